@@ -1,0 +1,155 @@
+/* ramscb_gpu.h -- C ABI of the B200-native RAM-SCB hot-path library
+ * (libramscb_gpu.so, built from ramscb_b200/csrc/ for sm_100a).
+ *
+ * This is the drop-in boundary.  The reference (lanl/RAM-SCB) has no FFI for
+ * these routines: they are Fortran module procedures that take only the
+ * species index and read/write module globals.  Each entry point below
+ * replaces the body of one such procedure; the Fortran shim modules in
+ * ramscb_b200/fortran/ keep the reference's names/signatures and forward
+ * c_loc() of the module arrays here (binding style copied from the
+ * reference's only existing ISO_C_BINDING boundary, src/ModRamGSL.f90:10-71
+ * <-> src/RamGSL.c).  INTEGRATION.md shows the shim a maintainer would add.
+ *
+ * Conventions
+ *  - plain C, pointers + sizes only; every function returns 0 on success and
+ *    a non-zero rsg_status otherwise (rsg_last_error() gives the text);
+ *    nothing throws, nothing calls exit().
+ *  - all host arrays are Fortran column-major with the reference's shapes
+ *    (src/ModRamInit.f90:68-151); species index S is 1-based as in Fortran.
+ *  - host pointers are never retained beyond the call.
+ *  - calls with different S may be issued concurrently from different host
+ *    threads (the reference calls them from `!$OMP PARALLEL DO` over species,
+ *    src/ModRamRun.f90:64); calls with the same S are ordered by the caller.
+ *  - there is no CPU fallback: without a CUDA device every call fails with
+ *    RSG_ERR_CUDA.
+ */
+#ifndef RAMSCB_GPU_H
+#define RAMSCB_GPU_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rsg_ram rsg_ram; /* opaque RAM state (device mirrors + streams) */
+
+enum rsg_status {
+  RSG_OK = 0,
+  RSG_ERR_CUDA = 1,     /* CUDA runtime error (no device, launch failure, ...) */
+  RSG_ERR_ARG = 2,      /* bad argument (NULL, species out of range, ...)      */
+  RSG_ERR_STATE = 3,    /* call order violated (e.g. DRIFTR before DRIFTPARA)  */
+  RSG_ERR_UNSUPPORTED = 4
+};
+
+/* arithmetic mode of the sweep kernels */
+enum rsg_mode {
+  RSG_MODE_EXACT = 0, /* reference operation order, no FMA contraction: drift
+                         sweeps / WPADIF are bit-identical to the CPU oracle   */
+  RSG_MODE_FAST = 1   /* separable coefficients a+w(K)*b, FMA, division-free
+                         limiter: same maths, results within ~1e-14 relative   */
+};
+
+/* species kinds: select the charge-exchange cross-section polynomial
+ * (src/ModRamLoss.f90:39-83) and the WPADIF coefficient pair (:677-685) */
+enum rsg_kind { RSG_KIND_H = 0, RSG_KIND_O = 1, RSG_KIND_HE = 2, RSG_KIND_E = 3 };
+
+/* flags of rsg_ram_run (src/ModRamParams.f90: DoUseWPI, DoUseCoulomb, DoUseEMIC) */
+enum { RSG_F_WPI = 1, RSG_F_COULOMB = 2, RSG_F_EMIC = 4 };
+
+const char* rsg_last_error(void);
+int rsg_device_count(void);
+/* name/SM count/L2 bytes of the current device; any pointer may be NULL */
+int rsg_device_info(char* name, int name_len, int* sm_count, long long* l2_bytes, long long* hbm_bytes);
+
+/* ---- life cycle ----------------------------------------------------------
+ * replaces ram_allocate / ram_deallocate for the device mirrors
+ * (src/ModRamInit.f90:13-154).  device < 0 keeps the current device. */
+int rsg_ram_create(rsg_ram** out, int nS, int NR, int NT, int NE, int NPA, int device);
+int rsg_ram_destroy(rsg_ram* h);
+int rsg_ram_set_mode(rsg_ram* h, int mode);
+/* run every species on `stream` (a cudaStream_t) instead of the library's own
+ * per-species streams; NULL restores the default.  Lets a host framework time
+ * the work with its own events. */
+int rsg_ram_set_stream(rsg_ram* h, void* stream);
+int rsg_ram_sync(rsg_ram* h);
+
+/* ---- static data ----------------------------------------------------------
+ * 1-D grids and per-species tables built by ARRAYS (src/ModRamInit.f90:364-587)
+ * RLZ(NR+1) LZ(NR+1) EKEV,WE,DE,EBND(NE) MU,WMU,DMU(NPA) UPA(NR)
+ * GREL,GRBND,V,VBND,EPP,ERNH(nS,NE) RMAS(nS) FFACTOR(nS,NR,NE,NPA)
+ * QS(nS)=species%s_charge, kind(nS)=rsg_kind, khi(5)=ANISCH band edges
+ * (src/ModRamRun.f90:303,322). */
+int rsg_ram_set_grids(rsg_ram* h, const double* RLZ, const double* LZ, const double* EKEV, const double* WE,
+                      const double* DE, const double* EBND, const double* MU, const double* WMU, const double* DMU,
+                      const double* UPA, const double* GREL, const double* GRBND, const double* V,
+                      const double* VBND, const double* EPP, const double* ERNH, const double* RMAS,
+                      const double* FFACTOR, const int* QS, const int* kind, const int* khi, double MDR,
+                      double DPHI, double CONF1, double CONF2, double BetaLim, double FracCFL);
+
+/* field-geometry arrays written by computehI (src/ModRamScb.f90:568-626):
+ * BNES,dBdt(NR+1,NT); FNHS,FNIS,BOUNHS,BOUNIS,HDNS,dIdt,dIbndt(NR+1,NT,NPA);
+ * outsideMGNP(NR,NT) integer. */
+int rsg_ram_set_fields(rsg_ram* h, const double* BNES, const double* dBdt, const double* FNHS, const double* FNIS,
+                       const double* BOUNHS, const double* BOUNIS, const double* HDNS, const double* dIdt,
+                       const double* dIbndt, const int* outsideMGNP);
+/* VT,EIR,EIP(NR+1,NT): src/ModRamRun.f90:45-54, src/ModRamEField.f90 */
+int rsg_ram_set_efield(rsg_ram* h, const double* VT, const double* EIR, const double* EIP);
+/* FGEOS(nS,NT,NE,NPA): src/ModRamBoundary.f90 (GEOSB) */
+int rsg_ram_set_boundary(rsg_ram* h, const double* FGEOS);
+/* WALOS1/2/3(NR,NE) (WAVEPARA1/2, src/ModRamWPI.f90:18-182), Kp, Kpmax12 */
+int rsg_ram_set_wavelo(rsg_ram* h, const double* WALOS1, const double* WALOS2, const double* WALOS3, double Kp,
+                       double Kpmax12);
+/* NECR(NR,NT) plasmaspheric density (Coulomb operators) */
+int rsg_ram_set_plasmasphere(rsg_ram* h, const double* NECR);
+/* pitch-angle diffusion coefficients (NR,NT,NE,NPA), src/ModRamRun.f90:422-605:
+ * which = 0 ATAW, 1 ATAC, 2 ATAW_emic_h, 3 ATAW_emic_he */
+int rsg_ram_set_diffcoef(rsg_ram* h, int which, const double* D);
+
+/* ---- phase-space density ---------------------------------------------------
+ * F2(nS,NR,NT,NE,NPA), species fastest (src/ModRamInit.f90:72).  S = 0 moves
+ * all species, S >= 1 one species (the host array is always the full one). */
+int rsg_ram_f2_h2d(rsg_ram* h, const double* F2, int S);
+int rsg_ram_f2_d2h(rsg_ram* h, double* F2, int S);
+/* device pointer of species S's block, layout [NPA][NE][Pp] with the (NT,NR)
+ * plane padded to Pp doubles (for NCCL plumbing and tests). */
+int rsg_ram_f2_device(rsg_ram* h, int S, void** ptr, long long* n_doubles, int* Pp);
+
+/* ---- operators: one per reference subroutine -------------------------------
+ * ModRamDrift (src/ModRamDrift.f90) */
+int rsg_driftpara(rsg_ram* h, int S, double DTs); /* :36-88   */
+int rsg_driftr(rsg_ram* h, int S);                /* :95-198  */
+int rsg_driftp(rsg_ram* h, int S);                /* :204-279 */
+int rsg_drifte(rsg_ram* h, int S);                /* :285-376 */
+int rsg_driftmu(rsg_ram* h, int S);               /* :382-473 */
+int rsg_driftend(rsg_ram* h);                     /* :23-30 (no-op: scratch is persistent) */
+/* DtDriftR/P/E/Mu(S) after the sweeps (synchronises species S) */
+int rsg_get_dtdrift(rsg_ram* h, int S, double out4[4]);
+/* ModRamLoss (src/ModRamLoss.f90) */
+int rsg_cepara(rsg_ram* h, int S, double DTs); /* :19-170  */
+int rsg_charexchange(rsg_ram* h, int S);       /* :457-478 */
+int rsg_atmol(rsg_ram* h, int S);              /* :485-507 */
+/* ModRamWPI (src/ModRamWPI.f90) */
+int rsg_wavelo(rsg_ram* h, int S, double DTs);                       /* :580-636 */
+int rsg_wpadif(rsg_ram* h, int S, double DTs, long long* nviolation); /* :643-714; nviolation may be NULL */
+/* ModRamCoul (src/ModRamCoul.f90) */
+int rsg_coulpara(rsg_ram* h, int S, double DTs); /* :17-125  */
+int rsg_coulen(rsg_ram* h, int S);               /* :133-221 */
+int rsg_coulmu(rsg_ram* h, int S, double T);     /* :229-296 */
+/* ModRamRun (src/ModRamRun.f90) */
+int rsg_sumrc(rsg_ram* h, int S, double* setrc, double* elorc);          /* :231-259 */
+int rsg_anisch(rsg_ram* h, int S, double* PPERT_S, double* PPART_S);     /* :343-415; (NR,NT) slices of species S */
+/* The whole species loop of ram_run plus its epilogue (:64-222) in one call,
+ * F2 resident on the device.  Outputs (any may be NULL): DtDrift(4,nS)
+ * [R,P,E,Mu fastest], losses(6,nS) = increments of LSDR,LSCHA,LSATM,LSWAE,
+ * LSCOE,LSCSC; SETRC(nS); PPERT,PPART(nS,NR,NT).  Returns DtsNext in *dts_next. */
+int rsg_ram_run(rsg_ram* h, double DTs, double DtsMin, double T, int flags, double* dts_next, double* DtDrift,
+                double* losses, double* SETRC, double* PPERT, double* PPART);
+/* FLUX = F2/FFACTOR/FNHS (src/ModRamRun.f90:210-221), host array like F2 */
+int rsg_ram_flux_d2h(rsg_ram* h, double* FLUX);
+
+/* number of kernel launches issued through this handle since creation */
+long long rsg_ram_launch_count(rsg_ram* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAMSCB_GPU_H */

@@ -1,0 +1,148 @@
+"""ctypes front-end of the CPU oracle (TEST INFRASTRUCTURE -- see the header of
+oracle/ram_oracle.cpp).  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs may import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_BUILD = os.path.join(_HERE, "_build")
+
+F_WPI, F_COULOMB, F_EMIC = 1, 2, 4
+
+
+def build(force: bool = False) -> None:
+    """Compile the oracle libraries (g++, a few seconds)."""
+    cmd = ["make", "-C", _HERE, "-s"] + (["-B"] if force else [])
+    subprocess.run(cmd, check=True)
+
+
+def _load(name):
+    path = os.path.join(_BUILD, name)
+    if not os.path.exists(path):
+        build()
+    return C.CDLL(path)
+
+
+_ram = None
+
+
+def ram_lib():
+    global _ram
+    if _ram is None:
+        lib = _load("libram_oracle.so")
+        lib.orc_create.restype = C.c_void_p
+        lib.orc_create.argtypes = [C.c_int] * 5
+        lib.orc_destroy.argtypes = [C.c_void_p]
+        lib.orc_set_array.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
+        lib.orc_set_iarray.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
+        lib.orc_set_scalar.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+        for f in ("driftpara", "driftr", "driftp", "drifte", "driftmu", "cepara", "charexchange", "atmol",
+                  "wavelo", "coulpara", "coulen", "coulmu", "sumrc", "anisch"):
+            fn = getattr(lib, "orc_" + f)
+            fn.argtypes = [C.c_void_p, C.c_int]
+            fn.restype = None
+        lib.orc_wpadif.argtypes = [C.c_void_p, C.c_int]
+        lib.orc_wpadif.restype = C.c_long
+        lib.orc_ram_run.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        lib.orc_ram_run.restype = C.c_double
+        lib.orc_get_cdrift.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        for f in ("gcoul", "funt", "funi"):
+            fn = getattr(lib, "orc_" + f)
+            fn.argtypes = [C.c_double]
+            fn.restype = C.c_double
+        lib.orc_max_threads.restype = C.c_int
+        _ram = lib
+    return _ram
+
+
+def _f(shape, dtype=np.float64):
+    return np.zeros(shape, dtype=dtype, order="F")
+
+
+class RamOracle:
+    """Holds one complete RAM state (reference layouts) and runs the restated
+    operators on it.  Species index S is 1-based, as in the reference."""
+
+    def __init__(self, g, inp, DTs=5.0):
+        self.lib = ram_lib()
+        self.g = g
+        nS, NR, NT, NE, NPA = g.nS, g.NR, g.NT, g.NE, g.NPA
+        self.h = self.lib.orc_create(nS, NR, NT, NE, NPA)
+        self.arr = {}
+        # grids
+        for name in ("LZ", "RLZ", "EKEV", "WE", "DE", "EBND", "MU", "WMU", "DMU", "UPA", "RMAS",
+                     "GREL", "GRBND", "V", "VBND", "EPP", "ERNH", "FFACTOR"):
+            self._set(name, np.asfortranarray(getattr(g, name), dtype=np.float64).copy(order="F"))
+        self._seti("QS", g.QS.copy())
+        self._seti("kind", g.kind.copy())
+        self._seti("khi", g.khi.copy())
+        # fields
+        for name in ("BNES", "dBdt", "VT", "EIR", "EIP", "FNHS", "FNIS", "BOUNHS", "BOUNIS", "HDNS", "dIdt",
+                     "dIbndt", "NECR", "FGEOS", "F2", "WALOS1", "WALOS2", "WALOS3"):
+            self._set(name, np.asfortranarray(getattr(inp, name), dtype=np.float64).copy(order="F"))
+        self._seti("outsideMGNP", np.asfortranarray(inp.outsideMGNP, dtype=np.int32).copy(order="F"))
+        # work / outputs
+        self._set("CHARGE", _f((nS, NR, NT, NE, NPA)))
+        self._set("FLUX", _f((nS, NR, NT, NE, NPA)))
+        self._set("ATLOS", _f((nS, NR, NE)))
+        for name in ("ATAW", "ATAC", "ATAW_emic_h", "ATAW_emic_he"):
+            self._set(name, _f((NR, NT, NE, NPA)))
+        for name in ("COULE", "COULI", "ATA", "GTA", "CEDR", "CIDR"):
+            self._set(name, _f((nS, NE, NPA)))
+        for name in ("DtDriftR", "DtDriftP", "DtDriftE", "DtDriftMu", "SETRC", "ELORC", "LSDR", "LSCHA", "LSATM",
+                     "LSWAE", "LSCOE", "LSCSC"):
+            self._set(name, _f((nS,)))
+        self._set("PPERT", _f((nS, NR, NT)))
+        self._set("PPART", _f((nS, NR, NT)))
+        for name, v in (("MDR", g.MDR), ("DPHI", g.DPHI), ("CONF1", g.CONF1), ("CONF2", g.CONF2),
+                        ("Kp", inp.Kp), ("Kpmax12", inp.Kpmax12), ("DTs", DTs)):
+            self.set_scalar(name, v)
+
+    def _set(self, name, a):
+        assert a.flags.f_contiguous and a.dtype == np.float64
+        self.arr[name] = a
+        self.lib.orc_set_array(self.h, name.encode(), a.ctypes.data)
+
+    def _seti(self, name, a):
+        assert a.dtype == np.int32
+        self.arr[name] = a
+        self.lib.orc_set_iarray(self.h, name.encode(), a.ctypes.data)
+
+    def set_scalar(self, name, v):
+        self.lib.orc_set_scalar(self.h, name.encode(), float(v))
+
+    def set_array(self, name, a):
+        """Replace the contents of a registered array."""
+        self.arr[name][...] = a
+
+    def __getattr__(self, name):
+        arr = self.__dict__.get("arr", {})
+        if name in arr:
+            return arr[name]
+        raise AttributeError(name)
+
+    def op(self, name, S):
+        return getattr(self.lib, "orc_" + name)(self.h, int(S))
+
+    def cdrift(self, S, which):
+        g = self.g
+        out = _f((g.NR, g.NT, g.NE, g.NPA))
+        self.lib.orc_get_cdrift(self.h, S, which, out.ctypes.data)
+        return out
+
+    def ram_run(self, flags=0, nthreads=None):
+        if nthreads is None:
+            nthreads = min(self.g.nS, self.lib.orc_max_threads())
+        return self.lib.orc_ram_run(self.h, flags, nthreads)
+
+    def __del__(self):
+        try:
+            self.lib.orc_destroy(self.h)
+        except Exception:
+            pass

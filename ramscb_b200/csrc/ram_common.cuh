@@ -1,0 +1,55 @@
+// Shared declarations of the RAM device library (sm_100a).
+//
+// Device data layout:
+//   F2dev[S][l][k][Pp]      species-major; the (MLT, R) plane (p = j*NR + i, R
+//                           fastest) is contiguous and padded to Pp (multiple of
+//                           16 doubles = 128 B); K (energy) next, L (pitch angle)
+//                           slowest.  All indices 0-based: I = i+1 etc.
+//   2-D fields  [j][i]      row length NR+1 (a raw copy of the Fortran array)
+//   3-D fields  [l][j][i]   row length NR+1 (raw copy)
+//   "plane" arrays [p] and [l][Pp]: coefficient pieces precomputed by the prep
+//                           kernels in the same p indexing as F2dev.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define RSG_MAX_SPECIES 8
+
+// everything a sweep kernel needs that is shared by all species
+struct RamDev {
+  int nS, NR, NT, NE, NPA, NR1, P, Pp;
+  double MDR, DPHI, CONF1, CONF2, BetaLim, FracCFL, DTs;
+  // 1-D grids
+  const double *RLZ, *EKEV, *WE, *DE, *MU, *WMU, *DMU;
+  const int* UPA;  // [NR] 1-based L index of the loss-cone edge
+  // raw fields
+  const double *BNES, *dBdt, *VT, *EIR, *EIP;                      // (NR+1,NT)
+  const double *FNHS, *FNIS, *BOUNHS, *BOUNIS, *HDNS, *dIdt, *dIbndt;  // (NR+1,NT,NPA)
+  const int* outside;                                              // (NR,NT)
+  // prep, 2-D planes [Pp]
+  double *CR, *sB, *pT1, *pT3, *sBp, *DRD1, *DPD1, *BNESc, *dBdt2, *RLZp;
+  unsigned char* outp;  // outsideMGNP per plane point
+  // prep, 3-D planes [NPA][Pp]
+  double *t1, *G, *sFp, *Gr, *Gp, *DRD2, *DPD2, *dBdt1, *dIdt1, *FNHSc;
+  double *CMUDOT, *Gmr, *Gmp, *DRM2, *DPM2, *dIbndt2, *BOUNHSc, *HDNSc;
+  // fast-mode separable coefficients [NPA][Pp]: c = gIK*(a + wK*b)
+  double *fRa, *fRb, *fPa, *fPb, *fEa, *fEb, *fMa, *fMb;
+};
+
+// per-species device tables (pointers into one buffer) + scalars
+struct SpecDev {
+  int S;            // 0-based species
+  int kind;
+  double QS;
+  double* F;        // species block of F2dev
+  const double* FGEOS;  // [l][k][j]
+  const double *P4, *eK, *epK, *aE, *sv;  // [NE]
+  const double *P2, *EDOT, *ATLOS;        // [NE][NR]
+  const double* aMU;                      // [NPA]
+  const double* FF;                       // FFACTOR [l][k][i]
+  const double* EPP;                      // [NE]
+  double GREL1, GREL2, sqrtA, GRZERO, sqrtB;  // DRIFTE ghost cells
+  double aRP;                             // FracCFL*DTs
+  double OMEt;                            // OME*DTs/DPHI
+  unsigned long long* dt;                 // [4] CFL minima as ordered bit patterns
+};

@@ -1,0 +1,977 @@
+// Host side of the RAM C ABI (include/ramscb_gpu.h): device mirrors, per-species
+// streams, small host tables (in the reference's operation order) and kernel
+// launches.  No CPU compute path exists here: without a CUDA device every entry
+// point fails with RSG_ERR_CUDA.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/ramscb_gpu.h"
+#include "ram_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CK(call)                                                                                      \
+  do {                                                                                                \
+    cudaError_t e_ = (call);                                                                          \
+    if (e_ != cudaSuccess)                                                                            \
+      return fail(RSG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" + \
+                                    std::to_string(__LINE__) + ")");                                  \
+  } while (0)
+#define CKL()                                                                                         \
+  do {                                                                                                \
+    cudaError_t e_ = cudaGetLastError();                                                              \
+    if (e_ != cudaSuccess)                                                                            \
+      return fail(RSG_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e_) + " (" __FILE__ ":" + \
+                                    std::to_string(__LINE__) + ")");                                  \
+  } while (0)
+#define RET(x)                   \
+  do {                           \
+    int r_ = (x);                \
+    if (r_ != RSG_OK) return r_; \
+  } while (0)
+
+constexpr double kQ = 1.602E-19, kCS = 2.998E8, kPI = 3.1415926535897932384626433832795;
+constexpr int NSUM = 16;  // moment slots per species
+
+struct Spec {
+  cudaStream_t own = nullptr;
+  cudaEvent_t ev = nullptr;
+  double DTs = -1.0;        // DTs of the last DRIFTPARA
+  double DTs_ce = -1.0;     // DTs of the last CEPARA
+  double DTs_wl = -1.0;     // DTs of the last WAVELO table
+  double setrc = 0.0;
+  // device tables
+  double* d_tab = nullptr;   // drift tables
+  double* h_tab = nullptr;   // pinned staging for d_tab
+  size_t n_tab = 0;
+  double* d_ce = nullptr;    // sv[NE], ATLOS[NE][NR]
+  double* h_ce = nullptr;
+  double* d_wfac = nullptr;  // [NE][Pp]
+  double* h_wfac = nullptr;
+  double* d_FF = nullptr;    // FFACTOR [l][k][i]
+  double* d_EPP = nullptr;   // [NE]
+  double* d_FGEOS = nullptr; // [l][k][j]
+  int* d_last = nullptr;     // DRIFTR inflow scan
+  double* d_part = nullptr;  // SUMRC partials
+  double* d_tE = nullptr;    // ANISCH scratch [NE][Pp] x2
+  double* d_pp = nullptr;    // ANISCH out [2][Pp]
+  // results
+  unsigned long long* d_res = nullptr;  // [4] dt bits, [4..4+NSUM) sums (as double), [4+NSUM] nviol
+  unsigned long long* h_res = nullptr;  // pinned
+  SpecDev sd{};
+};
+
+}  // namespace
+
+struct rsg_ram {
+  int nS, NR, NT, NE, NPA, NR1, P, Pp;
+  int device = 0, mode = RSG_MODE_EXACT;
+  bool grids_set = false, fields_set = false, efield_set = false;
+  double Kp = 0, Kpmax12 = 0;
+  std::vector<double> RLZ, LZ, EKEV, WE, DE, EBND, MU, WMU, DMU, UPA, GREL, GRBND, V, VBND, EPP, ERNH, RMAS;
+  std::vector<double> WALOS1, WALOS2, WALOS3;
+  std::vector<int> QS, kind, khi;
+  RamDev dev{};
+  std::vector<void*> allocs;
+  double* d_F2 = nullptr;
+  size_t specStride = 0;
+  double* d_stage = nullptr;  // host-layout image of F2 (nS*P*NE*NPA)
+  double* d_diff[4] = {nullptr, nullptr, nullptr, nullptr};
+  double* d_zero4 = nullptr;  // all-zero diffusion coefficient
+  double* d_NECR = nullptr;
+  double* d_dtinit = nullptr;
+  cudaStream_t ext = nullptr;   // user stream (rsg_ram_set_stream)
+  cudaStream_t prepst = nullptr;
+  cudaEvent_t prepev = nullptr;
+  double prep_DTs = -1.0;
+  bool step_dirty = true;       // e-field or fields changed since last k_prep_step
+  std::mutex mu;
+  Spec sp[RSG_MAX_SPECIES];
+  long long launches = 0;
+  int nblk_sum = 0;
+
+  cudaStream_t st(int s) { return ext ? ext : sp[s].own; }
+  cudaStream_t pst() { return ext ? ext : prepst; }
+  template <class T>
+  int dalloc(T** p, size_t n) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, n * sizeof(T));
+    if (e != cudaSuccess) return fail(RSG_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    e = cudaMemset(q, 0, n * sizeof(T));
+    if (e != cudaSuccess) return fail(RSG_ERR_CUDA, std::string("cudaMemset: ") + cudaGetErrorString(e));
+    allocs.push_back(q);
+    *p = (T*)q;
+    return RSG_OK;
+  }
+};
+
+namespace {
+
+inline int nblk(long long n, int b) { return (int)((n + b - 1) / b); }
+
+int check_S(rsg_ram* h, int S) {
+  if (!h) return fail(RSG_ERR_ARG, "null handle");
+  if (S < 1 || S > h->nS) return fail(RSG_ERR_ARG, "species index out of range");
+  return RSG_OK;
+}
+
+// upload helper: host -> device, synchronous w.r.t. the host buffer
+template <class T>
+int up(T* dst, const T* src, size_t n) {
+  CK(cudaMemcpy(dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+  return RSG_OK;
+}
+
+// (NR,NT,NE,NPA) Fortran array -> device [l][k][Pp]
+void to_planes4(const rsg_ram* h, const double* src, std::vector<double>& out) {
+  out.assign((size_t)h->NPA * h->NE * h->Pp, 0.0);
+  for (int l = 0; l < h->NPA; ++l)
+    for (int k = 0; k < h->NE; ++k)
+      std::memcpy(&out[((size_t)l * h->NE + k) * h->Pp], &src[((size_t)l * h->NE + k) * h->P], sizeof(double) * h->P);
+}
+
+int ensure_step(rsg_ram* h, double DTs) {
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (!h->step_dirty && h->prep_DTs == DTs) return RSG_OK;
+  if (!h->fields_set || !h->efield_set) return fail(RSG_ERR_STATE, "DRIFTPARA before set_fields/set_efield");
+  cudaStream_t ps = h->pst();
+  if (!h->ext)
+    for (int s = 0; s < h->nS; ++s) {
+      CK(cudaEventRecord(h->sp[s].ev, h->sp[s].own));
+      CK(cudaStreamWaitEvent(ps, h->sp[s].ev, 0));
+    }
+  RamDev dv = h->dev;
+  dv.DTs = DTs;
+  k_prep_step<<<nblk((long long)h->NPA * h->Pp, 256), 256, 0, ps>>>(dv);
+  CKL();
+  h->launches++;
+  if (!h->ext) {
+    CK(cudaEventRecord(h->prepev, ps));
+    for (int s = 0; s < h->nS; ++s) CK(cudaStreamWaitEvent(h->sp[s].own, h->prepev, 0));
+  }
+  h->prep_DTs = DTs;
+  h->step_dirty = false;
+  return RSG_OK;
+}
+
+RamDev devfor(rsg_ram* h, int s) {
+  RamDev dv = h->dev;
+  dv.DTs = h->sp[s].DTs;
+  return dv;
+}
+
+int launch_sumrc(rsg_ram* h, int s, int slot) {
+  Spec& sp = h->sp[s];
+  RamDev dv = devfor(h, s);
+  k_sumrc_partial<<<h->nblk_sum, 256, 0, h->st(s)>>>(dv, sp.sd, sp.d_part);
+  CKL();
+  k_sum_final<<<1, 256, 0, h->st(s)>>>(sp.d_part, h->nblk_sum, (double*)(sp.d_res + 4 + slot));
+  CKL();
+  h->launches += 2;
+  return RSG_OK;
+}
+
+int fetch_res(rsg_ram* h, int s) {
+  Spec& sp = h->sp[s];
+  CK(cudaMemcpyAsync(sp.h_res, sp.d_res, sizeof(unsigned long long) * (4 + NSUM + 1), cudaMemcpyDeviceToHost, h->st(s)));
+  CK(cudaStreamSynchronize(h->st(s)));
+  return RSG_OK;
+}
+
+// DtDrift* start values (:115,223,308,404) live in a device constant buffer so
+// the reset is a stream-ordered D2D copy
+int reset_dt(rsg_ram* h, int s, int which) {
+  CK(cudaMemcpyAsync(h->sp[s].d_res + which, h->d_dtinit + which, 8, cudaMemcpyDeviceToDevice, h->st(s)));
+  return RSG_OK;
+}
+
+}  // namespace
+
+// =============================================================================
+extern "C" {
+
+const char* rsg_last_error(void) { return g_err.c_str(); }
+
+int rsg_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int rsg_device_info(char* name, int name_len, int* sm_count, long long* l2_bytes, long long* hbm_bytes) {
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  CK(cudaGetDeviceProperties(&p, dev));
+  if (name && name_len > 0) {
+    std::strncpy(name, p.name, name_len - 1);
+    name[name_len - 1] = 0;
+  }
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (l2_bytes) *l2_bytes = p.l2CacheSize;
+  if (hbm_bytes) *hbm_bytes = (long long)p.totalGlobalMem;
+  return RSG_OK;
+}
+
+int rsg_ram_create(rsg_ram** out, int nS, int NR, int NT, int NE, int NPA, int device) {
+  if (!out) return fail(RSG_ERR_ARG, "null out");
+  if (nS < 1 || nS > RSG_MAX_SPECIES || NR < 4 || NT < 4 || NE < 4 || NPA < 6) return fail(RSG_ERR_ARG, "bad dimensions");
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (ndev < 1) return fail(RSG_ERR_CUDA, "no CUDA device");
+  if (device >= 0) CK(cudaSetDevice(device));
+  rsg_ram* h = new rsg_ram();
+  CK(cudaGetDevice(&h->device));
+  h->nS = nS; h->NR = NR; h->NT = NT; h->NE = NE; h->NPA = NPA;
+  h->NR1 = NR + 1;
+  h->P = NR * NT;
+  h->Pp = (h->P + 15) / 16 * 16;
+  RamDev& d = h->dev;
+  d.nS = nS; d.NR = NR; d.NT = NT; d.NE = NE; d.NPA = NPA; d.NR1 = h->NR1; d.P = h->P; d.Pp = h->Pp;
+  const size_t n2 = (size_t)h->NR1 * NT, n3 = n2 * NPA, np = h->Pp, n3p = (size_t)NPA * h->Pp;
+  double** g1[] = {(double**)&d.RLZ, (double**)&d.EKEV, (double**)&d.WE, (double**)&d.DE, (double**)&d.MU, (double**)&d.WMU, (double**)&d.DMU};
+  const size_t g1n[] = {(size_t)NR + 1, (size_t)NE, (size_t)NE, (size_t)NE, (size_t)NPA, (size_t)NPA, (size_t)NPA};
+  for (int q = 0; q < 7; ++q) RET(h->dalloc(g1[q], g1n[q]));
+  RET(h->dalloc((int**)&d.UPA, NR));
+  double** f2d[] = {(double**)&d.BNES, (double**)&d.dBdt, (double**)&d.VT, (double**)&d.EIR, (double**)&d.EIP};
+  for (auto p : f2d) RET(h->dalloc(p, n2));
+  double** f3d[] = {(double**)&d.FNHS, (double**)&d.FNIS, (double**)&d.BOUNHS, (double**)&d.BOUNIS, (double**)&d.HDNS, (double**)&d.dIdt, (double**)&d.dIbndt};
+  for (auto p : f3d) RET(h->dalloc(p, n3));
+  RET(h->dalloc((int**)&d.outside, (size_t)NR * NT));
+  double** p2d[] = {&d.CR, &d.sB, &d.pT1, &d.pT3, &d.sBp, &d.DRD1, &d.DPD1, &d.BNESc, &d.dBdt2, &d.RLZp};
+  for (auto p : p2d) RET(h->dalloc(p, np));
+  RET(h->dalloc(&d.outp, np));
+  double** p3d[] = {&d.t1, &d.G, &d.sFp, &d.Gr, &d.Gp, &d.DRD2, &d.DPD2, &d.dBdt1, &d.dIdt1, &d.FNHSc,
+                    &d.CMUDOT, &d.Gmr, &d.Gmp, &d.DRM2, &d.DPM2, &d.dIbndt2, &d.BOUNHSc, &d.HDNSc};
+  for (auto p : p3d) RET(h->dalloc(p, n3p));
+  h->specStride = (size_t)NPA * NE * h->Pp;
+  RET(h->dalloc(&h->d_F2, h->specStride * nS));
+  RET(h->dalloc(&h->d_stage, (size_t)nS * h->P * NE * NPA));
+  RET(h->dalloc(&h->d_zero4, h->specStride));
+  RET(h->dalloc(&h->d_NECR, (size_t)NR * NT));
+  RET(h->dalloc(&h->d_dtinit, 4));
+  {
+    const double init[4] = {100000.0, 100000.0, 10000.0, 10000.0};
+    RET(up(h->d_dtinit, init, 4));
+  }
+  CK(cudaStreamCreateWithFlags(&h->prepst, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&h->prepev, cudaEventDisableTiming));
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+  h->nblk_sum = sms * 4;
+  for (int s = 0; s < nS; ++s) {
+    Spec& sp = h->sp[s];
+    CK(cudaStreamCreateWithFlags(&sp.own, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&sp.ev, cudaEventDisableTiming));
+    sp.n_tab = (size_t)NE * 5 + (size_t)NE * NR * 2 + NPA;
+    RET(h->dalloc(&sp.d_tab, sp.n_tab));
+    CK(cudaMallocHost((void**)&sp.h_tab, sp.n_tab * sizeof(double)));
+    RET(h->dalloc(&sp.d_ce, (size_t)NE + (size_t)NE * NR));
+    CK(cudaMallocHost((void**)&sp.h_ce, ((size_t)NE + (size_t)NE * NR) * sizeof(double)));
+    RET(h->dalloc(&sp.d_wfac, (size_t)NE * h->Pp));
+    CK(cudaMallocHost((void**)&sp.h_wfac, (size_t)NE * h->Pp * sizeof(double)));
+    RET(h->dalloc(&sp.d_FF, (size_t)NPA * NE * NR));
+    RET(h->dalloc(&sp.d_EPP, (size_t)NE));
+    RET(h->dalloc(&sp.d_FGEOS, (size_t)NPA * NE * NT));
+    RET(h->dalloc(&sp.d_last, (size_t)NE * NPA * NT));
+    RET(h->dalloc(&sp.d_part, (size_t)h->nblk_sum));
+    RET(h->dalloc(&sp.d_tE, (size_t)2 * NE * h->Pp));
+    RET(h->dalloc(&sp.d_pp, (size_t)2 * h->Pp));
+    RET(h->dalloc(&sp.d_res, (size_t)4 + NSUM + 1));
+    CK(cudaMallocHost((void**)&sp.h_res, (4 + NSUM + 1) * sizeof(unsigned long long)));
+    SpecDev& sd = sp.sd;
+    sd.S = s;
+    sd.F = h->d_F2 + h->specStride * s;
+    sd.FGEOS = sp.d_FGEOS;
+    double* t = sp.d_tab;
+    sd.P4 = t; t += NE;
+    sd.eK = t; t += NE;
+    sd.epK = t; t += NE;
+    sd.aE = t; t += NE;
+    sd.sv = sp.d_ce;
+    sd.ATLOS = sp.d_ce + NE;
+    sd.P2 = t; t += (size_t)NE * NR;
+    sd.EDOT = t; t += (size_t)NE * NR;
+    sd.aMU = t; t += NPA;
+    sd.FF = sp.d_FF;
+    sd.EPP = sp.d_EPP;
+    sd.dt = sp.d_res;
+  }
+  *out = h;
+  return RSG_OK;
+}
+
+int rsg_ram_destroy(rsg_ram* h) {
+  if (!h) return RSG_OK;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (void* p : h->allocs) cudaFree(p);
+  for (int s = 0; s < h->nS; ++s) {
+    Spec& sp = h->sp[s];
+    if (sp.own) cudaStreamDestroy(sp.own);
+    if (sp.ev) cudaEventDestroy(sp.ev);
+    if (sp.h_tab) cudaFreeHost(sp.h_tab);
+    if (sp.h_ce) cudaFreeHost(sp.h_ce);
+    if (sp.h_wfac) cudaFreeHost(sp.h_wfac);
+    if (sp.h_res) cudaFreeHost(sp.h_res);
+  }
+  if (h->prepst) cudaStreamDestroy(h->prepst);
+  if (h->prepev) cudaEventDestroy(h->prepev);
+  delete h;
+  return RSG_OK;
+}
+
+int rsg_ram_set_mode(rsg_ram* h, int mode) {
+  if (!h) return fail(RSG_ERR_ARG, "null handle");
+  if (mode != RSG_MODE_EXACT) return fail(RSG_ERR_UNSUPPORTED, "only RSG_MODE_EXACT is implemented");
+  h->mode = mode;
+  return RSG_OK;
+}
+
+int rsg_ram_set_stream(rsg_ram* h, void* stream) {
+  if (!h) return fail(RSG_ERR_ARG, "null handle");
+  CK(cudaDeviceSynchronize());
+  h->ext = (cudaStream_t)stream;
+  return RSG_OK;
+}
+
+int rsg_ram_sync(rsg_ram* h) {
+  if (!h) return fail(RSG_ERR_ARG, "null handle");
+  if (h->ext) CK(cudaStreamSynchronize(h->ext));
+  for (int s = 0; s < h->nS; ++s) CK(cudaStreamSynchronize(h->sp[s].own));
+  CK(cudaStreamSynchronize(h->prepst));
+  return RSG_OK;
+}
+
+int rsg_ram_set_grids(rsg_ram* h, const double* RLZ, const double* LZ, const double* EKEV, const double* WE,
+                      const double* DE, const double* EBND, const double* MU, const double* WMU, const double* DMU,
+                      const double* UPA, const double* GREL, const double* GRBND, const double* V,
+                      const double* VBND, const double* EPP, const double* ERNH, const double* RMAS,
+                      const double* FFACTOR, const int* QS, const int* kind, const int* khi, double MDR,
+                      double DPHI, double CONF1, double CONF2, double BetaLim, double FracCFL) {
+  if (!h) return fail(RSG_ERR_ARG, "null handle");
+  if (!RLZ || !LZ || !EKEV || !WE || !DE || !EBND || !MU || !WMU || !DMU || !UPA || !GREL || !GRBND || !V || !VBND || !EPP ||
+      !ERNH || !RMAS || !FFACTOR || !QS || !kind || !khi)
+    return fail(RSG_ERR_ARG, "null grid pointer");
+  CK(cudaSetDevice(h->device));
+  RET(rsg_ram_sync(h));
+  const int nS = h->nS, NR = h->NR, NE = h->NE, NPA = h->NPA;
+  h->RLZ.assign(RLZ, RLZ + NR + 1); h->LZ.assign(LZ, LZ + NR + 1);
+  h->EKEV.assign(EKEV, EKEV + NE); h->WE.assign(WE, WE + NE); h->DE.assign(DE, DE + NE); h->EBND.assign(EBND, EBND + NE);
+  h->MU.assign(MU, MU + NPA); h->WMU.assign(WMU, WMU + NPA); h->DMU.assign(DMU, DMU + NPA);
+  h->UPA.assign(UPA, UPA + NR);
+  h->GREL.assign(GREL, GREL + (size_t)nS * NE); h->GRBND.assign(GRBND, GRBND + (size_t)nS * NE);
+  h->V.assign(V, V + (size_t)nS * NE); h->VBND.assign(VBND, VBND + (size_t)nS * NE);
+  h->EPP.assign(EPP, EPP + (size_t)nS * NE); h->ERNH.assign(ERNH, ERNH + (size_t)nS * NE);
+  h->RMAS.assign(RMAS, RMAS + nS);
+  h->QS.assign(QS, QS + nS); h->kind.assign(kind, kind + nS); h->khi.assign(khi, khi + 5);
+  RamDev& d = h->dev;
+  d.MDR = MDR; d.DPHI = DPHI; d.CONF1 = CONF1; d.CONF2 = CONF2; d.BetaLim = BetaLim; d.FracCFL = FracCFL;
+  RET(up((double*)d.RLZ, RLZ, NR + 1)); RET(up((double*)d.EKEV, EKEV, NE)); RET(up((double*)d.WE, WE, NE));
+  RET(up((double*)d.DE, DE, NE)); RET(up((double*)d.MU, MU, NPA)); RET(up((double*)d.WMU, WMU, NPA));
+  RET(up((double*)d.DMU, DMU, NPA));
+  std::vector<int> upa(NR);
+  for (int i = 0; i < NR; ++i) upa[i] = (int)UPA[i];
+  RET(up((int*)d.UPA, upa.data(), NR));
+  std::vector<double> ff((size_t)NPA * NE * NR), epp(NE);
+  for (int s = 0; s < nS; ++s) {
+    for (int l = 0; l < NPA; ++l)
+      for (int k = 0; k < NE; ++k)
+        for (int i = 0; i < NR; ++i)
+          ff[((size_t)l * NE + k) * NR + i] = FFACTOR[s + (size_t)nS * (i + (size_t)NR * (k + (size_t)NE * l))];
+    RET(up(h->sp[s].d_FF, ff.data(), ff.size()));
+    for (int k = 0; k < NE; ++k) epp[k] = EPP[s + (size_t)nS * k];
+    RET(up(h->sp[s].d_EPP, epp.data(), NE));
+    h->sp[s].sd.kind = kind[s];
+    h->sp[s].sd.QS = (double)QS[s];
+    h->sp[s].DTs = h->sp[s].DTs_ce = h->sp[s].DTs_wl = -1.0;
+  }
+  h->grids_set = true;
+  h->step_dirty = true;
+  return RSG_OK;
+}
+
+int rsg_ram_set_fields(rsg_ram* h, const double* BNES, const double* dBdt, const double* FNHS, const double* FNIS,
+                       const double* BOUNHS, const double* BOUNIS, const double* HDNS, const double* dIdt,
+                       const double* dIbndt, const int* outsideMGNP) {
+  if (!h) return fail(RSG_ERR_ARG, "null handle");
+  if (!BNES || !dBdt || !FNHS || !FNIS || !BOUNHS || !BOUNIS || !HDNS || !dIdt || !dIbndt || !outsideMGNP)
+    return fail(RSG_ERR_ARG, "null field pointer");
+  if (!h->grids_set) return fail(RSG_ERR_STATE, "set_fields before set_grids");
+  CK(cudaSetDevice(h->device));
+  RET(rsg_ram_sync(h));
+  RamDev& d = h->dev;
+  const size_t n2 = (size_t)h->NR1 * h->NT, n3 = n2 * h->NPA;
+  RET(up((double*)d.BNES, BNES, n2)); RET(up((double*)d.dBdt, dBdt, n2));
+  RET(up((double*)d.FNHS, FNHS, n3)); RET(up((double*)d.FNIS, FNIS, n3)); RET(up((double*)d.BOUNHS, BOUNHS, n3));
+  RET(up((double*)d.BOUNIS, BOUNIS, n3)); RET(up((double*)d.HDNS, HDNS, n3)); RET(up((double*)d.dIdt, dIdt, n3));
+  RET(up((double*)d.dIbndt, dIbndt, n3));
+  RET(up((int*)d.outside, outsideMGNP, (size_t)h->NR * h->NT));
+  k_prep_fields<<<nblk((long long)h->NPA * h->Pp, 256), 256, 0, h->pst()>>>(d);
+  CKL();
+  h->launches++;
+  CK(cudaStreamSynchronize(h->pst()));
+  h->fields_set = true;
+  h->step_dirty = true;
+  return RSG_OK;
+}
+
+int rsg_ram_set_efield(rsg_ram* h, const double* VT, const double* EIR, const double* EIP) {
+  if (!h) return fail(RSG_ERR_ARG, "null handle");
+  if (!VT || !EIR || !EIP) return fail(RSG_ERR_ARG, "null e-field pointer");
+  CK(cudaSetDevice(h->device));
+  RET(rsg_ram_sync(h));
+  const size_t n2 = (size_t)h->NR1 * h->NT;
+  RET(up((double*)h->dev.VT, VT, n2)); RET(up((double*)h->dev.EIR, EIR, n2)); RET(up((double*)h->dev.EIP, EIP, n2));
+  h->efield_set = true;
+  h->step_dirty = true;
+  return RSG_OK;
+}
+
+int rsg_ram_set_boundary(rsg_ram* h, const double* FGEOS) {
+  if (!h || !FGEOS) return fail(RSG_ERR_ARG, "null argument");
+  CK(cudaSetDevice(h->device));
+  RET(rsg_ram_sync(h));
+  const int nS = h->nS, NT = h->NT, NE = h->NE, NPA = h->NPA;
+  std::vector<double> b((size_t)NPA * NE * NT);
+  for (int s = 0; s < nS; ++s) {
+    for (int l = 0; l < NPA; ++l)
+      for (int k = 0; k < NE; ++k)
+        for (int j = 0; j < NT; ++j) b[((size_t)l * NE + k) * NT + j] = FGEOS[s + (size_t)nS * (j + (size_t)NT * (k + (size_t)NE * l))];
+    RET(up(h->sp[s].d_FGEOS, b.data(), b.size()));
+  }
+  return RSG_OK;
+}
+
+int rsg_ram_set_wavelo(rsg_ram* h, const double* W1, const double* W2, const double* W3, double Kp, double Kpmax12) {
+  if (!h || !W1 || !W2 || !W3) return fail(RSG_ERR_ARG, "null argument");
+  const size_t n = (size_t)h->NR * h->NE;
+  h->WALOS1.assign(W1, W1 + n); h->WALOS2.assign(W2, W2 + n); h->WALOS3.assign(W3, W3 + n);
+  h->Kp = Kp; h->Kpmax12 = Kpmax12;
+  for (int s = 0; s < h->nS; ++s) h->sp[s].DTs_wl = -1.0;
+  return RSG_OK;
+}
+
+int rsg_ram_set_plasmasphere(rsg_ram* h, const double* NECR) {
+  if (!h || !NECR) return fail(RSG_ERR_ARG, "null argument");
+  CK(cudaSetDevice(h->device));
+  RET(rsg_ram_sync(h));
+  RET(up(h->d_NECR, NECR, (size_t)h->NR * h->NT));
+  return RSG_OK;
+}
+
+int rsg_ram_set_diffcoef(rsg_ram* h, int which, const double* D) {
+  if (!h || !D) return fail(RSG_ERR_ARG, "null argument");
+  if (which < 0 || which > 3) return fail(RSG_ERR_ARG, "which must be 0..3");
+  CK(cudaSetDevice(h->device));
+  RET(rsg_ram_sync(h));
+  if (!h->d_diff[which]) RET(h->dalloc(&h->d_diff[which], h->specStride));
+  std::vector<double> b;
+  to_planes4(h, D, b);
+  RET(up(h->d_diff[which], b.data(), b.size()));
+  return RSG_OK;
+}
+
+// ---- F2 transfers -------------------------------------------------------------
+int rsg_ram_f2_h2d(rsg_ram* h, const double* F2, int S) {
+  if (!h || !F2) return fail(RSG_ERR_ARG, "null argument");
+  if (S < 0 || S > h->nS) return fail(RSG_ERR_ARG, "species index out of range");
+  CK(cudaSetDevice(h->device));
+  const size_t n = (size_t)h->nS * h->P * h->NE * h->NPA;
+  cudaStream_t st = h->st(S ? S - 1 : 0);
+  if (!h->ext && S == 0)
+    for (int s = 1; s < h->nS; ++s) CK(cudaStreamSynchronize(h->sp[s].own));
+  CK(cudaMemcpyAsync(h->d_stage, F2, n * sizeof(double), cudaMemcpyHostToDevice, st));
+  const long long ne = (long long)h->specStride;
+  for (int s = 0; s < h->nS; ++s) {
+    if (S != 0 && s != S - 1) continue;
+    k_f2_from_host<<<nblk(ne, 256), 256, 0, st>>>(h->dev, h->d_stage, h->d_F2 + h->specStride * s, s);
+    CKL();
+    h->launches++;
+  }
+  CK(cudaStreamSynchronize(st));
+  return RSG_OK;
+}
+
+int rsg_ram_f2_d2h(rsg_ram* h, double* F2, int S) {
+  if (!h || !F2) return fail(RSG_ERR_ARG, "null argument");
+  if (S < 0 || S > h->nS) return fail(RSG_ERR_ARG, "species index out of range");
+  CK(cudaSetDevice(h->device));
+  const size_t n = (size_t)h->nS * h->P * h->NE * h->NPA;
+  if (S == 0) RET(rsg_ram_sync(h));
+  cudaStream_t st = h->st(S ? S - 1 : 0);
+  const long long ne = (long long)h->specStride;
+  if (S != 0) {
+    // keep the other species' host values: start from the host image
+    CK(cudaMemcpyAsync(h->d_stage, F2, n * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
+  for (int s = 0; s < h->nS; ++s) {
+    if (S != 0 && s != S - 1) continue;
+    k_f2_to_host<<<nblk(ne, 256), 256, 0, st>>>(h->dev, h->d_stage, h->d_F2 + h->specStride * s, s);
+    CKL();
+    h->launches++;
+  }
+  CK(cudaMemcpyAsync(F2, h->d_stage, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return RSG_OK;
+}
+
+int rsg_ram_f2_device(rsg_ram* h, int S, void** ptr, long long* n_doubles, int* Pp) {
+  RET(check_S(h, S));
+  if (ptr) *ptr = h->d_F2 + h->specStride * (S - 1);
+  if (n_doubles) *n_doubles = (long long)h->specStride;
+  if (Pp) *Pp = h->Pp;
+  return RSG_OK;
+}
+
+// ---- ModRamDrift ----------------------------------------------------------------
+int rsg_driftpara(rsg_ram* h, int S, double DTs) {
+  RET(check_S(h, S));
+  if (!h->grids_set) return fail(RSG_ERR_STATE, "DRIFTPARA before set_grids");
+  CK(cudaSetDevice(h->device));
+  const int s = S - 1, nS = h->nS, NR = h->NR, NE = h->NE, NPA = h->NPA;
+  Spec& sp = h->sp[s];
+  RET(ensure_step(h, DTs));
+  // the previous contents of h_tab may still be in flight on the species stream
+  CK(cudaStreamSynchronize(h->st(s)));
+  const double MDR = h->dev.MDR, DPHI = h->dev.DPHI, FracCFL = h->dev.FracCFL;
+  const double QS = (double)h->QS[s];
+  double* t = sp.h_tab;
+  double *P4 = t, *eK = t + NE, *epK = t + 2 * NE, *aE = t + 3 * NE;
+  double* P2 = t + 4 * NE;
+  double* EDOT = P2 + (size_t)NE * NR;
+  double* aMU = EDOT + (size_t)NE * NR;
+#define GRELs(K) h->GREL[s + (size_t)nS * ((K)-1)]
+#define GRBNDs(K) h->GRBND[s + (size_t)nS * ((K)-1)]
+  for (int K = 1; K <= NE; ++K) {
+    // DRIFTR :131, DRIFTE :337 (energy-only prefix), DRIFTMU :424 (prefix)
+    P4[K - 1] = DTs * h->EKEV[K - 1] * 1000.0 * (GRELs(K) + 1) / GRELs(K) / DPHI / MDR / QS;
+    eK[K - 1] = h->EBND[K - 1] * 1e3 * (GRBNDs(K) + 1) / 2 / GRBNDs(K);
+    epK[K - 1] = h->EKEV[K - 1] * 1e3 * (GRELs(K) + 1) / 2 / GRELs(K);
+    aE[K - 1] = FracCFL * DTs * h->DE[K - 1];
+    for (int I = 1; I <= NR; ++I) {
+      // DRIFTPARA :71, :83
+      P2[(size_t)(K - 1) * NR + (I - 1)] =
+          DTs * h->EKEV[K - 1] * 1000 * (GRELs(K) + 1) / GRELs(K) / (h->RLZ[I - 1] * h->RLZ[I - 1]) / DPHI / QS;
+      EDOT[(size_t)(K - 1) * NR + (I - 1)] = h->EBND[K - 1] * DTs / h->RLZ[I - 1] * (GRBNDs(K) + 1) / GRBNDs(K) / 2.;
+    }
+  }
+  for (int L = 1; L <= NPA; ++L) aMU[L - 1] = FracCFL * DTs * h->DMU[L - 1];
+  CK(cudaMemcpyAsync(sp.d_tab, sp.h_tab, sp.n_tab * sizeof(double), cudaMemcpyHostToDevice, h->st(s)));
+  SpecDev& sd = sp.sd;
+  // DRIFTE :310-311, :334-335
+  const double EZERO = h->EKEV[0] - h->WE[0];
+  sd.GRZERO = 1. + EZERO * 1000. * kQ / h->RMAS[s] / kCS / kCS;
+  sd.GREL1 = GRELs(1);
+  sd.GREL2 = GRELs(2);
+  sd.sqrtA = std::sqrt((sd.GREL2 * sd.GREL2 - 1) / (sd.GREL1 * sd.GREL1 - 1));
+  sd.sqrtB = std::sqrt((sd.GREL1 * sd.GREL1 - 1) / (sd.GRZERO * sd.GRZERO - 1));
+  sd.aRP = FracCFL * DTs;
+  sd.OMEt = OME_EARTH * DTs / DPHI;
+  sp.DTs = DTs;
+  return RSG_OK;
+}
+
+int rsg_driftr(rsg_ram* h, int S) {
+  RET(check_S(h, S));
+  const int s = S - 1;
+  Spec& sp = h->sp[s];
+  if (sp.DTs < 0) return fail(RSG_ERR_STATE, "DRIFTR before DRIFTPARA");
+  CK(cudaSetDevice(h->device));
+  RamDev dv = devfor(h, s);
+  cudaStream_t st = h->st(s);
+  RET(reset_dt(h, s, 0));
+  const int nl = h->NE * h->NPA * h->NT;
+  k_driftr_inflow<<<nblk(nl, 256), 256, 0, st>>>(dv, sp.sd, sp.d_last);
+  CKL();
+  k_scan_last<<<1, 1024, 0, st>>>(sp.d_last, nl);
+  CKL();
+  // planes per CTA: fill ~256 threads, bounded by shared memory
+  const int NRc = h->NR | 1, NRf = (h->NR + 2) | 1;
+  int KC = std::max(1, 256 / h->NT);
+  size_t smem;
+  for (;;) {
+    smem = sizeof(double) * ((size_t)3 * h->NT * NRc + (size_t)KC * h->NT * NRf);
+    if (smem <= 96 * 1024 || KC == 1) break;
+    --KC;
+  }
+  if (smem > 220 * 1024) return fail(RSG_ERR_UNSUPPORTED, "DRIFTR: (NT,NR) plane too large for shared memory");
+  static thread_local size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    CK(cudaFuncSetAttribute(k_driftr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  const int threads = (KC * h->NT + 31) / 32 * 32;
+  dim3 grid((h->NE + KC - 1) / KC, h->NPA);
+  k_driftr<<<grid, threads, smem, st>>>(dv, sp.sd, sp.d_last, KC);
+  CKL();
+  h->launches += 3;
+  return RSG_OK;
+}
+
+int rsg_driftp(rsg_ram* h, int S) {
+  RET(check_S(h, S));
+  const int s = S - 1;
+  Spec& sp = h->sp[s];
+  if (sp.DTs < 0) return fail(RSG_ERR_STATE, "DRIFTP before DRIFTPARA");
+  CK(cudaSetDevice(h->device));
+  RET(reset_dt(h, s, 1));
+  k_driftp<<<nblk((long long)h->NPA * h->NE * h->NR, 128), 128, 0, h->st(s)>>>(devfor(h, s), sp.sd);
+  CKL();
+  h->launches++;
+  return RSG_OK;
+}
+
+int rsg_drifte(rsg_ram* h, int S) {
+  RET(check_S(h, S));
+  const int s = S - 1;
+  Spec& sp = h->sp[s];
+  if (sp.DTs < 0) return fail(RSG_ERR_STATE, "DRIFTE before DRIFTPARA");
+  CK(cudaSetDevice(h->device));
+  RET(reset_dt(h, s, 2));
+  k_drifte<<<nblk((long long)h->NPA * h->Pp, 128), 128, 0, h->st(s)>>>(devfor(h, s), sp.sd);
+  CKL();
+  h->launches++;
+  return RSG_OK;
+}
+
+int rsg_driftmu(rsg_ram* h, int S) {
+  RET(check_S(h, S));
+  const int s = S - 1;
+  Spec& sp = h->sp[s];
+  if (sp.DTs < 0) return fail(RSG_ERR_STATE, "DRIFTMU before DRIFTPARA");
+  CK(cudaSetDevice(h->device));
+  RET(reset_dt(h, s, 3));
+  k_driftmu<<<nblk((long long)h->NE * h->Pp, 128), 128, 0, h->st(s)>>>(devfor(h, s), sp.sd);
+  CKL();
+  h->launches++;
+  return RSG_OK;
+}
+
+int rsg_driftend(rsg_ram* h) {
+  if (!h) return fail(RSG_ERR_ARG, "null handle");
+  return RSG_OK;
+}
+
+int rsg_get_dtdrift(rsg_ram* h, int S, double out4[4]) {
+  RET(check_S(h, S));
+  if (!out4) return fail(RSG_ERR_ARG, "null out");
+  CK(cudaSetDevice(h->device));
+  RET(fetch_res(h, S - 1));
+  std::memcpy(out4, h->sp[S - 1].h_res, 4 * sizeof(double));
+  return RSG_OK;
+}
+
+// ---- ModRamLoss -------------------------------------------------------------------
+int rsg_cepara(rsg_ram* h, int S, double DTs) {
+  RET(check_S(h, S));
+  if (!h->grids_set) return fail(RSG_ERR_STATE, "CEPARA before set_grids");
+  CK(cudaSetDevice(h->device));
+  const int s = S - 1, nS = h->nS, NR = h->NR, NE = h->NE;
+  Spec& sp = h->sp[s];
+  CK(cudaStreamSynchronize(h->st(s)));
+  double* sv = sp.h_ce;
+  double* ATLOS = sp.h_ce + NE;
+  const int kind = h->kind[s];
+  for (int K = 1; K <= NE; ++K) {
+    const double Vk = h->V[s + (size_t)nS * (K - 1)];
+    double v = 0.0;
+    if (K >= 2 && kind != RSG_KIND_E) {
+      // src/ModRamLoss.f90:44-47, :59-62, :74-77
+      double X = std::log10(h->EKEV[K - 1]);
+      if (X < -2.) X = -2.;
+      double Y;
+      if (kind == RSG_KIND_H)
+        Y = -18.767 - 0.11017 * X - 3.8173e-2 * (X * X) - 0.1232 * (X * X * X) - 5.0488e-2 * ((X * X) * (X * X));
+      else if (kind == RSG_KIND_HE)
+        Y = -20.789 + 0.92316 * X - 0.68017 * (X * X) + 0.66153 * (X * X * X) - 0.20998 * ((X * X) * (X * X));
+      else
+        Y = -18.987 - 0.10613 * X - 5.4841E-3 * (X * X) - 1.6262E-2 * (X * X * X) - 7.0554E-3 * ((X * X) * (X * X));
+      v = std::pow(10., Y) * Vk;
+    }
+    sv[K - 1] = v;
+    for (int I = 1; I <= NR; ++I) {
+      double a = 1.0;
+      if (K >= 2 && I >= 2) {
+        const double TAUB = 2 * h->RLZ[I - 1] / Vk;  // :163-166
+        a = std::exp(-DTs / TAUB);
+      }
+      ATLOS[(size_t)(K - 1) * NR + (I - 1)] = a;
+    }
+  }
+  CK(cudaMemcpyAsync(sp.d_ce, sp.h_ce, ((size_t)NE + (size_t)NE * NR) * sizeof(double), cudaMemcpyHostToDevice, h->st(s)));
+  sp.DTs_ce = DTs;
+  return RSG_OK;
+}
+
+static int launch_loss(rsg_ram* h, int s, int op, double DTs) {
+  Spec& sp = h->sp[s];
+  RamDev dv = h->dev;
+  dv.DTs = DTs;
+  k_loss<<<nblk((long long)h->specStride, 256), 256, 0, h->st(s)>>>(dv, sp.sd, op, sp.d_wfac);
+  CKL();
+  h->launches++;
+  return RSG_OK;
+}
+
+int rsg_charexchange(rsg_ram* h, int S) {
+  RET(check_S(h, S));
+  Spec& sp = h->sp[S - 1];
+  if (sp.DTs_ce < 0) return fail(RSG_ERR_STATE, "CHAREXCHANGE before CEPARA");
+  if (!h->fields_set) return fail(RSG_ERR_STATE, "CHAREXCHANGE before set_fields");
+  CK(cudaSetDevice(h->device));
+  if (h->kind[S - 1] == RSG_KIND_E) return RSG_OK;  // CHARGE == 1 for electrons
+  return launch_loss(h, S - 1, 0, sp.DTs_ce);
+}
+
+int rsg_atmol(rsg_ram* h, int S) {
+  RET(check_S(h, S));
+  Spec& sp = h->sp[S - 1];
+  if (sp.DTs_ce < 0) return fail(RSG_ERR_STATE, "ATMOL before CEPARA");
+  if (!h->fields_set) return fail(RSG_ERR_STATE, "ATMOL before set_fields");
+  CK(cudaSetDevice(h->device));
+  return launch_loss(h, S - 1, 1, sp.DTs_ce);
+}
+
+// ---- ModRamWPI --------------------------------------------------------------------
+int rsg_wavelo(rsg_ram* h, int S, double DTs) {
+  RET(check_S(h, S));
+  if (h->WALOS1.empty()) return fail(RSG_ERR_STATE, "WAVELO before set_wavelo");
+  CK(cudaSetDevice(h->device));
+  const int s = S - 1, NR = h->NR, NT = h->NT, NE = h->NE;
+  Spec& sp = h->sp[s];
+  if (sp.DTs_wl != DTs) {
+    CK(cudaStreamSynchronize(h->st(s)));
+    // src/ModRamWPI.f90:599-632 with DoUsePlasmasphere=.false.
+    double Bw = 30.;
+    if (h->Kp >= 4.0) Bw = 100.;
+    const double RLpp = 5.39 - 0.382 * h->Kpmax12;
+    std::memset(sp.h_wfac, 0, (size_t)NE * h->Pp * sizeof(double));
+    for (int K = 2; K <= NE; ++K)
+      for (int I = 2; I <= NR; ++I) {
+        const double W1 = h->WALOS1[(I - 1) + (size_t)NR * (K - 1)], W2 = h->WALOS2[(I - 1) + (size_t)NR * (K - 1)],
+                     W3 = h->WALOS3[(I - 1) + (size_t)NR * (K - 1)];
+        const double E = h->EKEV[K - 1];
+        double TAU_LIF = 0.0;
+        if (h->LZ[I - 1] <= RLpp) {
+          TAU_LIF = W1 * ((10. / Bw) * (10. / Bw));
+        } else {
+          if (E <= 1000.) {
+            TAU_LIF = W2 * (1 + W3 / W2);
+            if (E <= 1.1) TAU_LIF = TAU_LIF * 37.5813 * std::exp(-1.81255 * E);
+            else if (E > 1.1 && E <= 5.) TAU_LIF = TAU_LIF * (7.5 - 1.15 * E);
+          } else {
+            TAU_LIF = 5. * 3600 * 24 / h->Kp;
+          }
+        }
+        const double fac = std::exp(-DTs / TAU_LIF);
+        for (int J = 1; J <= NT; ++J) sp.h_wfac[(size_t)(K - 1) * h->Pp + (size_t)(J - 1) * NR + (I - 1)] = fac;
+      }
+    CK(cudaMemcpyAsync(sp.d_wfac, sp.h_wfac, (size_t)NE * h->Pp * sizeof(double), cudaMemcpyHostToDevice, h->st(s)));
+    sp.DTs_wl = DTs;
+  }
+  return launch_loss(h, s, 2, DTs);
+}
+
+int rsg_wpadif(rsg_ram* h, int S, double DTs, long long* nviolation) {
+  RET(check_S(h, S));
+  if (!h->fields_set) return fail(RSG_ERR_STATE, "WPADIF before set_fields");
+  CK(cudaSetDevice(h->device));
+  const int s = S - 1;
+  Spec& sp = h->sp[s];
+  const double *DA, *DB;
+  if (h->kind[s] == RSG_KIND_E) { DA = h->d_diff[0]; DB = h->d_diff[1]; }
+  else { DA = h->d_diff[2]; DB = h->d_diff[3]; }
+  if (!DA && !DB) return fail(RSG_ERR_STATE, "WPADIF before set_diffcoef");
+  if (!DA) DA = h->d_zero4;
+  if (!DB) DB = h->d_zero4;
+  RamDev dv = h->dev;
+  dv.DTs = DTs;
+  const int T = 64;
+  const size_t smem = sizeof(double) * 2 * h->NPA * T;
+  static thread_local size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    CK(cudaFuncSetAttribute(k_wpadif, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  CK(cudaMemsetAsync(sp.d_res + 4 + NSUM, 0, sizeof(unsigned long long), h->st(s)));
+  k_wpadif<<<nblk((long long)h->NE * h->Pp, T), T, smem, h->st(s)>>>(dv, sp.sd, DA, DB, sp.d_res + 4 + NSUM);
+  CKL();
+  h->launches++;
+  if (nviolation) {
+    RET(fetch_res(h, s));
+    *nviolation = (long long)sp.h_res[4 + NSUM];
+  }
+  return RSG_OK;
+}
+
+// ---- ModRamCoul (optional operators; not yet on the device) --------------------------
+int rsg_coulpara(rsg_ram* h, int S, double) { RET(check_S(h, S)); return fail(RSG_ERR_UNSUPPORTED, "COULPARA not implemented"); }
+int rsg_coulen(rsg_ram* h, int S) { RET(check_S(h, S)); return fail(RSG_ERR_UNSUPPORTED, "COULEN not implemented"); }
+int rsg_coulmu(rsg_ram* h, int S, double) { RET(check_S(h, S)); return fail(RSG_ERR_UNSUPPORTED, "COULMU not implemented"); }
+
+// ---- ModRamRun --------------------------------------------------------------------
+int rsg_sumrc(rsg_ram* h, int S, double* setrc, double* elorc) {
+  RET(check_S(h, S));
+  CK(cudaSetDevice(h->device));
+  const int s = S - 1;
+  Spec& sp = h->sp[s];
+  RET(launch_sumrc(h, s, 0));
+  RET(fetch_res(h, s));
+  double v;
+  std::memcpy(&v, sp.h_res + 4, 8);
+  const double old = sp.setrc;
+  sp.setrc = v;
+  if (setrc) *setrc = v;
+  if (elorc) *elorc = old - v;
+  return RSG_OK;
+}
+
+static int launch_anisch(rsg_ram* h, int s) {
+  Spec& sp = h->sp[s];
+  RamDev dv = h->dev;
+  double* tE = sp.d_tE;
+  double* tA = sp.d_tE + (size_t)h->NE * h->Pp;
+  k_anisch_pa<<<nblk((long long)h->NE * h->Pp, 128), 128, 0, h->st(s)>>>(dv, sp.sd, tE, tA);
+  CKL();
+  const double cv = kCS * 100;
+  const double RFAC = 4 * kPI / cv;
+  k_anisch_en<<<nblk(h->P, 128), 128, 0, h->st(s)>>>(dv, tE, tA, RFAC, h->khi[0], h->khi[1], h->khi[2], h->khi[3], h->khi[4],
+                                                      sp.d_pp, sp.d_pp + h->Pp);
+  CKL();
+  h->launches += 2;
+  return RSG_OK;
+}
+
+// copy the (NR,NT) planes of species s into PPERT/PPART; stride = 1 for a
+// per-species slice, nS (with offset s) for the full (nS,NR,NT) arrays
+static int fetch_anisch(rsg_ram* h, int s, double* PPERT, double* PPART, int stride, int off) {
+  Spec& sp = h->sp[s];
+  std::vector<double> b((size_t)2 * h->Pp);
+  CK(cudaMemcpyAsync(b.data(), sp.d_pp, b.size() * sizeof(double), cudaMemcpyDeviceToHost, h->st(s)));
+  CK(cudaStreamSynchronize(h->st(s)));
+  for (int p = 0; p < h->P; ++p) {
+    if (PPERT) PPERT[(size_t)p * stride + off] = b[p];
+    if (PPART) PPART[(size_t)p * stride + off] = b[(size_t)h->Pp + p];
+  }
+  return RSG_OK;
+}
+
+int rsg_anisch(rsg_ram* h, int S, double* PPERT_S, double* PPART_S) {
+  RET(check_S(h, S));
+  if (!h->fields_set) return fail(RSG_ERR_STATE, "ANISCH before set_fields");
+  CK(cudaSetDevice(h->device));
+  RET(launch_anisch(h, S - 1));
+  return fetch_anisch(h, S - 1, PPERT_S, PPART_S, 1, 0);
+}
+
+int rsg_ram_run(rsg_ram* h, double DTs, double DtsMin, double T, int flags, double* dts_next, double* DtDrift,
+                double* losses, double* SETRC, double* PPERT, double* PPART) {
+  if (!h) return fail(RSG_ERR_ARG, "null handle");
+  if (flags & RSG_F_COULOMB) return fail(RSG_ERR_UNSUPPORTED, "Coulomb operators not implemented");
+  (void)T;
+  CK(cudaSetDevice(h->device));
+  const int nS = h->nS;
+  const bool DoUseWPI = flags & RSG_F_WPI, DoUseEMIC = flags & RSG_F_EMIC;
+  // category of each SUMRC slot: 0 LSDR 1 LSCHA 2 LSATM 3 LSWAE
+  int cat[RSG_MAX_SPECIES][NSUM];
+  int nslot[RSG_MAX_SPECIES];
+  for (int s = 0; s < nS; ++s) {
+    const int S = s + 1;
+    const int kind = h->kind[s];
+    const bool sWPI = (kind == RSG_KIND_E), sCEX = (kind != RSG_KIND_E), sEMIC = (kind == RSG_KIND_H);
+    int n = 0;
+#define SUMRC_(c)                     \
+  do {                                \
+    RET(launch_sumrc(h, s, n));       \
+    cat[s][n++] = (c);                \
+  } while (0)
+    RET(rsg_cepara(h, S, DTs));
+    RET(rsg_driftpara(h, S, DTs));
+    RET(rsg_driftr(h, S)); RET(rsg_driftp(h, S)); RET(rsg_drifte(h, S)); RET(rsg_driftmu(h, S));
+    SUMRC_(0);
+    if (sWPI) {
+      if (DoUseWPI) RET(rsg_wpadif(h, S, DTs, nullptr)); else RET(rsg_wavelo(h, S, DTs));
+      SUMRC_(3);
+    }
+    if (sEMIC && DoUseEMIC) { RET(rsg_wpadif(h, S, DTs, nullptr)); SUMRC_(3); }
+    if (sCEX) { RET(rsg_charexchange(h, S)); SUMRC_(1); }
+    RET(rsg_atmol(h, S)); SUMRC_(2);
+    RET(rsg_atmol(h, S)); SUMRC_(2);
+    if (sCEX) { RET(rsg_charexchange(h, S)); SUMRC_(1); }
+    if (sEMIC && DoUseEMIC) { RET(rsg_wpadif(h, S, DTs, nullptr)); SUMRC_(3); }
+    if (sWPI) {
+      if (DoUseWPI) RET(rsg_wpadif(h, S, DTs, nullptr)); else RET(rsg_wavelo(h, S, DTs));
+      SUMRC_(3);
+    }
+    RET(rsg_driftmu(h, S)); RET(rsg_drifte(h, S)); RET(rsg_driftp(h, S)); RET(rsg_driftr(h, S));
+    SUMRC_(0);
+#undef SUMRC_
+    nslot[s] = n;
+    // epilogue (:186-201) and pressures (:208-209)
+    k_epilogue<<<nblk((long long)h->specStride, 256), 256, 0, h->st(s)>>>(h->dev, h->d_F2 + h->specStride * s);
+    CKL();
+    h->launches++;
+    RET(launch_anisch(h, s));
+  }
+  double dtn = 1e300;
+  for (int s = 0; s < nS; ++s) {
+    Spec& sp = h->sp[s];
+    RET(fetch_res(h, s));
+    double dt4[4];
+    std::memcpy(dt4, sp.h_res, 32);
+    for (int q = 0; q < 4; ++q) {
+      dtn = std::min(dtn, dt4[q]);
+      if (DtDrift) DtDrift[q + 4 * s] = dt4[q];
+    }
+    double ls[6] = {0, 0, 0, 0, 0, 0};
+    double prev = sp.setrc;
+    for (int q = 0; q < nslot[s]; ++q) {
+      double v;
+      std::memcpy(&v, sp.h_res + 4 + q, 8);
+      ls[cat[s][q]] += prev - v;  // ELORC = ENOLD - SETRC (:256)
+      prev = v;
+    }
+    sp.setrc = prev;
+    if (losses)
+      for (int q = 0; q < 6; ++q) losses[q + 6 * s] = ls[q];
+    if (SETRC) SETRC[s] = prev;
+    if (PPERT || PPART) RET(fetch_anisch(h, s, PPERT, PPART, nS, s));
+  }
+  if (dts_next) *dts_next = std::max(dtn, DtsMin);
+  return RSG_OK;
+}
+
+int rsg_ram_flux_d2h(rsg_ram* h, double* FLUX) {
+  if (!h || !FLUX) return fail(RSG_ERR_ARG, "null argument");
+  CK(cudaSetDevice(h->device));
+  RET(rsg_ram_sync(h));
+  const size_t n = (size_t)h->nS * h->P * h->NE * h->NPA;
+  cudaStream_t st = h->st(0);
+  for (int s = 0; s < h->nS; ++s) {
+    k_flux_to_host<<<nblk((long long)h->specStride, 256), 256, 0, st>>>(h->dev, h->sp[s].sd, h->d_stage);
+    CKL();
+    h->launches++;
+  }
+  CK(cudaMemcpyAsync(FLUX, h->d_stage, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return RSG_OK;
+}
+
+long long rsg_ram_launch_count(rsg_ram* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,252 @@
+"""Host-side mirror of the reference's operator interface over the C ABI.
+
+The reference calls its hot routines as ``CALL DRIFTR(S)`` etc. on module
+globals (src/ModRamRun.f90:64-185).  ``RamGpu`` keeps that surface -- same
+routine names, 1-based species index, same call-order requirements (DRIFTPARA
+before the sweeps, CEPARA before CHAREXCHANGE/ATMOL) -- and forwards every call
+through ``libramscb_gpu.so`` (include/ramscb_gpu.h) with plain host pointers, the
+way the Fortran shim in ``ramscb_b200/fortran/`` does with ``c_loc``.
+
+There is no CPU fallback: if the CUDA library is missing or no device is
+present, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libramscb_gpu.so")
+
+MODE_EXACT, MODE_FAST = 0, 1
+F_WPI, F_COULOMB, F_EMIC = 1, 2, 4
+
+_lib = None
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+class RsgError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libramscb_gpu.so (built by ``python -m ramscb_b200.build``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RsgError(f"{LIB_PATH} not found: run `python -m ramscb_b200.build` (nvcc, sm_100a). "
+                       "There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, i, d, ll = C.c_void_p, C.c_int, C.c_double, C.c_longlong
+    L.rsg_last_error.restype = C.c_char_p
+    L.rsg_device_count.restype = i
+    L.rsg_device_info.argtypes = [C.c_char_p, i, _ip, C.POINTER(ll), C.POINTER(ll)]
+    L.rsg_ram_create.argtypes = [C.POINTER(vp), i, i, i, i, i, i]
+    L.rsg_ram_destroy.argtypes = [vp]
+    L.rsg_ram_set_mode.argtypes = [vp, i]
+    L.rsg_ram_set_stream.argtypes = [vp, vp]
+    L.rsg_ram_sync.argtypes = [vp]
+    L.rsg_ram_set_grids.argtypes = [vp] + [vp] * 18 + [vp, vp, vp] + [d] * 6
+    L.rsg_ram_set_fields.argtypes = [vp] + [vp] * 10
+    L.rsg_ram_set_efield.argtypes = [vp, vp, vp, vp]
+    L.rsg_ram_set_boundary.argtypes = [vp, vp]
+    L.rsg_ram_set_wavelo.argtypes = [vp, vp, vp, vp, d, d]
+    L.rsg_ram_set_plasmasphere.argtypes = [vp, vp]
+    L.rsg_ram_set_diffcoef.argtypes = [vp, i, vp]
+    L.rsg_ram_f2_h2d.argtypes = [vp, vp, i]
+    L.rsg_ram_f2_d2h.argtypes = [vp, vp, i]
+    L.rsg_ram_f2_device.argtypes = [vp, i, C.POINTER(vp), C.POINTER(ll), _ip]
+    for name in ("driftr", "driftp", "drifte", "driftmu", "charexchange", "atmol", "coulen"):
+        getattr(L, "rsg_" + name).argtypes = [vp, i]
+    for name in ("driftpara", "cepara", "wavelo", "coulpara", "coulmu"):
+        getattr(L, "rsg_" + name).argtypes = [vp, i, d]
+    L.rsg_driftend.argtypes = [vp]
+    L.rsg_get_dtdrift.argtypes = [vp, i, _dp]
+    L.rsg_wpadif.argtypes = [vp, i, d, C.POINTER(ll)]
+    L.rsg_sumrc.argtypes = [vp, i, _dp, _dp]
+    L.rsg_anisch.argtypes = [vp, i, vp, vp]
+    L.rsg_ram_run.argtypes = [vp, d, d, d, i, _dp, vp, vp, vp, vp, vp]
+    L.rsg_ram_flux_d2h.argtypes = [vp, vp]
+    L.rsg_ram_launch_count.argtypes = [vp]
+    L.rsg_ram_launch_count.restype = ll
+    _lib = L
+    return L
+
+
+def _ck(rc):
+    if rc != 0:
+        raise RsgError(f"rsg status {rc}: {lib().rsg_last_error().decode()}")
+
+
+def _p(a, dtype=np.float64):
+    """Pointer to a Fortran-contiguous array of the right dtype (no copy made)."""
+    if a.dtype != dtype or not (a.flags.f_contiguous or a.ndim <= 1 and a.flags.c_contiguous):
+        raise ValueError("array must be Fortran-contiguous " + str(dtype))
+    return a.ctypes.data
+
+
+def device_count() -> int:
+    return lib().rsg_device_count()
+
+
+def device_info():
+    name = C.create_string_buffer(256)
+    sm = C.c_int()
+    l2 = C.c_longlong()
+    hbm = C.c_longlong()
+    _ck(lib().rsg_device_info(name, 256, C.byref(sm), C.byref(l2), C.byref(hbm)))
+    return {"name": name.value.decode(), "sm_count": sm.value, "l2_bytes": l2.value, "hbm_bytes": hbm.value}
+
+
+class RamGpu:
+    """Device-resident RAM state + the reference's operator names."""
+
+    def __init__(self, g, device: int = -1, mode: int = MODE_EXACT):
+        self.L = lib()
+        self.g = g
+        self.h = C.c_void_p()
+        _ck(self.L.rsg_ram_create(C.byref(self.h), g.nS, g.NR, g.NT, g.NE, g.NPA, device))
+        self._keep = []
+        self.set_grids(g)
+        if mode != MODE_EXACT:
+            self.set_mode(mode)
+
+    # ---- configuration --------------------------------------------------------
+    def set_mode(self, mode):
+        _ck(self.L.rsg_ram_set_mode(self.h, mode))
+
+    def set_stream(self, stream_ptr):
+        _ck(self.L.rsg_ram_set_stream(self.h, C.c_void_p(stream_ptr) if stream_ptr else None))
+
+    def sync(self):
+        _ck(self.L.rsg_ram_sync(self.h))
+
+    def set_grids(self, g, BetaLim=1.5, FracCFL=0.8):
+        f = lambda a: _p(np.asfortranarray(a, dtype=np.float64))
+        arrs = [np.asfortranarray(getattr(g, n), dtype=np.float64) for n in
+                ("RLZ", "LZ", "EKEV", "WE", "DE", "EBND", "MU", "WMU", "DMU", "UPA", "GREL", "GRBND", "V", "VBND",
+                 "EPP", "ERNH", "RMAS", "FFACTOR")]
+        ints = [np.ascontiguousarray(getattr(g, n), dtype=np.int32) for n in ("QS", "kind", "khi")]
+        _ck(self.L.rsg_ram_set_grids(self.h, *[a.ctypes.data for a in arrs], *[a.ctypes.data for a in ints],
+                                     g.MDR, g.DPHI, g.CONF1, g.CONF2, BetaLim, FracCFL))
+
+    def set_fields(self, inp):
+        out = np.asfortranarray(inp.outsideMGNP, dtype=np.int32)
+        _ck(self.L.rsg_ram_set_fields(self.h, _p(inp.BNES), _p(inp.dBdt), _p(inp.FNHS), _p(inp.FNIS), _p(inp.BOUNHS),
+                                      _p(inp.BOUNIS), _p(inp.HDNS), _p(inp.dIdt), _p(inp.dIbndt), out.ctypes.data))
+
+    def set_efield(self, VT, EIR, EIP):
+        _ck(self.L.rsg_ram_set_efield(self.h, _p(VT), _p(EIR), _p(EIP)))
+
+    def set_boundary(self, FGEOS):
+        _ck(self.L.rsg_ram_set_boundary(self.h, _p(FGEOS)))
+
+    def set_wavelo(self, W1, W2, W3, Kp, Kpmax12):
+        _ck(self.L.rsg_ram_set_wavelo(self.h, _p(W1), _p(W2), _p(W3), Kp, Kpmax12))
+
+    def set_plasmasphere(self, NECR):
+        _ck(self.L.rsg_ram_set_plasmasphere(self.h, _p(NECR)))
+
+    def set_diffcoef(self, which, D):
+        _ck(self.L.rsg_ram_set_diffcoef(self.h, which, _p(D)))
+
+    def set_inputs(self, inp):
+        """Everything a RamInputs carries, F2 included."""
+        self.set_fields(inp)
+        self.set_efield(inp.VT, inp.EIR, inp.EIP)
+        self.set_boundary(inp.FGEOS)
+        self.set_wavelo(inp.WALOS1, inp.WALOS2, inp.WALOS3, inp.Kp, inp.Kpmax12)
+        self.set_plasmasphere(inp.NECR)
+        self.f2_h2d(inp.F2)
+
+    # ---- F2 -------------------------------------------------------------------
+    def f2_h2d(self, F2, S=0):
+        _ck(self.L.rsg_ram_f2_h2d(self.h, _p(F2), S))
+
+    def f2_d2h(self, F2=None, S=0):
+        g = self.g
+        if F2 is None:
+            F2 = np.zeros((g.nS, g.NR, g.NT, g.NE, g.NPA), order="F")
+        _ck(self.L.rsg_ram_f2_d2h(self.h, _p(F2), S))
+        return F2
+
+    def f2_device(self, S):
+        ptr, n, pp = C.c_void_p(), C.c_longlong(), C.c_int()
+        _ck(self.L.rsg_ram_f2_device(self.h, S, C.byref(ptr), C.byref(n), C.byref(pp)))
+        return ptr.value, n.value, pp.value
+
+    # ---- the reference's operator names (1-based species) ----------------------
+    def DRIFTPARA(self, S, DTs): _ck(self.L.rsg_driftpara(self.h, S, DTs))
+    def DRIFTR(self, S): _ck(self.L.rsg_driftr(self.h, S))
+    def DRIFTP(self, S): _ck(self.L.rsg_driftp(self.h, S))
+    def DRIFTE(self, S): _ck(self.L.rsg_drifte(self.h, S))
+    def DRIFTMU(self, S): _ck(self.L.rsg_driftmu(self.h, S))
+    def DRIFTEND(self): _ck(self.L.rsg_driftend(self.h))
+    def CEPARA(self, S, DTs): _ck(self.L.rsg_cepara(self.h, S, DTs))
+    def CHAREXCHANGE(self, S): _ck(self.L.rsg_charexchange(self.h, S))
+    def ATMOL(self, S): _ck(self.L.rsg_atmol(self.h, S))
+    def WAVELO(self, S, DTs): _ck(self.L.rsg_wavelo(self.h, S, DTs))
+    def COULPARA(self, S, DTs): _ck(self.L.rsg_coulpara(self.h, S, DTs))
+    def COULEN(self, S): _ck(self.L.rsg_coulen(self.h, S))
+    def COULMU(self, S, T=0.0): _ck(self.L.rsg_coulmu(self.h, S, T))
+
+    def WPADIF(self, S, DTs):
+        nv = C.c_longlong()
+        _ck(self.L.rsg_wpadif(self.h, S, DTs, C.byref(nv)))
+        return nv.value
+
+    def dtdrift(self, S):
+        out = (C.c_double * 4)()
+        _ck(self.L.rsg_get_dtdrift(self.h, S, out))
+        return np.array(out[:])
+
+    def SUMRC(self, S):
+        a, b = C.c_double(), C.c_double()
+        _ck(self.L.rsg_sumrc(self.h, S, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def ANISCH(self, S):
+        g = self.g
+        pper = np.zeros((g.NR, g.NT), order="F")
+        ppar = np.zeros((g.NR, g.NT), order="F")
+        _ck(self.L.rsg_anisch(self.h, S, _p(pper), _p(ppar)))
+        return pper, ppar
+
+    def ram_run(self, DTs, DtsMin=1.0, T=0.0, flags=0):
+        g = self.g
+        dtn = C.c_double()
+        out = {
+            "DtDrift": np.zeros((4, g.nS), order="F"),
+            "losses": np.zeros((6, g.nS), order="F"),
+            "SETRC": np.zeros(g.nS),
+            "PPERT": np.zeros((g.nS, g.NR, g.NT), order="F"),
+            "PPART": np.zeros((g.nS, g.NR, g.NT), order="F"),
+        }
+        _ck(self.L.rsg_ram_run(self.h, DTs, DtsMin, T, flags, C.byref(dtn), _p(out["DtDrift"]), _p(out["losses"]),
+                               _p(out["SETRC"]), _p(out["PPERT"]), _p(out["PPART"])))
+        out["DtsNext"] = dtn.value
+        return out
+
+    def flux_d2h(self):
+        g = self.g
+        FLUX = np.zeros((g.nS, g.NR, g.NT, g.NE, g.NPA), order="F")
+        _ck(self.L.rsg_ram_flux_d2h(self.h, _p(FLUX)))
+        return FLUX
+
+    def launch_count(self):
+        return self.L.rsg_ram_launch_count(self.h)
+
+    def close(self):
+        if self.h:
+            self.L.rsg_ram_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
