@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py -- RAM phase-space cell-updates/s per full RAM step (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload default|x4]
+
+One "step" = one pass of the RAM hot path (`ram_run`, src/ModRamRun.f90:64-222)
+over one synthetic input set: for each of the 4 species CEPARA, DRIFTPARA,
+DRIFTR/P/E/MU, SUMRC, [WAVELO | CHAREXCHANGE], ATMOL x2, reversed order back to
+DRIFTR, then the epilogue, ANISCH pressures and the CFL time step.  Work unit:
+one cell-update = one F2 cell advanced by one operator call; a step applies 12
+operators (8 drift sweeps + 2 ATMOL + 2 CHAREXCHANGE-or-WAVELO) to nS*NR*NT*NE*NPA
+cells.
+
+Printed JSON keys follow the driver contract: `value` is measured with F2 resident
+in HBM (CUDA events across the library's streams, L2 flushed between steps);
+`e2e` is the same metric through the C-ABI with HOST buffers (pinned), F2
+host->device and device->host copies inside the timed region (wall clock).
+`--impl reference` times the reference's CPU algorithm (the C++ oracle, the
+reference's own OpenMP-over-species parallelism) on the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+OPS_PER_STEP = 12  # operator applications per cell per ram_run (see module docstring)
+DTS = 5.0
+
+
+def workload(name):
+    from ramscb_b200 import grids, synthetic
+    if name == "default":
+        g = grids.build_grids()                                     # BASELINE configs[1]
+        desc = "configs[1]: RAM drift+loss step, reference default grid nS=4 NR=20 NT=25 NE=35 NPA=72 (5.04 M cells, 40 MB), synthetic F2"
+    elif name == "x4":
+        g = grids.build_grids(NR=80, NT=49, NE=70, energy_refine=2)  # BASELINE configs[2] grid
+        desc = "configs[2] grid: nS=4 NR=80 NT=49 NE=70 NPA=72 (79.0 M cells, 632 MB), synthetic F2"
+    else:
+        raise SystemExit("unknown workload " + name)
+    inp = synthetic.make_inputs(g, f2_kind="noisy", inductive=True)
+    return g, inp, desc
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_reference(g, inp, steps, warmup):
+    """The reference's CPU algorithm (C++ oracle; OpenMP over species like
+    src/ModRamRun.f90:64) on the same workload.  Returns (cell-updates/s, threads, s/step)."""
+    from oracle import oracle
+    oracle.build()
+    o = oracle.RamOracle(g, inp, DTs=DTS)
+    nthreads = min(g.nS, os.cpu_count() or 1)
+    for _ in range(warmup):
+        o.ram_run(flags=0, nthreads=nthreads)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.ram_run(flags=0, nthreads=nthreads)
+    dt = (time.perf_counter() - t0) / steps
+    cells = g.nS * g.NR * g.NT * g.NE * g.NPA
+    return OPS_PER_STEP * cells / dt, nthreads, dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="default", choices=["default", "x4"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    g, inp, desc = workload(a.workload)
+    cells = g.nS * g.NR * g.NT * g.NE * g.NPA
+    unit = "cell-updates/s"
+    metric = "RAM phase-space cell-updates/s per full RAM step (8 drift sweeps + losses, 4 species)"
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        steps = max(1, min(a.steps, 5))
+        v, nthreads, dt = cpu_reference(g, inp, steps, 1)
+        line = {"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": a.gpus, "steps": steps,
+                "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": desc},
+                "cpu_baseline": {"value": v, "unit": unit, "cores": nthreads, "kind": "port",
+                                 "sample": f"{steps} full ram_run steps of the same workload, OpenMP over species "
+                                           f"({nthreads} threads, the reference's own decomposition)"},
+                "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    from ramscb_b200 import host
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    # ---- species sharding: the species loop of ram_run has no cross-species data
+    # dependence (src/ModRamRun.f90:64-185), so ranks own disjoint species sets.
+    my_species = [s for s in range(g.nS) if s % world == rank]
+    gpu = host.RamGpu(g, device=local_rank)
+    gpu.set_inputs(inp)
+    F2_host = inp.F2.copy(order="F")
+    host.host_register(F2_host)
+    flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        return gpu.ram_run(DTS, DtsMin=1.0, flags=0) if world == 1 else run_my_species()
+
+    def run_my_species():
+        # same operator sequence as rsg_ram_run, restricted to this rank's species
+        for s in my_species:
+            S = s + 1
+            gpu.CEPARA(S, DTS); gpu.DRIFTPARA(S, DTS)
+            gpu.DRIFTR(S); gpu.DRIFTP(S); gpu.DRIFTE(S); gpu.DRIFTMU(S); gpu.SUMRC(S)
+            if g.species[s].WPI:
+                gpu.WAVELO(S, DTS); gpu.SUMRC(S)
+            if g.species[s].CEX:
+                gpu.CHAREXCHANGE(S); gpu.SUMRC(S)
+            gpu.ATMOL(S); gpu.SUMRC(S); gpu.ATMOL(S); gpu.SUMRC(S)
+            if g.species[s].CEX:
+                gpu.CHAREXCHANGE(S); gpu.SUMRC(S)
+            if g.species[s].WPI:
+                gpu.WAVELO(S, DTS); gpu.SUMRC(S)
+            gpu.DRIFTMU(S); gpu.DRIFTE(S); gpu.DRIFTP(S); gpu.DRIFTR(S); gpu.SUMRC(S)
+            gpu.ANISCH(S)
+
+    for _ in range(a.warmup):
+        step_resident()
+    launches0 = gpu.launch_count()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    barrier()
+    dev_ms = 0.0
+    t_wall0 = time.perf_counter()
+    for _ in range(a.steps):
+        flush.zero_()                      # evict F2 from the 126 MB L2 (untimed)
+        torch.cuda.synchronize()
+        gpu.timer_begin()
+        step_resident()
+        dev_ms += gpu.timer_end()
+    barrier()
+    wall_s = time.perf_counter() - t_wall0
+    clk = clocks.stop()
+    launches = gpu.launch_count() - launches0
+    if dist is not None:
+        t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms = float(t.item())
+    ms_per_step = dev_ms / a.steps
+    value = OPS_PER_STEP * cells / (ms_per_step * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers ---------------------------
+    e2e_steps = max(3, min(a.steps, 10))
+    VT = inp.VT
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        gpu.f2_h2d(F2_host)
+        gpu.set_efield(VT, inp.EIR, inp.EIP)
+        out = step_resident()
+        gpu.f2_d2h(F2_host)
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if dist is not None:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    h2d = F2_host.nbytes + 3 * VT.nbytes
+    d2h = F2_host.nbytes + (4 + 6 + 1) * g.nS * 8 + 2 * g.nS * g.NR * g.NT * 8
+    e2e = {"value": OPS_PER_STEP * cells / e2e_s, "unit": unit, "h2d_bytes_per_step": int(h2d),
+           "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3, "timer": "wall clock, pinned host F2"}
+
+    # ---- per-operator device times (CUDA events), dominant kernel roofline ----------
+    peak, peak_src = measured_peak()
+    per_op = {}
+    S = 1
+    gpu.CEPARA(S, DTS); gpu.DRIFTPARA(S, DTS)
+    sp_cells = cells // g.nS
+    for name in ("DRIFTR", "DRIFTP", "DRIFTE", "DRIFTMU", "CHAREXCHANGE", "ATMOL"):
+        reps = 5
+        tot = 0.0
+        for _ in range(reps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            gpu.timer_begin()
+            getattr(gpu, name)(S)
+            tot += gpu.timer_end()
+        per_op[name] = tot / reps
+    dom = max(("DRIFTR", "DRIFTP", "DRIFTE", "DRIFTMU"), key=lambda n: per_op[n])
+    achieved = 16.0 * sp_cells / (per_op[dom] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": {"DRIFTR": "k_driftr", "DRIFTP": "k_driftp", "DRIFTE": "k_drifte",
+                                           "DRIFTMU": "k_driftmu"}[dom],
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": 16 * sp_cells,
+                "note": "one species per launch (cold L2); 16 B per cell-update (SURVEY 8(d))",
+                "per_op_ms_one_species": per_op}
+
+    line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "ops_per_cell_per_step": OPS_PER_STEP, "mode": "exact (bit-identical to oracle)",
+                       "l2": "flushed between timed steps (512 MB memset, untimed)", "DTs": DTS,
+                       "parallelism": f"species-sharded x{world}" if world > 1 else "1 GPU, 4 species streams"},
+            "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "wall_s_timed_region": wall_s}
+    if rank == 0 and not a.no_cpu_baseline:
+        v, nthreads, dt = cpu_reference(g, inp, 3 if a.workload == "default" else 1, 1)
+        line["cpu_baseline"] = {"value": v, "unit": unit, "cores": nthreads, "kind": "port",
+                                "sample": "full ram_run steps of the same workload on the host cores "
+                                          f"({dt:.3f} s/step, OpenMP over species = the reference's decomposition)"}
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -149,6 +149,17 @@ int rsg_ram_flux_d2h(rsg_ram* h, double* FLUX);
 /* number of kernel launches issued through this handle since creation */
 long long rsg_ram_launch_count(rsg_ram* h);
 
+/* Device-side timing across the library's internal streams (CUDA events):
+ * begin() orders a start event before all later work of this handle, end()
+ * joins every stream, synchronises and returns the elapsed milliseconds. */
+int rsg_ram_timer_begin(rsg_ram* h);
+int rsg_ram_timer_end(rsg_ram* h, double* ms);
+
+/* Pin / unpin an existing host array (cudaHostRegister), e.g. the Fortran
+ * allocatable F2, so rsg_ram_f2_h2d/d2h run at full PCIe speed. */
+int rsg_host_register(void* p, long long bytes);
+int rsg_host_unregister(void* p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,6 +14,7 @@
 #include <stdint.h>
 
 #define RSG_MAX_SPECIES 8
+#define RSG_NMOM 4   // moments produced by the fused loss block
 
 // everything a sweep kernel needs that is shared by all species
 struct RamDev {
@@ -41,15 +42,27 @@ struct SpecDev {
   int S;            // 0-based species
   int kind;
   double QS;
-  double* F;        // species block of F2dev
+  double* F;        // species block of F2dev (current buffer)
+  double* Fo;       // the other ping-pong buffer (sweeps read F, write Fo)
+  const int* last;  // DRIFTR: index of the most recent inflow line (reference loop order)
+  double* part;     // per-CTA partial sums for the moment reductions
   const double* FGEOS;  // [l][k][j]
   const double *P4, *eK, *epK, *aE, *sv;  // [NE]
   const double *P2, *EDOT, *ATLOS;        // [NE][NR]
   const double* aMU;                      // [NPA]
   const double* FF;                       // FFACTOR [l][k][i]
   const double* EPP;                      // [NE]
+  const double* wfac;                     // WAVELO factor exp(-DTs/TAU_LIF) [NE][Pp]
+  const double *DA, *DB;                  // WPADIF coefficient pair [l][k][Pp]
+  double *tE, *tA;                        // ANISCH scratch [NE][Pp]
+  double *pper, *ppar;                    // ANISCH results [Pp]
   double GREL1, GREL2, sqrtA, GRZERO, sqrtB;  // DRIFTE ghost cells
   double aRP;                             // FracCFL*DTs
   double OMEt;                            // OME*DTs/DPHI
   unsigned long long* dt;                 // [4] CFL minima as ordered bit patterns
+};
+
+// all species of one launch (blockIdx.y selects the species)
+struct SpecPack {
+  SpecDev s[RSG_MAX_SPECIES];
 };

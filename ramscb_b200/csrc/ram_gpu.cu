@@ -2,7 +2,9 @@
 // streams, small host tables (in the reference's operation order) and kernel
 // launches.  No CPU compute path exists here: without a CUDA device every entry
 // point fails with RSG_ERR_CUDA.
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -42,7 +44,8 @@ int fail(int code, const std::string& msg) {
   } while (0)
 
 constexpr double kQ = 1.602E-19, kCS = 2.998E8, kPI = 3.1415926535897932384626433832795;
-constexpr int NSUM = 16;  // moment slots per species
+constexpr int NSUM = 16;           // moment slots per species
+constexpr int RES_N = 4 + NSUM + 1;  // [4] dt bits, [NSUM] sums, [1] WPADIF violations
 
 struct Spec {
   cudaStream_t own = nullptr;
@@ -51,7 +54,7 @@ struct Spec {
   double DTs_ce = -1.0;     // DTs of the last CEPARA
   double DTs_wl = -1.0;     // DTs of the last WAVELO table
   double setrc = 0.0;
-  // device tables
+  int cur = 0;              // which ping-pong buffer holds F2
   double* d_tab = nullptr;   // drift tables
   double* h_tab = nullptr;   // pinned staging for d_tab
   size_t n_tab = 0;
@@ -63,12 +66,11 @@ struct Spec {
   double* d_EPP = nullptr;   // [NE]
   double* d_FGEOS = nullptr; // [l][k][j]
   int* d_last = nullptr;     // DRIFTR inflow scan
-  double* d_part = nullptr;  // SUMRC partials
-  double* d_tE = nullptr;    // ANISCH scratch [NE][Pp] x2
-  double* d_pp = nullptr;    // ANISCH out [2][Pp]
-  // results
-  unsigned long long* d_res = nullptr;  // [4] dt bits, [4..4+NSUM) sums (as double), [4+NSUM] nviol
-  unsigned long long* h_res = nullptr;  // pinned
+  double* d_part = nullptr;  // moment partials [nblk_sum][RSG_NMOM]
+  double* d_tE = nullptr;    // ANISCH scratch [2][NE][Pp]
+  unsigned long long* d_res = nullptr;  // slice of rsg_ram::d_res_all
+  unsigned long long* h_res = nullptr;  // slice of rsg_ram::h_res_all (pinned)
+  double* d_pp = nullptr;    // slice of d_pp_all: [2][Pp]
   SpecDev sd{};
 };
 
@@ -84,22 +86,30 @@ struct rsg_ram {
   std::vector<int> QS, kind, khi;
   RamDev dev{};
   std::vector<void*> allocs;
-  double* d_F2 = nullptr;
+  double* d_F2[2] = {nullptr, nullptr};   // ping-pong buffers [nS][NPA][NE][Pp]
   size_t specStride = 0;
   double* d_stage = nullptr;  // host-layout image of F2 (nS*P*NE*NPA)
   double* d_diff[4] = {nullptr, nullptr, nullptr, nullptr};
   double* d_zero4 = nullptr;  // all-zero diffusion coefficient
   double* d_NECR = nullptr;
   double* d_dtinit = nullptr;
+  int* d_tilemax = nullptr;
+  int ntiles = 0;
+  unsigned long long* d_res_all = nullptr;
+  unsigned long long* h_res_all = nullptr;
+  double* d_pp_all = nullptr;
+  double* h_pp_all = nullptr;
   cudaStream_t ext = nullptr;   // user stream (rsg_ram_set_stream)
-  cudaStream_t prepst = nullptr;
+  cudaStream_t prepst = nullptr;  // prep kernels and the batched rsg_ram_run
   cudaEvent_t prepev = nullptr;
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
   double prep_DTs = -1.0;
   bool step_dirty = true;       // e-field or fields changed since last k_prep_step
   std::mutex mu;
   Spec sp[RSG_MAX_SPECIES];
   long long launches = 0;
   int nblk_sum = 0;
+  int segE = 12, segMU = 12, segP = 12;
 
   cudaStream_t st(int s) { return ext ? ext : sp[s].own; }
   cudaStream_t pst() { return ext ? ext : prepst; }
@@ -126,7 +136,6 @@ int check_S(rsg_ram* h, int S) {
   return RSG_OK;
 }
 
-// upload helper: host -> device, synchronous w.r.t. the host buffer
 template <class T>
 int up(T* dst, const T* src, size_t n) {
   CK(cudaMemcpy(dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
@@ -141,12 +150,28 @@ void to_planes4(const rsg_ram* h, const double* src, std::vector<double>& out) {
       std::memcpy(&out[((size_t)l * h->NE + k) * h->Pp], &src[((size_t)l * h->NE + k) * h->P], sizeof(double) * h->P);
 }
 
-int ensure_step(rsg_ram* h, double DTs) {
+// species pack with the current ping-pong assignment
+void make_pack(rsg_ram* h, SpecPack& pk, int s0 = 0, int ns = -1) {
+  if (ns < 0) ns = h->nS - s0;
+  for (int s = s0; s < s0 + ns; ++s) {
+    Spec& sp = h->sp[s];
+    sp.sd.F = h->d_F2[sp.cur] + h->specStride * s;
+    sp.sd.Fo = h->d_F2[sp.cur ^ 1] + h->specStride * s;
+    pk.s[s] = sp.sd;
+  }
+}
+void flip(rsg_ram* h, int s0, int ns) {
+  for (int s = s0; s < s0 + ns; ++s) h->sp[s].cur ^= 1;
+}
+
+// species-independent coefficient planes that depend on DTs / the E field
+int ensure_step(rsg_ram* h, double DTs, cudaStream_t only = nullptr) {
   std::lock_guard<std::mutex> lk(h->mu);
   if (!h->step_dirty && h->prep_DTs == DTs) return RSG_OK;
   if (!h->fields_set || !h->efield_set) return fail(RSG_ERR_STATE, "DRIFTPARA before set_fields/set_efield");
-  cudaStream_t ps = h->pst();
-  if (!h->ext)
+  cudaStream_t ps = only ? only : h->pst();
+  const bool join = !h->ext && !only;
+  if (join)
     for (int s = 0; s < h->nS; ++s) {
       CK(cudaEventRecord(h->sp[s].ev, h->sp[s].own));
       CK(cudaStreamWaitEvent(ps, h->sp[s].ev, 0));
@@ -156,7 +181,7 @@ int ensure_step(rsg_ram* h, double DTs) {
   k_prep_step<<<nblk((long long)h->NPA * h->Pp, 256), 256, 0, ps>>>(dv);
   CKL();
   h->launches++;
-  if (!h->ext) {
+  if (join) {
     CK(cudaEventRecord(h->prepev, ps));
     for (int s = 0; s < h->nS; ++s) CK(cudaStreamWaitEvent(h->sp[s].own, h->prepev, 0));
   }
@@ -165,34 +190,265 @@ int ensure_step(rsg_ram* h, double DTs) {
   return RSG_OK;
 }
 
-RamDev devfor(rsg_ram* h, int s) {
+RamDev devfor(rsg_ram* h, double DTs) {
   RamDev dv = h->dev;
-  dv.DTs = h->sp[s].DTs;
+  dv.DTs = DTs;
   return dv;
 }
 
-int launch_sumrc(rsg_ram* h, int s, int slot) {
-  Spec& sp = h->sp[s];
-  RamDev dv = devfor(h, s);
-  k_sumrc_partial<<<h->nblk_sum, 256, 0, h->st(s)>>>(dv, sp.sd, sp.d_part);
+int seg_count(int ncell, int seg) { return (ncell + seg - 1) / seg; }
+
+// ---- batched launches: species s0 .. s0+ns-1 on stream st ----------------------
+int L_inflow(rsg_ram* h, int s0, int ns, cudaStream_t st) {
+  SpecPack pk;
+  make_pack(h, pk, s0, ns);
+  RamDev dv = devfor(h, h->sp[s0].DTs);
+  dim3 g(h->ntiles, ns);
+  k_driftr_inflow<<<g, SCAN_TILE, 0, st>>>(dv, pk, s0, h->d_tilemax, h->ntiles);
   CKL();
-  k_sum_final<<<1, 256, 0, h->st(s)>>>(sp.d_part, h->nblk_sum, (double*)(sp.d_res + 4 + slot));
+  k_driftr_scan<<<g, SCAN_TILE, 0, st>>>(dv, pk, s0, h->d_tilemax, h->ntiles);
+  CKL();
+  h->launches += 2;
+  return RSG_OK;
+}
+int reset_dt(rsg_ram* h, int s0, int ns, int which, cudaStream_t st) {
+  for (int s = s0; s < s0 + ns; ++s)
+    CK(cudaMemcpyAsync(h->sp[s].d_res + which, h->d_dtinit + which, 8, cudaMemcpyDeviceToDevice, st));
+  return RSG_OK;
+}
+int L_driftr(rsg_ram* h, int s0, int ns, cudaStream_t st) {
+  RET(reset_dt(h, s0, ns, 0, st));
+  SpecPack pk;
+  make_pack(h, pk, s0, ns);
+  const long long N = (long long)h->specStride;
+  const long long warps = (N + 30) / 31 + 1;
+  dim3 g(nblk(warps * 32, 256), ns);
+  k_driftr<<<g, 256, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0);
+  CKL();
+  h->launches++;
+  flip(h, s0, ns);
+  return RSG_OK;
+}
+int L_driftp(rsg_ram* h, int s0, int ns, cudaStream_t st) {
+  RET(reset_dt(h, s0, ns, 1, st));
+  SpecPack pk;
+  make_pack(h, pk, s0, ns);
+  const int nseg = seg_count(h->NT - 1, h->segP);
+  dim3 g(nblk((long long)h->NPA * h->NE * h->NR * nseg, 128), ns);
+  k_driftp<<<g, 128, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0, h->segP, nseg);
+  CKL();
+  h->launches++;
+  flip(h, s0, ns);
+  return RSG_OK;
+}
+int L_drifte(rsg_ram* h, int s0, int ns, cudaStream_t st) {
+  RET(reset_dt(h, s0, ns, 2, st));
+  SpecPack pk;
+  make_pack(h, pk, s0, ns);
+  const int nseg = seg_count(h->NE, h->segE);
+  dim3 g(nblk((long long)h->NPA * h->Pp * nseg, 128), ns);
+  k_drifte<<<g, 128, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0, h->segE, nseg);
+  CKL();
+  h->launches++;
+  flip(h, s0, ns);
+  return RSG_OK;
+}
+int L_driftmu(rsg_ram* h, int s0, int ns, cudaStream_t st) {
+  RET(reset_dt(h, s0, ns, 3, st));
+  SpecPack pk;
+  make_pack(h, pk, s0, ns);
+  const int nseg = seg_count(h->NPA - 2, h->segMU);
+  dim3 g(nblk((long long)h->NE * h->Pp * nseg, 128), ns);
+  k_driftmu<<<g, 128, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0, h->segMU, nseg);
+  CKL();
+  h->launches++;
+  flip(h, s0, ns);
+  return RSG_OK;
+}
+int L_sumrc(rsg_ram* h, int s0, int ns, int slot, cudaStream_t st) {
+  SpecPack pk;
+  make_pack(h, pk, s0, ns);
+  k_sumrc_partial<<<dim3(h->nblk_sum, ns), 256, 0, st>>>(h->dev, pk, s0);
+  CKL();
+  k_sum_final<<<dim3(1, ns), 256, 0, st>>>(pk, s0, h->nblk_sum, 1, slot);
+  CKL();
+  h->launches += 2;
+  return RSG_OK;
+}
+int L_loss(rsg_ram* h, int s, int op, double DTs, cudaStream_t st) {
+  SpecPack pk;
+  make_pack(h, pk, s, 1);
+  k_loss<<<dim3(nblk((long long)h->specStride, 256), 1), 256, 0, st>>>(devfor(h, DTs), pk, s, op, h->sp[s].d_wfac);
+  CKL();
+  h->launches++;
+  return RSG_OK;
+}
+int L_loss_mid(rsg_ram* h, int s0, int ns, int doA, double DTs, int slot, cudaStream_t st) {
+  SpecPack pk;
+  make_pack(h, pk, s0, ns);
+  k_loss_mid<<<dim3(h->nblk_sum, ns), 256, 0, st>>>(devfor(h, DTs), pk, s0, doA);
+  CKL();
+  k_sum_final<<<dim3(4, ns), 256, 0, st>>>(pk, s0, h->nblk_sum, 4, slot);
+  CKL();
+  h->launches += 2;
+  return RSG_OK;
+}
+int L_wpadif(rsg_ram* h, int s, double DTs, cudaStream_t st) {
+  Spec& sp = h->sp[s];
+  const double *DA, *DB;
+  if (h->kind[s] == RSG_KIND_E) { DA = h->d_diff[0]; DB = h->d_diff[1]; }
+  else { DA = h->d_diff[2]; DB = h->d_diff[3]; }
+  if (!DA && !DB) return fail(RSG_ERR_STATE, "WPADIF before set_diffcoef");
+  sp.sd.DA = DA ? DA : h->d_zero4;
+  sp.sd.DB = DB ? DB : h->d_zero4;
+  SpecPack pk;
+  make_pack(h, pk, s, 1);
+  const int T = 64;
+  const size_t smem = sizeof(double) * 2 * h->NPA * T;
+  static thread_local size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    CK(cudaFuncSetAttribute(k_wpadif, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  CK(cudaMemsetAsync(sp.d_res + 4 + NSUM, 0, sizeof(unsigned long long), st));
+  k_wpadif<<<dim3(nblk((long long)h->NE * h->Pp, T), 1), T, smem, st>>>(devfor(h, DTs), pk, s);
+  CKL();
+  h->launches++;
+  return RSG_OK;
+}
+int L_anisch(rsg_ram* h, int s0, int ns, cudaStream_t st) {
+  SpecPack pk;
+  make_pack(h, pk, s0, ns);
+  k_anisch_pa<<<dim3(nblk((long long)h->NE * h->Pp, 128), ns), 128, 0, st>>>(h->dev, pk, s0);
+  CKL();
+  const double cv = kCS * 100;
+  const double RFAC = 4 * kPI / cv;
+  k_anisch_en<<<dim3(nblk(h->P, 128), ns), 128, 0, st>>>(h->dev, pk, s0, RFAC, h->khi[0], h->khi[1], h->khi[2], h->khi[3], h->khi[4]);
   CKL();
   h->launches += 2;
   return RSG_OK;
 }
 
-int fetch_res(rsg_ram* h, int s) {
+int fetch_res(rsg_ram* h, int s, cudaStream_t st) {
   Spec& sp = h->sp[s];
-  CK(cudaMemcpyAsync(sp.h_res, sp.d_res, sizeof(unsigned long long) * (4 + NSUM + 1), cudaMemcpyDeviceToHost, h->st(s)));
-  CK(cudaStreamSynchronize(h->st(s)));
+  CK(cudaMemcpyAsync(sp.h_res, sp.d_res, sizeof(unsigned long long) * RES_N, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
   return RSG_OK;
 }
 
-// DtDrift* start values (:115,223,308,404) live in a device constant buffer so
-// the reset is a stream-ordered D2D copy
-int reset_dt(rsg_ram* h, int s, int which) {
-  CK(cudaMemcpyAsync(h->sp[s].d_res + which, h->d_dtinit + which, 8, cudaMemcpyDeviceToDevice, h->st(s)));
+// ---- host tables of one species (reference operation order) ------------------------
+// DRIFTPARA (src/ModRamDrift.f90:36-88) + the energy-only prefixes of the sweeps
+int tables_drift(rsg_ram* h, int s, double DTs, cudaStream_t st) {
+  const int nS = h->nS, NR = h->NR, NE = h->NE, NPA = h->NPA;
+  Spec& sp = h->sp[s];
+  const double MDR = h->dev.MDR, DPHI = h->dev.DPHI, FracCFL = h->dev.FracCFL;
+  const double QS = (double)h->QS[s];
+  double* t = sp.h_tab;
+  double *P4 = t, *eK = t + NE, *epK = t + 2 * NE, *aE = t + 3 * NE;
+  double* P2 = t + 4 * NE;
+  double* EDOT = P2 + (size_t)NE * NR;
+  double* aMU = EDOT + (size_t)NE * NR;
+#define GRELs(K) h->GREL[s + (size_t)nS * ((K)-1)]
+#define GRBNDs(K) h->GRBND[s + (size_t)nS * ((K)-1)]
+  for (int K = 1; K <= NE; ++K) {
+    // DRIFTR :131, DRIFTE :337 (energy-only prefix), DRIFTMU :424 (prefix)
+    P4[K - 1] = DTs * h->EKEV[K - 1] * 1000.0 * (GRELs(K) + 1) / GRELs(K) / DPHI / MDR / QS;
+    eK[K - 1] = h->EBND[K - 1] * 1e3 * (GRBNDs(K) + 1) / 2 / GRBNDs(K);
+    epK[K - 1] = h->EKEV[K - 1] * 1e3 * (GRELs(K) + 1) / 2 / GRELs(K);
+    aE[K - 1] = FracCFL * DTs * h->DE[K - 1];
+    for (int I = 1; I <= NR; ++I) {
+      // DRIFTPARA :71, :83
+      P2[(size_t)(K - 1) * NR + (I - 1)] =
+          DTs * h->EKEV[K - 1] * 1000 * (GRELs(K) + 1) / GRELs(K) / (h->RLZ[I - 1] * h->RLZ[I - 1]) / DPHI / QS;
+      EDOT[(size_t)(K - 1) * NR + (I - 1)] = h->EBND[K - 1] * DTs / h->RLZ[I - 1] * (GRBNDs(K) + 1) / GRBNDs(K) / 2.;
+    }
+  }
+  for (int L = 1; L <= NPA; ++L) aMU[L - 1] = FracCFL * DTs * h->DMU[L - 1];
+  CK(cudaMemcpyAsync(sp.d_tab, sp.h_tab, sp.n_tab * sizeof(double), cudaMemcpyHostToDevice, st));
+  SpecDev& sd = sp.sd;
+  // DRIFTE :310-311, :334-335
+  const double EZERO = h->EKEV[0] - h->WE[0];
+  sd.GRZERO = 1. + EZERO * 1000. * kQ / h->RMAS[s] / kCS / kCS;
+  sd.GREL1 = GRELs(1);
+  sd.GREL2 = GRELs(2);
+  sd.sqrtA = std::sqrt((sd.GREL2 * sd.GREL2 - 1) / (sd.GREL1 * sd.GREL1 - 1));
+  sd.sqrtB = std::sqrt((sd.GREL1 * sd.GREL1 - 1) / (sd.GRZERO * sd.GRZERO - 1));
+  sd.aRP = FracCFL * DTs;
+  sd.OMEt = OME_EARTH * DTs / DPHI;
+  sp.DTs = DTs;
+  return RSG_OK;
+}
+
+// CEPARA (src/ModRamLoss.f90:19-170): energy-only factors
+int tables_cepara(rsg_ram* h, int s, double DTs, cudaStream_t st) {
+  const int nS = h->nS, NR = h->NR, NE = h->NE;
+  Spec& sp = h->sp[s];
+  double* sv = sp.h_ce;
+  double* ATLOS = sp.h_ce + NE;
+  const int kind = h->kind[s];
+  for (int K = 1; K <= NE; ++K) {
+    const double Vk = h->V[s + (size_t)nS * (K - 1)];
+    double v = 0.0;
+    if (K >= 2 && kind != RSG_KIND_E) {
+      // :44-47, :59-62, :74-77
+      double X = std::log10(h->EKEV[K - 1]);
+      if (X < -2.) X = -2.;
+      double Y;
+      if (kind == RSG_KIND_H)
+        Y = -18.767 - 0.11017 * X - 3.8173e-2 * (X * X) - 0.1232 * (X * X * X) - 5.0488e-2 * ((X * X) * (X * X));
+      else if (kind == RSG_KIND_HE)
+        Y = -20.789 + 0.92316 * X - 0.68017 * (X * X) + 0.66153 * (X * X * X) - 0.20998 * ((X * X) * (X * X));
+      else
+        Y = -18.987 - 0.10613 * X - 5.4841E-3 * (X * X) - 1.6262E-2 * (X * X * X) - 7.0554E-3 * ((X * X) * (X * X));
+      v = std::pow(10., Y) * Vk;
+    }
+    sv[K - 1] = v;
+    for (int I = 1; I <= NR; ++I) {
+      double a = 1.0;
+      if (K >= 2 && I >= 2) {
+        const double TAUB = 2 * h->RLZ[I - 1] / Vk;  // :163-166
+        a = std::exp(-DTs / TAUB);
+      }
+      ATLOS[(size_t)(K - 1) * NR + (I - 1)] = a;
+    }
+  }
+  CK(cudaMemcpyAsync(sp.d_ce, sp.h_ce, ((size_t)NE + (size_t)NE * NR) * sizeof(double), cudaMemcpyHostToDevice, st));
+  sp.DTs_ce = DTs;
+  return RSG_OK;
+}
+
+// WAVELO factor table exp(-DTs/TAU_LIF) (src/ModRamWPI.f90:599-632, DoUsePlasmasphere=.false.)
+int tables_wavelo(rsg_ram* h, int s, double DTs, cudaStream_t st) {
+  const int NR = h->NR, NT = h->NT, NE = h->NE;
+  Spec& sp = h->sp[s];
+  if (sp.DTs_wl == DTs) return RSG_OK;
+  if (h->WALOS1.empty()) return fail(RSG_ERR_STATE, "WAVELO before set_wavelo");
+  double Bw = 30.;
+  if (h->Kp >= 4.0) Bw = 100.;
+  const double RLpp = 5.39 - 0.382 * h->Kpmax12;
+  std::memset(sp.h_wfac, 0, (size_t)NE * h->Pp * sizeof(double));
+  for (int K = 2; K <= NE; ++K)
+    for (int I = 2; I <= NR; ++I) {
+      const double W1 = h->WALOS1[(I - 1) + (size_t)NR * (K - 1)], W2 = h->WALOS2[(I - 1) + (size_t)NR * (K - 1)],
+                   W3 = h->WALOS3[(I - 1) + (size_t)NR * (K - 1)];
+      const double E = h->EKEV[K - 1];
+      double TAU_LIF = 0.0;
+      if (h->LZ[I - 1] <= RLpp) {
+        TAU_LIF = W1 * ((10. / Bw) * (10. / Bw));
+      } else {
+        if (E <= 1000.) {
+          TAU_LIF = W2 * (1 + W3 / W2);
+          if (E <= 1.1) TAU_LIF = TAU_LIF * 37.5813 * std::exp(-1.81255 * E);
+          else if (E > 1.1 && E <= 5.) TAU_LIF = TAU_LIF * (7.5 - 1.15 * E);
+        } else {
+          TAU_LIF = 5. * 3600 * 24 / h->Kp;
+        }
+      }
+      const double fac = std::exp(-DTs / TAU_LIF);
+      for (int J = 1; J <= NT; ++J) sp.h_wfac[(size_t)(K - 1) * h->Pp + (size_t)(J - 1) * NR + (I - 1)] = fac;
+    }
+  CK(cudaMemcpyAsync(sp.d_wfac, sp.h_wfac, (size_t)NE * h->Pp * sizeof(double), cudaMemcpyHostToDevice, st));
+  sp.DTs_wl = DTs;
   return RSG_OK;
 }
 
@@ -240,6 +496,10 @@ int rsg_ram_create(rsg_ram** out, int nS, int NR, int NT, int NE, int NPA, int d
   h->NR1 = NR + 1;
   h->P = NR * NT;
   h->Pp = (h->P + 15) / 16 * 16;
+  if (const char* e = getenv("RSG_SEG")) h->segE = h->segMU = h->segP = std::max(2, atoi(e));
+  if (const char* e = getenv("RSG_SEG_E")) h->segE = std::max(2, atoi(e));
+  if (const char* e = getenv("RSG_SEG_MU")) h->segMU = std::max(2, atoi(e));
+  if (const char* e = getenv("RSG_SEG_P")) h->segP = std::max(2, atoi(e));
   RamDev& d = h->dev;
   d.nS = nS; d.NR = NR; d.NT = NT; d.NE = NE; d.NPA = NPA; d.NR1 = h->NR1; d.P = h->P; d.Pp = h->Pp;
   const size_t n2 = (size_t)h->NR1 * NT, n3 = n2 * NPA, np = h->Pp, n3p = (size_t)NPA * h->Pp;
@@ -259,25 +519,33 @@ int rsg_ram_create(rsg_ram** out, int nS, int NR, int NT, int NE, int NPA, int d
                     &d.CMUDOT, &d.Gmr, &d.Gmp, &d.DRM2, &d.DPM2, &d.dIbndt2, &d.BOUNHSc, &d.HDNSc};
   for (auto p : p3d) RET(h->dalloc(p, n3p));
   h->specStride = (size_t)NPA * NE * h->Pp;
-  RET(h->dalloc(&h->d_F2, h->specStride * nS));
+  RET(h->dalloc(&h->d_F2[0], h->specStride * nS));
+  RET(h->dalloc(&h->d_F2[1], h->specStride * nS));
   RET(h->dalloc(&h->d_stage, (size_t)nS * h->P * NE * NPA));
   RET(h->dalloc(&h->d_zero4, h->specStride));
   RET(h->dalloc(&h->d_NECR, (size_t)NR * NT));
   RET(h->dalloc(&h->d_dtinit, 4));
   {
-    const double init[4] = {100000.0, 100000.0, 10000.0, 10000.0};
+    const double init[4] = {100000.0, 100000.0, 10000.0, 10000.0};  // :115,223,308,404
     RET(up(h->d_dtinit, init, 4));
   }
+  h->ntiles = (NE * NPA * NT + SCAN_TILE - 1) / SCAN_TILE;
+  RET(h->dalloc(&h->d_tilemax, (size_t)nS * h->ntiles));
+  RET(h->dalloc(&h->d_res_all, (size_t)nS * RES_N));
+  CK(cudaMallocHost((void**)&h->h_res_all, (size_t)nS * RES_N * sizeof(unsigned long long)));
+  RET(h->dalloc(&h->d_pp_all, (size_t)nS * 2 * h->Pp));
+  CK(cudaMallocHost((void**)&h->h_pp_all, (size_t)nS * 2 * h->Pp * sizeof(double)));
   CK(cudaStreamCreateWithFlags(&h->prepst, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&h->prepev, cudaEventDisableTiming));
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-  h->nblk_sum = sms * 4;
+  // grid-stride reductions: a fixed grid => a fixed summation tree
+  h->nblk_sum = std::max(1, std::min(sms * 8, nblk((long long)h->specStride, 256)));
   for (int s = 0; s < nS; ++s) {
     Spec& sp = h->sp[s];
     CK(cudaStreamCreateWithFlags(&sp.own, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&sp.ev, cudaEventDisableTiming));
-    sp.n_tab = (size_t)NE * 5 + (size_t)NE * NR * 2 + NPA;
+    sp.n_tab = (size_t)NE * 4 + (size_t)NE * NR * 2 + NPA;
     RET(h->dalloc(&sp.d_tab, sp.n_tab));
     CK(cudaMallocHost((void**)&sp.h_tab, sp.n_tab * sizeof(double)));
     RET(h->dalloc(&sp.d_ce, (size_t)NE + (size_t)NE * NR));
@@ -288,14 +556,15 @@ int rsg_ram_create(rsg_ram** out, int nS, int NR, int NT, int NE, int NPA, int d
     RET(h->dalloc(&sp.d_EPP, (size_t)NE));
     RET(h->dalloc(&sp.d_FGEOS, (size_t)NPA * NE * NT));
     RET(h->dalloc(&sp.d_last, (size_t)NE * NPA * NT));
-    RET(h->dalloc(&sp.d_part, (size_t)h->nblk_sum));
+    RET(h->dalloc(&sp.d_part, (size_t)h->nblk_sum * RSG_NMOM));
     RET(h->dalloc(&sp.d_tE, (size_t)2 * NE * h->Pp));
-    RET(h->dalloc(&sp.d_pp, (size_t)2 * h->Pp));
-    RET(h->dalloc(&sp.d_res, (size_t)4 + NSUM + 1));
-    CK(cudaMallocHost((void**)&sp.h_res, (4 + NSUM + 1) * sizeof(unsigned long long)));
+    sp.d_res = h->d_res_all + (size_t)s * RES_N;
+    sp.h_res = h->h_res_all + (size_t)s * RES_N;
+    sp.d_pp = h->d_pp_all + (size_t)s * 2 * h->Pp;
     SpecDev& sd = sp.sd;
     sd.S = s;
-    sd.F = h->d_F2 + h->specStride * s;
+    sd.last = sp.d_last;
+    sd.part = sp.d_part;
     sd.FGEOS = sp.d_FGEOS;
     double* t = sp.d_tab;
     sd.P4 = t; t += NE;
@@ -309,6 +578,12 @@ int rsg_ram_create(rsg_ram** out, int nS, int NR, int NT, int NE, int NPA, int d
     sd.aMU = t; t += NPA;
     sd.FF = sp.d_FF;
     sd.EPP = sp.d_EPP;
+    sd.wfac = sp.d_wfac;
+    sd.DA = sd.DB = h->d_zero4;
+    sd.tE = sp.d_tE;
+    sd.tA = sp.d_tE + (size_t)NE * h->Pp;
+    sd.pper = sp.d_pp;
+    sd.ppar = sp.d_pp + h->Pp;
     sd.dt = sp.d_res;
   }
   *out = h;
@@ -327,10 +602,13 @@ int rsg_ram_destroy(rsg_ram* h) {
     if (sp.h_tab) cudaFreeHost(sp.h_tab);
     if (sp.h_ce) cudaFreeHost(sp.h_ce);
     if (sp.h_wfac) cudaFreeHost(sp.h_wfac);
-    if (sp.h_res) cudaFreeHost(sp.h_res);
   }
+  if (h->h_res_all) cudaFreeHost(h->h_res_all);
+  if (h->h_pp_all) cudaFreeHost(h->h_pp_all);
   if (h->prepst) cudaStreamDestroy(h->prepst);
   if (h->prepev) cudaEventDestroy(h->prepev);
+  if (h->t0) cudaEventDestroy(h->t0);
+  if (h->t1) cudaEventDestroy(h->t1);
   delete h;
   return RSG_OK;
 }
@@ -492,14 +770,13 @@ int rsg_ram_f2_h2d(rsg_ram* h, const double* F2, int S) {
   if (S < 0 || S > h->nS) return fail(RSG_ERR_ARG, "species index out of range");
   CK(cudaSetDevice(h->device));
   const size_t n = (size_t)h->nS * h->P * h->NE * h->NPA;
-  cudaStream_t st = h->st(S ? S - 1 : 0);
-  if (!h->ext && S == 0)
-    for (int s = 1; s < h->nS; ++s) CK(cudaStreamSynchronize(h->sp[s].own));
+  if (S == 0) RET(rsg_ram_sync(h));
+  cudaStream_t st = S ? h->st(S - 1) : h->pst();
   CK(cudaMemcpyAsync(h->d_stage, F2, n * sizeof(double), cudaMemcpyHostToDevice, st));
   const long long ne = (long long)h->specStride;
   for (int s = 0; s < h->nS; ++s) {
     if (S != 0 && s != S - 1) continue;
-    k_f2_from_host<<<nblk(ne, 256), 256, 0, st>>>(h->dev, h->d_stage, h->d_F2 + h->specStride * s, s);
+    k_f2_from_host<<<nblk(ne, 256), 256, 0, st>>>(h->dev, h->d_stage, h->d_F2[h->sp[s].cur] + h->specStride * s, s);
     CKL();
     h->launches++;
   }
@@ -513,7 +790,7 @@ int rsg_ram_f2_d2h(rsg_ram* h, double* F2, int S) {
   CK(cudaSetDevice(h->device));
   const size_t n = (size_t)h->nS * h->P * h->NE * h->NPA;
   if (S == 0) RET(rsg_ram_sync(h));
-  cudaStream_t st = h->st(S ? S - 1 : 0);
+  cudaStream_t st = S ? h->st(S - 1) : h->pst();
   const long long ne = (long long)h->specStride;
   if (S != 0) {
     // keep the other species' host values: start from the host image
@@ -521,7 +798,7 @@ int rsg_ram_f2_d2h(rsg_ram* h, double* F2, int S) {
   }
   for (int s = 0; s < h->nS; ++s) {
     if (S != 0 && s != S - 1) continue;
-    k_f2_to_host<<<nblk(ne, 256), 256, 0, st>>>(h->dev, h->d_stage, h->d_F2 + h->specStride * s, s);
+    k_f2_to_host<<<nblk(ne, 256), 256, 0, st>>>(h->dev, h->d_stage, h->d_F2[h->sp[s].cur] + h->specStride * s, s);
     CKL();
     h->launches++;
   }
@@ -532,7 +809,7 @@ int rsg_ram_f2_d2h(rsg_ram* h, double* F2, int S) {
 
 int rsg_ram_f2_device(rsg_ram* h, int S, void** ptr, long long* n_doubles, int* Pp) {
   RET(check_S(h, S));
-  if (ptr) *ptr = h->d_F2 + h->specStride * (S - 1);
+  if (ptr) *ptr = h->d_F2[h->sp[S - 1].cur] + h->specStride * (S - 1);
   if (n_doubles) *n_doubles = (long long)h->specStride;
   if (Pp) *Pp = h->Pp;
   return RSG_OK;
@@ -543,124 +820,25 @@ int rsg_driftpara(rsg_ram* h, int S, double DTs) {
   RET(check_S(h, S));
   if (!h->grids_set) return fail(RSG_ERR_STATE, "DRIFTPARA before set_grids");
   CK(cudaSetDevice(h->device));
-  const int s = S - 1, nS = h->nS, NR = h->NR, NE = h->NE, NPA = h->NPA;
-  Spec& sp = h->sp[s];
+  const int s = S - 1;
   RET(ensure_step(h, DTs));
   // the previous contents of h_tab may still be in flight on the species stream
   CK(cudaStreamSynchronize(h->st(s)));
-  const double MDR = h->dev.MDR, DPHI = h->dev.DPHI, FracCFL = h->dev.FracCFL;
-  const double QS = (double)h->QS[s];
-  double* t = sp.h_tab;
-  double *P4 = t, *eK = t + NE, *epK = t + 2 * NE, *aE = t + 3 * NE;
-  double* P2 = t + 4 * NE;
-  double* EDOT = P2 + (size_t)NE * NR;
-  double* aMU = EDOT + (size_t)NE * NR;
-#define GRELs(K) h->GREL[s + (size_t)nS * ((K)-1)]
-#define GRBNDs(K) h->GRBND[s + (size_t)nS * ((K)-1)]
-  for (int K = 1; K <= NE; ++K) {
-    // DRIFTR :131, DRIFTE :337 (energy-only prefix), DRIFTMU :424 (prefix)
-    P4[K - 1] = DTs * h->EKEV[K - 1] * 1000.0 * (GRELs(K) + 1) / GRELs(K) / DPHI / MDR / QS;
-    eK[K - 1] = h->EBND[K - 1] * 1e3 * (GRBNDs(K) + 1) / 2 / GRBNDs(K);
-    epK[K - 1] = h->EKEV[K - 1] * 1e3 * (GRELs(K) + 1) / 2 / GRELs(K);
-    aE[K - 1] = FracCFL * DTs * h->DE[K - 1];
-    for (int I = 1; I <= NR; ++I) {
-      // DRIFTPARA :71, :83
-      P2[(size_t)(K - 1) * NR + (I - 1)] =
-          DTs * h->EKEV[K - 1] * 1000 * (GRELs(K) + 1) / GRELs(K) / (h->RLZ[I - 1] * h->RLZ[I - 1]) / DPHI / QS;
-      EDOT[(size_t)(K - 1) * NR + (I - 1)] = h->EBND[K - 1] * DTs / h->RLZ[I - 1] * (GRBNDs(K) + 1) / GRBNDs(K) / 2.;
-    }
+  RET(tables_drift(h, s, DTs, h->st(s)));
+  return L_inflow(h, s, 1, h->st(s));
+}
+
+#define SWEEP_ENTRY(name, fn)                                                      \
+  int name(rsg_ram* h, int S) {                                                    \
+    RET(check_S(h, S));                                                            \
+    if (h->sp[S - 1].DTs < 0) return fail(RSG_ERR_STATE, #name " before DRIFTPARA"); \
+    CK(cudaSetDevice(h->device));                                                  \
+    return fn(h, S - 1, 1, h->st(S - 1));                                          \
   }
-  for (int L = 1; L <= NPA; ++L) aMU[L - 1] = FracCFL * DTs * h->DMU[L - 1];
-  CK(cudaMemcpyAsync(sp.d_tab, sp.h_tab, sp.n_tab * sizeof(double), cudaMemcpyHostToDevice, h->st(s)));
-  SpecDev& sd = sp.sd;
-  // DRIFTE :310-311, :334-335
-  const double EZERO = h->EKEV[0] - h->WE[0];
-  sd.GRZERO = 1. + EZERO * 1000. * kQ / h->RMAS[s] / kCS / kCS;
-  sd.GREL1 = GRELs(1);
-  sd.GREL2 = GRELs(2);
-  sd.sqrtA = std::sqrt((sd.GREL2 * sd.GREL2 - 1) / (sd.GREL1 * sd.GREL1 - 1));
-  sd.sqrtB = std::sqrt((sd.GREL1 * sd.GREL1 - 1) / (sd.GRZERO * sd.GRZERO - 1));
-  sd.aRP = FracCFL * DTs;
-  sd.OMEt = OME_EARTH * DTs / DPHI;
-  sp.DTs = DTs;
-  return RSG_OK;
-}
-
-int rsg_driftr(rsg_ram* h, int S) {
-  RET(check_S(h, S));
-  const int s = S - 1;
-  Spec& sp = h->sp[s];
-  if (sp.DTs < 0) return fail(RSG_ERR_STATE, "DRIFTR before DRIFTPARA");
-  CK(cudaSetDevice(h->device));
-  RamDev dv = devfor(h, s);
-  cudaStream_t st = h->st(s);
-  RET(reset_dt(h, s, 0));
-  const int nl = h->NE * h->NPA * h->NT;
-  k_driftr_inflow<<<nblk(nl, 256), 256, 0, st>>>(dv, sp.sd, sp.d_last);
-  CKL();
-  k_scan_last<<<1, 1024, 0, st>>>(sp.d_last, nl);
-  CKL();
-  // planes per CTA: fill ~256 threads, bounded by shared memory
-  const int NRc = h->NR | 1, NRf = (h->NR + 2) | 1;
-  int KC = std::max(1, 256 / h->NT);
-  size_t smem;
-  for (;;) {
-    smem = sizeof(double) * ((size_t)3 * h->NT * NRc + (size_t)KC * h->NT * NRf);
-    if (smem <= 96 * 1024 || KC == 1) break;
-    --KC;
-  }
-  if (smem > 220 * 1024) return fail(RSG_ERR_UNSUPPORTED, "DRIFTR: (NT,NR) plane too large for shared memory");
-  static thread_local size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
-    CK(cudaFuncSetAttribute(k_driftr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
-  const int threads = (KC * h->NT + 31) / 32 * 32;
-  dim3 grid((h->NE + KC - 1) / KC, h->NPA);
-  k_driftr<<<grid, threads, smem, st>>>(dv, sp.sd, sp.d_last, KC);
-  CKL();
-  h->launches += 3;
-  return RSG_OK;
-}
-
-int rsg_driftp(rsg_ram* h, int S) {
-  RET(check_S(h, S));
-  const int s = S - 1;
-  Spec& sp = h->sp[s];
-  if (sp.DTs < 0) return fail(RSG_ERR_STATE, "DRIFTP before DRIFTPARA");
-  CK(cudaSetDevice(h->device));
-  RET(reset_dt(h, s, 1));
-  k_driftp<<<nblk((long long)h->NPA * h->NE * h->NR, 128), 128, 0, h->st(s)>>>(devfor(h, s), sp.sd);
-  CKL();
-  h->launches++;
-  return RSG_OK;
-}
-
-int rsg_drifte(rsg_ram* h, int S) {
-  RET(check_S(h, S));
-  const int s = S - 1;
-  Spec& sp = h->sp[s];
-  if (sp.DTs < 0) return fail(RSG_ERR_STATE, "DRIFTE before DRIFTPARA");
-  CK(cudaSetDevice(h->device));
-  RET(reset_dt(h, s, 2));
-  k_drifte<<<nblk((long long)h->NPA * h->Pp, 128), 128, 0, h->st(s)>>>(devfor(h, s), sp.sd);
-  CKL();
-  h->launches++;
-  return RSG_OK;
-}
-
-int rsg_driftmu(rsg_ram* h, int S) {
-  RET(check_S(h, S));
-  const int s = S - 1;
-  Spec& sp = h->sp[s];
-  if (sp.DTs < 0) return fail(RSG_ERR_STATE, "DRIFTMU before DRIFTPARA");
-  CK(cudaSetDevice(h->device));
-  RET(reset_dt(h, s, 3));
-  k_driftmu<<<nblk((long long)h->NE * h->Pp, 128), 128, 0, h->st(s)>>>(devfor(h, s), sp.sd);
-  CKL();
-  h->launches++;
-  return RSG_OK;
-}
+SWEEP_ENTRY(rsg_driftr, L_driftr)
+SWEEP_ENTRY(rsg_driftp, L_driftp)
+SWEEP_ENTRY(rsg_drifte, L_drifte)
+SWEEP_ENTRY(rsg_driftmu, L_driftmu)
 
 int rsg_driftend(rsg_ram* h) {
   if (!h) return fail(RSG_ERR_ARG, "null handle");
@@ -671,7 +849,7 @@ int rsg_get_dtdrift(rsg_ram* h, int S, double out4[4]) {
   RET(check_S(h, S));
   if (!out4) return fail(RSG_ERR_ARG, "null out");
   CK(cudaSetDevice(h->device));
-  RET(fetch_res(h, S - 1));
+  RET(fetch_res(h, S - 1, h->st(S - 1)));
   std::memcpy(out4, h->sp[S - 1].h_res, 4 * sizeof(double));
   return RSG_OK;
 }
@@ -681,51 +859,8 @@ int rsg_cepara(rsg_ram* h, int S, double DTs) {
   RET(check_S(h, S));
   if (!h->grids_set) return fail(RSG_ERR_STATE, "CEPARA before set_grids");
   CK(cudaSetDevice(h->device));
-  const int s = S - 1, nS = h->nS, NR = h->NR, NE = h->NE;
-  Spec& sp = h->sp[s];
-  CK(cudaStreamSynchronize(h->st(s)));
-  double* sv = sp.h_ce;
-  double* ATLOS = sp.h_ce + NE;
-  const int kind = h->kind[s];
-  for (int K = 1; K <= NE; ++K) {
-    const double Vk = h->V[s + (size_t)nS * (K - 1)];
-    double v = 0.0;
-    if (K >= 2 && kind != RSG_KIND_E) {
-      // src/ModRamLoss.f90:44-47, :59-62, :74-77
-      double X = std::log10(h->EKEV[K - 1]);
-      if (X < -2.) X = -2.;
-      double Y;
-      if (kind == RSG_KIND_H)
-        Y = -18.767 - 0.11017 * X - 3.8173e-2 * (X * X) - 0.1232 * (X * X * X) - 5.0488e-2 * ((X * X) * (X * X));
-      else if (kind == RSG_KIND_HE)
-        Y = -20.789 + 0.92316 * X - 0.68017 * (X * X) + 0.66153 * (X * X * X) - 0.20998 * ((X * X) * (X * X));
-      else
-        Y = -18.987 - 0.10613 * X - 5.4841E-3 * (X * X) - 1.6262E-2 * (X * X * X) - 7.0554E-3 * ((X * X) * (X * X));
-      v = std::pow(10., Y) * Vk;
-    }
-    sv[K - 1] = v;
-    for (int I = 1; I <= NR; ++I) {
-      double a = 1.0;
-      if (K >= 2 && I >= 2) {
-        const double TAUB = 2 * h->RLZ[I - 1] / Vk;  // :163-166
-        a = std::exp(-DTs / TAUB);
-      }
-      ATLOS[(size_t)(K - 1) * NR + (I - 1)] = a;
-    }
-  }
-  CK(cudaMemcpyAsync(sp.d_ce, sp.h_ce, ((size_t)NE + (size_t)NE * NR) * sizeof(double), cudaMemcpyHostToDevice, h->st(s)));
-  sp.DTs_ce = DTs;
-  return RSG_OK;
-}
-
-static int launch_loss(rsg_ram* h, int s, int op, double DTs) {
-  Spec& sp = h->sp[s];
-  RamDev dv = h->dev;
-  dv.DTs = DTs;
-  k_loss<<<nblk((long long)h->specStride, 256), 256, 0, h->st(s)>>>(dv, sp.sd, op, sp.d_wfac);
-  CKL();
-  h->launches++;
-  return RSG_OK;
+  CK(cudaStreamSynchronize(h->st(S - 1)));
+  return tables_cepara(h, S - 1, DTs, h->st(S - 1));
 }
 
 int rsg_charexchange(rsg_ram* h, int S) {
@@ -735,7 +870,7 @@ int rsg_charexchange(rsg_ram* h, int S) {
   if (!h->fields_set) return fail(RSG_ERR_STATE, "CHAREXCHANGE before set_fields");
   CK(cudaSetDevice(h->device));
   if (h->kind[S - 1] == RSG_KIND_E) return RSG_OK;  // CHARGE == 1 for electrons
-  return launch_loss(h, S - 1, 0, sp.DTs_ce);
+  return L_loss(h, S - 1, 0, sp.DTs_ce, h->st(S - 1));
 }
 
 int rsg_atmol(rsg_ram* h, int S) {
@@ -744,47 +879,17 @@ int rsg_atmol(rsg_ram* h, int S) {
   if (sp.DTs_ce < 0) return fail(RSG_ERR_STATE, "ATMOL before CEPARA");
   if (!h->fields_set) return fail(RSG_ERR_STATE, "ATMOL before set_fields");
   CK(cudaSetDevice(h->device));
-  return launch_loss(h, S - 1, 1, sp.DTs_ce);
+  return L_loss(h, S - 1, 1, sp.DTs_ce, h->st(S - 1));
 }
 
 // ---- ModRamWPI --------------------------------------------------------------------
 int rsg_wavelo(rsg_ram* h, int S, double DTs) {
   RET(check_S(h, S));
-  if (h->WALOS1.empty()) return fail(RSG_ERR_STATE, "WAVELO before set_wavelo");
   CK(cudaSetDevice(h->device));
-  const int s = S - 1, NR = h->NR, NT = h->NT, NE = h->NE;
-  Spec& sp = h->sp[s];
-  if (sp.DTs_wl != DTs) {
-    CK(cudaStreamSynchronize(h->st(s)));
-    // src/ModRamWPI.f90:599-632 with DoUsePlasmasphere=.false.
-    double Bw = 30.;
-    if (h->Kp >= 4.0) Bw = 100.;
-    const double RLpp = 5.39 - 0.382 * h->Kpmax12;
-    std::memset(sp.h_wfac, 0, (size_t)NE * h->Pp * sizeof(double));
-    for (int K = 2; K <= NE; ++K)
-      for (int I = 2; I <= NR; ++I) {
-        const double W1 = h->WALOS1[(I - 1) + (size_t)NR * (K - 1)], W2 = h->WALOS2[(I - 1) + (size_t)NR * (K - 1)],
-                     W3 = h->WALOS3[(I - 1) + (size_t)NR * (K - 1)];
-        const double E = h->EKEV[K - 1];
-        double TAU_LIF = 0.0;
-        if (h->LZ[I - 1] <= RLpp) {
-          TAU_LIF = W1 * ((10. / Bw) * (10. / Bw));
-        } else {
-          if (E <= 1000.) {
-            TAU_LIF = W2 * (1 + W3 / W2);
-            if (E <= 1.1) TAU_LIF = TAU_LIF * 37.5813 * std::exp(-1.81255 * E);
-            else if (E > 1.1 && E <= 5.) TAU_LIF = TAU_LIF * (7.5 - 1.15 * E);
-          } else {
-            TAU_LIF = 5. * 3600 * 24 / h->Kp;
-          }
-        }
-        const double fac = std::exp(-DTs / TAU_LIF);
-        for (int J = 1; J <= NT; ++J) sp.h_wfac[(size_t)(K - 1) * h->Pp + (size_t)(J - 1) * NR + (I - 1)] = fac;
-      }
-    CK(cudaMemcpyAsync(sp.d_wfac, sp.h_wfac, (size_t)NE * h->Pp * sizeof(double), cudaMemcpyHostToDevice, h->st(s)));
-    sp.DTs_wl = DTs;
-  }
-  return launch_loss(h, s, 2, DTs);
+  const int s = S - 1;
+  if (h->sp[s].DTs_wl != DTs) CK(cudaStreamSynchronize(h->st(s)));
+  RET(tables_wavelo(h, s, DTs, h->st(s)));
+  return L_loss(h, s, 2, DTs, h->st(s));
 }
 
 int rsg_wpadif(rsg_ram* h, int S, double DTs, long long* nviolation) {
@@ -792,29 +897,10 @@ int rsg_wpadif(rsg_ram* h, int S, double DTs, long long* nviolation) {
   if (!h->fields_set) return fail(RSG_ERR_STATE, "WPADIF before set_fields");
   CK(cudaSetDevice(h->device));
   const int s = S - 1;
-  Spec& sp = h->sp[s];
-  const double *DA, *DB;
-  if (h->kind[s] == RSG_KIND_E) { DA = h->d_diff[0]; DB = h->d_diff[1]; }
-  else { DA = h->d_diff[2]; DB = h->d_diff[3]; }
-  if (!DA && !DB) return fail(RSG_ERR_STATE, "WPADIF before set_diffcoef");
-  if (!DA) DA = h->d_zero4;
-  if (!DB) DB = h->d_zero4;
-  RamDev dv = h->dev;
-  dv.DTs = DTs;
-  const int T = 64;
-  const size_t smem = sizeof(double) * 2 * h->NPA * T;
-  static thread_local size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
-    CK(cudaFuncSetAttribute(k_wpadif, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
-  CK(cudaMemsetAsync(sp.d_res + 4 + NSUM, 0, sizeof(unsigned long long), h->st(s)));
-  k_wpadif<<<nblk((long long)h->NE * h->Pp, T), T, smem, h->st(s)>>>(dv, sp.sd, DA, DB, sp.d_res + 4 + NSUM);
-  CKL();
-  h->launches++;
+  RET(L_wpadif(h, s, DTs, h->st(s)));
   if (nviolation) {
-    RET(fetch_res(h, s));
-    *nviolation = (long long)sp.h_res[4 + NSUM];
+    RET(fetch_res(h, s, h->st(s)));
+    *nviolation = (long long)h->sp[s].h_res[4 + NSUM];
   }
   return RSG_OK;
 }
@@ -830,8 +916,8 @@ int rsg_sumrc(rsg_ram* h, int S, double* setrc, double* elorc) {
   CK(cudaSetDevice(h->device));
   const int s = S - 1;
   Spec& sp = h->sp[s];
-  RET(launch_sumrc(h, s, 0));
-  RET(fetch_res(h, s));
+  RET(L_sumrc(h, s, 1, 0, h->st(s)));
+  RET(fetch_res(h, s, h->st(s)));
   double v;
   std::memcpy(&v, sp.h_res + 4, 8);
   const double old = sp.setrc;
@@ -841,97 +927,92 @@ int rsg_sumrc(rsg_ram* h, int S, double* setrc, double* elorc) {
   return RSG_OK;
 }
 
-static int launch_anisch(rsg_ram* h, int s) {
-  Spec& sp = h->sp[s];
-  RamDev dv = h->dev;
-  double* tE = sp.d_tE;
-  double* tA = sp.d_tE + (size_t)h->NE * h->Pp;
-  k_anisch_pa<<<nblk((long long)h->NE * h->Pp, 128), 128, 0, h->st(s)>>>(dv, sp.sd, tE, tA);
-  CKL();
-  const double cv = kCS * 100;
-  const double RFAC = 4 * kPI / cv;
-  k_anisch_en<<<nblk(h->P, 128), 128, 0, h->st(s)>>>(dv, tE, tA, RFAC, h->khi[0], h->khi[1], h->khi[2], h->khi[3], h->khi[4],
-                                                      sp.d_pp, sp.d_pp + h->Pp);
-  CKL();
-  h->launches += 2;
-  return RSG_OK;
-}
-
-// copy the (NR,NT) planes of species s into PPERT/PPART; stride = 1 for a
-// per-species slice, nS (with offset s) for the full (nS,NR,NT) arrays
-static int fetch_anisch(rsg_ram* h, int s, double* PPERT, double* PPART, int stride, int off) {
-  Spec& sp = h->sp[s];
-  std::vector<double> b((size_t)2 * h->Pp);
-  CK(cudaMemcpyAsync(b.data(), sp.d_pp, b.size() * sizeof(double), cudaMemcpyDeviceToHost, h->st(s)));
-  CK(cudaStreamSynchronize(h->st(s)));
+// (NR,NT) planes of species s out of the pinned image; stride = 1 for a
+// per-species slice, nS (offset s) for the full (nS,NR,NT) arrays
+static void scatter_anisch(rsg_ram* h, int s, double* PPERT, double* PPART, int stride, int off) {
+  const double* b = h->h_pp_all + (size_t)s * 2 * h->Pp;
   for (int p = 0; p < h->P; ++p) {
     if (PPERT) PPERT[(size_t)p * stride + off] = b[p];
     if (PPART) PPART[(size_t)p * stride + off] = b[(size_t)h->Pp + p];
   }
-  return RSG_OK;
 }
 
 int rsg_anisch(rsg_ram* h, int S, double* PPERT_S, double* PPART_S) {
   RET(check_S(h, S));
   if (!h->fields_set) return fail(RSG_ERR_STATE, "ANISCH before set_fields");
   CK(cudaSetDevice(h->device));
-  RET(launch_anisch(h, S - 1));
-  return fetch_anisch(h, S - 1, PPERT_S, PPART_S, 1, 0);
+  const int s = S - 1;
+  cudaStream_t st = h->st(s);
+  RET(L_anisch(h, s, 1, st));
+  CK(cudaMemcpyAsync(h->h_pp_all + (size_t)s * 2 * h->Pp, h->sp[s].d_pp, (size_t)2 * h->Pp * sizeof(double),
+                     cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  scatter_anisch(h, s, PPERT_S, PPART_S, 1, 0);
+  return RSG_OK;
 }
 
+// The whole species loop of ram_run (src/ModRamRun.f90:64-185) + epilogue
+// (:186-222), all species advanced by each launch, on one stream.
 int rsg_ram_run(rsg_ram* h, double DTs, double DtsMin, double T, int flags, double* dts_next, double* DtDrift,
                 double* losses, double* SETRC, double* PPERT, double* PPART) {
   if (!h) return fail(RSG_ERR_ARG, "null handle");
   if (flags & RSG_F_COULOMB) return fail(RSG_ERR_UNSUPPORTED, "Coulomb operators not implemented");
+  if (!h->grids_set || !h->fields_set || !h->efield_set) return fail(RSG_ERR_STATE, "ram_run before set_grids/fields/efield");
   (void)T;
   CK(cudaSetDevice(h->device));
   const int nS = h->nS;
   const bool DoUseWPI = flags & RSG_F_WPI, DoUseEMIC = flags & RSG_F_EMIC;
-  // category of each SUMRC slot: 0 LSDR 1 LSCHA 2 LSATM 3 LSWAE
-  int cat[RSG_MAX_SPECIES][NSUM];
-  int nslot[RSG_MAX_SPECIES];
+  RET(rsg_ram_sync(h));  // per-species streams idle; host staging tables free
+  cudaStream_t st = h->pst();
+  // SUMRC slots (global numbering): 0 fwd drifts | 1 WPI diffusion | 2 EMIC | 3-6 fused
+  // loss block | 7 EMIC | 8 WPI diffusion | 9 reverse drifts.  cat: -1 skip, 0 LSDR 1 LSCHA 2 LSATM 3 LSWAE
+  int cat[RSG_MAX_SPECIES][10];
+  int doA = 0;
   for (int s = 0; s < nS; ++s) {
-    const int S = s + 1;
     const int kind = h->kind[s];
     const bool sWPI = (kind == RSG_KIND_E), sCEX = (kind != RSG_KIND_E), sEMIC = (kind == RSG_KIND_H);
-    int n = 0;
-#define SUMRC_(c)                     \
-  do {                                \
-    RET(launch_sumrc(h, s, n));       \
-    cat[s][n++] = (c);                \
-  } while (0)
-    RET(rsg_cepara(h, S, DTs));
-    RET(rsg_driftpara(h, S, DTs));
-    RET(rsg_driftr(h, S)); RET(rsg_driftp(h, S)); RET(rsg_drifte(h, S)); RET(rsg_driftmu(h, S));
-    SUMRC_(0);
-    if (sWPI) {
-      if (DoUseWPI) RET(rsg_wpadif(h, S, DTs, nullptr)); else RET(rsg_wavelo(h, S, DTs));
-      SUMRC_(3);
-    }
-    if (sEMIC && DoUseEMIC) { RET(rsg_wpadif(h, S, DTs, nullptr)); SUMRC_(3); }
-    if (sCEX) { RET(rsg_charexchange(h, S)); SUMRC_(1); }
-    RET(rsg_atmol(h, S)); SUMRC_(2);
-    RET(rsg_atmol(h, S)); SUMRC_(2);
-    if (sCEX) { RET(rsg_charexchange(h, S)); SUMRC_(1); }
-    if (sEMIC && DoUseEMIC) { RET(rsg_wpadif(h, S, DTs, nullptr)); SUMRC_(3); }
-    if (sWPI) {
-      if (DoUseWPI) RET(rsg_wpadif(h, S, DTs, nullptr)); else RET(rsg_wavelo(h, S, DTs));
-      SUMRC_(3);
-    }
-    RET(rsg_driftmu(h, S)); RET(rsg_drifte(h, S)); RET(rsg_driftp(h, S)); RET(rsg_driftr(h, S));
-    SUMRC_(0);
-#undef SUMRC_
-    nslot[s] = n;
-    // epilogue (:186-201) and pressures (:208-209)
-    k_epilogue<<<nblk((long long)h->specStride, 256), 256, 0, h->st(s)>>>(h->dev, h->d_F2 + h->specStride * s);
+    const bool wavelo = sWPI && !DoUseWPI;
+    for (int q = 0; q < 10; ++q) cat[s][q] = -1;
+    cat[s][0] = 0; cat[s][9] = 0;
+    if (sWPI && DoUseWPI) cat[s][1] = cat[s][8] = 3;
+    if (sEMIC && DoUseEMIC) cat[s][2] = cat[s][7] = 3;
+    if (sCEX) { cat[s][3] = cat[s][6] = 1; doA |= 1 << s; }
+    if (wavelo) { cat[s][3] = cat[s][6] = 3; doA |= 1 << s; }
+    cat[s][4] = cat[s][5] = 2;
+    RET(tables_cepara(h, s, DTs, st));
+    RET(tables_drift(h, s, DTs, st));
+    if (wavelo) RET(tables_wavelo(h, s, DTs, st));
+  }
+  RET(ensure_step(h, DTs, st));
+  RET(L_inflow(h, 0, nS, st));
+  RET(L_driftr(h, 0, nS, st)); RET(L_driftp(h, 0, nS, st)); RET(L_drifte(h, 0, nS, st)); RET(L_driftmu(h, 0, nS, st));
+  RET(L_sumrc(h, 0, nS, 0, st));
+  for (int s = 0; s < nS; ++s)
+    if (cat[s][1] >= 0) { RET(L_wpadif(h, s, DTs, st)); RET(L_sumrc(h, s, 1, 1, st)); }
+  for (int s = 0; s < nS; ++s)
+    if (cat[s][2] >= 0) { RET(L_wpadif(h, s, DTs, st)); RET(L_sumrc(h, s, 1, 2, st)); }
+  RET(L_loss_mid(h, 0, nS, doA, DTs, 3, st));
+  for (int s = 0; s < nS; ++s)
+    if (cat[s][7] >= 0) { RET(L_wpadif(h, s, DTs, st)); RET(L_sumrc(h, s, 1, 7, st)); }
+  for (int s = 0; s < nS; ++s)
+    if (cat[s][8] >= 0) { RET(L_wpadif(h, s, DTs, st)); RET(L_sumrc(h, s, 1, 8, st)); }
+  RET(L_driftmu(h, 0, nS, st)); RET(L_drifte(h, 0, nS, st)); RET(L_driftp(h, 0, nS, st)); RET(L_driftr(h, 0, nS, st));
+  RET(L_sumrc(h, 0, nS, 9, st));
+  {
+    SpecPack pk;
+    make_pack(h, pk);
+    k_epilogue<<<dim3(nblk((long long)h->specStride, 256), nS), 256, 0, st>>>(h->dev, pk, 0);
     CKL();
     h->launches++;
-    RET(launch_anisch(h, s));
   }
+  RET(L_anisch(h, 0, nS, st));
+  CK(cudaMemcpyAsync(h->h_res_all, h->d_res_all, (size_t)nS * RES_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  if (PPERT || PPART)
+    CK(cudaMemcpyAsync(h->h_pp_all, h->d_pp_all, (size_t)nS * 2 * h->Pp * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
   double dtn = 1e300;
   for (int s = 0; s < nS; ++s) {
     Spec& sp = h->sp[s];
-    RET(fetch_res(h, s));
     double dt4[4];
     std::memcpy(dt4, sp.h_res, 32);
     for (int q = 0; q < 4; ++q) {
@@ -940,7 +1021,8 @@ int rsg_ram_run(rsg_ram* h, double DTs, double DtsMin, double T, int flags, doub
     }
     double ls[6] = {0, 0, 0, 0, 0, 0};
     double prev = sp.setrc;
-    for (int q = 0; q < nslot[s]; ++q) {
+    for (int q = 0; q < 10; ++q) {
+      if (cat[s][q] < 0) continue;
       double v;
       std::memcpy(&v, sp.h_res + 4 + q, 8);
       ls[cat[s][q]] += prev - v;  // ELORC = ENOLD - SETRC (:256)
@@ -950,7 +1032,7 @@ int rsg_ram_run(rsg_ram* h, double DTs, double DtsMin, double T, int flags, doub
     if (losses)
       for (int q = 0; q < 6; ++q) losses[q + 6 * s] = ls[q];
     if (SETRC) SETRC[s] = prev;
-    if (PPERT || PPART) RET(fetch_anisch(h, s, PPERT, PPART, nS, s));
+    if (PPERT || PPART) scatter_anisch(h, s, PPERT, PPART, nS, s);
   }
   if (dts_next) *dts_next = std::max(dtn, DtsMin);
   return RSG_OK;
@@ -961,9 +1043,11 @@ int rsg_ram_flux_d2h(rsg_ram* h, double* FLUX) {
   CK(cudaSetDevice(h->device));
   RET(rsg_ram_sync(h));
   const size_t n = (size_t)h->nS * h->P * h->NE * h->NPA;
-  cudaStream_t st = h->st(0);
+  cudaStream_t st = h->pst();
+  SpecPack pk;
+  make_pack(h, pk);
   for (int s = 0; s < h->nS; ++s) {
-    k_flux_to_host<<<nblk((long long)h->specStride, 256), 256, 0, st>>>(h->dev, h->sp[s].sd, h->d_stage);
+    k_flux_to_host<<<nblk((long long)h->specStride, 256), 256, 0, st>>>(h->dev, pk.s[s], h->d_stage);
     CKL();
     h->launches++;
   }
@@ -973,5 +1057,55 @@ int rsg_ram_flux_d2h(rsg_ram* h, double* FLUX) {
 }
 
 long long rsg_ram_launch_count(rsg_ram* h) { return h ? h->launches : 0; }
+
+// device-side timing across the library's streams: begin() puts a start event in
+// front of every species stream, end() joins them all and returns the elapsed ms
+int rsg_ram_timer_begin(rsg_ram* h) {
+  if (!h) return fail(RSG_ERR_ARG, "null handle");
+  CK(cudaSetDevice(h->device));
+  if (!h->t0) {
+    CK(cudaEventCreate(&h->t0));
+    CK(cudaEventCreate(&h->t1));
+  }
+  cudaStream_t ps = h->pst();
+  if (!h->ext)
+    for (int s = 0; s < h->nS; ++s) {
+      CK(cudaEventRecord(h->sp[s].ev, h->sp[s].own));
+      CK(cudaStreamWaitEvent(ps, h->sp[s].ev, 0));
+    }
+  CK(cudaEventRecord(h->t0, ps));
+  if (!h->ext)
+    for (int s = 0; s < h->nS; ++s) CK(cudaStreamWaitEvent(h->sp[s].own, h->t0, 0));
+  return RSG_OK;
+}
+int rsg_ram_timer_end(rsg_ram* h, double* ms) {
+  if (!h || !ms) return fail(RSG_ERR_ARG, "null argument");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t ps = h->pst();
+  if (!h->ext)
+    for (int s = 0; s < h->nS; ++s) {
+      CK(cudaEventRecord(h->sp[s].ev, h->sp[s].own));
+      CK(cudaStreamWaitEvent(ps, h->sp[s].ev, 0));
+    }
+  CK(cudaEventRecord(h->t1, ps));
+  CK(cudaEventSynchronize(h->t1));
+  float f = 0.f;
+  CK(cudaEventElapsedTime(&f, h->t0, h->t1));
+  *ms = (double)f;
+  return RSG_OK;
+}
+
+// pin / unpin an existing host array (e.g. the Fortran allocatable F2) so that
+// the F2 transfers run at full PCIe speed and asynchronously
+int rsg_host_register(void* p, long long bytes) {
+  if (!p || bytes <= 0) return fail(RSG_ERR_ARG, "bad argument");
+  CK(cudaHostRegister(p, (size_t)bytes, cudaHostRegisterDefault));
+  return RSG_OK;
+}
+int rsg_host_unregister(void* p) {
+  if (!p) return fail(RSG_ERR_ARG, "bad argument");
+  CK(cudaHostUnregister(p));
+  return RSG_OK;
+}
 
 }  // extern "C"

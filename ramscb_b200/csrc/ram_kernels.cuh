@@ -229,316 +229,459 @@ __device__ __forceinline__ double coef_mu(double epK, double BOUNHS, double RLZI
 }
 
 // =============================================================================
-// DRIFTR  (src/ModRamDrift.f90:95-198)
-// Lines run along the contiguous device dimension, so a CTA stages KC whole
-// (MLT,R) planes of one pitch angle in shared memory (coalesced loads), one
-// thread walks each line with a 4-cell register window, results go back in
-// place and are stored coalesced.  The energy-independent coefficient planes
-// t1/CR/sB are staged once per CTA and reused by the KC energies.
+// Sweep kernels.  Common design:
+//  * F2 is double-buffered per species: a sweep reads sp.F and writes sp.Fo
+//    (every cell, untouched ones are copied through), so threads never race on
+//    the limiter's 4-cell stencil and a line can be split between threads;
+//  * the thread index runs along the contiguous (MLT,R) plane index p, so for
+//    the strided sweeps (P, E, MU) every step of the walk is a coalesced row
+//    access; each thread walks a SEGMENT of a line with a 4-value register
+//    window, recomputing the one flux at the segment's lower edge;
+//  * DRIFTR's lines lie along p itself: one thread per cell, the neighbour's
+//    interface flux comes through a warp shuffle (31 cells + 1 halo lane / warp);
+//  * blockIdx.y selects the species: one launch advances all species.
 // =============================================================================
 
-// pre-pass: inflow flag of every line (sign of CDriftR at I=NR), reference
-// line order (K outer, L, J inner) -> inflow[(k*NPA + l)*NT + j] = own index or -1
-__global__ void k_driftr_inflow(RamDev d, SpecDev sp, int* __restrict__ last) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+// block-wide min -> one filtered atomicMin per CTA
+__device__ __forceinline__ void cta_min_to(unsigned long long* dst, double v) {
+  __shared__ unsigned long long s_min[32];
+  unsigned long long b = dbl_bits(v);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long t = __shfl_xor_sync(0xffffffffu, b, o);
+    b = t < b ? t : b;
+  }
+  if ((threadIdx.x & 31) == 0) s_min[threadIdx.x >> 5] = b;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    b = (threadIdx.x < ((blockDim.x + 31) >> 5)) ? s_min[threadIdx.x] : 0xffffffffffffffffull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      unsigned long long t = __shfl_xor_sync(0xffffffffu, b, o);
+      b = t < b ? t : b;
+    }
+    if (threadIdx.x == 0 && b < *((volatile unsigned long long*)dst)) atomicMin(dst, b);
+  }
+}
+
+// ---- DRIFTR pre-pass (src/ModRamDrift.f90:112-113,154-168): the line buffer's
+// ghost cells F(NR+1:NR+2) are only rewritten on inflow lines, so an outflow
+// line whose interface NR-1 is inflow reads the value left by the most recent
+// inflow line in the reference loop order (K outer, L, J inner).  The inflow
+// predicate (sign of CDriftR at I=NR) does not depend on F2, so the index of
+// that line is precomputed once per DRIFTPARA: last[(k*NPA+l)*NT+j].
+#define SCAN_TILE 1024
+__global__ void k_driftr_inflow(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0,
+                                int* __restrict__ tilemax_all, int ntiles) {
+  __shared__ int sm[32];
+  const SpecDev& sp = pk.s[s0 + blockIdx.y];
+  int* last = (int*)sp.last;
   const int n = d.NE * d.NPA * d.NT;
-  if (t >= n) return;
-  const int j = t % d.NT;
-  const int l = (t / d.NT) % d.NPA;
-  const int k = t / (d.NT * d.NPA);
-  const int i = d.NR - 1;
-  const int p = j * d.NR + i;
-  const double rl = d.RLZ[i] + 0.5 * d.MDR;
-  const double c = coef_r(d.CR[p], d.t1[(size_t)l * d.Pp + p], sp.P4[k], d.sB[p], rl);
-  last[t] = (c < 0.0) ? t : -1;
-}
-
-// inclusive running max over `last` (single CTA; n <= a few 1e5)
-__global__ void k_scan_last(int* __restrict__ last, int n) {
-  __shared__ int sm[1024];
-  const int T = blockDim.x, tid = threadIdx.x;
-  const int chunk = (n + T - 1) / T;
-  const int b = tid * chunk, e = min(n, b + chunk);
-  int m = -1;
-  for (int q = b; q < e; ++q) m = max(m, last[q]);
-  sm[tid] = m;
-  __syncthreads();
-  for (int o = 1; o < T; o <<= 1) {
-    int v = (tid >= o) ? sm[tid - o] : -1;
-    __syncthreads();
-    sm[tid] = max(sm[tid], v);
-    __syncthreads();
-  }
-  int run = (tid > 0) ? sm[tid - 1] : -1;
-  for (int q = b; q < e; ++q) {
-    run = max(run, last[q]);
-    last[q] = run;
-  }
-}
-
-__global__ void k_driftr(RamDev d, SpecDev sp, const int* __restrict__ last, int KC) {
-  extern __shared__ double smem[];
-  const int NR = d.NR, NT = d.NT, P = d.P, Pp = d.Pp;
-  const int NRc = NR | 1;          // odd row stride: conflict-free column walks
-  const int NRf = (NR + 2) | 1;
-  double* sT1 = smem;               // [NT][NRc]
-  double* sCR = sT1 + NT * NRc;
-  double* sSB = sCR + NT * NRc;
-  double* sF = sSB + NT * NRc;      // [KC][NT][NRf]
-  const int l = blockIdx.y;
-  const int k0 = blockIdx.x * KC;
-  const int kc = min(KC, d.NE - k0);
-  const int tid = threadIdx.x, nth = blockDim.x;
-
-  for (int p = tid; p < P; p += nth) {
-    const int j = p / NR, i = p - j * NR;
-    sT1[j * NRc + i] = d.t1[(size_t)l * Pp + p];
-    sCR[j * NRc + i] = d.CR[p];
-    sSB[j * NRc + i] = d.sB[p];
-  }
-  for (int q = tid; q < kc * P; q += nth) {
-    const int kk = q / P, p = q - kk * P;
-    const int j = p / NR, i = p - j * NR;
-    sF[(kk * NT + j) * NRf + i] = sp.F[((size_t)l * d.NE + (k0 + kk)) * Pp + p];
-  }
-  __syncthreads();
-
-  double cmax = 0.0;
-  if (tid < kc * NT) {
-    const int kk = tid / NT, j = tid - kk * NT;
-    const int k = k0 + kk;
-    double* F = sF + (kk * NT + j) * NRf;   // F[i] = F(I=i+1)
-    const double* T1 = sT1 + j * NRc;
-    const double* CRj = sCR + j * NRc;
-    const double* SBj = sSB + j * NRc;
-    const double P4 = sp.P4[k];
-    const double hMDR = 0.5 * d.MDR;
-    const double beta = d.BetaLim;
-    const unsigned char* outp = d.outp + j * NR;
-
-    const double cNR = coef_r(CRj[NR - 1], T1[NR - 1], P4, SBj[NR - 1], d.RLZ[NR - 1] + hMDR);
-    const bool inflow = (cNR < 0.0);
-    double g1, g2;  // F(NR+1), F(NR+2)
-    if (inflow) {
-      if (outp[NR - 1]) { g1 = 0.0; g2 = 0.0; }
-      else {
-        const double fg = sp.FGEOS[((size_t)l * d.NE + k) * NT + j];
-        const double fn = R3(d.FNHS, NR, j + 1, l + 1);
-        g1 = fg * d.CONF1 * fn;
-        g2 = fg * d.CONF2 * fn;
-      }
-    } else {
-      // ghost cells keep whatever the most recent inflow line (reference loop
-      // order K,L,J) left in the line buffer; 0 if none yet  (:112-113,:154-168)
-      g2 = 0.0;  // never read on an outflow line
-      const int line = (k * d.NPA + l) * NT + j;
-      const int src = last[line];
-      if (src < 0) g1 = 0.0;
-      else {
-        const int js = src % NT, ls = (src / NT) % d.NPA, ks = src / (NT * d.NPA);
-        if (d.outp[js * NR + NR - 1]) g1 = 0.0;
-        else g1 = sp.FGEOS[((size_t)ls * d.NE + ks) * NT + js] * d.CONF1 * R3(d.FNHS, NR, js + 1, ls + 1);
-      }
-    }
-    const int UR = inflow ? NR : NR - 1;
-    // I = 1
-    double c = coef_r(CRj[0], T1[0], P4, SBj[0], d.RLZ[0] + hMDR);
-    if (!outp[0]) cmax = fmax(cmax, fabs(c));
-    double Fm1 = 0.0, F0 = F[0], Fp1 = F[1], Fp2 = F[2];
-    double prev = c * (inflow ? Fp1 : 0.0);  // CDriftR(1)*FBND(1)
-    for (int I = 2; I <= NR; ++I) {
-      Fm1 = F0; F0 = Fp1; Fp1 = Fp2;
-      Fp2 = (I + 2 <= NR) ? F[I + 1] : ((I + 2 == NR + 1) ? g1 : g2);
-      c = coef_r(CRj[I - 1], T1[I - 1], P4, SBj[I - 1], d.RLZ[I - 1] + hMDR);
-      if (!outp[I - 1]) cmax = fmax(cmax, fabs(c));
-      double FB;
-      if (I <= UR) FB = limited_flux(Fm1, F0, Fp1, Fp2, c, c, beta);
-      else FB = F0;  // outflow: FBND(NR) = F(NR)
-      const double cur = c * FB;
-      double fn = F0 - cur + prev;
-      if (fn < 0.0) fn = 1E-15;
-      F[I - 1] = fn;
-      prev = cur;
-    }
-  }
-  // CFL: min over cells of FracCFL*DTs/max(|c|,1e-10) == FracCFL*DTs/max over cells
-  block_min_to(sp.dt + 0, sp.aRP / fmax(cmax, 1E-10));
-  __syncthreads();
-  for (int q = tid; q < kc * P; q += nth) {
-    const int kk = q / P, p = q - kk * P;
-    const int j = p / NR, i = p - j * NR;
-    if (i >= 1) sp.F[((size_t)l * d.NE + (k0 + kk)) * Pp + p] = sF[(kk * NT + j) * NRf + i];
-  }
-}
-
-// =============================================================================
-// DRIFTP  (src/ModRamDrift.f90:204-279): periodic lines along MLT.  One thread
-// per (L,K,I) line; at every J the warp reads NR-contiguous runs => coalesced
-// without staging.  The wrap-around flux (FBND(1)=FBND(NT)) is computed first.
-// =============================================================================
-__global__ void k_driftp(RamDev d, SpecDev sp) {
-  const int NR = d.NR, NT = d.NT, Pp = d.Pp;
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long n = (long long)d.NPA * d.NE * NR;
-  double cmax = 0.0;
+  const int t = blockIdx.x * SCAN_TILE + threadIdx.x;
+  int v = -1;
   if (t < n) {
-    const int i = (int)(t % NR);
-    const int plane = (int)(t / NR);
-    const int k = plane % d.NE, l = plane / d.NE;
+    const int j = t % d.NT;
+    const int l = (t / d.NT) % d.NPA;
+    const int k = t / (d.NT * d.NPA);
+    const int i = d.NR - 1;
+    const int p = j * d.NR + i;
+    const double c = coef_r(d.CR[p], d.t1[(size_t)l * d.Pp + p], sp.P4[k], d.sB[p], d.RLZ[i] + 0.5 * d.MDR);
+    v = (c < 0.0) ? t : -1;
+    last[t] = v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    v = sm[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (threadIdx.x == 0) tilemax_all[(size_t)(s0 + blockIdx.y) * ntiles + blockIdx.x] = v;
+  }
+}
+// inclusive running max of last[] (tile-local scan + carry from the tile maxima)
+__global__ void k_driftr_scan(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0,
+                              const int* __restrict__ tilemax_all, int ntiles) {
+  __shared__ int sm[32];
+  __shared__ int s_carry;
+  const SpecDev& sp = pk.s[s0 + blockIdx.y];
+  int* last = (int*)sp.last;
+  const int* tilemax = tilemax_all + (size_t)(s0 + blockIdx.y) * ntiles;
+  const int n = d.NE * d.NPA * d.NT;
+  const int t = blockIdx.x * SCAN_TILE + threadIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  // carry = max of all previous tiles
+  int c = -1;
+  for (int q = threadIdx.x; q < (int)blockIdx.x; q += blockDim.x) c = max(c, tilemax[q]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c = max(c, __shfl_xor_sync(0xffffffffu, c, o));
+  if (lane == 0) sm[w] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int m = -1;
+    for (int q = 0; q < 32; ++q) m = max(m, sm[q]);
+    s_carry = m;
+  }
+  __syncthreads();
+  int v = (t < n) ? last[t] : -1;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v = max(v, u);
+  }
+  __syncthreads();
+  if (lane == 31) sm[w] = v;
+  __syncthreads();
+  int pre = s_carry;
+  for (int q = 0; q < w; ++q) pre = max(pre, sm[q]);
+  v = max(v, pre);
+  if (t < n) last[t] = v;
+}
+
+// =============================================================================
+// DRIFTR  (src/ModRamDrift.f90:95-198): one thread per cell.
+// =============================================================================
+__global__ void __launch_bounds__(256) k_driftr(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0) {
+  const SpecDev& sp = pk.s[s0 + blockIdx.y];
+  const int NR = d.NR, NT = d.NT, NE = d.NE, P = d.P, Pp = d.Pp;
+  const long long N = (long long)d.NPA * NE * Pp;
+  const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const long long q = (gt >> 5) * 31 + lane - 1;   // 31 cells per warp + halo lane 0
+  const bool valid = (q >= 0) && (q < N);
+  double phi = 0.0, F0 = 0.0, cmax = 0.0;
+  int i = -1;
+  bool inplane = false;
+  if (valid) {
+    const int p = (int)(q % Pp);
+    const int plane = (int)(q / Pp);
+    if (p < P) {
+      inplane = true;
+      const int k = plane % NE, l = plane / NE;
+      const int j = p / NR;
+      i = p - j * NR;
+      const int I = i + 1;
+      const int line = (k * d.NPA + l) * NT + j;
+      const int src = sp.last[line];
+      const bool inflow = (src == line);
+      const double c = coef_r(d.CR[p], d.t1[(size_t)l * Pp + p], sp.P4[k], d.sB[p], d.RLZ[i] + 0.5 * d.MDR);
+      if (!d.outp[p]) cmax = fabs(c);
+      const double* F = sp.F + (size_t)plane * Pp + (size_t)j * NR;  // F[i'] = F(I=i'+1) of this line
+      F0 = F[i];
+      if (I == 1) {
+        phi = c * (inflow ? F[1] : 0.0);            // FBND(1) = F(2) | 0   (:155,:159)
+      } else if (I == NR && !inflow) {
+        phi = c * F0;                               // FBND(NR) = F(NR)     (:156)
+      } else {
+        double g1 = 0.0, g2 = 0.0;                  // F(NR+1), F(NR+2)
+        if (I + 2 > NR) {
+          if (inflow) {
+            if (!d.outp[j * NR + NR - 1]) {
+              const double fg = sp.FGEOS[((size_t)l * NE + k) * NT + j];
+              const double fn = R3(d.FNHS, NR, j + 1, l + 1);
+              g1 = fg * d.CONF1 * fn;
+              g2 = fg * d.CONF2 * fn;
+            }
+          } else if (src >= 0) {
+            const int js = src % NT, ls = (src / NT) % d.NPA, ks = src / (NT * d.NPA);
+            if (!d.outp[js * NR + NR - 1])
+              g1 = sp.FGEOS[((size_t)ls * NE + ks) * NT + js] * d.CONF1 * R3(d.FNHS, NR, js + 1, ls + 1);
+          }
+        }
+        const double Fm1 = F[i - 1];
+        const double Fp1 = (I + 1 <= NR) ? F[i + 1] : g1;
+        const double Fp2 = (I + 2 <= NR) ? F[i + 2] : ((I + 2 == NR + 1) ? g1 : g2);
+        phi = c * limited_flux(Fm1, F0, Fp1, Fp2, c, c, d.BetaLim);
+      }
+    }
+  }
+  const double phiPrev = __shfl_up_sync(0xffffffffu, phi, 1);
+  if (valid && lane >= 1 && inplane) {
+    double fn = F0;
     if (i >= 1) {
-      double* F = sp.F + (size_t)plane * Pp + i;  // F[j*NR] = F(J=j+1)
+      fn = F0 - phi + phiPrev;                      // :186
+      if (fn < 0.0) fn = 1E-15;
+    }
+    sp.Fo[q] = fn;
+  }
+  cta_min_to(sp.dt + 0, sp.aRP / fmax(cmax, 1E-10));
+}
+
+// =============================================================================
+// DRIFTP  (src/ModRamDrift.f90:204-279): periodic lines along MLT, segments of
+// SEG cells of J=2..NT per thread.  FBND(1)=FBND(NT), F2(J=1)=F2(J=NT).
+// =============================================================================
+__global__ void __launch_bounds__(128) k_driftp(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0, int SEG,
+                                                int nseg) {
+  const SpecDev& sp = pk.s[s0 + blockIdx.y];
+  const int NR = d.NR, NT = d.NT, Pp = d.Pp;
+  const long long nl = (long long)d.NPA * d.NE * NR;   // lines (incl. I=1)
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double cmax = 0.0;
+  if (t < nl * nseg) {
+    const int seg = (int)(t / nl);
+    const long long r = t - (long long)seg * nl;
+    const int i = (int)(r % NR);
+    const int plane = (int)(r / NR);
+    const int k = plane % d.NE, l = plane / d.NE;
+    const int ja = 2 + seg * SEG, jb = min(NT, ja + SEG - 1);
+    const double* F = sp.F + (size_t)plane * Pp + i;   // F[(J-1)*NR]
+    double* Fo = sp.Fo + (size_t)plane * Pp + i;
+    if (i == 0) {
+      for (int J = ja; J <= jb; ++J) Fo[(J - 1) * NR] = F[(J - 1) * NR];
+      if (jb == NT) Fo[0] = F[0];
+    } else {
       const double* G = d.G + (size_t)l * Pp + i;
       const double* sFp = d.sFp + (size_t)l * Pp + i;
       const double P2 = sp.P2[k * NR + i];
       const double beta = d.BetaLim, OMEt = sp.OMEt;
-      // interface J=NT first: window F(NT-1),F(NT),F(2),F(3)
-      const double f2 = F[1 * NR], f3 = F[2 * NR];
-      double cNT, phiNT;
+      const double f2 = F[NR], f3 = F[2 * NR];          // F(2), F(3): wrap-around values
+#define GETFJ(J) (((J) <= NT) ? F[((J)-1) * NR] : (((J) == NT + 1) ? f2 : f3))
+#define COEFP(J) coef_p(d.pT1[((J)-1) * NR + i], P2, G[((J)-1) * NR], sFp[((J)-1) * NR], d.pT3[((J)-1) * NR + i], d.sBp[((J)-1) * NR + i], OMEt)
+      // flux through the segment's lower edge: interface ja-1, or NT for ja==2 (:261-262)
+      const int Jh = (ja == 2) ? NT : ja - 1;
+      double prev;
       {
-        const int pj = (NT - 1) * NR;
-        cNT = coef_p(d.pT1[pj + i], P2, G[pj], sFp[pj], d.pT3[pj + i], d.sBp[pj + i], OMEt);
-        const double FB = limited_flux(F[(NT - 2) * NR], F[(NT - 1) * NR], f2, f3, cNT, cNT, beta);
-        phiNT = cNT * FB;
+        const double c = COEFP(Jh);
+        prev = c * limited_flux(F[(Jh - 2) * NR], F[(Jh - 1) * NR], GETFJ(Jh + 1), GETFJ(Jh + 2), c, c, beta);
       }
-      double Fm1 = F[0], F0 = f2, Fp1 = f3;
-      double prev = phiNT;
+      double Fm1 = F[(ja - 2) * NR], F0 = F[(ja - 1) * NR], Fp1 = GETFJ(ja + 1);
       double fnew = 0.0;
-      for (int J = 2; J <= NT; ++J) {
-        // window for interface J: F(J-1)=Fm1, F(J)=F0, F(J1)=Fp1, F(J+2 wrapped)=Fp2
-        double Fp2;
-        if (J + 2 <= NT) Fp2 = F[(J + 1) * NR];
-        else Fp2 = (J + 2 == NT + 1) ? f2 : f3;
-        const int pj = (J - 1) * NR;
-        double cur;
-        if (J < NT) {
-          const double c = coef_p(d.pT1[pj + i], P2, G[pj], sFp[pj], d.pT3[pj + i], d.sBp[pj + i], OMEt);
-          if (!d.outp[pj + i]) cmax = fmax(cmax, fabs(c));
-          cur = c * limited_flux(Fm1, F0, Fp1, Fp2, c, c, beta);
-        } else {
-          if (!d.outp[pj + i]) cmax = fmax(cmax, fabs(cNT));
-          cur = phiNT;
-        }
-        fnew = F0 - cur + prev;
+      for (int J = ja; J <= jb; ++J) {
+        const double Fp2 = GETFJ(J + 2);
+        const double c = COEFP(J);
+        if (!d.outp[(J - 1) * NR + i]) cmax = fmax(cmax, fabs(c));
+        const double cur = c * limited_flux(Fm1, F0, Fp1, Fp2, c, c, beta);
+        fnew = F0 - cur + prev;                         // :266
         if (fnew < 0.0) fnew = 1E-15;
-        F[pj] = fnew;
+        Fo[(J - 1) * NR] = fnew;
         prev = cur;
         Fm1 = F0; F0 = Fp1; Fp1 = Fp2;
       }
-      F[0] = fnew;  // F2(S,I,1,K,L) = F2(S,I,NT,K,L)
+      if (jb == NT) Fo[0] = fnew;                       // :272
+#undef GETFJ
+#undef COEFP
     }
   }
-  block_min_to(sp.dt + 1, sp.aRP / fmax(cmax, 1E-10));
+  cta_min_to(sp.dt + 1, sp.aRP / fmax(cmax, 1E-10));
 }
 
 // =============================================================================
-// DRIFTE  (src/ModRamDrift.f90:285-376): lines along energy.  One thread per
-// (L,J,I) line; consecutive threads are consecutive in the contiguous plane
-// index, so every K step is a coalesced row access.  Register window + one
-// step of software prefetch.
+// DRIFTE  (src/ModRamDrift.f90:285-376): lines along energy, segments of SEG
+// cells of K=1..NE per thread.  Ghosts F(1),F(0) from the relativistic
+// extrapolation of F2(K=2) (:334-335), F(NE+1)=F(NE+2)=0 (:312-313).
 // =============================================================================
-__global__ void k_drifte(RamDev d, SpecDev sp) {
+__global__ void __launch_bounds__(128) k_drifte(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0, int SEG,
+                                                int nseg) {
+  const SpecDev& sp = pk.s[s0 + blockIdx.y];
   const int NE = d.NE, Pp = d.Pp;
+  const long long nl = (long long)d.NPA * Pp;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   double dtmin = 1.0e300;
-  if (t < (long long)d.NPA * Pp) {
-    const int l = (int)(t / Pp), p = (int)(t - (long long)l * Pp);
-    const int i = p % d.NR;
-    if (p < d.P && i >= 1) {
-      const size_t o = (size_t)l * Pp + p;
-      const double FNHS = d.FNHSc[o], Gr = d.Gr[o], Gp = d.Gp[o], DRD2 = d.DRD2[o], DPD2 = d.DPD2[o], dBdt1 = d.dBdt1[o],
-                   dIdt1 = d.dIdt1[o];
-      const double DRD1 = d.DRD1[p], DPD1 = d.DPD1[p], BNES = d.BNESc[p], RLZI = d.RLZp[p];
-      const bool inside = !d.outp[p];
-      const double QS = sp.QS, beta = d.BetaLim;
-      double* F = sp.F + (size_t)l * NE * Pp + p;  // F[k*Pp] = F2(K=k+1)
-      const double* EDOT = sp.EDOT + i;             // [k*NR]
-      // ghost cells F(1), F(0)  (:334-335); F(NE+1)=F(NE+2)=0 (:312-313)
-      const double f2 = F[(size_t)1 * Pp];
-      const double F1 = f2 * sp.GREL1 / sp.GREL2 * sp.sqrtA;
-      const double Fz = F1 * sp.GRZERO / sp.GREL1 * sp.sqrtB;
-      double Fm1 = Fz, F0 = F1, Fp1 = f2, Fp2 = (NE >= 3) ? F[(size_t)2 * Pp] : 0.0;
-      double nxt = (NE >= 4) ? F[(size_t)3 * Pp] : 0.0;  // F(K+3) prefetch
-      double cprev = 0.0, FBprev = 0.0;
-      for (int K = 1; K <= NE; ++K) {
-        const double nn = (K + 4 <= NE) ? F[(size_t)(K + 3) * Pp] : 0.0;
-        const double c = coef_e(sp.eK[K - 1], FNHS, RLZI, BNES, QS, DRD1, DRD2, DPD1, DPD2, Gr, Gp, dBdt1, dIdt1,
-                                EDOT[(K - 1) * d.NR]);
-        const double DEK = d.DE[K - 1];
-        if (inside) dtmin = fmin(dtmin, sp.aE[K - 1] / fmax(fabs(c), 1E-10));
-        const double FB = limited_flux(Fm1, F0, Fp1, Fp2, c, c / DEK, beta);
-        if (K >= 2) {
-          const double WEK = d.WE[K - 1];
-          double fn = F0 - c / WEK * FB + cprev / WEK * FBprev;
-          if (fn < 0.0) fn = 1E-15;
-          F[(size_t)(K - 1) * Pp] = fn;
+  if (t < nl * nseg) {
+    const int seg = (int)(t / nl);
+    const long long r = t - (long long)seg * nl;
+    const int l = (int)(r / Pp), p = (int)(r - (long long)l * Pp);
+    const int ka = 1 + seg * SEG, kb = min(NE, ka + SEG - 1);
+    if (p < d.P) {
+      const int i = p % d.NR;
+      const double* F = sp.F + (size_t)l * NE * Pp + p;   // F[(K-1)*Pp]
+      double* Fo = sp.Fo + (size_t)l * NE * Pp + p;
+      if (i == 0) {
+        for (int K = ka; K <= kb; ++K) Fo[(size_t)(K - 1) * Pp] = F[(size_t)(K - 1) * Pp];
+      } else {
+        const size_t o = (size_t)l * Pp + p;
+        const double FNHS = d.FNHSc[o], Gr = d.Gr[o], Gp = d.Gp[o], DRD2 = d.DRD2[o], DPD2 = d.DPD2[o], dBdt1 = d.dBdt1[o],
+                     dIdt1 = d.dIdt1[o];
+        const double DRD1 = d.DRD1[p], DPD1 = d.DPD1[p], BNES = d.BNESc[p], RLZI = d.RLZp[p];
+        const bool inside = !d.outp[p];
+        const double QS = sp.QS, beta = d.BetaLim;
+        const double* EDOT = sp.EDOT + i;
+        double F1 = 0.0, Fz = 0.0;
+        if (ka <= 3) {
+          const double f2 = F[(size_t)Pp];
+          F1 = f2 * sp.GREL1 / sp.GREL2 * sp.sqrtA;
+          Fz = F1 * sp.GRZERO / sp.GREL1 * sp.sqrtB;
         }
-        cprev = c; FBprev = FB;
-        Fm1 = F0; F0 = Fp1; Fp1 = Fp2; Fp2 = nxt; nxt = nn;
+#define GETFK(K) (((K) > NE) ? 0.0 : (((K) >= 2) ? F[(size_t)((K)-1) * Pp] : (((K) == 1) ? F1 : Fz)))
+        if (ka == 1) Fo[0] = F[0];                        // F2(K=1) is not advanced by DRIFTE
+        const int K0 = max(ka - 1, 1);
+        double Fm1 = GETFK(K0 - 1), F0 = GETFK(K0), Fp1 = GETFK(K0 + 1), Fp2 = GETFK(K0 + 2);
+        double nxt = GETFK(K0 + 3);
+        double cprev = 0.0, FBprev = 0.0;
+        for (int K = K0; K <= kb; ++K) {
+          const double nn = GETFK(K + 4);
+          const double c = coef_e(sp.eK[K - 1], FNHS, RLZI, BNES, QS, DRD1, DRD2, DPD1, DPD2, Gr, Gp, dBdt1, dIdt1,
+                                  EDOT[(K - 1) * d.NR]);
+          if (inside && K >= ka) dtmin = fmin(dtmin, sp.aE[K - 1] / fmax(fabs(c), 1E-10));
+          const double FB = limited_flux(Fm1, F0, Fp1, Fp2, c, c / d.DE[K - 1], beta);
+          if (K >= ka && K >= 2) {
+            const double WEK = d.WE[K - 1];
+            double fn = F0 - c / WEK * FB + cprev / WEK * FBprev;   // :364
+            if (fn < 0.0) fn = 1E-15;
+            Fo[(size_t)(K - 1) * Pp] = fn;
+          }
+          cprev = c; FBprev = FB;
+          Fm1 = F0; F0 = Fp1; Fp1 = Fp2; Fp2 = nxt; nxt = nn;
+        }
+#undef GETFK
       }
     }
   }
-  block_min_to(sp.dt + 2, dtmin);
+  cta_min_to(sp.dt + 2, dtmin);
 }
 
 // =============================================================================
-// DRIFTMU  (src/ModRamDrift.f90:382-473): lines along pitch angle.  One thread
-// per (K,J,I) line, same coalescing argument as DRIFTE (row stride NE*Pp).
+// DRIFTMU  (src/ModRamDrift.f90:382-473): lines along pitch angle, segments of
+// SEG cells of L=2..NPA-1 per thread; the last segment also closes the line with
+// F2(NPA) = F2(NPA-1)*FNHS(NPA)*MU(NPA)/FNHS(NPA-1)/MU(NPA-1) (:466).
 // =============================================================================
-__global__ void k_driftmu(RamDev d, SpecDev sp) {
+__global__ void __launch_bounds__(128) k_driftmu(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0, int SEG,
+                                                 int nseg) {
+  const SpecDev& sp = pk.s[s0 + blockIdx.y];
   const int NE = d.NE, NPA = d.NPA, Pp = d.Pp;
+  const long long nl = (long long)NE * Pp;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   double dtmin = 1.0e300;
-  if (t < (long long)NE * Pp) {
-    const int k = (int)(t / Pp), p = (int)(t - (long long)k * Pp);
-    const int i = p % d.NR;
-    if (p < d.P && i >= 1) {
-      const size_t LS = (size_t)NE * Pp;  // stride between pitch angles
-      double* F = sp.F + (size_t)k * Pp + p;  // F[l*LS] = F2(L=l+1)
-      const double DRM1 = d.DRD1[p], DPM1 = d.DPD1[p], BNES = d.BNESc[p], RLZI = d.RLZp[p], dBdt2 = d.dBdt2[p];
-      const bool inside = !d.outp[p];
-      const double QS = sp.QS, beta = d.BetaLim, epK = sp.epK[k];
-      // F(1) = F(2)  (:414)
-      const double f2 = F[LS];
-      double Fm1 = f2, F0 = f2, Fp1 = F[2 * LS], Fp2 = F[3 * LS];   // window for L=2
-      double nxt = (NPA >= 5) ? F[4 * LS] : 0.0;
-      double cprev = 0.0, FBprev = 0.0;  // CDriftMu(..,1)=0, FBND(1)=0 (:456-457)
-      double fnew = 0.0;
-      for (int L = 2; L <= NPA; ++L) {
-        const double nn = (L + 4 <= NPA) ? F[(size_t)(L + 3) * LS] : 0.0;
-        const size_t o = (size_t)(L - 1) * Pp + p;
-        const double c = coef_mu(epK, d.BOUNHSc[o], RLZI, BNES, QS, DRM1, d.DRM2[o], DPM1, d.DPM2[o], d.Gmr[o], d.Gmp[o], dBdt2,
-                                 d.dIbndt2[o], d.CMUDOT[o]);
-        if (inside) dtmin = fmin(dtmin, sp.aMU[L - 1] / fmax(fabs(c), 1E-32));
-        if (L <= NPA - 1) {
+  if (t < nl * nseg) {
+    const int seg = (int)(t / nl);
+    const long long r = t - (long long)seg * nl;
+    const int k = (int)(r / Pp), p = (int)(r - (long long)k * Pp);
+    const int la = 2 + seg * SEG, lb = min(NPA - 1, la + SEG - 1);
+    const bool lastseg = (lb == NPA - 1);
+    if (p < d.P) {
+      const int i = p % d.NR;
+      const size_t LS = (size_t)NE * Pp;
+      const double* F = sp.F + (size_t)k * Pp + p;   // F[(L-1)*LS]
+      double* Fo = sp.Fo + (size_t)k * Pp + p;
+      if (seg == 0) Fo[0] = F[0];                     // F2(L=1) is not advanced by DRIFTMU
+      if (i == 0) {
+        for (int L = la; L <= lb; ++L) Fo[(size_t)(L - 1) * LS] = F[(size_t)(L - 1) * LS];
+        if (lastseg) Fo[(size_t)(NPA - 1) * LS] = F[(size_t)(NPA - 1) * LS];
+      } else {
+        const double DRM1 = d.DRD1[p], DPM1 = d.DPD1[p], BNES = d.BNESc[p], RLZI = d.RLZp[p], dBdt2 = d.dBdt2[p];
+        const bool inside = !d.outp[p];
+        const double QS = sp.QS, beta = d.BetaLim, epK = sp.epK[k];
+#define GETFL(L) (((L) >= 2) ? F[(size_t)((L)-1) * LS] : F[LS])   /* F(1) = F(2)  (:414) */
+#define COEFMU(L, o) coef_mu(epK, d.BOUNHSc[o], RLZI, BNES, QS, DRM1, d.DRM2[o], DPM1, d.DPM2[o], d.Gmr[o], d.Gmp[o], dBdt2, d.dIbndt2[o], d.CMUDOT[o])
+        const int L0 = max(la - 1, 2);
+        double Fm1 = GETFL(L0 - 1), F0 = GETFL(L0), Fp1 = GETFL(L0 + 1), Fp2 = (L0 + 2 <= NPA) ? GETFL(L0 + 2) : 0.0;
+        double nxt = (L0 + 3 <= NPA) ? GETFL(L0 + 3) : 0.0;
+        double cprev = 0.0, FBprev = 0.0;               // CDriftMu(..,1)=0, FBND(1)=0 (:456-457)
+        double fnew = 0.0;
+        for (int L = L0; L <= lb; ++L) {
+          const double nn = (L + 4 <= NPA) ? F[(size_t)(L + 3) * LS] : 0.0;
+          const size_t o = (size_t)(L - 1) * Pp + p;
+          const double c = COEFMU(L, o);
+          if (inside && L >= la) dtmin = fmin(dtmin, sp.aMU[L - 1] / fmax(fabs(c), 1E-32));
           double FB;
           if (L <= NPA - 2) FB = limited_flux(Fm1, F0, Fp1, Fp2, c, c / d.DMU[L - 1], beta);
-          else FB = Fp1;  // FBND(NPA-1) = F(NPA)  (:458)
-          const double WM = d.WMU[L - 1];
-          fnew = F0 - c / WM * FB + cprev / WM * FBprev;
-          if (fnew < 0.0) fnew = 1E-15;
-          F[(size_t)(L - 1) * LS] = fnew;
+          else FB = Fp1;                                // FBND(NPA-1) = F(NPA)  (:458)
+          if (L >= la) {
+            const double WM = d.WMU[L - 1];
+            fnew = F0 - c / WM * FB + cprev / WM * FBprev;   // :460
+            if (fnew < 0.0) fnew = 1E-15;
+            Fo[(size_t)(L - 1) * LS] = fnew;
+          }
           cprev = c; FBprev = FB;
-        } else {
-          // F2(NPA) = F2(NPA-1)*FNHS(NPA)*MU(NPA)/FNHS(NPA-1)/MU(NPA-1)  (:466)
-          const double r = fnew * d.FNHSc[(size_t)(NPA - 1) * Pp + p] * d.MU[NPA - 1] / d.FNHSc[(size_t)(NPA - 2) * Pp + p] / d.MU[NPA - 2];
-          F[(size_t)(NPA - 1) * LS] = r;
+          Fm1 = F0; F0 = Fp1; Fp1 = Fp2; Fp2 = nxt; nxt = nn;
         }
-        Fm1 = F0; F0 = Fp1; Fp1 = Fp2; Fp2 = nxt; nxt = nn;
+        if (lastseg) {
+          const size_t o = (size_t)(NPA - 1) * Pp + p;
+          const double c = COEFMU(NPA, o);
+          if (inside) dtmin = fmin(dtmin, sp.aMU[NPA - 1] / fmax(fabs(c), 1E-32));
+          Fo[(size_t)(NPA - 1) * LS] =
+              fnew * d.FNHSc[(size_t)(NPA - 1) * Pp + p] * d.MU[NPA - 1] / d.FNHSc[(size_t)(NPA - 2) * Pp + p] / d.MU[NPA - 2];
+        }
+#undef GETFL
+#undef COEFMU
       }
     }
   }
-  block_min_to(sp.dt + 3, dtmin);
+  cta_min_to(sp.dt + 3, dtmin);
 }
 
 // =============================================================================
-// pointwise losses.  CHAREXCHANGE (src/ModRamLoss.f90:457-478) with CEPARA's
-// CHARGE evaluated on the fly (:39-83; the energy-only factor sv(K)=10**Y*V is a
-// host table): F2 *= exp(-(sv*HDNS*DTs)).  ATMOL (:485-507): F2 *=
-// ATLOS(I,K)**(1/FNHS) inside the loss cone.  WAVELO (src/ModRamWPI.f90:580-636):
-// F2 *= exp(-DTs/TAU_LIF(I,J,K)), factor table built on the host.
-// op: 0 CHAREX, 1 ATMOL, 2 WAVELO
+// moment helper: per-thread values -> per-CTA partial sums part[blockIdx.x*NM+q]
+// (fixed tree => run-to-run reproducible)
 // =============================================================================
-__global__ void k_loss(RamDev d, SpecDev sp, int op, const double* __restrict__ wfac) {
+template <int NM>
+__device__ __forceinline__ void cta_sum_to(double* part, double (&acc)[NM]) {
+  __shared__ double s_sum[NM][32];
+#pragma unroll
+  for (int q = 0; q < NM; ++q) {
+    double v = acc[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) s_sum[q][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+#pragma unroll
+    for (int q = 0; q < NM; ++q) {
+      double v = (threadIdx.x < ((blockDim.x + 31) >> 5)) ? s_sum[q][threadIdx.x] : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (threadIdx.x == 0) part[(size_t)blockIdx.x * NM + q] = v;
+    }
+  }
+}
+
+// out[q] = sum_b part[b*nm + q]; grid = (nm, nspecies)
+__global__ void k_sum_final(const __grid_constant__ SpecPack pk, int s0, int nb, int nm, int slot0) {
+  __shared__ double sm[32];
+  const SpecDev& sp = pk.s[s0 + blockIdx.y];
+  const int q = blockIdx.x;
+  double acc = 0.0;
+  for (int b = threadIdx.x; b < nb; b += blockDim.x) acc += sp.part[(size_t)b * nm + q];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = (threadIdx.x < (blockDim.x >> 5)) ? sm[threadIdx.x] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) ((double*)(sp.dt + 4))[slot0 + q] = v;
+  }
+}
+
+// SUMRC weight of a cell (src/ModRamRun.f90:246-253): I>=2,K>=2,L>=2,J<=NT-1
+__device__ __forceinline__ bool in_sumrc(const RamDev& d, int p, int k, int l) {
+  if (p >= d.P || k < 1 || l < 1) return false;
+  const int j = p / d.NR, i = p - j * d.NR;
+  return i >= 1 && j <= d.NT - 2;
+}
+
+// =============================================================================
+// SUMRC  (src/ModRamRun.f90:231-259).  Two-stage deterministic tree; differs from
+// the reference's serial sum by summation order only (diagnostic quantity).
+// =============================================================================
+__global__ void __launch_bounds__(256) k_sumrc_partial(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0) {
+  const SpecDev& sp = pk.s[s0 + blockIdx.y];
+  const long long n = (long long)d.NPA * d.NE * d.Pp;
+  double acc[1] = {0.0};
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(t % d.Pp);
+    const int plane = (int)(t / d.Pp);
+    const int k = plane % d.NE, l = plane / d.NE;
+    if (!in_sumrc(d, p, k, l)) continue;
+    const double WEIGHT = sp.F[t] * d.WE[k] * d.WMU[l];
+    acc[0] += d.EKEV[k] * WEIGHT;
+  }
+  cta_sum_to<1>(sp.part, acc);
+}
+
+// =============================================================================
+// pointwise losses, one operator per launch (the per-routine ABI entry points):
+// op 0 CHAREXCHANGE (src/ModRamLoss.f90:457-478, CHARGE of CEPARA :39-83 on the
+// fly: the energy-only factor sv(K)=10**Y*V(S,K) is a host table), op 1 ATMOL
+// (:485-507), op 2 WAVELO (src/ModRamWPI.f90:580-636, factor table from the host).
+// =============================================================================
+__global__ void __launch_bounds__(256) k_loss(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0, int op,
+                                              const double* __restrict__ wfac) {
+  const SpecDev& sp = pk.s[s0 + blockIdx.y];
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long n = (long long)d.NPA * d.NE * d.Pp;
   if (t >= n) return;
@@ -564,13 +707,67 @@ __global__ void k_loss(RamDev d, SpecDev sp, int op, const double* __restrict__ 
 }
 
 // =============================================================================
+// The palindromic middle of ram_run fused into one pass over F2
+// (src/ModRamRun.f90:108-142 with the default flags):
+//   [CHAREXCHANGE | WAVELO], SUMRC, ATMOL, SUMRC, ATMOL, SUMRC, [same], SUMRC
+// 4 reference passes + 4 reductions -> one read and one write of F2; the four
+// SETRC moments come out as per-CTA partials.  doA: apply the species' first /
+// last operator (CHAREX for ions; WAVELO for electrons when DoUseWPI is off);
+// bit s of doA = species s.
+// Each factor is applied in the reference's order, so a cell's value is what
+// the four separate passes would give.
+// =============================================================================
+__global__ void __launch_bounds__(256) k_loss_mid(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0,
+                                                  int doA) {
+  const SpecDev& sp = pk.s[s0 + blockIdx.y];
+  const long long n = (long long)d.NPA * d.NE * d.Pp;
+  const bool ion = (sp.kind != 3);
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(t % d.Pp);
+    if (p >= d.P) continue;
+    const int plane = (int)(t / d.Pp);
+    const int k = plane % d.NE, l = plane / d.NE;
+    const int j = p / d.NR, i = p - j * d.NR;
+    if (i < 1 || k < 1) continue;                       // every operator here acts on I>=2, K>=2 only
+    double f = sp.F[t];
+    const bool mom = (l >= 1) && (j <= d.NT - 2);
+    const double w = d.WE[k] * 1.0, wm = d.WMU[l], e = d.EKEV[k];
+    const bool useA = ((doA >> (s0 + blockIdx.y)) & 1) && (l >= 1);
+    double facA = 1.0;
+    if (useA) {
+      if (ion) facA = exp(-(sp.sv[k] * d.HDNSc[(size_t)l * d.Pp + p] * d.DTs));
+      else facA = sp.wfac[(size_t)k * d.Pp + p];
+      f = f * facA;
+    }
+    if (mom) acc[0] += e * (f * w * wm);
+    if (l + 1 >= d.UPA[i]) {
+      const double a = pow(sp.ATLOS[k * d.NR + i], 1 / d.FNHSc[(size_t)l * d.Pp + p]);
+      f = f * a;
+      if (mom) acc[1] += e * (f * w * wm);
+      f = f * a;
+      if (mom) acc[2] += e * (f * w * wm);
+    } else if (mom) {
+      const double term = e * (f * w * wm);
+      acc[1] += term;
+      acc[2] += term;
+    }
+    if (useA) f = f * facA;
+    if (mom) acc[3] += e * (f * w * wm);
+    sp.F[t] = f;
+  }
+  cta_sum_to<4>(sp.part, acc);
+}
+
+// =============================================================================
 // WPADIF  (src/ModRamWPI.f90:643-714): implicit pitch-angle diffusion, Thomas
 // recurrences along L per (J,I,K) line.  One thread per line; RK/RL live in
 // shared memory [NPA][T] (conflict-free: T consecutive threads).  D = DA + DB.
+// In place (a thread owns its whole line).
 // =============================================================================
-__global__ void k_wpadif(RamDev d, SpecDev sp, const double* __restrict__ DA, const double* __restrict__ DB,
-                         unsigned long long* __restrict__ nviol) {
+__global__ void k_wpadif(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0) {
   extern __shared__ double smem[];
+  const SpecDev& sp = pk.s[s0 + blockIdx.y];
   const int NE = d.NE, NPA = d.NPA, Pp = d.Pp, T = blockDim.x;
   double* RK = smem;             // [NPA][T]
   double* RL = smem + NPA * T;
@@ -582,11 +779,10 @@ __global__ void k_wpadif(RamDev d, SpecDev sp, const double* __restrict__ DA, co
   if (p >= d.P || i < 1 || k < 1) return;
   const size_t LS = (size_t)NE * Pp;
   double* F = sp.F + (size_t)k * Pp + p;
-  const double* a = DA + (size_t)k * Pp + p;  // [l*LS]
-  const double* b = DB + (size_t)k * Pp + p;
+  const double* a = sp.DA + (size_t)k * Pp + p;  // [l*LS]
+  const double* b = sp.DB + (size_t)k * Pp + p;
   const double DTs = d.DTs;
   unsigned long long viol = 0;
-  // F(L) = F2/FACMU(L), F(1)=F(2); only F(L) is needed at step L
   RK[tx] = 0.;
   RL[tx] = -1.;
   double rkm = 0., rlm = -1.;
@@ -620,55 +816,7 @@ __global__ void k_wpadif(RamDev d, SpecDev sp, const double* __restrict__ DA, co
     const double FM = d.FNHSc[(size_t)(L - 1) * Pp + p] * d.MU[L - 1];
     F[(size_t)(L - 1) * LS] = f * FM;
   }
-  if (viol) atomicAdd(nviol, viol);
-}
-
-// =============================================================================
-// SUMRC  (src/ModRamRun.f90:231-259): SETRC = sum_{I>=2,K>=2,L>=2,J<=NT-1}
-// F2*WE(K)*WMU(L)*EKEV(K).  Two-stage deterministic tree (fixed grid), so the
-// result is run-to-run reproducible; it differs from the reference's serial
-// sum by summation order only (~1e-15 relative, diagnostic quantity).
-// =============================================================================
-__global__ void k_sumrc_partial(RamDev d, SpecDev sp, double* __restrict__ part) {
-  __shared__ double sm[32];
-  const long long n = (long long)d.NPA * d.NE * d.Pp;
-  double acc = 0.0;
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
-    const int p = (int)(t % d.Pp);
-    const int plane = (int)(t / d.Pp);
-    const int k = plane % d.NE, l = plane / d.NE;
-    if (p >= d.P || k < 1 || l < 1) continue;
-    const int j = p / d.NR, i = p - j * d.NR;
-    if (i < 1 || j > d.NT - 2) continue;
-    const double WEIGHT = sp.F[t] * d.WE[k] * d.WMU[l];
-    acc += d.EKEV[k] * WEIGHT;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    double v = (threadIdx.x < (blockDim.x >> 5)) ? sm[threadIdx.x] : 0.0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (threadIdx.x == 0) part[blockIdx.x] = v;
-  }
-}
-// out[slot] = sum(part[0..n))  (single warp-multiple CTA, fixed order)
-__global__ void k_sum_final(const double* __restrict__ part, int n, double* __restrict__ out) {
-  __shared__ double sm[32];
-  double acc = 0.0;
-  for (int q = threadIdx.x; q < n; q += blockDim.x) acc += part[q];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    double v = (threadIdx.x < (blockDim.x >> 5)) ? sm[threadIdx.x] : 0.0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (threadIdx.x == 0) *out = v;
-  }
+  if (viol) atomicAdd(sp.dt + 4 + 16, viol);
 }
 
 // =============================================================================
@@ -678,13 +826,14 @@ __global__ void k_sum_final(const double* __restrict__ part, int n, double* __re
 // one thread per p adds the energies band by band in the reference's order
 // => PPERT/PPART are bit-identical to the oracle.
 // =============================================================================
-__global__ void k_anisch_pa(RamDev d, SpecDev sp, double* __restrict__ tE, double* __restrict__ tA) {
+__global__ void __launch_bounds__(128) k_anisch_pa(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0) {
+  const SpecDev& sp = pk.s[s0 + blockIdx.y];
   const int NE = d.NE, Pp = d.Pp;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)NE * Pp) return;
   const int k = (int)(t / Pp), p = (int)(t - (long long)k * Pp);
   const int i = p % d.NR;
-  if (p >= d.P || i < 1 || k < 1) { tE[t] = 0; tA[t] = 0; return; }
+  if (p >= d.P || i < 1 || k < 1) { sp.tE[t] = 0; sp.tA[t] = 0; return; }
   const size_t LS = (size_t)NE * Pp;
   double* F = sp.F + (size_t)k * Pp + p;
   const double f2 = F[LS];
@@ -699,24 +848,25 @@ __global__ void k_anisch_pa(RamDev d, SpecDev sp, double* __restrict__ tE, doubl
     SUME = SUME + f * EPME;
     SUMA = SUMA + f * EPMA;
   }
-  tE[t] = sp.EPP[k] * SUME;
-  tA[t] = sp.EPP[k] * SUMA;
+  sp.tE[t] = sp.EPP[k] * SUME;
+  sp.tA[t] = sp.EPP[k] * SUMA;
 }
-// khi[5]: 1-based inclusive upper K of the 5 energy bands
-__global__ void k_anisch_en(RamDev d, const double* __restrict__ tE, const double* __restrict__ tA, double RFAC, int kh0, int kh1,
-                            int kh2, int kh3, int kh4, double* __restrict__ pper, double* __restrict__ ppar) {
+// kh0..kh4: 1-based inclusive upper K of the 5 energy bands (khi, :303,322)
+__global__ void k_anisch_en(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0, double RFAC, int kh0, int kh1,
+                            int kh2, int kh3, int kh4) {
+  const SpecDev& sp = pk.s[s0 + blockIdx.y];
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= d.P) return;
   const int i = p % d.NR;
-  if (i < 1) { pper[p] = 0; ppar[p] = 0; return; }
+  if (i < 1) { sp.pper[p] = 0; sp.ppar[p] = 0; return; }
   const int khi[5] = {kh0, kh1, kh2, kh3, kh4};
   int klo = 2;
   double PT = 0., AT = 0.;
   for (int w = 0; w < 5; ++w) {
     double PPER = 0., PPAR = 0.;
     for (int K = klo; K <= khi[w]; ++K) {
-      PPER = PPER + tE[(size_t)(K - 1) * d.Pp + p];
-      PPAR = PPAR + tA[(size_t)(K - 1) * d.Pp + p];
+      PPER = PPER + sp.tE[(size_t)(K - 1) * d.Pp + p];
+      PPAR = PPAR + sp.tA[(size_t)(K - 1) * d.Pp + p];
     }
     PPAR = 2 * RFAC * PPAR;
     PPER = RFAC * PPER;
@@ -724,8 +874,8 @@ __global__ void k_anisch_en(RamDev d, const double* __restrict__ tE, const doubl
     PT = PT + PPER;
     AT = AT + PPAR;
   }
-  pper[p] = PT;
-  ppar[p] = AT;
+  sp.pper[p] = PT;
+  sp.ppar[p] = AT;
 }
 
 // =============================================================================
@@ -753,7 +903,9 @@ __global__ void k_f2_to_host(RamDev d, double* __restrict__ stage, const double*
 }
 // F2(:,:,NT,:,:) = F2(:,:,1,:,:), then F2 = 1e-31 where outsideMGNP == 1.  The
 // J=1 thread owns both its own cell and the J=NT copy (no read/write race).
-__global__ void k_epilogue(RamDev d, double* __restrict__ Fs) {
+__global__ void __launch_bounds__(256) k_epilogue(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0) {
+  const SpecDev& sp = pk.s[s0 + blockIdx.y];
+  double* Fs = sp.F;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long n = (long long)d.NPA * d.NE * d.Pp;
   if (t >= n) return;

@@ -73,6 +73,10 @@ def lib():
     L.rsg_ram_flux_d2h.argtypes = [vp, vp]
     L.rsg_ram_launch_count.argtypes = [vp]
     L.rsg_ram_launch_count.restype = ll
+    L.rsg_ram_timer_begin.argtypes = [vp]
+    L.rsg_ram_timer_end.argtypes = [vp, _dp]
+    L.rsg_host_register.argtypes = [vp, ll]
+    L.rsg_host_unregister.argtypes = [vp]
     _lib = L
     return L
 
@@ -87,6 +91,15 @@ def _p(a, dtype=np.float64):
     if a.dtype != dtype or not (a.flags.f_contiguous or a.ndim <= 1 and a.flags.c_contiguous):
         raise ValueError("array must be Fortran-contiguous " + str(dtype))
     return a.ctypes.data
+
+
+def host_register(a):
+    """Pin a numpy array in place (cudaHostRegister)."""
+    _ck(lib().rsg_host_register(a.ctypes.data, a.nbytes))
+
+
+def host_unregister(a):
+    _ck(lib().rsg_host_unregister(a.ctypes.data))
 
 
 def device_count() -> int:
@@ -239,6 +252,14 @@ class RamGpu:
 
     def launch_count(self):
         return self.L.rsg_ram_launch_count(self.h)
+
+    def timer_begin(self):
+        _ck(self.L.rsg_ram_timer_begin(self.h))
+
+    def timer_end(self):
+        ms = C.c_double()
+        _ck(self.L.rsg_ram_timer_end(self.h, C.byref(ms)))
+        return ms.value
 
     def close(self):
         if self.h:
