@@ -33,8 +33,11 @@ struct RamDev {
   // prep, 3-D planes [NPA][Pp]
   double *t1, *G, *sFp, *Gr, *Gp, *DRD2, *DPD2, *dBdt1, *dIdt1, *FNHSc;
   double *CMUDOT, *Gmr, *Gmp, *DRM2, *DPM2, *dIbndt2, *BOUNHSc, *HDNSc;
-  // fast-mode separable coefficients [NPA][Pp]: c = gIK*(a + wK*b)
-  double *fRa, *fRb, *fPa, *fPb, *fEa, *fEb, *fMa, *fMb;
+  // FAST-mode separable coefficient planes: CDrift* = a + w(K)*b
+  //   R: CR[p] + P4[k]*fRb     P: fPa[p] - w2[k]*fPb
+  //   E: uE[k]*fEa + vE[k]*fEb MU: fMa + wM[k]*fMb          (3-D ones are [NPA][Pp])
+  double *fRb, *fPa, *fPb, *fEa, *fEb, *fMa, *fMb;
+  const double *rDMU, *rWMU;   // 1/DMU(L), 1/WMU(L)
 };
 
 // per-species device tables (pointers into one buffer) + scalars
@@ -50,6 +53,7 @@ struct SpecDev {
   const double *P4, *eK, *epK, *aE, *sv;  // [NE]
   const double *P2, *EDOT, *ATLOS;        // [NE][NR]
   const double* aMU;                      // [NPA]
+  const double *w2, *uE, *vE, *wM, *rDE, *rWE;  // FAST-mode energy tables [NE]
   const double* FF;                       // FFACTOR [l][k][i]
   const double* EPP;                      // [NE]
   const double* wfac;                     // WAVELO factor exp(-DTs/TAU_LIF) [NE][Pp]

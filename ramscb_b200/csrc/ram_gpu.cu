@@ -204,7 +204,8 @@ int L_inflow(rsg_ram* h, int s0, int ns, cudaStream_t st) {
   make_pack(h, pk, s0, ns);
   RamDev dv = devfor(h, h->sp[s0].DTs);
   dim3 g(h->ntiles, ns);
-  k_driftr_inflow<<<g, SCAN_TILE, 0, st>>>(dv, pk, s0, h->d_tilemax, h->ntiles);
+  if (h->mode == RSG_MODE_FAST) k_driftr_inflow<true><<<g, SCAN_TILE, 0, st>>>(dv, pk, s0, h->d_tilemax, h->ntiles);
+  else k_driftr_inflow<false><<<g, SCAN_TILE, 0, st>>>(dv, pk, s0, h->d_tilemax, h->ntiles);
   CKL();
   k_driftr_scan<<<g, SCAN_TILE, 0, st>>>(dv, pk, s0, h->d_tilemax, h->ntiles);
   CKL();
@@ -223,7 +224,8 @@ int L_driftr(rsg_ram* h, int s0, int ns, cudaStream_t st) {
   const long long N = (long long)h->specStride;
   const long long warps = (N + 30) / 31 + 1;
   dim3 g(nblk(warps * 32, 256), ns);
-  k_driftr<<<g, 256, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0);
+  if (h->mode == RSG_MODE_FAST) k_driftr<true><<<g, 256, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0);
+  else k_driftr<false><<<g, 256, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0);
   CKL();
   h->launches++;
   flip(h, s0, ns);
@@ -235,7 +237,8 @@ int L_driftp(rsg_ram* h, int s0, int ns, cudaStream_t st) {
   make_pack(h, pk, s0, ns);
   const int nseg = seg_count(h->NT - 1, h->segP);
   dim3 g(nblk((long long)h->NPA * h->NE * h->NR * nseg, 128), ns);
-  k_driftp<<<g, 128, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0, h->segP, nseg);
+  if (h->mode == RSG_MODE_FAST) k_driftp<true><<<g, 128, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0, h->segP, nseg);
+  else k_driftp<false><<<g, 128, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0, h->segP, nseg);
   CKL();
   h->launches++;
   flip(h, s0, ns);
@@ -247,7 +250,8 @@ int L_drifte(rsg_ram* h, int s0, int ns, cudaStream_t st) {
   make_pack(h, pk, s0, ns);
   const int nseg = seg_count(h->NE, h->segE);
   dim3 g(nblk((long long)h->NPA * h->Pp * nseg, 128), ns);
-  k_drifte<<<g, 128, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0, h->segE, nseg);
+  if (h->mode == RSG_MODE_FAST) k_drifte<true><<<g, 128, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0, h->segE, nseg);
+  else k_drifte<false><<<g, 128, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0, h->segE, nseg);
   CKL();
   h->launches++;
   flip(h, s0, ns);
@@ -259,7 +263,8 @@ int L_driftmu(rsg_ram* h, int s0, int ns, cudaStream_t st) {
   make_pack(h, pk, s0, ns);
   const int nseg = seg_count(h->NPA - 2, h->segMU);
   dim3 g(nblk((long long)h->NE * h->Pp * nseg, 128), ns);
-  k_driftmu<<<g, 128, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0, h->segMU, nseg);
+  if (h->mode == RSG_MODE_FAST) k_driftmu<true><<<g, 128, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0, h->segMU, nseg);
+  else k_driftmu<false><<<g, 128, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0, h->segMU, nseg);
   CKL();
   h->launches++;
   flip(h, s0, ns);
@@ -348,6 +353,7 @@ int tables_drift(rsg_ram* h, int s, double DTs, cudaStream_t st) {
   double* P2 = t + 4 * NE;
   double* EDOT = P2 + (size_t)NE * NR;
   double* aMU = EDOT + (size_t)NE * NR;
+  double* fast = aMU + NPA;  // w2, uE, vE, wM, rDE, rWE
 #define GRELs(K) h->GREL[s + (size_t)nS * ((K)-1)]
 #define GRBNDs(K) h->GRBND[s + (size_t)nS * ((K)-1)]
   for (int K = 1; K <= NE; ++K) {
@@ -356,6 +362,13 @@ int tables_drift(rsg_ram* h, int s, double DTs, cudaStream_t st) {
     eK[K - 1] = h->EBND[K - 1] * 1e3 * (GRBNDs(K) + 1) / 2 / GRBNDs(K);
     epK[K - 1] = h->EKEV[K - 1] * 1e3 * (GRELs(K) + 1) / 2 / GRELs(K);
     aE[K - 1] = FracCFL * DTs * h->DE[K - 1];
+    // FAST-mode energy factors
+    fast[K - 1] = DTs * h->EKEV[K - 1] * 1000 * (GRELs(K) + 1) / GRELs(K) / DPHI / QS;       // w2: P2 = w2/RLZ**2
+    fast[NE + K - 1] = h->EBND[K - 1] * DTs * (GRBNDs(K) + 1) / GRBNDs(K) / 2.;                // uE: EDOT = uE/RLZ
+    fast[2 * NE + K - 1] = fast[NE + K - 1] * eK[K - 1] / QS;                                  // vE
+    fast[3 * NE + K - 1] = epK[K - 1] / QS;                                                    // wM
+    fast[4 * NE + K - 1] = 1.0 / h->DE[K - 1];
+    fast[5 * NE + K - 1] = 1.0 / h->WE[K - 1];
     for (int I = 1; I <= NR; ++I) {
       // DRIFTPARA :71, :83
       P2[(size_t)(K - 1) * NR + (I - 1)] =
@@ -506,17 +519,20 @@ int rsg_ram_create(rsg_ram** out, int nS, int NR, int NT, int NE, int NPA, int d
   double** g1[] = {(double**)&d.RLZ, (double**)&d.EKEV, (double**)&d.WE, (double**)&d.DE, (double**)&d.MU, (double**)&d.WMU, (double**)&d.DMU};
   const size_t g1n[] = {(size_t)NR + 1, (size_t)NE, (size_t)NE, (size_t)NE, (size_t)NPA, (size_t)NPA, (size_t)NPA};
   for (int q = 0; q < 7; ++q) RET(h->dalloc(g1[q], g1n[q]));
+  RET(h->dalloc((double**)&d.rDMU, NPA));
+  RET(h->dalloc((double**)&d.rWMU, NPA));
   RET(h->dalloc((int**)&d.UPA, NR));
   double** f2d[] = {(double**)&d.BNES, (double**)&d.dBdt, (double**)&d.VT, (double**)&d.EIR, (double**)&d.EIP};
   for (auto p : f2d) RET(h->dalloc(p, n2));
   double** f3d[] = {(double**)&d.FNHS, (double**)&d.FNIS, (double**)&d.BOUNHS, (double**)&d.BOUNIS, (double**)&d.HDNS, (double**)&d.dIdt, (double**)&d.dIbndt};
   for (auto p : f3d) RET(h->dalloc(p, n3));
   RET(h->dalloc((int**)&d.outside, (size_t)NR * NT));
-  double** p2d[] = {&d.CR, &d.sB, &d.pT1, &d.pT3, &d.sBp, &d.DRD1, &d.DPD1, &d.BNESc, &d.dBdt2, &d.RLZp};
+  double** p2d[] = {&d.CR, &d.sB, &d.pT1, &d.pT3, &d.sBp, &d.DRD1, &d.DPD1, &d.BNESc, &d.dBdt2, &d.RLZp, &d.fPa};
   for (auto p : p2d) RET(h->dalloc(p, np));
   RET(h->dalloc(&d.outp, np));
   double** p3d[] = {&d.t1, &d.G, &d.sFp, &d.Gr, &d.Gp, &d.DRD2, &d.DPD2, &d.dBdt1, &d.dIdt1, &d.FNHSc,
-                    &d.CMUDOT, &d.Gmr, &d.Gmp, &d.DRM2, &d.DPM2, &d.dIbndt2, &d.BOUNHSc, &d.HDNSc};
+                    &d.CMUDOT, &d.Gmr, &d.Gmp, &d.DRM2, &d.DPM2, &d.dIbndt2, &d.BOUNHSc, &d.HDNSc,
+                    &d.fRb, &d.fPb, &d.fEa, &d.fEb, &d.fMa, &d.fMb};
   for (auto p : p3d) RET(h->dalloc(p, n3p));
   h->specStride = (size_t)NPA * NE * h->Pp;
   RET(h->dalloc(&h->d_F2[0], h->specStride * nS));
@@ -545,7 +561,7 @@ int rsg_ram_create(rsg_ram** out, int nS, int NR, int NT, int NE, int NPA, int d
     Spec& sp = h->sp[s];
     CK(cudaStreamCreateWithFlags(&sp.own, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&sp.ev, cudaEventDisableTiming));
-    sp.n_tab = (size_t)NE * 4 + (size_t)NE * NR * 2 + NPA;
+    sp.n_tab = (size_t)NE * 10 + (size_t)NE * NR * 2 + NPA;
     RET(h->dalloc(&sp.d_tab, sp.n_tab));
     CK(cudaMallocHost((void**)&sp.h_tab, sp.n_tab * sizeof(double)));
     RET(h->dalloc(&sp.d_ce, (size_t)NE + (size_t)NE * NR));
@@ -576,6 +592,12 @@ int rsg_ram_create(rsg_ram** out, int nS, int NR, int NT, int NE, int NPA, int d
     sd.P2 = t; t += (size_t)NE * NR;
     sd.EDOT = t; t += (size_t)NE * NR;
     sd.aMU = t; t += NPA;
+    sd.w2 = t; t += NE;
+    sd.uE = t; t += NE;
+    sd.vE = t; t += NE;
+    sd.wM = t; t += NE;
+    sd.rDE = t; t += NE;
+    sd.rWE = t; t += NE;
     sd.FF = sp.d_FF;
     sd.EPP = sp.d_EPP;
     sd.wfac = sp.d_wfac;
@@ -615,8 +637,11 @@ int rsg_ram_destroy(rsg_ram* h) {
 
 int rsg_ram_set_mode(rsg_ram* h, int mode) {
   if (!h) return fail(RSG_ERR_ARG, "null handle");
-  if (mode != RSG_MODE_EXACT) return fail(RSG_ERR_UNSUPPORTED, "only RSG_MODE_EXACT is implemented");
+  if (mode != RSG_MODE_EXACT && mode != RSG_MODE_FAST) return fail(RSG_ERR_ARG, "unknown mode");
+  CK(cudaSetDevice(h->device));
+  RET(rsg_ram_sync(h));
   h->mode = mode;
+  for (int s = 0; s < h->nS; ++s) h->sp[s].DTs = -1.0;  // the inflow pre-pass depends on the mode: redo DRIFTPARA
   return RSG_OK;
 }
 
@@ -662,6 +687,12 @@ int rsg_ram_set_grids(rsg_ram* h, const double* RLZ, const double* LZ, const dou
   RET(up((double*)d.RLZ, RLZ, NR + 1)); RET(up((double*)d.EKEV, EKEV, NE)); RET(up((double*)d.WE, WE, NE));
   RET(up((double*)d.DE, DE, NE)); RET(up((double*)d.MU, MU, NPA)); RET(up((double*)d.WMU, WMU, NPA));
   RET(up((double*)d.DMU, DMU, NPA));
+  {
+    std::vector<double> r1(NPA), r2(NPA);
+    for (int l = 0; l < NPA; ++l) { r1[l] = 1.0 / DMU[l]; r2[l] = 1.0 / WMU[l]; }
+    RET(up((double*)d.rDMU, r1.data(), NPA));
+    RET(up((double*)d.rWMU, r2.data(), NPA));
+  }
   std::vector<int> upa(NR);
   for (int i = 0; i < NR; ++i) upa[i] = (int)UPA[i];
   RET(up((int*)d.UPA, upa.data(), NR));

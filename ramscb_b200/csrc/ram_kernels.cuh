@@ -54,6 +54,22 @@ __device__ __forceinline__ double limited_flux(double Fm1, double F0, double Fp1
   return FB;
 }
 
+// FAST mode: the same limiter without the division (LIM*X is a min/max of |num|
+// and |X|) and with FUP selected instead of computed; mathematically identical,
+// rounding differs at the 1e-16 level.
+__device__ __forceinline__ double limited_flux_fast(double Fm1, double F0, double Fp1, double Fp2, double c, double chat,
+                                                    double beta) {
+  const bool neg = (c < 0.0);
+  const double X = Fp1 - F0;
+  const double FUP = neg ? Fp1 : F0;
+  const double num = neg ? (Fp2 - Fp1) : (F0 - Fm1);
+  const double aX = fabs(X), an = fabs(num);
+  const double limx = copysign(fmax(fmin(beta * an, aX), fmin(an, beta * aX)), X);   // LIM * X
+  const double corr = -0.5 * (chat - (neg ? -1.0 : 1.0));
+  const bool use = (aX > 1.E-27) && (num * X > 0.0);
+  return use ? fma(corr, limx, FUP) : FUP;
+}
+
 // =============================================================================
 // prep kernels: coefficient pieces that do not depend on energy, evaluated in
 // the reference's order so the sweeps only do the K-dependent tail.
@@ -69,6 +85,7 @@ __global__ void k_prep_fields(RamDev d) {
     d.t1[o] = 0; d.G[o] = 0; d.sFp[o] = 1; d.Gr[o] = 0; d.Gp[o] = 0; d.DRD2[o] = 0; d.DPD2[o] = 0;
     d.dBdt1[o] = 0; d.dIdt1[o] = 0; d.FNHSc[o] = 1; d.Gmr[o] = 0; d.Gmp[o] = 0; d.DRM2[o] = 0; d.DPM2[o] = 0;
     d.dIbndt2[o] = 0; d.BOUNHSc[o] = 1; d.HDNSc[o] = 0;
+    d.fRb[o] = 0; d.fPb[o] = 0; d.fEb[o] = 0;
     if (l == 0) { d.sB[p] = 1; d.sBp[p] = 1; d.BNESc[p] = 1; d.RLZp[p] = 1; d.outp[p] = 1; }
     return;
   }
@@ -99,6 +116,8 @@ __global__ void k_prep_fields(RamDev d) {
         CGR1 + (R3(FNIS, I + 1, J, L) + R3(FNIS, I, J, L) - 2 * R3(FNHS, I + 1, J, L) - 2 * R3(FNHS, I, J, L)) * CGR2 / 2. /
                    (R2(BNES, I + 1, J) + R2(BNES, I, J));
     d.t1[o] = CGR3 / (R3(FNHS, I, J, L) + R3(FNHS, I + 1, J, L));
+    // FAST: CGR = P4(K) * fRb
+    d.fRb[o] = d.t1[o] / 2. / (R2(BNES, I, J) + R2(BNES, I + 1, J)) / (RLZI + 0.5 * MDR);
   }
   if (I >= 2 && J >= 2) {  // DRIFTP :232-237
     const double GPA1 = R3(FNIS, I, J, L) + R3(FNIS, I, J1, L) +
@@ -108,9 +127,12 @@ __global__ void k_prep_fields(RamDev d) {
                         (R2(BNES, I, J) + R2(BNES, I, J1));
     d.G[o] = GPA1 + GPA2;
     d.sFp[o] = R3(FNHS, I, J, L) + R3(FNHS, I, J1, L);
+    // FAST: CDriftP = fPa - w2(K) * fPb   (P2(I,K) = w2(K)/RLZ(I)**2)
+    d.fPb[o] = (GPA1 + GPA2) / (R3(FNHS, I, J, L) + R3(FNHS, I, J1, L)) / (R2(BNES, I, J) + R2(BNES, I, J1)) / (RLZI * RLZI);
   } else {
     d.G[o] = 0;
     d.sFp[o] = 1;
+    d.fPb[o] = 0;
   }
   if (I >= 2) {
     // DRIFTE :323-332, :340-341
@@ -128,6 +150,8 @@ __global__ void k_prep_fields(RamDev d) {
                 RLZI * (R3(FNIS, I, J, L) - 2 * R3(FNHS, I, J, L)) / 4 / MDR * (R2(BNES, I + 1, J) - R2(BNES, I - 1, J)) / R2(BNES, I, J);
     d.dBdt1[o] = R2(d.dBdt, I, J) * (1. - R3(FNIS, I, J, L) / 2. / R3(FNHS, I, J, L)) * RLZI / R2(BNES, I, J);
     d.dIdt1[o] = -R3(d.dIdt, I, J, L) * RLZI / R3(FNHS, I, J, L);
+    // FAST: CDriftE = uE(K)*fEa + vE(K)*fEb  (EDOT(I,K) = uE(K)/RLZ(I), EDT1 = eK(K)/QS/(FNHS*RLZ*BNES))
+    d.fEb[o] = (d.Gr[o] * d.DRD2[o] * RLZI - d.Gp[o] * d.DPD2[o]) / (R3(FNHS, I, J, L) * RLZI * R2(BNES, I, J)) / RLZI;
     // DRIFTMU :419-428, :432
     const double GMR1 = (R2(BNES, I + 1, J) - R2(BNES, I - 1, J)) / 4 / MDR / R2(BNES, I, J);
     const double GMR2 = 1 / RLZI;
@@ -144,6 +168,7 @@ __global__ void k_prep_fields(RamDev d) {
   } else {
     d.Gr[o] = 0; d.Gp[o] = 0; d.DRD2[o] = 0; d.DPD2[o] = 0; d.dBdt1[o] = 0; d.dIdt1[o] = 0;
     d.Gmr[o] = 0; d.Gmp[o] = 0; d.DRM2[o] = 0; d.DPM2[o] = 0; d.dIbndt2[o] = 0;
+    d.fEb[o] = 0;
   }
 }
 
@@ -155,8 +180,8 @@ __global__ void k_prep_step(RamDev d) {
   const int l = t / d.Pp, p = t - l * d.Pp;
   const size_t o = (size_t)l * d.Pp + p;
   if (p >= d.P) {
-    d.CMUDOT[o] = 0;
-    if (l == 0) { d.CR[p] = 0; d.pT1[p] = 0; d.pT3[p] = 0; d.DRD1[p] = 0; d.DPD1[p] = 0; d.dBdt2[p] = 0; }
+    d.CMUDOT[o] = 0; d.fEa[o] = 0; d.fMa[o] = 0; d.fMb[o] = 0;
+    if (l == 0) { d.CR[p] = 0; d.pT1[p] = 0; d.pT3[p] = 0; d.DRD1[p] = 0; d.DPD1[p] = 0; d.dBdt2[p] = 0; d.fPa[p] = 0; }
     return;
   }
   const int j = p / d.NR, i = p - j * d.NR;
@@ -176,25 +201,38 @@ __global__ void k_prep_step(RamDev d) {
       if (J >= 2) {
         d.pT1[p] = (R2(VT, I + 1, J) + R2(VT, I + 1, J1) - R2(VT, I - 1, J) - R2(VT, I - 1, J1)) * P1;
         d.pT3[p] = (R2(EIR, I, J1) + R2(EIR, I, J)) / RLZI * DTs / DPHI;
+        d.fPa[p] = (d.pT1[p] - d.pT3[p]) / (R2(BNES, I, J) + R2(BNES, I, J1)) + OME_EARTH * DTs / DPHI;
       } else {
-        d.pT1[p] = 0; d.pT3[p] = 0;
+        d.pT1[p] = 0; d.pT3[p] = 0; d.fPa[p] = 0;
       }
       d.DRD1[p] = (R2(EIP, I, J) * RLZI - (R2(VT, I, J1) - R2(VT, I, J0)) / 2. / DPHI) / R2(BNES, I, J);
       d.DPD1[p] = OME_EARTH * RLZI + ((R2(VT, I + 1, J) - R2(VT, I - 1, J)) / 2 / MDR - R2(EIR, I, J)) / R2(BNES, I, J);
       d.dBdt2[p] = R2(d.dBdt, I, J) / 2. / R2(BNES, I, J) * RLZI;
     } else {
-      d.pT1[p] = 0; d.pT3[p] = 0; d.DRD1[p] = 0; d.DPD1[p] = 0; d.dBdt2[p] = 0;
+      d.pT1[p] = 0; d.pT3[p] = 0; d.DRD1[p] = 0; d.DPD1[p] = 0; d.dBdt2[p] = 0; d.fPa[p] = 0;
     }
   }
+  double CMUDOT = 0.;
   if (I >= 2 && L >= 2) {
     double MUDOT = 0.;
     if (L <= d.NPA - 1) {
       const double MUBOUN = d.MU[l] + 0.5 * d.WMU[l];
       MUDOT = (1. - MUBOUN * MUBOUN) * DTs / 2 / MUBOUN / RLZI;
     }
-    d.CMUDOT[o] = MUDOT * R3(d.BOUNIS, I, J, L) / R3(d.BOUNHS, I, J, L);
+    CMUDOT = MUDOT * R3(d.BOUNIS, I, J, L) / R3(d.BOUNHS, I, J, L);
+  }
+  d.CMUDOT[o] = CMUDOT;
+  // FAST-mode planes that depend on DTs / the E field (same expressions as the
+  // l==0 block above, recomputed here so no thread reads another's output)
+  if (I >= 2) {
+    const double DRD1 = (R2(EIP, I, J) * RLZI - (R2(VT, I, J1) - R2(VT, I, J0)) / 2. / DPHI) / R2(BNES, I, J);
+    const double DPD1 = OME_EARTH * RLZI + ((R2(VT, I + 1, J) - R2(VT, I - 1, J)) / 2 / MDR - R2(EIR, I, J)) / R2(BNES, I, J);
+    const double dBdt2 = R2(d.dBdt, I, J) / 2. / R2(BNES, I, J) * RLZI;
+    d.fEa[o] = (d.Gr[o] * DRD1 + d.Gp[o] * DPD1 + d.dBdt1[o] + d.dIdt1[o]) / RLZI;
+    d.fMa[o] = -CMUDOT * (d.Gmr[o] * DRD1 + d.Gmp[o] * DPD1 + dBdt2 + d.dIbndt2[o]);
+    d.fMb[o] = -CMUDOT * (d.Gmr[o] * d.DRM2[o] * RLZI - d.Gmp[o] * d.DPM2[o]) / (d.BOUNHSc[o] * RLZI * R2(BNES, I, J));
   } else {
-    d.CMUDOT[o] = 0;
+    d.fEa[o] = 0; d.fMa[o] = 0; d.fMb[o] = 0;
   }
 }
 
@@ -271,6 +309,7 @@ __device__ __forceinline__ void cta_min_to(unsigned long long* dst, double v) {
 // predicate (sign of CDriftR at I=NR) does not depend on F2, so the index of
 // that line is precomputed once per DRIFTPARA: last[(k*NPA+l)*NT+j].
 #define SCAN_TILE 1024
+template <bool FAST>
 __global__ void k_driftr_inflow(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0,
                                 int* __restrict__ tilemax_all, int ntiles) {
   __shared__ int sm[32];
@@ -285,7 +324,8 @@ __global__ void k_driftr_inflow(const __grid_constant__ RamDev d, const __grid_c
     const int k = t / (d.NT * d.NPA);
     const int i = d.NR - 1;
     const int p = j * d.NR + i;
-    const double c = coef_r(d.CR[p], d.t1[(size_t)l * d.Pp + p], sp.P4[k], d.sB[p], d.RLZ[i] + 0.5 * d.MDR);
+    const double c = FAST ? fma(sp.P4[k], d.fRb[(size_t)l * d.Pp + p], d.CR[p])
+                          : coef_r(d.CR[p], d.t1[(size_t)l * d.Pp + p], sp.P4[k], d.sB[p], d.RLZ[i] + 0.5 * d.MDR);
     v = (c < 0.0) ? t : -1;
     last[t] = v;
   }
@@ -342,6 +382,7 @@ __global__ void k_driftr_scan(const __grid_constant__ RamDev d, const __grid_con
 // =============================================================================
 // DRIFTR  (src/ModRamDrift.f90:95-198): one thread per cell.
 // =============================================================================
+template <bool FAST>
 __global__ void __launch_bounds__(256) k_driftr(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0) {
   const SpecDev& sp = pk.s[s0 + blockIdx.y];
   const int NR = d.NR, NT = d.NT, NE = d.NE, P = d.P, Pp = d.Pp;
@@ -365,7 +406,8 @@ __global__ void __launch_bounds__(256) k_driftr(const __grid_constant__ RamDev d
       const int line = (k * d.NPA + l) * NT + j;
       const int src = sp.last[line];
       const bool inflow = (src == line);
-      const double c = coef_r(d.CR[p], d.t1[(size_t)l * Pp + p], sp.P4[k], d.sB[p], d.RLZ[i] + 0.5 * d.MDR);
+      const double c = FAST ? fma(sp.P4[k], d.fRb[(size_t)l * Pp + p], d.CR[p])
+                            : coef_r(d.CR[p], d.t1[(size_t)l * Pp + p], sp.P4[k], d.sB[p], d.RLZ[i] + 0.5 * d.MDR);
       if (!d.outp[p]) cmax = fabs(c);
       const double* F = sp.F + (size_t)plane * Pp + (size_t)j * NR;  // F[i'] = F(I=i'+1) of this line
       F0 = F[i];
@@ -392,7 +434,7 @@ __global__ void __launch_bounds__(256) k_driftr(const __grid_constant__ RamDev d
         const double Fm1 = F[i - 1];
         const double Fp1 = (I + 1 <= NR) ? F[i + 1] : g1;
         const double Fp2 = (I + 2 <= NR) ? F[i + 2] : ((I + 2 == NR + 1) ? g1 : g2);
-        phi = c * limited_flux(Fm1, F0, Fp1, Fp2, c, c, d.BetaLim);
+        phi = c * (FAST ? limited_flux_fast(Fm1, F0, Fp1, Fp2, c, c, d.BetaLim) : limited_flux(Fm1, F0, Fp1, Fp2, c, c, d.BetaLim));
       }
     }
   }
@@ -412,6 +454,7 @@ __global__ void __launch_bounds__(256) k_driftr(const __grid_constant__ RamDev d
 // DRIFTP  (src/ModRamDrift.f90:204-279): periodic lines along MLT, segments of
 // SEG cells of J=2..NT per thread.  FBND(1)=FBND(NT), F2(J=1)=F2(J=NT).
 // =============================================================================
+template <bool FAST>
 __global__ void __launch_bounds__(128) k_driftp(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0, int SEG,
                                                 int nseg) {
   const SpecDev& sp = pk.s[s0 + blockIdx.y];
@@ -434,17 +477,21 @@ __global__ void __launch_bounds__(128) k_driftp(const __grid_constant__ RamDev d
     } else {
       const double* G = d.G + (size_t)l * Pp + i;
       const double* sFp = d.sFp + (size_t)l * Pp + i;
+      const double* fPb = d.fPb + (size_t)l * Pp + i;
       const double P2 = sp.P2[k * NR + i];
+      const double w2 = sp.w2[k];
       const double beta = d.BetaLim, OMEt = sp.OMEt;
       const double f2 = F[NR], f3 = F[2 * NR];          // F(2), F(3): wrap-around values
 #define GETFJ(J) (((J) <= NT) ? F[((J)-1) * NR] : (((J) == NT + 1) ? f2 : f3))
-#define COEFP(J) coef_p(d.pT1[((J)-1) * NR + i], P2, G[((J)-1) * NR], sFp[((J)-1) * NR], d.pT3[((J)-1) * NR + i], d.sBp[((J)-1) * NR + i], OMEt)
+#define COEFP(J) (FAST ? fma(-w2, fPb[((J)-1) * NR], d.fPa[((J)-1) * NR + i]) \
+                       : coef_p(d.pT1[((J)-1) * NR + i], P2, G[((J)-1) * NR], sFp[((J)-1) * NR], d.pT3[((J)-1) * NR + i], d.sBp[((J)-1) * NR + i], OMEt))
+#define LIMF(a, b, c_, d_, cc) (FAST ? limited_flux_fast(a, b, c_, d_, cc, cc, beta) : limited_flux(a, b, c_, d_, cc, cc, beta))
       // flux through the segment's lower edge: interface ja-1, or NT for ja==2 (:261-262)
       const int Jh = (ja == 2) ? NT : ja - 1;
       double prev;
       {
         const double c = COEFP(Jh);
-        prev = c * limited_flux(F[(Jh - 2) * NR], F[(Jh - 1) * NR], GETFJ(Jh + 1), GETFJ(Jh + 2), c, c, beta);
+        prev = c * LIMF(F[(Jh - 2) * NR], F[(Jh - 1) * NR], GETFJ(Jh + 1), GETFJ(Jh + 2), c);
       }
       double Fm1 = F[(ja - 2) * NR], F0 = F[(ja - 1) * NR], Fp1 = GETFJ(ja + 1);
       double fnew = 0.0;
@@ -452,7 +499,7 @@ __global__ void __launch_bounds__(128) k_driftp(const __grid_constant__ RamDev d
         const double Fp2 = GETFJ(J + 2);
         const double c = COEFP(J);
         if (!d.outp[(J - 1) * NR + i]) cmax = fmax(cmax, fabs(c));
-        const double cur = c * limited_flux(Fm1, F0, Fp1, Fp2, c, c, beta);
+        const double cur = c * LIMF(Fm1, F0, Fp1, Fp2, c);
         fnew = F0 - cur + prev;                         // :266
         if (fnew < 0.0) fnew = 1E-15;
         Fo[(J - 1) * NR] = fnew;
@@ -462,6 +509,7 @@ __global__ void __launch_bounds__(128) k_driftp(const __grid_constant__ RamDev d
       if (jb == NT) Fo[0] = fnew;                       // :272
 #undef GETFJ
 #undef COEFP
+#undef LIMF
     }
   }
   cta_min_to(sp.dt + 1, sp.aRP / fmax(cmax, 1E-10));
@@ -472,6 +520,7 @@ __global__ void __launch_bounds__(128) k_driftp(const __grid_constant__ RamDev d
 // cells of K=1..NE per thread.  Ghosts F(1),F(0) from the relativistic
 // extrapolation of F2(K=2) (:334-335), F(NE+1)=F(NE+2)=0 (:312-313).
 // =============================================================================
+template <bool FAST>
 __global__ void __launch_bounds__(128) k_drifte(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0, int SEG,
                                                 int nseg) {
   const SpecDev& sp = pk.s[s0 + blockIdx.y];
@@ -479,6 +528,7 @@ __global__ void __launch_bounds__(128) k_drifte(const __grid_constant__ RamDev d
   const long long nl = (long long)d.NPA * Pp;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   double dtmin = 1.0e300;
+  double mmax = 0.0;   // FAST: max over cells of max(|c|,1e-10)/DE(K)
   if (t < nl * nseg) {
     const int seg = (int)(t / nl);
     const long long r = t - (long long)seg * nl;
@@ -492,9 +542,13 @@ __global__ void __launch_bounds__(128) k_drifte(const __grid_constant__ RamDev d
         for (int K = ka; K <= kb; ++K) Fo[(size_t)(K - 1) * Pp] = F[(size_t)(K - 1) * Pp];
       } else {
         const size_t o = (size_t)l * Pp + p;
-        const double FNHS = d.FNHSc[o], Gr = d.Gr[o], Gp = d.Gp[o], DRD2 = d.DRD2[o], DPD2 = d.DPD2[o], dBdt1 = d.dBdt1[o],
-                     dIdt1 = d.dIdt1[o];
-        const double DRD1 = d.DRD1[p], DPD1 = d.DPD1[p], BNES = d.BNESc[p], RLZI = d.RLZp[p];
+        double FNHS = 0, Gr = 0, Gp = 0, DRD2 = 0, DPD2 = 0, dBdt1 = 0, dIdt1 = 0, DRD1 = 0, DPD1 = 0, BNES = 0, RLZI = 0, fA = 0, fB = 0;
+        if (FAST) {
+          fA = d.fEa[o]; fB = d.fEb[o];
+        } else {
+          FNHS = d.FNHSc[o]; Gr = d.Gr[o]; Gp = d.Gp[o]; DRD2 = d.DRD2[o]; DPD2 = d.DPD2[o]; dBdt1 = d.dBdt1[o]; dIdt1 = d.dIdt1[o];
+          DRD1 = d.DRD1[p]; DPD1 = d.DPD1[p]; BNES = d.BNESc[p]; RLZI = d.RLZp[p];
+        }
         const bool inside = !d.outp[p];
         const double QS = sp.QS, beta = d.BetaLim;
         const double* EDOT = sp.EDOT + i;
@@ -512,15 +566,27 @@ __global__ void __launch_bounds__(128) k_drifte(const __grid_constant__ RamDev d
         double cprev = 0.0, FBprev = 0.0;
         for (int K = K0; K <= kb; ++K) {
           const double nn = GETFK(K + 4);
-          const double c = coef_e(sp.eK[K - 1], FNHS, RLZI, BNES, QS, DRD1, DRD2, DPD1, DPD2, Gr, Gp, dBdt1, dIdt1,
-                                  EDOT[(K - 1) * d.NR]);
-          if (inside && K >= ka) dtmin = fmin(dtmin, sp.aE[K - 1] / fmax(fabs(c), 1E-10));
-          const double FB = limited_flux(Fm1, F0, Fp1, Fp2, c, c / d.DE[K - 1], beta);
-          if (K >= ka && K >= 2) {
-            const double WEK = d.WE[K - 1];
-            double fn = F0 - c / WEK * FB + cprev / WEK * FBprev;   // :364
-            if (fn < 0.0) fn = 1E-15;
-            Fo[(size_t)(K - 1) * Pp] = fn;
+          double c, FB;
+          if (FAST) {
+            c = fma(sp.vE[K - 1], fB, sp.uE[K - 1] * fA);
+            const double rDE = sp.rDE[K - 1];
+            if (inside && K >= ka) mmax = fmax(mmax, fmax(fabs(c), 1E-10) * rDE);
+            FB = c * limited_flux_fast(Fm1, F0, Fp1, Fp2, c, c * rDE, beta);   // FB holds the flux c*FBND
+            if (K >= ka && K >= 2) {
+              double fn = fma(-(FB - FBprev), sp.rWE[K - 1], F0);
+              if (fn < 0.0) fn = 1E-15;
+              Fo[(size_t)(K - 1) * Pp] = fn;
+            }
+          } else {
+            c = coef_e(sp.eK[K - 1], FNHS, RLZI, BNES, QS, DRD1, DRD2, DPD1, DPD2, Gr, Gp, dBdt1, dIdt1, EDOT[(K - 1) * d.NR]);
+            if (inside && K >= ka) dtmin = fmin(dtmin, sp.aE[K - 1] / fmax(fabs(c), 1E-10));
+            FB = limited_flux(Fm1, F0, Fp1, Fp2, c, c / d.DE[K - 1], beta);
+            if (K >= ka && K >= 2) {
+              const double WEK = d.WE[K - 1];
+              double fn = F0 - c / WEK * FB + cprev / WEK * FBprev;   // :364
+              if (fn < 0.0) fn = 1E-15;
+              Fo[(size_t)(K - 1) * Pp] = fn;
+            }
           }
           cprev = c; FBprev = FB;
           Fm1 = F0; F0 = Fp1; Fp1 = Fp2; Fp2 = nxt; nxt = nn;
@@ -529,6 +595,7 @@ __global__ void __launch_bounds__(128) k_drifte(const __grid_constant__ RamDev d
       }
     }
   }
+  if (FAST && mmax > 0.0) dtmin = sp.aRP / mmax;
   cta_min_to(sp.dt + 2, dtmin);
 }
 
@@ -537,6 +604,7 @@ __global__ void __launch_bounds__(128) k_drifte(const __grid_constant__ RamDev d
 // SEG cells of L=2..NPA-1 per thread; the last segment also closes the line with
 // F2(NPA) = F2(NPA-1)*FNHS(NPA)*MU(NPA)/FNHS(NPA-1)/MU(NPA-1) (:466).
 // =============================================================================
+template <bool FAST>
 __global__ void __launch_bounds__(128) k_driftmu(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0, int SEG,
                                                  int nseg) {
   const SpecDev& sp = pk.s[s0 + blockIdx.y];
@@ -544,6 +612,7 @@ __global__ void __launch_bounds__(128) k_driftmu(const __grid_constant__ RamDev 
   const long long nl = (long long)NE * Pp;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   double dtmin = 1.0e300;
+  double mmax = 0.0;   // FAST: max over cells of max(|c|,1e-32)/DMU(L)
   if (t < nl * nseg) {
     const int seg = (int)(t / nl);
     const long long r = t - (long long)seg * nl;
@@ -562,9 +631,10 @@ __global__ void __launch_bounds__(128) k_driftmu(const __grid_constant__ RamDev 
       } else {
         const double DRM1 = d.DRD1[p], DPM1 = d.DPD1[p], BNES = d.BNESc[p], RLZI = d.RLZp[p], dBdt2 = d.dBdt2[p];
         const bool inside = !d.outp[p];
-        const double QS = sp.QS, beta = d.BetaLim, epK = sp.epK[k];
+        const double QS = sp.QS, beta = d.BetaLim, epK = sp.epK[k], wM = sp.wM[k];
 #define GETFL(L) (((L) >= 2) ? F[(size_t)((L)-1) * LS] : F[LS])   /* F(1) = F(2)  (:414) */
-#define COEFMU(L, o) coef_mu(epK, d.BOUNHSc[o], RLZI, BNES, QS, DRM1, d.DRM2[o], DPM1, d.DPM2[o], d.Gmr[o], d.Gmp[o], dBdt2, d.dIbndt2[o], d.CMUDOT[o])
+#define COEFMU(L, o) (FAST ? fma(wM, d.fMb[o], d.fMa[o]) \
+                           : coef_mu(epK, d.BOUNHSc[o], RLZI, BNES, QS, DRM1, d.DRM2[o], DPM1, d.DPM2[o], d.Gmr[o], d.Gmp[o], dBdt2, d.dIbndt2[o], d.CMUDOT[o]))
         const int L0 = max(la - 1, 2);
         double Fm1 = GETFL(L0 - 1), F0 = GETFL(L0), Fp1 = GETFL(L0 + 1), Fp2 = (L0 + 2 <= NPA) ? GETFL(L0 + 2) : 0.0;
         double nxt = (L0 + 3 <= NPA) ? GETFL(L0 + 3) : 0.0;
@@ -574,15 +644,27 @@ __global__ void __launch_bounds__(128) k_driftmu(const __grid_constant__ RamDev 
           const double nn = (L + 4 <= NPA) ? F[(size_t)(L + 3) * LS] : 0.0;
           const size_t o = (size_t)(L - 1) * Pp + p;
           const double c = COEFMU(L, o);
-          if (inside && L >= la) dtmin = fmin(dtmin, sp.aMU[L - 1] / fmax(fabs(c), 1E-32));
           double FB;
-          if (L <= NPA - 2) FB = limited_flux(Fm1, F0, Fp1, Fp2, c, c / d.DMU[L - 1], beta);
-          else FB = Fp1;                                // FBND(NPA-1) = F(NPA)  (:458)
-          if (L >= la) {
-            const double WM = d.WMU[L - 1];
-            fnew = F0 - c / WM * FB + cprev / WM * FBprev;   // :460
-            if (fnew < 0.0) fnew = 1E-15;
-            Fo[(size_t)(L - 1) * LS] = fnew;
+          if (FAST) {
+            const double rDM = d.rDMU[L - 1];
+            if (inside && L >= la) mmax = fmax(mmax, fmax(fabs(c), 1E-32) * rDM);
+            if (L <= NPA - 2) FB = c * limited_flux_fast(Fm1, F0, Fp1, Fp2, c, c * rDM, beta);   // flux c*FBND
+            else FB = c * Fp1;
+            if (L >= la) {
+              fnew = fma(-(FB - FBprev), d.rWMU[L - 1], F0);
+              if (fnew < 0.0) fnew = 1E-15;
+              Fo[(size_t)(L - 1) * LS] = fnew;
+            }
+          } else {
+            if (inside && L >= la) dtmin = fmin(dtmin, sp.aMU[L - 1] / fmax(fabs(c), 1E-32));
+            if (L <= NPA - 2) FB = limited_flux(Fm1, F0, Fp1, Fp2, c, c / d.DMU[L - 1], beta);
+            else FB = Fp1;                                // FBND(NPA-1) = F(NPA)  (:458)
+            if (L >= la) {
+              const double WM = d.WMU[L - 1];
+              fnew = F0 - c / WM * FB + cprev / WM * FBprev;   // :460
+              if (fnew < 0.0) fnew = 1E-15;
+              Fo[(size_t)(L - 1) * LS] = fnew;
+            }
           }
           cprev = c; FBprev = FB;
           Fm1 = F0; F0 = Fp1; Fp1 = Fp2; Fp2 = nxt; nxt = nn;
@@ -590,7 +672,8 @@ __global__ void __launch_bounds__(128) k_driftmu(const __grid_constant__ RamDev 
         if (lastseg) {
           const size_t o = (size_t)(NPA - 1) * Pp + p;
           const double c = COEFMU(NPA, o);
-          if (inside) dtmin = fmin(dtmin, sp.aMU[NPA - 1] / fmax(fabs(c), 1E-32));
+          if (FAST) { if (inside) mmax = fmax(mmax, fmax(fabs(c), 1E-32) * d.rDMU[NPA - 1]); }
+          else if (inside) dtmin = fmin(dtmin, sp.aMU[NPA - 1] / fmax(fabs(c), 1E-32));
           Fo[(size_t)(NPA - 1) * LS] =
               fnew * d.FNHSc[(size_t)(NPA - 1) * Pp + p] * d.MU[NPA - 1] / d.FNHSc[(size_t)(NPA - 2) * Pp + p] / d.MU[NPA - 2];
         }
@@ -599,6 +682,7 @@ __global__ void __launch_bounds__(128) k_driftmu(const __grid_constant__ RamDev 
       }
     }
   }
+  if (FAST && mmax > 0.0) dtmin = sp.aRP / mmax;
   cta_min_to(sp.dt + 3, dtmin);
 }
 

