@@ -108,7 +108,7 @@ struct rsg_ram {
   std::mutex mu;
   Spec sp[RSG_MAX_SPECIES];
   long long launches = 0;
-  int nblk_sum = 0;
+  int nblk_sum = 0, sum_threads = 256;
   int segE = 12, segMU = 12, segP = 12;
 
   cudaStream_t st(int s) { return ext ? ext : sp[s].own; }
@@ -221,9 +221,7 @@ int L_driftr(rsg_ram* h, int s0, int ns, cudaStream_t st) {
   RET(reset_dt(h, s0, ns, 0, st));
   SpecPack pk;
   make_pack(h, pk, s0, ns);
-  const long long N = (long long)h->specStride;
-  const long long warps = (N + 30) / 31 + 1;
-  dim3 g(nblk(warps * 32, 256), ns);
+  dim3 g(nblk(h->P, 248), h->NPA * h->NE, ns);   // 8 warps x 31 cells per CTA
   if (h->mode == RSG_MODE_FAST) k_driftr<true><<<g, 256, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0);
   else k_driftr<false><<<g, 256, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0);
   CKL();
@@ -236,7 +234,7 @@ int L_driftp(rsg_ram* h, int s0, int ns, cudaStream_t st) {
   SpecPack pk;
   make_pack(h, pk, s0, ns);
   const int nseg = seg_count(h->NT - 1, h->segP);
-  dim3 g(nblk((long long)h->NPA * h->NE * h->NR * nseg, 128), ns);
+  dim3 g(nblk((long long)h->NE * h->NR, 128), h->NPA * nseg, ns);
   if (h->mode == RSG_MODE_FAST) k_driftp<true><<<g, 128, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0, h->segP, nseg);
   else k_driftp<false><<<g, 128, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0, h->segP, nseg);
   CKL();
@@ -249,7 +247,7 @@ int L_drifte(rsg_ram* h, int s0, int ns, cudaStream_t st) {
   SpecPack pk;
   make_pack(h, pk, s0, ns);
   const int nseg = seg_count(h->NE, h->segE);
-  dim3 g(nblk((long long)h->NPA * h->Pp * nseg, 128), ns);
+  dim3 g(nblk(h->P, 128), h->NPA * nseg, ns);
   if (h->mode == RSG_MODE_FAST) k_drifte<true><<<g, 128, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0, h->segE, nseg);
   else k_drifte<false><<<g, 128, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0, h->segE, nseg);
   CKL();
@@ -262,7 +260,7 @@ int L_driftmu(rsg_ram* h, int s0, int ns, cudaStream_t st) {
   SpecPack pk;
   make_pack(h, pk, s0, ns);
   const int nseg = seg_count(h->NPA - 2, h->segMU);
-  dim3 g(nblk((long long)h->NE * h->Pp * nseg, 128), ns);
+  dim3 g(nblk(h->P, 128), h->NE * nseg, ns);
   if (h->mode == RSG_MODE_FAST) k_driftmu<true><<<g, 128, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0, h->segMU, nseg);
   else k_driftmu<false><<<g, 128, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0, h->segMU, nseg);
   CKL();
@@ -273,7 +271,7 @@ int L_driftmu(rsg_ram* h, int s0, int ns, cudaStream_t st) {
 int L_sumrc(rsg_ram* h, int s0, int ns, int slot, cudaStream_t st) {
   SpecPack pk;
   make_pack(h, pk, s0, ns);
-  k_sumrc_partial<<<dim3(h->nblk_sum, ns), 256, 0, st>>>(h->dev, pk, s0);
+  k_sumrc_partial<<<dim3(h->nblk_sum, ns), h->sum_threads, 0, st>>>(h->dev, pk, s0);
   CKL();
   k_sum_final<<<dim3(1, ns), 256, 0, st>>>(pk, s0, h->nblk_sum, 1, slot);
   CKL();
@@ -283,7 +281,7 @@ int L_sumrc(rsg_ram* h, int s0, int ns, int slot, cudaStream_t st) {
 int L_loss(rsg_ram* h, int s, int op, double DTs, cudaStream_t st) {
   SpecPack pk;
   make_pack(h, pk, s, 1);
-  k_loss<<<dim3(nblk((long long)h->specStride, 256), 1), 256, 0, st>>>(devfor(h, DTs), pk, s, op, h->sp[s].d_wfac);
+  k_loss<<<dim3(nblk(h->P, 256), h->NPA * h->NE, 1), 256, 0, st>>>(devfor(h, DTs), pk, s, op);
   CKL();
   h->launches++;
   return RSG_OK;
@@ -291,7 +289,7 @@ int L_loss(rsg_ram* h, int s, int op, double DTs, cudaStream_t st) {
 int L_loss_mid(rsg_ram* h, int s0, int ns, int doA, double DTs, int slot, cudaStream_t st) {
   SpecPack pk;
   make_pack(h, pk, s0, ns);
-  k_loss_mid<<<dim3(h->nblk_sum, ns), 256, 0, st>>>(devfor(h, DTs), pk, s0, doA);
+  k_loss_mid<<<dim3(h->nblk_sum, ns), h->sum_threads, 0, st>>>(devfor(h, DTs), pk, s0, doA);
   CKL();
   k_sum_final<<<dim3(4, ns), 256, 0, st>>>(pk, s0, h->nblk_sum, 4, slot);
   CKL();
@@ -324,7 +322,7 @@ int L_wpadif(rsg_ram* h, int s, double DTs, cudaStream_t st) {
 int L_anisch(rsg_ram* h, int s0, int ns, cudaStream_t st) {
   SpecPack pk;
   make_pack(h, pk, s0, ns);
-  k_anisch_pa<<<dim3(nblk((long long)h->NE * h->Pp, 128), ns), 128, 0, st>>>(h->dev, pk, s0);
+  k_anisch_pa<<<dim3(nblk(h->Pp, 128), h->NE, ns), 128, 0, st>>>(h->dev, pk, s0);
   CKL();
   const double cv = kCS * 100;
   const double RFAC = 4 * kPI / cv;
@@ -556,7 +554,8 @@ int rsg_ram_create(rsg_ram** out, int nS, int NR, int NT, int NE, int NPA, int d
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
   // grid-stride reductions: a fixed grid => a fixed summation tree
-  h->nblk_sum = std::max(1, std::min(sms * 8, nblk((long long)h->specStride, 256)));
+  h->nblk_sum = NPA * NE;                       // one CTA per (K,L) plane
+  h->sum_threads = h->P >= 1024 ? 256 : 128;
   for (int s = 0; s < nS; ++s) {
     Spec& sp = h->sp[s];
     CK(cudaStreamCreateWithFlags(&sp.own, cudaStreamNonBlocking));
@@ -804,10 +803,9 @@ int rsg_ram_f2_h2d(rsg_ram* h, const double* F2, int S) {
   if (S == 0) RET(rsg_ram_sync(h));
   cudaStream_t st = S ? h->st(S - 1) : h->pst();
   CK(cudaMemcpyAsync(h->d_stage, F2, n * sizeof(double), cudaMemcpyHostToDevice, st));
-  const long long ne = (long long)h->specStride;
   for (int s = 0; s < h->nS; ++s) {
     if (S != 0 && s != S - 1) continue;
-    k_f2_from_host<<<nblk(ne, 256), 256, 0, st>>>(h->dev, h->d_stage, h->d_F2[h->sp[s].cur] + h->specStride * s, s);
+    k_f2_from_host<<<dim3(nblk(h->Pp, 256), h->NPA * h->NE), 256, 0, st>>>(h->dev, h->d_stage, h->d_F2[h->sp[s].cur] + h->specStride * s, s);
     CKL();
     h->launches++;
   }
@@ -822,14 +820,13 @@ int rsg_ram_f2_d2h(rsg_ram* h, double* F2, int S) {
   const size_t n = (size_t)h->nS * h->P * h->NE * h->NPA;
   if (S == 0) RET(rsg_ram_sync(h));
   cudaStream_t st = S ? h->st(S - 1) : h->pst();
-  const long long ne = (long long)h->specStride;
   if (S != 0) {
     // keep the other species' host values: start from the host image
     CK(cudaMemcpyAsync(h->d_stage, F2, n * sizeof(double), cudaMemcpyHostToDevice, st));
   }
   for (int s = 0; s < h->nS; ++s) {
     if (S != 0 && s != S - 1) continue;
-    k_f2_to_host<<<nblk(ne, 256), 256, 0, st>>>(h->dev, h->d_stage, h->d_F2[h->sp[s].cur] + h->specStride * s, s);
+    k_f2_to_host<<<dim3(nblk(h->Pp, 256), h->NPA * h->NE), 256, 0, st>>>(h->dev, h->d_stage, h->d_F2[h->sp[s].cur] + h->specStride * s, s);
     CKL();
     h->launches++;
   }
@@ -1032,7 +1029,7 @@ int rsg_ram_run(rsg_ram* h, double DTs, double DtsMin, double T, int flags, doub
   {
     SpecPack pk;
     make_pack(h, pk);
-    k_epilogue<<<dim3(nblk((long long)h->specStride, 256), nS), 256, 0, st>>>(h->dev, pk, 0);
+    k_epilogue<<<dim3(nblk(h->P, 256), h->NPA * h->NE, nS), 256, 0, st>>>(h->dev, pk, 0);
     CKL();
     h->launches++;
   }
@@ -1078,7 +1075,7 @@ int rsg_ram_flux_d2h(rsg_ram* h, double* FLUX) {
   SpecPack pk;
   make_pack(h, pk);
   for (int s = 0; s < h->nS; ++s) {
-    k_flux_to_host<<<nblk((long long)h->specStride, 256), 256, 0, st>>>(h->dev, pk.s[s], h->d_stage);
+    k_flux_to_host<<<dim3(nblk(h->P, 256), h->NPA * h->NE), 256, 0, st>>>(h->dev, pk.s[s], h->d_stage);
     CKL();
     h->launches++;
   }

@@ -280,26 +280,16 @@ __device__ __forceinline__ double coef_mu(double epK, double BOUNHS, double RLZI
 //  * blockIdx.y selects the species: one launch advances all species.
 // =============================================================================
 
-// block-wide min -> one filtered atomicMin per CTA
-__device__ __forceinline__ void cta_min_to(unsigned long long* dst, double v) {
-  __shared__ unsigned long long s_min[32];
+// warp-wide min -> one filtered atomicMin per warp (no CTA barrier: warps retire
+// independently; the racy pre-read only filters, atomicMin decides)
+__device__ __forceinline__ void warp_min_to(unsigned long long* dst, double v) {
   unsigned long long b = dbl_bits(v);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     unsigned long long t = __shfl_xor_sync(0xffffffffu, b, o);
     b = t < b ? t : b;
   }
-  if ((threadIdx.x & 31) == 0) s_min[threadIdx.x >> 5] = b;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    b = (threadIdx.x < ((blockDim.x + 31) >> 5)) ? s_min[threadIdx.x] : 0xffffffffffffffffull;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      unsigned long long t = __shfl_xor_sync(0xffffffffu, b, o);
-      b = t < b ? t : b;
-    }
-    if (threadIdx.x == 0 && b < *((volatile unsigned long long*)dst)) atomicMin(dst, b);
-  }
+  if ((threadIdx.x & 31) == 0 && b < *((volatile unsigned long long*)dst)) atomicMin(dst, b);
 }
 
 // ---- DRIFTR pre-pass (src/ModRamDrift.f90:112-113,154-168): the line buffer's
@@ -351,7 +341,6 @@ __global__ void k_driftr_scan(const __grid_constant__ RamDev d, const __grid_con
   const int n = d.NE * d.NPA * d.NT;
   const int t = blockIdx.x * SCAN_TILE + threadIdx.x;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  // carry = max of all previous tiles
   int c = -1;
   for (int q = threadIdx.x; q < (int)blockIdx.x; q += blockDim.x) c = max(c, tilemax[q]);
 #pragma unroll
@@ -381,93 +370,85 @@ __global__ void k_driftr_scan(const __grid_constant__ RamDev d, const __grid_con
 
 // =============================================================================
 // DRIFTR  (src/ModRamDrift.f90:95-198): one thread per cell.
+// grid: x = tiles of 248 cells (8 warps x 31) of one plane, y = plane l*NE+k, z = species
 // =============================================================================
 template <bool FAST>
 __global__ void __launch_bounds__(256) k_driftr(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0) {
-  const SpecDev& sp = pk.s[s0 + blockIdx.y];
+  const SpecDev& sp = pk.s[s0 + blockIdx.z];
   const int NR = d.NR, NT = d.NT, NE = d.NE, P = d.P, Pp = d.Pp;
-  const long long N = (long long)d.NPA * NE * Pp;
-  const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int plane = blockIdx.y;
   const int lane = threadIdx.x & 31;
-  const long long q = (gt >> 5) * 31 + lane - 1;   // 31 cells per warp + halo lane 0
-  const bool valid = (q >= 0) && (q < N);
+  const int p = (blockIdx.x * 8 + (threadIdx.x >> 5)) * 31 + lane - 1;   // 31 cells per warp + halo lane 0
   double phi = 0.0, F0 = 0.0, cmax = 0.0;
   int i = -1;
-  bool inplane = false;
-  if (valid) {
-    const int p = (int)(q % Pp);
-    const int plane = (int)(q / Pp);
-    if (p < P) {
-      inplane = true;
-      const int k = plane % NE, l = plane / NE;
-      const int j = p / NR;
-      i = p - j * NR;
-      const int I = i + 1;
-      const int line = (k * d.NPA + l) * NT + j;
-      const int src = sp.last[line];
-      const bool inflow = (src == line);
-      const double c = FAST ? fma(sp.P4[k], d.fRb[(size_t)l * Pp + p], d.CR[p])
-                            : coef_r(d.CR[p], d.t1[(size_t)l * Pp + p], sp.P4[k], d.sB[p], d.RLZ[i] + 0.5 * d.MDR);
-      if (!d.outp[p]) cmax = fabs(c);
-      const double* F = sp.F + (size_t)plane * Pp + (size_t)j * NR;  // F[i'] = F(I=i'+1) of this line
-      F0 = F[i];
-      if (I == 1) {
-        phi = c * (inflow ? F[1] : 0.0);            // FBND(1) = F(2) | 0   (:155,:159)
-      } else if (I == NR && !inflow) {
-        phi = c * F0;                               // FBND(NR) = F(NR)     (:156)
-      } else {
-        double g1 = 0.0, g2 = 0.0;                  // F(NR+1), F(NR+2)
-        if (I + 2 > NR) {
-          if (inflow) {
-            if (!d.outp[j * NR + NR - 1]) {
-              const double fg = sp.FGEOS[((size_t)l * NE + k) * NT + j];
-              const double fn = R3(d.FNHS, NR, j + 1, l + 1);
-              g1 = fg * d.CONF1 * fn;
-              g2 = fg * d.CONF2 * fn;
-            }
-          } else if (src >= 0) {
-            const int js = src % NT, ls = (src / NT) % d.NPA, ks = src / (NT * d.NPA);
-            if (!d.outp[js * NR + NR - 1])
-              g1 = sp.FGEOS[((size_t)ls * NE + ks) * NT + js] * d.CONF1 * R3(d.FNHS, NR, js + 1, ls + 1);
+  const bool inplane = (p >= 0) && (p < P);
+  if (inplane) {
+    const int l = plane / NE, k = plane - l * NE;
+    const int j = p / NR;
+    i = p - j * NR;
+    const int I = i + 1;
+    const int line = (k * d.NPA + l) * NT + j;
+    const int src = sp.last[line];
+    const bool inflow = (src == line);
+    const double c = FAST ? fma(sp.P4[k], d.fRb[(size_t)l * Pp + p], d.CR[p])
+                          : coef_r(d.CR[p], d.t1[(size_t)l * Pp + p], sp.P4[k], d.sB[p], d.RLZ[i] + 0.5 * d.MDR);
+    if (!d.outp[p]) cmax = fabs(c);
+    const double* F = sp.F + (size_t)plane * Pp + j * NR;  // F[i'] = F(I=i'+1) of this line
+    F0 = F[i];
+    if (I == 1) {
+      phi = c * (inflow ? F[1] : 0.0);            // FBND(1) = F(2) | 0   (:155,:159)
+    } else if (I == NR && !inflow) {
+      phi = c * F0;                               // FBND(NR) = F(NR)     (:156)
+    } else {
+      double g1 = 0.0, g2 = 0.0;                  // F(NR+1), F(NR+2)
+      if (I + 2 > NR) {
+        if (inflow) {
+          if (!d.outp[j * NR + NR - 1]) {
+            const double fg = sp.FGEOS[((size_t)l * NE + k) * NT + j];
+            const double fn = R3(d.FNHS, NR, j + 1, l + 1);
+            g1 = fg * d.CONF1 * fn;
+            g2 = fg * d.CONF2 * fn;
           }
+        } else if (src >= 0) {
+          const int js = src % NT, ls = (src / NT) % d.NPA, ks = src / (NT * d.NPA);
+          if (!d.outp[js * NR + NR - 1])
+            g1 = sp.FGEOS[((size_t)ls * NE + ks) * NT + js] * d.CONF1 * R3(d.FNHS, NR, js + 1, ls + 1);
         }
-        const double Fm1 = F[i - 1];
-        const double Fp1 = (I + 1 <= NR) ? F[i + 1] : g1;
-        const double Fp2 = (I + 2 <= NR) ? F[i + 2] : ((I + 2 == NR + 1) ? g1 : g2);
-        phi = c * (FAST ? limited_flux_fast(Fm1, F0, Fp1, Fp2, c, c, d.BetaLim) : limited_flux(Fm1, F0, Fp1, Fp2, c, c, d.BetaLim));
       }
+      const double Fm1 = F[i - 1];
+      const double Fp1 = (I + 1 <= NR) ? F[i + 1] : g1;
+      const double Fp2 = (I + 2 <= NR) ? F[i + 2] : ((I + 2 == NR + 1) ? g1 : g2);
+      phi = c * (FAST ? limited_flux_fast(Fm1, F0, Fp1, Fp2, c, c, d.BetaLim) : limited_flux(Fm1, F0, Fp1, Fp2, c, c, d.BetaLim));
     }
   }
   const double phiPrev = __shfl_up_sync(0xffffffffu, phi, 1);
-  if (valid && lane >= 1 && inplane) {
+  if (inplane && lane >= 1) {
     double fn = F0;
     if (i >= 1) {
       fn = F0 - phi + phiPrev;                      // :186
       if (fn < 0.0) fn = 1E-15;
     }
-    sp.Fo[q] = fn;
+    sp.Fo[(size_t)plane * Pp + p] = fn;
   }
-  cta_min_to(sp.dt + 0, sp.aRP / fmax(cmax, 1E-10));
+  warp_min_to(sp.dt + 0, sp.aRP / fmax(cmax, 1E-10));
 }
 
 // =============================================================================
 // DRIFTP  (src/ModRamDrift.f90:204-279): periodic lines along MLT, segments of
 // SEG cells of J=2..NT per thread.  FBND(1)=FBND(NT), F2(J=1)=F2(J=NT).
+// grid: x = tiles of (k,i) pairs, y = l*nseg + seg, z = species
 // =============================================================================
 template <bool FAST>
 __global__ void __launch_bounds__(128) k_driftp(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0, int SEG,
                                                 int nseg) {
-  const SpecDev& sp = pk.s[s0 + blockIdx.y];
+  const SpecDev& sp = pk.s[s0 + blockIdx.z];
   const int NR = d.NR, NT = d.NT, Pp = d.Pp;
-  const long long nl = (long long)d.NPA * d.NE * NR;   // lines (incl. I=1)
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
   double cmax = 0.0;
-  if (t < nl * nseg) {
-    const int seg = (int)(t / nl);
-    const long long r = t - (long long)seg * nl;
-    const int i = (int)(r % NR);
-    const int plane = (int)(r / NR);
-    const int k = plane % d.NE, l = plane / d.NE;
+  if (t < d.NE * NR) {
+    const int l = blockIdx.y / nseg, seg = blockIdx.y - l * nseg;
+    const int k = t / NR, i = t - k * NR;
+    const int plane = l * d.NE + k;
     const int ja = 2 + seg * SEG, jb = min(NT, ja + SEG - 1);
     const double* F = sp.F + (size_t)plane * Pp + i;   // F[(J-1)*NR]
     double* Fo = sp.Fo + (size_t)plane * Pp + i;
@@ -493,18 +474,22 @@ __global__ void __launch_bounds__(128) k_driftp(const __grid_constant__ RamDev d
         const double c = COEFP(Jh);
         prev = c * LIMF(F[(Jh - 2) * NR], F[(Jh - 1) * NR], GETFJ(Jh + 1), GETFJ(Jh + 2), c);
       }
-      double Fm1 = F[(ja - 2) * NR], F0 = F[(ja - 1) * NR], Fp1 = GETFJ(ja + 1);
+      double Fm1 = F[(ja - 2) * NR], F0 = F[(ja - 1) * NR], Fp1 = GETFJ(ja + 1), Fp2 = GETFJ(ja + 2);
+      double cn = COEFP(ja);
       double fnew = 0.0;
       for (int J = ja; J <= jb; ++J) {
-        const double Fp2 = GETFJ(J + 2);
-        const double c = COEFP(J);
+        // prefetch the next step's inputs before the dependent arithmetic
+        const double Fp3 = GETFJ(J + 3);
+        const int Jn = (J < NT) ? J + 1 : NT;
+        const double cnn = COEFP(Jn);
+        const double c = cn;
         if (!d.outp[(J - 1) * NR + i]) cmax = fmax(cmax, fabs(c));
         const double cur = c * LIMF(Fm1, F0, Fp1, Fp2, c);
         fnew = F0 - cur + prev;                         // :266
         if (fnew < 0.0) fnew = 1E-15;
         Fo[(J - 1) * NR] = fnew;
         prev = cur;
-        Fm1 = F0; F0 = Fp1; Fp1 = Fp2;
+        Fm1 = F0; F0 = Fp1; Fp1 = Fp2; Fp2 = Fp3; cn = cnn;
       }
       if (jb == NT) Fo[0] = fnew;                       // :272
 #undef GETFJ
@@ -512,186 +497,179 @@ __global__ void __launch_bounds__(128) k_driftp(const __grid_constant__ RamDev d
 #undef LIMF
     }
   }
-  cta_min_to(sp.dt + 1, sp.aRP / fmax(cmax, 1E-10));
+  warp_min_to(sp.dt + 1, sp.aRP / fmax(cmax, 1E-10));
 }
 
 // =============================================================================
 // DRIFTE  (src/ModRamDrift.f90:285-376): lines along energy, segments of SEG
 // cells of K=1..NE per thread.  Ghosts F(1),F(0) from the relativistic
 // extrapolation of F2(K=2) (:334-335), F(NE+1)=F(NE+2)=0 (:312-313).
+// grid: x = tiles of the plane index p, y = l*nseg + seg, z = species
 // =============================================================================
 template <bool FAST>
 __global__ void __launch_bounds__(128) k_drifte(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0, int SEG,
                                                 int nseg) {
-  const SpecDev& sp = pk.s[s0 + blockIdx.y];
+  const SpecDev& sp = pk.s[s0 + blockIdx.z];
   const int NE = d.NE, Pp = d.Pp;
-  const long long nl = (long long)d.NPA * Pp;
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
   double dtmin = 1.0e300;
   double mmax = 0.0;   // FAST: max over cells of max(|c|,1e-10)/DE(K)
-  if (t < nl * nseg) {
-    const int seg = (int)(t / nl);
-    const long long r = t - (long long)seg * nl;
-    const int l = (int)(r / Pp), p = (int)(r - (long long)l * Pp);
+  if (p < d.P) {
+    const int l = blockIdx.y / nseg, seg = blockIdx.y - l * nseg;
     const int ka = 1 + seg * SEG, kb = min(NE, ka + SEG - 1);
-    if (p < d.P) {
-      const int i = p % d.NR;
-      const double* F = sp.F + (size_t)l * NE * Pp + p;   // F[(K-1)*Pp]
-      double* Fo = sp.Fo + (size_t)l * NE * Pp + p;
-      if (i == 0) {
-        for (int K = ka; K <= kb; ++K) Fo[(size_t)(K - 1) * Pp] = F[(size_t)(K - 1) * Pp];
+    const int i = p % d.NR;
+    const double* F = sp.F + (size_t)l * NE * Pp + p;   // F[(K-1)*Pp]
+    double* Fo = sp.Fo + (size_t)l * NE * Pp + p;
+    if (i == 0) {
+      for (int K = ka; K <= kb; ++K) Fo[(size_t)(K - 1) * Pp] = F[(size_t)(K - 1) * Pp];
+    } else {
+      const size_t o = (size_t)l * Pp + p;
+      double FNHS = 0, Gr = 0, Gp = 0, DRD2 = 0, DPD2 = 0, dBdt1 = 0, dIdt1 = 0, DRD1 = 0, DPD1 = 0, BNES = 0, RLZI = 0, fA = 0, fB = 0;
+      if (FAST) {
+        fA = d.fEa[o]; fB = d.fEb[o];
       } else {
-        const size_t o = (size_t)l * Pp + p;
-        double FNHS = 0, Gr = 0, Gp = 0, DRD2 = 0, DPD2 = 0, dBdt1 = 0, dIdt1 = 0, DRD1 = 0, DPD1 = 0, BNES = 0, RLZI = 0, fA = 0, fB = 0;
-        if (FAST) {
-          fA = d.fEa[o]; fB = d.fEb[o];
-        } else {
-          FNHS = d.FNHSc[o]; Gr = d.Gr[o]; Gp = d.Gp[o]; DRD2 = d.DRD2[o]; DPD2 = d.DPD2[o]; dBdt1 = d.dBdt1[o]; dIdt1 = d.dIdt1[o];
-          DRD1 = d.DRD1[p]; DPD1 = d.DPD1[p]; BNES = d.BNESc[p]; RLZI = d.RLZp[p];
-        }
-        const bool inside = !d.outp[p];
-        const double QS = sp.QS, beta = d.BetaLim;
-        const double* EDOT = sp.EDOT + i;
-        double F1 = 0.0, Fz = 0.0;
-        if (ka <= 3) {
-          const double f2 = F[(size_t)Pp];
-          F1 = f2 * sp.GREL1 / sp.GREL2 * sp.sqrtA;
-          Fz = F1 * sp.GRZERO / sp.GREL1 * sp.sqrtB;
-        }
-#define GETFK(K) (((K) > NE) ? 0.0 : (((K) >= 2) ? F[(size_t)((K)-1) * Pp] : (((K) == 1) ? F1 : Fz)))
-        if (ka == 1) Fo[0] = F[0];                        // F2(K=1) is not advanced by DRIFTE
-        const int K0 = max(ka - 1, 1);
-        double Fm1 = GETFK(K0 - 1), F0 = GETFK(K0), Fp1 = GETFK(K0 + 1), Fp2 = GETFK(K0 + 2);
-        double nxt = GETFK(K0 + 3);
-        double cprev = 0.0, FBprev = 0.0;
-        for (int K = K0; K <= kb; ++K) {
-          const double nn = GETFK(K + 4);
-          double c, FB;
-          if (FAST) {
-            c = fma(sp.vE[K - 1], fB, sp.uE[K - 1] * fA);
-            const double rDE = sp.rDE[K - 1];
-            if (inside && K >= ka) mmax = fmax(mmax, fmax(fabs(c), 1E-10) * rDE);
-            FB = c * limited_flux_fast(Fm1, F0, Fp1, Fp2, c, c * rDE, beta);   // FB holds the flux c*FBND
-            if (K >= ka && K >= 2) {
-              double fn = fma(-(FB - FBprev), sp.rWE[K - 1], F0);
-              if (fn < 0.0) fn = 1E-15;
-              Fo[(size_t)(K - 1) * Pp] = fn;
-            }
-          } else {
-            c = coef_e(sp.eK[K - 1], FNHS, RLZI, BNES, QS, DRD1, DRD2, DPD1, DPD2, Gr, Gp, dBdt1, dIdt1, EDOT[(K - 1) * d.NR]);
-            if (inside && K >= ka) dtmin = fmin(dtmin, sp.aE[K - 1] / fmax(fabs(c), 1E-10));
-            FB = limited_flux(Fm1, F0, Fp1, Fp2, c, c / d.DE[K - 1], beta);
-            if (K >= ka && K >= 2) {
-              const double WEK = d.WE[K - 1];
-              double fn = F0 - c / WEK * FB + cprev / WEK * FBprev;   // :364
-              if (fn < 0.0) fn = 1E-15;
-              Fo[(size_t)(K - 1) * Pp] = fn;
-            }
-          }
-          cprev = c; FBprev = FB;
-          Fm1 = F0; F0 = Fp1; Fp1 = Fp2; Fp2 = nxt; nxt = nn;
-        }
-#undef GETFK
+        FNHS = d.FNHSc[o]; Gr = d.Gr[o]; Gp = d.Gp[o]; DRD2 = d.DRD2[o]; DPD2 = d.DPD2[o]; dBdt1 = d.dBdt1[o]; dIdt1 = d.dIdt1[o];
+        DRD1 = d.DRD1[p]; DPD1 = d.DPD1[p]; BNES = d.BNESc[p]; RLZI = d.RLZp[p];
       }
+      const bool inside = !d.outp[p];
+      const double QS = sp.QS, beta = d.BetaLim;
+      const double* EDOT = sp.EDOT + i;
+      double F1 = 0.0, Fz = 0.0;
+      if (ka <= 3) {
+        const double f2 = F[(size_t)Pp];
+        F1 = f2 * sp.GREL1 / sp.GREL2 * sp.sqrtA;
+        Fz = F1 * sp.GRZERO / sp.GREL1 * sp.sqrtB;
+      }
+#define GETFK(K) (((K) > NE) ? 0.0 : (((K) >= 2) ? F[(size_t)((K)-1) * Pp] : (((K) == 1) ? F1 : Fz)))
+      if (ka == 1) Fo[0] = F[0];                        // F2(K=1) is not advanced by DRIFTE
+      const int K0 = max(ka - 1, 1);
+      double Fm1 = GETFK(K0 - 1), F0 = GETFK(K0), Fp1 = GETFK(K0 + 1), Fp2 = GETFK(K0 + 2);
+      double nxt = GETFK(K0 + 3), nx2 = GETFK(K0 + 4);
+      double cprev = 0.0, FBprev = 0.0;
+      for (int K = K0; K <= kb; ++K) {
+        const double nn = GETFK(K + 5);
+        double c, FB;
+        if (FAST) {
+          c = fma(sp.vE[K - 1], fB, sp.uE[K - 1] * fA);
+          const double rDE = sp.rDE[K - 1];
+          if (inside && K >= ka) mmax = fmax(mmax, fmax(fabs(c), 1E-10) * rDE);
+          FB = c * limited_flux_fast(Fm1, F0, Fp1, Fp2, c, c * rDE, beta);   // FB holds the flux c*FBND
+          if (K >= ka && K >= 2) {
+            double fn = fma(-(FB - FBprev), sp.rWE[K - 1], F0);
+            if (fn < 0.0) fn = 1E-15;
+            Fo[(size_t)(K - 1) * Pp] = fn;
+          }
+        } else {
+          c = coef_e(sp.eK[K - 1], FNHS, RLZI, BNES, QS, DRD1, DRD2, DPD1, DPD2, Gr, Gp, dBdt1, dIdt1, EDOT[(K - 1) * d.NR]);
+          if (inside && K >= ka) dtmin = fmin(dtmin, sp.aE[K - 1] / fmax(fabs(c), 1E-10));
+          FB = limited_flux(Fm1, F0, Fp1, Fp2, c, c / d.DE[K - 1], beta);
+          if (K >= ka && K >= 2) {
+            const double WEK = d.WE[K - 1];
+            double fn = F0 - c / WEK * FB + cprev / WEK * FBprev;   // :364
+            if (fn < 0.0) fn = 1E-15;
+            Fo[(size_t)(K - 1) * Pp] = fn;
+          }
+        }
+        cprev = c; FBprev = FB;
+        Fm1 = F0; F0 = Fp1; Fp1 = Fp2; Fp2 = nxt; nxt = nx2; nx2 = nn;
+      }
+#undef GETFK
     }
   }
   if (FAST && mmax > 0.0) dtmin = sp.aRP / mmax;
-  cta_min_to(sp.dt + 2, dtmin);
+  warp_min_to(sp.dt + 2, dtmin);
 }
 
 // =============================================================================
 // DRIFTMU  (src/ModRamDrift.f90:382-473): lines along pitch angle, segments of
 // SEG cells of L=2..NPA-1 per thread; the last segment also closes the line with
 // F2(NPA) = F2(NPA-1)*FNHS(NPA)*MU(NPA)/FNHS(NPA-1)/MU(NPA-1) (:466).
+// grid: x = tiles of the plane index p, y = k*nseg + seg, z = species
 // =============================================================================
 template <bool FAST>
 __global__ void __launch_bounds__(128) k_driftmu(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0, int SEG,
                                                  int nseg) {
-  const SpecDev& sp = pk.s[s0 + blockIdx.y];
+  const SpecDev& sp = pk.s[s0 + blockIdx.z];
   const int NE = d.NE, NPA = d.NPA, Pp = d.Pp;
-  const long long nl = (long long)NE * Pp;
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
   double dtmin = 1.0e300;
   double mmax = 0.0;   // FAST: max over cells of max(|c|,1e-32)/DMU(L)
-  if (t < nl * nseg) {
-    const int seg = (int)(t / nl);
-    const long long r = t - (long long)seg * nl;
-    const int k = (int)(r / Pp), p = (int)(r - (long long)k * Pp);
+  if (p < d.P) {
+    const int k = blockIdx.y / nseg, seg = blockIdx.y - k * nseg;
     const int la = 2 + seg * SEG, lb = min(NPA - 1, la + SEG - 1);
     const bool lastseg = (lb == NPA - 1);
-    if (p < d.P) {
-      const int i = p % d.NR;
-      const size_t LS = (size_t)NE * Pp;
-      const double* F = sp.F + (size_t)k * Pp + p;   // F[(L-1)*LS]
-      double* Fo = sp.Fo + (size_t)k * Pp + p;
-      if (seg == 0) Fo[0] = F[0];                     // F2(L=1) is not advanced by DRIFTMU
-      if (i == 0) {
-        for (int L = la; L <= lb; ++L) Fo[(size_t)(L - 1) * LS] = F[(size_t)(L - 1) * LS];
-        if (lastseg) Fo[(size_t)(NPA - 1) * LS] = F[(size_t)(NPA - 1) * LS];
-      } else {
-        const double DRM1 = d.DRD1[p], DPM1 = d.DPD1[p], BNES = d.BNESc[p], RLZI = d.RLZp[p], dBdt2 = d.dBdt2[p];
-        const bool inside = !d.outp[p];
-        const double QS = sp.QS, beta = d.BetaLim, epK = sp.epK[k], wM = sp.wM[k];
+    const int i = p % d.NR;
+    const size_t LS = (size_t)NE * Pp;
+    const double* F = sp.F + (size_t)k * Pp + p;   // F[(L-1)*LS]
+    double* Fo = sp.Fo + (size_t)k * Pp + p;
+    if (seg == 0) Fo[0] = F[0];                     // F2(L=1) is not advanced by DRIFTMU
+    if (i == 0) {
+      for (int L = la; L <= lb; ++L) Fo[(size_t)(L - 1) * LS] = F[(size_t)(L - 1) * LS];
+      if (lastseg) Fo[(size_t)(NPA - 1) * LS] = F[(size_t)(NPA - 1) * LS];
+    } else {
+      double DRM1 = 0, DPM1 = 0, BNES = 0, RLZI = 0, dBdt2 = 0;
+      if (!FAST) { DRM1 = d.DRD1[p]; DPM1 = d.DPD1[p]; BNES = d.BNESc[p]; RLZI = d.RLZp[p]; dBdt2 = d.dBdt2[p]; }
+      const bool inside = !d.outp[p];
+      const double QS = sp.QS, beta = d.BetaLim, epK = sp.epK[k], wM = sp.wM[k];
 #define GETFL(L) (((L) >= 2) ? F[(size_t)((L)-1) * LS] : F[LS])   /* F(1) = F(2)  (:414) */
 #define COEFMU(L, o) (FAST ? fma(wM, d.fMb[o], d.fMa[o]) \
                            : coef_mu(epK, d.BOUNHSc[o], RLZI, BNES, QS, DRM1, d.DRM2[o], DPM1, d.DPM2[o], d.Gmr[o], d.Gmp[o], dBdt2, d.dIbndt2[o], d.CMUDOT[o]))
-        const int L0 = max(la - 1, 2);
-        double Fm1 = GETFL(L0 - 1), F0 = GETFL(L0), Fp1 = GETFL(L0 + 1), Fp2 = (L0 + 2 <= NPA) ? GETFL(L0 + 2) : 0.0;
-        double nxt = (L0 + 3 <= NPA) ? GETFL(L0 + 3) : 0.0;
-        double cprev = 0.0, FBprev = 0.0;               // CDriftMu(..,1)=0, FBND(1)=0 (:456-457)
-        double fnew = 0.0;
-        for (int L = L0; L <= lb; ++L) {
-          const double nn = (L + 4 <= NPA) ? F[(size_t)(L + 3) * LS] : 0.0;
-          const size_t o = (size_t)(L - 1) * Pp + p;
-          const double c = COEFMU(L, o);
-          double FB;
-          if (FAST) {
-            const double rDM = d.rDMU[L - 1];
-            if (inside && L >= la) mmax = fmax(mmax, fmax(fabs(c), 1E-32) * rDM);
-            if (L <= NPA - 2) FB = c * limited_flux_fast(Fm1, F0, Fp1, Fp2, c, c * rDM, beta);   // flux c*FBND
-            else FB = c * Fp1;
-            if (L >= la) {
-              fnew = fma(-(FB - FBprev), d.rWMU[L - 1], F0);
-              if (fnew < 0.0) fnew = 1E-15;
-              Fo[(size_t)(L - 1) * LS] = fnew;
-            }
-          } else {
-            if (inside && L >= la) dtmin = fmin(dtmin, sp.aMU[L - 1] / fmax(fabs(c), 1E-32));
-            if (L <= NPA - 2) FB = limited_flux(Fm1, F0, Fp1, Fp2, c, c / d.DMU[L - 1], beta);
-            else FB = Fp1;                                // FBND(NPA-1) = F(NPA)  (:458)
-            if (L >= la) {
-              const double WM = d.WMU[L - 1];
-              fnew = F0 - c / WM * FB + cprev / WM * FBprev;   // :460
-              if (fnew < 0.0) fnew = 1E-15;
-              Fo[(size_t)(L - 1) * LS] = fnew;
-            }
+      const int L0 = max(la - 1, 2);
+      double Fm1 = GETFL(L0 - 1), F0 = GETFL(L0), Fp1 = GETFL(L0 + 1), Fp2 = (L0 + 2 <= NPA) ? GETFL(L0 + 2) : 0.0;
+      double nxt = (L0 + 3 <= NPA) ? GETFL(L0 + 3) : 0.0;
+      double cn = COEFMU(L0, (size_t)(L0 - 1) * Pp + p);
+      double cprev = 0.0, FBprev = 0.0;               // CDriftMu(..,1)=0, FBND(1)=0 (:456-457)
+      double fnew = 0.0;
+      for (int L = L0; L <= lb; ++L) {
+        const double nn = (L + 4 <= NPA) ? F[(size_t)(L + 3) * LS] : 0.0;
+        const double cnn = COEFMU(L + 1, (size_t)L * Pp + p);   // L+1 <= NPA always
+        const double c = cn;
+        double FB;
+        if (FAST) {
+          const double rDM = d.rDMU[L - 1];
+          if (inside && L >= la) mmax = fmax(mmax, fmax(fabs(c), 1E-32) * rDM);
+          if (L <= NPA - 2) FB = c * limited_flux_fast(Fm1, F0, Fp1, Fp2, c, c * rDM, beta);   // flux c*FBND
+          else FB = c * Fp1;
+          if (L >= la) {
+            fnew = fma(-(FB - FBprev), d.rWMU[L - 1], F0);
+            if (fnew < 0.0) fnew = 1E-15;
+            Fo[(size_t)(L - 1) * LS] = fnew;
           }
-          cprev = c; FBprev = FB;
-          Fm1 = F0; F0 = Fp1; Fp1 = Fp2; Fp2 = nxt; nxt = nn;
+        } else {
+          if (inside && L >= la) dtmin = fmin(dtmin, sp.aMU[L - 1] / fmax(fabs(c), 1E-32));
+          if (L <= NPA - 2) FB = limited_flux(Fm1, F0, Fp1, Fp2, c, c / d.DMU[L - 1], beta);
+          else FB = Fp1;                                // FBND(NPA-1) = F(NPA)  (:458)
+          if (L >= la) {
+            const double WM = d.WMU[L - 1];
+            fnew = F0 - c / WM * FB + cprev / WM * FBprev;   // :460
+            if (fnew < 0.0) fnew = 1E-15;
+            Fo[(size_t)(L - 1) * LS] = fnew;
+          }
         }
-        if (lastseg) {
-          const size_t o = (size_t)(NPA - 1) * Pp + p;
-          const double c = COEFMU(NPA, o);
-          if (FAST) { if (inside) mmax = fmax(mmax, fmax(fabs(c), 1E-32) * d.rDMU[NPA - 1]); }
-          else if (inside) dtmin = fmin(dtmin, sp.aMU[NPA - 1] / fmax(fabs(c), 1E-32));
-          Fo[(size_t)(NPA - 1) * LS] =
-              fnew * d.FNHSc[(size_t)(NPA - 1) * Pp + p] * d.MU[NPA - 1] / d.FNHSc[(size_t)(NPA - 2) * Pp + p] / d.MU[NPA - 2];
-        }
+        cprev = c; FBprev = FB;
+        Fm1 = F0; F0 = Fp1; Fp1 = Fp2; Fp2 = nxt; nxt = nn; cn = cnn;
+      }
+      if (lastseg) {
+        const double c = cn;                            // CDriftMu(..,NPA)
+        if (FAST) { if (inside) mmax = fmax(mmax, fmax(fabs(c), 1E-32) * d.rDMU[NPA - 1]); }
+        else if (inside) dtmin = fmin(dtmin, sp.aMU[NPA - 1] / fmax(fabs(c), 1E-32));
+        Fo[(size_t)(NPA - 1) * LS] =
+            fnew * d.FNHSc[(size_t)(NPA - 1) * Pp + p] * d.MU[NPA - 1] / d.FNHSc[(size_t)(NPA - 2) * Pp + p] / d.MU[NPA - 2];
+      }
 #undef GETFL
 #undef COEFMU
-      }
     }
   }
   if (FAST && mmax > 0.0) dtmin = sp.aRP / mmax;
-  cta_min_to(sp.dt + 3, dtmin);
+  warp_min_to(sp.dt + 3, dtmin);
 }
 
 // =============================================================================
-// moment helper: per-thread values -> per-CTA partial sums part[blockIdx.x*NM+q]
+// moment helper: per-thread values -> per-CTA partial sums part[cta*NM+q]
 // (fixed tree => run-to-run reproducible)
 // =============================================================================
 template <int NM>
-__device__ __forceinline__ void cta_sum_to(double* part, double (&acc)[NM]) {
+__device__ __forceinline__ void cta_sum_to(double* part, int cta, double (&acc)[NM]) {
   __shared__ double s_sum[NM][32];
 #pragma unroll
   for (int q = 0; q < NM; ++q) {
@@ -707,7 +685,7 @@ __device__ __forceinline__ void cta_sum_to(double* part, double (&acc)[NM]) {
       double v = (threadIdx.x < ((blockDim.x + 31) >> 5)) ? s_sum[q][threadIdx.x] : 0.0;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (threadIdx.x == 0) part[(size_t)blockIdx.x * NM + q] = v;
+      if (threadIdx.x == 0) part[(size_t)cta * NM + q] = v;
     }
   }
 }
@@ -731,30 +709,29 @@ __global__ void k_sum_final(const __grid_constant__ SpecPack pk, int s0, int nb,
   }
 }
 
-// SUMRC weight of a cell (src/ModRamRun.f90:246-253): I>=2,K>=2,L>=2,J<=NT-1
-__device__ __forceinline__ bool in_sumrc(const RamDev& d, int p, int k, int l) {
-  if (p >= d.P || k < 1 || l < 1) return false;
-  const int j = p / d.NR, i = p - j * d.NR;
-  return i >= 1 && j <= d.NT - 2;
-}
-
 // =============================================================================
-// SUMRC  (src/ModRamRun.f90:231-259).  Two-stage deterministic tree; differs from
-// the reference's serial sum by summation order only (diagnostic quantity).
+// SUMRC  (src/ModRamRun.f90:231-259): SETRC = sum_{I>=2,K>=2,L>=2,J<=NT-1}
+// F2*WE(K)*WMU(L)*EKEV(K).  One CTA per (K,L) plane, then a second-stage tree
+// over the plane partials: deterministic; differs from the reference's serial
+// sum by summation order only (diagnostic quantity).
+// grid: x = plane l*NE+k, y = species
 // =============================================================================
 __global__ void __launch_bounds__(256) k_sumrc_partial(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0) {
   const SpecDev& sp = pk.s[s0 + blockIdx.y];
-  const long long n = (long long)d.NPA * d.NE * d.Pp;
+  const int plane = blockIdx.x;
+  const int l = plane / d.NE, k = plane - l * d.NE;
   double acc[1] = {0.0};
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
-    const int p = (int)(t % d.Pp);
-    const int plane = (int)(t / d.Pp);
-    const int k = plane % d.NE, l = plane / d.NE;
-    if (!in_sumrc(d, p, k, l)) continue;
-    const double WEIGHT = sp.F[t] * d.WE[k] * d.WMU[l];
-    acc[0] += d.EKEV[k] * WEIGHT;
+  if (k >= 1 && l >= 1) {
+    const double* F = sp.F + (size_t)plane * d.Pp;
+    const double w = d.WE[k], wm = d.WMU[l], e = d.EKEV[k];
+    const int pend = (d.NT - 1) * d.NR;      // J <= NT-1
+    for (int p = threadIdx.x; p < pend; p += blockDim.x) {
+      if (p % d.NR == 0) continue;            // I >= 2
+      const double WEIGHT = F[p] * w * wm;
+      acc[0] += e * WEIGHT;
+    }
   }
-  cta_sum_to<1>(sp.part, acc);
+  cta_sum_to<1>(sp.part, plane, acc);
 }
 
 // =============================================================================
@@ -762,20 +739,18 @@ __global__ void __launch_bounds__(256) k_sumrc_partial(const __grid_constant__ R
 // op 0 CHAREXCHANGE (src/ModRamLoss.f90:457-478, CHARGE of CEPARA :39-83 on the
 // fly: the energy-only factor sv(K)=10**Y*V(S,K) is a host table), op 1 ATMOL
 // (:485-507), op 2 WAVELO (src/ModRamWPI.f90:580-636, factor table from the host).
+// grid: x = tiles of p, y = plane, z = species
 // =============================================================================
-__global__ void __launch_bounds__(256) k_loss(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0, int op,
-                                              const double* __restrict__ wfac) {
-  const SpecDev& sp = pk.s[s0 + blockIdx.y];
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long n = (long long)d.NPA * d.NE * d.Pp;
-  if (t >= n) return;
-  const int p = (int)(t % d.Pp);
-  const int plane = (int)(t / d.Pp);
-  const int k = plane % d.NE, l = plane / d.NE;
+__global__ void __launch_bounds__(256) k_loss(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0, int op) {
+  const SpecDev& sp = pk.s[s0 + blockIdx.z];
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int plane = blockIdx.y;
+  const int l = plane / d.NE, k = plane - l * d.NE;
   if (p >= d.P || k < 1) return;
   const int i = p % d.NR;
   if (i < 1) return;
-  double f = sp.F[t];
+  double* Fp = sp.F + (size_t)plane * d.Pp + p;
+  double f = *Fp;
   if (op == 0) {
     if (l < 1) return;
     const double ALPHA = sp.sv[k] * d.HDNSc[(size_t)l * d.Pp + p] * d.DTs;
@@ -785,9 +760,9 @@ __global__ void __launch_bounds__(256) k_loss(const __grid_constant__ RamDev d, 
     f = f * pow(sp.ATLOS[k * d.NR + i], 1 / d.FNHSc[(size_t)l * d.Pp + p]);
   } else {
     if (l < 1) return;
-    f = f * wfac[(size_t)k * d.Pp + p];
+    f = f * sp.wfac[(size_t)k * d.Pp + p];
   }
-  sp.F[t] = f;
+  *Fp = f;
 }
 
 // =============================================================================
@@ -795,52 +770,53 @@ __global__ void __launch_bounds__(256) k_loss(const __grid_constant__ RamDev d, 
 // (src/ModRamRun.f90:108-142 with the default flags):
 //   [CHAREXCHANGE | WAVELO], SUMRC, ATMOL, SUMRC, ATMOL, SUMRC, [same], SUMRC
 // 4 reference passes + 4 reductions -> one read and one write of F2; the four
-// SETRC moments come out as per-CTA partials.  doA: apply the species' first /
+// SETRC moments come out as per-plane partials.  doA: apply the species' first /
 // last operator (CHAREX for ions; WAVELO for electrons when DoUseWPI is off);
-// bit s of doA = species s.
-// Each factor is applied in the reference's order, so a cell's value is what
-// the four separate passes would give.
+// bit s of doA = species s.  Each factor is applied in the reference's order,
+// so a cell's value is what the four separate passes would give.
+// grid: x = plane, y = species (one CTA per plane, same tree as k_sumrc_partial)
 // =============================================================================
 __global__ void __launch_bounds__(256) k_loss_mid(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0,
                                                   int doA) {
   const SpecDev& sp = pk.s[s0 + blockIdx.y];
-  const long long n = (long long)d.NPA * d.NE * d.Pp;
+  const int plane = blockIdx.x;
+  const int l = plane / d.NE, k = plane - l * d.NE;
   const bool ion = (sp.kind != 3);
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
-    const int p = (int)(t % d.Pp);
-    if (p >= d.P) continue;
-    const int plane = (int)(t / d.Pp);
-    const int k = plane % d.NE, l = plane / d.NE;
-    const int j = p / d.NR, i = p - j * d.NR;
-    if (i < 1 || k < 1) continue;                       // every operator here acts on I>=2, K>=2 only
-    double f = sp.F[t];
-    const bool mom = (l >= 1) && (j <= d.NT - 2);
-    const double w = d.WE[k] * 1.0, wm = d.WMU[l], e = d.EKEV[k];
+  if (k >= 1) {                                           // every operator here acts on K>=2 only
+    double* F = sp.F + (size_t)plane * d.Pp;
+    const double w = d.WE[k], wm = d.WMU[l], e = d.EKEV[k];
     const bool useA = ((doA >> (s0 + blockIdx.y)) & 1) && (l >= 1);
-    double facA = 1.0;
-    if (useA) {
-      if (ion) facA = exp(-(sp.sv[k] * d.HDNSc[(size_t)l * d.Pp + p] * d.DTs));
-      else facA = sp.wfac[(size_t)k * d.Pp + p];
-      f = f * facA;
+    const int pmom = (d.NT - 1) * d.NR;
+    for (int p = threadIdx.x; p < d.P; p += blockDim.x) {
+      const int i = p % d.NR;
+      if (i < 1) continue;                                // I >= 2
+      double f = F[p];
+      const bool mom = (l >= 1) && (p < pmom);
+      double facA = 1.0;
+      if (useA) {
+        if (ion) facA = exp(-(sp.sv[k] * d.HDNSc[(size_t)l * d.Pp + p] * d.DTs));
+        else facA = sp.wfac[(size_t)k * d.Pp + p];
+        f = f * facA;
+      }
+      if (mom) acc[0] += e * (f * w * wm);
+      if (l + 1 >= d.UPA[i]) {
+        const double a = pow(sp.ATLOS[k * d.NR + i], 1 / d.FNHSc[(size_t)l * d.Pp + p]);
+        f = f * a;
+        if (mom) acc[1] += e * (f * w * wm);
+        f = f * a;
+        if (mom) acc[2] += e * (f * w * wm);
+      } else if (mom) {
+        const double term = e * (f * w * wm);
+        acc[1] += term;
+        acc[2] += term;
+      }
+      if (useA) f = f * facA;
+      if (mom) acc[3] += e * (f * w * wm);
+      F[p] = f;
     }
-    if (mom) acc[0] += e * (f * w * wm);
-    if (l + 1 >= d.UPA[i]) {
-      const double a = pow(sp.ATLOS[k * d.NR + i], 1 / d.FNHSc[(size_t)l * d.Pp + p]);
-      f = f * a;
-      if (mom) acc[1] += e * (f * w * wm);
-      f = f * a;
-      if (mom) acc[2] += e * (f * w * wm);
-    } else if (mom) {
-      const double term = e * (f * w * wm);
-      acc[1] += term;
-      acc[2] += term;
-    }
-    if (useA) f = f * facA;
-    if (mom) acc[3] += e * (f * w * wm);
-    sp.F[t] = f;
   }
-  cta_sum_to<4>(sp.part, acc);
+  cta_sum_to<4>(sp.part, plane, acc);
 }
 
 // =============================================================================
@@ -911,11 +887,12 @@ __global__ void k_wpadif(const __grid_constant__ RamDev d, const __grid_constant
 // => PPERT/PPART are bit-identical to the oracle.
 // =============================================================================
 __global__ void __launch_bounds__(128) k_anisch_pa(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0) {
-  const SpecDev& sp = pk.s[s0 + blockIdx.y];
+  const SpecDev& sp = pk.s[s0 + blockIdx.z];
   const int NE = d.NE, Pp = d.Pp;
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (long long)NE * Pp) return;
-  const int k = (int)(t / Pp), p = (int)(t - (long long)k * Pp);
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = blockIdx.y;
+  if (p >= Pp) return;
+  const size_t t = (size_t)k * Pp + p;
   const int i = p % d.NR;
   if (p >= d.P || i < 1 || k < 1) { sp.tE[t] = 0; sp.tA[t] = 0; return; }
   const size_t LS = (size_t)NE * Pp;
@@ -967,55 +944,48 @@ __global__ void k_anisch_en(const __grid_constant__ RamDev d, const __grid_const
 // fastest) and F2dev; also the ram_run epilogue (src/ModRamRun.f90:186-201).
 // =============================================================================
 // stage: raw host image; one thread per device element of species s
+// grid: x = tiles of p, y = plane
 __global__ void k_f2_from_host(RamDev d, const double* __restrict__ stage, double* __restrict__ Fs, int s) {
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long n = (long long)d.NPA * d.NE * d.Pp;
-  if (t >= n) return;
-  const int p = (int)(t % d.Pp);
-  const long long plane = t / d.Pp;  // l*NE + k
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t plane = blockIdx.y;  // l*NE + k
+  if (p >= d.Pp) return;
   double v = 0.0;
-  if (p < d.P) v = stage[((size_t)plane * d.P + p) * d.nS + s];
-  Fs[t] = v;
+  if (p < d.P) v = stage[(plane * d.P + p) * d.nS + s];
+  Fs[plane * d.Pp + p] = v;
 }
 __global__ void k_f2_to_host(RamDev d, double* __restrict__ stage, const double* __restrict__ Fs, int s) {
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long n = (long long)d.NPA * d.NE * d.Pp;
-  if (t >= n) return;
-  const int p = (int)(t % d.Pp);
-  const long long plane = t / d.Pp;
-  if (p < d.P) stage[((size_t)plane * d.P + p) * d.nS + s] = Fs[t];
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t plane = blockIdx.y;
+  if (p < d.P) stage[(plane * d.P + p) * d.nS + s] = Fs[plane * d.Pp + p];
 }
 // F2(:,:,NT,:,:) = F2(:,:,1,:,:), then F2 = 1e-31 where outsideMGNP == 1.  The
 // J=1 thread owns both its own cell and the J=NT copy (no read/write race).
+// grid: x = tiles of p, y = plane, z = species
 __global__ void __launch_bounds__(256) k_epilogue(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0) {
-  const SpecDev& sp = pk.s[s0 + blockIdx.y];
-  double* Fs = sp.F;
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long n = (long long)d.NPA * d.NE * d.Pp;
-  if (t >= n) return;
-  const int p = (int)(t % d.Pp);
+  const SpecDev& sp = pk.s[s0 + blockIdx.z];
+  double* Fs = sp.F + (size_t)blockIdx.y * d.Pp;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= d.P) return;
   const int j = p / d.NR;
   if (j == d.NT - 1) return;
-  const double v = Fs[t];
+  const bool out = d.outp[p];
+  if (j != 0 && !out) return;              // nothing to do for the bulk of the cells
+  const double v = Fs[p];
   if (j == 0) {
     const int pN = p + (d.NT - 1) * d.NR;
-    Fs[t - p + pN] = d.outp[pN] ? 1.e-31 : v;
+    Fs[pN] = d.outp[pN] ? 1.e-31 : v;
   }
-  if (d.outp[p]) Fs[t] = 1.e-31;
+  if (out) Fs[p] = 1.e-31;
 }
 // FLUX = F2/FFACTOR/FNHS for I>=2,K>=2,L>=2,J<=NT-1 (src/ModRamRun.f90:210-221), host layout
 __global__ void k_flux_to_host(RamDev d, SpecDev sp, double* __restrict__ stage) {
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long n = (long long)d.NPA * d.NE * d.Pp;
-  if (t >= n) return;
-  const int p = (int)(t % d.Pp);
-  const long long plane = t / d.Pp;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t plane = blockIdx.y;
   if (p >= d.P) return;
-  const int k = (int)(plane % d.NE), l = (int)(plane / d.NE);
+  const int l = (int)(plane / d.NE), k = (int)(plane - (size_t)l * d.NE);
   const int j = p / d.NR, i = p - j * d.NR;
   double v = 0.0;
   if (i >= 1 && k >= 1 && l >= 1 && j <= d.NT - 2)
-    v = sp.F[t] / sp.FF[((size_t)l * d.NE + k) * d.NR + i] / d.FNHSc[(size_t)l * d.Pp + p];
-  stage[((size_t)plane * d.P + p) * d.nS + sp.S] = v;
+    v = sp.F[plane * d.Pp + p] / sp.FF[((size_t)l * d.NE + k) * d.NR + i] / d.FNHSc[(size_t)l * d.Pp + p];
+  stage[(plane * d.P + p) * d.nS + sp.S] = v;
 }
