@@ -53,7 +53,8 @@ struct SpecDev {
   const double *P4, *eK, *epK, *aE, *sv;  // [NE]
   const double *P2, *EDOT, *ATLOS;        // [NE][NR]
   const double* aMU;                      // [NPA]
-  const double *w2, *uE, *vE, *wM, *rDE, *rWE;  // FAST-mode energy tables [NE]
+  const double *w2, *wM;                  // FAST-mode energy tables [NE]
+  const double* tabE;                     // FAST DRIFTE: {uE, vE, 1/DE, 1/WE} per K, 32-byte records
   const double* FF;                       // FFACTOR [l][k][i]
   const double* EPP;                      // [NE]
   const double* wfac;                     // WAVELO factor exp(-DTs/TAU_LIF) [NE][Pp]

@@ -351,7 +351,8 @@ int tables_drift(rsg_ram* h, int s, double DTs, cudaStream_t st) {
   double* P2 = t + 4 * NE;
   double* EDOT = P2 + (size_t)NE * NR;
   double* aMU = EDOT + (size_t)NE * NR;
-  double* fast = aMU + NPA;  // w2, uE, vE, wM, rDE, rWE
+  double* fast = aMU + NPA;  // w2[NE], wM[NE], tabE[NE][4]
+  fast += (4 - ((fast - t) & 3)) & 3;  // tabE records are 32-byte aligned (d_tab is 256-byte aligned)
 #define GRELs(K) h->GREL[s + (size_t)nS * ((K)-1)]
 #define GRBNDs(K) h->GRBND[s + (size_t)nS * ((K)-1)]
   for (int K = 1; K <= NE; ++K) {
@@ -361,12 +362,16 @@ int tables_drift(rsg_ram* h, int s, double DTs, cudaStream_t st) {
     epK[K - 1] = h->EKEV[K - 1] * 1e3 * (GRELs(K) + 1) / 2 / GRELs(K);
     aE[K - 1] = FracCFL * DTs * h->DE[K - 1];
     // FAST-mode energy factors
-    fast[K - 1] = DTs * h->EKEV[K - 1] * 1000 * (GRELs(K) + 1) / GRELs(K) / DPHI / QS;       // w2: P2 = w2/RLZ**2
-    fast[NE + K - 1] = h->EBND[K - 1] * DTs * (GRBNDs(K) + 1) / GRBNDs(K) / 2.;                // uE: EDOT = uE/RLZ
-    fast[2 * NE + K - 1] = fast[NE + K - 1] * eK[K - 1] / QS;                                  // vE
-    fast[3 * NE + K - 1] = epK[K - 1] / QS;                                                    // wM
-    fast[4 * NE + K - 1] = 1.0 / h->DE[K - 1];
-    fast[5 * NE + K - 1] = 1.0 / h->WE[K - 1];
+    {
+      double* tabE = fast + 4 * (K - 1);
+      const double uE = h->EBND[K - 1] * DTs * (GRBNDs(K) + 1) / GRBNDs(K) / 2.;               // EDOT = uE/RLZ
+      tabE[0] = uE;
+      tabE[1] = uE * eK[K - 1] / QS;                                                            // vE
+      tabE[2] = 1.0 / h->DE[K - 1];
+      tabE[3] = 1.0 / h->WE[K - 1];
+      fast[4 * NE + K - 1] = DTs * h->EKEV[K - 1] * 1000 * (GRELs(K) + 1) / GRELs(K) / DPHI / QS;  // w2: P2 = w2/RLZ**2
+      fast[5 * NE + K - 1] = epK[K - 1] / QS;                                                   // wM
+    }
     for (int I = 1; I <= NR; ++I) {
       // DRIFTPARA :71, :83
       P2[(size_t)(K - 1) * NR + (I - 1)] =
@@ -560,7 +565,7 @@ int rsg_ram_create(rsg_ram** out, int nS, int NR, int NT, int NE, int NPA, int d
     Spec& sp = h->sp[s];
     CK(cudaStreamCreateWithFlags(&sp.own, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&sp.ev, cudaEventDisableTiming));
-    sp.n_tab = (size_t)NE * 10 + (size_t)NE * NR * 2 + NPA;
+    sp.n_tab = (size_t)NE * 10 + (size_t)NE * NR * 2 + NPA + 4;
     RET(h->dalloc(&sp.d_tab, sp.n_tab));
     CK(cudaMallocHost((void**)&sp.h_tab, sp.n_tab * sizeof(double)));
     RET(h->dalloc(&sp.d_ce, (size_t)NE + (size_t)NE * NR));
@@ -591,12 +596,10 @@ int rsg_ram_create(rsg_ram** out, int nS, int NR, int NT, int NE, int NPA, int d
     sd.P2 = t; t += (size_t)NE * NR;
     sd.EDOT = t; t += (size_t)NE * NR;
     sd.aMU = t; t += NPA;
+    t += (4 - ((t - sp.d_tab) & 3)) & 3;
+    sd.tabE = t; t += 4 * (size_t)NE;
     sd.w2 = t; t += NE;
-    sd.uE = t; t += NE;
-    sd.vE = t; t += NE;
     sd.wM = t; t += NE;
-    sd.rDE = t; t += NE;
-    sd.rWE = t; t += NE;
     sd.FF = sp.d_FF;
     sd.EPP = sp.d_EPP;
     sd.wfac = sp.d_wfac;

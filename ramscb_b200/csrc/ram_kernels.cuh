@@ -456,45 +456,52 @@ __global__ void __launch_bounds__(128) k_driftp(const __grid_constant__ RamDev d
       for (int J = ja; J <= jb; ++J) Fo[(J - 1) * NR] = F[(J - 1) * NR];
       if (jb == NT) Fo[0] = F[0];
     } else {
-      const double* G = d.G + (size_t)l * Pp + i;
-      const double* sFp = d.sFp + (size_t)l * Pp + i;
-      const double* fPb = d.fPb + (size_t)l * Pp + i;
       const double P2 = sp.P2[k * NR + i];
       const double w2 = sp.w2[k];
       const double beta = d.BetaLim, OMEt = sp.OMEt;
       const double f2 = F[NR], f3 = F[2 * NR];          // F(2), F(3): wrap-around values
-#define GETFJ(J) (((J) <= NT) ? F[((J)-1) * NR] : (((J) == NT + 1) ? f2 : f3))
-#define COEFP(J) (FAST ? fma(-w2, fPb[((J)-1) * NR], d.fPa[((J)-1) * NR + i]) \
-                       : coef_p(d.pT1[((J)-1) * NR + i], P2, G[((J)-1) * NR], sFp[((J)-1) * NR], d.pT3[((J)-1) * NR + i], d.sBp[((J)-1) * NR + i], OMEt))
-#define LIMF(a, b, c_, d_, cc) (FAST ? limited_flux_fast(a, b, c_, d_, cc, cc, beta) : limited_flux(a, b, c_, d_, cc, cc, beta))
+      // coefficient at plane offset q = (J-1)*NR  (CDriftP(I,J,K,L), :236-239)
+      const size_t lo = (size_t)l * Pp + i;
+      auto coef = [&](int q) -> double {
+        if (FAST) return fma(-w2, d.fPb[lo + q], d.fPa[q + i]);
+        return coef_p(d.pT1[q + i], P2, d.G[lo + q], d.sFp[lo + q], d.pT3[q + i], d.sBp[q + i], OMEt);
+      };
+      auto lim = [&](double a, double b, double c_, double e, double cc) -> double {
+        return FAST ? limited_flux_fast(a, b, c_, e, cc, cc, beta) : limited_flux(a, b, c_, e, cc, cc, beta);
+      };
       // flux through the segment's lower edge: interface ja-1, or NT for ja==2 (:261-262)
-      const int Jh = (ja == 2) ? NT : ja - 1;
       double prev;
-      {
-        const double c = COEFP(Jh);
-        prev = c * LIMF(F[(Jh - 2) * NR], F[(Jh - 1) * NR], GETFJ(Jh + 1), GETFJ(Jh + 2), c);
+      if (ja == 2) {
+        const double c = coef((NT - 1) * NR);
+        prev = c * lim(F[(NT - 2) * NR], F[(NT - 1) * NR], f2, f3, c);
+      } else {
+        const double c = coef((ja - 2) * NR);
+        const double e = (ja + 1 <= NT) ? F[ja * NR] : f2;
+        prev = c * lim(F[(ja - 3) * NR], F[(ja - 2) * NR], F[(ja - 1) * NR], e, c);
       }
-      double Fm1 = F[(ja - 2) * NR], F0 = F[(ja - 1) * NR], Fp1 = GETFJ(ja + 1), Fp2 = GETFJ(ja + 2);
-      double cn = COEFP(ja);
+      // rolling window F(J-1), F(J), F(J+1), F(J+2) with wrap J=NT+1->2, NT+2->3
+      int q = (ja - 1) * NR;                       // offset of F(J)
+      const int qNT = (NT - 1) * NR;
+      double Fm1 = F[q - NR], F0 = F[q];
+      double Fp1 = (ja + 1 <= NT) ? F[q + NR] : f2;
+      double Fp2 = (ja + 2 <= NT) ? F[q + 2 * NR] : ((ja + 2 == NT + 1) ? f2 : f3);
+      double cn = coef(q);
       double fnew = 0.0;
-      for (int J = ja; J <= jb; ++J) {
-        // prefetch the next step's inputs before the dependent arithmetic
-        const double Fp3 = GETFJ(J + 3);
-        const int Jn = (J < NT) ? J + 1 : NT;
-        const double cnn = COEFP(Jn);
+      for (int J = ja; J <= jb; ++J, q += NR) {
+        // next step's inputs first (independent of this step's arithmetic)
+        const int q3 = q + 3 * NR;
+        const double Fp3 = (q3 <= qNT) ? F[q3] : ((q3 == qNT + NR) ? f2 : f3);
+        const double cnn = coef(min(q + NR, qNT));
         const double c = cn;
-        if (!d.outp[(J - 1) * NR + i]) cmax = fmax(cmax, fabs(c));
-        const double cur = c * LIMF(Fm1, F0, Fp1, Fp2, c);
+        if (!d.outp[q + i]) cmax = fmax(cmax, fabs(c));
+        const double cur = c * lim(Fm1, F0, Fp1, Fp2, c);
         fnew = F0 - cur + prev;                         // :266
         if (fnew < 0.0) fnew = 1E-15;
-        Fo[(J - 1) * NR] = fnew;
+        Fo[q] = fnew;
         prev = cur;
         Fm1 = F0; F0 = Fp1; Fp1 = Fp2; Fp2 = Fp3; cn = cnn;
       }
       if (jb == NT) Fo[0] = fnew;                       // :272
-#undef GETFJ
-#undef COEFP
-#undef LIMF
     }
   }
   warp_min_to(sp.dt + 1, sp.aRP / fmax(cmax, 1E-10));
@@ -504,6 +511,8 @@ __global__ void __launch_bounds__(128) k_driftp(const __grid_constant__ RamDev d
 // DRIFTE  (src/ModRamDrift.f90:285-376): lines along energy, segments of SEG
 // cells of K=1..NE per thread.  Ghosts F(1),F(0) from the relativistic
 // extrapolation of F2(K=2) (:334-335), F(NE+1)=F(NE+2)=0 (:312-313).
+// The first interface of a segment (K=ka-1, or K=1 for the first segment) only
+// provides a flux: no cell is updated there, so it is peeled off the loop.
 // grid: x = tiles of the plane index p, y = l*nseg + seg, z = species
 // =============================================================================
 template <bool FAST>
@@ -533,47 +542,74 @@ __global__ void __launch_bounds__(128) k_drifte(const __grid_constant__ RamDev d
       }
       const bool inside = !d.outp[p];
       const double QS = sp.QS, beta = d.BetaLim;
-      const double* EDOT = sp.EDOT + i;
-      double F1 = 0.0, Fz = 0.0;
-      if (ka <= 3) {
-        const double f2 = F[(size_t)Pp];
-        F1 = f2 * sp.GREL1 / sp.GREL2 * sp.sqrtA;
-        Fz = F1 * sp.GRZERO / sp.GREL1 * sp.sqrtB;
-      }
-#define GETFK(K) (((K) > NE) ? 0.0 : (((K) >= 2) ? F[(size_t)((K)-1) * Pp] : (((K) == 1) ? F1 : Fz)))
-      if (ka == 1) Fo[0] = F[0];                        // F2(K=1) is not advanced by DRIFTE
       const int K0 = max(ka - 1, 1);
-      double Fm1 = GETFK(K0 - 1), F0 = GETFK(K0), Fp1 = GETFK(K0 + 1), Fp2 = GETFK(K0 + 2);
-      double nxt = GETFK(K0 + 3), nx2 = GETFK(K0 + 4);
-      double cprev = 0.0, FBprev = 0.0;
-      for (int K = K0; K <= kb; ++K) {
-        const double nn = GETFK(K + 5);
-        double c, FB;
-        if (FAST) {
-          c = fma(sp.vE[K - 1], fB, sp.uE[K - 1] * fA);
-          const double rDE = sp.rDE[K - 1];
-          if (inside && K >= ka) mmax = fmax(mmax, fmax(fabs(c), 1E-10) * rDE);
-          FB = c * limited_flux_fast(Fm1, F0, Fp1, Fp2, c, c * rDE, beta);   // FB holds the flux c*FBND
-          if (K >= ka && K >= 2) {
-            double fn = fma(-(FB - FBprev), sp.rWE[K - 1], F0);
-            if (fn < 0.0) fn = 1E-15;
-            Fo[(size_t)(K - 1) * Pp] = fn;
-          }
-        } else {
-          c = coef_e(sp.eK[K - 1], FNHS, RLZI, BNES, QS, DRD1, DRD2, DPD1, DPD2, Gr, Gp, dBdt1, dIdt1, EDOT[(K - 1) * d.NR]);
-          if (inside && K >= ka) dtmin = fmin(dtmin, sp.aE[K - 1] / fmax(fabs(c), 1E-10));
-          FB = limited_flux(Fm1, F0, Fp1, Fp2, c, c / d.DE[K - 1], beta);
-          if (K >= ka && K >= 2) {
-            const double WEK = d.WE[K - 1];
-            double fn = F0 - c / WEK * FB + cprev / WEK * FBprev;   // :364
-            if (fn < 0.0) fn = 1E-15;
-            Fo[(size_t)(K - 1) * Pp] = fn;
-          }
+      // rolling window F(K-1..K+2) + two prefetched values; pF walks ahead of the window
+      double Fm1, F0, Fp1, Fp2, nxt, nx2;
+      {
+        double F1 = 0.0, Fz = 0.0;
+        if (K0 <= 2) {
+          const double f2 = F[(size_t)Pp];
+          F1 = f2 * sp.GREL1 / sp.GREL2 * sp.sqrtA;
+          Fz = F1 * sp.GRZERO / sp.GREL1 * sp.sqrtB;
         }
-        cprev = c; FBprev = FB;
-        Fm1 = F0; F0 = Fp1; Fp1 = Fp2; Fp2 = nxt; nxt = nx2; nx2 = nn;
-      }
+#define GETFK(K) (((K) > NE) ? 0.0 : (((K) >= 2) ? F[(size_t)((K)-1) * Pp] : (((K) == 1) ? F1 : Fz)))
+        Fm1 = GETFK(K0 - 1); F0 = GETFK(K0); Fp1 = GETFK(K0 + 1); Fp2 = GETFK(K0 + 2);
+        nxt = GETFK(K0 + 3); nx2 = GETFK(K0 + 4);
 #undef GETFK
+      }
+      if (ka == 1) Fo[0] = F[0];                        // F2(K=1) is not advanced by DRIFTE
+      const double* pF = F + (size_t)(K0 + 4) * Pp;     // -> F(K0+5)
+      int nleft = NE - (K0 + 4);                        // loads still inside the array
+      double* pO = Fo + (size_t)K0 * Pp;                // -> Fo(K0+1)
+      double cprev, FBprev;
+      if (FAST) {
+        const double2* tab = (const double2*)sp.tabE + 2 * (K0 - 1);   // {uE,vE},{rDE,rWE} per K
+        {  // peeled first interface K0: flux only
+          const double2 uv = tab[0], rr = tab[1];
+          const double c = fma(uv.y, fB, uv.x * fA);
+          if (inside && seg == 0) mmax = fmax(mmax, fmax(fabs(c), 1E-10) * rr.x);
+          FBprev = c * limited_flux_fast(Fm1, F0, Fp1, Fp2, c, c * rr.x, beta);   // the flux c*FBND
+          cprev = c;
+        }
+        for (int K = K0 + 1; K <= kb; ++K) {
+          tab += 2;
+          const double nn = (nleft > 0) ? *pF : 0.0;
+          pF += Pp; --nleft;
+          Fm1 = F0; F0 = Fp1; Fp1 = Fp2; Fp2 = nxt; nxt = nx2; nx2 = nn;
+          const double2 uv = tab[0], rr = tab[1];
+          const double c = fma(uv.y, fB, uv.x * fA);
+          if (inside) mmax = fmax(mmax, fmax(fabs(c), 1E-10) * rr.x);
+          const double FB = c * limited_flux_fast(Fm1, F0, Fp1, Fp2, c, c * rr.x, beta);
+          double fn = fma(-(FB - FBprev), rr.y, F0);
+          if (fn < 0.0) fn = 1E-15;
+          *pO = fn;
+          pO += Pp;
+          FBprev = FB;
+        }
+      } else {
+        const double* EDOT = sp.EDOT + i + (size_t)(K0 - 1) * d.NR;
+        {
+          const double c = coef_e(sp.eK[K0 - 1], FNHS, RLZI, BNES, QS, DRD1, DRD2, DPD1, DPD2, Gr, Gp, dBdt1, dIdt1, *EDOT);
+          if (inside && seg == 0) dtmin = fmin(dtmin, sp.aE[K0 - 1] / fmax(fabs(c), 1E-10));
+          FBprev = limited_flux(Fm1, F0, Fp1, Fp2, c, c / d.DE[K0 - 1], beta);
+          cprev = c;
+        }
+        for (int K = K0 + 1; K <= kb; ++K) {
+          EDOT += d.NR;
+          const double nn = (nleft > 0) ? *pF : 0.0;
+          pF += Pp; --nleft;
+          Fm1 = F0; F0 = Fp1; Fp1 = Fp2; Fp2 = nxt; nxt = nx2; nx2 = nn;
+          const double c = coef_e(sp.eK[K - 1], FNHS, RLZI, BNES, QS, DRD1, DRD2, DPD1, DPD2, Gr, Gp, dBdt1, dIdt1, *EDOT);
+          if (inside) dtmin = fmin(dtmin, sp.aE[K - 1] / fmax(fabs(c), 1E-10));
+          const double FB = limited_flux(Fm1, F0, Fp1, Fp2, c, c / d.DE[K - 1], beta);
+          const double WEK = d.WE[K - 1];
+          double fn = F0 - c / WEK * FB + cprev / WEK * FBprev;   // :364
+          if (fn < 0.0) fn = 1E-15;
+          *pO = fn;
+          pO += Pp;
+          cprev = c; FBprev = FB;
+        }
+      }
     }
   }
   if (FAST && mmax > 0.0) dtmin = sp.aRP / mmax;
@@ -611,53 +647,66 @@ __global__ void __launch_bounds__(128) k_driftmu(const __grid_constant__ RamDev 
       if (!FAST) { DRM1 = d.DRD1[p]; DPM1 = d.DPD1[p]; BNES = d.BNESc[p]; RLZI = d.RLZp[p]; dBdt2 = d.dBdt2[p]; }
       const bool inside = !d.outp[p];
       const double QS = sp.QS, beta = d.BetaLim, epK = sp.epK[k], wM = sp.wM[k];
-#define GETFL(L) (((L) >= 2) ? F[(size_t)((L)-1) * LS] : F[LS])   /* F(1) = F(2)  (:414) */
-#define COEFMU(L, o) (FAST ? fma(wM, d.fMb[o], d.fMa[o]) \
-                           : coef_mu(epK, d.BOUNHSc[o], RLZI, BNES, QS, DRM1, d.DRM2[o], DPM1, d.DPM2[o], d.Gmr[o], d.Gmp[o], dBdt2, d.dIbndt2[o], d.CMUDOT[o]))
-      const int L0 = max(la - 1, 2);
-      double Fm1 = GETFL(L0 - 1), F0 = GETFL(L0), Fp1 = GETFL(L0 + 1), Fp2 = (L0 + 2 <= NPA) ? GETFL(L0 + 2) : 0.0;
-      double nxt = (L0 + 3 <= NPA) ? GETFL(L0 + 3) : 0.0;
-      double cn = COEFMU(L0, (size_t)(L0 - 1) * Pp + p);
-      double cprev = 0.0, FBprev = 0.0;               // CDriftMu(..,1)=0, FBND(1)=0 (:456-457)
+      // coefficient at plane offset o = (L-1)*Pp + p  (CDriftMu(I,J,K,L), :418-433)
+      auto coef = [&](size_t o) -> double {
+        if (FAST) return fma(wM, d.fMb[o], d.fMa[o]);
+        return coef_mu(epK, d.BOUNHSc[o], RLZI, BNES, QS, DRM1, d.DRM2[o], DPM1, d.DPM2[o], d.Gmr[o], d.Gmp[o], dBdt2, d.dIbndt2[o], d.CMUDOT[o]);
+      };
+      // window for the first updated cell L=la: F(la-1), F(la), F(la+1), F(la+2); F(1)=F(2) (:414)
+      const double* pF = F + (size_t)(la - 1) * LS;          // -> F(la)
+      double Fm1 = (la >= 3) ? pF[-(ptrdiff_t)LS] : pF[0];
+      double F0 = pF[0], Fp1 = pF[LS];
+      double Fp2 = (la + 2 <= NPA) ? pF[2 * LS] : 0.0;
+      double nxt = (la + 3 <= NPA) ? pF[3 * LS] : 0.0;
+      pF += 4 * LS;                                          // -> F(la+4)
+      int nleft = NPA - (la + 3);
+      size_t o = (size_t)(la - 1) * Pp + p;                  // coefficient offset of L=la
+      // flux through the segment's lower edge: CDriftMu(..,1)=0, FBND(1)=0 (:456-457) for la==2
+      double cprev = 0.0, FBprev = 0.0;
+      if (la > 2) {
+        const double c = coef(o - Pp);
+        const double Fm2 = (la >= 4) ? F[(size_t)(la - 3) * LS] : F[LS];   // F(la-2), F(1)=F(2)
+        if (FAST) FBprev = c * limited_flux_fast(Fm2, Fm1, F0, Fp1, c, c * d.rDMU[la - 2], beta);
+        else FBprev = limited_flux(Fm2, Fm1, F0, Fp1, c, c / d.DMU[la - 2], beta);
+        cprev = c;
+      }
+      double cn = coef(o);
       double fnew = 0.0;
-      for (int L = L0; L <= lb; ++L) {
-        const double nn = (L + 4 <= NPA) ? F[(size_t)(L + 3) * LS] : 0.0;
-        const double cnn = COEFMU(L + 1, (size_t)L * Pp + p);   // L+1 <= NPA always
+      double* pO = Fo + (size_t)(la - 1) * LS;
+      for (int L = la; L <= lb; ++L) {
+        o += Pp;
+        const double nn = (nleft > 0) ? *pF : 0.0;
+        pF += LS; --nleft;
+        const double cnn = coef(o);                           // CDriftMu(..,L+1), L+1 <= NPA
         const double c = cn;
-        double FB;
         if (FAST) {
           const double rDM = d.rDMU[L - 1];
-          if (inside && L >= la) mmax = fmax(mmax, fmax(fabs(c), 1E-32) * rDM);
+          if (inside) mmax = fmax(mmax, fmax(fabs(c), 1E-32) * rDM);
+          double FB;
           if (L <= NPA - 2) FB = c * limited_flux_fast(Fm1, F0, Fp1, Fp2, c, c * rDM, beta);   // flux c*FBND
-          else FB = c * Fp1;
-          if (L >= la) {
-            fnew = fma(-(FB - FBprev), d.rWMU[L - 1], F0);
-            if (fnew < 0.0) fnew = 1E-15;
-            Fo[(size_t)(L - 1) * LS] = fnew;
-          }
+          else FB = c * Fp1;                                  // FBND(NPA-1) = F(NPA)  (:458)
+          fnew = fma(-(FB - FBprev), d.rWMU[L - 1], F0);
+          FBprev = FB;
         } else {
-          if (inside && L >= la) dtmin = fmin(dtmin, sp.aMU[L - 1] / fmax(fabs(c), 1E-32));
+          if (inside) dtmin = fmin(dtmin, sp.aMU[L - 1] / fmax(fabs(c), 1E-32));
+          double FB;
           if (L <= NPA - 2) FB = limited_flux(Fm1, F0, Fp1, Fp2, c, c / d.DMU[L - 1], beta);
-          else FB = Fp1;                                // FBND(NPA-1) = F(NPA)  (:458)
-          if (L >= la) {
-            const double WM = d.WMU[L - 1];
-            fnew = F0 - c / WM * FB + cprev / WM * FBprev;   // :460
-            if (fnew < 0.0) fnew = 1E-15;
-            Fo[(size_t)(L - 1) * LS] = fnew;
-          }
+          else FB = Fp1;
+          const double WM = d.WMU[L - 1];
+          fnew = F0 - c / WM * FB + cprev / WM * FBprev;      // :460
+          cprev = c; FBprev = FB;
         }
-        cprev = c; FBprev = FB;
+        if (fnew < 0.0) fnew = 1E-15;
+        *pO = fnew;
+        pO += LS;
         Fm1 = F0; F0 = Fp1; Fp1 = Fp2; Fp2 = nxt; nxt = nn; cn = cnn;
       }
       if (lastseg) {
         const double c = cn;                            // CDriftMu(..,NPA)
         if (FAST) { if (inside) mmax = fmax(mmax, fmax(fabs(c), 1E-32) * d.rDMU[NPA - 1]); }
         else if (inside) dtmin = fmin(dtmin, sp.aMU[NPA - 1] / fmax(fabs(c), 1E-32));
-        Fo[(size_t)(NPA - 1) * LS] =
-            fnew * d.FNHSc[(size_t)(NPA - 1) * Pp + p] * d.MU[NPA - 1] / d.FNHSc[(size_t)(NPA - 2) * Pp + p] / d.MU[NPA - 2];
+        *pO = fnew * d.FNHSc[(size_t)(NPA - 1) * Pp + p] * d.MU[NPA - 1] / d.FNHSc[(size_t)(NPA - 2) * Pp + p] / d.MU[NPA - 2];
       }
-#undef GETFL
-#undef COEFMU
     }
   }
   if (FAST && mmax > 0.0) dtmin = sp.aRP / mmax;
