@@ -31,6 +31,12 @@ __device__ __forceinline__ void block_min_to(unsigned long long* dst, double v) 
   if ((threadIdx.x & 31) == 0) atomicMin(dst, b);
 }
 
+// compare-select min/max with std::min/std::max semantics (what the oracle and
+// Fortran MIN/MAX compute for ordered operands); IEEE fmin/fmax cost 6-7
+// instructions each on sm_100 because of their NaN rules.
+__device__ __forceinline__ double dmin(double a, double b) { return (b < a) ? b : a; }
+__device__ __forceinline__ double dmax(double a, double b) { return (a < b) ? b : a; }
+
 // =============================================================================
 // flux limiter, SURVEY appendix A.1 (ModRamDrift.f90:170-182, 246-259, 349-361,
 // 441-453).  Window: Fm1=F(m-1) F0=F(m) Fp1=F(m+1) Fp2=F(m+2); c = Courant
@@ -46,7 +52,7 @@ __device__ __forceinline__ double limited_flux(double Fm1, double F0, double Fp1
     const double num = (c < 0.0) ? (Fp2 - Fp1) : (F0 - Fm1);
     const double R = num / X;
     if (R > 0.0) {
-      const double LIM = fmax(fmin(beta * R, 1.0), fmin(R, beta));
+      const double LIM = dmax(dmin(beta * R, 1.0), dmin(R, beta));
       const double CORR = (-0.5 * (chat - sgn)) * X;
       FB = FUP + LIM * CORR;
     }
@@ -54,20 +60,25 @@ __device__ __forceinline__ double limited_flux(double Fm1, double F0, double Fp1
   return FB;
 }
 
-// FAST mode: the same limiter without the division (LIM*X is a min/max of |num|
-// and |X|) and with FUP selected instead of computed; mathematically identical,
-// rounding differs at the 1e-16 level.
-__device__ __forceinline__ double limited_flux_fast(double Fm1, double F0, double Fp1, double Fp2, double c, double chat,
+// FAST mode: the same limiter in upwind form, without the division.  With
+// U/D/UU the upwind, downwind and far-upwind cells, dU=U-UU, dD=D-U, R=dU/dD:
+//   FBND = U + 0.5*(1-|chat|) * LIM(R)*dD,  LIM(R)*|dD| = min(max(|dU|,|dD|), beta*min(|dU|,|dD|))
+// (max(min(bR,1),min(R,b)) = min(max(R,1), b*min(R,1)) for b >= 1).  achat = |chat|.
+// Mathematically identical to the reference; rounding differs at the 1e-16 level.
+__device__ __forceinline__ double limited_flux_fast(double Fm1, double F0, double Fp1, double Fp2, bool neg, double achat,
                                                     double beta) {
-  const bool neg = (c < 0.0);
-  const double X = Fp1 - F0;
-  const double FUP = neg ? Fp1 : F0;
-  const double num = neg ? (Fp2 - Fp1) : (F0 - Fm1);
-  const double aX = fabs(X), an = fabs(num);
-  const double limx = copysign(fmax(fmin(beta * an, aX), fmin(an, beta * aX)), X);   // LIM * X
-  const double corr = -0.5 * (chat - (neg ? -1.0 : 1.0));
-  const bool use = (aX > 1.E-27) && (num * X > 0.0);
-  return use ? fma(corr, limx, FUP) : FUP;
+  const double U = neg ? Fp1 : F0;
+  const double D = neg ? F0 : Fp1;
+  const double UU = neg ? Fp2 : Fm1;
+  const double dU = U - UU, dD = D - U;
+  const double an = fabs(dU), ad = fabs(dD);
+  const bool lt = an < ad;
+  const double m = lt ? an : ad, M = lt ? ad : an;
+  const double bm = beta * m;
+  const double lim = (bm < M) ? bm : M;
+  const bool use = (ad > 1.E-27) && (dU * dD > 0.0);
+  const double limx = use ? copysign(lim, dD) : 0.0;
+  return fma(fma(-0.5, achat, 0.5), limx, U);
 }
 
 // =============================================================================
@@ -418,7 +429,7 @@ __global__ void __launch_bounds__(256) k_driftr(const __grid_constant__ RamDev d
       const double Fm1 = F[i - 1];
       const double Fp1 = (I + 1 <= NR) ? F[i + 1] : g1;
       const double Fp2 = (I + 2 <= NR) ? F[i + 2] : ((I + 2 == NR + 1) ? g1 : g2);
-      phi = c * (FAST ? limited_flux_fast(Fm1, F0, Fp1, Fp2, c, c, d.BetaLim) : limited_flux(Fm1, F0, Fp1, Fp2, c, c, d.BetaLim));
+      phi = c * (FAST ? limited_flux_fast(Fm1, F0, Fp1, Fp2, c < 0.0, fabs(c), d.BetaLim) : limited_flux(Fm1, F0, Fp1, Fp2, c, c, d.BetaLim));
     }
   }
   const double phiPrev = __shfl_up_sync(0xffffffffu, phi, 1);
@@ -430,7 +441,7 @@ __global__ void __launch_bounds__(256) k_driftr(const __grid_constant__ RamDev d
     }
     sp.Fo[(size_t)plane * Pp + p] = fn;
   }
-  warp_min_to(sp.dt + 0, sp.aRP / fmax(cmax, 1E-10));
+  warp_min_to(sp.dt + 0, sp.aRP / dmax(cmax, 1E-10));
 }
 
 // =============================================================================
@@ -467,7 +478,7 @@ __global__ void __launch_bounds__(128) k_driftp(const __grid_constant__ RamDev d
         return coef_p(d.pT1[q + i], P2, d.G[lo + q], d.sFp[lo + q], d.pT3[q + i], d.sBp[q + i], OMEt);
       };
       auto lim = [&](double a, double b, double c_, double e, double cc) -> double {
-        return FAST ? limited_flux_fast(a, b, c_, e, cc, cc, beta) : limited_flux(a, b, c_, e, cc, cc, beta);
+        return FAST ? limited_flux_fast(a, b, c_, e, cc < 0.0, fabs(cc), beta) : limited_flux(a, b, c_, e, cc, cc, beta);
       };
       // flux through the segment's lower edge: interface ja-1, or NT for ja==2 (:261-262)
       double prev;
@@ -493,7 +504,7 @@ __global__ void __launch_bounds__(128) k_driftp(const __grid_constant__ RamDev d
         const double Fp3 = (q3 <= qNT) ? F[q3] : ((q3 == qNT + NR) ? f2 : f3);
         const double cnn = coef(min(q + NR, qNT));
         const double c = cn;
-        if (!d.outp[q + i]) cmax = fmax(cmax, fabs(c));
+        if (!d.outp[q + i]) cmax = dmax(cmax, fabs(c));
         const double cur = c * lim(Fm1, F0, Fp1, Fp2, c);
         fnew = F0 - cur + prev;                         // :266
         if (fnew < 0.0) fnew = 1E-15;
@@ -504,7 +515,7 @@ __global__ void __launch_bounds__(128) k_driftp(const __grid_constant__ RamDev d
       if (jb == NT) Fo[0] = fnew;                       // :272
     }
   }
-  warp_min_to(sp.dt + 1, sp.aRP / fmax(cmax, 1E-10));
+  warp_min_to(sp.dt + 1, sp.aRP / dmax(cmax, 1E-10));
 }
 
 // =============================================================================
@@ -564,12 +575,15 @@ __global__ void __launch_bounds__(128) k_drifte(const __grid_constant__ RamDev d
       double cprev, FBprev;
       if (FAST) {
         const double2* tab = (const double2*)sp.tabE + 2 * (K0 - 1);   // {uE,vE},{rDE,rWE} per K
+        double floorr = 0.0;
         {  // peeled first interface K0: flux only
           const double2 uv = tab[0], rr = tab[1];
           const double c = fma(uv.y, fB, uv.x * fA);
-          if (inside && seg == 0) mmax = fmax(mmax, fmax(fabs(c), 1E-10) * rr.x);
-          FBprev = c * limited_flux_fast(Fm1, F0, Fp1, Fp2, c, c * rr.x, beta);   // the flux c*FBND
+          const double ac = fabs(c) * rr.x;                                        // |CDriftE|/DE(K)
+          if (inside && seg == 0) mmax = ac;
+          FBprev = c * limited_flux_fast(Fm1, F0, Fp1, Fp2, c < 0.0, ac, beta);   // the flux c*FBND
           cprev = c;
+          floorr = rr.x;
         }
         for (int K = K0 + 1; K <= kb; ++K) {
           tab += 2;
@@ -578,19 +592,22 @@ __global__ void __launch_bounds__(128) k_drifte(const __grid_constant__ RamDev d
           Fm1 = F0; F0 = Fp1; Fp1 = Fp2; Fp2 = nxt; nxt = nx2; nx2 = nn;
           const double2 uv = tab[0], rr = tab[1];
           const double c = fma(uv.y, fB, uv.x * fA);
-          if (inside) mmax = fmax(mmax, fmax(fabs(c), 1E-10) * rr.x);
-          const double FB = c * limited_flux_fast(Fm1, F0, Fp1, Fp2, c, c * rr.x, beta);
+          const double ac = fabs(c) * rr.x;
+          mmax = dmax(mmax, ac);
+          const double FB = c * limited_flux_fast(Fm1, F0, Fp1, Fp2, c < 0.0, ac, beta);
           double fn = fma(-(FB - FBprev), rr.y, F0);
           if (fn < 0.0) fn = 1E-15;
           *pO = fn;
           pO += Pp;
           FBprev = FB;
         }
+        // the max(|c|,1e-10) floor of :344, hoisted: 1/DE is largest at the segment's first K
+        mmax = inside ? dmax(mmax, 1E-10 * floorr) : 0.0;
       } else {
         const double* EDOT = sp.EDOT + i + (size_t)(K0 - 1) * d.NR;
         {
           const double c = coef_e(sp.eK[K0 - 1], FNHS, RLZI, BNES, QS, DRD1, DRD2, DPD1, DPD2, Gr, Gp, dBdt1, dIdt1, *EDOT);
-          if (inside && seg == 0) dtmin = fmin(dtmin, sp.aE[K0 - 1] / fmax(fabs(c), 1E-10));
+          if (inside && seg == 0) dtmin = dmin(dtmin, sp.aE[K0 - 1] / dmax(fabs(c), 1E-10));
           FBprev = limited_flux(Fm1, F0, Fp1, Fp2, c, c / d.DE[K0 - 1], beta);
           cprev = c;
         }
@@ -600,7 +617,7 @@ __global__ void __launch_bounds__(128) k_drifte(const __grid_constant__ RamDev d
           pF += Pp; --nleft;
           Fm1 = F0; F0 = Fp1; Fp1 = Fp2; Fp2 = nxt; nxt = nx2; nx2 = nn;
           const double c = coef_e(sp.eK[K - 1], FNHS, RLZI, BNES, QS, DRD1, DRD2, DPD1, DPD2, Gr, Gp, dBdt1, dIdt1, *EDOT);
-          if (inside) dtmin = fmin(dtmin, sp.aE[K - 1] / fmax(fabs(c), 1E-10));
+          if (inside) dtmin = dmin(dtmin, sp.aE[K - 1] / dmax(fabs(c), 1E-10));
           const double FB = limited_flux(Fm1, F0, Fp1, Fp2, c, c / d.DE[K - 1], beta);
           const double WEK = d.WE[K - 1];
           double fn = F0 - c / WEK * FB + cprev / WEK * FBprev;   // :364
@@ -666,7 +683,7 @@ __global__ void __launch_bounds__(128) k_driftmu(const __grid_constant__ RamDev 
       if (la > 2) {
         const double c = coef(o - Pp);
         const double Fm2 = (la >= 4) ? F[(size_t)(la - 3) * LS] : F[LS];   // F(la-2), F(1)=F(2)
-        if (FAST) FBprev = c * limited_flux_fast(Fm2, Fm1, F0, Fp1, c, c * d.rDMU[la - 2], beta);
+        if (FAST) FBprev = c * limited_flux_fast(Fm2, Fm1, F0, Fp1, c < 0.0, fabs(c) * d.rDMU[la - 2], beta);
         else FBprev = limited_flux(Fm2, Fm1, F0, Fp1, c, c / d.DMU[la - 2], beta);
         cprev = c;
       }
@@ -680,15 +697,15 @@ __global__ void __launch_bounds__(128) k_driftmu(const __grid_constant__ RamDev 
         const double cnn = coef(o);                           // CDriftMu(..,L+1), L+1 <= NPA
         const double c = cn;
         if (FAST) {
-          const double rDM = d.rDMU[L - 1];
-          if (inside) mmax = fmax(mmax, fmax(fabs(c), 1E-32) * rDM);
+          const double ac = fabs(c) * d.rDMU[L - 1];         // |CDriftMu|/DMU(L)
+          mmax = dmax(mmax, ac);
           double FB;
-          if (L <= NPA - 2) FB = c * limited_flux_fast(Fm1, F0, Fp1, Fp2, c, c * rDM, beta);   // flux c*FBND
+          if (L <= NPA - 2) FB = c * limited_flux_fast(Fm1, F0, Fp1, Fp2, c < 0.0, ac, beta);   // flux c*FBND
           else FB = c * Fp1;                                  // FBND(NPA-1) = F(NPA)  (:458)
           fnew = fma(-(FB - FBprev), d.rWMU[L - 1], F0);
           FBprev = FB;
         } else {
-          if (inside) dtmin = fmin(dtmin, sp.aMU[L - 1] / fmax(fabs(c), 1E-32));
+          if (inside) dtmin = dmin(dtmin, sp.aMU[L - 1] / dmax(fabs(c), 1E-32));
           double FB;
           if (L <= NPA - 2) FB = limited_flux(Fm1, F0, Fp1, Fp2, c, c / d.DMU[L - 1], beta);
           else FB = Fp1;
@@ -701,15 +718,16 @@ __global__ void __launch_bounds__(128) k_driftmu(const __grid_constant__ RamDev 
         pO += LS;
         Fm1 = F0; F0 = Fp1; Fp1 = Fp2; Fp2 = nxt; nxt = nn; cn = cnn;
       }
+      if (FAST && !inside) mmax = 0.0;
       if (lastseg) {
         const double c = cn;                            // CDriftMu(..,NPA)
-        if (FAST) { if (inside) mmax = fmax(mmax, fmax(fabs(c), 1E-32) * d.rDMU[NPA - 1]); }
-        else if (inside) dtmin = fmin(dtmin, sp.aMU[NPA - 1] / fmax(fabs(c), 1E-32));
+        if (FAST) { if (inside) mmax = dmax(mmax, fabs(c) * d.rDMU[NPA - 1]); }
+        else if (inside) dtmin = dmin(dtmin, sp.aMU[NPA - 1] / dmax(fabs(c), 1E-32));
         *pO = fnew * d.FNHSc[(size_t)(NPA - 1) * Pp + p] * d.MU[NPA - 1] / d.FNHSc[(size_t)(NPA - 2) * Pp + p] / d.MU[NPA - 2];
       }
     }
   }
-  if (FAST && mmax > 0.0) dtmin = sp.aRP / mmax;
+  if (FAST && mmax > 0.0) dtmin = sp.aRP / mmax;   // (the 1e-32 floor of :435 can never bind: DMU/1e-32 >> 1e4)
   warp_min_to(sp.dt + 3, dtmin);
 }
 
