@@ -254,31 +254,32 @@ def main():
     e2e = {"value": OPS_PER_STEP * cells / e2e_s, "unit": unit, "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3, "timer": "wall clock, pinned host F2"}
 
-    # ---- per-operator device times (CUDA events), dominant kernel roofline ----------
+    # ---- per-kernel device times over timed steps (CUDA events recorded on the run
+    # stream between the stages of rsg_ram_run), dominant kernel roofline ------------
     peak, peak_src = measured_peak()
-    per_op = {}
-    S = 1
-    gpu.CEPARA(S, DTS); gpu.DRIFTPARA(S, DTS)
-    sp_cells = cells // g.nS
-    for name in ("DRIFTR", "DRIFTP", "DRIFTE", "DRIFTMU", "CHAREXCHANGE", "ATMOL"):
-        reps = 5
-        tot = 0.0
-        for _ in range(reps):
+    roofline = None
+    if world == 1:
+        gpu.profile(True)
+        for _ in range(a.steps):
             flush.zero_()
             torch.cuda.synchronize()
-            gpu.timer_begin()
-            getattr(gpu, name)(S)
-            tot += gpu.timer_end()
-        per_op[name] = tot / reps
-    dom = max(("DRIFTR", "DRIFTP", "DRIFTE", "DRIFTMU"), key=lambda n: per_op[n])
-    achieved = 16.0 * sp_cells / (per_op[dom] * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": {"DRIFTR": "k_driftr", "DRIFTP": "k_driftp", "DRIFTE": "k_drifte",
-                                           "DRIFTMU": "k_driftmu"}[dom],
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": 16 * sp_cells,
-                "note": "one species per launch (cold L2); 16 B per cell-update (SURVEY 8(d))",
-                "per_op_ms_one_species": per_op}
+            step_resident()
+        stages = gpu.profile_get()
+        gpu.profile(False)
+        per_kernel_ms = {k: v[0] / v[1] for k, v in stages.items() if v[1] and k != "end"}
+        sweeps = {k: per_kernel_ms[k] for k in ("k_driftr", "k_driftp", "k_drifte", "k_driftmu") if k in per_kernel_ms}
+        dom = max(sweeps, key=lambda n: sweeps[n])
+        alg_bytes = 16.0 * cells                       # one FP64 read + one write per cell, all species per launch
+        achieved = alg_bytes / (sweeps[dom] * 1e-3) / 1e9
+        step_sum = sum(v[0] for k, v in stages.items() if k != "end") / a.steps
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": int(alg_bytes),
+                    "note": "16 B per cell-update (SURVEY 8(d)) x all cells of the 4 species advanced by one launch; "
+                            "duration = CUDA events on the launching stream inside rsg_ram_run, L2 flushed per step",
+                    "per_kernel_ms": per_kernel_ms,
+                    "per_kernel_frac_of_peak": {k: alg_bytes / (v * 1e-3) / 1e9 / peak for k, v in sweeps.items()},
+                    "kernel_share_of_step": {k: (v[0] / a.steps) / step_sum for k, v in stages.items() if k != "end"}}
 
     line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

@@ -155,6 +155,14 @@ long long rsg_ram_launch_count(rsg_ram* h);
 int rsg_ram_timer_begin(rsg_ram* h);
 int rsg_ram_timer_end(rsg_ram* h, double* ms);
 
+/* Per-stage device timing of rsg_ram_run: when enabled, CUDA events are recorded
+ * on the run stream between the stages (one stage = the launch(es) of one
+ * kernel for all species) and accumulated; _get() enumerates the accumulators
+ * (returns non-zero past the end).  ms_total/count: summed milliseconds and
+ * number of intervals since the last rsg_ram_profile() call. */
+int rsg_ram_profile(rsg_ram* h, int on);
+int rsg_ram_profile_get(rsg_ram* h, int idx, char* name, int name_len, double* ms_total, long long* count);
+
 /* Pin / unpin an existing host array (cudaHostRegister), e.g. the Fortran
  * allocatable F2, so rsg_ram_f2_h2d/d2h run at full PCIe speed. */
 int rsg_host_register(void* p, long long bytes);

@@ -93,6 +93,8 @@ struct rsg_ram {
   double* d_zero4 = nullptr;  // all-zero diffusion coefficient
   double* d_NECR = nullptr;
   double* d_dtinit = nullptr;
+  int* d_outlist = nullptr;   // plane indices p of flagged (outsideMGNP) cells with 2 <= J <= NT-1
+  int nout = 0;
   int* d_tilemax = nullptr;
   int ntiles = 0;
   unsigned long long* d_res_all = nullptr;
@@ -108,8 +110,14 @@ struct rsg_ram {
   std::mutex mu;
   Spec sp[RSG_MAX_SPECIES];
   long long launches = 0;
+  // optional per-stage device timing of rsg_ram_run (CUDA events on the run stream)
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_ev;
+  std::vector<std::string> prof_stage;   // stage that starts at event i
+  size_t prof_n = 0;
+  std::vector<std::pair<std::string, std::pair<double, long long>>> prof_acc;  // name -> (ms, count)
   int nblk_sum = 0, sum_threads = 256;
-  int segE = 12, segMU = 12, segP = 12;
+  int segE = 12, segMU = 12, segP = 12, kcR = 7;
 
   cudaStream_t st(int s) { return ext ? ext : sp[s].own; }
   cudaStream_t pst() { return ext ? ext : prepst; }
@@ -190,6 +198,36 @@ int ensure_step(rsg_ram* h, double DTs, cudaStream_t only = nullptr) {
   return RSG_OK;
 }
 
+// mark the start of a stage of rsg_ram_run on stream st
+int prof_mark(rsg_ram* h, const char* stage, cudaStream_t st) {
+  if (!h->prof_on) return RSG_OK;
+  if (h->prof_n == h->prof_ev.size()) {
+    cudaEvent_t e;
+    CK(cudaEventCreate(&e));
+    h->prof_ev.push_back(e);
+    h->prof_stage.push_back("");
+  }
+  h->prof_stage[h->prof_n] = stage;
+  CK(cudaEventRecord(h->prof_ev[h->prof_n], st));
+  h->prof_n++;
+  return RSG_OK;
+}
+// after the stream has been synchronised: fold the intervals into the accumulators
+int prof_fold(rsg_ram* h) {
+  if (!h->prof_on) return RSG_OK;
+  for (size_t q = 0; q + 1 < h->prof_n; ++q) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->prof_ev[q], h->prof_ev[q + 1]));
+    const std::string& nm = h->prof_stage[q];
+    bool found = false;
+    for (auto& a : h->prof_acc)
+      if (a.first == nm) { a.second.first += ms; a.second.second++; found = true; break; }
+    if (!found) h->prof_acc.push_back({nm, {(double)ms, 1}});
+  }
+  h->prof_n = 0;
+  return RSG_OK;
+}
+
 RamDev devfor(rsg_ram* h, double DTs) {
   RamDev dv = h->dev;
   dv.DTs = DTs;
@@ -221,9 +259,10 @@ int L_driftr(rsg_ram* h, int s0, int ns, cudaStream_t st) {
   RET(reset_dt(h, s0, ns, 0, st));
   SpecPack pk;
   make_pack(h, pk, s0, ns);
-  dim3 g(nblk(h->P, 248), h->NPA * h->NE, ns);   // 8 warps x 31 cells per CTA
-  if (h->mode == RSG_MODE_FAST) k_driftr<true><<<g, 256, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0);
-  else k_driftr<false><<<g, 256, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0);
+  const int KC = h->kcR, KG = (h->NE + KC - 1) / KC;
+  dim3 g(nblk(h->P, 248), h->NPA * KG, ns);   // 8 warps x 31 cells per CTA, KC energies per thread
+  if (h->mode == RSG_MODE_FAST) k_driftr<true><<<g, 256, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0, KC, KG);
+  else k_driftr<false><<<g, 256, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0, KC, KG);
   CKL();
   h->launches++;
   flip(h, s0, ns);
@@ -516,6 +555,7 @@ int rsg_ram_create(rsg_ram** out, int nS, int NR, int NT, int NE, int NPA, int d
   if (const char* e = getenv("RSG_SEG_E")) h->segE = std::max(2, atoi(e));
   if (const char* e = getenv("RSG_SEG_MU")) h->segMU = std::max(2, atoi(e));
   if (const char* e = getenv("RSG_SEG_P")) h->segP = std::max(2, atoi(e));
+  if (const char* e = getenv("RSG_KC_R")) h->kcR = std::max(1, atoi(e));
   RamDev& d = h->dev;
   d.nS = nS; d.NR = NR; d.NT = NT; d.NE = NE; d.NPA = NPA; d.NR1 = h->NR1; d.P = h->P; d.Pp = h->Pp;
   const size_t n2 = (size_t)h->NR1 * NT, n3 = n2 * NPA, np = h->Pp, n3p = (size_t)NPA * h->Pp;
@@ -544,6 +584,7 @@ int rsg_ram_create(rsg_ram** out, int nS, int NR, int NT, int NE, int NPA, int d
   RET(h->dalloc(&h->d_zero4, h->specStride));
   RET(h->dalloc(&h->d_NECR, (size_t)NR * NT));
   RET(h->dalloc(&h->d_dtinit, 4));
+  RET(h->dalloc(&h->d_outlist, (size_t)NR * NT));
   {
     const double init[4] = {100000.0, 100000.0, 10000.0, 10000.0};  // :115,223,308,404
     RET(up(h->d_dtinit, init, 4));
@@ -633,6 +674,7 @@ int rsg_ram_destroy(rsg_ram* h) {
   if (h->prepev) cudaEventDestroy(h->prepev);
   if (h->t0) cudaEventDestroy(h->t0);
   if (h->t1) cudaEventDestroy(h->t1);
+  for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   delete h;
   return RSG_OK;
 }
@@ -732,6 +774,14 @@ int rsg_ram_set_fields(rsg_ram* h, const double* BNES, const double* dBdt, const
   RET(up((double*)d.BOUNIS, BOUNIS, n3)); RET(up((double*)d.HDNS, HDNS, n3)); RET(up((double*)d.dIdt, dIdt, n3));
   RET(up((double*)d.dIbndt, dIbndt, n3));
   RET(up((int*)d.outside, outsideMGNP, (size_t)h->NR * h->NT));
+  {
+    std::vector<int> lst;
+    for (int j = 1; j < h->NT - 1; ++j)
+      for (int i = 0; i < h->NR; ++i)
+        if (outsideMGNP[(size_t)j * h->NR + i] != 0) lst.push_back(j * h->NR + i);
+    h->nout = (int)lst.size();
+    if (h->nout) RET(up(h->d_outlist, lst.data(), lst.size()));
+  }
   k_prep_fields<<<nblk((long long)h->NPA * h->Pp, 256), 256, 0, h->pst()>>>(d);
   CKL();
   h->launches++;
@@ -1014,33 +1064,52 @@ int rsg_ram_run(rsg_ram* h, double DTs, double DtsMin, double T, int flags, doub
     RET(tables_drift(h, s, DTs, st));
     if (wavelo) RET(tables_wavelo(h, s, DTs, st));
   }
+  h->prof_n = 0;
+  RET(prof_mark(h, "prep_step", st));
   RET(ensure_step(h, DTs, st));
+  RET(prof_mark(h, "driftr_inflow", st));
   RET(L_inflow(h, 0, nS, st));
-  RET(L_driftr(h, 0, nS, st)); RET(L_driftp(h, 0, nS, st)); RET(L_drifte(h, 0, nS, st)); RET(L_driftmu(h, 0, nS, st));
+  RET(prof_mark(h, "k_driftr", st)); RET(L_driftr(h, 0, nS, st));
+  RET(prof_mark(h, "k_driftp", st)); RET(L_driftp(h, 0, nS, st));
+  RET(prof_mark(h, "k_drifte", st)); RET(L_drifte(h, 0, nS, st));
+  RET(prof_mark(h, "k_driftmu", st)); RET(L_driftmu(h, 0, nS, st));
+  RET(prof_mark(h, "k_sumrc", st));
   RET(L_sumrc(h, 0, nS, 0, st));
+  RET(prof_mark(h, "wpadif+sumrc", st));
   for (int s = 0; s < nS; ++s)
     if (cat[s][1] >= 0) { RET(L_wpadif(h, s, DTs, st)); RET(L_sumrc(h, s, 1, 1, st)); }
   for (int s = 0; s < nS; ++s)
     if (cat[s][2] >= 0) { RET(L_wpadif(h, s, DTs, st)); RET(L_sumrc(h, s, 1, 2, st)); }
+  RET(prof_mark(h, "k_loss_mid", st));
   RET(L_loss_mid(h, 0, nS, doA, DTs, 3, st));
+  RET(prof_mark(h, "wpadif+sumrc", st));
   for (int s = 0; s < nS; ++s)
     if (cat[s][7] >= 0) { RET(L_wpadif(h, s, DTs, st)); RET(L_sumrc(h, s, 1, 7, st)); }
   for (int s = 0; s < nS; ++s)
     if (cat[s][8] >= 0) { RET(L_wpadif(h, s, DTs, st)); RET(L_sumrc(h, s, 1, 8, st)); }
-  RET(L_driftmu(h, 0, nS, st)); RET(L_drifte(h, 0, nS, st)); RET(L_driftp(h, 0, nS, st)); RET(L_driftr(h, 0, nS, st));
+  RET(prof_mark(h, "k_driftmu", st)); RET(L_driftmu(h, 0, nS, st));
+  RET(prof_mark(h, "k_drifte", st)); RET(L_drifte(h, 0, nS, st));
+  RET(prof_mark(h, "k_driftp", st)); RET(L_driftp(h, 0, nS, st));
+  RET(prof_mark(h, "k_driftr", st)); RET(L_driftr(h, 0, nS, st));
+  RET(prof_mark(h, "k_sumrc", st));
   RET(L_sumrc(h, 0, nS, 9, st));
+  RET(prof_mark(h, "k_epilogue", st));
   {
     SpecPack pk;
     make_pack(h, pk);
-    k_epilogue<<<dim3(nblk(h->P, 256), h->NPA * h->NE, nS), 256, 0, st>>>(h->dev, pk, 0);
+    k_epilogue<<<dim3(nblk(h->NR + h->nout, 128), h->NPA * h->NE, nS), 128, 0, st>>>(h->dev, pk, 0, h->d_outlist, h->nout);
     CKL();
     h->launches++;
   }
+  RET(prof_mark(h, "k_anisch", st));
   RET(L_anisch(h, 0, nS, st));
+  RET(prof_mark(h, "d2h_results", st));
   CK(cudaMemcpyAsync(h->h_res_all, h->d_res_all, (size_t)nS * RES_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   if (PPERT || PPART)
     CK(cudaMemcpyAsync(h->h_pp_all, h->d_pp_all, (size_t)nS * 2 * h->Pp * sizeof(double), cudaMemcpyDeviceToHost, st));
+  RET(prof_mark(h, "end", st));
   CK(cudaStreamSynchronize(st));
+  RET(prof_fold(h));
   double dtn = 1e300;
   for (int s = 0; s < nS; ++s) {
     Spec& sp = h->sp[s];
@@ -1088,6 +1157,26 @@ int rsg_ram_flux_d2h(rsg_ram* h, double* FLUX) {
 }
 
 long long rsg_ram_launch_count(rsg_ram* h) { return h ? h->launches : 0; }
+
+int rsg_ram_profile(rsg_ram* h, int on) {
+  if (!h) return fail(RSG_ERR_ARG, "null handle");
+  h->prof_on = on != 0;
+  h->prof_acc.clear();
+  h->prof_n = 0;
+  return RSG_OK;
+}
+int rsg_ram_profile_get(rsg_ram* h, int idx, char* name, int name_len, double* ms_total, long long* count) {
+  if (!h) return fail(RSG_ERR_ARG, "null handle");
+  if (idx < 0 || idx >= (int)h->prof_acc.size()) return RSG_ERR_ARG;
+  const auto& a = h->prof_acc[idx];
+  if (name && name_len > 0) {
+    std::strncpy(name, a.first.c_str(), name_len - 1);
+    name[name_len - 1] = 0;
+  }
+  if (ms_total) *ms_total = a.second.first;
+  if (count) *count = a.second.second;
+  return RSG_OK;
+}
 
 // device-side timing across the library's streams: begin() puts a start event in
 // front of every species stream, end() joins them all and returns the elapsed ms

@@ -380,66 +380,91 @@ __global__ void k_driftr_scan(const __grid_constant__ RamDev d, const __grid_con
 }
 
 // =============================================================================
-// DRIFTR  (src/ModRamDrift.f90:95-198): one thread per cell.
-// grid: x = tiles of 248 cells (8 warps x 31) of one plane, y = plane l*NE+k, z = species
+// DRIFTR  (src/ModRamDrift.f90:95-198): lines lie along the contiguous plane
+// index, so a thread owns one (MLT,R) position and walks KC energies of one
+// pitch angle; the flux through the cell's lower face comes from the neighbour
+// lane by warp shuffle (31 cells + 1 halo lane per warp).  Everything that does
+// not depend on K (plane coefficients, boundary flags, index math) is hoisted.
+// grid: x = tiles of 248 cells (8 warps x 31) of one plane, y = l*KG + kgroup, z = species
 // =============================================================================
 template <bool FAST>
-__global__ void __launch_bounds__(256) k_driftr(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0) {
+__global__ void __launch_bounds__(256) k_driftr(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0, int KC,
+                                                int KG) {
   const SpecDev& sp = pk.s[s0 + blockIdx.z];
   const int NR = d.NR, NT = d.NT, NE = d.NE, P = d.P, Pp = d.Pp;
-  const int plane = blockIdx.y;
+  const int l = blockIdx.y / KG, kg = blockIdx.y - l * KG;
+  const int k0 = kg * KC, k1 = min(NE, k0 + KC);
   const int lane = threadIdx.x & 31;
   const int p = (blockIdx.x * 8 + (threadIdx.x >> 5)) * 31 + lane - 1;   // 31 cells per warp + halo lane 0
-  double phi = 0.0, F0 = 0.0, cmax = 0.0;
-  int i = -1;
   const bool inplane = (p >= 0) && (p < P);
+  double cmax = 0.0;
+  int i = -1, j = 0;
+  double CRp = 0, gR = 0, t1 = 0, sB = 1, rl = 1, fn_NR = 0;
+  bool count = false;
   if (inplane) {
-    const int l = plane / NE, k = plane - l * NE;
-    const int j = p / NR;
+    j = p / NR;
     i = p - j * NR;
-    const int I = i + 1;
-    const int line = (k * d.NPA + l) * NT + j;
-    const int src = sp.last[line];
-    const bool inflow = (src == line);
-    const double c = FAST ? fma(sp.P4[k], d.fRb[(size_t)l * Pp + p], d.CR[p])
-                          : coef_r(d.CR[p], d.t1[(size_t)l * Pp + p], sp.P4[k], d.sB[p], d.RLZ[i] + 0.5 * d.MDR);
-    if (!d.outp[p]) cmax = fabs(c);
-    const double* F = sp.F + (size_t)plane * Pp + j * NR;  // F[i'] = F(I=i'+1) of this line
-    F0 = F[i];
-    if (I == 1) {
-      phi = c * (inflow ? F[1] : 0.0);            // FBND(1) = F(2) | 0   (:155,:159)
-    } else if (I == NR && !inflow) {
-      phi = c * F0;                               // FBND(NR) = F(NR)     (:156)
-    } else {
-      double g1 = 0.0, g2 = 0.0;                  // F(NR+1), F(NR+2)
-      if (I + 2 > NR) {
-        if (inflow) {
-          if (!d.outp[j * NR + NR - 1]) {
-            const double fg = sp.FGEOS[((size_t)l * NE + k) * NT + j];
-            const double fn = R3(d.FNHS, NR, j + 1, l + 1);
-            g1 = fg * d.CONF1 * fn;
-            g2 = fg * d.CONF2 * fn;
+    CRp = d.CR[p];
+    if (FAST) gR = d.fRb[(size_t)l * Pp + p];
+    else { t1 = d.t1[(size_t)l * Pp + p]; sB = d.sB[p]; rl = d.RLZ[i] + 0.5 * d.MDR; }
+    count = !d.outp[p];
+  }
+  const int I = i + 1;
+  const bool edge = inplane && (i == 0 || i >= NR - 2);     // needs the line's boundary state
+  bool outNR = false;
+  if (edge) {
+    outNR = d.outp[j * NR + NR - 1];
+    fn_NR = R3(d.FNHS, NR, j + 1, l + 1);
+  }
+  const double beta = d.BetaLim;
+  const double* F = sp.F + ((size_t)l * NE + k0) * Pp + p;
+  double* Fo = sp.Fo + ((size_t)l * NE + k0) * Pp + p;
+  for (int k = k0; k < k1; ++k, F += Pp, Fo += Pp) {
+    double phi = 0.0, F0 = 0.0;
+    if (inplane) {
+      const double c = FAST ? fma(sp.P4[k], gR, CRp) : coef_r(CRp, t1, sp.P4[k], sB, rl);
+      if (count) cmax = dmax(cmax, fabs(c));
+      F0 = F[0];
+      if (!edge) {
+        phi = c * (FAST ? limited_flux_fast(F[-1], F0, F[1], F[2], c < 0.0, fabs(c), beta) : limited_flux(F[-1], F0, F[1], F[2], c, c, beta));
+      } else {
+        const int line = (k * d.NPA + l) * NT + j;
+        const int src = sp.last[line];
+        const bool inflow = (src == line);
+        if (I == 1) {
+          phi = c * (inflow ? F[1] : 0.0);            // FBND(1) = F(2) | 0   (:155,:159)
+        } else if (I == NR && !inflow) {
+          phi = c * F0;                               // FBND(NR) = F(NR)     (:156)
+        } else {
+          double g1 = 0.0, g2 = 0.0;                  // F(NR+1), F(NR+2)
+          if (inflow) {
+            if (!outNR) {
+              const double fg = sp.FGEOS[((size_t)l * NE + k) * NT + j];
+              g1 = fg * d.CONF1 * fn_NR;
+              g2 = fg * d.CONF2 * fn_NR;
+            }
+          } else if (src >= 0) {
+            // ghost cells left over by the most recent inflow line (:112-113,:154-168)
+            const int js = src % NT, ls = (src / NT) % d.NPA, ks = src / (NT * d.NPA);
+            if (!d.outp[js * NR + NR - 1])
+              g1 = sp.FGEOS[((size_t)ls * NE + ks) * NT + js] * d.CONF1 * R3(d.FNHS, NR, js + 1, ls + 1);
           }
-        } else if (src >= 0) {
-          const int js = src % NT, ls = (src / NT) % d.NPA, ks = src / (NT * d.NPA);
-          if (!d.outp[js * NR + NR - 1])
-            g1 = sp.FGEOS[((size_t)ls * NE + ks) * NT + js] * d.CONF1 * R3(d.FNHS, NR, js + 1, ls + 1);
+          const double Fm1 = F[-1];
+          const double Fp1 = (I + 1 <= NR) ? F[1] : g1;
+          const double Fp2 = (I + 2 <= NR) ? F[2] : ((I + 2 == NR + 1) ? g1 : g2);
+          phi = c * (FAST ? limited_flux_fast(Fm1, F0, Fp1, Fp2, c < 0.0, fabs(c), beta) : limited_flux(Fm1, F0, Fp1, Fp2, c, c, beta));
         }
       }
-      const double Fm1 = F[i - 1];
-      const double Fp1 = (I + 1 <= NR) ? F[i + 1] : g1;
-      const double Fp2 = (I + 2 <= NR) ? F[i + 2] : ((I + 2 == NR + 1) ? g1 : g2);
-      phi = c * (FAST ? limited_flux_fast(Fm1, F0, Fp1, Fp2, c < 0.0, fabs(c), d.BetaLim) : limited_flux(Fm1, F0, Fp1, Fp2, c, c, d.BetaLim));
     }
-  }
-  const double phiPrev = __shfl_up_sync(0xffffffffu, phi, 1);
-  if (inplane && lane >= 1) {
-    double fn = F0;
-    if (i >= 1) {
-      fn = F0 - phi + phiPrev;                      // :186
-      if (fn < 0.0) fn = 1E-15;
+    const double phiPrev = __shfl_up_sync(0xffffffffu, phi, 1);
+    if (inplane && lane >= 1) {
+      double fn = F0;
+      if (i >= 1) {
+        fn = F0 - phi + phiPrev;                      // :186
+        if (fn < 0.0) fn = 1E-15;
+      }
+      Fo[0] = fn;
     }
-    sp.Fo[(size_t)plane * Pp + p] = fn;
   }
   warp_min_to(sp.dt + 0, sp.aRP / dmax(cmax, 1E-10));
 }
@@ -1025,24 +1050,25 @@ __global__ void k_f2_to_host(RamDev d, double* __restrict__ stage, const double*
   const size_t plane = blockIdx.y;
   if (p < d.P) stage[(plane * d.P + p) * d.nS + s] = Fs[plane * d.Pp + p];
 }
-// F2(:,:,NT,:,:) = F2(:,:,1,:,:), then F2 = 1e-31 where outsideMGNP == 1.  The
-// J=1 thread owns both its own cell and the J=NT copy (no read/write race).
-// grid: x = tiles of p, y = plane, z = species
-__global__ void __launch_bounds__(256) k_epilogue(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0) {
+// F2(:,:,NT,:,:) = F2(:,:,1,:,:), then F2 = 1e-31 where outsideMGNP == 1
+// (src/ModRamRun.f90:186-201).  Only the J=1 row and the flagged columns are
+// touched: thread q < NR handles the seam cell I=q+1 (it owns both its own cell
+// and the J=NT copy, so there is no read/write race); thread q >= NR handles
+// the (q-NR)-th flagged (I,J) column with 2 <= J <= NT-1.
+// grid: x = tiles of q, y = plane, z = species
+__global__ void __launch_bounds__(128) k_epilogue(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0,
+                                                  const int* __restrict__ outlist, int nout) {
   const SpecDev& sp = pk.s[s0 + blockIdx.z];
   double* Fs = sp.F + (size_t)blockIdx.y * d.Pp;
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= d.P) return;
-  const int j = p / d.NR;
-  if (j == d.NT - 1) return;
-  const bool out = d.outp[p];
-  if (j != 0 && !out) return;              // nothing to do for the bulk of the cells
-  const double v = Fs[p];
-  if (j == 0) {
-    const int pN = p + (d.NT - 1) * d.NR;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < d.NR) {
+    const int pN = q + (d.NT - 1) * d.NR;
+    const double v = Fs[q];
     Fs[pN] = d.outp[pN] ? 1.e-31 : v;
+    if (d.outp[q]) Fs[q] = 1.e-31;
+  } else if (q - d.NR < nout) {
+    Fs[outlist[q - d.NR]] = 1.e-31;
   }
-  if (out) Fs[p] = 1.e-31;
 }
 // FLUX = F2/FFACTOR/FNHS for I>=2,K>=2,L>=2,J<=NT-1 (src/ModRamRun.f90:210-221), host layout
 __global__ void k_flux_to_host(RamDev d, SpecDev sp, double* __restrict__ stage) {

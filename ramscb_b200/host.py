@@ -75,6 +75,8 @@ def lib():
     L.rsg_ram_launch_count.restype = ll
     L.rsg_ram_timer_begin.argtypes = [vp]
     L.rsg_ram_timer_end.argtypes = [vp, _dp]
+    L.rsg_ram_profile.argtypes = [vp, i]
+    L.rsg_ram_profile_get.argtypes = [vp, i, C.c_char_p, i, _dp, C.POINTER(ll)]
     L.rsg_host_register.argtypes = [vp, ll]
     L.rsg_host_unregister.argtypes = [vp]
     _lib = L
@@ -252,6 +254,22 @@ class RamGpu:
 
     def launch_count(self):
         return self.L.rsg_ram_launch_count(self.h)
+
+    def profile(self, on=True):
+        _ck(self.L.rsg_ram_profile(self.h, 1 if on else 0))
+
+    def profile_get(self):
+        """{stage: (total_ms, count)} accumulated by rsg_ram_run since profile(True)."""
+        out = {}
+        idx = 0
+        while True:
+            name = C.create_string_buffer(64)
+            ms, cnt = C.c_double(), C.c_longlong()
+            if self.L.rsg_ram_profile_get(self.h, idx, name, 64, C.byref(ms), C.byref(cnt)) != 0:
+                break
+            out[name.value.decode()] = (ms.value, cnt.value)
+            idx += 1
+        return out
 
     def timer_begin(self):
         _ck(self.L.rsg_ram_timer_begin(self.h))
