@@ -168,6 +168,68 @@ int rsg_ram_profile_get(rsg_ram* h, int idx, char* name, int name_len, double* m
 int rsg_host_register(void* p, long long bytes);
 int rsg_host_unregister(void* p);
 
+/* ===========================================================================
+ * SCB: 3-D force-balance Euler-potential solve (second hot path)
+ *
+ * Replaces the bodies of the argument-less module procedures of ModScbCompute,
+ * ModScbEquation and ModScbEuler, which work on the ModScbVariables globals
+ * (src/ModScbVariables.f90:10-96, allocated src/ModScbInit.f90:22-119).  All 3-D
+ * host arrays are Fortran (nthe,npsi,nzeta+1) ["+1" arrays: x,y,z,alfa,psi,bf,
+ * bsq,pper,ppar,sigma] or (nthe,npsi,nzeta) [everything else].  The device keeps
+ * a mirror of every array; rsg_scb_get_field/set_field move any of them by its
+ * reference name ("jacobian", "vecd", "Bx", "GradRhoSq", ...), so the Fortran
+ * host only downloads what it reads.
+ * ========================================================================= */
+typedef struct rsg_scb rsg_scb;
+
+/* SOR sweep ordering */
+enum rsg_sor_order {
+  RSG_SOR_LEX = 0,    /* the reference's lexicographic Gauss-Seidel order, run as a skewed
+                         wavefront: iterates, iteration counts and residuals bit-identical */
+  RSG_SOR_COLOR4 = 1  /* 4-colour ordering (the 9-point stencil has corner couplings, so
+                         red-black is not enough): same fixed point, far more parallel   */
+};
+
+const char* rsg_scb_last_error(void);
+int rsg_scb_create(rsg_scb** out, int nthe, int npsi, int nzeta, int device); /* scb_allocate, src/ModScbInit.f90:13-155 */
+int rsg_scb_destroy(rsg_scb* h);
+/* thetaVal(nthe) rhoVal(npsi) zetaVal(nzeta) (src/ModScbInit.f90:278-290), f(npsi), fzet(nzeta+1) (src/ModScbIO.f90:179-205) */
+int rsg_scb_set_grid(rsg_scb* h, const double* thetaVal, const double* rhoVal, const double* zetaVal, const double* f,
+                     const double* fzet);
+int rsg_scb_set_geometry(rsg_scb* h, const double* x, const double* y, const double* z);
+/* outputs of `pressure` (src/ModScbRun.f90:753-1199) that the hot path reads; for isotropy = 1
+ * only dPdAlpha, dPdPsi are required */
+int rsg_scb_set_pressure(rsg_scb* h, int isotropy, const double* pper, const double* ppar, const double* sigma,
+                         const double* dPPerdTheta, const double* dPPerdRho, const double* dPPerdZeta, const double* dBsqdTheta,
+                         const double* dBsqdRho, const double* dBsqdZeta, const double* dPPerdPsi, const double* dPPerdAlpha,
+                         const double* dBsqdPsi, const double* dBsqdAlpha, const double* dPdAlpha, const double* dPdPsi);
+int rsg_scb_set_field(rsg_scb* h, const char* name, const double* src);
+int rsg_scb_get_field(rsg_scb* h, const char* name, double* dst);
+int rsg_scb_field_size(rsg_scb* h, const char* name, long long* n);
+
+int rsg_scb_bandjacob(rsg_scb* h, int* sorfail); /* computeBandJacob, src/ModScbCompute.f90:412-496 */
+int rsg_scb_metrica(rsg_scb* h);                 /* src/ModScbEquation.f90:18-280  */
+int rsg_scb_metric(rsg_scb* h);                  /* :283-540 */
+int rsg_scb_newk(rsg_scb* h);                    /* :546-604 (Picard) */
+int rsg_scb_newj(rsg_scb* h);                    /* :607-665 (Picard) */
+/* iterateAlpha / iteratePsi (src/ModScbEuler.f90:160-299 / :469-612) incl. the extap /
+ * theta-end / periodic-wrap post-processing.  Outputs mirror the module scalars nisave,
+ * sumb, sumdb, diffmx and the logical SORFail; ni (may be NULL) receives the per-surface
+ * iteration counts ni(1:npsi) / ni(1:nzeta). */
+int rsg_scb_iterate_alpha(rsg_scb* h, double InConAlpha, int nimax, int theChange, int psiChange, int ordering, int* nisave,
+                          double* sumb, double* sumdb, double* diffmx, int* sorfail, int* ni);
+int rsg_scb_iterate_psi(rsg_scb* h, double InConPsi, int nimax, int theChange, int psiChange, int ordering, int* nisave,
+                        double* sumb, double* sumdb, double* diffmx, int* sorfail, int* ni);
+/* Compute_convergence (src/ModScbCompute.f90:499-754): fills jGradRho/Zeta/Theta, Jx..Jz,
+ * GradPx..GradPz, jCrossB, GradP on the device and returns the three norms */
+int rsg_scb_convergence(rsg_scb* h, double* normDiff, double* normJxB, double* normGradP, int* sorfail);
+/* GSL_Derivs with the Steffen spline (src/ModRamGSL.f90:794-869) of a host (nthe,npsi,nzeta) field;
+ * any output may be NULL */
+int rsg_scb_derivs(rsg_scb* h, const double* f, double* dfdTheta, double* dfdRho, double* dfdZeta);
+/* device time (CUDA events on the launching stream) of the kernels of the last call */
+double rsg_scb_last_ms(rsg_scb* h);
+long long rsg_scb_launch_count(rsg_scb* h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -146,3 +146,119 @@ class RamOracle:
             self.lib.orc_destroy(self.h)
         except Exception:
             pass
+
+
+# =============================================================================
+# SCB oracle (oracle/scb_oracle.cpp)
+# =============================================================================
+_scb = None
+
+SCB_OUT3 = ("derivXTheta", "derivXRho", "derivXZeta", "derivYTheta", "derivYRho", "derivYZeta", "derivZTheta", "derivZRho",
+            "derivZZeta", "jacobian", "gradRhoX", "gradRhoY", "gradRhoZ", "gradZetaX", "gradZetaY", "gradZetaZ", "gradThetaX",
+            "gradThetaY", "gradThetaZ", "GradRhoSq", "GradThetaSq", "GradZetaSq", "GradRhoGradTheta", "GradRhoGradZeta",
+            "GradThetaGradZeta", "Bx", "By", "Bz", "vecd", "vec1", "vec2", "vec3", "vec4", "vec6", "vec7", "vec8", "vec9", "vecx",
+            "vecr", "jGradRho", "jGradZeta", "jGradTheta", "Jx", "Jy", "Jz", "GradPx", "GradPy", "GradPz", "jCrossB", "GradP")
+SCB_IN3 = ("dPPerdTheta", "dPPerdRho", "dPPerdZeta", "dBsqdTheta", "dBsqdRho", "dBsqdZeta", "dPPerdPsi", "dPPerdAlpha",
+           "dBsqdPsi", "dBsqdAlpha", "dPdAlpha", "dPdPsi")
+SCB_IN3P = ("x", "y", "z", "alfa", "psi", "pper", "ppar", "sigma")
+
+
+def scb_lib():
+    global _scb
+    if _scb is None:
+        lib = _load("libscb_oracle.so")
+        lib.scbo_create.restype = C.c_void_p
+        lib.scbo_create.argtypes = [C.c_int] * 3
+        lib.scbo_destroy.argtypes = [C.c_void_p]
+        lib.scbo_set_array.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
+        lib.scbo_set_scalar.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+        lib.scbo_set_int.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        lib.scbo_get_scalar.argtypes = [C.c_void_p, C.c_char_p]
+        lib.scbo_get_scalar.restype = C.c_double
+        for f in ("bandjacob", "convergence"):
+            getattr(lib, "scbo_" + f).argtypes = [C.c_void_p]
+            getattr(lib, "scbo_" + f).restype = C.c_int
+        for f in ("metrica", "metric", "newk", "newj"):
+            getattr(lib, "scbo_" + f).argtypes = [C.c_void_p]
+            getattr(lib, "scbo_" + f).restype = None
+        for f in ("iterate_alpha", "iterate_psi"):
+            getattr(lib, "scbo_" + f).argtypes = [C.c_void_p, C.c_void_p]
+            getattr(lib, "scbo_" + f).restype = C.c_int
+        lib.scbo_derivs3d.argtypes = [C.c_void_p] * 5
+        lib.scbo_steffen.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        _scb = lib
+    return _scb
+
+
+class ScbOracle:
+    """SCB state in the reference's layouts + the restated routines."""
+
+    def __init__(self, inp):
+        self.lib = scb_lib()
+        self.inp = inp
+        nthe, npsi, nzeta = inp.nthe, inp.npsi, inp.nzeta
+        self.h = self.lib.scbo_create(nthe, npsi, nzeta)
+        self.arr = {}
+        for n in ("thetaVal", "rhoVal", "zetaVal", "psiVal", "f", "alphaVal", "fzet"):
+            self._set(n, np.ascontiguousarray(getattr(inp, n), dtype=np.float64).copy())
+        for n in SCB_IN3P:
+            self._set(n, np.asfortranarray(getattr(inp, n)).copy(order="F"))
+        for n in SCB_IN3:
+            self._set(n, np.asfortranarray(getattr(inp, n)).copy(order="F"))
+        for n in ("bsq", "bf"):
+            self._set(n, _f((nthe, npsi, nzeta + 1)))
+        for n in SCB_OUT3:
+            self._set(n, _f((nthe, npsi, nzeta)))
+        self.set_int("isotropy", inp.isotropy)
+
+    def _set(self, name, a):
+        self.arr[name] = a
+        self.lib.scbo_set_array(self.h, name.encode(), a.ctypes.data)
+
+    def set_scalar(self, name, v):
+        self.lib.scbo_set_scalar(self.h, name.encode(), float(v))
+
+    def set_int(self, name, v):
+        self.lib.scbo_set_int(self.h, name.encode(), int(v))
+
+    def get(self, name):
+        return self.lib.scbo_get_scalar(self.h, name.encode())
+
+    def __getattr__(self, name):
+        arr = self.__dict__.get("arr", {})
+        if name in arr:
+            return arr[name]
+        raise AttributeError(name)
+
+    def bandjacob(self):
+        return self.lib.scbo_bandjacob(self.h)
+
+    def metrica(self): self.lib.scbo_metrica(self.h)
+    def metric(self): self.lib.scbo_metric(self.h)
+    def newk(self): self.lib.scbo_newk(self.h)
+    def newj(self): self.lib.scbo_newj(self.h)
+
+    def iterate_alpha(self):
+        ni = np.zeros(self.inp.npsi, dtype=np.int32)
+        fail = self.lib.scbo_iterate_alpha(self.h, ni.ctypes.data)
+        return fail, ni
+
+    def iterate_psi(self):
+        ni = np.zeros(self.inp.nzeta, dtype=np.int32)
+        fail = self.lib.scbo_iterate_psi(self.h, ni.ctypes.data)
+        return fail, ni
+
+    def convergence(self):
+        return self.lib.scbo_convergence(self.h)
+
+    def derivs3d(self, f3):
+        f3 = np.asfortranarray(f3, dtype=np.float64)
+        out = [_f(f3.shape) for _ in range(3)]
+        self.lib.scbo_derivs3d(self.h, f3.ctypes.data, *[o.ctypes.data for o in out])
+        return out
+
+    def __del__(self):
+        try:
+            self.lib.scbo_destroy(self.h)
+        except Exception:
+            pass

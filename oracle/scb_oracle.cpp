@@ -1,0 +1,698 @@
+// =============================================================================
+// TEST INFRASTRUCTURE -- NOT PRODUCT CODE.
+//
+// CPU oracle for the SCB hot path: a restatement in plain C++ (FP64, no
+// fast-math, no FMA contraction, reference loop order and operation order,
+// Fortran column-major (theta,psi,zeta) layout) of
+//
+//   computeBandJacob / Compute_convergence   src/ModScbCompute.f90:412-754
+//   metrica / metric / newk / newj           src/ModScbEquation.f90:18-665
+//   iterateAlpha / iteratePsi (+extap)       src/ModScbEuler.f90:160-299,469-612
+//                                            src/ModScbFunctions.f90:57-76
+//   GSL_Derivs (3-D driver)                  src/ModRamGSL.f90:794-869,
+//                                            src/RamGSL.c:228-291
+//
+// Only tests/, __graft_entry__.smoke() and bench.py's CPU arm may load this.
+//
+// PARITY PINNING: "parity unpinned".  The reference cannot be built here (no
+// Fortran compiler), and the Steffen spline itself lives in GNU GSL (system
+// package, libgsl 2.5/2.6 per the reference's Dockerfile / schemeSetup.sh; not
+// vendored): steffen_derivs() below restates GSL's interpolation/steffen.c
+// (Steffen 1990, A&A 239, 443) from its published algorithm.  The reference's
+// only tests touching this path are end-to-end (test3/test4 pressure.ref,
+// hI.ref) and need missing input blobs.  Checks that do exist: manufactured
+// solutions for the SOR, exactness of the derivative on linear data and
+// monotonicity preservation, dipole force balance (J x B ~ 0 for p = 0).
+// =============================================================================
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace {
+
+struct Scb {
+  int nthe, npsi, nzeta;
+  std::map<std::string, double*> d;
+  std::map<std::string, double> s;
+  std::map<std::string, int> iv;
+  double* D(const char* n) {
+    auto it = d.find(n);
+    if (it == d.end() || !it->second) { std::fprintf(stderr, "scb oracle: array %s not set\n", n); std::abort(); }
+    return it->second;
+  }
+  double S(const char* n) {
+    auto it = s.find(n);
+    if (it == s.end()) { std::fprintf(stderr, "scb oracle: scalar %s not set\n", n); std::abort(); }
+    return it->second;
+  }
+  int I(const char* n) {
+    auto it = iv.find(n);
+    if (it == iv.end()) { std::fprintf(stderr, "scb oracle: int %s not set\n", n); std::abort(); }
+    return it->second;
+  }
+};
+
+// 1-based column-major (nthe, npsi, *) accessor
+#define X3(a, i, j, k) (a)[(size_t)((i)-1) + (size_t)nthe * ((size_t)((j)-1) + (size_t)npsi * (size_t)((k)-1))]
+#define DIMS const int nthe = o->nthe, npsi = o->npsi, nzeta = o->nzeta; (void)nthe; (void)npsi; (void)nzeta;
+
+inline double sq(double x) { return x * x; }
+const double PI_D = 3.141592653589793238462643383279502884197;
+
+// ---- GSL steffen spline, derivative at the nodes -----------------------------
+// gsl interpolation/steffen.c (steffen_init + steffen_eval_deriv) as driven by
+// interpolation_derivs_c (src/RamGSL.c:255-277): node i < n-1 lies in interval
+// i with delx = 0 (=> y'_i); the last node is evaluated through the cubic of
+// interval n-2 with delx = h; exact zeros are nudged to 1e-31 (:276).
+inline double steffen_copysign(double x, double y) {
+  if ((x < 0 && y > 0) || (x > 0 && y < 0)) return -x;
+  return x;
+}
+void steffen_derivs(int n, const double* xa, const double* ya, double* dx, std::vector<double>& yp) {
+  yp.resize(n);
+  const double h0 = xa[1] - xa[0];
+  const double s0 = (ya[1] - ya[0]) / h0;
+  yp[0] = s0;
+  for (int i = 1; i < n - 1; ++i) {
+    const double hi = xa[i + 1] - xa[i];
+    const double him1 = xa[i] - xa[i - 1];
+    const double si = (ya[i + 1] - ya[i]) / hi;
+    const double sim1 = (ya[i] - ya[i - 1]) / him1;
+    const double pi = (sim1 * hi + si * him1) / (him1 + hi);
+    const double m1 = std::fabs(si) < 0.5 * std::fabs(pi) ? std::fabs(si) : 0.5 * std::fabs(pi);
+    const double m2 = std::fabs(sim1) < m1 ? std::fabs(sim1) : m1;
+    yp[i] = (steffen_copysign(1.0, sim1) + steffen_copysign(1.0, si)) * m2;
+  }
+  yp[n - 1] = (ya[n - 1] - ya[n - 2]) / (xa[n - 1] - xa[n - 2]);
+  for (int i = 0; i < n - 1; ++i) dx[i] = yp[i];  // c + 0*(...) with delx = 0
+  {
+    const int i = n - 2;
+    const double hi = xa[i + 1] - xa[i];
+    const double si = (ya[i + 1] - ya[i]) / hi;
+    const double a = (yp[i] + yp[i + 1] - 2 * si) / hi / hi;
+    const double b = (3 * si - 2 * yp[i] - yp[i + 1]) / hi;
+    const double c = yp[i];
+    const double delx = xa[n - 1] - xa[i];
+    dx[n - 1] = c + delx * (2.0 * b + delx * 3.0 * a);
+  }
+  for (int i = 0; i < n; ++i)
+    if (dx[i] == 0.0) dx[i] = dx[i] + 1e-31;
+}
+
+// Interpolation_3D_Derivs, src/ModRamGSL.f90:794-869; f, dT, dR, dZ are
+// (nthe,npsi,nzeta) views whose k-stride is that of the (possibly larger) parent
+void derivs3d(Scb* o, const double* f, double* dT, double* dR, double* dZ) {
+  DIMS
+  const double *tv = o->D("thetaVal"), *rv = o->D("rhoVal"), *zv = o->D("zetaVal");
+#pragma omp parallel
+  {
+    std::vector<double> ya(std::max(nthe, std::max(npsi, nzeta))), dd(ya.size()), yp;
+#pragma omp for collapse(2)
+    for (int i = 1; i <= nthe; ++i)
+      for (int j = 1; j <= npsi; ++j) {
+        for (int k = 1; k <= nzeta; ++k) ya[k - 1] = X3(f, i, j, k);
+        steffen_derivs(nzeta, zv, ya.data(), dd.data(), yp);
+        for (int k = 1; k <= nzeta; ++k) X3(dZ, i, j, k) = dd[k - 1];
+      }
+#pragma omp for collapse(2)
+    for (int i = 1; i <= nthe; ++i)
+      for (int k = 1; k <= nzeta; ++k) {
+        for (int j = 1; j <= npsi; ++j) ya[j - 1] = X3(f, i, j, k);
+        steffen_derivs(npsi, rv, ya.data(), dd.data(), yp);
+        for (int j = 1; j <= npsi; ++j) X3(dR, i, j, k) = dd[j - 1];
+      }
+#pragma omp for collapse(2)
+    for (int j = 1; j <= npsi; ++j)
+      for (int k = 1; k <= nzeta; ++k) {
+        for (int i = 1; i <= nthe; ++i) ya[i - 1] = X3(f, i, j, k);
+        steffen_derivs(nthe, tv, ya.data(), dd.data(), yp);
+        for (int i = 1; i <= nthe; ++i) X3(dT, i, j, k) = dd[i - 1];
+      }
+  }
+}
+
+// ---- computeBandJacob, src/ModScbCompute.f90:412-496 --------------------------------
+int computeBandJacob(Scb* o) {
+  DIMS
+  const double *x = o->D("x"), *y = o->D("y"), *z = o->D("z"), *f = o->D("f"), *fzet = o->D("fzet");
+  double *dXT = o->D("derivXTheta"), *dXR = o->D("derivXRho"), *dXZ = o->D("derivXZeta");
+  double *dYT = o->D("derivYTheta"), *dYR = o->D("derivYRho"), *dYZ = o->D("derivYZeta");
+  double *dZT = o->D("derivZTheta"), *dZR = o->D("derivZRho"), *dZZ = o->D("derivZZeta");
+  double *jac = o->D("jacobian");
+  double *gRX = o->D("gradRhoX"), *gRY = o->D("gradRhoY"), *gRZ = o->D("gradRhoZ");
+  double *gZX = o->D("gradZetaX"), *gZY = o->D("gradZetaY"), *gZZ = o->D("gradZetaZ");
+  double *gTX = o->D("gradThetaX"), *gTY = o->D("gradThetaY"), *gTZ = o->D("gradThetaZ");
+  double *GRS = o->D("GradRhoSq"), *GTS = o->D("GradThetaSq"), *GZS = o->D("GradZetaSq");
+  double *GRGT = o->D("GradRhoGradTheta"), *GRGZ = o->D("GradRhoGradZeta"), *GTGZ = o->D("GradThetaGradZeta");
+  double *Bx = o->D("Bx"), *By = o->D("By"), *Bz = o->D("Bz"), *bsq = o->D("bsq"), *bf = o->D("bf");
+  derivs3d(o, x, dXT, dXR, dXZ);
+  derivs3d(o, y, dYT, dYR, dYZ);
+  derivs3d(o, z, dZT, dZR, dZZ);
+  const size_t n = (size_t)nthe * npsi * nzeta;
+  for (size_t q = 0; q < n; ++q) {
+    jac[q] = dXR[q] * (dYZ[q] * dZT[q] - dYT[q] * dZZ[q]) + dXZ[q] * (dYT[q] * dZR[q] - dYR[q] * dZT[q]) +
+             dXT[q] * (dYR[q] * dZZ[q] - dYZ[q] * dZR[q]);
+    gRX[q] = (dYZ[q] * dZT[q] - dYT[q] * dZZ[q]) / jac[q];
+    gRY[q] = (dZZ[q] * dXT[q] - dZT[q] * dXZ[q]) / jac[q];
+    gRZ[q] = (dXZ[q] * dYT[q] - dXT[q] * dYZ[q]) / jac[q];
+    gZX[q] = (dYT[q] * dZR[q] - dYR[q] * dZT[q]) / jac[q];
+    gZY[q] = (dZT[q] * dXR[q] - dZR[q] * dXT[q]) / jac[q];
+    gZZ[q] = (dXT[q] * dYR[q] - dXR[q] * dYT[q]) / jac[q];
+    gTX[q] = (dYR[q] * dZZ[q] - dYZ[q] * dZR[q]) / jac[q];
+    gTY[q] = (dZR[q] * dXZ[q] - dZZ[q] * dXR[q]) / jac[q];
+    gTZ[q] = (dXR[q] * dYZ[q] - dXZ[q] * dYR[q]) / jac[q];
+    GRS[q] = gRX[q] * gRX[q] + gRY[q] * gRY[q] + gRZ[q] * gRZ[q];
+    GRGZ[q] = gRX[q] * gZX[q] + gRY[q] * gZY[q] + gRZ[q] * gZZ[q];
+    GRGT[q] = gRX[q] * gTX[q] + gRY[q] * gTY[q] + gRZ[q] * gTZ[q];
+    GTS[q] = gTX[q] * gTX[q] + gTY[q] * gTY[q] + gTZ[q] * gTZ[q];
+    GTGZ[q] = gTX[q] * gZX[q] + gTY[q] * gZY[q] + gTZ[q] * gZZ[q];
+    GZS[q] = gZX[q] * gZX[q] + gZY[q] * gZY[q] + gZZ[q] * gZZ[q];
+  }
+  int fail = 0;
+  for (int k = 2; k <= nzeta && !fail; ++k)
+    for (int j = 1; j <= npsi && !fail; ++j)
+      for (int i = 1; i <= nthe; ++i) {
+        X3(Bx, i, j, k) = (f[j - 1] * fzet[k - 1] * X3(dXT, i, j, k) / X3(jac, i, j, k));
+        X3(By, i, j, k) = (f[j - 1] * fzet[k - 1] * X3(dYT, i, j, k) / X3(jac, i, j, k));
+        X3(Bz, i, j, k) = (f[j - 1] * fzet[k - 1] * X3(dZT, i, j, k) / X3(jac, i, j, k));
+        X3(bsq, i, j, k) = (X3(GRS, i, j, k) * X3(GZS, i, j, k) - sq(X3(GRGZ, i, j, k))) * sq(f[j - 1] * fzet[k - 1]);
+        X3(bf, i, j, k) = std::sqrt(X3(bsq, i, j, k));
+        if (std::isnan(X3(bf, i, j, k))) { fail = 1; break; }
+      }
+  if (fail) return 1;
+  for (int j = 1; j <= npsi; ++j)
+    for (int i = 1; i <= nthe; ++i) {
+      X3(Bx, i, j, 1) = X3(Bx, i, j, nzeta);
+      X3(By, i, j, 1) = X3(By, i, j, nzeta);
+      X3(Bz, i, j, 1) = X3(Bz, i, j, nzeta);
+      X3(bf, i, j, 1) = X3(bf, i, j, nzeta);
+      X3(bsq, i, j, 1) = X3(bsq, i, j, nzeta);
+    }
+  return 0;
+}
+
+// ---- one stencil position of metrica / metric: Jacobian, contravariant gradients,
+// their squares and dot products (src/ModScbEquation.f90:154-250 / :404-510)
+struct Pos {
+  double aj, grs, gps, gts, grgp, gpgt, gtgr;
+};
+inline Pos geom(double xt, double yt, double zt, double xp, double yp, double zp, double xr, double yr, double zr) {
+  Pos g;
+  g.aj = xr * (yp * zt - yt * zp) + xp * (yt * zr - yr * zt) + xt * (yr * zp - yp * zr);
+  const double grx = (yp * zt - yt * zp) / g.aj, gry = (zp * xt - zt * xp) / g.aj, grz = (xp * yt - xt * yp) / g.aj;
+  const double gpx = (yt * zr - yr * zt) / g.aj, gpy = (zt * xr - zr * xt) / g.aj, gpz = (xt * yr - xr * yt) / g.aj;
+  const double gtx = (yr * zp - yp * zr) / g.aj, gty = (zr * xp - zp * xr) / g.aj, gtz = (xr * yp - xp * yr) / g.aj;
+  g.grs = (grx * grx + gry * gry + grz * grz);
+  g.gps = (gpx * gpx + gpy * gpy + gpz * gpz);
+  g.gts = (gtx * gtx + gty * gty + gtz * gtz);
+  g.grgp = (gpx * grx + gpy * gry + gpz * grz);
+  g.gpgt = (gpx * gtx + gpy * gty + gpz * gtz);
+  g.gtgr = (gtx * grx + gty * gry + gtz * grz);
+  return g;
+}
+
+struct Spacing {
+  double rdr, rdt, rdp, rdrsq, rdtsq, rdpsq, rdr2, rdt2, rdp2, rdr4, rdt4, rdp4, rdpdt4, rdtdr4, dr, dt, dpPrime;
+};
+Spacing spacing(Scb* o) {  // src/ModScbInit.f90:131-148
+  DIMS
+  Spacing s;
+  s.dr = 1.0 / (double)(npsi - 1);
+  s.dt = PI_D / (double)(nthe - 1);
+  s.dpPrime = 2 * PI_D / (double)(nzeta - 1);
+  s.rdr = 1.0 / s.dr; s.rdt = 1.0 / s.dt; s.rdp = 1.0 / s.dpPrime;
+  s.rdrsq = s.rdr * s.rdr; s.rdtsq = s.rdt * s.rdt; s.rdpsq = s.rdp * s.rdp;
+  s.rdr2 = 0.5 * s.rdr; s.rdt2 = 0.5 * s.rdt; s.rdp2 = 0.5 * s.rdp;
+  s.rdr4 = 0.25 * s.rdr; s.rdt4 = 0.25 * s.rdt; s.rdp4 = 0.25 * s.rdp;
+  s.rdpdt4 = 0.25 * s.rdp * s.rdt;
+  s.rdtdr4 = 0.25 * s.rdt * s.rdr;
+  return s;
+}
+
+void zero_vecs(Scb* o) {
+  DIMS
+  const size_t n = (size_t)nthe * npsi * nzeta;
+  for (const char* nm : {"vecd", "vec1", "vec2", "vec3", "vec4", "vec6", "vec7", "vec8", "vec9"}) std::memset(o->D(nm), 0, n * sizeof(double));
+}
+
+// ---- metrica, src/ModScbEquation.f90:18-280 (alpha equation, (theta,zeta) stencil) ----
+void metrica(Scb* o) {
+  DIMS
+  const Spacing s = spacing(o);
+  const double *x = o->D("x"), *y = o->D("y"), *z = o->D("z");
+  double *vecd = o->D("vecd"), *vec1 = o->D("vec1"), *vec2 = o->D("vec2"), *vec3 = o->D("vec3"), *vec4 = o->D("vec4"),
+         *vec6 = o->D("vec6"), *vec7 = o->D("vec7"), *vec8 = o->D("vec8"), *vec9 = o->D("vec9");
+  zero_vecs(o);
+#define DT_A(a) ((X3(a, i + 1, j, k) - X3(a, i, j, k)) * s.rdt)
+#define DT_B(a) ((X3(a, i + 1, j, k + 1) + X3(a, i + 1, j, k) - X3(a, i - 1, j, k + 1) - X3(a, i - 1, j, k)) * s.rdt4)
+#define DT_C(a) ((X3(a, i, j, k) - X3(a, i - 1, j, k)) * s.rdt)
+#define DT_D(a) ((X3(a, i + 1, j, k) + X3(a, i + 1, j, k - 1) - X3(a, i - 1, j, k) - X3(a, i - 1, j, k - 1)) * s.rdt4)
+#define DT_E(a) ((X3(a, i + 1, j, k) - X3(a, i - 1, j, k)) * s.rdt2)
+#define DP_A(a) ((X3(a, i + 1, j, k + 1) + X3(a, i, j, k + 1) - X3(a, i + 1, j, k - 1) - X3(a, i, j, k - 1)) * s.rdp4)
+#define DP_B(a) ((X3(a, i, j, k + 1) - X3(a, i, j, k)) * s.rdp)
+#define DP_C(a) ((X3(a, i, j, k + 1) + X3(a, i - 1, j, k + 1) - X3(a, i, j, k - 1) - X3(a, i - 1, j, k - 1)) * s.rdp4)
+#define DP_D(a) ((X3(a, i, j, k) - X3(a, i, j, k - 1)) * s.rdp)
+#define DP_E(a) ((X3(a, i, j, k + 1) - X3(a, i, j, k - 1)) * s.rdp2)
+#define DR_A(a) ((X3(a, i + 1, j + 1, k) + X3(a, i, j + 1, k) - X3(a, i + 1, j - 1, k) - X3(a, i, j - 1, k)) * s.rdr4)
+#define DR_B(a) ((X3(a, i, j + 1, k + 1) + X3(a, i, j + 1, k) - X3(a, i, j - 1, k + 1) - X3(a, i, j - 1, k)) * s.rdr4)
+#define DR_C(a) ((X3(a, i, j + 1, k) + X3(a, i - 1, j + 1, k) - X3(a, i, j - 1, k) - X3(a, i - 1, j - 1, k)) * s.rdr4)
+#define DR_D(a) ((X3(a, i, j + 1, k - 1) + X3(a, i, j + 1, k) - X3(a, i, j - 1, k - 1) - X3(a, i, j - 1, k)) * s.rdr4)
+#define DR_E(a) ((X3(a, i, j + 1, k) - X3(a, i, j - 1, k)) * s.rdr2)
+#pragma omp parallel for collapse(2)
+  for (int j = 2; j <= npsi - 1; ++j)
+    for (int k = 2; k <= nzeta; ++k)
+      for (int i = 2; i <= nthe - 1; ++i) {
+        const Pos a = geom(DT_A(x), DT_A(y), DT_A(z), DP_A(x), DP_A(y), DP_A(z), DR_A(x), DR_A(y), DR_A(z));
+        const Pos b = geom(DT_B(x), DT_B(y), DT_B(z), DP_B(x), DP_B(y), DP_B(z), DR_B(x), DR_B(y), DR_B(z));
+        const Pos c = geom(DT_C(x), DT_C(y), DT_C(z), DP_C(x), DP_C(y), DP_C(z), DR_C(x), DR_C(y), DR_C(z));
+        const Pos d = geom(DT_D(x), DT_D(y), DT_D(z), DP_D(x), DP_D(y), DP_D(z), DR_D(x), DR_D(y), DR_D(z));
+        const double v1a = (a.grs * a.gts - sq(a.gtgr)) * a.aj * s.rdtsq;
+        const double v1c = (c.grs * c.gts - sq(c.gtgr)) * c.aj * s.rdtsq;
+        const double v2a = (a.grs * a.gpgt - a.grgp * a.gtgr) * a.aj * s.rdpdt4;
+        const double v2b = (b.grs * b.gpgt - b.grgp * b.gtgr) * b.aj * s.rdpdt4;
+        const double v2c = (c.grs * c.gpgt - c.grgp * c.gtgr) * c.aj * s.rdpdt4;
+        const double v2d = (d.grs * d.gpgt - d.grgp * d.gtgr) * d.aj * s.rdpdt4;
+        const double v3b = (b.grs * b.gps - sq(b.grgp)) * b.aj * s.rdpsq;
+        const double v3d = (d.grs * d.gps - sq(d.grgp)) * d.aj * s.rdpsq;
+        X3(vecd, i, j, k) = (v1a + v1c) + (v3b + v3d);
+        X3(vec1, i, j, k) = (v2c + v2d);
+        X3(vec2, i, j, k) = (v2c - v2a) + v3d;
+        X3(vec3, i, j, k) = -(v2a + v2d);
+        X3(vec4, i, j, k) = v1c + (v2d - v2b);
+        X3(vec6, i, j, k) = v1a + (v2b - v2d);
+        X3(vec7, i, j, k) = -(v2c + v2b);
+        X3(vec8, i, j, k) = v3b + (v2a - v2c);
+        X3(vec9, i, j, k) = (v2a + v2b);
+      }
+}
+
+// ---- metric, src/ModScbEquation.f90:283-540 (psi equation, (theta,rho) stencil) -------
+void metric(Scb* o) {
+  DIMS
+  const Spacing s = spacing(o);
+  const double *x = o->D("x"), *y = o->D("y"), *z = o->D("z");
+  double *vecd = o->D("vecd"), *vec1 = o->D("vec1"), *vec2 = o->D("vec2"), *vec3 = o->D("vec3"), *vec4 = o->D("vec4"),
+         *vec6 = o->D("vec6"), *vec7 = o->D("vec7"), *vec8 = o->D("vec8"), *vec9 = o->D("vec9");
+  zero_vecs(o);
+#define MT_B(a) ((X3(a, i + 1, j + 1, k) + X3(a, i + 1, j, k) - X3(a, i - 1, j + 1, k) - X3(a, i - 1, j, k)) * s.rdt4)
+#define MT_D(a) ((X3(a, i + 1, j, k) + X3(a, i + 1, j - 1, k) - X3(a, i - 1, j, k) - X3(a, i - 1, j - 1, k)) * s.rdt4)
+#define MP_B(a) ((X3(a, i, j + 1, k + 1) + X3(a, i, j, k + 1) - X3(a, i, j + 1, k - 1) - X3(a, i, j, k - 1)) * s.rdp4)
+#define MP_D(a) ((X3(a, i, j, k + 1) + X3(a, i, j - 1, k + 1) - X3(a, i, j, k - 1) - X3(a, i, j - 1, k - 1)) * s.rdp4)
+#define MR_B(a) ((X3(a, i, j + 1, k) - X3(a, i, j, k)) * s.rdr)
+#define MR_D(a) ((X3(a, i, j, k) - X3(a, i, j - 1, k)) * s.rdr)
+#pragma omp parallel for collapse(2)
+  for (int j = 2; j <= npsi - 1; ++j)
+    for (int k = 2; k <= nzeta; ++k)
+      for (int i = 2; i <= nthe - 1; ++i) {
+        const Pos a = geom(DT_A(x), DT_A(y), DT_A(z), DP_A(x), DP_A(y), DP_A(z), DR_A(x), DR_A(y), DR_A(z));
+        const Pos b = geom(MT_B(x), MT_B(y), MT_B(z), MP_B(x), MP_B(y), MP_B(z), MR_B(x), MR_B(y), MR_B(z));
+        const Pos c = geom(DT_C(x), DT_C(y), DT_C(z), DP_C(x), DP_C(y), DP_C(z), DR_C(x), DR_C(y), DR_C(z));
+        const Pos d = geom(MT_D(x), MT_D(y), MT_D(z), MP_D(x), MP_D(y), MP_D(z), MR_D(x), MR_D(y), MR_D(z));
+        const double v1a = (sq(a.gpgt) - a.gps * a.gts) * a.aj * s.rdtsq;
+        const double v1c = (sq(c.gpgt) - c.gps * c.gts) * c.aj * s.rdtsq;
+        const double v2a = (a.grgp * a.gpgt - a.gps * a.gtgr) * a.aj * s.rdtdr4;
+        const double v2b = (b.grgp * b.gpgt - b.gps * b.gtgr) * b.aj * s.rdtdr4;
+        const double v2c = (c.grgp * c.gpgt - c.gps * c.gtgr) * c.aj * s.rdtdr4;
+        const double v2d = (d.grgp * d.gpgt - d.gps * d.gtgr) * d.aj * s.rdtdr4;
+        const double v3b = (sq(b.grgp) - b.grs * b.gps) * b.aj * s.rdrsq;
+        const double v3d = (sq(d.grgp) - d.grs * d.gps) * d.aj * s.rdrsq;
+        X3(vecd, i, j, k) = (v1a + v1c + v3b + v3d);
+        X3(vec1, i, j, k) = (v2c + v2d);
+        X3(vec2, i, j, k) = ((v2c - v2a) + v3d);
+        X3(vec3, i, j, k) = -(v2a + v2d);
+        X3(vec4, i, j, k) = (v1c + (v2d - v2b));
+        X3(vec6, i, j, k) = (v1a + (v2b - v2d));
+        X3(vec7, i, j, k) = -(v2c + v2b);
+        X3(vec8, i, j, k) = (v3b + (v2a - v2c));
+        X3(vec9, i, j, k) = (v2b + v2a);
+      }
+}
+
+// ---- newk / newj, src/ModScbEquation.f90:546-665 (Picard; isotropy 0 or 1) -----------
+void newk(Scb* o) {
+  DIMS
+  const int isotropy = o->I("isotropy");
+  const double *jac = o->D("jacobian"), *f = o->D("f");
+  double* vecx = o->D("vecx");
+  if (isotropy == 1) {
+    const double* dPdAlpha = o->D("dPdAlpha");
+    for (int j = 1; j <= npsi; ++j)
+      for (int k = 1; k <= nzeta; ++k)
+        for (int i = 1; i <= nthe; ++i) X3(vecx, i, j, k) = -X3(dPdAlpha, i, j, k) * X3(jac, i, j, k) / (f[j - 1] * f[j - 1]);
+    return;
+  }
+  const double *fzet = o->D("fzet"), *bsq = o->D("bsq"), *sigma = o->D("sigma");
+  const double *GRS = o->D("GradRhoSq"), *GZS = o->D("GradZetaSq"), *GRGT = o->D("GradRhoGradTheta"), *GRGZ = o->D("GradRhoGradZeta"),
+               *GTGZ = o->D("GradThetaGradZeta");
+  const double *dPZ = o->D("dPPerdZeta"), *dPT = o->D("dPPerdTheta"), *dBZ = o->D("dBsqdZeta"), *dBT = o->D("dBsqdTheta");
+  for (int i = 1; i <= nthe; ++i)
+    for (int j = 1; j <= npsi; ++j)
+      for (int k = 1; k <= nzeta; ++k) {
+        const double xpz = (X3(GRS, i, j, k) * X3(GZS, i, j, k) - sq(X3(GRGZ, i, j, k)));
+        const double xpt = (X3(GRS, i, j, k) * X3(GTGZ, i, j, k) - X3(GRGZ, i, j, k) * X3(GRGT, i, j, k));
+        const double c0 = -(f[j - 1] * f[j - 1] * fzet[k - 1]) / X3(sigma, i, j, k) / X3(bsq, i, j, k);
+        const double tz = X3(dPZ, i, j, k) + 0.5 * (1. - X3(sigma, i, j, k)) * X3(dBZ, i, j, k);
+        const double tt = X3(dPT, i, j, k) + 0.5 * (1. - X3(sigma, i, j, k)) * X3(dBT, i, j, k);
+        X3(vecx, i, j, k) = X3(jac, i, j, k) / (f[j - 1] * f[j - 1]) * c0 * (tz * xpz + tt * xpt);
+      }
+}
+void newj(Scb* o) {
+  DIMS
+  const int isotropy = o->I("isotropy");
+  const double *jac = o->D("jacobian"), *fzet = o->D("fzet");
+  double* vecr = o->D("vecr");
+  if (isotropy == 1) {
+    const double* dPdPsi = o->D("dPdPsi");
+    for (int k = 1; k <= nzeta; ++k)
+      for (int j = 1; j <= npsi; ++j)
+        for (int i = 1; i <= nthe; ++i) X3(vecr, i, j, k) = X3(jac, i, j, k) * X3(dPdPsi, i, j, k) / (fzet[k - 1] * fzet[k - 1]);
+    return;
+  }
+  const double *f = o->D("f"), *bsq = o->D("bsq"), *sigma = o->D("sigma");
+  const double *GRS = o->D("GradRhoSq"), *GZS = o->D("GradZetaSq"), *GRGT = o->D("GradRhoGradTheta"), *GRGZ = o->D("GradRhoGradZeta"),
+               *GTGZ = o->D("GradThetaGradZeta");
+  const double *dPR = o->D("dPPerdRho"), *dPT = o->D("dPPerdTheta"), *dBR = o->D("dBsqdRho"), *dBT = o->D("dBsqdTheta");
+  for (int k = 1; k <= nzeta; ++k)
+    for (int j = 1; j <= npsi; ++j)
+      for (int i = 1; i <= nthe; ++i) {
+        const double xpr = (sq(X3(GRGZ, i, j, k)) - X3(GRS, i, j, k) * X3(GZS, i, j, k));
+        const double xpt = (X3(GRGZ, i, j, k) * X3(GTGZ, i, j, k) - X3(GZS, i, j, k) * X3(GRGT, i, j, k));
+        const double c0 = -(f[j - 1] * (fzet[k - 1] * fzet[k - 1])) / X3(sigma, i, j, k) / X3(bsq, i, j, k);
+        const double tr = X3(dPR, i, j, k) + 0.5 * (1. - X3(sigma, i, j, k)) * X3(dBR, i, j, k);
+        const double tt = X3(dPT, i, j, k) + 0.5 * (1. - X3(sigma, i, j, k)) * X3(dBT, i, j, k);
+        X3(vecr, i, j, k) = X3(jac, i, j, k) / (fzet[k - 1] * fzet[k - 1]) * c0 * (tr * xpr + tt * xpt);
+      }
+}
+
+// extap, src/ModScbFunctions.f90:57-76
+inline void extap(double x1, double x2, double x3, double& x4) {
+  x4 = 3. * x3 - 3. * x2 + x1;
+  const double ddx1 = x3 - x2, ddx2 = x2 - x1;
+  double ddx = x4 - x3;
+  const double pm = ddx * ddx1;
+  if (pm > 0.) return;
+  if (std::fabs(ddx2) <= 1e-9) { x4 = 2. * x3 - x2; return; }
+  ddx = (ddx1 * ddx1) / ddx2;
+  x4 = x3 + ddx;
+}
+
+// post-processing shared by iterateAlpha / iteratePsi (:262-292 / :575-605)
+void sor_post(Scb* o, double* u, int nT, int nP, double wrap) {
+  DIMS
+  for (int k = 2; k <= nzeta; ++k)
+    for (int i = 1 + nT; i <= nthe - nT; ++i)
+      for (int j = nP; j >= 1; --j) extap(X3(u, i, npsi - j - 2, k), X3(u, i, npsi - j - 1, k), X3(u, i, npsi - j + 0, k), X3(u, i, npsi - j + 1, k));
+  if (nT == 1) {
+    // NOTE: the alpha variant loops k = 2..nthe-1 here (:274, a reference quirk that only
+    // matters for theChange <= 1); the psi variant loops k = 2..nzeta.  nT = 1 is not a
+    // configuration any shipped PARAM uses (theChange = 4); not restated.
+    std::fprintf(stderr, "scb oracle: theChange <= 1 is not supported\n");
+    std::abort();
+  } else {
+    for (int j = 1; j <= npsi; ++j)
+      for (int k = 1; k <= nzeta; ++k)
+        for (int i = 1; i <= nT; ++i) {
+          X3(u, i, j, k) = X3(u, nT + 1, j, k) + (nT + 1 - i) * (X3(u, 1, j, k) - X3(u, nT + 1, j, k)) / nT;
+          X3(u, nthe - i + 1, j, k) = X3(u, nthe - nT - 1, j, k) + (nT + 1 - i) * (X3(u, nthe, j, k) - X3(u, nthe - nT - 1, j, k)) / (nT);
+        }
+  }
+  for (int j = 1; j <= npsi; ++j)
+    for (int i = 1; i <= nthe; ++i) {
+      X3(u, i, j, 1) = X3(u, i, j, nzeta) - wrap;
+      X3(u, i, j, nzeta + 1) = X3(u, i, j, 2) + wrap;
+    }
+}
+
+// ---- iterateAlpha, src/ModScbEuler.f90:160-299 ----------------------------------------
+// outputs: nisave, sumb, sumdb, diffmx (scalars), ni per surface; returns SORFail
+int iterateAlpha(Scb* o, int* ni_out) {
+  DIMS
+  const int nimax = o->I("nimax"), nT = std::max(o->I("theChange"), 1), nP = std::max(o->I("psiChange"), 1);
+  const double InCon = o->S("InConAlpha");
+  const double *vecd = o->D("vecd"), *vec1 = o->D("vec1"), *vec2 = o->D("vec2"), *vec3 = o->D("vec3"), *vec4 = o->D("vec4"),
+               *vec6 = o->D("vec6"), *vec7 = o->D("vec7"), *vec8 = o->D("vec8"), *vec9 = o->D("vec9"), *vecx = o->D("vecx");
+  double* alfa = o->D("alfa");
+  const size_t n1 = (size_t)nthe * npsi * (nzeta + 1);
+  std::vector<double> prev(alfa, alfa + n1), resid(n1, 0.0);
+  std::vector<int> ni(npsi + 1, 0);
+  const double rjac = 1.0 - 2.0 * PI_D * PI_D / ((double)nzeta * (double)nzeta + (double)nthe * (double)nthe);
+  const double omegaOpt = 2.0 / (1.0 + std::sqrt(1.0 - rjac * rjac));
+  int fail = 0;
+  double* res = resid.data();
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int jz = 2; jz <= npsi - nP; ++jz) {
+    double om = 1.0;
+    ni[jz] = 1;
+    bool stop = false;
+    while (ni[jz] <= nimax && !stop) {
+      for (int k = 2; k <= nzeta && !stop; ++k) {
+        const int kp = k + 1, km = k - 1;
+        for (int iz = 1 + nT; iz <= nthe - nT; ++iz) {
+          const int im = iz - 1, ip = iz + 1;
+          X3(res, iz, jz, k) = -X3(vecd, iz, jz, k) * X3(alfa, iz, jz, k) + X3(vec1, iz, jz, k) * X3(alfa, im, jz, km) +
+                               X3(vec2, iz, jz, k) * X3(alfa, iz, jz, km) + X3(vec3, iz, jz, k) * X3(alfa, ip, jz, km) +
+                               X3(vec4, iz, jz, k) * X3(alfa, im, jz, k) + X3(vec6, iz, jz, k) * X3(alfa, ip, jz, k) +
+                               X3(vec7, iz, jz, k) * X3(alfa, im, jz, kp) + X3(vec8, iz, jz, k) * X3(alfa, iz, jz, kp) +
+                               X3(vec9, iz, jz, k) * X3(alfa, ip, jz, kp) - X3(vecx, iz, jz, k);
+          X3(alfa, iz, jz, k) = X3(alfa, iz, jz, k) + om * (X3(res, iz, jz, k) / X3(vecd, iz, jz, k));
+          if (std::isnan(X3(alfa, iz, jz, k)) || X3(alfa, iz, jz, k) >= 1e10) {
+            X3(alfa, iz, jz, k) = prev[(&X3(alfa, iz, jz, k)) - alfa];
+            X3(res, iz, jz, k) = 0.0;
+#pragma omp atomic write
+            fail = 1;
+            stop = true;
+            break;
+          }
+        }
+      }
+      if (stop) break;
+      om = omegaOpt;
+      double mx = 0.0;
+      for (int k = 2; k <= nzeta; ++k)
+        for (int i = 2; i <= nthe - 1; ++i) mx = std::max(mx, std::fabs(X3(res, i, jz, k)));
+      if (mx < InCon) break;
+      ni[jz] = ni[jz] + 1;
+    }
+  }
+  int nisave = 0;
+  for (int jz = 1; jz <= npsi; ++jz) nisave = std::max(nisave, ni[jz]);
+  double sumdb = 0.0, sumb = 0.0, diffmx = 0.0;
+  for (int k = 2; k <= nzeta; ++k)
+    for (int j = 2; j <= npsi - 1; ++j)
+      for (int i = 2; i <= nthe - 1; ++i) {
+        sumdb += std::fabs(X3(alfa, i, j, k) - X3(prev.data(), i, j, k));
+        sumb += std::fabs(X3(alfa, i, j, k));
+        diffmx = std::max(diffmx, std::fabs(X3(res, i, j, k)));
+      }
+  o->s["nisave"] = nisave; o->s["sumdb"] = sumdb; o->s["sumb"] = sumb; o->s["diffmx"] = diffmx;
+  if (ni_out)
+    for (int jz = 1; jz <= npsi; ++jz) ni_out[jz - 1] = ni[jz];
+  sor_post(o, alfa, nT, nP, 2.0 * PI_D);
+  return fail;
+}
+
+// ---- iteratePsi, src/ModScbEuler.f90:469-612 ------------------------------------------
+int iteratePsi(Scb* o, int* ni_out) {
+  DIMS
+  const int nimax = o->I("nimax"), nT = std::max(o->I("theChange"), 1), nP = std::max(o->I("psiChange"), 1);
+  const double InCon = o->S("InConPsi");
+  const double *vecd = o->D("vecd"), *vec1 = o->D("vec1"), *vec2 = o->D("vec2"), *vec3 = o->D("vec3"), *vec4 = o->D("vec4"),
+               *vec6 = o->D("vec6"), *vec7 = o->D("vec7"), *vec8 = o->D("vec8"), *vec9 = o->D("vec9"), *vecr = o->D("vecr");
+  double* psi = o->D("psi");
+  const size_t n1 = (size_t)nthe * npsi * (nzeta + 1);
+  std::vector<double> prev(psi, psi + n1), resid(n1, 0.0);
+  std::vector<int> ni(nzeta + 1, 0);
+  const double rjac = 1.0 - 2.0 * PI_D * PI_D / ((double)nthe * (double)nthe + (double)npsi * (double)npsi);
+  const double omegaOpt = 2.0 / (1.0 + std::sqrt(1.0 - rjac * rjac));
+  int fail = 0;
+  double* res = resid.data();
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int k = 2; k <= nzeta; ++k) {
+    double om = 1.0;
+    ni[k] = 1;
+    bool stop = false;
+    while (ni[k] <= nimax && !stop) {
+      for (int jz = 2; jz <= npsi - nP && !stop; ++jz) {
+        const int jp = jz + 1, jm = jz - 1;
+        for (int iz = 1 + nT; iz <= nthe - nT; ++iz) {
+          const int im = iz - 1, ip = iz + 1;
+          X3(res, iz, jz, k) = -X3(vecd, iz, jz, k) * X3(psi, iz, jz, k) + X3(vec1, iz, jz, k) * X3(psi, im, jm, k) +
+                               X3(vec2, iz, jz, k) * X3(psi, iz, jm, k) + X3(vec3, iz, jz, k) * X3(psi, ip, jm, k) +
+                               X3(vec4, iz, jz, k) * X3(psi, im, jz, k) + X3(vec6, iz, jz, k) * X3(psi, ip, jz, k) +
+                               X3(vec7, iz, jz, k) * X3(psi, im, jp, k) + X3(vec8, iz, jz, k) * X3(psi, iz, jp, k) +
+                               X3(vec9, iz, jz, k) * X3(psi, ip, jp, k) - X3(vecr, iz, jz, k);
+          X3(psi, iz, jz, k) = X3(psi, iz, jz, k) + om * X3(res, iz, jz, k) / X3(vecd, iz, jz, k);
+          if (std::isnan(X3(psi, iz, jz, k)) || X3(psi, iz, jz, k) >= 1e10) {
+            X3(psi, iz, jz, k) = prev[(&X3(psi, iz, jz, k)) - psi];
+            X3(res, iz, jz, k) = 0.0;
+#pragma omp atomic write
+            fail = 1;
+            stop = true;
+            break;
+          }
+        }
+      }
+      if (stop) break;
+      om = omegaOpt;
+      double mx = 0.0;
+      for (int j = 2; j <= npsi - 1; ++j)
+        for (int i = 2; i <= nthe - 1; ++i) mx = std::max(mx, std::fabs(X3(res, i, j, k)));
+      if (mx < InCon) break;
+      ni[k] = ni[k] + 1;
+    }
+  }
+  int nisave = 0;
+  for (int k = 1; k <= nzeta; ++k) nisave = std::max(nisave, ni[k]);
+  double sumdb = 0.0, sumb = 0.0, diffmx = 0.0;
+  for (int k = 2; k <= nzeta; ++k)
+    for (int j = 2; j <= npsi - 1; ++j)
+      for (int i = 2; i <= nthe - 1; ++i) {
+        sumdb += std::fabs(X3(psi, i, j, k) - X3(prev.data(), i, j, k));
+        sumb += std::fabs(X3(psi, i, j, k));
+        diffmx = std::max(diffmx, std::fabs(X3(res, i, j, k)));
+      }
+  o->s["nisave"] = nisave; o->s["sumdb"] = sumdb; o->s["sumb"] = sumb; o->s["diffmx"] = diffmx;
+  if (ni_out)
+    for (int k = 1; k <= nzeta; ++k) ni_out[k - 1] = ni[k];
+  sor_post(o, psi, nT, nP, 0.0);
+  return fail;
+}
+
+// ---- Compute_convergence, src/ModScbCompute.f90:499-754 (anisotropic branch) ------------
+// produces jGradRho/jGradZeta/jGradTheta, Jx..Jz, GradPx..GradPz, jCrossB, GradP and
+// the three norms
+int compute_convergence(Scb* o) {
+  DIMS
+  const int isotropy = o->I("isotropy");
+  if (isotropy != 0) { std::fprintf(stderr, "scb oracle: Compute_convergence restated for isotropy=0 only\n"); std::abort(); }
+  const Spacing s = spacing(o);
+  const double bnormal = o->S("bnormal"), pnormal = o->S("pnormal"), pjconst = o->S("pjconst");
+  const double *f = o->D("f"), *fzet = o->D("fzet"), *jac = o->D("jacobian"), *bsq = o->D("bsq"), *sigma = o->D("sigma");
+  const double *GRS = o->D("GradRhoSq"), *GTS = o->D("GradThetaSq"), *GZS = o->D("GradZetaSq"), *GRGT = o->D("GradRhoGradTheta"),
+               *GRGZ = o->D("GradRhoGradZeta"), *GTGZ = o->D("GradThetaGradZeta");
+  const double *dPA = o->D("dPPerdAlpha"), *dPP = o->D("dPPerdPsi"), *dPT = o->D("dPPerdTheta"), *dPR = o->D("dPPerdRho"),
+               *dPZ = o->D("dPPerdZeta"), *dBA = o->D("dBsqdAlpha"), *dBP = o->D("dBsqdPsi"), *dBT = o->D("dBsqdTheta");
+  const double *pper = o->D("pper"), *ppar = o->D("ppar");
+  const double *dXT = o->D("derivXTheta"), *dXR = o->D("derivXRho"), *dXZ = o->D("derivXZeta");
+  const double *dYT = o->D("derivYTheta"), *dYR = o->D("derivYRho"), *dYZ = o->D("derivYZeta");
+  const double *dZT = o->D("derivZTheta"), *dZR = o->D("derivZRho"), *dZZ = o->D("derivZZeta");
+  double *jGR = o->D("jGradRho"), *jGZ = o->D("jGradZeta"), *jGT = o->D("jGradTheta");
+  double *Jx = o->D("Jx"), *Jy = o->D("Jy"), *Jz = o->D("Jz"), *GPx = o->D("GradPx"), *GPy = o->D("GradPy"), *GPz = o->D("GradPz");
+  double *jCrossB = o->D("jCrossB"), *GradP = o->D("GradP");
+  const size_t n = (size_t)nthe * npsi * nzeta;
+  std::vector<double> pR(n), pZ(n), dpR(n), dpZ(n), nu1(n), nu2(n), dDiff(n), jdiff(n), jCBsq(n), gPsq(n);
+  for (int i = 1; i <= nthe; ++i)
+    for (int j = 1; j <= npsi; ++j)
+      for (int k = 1; k <= nzeta; ++k) {
+        const double sg = X3(sigma, i, j, k), fj = f[j - 1], fk = fzet[k - 1];
+        X3(jGR, i, j, k) = 1.0 / fj * (-1. / sg * X3(dPA, i, j, k) -
+                                       1. / (sg * X3(bsq, i, j, k)) * (fj * fj) * fk *
+                                           (X3(GRS, i, j, k) * X3(GTGZ, i, j, k) - X3(GRGT, i, j, k) * X3(GRGZ, i, j, k)) *
+                                           (X3(dPT, i, j, k) + (1. - sg) * 0.5 * X3(dBT, i, j, k)) -
+                                       (1. - sg) / sg * 0.5 * X3(dBA, i, j, k));
+        X3(jGZ, i, j, k) = 1.0 / fk * (1. / sg * X3(dPP, i, j, k) -
+                                       1. / (sg * X3(bsq, i, j, k)) * fj * (fk * fk) *
+                                           (X3(GRGZ, i, j, k) * X3(GTGZ, i, j, k) - X3(GRGT, i, j, k) * X3(GZS, i, j, k)) *
+                                           (X3(dPT, i, j, k) + (1. - sg) * 0.5 * X3(dBT, i, j, k)) +
+                                       (1. - sg) / sg * 0.5 * X3(dBP, i, j, k));
+      }
+  for (int j = 1; j <= npsi; ++j)
+    for (int k = 1; k <= nzeta; ++k)
+      for (int i = 1; i <= nthe; ++i) {
+        X3(pR.data(), i, j, k) = X3(jac, i, j, k) * f[j - 1] * fzet[k - 1] * (X3(GRGT, i, j, k) * X3(GRGZ, i, j, k) - X3(GTGZ, i, j, k) * X3(GRS, i, j, k));
+        X3(pZ.data(), i, j, k) = X3(jac, i, j, k) * f[j - 1] * fzet[k - 1] * (X3(GRGT, i, j, k) * X3(GZS, i, j, k) - X3(GRGZ, i, j, k) * X3(GTGZ, i, j, k));
+      }
+  derivs3d(o, pR.data(), nu1.data(), dpR.data(), nu2.data());
+  derivs3d(o, pZ.data(), nu1.data(), nu2.data(), dpZ.data());
+  for (size_t q = 0; q < n; ++q) jGT[q] = (dpR[q] + dpZ[q]) / jac[q];
+  for (size_t q = 0; q < n; ++q) {
+    // pper/ppar are (nthe,npsi,nzeta+1): same linear index for k <= nzeta
+    jdiff[q] = jac[q] * (pper[q] - ppar[q]);
+  }
+  derivs3d(o, jdiff.data(), dDiff.data(), nu1.data(), nu2.data());
+  for (size_t q = 0; q < n; ++q) {
+    Jx[q] = (jGR[q] * dXR[q] + jGZ[q] * dXZ[q] + jGT[q] * dXT[q]);
+    Jy[q] = (jGR[q] * dYR[q] + jGZ[q] * dYZ[q] + jGT[q] * dYT[q]);
+    Jz[q] = (jGR[q] * dZR[q] + jGZ[q] * dZZ[q] + jGT[q] * dZT[q]);
+  }
+  for (int k = 1; k <= nzeta; ++k)
+    for (int j = 1; j <= npsi; ++j)
+      for (int i = 1; i <= nthe; ++i) {
+        const size_t q = &X3(jac, i, j, k) - jac;
+        const double fj = f[j - 1], fk = fzet[k - 1];
+        jCBsq[q] = (fj * fj) * (fk * fk) *
+                   (GRS[q] * sq(jGZ[q]) + GZS[q] * sq(jGR[q]) - 2.0 * jGZ[q] * jGR[q] * GRGZ[q]);
+        gPsq[q] = GRS[q] * sq(dPR[q]) + GZS[q] * sq(dPZ[q]) + GTS[q] * sq(dPT[q]) + 2. * dPR[q] * dPZ[q] * GRGZ[q] +
+                  2. * dPR[q] * dPT[q] * GRGT[q] + 2. * dPZ[q] * dPT[q] * GTGZ[q] + sq(dDiff[q] / jac[q]) -
+                  2. * dPT[q] * dDiff[q] / jac[q];
+        const double t1 = (dPR[q] * GRS[q] + dPZ[q] * GRGZ[q] + dPT[q] * GRGT[q]);
+        const double t2 = (dPR[q] * GRGZ[q] + dPZ[q] * GZS[q] + dPT[q] * GTGZ[q]);
+        const double t3 = (dPR[q] * GRGT[q] + dPZ[q] * GTGZ[q] + dPT[q] * GTS[q]);
+        GPx[q] = t1 * dXR[q] + t2 * dXZ[q] + t3 * dXT[q] + dDiff[q] * GRGT[q] * dXR[q] + dDiff[q] * GTGZ[q] * dXZ[q] + dDiff[q] * GTS[q] * dXT[q];
+        GPy[q] = t1 * dYR[q] + t2 * dYZ[q] + t3 * dYT[q] + dDiff[q] * GRGT[q] * dYR[q] + dDiff[q] * GTGZ[q] * dYZ[q] + dDiff[q] * GTS[q] * dYT[q];
+        GPz[q] = t1 * dZR[q] + t2 * dZZ[q] + t3 * dZT[q] + dDiff[q] * GRGT[q] * dZR[q] + dDiff[q] * GTGZ[q] * dZZ[q] + dDiff[q] * GTS[q] * dZT[q];
+      }
+  for (size_t q = 0; q < n; ++q) {
+    jCrossB[q] = std::sqrt(jCBsq[q]) * bnormal * pjconst;
+    GradP[q] = std::sqrt(std::fabs(gPsq[q])) * pnormal / 6.4;
+  }
+  double normDiff = 0, normJxB = 0, normGradP = 0, volume = 0;
+  for (int i = 2; i <= nthe - 1; ++i)
+    for (int j = 2; j <= npsi - 1; ++j)
+      for (int k = 2; k <= nzeta; ++k) {
+        const size_t q = &X3(jac, i, j, k) - jac;
+        normDiff = normDiff + jac[q] * s.dr * s.dpPrime * s.dt * (jCrossB[q] - GradP[q]);
+        normJxB = normJxB + jac[q] * s.dr * s.dpPrime * s.dt * jCrossB[q];
+        normGradP = normGradP + jac[q] * s.dr * s.dpPrime * s.dt * GradP[q];
+        volume = volume + jac[q] * s.dr * s.dpPrime * s.dt;
+      }
+  normDiff /= volume; normJxB /= volume; normGradP /= volume;
+  o->s["normDiff"] = normDiff; o->s["normJxB"] = normJxB; o->s["normGradP"] = normGradP; o->s["volume"] = volume;
+  return (std::isnan(normDiff) || std::isnan(normJxB) || std::isnan(normGradP)) ? 1 : 0;
+}
+
+}  // namespace
+
+extern "C" {
+void* scbo_create(int nthe, int npsi, int nzeta) {
+  Scb* o = new Scb();
+  o->nthe = nthe; o->npsi = npsi; o->nzeta = nzeta;
+  o->iv["nimax"] = 5001;        // src/ModScbMain.f90:45
+  o->iv["theChange"] = 4;       // src/ModScbParams.f90
+  o->iv["psiChange"] = 0;
+  o->iv["isotropy"] = 0;
+  o->s["InConAlpha"] = 1e-6;    // src/ModScbParams.f90:37-38
+  o->s["InConPsi"] = 1e-6;
+  const double xzero3 = 6.6 * 6.6 * 6.6;   // src/ModScbInit.f90:246-273
+  const double bnormal = 0.31 / xzero3 * 1.E5;
+  o->s["bnormal"] = bnormal;
+  o->s["pnormal"] = bnormal * bnormal / (4. * PI_D * 1.E-7) * 1.E-9;
+  o->s["pjconst"] = 1.e6 * 0.31E-4 / (xzero3 * 4. * PI_D * 1.E-7 * 6.4E6);
+  return o;
+}
+void scbo_destroy(void* h) { delete (Scb*)h; }
+void scbo_set_array(void* h, const char* n, double* p) { ((Scb*)h)->d[n] = p; }
+void scbo_set_scalar(void* h, const char* n, double v) { ((Scb*)h)->s[n] = v; }
+void scbo_set_int(void* h, const char* n, int v) { ((Scb*)h)->iv[n] = v; }
+double scbo_get_scalar(void* h, const char* n) { return ((Scb*)h)->S(n); }
+int scbo_bandjacob(void* h) { return computeBandJacob((Scb*)h); }
+void scbo_metrica(void* h) { metrica((Scb*)h); }
+void scbo_metric(void* h) { metric((Scb*)h); }
+void scbo_newk(void* h) { newk((Scb*)h); }
+void scbo_newj(void* h) { newj((Scb*)h); }
+int scbo_iterate_alpha(void* h, int* ni) { return iterateAlpha((Scb*)h, ni); }
+int scbo_iterate_psi(void* h, int* ni) { return iteratePsi((Scb*)h, ni); }
+int scbo_convergence(void* h) { return compute_convergence((Scb*)h); }
+void scbo_derivs3d(void* h, const double* f, double* dT, double* dR, double* dZ) { derivs3d((Scb*)h, f, dT, dR, dZ); }
+void scbo_steffen(int n, const double* xa, const double* ya, double* dx) {
+  std::vector<double> yp;
+  steffen_derivs(n, xa, ya, dx, yp);
+}
+}

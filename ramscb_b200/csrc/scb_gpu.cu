@@ -1,0 +1,458 @@
+// Host side of the SCB C ABI (include/ramscb_gpu.h, rsg_scb_*): device mirrors of
+// the ModScbVariables arrays and kernel launches.  No CPU compute path: without
+// a CUDA device every entry point fails with RSG_ERR_CUDA.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/ramscb_gpu.h"
+#include "scb_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_serr;
+int sfail(int code, const std::string& msg) {
+  g_serr = msg;
+  return code;
+}
+#define SCK(call)                                                                                         \
+  do {                                                                                                    \
+    cudaError_t e_ = (call);                                                                              \
+    if (e_ != cudaSuccess)                                                                                \
+      return sfail(RSG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" + \
+                                     std::to_string(__LINE__) + ")");                                     \
+  } while (0)
+#define SCKL()                                                                                            \
+  do {                                                                                                    \
+    cudaError_t e_ = cudaGetLastError();                                                                  \
+    if (e_ != cudaSuccess)                                                                                \
+      return sfail(RSG_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e_) + " (" __FILE__ ":" + \
+                                     std::to_string(__LINE__) + ")");                                     \
+  } while (0)
+#define SRET(x)                  \
+  do {                           \
+    int r_ = (x);                \
+    if (r_ != RSG_OK) return r_; \
+  } while (0)
+
+const double PI_D = 3.141592653589793238462643383279502884197;
+inline int nblk(long long n, int b) { return (int)((n + b - 1) / b); }
+
+}  // namespace
+
+extern "C" const char* rsg_scb_last_error(void) { return g_serr.c_str(); }
+
+struct rsg_scb {
+  int nthe, npsi, nzeta, device = 0;
+  int isotropy = 0;
+  ScbDev dev{};
+  std::map<std::string, std::pair<double*, size_t>> arr;   // name -> (device ptr, elements)
+  std::vector<void*> allocs;
+  cudaStream_t st = nullptr;
+  double *d_prev = nullptr, *d_part = nullptr, *d_resmax = nullptr;
+  int *d_ni = nullptr, *d_fail = nullptr;
+  size_t npart = 0;
+  long long launches = 0;
+  double bnormal, pnormal, pjconst;
+  bool grid_set = false, geom_set = false, press_set = false, band_done = false;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  double last_ms = 0.0;
+
+  int dalloc(double** p, size_t n, const char* name) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, n * sizeof(double));
+    if (e != cudaSuccess) return sfail(RSG_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    cudaMemset(q, 0, n * sizeof(double));
+    allocs.push_back(q);
+    *p = (double*)q;
+    if (name) arr[name] = {(double*)q, n};
+    return RSG_OK;
+  }
+};
+
+extern "C" {
+
+int rsg_scb_create(rsg_scb** out, int nthe, int npsi, int nzeta, int device) {
+  if (!out) return sfail(RSG_ERR_ARG, "null out");
+  if (nthe < 12 || npsi < 6 || nzeta < 6) return sfail(RSG_ERR_ARG, "bad dimensions");
+  int ndev = 0;
+  SCK(cudaGetDeviceCount(&ndev));
+  if (ndev < 1) return sfail(RSG_ERR_CUDA, "no CUDA device");
+  if (device >= 0) SCK(cudaSetDevice(device));
+  rsg_scb* h = new rsg_scb();
+  SCK(cudaGetDevice(&h->device));
+  h->nthe = nthe; h->npsi = npsi; h->nzeta = nzeta;
+  ScbDev& d = h->dev;
+  d.nthe = nthe; d.npsi = npsi; d.nzeta = nzeta;
+  // src/ModScbInit.f90:131-148
+  d.dr = 1.0 / (double)(npsi - 1);
+  d.dt = PI_D / (double)(nthe - 1);
+  d.dpPrime = 2 * PI_D / (double)(nzeta - 1);
+  d.rdr = 1.0 / d.dr; d.rdt = 1.0 / d.dt; d.rdp = 1.0 / d.dpPrime;
+  d.rdrsq = d.rdr * d.rdr; d.rdtsq = d.rdt * d.rdt; d.rdpsq = d.rdp * d.rdp;
+  d.rdr2 = 0.5 * d.rdr; d.rdt2 = 0.5 * d.rdt; d.rdp2 = 0.5 * d.rdp;
+  d.rdr4 = 0.25 * d.rdr; d.rdt4 = 0.25 * d.rdt; d.rdp4 = 0.25 * d.rdp;
+  d.rdpdt4 = 0.25 * d.rdp * d.rdt;
+  d.rdtdr4 = 0.25 * d.rdt * d.rdr;
+  // src/ModScbInit.f90:246-273
+  const double xzero3 = 6.6 * 6.6 * 6.6;
+  h->bnormal = 0.31 / xzero3 * 1.E5;
+  h->pnormal = h->bnormal * h->bnormal / (4. * PI_D * 1.E-7) * 1.E-9;
+  h->pjconst = 1.e6 * 0.31E-4 / (xzero3 * 4. * PI_D * 1.E-7 * 6.4E6);
+  const size_t n3 = (size_t)nthe * npsi * nzeta, n3p = (size_t)nthe * npsi * (nzeta + 1);
+  SRET(h->dalloc((double**)&d.thetaVal, nthe, "thetaVal"));
+  SRET(h->dalloc((double**)&d.rhoVal, npsi, "rhoVal"));
+  SRET(h->dalloc((double**)&d.zetaVal, nzeta, "zetaVal"));
+  SRET(h->dalloc((double**)&d.f, npsi, "f"));
+  SRET(h->dalloc((double**)&d.fzet, nzeta + 1, "fzet"));
+  struct { double** p; const char* n; } p1[] = {{&d.x, "x"}, {&d.y, "y"}, {&d.z, "z"}, {&d.alfa, "alfa"}, {&d.psi, "psi"},
+      {&d.pper, "pper"}, {&d.ppar, "ppar"}, {&d.sigma, "sigma"}, {&d.bsq, "bsq"}, {&d.bf, "bf"}};
+  for (auto& e : p1) SRET(h->dalloc(e.p, n3p, e.n));
+  struct { double** p; const char* n; } p0[] = {
+      {&d.dXT, "derivXTheta"}, {&d.dXR, "derivXRho"}, {&d.dXZ, "derivXZeta"}, {&d.dYT, "derivYTheta"}, {&d.dYR, "derivYRho"},
+      {&d.dYZ, "derivYZeta"}, {&d.dZT, "derivZTheta"}, {&d.dZR, "derivZRho"}, {&d.dZZ, "derivZZeta"}, {&d.jac, "jacobian"},
+      {&d.gRX, "gradRhoX"}, {&d.gRY, "gradRhoY"}, {&d.gRZ, "gradRhoZ"}, {&d.gZX, "gradZetaX"}, {&d.gZY, "gradZetaY"},
+      {&d.gZZ, "gradZetaZ"}, {&d.gTX, "gradThetaX"}, {&d.gTY, "gradThetaY"}, {&d.gTZ, "gradThetaZ"}, {&d.GRS, "GradRhoSq"},
+      {&d.GTS, "GradThetaSq"}, {&d.GZS, "GradZetaSq"}, {&d.GRGT, "GradRhoGradTheta"}, {&d.GRGZ, "GradRhoGradZeta"},
+      {&d.GTGZ, "GradThetaGradZeta"}, {&d.Bx, "Bx"}, {&d.By, "By"}, {&d.Bz, "Bz"}, {&d.vecd, "vecd"}, {&d.vec1, "vec1"},
+      {&d.vec2, "vec2"}, {&d.vec3, "vec3"}, {&d.vec4, "vec4"}, {&d.vec6, "vec6"}, {&d.vec7, "vec7"}, {&d.vec8, "vec8"},
+      {&d.vec9, "vec9"}, {&d.vecx, "vecx"}, {&d.vecr, "vecr"}, {&d.dPT, "dPPerdTheta"}, {&d.dPR, "dPPerdRho"},
+      {&d.dPZ, "dPPerdZeta"}, {&d.dBT, "dBsqdTheta"}, {&d.dBR, "dBsqdRho"}, {&d.dBZ, "dBsqdZeta"}, {&d.dPP, "dPPerdPsi"},
+      {&d.dPA, "dPPerdAlpha"}, {&d.dBP, "dBsqdPsi"}, {&d.dBA, "dBsqdAlpha"}, {&d.dPdAlpha, "dPdAlpha"}, {&d.dPdPsi, "dPdPsi"},
+      {&d.jGR, "jGradRho"}, {&d.jGZ, "jGradZeta"}, {&d.jGT, "jGradTheta"}, {&d.Jx, "Jx"}, {&d.Jy, "Jy"}, {&d.Jz, "Jz"},
+      {&d.GPx, "GradPx"}, {&d.GPy, "GradPy"}, {&d.GPz, "GradPz"}, {&d.jCrossB, "jCrossB"}, {&d.GradP, "GradP"},
+      {&d.w1, nullptr}, {&d.w2, nullptr}, {&d.w3, nullptr}, {&d.w4, nullptr}, {&d.w5, nullptr}};
+  for (auto& e : p0) SRET(h->dalloc(e.p, n3, e.n));
+  SRET(h->dalloc(&h->d_prev, n3p, nullptr));
+  h->npart = (size_t)4 * nblk(nthe, 128) * npsi * nzeta + 2 * (size_t)nzeta;
+  SRET(h->dalloc(&h->d_part, h->npart, nullptr));
+  const int nsub = std::max(npsi, nzeta) + 1;
+  SRET(h->dalloc(&h->d_resmax, nsub, nullptr));
+  void* q = nullptr;
+  SCK(cudaMalloc(&q, sizeof(int) * (nsub + 1)));
+  h->allocs.push_back(q);
+  h->d_ni = (int*)q;
+  h->d_fail = h->d_ni + nsub;
+  SCK(cudaMemset(q, 0, sizeof(int) * (nsub + 1)));
+  SCK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+  SCK(cudaEventCreate(&h->e0));
+  SCK(cudaEventCreate(&h->e1));
+  *out = h;
+  return RSG_OK;
+}
+
+int rsg_scb_destroy(rsg_scb* h) {
+  if (!h) return RSG_OK;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->st) cudaStreamDestroy(h->st);
+  if (h->e0) cudaEventDestroy(h->e0);
+  if (h->e1) cudaEventDestroy(h->e1);
+  delete h;
+  return RSG_OK;
+}
+
+static int scb_up(rsg_scb* h, const char* name, const double* src) {
+  auto it = h->arr.find(name);
+  if (it == h->arr.end()) return sfail(RSG_ERR_ARG, std::string("unknown array ") + name);
+  if (!src) return sfail(RSG_ERR_ARG, std::string("null pointer for ") + name);
+  SCK(cudaMemcpyAsync(it->second.first, src, it->second.second * sizeof(double), cudaMemcpyHostToDevice, h->st));
+  return RSG_OK;
+}
+
+int rsg_scb_set_grid(rsg_scb* h, const double* thetaVal, const double* rhoVal, const double* zetaVal, const double* f,
+                     const double* fzet) {
+  if (!h) return sfail(RSG_ERR_ARG, "null handle");
+  SCK(cudaSetDevice(h->device));
+  SRET(scb_up(h, "thetaVal", thetaVal)); SRET(scb_up(h, "rhoVal", rhoVal)); SRET(scb_up(h, "zetaVal", zetaVal));
+  SRET(scb_up(h, "f", f)); SRET(scb_up(h, "fzet", fzet));
+  SCK(cudaStreamSynchronize(h->st));
+  h->grid_set = true;
+  return RSG_OK;
+}
+
+int rsg_scb_set_geometry(rsg_scb* h, const double* x, const double* y, const double* z) {
+  if (!h) return sfail(RSG_ERR_ARG, "null handle");
+  SCK(cudaSetDevice(h->device));
+  SRET(scb_up(h, "x", x)); SRET(scb_up(h, "y", y)); SRET(scb_up(h, "z", z));
+  SCK(cudaStreamSynchronize(h->st));
+  h->geom_set = true;
+  h->band_done = false;
+  return RSG_OK;
+}
+
+int rsg_scb_set_pressure(rsg_scb* h, int isotropy, const double* pper, const double* ppar, const double* sigma,
+                         const double* dPPerdTheta, const double* dPPerdRho, const double* dPPerdZeta, const double* dBsqdTheta,
+                         const double* dBsqdRho, const double* dBsqdZeta, const double* dPPerdPsi, const double* dPPerdAlpha,
+                         const double* dBsqdPsi, const double* dBsqdAlpha, const double* dPdAlpha, const double* dPdPsi) {
+  if (!h) return sfail(RSG_ERR_ARG, "null handle");
+  SCK(cudaSetDevice(h->device));
+  h->isotropy = isotropy;
+  if (isotropy == 1) {
+    SRET(scb_up(h, "dPdAlpha", dPdAlpha)); SRET(scb_up(h, "dPdPsi", dPdPsi));
+    if (pper) SRET(scb_up(h, "pper", pper));
+    if (ppar) SRET(scb_up(h, "ppar", ppar));
+  } else {
+    SRET(scb_up(h, "pper", pper)); SRET(scb_up(h, "ppar", ppar)); SRET(scb_up(h, "sigma", sigma));
+    SRET(scb_up(h, "dPPerdTheta", dPPerdTheta)); SRET(scb_up(h, "dPPerdRho", dPPerdRho)); SRET(scb_up(h, "dPPerdZeta", dPPerdZeta));
+    SRET(scb_up(h, "dBsqdTheta", dBsqdTheta)); SRET(scb_up(h, "dBsqdRho", dBsqdRho)); SRET(scb_up(h, "dBsqdZeta", dBsqdZeta));
+    SRET(scb_up(h, "dPPerdPsi", dPPerdPsi)); SRET(scb_up(h, "dPPerdAlpha", dPPerdAlpha));
+    SRET(scb_up(h, "dBsqdPsi", dBsqdPsi)); SRET(scb_up(h, "dBsqdAlpha", dBsqdAlpha));
+  }
+  SCK(cudaStreamSynchronize(h->st));
+  h->press_set = true;
+  return RSG_OK;
+}
+
+int rsg_scb_set_field(rsg_scb* h, const char* name, const double* src) {
+  if (!h || !name) return sfail(RSG_ERR_ARG, "null argument");
+  SCK(cudaSetDevice(h->device));
+  SRET(scb_up(h, name, src));
+  SCK(cudaStreamSynchronize(h->st));
+  return RSG_OK;
+}
+
+int rsg_scb_get_field(rsg_scb* h, const char* name, double* dst) {
+  if (!h || !name || !dst) return sfail(RSG_ERR_ARG, "null argument");
+  SCK(cudaSetDevice(h->device));
+  auto it = h->arr.find(name);
+  if (it == h->arr.end()) return sfail(RSG_ERR_ARG, std::string("unknown array ") + name);
+  SCK(cudaMemcpyAsync(dst, it->second.first, it->second.second * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  SCK(cudaStreamSynchronize(h->st));
+  return RSG_OK;
+}
+
+int rsg_scb_field_size(rsg_scb* h, const char* name, long long* n) {
+  if (!h || !name || !n) return sfail(RSG_ERR_ARG, "null argument");
+  auto it = h->arr.find(name);
+  if (it == h->arr.end()) return sfail(RSG_ERR_ARG, std::string("unknown array ") + name);
+  *n = (long long)it->second.second;
+  return RSG_OK;
+}
+
+// computeBandJacob, src/ModScbCompute.f90:412-496
+int rsg_scb_bandjacob(rsg_scb* h, int* sorfail) {
+  if (!h) return sfail(RSG_ERR_ARG, "null handle");
+  if (!h->grid_set || !h->geom_set) return sfail(RSG_ERR_STATE, "computeBandJacob before set_grid/set_geometry");
+  SCK(cudaSetDevice(h->device));
+  SCK(cudaMemsetAsync(h->d_fail, 0, sizeof(int), h->st));
+  SCK(cudaEventRecord(h->e0, h->st));
+  dim3 g(nblk(h->nthe, 128), h->npsi, h->nzeta);
+  k_scb_bandjacob<<<g, 128, 0, h->st>>>(h->dev, h->d_fail);
+  SCKL();
+  k_scb_bwrap<<<dim3(nblk(h->nthe, 128), h->npsi), 128, 0, h->st>>>(h->dev);
+  SCKL();
+  SCK(cudaEventRecord(h->e1, h->st));
+  h->launches += 2;
+  int f = 0;
+  SCK(cudaMemcpyAsync(&f, h->d_fail, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  SCK(cudaStreamSynchronize(h->st));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->e0, h->e1);
+  h->last_ms = ms;
+  if (sorfail) *sorfail = f;
+  h->band_done = true;
+  return RSG_OK;
+}
+
+static int scb_metric(rsg_scb* h, bool alpha) {
+  if (!h) return sfail(RSG_ERR_ARG, "null handle");
+  if (!h->geom_set) return sfail(RSG_ERR_STATE, "metric before set_geometry");
+  SCK(cudaSetDevice(h->device));
+  const size_t n3 = (size_t)h->nthe * h->npsi * h->nzeta;
+  SCK(cudaEventRecord(h->e0, h->st));
+  double* vs[] = {h->dev.vecd, h->dev.vec1, h->dev.vec2, h->dev.vec3, h->dev.vec4, h->dev.vec6, h->dev.vec7, h->dev.vec8, h->dev.vec9};
+  for (double* v : vs) SCK(cudaMemsetAsync(v, 0, n3 * sizeof(double), h->st));
+  dim3 g(nblk(h->nthe - 2, 128), h->npsi - 2, h->nzeta - 1);
+  if (alpha) k_scb_metric<true><<<g, 128, 0, h->st>>>(h->dev);
+  else k_scb_metric<false><<<g, 128, 0, h->st>>>(h->dev);
+  SCKL();
+  SCK(cudaEventRecord(h->e1, h->st));
+  h->launches++;
+  SCK(cudaStreamSynchronize(h->st));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->e0, h->e1);
+  h->last_ms = ms;
+  return RSG_OK;
+}
+int rsg_scb_metrica(rsg_scb* h) { return scb_metric(h, true); }   // src/ModScbEquation.f90:18-280
+int rsg_scb_metric(rsg_scb* h) { return scb_metric(h, false); }   // :283-540
+
+static int scb_rhs(rsg_scb* h, bool alpha) {
+  if (!h) return sfail(RSG_ERR_ARG, "null handle");
+  if (!h->band_done || !h->press_set) return sfail(RSG_ERR_STATE, "newk/newj before computeBandJacob/set_pressure");
+  SCK(cudaSetDevice(h->device));
+  dim3 g(nblk(h->nthe, 128), h->npsi, h->nzeta);
+  if (alpha) k_scb_rhs<true><<<g, 128, 0, h->st>>>(h->dev, h->isotropy);
+  else k_scb_rhs<false><<<g, 128, 0, h->st>>>(h->dev, h->isotropy);
+  SCKL();
+  h->launches++;
+  SCK(cudaStreamSynchronize(h->st));
+  return RSG_OK;
+}
+int rsg_scb_newk(rsg_scb* h) { return scb_rhs(h, true); }    // :546-604
+int rsg_scb_newj(rsg_scb* h) { return scb_rhs(h, false); }   // :607-665
+
+// iterateAlpha / iteratePsi, src/ModScbEuler.f90:160-299 / :469-612
+static int scb_iterate(rsg_scb* h, bool alpha, double tol, int nimax, int theChange, int psiChange, int ordering, int* nisave,
+                       double* sumb, double* sumdb, double* diffmx, int* sorfail, int* ni_out) {
+  if (!h) return sfail(RSG_ERR_ARG, "null handle");
+  if (ordering != RSG_SOR_LEX && ordering != RSG_SOR_COLOR4) return sfail(RSG_ERR_ARG, "unknown SOR ordering");
+  SCK(cudaSetDevice(h->device));
+  const int nthe = h->nthe, npsi = h->npsi, nzeta = h->nzeta;
+  const int nT = std::max(theChange, 1), nP = std::max(psiChange, 1);
+  if (nT == 1) return sfail(RSG_ERR_UNSUPPORTED, "theChange <= 1 is not supported");
+  if (nthe - 2 * nT < 3) return sfail(RSG_ERR_ARG, "theChange too large for nthe");
+  double* u = alpha ? h->dev.alfa : h->dev.psi;
+  const size_t n3p = (size_t)nthe * npsi * (nzeta + 1);
+  SCK(cudaMemcpyAsync(h->d_prev, u, n3p * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+  const int nsub = alpha ? (npsi - nP - 1) : (nzeta - 1);
+  SCK(cudaMemsetAsync(h->d_ni, 0, sizeof(int) * (std::max(npsi, nzeta) + 2), h->st));
+  SorArgs a;
+  a.tol = tol;
+  a.nimax = nimax;
+  a.nT = nT;
+  a.nP = nP;
+  a.ni = h->d_ni;
+  a.resmax = h->d_resmax;
+  a.fail = h->d_fail;
+  const double rjac = alpha ? 1.0 - 2.0 * PI_D * PI_D / ((double)nzeta * (double)nzeta + (double)nthe * (double)nthe)
+                            : 1.0 - 2.0 * PI_D * PI_D / ((double)nthe * (double)nthe + (double)npsi * (double)npsi);
+  a.omegaOpt = 2.0 / (1.0 + std::sqrt(1.0 - rjac * rjac));
+  const int nrows = alpha ? nzeta + 1 : npsi;
+  const size_t smem = sizeof(double) * (size_t)nrows * nthe;
+  if (smem > 220 * 1024) return sfail(RSG_ERR_UNSUPPORTED, "SOR plane does not fit in shared memory");
+  const int nr = alpha ? (nzeta - 1) : (npsi - nP - 1);
+  const int threads = ordering == RSG_SOR_LEX ? std::min(1024, (nr + 31) / 32 * 32) : 1024;
+  if (ordering == RSG_SOR_LEX && nr > 1024) return sfail(RSG_ERR_UNSUPPORTED, "too many rows for the lexicographic SOR kernel");
+  SCK(cudaEventRecord(h->e0, h->st));
+#define LAUNCH_SOR(A, O)                                                                                   \
+  do {                                                                                                     \
+    SCK(cudaFuncSetAttribute(k_scb_sor<A, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    k_scb_sor<A, O><<<nsub, threads, smem, h->st>>>(h->dev, a);                                            \
+  } while (0)
+  if (alpha && ordering == RSG_SOR_LEX) LAUNCH_SOR(true, 0);
+  else if (alpha) LAUNCH_SOR(true, 1);
+  else if (ordering == RSG_SOR_LEX) LAUNCH_SOR(false, 0);
+  else LAUNCH_SOR(false, 1);
+#undef LAUNCH_SOR
+  SCKL();
+  SCK(cudaEventRecord(h->e1, h->st));
+  k_scb_sums<<<nzeta - 1, 256, 0, h->st>>>(h->dev, u, h->d_prev, h->d_part);
+  SCKL();
+  k_scb_post_extap<<<dim3(nblk(nthe, 128), nzeta - 1), 128, 0, h->st>>>(h->dev, u, nT, nP);
+  SCKL();
+  k_scb_post_theta<<<dim3(nblk(npsi, 64), nzeta), 64, 0, h->st>>>(h->dev, u, nT);
+  SCKL();
+  k_scb_post_wrap<<<dim3(nblk(nthe, 128), npsi), 128, 0, h->st>>>(h->dev, u, alpha ? 2.0 * PI_D : 0.0);
+  SCKL();
+  h->launches += 5;
+  std::vector<int> ni(nsub + 1);
+  std::vector<double> rm(nsub), part(2 * (size_t)(nzeta - 1));
+  int f = 0;
+  SCK(cudaMemcpyAsync(ni.data(), h->d_ni, sizeof(int) * nsub, cudaMemcpyDeviceToHost, h->st));
+  SCK(cudaMemcpyAsync(rm.data(), h->d_resmax, sizeof(double) * nsub, cudaMemcpyDeviceToHost, h->st));
+  SCK(cudaMemcpyAsync(part.data(), h->d_part, sizeof(double) * part.size(), cudaMemcpyDeviceToHost, h->st));
+  SCK(cudaMemcpyAsync(&f, h->d_fail, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  SCK(cudaStreamSynchronize(h->st));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->e0, h->e1);
+  h->last_ms = ms;
+  int nmax = 0;
+  double dmx = 0.0, sb = 0.0, sdb = 0.0;
+  for (int q = 0; q < nsub; ++q) {
+    nmax = std::max(nmax, ni[q]);
+    dmx = std::max(dmx, rm[q]);
+  }
+  for (int k = 0; k < nzeta - 1; ++k) {
+    sb += part[2 * k];
+    sdb += part[2 * k + 1];
+  }
+  if (nisave) *nisave = nmax;
+  if (sumb) *sumb = sb;
+  if (sumdb) *sumdb = sdb;
+  if (diffmx) *diffmx = dmx;
+  if (sorfail) *sorfail = f;
+  if (ni_out) {
+    // Fortran ni(1:npsi) (alpha, entries jz=2..npsi-nP) / ni(1:nzeta) (psi, entries k=2..nzeta)
+    const int n = alpha ? npsi : nzeta;
+    for (int q = 0; q < n; ++q) ni_out[q] = 0;
+    for (int q = 0; q < nsub; ++q) ni_out[q + 1] = ni[q];
+  }
+  if (f) SCK(cudaMemsetAsync(h->d_fail, 0, sizeof(int), h->st));
+  return RSG_OK;
+}
+int rsg_scb_iterate_alpha(rsg_scb* h, double InConAlpha, int nimax, int theChange, int psiChange, int ordering, int* nisave,
+                          double* sumb, double* sumdb, double* diffmx, int* sorfail, int* ni) {
+  return scb_iterate(h, true, InConAlpha, nimax, theChange, psiChange, ordering, nisave, sumb, sumdb, diffmx, sorfail, ni);
+}
+int rsg_scb_iterate_psi(rsg_scb* h, double InConPsi, int nimax, int theChange, int psiChange, int ordering, int* nisave,
+                        double* sumb, double* sumdb, double* diffmx, int* sorfail, int* ni) {
+  return scb_iterate(h, false, InConPsi, nimax, theChange, psiChange, ordering, nisave, sumb, sumdb, diffmx, sorfail, ni);
+}
+
+// Compute_convergence, src/ModScbCompute.f90:499-754 (anisotropic branch)
+int rsg_scb_convergence(rsg_scb* h, double* normDiff, double* normJxB, double* normGradP, int* sorfail) {
+  if (!h) return sfail(RSG_ERR_ARG, "null handle");
+  if (!h->band_done || !h->press_set) return sfail(RSG_ERR_STATE, "Compute_convergence before computeBandJacob/set_pressure");
+  if (h->isotropy != 0) return sfail(RSG_ERR_UNSUPPORTED, "Compute_convergence: only the anisotropic branch is implemented");
+  SCK(cudaSetDevice(h->device));
+  dim3 g(nblk(h->nthe, 128), h->npsi, h->nzeta);
+  SCK(cudaEventRecord(h->e0, h->st));
+  k_scb_conv1<<<g, 128, 0, h->st>>>(h->dev);
+  SCKL();
+  k_scb_derivs<<<g, 128, 0, h->st>>>(h->dev, h->dev.w1, nullptr, h->dev.w4, nullptr);   // d/drho of jGradThetaPartialRho
+  SCKL();
+  k_scb_derivs<<<g, 128, 0, h->st>>>(h->dev, h->dev.w2, nullptr, nullptr, h->dev.w5);   // d/dzeta of jGradThetaPartialZeta
+  SCKL();
+  k_scb_derivs<<<g, 128, 0, h->st>>>(h->dev, h->dev.w3, h->dev.w1, nullptr, nullptr);   // d/dtheta of J(pper-ppar) -> w1
+  SCKL();
+  k_scb_conv2<<<g, 128, 0, h->st>>>(h->dev, h->bnormal, h->pnormal, h->pjconst, h->d_part);
+  SCKL();
+  SCK(cudaEventRecord(h->e1, h->st));
+  h->launches += 5;
+  const size_t ncta = (size_t)g.x * g.y * g.z;
+  std::vector<double> part(4 * ncta);
+  SCK(cudaMemcpyAsync(part.data(), h->d_part, part.size() * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  SCK(cudaStreamSynchronize(h->st));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->e0, h->e1);
+  h->last_ms = ms;
+  double s[4] = {0, 0, 0, 0};
+  for (size_t c = 0; c < ncta; ++c)
+    for (int m = 0; m < 4; ++m) s[m] += part[4 * c + m];
+  const double nd = s[0] / s[3], nj = s[1] / s[3], ng = s[2] / s[3];
+  if (normDiff) *normDiff = nd;
+  if (normJxB) *normJxB = nj;
+  if (normGradP) *normGradP = ng;
+  if (sorfail) *sorfail = (std::isnan(nd) || std::isnan(nj) || std::isnan(ng)) ? 1 : 0;
+  return RSG_OK;
+}
+
+// GSL_Derivs (Steffen) of an arbitrary (nthe,npsi,nzeta) host field -- exposed for tests and
+// for host code that still needs the derivative of its own arrays (e.g. `pressure`)
+int rsg_scb_derivs(rsg_scb* h, const double* f, double* dT, double* dR, double* dZ) {
+  if (!h || !f) return sfail(RSG_ERR_ARG, "null argument");
+  if (!h->grid_set) return sfail(RSG_ERR_STATE, "derivs before set_grid");
+  SCK(cudaSetDevice(h->device));
+  const size_t n3 = (size_t)h->nthe * h->npsi * h->nzeta;
+  SCK(cudaMemcpyAsync(h->dev.w1, f, n3 * sizeof(double), cudaMemcpyHostToDevice, h->st));
+  dim3 g(nblk(h->nthe, 128), h->npsi, h->nzeta);
+  k_scb_derivs<<<g, 128, 0, h->st>>>(h->dev, h->dev.w1, dT ? h->dev.w2 : nullptr, dR ? h->dev.w3 : nullptr, dZ ? h->dev.w4 : nullptr);
+  SCKL();
+  h->launches++;
+  if (dT) SCK(cudaMemcpyAsync(dT, h->dev.w2, n3 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  if (dR) SCK(cudaMemcpyAsync(dR, h->dev.w3, n3 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  if (dZ) SCK(cudaMemcpyAsync(dZ, h->dev.w4, n3 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  SCK(cudaStreamSynchronize(h->st));
+  return RSG_OK;
+}
+
+double rsg_scb_last_ms(rsg_scb* h) { return h ? h->last_ms : 0.0; }
+long long rsg_scb_launch_count(rsg_scb* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

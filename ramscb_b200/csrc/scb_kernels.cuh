@@ -1,0 +1,554 @@
+// SCB hot-path kernels for sm_100a (FP64).  Compiled with -fmad=false: every
+// expression keeps the reference's operation order, so the pointwise kernels
+// (Steffen derivatives, computeBandJacob, metrica/metric, newk/newj) and the
+// lexicographic SOR are bit-identical to the CPU oracle.
+//
+// Layout: the reference's Fortran arrays are mirrored as they are, theta
+// fastest: a(i,j,k) -> a[i + nthe*(j + npsi*k)] (0-based), so consecutive
+// threads walk theta and every access is coalesced.  Arrays with a periodic
+// ghost plane have nzeta+1 planes, the others nzeta (src/ModScbInit.f90:22-119).
+//
+// Reference routines restated: src/ModScbCompute.f90:412-754,
+// src/ModScbEquation.f90:18-665, src/ModScbEuler.f90:160-299,469-612,
+// src/ModScbFunctions.f90:57-76, src/RamGSL.c:228-291 (GSL steffen spline).
+#pragma once
+#include <cuda_runtime.h>
+
+struct ScbDev {
+  int nthe, npsi, nzeta;
+  // spacing constants, src/ModScbInit.f90:131-148
+  double rdr, rdt, rdp, rdrsq, rdtsq, rdpsq, rdr2, rdt2, rdp2, rdr4, rdt4, rdp4, rdpdt4, rdtdr4, dr, dt, dpPrime;
+  const double *thetaVal, *rhoVal, *zetaVal, *f, *fzet;
+  double *x, *y, *z, *alfa, *psi, *pper, *ppar, *sigma, *bsq, *bf;  // (nthe,npsi,nzeta+1)
+  double *dXT, *dXR, *dXZ, *dYT, *dYR, *dYZ, *dZT, *dZR, *dZZ, *jac;
+  double *gRX, *gRY, *gRZ, *gZX, *gZY, *gZZ, *gTX, *gTY, *gTZ;
+  double *GRS, *GTS, *GZS, *GRGT, *GRGZ, *GTGZ, *Bx, *By, *Bz;
+  double *vecd, *vec1, *vec2, *vec3, *vec4, *vec6, *vec7, *vec8, *vec9, *vecx, *vecr;
+  double *dPT, *dPR, *dPZ, *dBT, *dBR, *dBZ, *dPP, *dPA, *dBP, *dBA, *dPdAlpha, *dPdPsi;
+  double *jGR, *jGZ, *jGT, *Jx, *Jy, *Jz, *GPx, *GPy, *GPz, *jCrossB, *GradP;
+  double *w1, *w2, *w3, *w4, *w5;   // scratch (nthe,npsi,nzeta)
+};
+
+#define S3(a, i, j, k) (a)[(size_t)(i) + (size_t)d.nthe * ((size_t)(j) + (size_t)d.npsi * (size_t)(k))]   /* 0-based */
+
+__device__ __forceinline__ double sq(double x) { return x * x; }
+
+// ---- GSL steffen spline: derivative at node `i` of the data ya(0..n-1) on the
+// abscissae xa.  ya is addressed as base[idx*stride].
+__device__ __forceinline__ double steffen_sgn(double y) { return (y < 0) ? -1.0 : 1.0; }   // steffen_copysign(1.0, y)
+__device__ __forceinline__ double steffen_yp(const double* xa, const double* base, size_t stride, int n, int i) {
+  if (i == 0) return (base[stride] - base[0]) / (xa[1] - xa[0]);
+  if (i == n - 1) return (base[(size_t)(n - 1) * stride] - base[(size_t)(n - 2) * stride]) / (xa[n - 1] - xa[n - 2]);
+  const double hi = xa[i + 1] - xa[i];
+  const double him1 = xa[i] - xa[i - 1];
+  const double yi = base[(size_t)i * stride];
+  const double si = (base[(size_t)(i + 1) * stride] - yi) / hi;
+  const double sim1 = (yi - base[(size_t)(i - 1) * stride]) / him1;
+  const double pi = (sim1 * hi + si * him1) / (him1 + hi);
+  const double m1 = fabs(si) < 0.5 * fabs(pi) ? fabs(si) : 0.5 * fabs(pi);
+  const double m2 = fabs(sim1) < m1 ? fabs(sim1) : m1;
+  return (steffen_sgn(sim1) + steffen_sgn(si)) * m2;
+}
+__device__ __forceinline__ double steffen_node(const double* xa, const double* base, size_t stride, int n, int i) {
+  double dx;
+  if (i < n - 1) {
+    dx = steffen_yp(xa, base, stride, n, i);
+  } else {
+    // last node: evaluated through the cubic of interval n-2 at delx = h (src/RamGSL.c:274-275)
+    const int q = n - 2;
+    const double hi = xa[q + 1] - xa[q];
+    const double si = (base[(size_t)(q + 1) * stride] - base[(size_t)q * stride]) / hi;
+    const double ypq = steffen_yp(xa, base, stride, n, q), ypq1 = steffen_yp(xa, base, stride, n, q + 1);
+    const double a = (ypq + ypq1 - 2 * si) / hi / hi;
+    const double b = (3 * si - 2 * ypq - ypq1) / hi;
+    const double c = ypq;
+    const double delx = xa[n - 1] - xa[q];
+    dx = c + delx * (2.0 * b + delx * 3.0 * a);
+  }
+  if (dx == 0.0) dx = dx + 1e-31;
+  return dx;
+}
+
+// GSL_Derivs of one field: any of the three outputs may be NULL.
+__global__ void __launch_bounds__(128) k_scb_derivs(ScbDev d, const double* __restrict__ f, double* __restrict__ dT,
+                                                    double* __restrict__ dR, double* __restrict__ dZ) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y, k = blockIdx.z;
+  if (i >= d.nthe) return;
+  const size_t sj = d.nthe, sk = (size_t)d.nthe * d.npsi;
+  const size_t q = i + sj * j + sk * k;
+  if (dT) dT[q] = steffen_node(d.thetaVal, f + sj * j + sk * k, 1, d.nthe, i);
+  if (dR) dR[q] = steffen_node(d.rhoVal, f + i + sk * k, sj, d.npsi, j);
+  if (dZ) dZ[q] = steffen_node(d.zetaVal, f + i + sj * j, sk, d.nzeta, k);
+}
+
+// computeBandJacob (src/ModScbCompute.f90:435-483): derivatives of x,y,z, Jacobian,
+// contravariant gradients, metric products, B (k >= 2).  One thread per point.
+__global__ void __launch_bounds__(128) k_scb_bandjacob(ScbDev d, int* __restrict__ fail) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y, k = blockIdx.z;   // k = 0..nzeta-1
+  if (i >= d.nthe) return;
+  const size_t sj = d.nthe, sk = (size_t)d.nthe * d.npsi;
+  const size_t q = i + sj * j + sk * k;
+  const size_t oT = sj * j + sk * k, oR = i + sk * k, oZ = i + sj * j;
+  const double xT = steffen_node(d.thetaVal, d.x + oT, 1, d.nthe, i), xR = steffen_node(d.rhoVal, d.x + oR, sj, d.npsi, j),
+               xZ = steffen_node(d.zetaVal, d.x + oZ, sk, d.nzeta, k);
+  const double yT = steffen_node(d.thetaVal, d.y + oT, 1, d.nthe, i), yR = steffen_node(d.rhoVal, d.y + oR, sj, d.npsi, j),
+               yZ = steffen_node(d.zetaVal, d.y + oZ, sk, d.nzeta, k);
+  const double zT = steffen_node(d.thetaVal, d.z + oT, 1, d.nthe, i), zR = steffen_node(d.rhoVal, d.z + oR, sj, d.npsi, j),
+               zZ = steffen_node(d.zetaVal, d.z + oZ, sk, d.nzeta, k);
+  d.dXT[q] = xT; d.dXR[q] = xR; d.dXZ[q] = xZ;
+  d.dYT[q] = yT; d.dYR[q] = yR; d.dYZ[q] = yZ;
+  d.dZT[q] = zT; d.dZR[q] = zR; d.dZZ[q] = zZ;
+  const double jac = xR * (yZ * zT - yT * zZ) + xZ * (yT * zR - yR * zT) + xT * (yR * zZ - yZ * zR);
+  d.jac[q] = jac;
+  const double gRX = (yZ * zT - yT * zZ) / jac, gRY = (zZ * xT - zT * xZ) / jac, gRZ = (xZ * yT - xT * yZ) / jac;
+  const double gZX = (yT * zR - yR * zT) / jac, gZY = (zT * xR - zR * xT) / jac, gZZ = (xT * yR - xR * yT) / jac;
+  const double gTX = (yR * zZ - yZ * zR) / jac, gTY = (zR * xZ - zZ * xR) / jac, gTZ = (xR * yZ - xZ * yR) / jac;
+  d.gRX[q] = gRX; d.gRY[q] = gRY; d.gRZ[q] = gRZ;
+  d.gZX[q] = gZX; d.gZY[q] = gZY; d.gZZ[q] = gZZ;
+  d.gTX[q] = gTX; d.gTY[q] = gTY; d.gTZ[q] = gTZ;
+  const double GRS = gRX * gRX + gRY * gRY + gRZ * gRZ;
+  const double GRGZ = gRX * gZX + gRY * gZY + gRZ * gZZ;
+  const double GRGT = gRX * gTX + gRY * gTY + gRZ * gTZ;
+  const double GTS = gTX * gTX + gTY * gTY + gTZ * gTZ;
+  const double GTGZ = gTX * gZX + gTY * gZY + gTZ * gZZ;
+  const double GZS = gZX * gZX + gZY * gZY + gZZ * gZZ;
+  d.GRS[q] = GRS; d.GRGZ[q] = GRGZ; d.GRGT[q] = GRGT; d.GTS[q] = GTS; d.GTGZ[q] = GTGZ; d.GZS[q] = GZS;
+  if (k >= 1) {   // Fortran k = 2..nzeta
+    const double ff = d.f[j] * d.fzet[k];
+    d.Bx[q] = (ff * xT / jac);
+    d.By[q] = (ff * yT / jac);
+    d.Bz[q] = (ff * zT / jac);
+    const double bsq = (GRS * GZS - sq(GRGZ)) * sq(ff);
+    d.bsq[q] = bsq;
+    const double bf = sqrt(bsq);
+    d.bf[q] = bf;
+    if (isnan(bf)) *fail = 1;
+  }
+}
+// bX(:,:,1) = bX(:,:,nZeta) etc. (:490-494)
+__global__ void k_scb_bwrap(ScbDev d) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y;
+  if (i >= d.nthe) return;
+  const size_t q0 = i + (size_t)d.nthe * j, qn = q0 + (size_t)d.nthe * d.npsi * (d.nzeta - 1);
+  d.Bx[q0] = d.Bx[qn]; d.By[q0] = d.By[qn]; d.Bz[q0] = d.Bz[qn]; d.bf[q0] = d.bf[qn]; d.bsq[q0] = d.bsq[qn];
+}
+
+// ---- one stencil position of metrica / metric (src/ModScbEquation.f90:154-250) ----------
+struct Pos {
+  double aj, grs, gps, gts, grgp, gpgt, gtgr;
+};
+__device__ __forceinline__ Pos geom(double xt, double yt, double zt, double xp, double yp, double zp, double xr, double yr,
+                                    double zr) {
+  Pos g;
+  g.aj = xr * (yp * zt - yt * zp) + xp * (yt * zr - yr * zt) + xt * (yr * zp - yp * zr);
+  const double grx = (yp * zt - yt * zp) / g.aj, gry = (zp * xt - zt * xp) / g.aj, grz = (xp * yt - xt * yp) / g.aj;
+  const double gpx = (yt * zr - yr * zt) / g.aj, gpy = (zt * xr - zr * xt) / g.aj, gpz = (xt * yr - xr * yt) / g.aj;
+  const double gtx = (yr * zp - yp * zr) / g.aj, gty = (zr * xp - zp * xr) / g.aj, gtz = (xr * yp - xp * yr) / g.aj;
+  g.grs = (grx * grx + gry * gry + grz * grz);
+  g.gps = (gpx * gpx + gpy * gpy + gpz * gpz);
+  g.gts = (gtx * gtx + gty * gty + gtz * gtz);
+  g.grgp = (gpx * grx + gpy * gry + gpz * grz);
+  g.gpgt = (gpx * gtx + gpy * gty + gpz * gtz);
+  g.gtgr = (gtx * grx + gty * gry + gtz * grz);
+  return g;
+}
+
+// difference stencils (0-based i,j,k of the centre), a = x, y or z
+#define V(a, di, dj, dk) S3(a, i + (di), j + (dj), k + (dk))
+#define DT_A(a) ((V(a, 1, 0, 0) - V(a, 0, 0, 0)) * d.rdt)
+#define DT_C(a) ((V(a, 0, 0, 0) - V(a, -1, 0, 0)) * d.rdt)
+#define DP_A(a) ((V(a, 1, 0, 1) + V(a, 0, 0, 1) - V(a, 1, 0, -1) - V(a, 0, 0, -1)) * d.rdp4)
+#define DP_C(a) ((V(a, 0, 0, 1) + V(a, -1, 0, 1) - V(a, 0, 0, -1) - V(a, -1, 0, -1)) * d.rdp4)
+#define DR_A(a) ((V(a, 1, 1, 0) + V(a, 0, 1, 0) - V(a, 1, -1, 0) - V(a, 0, -1, 0)) * d.rdr4)
+#define DR_C(a) ((V(a, 0, 1, 0) + V(a, -1, 1, 0) - V(a, 0, -1, 0) - V(a, -1, -1, 0)) * d.rdr4)
+// metrica b,d = (k +- 1/2)
+#define AT_B(a) ((V(a, 1, 0, 1) + V(a, 1, 0, 0) - V(a, -1, 0, 1) - V(a, -1, 0, 0)) * d.rdt4)
+#define AT_D(a) ((V(a, 1, 0, 0) + V(a, 1, 0, -1) - V(a, -1, 0, 0) - V(a, -1, 0, -1)) * d.rdt4)
+#define AP_B(a) ((V(a, 0, 0, 1) - V(a, 0, 0, 0)) * d.rdp)
+#define AP_D(a) ((V(a, 0, 0, 0) - V(a, 0, 0, -1)) * d.rdp)
+#define AR_B(a) ((V(a, 0, 1, 1) + V(a, 0, 1, 0) - V(a, 0, -1, 1) - V(a, 0, -1, 0)) * d.rdr4)
+#define AR_D(a) ((V(a, 0, 1, -1) + V(a, 0, 1, 0) - V(a, 0, -1, -1) - V(a, 0, -1, 0)) * d.rdr4)
+// metric b,d = (j +- 1/2)
+#define MT_B(a) ((V(a, 1, 1, 0) + V(a, 1, 0, 0) - V(a, -1, 1, 0) - V(a, -1, 0, 0)) * d.rdt4)
+#define MT_D(a) ((V(a, 1, 0, 0) + V(a, 1, -1, 0) - V(a, -1, 0, 0) - V(a, -1, -1, 0)) * d.rdt4)
+#define MP_B(a) ((V(a, 0, 1, 1) + V(a, 0, 0, 1) - V(a, 0, 1, -1) - V(a, 0, 0, -1)) * d.rdp4)
+#define MP_D(a) ((V(a, 0, 0, 1) + V(a, 0, -1, 1) - V(a, 0, 0, -1) - V(a, 0, -1, -1)) * d.rdp4)
+#define MR_B(a) ((V(a, 0, 1, 0) - V(a, 0, 0, 0)) * d.rdr)
+#define MR_D(a) ((V(a, 0, 0, 0) - V(a, 0, -1, 0)) * d.rdr)
+
+// metrica (ALPHA=true, src/ModScbEquation.f90:18-280) / metric (ALPHA=false, :283-540).
+// One thread per interior point j=2..npsi-1, k=2..nzeta, i=2..nthe-1 (Fortran); the
+// 27-point neighbourhood of x,y,z is served by L1/L2.
+template <bool ALPHA>
+__global__ void __launch_bounds__(128) k_scb_metric(ScbDev d) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;   // 1..nthe-2
+  const int j = blockIdx.y + 1;                              // 1..npsi-2
+  const int k = blockIdx.z + 1;                              // 1..nzeta-1
+  if (i > d.nthe - 2) return;
+  const double *x = d.x, *y = d.y, *z = d.z;
+  const Pos a = geom(DT_A(x), DT_A(y), DT_A(z), DP_A(x), DP_A(y), DP_A(z), DR_A(x), DR_A(y), DR_A(z));
+  const Pos c = geom(DT_C(x), DT_C(y), DT_C(z), DP_C(x), DP_C(y), DP_C(z), DR_C(x), DR_C(y), DR_C(z));
+  const size_t q = (size_t)i + (size_t)d.nthe * ((size_t)j + (size_t)d.npsi * (size_t)k);
+  if (ALPHA) {
+    const Pos b = geom(AT_B(x), AT_B(y), AT_B(z), AP_B(x), AP_B(y), AP_B(z), AR_B(x), AR_B(y), AR_B(z));
+    const Pos e = geom(AT_D(x), AT_D(y), AT_D(z), AP_D(x), AP_D(y), AP_D(z), AR_D(x), AR_D(y), AR_D(z));
+    const double v1a = (a.grs * a.gts - sq(a.gtgr)) * a.aj * d.rdtsq;
+    const double v1c = (c.grs * c.gts - sq(c.gtgr)) * c.aj * d.rdtsq;
+    const double v2a = (a.grs * a.gpgt - a.grgp * a.gtgr) * a.aj * d.rdpdt4;
+    const double v2b = (b.grs * b.gpgt - b.grgp * b.gtgr) * b.aj * d.rdpdt4;
+    const double v2c = (c.grs * c.gpgt - c.grgp * c.gtgr) * c.aj * d.rdpdt4;
+    const double v2d = (e.grs * e.gpgt - e.grgp * e.gtgr) * e.aj * d.rdpdt4;
+    const double v3b = (b.grs * b.gps - sq(b.grgp)) * b.aj * d.rdpsq;
+    const double v3d = (e.grs * e.gps - sq(e.grgp)) * e.aj * d.rdpsq;
+    d.vecd[q] = (v1a + v1c) + (v3b + v3d);
+    d.vec1[q] = (v2c + v2d);
+    d.vec2[q] = (v2c - v2a) + v3d;
+    d.vec3[q] = -(v2a + v2d);
+    d.vec4[q] = v1c + (v2d - v2b);
+    d.vec6[q] = v1a + (v2b - v2d);
+    d.vec7[q] = -(v2c + v2b);
+    d.vec8[q] = v3b + (v2a - v2c);
+    d.vec9[q] = (v2a + v2b);
+  } else {
+    const Pos b = geom(MT_B(x), MT_B(y), MT_B(z), MP_B(x), MP_B(y), MP_B(z), MR_B(x), MR_B(y), MR_B(z));
+    const Pos e = geom(MT_D(x), MT_D(y), MT_D(z), MP_D(x), MP_D(y), MP_D(z), MR_D(x), MR_D(y), MR_D(z));
+    const double v1a = (sq(a.gpgt) - a.gps * a.gts) * a.aj * d.rdtsq;
+    const double v1c = (sq(c.gpgt) - c.gps * c.gts) * c.aj * d.rdtsq;
+    const double v2a = (a.grgp * a.gpgt - a.gps * a.gtgr) * a.aj * d.rdtdr4;
+    const double v2b = (b.grgp * b.gpgt - b.gps * b.gtgr) * b.aj * d.rdtdr4;
+    const double v2c = (c.grgp * c.gpgt - c.gps * c.gtgr) * c.aj * d.rdtdr4;
+    const double v2d = (e.grgp * e.gpgt - e.gps * e.gtgr) * e.aj * d.rdtdr4;
+    const double v3b = (sq(b.grgp) - b.grs * b.gps) * b.aj * d.rdrsq;
+    const double v3d = (sq(e.grgp) - e.grs * e.gps) * e.aj * d.rdrsq;
+    d.vecd[q] = (v1a + v1c + v3b + v3d);
+    d.vec1[q] = (v2c + v2d);
+    d.vec2[q] = ((v2c - v2a) + v3d);
+    d.vec3[q] = -(v2a + v2d);
+    d.vec4[q] = (v1c + (v2d - v2b));
+    d.vec6[q] = (v1a + (v2b - v2d));
+    d.vec7[q] = -(v2c + v2b);
+    d.vec8[q] = (v3b + (v2a - v2c));
+    d.vec9[q] = (v2b + v2a);
+  }
+}
+
+// newk (ALPHA) / newj, Picard, src/ModScbEquation.f90:546-665.  All points of (nthe,npsi,nzeta).
+template <bool ALPHA>
+__global__ void __launch_bounds__(128) k_scb_rhs(ScbDev d, int isotropy) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y, k = blockIdx.z;
+  if (i >= d.nthe) return;
+  const size_t q = (size_t)i + (size_t)d.nthe * ((size_t)j + (size_t)d.npsi * (size_t)k);
+  const double fj = d.f[j], fk = d.fzet[k];
+  if (isotropy == 1) {
+    if (ALPHA) d.vecx[q] = -d.dPdAlpha[q] * d.jac[q] / (fj * fj);
+    else d.vecr[q] = d.jac[q] * d.dPdPsi[q] / (fk * fk);
+    return;
+  }
+  const double sg = d.sigma[q];
+  const double tt = d.dPT[q] + 0.5 * (1. - sg) * d.dBT[q];
+  if (ALPHA) {
+    const double xpz = (d.GRS[q] * d.GZS[q] - sq(d.GRGZ[q]));
+    const double xpt = (d.GRS[q] * d.GTGZ[q] - d.GRGZ[q] * d.GRGT[q]);
+    const double c0 = -(fj * fj * fk) / sg / d.bsq[q];
+    const double tz = d.dPZ[q] + 0.5 * (1. - sg) * d.dBZ[q];
+    d.vecx[q] = d.jac[q] / (fj * fj) * c0 * (tz * xpz + tt * xpt);
+  } else {
+    const double xpr = (sq(d.GRGZ[q]) - d.GRS[q] * d.GZS[q]);
+    const double xpt = (d.GRGZ[q] * d.GTGZ[q] - d.GZS[q] * d.GRGT[q]);
+    const double c0 = -(fj * (fk * fk)) / sg / d.bsq[q];
+    const double tr = d.dPR[q] + 0.5 * (1. - sg) * d.dBR[q];
+    d.vecr[q] = d.jac[q] / (fk * fk) * c0 * (tr * xpr + tt * xpt);
+  }
+}
+
+// =============================================================================
+// SOR.  Each sub-problem (a psi surface for alpha, a zeta slice for psi) is a 2-D
+// 9-point problem owned by one CTA; the unknown plane lives in shared memory,
+// the 10 coefficient planes are streamed from L2 (the whole coefficient set of
+// the default grid is 39 MB: L2 resident).  The CTA iterates to convergence in
+// one launch (in-kernel convergence test, per-sub-problem early exit).
+//
+// Plane indexing: column c = theta (0..nthe-1), row r = the second stencil
+// direction (zeta planes 0..nzeta for alpha, psi 0..npsi-1 for psi).
+//   ORDER 0 (LEX): the reference's lexicographic Gauss-Seidel order reproduced
+//     as a skewed wavefront -- thread = row, at step t row r updates column
+//     t-2r -- bit-identical iterates, iteration counts and residuals.
+//   ORDER 1 (COLOR4): 4-colour ordering ((c mod 2, r mod 2)); the 9-point
+//     stencil has corner couplings, so 4 colours (not red-black) are needed for
+//     a race-free Gauss-Seidel; converges to the same fixed point.
+// =============================================================================
+struct SorArgs {
+  double tol, omegaOpt;
+  int nimax, nT, nP;
+  int* ni;          // per sub-problem iteration count (Fortran ni(jz) / ni(k))
+  double* resmax;   // per sub-problem max|resid| of the last sweep
+  int* fail;
+};
+
+template <bool ALPHA, int ORDER>
+__global__ void __launch_bounds__(1024) k_scb_sor(ScbDev d, SorArgs a) {
+  extern __shared__ double su[];
+  __shared__ double s_red[32];
+  __shared__ int s_stop;
+  const int nthe = d.nthe, npsi = d.npsi, nzeta = d.nzeta;
+  const int tid = threadIdx.x, T = blockDim.x;
+  // sub-problem and its plane geometry
+  const int sub = blockIdx.x;                       // alpha: jz-2 (Fortran jz = 2..npsi-nP); psi: k-2 (k = 2..nzeta)
+  const int nrows = ALPHA ? nzeta + 1 : npsi;       // rows held in shared memory
+  const int r0 = 1, r1 = ALPHA ? nzeta - 1 : npsi - a.nP - 1;   // updated rows (0-based, inclusive)
+  const int c0 = a.nT, c1 = nthe - a.nT - 1;                    // updated columns
+  const size_t sj = nthe, sk = (size_t)nthe * npsi;
+  double* u = ALPHA ? d.alfa : d.psi;
+  const size_t base = ALPHA ? sj * (size_t)(sub + 1) : sk * (size_t)(sub + 1);   // plane origin (jz or k fixed)
+  const size_t rstride = ALPHA ? sk : sj;                                        // between rows
+  for (int q = tid; q < nrows * nthe; q += T) {
+    const int r = q / nthe, c = q - r * nthe;
+    su[q] = u[base + (size_t)r * rstride + c];
+  }
+  if (tid == 0) s_stop = 0;
+  __syncthreads();
+  const double* rhs = ALPHA ? d.vecx : d.vecr;
+  double om = 1.0;
+  int ni = 1;
+  double lastmax = 0.0;
+  bool failed = false;
+  while (ni <= a.nimax) {
+    double rmax = 0.0;
+    if (ORDER == 0) {
+      const int nr = r1 - r0 + 1, nc = c1 - c0 + 1;
+      const int r = r0 + tid;
+      const bool active = tid < nr;
+      const size_t rowoff = base + (size_t)r * rstride;
+      for (int t = 0; t < 2 * (nr - 1) + nc; ++t) {
+        const int c = c0 + t - 2 * tid;
+        if (active && c >= c0 && c <= c1) {
+          const size_t q = rowoff + c;
+          const double* um = su + (r - 1) * nthe + c;
+          const double* uc = su + r * nthe + c;
+          const double* up = su + (r + 1) * nthe + c;
+          const double vd = d.vecd[q];
+          const double res = -vd * uc[0] + d.vec1[q] * um[-1] + d.vec2[q] * um[0] + d.vec3[q] * um[1] + d.vec4[q] * uc[-1] +
+                             d.vec6[q] * uc[1] + d.vec7[q] * up[-1] + d.vec8[q] * up[0] + d.vec9[q] * up[1] - rhs[q];
+          double un = ALPHA ? (uc[0] + om * (res / vd)) : (uc[0] + om * res / vd);
+          double rr = res;
+          if (isnan(un) || un >= 1e10) {   // :226-240 / :539-553
+            un = u[q];                      // global memory still holds the pre-solve value
+            rr = 0.0;
+            failed = true;
+          }
+          su[r * nthe + c] = un;
+          if (c >= 1 && c <= nthe - 2) rmax = fmax(rmax, fabs(rr));
+        }
+        __syncthreads();
+      }
+    } else {
+      for (int col = 0; col < 4; ++col) {
+        const int pc = col & 1, pr = col >> 1;
+        // points of this colour: c in [c0,c1] with c%2==pc, r in [r0,r1] with r%2==pr
+        const int cs = c0 + (((c0 & 1) == pc) ? 0 : 1), rs = r0 + (((r0 & 1) == pr) ? 0 : 1);
+        const int ncc = (c1 - cs) / 2 + 1, nrr = (r1 - rs) / 2 + 1;
+        if (cs <= c1 && rs <= r1)
+          for (int w = tid; w < ncc * nrr; w += T) {
+            const int rr_ = w / ncc, cc = w - rr_ * ncc;
+            const int r = rs + 2 * rr_, c = cs + 2 * cc;
+            const size_t q = base + (size_t)r * rstride + c;
+            const double* um = su + (r - 1) * nthe + c;
+            const double* uc = su + r * nthe + c;
+            const double* up = su + (r + 1) * nthe + c;
+            const double vd = d.vecd[q];
+            const double res = -vd * uc[0] + d.vec1[q] * um[-1] + d.vec2[q] * um[0] + d.vec3[q] * um[1] + d.vec4[q] * uc[-1] +
+                               d.vec6[q] * uc[1] + d.vec7[q] * up[-1] + d.vec8[q] * up[0] + d.vec9[q] * up[1] - rhs[q];
+            double un = ALPHA ? (uc[0] + om * (res / vd)) : (uc[0] + om * res / vd);
+            double rr = res;
+            if (isnan(un) || un >= 1e10) {
+              un = u[q];
+              rr = 0.0;
+              failed = true;
+            }
+            su[r * nthe + c] = un;
+            if (c >= 1 && c <= nthe - 2) rmax = fmax(rmax, fabs(rr));
+          }
+        __syncthreads();
+      }
+    }
+    // block max of |resid| over the sweep, failure flag
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+    if ((tid & 31) == 0) s_red[tid >> 5] = rmax;
+    if (failed) s_stop = 1;
+    __syncthreads();
+    double m = 0.0;
+    for (int q = 0; q < (T + 31) / 32; ++q) m = fmax(m, s_red[q]);
+    lastmax = m;
+    const int stop = s_stop;
+    __syncthreads();
+    if (stop) break;              // EXIT Iterations on failure (ni not advanced)
+    om = a.omegaOpt;
+    if (m < a.tol) break;         // converged
+    ni = ni + 1;
+  }
+  for (int q = tid; q < nrows * nthe; q += T) {
+    const int r = q / nthe, c = q - r * nthe;
+    if (r >= r0 && r <= r1 && c >= c0 && c <= c1) u[base + (size_t)r * rstride + c] = su[q];
+  }
+  if (tid == 0) {
+    a.ni[sub] = ni;
+    a.resmax[sub] = lastmax;
+    if (s_stop) *a.fail = 1;
+  }
+}
+
+// sumb, sumdb over (2:nthe-1, 2:npsi-1, 2:nzeta) (Fortran), one CTA per zeta plane -> partials
+__global__ void __launch_bounds__(256) k_scb_sums(ScbDev d, const double* __restrict__ u, const double* __restrict__ uprev,
+                                                  double* __restrict__ part) {
+  __shared__ double sm[2][32];
+  const int k = blockIdx.x + 1;
+  double sb = 0.0, sdb = 0.0;
+  const int ni = d.nthe - 2, nj = d.npsi - 2;
+  for (int w = threadIdx.x; w < ni * nj; w += blockDim.x) {
+    const int jj = w / ni, ii = w - jj * ni;
+    const size_t q = (size_t)(ii + 1) + (size_t)d.nthe * ((size_t)(jj + 1) + (size_t)d.npsi * (size_t)k);
+    sb += fabs(u[q]);
+    sdb += fabs(u[q] - uprev[q]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sb += __shfl_xor_sync(0xffffffffu, sb, o);
+    sdb += __shfl_xor_sync(0xffffffffu, sdb, o);
+  }
+  if ((threadIdx.x & 31) == 0) { sm[0][threadIdx.x >> 5] = sb; sm[1][threadIdx.x >> 5] = sdb; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, b = 0;
+    for (int q = 0; q < (int)(blockDim.x >> 5); ++q) { a += sm[0][q]; b += sm[1][q]; }
+    part[2 * blockIdx.x] = a;
+    part[2 * blockIdx.x + 1] = b;
+  }
+}
+
+// extap, src/ModScbFunctions.f90:57-76
+__device__ __forceinline__ double extap(double x1, double x2, double x3) {
+  double x4 = 3. * x3 - 3. * x2 + x1;
+  const double ddx1 = x3 - x2, ddx2 = x2 - x1;
+  double ddx = x4 - x3;
+  const double pm = ddx * ddx1;
+  if (pm > 0.) return x4;
+  if (fabs(ddx2) <= 1e-9) return 2. * x3 - x2;
+  ddx = (ddx1 * ddx1) / ddx2;
+  return x3 + ddx;
+}
+// post-processing of iterateAlpha/iteratePsi (src/ModScbEuler.f90:262-292, :575-605), stage 1:
+// extrapolation onto the outer psi surfaces; one thread per (i, k)
+__global__ void k_scb_post_extap(ScbDev d, double* __restrict__ u, int nT, int nP) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // 0-based theta
+  const int k = blockIdx.y + 1;                           // Fortran k = 2..nzeta
+  if (i < nT || i > d.nthe - nT - 1) return;
+  for (int j = nP; j >= 1; --j) {
+    // extap(u(i,npsi-j-2), u(i,npsi-j-1), u(i,npsi-j), u(i,npsi-j+1)), Fortran 1-based psi index
+    const int j4 = d.npsi - j + 1 - 1;
+    S3(u, i, j4, k) = extap(S3(u, i, j4 - 3, k), S3(u, i, j4 - 2, k), S3(u, i, j4 - 1, k));
+  }
+}
+// stage 2: linear fill of the theta ends for k = 1..nzeta (Fortran), all j
+__global__ void k_scb_post_theta(ScbDev d, double* __restrict__ u, int nT) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = blockIdx.y;   // 0..nzeta-1
+  if (j >= d.npsi) return;
+  const int nthe = d.nthe;
+  for (int i = 1; i <= nT; ++i) {   // Fortran i
+    // u(i) = u(nT+1) + (nT+1-i)*(u(1)-u(nT+1))/nT ; u(nthe-i+1) = u(nthe-nT-1) + (nT+1-i)*(u(nthe)-u(nthe-nT-1))/nT
+    S3(u, i - 1, j, k) = S3(u, nT, j, k) + (nT + 1 - i) * (S3(u, 0, j, k) - S3(u, nT, j, k)) / nT;
+    S3(u, nthe - i, j, k) = S3(u, nthe - nT - 2, j, k) + (nT + 1 - i) * (S3(u, nthe - 1, j, k) - S3(u, nthe - nT - 2, j, k)) / (nT);
+  }
+}
+// stage 3: periodic wrap u(:,:,1) = u(:,:,nzeta) - wrap ; u(:,:,nzeta+1) = u(:,:,2) + wrap
+__global__ void k_scb_post_wrap(ScbDev d, double* __restrict__ u, double wrap) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y;
+  if (i >= d.nthe) return;
+  S3(u, i, j, 0) = S3(u, i, j, d.nzeta - 1) - wrap;
+  S3(u, i, j, d.nzeta) = S3(u, i, j, 1) + wrap;
+}
+
+// ---- Compute_convergence (src/ModScbCompute.f90:553-733), anisotropic branch --------------
+// stage 1: j.gradRho, j.gradZeta, and the two flux-like fields whose derivatives give j.gradTheta,
+// plus jacobian*(pper-ppar)
+__global__ void __launch_bounds__(128) k_scb_conv1(ScbDev d) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y, k = blockIdx.z;
+  if (i >= d.nthe) return;
+  const size_t q = (size_t)i + (size_t)d.nthe * ((size_t)j + (size_t)d.npsi * (size_t)k);
+  const double sg = d.sigma[q], fj = d.f[j], fk = d.fzet[k];
+  d.jGR[q] = 1.0 / fj * (-1. / sg * d.dPA[q] -
+                         1. / (sg * d.bsq[q]) * (fj * fj) * fk * (d.GRS[q] * d.GTGZ[q] - d.GRGT[q] * d.GRGZ[q]) *
+                             (d.dPT[q] + (1. - sg) * 0.5 * d.dBT[q]) -
+                         (1. - sg) / sg * 0.5 * d.dBA[q]);
+  d.jGZ[q] = 1.0 / fk * (1. / sg * d.dPP[q] -
+                         1. / (sg * d.bsq[q]) * fj * (fk * fk) * (d.GRGZ[q] * d.GTGZ[q] - d.GRGT[q] * d.GZS[q]) *
+                             (d.dPT[q] + (1. - sg) * 0.5 * d.dBT[q]) +
+                         (1. - sg) / sg * 0.5 * d.dBP[q]);
+  d.w1[q] = d.jac[q] * fj * fk * (d.GRGT[q] * d.GRGZ[q] - d.GTGZ[q] * d.GRS[q]);   // jGradThetaPartialRho
+  d.w2[q] = d.jac[q] * fj * fk * (d.GRGT[q] * d.GZS[q] - d.GRGZ[q] * d.GTGZ[q]);   // jGradThetaPartialZeta
+  d.w3[q] = d.jac[q] * (d.pper[q] - d.ppar[q]);
+}
+// stage 2 (after the derivative passes: w4 = d(w1)/drho, w5 = d(w2)/dzeta, w1 <- d(w3)/dtheta):
+// J, grad P, |J x B|, |grad P| and the per-plane partial sums of the four norms
+__global__ void __launch_bounds__(128) k_scb_conv2(ScbDev d, double bnormal, double pnormal, double pjconst, double* __restrict__ part) {
+  __shared__ double sm[4][4];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y, k = blockIdx.z;
+  double acc[4] = {0, 0, 0, 0};
+  if (i < d.nthe) {
+    const size_t q = (size_t)i + (size_t)d.nthe * ((size_t)j + (size_t)d.npsi * (size_t)k);
+    const double jac = d.jac[q];
+    const double jGT = (d.w4[q] + d.w5[q]) / jac;
+    d.jGT[q] = jGT;
+    const double jGR = d.jGR[q], jGZ = d.jGZ[q], dD = d.w1[q];
+    d.Jx[q] = (jGR * d.dXR[q] + jGZ * d.dXZ[q] + jGT * d.dXT[q]);
+    d.Jy[q] = (jGR * d.dYR[q] + jGZ * d.dYZ[q] + jGT * d.dYT[q]);
+    d.Jz[q] = (jGR * d.dZR[q] + jGZ * d.dZZ[q] + jGT * d.dZT[q]);
+    const double fj = d.f[j], fk = d.fzet[k];
+    const double GRS = d.GRS[q], GZS = d.GZS[q], GTS = d.GTS[q], GRGZ = d.GRGZ[q], GRGT = d.GRGT[q], GTGZ = d.GTGZ[q];
+    const double dPR = d.dPR[q], dPZ = d.dPZ[q], dPT = d.dPT[q];
+    const double jCBsq = (fj * fj) * (fk * fk) * (GRS * sq(jGZ) + GZS * sq(jGR) - 2.0 * jGZ * jGR * GRGZ);
+    const double gPsq = GRS * sq(dPR) + GZS * sq(dPZ) + GTS * sq(dPT) + 2. * dPR * dPZ * GRGZ + 2. * dPR * dPT * GRGT +
+                        2. * dPZ * dPT * GTGZ + sq(dD / jac) - 2. * dPT * dD / jac;
+    const double t1 = (dPR * GRS + dPZ * GRGZ + dPT * GRGT);
+    const double t2 = (dPR * GRGZ + dPZ * GZS + dPT * GTGZ);
+    const double t3 = (dPR * GRGT + dPZ * GTGZ + dPT * GTS);
+    d.GPx[q] = t1 * d.dXR[q] + t2 * d.dXZ[q] + t3 * d.dXT[q] + dD * GRGT * d.dXR[q] + dD * GTGZ * d.dXZ[q] + dD * GTS * d.dXT[q];
+    d.GPy[q] = t1 * d.dYR[q] + t2 * d.dYZ[q] + t3 * d.dYT[q] + dD * GRGT * d.dYR[q] + dD * GTGZ * d.dYZ[q] + dD * GTS * d.dYT[q];
+    d.GPz[q] = t1 * d.dZR[q] + t2 * d.dZZ[q] + t3 * d.dZT[q] + dD * GRGT * d.dZR[q] + dD * GTGZ * d.dZZ[q] + dD * GTS * d.dZT[q];
+    const double jCB = sqrt(jCBsq) * bnormal * pjconst;
+    const double gP = sqrt(fabs(gPsq)) * pnormal / 6.4;
+    d.jCrossB[q] = jCB;
+    d.GradP[q] = gP;
+    if (i >= 1 && i <= d.nthe - 2 && j >= 1 && j <= d.npsi - 2 && k >= 1) {
+      const double vol = jac * d.dr * d.dpPrime * d.dt;
+      acc[0] = vol * (jCB - gP);
+      acc[1] = vol * jCB;
+      acc[2] = vol * gP;
+      acc[3] = vol;
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    double v = acc[m];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sm[m][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const size_t cta = blockIdx.x + (size_t)gridDim.x * (blockIdx.y + (size_t)gridDim.y * blockIdx.z);
+    for (int m = 0; m < 4; ++m) {
+      double v = 0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += sm[m][w];
+      part[cta * 4 + m] = v;
+    }
+  }
+}

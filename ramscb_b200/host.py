@@ -289,3 +289,139 @@ class RamGpu:
             self.close()
         except Exception:
             pass
+
+
+# =============================================================================
+# SCB: mirror of ModScbCompute / ModScbEquation / ModScbEuler over the C ABI
+# =============================================================================
+SOR_LEX, SOR_COLOR4 = 0, 1
+_scb_ready = False
+
+
+def _scb_lib():
+    global _scb_ready
+    L = lib()
+    if not _scb_ready:
+        vp, i, d, ll = C.c_void_p, C.c_int, C.c_double, C.c_longlong
+        L.rsg_scb_last_error.restype = C.c_char_p
+        L.rsg_scb_create.argtypes = [C.POINTER(vp), i, i, i, i]
+        L.rsg_scb_destroy.argtypes = [vp]
+        L.rsg_scb_set_grid.argtypes = [vp] * 6
+        L.rsg_scb_set_geometry.argtypes = [vp] * 4
+        L.rsg_scb_set_pressure.argtypes = [vp, i] + [vp] * 15
+        L.rsg_scb_set_field.argtypes = [vp, C.c_char_p, vp]
+        L.rsg_scb_get_field.argtypes = [vp, C.c_char_p, vp]
+        L.rsg_scb_field_size.argtypes = [vp, C.c_char_p, C.POINTER(ll)]
+        L.rsg_scb_bandjacob.argtypes = [vp, _ip]
+        for n in ("metrica", "metric", "newk", "newj"):
+            getattr(L, "rsg_scb_" + n).argtypes = [vp]
+        for n in ("iterate_alpha", "iterate_psi"):
+            getattr(L, "rsg_scb_" + n).argtypes = [vp, d, i, i, i, i, _ip, _dp, _dp, _dp, _ip, vp]
+        L.rsg_scb_convergence.argtypes = [vp, _dp, _dp, _dp, _ip]
+        L.rsg_scb_derivs.argtypes = [vp] * 5
+        L.rsg_scb_last_ms.argtypes = [vp]
+        L.rsg_scb_last_ms.restype = d
+        L.rsg_scb_launch_count.argtypes = [vp]
+        L.rsg_scb_launch_count.restype = ll
+        _scb_ready = True
+    return L
+
+
+def _sck(rc):
+    if rc != 0:
+        raise RsgError(f"rsg_scb status {rc}: {_scb_lib().rsg_scb_last_error().decode()}")
+
+
+class ScbGpu:
+    """Device-resident SCB state with the reference's routine names
+    (computeBandJacob, metrica, metric, newk, newj, iterateAlpha, iteratePsi,
+    Compute_convergence -- all argument-less in the reference)."""
+
+    def __init__(self, inp, device: int = -1):
+        self.L = _scb_lib()
+        self.inp = inp
+        self.nthe, self.npsi, self.nzeta = inp.nthe, inp.npsi, inp.nzeta
+        self.h = C.c_void_p()
+        _sck(self.L.rsg_scb_create(C.byref(self.h), inp.nthe, inp.npsi, inp.nzeta, device))
+        c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        g = [c(inp.thetaVal), c(inp.rhoVal), c(inp.zetaVal), c(inp.f), c(inp.fzet)]
+        _sck(self.L.rsg_scb_set_grid(self.h, *[a.ctypes.data for a in g]))
+        _sck(self.L.rsg_scb_set_geometry(self.h, _p(inp.x), _p(inp.y), _p(inp.z)))
+        self.set_pressure(inp)
+        self.set_field("alfa", inp.alfa)
+        self.set_field("psi", inp.psi)
+
+    def set_pressure(self, inp):
+        names = ("pper", "ppar", "sigma", "dPPerdTheta", "dPPerdRho", "dPPerdZeta", "dBsqdTheta", "dBsqdRho", "dBsqdZeta",
+                 "dPPerdPsi", "dPPerdAlpha", "dBsqdPsi", "dBsqdAlpha", "dPdAlpha", "dPdPsi")
+        _sck(self.L.rsg_scb_set_pressure(self.h, inp.isotropy, *[_p(getattr(inp, n)) for n in names]))
+
+    def set_geometry(self, x, y, z):
+        _sck(self.L.rsg_scb_set_geometry(self.h, _p(x), _p(y), _p(z)))
+
+    def set_field(self, name, a):
+        _sck(self.L.rsg_scb_set_field(self.h, name.encode(), _p(np.asfortranarray(a, dtype=np.float64))))
+
+    def get_field(self, name):
+        n = C.c_longlong()
+        _sck(self.L.rsg_scb_field_size(self.h, name.encode(), C.byref(n)))
+        plane = self.nthe * self.npsi
+        if n.value % plane == 0 and n.value // plane in (self.nzeta, self.nzeta + 1):
+            out = np.zeros((self.nthe, self.npsi, n.value // plane), order="F")
+        else:
+            out = np.zeros(n.value)
+        _sck(self.L.rsg_scb_get_field(self.h, name.encode(), out.ctypes.data))
+        return out
+
+    def computeBandJacob(self):
+        f = C.c_int()
+        _sck(self.L.rsg_scb_bandjacob(self.h, C.byref(f)))
+        return f.value
+
+    def metrica(self): _sck(self.L.rsg_scb_metrica(self.h))
+    def metric(self): _sck(self.L.rsg_scb_metric(self.h))
+    def newk(self): _sck(self.L.rsg_scb_newk(self.h))
+    def newj(self): _sck(self.L.rsg_scb_newj(self.h))
+
+    def _iterate(self, fn, tol, nimax, theChange, psiChange, ordering, n):
+        nisave, fail = C.c_int(), C.c_int()
+        sumb, sumdb, diffmx = C.c_double(), C.c_double(), C.c_double()
+        ni = np.zeros(n, dtype=np.int32)
+        _sck(fn(self.h, tol, nimax, theChange, psiChange, ordering, C.byref(nisave), C.byref(sumb), C.byref(sumdb),
+                C.byref(diffmx), C.byref(fail), ni.ctypes.data))
+        return {"nisave": nisave.value, "sumb": sumb.value, "sumdb": sumdb.value, "diffmx": diffmx.value,
+                "SORFail": fail.value, "ni": ni, "ms": self.last_ms()}
+
+    def iterateAlpha(self, InConAlpha=1e-6, nimax=5001, theChange=4, psiChange=0, ordering=SOR_LEX):
+        return self._iterate(self.L.rsg_scb_iterate_alpha, InConAlpha, nimax, theChange, psiChange, ordering, self.npsi)
+
+    def iteratePsi(self, InConPsi=1e-6, nimax=5001, theChange=4, psiChange=0, ordering=SOR_LEX):
+        return self._iterate(self.L.rsg_scb_iterate_psi, InConPsi, nimax, theChange, psiChange, ordering, self.nzeta)
+
+    def Compute_convergence(self):
+        a, b, c, f = C.c_double(), C.c_double(), C.c_double(), C.c_int()
+        _sck(self.L.rsg_scb_convergence(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(f)))
+        return {"normDiff": a.value, "normJxB": b.value, "normGradP": c.value, "SORFail": f.value}
+
+    def derivs(self, f3):
+        f3 = np.asfortranarray(f3, dtype=np.float64)
+        out = [np.zeros(f3.shape, order="F") for _ in range(3)]
+        _sck(self.L.rsg_scb_derivs(self.h, _p(f3), *[_p(o) for o in out]))
+        return out
+
+    def last_ms(self):
+        return self.L.rsg_scb_last_ms(self.h)
+
+    def launch_count(self):
+        return self.L.rsg_scb_launch_count(self.h)
+
+    def close(self):
+        if self.h:
+            self.L.rsg_scb_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
