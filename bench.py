@@ -173,14 +173,22 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    # ---- species sharding: the species loop of ram_run has no cross-species data
-    # dependence (src/ModRamRun.f90:64-185), so ranks own disjoint species sets.
-    my_species = [s for s in range(g.nS) if s % world == rank]
+    # ---- sharding (ramscb_b200/parallel.py): species over ranks (no data-path collective);
+    # beyond nS ranks, (L,K) slabs inside a species with two NCCL re-shardings per step
+    from ramscb_b200 import parallel
+    plan = parallel.make_plan(world, rank, g.nS, g.NPA, g.NE)
     gpu = host.RamGpu(g, device=local_rank, mode=host.MODE_FAST if a.mode == "fast" else host.MODE_EXACT)
     gpu.set_inputs(inp)
     F2_host = inp.F2.copy(order="F")
     host.host_register(F2_host)
     flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
+    sharded = None
+    if world > 1:
+        # a non-default torch stream carries both the library's kernels and the NCCL traffic
+        run_stream = torch.cuda.Stream()
+        torch.cuda.set_stream(run_stream)
+        gpu.set_stream(run_stream.cuda_stream)
+        sharded = parallel.RamSharded(gpu, plan, dist)
 
     def barrier():
         if dist is not None:
@@ -188,25 +196,7 @@ def main():
         torch.cuda.synchronize()
 
     def step_resident():
-        return gpu.ram_run(DTS, DtsMin=1.0, flags=0) if world == 1 else run_my_species()
-
-    def run_my_species():
-        # same operator sequence as rsg_ram_run, restricted to this rank's species
-        for s in my_species:
-            S = s + 1
-            gpu.CEPARA(S, DTS); gpu.DRIFTPARA(S, DTS)
-            gpu.DRIFTR(S); gpu.DRIFTP(S); gpu.DRIFTE(S); gpu.DRIFTMU(S); gpu.SUMRC(S)
-            if g.species[s].WPI:
-                gpu.WAVELO(S, DTS); gpu.SUMRC(S)
-            if g.species[s].CEX:
-                gpu.CHAREXCHANGE(S); gpu.SUMRC(S)
-            gpu.ATMOL(S); gpu.SUMRC(S); gpu.ATMOL(S); gpu.SUMRC(S)
-            if g.species[s].CEX:
-                gpu.CHAREXCHANGE(S); gpu.SUMRC(S)
-            if g.species[s].WPI:
-                gpu.WAVELO(S, DTS); gpu.SUMRC(S)
-            gpu.DRIFTMU(S); gpu.DRIFTE(S); gpu.DRIFTP(S); gpu.DRIFTR(S); gpu.SUMRC(S)
-            gpu.ANISCH(S)
+        return gpu.ram_run(DTS, DtsMin=1.0, flags=0) if world == 1 else sharded.ram_run(DTS)
 
     for _ in range(a.warmup):
         step_resident()
@@ -216,12 +206,20 @@ def main():
     barrier()
     dev_ms = 0.0
     t_wall0 = time.perf_counter()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for _ in range(a.steps):
         flush.zero_()                      # evict F2 from the 126 MB L2 (untimed)
         torch.cuda.synchronize()
-        gpu.timer_begin()
-        step_resident()
-        dev_ms += gpu.timer_end()
+        if world == 1:
+            gpu.timer_begin()
+            step_resident()
+            dev_ms += gpu.timer_end()
+        else:                              # library work and NCCL are on / ordered with torch's current stream
+            ev0.record()
+            step_resident()
+            ev1.record()
+            torch.cuda.synchronize()
+            dev_ms += ev0.elapsed_time(ev1)
     barrier()
     wall_s = time.perf_counter() - t_wall0
     clk = clocks.stop()
@@ -288,7 +286,9 @@ def main():
                                 "stencil neighbourhood (tests/test_ram_parity_gpu.py)") if a.mode == "fast"
                        else "exact: reference operation order, bit-identical to the oracle",
                        "l2": "flushed between timed steps (512 MB memset, untimed)", "DTs": DTS,
-                       "parallelism": f"species-sharded x{world}" if world > 1 else "1 GPU, 4 species streams"},
+                       "parallelism": (f"{world} ranks: species x (L,K)-slab groups of {plan.G}, NCCL re-sharding twice per step"
+                                       if plan.G > 1 else f"{world} ranks, species-sharded, no data-path collective")
+                       if world > 1 else "1 GPU, all species per launch"},
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "wall_s_timed_region": wall_s}
     if rank == 0 and not a.no_cpu_baseline:

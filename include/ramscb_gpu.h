@@ -143,6 +143,21 @@ int rsg_anisch(rsg_ram* h, int S, double* PPERT_S, double* PPART_S);     /* :343
  * LSCOE,LSCSC; SETRC(nS); PPERT,PPART(nS,NR,NT).  Returns DtsNext in *dts_next. */
 int rsg_ram_run(rsg_ram* h, double DTs, double DtsMin, double T, int flags, double* dts_next, double* DtDrift,
                 double* losses, double* SETRC, double* PPERT, double* PPART);
+/* Multi-GPU: rsg_ram_run split at its two exchange points.  A rank owns species
+ * [s0, s0+ns) (0-based) and, inside them, the pitch-angle slab [l0, l0+nl) for the
+ * R/P/E sweeps and the energy slab [k0, k0+nk) for the pitch-angle block; between the
+ * parts the ranks sharing a species swap the complementary (L,K) blocks of the current
+ * F2 buffer (rsg_ram_f2_device) with NCCL send/recv -- there is no other data-path
+ * collective.  The calls only enqueue work (on the stream of rsg_ram_set_stream, or the
+ * library's run stream); rsg_ram_part_results synchronises and returns the rank's raw
+ * results: DtDrift(4,ns) [min over ranks], SUMRC partial sums moments(10,ns) and partial
+ * pressures PPER/PPAR(NR,NT,ns) [sum over the ranks of a species].  One GPU:
+ * rsg_ram_run == fwd(all) + mid(all) + rev(all) + results. */
+int rsg_ram_part_fwd(rsg_ram* h, double DTs, int flags, int s0, int ns, int l0, int nl);
+int rsg_ram_part_mid(rsg_ram* h, double DTs, int flags, int s0, int ns, int k0, int nk);
+int rsg_ram_part_rev(rsg_ram* h, int s0, int ns, int l0, int nl);
+int rsg_ram_part_results(rsg_ram* h, int s0, int ns, double* DtDrift, double* moments, double* PPER, double* PPAR);
+
 /* FLUX = F2/FFACTOR/FNHS (src/ModRamRun.f90:210-221), host array like F2 */
 int rsg_ram_flux_d2h(rsg_ram* h, double* FLUX);
 

@@ -67,6 +67,12 @@ struct SpecDev {
   unsigned long long* dt;                 // [4] CFL minima as ordered bit patterns
 };
 
+// Sub-range of the (L,K) planes a launch works on (multi-GPU slabs): planes
+// (l0 + a, k0 + b), a < nl, b < nk.  A single GPU uses {0, NPA, 0, NE}.
+struct PlaneRange {
+  int l0, nl, k0, nk;
+};
+
 // all species of one launch (blockIdx.y selects the species)
 struct SpecPack {
   SpecDev s[RSG_MAX_SPECIES];

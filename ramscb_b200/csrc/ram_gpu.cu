@@ -255,64 +255,71 @@ int reset_dt(rsg_ram* h, int s0, int ns, int which, cudaStream_t st) {
     CK(cudaMemcpyAsync(h->sp[s].d_res + which, h->d_dtinit + which, 8, cudaMemcpyDeviceToDevice, st));
   return RSG_OK;
 }
-int L_driftr(rsg_ram* h, int s0, int ns, cudaStream_t st) {
+int L_driftr(rsg_ram* h, int s0, int ns, cudaStream_t st, int l0 = 0, int nl = -1) {
+  if (nl < 0) nl = h->NPA - l0;
   RET(reset_dt(h, s0, ns, 0, st));
   SpecPack pk;
   make_pack(h, pk, s0, ns);
   const int KC = h->kcR, KG = (h->NE + KC - 1) / KC;
-  dim3 g(nblk(h->P, 248), h->NPA * KG, ns);   // 8 warps x 31 cells per CTA, KC energies per thread
-  if (h->mode == RSG_MODE_FAST) k_driftr<true><<<g, 256, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0, KC, KG);
-  else k_driftr<false><<<g, 256, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0, KC, KG);
+  dim3 g(nblk(h->P, 248), nl * KG, ns);   // 8 warps x 31 cells per CTA, KC energies per thread
+  if (h->mode == RSG_MODE_FAST) k_driftr<true><<<g, 256, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0, KC, KG, l0);
+  else k_driftr<false><<<g, 256, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0, KC, KG, l0);
   CKL();
   h->launches++;
   flip(h, s0, ns);
   return RSG_OK;
 }
-int L_driftp(rsg_ram* h, int s0, int ns, cudaStream_t st) {
+int L_driftp(rsg_ram* h, int s0, int ns, cudaStream_t st, int l0 = 0, int nl = -1) {
+  if (nl < 0) nl = h->NPA - l0;
   RET(reset_dt(h, s0, ns, 1, st));
   SpecPack pk;
   make_pack(h, pk, s0, ns);
   const int nseg = seg_count(h->NT - 1, h->segP);
-  dim3 g(nblk((long long)h->NE * h->NR, 128), h->NPA * nseg, ns);
-  if (h->mode == RSG_MODE_FAST) k_driftp<true><<<g, 128, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0, h->segP, nseg);
-  else k_driftp<false><<<g, 128, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0, h->segP, nseg);
+  dim3 g(nblk((long long)h->NE * h->NR, 128), nl * nseg, ns);
+  if (h->mode == RSG_MODE_FAST) k_driftp<true><<<g, 128, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0, h->segP, nseg, l0);
+  else k_driftp<false><<<g, 128, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0, h->segP, nseg, l0);
   CKL();
   h->launches++;
   flip(h, s0, ns);
   return RSG_OK;
 }
-int L_drifte(rsg_ram* h, int s0, int ns, cudaStream_t st) {
+int L_drifte(rsg_ram* h, int s0, int ns, cudaStream_t st, int l0 = 0, int nl = -1) {
+  if (nl < 0) nl = h->NPA - l0;
   RET(reset_dt(h, s0, ns, 2, st));
   SpecPack pk;
   make_pack(h, pk, s0, ns);
   const int nseg = seg_count(h->NE, h->segE);
-  dim3 g(nblk(h->P, 128), h->NPA * nseg, ns);
-  if (h->mode == RSG_MODE_FAST) k_drifte<true><<<g, 128, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0, h->segE, nseg);
-  else k_drifte<false><<<g, 128, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0, h->segE, nseg);
+  dim3 g(nblk(h->P, 128), nl * nseg, ns);
+  if (h->mode == RSG_MODE_FAST) k_drifte<true><<<g, 128, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0, h->segE, nseg, l0);
+  else k_drifte<false><<<g, 128, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0, h->segE, nseg, l0);
   CKL();
   h->launches++;
   flip(h, s0, ns);
   return RSG_OK;
 }
-int L_driftmu(rsg_ram* h, int s0, int ns, cudaStream_t st) {
+int L_driftmu(rsg_ram* h, int s0, int ns, cudaStream_t st, int k0 = 0, int nk = -1) {
+  if (nk < 0) nk = h->NE - k0;
   RET(reset_dt(h, s0, ns, 3, st));
   SpecPack pk;
   make_pack(h, pk, s0, ns);
   const int nseg = seg_count(h->NPA - 2, h->segMU);
-  dim3 g(nblk(h->P, 128), h->NE * nseg, ns);
-  if (h->mode == RSG_MODE_FAST) k_driftmu<true><<<g, 128, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0, h->segMU, nseg);
-  else k_driftmu<false><<<g, 128, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0, h->segMU, nseg);
+  dim3 g(nblk(h->P, 128), nk * nseg, ns);
+  if (h->mode == RSG_MODE_FAST) k_driftmu<true><<<g, 128, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0, h->segMU, nseg, k0);
+  else k_driftmu<false><<<g, 128, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0, h->segMU, nseg, k0);
   CKL();
   h->launches++;
   flip(h, s0, ns);
   return RSG_OK;
 }
-int L_sumrc(rsg_ram* h, int s0, int ns, int slot, cudaStream_t st) {
+PlaneRange full_range(rsg_ram* h) { return PlaneRange{0, h->NPA, 0, h->NE}; }
+int L_sumrc(rsg_ram* h, int s0, int ns, int slot, cudaStream_t st, PlaneRange pr = PlaneRange{0, -1, 0, -1}) {
+  if (pr.nl < 0) pr = full_range(h);
   SpecPack pk;
   make_pack(h, pk, s0, ns);
-  k_sumrc_partial<<<dim3(h->nblk_sum, ns), h->sum_threads, 0, st>>>(h->dev, pk, s0);
+  const int nb = pr.nl * pr.nk;
+  k_sumrc_partial<<<dim3(nb, ns), h->sum_threads, 0, st>>>(h->dev, pk, s0, pr);
   CKL();
-  k_sum_final<<<dim3(1, ns), 256, 0, st>>>(pk, s0, h->nblk_sum, 1, slot);
+  k_sum_final<<<dim3(1, ns), 256, 0, st>>>(pk, s0, nb, 1, slot);
   CKL();
   h->launches += 2;
   return RSG_OK;
@@ -325,17 +332,20 @@ int L_loss(rsg_ram* h, int s, int op, double DTs, cudaStream_t st) {
   h->launches++;
   return RSG_OK;
 }
-int L_loss_mid(rsg_ram* h, int s0, int ns, int doA, double DTs, int slot, cudaStream_t st) {
+int L_loss_mid(rsg_ram* h, int s0, int ns, int doA, double DTs, int slot, cudaStream_t st, PlaneRange pr = PlaneRange{0, -1, 0, -1}) {
+  if (pr.nl < 0) pr = full_range(h);
   SpecPack pk;
   make_pack(h, pk, s0, ns);
-  k_loss_mid<<<dim3(h->nblk_sum, ns), h->sum_threads, 0, st>>>(devfor(h, DTs), pk, s0, doA);
+  const int nb = pr.nl * pr.nk;
+  k_loss_mid<<<dim3(nb, ns), h->sum_threads, 0, st>>>(devfor(h, DTs), pk, s0, doA, pr);
   CKL();
-  k_sum_final<<<dim3(4, ns), 256, 0, st>>>(pk, s0, h->nblk_sum, 4, slot);
+  k_sum_final<<<dim3(4, ns), 256, 0, st>>>(pk, s0, nb, 4, slot);
   CKL();
   h->launches += 2;
   return RSG_OK;
 }
-int L_wpadif(rsg_ram* h, int s, double DTs, cudaStream_t st) {
+int L_wpadif(rsg_ram* h, int s, double DTs, cudaStream_t st, int k0 = 0, int nk = -1) {
+  if (nk < 0) nk = h->NE - k0;
   Spec& sp = h->sp[s];
   const double *DA, *DB;
   if (h->kind[s] == RSG_KIND_E) { DA = h->d_diff[0]; DB = h->d_diff[1]; }
@@ -353,15 +363,16 @@ int L_wpadif(rsg_ram* h, int s, double DTs, cudaStream_t st) {
     smem_set = smem;
   }
   CK(cudaMemsetAsync(sp.d_res + 4 + NSUM, 0, sizeof(unsigned long long), st));
-  k_wpadif<<<dim3(nblk((long long)h->NE * h->Pp, T), 1), T, smem, st>>>(devfor(h, DTs), pk, s);
+  k_wpadif<<<dim3(nblk((long long)nk * h->Pp, T), 1), T, smem, st>>>(devfor(h, DTs), pk, s, k0, nk);
   CKL();
   h->launches++;
   return RSG_OK;
 }
-int L_anisch(rsg_ram* h, int s0, int ns, cudaStream_t st) {
+int L_anisch(rsg_ram* h, int s0, int ns, cudaStream_t st, int l0 = 0, int nl = -1) {
+  if (nl < 0) nl = h->NPA - l0;
   SpecPack pk;
   make_pack(h, pk, s0, ns);
-  k_anisch_pa<<<dim3(nblk(h->Pp, 128), h->NE, ns), 128, 0, st>>>(h->dev, pk, s0);
+  k_anisch_pa<<<dim3(nblk(h->Pp, 128), h->NE, ns), 128, 0, st>>>(h->dev, pk, s0, l0, nl);
   CKL();
   const double cv = kCS * 100;
   const double RFAC = 4 * kPI / cv;
@@ -1032,99 +1043,173 @@ int rsg_anisch(rsg_ram* h, int S, double* PPERT_S, double* PPART_S) {
   return RSG_OK;
 }
 
-// The whole species loop of ram_run (src/ModRamRun.f90:64-185) + epilogue
-// (:186-222), all species advanced by each launch, on one stream.
-int rsg_ram_run(rsg_ram* h, double DTs, double DtsMin, double T, int flags, double* dts_next, double* DtDrift,
-                double* losses, double* SETRC, double* PPERT, double* PPART) {
-  if (!h) return fail(RSG_ERR_ARG, "null handle");
-  if (flags & RSG_F_COULOMB) return fail(RSG_ERR_UNSUPPORTED, "Coulomb operators not implemented");
-  if (!h->grids_set || !h->fields_set || !h->efield_set) return fail(RSG_ERR_STATE, "ram_run before set_grids/fields/efield");
-  (void)T;
-  CK(cudaSetDevice(h->device));
-  const int nS = h->nS;
+// ---- ram_run split at its two exchange points ------------------------------------------
+// SUMRC slots (global numbering): 0 fwd drifts | 1 WPI diffusion | 2 EMIC | 3-6 fused loss
+// block | 7 EMIC | 8 WPI diffusion | 9 reverse drifts.  cat: -1 unused, 0 LSDR 1 LSCHA 2 LSATM 3 LSWAE
+namespace {
+constexpr int NSLOT = 10;
+void slot_cats(rsg_ram* h, int flags, int cat[RSG_MAX_SPECIES][NSLOT], int* doA, bool* wavelo_sp) {
   const bool DoUseWPI = flags & RSG_F_WPI, DoUseEMIC = flags & RSG_F_EMIC;
-  RET(rsg_ram_sync(h));  // per-species streams idle; host staging tables free
-  cudaStream_t st = h->pst();
-  // SUMRC slots (global numbering): 0 fwd drifts | 1 WPI diffusion | 2 EMIC | 3-6 fused
-  // loss block | 7 EMIC | 8 WPI diffusion | 9 reverse drifts.  cat: -1 skip, 0 LSDR 1 LSCHA 2 LSATM 3 LSWAE
-  int cat[RSG_MAX_SPECIES][10];
-  int doA = 0;
-  for (int s = 0; s < nS; ++s) {
+  *doA = 0;
+  for (int s = 0; s < h->nS; ++s) {
     const int kind = h->kind[s];
     const bool sWPI = (kind == RSG_KIND_E), sCEX = (kind != RSG_KIND_E), sEMIC = (kind == RSG_KIND_H);
     const bool wavelo = sWPI && !DoUseWPI;
-    for (int q = 0; q < 10; ++q) cat[s][q] = -1;
+    for (int q = 0; q < NSLOT; ++q) cat[s][q] = -1;
     cat[s][0] = 0; cat[s][9] = 0;
     if (sWPI && DoUseWPI) cat[s][1] = cat[s][8] = 3;
     if (sEMIC && DoUseEMIC) cat[s][2] = cat[s][7] = 3;
-    if (sCEX) { cat[s][3] = cat[s][6] = 1; doA |= 1 << s; }
-    if (wavelo) { cat[s][3] = cat[s][6] = 3; doA |= 1 << s; }
+    if (sCEX) { cat[s][3] = cat[s][6] = 1; *doA |= 1 << s; }
+    if (wavelo) { cat[s][3] = cat[s][6] = 3; *doA |= 1 << s; }
     cat[s][4] = cat[s][5] = 2;
-    RET(tables_cepara(h, s, DTs, st));
-    RET(tables_drift(h, s, DTs, st));
-    if (wavelo) RET(tables_wavelo(h, s, DTs, st));
+    if (wavelo_sp) wavelo_sp[s] = wavelo;
   }
+}
+int check_part(rsg_ram* h, int s0, int ns, int a0, int na, int amax) {
+  if (!h) return fail(RSG_ERR_ARG, "null handle");
+  if (!h->grids_set || !h->fields_set || !h->efield_set) return fail(RSG_ERR_STATE, "ram_run before set_grids/fields/efield");
+  if (s0 < 0 || ns < 1 || s0 + ns > h->nS) return fail(RSG_ERR_ARG, "species range out of bounds");
+  if (a0 < 0 || na < 1 || a0 + na > amax) return fail(RSG_ERR_ARG, "slab range out of bounds");
+  return RSG_OK;
+}
+}  // namespace
+
+// part 1: tables, coefficient planes, DRIFTR inflow scan, forward DRIFTR/P/E on the
+// pitch-angle slab [l0, l0+nl) of species [s0, s0+ns)        (src/ModRamRun.f90:67-75)
+int rsg_ram_part_fwd(rsg_ram* h, double DTs, int flags, int s0, int ns, int l0, int nl) {
+  RET(check_part(h, s0, ns, l0, nl, h ? h->NPA : 0));
+  if (flags & RSG_F_COULOMB) return fail(RSG_ERR_UNSUPPORTED, "Coulomb operators not implemented");
+  CK(cudaSetDevice(h->device));
+  RET(rsg_ram_sync(h));  // per-species streams idle; host staging tables free
+  cudaStream_t st = h->pst();
+  int cat[RSG_MAX_SPECIES][NSLOT], doA;
+  bool wl[RSG_MAX_SPECIES];
+  slot_cats(h, flags, cat, &doA, wl);
   h->prof_n = 0;
   RET(prof_mark(h, "prep_step", st));
+  for (int s = s0; s < s0 + ns; ++s) {
+    RET(tables_cepara(h, s, DTs, st));
+    RET(tables_drift(h, s, DTs, st));
+    if (wl[s]) RET(tables_wavelo(h, s, DTs, st));
+  }
   RET(ensure_step(h, DTs, st));
   RET(prof_mark(h, "driftr_inflow", st));
-  RET(L_inflow(h, 0, nS, st));
-  RET(prof_mark(h, "k_driftr", st)); RET(L_driftr(h, 0, nS, st));
-  RET(prof_mark(h, "k_driftp", st)); RET(L_driftp(h, 0, nS, st));
-  RET(prof_mark(h, "k_drifte", st)); RET(L_drifte(h, 0, nS, st));
-  RET(prof_mark(h, "k_driftmu", st)); RET(L_driftmu(h, 0, nS, st));
+  RET(L_inflow(h, s0, ns, st));
+  RET(prof_mark(h, "k_driftr", st)); RET(L_driftr(h, s0, ns, st, l0, nl));
+  RET(prof_mark(h, "k_driftp", st)); RET(L_driftp(h, s0, ns, st, l0, nl));
+  RET(prof_mark(h, "k_drifte", st)); RET(L_drifte(h, s0, ns, st, l0, nl));
+  RET(prof_mark(h, "exchange", st));
+  return RSG_OK;
+}
+
+// part 2: the pitch-angle block on the energy slab [k0, k0+nk): DRIFTMU, SUMRC, [WPADIF],
+// fused losses, [WPADIF], DRIFTMU                                         (:76-170)
+int rsg_ram_part_mid(rsg_ram* h, double DTs, int flags, int s0, int ns, int k0, int nk) {
+  RET(check_part(h, s0, ns, k0, nk, h ? h->NE : 0));
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = h->pst();
+  int cat[RSG_MAX_SPECIES][NSLOT], doA;
+  slot_cats(h, flags, cat, &doA, nullptr);
+  const PlaneRange pr{0, h->NPA, k0, nk};
+  RET(prof_mark(h, "k_driftmu", st)); RET(L_driftmu(h, s0, ns, st, k0, nk));
   RET(prof_mark(h, "k_sumrc", st));
-  RET(L_sumrc(h, 0, nS, 0, st));
+  RET(L_sumrc(h, s0, ns, 0, st, pr));
   RET(prof_mark(h, "wpadif+sumrc", st));
-  for (int s = 0; s < nS; ++s)
-    if (cat[s][1] >= 0) { RET(L_wpadif(h, s, DTs, st)); RET(L_sumrc(h, s, 1, 1, st)); }
-  for (int s = 0; s < nS; ++s)
-    if (cat[s][2] >= 0) { RET(L_wpadif(h, s, DTs, st)); RET(L_sumrc(h, s, 1, 2, st)); }
+  for (int s = s0; s < s0 + ns; ++s)
+    if (cat[s][1] >= 0) { RET(L_wpadif(h, s, DTs, st, k0, nk)); RET(L_sumrc(h, s, 1, 1, st, pr)); }
+  for (int s = s0; s < s0 + ns; ++s)
+    if (cat[s][2] >= 0) { RET(L_wpadif(h, s, DTs, st, k0, nk)); RET(L_sumrc(h, s, 1, 2, st, pr)); }
   RET(prof_mark(h, "k_loss_mid", st));
-  RET(L_loss_mid(h, 0, nS, doA, DTs, 3, st));
+  RET(L_loss_mid(h, s0, ns, doA, DTs, 3, st, pr));
   RET(prof_mark(h, "wpadif+sumrc", st));
-  for (int s = 0; s < nS; ++s)
-    if (cat[s][7] >= 0) { RET(L_wpadif(h, s, DTs, st)); RET(L_sumrc(h, s, 1, 7, st)); }
-  for (int s = 0; s < nS; ++s)
-    if (cat[s][8] >= 0) { RET(L_wpadif(h, s, DTs, st)); RET(L_sumrc(h, s, 1, 8, st)); }
-  RET(prof_mark(h, "k_driftmu", st)); RET(L_driftmu(h, 0, nS, st));
-  RET(prof_mark(h, "k_drifte", st)); RET(L_drifte(h, 0, nS, st));
-  RET(prof_mark(h, "k_driftp", st)); RET(L_driftp(h, 0, nS, st));
-  RET(prof_mark(h, "k_driftr", st)); RET(L_driftr(h, 0, nS, st));
+  for (int s = s0; s < s0 + ns; ++s)
+    if (cat[s][7] >= 0) { RET(L_wpadif(h, s, DTs, st, k0, nk)); RET(L_sumrc(h, s, 1, 7, st, pr)); }
+  for (int s = s0; s < s0 + ns; ++s)
+    if (cat[s][8] >= 0) { RET(L_wpadif(h, s, DTs, st, k0, nk)); RET(L_sumrc(h, s, 1, 8, st, pr)); }
+  RET(prof_mark(h, "k_driftmu", st)); RET(L_driftmu(h, s0, ns, st, k0, nk));
+  RET(prof_mark(h, "exchange", st));
+  return RSG_OK;
+}
+
+// part 3: reverse DRIFTE/P/R, SUMRC, epilogue and the pitch-angle sums of ANISCH on the
+// pitch-angle slab                                                      (:171-175, :186-209)
+int rsg_ram_part_rev(rsg_ram* h, int s0, int ns, int l0, int nl) {
+  RET(check_part(h, s0, ns, l0, nl, h ? h->NPA : 0));
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = h->pst();
+  const PlaneRange pr{l0, nl, 0, h->NE};
+  RET(prof_mark(h, "k_drifte", st)); RET(L_drifte(h, s0, ns, st, l0, nl));
+  RET(prof_mark(h, "k_driftp", st)); RET(L_driftp(h, s0, ns, st, l0, nl));
+  RET(prof_mark(h, "k_driftr", st)); RET(L_driftr(h, s0, ns, st, l0, nl));
   RET(prof_mark(h, "k_sumrc", st));
-  RET(L_sumrc(h, 0, nS, 9, st));
+  RET(L_sumrc(h, s0, ns, 9, st, pr));
   RET(prof_mark(h, "k_epilogue", st));
   {
     SpecPack pk;
-    make_pack(h, pk);
-    k_epilogue<<<dim3(nblk(h->NR + h->nout, 128), h->NPA * h->NE, nS), 128, 0, st>>>(h->dev, pk, 0, h->d_outlist, h->nout);
+    make_pack(h, pk, s0, ns);
+    k_epilogue<<<dim3(nblk(h->NR + h->nout, 128), nl * h->NE, ns), 128, 0, st>>>(h->dev, pk, s0, h->d_outlist, h->nout, pr);
     CKL();
     h->launches++;
   }
   RET(prof_mark(h, "k_anisch", st));
-  RET(L_anisch(h, 0, nS, st));
+  RET(L_anisch(h, s0, ns, st, l0, nl));
   RET(prof_mark(h, "d2h_results", st));
-  CK(cudaMemcpyAsync(h->h_res_all, h->d_res_all, (size_t)nS * RES_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-  if (PPERT || PPART)
-    CK(cudaMemcpyAsync(h->h_pp_all, h->d_pp_all, (size_t)nS * 2 * h->Pp * sizeof(double), cudaMemcpyDeviceToHost, st));
+  return RSG_OK;
+}
+
+// raw per-rank results of the three parts: DtDrift(4,ns) minima, SUMRC partial sums
+// moments(10,ns) over the local slab (unused slots are 0), partial PPERT/PPART(NR,NT,ns).
+// Ranks sharing a species add moments and pressures and take the min of DtDrift.
+int rsg_ram_part_results(rsg_ram* h, int s0, int ns, double* DtDrift, double* moments, double* PPER, double* PPAR) {
+  RET(check_part(h, s0, ns, 0, 1, 1));
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = h->pst();
+  CK(cudaMemcpyAsync(h->h_res_all + (size_t)s0 * RES_N, h->d_res_all + (size_t)s0 * RES_N, (size_t)ns * RES_N * sizeof(unsigned long long),
+                     cudaMemcpyDeviceToHost, st));
+  if (PPER || PPAR)
+    CK(cudaMemcpyAsync(h->h_pp_all + (size_t)s0 * 2 * h->Pp, h->d_pp_all + (size_t)s0 * 2 * h->Pp,
+                       (size_t)ns * 2 * h->Pp * sizeof(double), cudaMemcpyDeviceToHost, st));
   RET(prof_mark(h, "end", st));
   CK(cudaStreamSynchronize(st));
   RET(prof_fold(h));
+  for (int s = s0; s < s0 + ns; ++s) {
+    Spec& sp = h->sp[s];
+    if (DtDrift) std::memcpy(DtDrift + 4 * (s - s0), sp.h_res, 32);
+    if (moments) std::memcpy(moments + NSLOT * (s - s0), sp.h_res + 4, NSLOT * 8);
+    const double* b = h->h_pp_all + (size_t)s * 2 * h->Pp;
+    if (PPER) std::memcpy(PPER + (size_t)h->P * (s - s0), b, h->P * sizeof(double));
+    if (PPAR) std::memcpy(PPAR + (size_t)h->P * (s - s0), b + h->Pp, h->P * sizeof(double));
+  }
+  return RSG_OK;
+}
+
+// The whole species loop of ram_run (src/ModRamRun.f90:64-185) + epilogue (:186-222) on one
+// GPU: the three parts back to back, all species advanced by each launch, on one stream.
+int rsg_ram_run(rsg_ram* h, double DTs, double DtsMin, double T, int flags, double* dts_next, double* DtDrift,
+                double* losses, double* SETRC, double* PPERT, double* PPART) {
+  if (!h) return fail(RSG_ERR_ARG, "null handle");
+  (void)T;
+  const int nS = h->nS;
+  RET(rsg_ram_part_fwd(h, DTs, flags, 0, nS, 0, h->NPA));
+  RET(rsg_ram_part_mid(h, DTs, flags, 0, nS, 0, h->NE));
+  RET(rsg_ram_part_rev(h, 0, nS, 0, h->NPA));
+  std::vector<double> dt((size_t)4 * nS), mom((size_t)NSLOT * nS), pe, pa;
+  if (PPERT || PPART) { pe.resize((size_t)h->P * nS); pa.resize((size_t)h->P * nS); }
+  RET(rsg_ram_part_results(h, 0, nS, dt.data(), mom.data(), pe.empty() ? nullptr : pe.data(), pa.empty() ? nullptr : pa.data()));
+  int cat[RSG_MAX_SPECIES][NSLOT], doA;
+  slot_cats(h, flags, cat, &doA, nullptr);
   double dtn = 1e300;
   for (int s = 0; s < nS; ++s) {
     Spec& sp = h->sp[s];
-    double dt4[4];
-    std::memcpy(dt4, sp.h_res, 32);
     for (int q = 0; q < 4; ++q) {
-      dtn = std::min(dtn, dt4[q]);
-      if (DtDrift) DtDrift[q + 4 * s] = dt4[q];
+      dtn = std::min(dtn, dt[q + 4 * s]);
+      if (DtDrift) DtDrift[q + 4 * s] = dt[q + 4 * s];
     }
     double ls[6] = {0, 0, 0, 0, 0, 0};
     double prev = sp.setrc;
-    for (int q = 0; q < 10; ++q) {
+    for (int q = 0; q < NSLOT; ++q) {
       if (cat[s][q] < 0) continue;
-      double v;
-      std::memcpy(&v, sp.h_res + 4 + q, 8);
+      const double v = mom[q + (size_t)NSLOT * s];
       ls[cat[s][q]] += prev - v;  // ELORC = ENOLD - SETRC (:256)
       prev = v;
     }
@@ -1132,7 +1217,10 @@ int rsg_ram_run(rsg_ram* h, double DTs, double DtsMin, double T, int flags, doub
     if (losses)
       for (int q = 0; q < 6; ++q) losses[q + 6 * s] = ls[q];
     if (SETRC) SETRC[s] = prev;
-    if (PPERT || PPART) scatter_anisch(h, s, PPERT, PPART, nS, s);
+    for (int p = 0; p < h->P; ++p) {
+      if (PPERT) PPERT[(size_t)p * nS + s] = pe[(size_t)h->P * s + p];
+      if (PPART) PPART[(size_t)p * nS + s] = pa[(size_t)h->P * s + p];
+    }
   }
   if (dts_next) *dts_next = std::max(dtn, DtsMin);
   return RSG_OK;

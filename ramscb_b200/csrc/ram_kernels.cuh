@@ -389,10 +389,11 @@ __global__ void k_driftr_scan(const __grid_constant__ RamDev d, const __grid_con
 // =============================================================================
 template <bool FAST>
 __global__ void __launch_bounds__(256) k_driftr(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0, int KC,
-                                                int KG) {
+                                                int KG, int l0) {
   const SpecDev& sp = pk.s[s0 + blockIdx.z];
   const int NR = d.NR, NT = d.NT, NE = d.NE, P = d.P, Pp = d.Pp;
-  const int l = blockIdx.y / KG, kg = blockIdx.y - l * KG;
+  const int lq = blockIdx.y / KG, kg = blockIdx.y - lq * KG;
+  const int l = l0 + lq;
   const int k0 = kg * KC, k1 = min(NE, k0 + KC);
   const int lane = threadIdx.x & 31;
   const int p = (blockIdx.x * 8 + (threadIdx.x >> 5)) * 31 + lane - 1;   // 31 cells per warp + halo lane 0
@@ -476,13 +477,14 @@ __global__ void __launch_bounds__(256) k_driftr(const __grid_constant__ RamDev d
 // =============================================================================
 template <bool FAST>
 __global__ void __launch_bounds__(128) k_driftp(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0, int SEG,
-                                                int nseg) {
+                                                int nseg, int l0) {
   const SpecDev& sp = pk.s[s0 + blockIdx.z];
   const int NR = d.NR, NT = d.NT, Pp = d.Pp;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   double cmax = 0.0;
   if (t < d.NE * NR) {
-    const int l = blockIdx.y / nseg, seg = blockIdx.y - l * nseg;
+    const int lq = blockIdx.y / nseg, seg = blockIdx.y - lq * nseg;
+    const int l = l0 + lq;
     const int k = t / NR, i = t - k * NR;
     const int plane = l * d.NE + k;
     const int ja = 2 + seg * SEG, jb = min(NT, ja + SEG - 1);
@@ -553,14 +555,15 @@ __global__ void __launch_bounds__(128) k_driftp(const __grid_constant__ RamDev d
 // =============================================================================
 template <bool FAST>
 __global__ void __launch_bounds__(128) k_drifte(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0, int SEG,
-                                                int nseg) {
+                                                int nseg, int l0) {
   const SpecDev& sp = pk.s[s0 + blockIdx.z];
   const int NE = d.NE, Pp = d.Pp;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   double dtmin = 1.0e300;
   double mmax = 0.0;   // FAST: max over cells of max(|c|,1e-10)/DE(K)
   if (p < d.P) {
-    const int l = blockIdx.y / nseg, seg = blockIdx.y - l * nseg;
+    const int lq = blockIdx.y / nseg, seg = blockIdx.y - lq * nseg;
+    const int l = l0 + lq;
     const int ka = 1 + seg * SEG, kb = min(NE, ka + SEG - 1);
     const int i = p % d.NR;
     const double* F = sp.F + (size_t)l * NE * Pp + p;   // F[(K-1)*Pp]
@@ -666,14 +669,15 @@ __global__ void __launch_bounds__(128) k_drifte(const __grid_constant__ RamDev d
 // =============================================================================
 template <bool FAST>
 __global__ void __launch_bounds__(128) k_driftmu(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0, int SEG,
-                                                 int nseg) {
+                                                 int nseg, int k0) {
   const SpecDev& sp = pk.s[s0 + blockIdx.z];
   const int NE = d.NE, NPA = d.NPA, Pp = d.Pp;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   double dtmin = 1.0e300;
   double mmax = 0.0;   // FAST: max over cells of max(|c|,1e-32)/DMU(L)
   if (p < d.P) {
-    const int k = blockIdx.y / nseg, seg = blockIdx.y - k * nseg;
+    const int kq = blockIdx.y / nseg, seg = blockIdx.y - kq * nseg;
+    const int k = k0 + kq;
     const int la = 2 + seg * SEG, lb = min(NPA - 1, la + SEG - 1);
     const bool lastseg = (lb == NPA - 1);
     const int i = p % d.NR;
@@ -808,10 +812,12 @@ __global__ void k_sum_final(const __grid_constant__ SpecPack pk, int s0, int nb,
 // sum by summation order only (diagnostic quantity).
 // grid: x = plane l*NE+k, y = species
 // =============================================================================
-__global__ void __launch_bounds__(256) k_sumrc_partial(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0) {
+__global__ void __launch_bounds__(256) k_sumrc_partial(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0,
+                                                       PlaneRange pr) {
   const SpecDev& sp = pk.s[s0 + blockIdx.y];
-  const int plane = blockIdx.x;
-  const int l = plane / d.NE, k = plane - l * d.NE;
+  const int lq = blockIdx.x / pr.nk;
+  const int l = pr.l0 + lq, k = pr.k0 + (blockIdx.x - lq * pr.nk);
+  const int plane = l * d.NE + k;
   double acc[1] = {0.0};
   if (k >= 1 && l >= 1) {
     const double* F = sp.F + (size_t)plane * d.Pp;
@@ -823,7 +829,7 @@ __global__ void __launch_bounds__(256) k_sumrc_partial(const __grid_constant__ R
       acc[0] += e * WEIGHT;
     }
   }
-  cta_sum_to<1>(sp.part, plane, acc);
+  cta_sum_to<1>(sp.part, blockIdx.x, acc);
 }
 
 // =============================================================================
@@ -869,10 +875,11 @@ __global__ void __launch_bounds__(256) k_loss(const __grid_constant__ RamDev d, 
 // grid: x = plane, y = species (one CTA per plane, same tree as k_sumrc_partial)
 // =============================================================================
 __global__ void __launch_bounds__(256) k_loss_mid(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0,
-                                                  int doA) {
+                                                  int doA, PlaneRange pr) {
   const SpecDev& sp = pk.s[s0 + blockIdx.y];
-  const int plane = blockIdx.x;
-  const int l = plane / d.NE, k = plane - l * d.NE;
+  const int lq = blockIdx.x / pr.nk;
+  const int l = pr.l0 + lq, k = pr.k0 + (blockIdx.x - lq * pr.nk);
+  const int plane = l * d.NE + k;
   const bool ion = (sp.kind != 3);
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
   if (k >= 1) {                                           // every operator here acts on K>=2 only
@@ -908,7 +915,7 @@ __global__ void __launch_bounds__(256) k_loss_mid(const __grid_constant__ RamDev
       F[p] = f;
     }
   }
-  cta_sum_to<4>(sp.part, plane, acc);
+  cta_sum_to<4>(sp.part, blockIdx.x, acc);
 }
 
 // =============================================================================
@@ -917,7 +924,7 @@ __global__ void __launch_bounds__(256) k_loss_mid(const __grid_constant__ RamDev
 // shared memory [NPA][T] (conflict-free: T consecutive threads).  D = DA + DB.
 // In place (a thread owns its whole line).
 // =============================================================================
-__global__ void k_wpadif(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0) {
+__global__ void k_wpadif(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0, int k0, int nk) {
   extern __shared__ double smem[];
   const SpecDev& sp = pk.s[s0 + blockIdx.y];
   const int NE = d.NE, NPA = d.NPA, Pp = d.Pp, T = blockDim.x;
@@ -925,8 +932,9 @@ __global__ void k_wpadif(const __grid_constant__ RamDev d, const __grid_constant
   double* RL = smem + NPA * T;
   const long long t = (long long)blockIdx.x * T + threadIdx.x;
   const int tx = threadIdx.x;
-  if (t >= (long long)NE * Pp) return;
-  const int k = (int)(t / Pp), p = (int)(t - (long long)k * Pp);
+  if (t >= (long long)nk * Pp) return;
+  const int kq = (int)(t / Pp), p = (int)(t - (long long)kq * Pp);
+  const int k = k0 + kq;
   const int i = p % d.NR;
   if (p >= d.P || i < 1 || k < 1) return;
   const size_t LS = (size_t)NE * Pp;
@@ -978,7 +986,8 @@ __global__ void k_wpadif(const __grid_constant__ RamDev d, const __grid_constant
 // one thread per p adds the energies band by band in the reference's order
 // => PPERT/PPART are bit-identical to the oracle.
 // =============================================================================
-__global__ void __launch_bounds__(128) k_anisch_pa(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0) {
+__global__ void __launch_bounds__(128) k_anisch_pa(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0, int l0,
+                                                   int nl) {
   const SpecDev& sp = pk.s[s0 + blockIdx.z];
   const int NE = d.NE, Pp = d.Pp;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -989,11 +998,14 @@ __global__ void __launch_bounds__(128) k_anisch_pa(const __grid_constant__ RamDe
   if (p >= d.P || i < 1 || k < 1) { sp.tE[t] = 0; sp.tA[t] = 0; return; }
   const size_t LS = (size_t)NE * Pp;
   double* F = sp.F + (size_t)k * Pp + p;
-  const double f2 = F[LS];
-  F[0] = f2;  // F2(S,I,J,K,1) = F2(S,I,J,K,2)
-  const int u = d.UPA[i] - 1;
+  double f2 = 0.0;
+  if (l0 == 0) {                 // the slab that owns L=1,2 (a slab always holds >= 2 pitch angles)
+    f2 = F[LS];
+    F[0] = f2;  // F2(S,I,J,K,1) = F2(S,I,J,K,2)
+  }
+  const int u = min(d.UPA[i] - 1, l0 + nl);
   double SUME = 0., SUMA = 0.;
-  for (int L = 1; L <= u; ++L) {
+  for (int L = l0 + 1; L <= u; ++L) {
     const double f = (L == 1) ? f2 : F[(size_t)(L - 1) * LS];
     const double ERNM = d.WMU[L - 1] / sp.FF[((size_t)(L - 1) * NE + k) * d.NR + i] / d.FNHSc[(size_t)(L - 1) * Pp + p];
     const double EPMA = ERNM * d.MU[L - 1] * d.MU[L - 1];
@@ -1057,9 +1069,11 @@ __global__ void k_f2_to_host(RamDev d, double* __restrict__ stage, const double*
 // the (q-NR)-th flagged (I,J) column with 2 <= J <= NT-1.
 // grid: x = tiles of q, y = plane, z = species
 __global__ void __launch_bounds__(128) k_epilogue(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0,
-                                                  const int* __restrict__ outlist, int nout) {
+                                                  const int* __restrict__ outlist, int nout, PlaneRange pr) {
   const SpecDev& sp = pk.s[s0 + blockIdx.z];
-  double* Fs = sp.F + (size_t)blockIdx.y * d.Pp;
+  const int lq = blockIdx.y / pr.nk;
+  const int plane = (pr.l0 + lq) * d.NE + pr.k0 + (blockIdx.y - lq * pr.nk);
+  double* Fs = sp.F + (size_t)plane * d.Pp;
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q < d.NR) {
     const int pN = q + (d.NT - 1) * d.NR;

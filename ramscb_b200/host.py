@@ -70,6 +70,10 @@ def lib():
     L.rsg_sumrc.argtypes = [vp, i, _dp, _dp]
     L.rsg_anisch.argtypes = [vp, i, vp, vp]
     L.rsg_ram_run.argtypes = [vp, d, d, d, i, _dp, vp, vp, vp, vp, vp]
+    L.rsg_ram_part_fwd.argtypes = [vp, d, i, i, i, i, i]
+    L.rsg_ram_part_mid.argtypes = [vp, d, i, i, i, i, i]
+    L.rsg_ram_part_rev.argtypes = [vp, i, i, i, i]
+    L.rsg_ram_part_results.argtypes = [vp, i, i, vp, vp, vp, vp]
     L.rsg_ram_flux_d2h.argtypes = [vp, vp]
     L.rsg_ram_launch_count.argtypes = [vp]
     L.rsg_ram_launch_count.restype = ll
@@ -245,6 +249,25 @@ class RamGpu:
                                _p(out["SETRC"]), _p(out["PPERT"]), _p(out["PPART"])))
         out["DtsNext"] = dtn.value
         return out
+
+    # ---- multi-GPU parts (include/ramscb_gpu.h: rsg_ram_part_*) ---------------------
+    def part_fwd(self, DTs, flags, s0, ns, l0, nl):
+        _ck(self.L.rsg_ram_part_fwd(self.h, DTs, flags, s0, ns, l0, nl))
+
+    def part_mid(self, DTs, flags, s0, ns, k0, nk):
+        _ck(self.L.rsg_ram_part_mid(self.h, DTs, flags, s0, ns, k0, nk))
+
+    def part_rev(self, s0, ns, l0, nl):
+        _ck(self.L.rsg_ram_part_rev(self.h, s0, ns, l0, nl))
+
+    def part_results(self, s0, ns):
+        g = self.g
+        dt = np.zeros((4, ns), order="F")
+        mom = np.zeros((10, ns), order="F")
+        pper = np.zeros((g.NR, g.NT, ns), order="F")
+        ppar = np.zeros((g.NR, g.NT, ns), order="F")
+        _ck(self.L.rsg_ram_part_results(self.h, s0, ns, _p(dt), _p(mom), _p(pper), _p(ppar)))
+        return dt, mom, pper, ppar
 
     def flux_d2h(self):
         g = self.g

@@ -1,0 +1,183 @@
+"""Multi-GPU execution of the RAM step: one process per GPU, torch.distributed for the plumbing.
+
+The reference has no domain decomposition (MPI is init/finalize only,
+src/Main.f90:54-57); this sharding is a new design:
+
+* species are independent inside ``ram_run`` (src/ModRamRun.f90:64-185), so up to
+  nS ranks need **no data-path communication at all**;
+* beyond nS ranks a species is shared by a group of G ranks.  DRIFTR/P/E and the
+  pointwise losses are independent across pitch angle L, DRIFTMU / WPADIF couple all
+  L but are independent across energy K: a rank owns an L-slab for the R,P,E sweeps
+  and a K-slab for the pitch-angle block.  The step is palindromic
+  (R,P,E | MU, losses, MU | E,P,R), so there are exactly **two** re-shardings per
+  step, each an all-to-all *inside the group* done with NCCL send/recv of the
+  complementary (L,K) blocks straight out of / into the resident F2 buffer (the
+  device layout [L][K][plane] makes every block a run of contiguous planes).
+
+Control-plane reductions (CFL minima, SUMRC partial sums, partial pressures: a few
+KB) are all-reduces after the step.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+
+def _split(n, parts, idx):
+    """[start, count) of slab ``idx`` when n items are split into ``parts`` near-equal slabs."""
+    base, rem = divmod(n, parts)
+    start = idx * base + min(idx, rem)
+    return start, base + (1 if idx < rem else 0)
+
+
+@dataclass
+class ShardPlan:
+    world: int
+    rank: int
+    nS: int
+    NPA: int
+    NE: int
+    s0: int = 0          # first owned species (0-based)
+    ns: int = 0          # number of owned species
+    group: tuple = ()    # ranks sharing this rank's species (sorted); len 1 => no exchange
+    gidx: int = 0        # index of this rank in its group
+    l0: int = 0
+    nl: int = 0
+    k0: int = 0
+    nk: int = 0
+
+    @property
+    def G(self):
+        return len(self.group)
+
+
+def make_plan(world: int, rank: int, nS: int, NPA: int, NE: int) -> ShardPlan:
+    p = ShardPlan(world=world, rank=rank, nS=nS, NPA=NPA, NE=NE)
+    if world <= nS:
+        if nS % world != 0:
+            raise ValueError(f"{nS} species cannot be split evenly over {world} ranks")
+        per = nS // world
+        p.s0, p.ns = rank * per, per
+        p.group, p.gidx = (rank,), 0
+    else:
+        if world % nS != 0:
+            raise ValueError(f"{world} ranks must be a multiple of the {nS} species")
+        G = world // nS
+        if G > min(NPA // 2, NE):
+            raise ValueError("too many ranks per species for the (L,K) slabs")
+        p.s0, p.ns = rank // G, 1
+        p.group = tuple(range((rank // G) * G, (rank // G + 1) * G))
+        p.gidx = rank % G
+    p.l0, p.nl = _split(NPA, p.G, p.gidx)
+    p.k0, p.nk = _split(NE, p.G, p.gidx)
+    return p
+
+
+def exchange_blocks(p: ShardPlan, to_kslab: bool):
+    """Blocks to swap with every other rank of the group.
+
+    Returns a list of (peer_rank, send (l0,nl,k0,nk), recv (l0,nl,k0,nk)).
+    to_kslab=True : L-slab -> K-slab layout (before DRIFTMU): send my pitch angles of the
+                    peer's energies, receive the peer's pitch angles of my energies.
+    to_kslab=False: the way back (after the second DRIFTMU).
+    """
+    out = []
+    for gi, peer in enumerate(p.group):
+        if peer == p.rank:
+            continue
+        pl0, pnl = _split(p.NPA, p.G, gi)
+        pk0, pnk = _split(p.NE, p.G, gi)
+        mine_L_peer_K = (p.l0, p.nl, pk0, pnk)
+        peer_L_my_K = (pl0, pnl, p.k0, p.nk)
+        if to_kslab:
+            out.append((peer, mine_L_peer_K, peer_L_my_K))
+        else:
+            out.append((peer, peer_L_my_K, mine_L_peer_K))
+    return out
+
+
+def block_chunks(block, NE, Pp):
+    """Contiguous runs (offset, length in doubles) of an (l0,nl,k0,nk) block of a species
+    buffer laid out [L][K][Pp]."""
+    l0, nl, k0, nk = block
+    return [((l * NE + k0) * Pp, nk * Pp) for l in range(l0, l0 + nl)]
+
+
+def exchange(p: ShardPlan, bufs, Pp: int, to_kslab: bool, dist):
+    """Re-shard the species buffers of this rank inside its group.
+
+    ``bufs``: list of 1-D torch tensors (one per owned species) aliasing the resident F2
+    buffers, on whatever device the process group's backend moves (CUDA for nccl, CPU for
+    gloo).  Every run of contiguous planes is one send/recv; all of them are posted as one
+    batch (ncclGroupStart/End underneath).
+    """
+    if p.G == 1:
+        return
+    import torch.distributed as td
+    ops = []
+    for peer, sblk, rblk in exchange_blocks(p, to_kslab):
+        for buf in bufs:
+            for off, n in block_chunks(sblk, p.NE, Pp):
+                ops.append(td.P2POp(td.isend, buf[off:off + n], peer))
+            for off, n in block_chunks(rblk, p.NE, Pp):
+                ops.append(td.P2POp(td.irecv, buf[off:off + n], peer))
+    for w in td.batch_isend_irecv(ops):
+        w.wait()
+
+
+class _DevBuf:
+    """Zero-copy view of library-owned device memory for torch (CUDA array interface)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+
+class RamSharded:
+    """One rank's share of the RAM step (drop-in for ``RamGpu.ram_run`` at N > 1)."""
+
+    def __init__(self, gpu, plan: ShardPlan, dist=None):
+        self.gpu, self.p, self.dist = gpu, plan, dist
+        self.setrc = np.zeros(gpu.g.nS)
+
+    def _bufs(self):
+        import torch
+        out = []
+        for s in range(self.p.s0, self.p.s0 + self.p.ns):
+            ptr, n, pp = self.gpu.f2_device(s + 1)
+            out.append(torch.as_tensor(_DevBuf(ptr, n), device="cuda"))
+        return out, pp
+
+    def ram_run(self, DTs, DtsMin=1.0, flags=0):
+        import torch
+        g, p, gpu = self.gpu.g, self.p, self.gpu
+        gpu.part_fwd(DTs, flags, p.s0, p.ns, p.l0, p.nl)
+        if p.G > 1:
+            bufs, pp = self._bufs()
+            exchange(p, bufs, pp, True, self.dist)
+        gpu.part_mid(DTs, flags, p.s0, p.ns, p.k0, p.nk)
+        if p.G > 1:
+            bufs, pp = self._bufs()
+            exchange(p, bufs, pp, False, self.dist)
+        gpu.part_rev(p.s0, p.ns, p.l0, p.nl)
+        dt, mom, pper, ppar = gpu.part_results(p.s0, p.ns)
+        # control-plane reductions over all ranks (a few KB)
+        DT = np.full((4, g.nS), np.inf)
+        MOM = np.zeros((10, g.nS))
+        PE = np.zeros((g.NR, g.NT, g.nS))
+        PA = np.zeros((g.NR, g.NT, g.nS))
+        sl = slice(p.s0, p.s0 + p.ns)
+        DT[:, sl], MOM[:, sl], PE[:, :, sl], PA[:, :, sl] = dt, mom, pper, ppar
+        if self.dist is not None and p.world > 1:
+            dev = "cuda" if self.dist.get_backend() == "nccl" else "cpu"
+            t_min = torch.as_tensor(DT, device=dev)
+            t_sum = torch.as_tensor(np.concatenate([MOM.ravel(), PE.ravel(), PA.ravel()]), device=dev)
+            self.dist.all_reduce(t_min, op=self.dist.ReduceOp.MIN)
+            self.dist.all_reduce(t_sum, op=self.dist.ReduceOp.SUM)
+            DT = t_min.cpu().numpy()
+            v = t_sum.cpu().numpy()
+            MOM = v[:MOM.size].reshape(MOM.shape)
+            PE = v[MOM.size:MOM.size + PE.size].reshape(PE.shape)
+            PA = v[MOM.size + PE.size:].reshape(PA.shape)
+        return {"DtDrift": DT, "DtsNext": max(float(DT.min()), DtsMin), "moments": MOM,
+                "PPERT": np.asfortranarray(np.moveaxis(PE, 2, 0)), "PPART": np.asfortranarray(np.moveaxis(PA, 2, 0))}

@@ -1,0 +1,80 @@
+"""Host-side logic of the multi-GPU path on CPU: the sharding plan, and the (L,K)-slab
+re-sharding exchanged over a world_size-2 gloo process group (the same code path the
+nccl backend drives on GPUs: ramscb_b200.parallel.exchange)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from ramscb_b200 import parallel
+
+
+def test_plan_species_sharding():
+    for world in (1, 2, 4):
+        owned = []
+        for r in range(world):
+            p = parallel.make_plan(world, r, 4, 72, 35)
+            assert p.G == 1 and (p.l0, p.nl, p.k0, p.nk) == (0, 72, 0, 35)
+            owned += list(range(p.s0, p.s0 + p.ns))
+        assert owned == [0, 1, 2, 3]
+    with pytest.raises(ValueError):
+        parallel.make_plan(3, 0, 4, 72, 35)
+
+
+def test_plan_slab_sharding_covers_everything():
+    for world, NE in ((8, 35), (16, 70)):
+        G = world // 4
+        for s in range(4):
+            Ls, Ks = [], []
+            for r in range(s * G, (s + 1) * G):
+                p = parallel.make_plan(world, r, 4, 72, NE)
+                assert (p.s0, p.ns) == (s, 1) and p.group == tuple(range(s * G, (s + 1) * G))
+                Ls += list(range(p.l0, p.l0 + p.nl))
+                Ks += list(range(p.k0, p.k0 + p.nk))
+            assert Ls == list(range(72)) and Ks == list(range(NE))
+        # what a sends to b is what b receives from a
+        pa, pb = parallel.make_plan(world, 0, 4, 72, NE), parallel.make_plan(world, 1, 4, 72, NE)
+        for to_k in (True, False):
+            sa = [b for b in parallel.exchange_blocks(pa, to_k) if b[0] == 1][0]
+            sb = [b for b in parallel.exchange_blocks(pb, to_k) if b[0] == 0][0]
+            assert sa[1] == sb[2] and sa[2] == sb[1]
+
+
+def _worker(rank, world, port, NPA, NE, Pp, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # one species shared by the two ranks (nS = 1, world = 2)
+    p = parallel.make_plan(world, rank, 1, NPA, NE)
+    full = torch.arange(NPA * NE * Pp, dtype=torch.float64)          # the global species block [L][K][Pp]
+    buf = torch.full_like(full, -1.0)
+    v = buf.view(NPA, NE, Pp)
+    v[p.l0:p.l0 + p.nl] = full.view(NPA, NE, Pp)[p.l0:p.l0 + p.nl]   # L-slab layout: I hold my pitch angles, all energies
+    parallel.exchange(p, [buf], Pp, True, dist)
+    ok1 = bool(torch.equal(v[:, p.k0:p.k0 + p.nk], full.view(NPA, NE, Pp)[:, p.k0:p.k0 + p.nk]))  # all L of my energies
+    # "pitch-angle block": touch my K-slab, then go back
+    v[:, p.k0:p.k0 + p.nk] += 0.5
+    parallel.exchange(p, [buf], Pp, False, dist)
+    ok2 = bool(torch.equal(v[p.l0:p.l0 + p.nl], full.view(NPA, NE, Pp)[p.l0:p.l0 + p.nl] + 0.5))  # my L-slab, all energies updated
+    q.put((rank, ok1, ok2))
+    dist.destroy_process_group()
+
+
+def test_slab_exchange_gloo_world2():
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 10, 7, 16, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for pr in procs:
+        pr.join(timeout=60)
+    assert sorted(res) == [(0, True, True), (1, True, True)]

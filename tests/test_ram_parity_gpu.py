@@ -309,3 +309,54 @@ def test_fast_mode_full_ram_run(default_grids, oracle_built):
         assert _relerr(out["PPERT"][:, 1:], o.PPERT[:, 1:]) <= 1e-12
         assert _relerr(out["PPART"][:, 1:], o.PPART[:, 1:]) <= 1e-12
         assert np.allclose(out["SETRC"], o.SETRC, rtol=1e-12, atol=0)
+
+
+# ---------------------------------------------------------------------------------
+# multi-GPU parts (rsg_ram_part_*): slab-wise execution on one device must reproduce
+# the single-launch step bit for bit (the exchange between the parts is then a no-op:
+# every slab lives in the same buffer)
+# ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+def test_slabwise_parts_equal_full_step(default_grids, mode):
+    from ramscb_b200 import host
+    from ramscb_b200.parallel import _split
+    g = default_grids
+    inp = _mk(g, f2_kind="noisy", inductive=True, mgnp=True)
+    m = host.MODE_FAST if mode == "fast" else host.MODE_EXACT
+    a = host.RamGpu(g, mode=m); a.set_inputs(inp)
+    b = host.RamGpu(g, mode=m); b.set_inputs(inp)
+    ref = a.ram_run(DTS)
+    G = 3
+    for gi in range(G):
+        b.part_fwd(DTS, 0, 0, g.nS, *_split(g.NPA, G, gi))
+    mom = np.zeros((10, g.nS))
+    for gi in range(G):
+        b.part_mid(DTS, 0, 0, g.nS, *_split(g.NE, G, gi))
+        mom[:9] += b.part_results(0, g.nS)[1][:9]
+    dts, pe = [], np.zeros((g.NR, g.NT, g.nS))
+    for gi in range(G):
+        b.part_rev(0, g.nS, *_split(g.NPA, G, gi))
+        dt, m2, pper, _ = b.part_results(0, g.nS)
+        dts.append(dt); pe += pper; mom[9] += m2[9]
+    assert np.array_equal(b.f2_d2h(), a.f2_d2h())
+    # CFL minima of the last sweeps: min over slabs == single launch (R, P, E run in part_rev)
+    assert np.array_equal(np.min(dts, axis=0)[:3], ref["DtDrift"][:3])
+    assert np.allclose(np.moveaxis(pe, 2, 0)[:, 1:], ref["PPERT"][:, 1:], rtol=1e-13, atol=0)
+    assert np.allclose(mom[9], ref["SETRC"], rtol=1e-13, atol=0)
+
+
+def test_multi_gpu_nccl_exchange():
+    """2 GPUs, one species shared by both ranks (G = 2): L-slab <-> K-slab re-sharding over
+    NCCL must reproduce the single-GPU step bit for bit.  Skipped on a 1-GPU box."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29517", os.path.join(root, "tests", "multi_gpu_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "MULTI_GPU_CHECK_OK" in r.stdout
