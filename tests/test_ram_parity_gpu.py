@@ -317,32 +317,62 @@ def test_fast_mode_full_ram_run(default_grids, oracle_built):
 # every slab lives in the same buffer)
 # ---------------------------------------------------------------------------------
 @pytest.mark.parametrize("mode", ["exact", "fast"])
-def test_slabwise_parts_equal_full_step(default_grids, mode):
-    from ramscb_b200 import host
-    from ramscb_b200.parallel import _split
-    g = default_grids
+def test_slab_ranks_emulated_on_one_gpu(mode):
+    """G = 3 'ranks' (three handles on one device) share one species: each runs its parts on
+    its (L,K) slabs and the NCCL re-sharding is emulated with device-to-device copies of the
+    very blocks parallel.exchange_blocks() names.  F2 must equal the single-launch step bit
+    for bit; CFL minima, SUMRC sums and pressures must combine to the single-GPU values."""
+    import torch
+    from ramscb_b200 import host, parallel
+    g = grids.build_grids(nS=1)
     inp = _mk(g, f2_kind="noisy", inductive=True, mgnp=True)
     m = host.MODE_FAST if mode == "fast" else host.MODE_EXACT
-    a = host.RamGpu(g, mode=m); a.set_inputs(inp)
-    b = host.RamGpu(g, mode=m); b.set_inputs(inp)
-    ref = a.ram_run(DTS)
+    ref = host.RamGpu(g, mode=m); ref.set_inputs(inp)
     G = 3
-    for gi in range(G):
-        b.part_fwd(DTS, 0, 0, g.nS, *_split(g.NPA, G, gi))
-    mom = np.zeros((10, g.nS))
-    for gi in range(G):
-        b.part_mid(DTS, 0, 0, g.nS, *_split(g.NE, G, gi))
-        mom[:9] += b.part_results(0, g.nS)[1][:9]
-    dts, pe = [], np.zeros((g.NR, g.NT, g.nS))
-    for gi in range(G):
-        b.part_rev(0, g.nS, *_split(g.NPA, G, gi))
-        dt, m2, pper, _ = b.part_results(0, g.nS)
-        dts.append(dt); pe += pper; mom[9] += m2[9]
-    assert np.array_equal(b.f2_d2h(), a.f2_d2h())
-    # CFL minima of the last sweeps: min over slabs == single launch (R, P, E run in part_rev)
-    assert np.array_equal(np.min(dts, axis=0)[:3], ref["DtDrift"][:3])
-    assert np.allclose(np.moveaxis(pe, 2, 0)[:, 1:], ref["PPERT"][:, 1:], rtol=1e-13, atol=0)
-    assert np.allclose(mom[9], ref["SETRC"], rtol=1e-13, atol=0)
+    ranks = [host.RamGpu(g, mode=m) for _ in range(G)]
+    plans = [parallel.make_plan(G, r, 1, g.NPA, g.NE) for r in range(G)]
+    for r in ranks:
+        r.set_inputs(inp)
+
+    def bufs():
+        out = []
+        for r in ranks:
+            ptr, n, pp = r.f2_device(1)
+            out.append(torch.as_tensor(parallel._DevBuf(ptr, n), device="cuda"))
+        return out, pp
+
+    def exchange(to_k):
+        for r in ranks:
+            r.sync()
+        b, pp = bufs()
+        for me, p in enumerate(plans):
+            for peer, sblk, _ in parallel.exchange_blocks(p, to_k):
+                for off, n in parallel.block_chunks(sblk, g.NE, pp):
+                    b[peer][off:off + n].copy_(b[me][off:off + n])
+        torch.cuda.synchronize()
+
+    for dts in (DTS, 7.5):
+        out_ref = ref.ram_run(dts)
+        for r, p in zip(ranks, plans):
+            r.part_fwd(dts, 0, 0, 1, p.l0, p.nl)
+        exchange(True)
+        for r, p in zip(ranks, plans):
+            r.part_mid(dts, 0, 0, 1, p.k0, p.nk)
+        exchange(False)
+        res = []
+        for r, p in zip(ranks, plans):
+            r.part_rev(0, 1, p.l0, p.nl)
+            res.append(r.part_results(0, 1))
+        full = ref.f2_d2h()
+        for r, p in zip(ranks, plans):
+            mine = r.f2_d2h()
+            sl = slice(p.l0, p.l0 + p.nl)
+            assert np.array_equal(mine[..., sl], full[..., sl])
+        dt = np.min([x[0] for x in res], axis=0)
+        assert np.array_equal(dt, out_ref["DtDrift"])
+        pper = sum(x[2] for x in res)
+        assert np.allclose(np.moveaxis(pper, 2, 0)[:, 1:], out_ref["PPERT"][:, 1:], rtol=1e-13, atol=0)
+        assert np.allclose(sum(x[1] for x in res)[9], out_ref["SETRC"], rtol=1e-13, atol=0)
 
 
 def test_multi_gpu_nccl_exchange():
