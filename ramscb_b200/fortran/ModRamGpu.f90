@@ -1,0 +1,218 @@
+!============================================================================
+! ModRamGpu -- ISO_C_BINDING interface to libramscb_gpu.so (include/ramscb_gpu.h)
+!
+! Drop-in shim for the RAM hot path of lanl/RAM-SCB.  The reference's operators
+! are module procedures that take only the species index and work on the
+! ModRamVariables globals (src/ModRamRun.f90:64-185).  With this file and the
+! replacement bodies below, ModRamDrift / ModRamLoss / ModRamWPI / ModRamRun keep
+! their names and signatures; the bodies forward c_loc() of the module arrays to
+! the C ABI.  Binding style follows the reference's only existing C boundary,
+! src/ModRamGSL.f90:10-71 <-> src/RamGSL.c, but passes the contiguous
+! allocatables directly instead of copying them.
+!
+! NOTE: there is no Fortran compiler in the build container of this repository,
+! so this file is shipped uncompiled; the C ABI it binds is exercised from
+! Python/ctypes with the same pointers-and-sizes calling convention
+! (ramscb_b200/host.py) and checked symbol by symbol in tests/test_cpu.py.
+!============================================================================
+module ModRamGpu
+
+  use, intrinsic :: iso_c_binding
+  implicit none
+
+  type(c_ptr), save :: hRam = c_null_ptr     ! rsg_ram*
+
+  integer(c_int), parameter :: RSG_MODE_EXACT = 0, RSG_MODE_FAST = 1
+  integer(c_int), parameter :: RSG_F_WPI = 1, RSG_F_COULOMB = 2, RSG_F_EMIC = 4
+
+  interface
+     function rsg_ram_create(h, nS, nR, nT, nE, nPa, device) bind(C, name='rsg_ram_create') result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), intent(out) :: h
+       integer(c_int), value :: nS, nR, nT, nE, nPa, device
+       integer(c_int) :: ierr
+     end function
+     function rsg_ram_destroy(h) bind(C, name='rsg_ram_destroy') result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       integer(c_int) :: ierr
+     end function
+     function rsg_ram_set_mode(h, mode) bind(C, name='rsg_ram_set_mode') result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       integer(c_int), value :: mode
+       integer(c_int) :: ierr
+     end function
+     function rsg_ram_set_grids(h, RLZ, LZ, EKEV, WE, DE, EBND, MU, WMU, DMU, UPA, GREL, GRBND, V, VBND, EPP, ERNH, &
+                                RMAS, FFACTOR, QS, kind, khi, MDR, DPHI, CONF1, CONF2, BetaLim, FracCFL) &
+          bind(C, name='rsg_ram_set_grids') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       real(c_double), intent(in) :: RLZ(*), LZ(*), EKEV(*), WE(*), DE(*), EBND(*), MU(*), WMU(*), DMU(*), UPA(*), &
+                                     GREL(*), GRBND(*), V(*), VBND(*), EPP(*), ERNH(*), RMAS(*), FFACTOR(*)
+       integer(c_int), intent(in) :: QS(*), kind(*), khi(*)
+       real(c_double), value :: MDR, DPHI, CONF1, CONF2, BetaLim, FracCFL
+       integer(c_int) :: ierr
+     end function
+     function rsg_ram_set_fields(h, BNES, dBdt, FNHS, FNIS, BOUNHS, BOUNIS, HDNS, dIdt, dIbndt, outsideMGNP) &
+          bind(C, name='rsg_ram_set_fields') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       real(c_double), intent(in) :: BNES(*), dBdt(*), FNHS(*), FNIS(*), BOUNHS(*), BOUNIS(*), HDNS(*), dIdt(*), dIbndt(*)
+       integer(c_int), intent(in) :: outsideMGNP(*)
+       integer(c_int) :: ierr
+     end function
+     function rsg_ram_set_efield(h, VT, EIR, EIP) bind(C, name='rsg_ram_set_efield') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       real(c_double), intent(in) :: VT(*), EIR(*), EIP(*)
+       integer(c_int) :: ierr
+     end function
+     function rsg_ram_set_boundary(h, FGEOS) bind(C, name='rsg_ram_set_boundary') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       real(c_double), intent(in) :: FGEOS(*)
+       integer(c_int) :: ierr
+     end function
+     function rsg_ram_set_wavelo(h, WALOS1, WALOS2, WALOS3, Kp, Kpmax12) bind(C, name='rsg_ram_set_wavelo') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       real(c_double), intent(in) :: WALOS1(*), WALOS2(*), WALOS3(*)
+       real(c_double), value :: Kp, Kpmax12
+       integer(c_int) :: ierr
+     end function
+     function rsg_ram_set_diffcoef(h, which, D) bind(C, name='rsg_ram_set_diffcoef') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       integer(c_int), value :: which
+       real(c_double), intent(in) :: D(*)
+       integer(c_int) :: ierr
+     end function
+     function rsg_ram_f2_h2d(h, F2, S) bind(C, name='rsg_ram_f2_h2d') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       real(c_double), intent(in) :: F2(*)
+       integer(c_int), value :: S
+       integer(c_int) :: ierr
+     end function
+     function rsg_ram_f2_d2h(h, F2, S) bind(C, name='rsg_ram_f2_d2h') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       real(c_double), intent(inout) :: F2(*)
+       integer(c_int), value :: S
+       integer(c_int) :: ierr
+     end function
+     function rsg_driftpara(h, S, DTs) bind(C, name='rsg_driftpara') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       integer(c_int), value :: S
+       real(c_double), value :: DTs
+       integer(c_int) :: ierr
+     end function
+     function rsg_driftr(h, S) bind(C, name='rsg_driftr') result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       integer(c_int), value :: S
+       integer(c_int) :: ierr
+     end function
+     function rsg_driftp(h, S) bind(C, name='rsg_driftp') result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       integer(c_int), value :: S
+       integer(c_int) :: ierr
+     end function
+     function rsg_drifte(h, S) bind(C, name='rsg_drifte') result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       integer(c_int), value :: S
+       integer(c_int) :: ierr
+     end function
+     function rsg_driftmu(h, S) bind(C, name='rsg_driftmu') result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       integer(c_int), value :: S
+       integer(c_int) :: ierr
+     end function
+     function rsg_get_dtdrift(h, S, out4) bind(C, name='rsg_get_dtdrift') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       integer(c_int), value :: S
+       real(c_double), intent(out) :: out4(4)
+       integer(c_int) :: ierr
+     end function
+     function rsg_cepara(h, S, DTs) bind(C, name='rsg_cepara') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       integer(c_int), value :: S
+       real(c_double), value :: DTs
+       integer(c_int) :: ierr
+     end function
+     function rsg_charexchange(h, S) bind(C, name='rsg_charexchange') result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       integer(c_int), value :: S
+       integer(c_int) :: ierr
+     end function
+     function rsg_atmol(h, S) bind(C, name='rsg_atmol') result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       integer(c_int), value :: S
+       integer(c_int) :: ierr
+     end function
+     function rsg_wavelo(h, S, DTs) bind(C, name='rsg_wavelo') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       integer(c_int), value :: S
+       real(c_double), value :: DTs
+       integer(c_int) :: ierr
+     end function
+     function rsg_wpadif(h, S, DTs, nviolation) bind(C, name='rsg_wpadif') result(ierr)
+       import :: c_ptr, c_int, c_double, c_long_long
+       type(c_ptr), value :: h
+       integer(c_int), value :: S
+       real(c_double), value :: DTs
+       integer(c_long_long), intent(out) :: nviolation
+       integer(c_int) :: ierr
+     end function
+     function rsg_sumrc(h, S, setrc, elorc) bind(C, name='rsg_sumrc') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       integer(c_int), value :: S
+       real(c_double), intent(out) :: setrc, elorc
+       integer(c_int) :: ierr
+     end function
+     function rsg_anisch(h, S, PPERT_S, PPART_S) bind(C, name='rsg_anisch') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       integer(c_int), value :: S
+       real(c_double), intent(out) :: PPERT_S(*), PPART_S(*)
+       integer(c_int) :: ierr
+     end function
+     function rsg_ram_run(h, DTs, DtsMin, T, flags, dts_next, DtDrift, losses, SETRC, PPERT, PPART) &
+          bind(C, name='rsg_ram_run') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       real(c_double), value :: DTs, DtsMin, T
+       integer(c_int), value :: flags
+       real(c_double), intent(out) :: dts_next, DtDrift(*), losses(*), SETRC(*), PPERT(*), PPART(*)
+       integer(c_int) :: ierr
+     end function
+     function rsg_host_register(p, bytes) bind(C, name='rsg_host_register') result(ierr)
+       import :: c_ptr, c_int, c_long_long
+       type(c_ptr), value :: p
+       integer(c_long_long), value :: bytes
+       integer(c_int) :: ierr
+     end function
+  end interface
+
+contains
+
+  subroutine rsg_check(ierr, where)
+    ! No return codes cross the reference's interfaces: a failure of the device path is fatal,
+    ! exactly like the reference's CON_stop (src/Main.f90:135-168).
+    integer(c_int), intent(in) :: ierr
+    character(len=*), intent(in) :: where
+    if (ierr /= 0) call CON_stop('ramscb_gpu failure in '//where)
+  end subroutine rsg_check
+
+end module ModRamGpu
