@@ -38,6 +38,8 @@ struct RamDev {
   //   E: uE[k]*fEa + vE[k]*fEb MU: fMa + wM[k]*fMb          (3-D ones are [NPA][Pp])
   double *fRb, *fPa, *fPb, *fEa, *fEb, *fMa, *fMb;
   const double *rDMU, *rWMU;   // 1/DMU(L), 1/WMU(L)
+  double* rFNHS;               // FAST: 1/FNHS plane [NPA][Pp]
+  const double *wPE, *wPA;     // FAST ANISCH pitch-angle weights [NPA]: WMU/MU*(1-MU^2), WMU*MU (MU(1):=MU(2) as FFACTOR(..,1)=FFACTOR(..,2))
 };
 
 // per-species device tables (pointers into one buffer) + scalars
@@ -48,6 +50,7 @@ struct SpecDev {
   double* F;        // species block of F2dev (current buffer)
   double* Fo;       // the other ping-pong buffer (sweeps read F, write Fo)
   const int* last;  // DRIFTR: index of the most recent inflow line (reference loop order)
+  double* ghost;    // DRIFTR: F(NR+1), F(NR+2) of every line [(k*NPA+l)*NT+j][2]
   double* part;     // per-CTA partial sums for the moment reductions
   const double* FGEOS;  // [l][k][j]
   const double *P4, *eK, *epK, *aE, *sv;  // [NE]
@@ -56,6 +59,8 @@ struct SpecDev {
   const double *w2, *wM;                  // FAST-mode energy tables [NE]
   const double* tabE;                     // FAST DRIFTE: {uE, vE, 1/DE, 1/WE} per K, 32-byte records
   const double* FF;                       // FFACTOR [l][k][i]
+  const double* rFFA;                     // FAST ANISCH: MU(2)/FFACTOR(S,I,K,2) = 1/(LZ^2*GREL/sqrt(GREL^2-1)) [k][i]
+  const double* xATL;                     // FAST: log(ATLOS(S,I,K)) = -DTs*V/(2*RLZ) [k][i]
   const double* EPP;                      // [NE]
   const double* wfac;                     // WAVELO factor exp(-DTs/TAU_LIF) [NE][Pp]
   const double *DA, *DB;                  // WPADIF coefficient pair [l][k][Pp]
@@ -64,7 +69,8 @@ struct SpecDev {
   double GREL1, GREL2, sqrtA, GRZERO, sqrtB;  // DRIFTE ghost cells
   double aRP;                             // FracCFL*DTs
   double OMEt;                            // OME*DTs/DPHI
-  unsigned long long* dt;                 // [4] CFL minima as ordered bit patterns
+  unsigned long long* dt;                 // result block: [4] CFL minima (ordered bit patterns), moments, counters
+  unsigned long long* dtw;                // where the sweeps of this launch accumulate their CFL minima [4]
 };
 
 // Sub-range of the (L,K) planes a launch works on (multi-GPU slabs): planes

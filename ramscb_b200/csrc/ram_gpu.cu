@@ -45,7 +45,8 @@ int fail(int code, const std::string& msg) {
 
 constexpr double kQ = 1.602E-19, kCS = 2.998E8, kPI = 3.1415926535897932384626433832795;
 constexpr int NSUM = 16;           // moment slots per species
-constexpr int RES_N = 4 + NSUM + 1;  // [4] dt bits, [NSUM] sums, [1] WPADIF violations
+constexpr int RES_N = 4 + NSUM + 1 + 4;  // [4] dt bits, [NSUM] sums, [1] WPADIF violations, [4] dt of the forward half step
+constexpr int DTF_OFF = 4 + NSUM + 1;
 
 struct Spec {
   cudaStream_t own = nullptr;
@@ -66,8 +67,10 @@ struct Spec {
   double* d_EPP = nullptr;   // [NE]
   double* d_FGEOS = nullptr; // [l][k][j]
   int* d_last = nullptr;     // DRIFTR inflow scan
+  double* d_ghost = nullptr; // DRIFTR ghost cells per line
   double* d_part = nullptr;  // moment partials [nblk_sum][RSG_NMOM]
-  double* d_tE = nullptr;    // ANISCH scratch [2][NE][Pp]
+  double* d_tE = nullptr;    // ANISCH scratch [2][nch][NE][Pp]
+  double* d_rFFA = nullptr;  // FAST ANISCH: 1/A(S,I,K) [k][i]
   unsigned long long* d_res = nullptr;  // slice of rsg_ram::d_res_all
   unsigned long long* h_res = nullptr;  // slice of rsg_ram::h_res_all (pinned)
   double* d_pp = nullptr;    // slice of d_pp_all: [2][Pp]
@@ -118,6 +121,8 @@ struct rsg_ram {
   std::vector<std::pair<std::string, std::pair<double, long long>>> prof_acc;  // name -> (ms, count)
   int nblk_sum = 0, sum_threads = 256;
   int segE = 12, segMU = 12, segP = 12, kcR = 7;
+  bool in_step = false, fwd_half = false;   // set by rsg_ram_part_*: CFL slots are reset once per step
+  unsigned long long* d_res_init = nullptr;
 
   cudaStream_t st(int s) { return ext ? ext : sp[s].own; }
   cudaStream_t pst() { return ext ? ext : prepst; }
@@ -165,6 +170,9 @@ void make_pack(rsg_ram* h, SpecPack& pk, int s0 = 0, int ns = -1) {
     Spec& sp = h->sp[s];
     sp.sd.F = h->d_F2[sp.cur] + h->specStride * s;
     sp.sd.Fo = h->d_F2[sp.cur ^ 1] + h->specStride * s;
+    // inside the fused step the forward sweeps park their CFL minima in a scratch slot: the
+    // reference resets DtDrift* at every call, so only the reverse half step's values survive
+    sp.sd.dtw = sp.d_res + ((h->in_step && h->fwd_half) ? DTF_OFF : 0);
     pk.s[s] = sp.sd;
   }
 }
@@ -251,6 +259,7 @@ int L_inflow(rsg_ram* h, int s0, int ns, cudaStream_t st) {
   return RSG_OK;
 }
 int reset_dt(rsg_ram* h, int s0, int ns, int which, cudaStream_t st) {
+  if (h->in_step) return RSG_OK;   // done once for the whole step in rsg_ram_part_fwd
   for (int s = s0; s < s0 + ns; ++s)
     CK(cudaMemcpyAsync(h->sp[s].d_res + which, h->d_dtinit + which, 8, cudaMemcpyDeviceToDevice, st));
   return RSG_OK;
@@ -337,7 +346,8 @@ int L_loss_mid(rsg_ram* h, int s0, int ns, int doA, double DTs, int slot, cudaSt
   SpecPack pk;
   make_pack(h, pk, s0, ns);
   const int nb = pr.nl * pr.nk;
-  k_loss_mid<<<dim3(nb, ns), h->sum_threads, 0, st>>>(devfor(h, DTs), pk, s0, doA, pr);
+  if (h->mode == RSG_MODE_FAST) k_loss_mid<true><<<dim3(nb, ns), h->sum_threads, 0, st>>>(devfor(h, DTs), pk, s0, doA, pr);
+  else k_loss_mid<false><<<dim3(nb, ns), h->sum_threads, 0, st>>>(devfor(h, DTs), pk, s0, doA, pr);
   CKL();
   k_sum_final<<<dim3(4, ns), 256, 0, st>>>(pk, s0, nb, 4, slot);
   CKL();
@@ -372,7 +382,14 @@ int L_anisch(rsg_ram* h, int s0, int ns, cudaStream_t st, int l0 = 0, int nl = -
   if (nl < 0) nl = h->NPA - l0;
   SpecPack pk;
   make_pack(h, pk, s0, ns);
-  k_anisch_pa<<<dim3(nblk(h->Pp, 128), h->NE, ns), 128, 0, st>>>(h->dev, pk, s0, l0, nl);
+  if (h->mode == RSG_MODE_FAST) {
+    const int LCH = 6;
+    const int nch = std::max(1, std::min(16, (nl + LCH - 1) / LCH));
+    const int lch = (nl + nch - 1) / nch;
+    k_anisch_pa_fast<<<dim3(nblk(h->Pp, 32), h->NE, ns), dim3(32, nch), 0, st>>>(h->dev, pk, s0, l0, nl, lch);
+  } else {
+    k_anisch_pa<<<dim3(nblk(h->Pp, 128), h->NE, ns), 128, 0, st>>>(h->dev, pk, s0, l0, nl);
+  }
   CKL();
   const double cv = kCS * 100;
   const double RFAC = 4 * kPI / cv;
@@ -394,6 +411,7 @@ int fetch_res(rsg_ram* h, int s, cudaStream_t st) {
 int tables_drift(rsg_ram* h, int s, double DTs, cudaStream_t st) {
   const int nS = h->nS, NR = h->NR, NE = h->NE, NPA = h->NPA;
   Spec& sp = h->sp[s];
+  if (sp.DTs == DTs) return RSG_OK;   // pure function of DTs (and the grids)
   const double MDR = h->dev.MDR, DPHI = h->dev.DPHI, FracCFL = h->dev.FracCFL;
   const double QS = (double)h->QS[s];
   double* t = sp.h_tab;
@@ -449,8 +467,10 @@ int tables_drift(rsg_ram* h, int s, double DTs, cudaStream_t st) {
 int tables_cepara(rsg_ram* h, int s, double DTs, cudaStream_t st) {
   const int nS = h->nS, NR = h->NR, NE = h->NE;
   Spec& sp = h->sp[s];
+  if (sp.DTs_ce == DTs) return RSG_OK;   // pure function of DTs
   double* sv = sp.h_ce;
   double* ATLOS = sp.h_ce + NE;
+  double* xATL = ATLOS + (size_t)NE * NR;
   const int kind = h->kind[s];
   for (int K = 1; K <= NE; ++K) {
     const double Vk = h->V[s + (size_t)nS * (K - 1)];
@@ -470,15 +490,17 @@ int tables_cepara(rsg_ram* h, int s, double DTs, cudaStream_t st) {
     }
     sv[K - 1] = v;
     for (int I = 1; I <= NR; ++I) {
-      double a = 1.0;
+      double a = 1.0, xa = 0.0;
       if (K >= 2 && I >= 2) {
         const double TAUB = 2 * h->RLZ[I - 1] / Vk;  // :163-166
-        a = std::exp(-DTs / TAUB);
+        xa = -DTs / TAUB;
+        a = std::exp(xa);
       }
       ATLOS[(size_t)(K - 1) * NR + (I - 1)] = a;
+      xATL[(size_t)(K - 1) * NR + (I - 1)] = xa;
     }
   }
-  CK(cudaMemcpyAsync(sp.d_ce, sp.h_ce, ((size_t)NE + (size_t)NE * NR) * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(sp.d_ce, sp.h_ce, ((size_t)NE + 2 * (size_t)NE * NR) * sizeof(double), cudaMemcpyHostToDevice, st));
   sp.DTs_ce = DTs;
   return RSG_OK;
 }
@@ -575,6 +597,8 @@ int rsg_ram_create(rsg_ram** out, int nS, int NR, int NT, int NE, int NPA, int d
   for (int q = 0; q < 7; ++q) RET(h->dalloc(g1[q], g1n[q]));
   RET(h->dalloc((double**)&d.rDMU, NPA));
   RET(h->dalloc((double**)&d.rWMU, NPA));
+  RET(h->dalloc((double**)&d.wPE, NPA));
+  RET(h->dalloc((double**)&d.wPA, NPA));
   RET(h->dalloc((int**)&d.UPA, NR));
   double** f2d[] = {(double**)&d.BNES, (double**)&d.dBdt, (double**)&d.VT, (double**)&d.EIR, (double**)&d.EIP};
   for (auto p : f2d) RET(h->dalloc(p, n2));
@@ -586,7 +610,7 @@ int rsg_ram_create(rsg_ram** out, int nS, int NR, int NT, int NE, int NPA, int d
   RET(h->dalloc(&d.outp, np));
   double** p3d[] = {&d.t1, &d.G, &d.sFp, &d.Gr, &d.Gp, &d.DRD2, &d.DPD2, &d.dBdt1, &d.dIdt1, &d.FNHSc,
                     &d.CMUDOT, &d.Gmr, &d.Gmp, &d.DRM2, &d.DPM2, &d.dIbndt2, &d.BOUNHSc, &d.HDNSc,
-                    &d.fRb, &d.fPb, &d.fEa, &d.fEb, &d.fMa, &d.fMb};
+                    &d.fRb, &d.fPb, &d.fEa, &d.fEb, &d.fMa, &d.fMb, &d.rFNHS};
   for (auto p : p3d) RET(h->dalloc(p, n3p));
   h->specStride = (size_t)NPA * NE * h->Pp;
   RET(h->dalloc(&h->d_F2[0], h->specStride * nS));
@@ -603,6 +627,17 @@ int rsg_ram_create(rsg_ram** out, int nS, int NR, int NT, int NE, int NPA, int d
   h->ntiles = (NE * NPA * NT + SCAN_TILE - 1) / SCAN_TILE;
   RET(h->dalloc(&h->d_tilemax, (size_t)nS * h->ntiles));
   RET(h->dalloc(&h->d_res_all, (size_t)nS * RES_N));
+  RET(h->dalloc(&h->d_res_init, (size_t)nS * RES_N));
+  {
+    std::vector<unsigned long long> init((size_t)nS * RES_N, 0ull);
+    const double dflt[4] = {100000.0, 100000.0, 10000.0, 10000.0};  // :115,223,308,404
+    for (int s = 0; s < nS; ++s)
+      for (int q = 0; q < 4; ++q) {
+        std::memcpy(&init[(size_t)s * RES_N + q], &dflt[q], 8);
+        std::memcpy(&init[(size_t)s * RES_N + DTF_OFF + q], &dflt[q], 8);
+      }
+    RET(up(h->d_res_init, init.data(), init.size()));
+  }
   CK(cudaMallocHost((void**)&h->h_res_all, (size_t)nS * RES_N * sizeof(unsigned long long)));
   RET(h->dalloc(&h->d_pp_all, (size_t)nS * 2 * h->Pp));
   CK(cudaMallocHost((void**)&h->h_pp_all, (size_t)nS * 2 * h->Pp * sizeof(double)));
@@ -620,22 +655,25 @@ int rsg_ram_create(rsg_ram** out, int nS, int NR, int NT, int NE, int NPA, int d
     sp.n_tab = (size_t)NE * 10 + (size_t)NE * NR * 2 + NPA + 4;
     RET(h->dalloc(&sp.d_tab, sp.n_tab));
     CK(cudaMallocHost((void**)&sp.h_tab, sp.n_tab * sizeof(double)));
-    RET(h->dalloc(&sp.d_ce, (size_t)NE + (size_t)NE * NR));
-    CK(cudaMallocHost((void**)&sp.h_ce, ((size_t)NE + (size_t)NE * NR) * sizeof(double)));
+    RET(h->dalloc(&sp.d_ce, (size_t)NE + 2 * (size_t)NE * NR));
+    CK(cudaMallocHost((void**)&sp.h_ce, ((size_t)NE + 2 * (size_t)NE * NR) * sizeof(double)));
     RET(h->dalloc(&sp.d_wfac, (size_t)NE * h->Pp));
     CK(cudaMallocHost((void**)&sp.h_wfac, (size_t)NE * h->Pp * sizeof(double)));
     RET(h->dalloc(&sp.d_FF, (size_t)NPA * NE * NR));
     RET(h->dalloc(&sp.d_EPP, (size_t)NE));
     RET(h->dalloc(&sp.d_FGEOS, (size_t)NPA * NE * NT));
     RET(h->dalloc(&sp.d_last, (size_t)NE * NPA * NT));
+    RET(h->dalloc(&sp.d_ghost, (size_t)2 * NE * NPA * NT));
     RET(h->dalloc(&sp.d_part, (size_t)h->nblk_sum * RSG_NMOM));
     RET(h->dalloc(&sp.d_tE, (size_t)2 * NE * h->Pp));
+    RET(h->dalloc(&sp.d_rFFA, (size_t)NE * NR));
     sp.d_res = h->d_res_all + (size_t)s * RES_N;
     sp.h_res = h->h_res_all + (size_t)s * RES_N;
     sp.d_pp = h->d_pp_all + (size_t)s * 2 * h->Pp;
     SpecDev& sd = sp.sd;
     sd.S = s;
     sd.last = sp.d_last;
+    sd.ghost = sp.d_ghost;
     sd.part = sp.d_part;
     sd.FGEOS = sp.d_FGEOS;
     double* t = sp.d_tab;
@@ -645,6 +683,7 @@ int rsg_ram_create(rsg_ram** out, int nS, int NR, int NT, int NE, int NPA, int d
     sd.aE = t; t += NE;
     sd.sv = sp.d_ce;
     sd.ATLOS = sp.d_ce + NE;
+    sd.xATL = sp.d_ce + NE + (size_t)NE * NR;
     sd.P2 = t; t += (size_t)NE * NR;
     sd.EDOT = t; t += (size_t)NE * NR;
     sd.aMU = t; t += NPA;
@@ -658,9 +697,11 @@ int rsg_ram_create(rsg_ram** out, int nS, int NR, int NT, int NE, int NPA, int d
     sd.DA = sd.DB = h->d_zero4;
     sd.tE = sp.d_tE;
     sd.tA = sp.d_tE + (size_t)NE * h->Pp;
+    sd.rFFA = sp.d_rFFA;
     sd.pper = sp.d_pp;
     sd.ppar = sp.d_pp + h->Pp;
     sd.dt = sp.d_res;
+    sd.dtw = sp.d_res;
   }
   *out = h;
   return RSG_OK;
@@ -743,10 +784,19 @@ int rsg_ram_set_grids(rsg_ram* h, const double* RLZ, const double* LZ, const dou
   RET(up((double*)d.DE, DE, NE)); RET(up((double*)d.MU, MU, NPA)); RET(up((double*)d.WMU, WMU, NPA));
   RET(up((double*)d.DMU, DMU, NPA));
   {
-    std::vector<double> r1(NPA), r2(NPA);
-    for (int l = 0; l < NPA; ++l) { r1[l] = 1.0 / DMU[l]; r2[l] = 1.0 / WMU[l]; }
+    std::vector<double> r1(NPA), r2(NPA), w1(NPA), w2(NPA);
+    for (int l = 0; l < NPA; ++l) {
+      r1[l] = 1.0 / DMU[l];
+      r2[l] = 1.0 / WMU[l];
+      // ANISCH :372-374 with FFACTOR(S,I,K,L) = A(S,I,K)*MU(L), FFACTOR(..,1) = FFACTOR(..,2) (src/ModRamInit.f90:561-569)
+      const double mueff = (l == 0) ? MU[1] : MU[l];
+      w1[l] = WMU[l] / mueff * (1.0 - MU[l] * MU[l]);
+      w2[l] = WMU[l] / mueff * (MU[l] * MU[l]);
+    }
     RET(up((double*)d.rDMU, r1.data(), NPA));
     RET(up((double*)d.rWMU, r2.data(), NPA));
+    RET(up((double*)d.wPE, w1.data(), NPA));
+    RET(up((double*)d.wPA, w2.data(), NPA));
   }
   std::vector<int> upa(NR);
   for (int i = 0; i < NR; ++i) upa[i] = (int)UPA[i];
@@ -758,6 +808,12 @@ int rsg_ram_set_grids(rsg_ram* h, const double* RLZ, const double* LZ, const dou
         for (int i = 0; i < NR; ++i)
           ff[((size_t)l * NE + k) * NR + i] = FFACTOR[s + (size_t)nS * (i + (size_t)NR * (k + (size_t)NE * l))];
     RET(up(h->sp[s].d_FF, ff.data(), ff.size()));
+    {
+      std::vector<double> ra((size_t)NE * NR);
+      for (int k = 0; k < NE; ++k)
+        for (int i = 0; i < NR; ++i) ra[(size_t)k * NR + i] = MU[1] / ff[((size_t)1 * NE + k) * NR + i];
+      RET(up(h->sp[s].d_rFFA, ra.data(), ra.size()));
+    }
     for (int k = 0; k < NE; ++k) epp[k] = EPP[s + (size_t)nS * k];
     RET(up(h->sp[s].d_EPP, epp.data(), NE));
     h->sp[s].sd.kind = kind[s];
@@ -915,7 +971,7 @@ int rsg_driftpara(rsg_ram* h, int S, double DTs) {
   const int s = S - 1;
   RET(ensure_step(h, DTs));
   // the previous contents of h_tab may still be in flight on the species stream
-  CK(cudaStreamSynchronize(h->st(s)));
+  if (h->sp[s].DTs != DTs) CK(cudaStreamSynchronize(h->st(s)));
   RET(tables_drift(h, s, DTs, h->st(s)));
   return L_inflow(h, s, 1, h->st(s));
 }
@@ -1093,13 +1149,25 @@ int rsg_ram_part_fwd(rsg_ram* h, double DTs, int flags, int s0, int ns, int l0, 
     if (wl[s]) RET(tables_wavelo(h, s, DTs, st));
   }
   RET(ensure_step(h, DTs, st));
+  // CFL minima, moment slots and counters of the owned species: one reset per step
+  CK(cudaMemcpyAsync(h->d_res_all + (size_t)s0 * RES_N, h->d_res_init + (size_t)s0 * RES_N,
+                     (size_t)ns * RES_N * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
   RET(prof_mark(h, "driftr_inflow", st));
   RET(L_inflow(h, s0, ns, st));
-  RET(prof_mark(h, "k_driftr", st)); RET(L_driftr(h, s0, ns, st, l0, nl));
-  RET(prof_mark(h, "k_driftp", st)); RET(L_driftp(h, s0, ns, st, l0, nl));
-  RET(prof_mark(h, "k_drifte", st)); RET(L_drifte(h, s0, ns, st, l0, nl));
-  RET(prof_mark(h, "exchange", st));
-  return RSG_OK;
+  h->in_step = true;
+  h->fwd_half = true;
+  int rc = RSG_OK;
+  do {
+    if ((rc = prof_mark(h, "k_driftr", st)) != RSG_OK) break;
+    if ((rc = L_driftr(h, s0, ns, st, l0, nl)) != RSG_OK) break;
+    if ((rc = prof_mark(h, "k_driftp", st)) != RSG_OK) break;
+    if ((rc = L_driftp(h, s0, ns, st, l0, nl)) != RSG_OK) break;
+    if ((rc = prof_mark(h, "k_drifte", st)) != RSG_OK) break;
+    if ((rc = L_drifte(h, s0, ns, st, l0, nl)) != RSG_OK) break;
+    rc = prof_mark(h, "exchange", st);
+  } while (0);
+  h->in_step = false;
+  return rc;
 }
 
 // part 2: the pitch-angle block on the energy slab [k0, k0+nk): DRIFTMU, SUMRC, [WPADIF],
@@ -1111,7 +1179,14 @@ int rsg_ram_part_mid(rsg_ram* h, double DTs, int flags, int s0, int ns, int k0, 
   int cat[RSG_MAX_SPECIES][NSLOT], doA;
   slot_cats(h, flags, cat, &doA, nullptr);
   const PlaneRange pr{0, h->NPA, k0, nk};
-  RET(prof_mark(h, "k_driftmu", st)); RET(L_driftmu(h, s0, ns, st, k0, nk));
+  h->in_step = true;
+  h->fwd_half = true;
+  RET(prof_mark(h, "k_driftmu", st));
+  {
+    const int rc = L_driftmu(h, s0, ns, st, k0, nk);
+    h->in_step = false;
+    if (rc != RSG_OK) return rc;
+  }
   RET(prof_mark(h, "k_sumrc", st));
   RET(L_sumrc(h, s0, ns, 0, st, pr));
   RET(prof_mark(h, "wpadif+sumrc", st));
@@ -1126,7 +1201,14 @@ int rsg_ram_part_mid(rsg_ram* h, double DTs, int flags, int s0, int ns, int k0, 
     if (cat[s][7] >= 0) { RET(L_wpadif(h, s, DTs, st, k0, nk)); RET(L_sumrc(h, s, 1, 7, st, pr)); }
   for (int s = s0; s < s0 + ns; ++s)
     if (cat[s][8] >= 0) { RET(L_wpadif(h, s, DTs, st, k0, nk)); RET(L_sumrc(h, s, 1, 8, st, pr)); }
-  RET(prof_mark(h, "k_driftmu", st)); RET(L_driftmu(h, s0, ns, st, k0, nk));
+  RET(prof_mark(h, "k_driftmu", st));
+  h->in_step = true;
+  h->fwd_half = false;
+  {
+    const int rc = L_driftmu(h, s0, ns, st, k0, nk);
+    h->in_step = false;
+    if (rc != RSG_OK) return rc;
+  }
   RET(prof_mark(h, "exchange", st));
   return RSG_OK;
 }
@@ -1138,9 +1220,21 @@ int rsg_ram_part_rev(rsg_ram* h, int s0, int ns, int l0, int nl) {
   CK(cudaSetDevice(h->device));
   cudaStream_t st = h->pst();
   const PlaneRange pr{l0, nl, 0, h->NE};
-  RET(prof_mark(h, "k_drifte", st)); RET(L_drifte(h, s0, ns, st, l0, nl));
-  RET(prof_mark(h, "k_driftp", st)); RET(L_driftp(h, s0, ns, st, l0, nl));
-  RET(prof_mark(h, "k_driftr", st)); RET(L_driftr(h, s0, ns, st, l0, nl));
+  h->in_step = true;
+  h->fwd_half = false;
+  {
+    int rc = RSG_OK;
+    do {
+      if ((rc = prof_mark(h, "k_drifte", st)) != RSG_OK) break;
+      if ((rc = L_drifte(h, s0, ns, st, l0, nl)) != RSG_OK) break;
+      if ((rc = prof_mark(h, "k_driftp", st)) != RSG_OK) break;
+      if ((rc = L_driftp(h, s0, ns, st, l0, nl)) != RSG_OK) break;
+      if ((rc = prof_mark(h, "k_driftr", st)) != RSG_OK) break;
+      rc = L_driftr(h, s0, ns, st, l0, nl);
+    } while (0);
+    h->in_step = false;
+    if (rc != RSG_OK) return rc;
+  }
   RET(prof_mark(h, "k_sumrc", st));
   RET(L_sumrc(h, s0, ns, 9, st, pr));
   RET(prof_mark(h, "k_epilogue", st));

@@ -96,7 +96,7 @@ __global__ void k_prep_fields(RamDev d) {
     d.t1[o] = 0; d.G[o] = 0; d.sFp[o] = 1; d.Gr[o] = 0; d.Gp[o] = 0; d.DRD2[o] = 0; d.DPD2[o] = 0;
     d.dBdt1[o] = 0; d.dIdt1[o] = 0; d.FNHSc[o] = 1; d.Gmr[o] = 0; d.Gmp[o] = 0; d.DRM2[o] = 0; d.DPM2[o] = 0;
     d.dIbndt2[o] = 0; d.BOUNHSc[o] = 1; d.HDNSc[o] = 0;
-    d.fRb[o] = 0; d.fPb[o] = 0; d.fEb[o] = 0;
+    d.fRb[o] = 0; d.fPb[o] = 0; d.fEb[o] = 0; d.rFNHS[o] = 1;
     if (l == 0) { d.sB[p] = 1; d.sBp[p] = 1; d.BNESc[p] = 1; d.RLZp[p] = 1; d.outp[p] = 1; }
     return;
   }
@@ -117,6 +117,7 @@ __global__ void k_prep_fields(RamDev d) {
     d.sBp[p] = (I >= 2 && J >= 2) ? (R2(BNES, I, J) + R2(BNES, I, J1)) : 1.0;
   }
   d.FNHSc[o] = R3(FNHS, I, J, L);
+  d.rFNHS[o] = 1.0 / R3(FNHS, I, J, L);
   d.BOUNHSc[o] = R3(BOUNHS, I, J, L);
   d.HDNSc[o] = R3(d.HDNS, I, J, L);
 
@@ -376,7 +377,23 @@ __global__ void k_driftr_scan(const __grid_constant__ RamDev d, const __grid_con
   int pre = s_carry;
   for (int q = 0; q < w; ++q) pre = max(pre, sm[q]);
   v = max(v, pre);
-  if (t < n) last[t] = v;
+  if (t < n) {
+    last[t] = v;
+    // ghost cells F(NR+1), F(NR+2) this line will see (:154-168): its own boundary flux on an
+    // inflow line, otherwise F(NR+1) as left by the most recent inflow line (0 if none yet)
+    double g1 = 0.0, g2 = 0.0;
+    if (v >= 0) {
+      const int js = v % d.NT, ls = (v / d.NT) % d.NPA, ks = v / (d.NT * d.NPA);
+      if (!d.outp[js * d.NR + d.NR - 1]) {
+        const double fg = sp.FGEOS[((size_t)ls * d.NE + ks) * d.NT + js];
+        const double fn = R3(d.FNHS, d.NR, js + 1, ls + 1);
+        g1 = fg * d.CONF1 * fn;
+        if (v == t) g2 = fg * d.CONF2 * fn;
+      }
+    }
+    sp.ghost[2 * (size_t)t] = g1;
+    sp.ghost[2 * (size_t)t + 1] = g2;
+  }
 }
 
 // =============================================================================
@@ -400,7 +417,7 @@ __global__ void __launch_bounds__(256) k_driftr(const __grid_constant__ RamDev d
   const bool inplane = (p >= 0) && (p < P);
   double cmax = 0.0;
   int i = -1, j = 0;
-  double CRp = 0, gR = 0, t1 = 0, sB = 1, rl = 1, fn_NR = 0;
+  double CRp = 0, gR = 0, t1 = 0, sB = 1, rl = 1;
   bool count = false;
   if (inplane) {
     j = p / NR;
@@ -412,11 +429,6 @@ __global__ void __launch_bounds__(256) k_driftr(const __grid_constant__ RamDev d
   }
   const int I = i + 1;
   const bool edge = inplane && (i == 0 || i >= NR - 2);     // needs the line's boundary state
-  bool outNR = false;
-  if (edge) {
-    outNR = d.outp[j * NR + NR - 1];
-    fn_NR = R3(d.FNHS, NR, j + 1, l + 1);
-  }
   const double beta = d.BetaLim;
   const double* F = sp.F + ((size_t)l * NE + k0) * Pp + p;
   double* Fo = sp.Fo + ((size_t)l * NE + k0) * Pp + p;
@@ -430,26 +442,14 @@ __global__ void __launch_bounds__(256) k_driftr(const __grid_constant__ RamDev d
         phi = c * (FAST ? limited_flux_fast(F[-1], F0, F[1], F[2], c < 0.0, fabs(c), beta) : limited_flux(F[-1], F0, F[1], F[2], c, c, beta));
       } else {
         const int line = (k * d.NPA + l) * NT + j;
-        const int src = sp.last[line];
-        const bool inflow = (src == line);
+        const bool inflow = (sp.last[line] == line);
         if (I == 1) {
           phi = c * (inflow ? F[1] : 0.0);            // FBND(1) = F(2) | 0   (:155,:159)
         } else if (I == NR && !inflow) {
           phi = c * F0;                               // FBND(NR) = F(NR)     (:156)
         } else {
-          double g1 = 0.0, g2 = 0.0;                  // F(NR+1), F(NR+2)
-          if (inflow) {
-            if (!outNR) {
-              const double fg = sp.FGEOS[((size_t)l * NE + k) * NT + j];
-              g1 = fg * d.CONF1 * fn_NR;
-              g2 = fg * d.CONF2 * fn_NR;
-            }
-          } else if (src >= 0) {
-            // ghost cells left over by the most recent inflow line (:112-113,:154-168)
-            const int js = src % NT, ls = (src / NT) % d.NPA, ks = src / (NT * d.NPA);
-            if (!d.outp[js * NR + NR - 1])
-              g1 = sp.FGEOS[((size_t)ls * NE + ks) * NT + js] * d.CONF1 * R3(d.FNHS, NR, js + 1, ls + 1);
-          }
+          // F(NR+1), F(NR+2): precomputed per line by k_driftr_scan (incl. the carry-over quirk)
+          const double g1 = sp.ghost[2 * (size_t)line], g2 = sp.ghost[2 * (size_t)line + 1];
           const double Fm1 = F[-1];
           const double Fp1 = (I + 1 <= NR) ? F[1] : g1;
           const double Fp2 = (I + 2 <= NR) ? F[2] : ((I + 2 == NR + 1) ? g1 : g2);
@@ -467,7 +467,7 @@ __global__ void __launch_bounds__(256) k_driftr(const __grid_constant__ RamDev d
       Fo[0] = fn;
     }
   }
-  warp_min_to(sp.dt + 0, sp.aRP / dmax(cmax, 1E-10));
+  warp_min_to(sp.dtw + 0, sp.aRP / dmax(cmax, 1E-10));
 }
 
 // =============================================================================
@@ -542,7 +542,7 @@ __global__ void __launch_bounds__(128) k_driftp(const __grid_constant__ RamDev d
       if (jb == NT) Fo[0] = fnew;                       // :272
     }
   }
-  warp_min_to(sp.dt + 1, sp.aRP / dmax(cmax, 1E-10));
+  warp_min_to(sp.dtw + 1, sp.aRP / dmax(cmax, 1E-10));
 }
 
 // =============================================================================
@@ -658,7 +658,7 @@ __global__ void __launch_bounds__(128) k_drifte(const __grid_constant__ RamDev d
     }
   }
   if (FAST && mmax > 0.0) dtmin = sp.aRP / mmax;
-  warp_min_to(sp.dt + 2, dtmin);
+  warp_min_to(sp.dtw + 2, dtmin);
 }
 
 // =============================================================================
@@ -757,7 +757,7 @@ __global__ void __launch_bounds__(128) k_driftmu(const __grid_constant__ RamDev 
     }
   }
   if (FAST && mmax > 0.0) dtmin = sp.aRP / mmax;   // (the 1e-32 floor of :435 can never bind: DMU/1e-32 >> 1e4)
-  warp_min_to(sp.dt + 3, dtmin);
+  warp_min_to(sp.dtw + 3, dtmin);
 }
 
 // =============================================================================
@@ -874,6 +874,7 @@ __global__ void __launch_bounds__(256) k_loss(const __grid_constant__ RamDev d, 
 // so a cell's value is what the four separate passes would give.
 // grid: x = plane, y = species (one CTA per plane, same tree as k_sumrc_partial)
 // =============================================================================
+template <bool FAST>
 __global__ void __launch_bounds__(256) k_loss_mid(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0,
                                                   int doA, PlaneRange pr) {
   const SpecDev& sp = pk.s[s0 + blockIdx.y];
@@ -900,7 +901,9 @@ __global__ void __launch_bounds__(256) k_loss_mid(const __grid_constant__ RamDev
       }
       if (mom) acc[0] += e * (f * w * wm);
       if (l + 1 >= d.UPA[i]) {
-        const double a = pow(sp.ATLOS[k * d.NR + i], 1 / d.FNHSc[(size_t)l * d.Pp + p]);
+        // ATLOS**(1/FNHS) (:502).  FAST: exp(log(ATLOS)/FNHS) with log(ATLOS) = -DTs/TAUB exact from the host
+        const double a = FAST ? exp(sp.xATL[k * d.NR + i] * d.rFNHS[(size_t)l * d.Pp + p])
+                              : pow(sp.ATLOS[k * d.NR + i], 1 / d.FNHSc[(size_t)l * d.Pp + p]);
         f = f * a;
         if (mom) acc[1] += e * (f * w * wm);
         f = f * a;
@@ -1016,6 +1019,45 @@ __global__ void __launch_bounds__(128) k_anisch_pa(const __grid_constant__ RamDe
   sp.tE[t] = sp.EPP[k] * SUME;
   sp.tA[t] = sp.EPP[k] * SUMA;
 }
+// FAST variant of stage 1: the pitch-angle sum is split into NCH chunks of LCH cells (one
+// thread each; threadIdx.y = chunk), combined in a fixed order through shared memory, and
+// FFACTOR's separable form A(S,I,K)*MU(L) moves the division out of the loop:
+//   SUME = rFFA(k,i) * sum_L f * wPE(L) / FNHS,   SUMA likewise with wPA.
+// grid: x = tiles of 32 plane points, y = k, z = species; block = (32, nch)
+__global__ void __launch_bounds__(512) k_anisch_pa_fast(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0,
+                                                        int l0, int nl, int LCH) {
+  __shared__ double sE[16][32], sA[16][32];
+  const SpecDev& sp = pk.s[s0 + blockIdx.z];
+  const int NE = d.NE, Pp = d.Pp;
+  const int p = blockIdx.x * 32 + threadIdx.x;
+  const int k = blockIdx.y, ch = threadIdx.y, nch = blockDim.y;
+  const int i = (p < d.P) ? p % d.NR : 0;
+  const bool act = (p < d.P) && i >= 1 && k >= 1;
+  double se = 0., sa = 0.;
+  if (act) {
+    const size_t LS = (size_t)NE * Pp;
+    double* F = sp.F + (size_t)k * Pp + p;
+    const int La = l0 + 1 + ch * LCH;                               // Fortran L range of this chunk
+    const int Lb = min(min(d.UPA[i] - 1, l0 + nl), La + LCH - 1);
+    for (int L = La; L <= Lb; ++L) {
+      double f;
+      if (L == 1) { f = F[LS]; F[0] = f; }                         // F2(S,I,J,K,1) = F2(S,I,J,K,2)  (:366)
+      else f = F[(size_t)(L - 1) * LS];
+      const double g = f * d.rFNHS[(size_t)(L - 1) * Pp + p];
+      se = fma(g, d.wPE[L - 1], se);
+      sa = fma(g, d.wPA[L - 1], sa);
+    }
+  }
+  sE[ch][threadIdx.x] = se;
+  sA[ch][threadIdx.x] = sa;
+  __syncthreads();
+  if (ch == 0 && p < Pp) {
+    for (int c = 1; c < nch; ++c) { se += sE[c][threadIdx.x]; sa += sA[c][threadIdx.x]; }
+    const double c0 = act ? sp.EPP[k] * sp.rFFA[k * d.NR + i] : 0.0;
+    sp.tE[(size_t)k * Pp + p] = c0 * se;
+    sp.tA[(size_t)k * Pp + p] = c0 * sa;
+  }
+}
 // kh0..kh4: 1-based inclusive upper K of the 5 energy bands (khi, :303,322)
 __global__ void k_anisch_en(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0, double RFAC, int kh0, int kh1,
                             int kh2, int kh3, int kh4) {
@@ -1029,6 +1071,7 @@ __global__ void k_anisch_en(const __grid_constant__ RamDev d, const __grid_const
   double PT = 0., AT = 0.;
   for (int w = 0; w < 5; ++w) {
     double PPER = 0., PPAR = 0.;
+#pragma unroll 8
     for (int K = klo; K <= khi[w]; ++K) {
       PPER = PPER + sp.tE[(size_t)(K - 1) * d.Pp + p];
       PPAR = PPAR + sp.tA[(size_t)(K - 1) * d.Pp + p];
