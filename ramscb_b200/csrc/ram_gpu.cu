@@ -264,18 +264,31 @@ int reset_dt(rsg_ram* h, int s0, int ns, int which, cudaStream_t st) {
     CK(cudaMemcpyAsync(h->sp[s].d_res + which, h->d_dtinit + which, 8, cudaMemcpyDeviceToDevice, st));
   return RSG_OK;
 }
-int L_driftr(rsg_ram* h, int s0, int ns, cudaStream_t st, int l0 = 0, int nl = -1) {
+// mom_slot >= 0: also produce the SUMRC moment of the updated F2 into that result slot
+int L_driftr(rsg_ram* h, int s0, int ns, cudaStream_t st, int l0 = 0, int nl = -1, int mom_slot = -1) {
   if (nl < 0) nl = h->NPA - l0;
   RET(reset_dt(h, s0, ns, 0, st));
   SpecPack pk;
   make_pack(h, pk, s0, ns);
   const int KC = h->kcR, KG = (h->NE + KC - 1) / KC;
   dim3 g(nblk(h->P, 248), nl * KG, ns);   // 8 warps x 31 cells per CTA, KC energies per thread
-  if (h->mode == RSG_MODE_FAST) k_driftr<true><<<g, 256, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0, KC, KG, l0);
-  else k_driftr<false><<<g, 256, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0, KC, KG, l0);
+  const RamDev dv = devfor(h, h->sp[s0].DTs);
+  const bool fast = h->mode == RSG_MODE_FAST;
+  if (mom_slot >= 0) {
+    if (fast) k_driftr<true, true><<<g, 256, 0, st>>>(dv, pk, s0, KC, KG, l0);
+    else k_driftr<false, true><<<g, 256, 0, st>>>(dv, pk, s0, KC, KG, l0);
+  } else {
+    if (fast) k_driftr<true, false><<<g, 256, 0, st>>>(dv, pk, s0, KC, KG, l0);
+    else k_driftr<false, false><<<g, 256, 0, st>>>(dv, pk, s0, KC, KG, l0);
+  }
   CKL();
   h->launches++;
   flip(h, s0, ns);
+  if (mom_slot >= 0) {
+    k_sum_final<<<dim3(1, ns), 256, 0, st>>>(pk, s0, (int)(g.x * g.y * 8), 1, mom_slot);
+    CKL();
+    h->launches++;
+  }
   return RSG_OK;
 }
 int L_driftp(rsg_ram* h, int s0, int ns, cudaStream_t st, int l0 = 0, int nl = -1) {
@@ -306,18 +319,30 @@ int L_drifte(rsg_ram* h, int s0, int ns, cudaStream_t st, int l0 = 0, int nl = -
   flip(h, s0, ns);
   return RSG_OK;
 }
-int L_driftmu(rsg_ram* h, int s0, int ns, cudaStream_t st, int k0 = 0, int nk = -1) {
+int L_driftmu(rsg_ram* h, int s0, int ns, cudaStream_t st, int k0 = 0, int nk = -1, int mom_slot = -1) {
   if (nk < 0) nk = h->NE - k0;
   RET(reset_dt(h, s0, ns, 3, st));
   SpecPack pk;
   make_pack(h, pk, s0, ns);
   const int nseg = seg_count(h->NPA - 2, h->segMU);
   dim3 g(nblk(h->P, 128), nk * nseg, ns);
-  if (h->mode == RSG_MODE_FAST) k_driftmu<true><<<g, 128, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0, h->segMU, nseg, k0);
-  else k_driftmu<false><<<g, 128, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0, h->segMU, nseg, k0);
+  const RamDev dv = devfor(h, h->sp[s0].DTs);
+  const bool fast = h->mode == RSG_MODE_FAST;
+  if (mom_slot >= 0) {
+    if (fast) k_driftmu<true, true><<<g, 128, 0, st>>>(dv, pk, s0, h->segMU, nseg, k0);
+    else k_driftmu<false, true><<<g, 128, 0, st>>>(dv, pk, s0, h->segMU, nseg, k0);
+  } else {
+    if (fast) k_driftmu<true, false><<<g, 128, 0, st>>>(dv, pk, s0, h->segMU, nseg, k0);
+    else k_driftmu<false, false><<<g, 128, 0, st>>>(dv, pk, s0, h->segMU, nseg, k0);
+  }
   CKL();
   h->launches++;
   flip(h, s0, ns);
+  if (mom_slot >= 0) {
+    k_sum_final<<<dim3(1, ns), 256, 0, st>>>(pk, s0, (int)(g.x * g.y * 4), 1, mom_slot);
+    CKL();
+    h->launches++;
+  }
   return RSG_OK;
 }
 PlaneRange full_range(rsg_ram* h) { return PlaneRange{0, h->NPA, 0, h->NE}; }
@@ -664,7 +689,12 @@ int rsg_ram_create(rsg_ram** out, int nS, int NR, int NT, int NE, int NPA, int d
     RET(h->dalloc(&sp.d_FGEOS, (size_t)NPA * NE * NT));
     RET(h->dalloc(&sp.d_last, (size_t)NE * NPA * NT));
     RET(h->dalloc(&sp.d_ghost, (size_t)2 * NE * NPA * NT));
-    RET(h->dalloc(&sp.d_part, (size_t)h->nblk_sum * RSG_NMOM));
+    {
+      // per-plane partials of the reductions, or per-warp partials of the sweeps with a fused SUMRC
+      const size_t wR = (size_t)nblk(h->P, 248) * NPA * NE * 8;                       // KC = 1 worst case
+      const size_t wM = (size_t)nblk(h->P, 128) * NE * ((NPA - 2 + 1) / 2) * 4;       // SEG = 2 worst case
+      RET(h->dalloc(&sp.d_part, std::max({(size_t)h->nblk_sum * RSG_NMOM, wR, wM})));
+    }
     RET(h->dalloc(&sp.d_tE, (size_t)2 * NE * h->Pp));
     RET(h->dalloc(&sp.d_rFFA, (size_t)NE * NR));
     sp.d_res = h->d_res_all + (size_t)s * RES_N;
@@ -1183,12 +1213,10 @@ int rsg_ram_part_mid(rsg_ram* h, double DTs, int flags, int s0, int ns, int k0, 
   h->fwd_half = true;
   RET(prof_mark(h, "k_driftmu", st));
   {
-    const int rc = L_driftmu(h, s0, ns, st, k0, nk);
+    const int rc = L_driftmu(h, s0, ns, st, k0, nk, 0);   // SUMRC of :77 fused into the sweep
     h->in_step = false;
     if (rc != RSG_OK) return rc;
   }
-  RET(prof_mark(h, "k_sumrc", st));
-  RET(L_sumrc(h, s0, ns, 0, st, pr));
   RET(prof_mark(h, "wpadif+sumrc", st));
   for (int s = s0; s < s0 + ns; ++s)
     if (cat[s][1] >= 0) { RET(L_wpadif(h, s, DTs, st, k0, nk)); RET(L_sumrc(h, s, 1, 1, st, pr)); }
@@ -1230,13 +1258,11 @@ int rsg_ram_part_rev(rsg_ram* h, int s0, int ns, int l0, int nl) {
       if ((rc = prof_mark(h, "k_driftp", st)) != RSG_OK) break;
       if ((rc = L_driftp(h, s0, ns, st, l0, nl)) != RSG_OK) break;
       if ((rc = prof_mark(h, "k_driftr", st)) != RSG_OK) break;
-      rc = L_driftr(h, s0, ns, st, l0, nl);
+      rc = L_driftr(h, s0, ns, st, l0, nl, 9);             // SUMRC of :174 fused into the sweep
     } while (0);
     h->in_step = false;
     if (rc != RSG_OK) return rc;
   }
-  RET(prof_mark(h, "k_sumrc", st));
-  RET(L_sumrc(h, s0, ns, 9, st, pr));
   RET(prof_mark(h, "k_epilogue", st));
   {
     SpecPack pk;

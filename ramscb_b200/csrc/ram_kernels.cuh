@@ -404,7 +404,14 @@ __global__ void k_driftr_scan(const __grid_constant__ RamDev d, const __grid_con
 // not depend on K (plane coefficients, boundary flags, index math) is hoisted.
 // grid: x = tiles of 248 cells (8 warps x 31) of one plane, y = l*KG + kgroup, z = species
 // =============================================================================
-template <bool FAST>
+// warp-wide sum -> one partial per warp (no CTA barrier), fixed order => reproducible
+__device__ __forceinline__ void warp_sum_to(double* part, size_t warp_index, double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) part[warp_index] = v;
+}
+
+template <bool FAST, bool MOM>
 __global__ void __launch_bounds__(256) k_driftr(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0, int KC,
                                                 int KG, int l0) {
   const SpecDev& sp = pk.s[s0 + blockIdx.z];
@@ -415,7 +422,7 @@ __global__ void __launch_bounds__(256) k_driftr(const __grid_constant__ RamDev d
   const int lane = threadIdx.x & 31;
   const int p = (blockIdx.x * 8 + (threadIdx.x >> 5)) * 31 + lane - 1;   // 31 cells per warp + halo lane 0
   const bool inplane = (p >= 0) && (p < P);
-  double cmax = 0.0;
+  double cmax = 0.0, macc = 0.0;
   int i = -1, j = 0;
   double CRp = 0, gR = 0, t1 = 0, sB = 1, rl = 1;
   bool count = false;
@@ -429,6 +436,7 @@ __global__ void __launch_bounds__(256) k_driftr(const __grid_constant__ RamDev d
   }
   const int I = i + 1;
   const bool edge = inplane && (i == 0 || i >= NR - 2);     // needs the line's boundary state
+  const bool inmom = MOM && inplane && i >= 1 && l >= 1 && j <= NT - 2;
   const double beta = d.BetaLim;
   const double* F = sp.F + ((size_t)l * NE + k0) * Pp + p;
   double* Fo = sp.Fo + ((size_t)l * NE + k0) * Pp + p;
@@ -438,24 +446,20 @@ __global__ void __launch_bounds__(256) k_driftr(const __grid_constant__ RamDev d
       const double c = FAST ? fma(sp.P4[k], gR, CRp) : coef_r(CRp, t1, sp.P4[k], sB, rl);
       if (count) cmax = dmax(cmax, fabs(c));
       F0 = F[0];
-      if (!edge) {
-        phi = c * (FAST ? limited_flux_fast(F[-1], F0, F[1], F[2], c < 0.0, fabs(c), beta) : limited_flux(F[-1], F0, F[1], F[2], c, c, beta));
-      } else {
+      bool inflow = false;
+      double g1 = 0.0, g2 = 0.0;                    // F(NR+1), F(NR+2): per line, from k_driftr_scan
+      if (edge) {
         const int line = (k * d.NPA + l) * NT + j;
-        const bool inflow = (sp.last[line] == line);
-        if (I == 1) {
-          phi = c * (inflow ? F[1] : 0.0);            // FBND(1) = F(2) | 0   (:155,:159)
-        } else if (I == NR && !inflow) {
-          phi = c * F0;                               // FBND(NR) = F(NR)     (:156)
-        } else {
-          // F(NR+1), F(NR+2): precomputed per line by k_driftr_scan (incl. the carry-over quirk)
-          const double g1 = sp.ghost[2 * (size_t)line], g2 = sp.ghost[2 * (size_t)line + 1];
-          const double Fm1 = F[-1];
-          const double Fp1 = (I + 1 <= NR) ? F[1] : g1;
-          const double Fp2 = (I + 2 <= NR) ? F[2] : ((I + 2 == NR + 1) ? g1 : g2);
-          phi = c * (FAST ? limited_flux_fast(Fm1, F0, Fp1, Fp2, c < 0.0, fabs(c), beta) : limited_flux(Fm1, F0, Fp1, Fp2, c, c, beta));
-        }
+        inflow = (sp.last[line] == line);
+        if (i >= NR - 2) { g1 = sp.ghost[2 * (size_t)line]; g2 = sp.ghost[2 * (size_t)line + 1]; }
       }
+      const double Fm1 = (i >= 1) ? F[-1] : 0.0;
+      const double Fp1 = (I + 1 <= NR) ? F[1] : g1;
+      const double Fp2 = (I + 2 <= NR) ? F[2] : ((I + 2 == NR + 1) ? g1 : g2);
+      double FB = FAST ? limited_flux_fast(Fm1, F0, Fp1, Fp2, c < 0.0, fabs(c), beta) : limited_flux(Fm1, F0, Fp1, Fp2, c, c, beta);
+      if (I == 1) FB = inflow ? Fp1 : 0.0;          // FBND(1) = F(2) | 0   (:155,:159)
+      if (I == NR && !inflow) FB = F0;              // FBND(NR) = F(NR)     (:156)
+      phi = c * FB;
     }
     const double phiPrev = __shfl_up_sync(0xffffffffu, phi, 1);
     if (inplane && lane >= 1) {
@@ -465,9 +469,14 @@ __global__ void __launch_bounds__(256) k_driftr(const __grid_constant__ RamDev d
         if (fn < 0.0) fn = 1E-15;
       }
       Fo[0] = fn;
+      if (MOM && inmom && k >= 1) macc = fma(fn, d.WE[k] * d.EKEV[k], macc);
     }
   }
   warp_min_to(sp.dtw + 0, sp.aRP / dmax(cmax, 1E-10));
+  if (MOM) {   // fused SUMRC (src/ModRamRun.f90:246-253) of the updated F2
+    const size_t widx = ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + (threadIdx.x >> 5);
+    warp_sum_to(sp.part, widx, inmom ? macc * d.WMU[l] : 0.0);
+  }
 }
 
 // =============================================================================
@@ -667,7 +676,7 @@ __global__ void __launch_bounds__(128) k_drifte(const __grid_constant__ RamDev d
 // F2(NPA) = F2(NPA-1)*FNHS(NPA)*MU(NPA)/FNHS(NPA-1)/MU(NPA-1) (:466).
 // grid: x = tiles of the plane index p, y = k*nseg + seg, z = species
 // =============================================================================
-template <bool FAST>
+template <bool FAST, bool MOM>
 __global__ void __launch_bounds__(128) k_driftmu(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0, int SEG,
                                                  int nseg, int k0) {
   const SpecDev& sp = pk.s[s0 + blockIdx.z];
@@ -675,6 +684,7 @@ __global__ void __launch_bounds__(128) k_driftmu(const __grid_constant__ RamDev 
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   double dtmin = 1.0e300;
   double mmax = 0.0;   // FAST: max over cells of max(|c|,1e-32)/DMU(L)
+  double macc = 0.0;
   if (p < d.P) {
     const int kq = blockIdx.y / nseg, seg = blockIdx.y - kq * nseg;
     const int k = k0 + kq;
@@ -745,6 +755,7 @@ __global__ void __launch_bounds__(128) k_driftmu(const __grid_constant__ RamDev 
         if (fnew < 0.0) fnew = 1E-15;
         *pO = fnew;
         pO += LS;
+        if (MOM) macc = fma(fnew, d.WMU[L - 1], macc);
         Fm1 = F0; F0 = Fp1; Fp1 = Fp2; Fp2 = nxt; nxt = nn; cn = cnn;
       }
       if (FAST && !inside) mmax = 0.0;
@@ -752,9 +763,17 @@ __global__ void __launch_bounds__(128) k_driftmu(const __grid_constant__ RamDev 
         const double c = cn;                            // CDriftMu(..,NPA)
         if (FAST) { if (inside) mmax = dmax(mmax, fabs(c) * d.rDMU[NPA - 1]); }
         else if (inside) dtmin = dmin(dtmin, sp.aMU[NPA - 1] / dmax(fabs(c), 1E-32));
-        *pO = fnew * d.FNHSc[(size_t)(NPA - 1) * Pp + p] * d.MU[NPA - 1] / d.FNHSc[(size_t)(NPA - 2) * Pp + p] / d.MU[NPA - 2];
+        const double fN = fnew * d.FNHSc[(size_t)(NPA - 1) * Pp + p] * d.MU[NPA - 1] / d.FNHSc[(size_t)(NPA - 2) * Pp + p] / d.MU[NPA - 2];
+        *pO = fN;
+        if (MOM) macc = fma(fN, d.WMU[NPA - 1], macc);
       }
+      // fused SUMRC (src/ModRamRun.f90:246-253): I>=2 (here), K>=2, J<=NT-1
+      if (MOM) macc = (k >= 1 && p < (d.NT - 1) * d.NR) ? macc * (d.WE[k] * d.EKEV[k]) : 0.0;
     }
+  }
+  if (MOM) {
+    const size_t widx = ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    warp_sum_to(sp.part, widx, macc);
   }
   if (FAST && mmax > 0.0) dtmin = sp.aRP / mmax;   // (the 1e-32 floor of :435 can never bind: DMU/1e-32 >> 1e4)
   warp_min_to(sp.dtw + 3, dtmin);
