@@ -71,6 +71,9 @@ int rsg_ram_set_mode(rsg_ram* h, int mode);
  * the work with its own events. */
 int rsg_ram_set_stream(rsg_ram* h, void* stream);
 int rsg_ram_sync(rsg_ram* h);
+/* rsg_ram_run replays its launch sequence from a CUDA graph when DTs/flags/mode repeat
+ * (default on); 0 disables (every call launches kernel by kernel). */
+int rsg_ram_use_graph(rsg_ram* h, int on);
 
 /* ---- static data ----------------------------------------------------------
  * 1-D grids and per-species tables built by ARRAYS (src/ModRamInit.f90:364-587)

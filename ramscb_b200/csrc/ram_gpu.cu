@@ -121,6 +121,14 @@ struct rsg_ram {
   std::vector<std::pair<std::string, std::pair<double, long long>>> prof_acc;  // name -> (ms, count)
   int nblk_sum = 0, sum_threads = 256;
   int segE = 12, segMU = 12, segP = 12, kcR = 7;
+  // DRIFTR inflow scan: valid while DTs, the E field, the fields and the mode are unchanged
+  bool inflow_ok[RSG_MAX_SPECIES] = {false};
+  // CUDA graph of the single-GPU step (valid for one (DTs, flags, mode); rebuilt when they change)
+  cudaGraphExec_t gexec = nullptr;
+  double g_DTs = -1.0;
+  int g_flags = -1, g_mode = -1;
+  long long g_launches = 0;
+  bool use_graph = true;
   bool in_step = false, fwd_half = false;   // set by rsg_ram_part_*: CFL slots are reset once per step
   unsigned long long* d_res_init = nullptr;
 
@@ -203,6 +211,7 @@ int ensure_step(rsg_ram* h, double DTs, cudaStream_t only = nullptr) {
   }
   h->prep_DTs = DTs;
   h->step_dirty = false;
+  for (int s = 0; s < h->nS; ++s) h->inflow_ok[s] = false;   // CR changed
   return RSG_OK;
 }
 
@@ -246,6 +255,9 @@ int seg_count(int ncell, int seg) { return (ncell + seg - 1) / seg; }
 
 // ---- batched launches: species s0 .. s0+ns-1 on stream st ----------------------
 int L_inflow(rsg_ram* h, int s0, int ns, cudaStream_t st) {
+  bool all_ok = true;
+  for (int s = s0; s < s0 + ns; ++s) all_ok = all_ok && h->inflow_ok[s];
+  if (all_ok) return RSG_OK;   // coefficients unchanged since the last scan
   SpecPack pk;
   make_pack(h, pk, s0, ns);
   RamDev dv = devfor(h, h->sp[s0].DTs);
@@ -256,6 +268,7 @@ int L_inflow(rsg_ram* h, int s0, int ns, cudaStream_t st) {
   k_driftr_scan<<<g, SCAN_TILE, 0, st>>>(dv, pk, s0, h->d_tilemax, h->ntiles);
   CKL();
   h->launches += 2;
+  for (int s = s0; s < s0 + ns; ++s) h->inflow_ok[s] = true;
   return RSG_OK;
 }
 int reset_dt(rsg_ram* h, int s0, int ns, int which, cudaStream_t st) {
@@ -485,6 +498,7 @@ int tables_drift(rsg_ram* h, int s, double DTs, cudaStream_t st) {
   sd.aRP = FracCFL * DTs;
   sd.OMEt = OME_EARTH * DTs / DPHI;
   sp.DTs = DTs;
+  h->inflow_ok[s] = false;   // P4 changed
   return RSG_OK;
 }
 
@@ -614,6 +628,7 @@ int rsg_ram_create(rsg_ram** out, int nS, int NR, int NT, int NE, int NPA, int d
   if (const char* e = getenv("RSG_SEG_MU")) h->segMU = std::max(2, atoi(e));
   if (const char* e = getenv("RSG_SEG_P")) h->segP = std::max(2, atoi(e));
   if (const char* e = getenv("RSG_KC_R")) h->kcR = std::max(1, atoi(e));
+  if (getenv("RSG_NO_GRAPH")) h->use_graph = false;   // kernel-by-kernel launches (profilers)
   RamDev& d = h->dev;
   d.nS = nS; d.NR = NR; d.NT = NT; d.NE = NE; d.NPA = NPA; d.NR1 = h->NR1; d.P = h->P; d.Pp = h->Pp;
   const size_t n2 = (size_t)h->NR1 * NT, n3 = n2 * NPA, np = h->Pp, n3p = (size_t)NPA * h->Pp;
@@ -756,6 +771,7 @@ int rsg_ram_destroy(rsg_ram* h) {
   if (h->prepev) cudaEventDestroy(h->prepev);
   if (h->t0) cudaEventDestroy(h->t0);
   if (h->t1) cudaEventDestroy(h->t1);
+  if (h->gexec) cudaGraphExecDestroy(h->gexec);
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   delete h;
   return RSG_OK;
@@ -767,7 +783,8 @@ int rsg_ram_set_mode(rsg_ram* h, int mode) {
   CK(cudaSetDevice(h->device));
   RET(rsg_ram_sync(h));
   h->mode = mode;
-  for (int s = 0; s < h->nS; ++s) h->sp[s].DTs = -1.0;  // the inflow pre-pass depends on the mode: redo DRIFTPARA
+  for (int s = 0; s < h->nS; ++s) { h->sp[s].DTs = -1.0; h->inflow_ok[s] = false; }  // the inflow pre-pass depends on the mode
+  if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
   return RSG_OK;
 }
 
@@ -775,6 +792,13 @@ int rsg_ram_set_stream(rsg_ram* h, void* stream) {
   if (!h) return fail(RSG_ERR_ARG, "null handle");
   CK(cudaDeviceSynchronize());
   h->ext = (cudaStream_t)stream;
+  return RSG_OK;
+}
+
+int rsg_ram_use_graph(rsg_ram* h, int on) {
+  if (!h) return fail(RSG_ERR_ARG, "null handle");
+  h->use_graph = on != 0;
+  if (!on && h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
   return RSG_OK;
 }
 
@@ -911,6 +935,7 @@ int rsg_ram_set_boundary(rsg_ram* h, const double* FGEOS) {
       for (int k = 0; k < NE; ++k)
         for (int j = 0; j < NT; ++j) b[((size_t)l * NE + k) * NT + j] = FGEOS[s + (size_t)nS * (j + (size_t)NT * (k + (size_t)NE * l))];
     RET(up(h->sp[s].d_FGEOS, b.data(), b.size()));
+    h->inflow_ok[s] = false;
   }
   return RSG_OK;
 }
@@ -937,7 +962,10 @@ int rsg_ram_set_diffcoef(rsg_ram* h, int which, const double* D) {
   if (which < 0 || which > 3) return fail(RSG_ERR_ARG, "which must be 0..3");
   CK(cudaSetDevice(h->device));
   RET(rsg_ram_sync(h));
-  if (!h->d_diff[which]) RET(h->dalloc(&h->d_diff[which], h->specStride));
+  if (!h->d_diff[which]) {
+    RET(h->dalloc(&h->d_diff[which], h->specStride));
+    if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }   // a kernel argument changes
+  }
   std::vector<double> b;
   to_planes4(h, D, b);
   RET(up(h->d_diff[which], b.data(), b.size()));
@@ -1162,10 +1190,10 @@ int check_part(rsg_ram* h, int s0, int ns, int a0, int na, int amax) {
 
 // part 1: tables, coefficient planes, DRIFTR inflow scan, forward DRIFTR/P/E on the
 // pitch-angle slab [l0, l0+nl) of species [s0, s0+ns)        (src/ModRamRun.f90:67-75)
-int rsg_ram_part_fwd(rsg_ram* h, double DTs, int flags, int s0, int ns, int l0, int nl) {
-  RET(check_part(h, s0, ns, l0, nl, h ? h->NPA : 0));
-  if (flags & RSG_F_COULOMB) return fail(RSG_ERR_UNSUPPORTED, "Coulomb operators not implemented");
-  CK(cudaSetDevice(h->device));
+namespace {
+// host part of a step: tables (pure functions of DTs), coefficient planes, DRIFTR inflow scan.
+// Contains synchronisation, so it stays outside any stream capture.
+int step_prepare(rsg_ram* h, double DTs, int flags, int s0, int ns) {
   RET(rsg_ram_sync(h));  // per-species streams idle; host staging tables free
   cudaStream_t st = h->pst();
   int cat[RSG_MAX_SPECIES][NSLOT], doA;
@@ -1179,11 +1207,27 @@ int rsg_ram_part_fwd(rsg_ram* h, double DTs, int flags, int s0, int ns, int l0, 
     if (wl[s]) RET(tables_wavelo(h, s, DTs, st));
   }
   RET(ensure_step(h, DTs, st));
+  RET(prof_mark(h, "driftr_inflow", st));
+  RET(L_inflow(h, s0, ns, st));
+  return RSG_OK;
+}
+int enqueue_fwd(rsg_ram* h, int s0, int ns, int l0, int nl);
+}  // namespace
+
+int rsg_ram_part_fwd(rsg_ram* h, double DTs, int flags, int s0, int ns, int l0, int nl) {
+  RET(check_part(h, s0, ns, l0, nl, h ? h->NPA : 0));
+  if (flags & RSG_F_COULOMB) return fail(RSG_ERR_UNSUPPORTED, "Coulomb operators not implemented");
+  CK(cudaSetDevice(h->device));
+  RET(step_prepare(h, DTs, flags, s0, ns));
+  return enqueue_fwd(h, s0, ns, l0, nl);
+}
+
+namespace {
+int enqueue_fwd(rsg_ram* h, int s0, int ns, int l0, int nl) {
+  cudaStream_t st = h->pst();
   // CFL minima, moment slots and counters of the owned species: one reset per step
   CK(cudaMemcpyAsync(h->d_res_all + (size_t)s0 * RES_N, h->d_res_init + (size_t)s0 * RES_N,
                      (size_t)ns * RES_N * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
-  RET(prof_mark(h, "driftr_inflow", st));
-  RET(L_inflow(h, s0, ns, st));
   h->in_step = true;
   h->fwd_half = true;
   int rc = RSG_OK;
@@ -1199,6 +1243,7 @@ int rsg_ram_part_fwd(rsg_ram* h, double DTs, int flags, int s0, int ns, int l0, 
   h->in_step = false;
   return rc;
 }
+}  // namespace
 
 // part 2: the pitch-angle block on the energy slab [k0, k0+nk): DRIFTMU, SUMRC, [WPADIF],
 // fused losses, [WPADIF], DRIFTMU                                         (:76-170)
@@ -1280,15 +1325,29 @@ int rsg_ram_part_rev(rsg_ram* h, int s0, int ns, int l0, int nl) {
 // raw per-rank results of the three parts: DtDrift(4,ns) minima, SUMRC partial sums
 // moments(10,ns) over the local slab (unused slots are 0), partial PPERT/PPART(NR,NT,ns).
 // Ranks sharing a species add moments and pressures and take the min of DtDrift.
-int rsg_ram_part_results(rsg_ram* h, int s0, int ns, double* DtDrift, double* moments, double* PPER, double* PPAR) {
-  RET(check_part(h, s0, ns, 0, 1, 1));
-  CK(cudaSetDevice(h->device));
+namespace {
+int enqueue_results(rsg_ram* h, int s0, int ns, bool pressures) {
   cudaStream_t st = h->pst();
   CK(cudaMemcpyAsync(h->h_res_all + (size_t)s0 * RES_N, h->d_res_all + (size_t)s0 * RES_N, (size_t)ns * RES_N * sizeof(unsigned long long),
                      cudaMemcpyDeviceToHost, st));
-  if (PPER || PPAR)
+  if (pressures)
     CK(cudaMemcpyAsync(h->h_pp_all + (size_t)s0 * 2 * h->Pp, h->d_pp_all + (size_t)s0 * 2 * h->Pp,
                        (size_t)ns * 2 * h->Pp * sizeof(double), cudaMemcpyDeviceToHost, st));
+  return RSG_OK;
+}
+int collect_results(rsg_ram* h, int s0, int ns, double* DtDrift, double* moments, double* PPER, double* PPAR);
+}  // namespace
+
+int rsg_ram_part_results(rsg_ram* h, int s0, int ns, double* DtDrift, double* moments, double* PPER, double* PPAR) {
+  RET(check_part(h, s0, ns, 0, 1, 1));
+  CK(cudaSetDevice(h->device));
+  RET(enqueue_results(h, s0, ns, PPER || PPAR));
+  return collect_results(h, s0, ns, DtDrift, moments, PPER, PPAR);
+}
+
+namespace {
+int collect_results(rsg_ram* h, int s0, int ns, double* DtDrift, double* moments, double* PPER, double* PPAR) {
+  cudaStream_t st = h->pst();
   RET(prof_mark(h, "end", st));
   CK(cudaStreamSynchronize(st));
   RET(prof_fold(h));
@@ -1302,6 +1361,7 @@ int rsg_ram_part_results(rsg_ram* h, int s0, int ns, double* DtDrift, double* mo
   }
   return RSG_OK;
 }
+}  // namespace
 
 // The whole species loop of ram_run (src/ModRamRun.f90:64-185) + epilogue (:186-222) on one
 // GPU: the three parts back to back, all species advanced by each launch, on one stream.
@@ -1310,12 +1370,44 @@ int rsg_ram_run(rsg_ram* h, double DTs, double DtsMin, double T, int flags, doub
   if (!h) return fail(RSG_ERR_ARG, "null handle");
   (void)T;
   const int nS = h->nS;
-  RET(rsg_ram_part_fwd(h, DTs, flags, 0, nS, 0, h->NPA));
-  RET(rsg_ram_part_mid(h, DTs, flags, 0, nS, 0, h->NE));
-  RET(rsg_ram_part_rev(h, 0, nS, 0, h->NPA));
-  std::vector<double> dt((size_t)4 * nS), mom((size_t)NSLOT * nS), pe, pa;
-  if (PPERT || PPART) { pe.resize((size_t)h->P * nS); pa.resize((size_t)h->P * nS); }
-  RET(rsg_ram_part_results(h, 0, nS, dt.data(), mom.data(), pe.empty() ? nullptr : pe.data(), pa.empty() ? nullptr : pa.data()));
+  RET(check_part(h, 0, nS, 0, h->NPA, h->NPA));
+  if (flags & RSG_F_COULOMB) return fail(RSG_ERR_UNSUPPORTED, "Coulomb operators not implemented");
+  CK(cudaSetDevice(h->device));
+  RET(step_prepare(h, DTs, flags, 0, nS));
+  cudaStream_t st = h->pst();
+  // The launch sequence of a step is fixed for a given (DTs, flags, mode): kernel arguments
+  // carry DTs by value and the ping-pong buffers return to their start after 8 sweeps.  It is
+  // captured once into a CUDA graph and replayed (no per-launch gaps); a change of DTs / flags /
+  // mode re-captures.  Stage profiling needs the events between launches: no graph then.
+  const bool graph_ok = h->use_graph && !h->prof_on;
+  if (graph_ok && h->gexec && h->g_DTs == DTs && h->g_flags == flags && h->g_mode == h->mode) {
+    CK(cudaGraphLaunch(h->gexec, st));
+    h->launches += h->g_launches;
+  } else {
+    if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+    const long long l0 = h->launches;
+    if (graph_ok) CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue_fwd(h, 0, nS, 0, h->NPA);
+    if (rc == RSG_OK) rc = rsg_ram_part_mid(h, DTs, flags, 0, nS, 0, h->NE);
+    if (rc == RSG_OK) rc = rsg_ram_part_rev(h, 0, nS, 0, h->NPA);
+    if (rc == RSG_OK) rc = enqueue_results(h, 0, nS, true);
+    if (graph_ok) {
+      cudaGraph_t g = nullptr;
+      cudaError_t e = cudaStreamEndCapture(st, &g);
+      if (rc != RSG_OK) { if (g) cudaGraphDestroy(g); return rc; }
+      if (e != cudaSuccess) return fail(RSG_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+      e = cudaGraphInstantiate(&h->gexec, g, 0);
+      cudaGraphDestroy(g);
+      if (e != cudaSuccess) { h->gexec = nullptr; return fail(RSG_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
+      h->g_DTs = DTs; h->g_flags = flags; h->g_mode = h->mode;
+      h->g_launches = h->launches - l0;
+      CK(cudaGraphLaunch(h->gexec, st));
+    } else if (rc != RSG_OK) {
+      return rc;
+    }
+  }
+  std::vector<double> dt((size_t)4 * nS), mom((size_t)NSLOT * nS), pe((size_t)h->P * nS), pa((size_t)h->P * nS);
+  RET(collect_results(h, 0, nS, dt.data(), mom.data(), pe.data(), pa.data()));
   int cat[RSG_MAX_SPECIES][NSLOT], doA;
   slot_cats(h, flags, cat, &doA, nullptr);
   double dtn = 1e300;

@@ -50,6 +50,7 @@ def lib():
     L.rsg_ram_set_mode.argtypes = [vp, i]
     L.rsg_ram_set_stream.argtypes = [vp, vp]
     L.rsg_ram_sync.argtypes = [vp]
+    L.rsg_ram_use_graph.argtypes = [vp, i]
     L.rsg_ram_set_grids.argtypes = [vp] + [vp] * 18 + [vp, vp, vp] + [d] * 6
     L.rsg_ram_set_fields.argtypes = [vp] + [vp] * 10
     L.rsg_ram_set_efield.argtypes = [vp, vp, vp, vp]
@@ -143,6 +144,9 @@ class RamGpu:
 
     def sync(self):
         _ck(self.L.rsg_ram_sync(self.h))
+
+    def use_graph(self, on=True):
+        _ck(self.L.rsg_ram_use_graph(self.h, 1 if on else 0))
 
     def set_grids(self, g, BetaLim=1.5, FracCFL=0.8):
         f = lambda a: _p(np.asfortranarray(a, dtype=np.float64))

@@ -198,6 +198,38 @@ def test_full_ram_run(default_grids, oracle_built, flags):
     assert _relerr(flux[:, 1:, :-1, 1:, 1:], o.FLUX[:, 1:, :-1, 1:, 1:]) <= 1e-12
 
 
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+def test_graph_replay_matches_kernel_by_kernel(default_grids, mode):
+    """rsg_ram_run replays a captured CUDA graph when (DTs, flags, mode) repeat: the
+    replayed steps, the re-capture on a DTs / flags change and the plain launch
+    sequence must give bit-identical states and results."""
+    from ramscb_b200 import host
+    from ramscb_b200.host import RamGpu
+    g = default_grids
+    inp = _mk(g, f2_kind="noisy", inductive=True, mgnp=True)
+    D = synthetic.synthetic_daa(g, inp)
+    runs = []
+    for use_graph in (False, True):
+        gpu = RamGpu(g)
+        gpu.set_mode(host.MODE_FAST if mode == "fast" else host.MODE_EXACT)
+        gpu.set_inputs(inp)
+        gpu.set_diffcoef(1, D)
+        gpu.set_diffcoef(2, D)
+        gpu.use_graph(use_graph)
+        outs = []
+        for dts, flags in ((5.0, 0), (5.0, 0), (5.0, 0), (7.5, 0), (7.5, 5), (7.5, 5), (5.0, 0)):
+            outs.append(gpu.ram_run(dts, DtsMin=1.0, flags=flags))
+        runs.append((gpu.f2_d2h(), outs, gpu.launch_count()))
+        gpu.close()
+    (f_a, o_a, n_a), (f_b, o_b, n_b) = runs
+    assert np.array_equal(f_a, f_b)
+    assert n_a == n_b, "replayed launches must be counted like direct ones"
+    for a, b in zip(o_a, o_b):
+        for k in ("DtDrift", "PPERT", "PPART", "SETRC", "losses"):
+            assert np.array_equal(a[k], b[k]), k
+        assert a["DtsNext"] == b["DtsNext"]
+
+
 def test_scaled_grid_properties():
     """BASELINE config 3 grid (4x: NR=80, NT=49, NE=70): size-independent
     properties -- positivity, untouched ghost shells, periodic seam, and particle
