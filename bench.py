@@ -270,8 +270,14 @@ def main():
         alg_bytes = 16.0 * cells                       # one FP64 read + one write per cell, all species per launch
         achieved = alg_bytes / (sweeps[dom] * 1e-3) / 1e9
         step_sum = sum(v[0] for k, v in stages.items() if k != "end") / a.steps
+        traffic = None   # dram read+write bytes per launch from the committed `ncu --set full` capture
+        try:
+            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get(a.workload, {}).get(dom)
+        except OSError:
+            pass
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": int(alg_bytes),
                     "note": "16 B per cell-update (SURVEY 8(d)) x all cells of the 4 species advanced by one launch; "
                             "duration = CUDA events on the launching stream inside rsg_ram_run, L2 flushed per step",
