@@ -74,6 +74,10 @@ int rsg_ram_sync(rsg_ram* h);
 /* rsg_ram_run replays its launch sequence from a CUDA graph when DTs/flags/mode repeat
  * (default on); 0 disables (every call launches kernel by kernel). */
 int rsg_ram_use_graph(rsg_ram* h, int on);
+/* FAST mode, flags == 0: rsg_ram_run advances F2 with the fused shared-memory kernels
+ * (DRIFTR+DRIFTP per plane; DRIFTE, DRIFTMU, losses, DRIFTMU, DRIFTE per column block), default on.
+ * 0 selects the one-kernel-per-operator FAST path; F2 is bit-identical either way. */
+int rsg_ram_use_fused(rsg_ram* h, int on);
 
 /* ---- static data ----------------------------------------------------------
  * 1-D grids and per-species tables built by ARRAYS (src/ModRamInit.f90:364-587)

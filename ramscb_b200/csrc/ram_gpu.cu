@@ -13,6 +13,7 @@
 
 #include "../../include/ramscb_gpu.h"
 #include "ram_kernels.cuh"
+#include "ram_fused.cuh"
 
 namespace {
 
@@ -129,6 +130,9 @@ struct rsg_ram {
   int g_flags = -1, g_mode = -1;
   long long g_launches = 0;
   bool use_graph = true;
+  // fused FAST path (ram_fused.cuh): shared-memory plane / column kernels
+  bool use_fused = true;
+  int kcPlane = 7, colT = 0;
   bool in_step = false, fwd_half = false;   // set by rsg_ram_part_*: CFL slots are reset once per step
   unsigned long long* d_res_init = nullptr;
 
@@ -437,6 +441,79 @@ int L_anisch(rsg_ram* h, int s0, int ns, cudaStream_t st, int l0 = 0, int nl = -
   return RSG_OK;
 }
 
+// ---- fused FAST path --------------------------------------------------------------
+constexpr int COL_PG = 4;
+struct ColPlan { ColCfg cfg; int T; size_t smem; };
+ColPlan col_plan(const rsg_ram* h) {
+  ColPlan c{};
+  const int NE = h->NE, NPA = h->NPA;
+  c.cfg.NEs = NE | 1;
+  const int linesE = NPA * COL_PG, linesM = NE * COL_PG;
+  int T = h->colT ? h->colT : ((linesE + 31) / 32 * 32) * (NE > 48 ? 3 : 1);
+  c.T = std::min(1024, (T + 31) / 32 * 32);
+  auto segs = [](int n, int want, int* nseg, int* seg) {
+    want = std::max(1, want);
+    *seg = (n + want - 1) / want;
+    *nseg = (n + *seg - 1) / *seg;
+  };
+  segs(NE, c.T / linesE, &c.cfg.nsegE, &c.cfg.segE);
+  segs(NPA - 2, c.T / linesM, &c.cfg.nsegM, &c.cfg.segM);
+  c.smem = sizeof(double) * ((size_t)NPA * c.cfg.NEs * COL_PG + 6 * (size_t)NPA * COL_PG + 8 * (size_t)NE + 2 * (size_t)NE * COL_PG +
+                             3 * (size_t)NPA + 5 * 32);
+  return c;
+}
+size_t plane_smem(const rsg_ram* h) { return sizeof(double) * (2 * (size_t)h->Pp + 2 * (size_t)h->NT) + sizeof(int) * (size_t)h->NT; }
+// the fused kernels cover the default operator set on a whole grid in FAST mode
+bool fused_ok(const rsg_ram* h, int flags) {
+  if (!h->use_fused || h->mode != RSG_MODE_FAST || flags != 0) return false;
+  if (h->P > 4096 || h->NR < 3 || h->NT < 4 || h->NT > 1024 || h->NR > 4095 || h->NE < 3 || h->NPA < 4) return false;
+  return col_plan(h).smem <= 220 * 1024 && plane_smem(h) <= 220 * 1024;
+}
+template <typename K>
+int opt_in_smem(K kernel, size_t smem) {
+  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  return RSG_OK;
+}
+int L_plane_rp(rsg_ram* h, int s0, int ns, cudaStream_t st, bool rev) {
+  SpecPack pk;
+  make_pack(h, pk, s0, ns);
+  const RamDev dv = devfor(h, h->sp[s0].DTs);
+  const int KC = std::min(h->kcPlane, h->NE), KG = (h->NE + KC - 1) / KC;
+  const dim3 g(KG, h->NPA, ns);
+  const size_t smem = plane_smem(h);
+  if (h->P <= 512) {
+    const int T = 256;
+    if (rev) { RET(opt_in_smem(k_plane_rp<2, true>, smem)); k_plane_rp<2, true><<<g, T, smem, st>>>(dv, pk, s0, KC); }
+    else { RET(opt_in_smem(k_plane_rp<2, false>, smem)); k_plane_rp<2, false><<<g, T, smem, st>>>(dv, pk, s0, KC); }
+  } else {
+    const int T = ((h->P + 3) / 4 + 31) / 32 * 32;
+    if (rev) { RET(opt_in_smem(k_plane_rp<4, true>, smem)); k_plane_rp<4, true><<<g, T, smem, st>>>(dv, pk, s0, KC); }
+    else { RET(opt_in_smem(k_plane_rp<4, false>, smem)); k_plane_rp<4, false><<<g, T, smem, st>>>(dv, pk, s0, KC); }
+  }
+  CKL();
+  h->launches++;
+  if (rev) {
+    k_sum_final<<<dim3(1, ns), 256, 0, st>>>(pk, s0, KG * h->NPA, 1, 9);   // SUMRC of src/ModRamRun.f90:174
+    CKL();
+    h->launches++;
+  }
+  return RSG_OK;
+}
+int L_col(rsg_ram* h, int s0, int ns, int doA, double DTs, cudaStream_t st) {
+  SpecPack pk;
+  make_pack(h, pk, s0, ns);
+  ColPlan c = col_plan(h);
+  c.cfg.doA = doA;
+  RET(opt_in_smem(k_col_fused<COL_PG>, c.smem));
+  const int nb = (h->P + COL_PG - 1) / COL_PG;
+  k_col_fused<COL_PG><<<dim3(nb, ns), c.T, c.smem, st>>>(devfor(h, DTs), pk, s0, c.cfg);
+  CKL();
+  k_sum_final<<<dim3(5, ns), 256, 0, st>>>(pk, s0, nb, 5, 0, 2);   // slot 0 (:77) and slots 3..6 (:108-142)
+  CKL();
+  h->launches += 2;
+  return RSG_OK;
+}
+
 int fetch_res(rsg_ram* h, int s, cudaStream_t st) {
   Spec& sp = h->sp[s];
   CK(cudaMemcpyAsync(sp.h_res, sp.d_res, sizeof(unsigned long long) * RES_N, cudaMemcpyDeviceToHost, st));
@@ -628,6 +705,9 @@ int rsg_ram_create(rsg_ram** out, int nS, int NR, int NT, int NE, int NPA, int d
   if (const char* e = getenv("RSG_SEG_MU")) h->segMU = std::max(2, atoi(e));
   if (const char* e = getenv("RSG_SEG_P")) h->segP = std::max(2, atoi(e));
   if (const char* e = getenv("RSG_KC_R")) h->kcR = std::max(1, atoi(e));
+  if (getenv("RSG_NO_FUSE")) h->use_fused = false;
+  if (const char* e = getenv("RSG_KC_PLANE")) h->kcPlane = std::max(1, atoi(e));
+  if (const char* e = getenv("RSG_COL_T")) h->colT = std::max(32, atoi(e));
   if (getenv("RSG_NO_GRAPH")) h->use_graph = false;   // kernel-by-kernel launches (profilers)
   RamDev& d = h->dev;
   d.nS = nS; d.NR = NR; d.NT = NT; d.NE = NE; d.NPA = NPA; d.NR1 = h->NR1; d.P = h->P; d.Pp = h->Pp;
@@ -799,6 +879,13 @@ int rsg_ram_use_graph(rsg_ram* h, int on) {
   if (!h) return fail(RSG_ERR_ARG, "null handle");
   h->use_graph = on != 0;
   if (!on && h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+  return RSG_OK;
+}
+
+int rsg_ram_use_fused(rsg_ram* h, int on) {
+  if (!h) return fail(RSG_ERR_ARG, "null handle");
+  h->use_fused = on != 0;
+  if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
   return RSG_OK;
 }
 
@@ -1212,6 +1299,8 @@ int step_prepare(rsg_ram* h, double DTs, int flags, int s0, int ns) {
   return RSG_OK;
 }
 int enqueue_fwd(rsg_ram* h, int s0, int ns, int l0, int nl);
+int enqueue_fused(rsg_ram* h, double DTs, int flags);
+int enqueue_tail(rsg_ram* h, int s0, int ns, int l0, int nl, cudaStream_t st);
 }  // namespace
 
 int rsg_ram_part_fwd(rsg_ram* h, double DTs, int flags, int s0, int ns, int l0, int nl) {
@@ -1242,6 +1331,38 @@ int enqueue_fwd(rsg_ram* h, int s0, int ns, int l0, int nl) {
   } while (0);
   h->in_step = false;
   return rc;
+}
+// epilogue of ram_run (src/ModRamRun.f90:186-209) and the pitch-angle sums of ANISCH
+int enqueue_tail(rsg_ram* h, int s0, int ns, int l0, int nl, cudaStream_t st) {
+  const PlaneRange pr{l0, nl, 0, h->NE};
+  RET(prof_mark(h, "k_epilogue", st));
+  {
+    SpecPack pk;
+    make_pack(h, pk, s0, ns);
+    k_epilogue<<<dim3(nblk(h->NR + h->nout, 128), nl * h->NE, ns), 128, 0, st>>>(h->dev, pk, s0, h->d_outlist, h->nout, pr);
+    CKL();
+    h->launches++;
+  }
+  RET(prof_mark(h, "k_anisch", st));
+  RET(L_anisch(h, s0, ns, st, l0, nl));
+  RET(prof_mark(h, "d2h_results", st));
+  return RSG_OK;
+}
+// the whole step of all species on the fused FAST kernels: F2 makes three round trips
+int enqueue_fused(rsg_ram* h, double DTs, int flags) {
+  cudaStream_t st = h->pst();
+  const int nS = h->nS;
+  CK(cudaMemcpyAsync(h->d_res_all, h->d_res_init, (size_t)nS * RES_N * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+  int cat[RSG_MAX_SPECIES][NSLOT], doA;
+  slot_cats(h, flags, cat, &doA, nullptr);
+  h->in_step = false;
+  RET(prof_mark(h, "k_plane_rp", st));
+  RET(L_plane_rp(h, 0, nS, st, false));
+  RET(prof_mark(h, "k_col_fused", st));
+  RET(L_col(h, 0, nS, doA, DTs, st));
+  RET(prof_mark(h, "k_plane_rp", st));
+  RET(L_plane_rp(h, 0, nS, st, true));
+  return enqueue_tail(h, 0, nS, 0, h->NPA, st);
 }
 }  // namespace
 
@@ -1292,7 +1413,6 @@ int rsg_ram_part_rev(rsg_ram* h, int s0, int ns, int l0, int nl) {
   RET(check_part(h, s0, ns, l0, nl, h ? h->NPA : 0));
   CK(cudaSetDevice(h->device));
   cudaStream_t st = h->pst();
-  const PlaneRange pr{l0, nl, 0, h->NE};
   h->in_step = true;
   h->fwd_half = false;
   {
@@ -1308,18 +1428,7 @@ int rsg_ram_part_rev(rsg_ram* h, int s0, int ns, int l0, int nl) {
     h->in_step = false;
     if (rc != RSG_OK) return rc;
   }
-  RET(prof_mark(h, "k_epilogue", st));
-  {
-    SpecPack pk;
-    make_pack(h, pk, s0, ns);
-    k_epilogue<<<dim3(nblk(h->NR + h->nout, 128), nl * h->NE, ns), 128, 0, st>>>(h->dev, pk, s0, h->d_outlist, h->nout, pr);
-    CKL();
-    h->launches++;
-  }
-  RET(prof_mark(h, "k_anisch", st));
-  RET(L_anisch(h, s0, ns, st, l0, nl));
-  RET(prof_mark(h, "d2h_results", st));
-  return RSG_OK;
+  return enqueue_tail(h, s0, ns, l0, nl, st);
 }
 
 // raw per-rank results of the three parts: DtDrift(4,ns) minima, SUMRC partial sums
@@ -1387,9 +1496,13 @@ int rsg_ram_run(rsg_ram* h, double DTs, double DtsMin, double T, int flags, doub
     if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
     const long long l0 = h->launches;
     if (graph_ok) CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    int rc = enqueue_fwd(h, 0, nS, 0, h->NPA);
-    if (rc == RSG_OK) rc = rsg_ram_part_mid(h, DTs, flags, 0, nS, 0, h->NE);
-    if (rc == RSG_OK) rc = rsg_ram_part_rev(h, 0, nS, 0, h->NPA);
+    int rc;
+    if (fused_ok(h, flags)) rc = enqueue_fused(h, DTs, flags);
+    else {
+      rc = enqueue_fwd(h, 0, nS, 0, h->NPA);
+      if (rc == RSG_OK) rc = rsg_ram_part_mid(h, DTs, flags, 0, nS, 0, h->NE);
+      if (rc == RSG_OK) rc = rsg_ram_part_rev(h, 0, nS, 0, h->NPA);
+    }
     if (rc == RSG_OK) rc = enqueue_results(h, 0, nS, true);
     if (graph_ok) {
       cudaGraph_t g = nullptr;

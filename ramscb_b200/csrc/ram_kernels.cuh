@@ -806,7 +806,8 @@ __device__ __forceinline__ void cta_sum_to(double* part, int cta, double (&acc)[
 }
 
 // out[q] = sum_b part[b*nm + q]; grid = (nm, nspecies)
-__global__ void k_sum_final(const __grid_constant__ SpecPack pk, int s0, int nb, int nm, int slot0) {
+// (gap: result slots of q >= 1 are shifted by gap -- the fused column kernel produces slot 0 and slots 3..6)
+__global__ void k_sum_final(const __grid_constant__ SpecPack pk, int s0, int nb, int nm, int slot0, int gap = 0) {
   __shared__ double sm[32];
   const SpecDev& sp = pk.s[s0 + blockIdx.y];
   const int q = blockIdx.x;
@@ -820,7 +821,7 @@ __global__ void k_sum_final(const __grid_constant__ SpecPack pk, int s0, int nb,
     double v = (threadIdx.x < (blockDim.x >> 5)) ? sm[threadIdx.x] : 0.0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (threadIdx.x == 0) ((double*)(sp.dt + 4))[slot0 + q] = v;
+    if (threadIdx.x == 0) ((double*)(sp.dt + 4))[slot0 + q + (q > 0 ? gap : 0)] = v;
   }
 }
 

@@ -51,6 +51,7 @@ def lib():
     L.rsg_ram_set_stream.argtypes = [vp, vp]
     L.rsg_ram_sync.argtypes = [vp]
     L.rsg_ram_use_graph.argtypes = [vp, i]
+    L.rsg_ram_use_fused.argtypes = [vp, i]
     L.rsg_ram_set_grids.argtypes = [vp] + [vp] * 18 + [vp, vp, vp] + [d] * 6
     L.rsg_ram_set_fields.argtypes = [vp] + [vp] * 10
     L.rsg_ram_set_efield.argtypes = [vp, vp, vp, vp]
@@ -144,6 +145,9 @@ class RamGpu:
 
     def sync(self):
         _ck(self.L.rsg_ram_sync(self.h))
+
+    def use_fused(self, on=True):
+        _ck(self.L.rsg_ram_use_fused(self.h, 1 if on else 0))
 
     def use_graph(self, on=True):
         _ck(self.L.rsg_ram_use_graph(self.h, 1 if on else 0))

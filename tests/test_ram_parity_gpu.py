@@ -230,6 +230,41 @@ def test_graph_replay_matches_kernel_by_kernel(default_grids, mode):
         assert a["DtsNext"] == b["DtsNext"]
 
 
+@pytest.mark.parametrize("grid", ["default", "odd", "x4"])
+def test_fused_step_matches_unfused_fast(default_grids, grid):
+    """The fused shared-memory kernels (ram_fused.cuh) restate the FAST arithmetic cell by cell:
+    F2 and the CFL limits must be bit-identical to the one-kernel-per-operator FAST path, the
+    SUMRC moments / pressures equal up to summation order.  'odd': a grid whose sizes exercise the
+    padded energy stride, ragged plane tiles and segmented lines; 'x4': BASELINE configs[2]."""
+    from ramscb_b200 import host
+    from ramscb_b200.host import RamGpu
+    if grid == "default":
+        g = default_grids
+    elif grid == "odd":
+        g = grids.build_grids(NR=23, NT=31, NE=46, energy_refine=1)
+    else:
+        g = grids.build_grids(NR=80, NT=49, NE=70, energy_refine=2)
+    inp = _mk(g, f2_kind="noisy", inductive=True, mgnp=True)
+    runs = []
+    for fused in (False, True):
+        gpu = RamGpu(g)
+        gpu.set_mode(host.MODE_FAST)
+        gpu.set_inputs(inp)
+        gpu.use_fused(fused)
+        outs = [gpu.ram_run(dts, DtsMin=1.0, flags=0) for dts in (5.0, 5.0, 2.5)]
+        runs.append((gpu.f2_d2h(), outs))
+        gpu.close()
+    (f_a, o_a), (f_b, o_b) = runs
+    assert np.array_equal(f_a, f_b), f"max |diff| {np.abs(f_a - f_b).max():.3e}"
+    for a, b in zip(o_a, o_b):
+        assert np.array_equal(a["DtDrift"], b["DtDrift"])
+        assert a["DtsNext"] == b["DtsNext"]
+        for k in ("PPERT", "PPART", "SETRC"):
+            assert np.allclose(a[k], b[k], rtol=1e-12, atol=0), k
+        # the loss increments are differences of consecutive SETRC moments
+        assert np.all(np.abs(a["losses"] - b["losses"]) <= 1e-11 * np.abs(a["SETRC"])[None, :])
+
+
 def test_scaled_grid_properties():
     """BASELINE config 3 grid (4x: NR=80, NT=49, NE=70): size-independent
     properties -- positivity, untouched ghost shells, periodic seam, and particle
