@@ -163,6 +163,12 @@ int rsg_ram_run(rsg_ram* h, double DTs, double DtsMin, double T, int flags, doub
 int rsg_ram_part_fwd(rsg_ram* h, double DTs, int flags, int s0, int ns, int l0, int nl);
 int rsg_ram_part_mid(rsg_ram* h, double DTs, int flags, int s0, int ns, int k0, int nk);
 int rsg_ram_part_rev(rsg_ram* h, int s0, int ns, int l0, int nl);
+/* All three parts at once for species [s0, s0+ns) when every pitch angle and energy is local
+ * (species-sharded ranks, or one GPU): uses the fused kernels / graph replay of rsg_ram_run. */
+int rsg_ram_part_all(rsg_ram* h, double DTs, int flags, int s0, int ns);
+/* Device result blocks, species-major: res = nS x *res_n 8-byte words, pp = nS x *pp_n doubles.
+ * Species-sharded ranks all-gather them in place (NCCL) and decode with rsg_ram_part_results(0, nS). */
+int rsg_ram_results_device(rsg_ram* h, void** res, long long* res_n, void** pp, long long* pp_n);
 int rsg_ram_part_results(rsg_ram* h, int s0, int ns, double* DtDrift, double* moments, double* PPER, double* PPAR);
 
 /* FLUX = F2/FFACTOR/FNHS (src/ModRamRun.f90:210-221), host array like F2 */

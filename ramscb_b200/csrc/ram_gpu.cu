@@ -129,6 +129,8 @@ struct rsg_ram {
   double g_DTs = -1.0;
   int g_flags = -1, g_mode = -1;
   long long g_launches = 0;
+  int g_s0 = 0, g_ns = 0;
+  cudaStream_t g_stream = nullptr;
   bool use_graph = true;
   // fused FAST path (ram_fused.cuh): shared-memory plane / column kernels
   bool use_fused = true;
@@ -1299,7 +1301,7 @@ int step_prepare(rsg_ram* h, double DTs, int flags, int s0, int ns) {
   return RSG_OK;
 }
 int enqueue_fwd(rsg_ram* h, int s0, int ns, int l0, int nl);
-int enqueue_fused(rsg_ram* h, double DTs, int flags);
+int enqueue_fused(rsg_ram* h, double DTs, int flags, int s0, int ns);
 int enqueue_tail(rsg_ram* h, int s0, int ns, int l0, int nl, cudaStream_t st);
 }  // namespace
 
@@ -1349,20 +1351,20 @@ int enqueue_tail(rsg_ram* h, int s0, int ns, int l0, int nl, cudaStream_t st) {
   return RSG_OK;
 }
 // the whole step of all species on the fused FAST kernels: F2 makes three round trips
-int enqueue_fused(rsg_ram* h, double DTs, int flags) {
+int enqueue_fused(rsg_ram* h, double DTs, int flags, int s0, int ns) {
   cudaStream_t st = h->pst();
-  const int nS = h->nS;
-  CK(cudaMemcpyAsync(h->d_res_all, h->d_res_init, (size_t)nS * RES_N * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(h->d_res_all + (size_t)s0 * RES_N, h->d_res_init + (size_t)s0 * RES_N,
+                     (size_t)ns * RES_N * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
   int cat[RSG_MAX_SPECIES][NSLOT], doA;
   slot_cats(h, flags, cat, &doA, nullptr);
   h->in_step = false;
   RET(prof_mark(h, "k_plane_rp", st));
-  RET(L_plane_rp(h, 0, nS, st, false));
+  RET(L_plane_rp(h, s0, ns, st, false));
   RET(prof_mark(h, "k_col_fused", st));
-  RET(L_col(h, 0, nS, doA, DTs, st));
+  RET(L_col(h, s0, ns, doA, DTs, st));
   RET(prof_mark(h, "k_plane_rp", st));
-  RET(L_plane_rp(h, 0, nS, st, true));
-  return enqueue_tail(h, 0, nS, 0, h->NPA, st);
+  RET(L_plane_rp(h, s0, ns, st, true));
+  return enqueue_tail(h, s0, ns, 0, h->NPA, st);
 }
 }  // namespace
 
@@ -1472,6 +1474,70 @@ int collect_results(rsg_ram* h, int s0, int ns, double* DtDrift, double* moments
 }
 }  // namespace
 
+namespace {
+// One full step of species [s0, s0+ns) on this GPU, results left in the pinned result block.
+// The launch sequence of a step is fixed for a given (DTs, flags, mode, species range): kernel
+// arguments carry DTs by value and the ping-pong buffers return to their start after 8 sweeps.
+// It is captured once into a CUDA graph and replayed (no per-launch gaps); any change of the key
+// re-captures.  Stage profiling needs the events between launches: no graph then.
+int run_core(rsg_ram* h, double DTs, int flags, int s0, int ns) {
+  RET(check_part(h, s0, ns, 0, h ? h->NPA : 0, h ? h->NPA : 0));
+  if (flags & RSG_F_COULOMB) return fail(RSG_ERR_UNSUPPORTED, "Coulomb operators not implemented");
+  CK(cudaSetDevice(h->device));
+  RET(step_prepare(h, DTs, flags, s0, ns));
+  cudaStream_t st = h->pst();
+  const bool graph_ok = h->use_graph && !h->prof_on;
+  if (graph_ok && h->gexec && h->g_DTs == DTs && h->g_flags == flags && h->g_mode == h->mode && h->g_s0 == s0 && h->g_ns == ns &&
+      h->g_stream == st) {
+    CK(cudaGraphLaunch(h->gexec, st));
+    h->launches += h->g_launches;
+    return RSG_OK;
+  }
+  if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+  const long long l0 = h->launches;
+  if (graph_ok) CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  int rc;
+  if (fused_ok(h, flags)) rc = enqueue_fused(h, DTs, flags, s0, ns);
+  else {
+    rc = enqueue_fwd(h, s0, ns, 0, h->NPA);
+    if (rc == RSG_OK) rc = rsg_ram_part_mid(h, DTs, flags, s0, ns, 0, h->NE);
+    if (rc == RSG_OK) rc = rsg_ram_part_rev(h, s0, ns, 0, h->NPA);
+  }
+  if (rc == RSG_OK) rc = enqueue_results(h, s0, ns, true);
+  if (graph_ok) {
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(st, &g);
+    if (rc != RSG_OK) { if (g) cudaGraphDestroy(g); return rc; }
+    if (e != cudaSuccess) return fail(RSG_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&h->gexec, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) { h->gexec = nullptr; return fail(RSG_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
+    h->g_DTs = DTs; h->g_flags = flags; h->g_mode = h->mode; h->g_s0 = s0; h->g_ns = ns; h->g_stream = st;
+    h->g_launches = h->launches - l0;
+    CK(cudaGraphLaunch(h->gexec, st));
+  }
+  return rc;
+}
+}  // namespace
+
+// Device result blocks (species-major): res = nS x res_n 8-byte words (CFL minima as ordered bit
+// patterns, moments, counters), pp = nS x pp_n doubles (PPER plane, PPAR plane).  Species-sharded
+// ranks all-gather these in place and then decode every species with rsg_ram_part_results.
+int rsg_ram_results_device(rsg_ram* h, void** res, long long* res_n, void** pp, long long* pp_n) {
+  if (!h || !res || !res_n || !pp || !pp_n) return fail(RSG_ERR_ARG, "null argument");
+  *res = h->d_res_all; *res_n = RES_N;
+  *pp = h->d_pp_all; *pp_n = 2 * (long long)h->Pp;
+  return RSG_OK;
+}
+
+// All three parts of a step for species [s0, s0+ns) with every pitch angle and energy local
+// (species-sharded ranks): same fused kernels and graph replay as rsg_ram_run.  Results through
+// rsg_ram_part_results.
+int rsg_ram_part_all(rsg_ram* h, double DTs, int flags, int s0, int ns) {
+  if (!h) return fail(RSG_ERR_ARG, "null handle");
+  return run_core(h, DTs, flags, s0, ns);
+}
+
 // The whole species loop of ram_run (src/ModRamRun.f90:64-185) + epilogue (:186-222) on one
 // GPU: the three parts back to back, all species advanced by each launch, on one stream.
 int rsg_ram_run(rsg_ram* h, double DTs, double DtsMin, double T, int flags, double* dts_next, double* DtDrift,
@@ -1479,46 +1545,7 @@ int rsg_ram_run(rsg_ram* h, double DTs, double DtsMin, double T, int flags, doub
   if (!h) return fail(RSG_ERR_ARG, "null handle");
   (void)T;
   const int nS = h->nS;
-  RET(check_part(h, 0, nS, 0, h->NPA, h->NPA));
-  if (flags & RSG_F_COULOMB) return fail(RSG_ERR_UNSUPPORTED, "Coulomb operators not implemented");
-  CK(cudaSetDevice(h->device));
-  RET(step_prepare(h, DTs, flags, 0, nS));
-  cudaStream_t st = h->pst();
-  // The launch sequence of a step is fixed for a given (DTs, flags, mode): kernel arguments
-  // carry DTs by value and the ping-pong buffers return to their start after 8 sweeps.  It is
-  // captured once into a CUDA graph and replayed (no per-launch gaps); a change of DTs / flags /
-  // mode re-captures.  Stage profiling needs the events between launches: no graph then.
-  const bool graph_ok = h->use_graph && !h->prof_on;
-  if (graph_ok && h->gexec && h->g_DTs == DTs && h->g_flags == flags && h->g_mode == h->mode) {
-    CK(cudaGraphLaunch(h->gexec, st));
-    h->launches += h->g_launches;
-  } else {
-    if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
-    const long long l0 = h->launches;
-    if (graph_ok) CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    int rc;
-    if (fused_ok(h, flags)) rc = enqueue_fused(h, DTs, flags);
-    else {
-      rc = enqueue_fwd(h, 0, nS, 0, h->NPA);
-      if (rc == RSG_OK) rc = rsg_ram_part_mid(h, DTs, flags, 0, nS, 0, h->NE);
-      if (rc == RSG_OK) rc = rsg_ram_part_rev(h, 0, nS, 0, h->NPA);
-    }
-    if (rc == RSG_OK) rc = enqueue_results(h, 0, nS, true);
-    if (graph_ok) {
-      cudaGraph_t g = nullptr;
-      cudaError_t e = cudaStreamEndCapture(st, &g);
-      if (rc != RSG_OK) { if (g) cudaGraphDestroy(g); return rc; }
-      if (e != cudaSuccess) return fail(RSG_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
-      e = cudaGraphInstantiate(&h->gexec, g, 0);
-      cudaGraphDestroy(g);
-      if (e != cudaSuccess) { h->gexec = nullptr; return fail(RSG_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
-      h->g_DTs = DTs; h->g_flags = flags; h->g_mode = h->mode;
-      h->g_launches = h->launches - l0;
-      CK(cudaGraphLaunch(h->gexec, st));
-    } else if (rc != RSG_OK) {
-      return rc;
-    }
-  }
+  RET(run_core(h, DTs, flags, 0, nS));
   std::vector<double> dt((size_t)4 * nS), mom((size_t)NSLOT * nS), pe((size_t)h->P * nS), pa((size_t)h->P * nS);
   RET(collect_results(h, 0, nS, dt.data(), mom.data(), pe.data(), pa.data()));
   int cat[RSG_MAX_SPECIES][NSLOT], doA;

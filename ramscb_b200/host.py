@@ -73,6 +73,8 @@ def lib():
     L.rsg_anisch.argtypes = [vp, i, vp, vp]
     L.rsg_ram_run.argtypes = [vp, d, d, d, i, _dp, vp, vp, vp, vp, vp]
     L.rsg_ram_part_fwd.argtypes = [vp, d, i, i, i, i, i]
+    L.rsg_ram_part_all.argtypes = [vp, d, i, i, i]
+    L.rsg_ram_results_device.argtypes = [vp, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong), C.POINTER(C.c_void_p), C.POINTER(C.c_longlong)]
     L.rsg_ram_part_mid.argtypes = [vp, d, i, i, i, i, i]
     L.rsg_ram_part_rev.argtypes = [vp, i, i, i, i]
     L.rsg_ram_part_results.argtypes = [vp, i, i, vp, vp, vp, vp]
@@ -261,6 +263,15 @@ class RamGpu:
     # ---- multi-GPU parts (include/ramscb_gpu.h: rsg_ram_part_*) ---------------------
     def part_fwd(self, DTs, flags, s0, ns, l0, nl):
         _ck(self.L.rsg_ram_part_fwd(self.h, DTs, flags, s0, ns, l0, nl))
+
+    def results_device(self):
+        """(res_ptr, words per species, pp_ptr, doubles per species) of the device result blocks."""
+        r, rn, q, qn = C.c_void_p(), C.c_longlong(), C.c_void_p(), C.c_longlong()
+        _ck(self.L.rsg_ram_results_device(self.h, C.byref(r), C.byref(rn), C.byref(q), C.byref(qn)))
+        return r.value, rn.value, q.value, qn.value
+
+    def part_all(self, DTs, flags, s0, ns):
+        _ck(self.L.rsg_ram_part_all(self.h, DTs, flags, s0, ns))
 
     def part_mid(self, DTs, flags, s0, ns, k0, nk):
         _ck(self.L.rsg_ram_part_mid(self.h, DTs, flags, s0, ns, k0, nk))

@@ -139,6 +139,7 @@ class RamSharded:
     def __init__(self, gpu, plan: ShardPlan, dist=None):
         self.gpu, self.p, self.dist = gpu, plan, dist
         self.setrc = np.zeros(gpu.g.nS)
+        self._views = None
 
     def _bufs(self):
         import torch
@@ -148,18 +149,37 @@ class RamSharded:
             out.append(torch.as_tensor(_DevBuf(ptr, n), device="cuda"))
         return out, pp
 
+    def _result_views(self):
+        if self._views is None:
+            import torch
+            r, rn, q, qn = self.gpu.results_device()
+            nS = self.gpu.g.nS
+            self._views = (torch.as_tensor(_DevBuf(r, nS * rn), device="cuda"), torch.as_tensor(_DevBuf(q, nS * qn), device="cuda"), rn, qn)
+        return self._views
+
     def ram_run(self, DTs, DtsMin=1.0, flags=0):
         import torch
         g, p, gpu = self.gpu.g, self.p, self.gpu
-        gpu.part_fwd(DTs, flags, p.s0, p.ns, p.l0, p.nl)
-        if p.G > 1:
+        if p.G == 1:
+            # species-sharded: the whole step is local (fused kernels, graph replay)
+            gpu.part_all(DTs, flags, p.s0, p.ns)
+        else:
+            gpu.part_fwd(DTs, flags, p.s0, p.ns, p.l0, p.nl)
             bufs, pp = self._bufs()
             exchange(p, bufs, pp, True, self.dist)
-        gpu.part_mid(DTs, flags, p.s0, p.ns, p.k0, p.nk)
-        if p.G > 1:
+            gpu.part_mid(DTs, flags, p.s0, p.ns, p.k0, p.nk)
             bufs, pp = self._bufs()
             exchange(p, bufs, pp, False, self.dist)
-        gpu.part_rev(p.s0, p.ns, p.l0, p.nl)
+            gpu.part_rev(p.s0, p.ns, p.l0, p.nl)
+        if p.G == 1 and p.world > 1 and self.dist is not None and self.dist.get_backend() == "nccl":
+            # every rank owns whole species: the result blocks of all ranks are concatenated by two
+            # in-place all-gathers on the device (same stream as the step), then decoded once
+            res, pp_t, rn, qn = self._result_views()
+            self.dist.all_gather_into_tensor(res, res[p.s0 * rn:(p.s0 + p.ns) * rn])
+            self.dist.all_gather_into_tensor(pp_t, pp_t[p.s0 * qn:(p.s0 + p.ns) * qn])
+            DT, MOM, PE, PA = gpu.part_results(0, g.nS)
+            return {"DtDrift": DT, "DtsNext": max(float(DT.min()), DtsMin), "moments": MOM,
+                    "PPERT": np.asfortranarray(np.moveaxis(PE, 2, 0)), "PPART": np.asfortranarray(np.moveaxis(PA, 2, 0))}
         dt, mom, pper, ppar = gpu.part_results(p.s0, p.ns)
         # control-plane reductions over all ranks (a few KB)
         DT = np.full((4, g.nS), np.inf)
