@@ -39,6 +39,7 @@ struct RamDev {
   double *fRb, *fPa, *fPb, *fEa, *fEb, *fMa, *fMb;
   const double *rDMU, *rWMU;   // 1/DMU(L), 1/WMU(L)
   double* rFNHS;               // FAST: 1/FNHS plane [NPA][Pp]
+  const double* exp2tab;       // FAST: 2^(j/64), j < 64 (table of fast_exp)
   const double *wPE, *wPA;     // FAST ANISCH pitch-angle weights [NPA]: WMU/MU*(1-MU^2), WMU*MU (MU(1):=MU(2) as FFACTOR(..,1)=FFACTOR(..,2))
 };
 

@@ -37,169 +37,257 @@ __device__ __forceinline__ void block_sum_to(double* part, size_t cta, double (&
 }
 
 // =============================================================================
-// k_plane_rp: DRIFTR (src/ModRamDrift.f90:95-198) and DRIFTP (:204-279) of one
-// (K,L) plane, back to back on a shared-memory copy; REV = reverse half step
-// (DRIFTP first, then DRIFTR with the fused SUMRC of src/ModRamRun.f90:174).
-// A CTA owns pitch angle l and KC consecutive energies; thread t owns the cells
-// p = t + m*blockDim.x (m < NC) of every plane: their K-independent coefficients
-// stay in registers, the next plane's values are prefetched while the current
-// plane is advanced.  Both sweeps are cell-parallel: interface fluxes to shared
-// memory, barrier, update.
-// grid: x = energy chunk, y = l, z = species;  smem: 2*Pp + 2*NT doubles + NT ints
+// k_cfl_fast: the four CFL limits DtDriftR/P/E/Mu (src/ModRamDrift.f90:147, :240,
+// :344, :435).  They are functions of the drift coefficients only, not of F2, so
+// the fused path evaluates them here -- once per coefficient set (DRIFTPARA /
+// field / mode change), cached by the host -- instead of inside every sweep.
+// Same expressions and therefore the same bits as the sweeps' own tracking.
+// grid: x = l, y = species
 // =============================================================================
-template <int NC, bool REV>
-__global__ void __launch_bounds__(NC >= 4 ? 1024 : 256)
-k_plane_rp(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0, int KC) {
+__global__ void __launch_bounds__(256) k_cfl_fast(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0,
+                                                  unsigned long long* __restrict__ cfl_all) {
+  const SpecDev& sp = pk.s[s0 + blockIdx.y];
+  unsigned long long* out = cfl_all + 4 * (size_t)(s0 + blockIdx.y);
+  const int NR = d.NR, NE = d.NE, P = d.P, Pp = d.Pp;
+  const int l = blockIdx.x;
+  double mR = 0.0, mP = 0.0, mE = 0.0, mM = 0.0;
+  for (int p = threadIdx.x; p < P; p += blockDim.x) {
+    if (d.outp[p]) continue;
+    const int j = p / NR, i = p - j * NR;
+    const size_t o = (size_t)l * Pp + p;
+    const double CRp = d.CR[p], gR = d.fRb[o], pa = d.fPa[p], pb = d.fPb[o];
+    const double fA = d.fEa[o], fB = d.fEb[o], mA = d.fMa[o], mB = d.fMb[o];
+    const double rdmu = d.rDMU[l];
+    for (int k = 0; k < NE; ++k) {
+      mR = dmax(mR, fabs(fma(sp.P4[k], gR, CRp)));
+      if (i >= 1) {
+        if (j >= 1) mP = dmax(mP, fabs(fma(-sp.w2[k], pb, pa)));
+        const double* tb = sp.tabE + 4 * k;
+        mE = dmax(mE, fabs(fma(tb[1], fB, tb[0] * fA)) * tb[2]);
+        if (l >= 1) mM = dmax(mM, fabs(fma(sp.wM[k], mB, mA)) * rdmu);
+      }
+    }
+    if (i >= 1) mE = dmax(mE, 1E-10 * sp.tabE[2]);      // the max(|c|,1e-10) floor of :344 (1/DE largest at K=1)
+  }
+  warp_min_to(out + 0, sp.aRP / dmax(mR, 1E-10));
+  warp_min_to(out + 1, sp.aRP / dmax(mP, 1E-10));
+  warp_min_to(out + 2, mE > 0.0 ? sp.aRP / mE : 1.0e300);
+  warp_min_to(out + 3, mM > 0.0 ? sp.aRP / mM : 1.0e300);
+}
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
+}
+
+// =============================================================================
+// k_plane_rp: DRIFTR (src/ModRamDrift.f90:95-198) and DRIFTP (:204-279) of KC
+// consecutive (K,L) planes, back to back on a shared-memory copy; REV = reverse half
+// step (DRIFTP first, then DRIFTR with the fused SUMRC of src/ModRamRun.f90:174).
+// Planes are stored with an odd row stride NRp so that the radial walks of
+// consecutive MLT lines hit different banks.  Both sweeps walk line segments in
+// place with a rolling register window (one thread per segment); the foreign halo
+// cells of a segment are read before the barrier that precedes the walk.
+// grid: x = energy chunk, y = l, z = species
+// =============================================================================
+struct PlaneCfg {
+  int KC;             // planes (energies) per CTA
+  int NRp, PS;        // padded row stride and plane stride of the shared copy (doubles)
+  int nsegR, segR;    // DRIFTR: segments per line, cells per segment (cells I=2..NR)
+  int nsegP, segP;    // DRIFTP (cells J=2..NT)
+};
+
+template <bool REV>
+__global__ void __launch_bounds__(512) k_plane_rp(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0,
+                                                  PlaneCfg cfg) {
   extern __shared__ double smem[];
   const SpecDev& sp = pk.s[s0 + blockIdx.z];
-  const int NR = d.NR, NT = d.NT, NE = d.NE, P = d.P, Pp = d.Pp;
+  const int NR = d.NR, NT = d.NT, NE = d.NE, Pp = d.Pp;
   const int T = blockDim.x, tid = threadIdx.x;
-  double* sF = smem;                   // the plane
-  double* sPhi = smem + Pp;            // interface fluxes
-  double* sG = smem + 2 * Pp;          // ghost cells F(NR+1), F(NR+2) of the NT lines
-  int* sIn = (int*)(sG + 2 * NT);      // inflow flag of the lines
+  const int NRp = cfg.NRp, PS = cfg.PS;
   const int l = blockIdx.y;
-  const int k0 = blockIdx.x * KC, k1 = min(NE, k0 + KC);
+  const int k0 = blockIdx.x * cfg.KC, KCa = min(NE, k0 + cfg.KC) - k0;
+  double* sP = smem;                                   // [KC][PS]
+  double* sG = smem + (size_t)cfg.KC * PS;             // [KC][NT][2] ghost cells F(NR+1), F(NR+2)
+  int* sIn = (int*)(sG + 2 * (size_t)cfg.KC * NT);     // [KC][NT] inflow flag
+  double* sRed = (double*)(sIn + ((cfg.KC * NT + 1) & ~1));   // [32]
   const double beta = d.BetaLim;
-
-  double CRc[NC], gR[NC], pa[NC], pb[NC];
-  int ij[NC];                          // i | j << 12 | counted << 30; -1: no cell
-#pragma unroll
-  for (int m = 0; m < NC; ++m) {
-    const int p = tid + m * T;
-    ij[m] = -1;
-    CRc[m] = gR[m] = pa[m] = pb[m] = 0.0;
-    if (p < P) {
-      const int j = p / NR, i = p - j * NR;
-      ij[m] = i | (j << 12) | (d.outp[p] ? 0 : (1 << 30));
-      CRc[m] = d.CR[p];
-      gR[m] = d.fRb[(size_t)l * Pp + p];
-      pa[m] = d.fPa[p];
-      pb[m] = d.fPb[(size_t)l * Pp + p];
-    }
-  }
   double* Fg = sp.F + ((size_t)l * NE + k0) * Pp;
-  double Fn[NC];
-#pragma unroll
-  for (int m = 0; m < NC; ++m) Fn[m] = (ij[m] >= 0) ? Fg[tid + m * T] : 0.0;
-  int line = (k0 * d.NPA + l) * NT + tid;   // threads < NT carry the line state
-  int inN = 0;
-  double g1N = 0.0, g2N = 0.0;
-  if (tid < NT) { inN = (sp.last[line] == line); g1N = sp.ghost[2 * (size_t)line]; g2N = sp.ghost[2 * (size_t)line + 1]; }
-  double cmaxR = 0.0, cmaxP = 0.0, macc = 0.0;
 
-  for (int k = k0; k < k1; ++k, Fg += Pp) {
-    double Fc[NC];
-#pragma unroll
-    for (int m = 0; m < NC; ++m) {
-      Fc[m] = Fn[m];
-      if (ij[m] >= 0) sF[tid + m * T] = Fc[m];
+  // ---- stage the planes (a warp copies whole rows: one address update per row) and the line state
+  {
+    const int lane = tid & 31, nw = T >> 5;
+    int q = 0, j = tid >> 5;
+    while (j >= NT) { j -= NT; ++q; }
+    while (q < KCa) {
+      const double* src = Fg + (size_t)q * Pp + j * NR;
+      double* dst = sP + (size_t)q * PS + j * NRp;
+      for (int i = lane; i < NR; i += 32) cp_async8(dst + i, src + i);
+      j += nw;
+      while (j >= NT) { j -= NT; ++q; }
     }
-    if (tid < NT) { sIn[tid] = inN; sG[2 * tid] = g1N; sG[2 * tid + 1] = g2N; }
-    __syncthreads();
-    if (k + 1 < k1) {                  // next plane: in flight during this plane's arithmetic
-#pragma unroll
-      for (int m = 0; m < NC; ++m) Fn[m] = (ij[m] >= 0) ? Fg[Pp + tid + m * T] : 0.0;
-      if (tid < NT) {
-        line += d.NPA * NT;
-        inN = (sp.last[line] == line); g1N = sp.ghost[2 * (size_t)line]; g2N = sp.ghost[2 * (size_t)line + 1];
-      }
+    asm volatile("cp.async.commit_group;");
+    for (int t = tid; t < KCa * NT; t += T) {
+      const int q2 = t / NT, j2 = t - q2 * NT;
+      const int line = ((k0 + q2) * d.NPA + l) * NT + j2;
+      sIn[t] = (sp.last[line] == line);
+      sG[2 * t] = sp.ghost[2 * (size_t)line];
+      sG[2 * t + 1] = sp.ghost[2 * (size_t)line + 1];
     }
-    const double P4k = sp.P4[k], w2k = sp.w2[k];
-    const double wk = (REV && k >= 1) ? d.WE[k] * d.EKEV[k] : 0.0;
+    asm volatile("cp.async.wait_group 0;");
+  }
+  __syncthreads();
+  double macc = 0.0;
 
-    // ---- DRIFTP: cells J=2..NT, I>=2; F(NT+1)=F(2), F(NT+2)=F(3), FBND(1)=FBND(NT) (:246-262)
-    auto driftp = [&]() {
-      double cur[NC];
-#pragma unroll
-      for (int m = 0; m < NC; ++m) {
-        const int p = tid + m * T, i = ij[m] & 4095, j = (ij[m] >> 12) & 4095;
-        cur[m] = 0.0;
-        if (ij[m] >= 0 && i >= 1 && j >= 1) {
-          const double c = fma(-w2k, pb[m], pa[m]);
-          if (REV && (ij[m] >> 30)) cmaxP = dmax(cmaxP, fabs(c));
-          const double F0 = REV ? Fc[m] : sF[p];
-          const double Fm1 = sF[p - NR];
-          const double f2 = sF[NR + i], f3 = sF[2 * NR + i];
-          const double Fp1 = (j + 1 <= NT - 1) ? sF[p + NR] : f2;
-          const double Fp2 = (j + 2 <= NT - 1) ? sF[p + 2 * NR] : ((j + 2 == NT) ? f2 : f3);
-          if (!REV) Fc[m] = F0;
-          cur[m] = c * limited_flux_fast(Fm1, F0, Fp1, Fp2, c < 0.0, fabs(c), beta);
-          sPhi[p] = cur[m];
-        }
+  // ---- DRIFTR: cells I=2..NR of every line (j, plane q) ------------------------------
+  auto driftr = [&]() {
+    const int ntask = NT * KCa * cfg.nsegR;
+    const int nround = (ntask + T - 1) / T;
+    for (int rd = 0; rd < nround; ++rd) {
+      const int e = tid + rd * T;
+      const int j = e % NT, qq = e / NT;
+      const int q = qq % KCa, seg = qq / KCa;
+      const bool act = e < ntask;
+      const int ia = 2 + seg * cfg.segR, ib = min(NR, ia + cfg.segR - 1);
+      double* row = sP + (size_t)q * PS + j * NRp;     // F(I) at row[I-1]
+      double Fm1 = 0, F0 = 0, Fp1 = 0, Fp2 = 0, hi1 = 0, hi2 = 0, g1 = 0, g2 = 0;
+      bool inflow = false;
+      if (act) {
+        g1 = sG[2 * (q * NT + j)]; g2 = sG[2 * (q * NT + j) + 1];
+        inflow = sIn[q * NT + j] != 0;
+#define GETR(I) (((I) < 1) ? 0.0 : (((I) <= NR) ? row[(I)-1] : (((I) == NR + 1) ? g1 : g2)))
+        Fm1 = GETR(ia - 2); F0 = GETR(ia - 1); Fp1 = GETR(ia); Fp2 = GETR(ia + 1);
+        hi1 = GETR(ib + 1); hi2 = GETR(ib + 2);
+#undef GETR
       }
-      __syncthreads();
-#pragma unroll
-      for (int m = 0; m < NC; ++m) {
-        const int p = tid + m * T, i = ij[m] & 4095, j = (ij[m] >> 12) & 4095;
-        if (ij[m] >= 0 && i >= 1 && j >= 1) {
-          const double prev = (j == 1) ? sPhi[(NT - 1) * NR + i] : sPhi[p - NR];
-          double fnew = Fc[m] - cur[m] + prev;               // :266
-          if (fnew < 0.0) fnew = 1E-15;
-          if (REV) {
-            sF[p] = fnew;
-            if (j == NT - 1) sF[i] = fnew;                   // F2(J=1) = F2(J=NT)  (:272)
-          } else {
-            Fg[p] = fnew;
-            if (j == NT - 1) Fg[i] = fnew;
-          }
+      if (cfg.nsegR > 1) __syncthreads();
+      if (act) {
+        const int k = k0 + q;
+        const double P4k = sp.P4[k];
+        const double* cr = d.CR + j * NR + (ia - 2);                     // coefficient pieces of I = ia-1
+        const double* gr = d.fRb + (size_t)l * Pp + j * NR + (ia - 2);
+        double dm1 = F0 - Fm1, d0 = Fp1 - F0, dp1 = Fp2 - Fp1;
+        double phiPrev;
+        {                                               // interface ia-1: flux only
+          const double c = fma(P4k, *gr, *cr);
+          double FB = limited_flux_d(F0, Fp1, dm1, d0, dp1, c < 0.0, fabs(c), beta);
+          if (ia == 2) FB = inflow ? Fp1 : 0.0;         // FBND(1) = F(2) | 0   (:155,:159)
+          phiPrev = c * FB;
         }
-      }
-    };
-    // ---- DRIFTR: all cells; FBND(1), FBND(NR) and the ghost cells from the line state (:154-168)
-    auto driftr = [&]() {
-      double phi[NC], F0v[NC];
-#pragma unroll
-      for (int m = 0; m < NC; ++m) {
-        const int p = tid + m * T, i = ij[m] & 4095, j = (ij[m] >> 12) & 4095;
-        phi[m] = 0.0;
-        F0v[m] = 0.0;
-        if (ij[m] >= 0) {
-          const double c = fma(P4k, gR[m], CRc[m]);
-          if (REV && (ij[m] >> 30)) cmaxR = dmax(cmaxR, fabs(c));
-          const double F0 = REV ? sF[p] : Fc[m];
-          F0v[m] = F0;
-          const int I = i + 1;
-          const double g1 = sG[2 * j], g2 = sG[2 * j + 1];
-          const bool inflow = sIn[j] != 0;
-          const double Fm1 = (i >= 1) ? sF[p - 1] : 0.0;
-          const double Fp1 = (I + 1 <= NR) ? sF[p + 1] : g1;
-          const double Fp2 = (I + 2 <= NR) ? sF[p + 2] : ((I + 2 == NR + 1) ? g1 : g2);
-          double FB = limited_flux_fast(Fm1, F0, Fp1, Fp2, c < 0.0, fabs(c), beta);
-          if (I == 1) FB = inflow ? Fp1 : 0.0;
-          if (I == NR && !inflow) FB = F0;
-          phi[m] = c * FB;
-          sPhi[p] = phi[m];
-        }
-      }
-      __syncthreads();
-#pragma unroll
-      for (int m = 0; m < NC; ++m) {
-        const int p = tid + m * T, i = ij[m] & 4095, j = (ij[m] >> 12) & 4095;
-        if (ij[m] >= 0 && i >= 1) {
-          double fn = F0v[m] - phi[m] + sPhi[p - 1];         // :186
+        double cnext = fma(P4k, gr[1], cr[1]);          // CDriftR of I = ia
+        cr += 2; gr += 2;
+        double* pO = row + (ia - 1);
+        const bool inmom = REV && l >= 1 && j <= NT - 2 && k >= 1;
+        const double wk = inmom ? d.WE[k] * d.EKEV[k] : 0.0;
+        auto step = [&](const double nn, const bool lastI) {
+          F0 = Fp1; Fp1 = Fp2; Fp2 = nn;
+          dm1 = d0; d0 = dp1; dp1 = Fp2 - Fp1;
+          const double c = cnext;
+          if (!lastI) cnext = fma(P4k, *gr, *cr);       // next cell's coefficient, off the critical path
+          ++cr; ++gr;
+          double FB = limited_flux_d(F0, Fp1, dm1, d0, dp1, c < 0.0, fabs(c), beta);
+          if (lastI && !inflow) FB = F0;                // FBND(NR) = F(NR)     (:156)
+          const double phi = c * FB;
+          double fn = F0 - phi + phiPrev;               // :186
           if (fn < 0.0) fn = 1E-15;
-          if (REV) {
-            Fg[p] = fn;
-            if (l >= 1 && j <= NT - 2) macc = fma(fn, wk, macc);
-          } else {
-            sF[p] = fn;
-          }
-        }
+          *pO++ = fn;
+          phiPrev = phi;
+          if (REV) macc = fma(fn, wk, macc);
+        };
+        int I = ia;
+#pragma unroll 4
+        for (; I + 2 <= ib; ++I) step(pO[2], false);
+        if (I + 1 <= ib) { step(hi1, false); ++I; }
+        if (I <= ib) step(hi2, ib == NR);
       }
-    };
-    if (REV) { driftp(); __syncthreads(); driftr(); }
-    else { driftr(); __syncthreads(); driftp(); }
-    // the next iteration's first shared-memory writes go to sF / the line state, whose readers
-    // are all behind the barrier inside the second sweep; sPhi is rewritten only after the
-    // next iteration's first barrier.
+    }
+  };
+
+  // ---- DRIFTP: cells J=2..NT of every line (i >= 1, plane q); periodic in J -----------
+  auto driftp = [&]() {
+    const int ntask = NR * KCa * cfg.nsegP;
+    const int nround = (ntask + T - 1) / T;
+    for (int rd = 0; rd < nround; ++rd) {
+      const int e = tid + rd * T;
+      const int i = e % NR, qq = e / NR;
+      const int q = qq % KCa, seg = qq / KCa;
+      const bool act = (e < ntask) && (i >= 1);
+      const int ja = 2 + seg * cfg.segP, jb = min(NT, ja + cfg.segP - 1);
+      double* colp = sP + (size_t)q * PS + i;           // F(J) at colp[(J-1)*NRp]
+      double Fm1 = 0, F0 = 0, Fp1 = 0, Fp2 = 0, hi1 = 0, hi2 = 0, F1row = 0;
+      if (act) {
+#define GETP(J) colp[(size_t)(((J) > NT ? (J) - NT + 1 : (J)) - 1) * NRp]   /* F(NT+1)=F(2), F(NT+2)=F(3) */
+        const int Jpe = (ja == 2) ? NT : ja - 1;        // interface below the segment (:261-262)
+        Fm1 = GETP(Jpe - 1); F0 = GETP(Jpe); Fp1 = GETP(Jpe + 1); Fp2 = GETP(Jpe + 2);
+        hi1 = GETP(jb + 1); hi2 = GETP(jb + 2);
+        F1row = colp[0];
+#undef GETP
+      }
+      if (cfg.nsegP > 1) __syncthreads();
+      if (act) {
+        const int k = k0 + q;
+        const double w2k = sp.w2[k];
+        const int Jpe = (ja == 2) ? NT : ja - 1;
+        const double* pa = d.fPa + (Jpe - 1) * NR + i;
+        const double* pb = d.fPb + (size_t)l * Pp + (Jpe - 1) * NR + i;
+        double dm1 = F0 - Fm1, d0 = Fp1 - F0, dp1 = Fp2 - Fp1;
+        double prev;
+        {
+          const double c = fma(-w2k, *pb, *pa);
+          prev = c * limited_flux_d(F0, Fp1, dm1, d0, dp1, c < 0.0, fabs(c), beta);
+        }
+        if (ja == 2) d0 = Fp1 - F1row;                  // cell J=2 sees the stored F(1), not F(NT)
+        pa = d.fPa + (ja - 1) * NR + i;
+        pb = d.fPb + (size_t)l * Pp + (ja - 1) * NR + i;
+        double cnext = fma(-w2k, *pb, *pa);
+        double* pO = colp + (size_t)(ja - 1) * NRp;
+        double fnew = 0.0;
+        auto step = [&](const double nn, const bool more) {
+          F0 = Fp1; Fp1 = Fp2; Fp2 = nn;
+          dm1 = d0; d0 = dp1; dp1 = Fp2 - Fp1;
+          const double c = cnext;
+          pa += NR; pb += NR;
+          if (more) cnext = fma(-w2k, *pb, *pa);
+          const double cur = c * limited_flux_d(F0, Fp1, dm1, d0, dp1, c < 0.0, fabs(c), beta);
+          fnew = F0 - cur + prev;                       // :266
+          if (fnew < 0.0) fnew = 1E-15;
+          *pO = fnew;
+          pO += NRp;
+          prev = cur;
+        };
+        int J = ja;
+#pragma unroll 4
+        for (; J + 2 <= jb; ++J) step(pO[2 * (size_t)NRp], true);
+        if (J + 1 <= jb) { step(hi1, true); ++J; }
+        if (J <= jb) step(hi2, false);
+        if (jb == NT) colp[0] = fnew;                   // F2(J=1) = F2(J=NT)  (:272)
+      }
+    }
+  };
+
+  if (REV) { driftp(); __syncthreads(); driftr(); }
+  else { driftr(); __syncthreads(); driftp(); }
+  __syncthreads();
+
+  // ---- write the planes back (I=1 is never advanced) ---------------------------------------
+  {
+    const int lane = tid & 31, nw = T >> 5;
+    int q = 0, j = tid >> 5;
+    while (j >= NT) { j -= NT; ++q; }
+    while (q < KCa) {
+      double* dst = Fg + (size_t)q * Pp + j * NR;
+      const double* src = sP + (size_t)q * PS + j * NRp;
+      for (int i = lane; i < NR; i += 32)
+        if (i >= 1) dst[i] = src[i];
+      j += nw;
+      while (j >= NT) { j -= NT; ++q; }
+    }
   }
   if (REV) {
-    warp_min_to(sp.dtw + 0, sp.aRP / dmax(cmaxR, 1E-10));
-    warp_min_to(sp.dtw + 1, sp.aRP / dmax(cmaxP, 1E-10));
-    __syncthreads();
     double acc[1] = {macc * d.WMU[l]};
-    block_sum_to<1>(sp.part, (size_t)blockIdx.y * gridDim.x + blockIdx.x, acc, sPhi);
+    block_sum_to<1>(sp.part, (size_t)blockIdx.y * gridDim.x + blockIdx.x, acc, sRed);
   }
 }
 
@@ -219,11 +307,12 @@ struct ColCfg {
   int NEs;            // padded energy stride of the block
   int nsegE, segE;    // DRIFTE: segments per line, cells per segment
   int nsegM, segM;    // DRIFTMU
+  int nsegL, segL;    // loss block: pitch-angle segments per (k, position) column
   int doA;            // bit s: species s applies its first/last loss operator
 };
 
-template <int PG>
-__global__ void __launch_bounds__(1024) k_col_fused(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0,
+template <int PG, int MAXT>
+__global__ void __launch_bounds__(MAXT) k_col_fused(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0,
                                                     ColCfg cfg) {
   extern __shared__ double smem[];
   const SpecDev& sp = pk.s[s0 + blockIdx.y];
@@ -245,12 +334,14 @@ __global__ void __launch_bounds__(1024) k_col_fused(const __grid_constant__ RamD
   double* sEK = sWE + NE;
   double* sX = sEK + NE;                     // [NE][PG] log(ATLOS) at this block's radii
   double* sW = sX + NE * PG;                 // [NE][PG] WAVELO factor
-  double* sRD = sW + NE * PG;                // [NPA] each: 1/DMU, 1/WMU, WMU
+  double* sRD = sW + NE * PG;                // [NPA] each: 1/DMU, 1/WMU, WMU, WMU with L=1 zeroed
   double* sRW = sRD + NPA;
   double* sWMU = sRW + NPA;
-  double* sRed = sWMU + NPA;                 // [5][32]
+  double* sWMZ = sWMU + NPA;
+  double* sE2 = sWMZ + NPA;                  // [64] 2^(j/64)
+  double* sRed = sE2 + 64;                   // [5][32]
 
-  // ---- stage the block and its coefficient tables ----------------------------
+  // ---- stage the block (asynchronous 16-byte copies, all in flight) and its tables -----
   {
     constexpr int H = PG / 2;                // 16-byte items per (l,k) row
     const int rowItems = NE * H;
@@ -258,11 +349,11 @@ __global__ void __launch_bounds__(1024) k_col_fused(const __grid_constant__ RamD
     const int dl = T / rowItems, dr = T - dl * rowItems;
     while (l < NPA) {
       const int k = r / H, hh = r - k * H;
-      const double2 v = *(const double2*)(sp.F + ((size_t)l * NE + k) * Pp + p0 + 2 * hh);
-      *(double2*)(sT + (size_t)l * RS + k * PG + 2 * hh) = v;
+      cp_async16(sT + (size_t)l * RS + k * PG + 2 * hh, sp.F + ((size_t)l * NE + k) * Pp + p0 + 2 * hh);
       r += dr; l += dl;
       if (r >= rowItems) { r -= rowItems; ++l; }
     }
+    asm volatile("cp.async.commit_group;");
     for (int t = tid; t < NPA * PG; t += T) {
       const int l2 = t / PG, pp = t - l2 * PG;
       const size_t o = (size_t)l2 * Pp + p0 + pp;
@@ -277,7 +368,12 @@ __global__ void __launch_bounds__(1024) k_col_fused(const __grid_constant__ RamD
       sX[t] = sp.xATL[k * NR + p % NR];
       sW[t] = sp.wfac[(size_t)k * Pp + p0 + pp];
     }
-    for (int t = tid; t < NPA; t += T) { sRD[t] = d.rDMU[t]; sRW[t] = d.rWMU[t]; sWMU[t] = d.WMU[t]; }
+    for (int t = tid; t < NPA; t += T) {
+      sRD[t] = d.rDMU[t]; sRW[t] = d.rWMU[t]; sWMU[t] = d.WMU[t];
+      sWMZ[t] = (t >= 1) ? d.WMU[t] : 0.0;
+    }
+    for (int t = tid; t < 64; t += T) sE2[t] = d.exp2tab[t];
+    asm volatile("cp.async.wait_group 0;");
   }
   __syncthreads();
 
@@ -315,30 +411,35 @@ __global__ void __launch_bounds__(1024) k_col_fused(const __grid_constant__ RamD
       if (act) {
         const bool inside = !d.outp[p];
         const double fA = sEa[l * PG + pp], fB = sEb[l * PG + pp];
-        const double* tab = sTab + 4 * (K0 - 1);
+        const double4* tab = (const double4*)sTab + (K0 - 1);
         double FBprev, mmax = 0.0;
-        const double floorr = tab[2];
+        double dm1 = F0 - Fm1, d0 = Fp1 - F0, dp1 = Fp2 - Fp1;
+        const double floorr = tab->z;
         {                                               // peeled first interface K0: flux only
-          const double c = fma(tab[1], fB, tab[0] * fA);
-          const double ac = fabs(c) * tab[2];
+          const double4 tb = *tab;
+          const double c = fma(tb.y, fB, tb.x * fA);
+          const double ac = fabs(c) * tb.z;
           if (inside && seg == 0) mmax = ac;
-          FBprev = c * limited_flux_fast(Fm1, F0, Fp1, Fp2, c < 0.0, ac, beta);
+          FBprev = c * limited_flux_d(F0, Fp1, dm1, d0, dp1, c < 0.0, ac, beta);
         }
         double* pO = col + (size_t)K0 * PG;             // -> F(K0+1)
         auto step = [&](const double nn) {
-          tab += 4;
-          Fm1 = F0; F0 = Fp1; Fp1 = Fp2; Fp2 = nn;
-          const double c = fma(tab[1], fB, tab[0] * fA);
-          const double ac = fabs(c) * tab[2];
+          ++tab;
+          F0 = Fp1; Fp1 = Fp2; Fp2 = nn;
+          dm1 = d0; d0 = dp1; dp1 = Fp2 - Fp1;
+          const double4 tb = *tab;
+          const double c = fma(tb.y, fB, tb.x * fA);
+          const double ac = fabs(c) * tb.z;
           if (cfl) mmax = dmax(mmax, ac);
-          const double FB = c * limited_flux_fast(Fm1, F0, Fp1, Fp2, c < 0.0, ac, beta);
-          double fn = fma(-(FB - FBprev), tab[3], F0);
+          const double FB = c * limited_flux_d(F0, Fp1, dm1, d0, dp1, c < 0.0, ac, beta);
+          double fn = fma(-(FB - FBprev), tb.w, F0);
           if (fn < 0.0) fn = 1E-15;
           *pO = fn;
           pO += PG;
           FBprev = FB;
         };
         int K = K0 + 1;
+#pragma unroll 4
         for (; K + 2 <= kb; ++K) step(pO[2 * PG]);      // F(K+2): own cell, not yet rewritten
         if (K + 1 <= kb) { step(hi1); ++K; }            // K = kb-1: F(kb+1)
         if (K <= kb) step(hi2);                         // K = kb:   F(kb+2)
@@ -374,34 +475,42 @@ __global__ void __launch_bounds__(1024) k_col_fused(const __grid_constant__ RamD
         const double* ca = sMa + (la - 1) * PG + pp;    // coefficient pieces of L = la
         const double* cb = sMb + (la - 1) * PG + pp;
         double FBprev = 0.0, mmax = 0.0, macc = 0.0, fnew = 0.0;
+        double dm1 = F0 - Fm1, d0 = Fp1 - F0, dp1 = Fp2 - Fp1;
         if (la > 2) {                                   // flux through the segment's lower edge
           const double c = fma(wM, cb[-PG], ca[-PG]);
-          FBprev = c * limited_flux_fast(Fm2, Fm1, F0, Fp1, c < 0.0, fabs(c) * sRD[la - 2], beta);
+          FBprev = c * limited_flux_d(Fm1, F0, Fm1 - Fm2, dm1, d0, c < 0.0, fabs(c) * sRD[la - 2], beta);
         }
         double* pO = col + (size_t)(la - 1) * RS;
-        int L = la;
-        auto step = [&](const double nn) {
+        const double* rd_ = sRD + (la - 1);
+        const double* rw_ = sRW + (la - 1);
+        const double* wm_ = sWMU + (la - 1);
+        // cells L <= NPA-2 (limited flux); the value entering the window after cell L is F(L+3)
+        auto step = [&](const double nn, const bool limited) {
           const double c = fma(wM, *cb, *ca);
           ca += PG; cb += PG;
-          const double ac = fabs(c) * sRD[L - 1];
+          const double ac = fabs(c) * (*rd_++);
           if (cfl) mmax = dmax(mmax, ac);
           double FB;
-          if (L <= NPA - 2) FB = c * limited_flux_fast(Fm1, F0, Fp1, Fp2, c < 0.0, ac, beta);
+          if (limited) FB = c * limited_flux_d(F0, Fp1, dm1, d0, dp1, c < 0.0, ac, beta);
           else FB = c * Fp1;                            // FBND(NPA-1) = F(NPA)  (:458)
-          fnew = fma(-(FB - FBprev), sRW[L - 1], F0);
+          fnew = fma(-(FB - FBprev), *rw_++, F0);
           FBprev = FB;
           if (fnew < 0.0) fnew = 1E-15;
           *pO = fnew;
           pO += RS;
-          if (mom) macc = fma(fnew, sWMU[L - 1], macc);
-          Fm1 = F0; F0 = Fp1; Fp1 = Fp2; Fp2 = nn;
-          ++L;
+          if (mom) macc = fma(fnew, *wm_, macc);
+          ++wm_;
+          F0 = Fp1; Fp1 = Fp2; Fp2 = nn;
+          dm1 = d0; d0 = dp1; dp1 = Fp2 - Fp1;
         };
-        // the value entering the window after cell L is F(L+3)
-        for (; L + 3 <= lb;) step(pO[3 * (size_t)RS]);
-        if (L + 2 <= lb) step(hi1);                     // L = lb-2: F(lb+1)
-        if (L + 1 <= lb) step(hi2);                     // L = lb-1: F(lb+2)
-        if (L <= lb) step(0.0);
+        int L = la;
+        const int lim_end = min(lb, NPA - 2);           // last cell with a limited upper flux
+#pragma unroll 4
+        for (; L + 3 <= lim_end; ++L) step(pO[3 * (size_t)RS], true);
+        for (; L <= lb; ++L) {                          // the (at most 3) cells that read the halo
+          const double nn = (L + 3 <= lb) ? pO[3 * (size_t)RS] : ((L + 3 == lb + 1) ? hi1 : ((L + 3 == lb + 2) ? hi2 : 0.0));
+          step(nn, L <= NPA - 2);
+        }
         if (!inside) mmax = 0.0;
         if (lastseg) {
           const double c = fma(wM, *cb, *ca);           // CDriftMu(..,NPA)
@@ -416,48 +525,62 @@ __global__ void __launch_bounds__(1024) k_col_fused(const __grid_constant__ RamD
     }
   };
 
-  // ---- the loss block (k_loss_mid): pointwise, four SUMRC moments ------------------
+  // ---- the loss block (k_loss_mid): pointwise; a thread walks the pitch angles of one
+  // (energy, position) so everything but the pitch-angle factors is hoisted ------------
   auto losses = [&]() {
     const bool ion = (sp.kind != 3);
     const bool doA = (cfg.doA >> (s0 + blockIdx.y)) & 1;
-    const int rowItems = NE * PG;
-    int l = tid / rowItems, r = tid - l * rowItems;
-    const int dl = T / rowItems, dr = T - dl * rowItems;
-    const int pmom = (NT - 1) * NR;
-    while (l < NPA) {
-      const int k = r / PG, pp = r - k * PG;
+    const int ntask = NE * PG * cfg.nsegL;
+    const int nround = (ntask + T - 1) / T;
+    const double DTs = d.DTs;
+    for (int rd = 0; rd < nround; ++rd) {
+      const int e = tid + rd * T;
+      const int pp = e % PG, kq = e / PG;
+      const int k = kq % NE, seg = kq / NE;
       const int p = p0 + pp;
       const int i = p % NR;
-      if (k >= 1 && p < P && i >= 1) {
-        double* c = sT + (size_t)l * RS + r;
-        double f = *c;
-        const double w = sWE[k], wm = sWMU[l], e = sEK[k];
-        const bool mom = (l >= 1) && (p < pmom);
-        const bool useA = doA && (l >= 1);
+      if (e >= ntask || k < 1 || p >= P || i < 1) continue;
+      const int la = seg * cfg.segL, lb = min(NPA, la + cfg.segL);     // 0-based [la, lb)
+      const int lcone = max(la, min(lb, d.UPA[i] - 1));                 // ATMOL acts on l >= UPA-1
+      const double svk = sSV[k], xk = sX[k * PG + pp], wfk = sW[k * PG + pp];
+      double* col = sT + k * PG + pp;
+      double s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0;
+      auto cell = [&](const int l, const bool useA, const bool cone) {
+        double f = col[(size_t)l * RS];
+        const double wm = sWMZ[l];
         double facA = 1.0;
         if (useA) {
-          if (ion) facA = exp(-(sSV[k] * sH[l * PG + pp] * d.DTs));
-          else facA = sW[r];
+          facA = ion ? fast_exp(-(svk * sH[l * PG + pp] * DTs), sE2) : wfk;
           f = f * facA;
         }
-        if (mom) acc[1] += e * (f * w * wm);
-        if (l + 1 >= d.UPA[i]) {
-          const double a = exp(sX[r] * sRF[l * PG + pp]);
+        s1 = fma(wm, f, s1);
+        if (cone) {
+          const double a = fast_exp(xk * sRF[l * PG + pp], sE2);
           f = f * a;
-          if (mom) acc[2] += e * (f * w * wm);
+          s2 = fma(wm, f, s2);
           f = f * a;
-          if (mom) acc[3] += e * (f * w * wm);
-        } else if (mom) {
-          const double term = e * (f * w * wm);
-          acc[2] += term;
-          acc[3] += term;
+          s3 = fma(wm, f, s3);
+        } else {
+          s2 = fma(wm, f, s2);
+          s3 = fma(wm, f, s3);
         }
         if (useA) f = f * facA;
-        if (mom) acc[4] += e * (f * w * wm);
-        *c = f;
+        s4 = fma(wm, f, s4);
+        col[(size_t)l * RS] = f;
+      };
+      int l = la;
+      if (l == 0 && l < lb) { cell(0, false, lcone == 0); ++l; }      // L=1: the first/last operator skips it
+      if (doA) {
+        for (; l < lcone; ++l) cell(l, true, false);
+        for (; l < lb; ++l) cell(l, true, true);
+      } else {
+        for (; l < lcone; ++l) cell(l, false, false);
+        for (; l < lb; ++l) cell(l, false, true);
       }
-      r += dr; l += dl;
-      if (r >= rowItems) { r -= rowItems; ++l; }
+      if (p < (NT - 1) * NR) {
+        const double we = sEK[k] * sWE[k];
+        acc[1] += we * s1; acc[2] += we * s2; acc[3] += we * s3; acc[4] += we * s4;
+      }
     }
   };
 
@@ -467,9 +590,9 @@ __global__ void __launch_bounds__(1024) k_col_fused(const __grid_constant__ RamD
   __syncthreads();
   losses();
   __syncthreads();
-  driftmu(false, true);
+  driftmu(false, false);
   __syncthreads();
-  drifte(true);
+  drifte(false);                               // (the CFL limits come from k_cfl_fast)
   __syncthreads();
 
   // ---- write the block back, reductions -------------------------------------------
@@ -485,10 +608,6 @@ __global__ void __launch_bounds__(1024) k_col_fused(const __grid_constant__ RamD
       if (r >= rowItems) { r -= rowItems; ++l; }
     }
   }
-  double dtE = 1.0e300, dtM = 1.0e300;
-  if (mmaxE > 0.0) dtE = sp.aRP / mmaxE;
-  if (mmaxM > 0.0) dtM = sp.aRP / mmaxM;
-  warp_min_to(sp.dtw + 2, dtE);
-  warp_min_to(sp.dtw + 3, dtM);
+  (void)mmaxE; (void)mmaxM;
   block_sum_to<5>(sp.part, blockIdx.x, acc, sRed);
 }

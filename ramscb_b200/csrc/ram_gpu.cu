@@ -124,6 +124,8 @@ struct rsg_ram {
   int segE = 12, segMU = 12, segP = 12, kcR = 7;
   // DRIFTR inflow scan: valid while DTs, the E field, the fields and the mode are unchanged
   bool inflow_ok[RSG_MAX_SPECIES] = {false};
+  bool cfl_ok[RSG_MAX_SPECIES] = {false};   // cached CFL limits of the fused path (same dependencies)
+  unsigned long long* d_cfl_all = nullptr;  // [nS][4]
   // CUDA graph of the single-GPU step (valid for one (DTs, flags, mode); rebuilt when they change)
   cudaGraphExec_t gexec = nullptr;
   double g_DTs = -1.0;
@@ -134,7 +136,7 @@ struct rsg_ram {
   bool use_graph = true;
   // fused FAST path (ram_fused.cuh): shared-memory plane / column kernels
   bool use_fused = true;
-  int kcPlane = 7, colT = 0;
+  int kcPlane = 0, colT = 0, planeT = 0;
   bool in_step = false, fwd_half = false;   // set by rsg_ram_part_*: CFL slots are reset once per step
   unsigned long long* d_res_init = nullptr;
 
@@ -217,7 +219,7 @@ int ensure_step(rsg_ram* h, double DTs, cudaStream_t only = nullptr) {
   }
   h->prep_DTs = DTs;
   h->step_dirty = false;
-  for (int s = 0; s < h->nS; ++s) h->inflow_ok[s] = false;   // CR changed
+  for (int s = 0; s < h->nS; ++s) h->inflow_ok[s] = h->cfl_ok[s] = false;   // CR changed
   return RSG_OK;
 }
 
@@ -460,15 +462,45 @@ ColPlan col_plan(const rsg_ram* h) {
   };
   segs(NE, c.T / linesE, &c.cfg.nsegE, &c.cfg.segE);
   segs(NPA - 2, c.T / linesM, &c.cfg.nsegM, &c.cfg.segM);
+  segs(NPA, c.T / linesM, &c.cfg.nsegL, &c.cfg.segL);
   c.smem = sizeof(double) * ((size_t)NPA * c.cfg.NEs * COL_PG + 6 * (size_t)NPA * COL_PG + 8 * (size_t)NE + 2 * (size_t)NE * COL_PG +
-                             3 * (size_t)NPA + 5 * 32);
+                             4 * (size_t)NPA + 64 + 5 * 32);
   return c;
 }
-size_t plane_smem(const rsg_ram* h) { return sizeof(double) * (2 * (size_t)h->Pp + 2 * (size_t)h->NT) + sizeof(int) * (size_t)h->NT; }
+struct PlanePlan { PlaneCfg cfg; int T; size_t smem; };
+PlanePlan plane_plan(const rsg_ram* h) {
+  PlanePlan c{};
+  const int NR = h->NR, NT = h->NT;
+  c.cfg.NRp = NR | 1;
+  c.cfg.PS = (NT * c.cfg.NRp + 1) & ~1;
+  const size_t plane_bytes = sizeof(double) * (size_t)c.cfg.PS;
+  // planes per CTA: enough lines for a few warps, at most ~100 KB so two CTAs share an SM
+  int KC = h->kcPlane > 0 ? h->kcPlane : std::max(1, std::min(8, (int)(50 * 1024 / plane_bytes)));
+  KC = std::max(1, std::min({KC, h->NE, (int)(100 * 1024 / plane_bytes)}));   // F2 planes + coefficient planes
+  c.cfg.KC = KC;
+  const int linesR = NT * KC, linesP = NR * KC;
+  // one thread per line; lines longer than ~32 cells are split so that a CTA has >= 8 warps
+  int T = h->planeT ? h->planeT : std::max(linesR, linesP);
+  if (!h->planeT) {
+    const int longest = std::max(NR, NT);
+    if (longest > 40) T = std::min(512, T * ((longest + 31) / 32));
+  }
+  c.T = std::max(64, std::min(512, (T + 31) / 32 * 32));
+  auto segs = [](int n, int want, int* nseg, int* seg) {
+    want = std::max(1, want);
+    *seg = std::max(2, (n + want - 1) / want);
+    *nseg = (n + *seg - 1) / *seg;
+  };
+  segs(NR - 1, c.T / linesR, &c.cfg.nsegR, &c.cfg.segR);
+  segs(NT - 1, c.T / linesP, &c.cfg.nsegP, &c.cfg.segP);
+  c.smem = sizeof(double) * (2 * (size_t)KC * c.cfg.PS + 2 * (size_t)KC * NT + 32) + sizeof(int) * (((size_t)KC * NT + 1) & ~(size_t)1);
+  return c;
+}
+size_t plane_smem(const rsg_ram* h) { return plane_plan(h).smem; }
 // the fused kernels cover the default operator set on a whole grid in FAST mode
 bool fused_ok(const rsg_ram* h, int flags) {
   if (!h->use_fused || h->mode != RSG_MODE_FAST || flags != 0) return false;
-  if (h->P > 4096 || h->NR < 3 || h->NT < 4 || h->NT > 1024 || h->NR > 4095 || h->NE < 3 || h->NPA < 4) return false;
+  if (h->NR < 4 || h->NT < 5 || h->NE < 3 || h->NPA < 4) return false;
   return col_plan(h).smem <= 220 * 1024 && plane_smem(h) <= 220 * 1024;
 }
 template <typename K>
@@ -480,18 +512,11 @@ int L_plane_rp(rsg_ram* h, int s0, int ns, cudaStream_t st, bool rev) {
   SpecPack pk;
   make_pack(h, pk, s0, ns);
   const RamDev dv = devfor(h, h->sp[s0].DTs);
-  const int KC = std::min(h->kcPlane, h->NE), KG = (h->NE + KC - 1) / KC;
+  const PlanePlan c = plane_plan(h);
+  const int KG = (h->NE + c.cfg.KC - 1) / c.cfg.KC;
   const dim3 g(KG, h->NPA, ns);
-  const size_t smem = plane_smem(h);
-  if (h->P <= 512) {
-    const int T = 256;
-    if (rev) { RET(opt_in_smem(k_plane_rp<2, true>, smem)); k_plane_rp<2, true><<<g, T, smem, st>>>(dv, pk, s0, KC); }
-    else { RET(opt_in_smem(k_plane_rp<2, false>, smem)); k_plane_rp<2, false><<<g, T, smem, st>>>(dv, pk, s0, KC); }
-  } else {
-    const int T = ((h->P + 3) / 4 + 31) / 32 * 32;
-    if (rev) { RET(opt_in_smem(k_plane_rp<4, true>, smem)); k_plane_rp<4, true><<<g, T, smem, st>>>(dv, pk, s0, KC); }
-    else { RET(opt_in_smem(k_plane_rp<4, false>, smem)); k_plane_rp<4, false><<<g, T, smem, st>>>(dv, pk, s0, KC); }
-  }
+  if (rev) { RET(opt_in_smem(k_plane_rp<true>, c.smem)); k_plane_rp<true><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg); }
+  else { RET(opt_in_smem(k_plane_rp<false>, c.smem)); k_plane_rp<false><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg); }
   CKL();
   h->launches++;
   if (rev) {
@@ -501,14 +526,39 @@ int L_plane_rp(rsg_ram* h, int s0, int ns, cudaStream_t st, bool rev) {
   }
   return RSG_OK;
 }
+// CFL limits of the fused path: evaluated when the coefficient set changed, else cached
+int L_cfl(rsg_ram* h, int s0, int ns, cudaStream_t st) {
+  bool all_ok = true;
+  for (int s = s0; s < s0 + ns; ++s) all_ok = all_ok && h->cfl_ok[s];
+  if (all_ok) return RSG_OK;
+  SpecPack pk;
+  make_pack(h, pk, s0, ns);
+  CK(cudaMemcpy2DAsync(h->d_cfl_all + (size_t)s0 * 4, 4 * sizeof(unsigned long long), h->d_res_init + (size_t)s0 * RES_N,
+                       RES_N * sizeof(unsigned long long), 4 * sizeof(unsigned long long), ns, cudaMemcpyDeviceToDevice, st));
+  k_cfl_fast<<<dim3(h->NPA, ns), 256, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0, h->d_cfl_all);
+  CKL();
+  h->launches++;
+  for (int s = s0; s < s0 + ns; ++s) h->cfl_ok[s] = true;
+  return RSG_OK;
+}
 int L_col(rsg_ram* h, int s0, int ns, int doA, double DTs, cudaStream_t st) {
   SpecPack pk;
   make_pack(h, pk, s0, ns);
   ColPlan c = col_plan(h);
   c.cfg.doA = doA;
-  RET(opt_in_smem(k_col_fused<COL_PG>, c.smem));
   const int nb = (h->P + COL_PG - 1) / COL_PG;
-  k_col_fused<COL_PG><<<dim3(nb, ns), c.T, c.smem, st>>>(devfor(h, DTs), pk, s0, c.cfg);
+  const dim3 g(nb, ns);
+  const RamDev dv = devfor(h, DTs);
+  if (c.T <= 320) {          // register budget follows the CTA size
+    RET(opt_in_smem(k_col_fused<COL_PG, 320>, c.smem));
+    k_col_fused<COL_PG, 320><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg);
+  } else if (c.T <= 640) {
+    RET(opt_in_smem(k_col_fused<COL_PG, 640>, c.smem));
+    k_col_fused<COL_PG, 640><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg);
+  } else {
+    RET(opt_in_smem(k_col_fused<COL_PG, 1024>, c.smem));
+    k_col_fused<COL_PG, 1024><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg);
+  }
   CKL();
   k_sum_final<<<dim3(5, ns), 256, 0, st>>>(pk, s0, nb, 5, 0, 2);   // slot 0 (:77) and slots 3..6 (:108-142)
   CKL();
@@ -577,7 +627,7 @@ int tables_drift(rsg_ram* h, int s, double DTs, cudaStream_t st) {
   sd.aRP = FracCFL * DTs;
   sd.OMEt = OME_EARTH * DTs / DPHI;
   sp.DTs = DTs;
-  h->inflow_ok[s] = false;   // P4 changed
+  h->inflow_ok[s] = h->cfl_ok[s] = false;   // P4 changed
   return RSG_OK;
 }
 
@@ -710,6 +760,7 @@ int rsg_ram_create(rsg_ram** out, int nS, int NR, int NT, int NE, int NPA, int d
   if (getenv("RSG_NO_FUSE")) h->use_fused = false;
   if (const char* e = getenv("RSG_KC_PLANE")) h->kcPlane = std::max(1, atoi(e));
   if (const char* e = getenv("RSG_COL_T")) h->colT = std::max(32, atoi(e));
+  if (const char* e = getenv("RSG_PLANE_T")) h->planeT = std::max(32, atoi(e));
   if (getenv("RSG_NO_GRAPH")) h->use_graph = false;   // kernel-by-kernel launches (profilers)
   RamDev& d = h->dev;
   d.nS = nS; d.NR = NR; d.NT = NT; d.NE = NE; d.NPA = NPA; d.NR1 = h->NR1; d.P = h->P; d.Pp = h->Pp;
@@ -719,6 +770,7 @@ int rsg_ram_create(rsg_ram** out, int nS, int NR, int NT, int NE, int NPA, int d
   for (int q = 0; q < 7; ++q) RET(h->dalloc(g1[q], g1n[q]));
   RET(h->dalloc((double**)&d.rDMU, NPA));
   RET(h->dalloc((double**)&d.rWMU, NPA));
+  RET(h->dalloc((double**)&d.exp2tab, 64));
   RET(h->dalloc((double**)&d.wPE, NPA));
   RET(h->dalloc((double**)&d.wPA, NPA));
   RET(h->dalloc((int**)&d.UPA, NR));
@@ -750,6 +802,7 @@ int rsg_ram_create(rsg_ram** out, int nS, int NR, int NT, int NE, int NPA, int d
   RET(h->dalloc(&h->d_tilemax, (size_t)nS * h->ntiles));
   RET(h->dalloc(&h->d_res_all, (size_t)nS * RES_N));
   RET(h->dalloc(&h->d_res_init, (size_t)nS * RES_N));
+  RET(h->dalloc(&h->d_cfl_all, (size_t)nS * 4));
   {
     std::vector<unsigned long long> init((size_t)nS * RES_N, 0ull);
     const double dflt[4] = {100000.0, 100000.0, 10000.0, 10000.0};  // :115,223,308,404
@@ -865,7 +918,7 @@ int rsg_ram_set_mode(rsg_ram* h, int mode) {
   CK(cudaSetDevice(h->device));
   RET(rsg_ram_sync(h));
   h->mode = mode;
-  for (int s = 0; s < h->nS; ++s) { h->sp[s].DTs = -1.0; h->inflow_ok[s] = false; }  // the inflow pre-pass depends on the mode
+  for (int s = 0; s < h->nS; ++s) { h->sp[s].DTs = -1.0; h->inflow_ok[s] = h->cfl_ok[s] = false; }  // the inflow pre-pass depends on the mode
   if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
   return RSG_OK;
 }
@@ -936,6 +989,9 @@ int rsg_ram_set_grids(rsg_ram* h, const double* RLZ, const double* LZ, const dou
       w1[l] = WMU[l] / mueff * (1.0 - MU[l] * MU[l]);
       w2[l] = WMU[l] / mueff * (MU[l] * MU[l]);
     }
+    double e2[64];
+    for (int j = 0; j < 64; ++j) e2[j] = std::exp2((double)j / 64.0);
+    RET(up((double*)d.exp2tab, e2, 64));
     RET(up((double*)d.rDMU, r1.data(), NPA));
     RET(up((double*)d.rWMU, r2.data(), NPA));
     RET(up((double*)d.wPE, w1.data(), NPA));
@@ -1024,7 +1080,7 @@ int rsg_ram_set_boundary(rsg_ram* h, const double* FGEOS) {
       for (int k = 0; k < NE; ++k)
         for (int j = 0; j < NT; ++j) b[((size_t)l * NE + k) * NT + j] = FGEOS[s + (size_t)nS * (j + (size_t)NT * (k + (size_t)NE * l))];
     RET(up(h->sp[s].d_FGEOS, b.data(), b.size()));
-    h->inflow_ok[s] = false;
+    h->inflow_ok[s] = h->cfl_ok[s] = false;
   }
   return RSG_OK;
 }
@@ -1298,6 +1354,7 @@ int step_prepare(rsg_ram* h, double DTs, int flags, int s0, int ns) {
   RET(ensure_step(h, DTs, st));
   RET(prof_mark(h, "driftr_inflow", st));
   RET(L_inflow(h, s0, ns, st));
+  if (fused_ok(h, flags)) RET(L_cfl(h, s0, ns, st));
   return RSG_OK;
 }
 int enqueue_fwd(rsg_ram* h, int s0, int ns, int l0, int nl);
@@ -1355,6 +1412,9 @@ int enqueue_fused(rsg_ram* h, double DTs, int flags, int s0, int ns) {
   cudaStream_t st = h->pst();
   CK(cudaMemcpyAsync(h->d_res_all + (size_t)s0 * RES_N, h->d_res_init + (size_t)s0 * RES_N,
                      (size_t)ns * RES_N * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+  // DtDriftR/P/E/Mu: properties of the coefficient set, cached by L_cfl
+  CK(cudaMemcpy2DAsync(h->d_res_all + (size_t)s0 * RES_N, RES_N * sizeof(unsigned long long), h->d_cfl_all + (size_t)s0 * 4,
+                       4 * sizeof(unsigned long long), 4 * sizeof(unsigned long long), ns, cudaMemcpyDeviceToDevice, st));
   int cat[RSG_MAX_SPECIES][NSLOT], doA;
   slot_cats(h, flags, cat, &doA, nullptr);
   h->in_step = false;

@@ -65,20 +65,49 @@ __device__ __forceinline__ double limited_flux(double Fm1, double F0, double Fp1
 //   FBND = U + 0.5*(1-|chat|) * LIM(R)*dD,  LIM(R)*|dD| = min(max(|dU|,|dD|), beta*min(|dU|,|dD|))
 // (max(min(bR,1),min(R,b)) = min(max(R,1), b*min(R,1)) for b >= 1).  achat = |chat|.
 // Mathematically identical to the reference; rounding differs at the 1e-16 level.
-__device__ __forceinline__ double limited_flux_fast(double Fm1, double F0, double Fp1, double Fp2, bool neg, double achat,
-                                                    double beta) {
+// Written on the cell differences so a walking sweep computes each difference once:
+//   dm1 = F0-Fm1, d0 = Fp1-F0, dp1 = Fp2-Fp1;  dU = neg ? -dp1 : dm1,  dD = neg ? -d0 : d0.
+// |.| and the sign tests are done on the high words (dU*dD > 0 <=> same sign, and a zero dU
+// gives lim = 0 anyway; the product's underflow to 0 below 1e-308 is the only difference).
+__device__ __forceinline__ double limited_flux_d(double F0, double Fp1, double dm1, double d0, double dp1, bool neg, double achat,
+                                                 double beta) {
   const double U = neg ? Fp1 : F0;
-  const double D = neg ? F0 : Fp1;
-  const double UU = neg ? Fp2 : Fm1;
-  const double dU = U - UU, dD = D - U;
-  const double an = fabs(dU), ad = fabs(dD);
+  const double ds = neg ? dp1 : dm1;
+  const int hs = __double2hiint(ds), h0 = __double2hiint(d0);
+  const double an = __hiloint2double(hs & 0x7fffffff, __double2loint(ds));
+  const double ad = __hiloint2double(h0 & 0x7fffffff, __double2loint(d0));
   const bool lt = an < ad;
   const double m = lt ? an : ad, M = lt ? ad : an;
   const double bm = beta * m;
   const double lim = (bm < M) ? bm : M;
-  const bool use = (ad > 1.E-27) && (dU * dD > 0.0);
-  const double limx = use ? copysign(lim, dD) : 0.0;
+  const bool use = (ad > 1.E-27) && ((hs ^ h0) >= 0);
+  const int sgn = (h0 ^ (neg ? (int)0x80000000 : 0)) & (int)0x80000000;   // sign of dD
+  const double limx = use ? __hiloint2double(__double2hiint(lim) | sgn, __double2loint(lim)) : 0.0;
   return fma(fma(-0.5, achat, 0.5), limx, U);
+}
+__device__ __forceinline__ double limited_flux_fast(double Fm1, double F0, double Fp1, double Fp2, bool neg, double achat,
+                                                    double beta) {
+  return limited_flux_d(F0, Fp1, F0 - Fm1, Fp1 - F0, Fp2 - Fp1, neg, achat, beta);
+}
+
+// FAST mode exp(x) for x <= 0 (loss factors): x = (64 n + j) ln2/64 + r, |r| <= ln2/128,
+// exp(x) = 2^n * 2^(j/64) * (1 + r + r^2/2 + ... + r^5/120)   (next term 3.5e-17), ~1 ulp.
+// tab = 2^(j/64).  Arguments below -708 (result < 3e-308) are clamped: no denormal scaling.
+__device__ __forceinline__ double fast_exp(double x, const double* __restrict__ tab) {
+  x = (x < -708.0) ? -708.0 : x;
+  const double MAGIC = 6755399441055744.0;                  // 1.5 * 2^52: rint in the low word
+  const double t = fma(x, 92.33248261689366, MAGIC);     // 64/ln2
+  const int ki = __double2loint(t);
+  const double kf = t - MAGIC;
+  double r = fma(kf, -0.01083042469326756, x);               // ln2/64 high part (21 trailing zero bits)
+  r = fma(kf, -2.9815858269852933e-12, r);                   // low part
+  const double T = tab[ki & 63];
+  double q = fma(r, 8.3333333333333332e-03, 4.1666666666666664e-02);
+  q = fma(q, r, 1.6666666666666666e-01);
+  q = fma(q, r, 0.5);
+  q = fma(q * r, r, r);                                      // r + r^2/2 + ... + r^5/120
+  const double v = fma(T, q, T);
+  return __hiloint2double(__double2hiint(v) + ((ki >> 6) << 20), __double2loint(v));
 }
 
 // =============================================================================
@@ -915,14 +944,17 @@ __global__ void __launch_bounds__(256) k_loss_mid(const __grid_constant__ RamDev
       const bool mom = (l >= 1) && (p < pmom);
       double facA = 1.0;
       if (useA) {
-        if (ion) facA = exp(-(sp.sv[k] * d.HDNSc[(size_t)l * d.Pp + p] * d.DTs));
+        if (ion) {
+          const double x = -(sp.sv[k] * d.HDNSc[(size_t)l * d.Pp + p] * d.DTs);
+          facA = FAST ? fast_exp(x, d.exp2tab) : exp(x);
+        }
         else facA = sp.wfac[(size_t)k * d.Pp + p];
         f = f * facA;
       }
       if (mom) acc[0] += e * (f * w * wm);
       if (l + 1 >= d.UPA[i]) {
         // ATLOS**(1/FNHS) (:502).  FAST: exp(log(ATLOS)/FNHS) with log(ATLOS) = -DTs/TAUB exact from the host
-        const double a = FAST ? exp(sp.xATL[k * d.NR + i] * d.rFNHS[(size_t)l * d.Pp + p])
+        const double a = FAST ? fast_exp(sp.xATL[k * d.NR + i] * d.rFNHS[(size_t)l * d.Pp + p], d.exp2tab)
                               : pow(sp.ATLOS[k * d.NR + i], 1 / d.FNHSc[(size_t)l * d.Pp + p]);
         f = f * a;
         if (mom) acc[1] += e * (f * w * wm);
