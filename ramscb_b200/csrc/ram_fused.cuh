@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(512) k_plane_rp(const __grid_constant__ RamDev
                                                   PlaneCfg cfg) {
   extern __shared__ double smem[];
   const SpecDev& sp = pk.s[s0 + blockIdx.z];
-  const int NR = d.NR, NT = d.NT, NE = d.NE, Pp = d.Pp;
+  const int NR = d.NR, NT = d.NT, NE = d.NE, P = d.P, Pp = d.Pp;
   const int T = blockDim.x, tid = threadIdx.x;
   const int NRp = cfg.NRp, PS = cfg.PS;
   const int l = blockIdx.y;
@@ -116,18 +116,27 @@ __global__ void __launch_bounds__(512) k_plane_rp(const __grid_constant__ RamDev
   const double beta = d.BetaLim;
   double* Fg = sp.F + ((size_t)l * NE + k0) * Pp;
 
-  // ---- stage the planes (a warp copies whole rows: one address update per row) and the line state
-  {
-    const int lane = tid & 31, nw = T >> 5;
-    int q = 0, j = tid >> 5;
-    while (j >= NT) { j -= NT; ++q; }
+  // ---- stage the planes and the line state.  A plane is contiguous in global memory; element
+  // e = q*P + j*NR + i goes to q*PS + j*NRp + i.  16-byte chunks when NR is even (a chunk never
+  // straddles a row; NRp is even then), else 8-byte; the offsets advance incrementally.
+  const int E = (NR & 1) ? 1 : 2;
+  auto for_chunks = [&](auto&& body) {
+    const int e0 = tid * E;
+    int q = e0 / P, p = e0 - q * P;
+    int j = p / NR, i = p - j * NR;
+    const int stp = T * E, dj = stp / NR, di = stp - dj * NR;
+    int so = q * PS + j * NRp + i, go = q * Pp + j * NR + i;
+    const int dso = dj * NRp + di, dgo = dj * NR + di;
     while (q < KCa) {
-      const double* src = Fg + (size_t)q * Pp + j * NR;
-      double* dst = sP + (size_t)q * PS + j * NRp;
-      for (int i = lane; i < NR; i += 32) cp_async8(dst + i, src + i);
-      j += nw;
-      while (j >= NT) { j -= NT; ++q; }
+      body(so, go);
+      i += di; j += dj; so += dso; go += dgo;
+      if (i >= NR) { i -= NR; ++j; so += NRp - NR; }
+      while (j >= NT) { j -= NT; ++q; so += PS - NT * NRp; go += Pp - P; }
     }
+  };
+  {
+    if (E == 2) for_chunks([&](int so, int go) { cp_async16(sP + so, Fg + go); });
+    else for_chunks([&](int so, int go) { cp_async8(sP + so, Fg + go); });
     asm volatile("cp.async.commit_group;");
     for (int t = tid; t < KCa * NT; t += T) {
       const int q2 = t / NT, j2 = t - q2 * NT;
@@ -271,20 +280,9 @@ __global__ void __launch_bounds__(512) k_plane_rp(const __grid_constant__ RamDev
   else { driftr(); __syncthreads(); driftp(); }
   __syncthreads();
 
-  // ---- write the planes back (I=1 is never advanced) ---------------------------------------
-  {
-    const int lane = tid & 31, nw = T >> 5;
-    int q = 0, j = tid >> 5;
-    while (j >= NT) { j -= NT; ++q; }
-    while (q < KCa) {
-      double* dst = Fg + (size_t)q * Pp + j * NR;
-      const double* src = sP + (size_t)q * PS + j * NRp;
-      for (int i = lane; i < NR; i += 32)
-        if (i >= 1) dst[i] = src[i];
-      j += nw;
-      while (j >= NT) { j -= NT; ++q; }
-    }
-  }
+  // ---- write the planes back (the never-advanced I=1 cells are rewritten with their own value)
+  if (E == 2) for_chunks([&](int so, int go) { *(double2*)(Fg + go) = *(const double2*)(sP + so); });
+  else for_chunks([&](int so, int go) { Fg[go] = sP[so]; });
   if (REV) {
     double acc[1] = {macc * d.WMU[l]};
     block_sum_to<1>(sp.part, (size_t)blockIdx.y * gridDim.x + blockIdx.x, acc, sRed);

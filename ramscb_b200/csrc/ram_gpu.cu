@@ -471,12 +471,14 @@ struct PlanePlan { PlaneCfg cfg; int T; size_t smem; };
 PlanePlan plane_plan(const rsg_ram* h) {
   PlanePlan c{};
   const int NR = h->NR, NT = h->NT;
-  c.cfg.NRp = NR | 1;
+  // row stride of the shared copy: odd, or 2*odd when NR is even (16-byte rows; the radial walks of
+  // 16 consecutive MLT lines then hit 8 different 8-byte banks instead of 1-4)
+  c.cfg.NRp = (NR & 1) ? NR : (((NR / 2) & 1) ? NR : NR + 2);
   c.cfg.PS = (NT * c.cfg.NRp + 1) & ~1;
   const size_t plane_bytes = sizeof(double) * (size_t)c.cfg.PS;
   // planes per CTA: enough lines for a few warps, at most ~100 KB so two CTAs share an SM
-  int KC = h->kcPlane > 0 ? h->kcPlane : std::max(1, std::min(8, (int)(50 * 1024 / plane_bytes)));
-  KC = std::max(1, std::min({KC, h->NE, (int)(100 * 1024 / plane_bytes)}));   // F2 planes + coefficient planes
+  int KC = h->kcPlane > 0 ? h->kcPlane : std::max(1, std::min(8, (int)(100 * 1024 / plane_bytes)));
+  KC = std::max(1, std::min({KC, h->NE, (int)(200 * 1024 / plane_bytes)}));
   c.cfg.KC = KC;
   const int linesR = NT * KC, linesP = NR * KC;
   // one thread per line; lines longer than ~32 cells are split so that a CTA has >= 8 warps
@@ -493,7 +495,7 @@ PlanePlan plane_plan(const rsg_ram* h) {
   };
   segs(NR - 1, c.T / linesR, &c.cfg.nsegR, &c.cfg.segR);
   segs(NT - 1, c.T / linesP, &c.cfg.nsegP, &c.cfg.segP);
-  c.smem = sizeof(double) * (2 * (size_t)KC * c.cfg.PS + 2 * (size_t)KC * NT + 32) + sizeof(int) * (((size_t)KC * NT + 1) & ~(size_t)1);
+  c.smem = sizeof(double) * ((size_t)KC * c.cfg.PS + 2 * (size_t)KC * NT + 32) + sizeof(int) * (((size_t)KC * NT + 1) & ~(size_t)1);
   return c;
 }
 size_t plane_smem(const rsg_ram* h) { return plane_plan(h).smem; }
