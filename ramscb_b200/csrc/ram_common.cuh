@@ -37,6 +37,7 @@ struct RamDev {
   //   R: CR[p] + P4[k]*fRb     P: fPa[p] - w2[k]*fPb
   //   E: uE[k]*fEa + vE[k]*fEb MU: fMa + wM[k]*fMb          (3-D ones are [NPA][Pp])
   double *fRb, *fPa, *fPb, *fEa, *fEb, *fMa, *fMb;
+  double *CRt, *fRbt;          // CR, fRb transposed to [i][j] / [l][i][j]: coalesced for the radial walks (lane = MLT line)
   const double *rDMU, *rWMU;   // 1/DMU(L), 1/WMU(L)
   double* rFNHS;               // FAST: 1/FNHS plane [NPA][Pp]
   const double* exp2tab;       // FAST: 2^(j/64), j < 64 (table of fast_exp)

@@ -75,6 +75,16 @@ __global__ void __launch_bounds__(256) k_cfl_fast(const __grid_constant__ RamDev
   warp_min_to(out + 3, mM > 0.0 ? sp.aRP / mM : 1.0e300);
 }
 
+// CR, fRb in [i][j] order for the radial walks of k_plane_rp (grid: x = tiles of the plane, y = l)
+__global__ void k_transpose_rcoef(RamDev d) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;   // t = i*NT + j
+  if (t >= d.P) return;
+  const int i = t / d.NT, j = t - i * d.NT;
+  const int l = blockIdx.y;
+  if (l == 0) d.CRt[t] = d.CR[j * d.NR + i];
+  d.fRbt[(size_t)l * d.Pp + t] = d.fRb[(size_t)l * d.Pp + j * d.NR + i];
+}
+
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
 }
@@ -119,7 +129,7 @@ __global__ void __launch_bounds__(512) k_plane_rp(const __grid_constant__ RamDev
   // ---- stage the planes and the line state.  A plane is contiguous in global memory; element
   // e = q*P + j*NR + i goes to q*PS + j*NRp + i.  16-byte chunks when NR is even (a chunk never
   // straddles a row; NRp is even then), else 8-byte; the offsets advance incrementally.
-  const int E = (NR & 1) ? 1 : 2;
+  const int E = (NRp & 1) ? 1 : 2;
   auto for_chunks = [&](auto&& body) {
     const int e0 = tid * E;
     int q = e0 / P, p = e0 - q * P;
@@ -175,8 +185,8 @@ __global__ void __launch_bounds__(512) k_plane_rp(const __grid_constant__ RamDev
       if (act) {
         const int k = k0 + q;
         const double P4k = sp.P4[k];
-        const double* cr = d.CR + j * NR + (ia - 2);                     // coefficient pieces of I = ia-1
-        const double* gr = d.fRb + (size_t)l * Pp + j * NR + (ia - 2);
+        const double* cr = d.CRt + (ia - 2) * NT + j;                    // coefficient pieces of I = ia-1, [i][j] order
+        const double* gr = d.fRbt + (size_t)l * Pp + (ia - 2) * NT + j;
         double dm1 = F0 - Fm1, d0 = Fp1 - F0, dp1 = Fp2 - Fp1;
         double phiPrev;
         {                                               // interface ia-1: flux only
@@ -185,8 +195,8 @@ __global__ void __launch_bounds__(512) k_plane_rp(const __grid_constant__ RamDev
           if (ia == 2) FB = inflow ? Fp1 : 0.0;         // FBND(1) = F(2) | 0   (:155,:159)
           phiPrev = c * FB;
         }
-        double cnext = fma(P4k, gr[1], cr[1]);          // CDriftR of I = ia
-        cr += 2; gr += 2;
+        double cnext = fma(P4k, gr[NT], cr[NT]);        // CDriftR of I = ia
+        cr += 2 * NT; gr += 2 * NT;
         double* pO = row + (ia - 1);
         const bool inmom = REV && l >= 1 && j <= NT - 2 && k >= 1;
         const double wk = inmom ? d.WE[k] * d.EKEV[k] : 0.0;
@@ -195,7 +205,7 @@ __global__ void __launch_bounds__(512) k_plane_rp(const __grid_constant__ RamDev
           dm1 = d0; d0 = dp1; dp1 = Fp2 - Fp1;
           const double c = cnext;
           if (!lastI) cnext = fma(P4k, *gr, *cr);       // next cell's coefficient, off the critical path
-          ++cr; ++gr;
+          cr += NT; gr += NT;
           double FB = limited_flux_d(F0, Fp1, dm1, d0, dp1, c < 0.0, fabs(c), beta);
           if (lastI && !inflow) FB = F0;                // FBND(NR) = F(NR)     (:156)
           const double phi = c * FB;

@@ -137,6 +137,7 @@ struct rsg_ram {
   // fused FAST path (ram_fused.cuh): shared-memory plane / column kernels
   bool use_fused = true;
   int kcPlane = 0, colT = 0, planeT = 0;
+  bool planeOdd = false;
   bool in_step = false, fwd_half = false;   // set by rsg_ram_part_*: CFL slots are reset once per step
   unsigned long long* d_res_init = nullptr;
 
@@ -212,7 +213,9 @@ int ensure_step(rsg_ram* h, double DTs, cudaStream_t only = nullptr) {
   dv.DTs = DTs;
   k_prep_step<<<nblk((long long)h->NPA * h->Pp, 256), 256, 0, ps>>>(dv);
   CKL();
-  h->launches++;
+  k_transpose_rcoef<<<dim3(nblk(h->P, 256), h->NPA), 256, 0, ps>>>(dv);
+  CKL();
+  h->launches += 2;
   if (join) {
     CK(cudaEventRecord(h->prepev, ps));
     for (int s = 0; s < h->nS; ++s) CK(cudaStreamWaitEvent(h->sp[s].own, h->prepev, 0));
@@ -474,6 +477,7 @@ PlanePlan plane_plan(const rsg_ram* h) {
   // row stride of the shared copy: odd, or 2*odd when NR is even (16-byte rows; the radial walks of
   // 16 consecutive MLT lines then hit 8 different 8-byte banks instead of 1-4)
   c.cfg.NRp = (NR & 1) ? NR : (((NR / 2) & 1) ? NR : NR + 2);
+  if (h->planeOdd) c.cfg.NRp = NR | 1;   // odd stride: conflict-free walks, 8-byte staging
   c.cfg.PS = (NT * c.cfg.NRp + 1) & ~1;
   const size_t plane_bytes = sizeof(double) * (size_t)c.cfg.PS;
   // planes per CTA: enough lines for a few warps, at most ~100 KB so two CTAs share an SM
@@ -763,6 +767,7 @@ int rsg_ram_create(rsg_ram** out, int nS, int NR, int NT, int NE, int NPA, int d
   if (const char* e = getenv("RSG_KC_PLANE")) h->kcPlane = std::max(1, atoi(e));
   if (const char* e = getenv("RSG_COL_T")) h->colT = std::max(32, atoi(e));
   if (const char* e = getenv("RSG_PLANE_T")) h->planeT = std::max(32, atoi(e));
+  if (const char* e = getenv("RSG_PLANE_ODD")) h->planeOdd = atoi(e) != 0;
   if (getenv("RSG_NO_GRAPH")) h->use_graph = false;   // kernel-by-kernel launches (profilers)
   RamDev& d = h->dev;
   d.nS = nS; d.NR = NR; d.NT = NT; d.NE = NE; d.NPA = NPA; d.NR1 = h->NR1; d.P = h->P; d.Pp = h->Pp;
@@ -784,6 +789,8 @@ int rsg_ram_create(rsg_ram** out, int nS, int NR, int NT, int NE, int NPA, int d
   double** p2d[] = {&d.CR, &d.sB, &d.pT1, &d.pT3, &d.sBp, &d.DRD1, &d.DPD1, &d.BNESc, &d.dBdt2, &d.RLZp, &d.fPa};
   for (auto p : p2d) RET(h->dalloc(p, np));
   RET(h->dalloc(&d.outp, np));
+  RET(h->dalloc(&d.CRt, np));
+  RET(h->dalloc(&d.fRbt, n3p));
   double** p3d[] = {&d.t1, &d.G, &d.sFp, &d.Gr, &d.Gp, &d.DRD2, &d.DPD2, &d.dBdt1, &d.dIdt1, &d.FNHSc,
                     &d.CMUDOT, &d.Gmr, &d.Gmp, &d.DRM2, &d.DPM2, &d.dIbndt2, &d.BOUNHSc, &d.HDNSc,
                     &d.fRb, &d.fPb, &d.fEa, &d.fEb, &d.fMa, &d.fMb, &d.rFNHS};
