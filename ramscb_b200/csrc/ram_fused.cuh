@@ -107,6 +107,7 @@ struct PlaneCfg {
   int NRp, PS;        // padded row stride and plane stride of the shared copy (doubles)
   int nsegR, segR;    // DRIFTR: segments per line, cells per segment (cells I=2..NR)
   int nsegP, segP;    // DRIFTP (cells J=2..NT)
+  int part_off;       // REV: offset of this kernel's SUMRC partials in SpecDev::part
 };
 
 template <bool REV>
@@ -138,15 +139,15 @@ __global__ void __launch_bounds__(512) k_plane_rp(const __grid_constant__ RamDev
     int so = q * PS + j * NRp + i, go = q * Pp + j * NR + i;
     const int dso = dj * NRp + di, dgo = dj * NR + di;
     while (q < KCa) {
-      body(so, go);
-      i += di; j += dj; so += dso; go += dgo;
+      body(so, go, p);
+      i += di; j += dj; so += dso; go += dgo; p += dgo;
       if (i >= NR) { i -= NR; ++j; so += NRp - NR; }
-      while (j >= NT) { j -= NT; ++q; so += PS - NT * NRp; go += Pp - P; }
+      while (j >= NT) { j -= NT; ++q; so += PS - NT * NRp; go += Pp - P; p -= P; }
     }
   };
   {
-    if (E == 2) for_chunks([&](int so, int go) { cp_async16(sP + so, Fg + go); });
-    else for_chunks([&](int so, int go) { cp_async8(sP + so, Fg + go); });
+    if (E == 2) for_chunks([&](int so, int go, int) { cp_async16(sP + so, Fg + go); });
+    else for_chunks([&](int so, int go, int) { cp_async8(sP + so, Fg + go); });
     asm volatile("cp.async.commit_group;");
     for (int t = tid; t < KCa * NT; t += T) {
       const int q2 = t / NT, j2 = t - q2 * NT;
@@ -290,12 +291,32 @@ __global__ void __launch_bounds__(512) k_plane_rp(const __grid_constant__ RamDev
   else { driftr(); __syncthreads(); driftp(); }
   __syncthreads();
 
-  // ---- write the planes back (the never-advanced I=1 cells are rewritten with their own value)
-  if (E == 2) for_chunks([&](int so, int go) { *(double2*)(Fg + go) = *(const double2*)(sP + so); });
-  else for_chunks([&](int so, int go) { Fg[go] = sP[so]; });
+  // ---- write the planes back (the never-advanced I=1 cells are rewritten with their own value).
+  // REV: the step ends here, so the epilogue of ram_run (src/ModRamRun.f90:186-201) rides along:
+  // F2(J=NT) = F2(J=1), then F2 = 1e-31 outside the magnetopause.
+  if (REV) {
+    for (int t = tid; t < KCa * NR; t += T) {
+      const int q = t / NR, i = t - q * NR;
+      sP[(size_t)q * PS + (NT - 1) * NRp + i] = sP[(size_t)q * PS + i];
+    }
+    __syncthreads();
+    if (E == 2)
+      for_chunks([&](int so, int go, int pl) {
+        double2 v = *(const double2*)(sP + so);
+        const unsigned short o2 = *(const unsigned short*)(d.outp + pl);
+        if (o2 & 0xff) v.x = 1.e-31;
+        if (o2 >> 8) v.y = 1.e-31;
+        *(double2*)(Fg + go) = v;
+      });
+    else
+      for_chunks([&](int so, int go, int pl) { Fg[go] = d.outp[pl] ? 1.e-31 : sP[so]; });
+  } else {
+    if (E == 2) for_chunks([&](int so, int go, int) { *(double2*)(Fg + go) = *(const double2*)(sP + so); });
+    else for_chunks([&](int so, int go, int) { Fg[go] = sP[so]; });
+  }
   if (REV) {
     double acc[1] = {macc * d.WMU[l]};
-    block_sum_to<1>(sp.part, (size_t)blockIdx.y * gridDim.x + blockIdx.x, acc, sRed);
+    block_sum_to<1>(sp.part + cfg.part_off, (size_t)blockIdx.y * gridDim.x + blockIdx.x, acc, sRed);
   }
 }
 
@@ -618,4 +639,76 @@ __global__ void __launch_bounds__(MAXT) k_col_fused(const __grid_constant__ RamD
   }
   (void)mmaxE; (void)mmaxM;
   block_sum_to<5>(sp.part, blockIdx.x, acc, sRed);
+}
+
+// =============================================================================
+// k_finalize: second stage of the SUMRC reductions of the fused step and the result
+// block of every species: DtDrift* from the cached CFL limits, moment slots 0, 3..6
+// (column kernel partials) and 9 (reverse plane kernel partials), zero elsewhere.
+// Blocks x >= 6 do the energy sums of ANISCH (src/ModRamRun.f90:379-400) for a tile of plane
+// positions: PPERT/PPART = RFAC * sum_K tE|tA (the reference groups K into five bands with the
+// same factor; only the summation order differs).
+// Everything is written to the device blocks and to the host-mapped copies: no memcpy nodes.
+// grid: x = 6 moments + tiles of 32 positions, y = species; block = 256
+// =============================================================================
+__global__ void __launch_bounds__(256) k_finalize(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0,
+                                                  int nb_col, int off_rev, int nb_rev,
+                                                  const unsigned long long* __restrict__ cfl_all, int res_n, int nsum,
+                                                  unsigned long long* __restrict__ host_res, double RFAC, double* __restrict__ host_pp) {
+  __shared__ double sm[32];
+  const int s = s0 + blockIdx.y;
+  const SpecDev& sp = pk.s[s];
+  if (blockIdx.x >= 6) {
+    // 32 positions x 8 energy lanes; the 8 partial sums are combined in a fixed order
+    __shared__ double sE[8][32], sA[8][32];
+    const int pl = threadIdx.x & 31, kl = threadIdx.x >> 5;
+    const int p = (blockIdx.x - 6) * 32 + pl;
+    double pe = 0.0, pa = 0.0;
+    const bool act = (p < d.P) && (p % d.NR >= 1);
+    if (act)
+      for (int k = 1 + kl; k < d.NE; k += 8) { pe += sp.tE[(size_t)k * d.Pp + p]; pa += sp.tA[(size_t)k * d.Pp + p]; }
+    sE[kl][pl] = pe;
+    sA[kl][pl] = pa;
+    __syncthreads();
+    if (kl == 0 && p < d.P) {
+      for (int c = 1; c < 8; ++c) { pe += sE[c][pl]; pa += sA[c][pl]; }
+      pe = RFAC * pe;
+      pa = 2 * RFAC * pa;
+      sp.pper[p] = pe;
+      sp.ppar[p] = pa;
+      double* hb = host_pp + (size_t)s * 2 * d.Pp;
+      hb[p] = pe;
+      hb[d.Pp + p] = pa;
+    }
+    return;
+  }
+  const int q = blockIdx.x;                              // 0..4: column moments, 5: reverse DRIFTR
+  double acc = 0.0;
+  if (q < 5) for (int b = threadIdx.x; b < nb_col; b += blockDim.x) acc += sp.part[(size_t)b * 5 + q];
+  else for (int b = threadIdx.x; b < nb_rev; b += blockDim.x) acc += sp.part[off_rev + b];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  unsigned long long* hr = host_res + (size_t)s * res_n;
+  if (threadIdx.x < 32) {
+    double v = (threadIdx.x < (blockDim.x >> 5)) ? sm[threadIdx.x] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) {
+      const int slot = (q == 0) ? 0 : ((q < 5) ? q + 2 : 9);
+      sp.dt[4 + slot] = dbl_bits(v);
+      hr[4 + slot] = dbl_bits(v);
+    }
+  }
+  if (q == 0) {
+    // the rest of the block: CFL limits, unused moment slots, counters
+    for (int t = threadIdx.x; t < res_n; t += blockDim.x) {
+      const int slot = t - 4;
+      if (t >= 4 && t < 4 + nsum && (slot == 0 || (slot >= 3 && slot <= 6) || slot == 9)) continue;
+      const unsigned long long v = (t < 4) ? cfl_all[4 * (size_t)s + t] : 0ull;
+      sp.dt[t] = v;
+      hr[t] = v;
+    }
+  }
 }

@@ -126,6 +126,8 @@ struct rsg_ram {
   bool inflow_ok[RSG_MAX_SPECIES] = {false};
   bool cfl_ok[RSG_MAX_SPECIES] = {false};   // cached CFL limits of the fused path (same dependencies)
   unsigned long long* d_cfl_all = nullptr;  // [nS][4]
+  unsigned long long* hd_res_all = nullptr; // device-side addresses of the pinned h_res_all / h_pp_all
+  double* hd_pp_all = nullptr;
   // CUDA graph of the single-GPU step (valid for one (DTs, flags, mode); rebuilt when they change)
   cudaGraphExec_t gexec = nullptr;
   double g_DTs = -1.0;
@@ -456,7 +458,7 @@ ColPlan col_plan(const rsg_ram* h) {
   const int NE = h->NE, NPA = h->NPA;
   c.cfg.NEs = NE | 1;
   const int linesE = NPA * COL_PG, linesM = NE * COL_PG;
-  int T = h->colT ? h->colT : ((linesE + 31) / 32 * 32) * (NE > 48 ? 3 : 1);
+  int T = h->colT ? h->colT : ((linesE + 31) / 32 * 32) * (NE > 48 ? 2 : 1);
   c.T = std::min(1024, (T + 31) / 32 * 32);
   auto segs = [](int n, int want, int* nseg, int* seg) {
     want = std::max(1, want);
@@ -470,6 +472,7 @@ ColPlan col_plan(const rsg_ram* h) {
                              4 * (size_t)NPA + 64 + 5 * 32);
   return c;
 }
+int fused_part_off(const rsg_ram* h) { return (((h->P + COL_PG - 1) / COL_PG) * 5 + 15) & ~15; }
 struct PlanePlan { PlaneCfg cfg; int T; size_t smem; };
 PlanePlan plane_plan(const rsg_ram* h) {
   PlanePlan c{};
@@ -481,7 +484,7 @@ PlanePlan plane_plan(const rsg_ram* h) {
   c.cfg.PS = (NT * c.cfg.NRp + 1) & ~1;
   const size_t plane_bytes = sizeof(double) * (size_t)c.cfg.PS;
   // planes per CTA: enough lines for a few warps, at most ~100 KB so two CTAs share an SM
-  int KC = h->kcPlane > 0 ? h->kcPlane : std::max(1, std::min(8, (int)(100 * 1024 / plane_bytes)));
+  int KC = h->kcPlane > 0 ? h->kcPlane : std::max(1, std::min(12, (int)(100 * 1024 / plane_bytes)));
   KC = std::max(1, std::min({KC, h->NE, (int)(200 * 1024 / plane_bytes)}));
   c.cfg.KC = KC;
   const int linesR = NT * KC, linesP = NR * KC;
@@ -518,18 +521,14 @@ int L_plane_rp(rsg_ram* h, int s0, int ns, cudaStream_t st, bool rev) {
   SpecPack pk;
   make_pack(h, pk, s0, ns);
   const RamDev dv = devfor(h, h->sp[s0].DTs);
-  const PlanePlan c = plane_plan(h);
+  PlanePlan c = plane_plan(h);
   const int KG = (h->NE + c.cfg.KC - 1) / c.cfg.KC;
   const dim3 g(KG, h->NPA, ns);
+  c.cfg.part_off = fused_part_off(h);      // after the column kernel's partials
   if (rev) { RET(opt_in_smem(k_plane_rp<true>, c.smem)); k_plane_rp<true><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg); }
   else { RET(opt_in_smem(k_plane_rp<false>, c.smem)); k_plane_rp<false><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg); }
   CKL();
   h->launches++;
-  if (rev) {
-    k_sum_final<<<dim3(1, ns), 256, 0, st>>>(pk, s0, KG * h->NPA, 1, 9);   // SUMRC of src/ModRamRun.f90:174
-    CKL();
-    h->launches++;
-  }
   return RSG_OK;
 }
 // CFL limits of the fused path: evaluated when the coefficient set changed, else cached
@@ -566,7 +565,28 @@ int L_col(rsg_ram* h, int s0, int ns, int doA, double DTs, cudaStream_t st) {
     k_col_fused<COL_PG, 1024><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg);
   }
   CKL();
-  k_sum_final<<<dim3(5, ns), 256, 0, st>>>(pk, s0, nb, 5, 0, 2);   // slot 0 (:77) and slots 3..6 (:108-142)
+  h->launches++;
+  return RSG_OK;
+}
+// pressures of ANISCH in one pass + the result block of the step, both also written to the
+// host-mapped copies (no memcpy nodes in the fused step)
+int L_finish_fused(rsg_ram* h, int s0, int ns, cudaStream_t st) {
+  SpecPack pk;
+  make_pack(h, pk, s0, ns);
+  const double RFAC = 4 * kPI / (kCS * 100);
+  RET(prof_mark(h, "k_anisch", st));
+  {
+    const int LCH = 6;
+    const int nch = std::max(1, std::min(16, (h->NPA + LCH - 1) / LCH));
+    const int lch = (h->NPA + nch - 1) / nch;
+    k_anisch_pa_fast<<<dim3(nblk(h->Pp, 32), h->NE, ns), dim3(32, nch), 0, st>>>(h->dev, pk, s0, 0, h->NPA, lch);
+    CKL();
+  }
+  RET(prof_mark(h, "k_finalize", st));
+  const PlanePlan c = plane_plan(h);
+  const int KG = (h->NE + c.cfg.KC - 1) / c.cfg.KC;
+  k_finalize<<<dim3(6 + nblk(h->P, 32), ns), 256, 0, st>>>(h->dev, pk, s0, (h->P + COL_PG - 1) / COL_PG, fused_part_off(h), KG * h->NPA,
+                                                            h->d_cfl_all, RES_N, NSUM, h->hd_res_all, RFAC, h->hd_pp_all);
   CKL();
   h->launches += 2;
   return RSG_OK;
@@ -825,6 +845,8 @@ int rsg_ram_create(rsg_ram** out, int nS, int NR, int NT, int NE, int NPA, int d
   CK(cudaMallocHost((void**)&h->h_res_all, (size_t)nS * RES_N * sizeof(unsigned long long)));
   RET(h->dalloc(&h->d_pp_all, (size_t)nS * 2 * h->Pp));
   CK(cudaMallocHost((void**)&h->h_pp_all, (size_t)nS * 2 * h->Pp * sizeof(double)));
+  CK(cudaHostGetDevicePointer((void**)&h->hd_res_all, h->h_res_all, 0));
+  CK(cudaHostGetDevicePointer((void**)&h->hd_pp_all, h->h_pp_all, 0));
   CK(cudaStreamCreateWithFlags(&h->prepst, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&h->prepev, cudaEventDisableTiming));
   int sms = 148;
@@ -1419,11 +1441,6 @@ int enqueue_tail(rsg_ram* h, int s0, int ns, int l0, int nl, cudaStream_t st) {
 // the whole step of all species on the fused FAST kernels: F2 makes three round trips
 int enqueue_fused(rsg_ram* h, double DTs, int flags, int s0, int ns) {
   cudaStream_t st = h->pst();
-  CK(cudaMemcpyAsync(h->d_res_all + (size_t)s0 * RES_N, h->d_res_init + (size_t)s0 * RES_N,
-                     (size_t)ns * RES_N * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
-  // DtDriftR/P/E/Mu: properties of the coefficient set, cached by L_cfl
-  CK(cudaMemcpy2DAsync(h->d_res_all + (size_t)s0 * RES_N, RES_N * sizeof(unsigned long long), h->d_cfl_all + (size_t)s0 * 4,
-                       4 * sizeof(unsigned long long), 4 * sizeof(unsigned long long), ns, cudaMemcpyDeviceToDevice, st));
   int cat[RSG_MAX_SPECIES][NSLOT], doA;
   slot_cats(h, flags, cat, &doA, nullptr);
   h->in_step = false;
@@ -1432,8 +1449,9 @@ int enqueue_fused(rsg_ram* h, double DTs, int flags, int s0, int ns) {
   RET(prof_mark(h, "k_col_fused", st));
   RET(L_col(h, s0, ns, doA, DTs, st));
   RET(prof_mark(h, "k_plane_rp", st));
-  RET(L_plane_rp(h, s0, ns, st, true));
-  return enqueue_tail(h, s0, ns, 0, h->NPA, st);
+  RET(L_plane_rp(h, s0, ns, st, true));          // ends with the epilogue of ram_run
+  RET(L_finish_fused(h, s0, ns, st));
+  return prof_mark(h, "d2h_results", st);
 }
 }  // namespace
 
@@ -1566,13 +1584,13 @@ int run_core(rsg_ram* h, double DTs, int flags, int s0, int ns) {
   const long long l0 = h->launches;
   if (graph_ok) CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
   int rc;
-  if (fused_ok(h, flags)) rc = enqueue_fused(h, DTs, flags, s0, ns);
+  if (fused_ok(h, flags)) rc = enqueue_fused(h, DTs, flags, s0, ns);   // results land in the pinned blocks directly
   else {
     rc = enqueue_fwd(h, s0, ns, 0, h->NPA);
     if (rc == RSG_OK) rc = rsg_ram_part_mid(h, DTs, flags, s0, ns, 0, h->NE);
     if (rc == RSG_OK) rc = rsg_ram_part_rev(h, s0, ns, 0, h->NPA);
+    if (rc == RSG_OK) rc = enqueue_results(h, s0, ns, true);
   }
-  if (rc == RSG_OK) rc = enqueue_results(h, s0, ns, true);
   if (graph_ok) {
     cudaGraph_t g = nullptr;
     cudaError_t e = cudaStreamEndCapture(st, &g);
