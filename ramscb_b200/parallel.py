@@ -109,21 +109,29 @@ def exchange(p: ShardPlan, bufs, Pp: int, to_kslab: bool, dist):
 
     ``bufs``: list of 1-D torch tensors (one per owned species) aliasing the resident F2
     buffers, on whatever device the process group's backend moves (CUDA for nccl, CPU for
-    gloo).  Every run of contiguous planes is one send/recv; all of them are posted as one
-    batch (ncclGroupStart/End underneath).
+    gloo).  An (l0,nl,k0,nk) block is nl runs of nk*Pp contiguous doubles: it is packed into one
+    message per peer (a strided 2-D copy), all messages are posted as one batch
+    (ncclGroupStart/End underneath) and the received blocks are scattered back.
     """
     if p.G == 1:
         return
+    import torch
     import torch.distributed as td
-    ops = []
+    ops, pending = [], []
     for peer, sblk, rblk in exchange_blocks(p, to_kslab):
         for buf in bufs:
-            for off, n in block_chunks(sblk, p.NE, Pp):
-                ops.append(td.P2POp(td.isend, buf[off:off + n], peer))
-            for off, n in block_chunks(rblk, p.NE, Pp):
-                ops.append(td.P2POp(td.irecv, buf[off:off + n], peer))
+            v = buf[:p.NPA * p.NE * Pp].view(p.NPA, p.NE * Pp)
+            sl0, snl, sk0, snk = sblk
+            rl0, rnl, rk0, rnk = rblk
+            send = v[sl0:sl0 + snl, sk0 * Pp:(sk0 + snk) * Pp].contiguous()
+            recv = torch.empty((rnl, rnk * Pp), dtype=buf.dtype, device=buf.device)
+            ops.append(td.P2POp(td.isend, send, peer))
+            ops.append(td.P2POp(td.irecv, recv, peer))
+            pending.append((v[rl0:rl0 + rnl, rk0 * Pp:(rk0 + rnk) * Pp], recv))
     for w in td.batch_isend_irecv(ops):
         w.wait()
+    for dst, recv in pending:
+        dst.copy_(recv)
 
 
 class _DevBuf:
