@@ -137,7 +137,9 @@ int rsg_atmol(rsg_ram* h, int S);              /* :485-507 */
 /* ModRamWPI (src/ModRamWPI.f90) */
 int rsg_wavelo(rsg_ram* h, int S, double DTs);                       /* :580-636 */
 int rsg_wpadif(rsg_ram* h, int S, double DTs, long long* nviolation); /* :643-714; nviolation may be NULL */
-/* ModRamCoul (src/ModRamCoul.f90) */
+/* ModRamCoul (src/ModRamCoul.f90): COULPARA builds the rate tables from the grids of
+ * rsg_ram_set_grids (host side, cached by DTs); COULEN / COULMU need rsg_ram_set_plasmasphere
+ * (NECR) and the fields; T = TimeRamElapsed arms COULMU's negative clamp (:289). */
 int rsg_coulpara(rsg_ram* h, int S, double DTs); /* :17-125  */
 int rsg_coulen(rsg_ram* h, int S);               /* :133-221 */
 int rsg_coulmu(rsg_ram* h, int S, double T);     /* :229-296 */
@@ -157,7 +159,7 @@ int rsg_ram_run(rsg_ram* h, double DTs, double DtsMin, double T, int flags, doub
  * F2 buffer (rsg_ram_f2_device) with NCCL send/recv -- there is no other data-path
  * collective.  The calls only enqueue work (on the stream of rsg_ram_set_stream, or the
  * library's run stream); rsg_ram_part_results synchronises and returns the rank's raw
- * results: DtDrift(4,ns) [min over ranks], SUMRC partial sums moments(10,ns) and partial
+ * results: DtDrift(4,ns) [min over ranks], SUMRC partial sums moments(14,ns) and partial
  * pressures PPER/PPAR(NR,NT,ns) [sum over the ranks of a species].  One GPU:
  * rsg_ram_run == fwd(all) + mid(all) + rev(all) + results. */
 int rsg_ram_part_fwd(rsg_ram* h, double DTs, int flags, int s0, int ns, int l0, int nl);

@@ -14,6 +14,7 @@
 #include "../../include/ramscb_gpu.h"
 #include "ram_kernels.cuh"
 #include "ram_fused.cuh"
+#include "ram_coulomb.cuh"
 
 namespace {
 
@@ -72,6 +73,8 @@ struct Spec {
   double* d_part = nullptr;  // moment partials [nblk_sum][RSG_NMOM]
   double* d_tE = nullptr;    // ANISCH scratch [2][nch][NE][Pp]
   double* d_rFFA = nullptr;  // FAST ANISCH: 1/A(S,I,K) [k][i]
+  double* d_coul = nullptr;  // COULPARA tables COULE, COULI, ATA, GTA, each [k][l]
+  double DTs_coul = -1.0;    // DTs of the last COULPARA
   unsigned long long* d_res = nullptr;  // slice of rsg_ram::d_res_all
   unsigned long long* h_res = nullptr;  // slice of rsg_ram::h_res_all (pinned)
   double* d_pp = nullptr;    // slice of d_pp_all: [2][Pp]
@@ -134,7 +137,9 @@ struct rsg_ram {
   int g_flags = -1, g_mode = -1;
   long long g_launches = 0;
   int g_s0 = 0, g_ns = 0;
+  bool g_tpos = false;   // COULMU's T > 0 switch is baked into the captured launch
   cudaStream_t g_stream = nullptr;
+  double T_elapsed = 0.0;
   bool use_graph = true;
   // fused FAST path (ram_fused.cuh): shared-memory plane / column kernels
   bool use_fused = true;
@@ -878,6 +883,7 @@ int rsg_ram_create(rsg_ram** out, int nS, int NR, int NT, int NE, int NPA, int d
     }
     RET(h->dalloc(&sp.d_tE, (size_t)2 * NE * h->Pp));
     RET(h->dalloc(&sp.d_rFFA, (size_t)NE * NR));
+    RET(h->dalloc(&sp.d_coul, (size_t)4 * NE * NPA));
     sp.d_res = h->d_res_all + (size_t)s * RES_N;
     sp.h_res = h->h_res_all + (size_t)s * RES_N;
     sp.d_pp = h->d_pp_all + (size_t)s * 2 * h->Pp;
@@ -1287,10 +1293,154 @@ int rsg_wpadif(rsg_ram* h, int S, double DTs, long long* nviolation) {
   return RSG_OK;
 }
 
-// ---- ModRamCoul (optional operators; not yet on the device) --------------------------
-int rsg_coulpara(rsg_ram* h, int S, double) { RET(check_S(h, S)); return fail(RSG_ERR_UNSUPPORTED, "COULPARA not implemented"); }
-int rsg_coulen(rsg_ram* h, int S) { RET(check_S(h, S)); return fail(RSG_ERR_UNSUPPORTED, "COULEN not implemented"); }
-int rsg_coulmu(rsg_ram* h, int S, double) { RET(check_S(h, S)); return fail(RSG_ERR_UNSUPPORTED, "COULMU not implemented"); }
+// ---- ModRamCoul -----------------------------------------------------------------------
+namespace {
+// src/ModRamFunctions.f90:72-143
+double gcoul_h(double x) {
+  const double g1 = std::erf(x) - 2. * x / std::sqrt(kPI) * std::exp(-x * x);
+  return g1 / 2. / x / x;
+}
+double funt_h(double x) {
+  const double y = std::sqrt(1 - x * x);
+  const double alpha = 1. + std::log(2. + std::sqrt(3.)) / 2. / std::sqrt(3.);
+  const double beta = alpha / 2. - kPI * std::sqrt(2.) / 12.;
+  return alpha - beta * (y + std::sqrt(y)) + 0.055 * std::pow(y, 1. / 3.) + -0.037 * std::pow(y, 2. / 3.) + -0.074 * y +
+         0.056 * std::pow(y, 4. / 3.);
+}
+double funi_h(double x) {
+  const double y = std::sqrt(1 - x * x);
+  const double ylog = (y > 0) ? std::log(y) : 0.0;
+  const double alpha = 1. + std::log(2. + std::sqrt(3.)) / 2. / std::sqrt(3.);
+  const double beta = alpha / 2. - kPI * std::sqrt(2.) / 12.;
+  const double a1 = 0.055, a2 = -0.037, a3 = -0.074, a4 = 0.056;
+  return 2. * alpha * (1. - y) + 2. * beta * y * ylog + 4. * beta * (y - std::sqrt(y)) + 3. * a1 * (std::pow(y, 1. / 3.) - y) +
+         6. * a2 * (std::pow(y, 2. / 3.) - y) + 6. * a4 * (y - std::pow(y, 4. / 3.)) - 2. * a3 * y * ylog;
+}
+// COULPARA (src/ModRamCoul.f90:17-125): energy / pitch-angle tables of the Coulomb drag and
+// scattering rates against the plasmasphere population (RAMSpecies(1:6): e-, H+, He+, O+, N+, Sr+
+// with plasmasphereRatio 1, 0.77, 0.2, 0.03, 0, 0; src/ModRamSpecies.f90:42-133).  As in the
+// reference the collision sums are NOT reset inside the energy loop (they accumulate over K).
+// Tables are laid out [k][l]; entries the reference never assigns stay 0.
+int tables_coulomb(rsg_ram* h, int s, double DTs) {
+  Spec& sp = h->sp[s];
+  if (sp.DTs_coul == DTs) return RSG_OK;
+  const int nS = h->nS, NE = h->NE, NPA = h->NPA;
+  const double MP = 1.673E-27, RE = 6.371E6, EPS = 8.854E-12, DLN = 21.5;
+  static const double ps_mass[6] = {5.4462E-4, 1.0, 4.0, 16.0, 14.0, 87.62};
+  static const double ps_charge[6] = {-1, 1, 1, 1, 1, 1};
+  static const double ps_ratio[6] = {1.0, 0.77, 0.2, 0.03, 0.0, 0.0};
+  std::vector<double> tab((size_t)4 * NE * NPA, 0.0), de(NPA, 0.0), di(NPA, 0.0);
+  double* COULE = tab.data();
+  double* COULI = COULE + (size_t)NE * NPA;
+  double* ATA = COULI + (size_t)NE * NPA;
+  double* GTA = ATA + (size_t)NE * NPA;
+  const double Zt = (double)h->QS[s];
+  const double QE = (kQ * kQ / EPS);
+  const double GAMA = Zt * Zt * DLN / 4. / kPI * QE * 1E6 * QE;
+  const double CCO = GAMA / kQ * DTs / kQ / 1E3;
+  const double CCD = GAMA * DTs / (h->RMAS[s] * h->RMAS[s]) / (kCS * kCS * kCS);
+  double CCE = 0, CDE = 0, CCI = 0, CDI = 0;
+  const double *MU = h->MU.data(), *WMU = h->WMU.data(), *DMU = h->DMU.data();
+  for (int k = 0; k < NE; ++k) {
+    const double Vk = h->V[s + (size_t)nS * k], VBk = h->VBND[s + (size_t)nS * k];
+    const double GRk = h->GREL[s + (size_t)nS * k], GRBk = h->GRBND[s + (size_t)nS * k];
+    for (int b = 0; b < 6; ++b) {
+      const double RA = ps_ratio[b];
+      if (RA < 1e-9) continue;
+      const double VF = std::sqrt(2. * kQ / (MP * ps_mass[b]));
+      const double Zb = ps_charge[b];
+      const double X = VBk / VF, XD = Vk / VF;
+      if (Zb < 0.0) {
+        CCE = CCE + RA * gcoul_h(X);
+        CDE = CDE + RA * (std::erf(XD) - gcoul_h(XD));
+      } else {
+        CCI = CCI + RA * (Zb * Zb) * gcoul_h(X);
+        CDI = CDI + RA * (Zb * Zb) * (std::erf(XD) - gcoul_h(XD));
+      }
+    }
+    const double ce1 = -CCE * VBk * CCO * (GRBk * GRBk);
+    const double ci1 = -CCI * VBk * CCO * (GRBk * GRBk);
+    COULE[(size_t)k * NPA] = ce1;
+    COULI[(size_t)k * NPA] = ci1;
+    const double CCDE = CCD * CDE * GRk / std::pow(GRk * GRk - 1, 1.5);
+    const double CCDI = CCD * CDI * GRk / std::pow(GRk * GRk - 1, 1.5);
+    for (int l = 1; l <= NPA - 2; ++l) {      // L = 2..NPA-1
+      COULE[(size_t)k * NPA + l] = ce1;
+      COULI[(size_t)k * NPA + l] = ci1;
+      const double MUBOUN = MU[l] + 0.5 * WMU[l];
+      const double BADIF = (1. - MUBOUN * MUBOUN) / MUBOUN / 2.;
+      de[l] = CCDE * BADIF;
+      const double AFER = de[l] / MU[l] / DMU[l] / WMU[l];
+      const double ASEC = de[l - 1] / MU[l] / DMU[l - 1] / WMU[l];
+      di[l] = CCDI * BADIF;
+      const double AFIR = di[l] / MU[l] / DMU[l] / WMU[l];
+      const double ASIC = di[l - 1] / MU[l] / DMU[l - 1] / WMU[l];
+      ATA[(size_t)k * NPA + l] = AFIR + AFER;
+      GTA[(size_t)k * NPA + l] = ASIC + ASEC;
+    }
+  }
+  (void)RE; (void)funt_h; (void)funi_h;
+  CK(cudaStreamSynchronize(h->st(s)));
+  RET(up(sp.d_coul, tab.data(), tab.size()));
+  sp.DTs_coul = DTs;
+  return RSG_OK;
+}
+int L_coulen(rsg_ram* h, int s, cudaStream_t st) {
+  Spec& sp = h->sp[s];
+  if (sp.DTs_coul < 0) return fail(RSG_ERR_STATE, "COULEN before COULPARA");
+  SpecPack pk;
+  make_pack(h, pk, s, 1);
+  // ghost cells F(1), F(0) (:154-156, :182-183)
+  const double EZERO = h->EKEV[0] - h->WE[0];
+  const double GRZERO = 1. + EZERO * 1000. * kQ / h->RMAS[s] / kCS / kCS;
+  const double GREL1 = h->GREL[s], GREL2 = h->GREL[s + (size_t)h->nS];
+  const double g1 = std::sqrt((GREL1 * GREL1 - 1) / (GREL2 * GREL2 - 1));
+  const double g0 = std::sqrt((GRZERO * GRZERO - 1) / (GREL1 * GREL1 - 1));
+  const size_t n = (size_t)h->NE * h->NPA;
+  k_coulen<<<dim3(nblk(h->P, 128), h->NPA - 1), 128, 0, st>>>(h->dev, pk.s[s], sp.d_coul, sp.d_coul + n, h->d_NECR, GREL1, GREL2,
+                                                              GRZERO, g1, g0);
+  CKL();
+  h->launches++;
+  return RSG_OK;
+}
+int L_coulmu(rsg_ram* h, int s, double T, cudaStream_t st) {
+  Spec& sp = h->sp[s];
+  if (sp.DTs_coul < 0) return fail(RSG_ERR_STATE, "COULMU before COULPARA");
+  SpecPack pk;
+  make_pack(h, pk, s, 1);
+  const int TB = 64;
+  const size_t smem = sizeof(double) * 2 * h->NPA * TB;
+  static thread_local size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    CK(cudaFuncSetAttribute(k_coulmu, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  const size_t n = (size_t)h->NE * h->NPA;
+  k_coulmu<<<nblk((long long)h->NE * h->Pp, TB), TB, smem, st>>>(h->dev, pk.s[s], sp.d_coul + 2 * n, sp.d_coul + 3 * n, h->d_NECR, T);
+  CKL();
+  h->launches++;
+  return RSG_OK;
+}
+}  // namespace
+
+int rsg_coulpara(rsg_ram* h, int S, double DTs) {
+  RET(check_S(h, S));
+  if (!h->grids_set) return fail(RSG_ERR_STATE, "COULPARA before set_grids");
+  CK(cudaSetDevice(h->device));
+  return tables_coulomb(h, S - 1, DTs);
+}
+int rsg_coulen(rsg_ram* h, int S) {
+  RET(check_S(h, S));
+  if (!h->fields_set) return fail(RSG_ERR_STATE, "COULEN before set_fields");
+  CK(cudaSetDevice(h->device));
+  return L_coulen(h, S - 1, h->st(S - 1));
+}
+int rsg_coulmu(rsg_ram* h, int S, double T) {
+  RET(check_S(h, S));
+  if (!h->fields_set) return fail(RSG_ERR_STATE, "COULMU before set_fields");
+  CK(cudaSetDevice(h->device));
+  return L_coulmu(h, S - 1, T, h->st(S - 1));
+}
 
 // ---- ModRamRun --------------------------------------------------------------------
 int rsg_sumrc(rsg_ram* h, int S, double* setrc, double* elorc) {
@@ -1337,9 +1487,12 @@ int rsg_anisch(rsg_ram* h, int S, double* PPERT_S, double* PPART_S) {
 // SUMRC slots (global numbering): 0 fwd drifts | 1 WPI diffusion | 2 EMIC | 3-6 fused loss
 // block | 7 EMIC | 8 WPI diffusion | 9 reverse drifts.  cat: -1 unused, 0 LSDR 1 LSCHA 2 LSATM 3 LSWAE
 namespace {
-constexpr int NSLOT = 10;
+constexpr int NSLOT = 14;
+// SUMRC slots in the order ram_run takes them (src/ModRamRun.f90:77-174); slots 10..13 are the
+// Coulomb ones (COULEN, COULMU | COULMU, COULEN), appended so that the others keep their index
+constexpr int kSlotOrder[NSLOT] = {0, 10, 11, 1, 2, 3, 4, 5, 6, 7, 8, 12, 13, 9};
 void slot_cats(rsg_ram* h, int flags, int cat[RSG_MAX_SPECIES][NSLOT], int* doA, bool* wavelo_sp) {
-  const bool DoUseWPI = flags & RSG_F_WPI, DoUseEMIC = flags & RSG_F_EMIC;
+  const bool DoUseWPI = flags & RSG_F_WPI, DoUseEMIC = flags & RSG_F_EMIC, DoUseCoulomb = flags & RSG_F_COULOMB;
   *doA = 0;
   for (int s = 0; s < h->nS; ++s) {
     const int kind = h->kind[s];
@@ -1352,6 +1505,7 @@ void slot_cats(rsg_ram* h, int flags, int cat[RSG_MAX_SPECIES][NSLOT], int* doA,
     if (sCEX) { cat[s][3] = cat[s][6] = 1; *doA |= 1 << s; }
     if (wavelo) { cat[s][3] = cat[s][6] = 3; *doA |= 1 << s; }
     cat[s][4] = cat[s][5] = 2;
+    if (DoUseCoulomb) { cat[s][10] = cat[s][13] = 4; cat[s][11] = cat[s][12] = 5; }   // LSCOE, LSCSC
     if (wavelo_sp) wavelo_sp[s] = wavelo;
   }
 }
@@ -1378,6 +1532,7 @@ int step_prepare(rsg_ram* h, double DTs, int flags, int s0, int ns) {
   h->prof_n = 0;
   RET(prof_mark(h, "prep_step", st));
   for (int s = s0; s < s0 + ns; ++s) {
+    if (flags & RSG_F_COULOMB) RET(tables_coulomb(h, s, DTs));
     RET(tables_cepara(h, s, DTs, st));
     RET(tables_drift(h, s, DTs, st));
     if (wl[s]) RET(tables_wavelo(h, s, DTs, st));
@@ -1395,7 +1550,6 @@ int enqueue_tail(rsg_ram* h, int s0, int ns, int l0, int nl, cudaStream_t st);
 
 int rsg_ram_part_fwd(rsg_ram* h, double DTs, int flags, int s0, int ns, int l0, int nl) {
   RET(check_part(h, s0, ns, l0, nl, h ? h->NPA : 0));
-  if (flags & RSG_F_COULOMB) return fail(RSG_ERR_UNSUPPORTED, "Coulomb operators not implemented");
   CK(cudaSetDevice(h->device));
   RET(step_prepare(h, DTs, flags, s0, ns));
   return enqueue_fwd(h, s0, ns, l0, nl);
@@ -1472,7 +1626,15 @@ int rsg_ram_part_mid(rsg_ram* h, double DTs, int flags, int s0, int ns, int k0, 
     h->in_step = false;
     if (rc != RSG_OK) return rc;
   }
+  const bool coul = flags & RSG_F_COULOMB;
+  if (coul && (k0 != 0 || nk != h->NE))
+    return fail(RSG_ERR_UNSUPPORTED, "Coulomb operators need every energy and pitch angle local (no slab sharding)");
   RET(prof_mark(h, "wpadif+sumrc", st));
+  if (coul)                                        // COULEN, SUMRC, COULMU, SUMRC  (:79-84)
+    for (int s = s0; s < s0 + ns; ++s) {
+      RET(L_coulen(h, s, st)); RET(L_sumrc(h, s, 1, 10, st, pr));
+      RET(L_coulmu(h, s, h->T_elapsed, st)); RET(L_sumrc(h, s, 1, 11, st, pr));
+    }
   for (int s = s0; s < s0 + ns; ++s)
     if (cat[s][1] >= 0) { RET(L_wpadif(h, s, DTs, st, k0, nk)); RET(L_sumrc(h, s, 1, 1, st, pr)); }
   for (int s = s0; s < s0 + ns; ++s)
@@ -1484,6 +1646,11 @@ int rsg_ram_part_mid(rsg_ram* h, double DTs, int flags, int s0, int ns, int k0, 
     if (cat[s][7] >= 0) { RET(L_wpadif(h, s, DTs, st, k0, nk)); RET(L_sumrc(h, s, 1, 7, st, pr)); }
   for (int s = s0; s < s0 + ns; ++s)
     if (cat[s][8] >= 0) { RET(L_wpadif(h, s, DTs, st, k0, nk)); RET(L_sumrc(h, s, 1, 8, st, pr)); }
+  if (coul)                                        // COULMU, SUMRC, COULEN, SUMRC  (:161-166)
+    for (int s = s0; s < s0 + ns; ++s) {
+      RET(L_coulmu(h, s, h->T_elapsed, st)); RET(L_sumrc(h, s, 1, 12, st, pr));
+      RET(L_coulen(h, s, st)); RET(L_sumrc(h, s, 1, 13, st, pr));
+    }
   RET(prof_mark(h, "k_driftmu", st));
   h->in_step = true;
   h->fwd_half = false;
@@ -1521,7 +1688,7 @@ int rsg_ram_part_rev(rsg_ram* h, int s0, int ns, int l0, int nl) {
 }
 
 // raw per-rank results of the three parts: DtDrift(4,ns) minima, SUMRC partial sums
-// moments(10,ns) over the local slab (unused slots are 0), partial PPERT/PPART(NR,NT,ns).
+// moments(14,ns) over the local slab (unused slots are 0), partial PPERT/PPART(NR,NT,ns).
 // Ranks sharing a species add moments and pressures and take the min of DtDrift.
 namespace {
 int enqueue_results(rsg_ram* h, int s0, int ns, bool pressures) {
@@ -1569,12 +1736,11 @@ namespace {
 // re-captures.  Stage profiling needs the events between launches: no graph then.
 int run_core(rsg_ram* h, double DTs, int flags, int s0, int ns) {
   RET(check_part(h, s0, ns, 0, h ? h->NPA : 0, h ? h->NPA : 0));
-  if (flags & RSG_F_COULOMB) return fail(RSG_ERR_UNSUPPORTED, "Coulomb operators not implemented");
   CK(cudaSetDevice(h->device));
   RET(step_prepare(h, DTs, flags, s0, ns));
   cudaStream_t st = h->pst();
   const bool graph_ok = h->use_graph && !h->prof_on;
-  if (graph_ok && h->gexec && h->g_DTs == DTs && h->g_flags == flags && h->g_mode == h->mode && h->g_s0 == s0 && h->g_ns == ns &&
+  if (graph_ok && h->gexec && h->g_DTs == DTs && h->g_flags == flags && h->g_mode == h->mode && h->g_s0 == s0 && h->g_ns == ns && h->g_tpos == (h->T_elapsed > 0.0) &&
       h->g_stream == st) {
     CK(cudaGraphLaunch(h->gexec, st));
     h->launches += h->g_launches;
@@ -1599,7 +1765,7 @@ int run_core(rsg_ram* h, double DTs, int flags, int s0, int ns) {
     e = cudaGraphInstantiate(&h->gexec, g, 0);
     cudaGraphDestroy(g);
     if (e != cudaSuccess) { h->gexec = nullptr; return fail(RSG_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
-    h->g_DTs = DTs; h->g_flags = flags; h->g_mode = h->mode; h->g_s0 = s0; h->g_ns = ns; h->g_stream = st;
+    h->g_DTs = DTs; h->g_flags = flags; h->g_mode = h->mode; h->g_s0 = s0; h->g_ns = ns; h->g_stream = st; h->g_tpos = (h->T_elapsed > 0.0);
     h->g_launches = h->launches - l0;
     CK(cudaGraphLaunch(h->gexec, st));
   }
@@ -1630,7 +1796,7 @@ int rsg_ram_part_all(rsg_ram* h, double DTs, int flags, int s0, int ns) {
 int rsg_ram_run(rsg_ram* h, double DTs, double DtsMin, double T, int flags, double* dts_next, double* DtDrift,
                 double* losses, double* SETRC, double* PPERT, double* PPART) {
   if (!h) return fail(RSG_ERR_ARG, "null handle");
-  (void)T;
+  h->T_elapsed = T;                    // COULMU clamps negatives only once T > 0 (src/ModRamCoul.f90:289)
   const int nS = h->nS;
   RET(run_core(h, DTs, flags, 0, nS));
   std::vector<double> dt((size_t)4 * nS), mom((size_t)NSLOT * nS), pe((size_t)h->P * nS), pa((size_t)h->P * nS);
@@ -1646,7 +1812,8 @@ int rsg_ram_run(rsg_ram* h, double DTs, double DtsMin, double T, int flags, doub
     }
     double ls[6] = {0, 0, 0, 0, 0, 0};
     double prev = sp.setrc;
-    for (int q = 0; q < NSLOT; ++q) {
+    for (int qi = 0; qi < NSLOT; ++qi) {
+      const int q = kSlotOrder[qi];
       if (cat[s][q] < 0) continue;
       const double v = mom[q + (size_t)NSLOT * s];
       ls[cat[s][q]] += prev - v;  // ELORC = ENOLD - SETRC (:256)

@@ -282,7 +282,7 @@ class RamGpu:
     def part_results(self, s0, ns):
         g = self.g
         dt = np.zeros((4, ns), order="F")
-        mom = np.zeros((10, ns), order="F")
+        mom = np.zeros((14, ns), order="F")
         pper = np.zeros((g.NR, g.NT, ns), order="F")
         ppar = np.zeros((g.NR, g.NT, ns), order="F")
         _ck(self.L.rsg_ram_part_results(self.h, s0, ns, _p(dt), _p(mom), _p(pper), _p(ppar)))

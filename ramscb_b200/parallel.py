@@ -191,7 +191,7 @@ class RamSharded:
         dt, mom, pper, ppar = gpu.part_results(p.s0, p.ns)
         # control-plane reductions over all ranks (a few KB)
         DT = np.full((4, g.nS), np.inf)
-        MOM = np.zeros((10, g.nS))
+        MOM = np.zeros((14, g.nS))
         PE = np.zeros((g.NR, g.NT, g.nS))
         PA = np.zeros((g.NR, g.NT, g.nS))
         sl = slice(p.s0, p.s0 + p.ns)

@@ -164,7 +164,33 @@ def test_wpadif_bit_exact(default_grids, oracle_built, kind):
     assert not np.array_equal(got[S - 1], inp.F2[S - 1])
 
 
-@pytest.mark.parametrize("flags", [0, 1 | 4])
+@pytest.mark.parametrize("S", [1, 2, 4])
+def test_coulomb_operators_bit_exact(default_grids, oracle_built, S):
+    """COULPARA tables + COULEN (energy drag) + COULMU (pitch-angle scattering),
+    src/ModRamCoul.f90:17-296, for H+, O+ and electrons; T > 0 arms the negative clamp."""
+    g = default_grids
+    inp = _mk(g, f2_kind="noisy", inductive=True)
+    o, gpu = _pair(g, inp, oracle_built)
+    o.set_scalar("T", 10.0)
+    o.op("coulpara", S)
+    gpu.COULPARA(S, DTS)
+    o.op("coulen", S)
+    gpu.COULEN(S)
+    got = gpu.f2_d2h()
+    assert np.array_equal(got[S - 1], o.F2[S - 1]), f"COULEN rel err {_relerr(got[S - 1], o.F2[S - 1]):.3e}"
+    assert not np.array_equal(got[S - 1], inp.F2[S - 1])
+    o.op("coulmu", S)
+    gpu.COULMU(S, 10.0)
+    got2 = gpu.f2_d2h()
+    assert np.array_equal(got2[S - 1], o.F2[S - 1]), f"COULMU rel err {_relerr(got2[S - 1], o.F2[S - 1]):.3e}"
+    assert not np.array_equal(got2[S - 1], got[S - 1])
+    # other species untouched
+    for q in range(g.nS):
+        if q != S - 1:
+            assert np.array_equal(got2[q], inp.F2[q])
+
+
+@pytest.mark.parametrize("flags", [0, 1 | 4, 2, 1 | 2 | 4])
 def test_full_ram_run(default_grids, oracle_built, flags):
     """Whole species loop + epilogue of ram_run (src/ModRamRun.f90:64-222), two
     consecutive calls (the second starts from the first's state and SETRC)."""
@@ -179,9 +205,10 @@ def test_full_ram_run(default_grids, oracle_built, flags):
     for step in range(2):
         dts = DTS if step == 0 else 7.5
         o.set_scalar("DTs", dts)
-        before = {k: o.arr[k].copy() for k in ("LSDR", "LSCHA", "LSATM", "LSWAE")}
+        before = {k: o.arr[k].copy() for k in ("LSDR", "LSCHA", "LSATM", "LSWAE", "LSCOE", "LSCSC")}
+        o.set_scalar("T", 5.0 * step)
         dtn_ref = o.ram_run(flags=flags)
-        out = gpu.ram_run(dts, DtsMin=1.0, flags=flags)
+        out = gpu.ram_run(dts, DtsMin=1.0, flags=flags, T=5.0 * step)
         got = gpu.f2_d2h()
         assert _relerr(got, o.F2) <= 1e-12, f"step {step}: F2 rel err {_relerr(got, o.F2):.3e}"
         assert out["DtsNext"] == dtn_ref
@@ -191,7 +218,7 @@ def test_full_ram_run(default_grids, oracle_built, flags):
         assert _relerr(out["PPART"][:, 1:], o.PPART[:, 1:]) <= 1e-12
         assert np.allclose(out["SETRC"], o.SETRC, rtol=1e-12, atol=0)
         scale = np.abs(o.SETRC)
-        for q, name in enumerate(("LSDR", "LSCHA", "LSATM", "LSWAE")):
+        for q, name in enumerate(("LSDR", "LSCHA", "LSATM", "LSWAE", "LSCOE", "LSCSC")):
             inc = o.arr[name] - before[name]
             assert np.all(np.abs(out["losses"][q] - inc) <= 1e-11 * scale), name
     flux = gpu.flux_d2h()
