@@ -134,6 +134,10 @@ int rsg_get_dtdrift(rsg_ram* h, int S, double out4[4]);
 int rsg_cepara(rsg_ram* h, int S, double DTs); /* :19-170  */
 int rsg_charexchange(rsg_ram* h, int S);       /* :457-478 */
 int rsg_atmol(rsg_ram* h, int S);              /* :485-507 */
+/* FLCscatter :513-575 (skipped while T < Dt_bc, :523).  FLC_coef(S,:,:,:,:) -- the output of
+ * PARA_FLC, which stays on the host -- is set per species as a contiguous (NR,NT,NE,NPA) array. */
+int rsg_ram_set_flc_coef(rsg_ram* h, int S, const double* FLC_coef);
+int rsg_flcscatter(rsg_ram* h, int S, double DTs, double T, double Dt_bc, long long* nviolation);
 /* ModRamWPI (src/ModRamWPI.f90) */
 int rsg_wavelo(rsg_ram* h, int S, double DTs);                       /* :580-636 */
 int rsg_wpadif(rsg_ram* h, int S, double DTs, long long* nviolation); /* :643-714; nviolation may be NULL */

@@ -49,6 +49,8 @@ def ram_lib():
             fn.restype = None
         lib.orc_wpadif.argtypes = [C.c_void_p, C.c_int]
         lib.orc_wpadif.restype = C.c_long
+        lib.orc_flcscatter.argtypes = [C.c_void_p, C.c_int]
+        lib.orc_flcscatter.restype = C.c_long
         lib.orc_ram_run.argtypes = [C.c_void_p, C.c_int, C.c_int]
         lib.orc_ram_run.restype = C.c_double
         lib.orc_get_cdrift.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
@@ -91,7 +93,7 @@ class RamOracle:
         self._set("CHARGE", _f((nS, NR, NT, NE, NPA)))
         self._set("FLUX", _f((nS, NR, NT, NE, NPA)))
         self._set("ATLOS", _f((nS, NR, NE)))
-        for name in ("ATAW", "ATAC", "ATAW_emic_h", "ATAW_emic_he"):
+        for name in ("ATAW", "ATAC", "ATAW_emic_h", "ATAW_emic_he", "FLC_coef"):
             self._set(name, _f((NR, NT, NE, NPA)))
         for name in ("COULE", "COULI", "ATA", "GTA", "CEDR", "CIDR"):
             self._set(name, _f((nS, NE, NPA)))
@@ -101,7 +103,7 @@ class RamOracle:
         self._set("PPERT", _f((nS, NR, NT)))
         self._set("PPART", _f((nS, NR, NT)))
         for name, v in (("MDR", g.MDR), ("DPHI", g.DPHI), ("CONF1", g.CONF1), ("CONF2", g.CONF2),
-                        ("Kp", inp.Kp), ("Kpmax12", inp.Kpmax12), ("DTs", DTs)):
+                        ("Kp", inp.Kp), ("Kpmax12", inp.Kpmax12), ("DTs", DTs), ("T", 0.0), ("Dt_bc", 300.0)):
             self.set_scalar(name, v)
 
     def _set(self, name, a):

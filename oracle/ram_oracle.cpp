@@ -9,6 +9,7 @@
 //   CEPARA/CHAREXCHANGE/ATMOL                src/ModRamLoss.f90:19-170,457-507
 //   WAVELO/WPADIF                            src/ModRamWPI.f90:580-714
 //   COULPARA/COULEN/COULMU                   src/ModRamCoul.f90:17-296
+//   FLCscatter                               src/ModRamLoss.f90:513-575
 //   SUMRC/ANISCH(moments)/ram_run            src/ModRamRun.f90:16-415
 //   Gcoul/FUNT/FUNI                          src/ModRamFunctions.f90:72-143
 //
@@ -587,6 +588,50 @@ long wpadif(Orc* o, int S) {
   return nviol;
 }
 
+// FLCscatter  src/ModRamLoss.f90:513-575: field-line-curvature scattering, the same
+// implicit pitch-angle diffusion with the single coefficient array FLC_coef(S,I,J,K,L)
+// (here the (I,J,K,L) slab of species S, "FLC_coef").  Skipped during the first
+// boundary cycle (TimeRamElapsed < Dt_bc, :523).  Returns the number of lines the
+// reference would have logged to flc_cf_ion.dat (:548-555).
+long flcscatter(Orc* o, int S) {
+  DIMS
+  const double DTs = o->S("DTs");
+  if (o->S("T") < o->S("Dt_bc")) return 0;
+  double* F2 = o->D("F2");
+  const double *FNHS = o->D("FNHS"), *MU = o->D("MU"), *DMU = o->D("DMU"), *WMU = o->D("WMU"), *D = o->D("FLC_coef");
+  std::vector<double> F(NPA, 0.0), RK(NPA, 0.0), RL(NPA, 0.0), FACMU(NPA, 0.0);
+  long nviol = 0;
+  for (int J = 1; J <= NT; ++J)
+    for (int I = 2; I <= NR; ++I)
+      for (int K = 2; K <= NE; ++K) {
+        for (int L = 2; L <= NPA; ++L) {
+          A1(FACMU, L) = FNHS_(I, J, L) * A1(MU, L);
+          A1(F, L) = F2_(S, I, J, K, L) / A1(FACMU, L);
+        }
+        A1(FACMU, 1) = FNHS_(I, J, 1) * A1(MU, 1);
+        A1(F, 1) = A1(F, 2);
+        A1(RK, 1) = 0.;
+        A1(RL, 1) = -1.;
+        for (int L = 2; L <= NPA - 1; ++L) {
+          double AN = A4(D, NR, NT, NE, I, J, K, L) / A1(DMU, L);
+          double GN = A4(D, NR, NT, NE, I, J, K, L - 1) / A1(DMU, L - 1);
+          AN = AN * DTs / A1(FACMU, L) / A1(WMU, L);
+          GN = GN * DTs / A1(FACMU, L) / A1(WMU, L);
+          double BN = AN + GN;
+          if (std::fabs(-1 - BN) < (std::fabs(AN) + std::fabs(GN))) ++nviol;
+          double RP = A1(F, L);
+          double DENOM = BN + GN * A1(RL, L - 1) + 1;
+          A1(RK, L) = (RP + GN * A1(RK, L - 1)) / DENOM;
+          A1(RL, L) = -AN / DENOM;
+        }
+        F2_(S, I, J, K, NPA - 1) = A1(RK, NPA - 1) / (1 + A1(RL, NPA - 1));
+        for (int L = NPA - 2; L >= 1; --L) F2_(S, I, J, K, L) = A1(RK, L) - A1(RL, L) * F2_(S, I, J, K, L + 1);
+        F2_(S, I, J, K, NPA) = F2_(S, I, J, K, NPA - 1);
+        for (int L = 1; L <= NPA; ++L) F2_(S, I, J, K, L) = F2_(S, I, J, K, L) * A1(FACMU, L);
+      }
+  return nviol;
+}
+
 // -----------------------------------------------------------------------------
 // COULPARA  src/ModRamCoul.f90:17-125.  The plasmasphere species table is the
 // reference's RAMSpecies(1:6) (src/ModRamSpecies.f90:42-133): mass, charge,
@@ -911,6 +956,7 @@ void orc_charexchange(void* h, int S) { charexchange((Orc*)h, S); }
 void orc_atmol(void* h, int S) { atmol((Orc*)h, S); }
 void orc_wavelo(void* h, int S) { wavelo((Orc*)h, S); }
 long orc_wpadif(void* h, int S) { return wpadif((Orc*)h, S); }
+long orc_flcscatter(void* h, int S) { return flcscatter((Orc*)h, S); }
 void orc_coulpara(void* h, int S) { coulpara((Orc*)h, S); }
 void orc_coulen(void* h, int S) { coulen((Orc*)h, S); }
 void orc_coulmu(void* h, int S) { coulmu((Orc*)h, S); }

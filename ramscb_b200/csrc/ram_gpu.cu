@@ -73,6 +73,7 @@ struct Spec {
   double* d_part = nullptr;  // moment partials [nblk_sum][RSG_NMOM]
   double* d_tE = nullptr;    // ANISCH scratch [2][nch][NE][Pp]
   double* d_rFFA = nullptr;  // FAST ANISCH: 1/A(S,I,K) [k][i]
+  double* d_flc = nullptr;   // FLC_coef of this species [l][k][Pp] (allocated by rsg_ram_set_flc_coef)
   double* d_coul = nullptr;  // COULPARA tables COULE, COULI, ATA, GTA, each [k][l]
   double DTs_coul = -1.0;    // DTs of the last COULPARA
   unsigned long long* d_res = nullptr;  // slice of rsg_ram::d_res_all
@@ -410,13 +411,16 @@ int L_loss_mid(rsg_ram* h, int s0, int ns, int doA, double DTs, int slot, cudaSt
   h->launches += 2;
   return RSG_OK;
 }
-int L_wpadif(rsg_ram* h, int s, double DTs, cudaStream_t st, int k0 = 0, int nk = -1) {
+// flc: FLCscatter (src/ModRamLoss.f90:513-575) = the same kernel with the species' FLC_coef as
+// the only coefficient array
+int L_wpadif(rsg_ram* h, int s, double DTs, cudaStream_t st, int k0 = 0, int nk = -1, bool flc = false) {
   if (nk < 0) nk = h->NE - k0;
   Spec& sp = h->sp[s];
   const double *DA, *DB;
-  if (h->kind[s] == RSG_KIND_E) { DA = h->d_diff[0]; DB = h->d_diff[1]; }
+  if (flc) { DA = sp.d_flc; DB = nullptr; }
+  else if (h->kind[s] == RSG_KIND_E) { DA = h->d_diff[0]; DB = h->d_diff[1]; }
   else { DA = h->d_diff[2]; DB = h->d_diff[3]; }
-  if (!DA && !DB) return fail(RSG_ERR_STATE, "WPADIF before set_diffcoef");
+  if (!DA && !DB) return fail(RSG_ERR_STATE, flc ? "FLCscatter before set_flc_coef" : "WPADIF before set_diffcoef");
   sp.sd.DA = DA ? DA : h->d_zero4;
   sp.sd.DB = DB ? DB : h->d_zero4;
   SpecPack pk;
@@ -1154,6 +1158,20 @@ int rsg_ram_set_diffcoef(rsg_ram* h, int which, const double* D) {
   return RSG_OK;
 }
 
+// FLC_coef(S,:,:,:,:) of one species, as a contiguous (NR,NT,NE,NPA) array (the output of PARA_FLC)
+int rsg_ram_set_flc_coef(rsg_ram* h, int S, const double* D) {
+  RET(check_S(h, S));
+  if (!D) return fail(RSG_ERR_ARG, "null argument");
+  CK(cudaSetDevice(h->device));
+  RET(rsg_ram_sync(h));
+  Spec& sp = h->sp[S - 1];
+  if (!sp.d_flc) RET(h->dalloc(&sp.d_flc, h->specStride));
+  std::vector<double> b;
+  to_planes4(h, D, b);
+  RET(up(sp.d_flc, b.data(), b.size()));
+  return RSG_OK;
+}
+
 // ---- F2 transfers -------------------------------------------------------------
 int rsg_ram_f2_h2d(rsg_ram* h, const double* F2, int S) {
   if (!h || !F2) return fail(RSG_ERR_ARG, "null argument");
@@ -1286,6 +1304,23 @@ int rsg_wpadif(rsg_ram* h, int S, double DTs, long long* nviolation) {
   CK(cudaSetDevice(h->device));
   const int s = S - 1;
   RET(L_wpadif(h, s, DTs, h->st(s)));
+  if (nviolation) {
+    RET(fetch_res(h, s, h->st(s)));
+    *nviolation = (long long)h->sp[s].h_res[4 + NSUM];
+  }
+  return RSG_OK;
+}
+
+// FLCscatter (src/ModRamLoss.f90:513-575).  The reference skips it during the first boundary
+// cycle (TimeRamElapsed < Dt_bc): the caller passes both times.
+int rsg_flcscatter(rsg_ram* h, int S, double DTs, double T, double Dt_bc, long long* nviolation) {
+  RET(check_S(h, S));
+  if (!h->fields_set) return fail(RSG_ERR_STATE, "FLCscatter before set_fields");
+  if (nviolation) *nviolation = 0;
+  if (T < Dt_bc) return RSG_OK;
+  CK(cudaSetDevice(h->device));
+  const int s = S - 1;
+  RET(L_wpadif(h, s, DTs, h->st(s), 0, -1, true));
   if (nviolation) {
     RET(fetch_res(h, s, h->st(s)));
     *nviolation = (long long)h->sp[s].h_res[4 + NSUM];

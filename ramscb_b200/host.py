@@ -58,6 +58,8 @@ def lib():
     L.rsg_ram_set_boundary.argtypes = [vp, vp]
     L.rsg_ram_set_wavelo.argtypes = [vp, vp, vp, vp, d, d]
     L.rsg_ram_set_plasmasphere.argtypes = [vp, vp]
+    L.rsg_ram_set_flc_coef.argtypes = [vp, i, vp]
+    L.rsg_flcscatter.argtypes = [vp, i, d, d, d, C.POINTER(C.c_longlong)]
     L.rsg_ram_set_diffcoef.argtypes = [vp, i, vp]
     L.rsg_ram_f2_h2d.argtypes = [vp, vp, i]
     L.rsg_ram_f2_d2h.argtypes = [vp, vp, i]
@@ -219,6 +221,14 @@ class RamGpu:
     def CHAREXCHANGE(self, S): _ck(self.L.rsg_charexchange(self.h, S))
     def ATMOL(self, S): _ck(self.L.rsg_atmol(self.h, S))
     def WAVELO(self, S, DTs): _ck(self.L.rsg_wavelo(self.h, S, DTs))
+    def set_flc_coef(self, S, D):
+        _ck(self.L.rsg_ram_set_flc_coef(self.h, S, _p(np.asfortranarray(D, dtype=np.float64))))
+
+    def FLCscatter(self, S, DTs, T, Dt_bc=300.0):
+        nv = C.c_longlong()
+        _ck(self.L.rsg_flcscatter(self.h, S, DTs, T, Dt_bc, C.byref(nv)))
+        return nv.value
+
     def COULPARA(self, S, DTs): _ck(self.L.rsg_coulpara(self.h, S, DTs))
     def COULEN(self, S): _ck(self.L.rsg_coulen(self.h, S))
     def COULMU(self, S, T=0.0): _ck(self.L.rsg_coulmu(self.h, S, T))

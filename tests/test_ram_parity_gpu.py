@@ -164,6 +164,28 @@ def test_wpadif_bit_exact(default_grids, oracle_built, kind):
     assert not np.array_equal(got[S - 1], inp.F2[S - 1])
 
 
+def test_flcscatter_bit_exact(default_grids, oracle_built):
+    """FLCscatter (src/ModRamLoss.f90:513-575): implicit pitch-angle diffusion with the
+    species' FLC_coef; a no-op during the first boundary cycle (T < Dt_bc)."""
+    g = default_grids
+    inp = _mk(g, f2_kind="noisy")
+    D = 3.0 * synthetic.synthetic_daa(g, inp)
+    o, gpu = _pair(g, inp, oracle_built)
+    S = 2
+    o.set_array("FLC_coef", D)
+    gpu.set_flc_coef(S, D)
+    o.set_scalar("T", 100.0)
+    assert o.op("flcscatter", S) == 0 and gpu.FLCscatter(S, DTS, 100.0) == 0
+    assert np.array_equal(gpu.f2_d2h(), inp.F2)                 # first cycle: skipped
+    o.set_scalar("T", 900.0)
+    nv_ref = o.op("flcscatter", S)
+    nv = gpu.FLCscatter(S, DTS, 900.0)
+    got = gpu.f2_d2h()
+    assert np.array_equal(got[S - 1], o.F2[S - 1]), _relerr(got[S - 1], o.F2[S - 1])
+    assert nv == nv_ref
+    assert not np.array_equal(got[S - 1], inp.F2[S - 1])
+
+
 @pytest.mark.parametrize("S", [1, 2, 4])
 def test_coulomb_operators_bit_exact(default_grids, oracle_built, S):
     """COULPARA tables + COULEN (energy drag) + COULMU (pitch-angle scattering),
