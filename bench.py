@@ -125,6 +125,46 @@ def cpu_reference(g, inp, steps, warmup):
     return OPS_PER_STEP * cells / dt, nthreads, dt
 
 
+def scb_metrics(device):
+    """The second half of BASELINE.json's metric: SCB SOR sweeps/s.  One Euler-potential solve on
+    the default SCB grid (configs[3]: 101 x 45 x 97, synthetic anisotropic pressure) through the
+    C ABI: computeBandJacob, metrica+newk, iterateAlpha, metric+newj, iteratePsi to the reference's
+    tolerance (InConAlpha = InConPsi = 1e-6), 4-colour ordering.  Device times of the calls
+    (rsg_scb_last_ms, CUDA events), median of 3 solves from the same start."""
+    from ramscb_b200 import host, scb_synthetic
+    inp = scb_synthetic.build_scb(nthe=101, npsi=45, nzeta=97, warp=0.2)
+    gpu = host.ScbGpu(inp, device=device)
+    alfa0, psi0 = gpu.get_field("alfa").copy(), gpu.get_field("psi").copy()
+    npts_a = (inp.npsi - 2) * (inp.nzeta - 1) * (inp.nthe - 8)   # jz=2..npsi-1, k=2..nzeta, iz=1+nT..nthe-nT (nT=4)
+    npts_p = (inp.nzeta - 1) * (inp.npsi - 2) * (inp.nthe - 8)
+    runs = []
+    for _ in range(3):
+        gpu.set_field("alfa", alfa0)
+        gpu.set_field("psi", psi0)
+        r = {}
+        gpu.computeBandJacob(); r["bandjacob_ms"] = gpu.last_ms()
+        gpu.metrica(); r["metrica_ms"] = gpu.last_ms()
+        gpu.newk()
+        ra = gpu.iterateAlpha(1e-6, ordering=host.SOR_COLOR4)
+        gpu.metric(); r["metric_ms"] = gpu.last_ms()
+        gpu.newj()
+        rp = gpu.iteratePsi(1e-6, ordering=host.SOR_COLOR4)
+        r["alpha"], r["psi"] = ra, rp
+        runs.append(r)
+    runs.sort(key=lambda r: r["alpha"]["ms"] + r["psi"]["ms"])
+    r = runs[1]
+    out = {"grid": "nthe=101 npsi=45 nzeta=97 (configs[3]), synthetic anisotropic pressure, tol 1e-6, 4-colour SOR",
+           "bandjacob_ms": r["bandjacob_ms"], "metrica_ms": r["metrica_ms"], "metric_ms": r["metric_ms"]}
+    for name, rr, npts in (("iterate_alpha", r["alpha"], npts_a), ("iterate_psi", r["psi"], npts_p)):
+        sweeps = int(np.sum(rr["ni"]))          # sub-problem sweeps, summed over the independent sub-problems
+        nsub = int(np.count_nonzero(rr["ni"]))
+        full = sweeps / max(nsub, 1)             # equivalent sweeps over all sub-problems
+        out[name] = {"ms": rr["ms"], "max_sweeps": int(rr["nisave"]), "mean_sweeps": full, "SORFail": int(rr["SORFail"]),
+                     "sweeps_per_s": full / (rr["ms"] * 1e-3), "point_updates_per_s": full * npts / (rr["ms"] * 1e-3)}
+    gpu.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -132,6 +172,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="default", choices=["default", "x4"])
+    ap.add_argument("--no-scb", action="store_true", help="skip the SCB solve metrics")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"],
                     help="arithmetic mode of the sweeps (include/ramscb_gpu.h rsg_mode)")
@@ -303,6 +344,8 @@ def main():
                        if world > 1 else "1 GPU, all species per launch"},
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "wall_s_timed_region": wall_s}
+    if rank == 0 and world == 1 and not a.no_scb:
+        line["scb"] = scb_metrics(local_rank)
     if rank == 0 and not a.no_cpu_baseline:
         v, nthreads, dt = cpu_reference(g, inp, 3 if a.workload == "default" else 1, 1)
         line["cpu_baseline"] = {"value": v, "unit": unit, "cores": nthreads, "kind": "port",

@@ -262,6 +262,12 @@ int rsg_scb_convergence(rsg_scb* h, double* normDiff, double* normJxB, double* n
 int rsg_scb_derivs(rsg_scb* h, const double* f, double* dfdTheta, double* dfdRho, double* dfdZeta);
 /* device time (CUDA events on the launching stream) of the kernels of the last call */
 double rsg_scb_last_ms(rsg_scb* h);
+/* RSG_SOR_COLOR4 runs on thread-block clusters (2..8 CTAs per sub-problem) with the unknown and all
+ * ten coefficient arrays resident in distributed shared memory for the whole solve when they fit
+ * (default on); 0 selects one CTA per sub-problem with coefficients streamed from L2.  Results are
+ * bit-identical either way.  rsg_scb_last_cluster: cluster size the last solve used (0 = none). */
+int rsg_scb_use_cluster(rsg_scb* h, int on);
+int rsg_scb_last_cluster(rsg_scb* h);
 long long rsg_scb_launch_count(rsg_scb* h);
 
 #ifdef __cplusplus

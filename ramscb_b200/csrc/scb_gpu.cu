@@ -60,6 +60,8 @@ struct rsg_scb {
   bool grid_set = false, geom_set = false, press_set = false, band_done = false;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   double last_ms = 0.0;
+  bool use_cluster = true;   // 4-colour SOR on thread-block clusters with the problem resident on chip
+  int last_cluster = 0;      // cluster size of the last SOR launch (0: one CTA per sub-problem)
 
   int dalloc(double** p, size_t n, const char* name) {
     void* q = nullptr;
@@ -329,7 +331,59 @@ static int scb_iterate(rsg_scb* h, bool alpha, double tol, int nimax, int theCha
   const int nr = alpha ? (nzeta - 1) : (npsi - nP - 1);
   const int threads = ordering == RSG_SOR_LEX ? std::min(1024, (nr + 31) / 32 * 32) : 1024;
   if (ordering == RSG_SOR_LEX && nr > 1024) return sfail(RSG_ERR_UNSUPPORTED, "too many rows for the lexicographic SOR kernel");
+  // 4-colour ordering: a cluster of CL CTAs per sub-problem keeps the unknown AND the ten
+  // coefficient arrays in (distributed) shared memory for the whole solve
+  int CL = 0, nloc_max = 0, npc_max = 0;
+  size_t csmem = 0;
+  bool in_regs = false;     // coefficients in registers: one point per colour per thread (<= 576)
+  if (ordering != RSG_SOR_LEX && h->use_cluster && !getenv("RSG_SCB_NO_CLUSTER")) {
+    const int nc = nthe - 2 * nT;
+    if (!getenv("RSG_SCB_NO_REGS"))
+      for (int c = 1; c <= 8; c *= 2) {
+        const int nl = (nr + c - 1) / c;
+        const int npc = ((nl + 1) / 2) * ((nc + 1) / 2);
+        if (npc <= 576 && nl >= 2) {
+          CL = c; nloc_max = nl; npc_max = npc; in_regs = true;
+          csmem = sizeof(double) * (size_t)(nl + 2) * nthe;
+          break;
+        }
+      }
+    for (int c = 1; c <= 8 && !in_regs; c *= 2) {
+      const int nl = (nr + c - 1) / c;
+      const int npc = ((nl + 1) / 2) * ((nc + 1) / 2);
+      const size_t b = sizeof(double) * ((size_t)(nl + 2) * nthe + (size_t)40 * npc);
+      if (b <= 220 * 1024 && nl >= 2) { CL = c; nloc_max = nl; npc_max = npc; csmem = b; break; }
+    }
+  }
+  h->last_cluster = CL;
   SCK(cudaEventRecord(h->e0, h->st));
+  if (CL > 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(nsub * CL);
+    cfg.blockDim = dim3(std::min(1024, (npc_max + 31) / 32 * 32));
+    cfg.dynamicSmemBytes = csmem;
+    cfg.stream = h->st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    if (in_regs && alpha) {
+      SCK(cudaFuncSetAttribute(k_scb_sor_cluster_reg<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+      SCK(cudaLaunchKernelEx(&cfg, k_scb_sor_cluster_reg<true>, h->dev, a, nloc_max));
+    } else if (in_regs) {
+      SCK(cudaFuncSetAttribute(k_scb_sor_cluster_reg<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+      SCK(cudaLaunchKernelEx(&cfg, k_scb_sor_cluster_reg<false>, h->dev, a, nloc_max));
+    } else if (alpha) {
+      SCK(cudaFuncSetAttribute(k_scb_sor_cluster<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+      SCK(cudaLaunchKernelEx(&cfg, k_scb_sor_cluster<true>, h->dev, a, nloc_max, npc_max));
+    } else {
+      SCK(cudaFuncSetAttribute(k_scb_sor_cluster<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+      SCK(cudaLaunchKernelEx(&cfg, k_scb_sor_cluster<false>, h->dev, a, nloc_max, npc_max));
+    }
+  } else {
 #define LAUNCH_SOR(A, O)                                                                                   \
   do {                                                                                                     \
     SCK(cudaFuncSetAttribute(k_scb_sor<A, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
@@ -340,6 +394,7 @@ static int scb_iterate(rsg_scb* h, bool alpha, double tol, int nimax, int theCha
   else if (ordering == RSG_SOR_LEX) LAUNCH_SOR(false, 0);
   else LAUNCH_SOR(false, 1);
 #undef LAUNCH_SOR
+  }
   SCKL();
   SCK(cudaEventRecord(h->e1, h->st));
   k_scb_sums<<<nzeta - 1, 256, 0, h->st>>>(h->dev, u, h->d_prev, h->d_part);
@@ -453,6 +508,12 @@ int rsg_scb_derivs(rsg_scb* h, const double* f, double* dT, double* dR, double* 
 }
 
 double rsg_scb_last_ms(rsg_scb* h) { return h ? h->last_ms : 0.0; }
+int rsg_scb_use_cluster(rsg_scb* h, int on) {
+  if (!h) return sfail(RSG_ERR_ARG, "null handle");
+  h->use_cluster = on != 0;
+  return RSG_OK;
+}
+int rsg_scb_last_cluster(rsg_scb* h) { return h ? h->last_cluster : 0; }
 long long rsg_scb_launch_count(rsg_scb* h) { return h ? h->launches : 0; }
 
 }  // extern "C"

@@ -552,3 +552,291 @@ __global__ void __launch_bounds__(128) k_scb_conv2(ScbDev d, double bnormal, dou
     }
   }
 }
+
+// =============================================================================
+// k_scb_sor_cluster: the 4-colour SOR of iterateAlpha / iteratePsi with the WHOLE
+// problem resident on chip.  A thread-block cluster of CL CTAs owns one independent
+// sub-problem (a psi surface for alpha, a zeta plane for psi); the updated rows are cut
+// into CL slabs.  Each CTA keeps in shared memory, for the life of the solve,
+//   * its rows of the unknown plus one halo row on either side, and
+//   * the nine stencil coefficients and the right-hand side of its points, packed
+//     colour-major (unit-stride, conflict-free reads),
+// i.e. after the initial load no sweep touches L2/HBM ("coefficients held in
+// (distributed) shared memory for the whole solve").  After a colour phase the boundary-row
+// updates are pushed into the neighbour CTA's halo row through distributed shared memory;
+// two cluster barriers per sweep (at the row-parity switches of the colour sequence) make them
+// visible; the per-sweep max|resid| and the failure flag travel the same way.  Per point the arithmetic and the colour order are those of
+// k_scb_sor<.,1>: potentials, iteration counts and residual maxima are bit-identical.
+// grid: nsub*CL CTAs, cluster (CL,1,1); smem: see scb_gpu.cu
+// =============================================================================
+#include <cooperative_groups.h>
+
+template <bool ALPHA>
+__global__ void __launch_bounds__(1024) k_scb_sor_cluster(ScbDev d, SorArgs a, int nloc_max, int npc_max) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ double sm[];
+  __shared__ double s_red[32];
+  __shared__ double s_xmax[8];   // per-rank max|resid| of the sweep (every rank's written by its owner)
+  __shared__ int s_xfail[8];
+  const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+  const int nthe = d.nthe, npsi = d.npsi, nzeta = d.nzeta;
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int sub = blockIdx.x / CL;
+  const int r0 = 1, r1 = ALPHA ? nzeta - 1 : npsi - a.nP - 1;   // updated rows (0-based, inclusive)
+  const int c0 = a.nT, c1 = nthe - a.nT - 1;                    // updated columns
+  const int nr = r1 - r0 + 1;
+  const int nloc_nom = (nr + CL - 1) / CL;
+  const int rb = r0 + rank * nloc_nom;                          // my first row
+  const int nloc = max(0, min(nloc_nom, r1 - rb + 1));          // my rows: rb .. rb+nloc-1
+  const size_t sj = nthe, sk = (size_t)nthe * npsi;
+  double* u = ALPHA ? d.alfa : d.psi;
+  const size_t base = ALPHA ? sj * (size_t)(sub + 1) : sk * (size_t)(sub + 1);
+  const size_t rstride = ALPHA ? sk : sj;
+  // shared layout: su[(nloc_max+2)][nthe] | coef[4 colours][10][npc_max]
+  double* su = sm;
+  double* sc = sm + (size_t)(nloc_max + 2) * nthe;
+  // local row lr = 0 is global row rb-1, lr = 1..nloc my rows, lr = nloc+1 global row rb+nloc
+  for (int q = tid; q < (nloc + 2) * nthe; q += T) {
+    const int lr = q / nthe, c = q - lr * nthe;
+    su[q] = u[base + (size_t)(rb - 1 + lr) * rstride + c];
+  }
+  const double* rhs = ALPHA ? d.vecx : d.vecr;
+  const double* cf[10] = {d.vecd, d.vec1, d.vec2, d.vec3, d.vec4, d.vec6, d.vec7, d.vec8, d.vec9, rhs};
+  int rs_[4], cs_[4], ncc_[4], np_[4];
+  for (int col = 0; col < 4; ++col) {
+    const int pc = col & 1, pr = col >> 1;
+    const int cs = c0 + (((c0 & 1) == pc) ? 0 : 1);
+    const int rs = rb + (((rb & 1) == pr) ? 0 : 1);             // global row parity, as the one-CTA kernel
+    const int rend = rb + nloc - 1;
+    const int ncc = (cs <= c1) ? (c1 - cs) / 2 + 1 : 0;
+    const int nrr = (rs <= rend) ? (rend - rs) / 2 + 1 : 0;
+    rs_[col] = rs; cs_[col] = cs; ncc_[col] = ncc; np_[col] = ncc * nrr;
+    for (int w = tid; w < ncc * nrr; w += T) {
+      const int rr = w / ncc, cc = w - rr * ncc;
+      const size_t q = base + (size_t)(rs + 2 * rr) * rstride + (cs + 2 * cc);
+#pragma unroll
+      for (int m = 0; m < 10; ++m) sc[((size_t)col * 10 + m) * npc_max + w] = cf[m][q];
+    }
+  }
+  if (tid < 8) { s_xmax[tid] = 0.0; s_xfail[tid] = 0; }
+  cluster.sync();
+  double* su_prev = (rank > 0) ? cluster.map_shared_rank(su, rank - 1) : nullptr;
+  double* su_next = (rank < CL - 1) ? cluster.map_shared_rank(su, rank + 1) : nullptr;
+  const int nloc_prev = nloc_nom;                               // every rank before the last has nloc_nom rows
+  double om = 1.0;
+  int ni = 1;
+  double lastmax = 0.0;
+  bool failed = false, stopped = false;
+  while (ni <= a.nimax) {
+    double rmax = 0.0;
+    for (int col = 0; col < 4; ++col) {
+      const int rs = rs_[col], cs = cs_[col], ncc = ncc_[col], np = np_[col];
+      const double* k0 = sc + (size_t)col * 10 * npc_max;
+      for (int w = tid; w < np; w += T) {
+        const int rr = w / ncc, cc = w - rr * ncc;
+        const int r = rs + 2 * rr, c = cs + 2 * cc;
+        const int lr = r - rb + 1;
+        const double* um = su + (lr - 1) * nthe + c;
+        double* uc = su + lr * nthe + c;
+        const double* up = su + (lr + 1) * nthe + c;
+        const double vd = k0[w];
+        const double res = -vd * uc[0] + k0[npc_max + w] * um[-1] + k0[2 * npc_max + w] * um[0] + k0[3 * npc_max + w] * um[1] +
+                           k0[4 * npc_max + w] * uc[-1] + k0[5 * npc_max + w] * uc[1] + k0[6 * npc_max + w] * up[-1] +
+                           k0[7 * npc_max + w] * up[0] + k0[8 * npc_max + w] * up[1] - k0[9 * npc_max + w];
+        double un = ALPHA ? (uc[0] + om * (res / vd)) : (uc[0] + om * res / vd);
+        double rr2 = res;
+        if (isnan(un) || un >= 1e10) {   // :226-240 / :539-553
+          un = u[base + (size_t)r * rstride + c];
+          rr2 = 0.0;
+          failed = true;
+        }
+        uc[0] = un;
+        if (lr == 1 && su_prev) su_prev[(nloc_prev + 1) * nthe + c] = un;     // neighbour's lower halo row
+        if (lr == nloc && su_next) su_next[c] = un;                           // neighbour's upper halo row
+        if (c >= 1 && c <= nthe - 2) rmax = fmax(rmax, fabs(rr2));
+      }
+      // Colours 0,1 update the even rows, 2,3 the odd rows.  A point reads the neighbour CTA's
+      // rows only through its halo row, whose parity is the opposite of the point's own row: the
+      // halo values a colour needs were written two or three colours earlier.  So a CTA barrier
+      // separates 0|1 and 2|3, and only the row-parity switches 1|2 and 3|0 need the cluster.
+      if (col == 0 || col == 2) {
+        __syncthreads();
+      } else if (col == 1) {
+        cluster.sync();
+      } else {
+        // last colour: CTA max of |resid| over the sweep + failure flag, published to every rank
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+        if ((tid & 31) == 0) s_red[tid >> 5] = rmax;
+        const int anyfail = __syncthreads_or(failed ? 1 : 0);
+        if (tid < CL) {
+          double m = 0.0;
+          for (int q = 0; q < (T + 31) / 32; ++q) m = fmax(m, s_red[q]);
+          double* xm = cluster.map_shared_rank(s_xmax, tid);
+          int* xf = cluster.map_shared_rank(s_xfail, tid);
+          xm[rank] = m;
+          xf[rank] = anyfail;
+        }
+        cluster.sync();
+      }
+    }
+    double m = 0.0;
+    int stop = 0;
+    for (int q = 0; q < CL; ++q) { m = fmax(m, s_xmax[q]); stop |= s_xfail[q]; }
+    lastmax = m;
+    if (stop) { stopped = true; break; }   // EXIT Iterations on failure (ni not advanced)
+    om = a.omegaOpt;
+    if (m < a.tol) break;                  // converged
+    ni = ni + 1;
+  }
+  for (int q = tid; q < nloc * nthe; q += T) {
+    const int lr = 1 + q / nthe, c = q % nthe;
+    if (c >= c0 && c <= c1) u[base + (size_t)(rb + lr - 1) * rstride + c] = su[lr * nthe + c];
+  }
+  if (rank == 0 && tid == 0) {
+    a.ni[sub] = ni;
+    a.resmax[sub] = lastmax;
+    if (stopped) *a.fail = 1;
+  }
+  cluster.sync();   // no CTA may exit while a neighbour can still write into its shared memory
+}
+
+// =============================================================================
+// k_scb_sor_cluster_reg: the same cluster solve with the coefficients in REGISTERS.  When a
+// CTA has at most one point per colour per thread (<= 576 points per colour), thread t owns
+// the t-th point of each of the four colours for the whole solve: its 4 x 10 coefficients
+// stay in 80 registers, and shared memory holds only the unknown (rows + 2 halo rows).  A
+// sweep then is 9 shared loads, the stencil arithmetic and one store per point: no
+// coefficient traffic at all, not even from shared memory.  Same arithmetic, colour order,
+// halo pushes and barriers as k_scb_sor_cluster: bit-identical results.
+// =============================================================================
+template <bool ALPHA>
+__global__ void __launch_bounds__(576, 1) k_scb_sor_cluster_reg(ScbDev d, SorArgs a, int nloc_max) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ double su[];
+  __shared__ double s_red[32];
+  __shared__ double s_xmax[8];
+  __shared__ int s_xfail[8];
+  const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+  const int nthe = d.nthe, npsi = d.npsi, nzeta = d.nzeta;
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int sub = blockIdx.x / CL;
+  const int r0 = 1, r1 = ALPHA ? nzeta - 1 : npsi - a.nP - 1;
+  const int c0 = a.nT, c1 = nthe - a.nT - 1;
+  const int nr = r1 - r0 + 1;
+  const int nloc_nom = (nr + CL - 1) / CL;
+  const int rb = r0 + rank * nloc_nom;
+  const int nloc = max(0, min(nloc_nom, r1 - rb + 1));
+  const size_t sj = nthe, sk = (size_t)nthe * npsi;
+  double* u = ALPHA ? d.alfa : d.psi;
+  const size_t base = ALPHA ? sj * (size_t)(sub + 1) : sk * (size_t)(sub + 1);
+  const size_t rstride = ALPHA ? sk : sj;
+  for (int q = tid; q < (nloc + 2) * nthe; q += T) {
+    const int lr = q / nthe, c = q - lr * nthe;
+    su[q] = u[base + (size_t)(rb - 1 + lr) * rstride + c];
+  }
+  const double* rhs = ALPHA ? d.vecx : d.vecr;
+  const double* cf[10] = {d.vecd, d.vec1, d.vec2, d.vec3, d.vec4, d.vec6, d.vec7, d.vec8, d.vec9, rhs};
+  double* su_prev = (rank > 0) ? cluster.map_shared_rank(su, rank - 1) : nullptr;
+  double* su_next = (rank < CL - 1) ? cluster.map_shared_rank(su, rank + 1) : nullptr;
+  const int nloc_prev = nloc_nom;
+  // my point of every colour: coefficients, shared-memory offset, global index, halo targets
+  double kk[4][10];
+  int off[4];       // shared-memory offset of the point (0: no point of this colour)
+  int pushoff[4];   // > 0: offset in the next CTA's block, < 0: -(offset in the previous CTA's block), 0: none
+#pragma unroll
+  for (int col = 0; col < 4; ++col) {
+    const int pc = col & 1, pr = col >> 1;
+    const int cs = c0 + (((c0 & 1) == pc) ? 0 : 1);
+    const int rs = rb + (((rb & 1) == pr) ? 0 : 1);
+    const int rend = rb + nloc - 1;
+    const int ncc = (cs <= c1) ? (c1 - cs) / 2 + 1 : 0;
+    const int nrr = (rs <= rend) ? (rend - rs) / 2 + 1 : 0;
+    const bool valid = tid < ncc * nrr;
+    off[col] = 0; pushoff[col] = 0;
+#pragma unroll
+    for (int m = 0; m < 10; ++m) kk[col][m] = (m == 0) ? 1.0 : 0.0;
+    if (valid) {
+      const int rr = tid / ncc, cc = tid - rr * ncc;
+      const int r = rs + 2 * rr, c = cs + 2 * cc;
+      const int lr = r - rb + 1;
+      off[col] = lr * nthe + c;                                 // >= nthe
+      const size_t gq = base + (size_t)r * rstride + c;
+#pragma unroll
+      for (int m = 0; m < 10; ++m) kk[col][m] = cf[m][gq];
+      if (lr == 1 && su_prev) pushoff[col] = -((nloc_prev + 1) * nthe + c);
+      if (lr == nloc && su_next) pushoff[col] = c;              // (a one-row slab is excluded by the host)
+    }
+  }
+  if (tid < 8) { s_xmax[tid] = 0.0; s_xfail[tid] = 0; }
+  cluster.sync();
+  double om = 1.0;
+  int ni = 1;
+  double lastmax = 0.0;
+  bool failed = false, stopped = false;
+  while (ni <= a.nimax) {
+    double rmax = 0.0;
+#pragma unroll
+    for (int col = 0; col < 4; ++col) {
+      if (off[col]) {
+        double* uc = su + off[col];
+        const double* um = uc - nthe;
+        const double* up = uc + nthe;
+        const double vd = kk[col][0];
+        const double res = -vd * uc[0] + kk[col][1] * um[-1] + kk[col][2] * um[0] + kk[col][3] * um[1] + kk[col][4] * uc[-1] +
+                           kk[col][5] * uc[1] + kk[col][6] * up[-1] + kk[col][7] * up[0] + kk[col][8] * up[1] - kk[col][9];
+        double un = ALPHA ? (uc[0] + om * (res / vd)) : (uc[0] + om * res / vd);
+        double rr2 = res;
+        if (isnan(un) || un >= 1e10) {
+          const int lr = off[col] / nthe, c = off[col] - lr * nthe;
+          un = u[base + (size_t)(rb + lr - 1) * rstride + c];
+          rr2 = 0.0;
+          failed = true;
+        }
+        uc[0] = un;
+        if (pushoff[col] > 0) su_next[pushoff[col]] = un;
+        else if (pushoff[col] < 0) su_prev[-pushoff[col]] = un;
+        rmax = fmax(rmax, fabs(rr2));      // every updated column lies in 1..nthe-2 (nT >= 2)
+      }
+      if (col == 0 || col == 2) {
+        __syncthreads();
+      } else if (col == 1) {
+        cluster.sync();
+      } else {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+        if ((tid & 31) == 0) s_red[tid >> 5] = rmax;
+        const int anyfail = __syncthreads_or(failed ? 1 : 0);
+        if (tid < CL) {
+          double m = 0.0;
+          for (int q = 0; q < (T + 31) / 32; ++q) m = fmax(m, s_red[q]);
+          double* xm = cluster.map_shared_rank(s_xmax, tid);
+          int* xf = cluster.map_shared_rank(s_xfail, tid);
+          xm[rank] = m;
+          xf[rank] = anyfail;
+        }
+        cluster.sync();
+      }
+    }
+    double m = 0.0;
+    int stop = 0;
+    for (int q = 0; q < CL; ++q) { m = fmax(m, s_xmax[q]); stop |= s_xfail[q]; }
+    lastmax = m;
+    if (stop) { stopped = true; break; }
+    om = a.omegaOpt;
+    if (m < a.tol) break;
+    ni = ni + 1;
+  }
+  for (int q = tid; q < nloc * nthe; q += T) {
+    const int lr = 1 + q / nthe, c = q % nthe;
+    if (c >= c0 && c <= c1) u[base + (size_t)(rb + lr - 1) * rstride + c] = su[lr * nthe + c];
+  }
+  if (rank == 0 && tid == 0) {
+    a.ni[sub] = ni;
+    a.resmax[sub] = lastmax;
+    if (stopped) *a.fail = 1;
+  }
+  cluster.sync();
+}

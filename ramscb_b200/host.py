@@ -373,6 +373,8 @@ def _scb_lib():
         L.rsg_scb_derivs.argtypes = [vp] * 5
         L.rsg_scb_last_ms.argtypes = [vp]
         L.rsg_scb_last_ms.restype = d
+        L.rsg_scb_use_cluster.argtypes = [vp, i]
+        L.rsg_scb_last_cluster.argtypes = [vp]
         L.rsg_scb_launch_count.argtypes = [vp]
         L.rsg_scb_launch_count.restype = ll
         _scb_ready = True
@@ -463,6 +465,12 @@ class ScbGpu:
 
     def last_ms(self):
         return self.L.rsg_scb_last_ms(self.h)
+
+    def use_cluster(self, on=True):
+        _sck(self.L.rsg_scb_use_cluster(self.h, 1 if on else 0))
+
+    def last_cluster(self):
+        return self.L.rsg_scb_last_cluster(self.h)
 
     def launch_count(self):
         return self.L.rsg_scb_launch_count(self.h)

@@ -111,6 +111,38 @@ def test_sor_color4_converged_fields(oracle_built):
     assert np.max(np.abs(a - b) / np.abs(b)) <= 1e-8
 
 
+@pytest.mark.parametrize("grid", [SMALL, dict(nthe=101, npsi=45, nzeta=97, warp=0.2), dict(nthe=75, npsi=30, nzeta=64, warp=0.25)])
+def test_sor_cluster_matches_single_cta(grid):
+    """The cluster/distributed-shared-memory SOR kernel (coefficients resident on chip, halo rows
+    pushed between the CTAs of a cluster) keeps the per-point arithmetic and the colour order of
+    the one-CTA 4-colour kernel: potentials, per-sub-problem sweep counts and residual maxima
+    must be bit-identical."""
+    from ramscb_b200.host import ScbGpu, SOR_COLOR4
+    inp = S.build_scb(**grid)
+    res = []
+    for cluster in (False, True):
+        gpu = ScbGpu(inp)
+        gpu.use_cluster(cluster)
+        gpu.computeBandJacob()
+        gpu.metrica(); gpu.newk()
+        ra = gpu.iterateAlpha(1e-7, ordering=SOR_COLOR4)
+        ca = gpu.last_cluster()
+        gpu.metric(); gpu.newj()
+        rp = gpu.iteratePsi(1e-7, ordering=SOR_COLOR4)
+        cp = gpu.last_cluster()
+        res.append((gpu.get_field("alfa"), gpu.get_field("psi"), ra, rp, ca, cp))
+        gpu.close()
+    (a0, p0, ra0, rp0, ca0, cp0), (a1, p1, ra1, rp1, ca1, cp1) = res
+    assert ca0 == 0 and cp0 == 0 and ca1 >= 1 and cp1 >= 1, (ca1, cp1)
+    if grid["nthe"] == 101:
+        assert ca1 == 4 and cp1 == 2      # default grid: 200 KB / 183 KB of shared memory per CTA
+    assert np.array_equal(ra0["ni"], ra1["ni"]) and np.array_equal(rp0["ni"], rp1["ni"])
+    assert ra0["diffmx"] == ra1["diffmx"] and rp0["diffmx"] == rp1["diffmx"]
+    assert ra0["SORFail"] == ra1["SORFail"] == 0 and rp0["SORFail"] == rp1["SORFail"] == 0
+    assert np.array_equal(a0, a1)
+    assert np.array_equal(p0, p1)
+
+
 def test_sor_manufactured_solution(oracle_built):
     """Known answer: pick a smooth alpha*, build the RHS as L(alpha*) with the oracle's
     own coefficients, solve on the GPU from the coordinate-aligned guess: alpha* comes back."""
