@@ -191,10 +191,12 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return
-        steps = max(1, min(a.steps, 5))
-        v, nthreads, dt = cpu_reference(g, inp, steps, 1)
+        # ~0.5 s per step on 4 cores at the default grid: bound the run to about a minute
+        cap = 40 if a.workload == "default" else 4
+        steps, wu = max(1, min(a.steps, cap)), max(1, min(a.warmup, 3 if a.workload == "default" else 1))
+        v, nthreads, dt = cpu_reference(g, inp, steps, wu)
         line = {"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": a.gpus, "steps": steps,
-                "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+                "warmup": wu, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": desc},
                 "cpu_baseline": {"value": v, "unit": unit, "cores": nthreads, "kind": "port",
