@@ -172,6 +172,16 @@ int rsg_ram_part_rev(rsg_ram* h, int s0, int ns, int l0, int nl);
 /* All three parts at once for species [s0, s0+ns) when every pitch angle and energy is local
  * (species-sharded ranks, or one GPU): uses the fused kernels / graph replay of rsg_ram_run. */
 int rsg_ram_part_all(rsg_ram* h, double DTs, int flags, int s0, int ns);
+/* The fused FAST step for ranks that SHARE a species (flags == 0): the plane kernels shard by pitch
+ * angle [l0, l0+nl), the column kernel by blocks [b0, b0+nb) of *positions_per_block consecutive
+ * plane positions (rsg_ram_col_blocks).  Between the calls the caller re-shards F2 (rows l x
+ * columns p of the [NPA*NE][Pp] species buffer).  planes_rev also runs the epilogue, ANISCH and
+ * the result block; moments and pressures are partial sums over the slab / block range. */
+int rsg_ram_fused_available(rsg_ram* h, int flags);
+int rsg_ram_col_blocks(rsg_ram* h, int* nblocks, int* positions_per_block);
+int rsg_ram_fpart_planes_fwd(rsg_ram* h, double DTs, int flags, int s0, int ns, int l0, int nl);
+int rsg_ram_fpart_columns(rsg_ram* h, double DTs, int flags, int s0, int ns, int b0, int nb);
+int rsg_ram_fpart_planes_rev(rsg_ram* h, int s0, int ns, int l0, int nl);
 /* Device result blocks, species-major: res = nS x *res_n 8-byte words, pp = nS x *pp_n doubles.
  * Species-sharded ranks all-gather them in place (NCCL) and decode with rsg_ram_part_results(0, nS). */
 int rsg_ram_results_device(rsg_ram* h, void** res, long long* res_n, void** pp, long long* pp_n);

@@ -108,6 +108,7 @@ struct PlaneCfg {
   int nsegR, segR;    // DRIFTR: segments per line, cells per segment (cells I=2..NR)
   int nsegP, segP;    // DRIFTP (cells J=2..NT)
   int part_off;       // REV: offset of this kernel's SUMRC partials in SpecDev::part
+  int l0;             // first pitch angle of the launch (slab-sharded ranks); blockIdx.y counts from it
 };
 
 template <bool REV>
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(512) k_plane_rp(const __grid_constant__ RamDev
   const int NR = d.NR, NT = d.NT, NE = d.NE, P = d.P, Pp = d.Pp;
   const int T = blockDim.x, tid = threadIdx.x;
   const int NRp = cfg.NRp, PS = cfg.PS;
-  const int l = blockIdx.y;
+  const int l = cfg.l0 + blockIdx.y;
   const int k0 = blockIdx.x * cfg.KC, KCa = min(NE, k0 + cfg.KC) - k0;
   double* sP = smem;                                   // [KC][PS]
   double* sG = smem + (size_t)cfg.KC * PS;             // [KC][NT][2] ghost cells F(NR+1), F(NR+2)
@@ -338,6 +339,7 @@ struct ColCfg {
   int nsegM, segM;    // DRIFTMU
   int nsegL, segL;    // loss block: pitch-angle segments per (k, position) column
   int doA;            // bit s: species s applies its first/last loss operator
+  int b0;             // first block of plane positions of the launch (column-sharded ranks)
 };
 
 template <int PG, int MAXT>
@@ -347,7 +349,7 @@ __global__ void __launch_bounds__(MAXT) k_col_fused(const __grid_constant__ RamD
   const SpecDev& sp = pk.s[s0 + blockIdx.y];
   const int NR = d.NR, NT = d.NT, NE = d.NE, NPA = d.NPA, P = d.P, Pp = d.Pp;
   const int T = blockDim.x, tid = threadIdx.x;
-  const int p0 = blockIdx.x * PG;
+  const int p0 = (cfg.b0 + blockIdx.x) * PG;
   const int NEs = cfg.NEs, RS = NEs * PG;
   double* sT = smem;                         // [NPA][NEs][PG]
   double* sEa = sT + (size_t)NPA * RS;       // [NPA][PG] each

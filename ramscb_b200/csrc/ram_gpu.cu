@@ -141,6 +141,7 @@ struct rsg_ram {
   bool g_tpos = false;   // COULMU's T > 0 switch is baked into the captured launch
   cudaStream_t g_stream = nullptr;
   double T_elapsed = 0.0;
+  int fp_nb = 0;   // column blocks of the last rsg_ram_fpart_columns (k_finalize sums that many partials)
   bool use_graph = true;
   // fused FAST path (ram_fused.cuh): shared-memory plane / column kernels
   bool use_fused = true;
@@ -526,14 +527,16 @@ int opt_in_smem(K kernel, size_t smem) {
   if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   return RSG_OK;
 }
-int L_plane_rp(rsg_ram* h, int s0, int ns, cudaStream_t st, bool rev) {
+int L_plane_rp(rsg_ram* h, int s0, int ns, cudaStream_t st, bool rev, int l0 = 0, int nl = -1) {
+  if (nl < 0) nl = h->NPA - l0;
   SpecPack pk;
   make_pack(h, pk, s0, ns);
   const RamDev dv = devfor(h, h->sp[s0].DTs);
   PlanePlan c = plane_plan(h);
   const int KG = (h->NE + c.cfg.KC - 1) / c.cfg.KC;
-  const dim3 g(KG, h->NPA, ns);
+  const dim3 g(KG, nl, ns);
   c.cfg.part_off = fused_part_off(h);      // after the column kernel's partials
+  c.cfg.l0 = l0;
   if (rev) { RET(opt_in_smem(k_plane_rp<true>, c.smem)); k_plane_rp<true><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg); }
   else { RET(opt_in_smem(k_plane_rp<false>, c.smem)); k_plane_rp<false><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg); }
   CKL();
@@ -555,12 +558,13 @@ int L_cfl(rsg_ram* h, int s0, int ns, cudaStream_t st) {
   for (int s = s0; s < s0 + ns; ++s) h->cfl_ok[s] = true;
   return RSG_OK;
 }
-int L_col(rsg_ram* h, int s0, int ns, int doA, double DTs, cudaStream_t st) {
+int L_col(rsg_ram* h, int s0, int ns, int doA, double DTs, cudaStream_t st, int b0 = 0, int nb = -1) {
   SpecPack pk;
   make_pack(h, pk, s0, ns);
   ColPlan c = col_plan(h);
   c.cfg.doA = doA;
-  const int nb = (h->P + COL_PG - 1) / COL_PG;
+  c.cfg.b0 = b0;
+  if (nb < 0) nb = (h->P + COL_PG - 1) / COL_PG - b0;
   const dim3 g(nb, ns);
   const RamDev dv = devfor(h, DTs);
   if (c.T <= 320) {          // register budget follows the CTA size
@@ -579,23 +583,25 @@ int L_col(rsg_ram* h, int s0, int ns, int doA, double DTs, cudaStream_t st) {
 }
 // pressures of ANISCH in one pass + the result block of the step, both also written to the
 // host-mapped copies (no memcpy nodes in the fused step)
-int L_finish_fused(rsg_ram* h, int s0, int ns, cudaStream_t st) {
+int L_finish_fused(rsg_ram* h, int s0, int ns, cudaStream_t st, int l0 = 0, int nl = -1, int nb_col = -1) {
+  if (nl < 0) nl = h->NPA - l0;
+  if (nb_col < 0) nb_col = (h->P + COL_PG - 1) / COL_PG;
   SpecPack pk;
   make_pack(h, pk, s0, ns);
   const double RFAC = 4 * kPI / (kCS * 100);
   RET(prof_mark(h, "k_anisch", st));
   {
     const int LCH = 6;
-    const int nch = std::max(1, std::min(16, (h->NPA + LCH - 1) / LCH));
-    const int lch = (h->NPA + nch - 1) / nch;
-    k_anisch_pa_fast<<<dim3(nblk(h->Pp, 32), h->NE, ns), dim3(32, nch), 0, st>>>(h->dev, pk, s0, 0, h->NPA, lch);
+    const int nch = std::max(1, std::min(16, (nl + LCH - 1) / LCH));
+    const int lch = (nl + nch - 1) / nch;
+    k_anisch_pa_fast<<<dim3(nblk(h->Pp, 32), h->NE, ns), dim3(32, nch), 0, st>>>(h->dev, pk, s0, l0, nl, lch);
     CKL();
   }
   RET(prof_mark(h, "k_finalize", st));
   const PlanePlan c = plane_plan(h);
   const int KG = (h->NE + c.cfg.KC - 1) / c.cfg.KC;
-  k_finalize<<<dim3(6 + nblk(h->P, 32), ns), 256, 0, st>>>(h->dev, pk, s0, (h->P + COL_PG - 1) / COL_PG, fused_part_off(h), KG * h->NPA,
-                                                            h->d_cfl_all, RES_N, NSUM, h->hd_res_all, RFAC, h->hd_pp_all);
+  k_finalize<<<dim3(6 + nblk(h->P, 32), ns), 256, 0, st>>>(h->dev, pk, s0, nb_col, fused_part_off(h), KG * nl, h->d_cfl_all, RES_N, NSUM,
+                                                           h->hd_res_all, RFAC, h->hd_pp_all);
   CKL();
   h->launches += 2;
   return RSG_OK;
@@ -1720,6 +1726,43 @@ int rsg_ram_part_rev(rsg_ram* h, int s0, int ns, int l0, int nl) {
     if (rc != RSG_OK) return rc;
   }
   return enqueue_tail(h, s0, ns, l0, nl, st);
+}
+
+// ---- fused step for ranks that share a species (FAST mode, default operators) ---------------
+// The plane kernels shard by pitch angle, the column kernel by blocks of 4 plane positions:
+//   planes_fwd(l-slab) | exchange | columns(block range) | exchange | planes_rev(l-slab) + finish
+// Moments and pressures are partial sums over the rank's slab / block range.
+int rsg_ram_fused_available(rsg_ram* h, int flags) { return (h && fused_ok(h, flags)) ? 1 : 0; }
+int rsg_ram_fpart_planes_fwd(rsg_ram* h, double DTs, int flags, int s0, int ns, int l0, int nl) {
+  RET(check_part(h, s0, ns, l0, nl, h ? h->NPA : 0));
+  if (!fused_ok(h, flags)) return fail(RSG_ERR_UNSUPPORTED, "fused kernels not available for this mode / flags / grid");
+  CK(cudaSetDevice(h->device));
+  RET(step_prepare(h, DTs, flags, s0, ns));
+  h->in_step = false;
+  return L_plane_rp(h, s0, ns, h->pst(), false, l0, nl);
+}
+int rsg_ram_fpart_columns(rsg_ram* h, double DTs, int flags, int s0, int ns, int b0, int nb) {
+  const int nbtot = h ? (h->P + COL_PG - 1) / COL_PG : 0;
+  RET(check_part(h, s0, ns, b0, nb, nbtot));
+  if (!fused_ok(h, flags)) return fail(RSG_ERR_UNSUPPORTED, "fused kernels not available for this mode / flags / grid");
+  CK(cudaSetDevice(h->device));
+  int cat[RSG_MAX_SPECIES][NSLOT], doA;
+  slot_cats(h, flags, cat, &doA, nullptr);
+  h->fp_nb = nb;
+  return L_col(h, s0, ns, doA, DTs, h->pst(), b0, nb);
+}
+int rsg_ram_fpart_planes_rev(rsg_ram* h, int s0, int ns, int l0, int nl) {
+  RET(check_part(h, s0, ns, l0, nl, h ? h->NPA : 0));
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = h->pst();
+  RET(L_plane_rp(h, s0, ns, st, true, l0, nl));
+  return L_finish_fused(h, s0, ns, st, l0, nl, h->fp_nb);
+}
+int rsg_ram_col_blocks(rsg_ram* h, int* nblocks, int* positions_per_block) {
+  if (!h || !nblocks || !positions_per_block) return fail(RSG_ERR_ARG, "null argument");
+  *nblocks = (h->P + COL_PG - 1) / COL_PG;
+  *positions_per_block = COL_PG;
+  return RSG_OK;
 }
 
 // raw per-rank results of the three parts: DtDrift(4,ns) minima, SUMRC partial sums

@@ -76,6 +76,11 @@ def lib():
     L.rsg_ram_run.argtypes = [vp, d, d, d, i, _dp, vp, vp, vp, vp, vp]
     L.rsg_ram_part_fwd.argtypes = [vp, d, i, i, i, i, i]
     L.rsg_ram_part_all.argtypes = [vp, d, i, i, i]
+    L.rsg_ram_fused_available.argtypes = [vp, i]
+    L.rsg_ram_col_blocks.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.rsg_ram_fpart_planes_fwd.argtypes = [vp, d, i, i, i, i, i]
+    L.rsg_ram_fpart_columns.argtypes = [vp, d, i, i, i, i, i]
+    L.rsg_ram_fpart_planes_rev.argtypes = [vp, i, i, i, i]
     L.rsg_ram_results_device.argtypes = [vp, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong), C.POINTER(C.c_void_p), C.POINTER(C.c_longlong)]
     L.rsg_ram_part_mid.argtypes = [vp, d, i, i, i, i, i]
     L.rsg_ram_part_rev.argtypes = [vp, i, i, i, i]
@@ -279,6 +284,23 @@ class RamGpu:
         r, rn, q, qn = C.c_void_p(), C.c_longlong(), C.c_void_p(), C.c_longlong()
         _ck(self.L.rsg_ram_results_device(self.h, C.byref(r), C.byref(rn), C.byref(q), C.byref(qn)))
         return r.value, rn.value, q.value, qn.value
+
+    def fused_available(self, flags=0):
+        return bool(self.L.rsg_ram_fused_available(self.h, flags))
+
+    def col_blocks(self):
+        n, per = C.c_int(), C.c_int()
+        _ck(self.L.rsg_ram_col_blocks(self.h, C.byref(n), C.byref(per)))
+        return n.value, per.value
+
+    def fpart_planes_fwd(self, DTs, flags, s0, ns, l0, nl):
+        _ck(self.L.rsg_ram_fpart_planes_fwd(self.h, DTs, flags, s0, ns, l0, nl))
+
+    def fpart_columns(self, DTs, flags, s0, ns, b0, nb):
+        _ck(self.L.rsg_ram_fpart_columns(self.h, DTs, flags, s0, ns, b0, nb))
+
+    def fpart_planes_rev(self, s0, ns, l0, nl):
+        _ck(self.L.rsg_ram_fpart_planes_rev(self.h, s0, ns, l0, nl))
 
     def part_all(self, DTs, flags, s0, ns):
         _ck(self.L.rsg_ram_part_all(self.h, DTs, flags, s0, ns))

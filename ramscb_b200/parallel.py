@@ -134,6 +134,45 @@ def exchange(p: ShardPlan, bufs, Pp: int, to_kslab: bool, dist):
         dst.copy_(recv)
 
 
+def exchange_lp(p: ShardPlan, bufs, Pp: int, nblocks: int, per: int, to_columns: bool, dist):
+    """Re-sharding of the FUSED step inside a group: pitch-angle slabs (plane kernels) <-> ranges of
+    plane positions (column kernel).  The species buffer is [NPA*NE][Pp]; rank g owns rows
+    l in slab_g (all positions) in the plane layout and columns p in range_g (all rows) in the
+    column layout.  to_columns: send my rows of the peer's columns, receive the peer's rows of my
+    columns; the way back swaps the roles.  One packed message per peer (strided 2-D copies)."""
+    if p.G == 1:
+        return
+    import torch
+    import torch.distributed as td
+
+    def cols(gi):
+        b0, nb = _split(nblocks, p.G, gi)
+        return b0 * per, min((b0 + nb) * per, Pp)
+
+    def rows(gi):
+        l0, nl = _split(p.NPA, p.G, gi)
+        return l0 * p.NE, (l0 + nl) * p.NE
+
+    ops, pending = [], []
+    my_r, my_c = rows(p.gidx), cols(p.gidx)
+    for gi, peer in enumerate(p.group):
+        if peer == p.rank:
+            continue
+        pr, pc = rows(gi), cols(gi)
+        (sr, sc), (rr, rc) = ((my_r, pc), (pr, my_c)) if to_columns else ((pr, my_c), (my_r, pc))
+        for buf in bufs:
+            v = buf[:p.NPA * p.NE * Pp].view(p.NPA * p.NE, Pp)
+            send = v[sr[0]:sr[1], sc[0]:sc[1]].contiguous()
+            recv = torch.empty((rr[1] - rr[0], rc[1] - rc[0]), dtype=buf.dtype, device=buf.device)
+            ops.append(td.P2POp(td.isend, send, peer))
+            ops.append(td.P2POp(td.irecv, recv, peer))
+            pending.append((v[rr[0]:rr[1], rc[0]:rc[1]], recv))
+    for w in td.batch_isend_irecv(ops):
+        w.wait()
+    for dst, recv in pending:
+        dst.copy_(recv)
+
+
 class _DevBuf:
     """Zero-copy view of library-owned device memory for torch (CUDA array interface)."""
 
@@ -171,6 +210,17 @@ class RamSharded:
         if p.G == 1:
             # species-sharded: the whole step is local (fused kernels, graph replay)
             gpu.part_all(DTs, flags, p.s0, p.ns)
+        elif gpu.fused_available(flags):
+            # ranks sharing a species, fused kernels: pitch-angle slabs for the plane kernels,
+            # ranges of plane positions for the column kernel, two re-shardings per step
+            nblocks, per = gpu.col_blocks()
+            b0, nb = _split(nblocks, p.G, p.gidx)
+            gpu.fpart_planes_fwd(DTs, flags, p.s0, p.ns, p.l0, p.nl)
+            bufs, pp = self._bufs()
+            exchange_lp(p, bufs, pp, nblocks, per, True, self.dist)
+            gpu.fpart_columns(DTs, flags, p.s0, p.ns, b0, nb)
+            exchange_lp(p, bufs, pp, nblocks, per, False, self.dist)
+            gpu.fpart_planes_rev(p.s0, p.ns, p.l0, p.nl)
         else:
             gpu.part_fwd(DTs, flags, p.s0, p.ns, p.l0, p.nl)
             bufs, pp = self._bufs()

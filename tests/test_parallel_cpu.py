@@ -59,7 +59,21 @@ def _worker(rank, world, port, NPA, NE, Pp, q):
     v[:, p.k0:p.k0 + p.nk] += 0.5
     parallel.exchange(p, [buf], Pp, False, dist)
     ok2 = bool(torch.equal(v[p.l0:p.l0 + p.nl], full.view(NPA, NE, Pp)[p.l0:p.l0 + p.nl] + 0.5))  # my L-slab, all energies updated
-    q.put((rank, ok1, ok2))
+    # the fused step's re-sharding: pitch-angle slabs <-> ranges of plane positions (blocks of 4)
+    nblocks, per = (Pp - 3 + 3) // 4, 4          # P = Pp - 3 positions in use, as a ragged case
+    buf2 = torch.full_like(full, -1.0)
+    w = buf2.view(NPA * NE, Pp)
+    fw = full.view(NPA * NE, Pp)
+    w[p.l0 * NE:(p.l0 + p.nl) * NE] = fw[p.l0 * NE:(p.l0 + p.nl) * NE]      # my rows, all positions
+    parallel.exchange_lp(p, [buf2], Pp, nblocks, per, True, dist)
+    b0, nb = parallel._split(nblocks, p.G, p.gidx)
+    c0, c1 = b0 * per, min((b0 + nb) * per, Pp)
+    ok3 = bool(torch.equal(w[:, c0:c1], fw[:, c0:c1]))                        # all rows of my positions
+    w[:, c0:c1] += 0.25
+    parallel.exchange_lp(p, [buf2], Pp, nblocks, per, False, dist)
+    last = nblocks * per                                                      # columns beyond the last block are padding
+    ok4 = bool(torch.equal(w[p.l0 * NE:(p.l0 + p.nl) * NE, :last], fw[p.l0 * NE:(p.l0 + p.nl) * NE, :last] + 0.25))
+    q.put((rank, ok1 and ok3, ok2 and ok4))
     dist.destroy_process_group()
 
 
