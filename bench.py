@@ -219,7 +219,8 @@ def main():
     # ---- sharding (ramscb_b200/parallel.py): species over ranks (no data-path collective);
     # beyond nS ranks, (L,K) slabs inside a species with two NCCL re-shardings per step
     from ramscb_b200 import parallel
-    plan = parallel.make_plan(world, rank, g.nS, g.NPA, g.NE)
+    plan = parallel.make_plan(world, rank, g.nS, g.NPA, g.NE, cells_per_species=g.NR * g.NT * g.NE * g.NPA)
+    idle = plan.ns == 0     # more ranks than species on a grid too small to split a species
     gpu = host.RamGpu(g, device=local_rank, mode=host.MODE_FAST if a.mode == "fast" else host.MODE_EXACT)
     gpu.set_inputs(inp)
     F2_host = inp.F2.copy(order="F")
@@ -280,6 +281,8 @@ def main():
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
+        if idle:
+            continue
         gpu.f2_h2d(F2_host)
         gpu.set_efield(VT, inp.EIR, inp.EIP)
         out = step_resident()
@@ -341,8 +344,13 @@ def main():
                                 "stencil neighbourhood (tests/test_ram_parity_gpu.py)") if a.mode == "fast"
                        else "exact: reference operation order, bit-identical to the oracle",
                        "l2": "flushed between timed steps (512 MB memset, untimed)", "DTs": DTS,
-                       "parallelism": (f"{world} ranks: species x (L,K)-slab groups of {plan.G}, NCCL re-sharding twice per step"
-                                       if plan.G > 1 else f"{world} ranks, species-sharded, no data-path collective")
+                       "parallelism": (f"{world} ranks: species x slab groups of {plan.G}, NCCL re-sharding twice per step"
+                                       if plan.G > 1 else
+                                       (f"{world} ranks, {len(plan.active)} active (one species each, no data-path collective), "
+                                        f"{world - len(plan.active)} idle: a species is split only above "
+                                        f"{parallel.SPLIT_MIN_CELLS:.0e} cells (ramscb_b200/parallel.py)"
+                                        if len(plan.active) < world else
+                                        f"{world} ranks, species-sharded, no data-path collective"))
                        if world > 1 else "1 GPU, all species per launch"},
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "wall_s_timed_region": wall_s}

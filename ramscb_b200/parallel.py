@@ -19,6 +19,7 @@ KB) are all-reduces after the step.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -46,14 +47,31 @@ class ShardPlan:
     nl: int = 0
     k0: int = 0
     nk: int = 0
+    active: tuple = ()   # ranks that hold species (all of them unless small grids leave ranks idle)
 
     @property
     def G(self):
         return len(self.group)
 
 
-def make_plan(world: int, rank: int, nS: int, NPA: int, NE: int) -> ShardPlan:
+# A species is split among several ranks only when it has at least this many cells: the two
+# re-shardings per step move half of a rank's data each and cost ~0.1 ms of launch/NCCL latency,
+# which only pays off for grids well beyond the 4x one (19.8 M cells per species); measured in
+# profiles/r1/scaling_r1.txt.  Below it, ranks beyond nS stay idle.
+SPLIT_MIN_CELLS = int(float(os.environ.get("RSG_SPLIT_MIN_CELLS", "5e7")))
+
+
+def make_plan(world: int, rank: int, nS: int, NPA: int, NE: int, cells_per_species=None) -> ShardPlan:
+    """cells_per_species=None: always split a species when world > nS (tests, large grids)."""
     p = ShardPlan(world=world, rank=rank, nS=nS, NPA=NPA, NE=NE)
+    p.active = tuple(range(world))
+    if world > nS and cells_per_species is not None and cells_per_species < SPLIT_MIN_CELLS:
+        # one species per rank on the first nS ranks, the others idle
+        p.active = tuple(range(nS))
+        p.group, p.gidx = (rank,), 0
+        p.s0, p.ns = (rank, 1) if rank < nS else (0, 0)
+        p.l0, p.nl, p.k0, p.nk = 0, NPA, 0, NE
+        return p
     if world <= nS:
         if nS % world != 0:
             raise ValueError(f"{nS} species cannot be split evenly over {world} ranks")
@@ -187,6 +205,9 @@ class RamSharded:
         self.gpu, self.p, self.dist = gpu, plan, dist
         self.setrc = np.zeros(gpu.g.nS)
         self._views = None
+        self._agroup = None
+        if dist is not None and plan.world > 1 and len(plan.active) < plan.world:
+            self._agroup = dist.new_group(ranks=list(plan.active))   # collective: every rank calls it
 
     def _bufs(self):
         import torch
@@ -207,6 +228,8 @@ class RamSharded:
     def ram_run(self, DTs, DtsMin=1.0, flags=0):
         import torch
         g, p, gpu = self.gpu.g, self.p, self.gpu
+        if p.ns == 0:
+            return None                      # idle rank (small grid, more ranks than species)
         if p.G == 1:
             # species-sharded: the whole step is local (fused kernels, graph replay)
             gpu.part_all(DTs, flags, p.s0, p.ns)
@@ -229,12 +252,12 @@ class RamSharded:
             bufs, pp = self._bufs()
             exchange(p, bufs, pp, False, self.dist)
             gpu.part_rev(p.s0, p.ns, p.l0, p.nl)
-        if p.G == 1 and p.world > 1 and self.dist is not None and self.dist.get_backend() == "nccl":
+        if p.G == 1 and len(p.active) > 1 and self.dist is not None and self.dist.get_backend() == "nccl":
             # every rank owns whole species: the result blocks of all ranks are concatenated by two
             # in-place all-gathers on the device (same stream as the step), then decoded once
             res, pp_t, rn, qn = self._result_views()
-            self.dist.all_gather_into_tensor(res, res[p.s0 * rn:(p.s0 + p.ns) * rn])
-            self.dist.all_gather_into_tensor(pp_t, pp_t[p.s0 * qn:(p.s0 + p.ns) * qn])
+            self.dist.all_gather_into_tensor(res, res[p.s0 * rn:(p.s0 + p.ns) * rn], group=self._agroup)
+            self.dist.all_gather_into_tensor(pp_t, pp_t[p.s0 * qn:(p.s0 + p.ns) * qn], group=self._agroup)
             DT, MOM, PE, PA = gpu.part_results(0, g.nS)
             return {"DtDrift": DT, "DtsNext": max(float(DT.min()), DtsMin), "moments": MOM,
                     "PPERT": np.asfortranarray(np.moveaxis(PE, 2, 0)), "PPART": np.asfortranarray(np.moveaxis(PA, 2, 0))}
