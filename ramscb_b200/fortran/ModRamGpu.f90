@@ -188,6 +188,61 @@ module ModRamGpu
        real(c_double), intent(out) :: PPERT_S(*), PPART_S(*)
        integer(c_int) :: ierr
      end function
+     ! ModRamCoul / FLCscatter (optional operators)
+     function rsg_ram_set_plasmasphere(h, NECR) bind(C, name='rsg_ram_set_plasmasphere') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       real(c_double), intent(in) :: NECR(*)
+       integer(c_int) :: ierr
+     end function
+     function rsg_coulpara(h, S, DTs) bind(C, name='rsg_coulpara') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       integer(c_int), value :: S
+       real(c_double), value :: DTs
+       integer(c_int) :: ierr
+     end function
+     function rsg_coulen(h, S) bind(C, name='rsg_coulen') result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       integer(c_int), value :: S
+       integer(c_int) :: ierr
+     end function
+     function rsg_coulmu(h, S, T) bind(C, name='rsg_coulmu') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       integer(c_int), value :: S
+       real(c_double), value :: T
+       integer(c_int) :: ierr
+     end function
+     function rsg_ram_set_flc_coef(h, S, FLC_coef) bind(C, name='rsg_ram_set_flc_coef') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       integer(c_int), value :: S
+       real(c_double), intent(in) :: FLC_coef(*)     ! contiguous copy of FLC_coef(S,:,:,:,:)
+       integer(c_int) :: ierr
+     end function
+     function rsg_flcscatter(h, S, DTs, T, Dt_bc, nviolation) bind(C, name='rsg_flcscatter') result(ierr)
+       import :: c_ptr, c_int, c_double, c_long_long
+       type(c_ptr), value :: h
+       integer(c_int), value :: S
+       real(c_double), value :: DTs, T, Dt_bc
+       integer(c_long_long), intent(out) :: nviolation
+       integer(c_int) :: ierr
+     end function
+     ! execution options of rsg_ram_run (both default on; results do not depend on them)
+     function rsg_ram_use_fused(h, on) bind(C, name='rsg_ram_use_fused') result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       integer(c_int), value :: on
+       integer(c_int) :: ierr
+     end function
+     function rsg_ram_use_graph(h, on) bind(C, name='rsg_ram_use_graph') result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       integer(c_int), value :: on
+       integer(c_int) :: ierr
+     end function
      function rsg_ram_run(h, DTs, DtsMin, T, flags, dts_next, DtDrift, losses, SETRC, PPERT, PPART) &
           bind(C, name='rsg_ram_run') result(ierr)
        import :: c_ptr, c_int, c_double
