@@ -409,11 +409,10 @@ __global__ void __launch_bounds__(MAXT) k_col_fused(const __grid_constant__ RamD
   __syncthreads();
 
   const double beta = d.BetaLim;
-  double mmaxE = 0.0, mmaxM = 0.0;
   double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};   // SUMRC after DRIFTMU, and the four of the loss block
 
   // ---- DRIFTE (src/ModRamDrift.f90:285-376) ------------------------------------
-  auto drifte = [&](const bool cfl) {
+  auto drifte = [&]() {
     const int ntask = NPA * PG * cfg.nsegE;
     const int nround = (ntask + T - 1) / T;
     for (int rd = 0; rd < nround; ++rd) {
@@ -440,17 +439,14 @@ __global__ void __launch_bounds__(MAXT) k_col_fused(const __grid_constant__ RamD
       }
       if (cfg.nsegE > 1) __syncthreads();               // halo reads before anybody's in-place walk
       if (act) {
-        const bool inside = !d.outp[p];
         const double fA = sEa[l * PG + pp], fB = sEb[l * PG + pp];
         const double4* tab = (const double4*)sTab + (K0 - 1);
-        double FBprev, mmax = 0.0;
+        double FBprev;
         double dm1 = F0 - Fm1, d0 = Fp1 - F0, dp1 = Fp2 - Fp1;
-        const double floorr = tab->z;
         {                                               // peeled first interface K0: flux only
           const double4 tb = *tab;
           const double c = fma(tb.y, fB, tb.x * fA);
           const double ac = fabs(c) * tb.z;
-          if (inside && seg == 0) mmax = ac;
           FBprev = c * limited_flux_d(F0, Fp1, dm1, d0, dp1, c < 0.0, ac, beta);
         }
         double* pO = col + (size_t)K0 * PG;             // -> F(K0+1)
@@ -461,7 +457,6 @@ __global__ void __launch_bounds__(MAXT) k_col_fused(const __grid_constant__ RamD
           const double4 tb = *tab;
           const double c = fma(tb.y, fB, tb.x * fA);
           const double ac = fabs(c) * tb.z;
-          if (cfl) mmax = dmax(mmax, ac);
           const double FB = c * limited_flux_d(F0, Fp1, dm1, d0, dp1, c < 0.0, ac, beta);
           double fn = fma(-(FB - FBprev), tb.w, F0);
           if (fn < 0.0) fn = 1E-15;
@@ -474,13 +469,12 @@ __global__ void __launch_bounds__(MAXT) k_col_fused(const __grid_constant__ RamD
         for (; K + 2 <= kb; ++K) step(pO[2 * PG]);      // F(K+2): own cell, not yet rewritten
         if (K + 1 <= kb) { step(hi1); ++K; }            // K = kb-1: F(kb+1)
         if (K <= kb) step(hi2);                         // K = kb:   F(kb+2)
-        if (cfl) mmaxE = dmax(mmaxE, inside ? dmax(mmax, 1E-10 * floorr) : 0.0);
       }
     }
   };
 
   // ---- DRIFTMU (src/ModRamDrift.f90:382-473), optionally with the SUMRC moment ----
-  auto driftmu = [&](const bool mom, const bool cfl) {
+  auto driftmu = [&](const bool mom) {
     const int ntask = NE * PG * cfg.nsegM;
     const int nround = (ntask + T - 1) / T;
     for (int rd = 0; rd < nround; ++rd) {
@@ -501,11 +495,10 @@ __global__ void __launch_bounds__(MAXT) k_col_fused(const __grid_constant__ RamD
       }
       if (cfg.nsegM > 1) __syncthreads();
       if (act) {
-        const bool inside = !d.outp[p];
         const double wM = sWM[k];
         const double* ca = sMa + (la - 1) * PG + pp;    // coefficient pieces of L = la
         const double* cb = sMb + (la - 1) * PG + pp;
-        double FBprev = 0.0, mmax = 0.0, macc = 0.0, fnew = 0.0;
+        double FBprev = 0.0, macc = 0.0, fnew = 0.0;
         double dm1 = F0 - Fm1, d0 = Fp1 - F0, dp1 = Fp2 - Fp1;
         if (la > 2) {                                   // flux through the segment's lower edge
           const double c = fma(wM, cb[-PG], ca[-PG]);
@@ -520,7 +513,6 @@ __global__ void __launch_bounds__(MAXT) k_col_fused(const __grid_constant__ RamD
           const double c = fma(wM, *cb, *ca);
           ca += PG; cb += PG;
           const double ac = fabs(c) * (*rd_++);
-          if (cfl) mmax = dmax(mmax, ac);
           double FB;
           if (limited) FB = c * limited_flux_d(F0, Fp1, dm1, d0, dp1, c < 0.0, ac, beta);
           else FB = c * Fp1;                            // FBND(NPA-1) = F(NPA)  (:458)
@@ -542,16 +534,12 @@ __global__ void __launch_bounds__(MAXT) k_col_fused(const __grid_constant__ RamD
           const double nn = (L + 3 <= lb) ? pO[3 * (size_t)RS] : ((L + 3 == lb + 1) ? hi1 : ((L + 3 == lb + 2) ? hi2 : 0.0));
           step(nn, L <= NPA - 2);
         }
-        if (!inside) mmax = 0.0;
         if (lastseg) {
-          const double c = fma(wM, *cb, *ca);           // CDriftMu(..,NPA)
-          if (cfl && inside) mmax = dmax(mmax, fabs(c) * sRD[NPA - 1]);
           const double fN = fnew * d.FNHSc[(size_t)(NPA - 1) * Pp + p] * d.MU[NPA - 1] / d.FNHSc[(size_t)(NPA - 2) * Pp + p] / d.MU[NPA - 2];
           *pO = fN;                                     // :466
           if (mom) macc = fma(fN, sWMU[NPA - 1], macc);
         }
         if (mom && k >= 1 && p < (NT - 1) * NR) acc[0] += macc * (sWE[k] * sEK[k]);
-        if (cfl) mmaxM = dmax(mmaxM, mmax);
       }
     }
   };
@@ -615,15 +603,16 @@ __global__ void __launch_bounds__(MAXT) k_col_fused(const __grid_constant__ RamD
     }
   };
 
-  drifte(false);
+  // (the CFL limits DtDriftE/Mu come from k_cfl_fast, not from the sweeps)
+  drifte();
   __syncthreads();
-  driftmu(true, false);
+  driftmu(true);
   __syncthreads();
   losses();
   __syncthreads();
-  driftmu(false, false);
+  driftmu(false);
   __syncthreads();
-  drifte(false);                               // (the CFL limits come from k_cfl_fast)
+  drifte();
   __syncthreads();
 
   // ---- write the block back, reductions -------------------------------------------
@@ -639,7 +628,6 @@ __global__ void __launch_bounds__(MAXT) k_col_fused(const __grid_constant__ RamD
       if (r >= rowItems) { r -= rowItems; ++l; }
     }
   }
-  (void)mmaxE; (void)mmaxM;
   block_sum_to<5>(sp.part, blockIdx.x, acc, sRed);
 }
 

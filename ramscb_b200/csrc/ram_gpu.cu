@@ -573,6 +573,9 @@ int L_col(rsg_ram* h, int s0, int ns, int doA, double DTs, cudaStream_t st, int 
   } else if (c.T <= 640) {
     RET(opt_in_smem(k_col_fused<COL_PG, 640>, c.smem));
     k_col_fused<COL_PG, 640><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg);
+  } else if (c.T <= 896) {
+    RET(opt_in_smem(k_col_fused<COL_PG, 896>, c.smem));
+    k_col_fused<COL_PG, 896><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg);
   } else {
     RET(opt_in_smem(k_col_fused<COL_PG, 1024>, c.smem));
     k_col_fused<COL_PG, 1024><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg);
