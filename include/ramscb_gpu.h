@@ -271,6 +271,18 @@ int rsg_scb_convergence(rsg_scb* h, double* normDiff, double* normJxB, double* n
  * any output may be NULL */
 int rsg_scb_derivs(rsg_scb* h, const double* f, double* dfdTheta, double* dfdRho, double* dfdZeta);
 /* device time (CUDA events on the launching stream) of the kernels of the last call */
+/* Multi-GPU: the independent sub-problems of a solve (psi surfaces for alpha, zeta planes for psi)
+ * split among ranks.  part solves sub-problems [sub0, sub0+nsub) (0-based: q is jz = q+2 / k = q+2);
+ * the caller all-gathers the solved planes of the field (rsg_scb_field_device gives the device
+ * array, theta fastest: a[i + nthe*(j + npsi*k)]) and calls finish (sums, extrapolation, periodic
+ * wrap) on every rank; nisave / diffmx / ni of finish cover this rank's sub-problems only.
+ * rsg_scb_set_stream: run on the caller's stream (NULL: back to the handle's own). */
+int rsg_scb_iterate_part(rsg_scb* h, int alpha, double tol, int nimax, int theChange, int psiChange, int ordering, int sub0,
+                         int nsub);
+int rsg_scb_iterate_finish(rsg_scb* h, int alpha, int theChange, int psiChange, int* nisave, double* sumb, double* sumdb,
+                           double* diffmx, int* sorfail, int* ni);
+int rsg_scb_field_device(rsg_scb* h, const char* name, void** ptr, long long* n);
+int rsg_scb_set_stream(rsg_scb* h, void* stream);
 double rsg_scb_last_ms(rsg_scb* h);
 /* RSG_SOR_COLOR4 runs on thread-block clusters (2..8 CTAs per sub-problem) with the unknown and all
  * ten coefficient arrays resident in distributed shared memory for the whole solve when they fit

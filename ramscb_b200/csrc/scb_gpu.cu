@@ -51,7 +51,7 @@ struct rsg_scb {
   ScbDev dev{};
   std::map<std::string, std::pair<double*, size_t>> arr;   // name -> (device ptr, elements)
   std::vector<void*> allocs;
-  cudaStream_t st = nullptr;
+  cudaStream_t st = nullptr, own_st = nullptr;   // st: where the work goes (own_st unless rsg_scb_set_stream)
   double *d_prev = nullptr, *d_part = nullptr, *d_resmax = nullptr;
   int *d_ni = nullptr, *d_fail = nullptr;
   size_t npart = 0;
@@ -139,7 +139,8 @@ int rsg_scb_create(rsg_scb** out, int nthe, int npsi, int nzeta, int device) {
   h->d_ni = (int*)q;
   h->d_fail = h->d_ni + nsub;
   SCK(cudaMemset(q, 0, sizeof(int) * (nsub + 1)));
-  SCK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+  SCK(cudaStreamCreateWithFlags(&h->own_st, cudaStreamNonBlocking));
+  h->st = h->own_st;
   SCK(cudaEventCreate(&h->e0));
   SCK(cudaEventCreate(&h->e1));
   *out = h;
@@ -151,7 +152,7 @@ int rsg_scb_destroy(rsg_scb* h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   for (void* p : h->allocs) cudaFree(p);
-  if (h->st) cudaStreamDestroy(h->st);
+  if (h->own_st) cudaStreamDestroy(h->own_st);
   if (h->e0) cudaEventDestroy(h->e0);
   if (h->e1) cudaEventDestroy(h->e1);
   delete h;
@@ -300,8 +301,13 @@ int rsg_scb_newk(rsg_scb* h) { return scb_rhs(h, true); }    // :546-604
 int rsg_scb_newj(rsg_scb* h) { return scb_rhs(h, false); }   // :607-665
 
 // iterateAlpha / iteratePsi, src/ModScbEuler.f90:160-299 / :469-612
-static int scb_iterate(rsg_scb* h, bool alpha, double tol, int nimax, int theChange, int psiChange, int ordering, int* nisave,
-                       double* sumb, double* sumdb, double* diffmx, int* sorfail, int* ni_out) {
+// part 1: the SOR solves of sub-problems [sub0, sub0+nsub_l) (nsub_l < 0: all); part 2
+// (scb_iterate_finish): sums, extrapolation / theta fill / periodic wrap, results.  Ranks that
+// shard the independent sub-problems all-gather the solved planes between the two.
+static int scb_iterate_finish(rsg_scb* h, bool alpha, int theChange, int psiChange, int* nisave, double* sumb, double* sumdb,
+                              double* diffmx, int* sorfail, int* ni_out);
+static int scb_iterate_part(rsg_scb* h, bool alpha, double tol, int nimax, int theChange, int psiChange, int ordering, int sub0,
+                            int nsub_l) {
   if (!h) return sfail(RSG_ERR_ARG, "null handle");
   if (ordering != RSG_SOR_LEX && ordering != RSG_SOR_COLOR4) return sfail(RSG_ERR_ARG, "unknown SOR ordering");
   SCK(cudaSetDevice(h->device));
@@ -312,9 +318,14 @@ static int scb_iterate(rsg_scb* h, bool alpha, double tol, int nimax, int theCha
   double* u = alpha ? h->dev.alfa : h->dev.psi;
   const size_t n3p = (size_t)nthe * npsi * (nzeta + 1);
   SCK(cudaMemcpyAsync(h->d_prev, u, n3p * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
-  const int nsub = alpha ? (npsi - nP - 1) : (nzeta - 1);
+  const int nsub_all = alpha ? (npsi - nP - 1) : (nzeta - 1);
+  if (nsub_l < 0) { sub0 = 0; nsub_l = nsub_all; }
+  if (sub0 < 0 || nsub_l < 0 || sub0 + nsub_l > nsub_all) return sfail(RSG_ERR_ARG, "sub-problem range out of bounds");
+  const int nsub = nsub_l;
   SCK(cudaMemsetAsync(h->d_ni, 0, sizeof(int) * (std::max(npsi, nzeta) + 2), h->st));
+  SCK(cudaMemsetAsync(h->d_resmax, 0, sizeof(double) * (std::max(npsi, nzeta) + 1), h->st));
   SorArgs a;
+  a.sub0 = sub0;
   a.tol = tol;
   a.nimax = nimax;
   a.nT = nT;
@@ -357,7 +368,9 @@ static int scb_iterate(rsg_scb* h, bool alpha, double tol, int nimax, int theCha
   }
   h->last_cluster = CL;
   SCK(cudaEventRecord(h->e0, h->st));
-  if (CL > 0) {
+  if (nsub == 0) {
+    // nothing to solve on this rank
+  } else if (CL > 0) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(nsub * CL);
     cfg.blockDim = dim3(std::min(1024, (npc_max + 31) / 32 * 32));
@@ -397,6 +410,17 @@ static int scb_iterate(rsg_scb* h, bool alpha, double tol, int nimax, int theCha
   }
   SCKL();
   SCK(cudaEventRecord(h->e1, h->st));
+  if (nsub > 0) h->launches++;
+  return RSG_OK;
+}
+static int scb_iterate_finish(rsg_scb* h, bool alpha, int theChange, int psiChange, int* nisave, double* sumb, double* sumdb,
+                              double* diffmx, int* sorfail, int* ni_out) {
+  if (!h) return sfail(RSG_ERR_ARG, "null handle");
+  SCK(cudaSetDevice(h->device));
+  const int nthe = h->nthe, npsi = h->npsi, nzeta = h->nzeta;
+  const int nT = std::max(theChange, 1), nP = std::max(psiChange, 1);
+  double* u = alpha ? h->dev.alfa : h->dev.psi;
+  const int nsub = alpha ? (npsi - nP - 1) : (nzeta - 1);
   k_scb_sums<<<nzeta - 1, 256, 0, h->st>>>(h->dev, u, h->d_prev, h->d_part);
   SCKL();
   k_scb_post_extap<<<dim3(nblk(nthe, 128), nzeta - 1), 128, 0, h->st>>>(h->dev, u, nT, nP);
@@ -405,7 +429,7 @@ static int scb_iterate(rsg_scb* h, bool alpha, double tol, int nimax, int theCha
   SCKL();
   k_scb_post_wrap<<<dim3(nblk(nthe, 128), npsi), 128, 0, h->st>>>(h->dev, u, alpha ? 2.0 * PI_D : 0.0);
   SCKL();
-  h->launches += 5;
+  h->launches += 4;
   std::vector<int> ni(nsub + 1);
   std::vector<double> rm(nsub), part(2 * (size_t)(nzeta - 1));
   int f = 0;
@@ -439,6 +463,40 @@ static int scb_iterate(rsg_scb* h, bool alpha, double tol, int nimax, int theCha
     for (int q = 0; q < nsub; ++q) ni_out[q + 1] = ni[q];
   }
   if (f) SCK(cudaMemsetAsync(h->d_fail, 0, sizeof(int), h->st));
+  return RSG_OK;
+}
+static int scb_iterate(rsg_scb* h, bool alpha, double tol, int nimax, int theChange, int psiChange, int ordering, int* nisave,
+                       double* sumb, double* sumdb, double* diffmx, int* sorfail, int* ni_out) {
+  const int rc = scb_iterate_part(h, alpha, tol, nimax, theChange, psiChange, ordering, 0, -1);
+  if (rc != RSG_OK) return rc;
+  return scb_iterate_finish(h, alpha, theChange, psiChange, nisave, sumb, sumdb, diffmx, sorfail, ni_out);
+}
+// The independent sub-problems (psi surfaces jz for alpha, zeta planes k for psi) of one solve split
+// among ranks: part solves [sub0, sub0+nsub) (0-based; sub-problem q is jz = q+2 / k = q+2); the
+// caller all-gathers the solved planes of the field (rsg_scb_field_device) and calls finish,
+// whose nisave / diffmx / ni cover this rank's sub-problems only (reduce with max over ranks).
+int rsg_scb_iterate_part(rsg_scb* h, int alpha, double tol, int nimax, int theChange, int psiChange, int ordering, int sub0,
+                         int nsub) {
+  if (nsub < 0) return sfail(RSG_ERR_ARG, "negative sub-problem count");
+  return scb_iterate_part(h, alpha != 0, tol, nimax, theChange, psiChange, ordering, sub0, nsub);
+}
+int rsg_scb_iterate_finish(rsg_scb* h, int alpha, int theChange, int psiChange, int* nisave, double* sumb, double* sumdb,
+                           double* diffmx, int* sorfail, int* ni) {
+  return scb_iterate_finish(h, alpha != 0, theChange, psiChange, nisave, sumb, sumdb, diffmx, sorfail, ni);
+}
+int rsg_scb_field_device(rsg_scb* h, const char* name, void** ptr, long long* n) {
+  if (!h || !name || !ptr || !n) return sfail(RSG_ERR_ARG, "null argument");
+  auto it = h->arr.find(name);
+  if (it == h->arr.end()) return sfail(RSG_ERR_ARG, std::string("unknown field ") + name);
+  *ptr = it->second.first;
+  *n = (long long)it->second.second;
+  return RSG_OK;
+}
+int rsg_scb_set_stream(rsg_scb* h, void* stream) {
+  if (!h) return sfail(RSG_ERR_ARG, "null handle");
+  SCK(cudaSetDevice(h->device));
+  SCK(cudaStreamSynchronize(h->st));
+  h->st = stream ? (cudaStream_t)stream : h->own_st;
   return RSG_OK;
 }
 int rsg_scb_iterate_alpha(rsg_scb* h, double InConAlpha, int nimax, int theChange, int psiChange, int ordering, int* nisave,

@@ -284,6 +284,7 @@ __global__ void __launch_bounds__(128) k_scb_rhs(ScbDev d, int isotropy) {
 struct SorArgs {
   double tol, omegaOpt;
   int nimax, nT, nP;
+  int sub0;         // first sub-problem of this launch (ranks sharding the independent sub-problems)
   int* ni;          // per sub-problem iteration count (Fortran ni(jz) / ni(k))
   double* resmax;   // per sub-problem max|resid| of the last sweep
   int* fail;
@@ -297,7 +298,7 @@ __global__ void __launch_bounds__(1024) k_scb_sor(ScbDev d, SorArgs a) {
   const int nthe = d.nthe, npsi = d.npsi, nzeta = d.nzeta;
   const int tid = threadIdx.x, T = blockDim.x;
   // sub-problem and its plane geometry
-  const int sub = blockIdx.x;                       // alpha: jz-2 (Fortran jz = 2..npsi-nP); psi: k-2 (k = 2..nzeta)
+  const int sub = a.sub0 + blockIdx.x;              // alpha: jz-2 (Fortran jz = 2..npsi-nP); psi: k-2 (k = 2..nzeta)
   const int nrows = ALPHA ? nzeta + 1 : npsi;       // rows held in shared memory
   const int r0 = 1, r1 = ALPHA ? nzeta - 1 : npsi - a.nP - 1;   // updated rows (0-based, inclusive)
   const int c0 = a.nT, c1 = nthe - a.nT - 1;                    // updated columns
@@ -582,7 +583,7 @@ __global__ void __launch_bounds__(1024) k_scb_sor_cluster(ScbDev d, SorArgs a, i
   const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
   const int nthe = d.nthe, npsi = d.npsi, nzeta = d.nzeta;
   const int tid = threadIdx.x, T = blockDim.x;
-  const int sub = blockIdx.x / CL;
+  const int sub = a.sub0 + blockIdx.x / CL;
   const int r0 = 1, r1 = ALPHA ? nzeta - 1 : npsi - a.nP - 1;   // updated rows (0-based, inclusive)
   const int c0 = a.nT, c1 = nthe - a.nT - 1;                    // updated columns
   const int nr = r1 - r0 + 1;
@@ -722,7 +723,7 @@ __global__ void __launch_bounds__(576, 1) k_scb_sor_cluster_reg(ScbDev d, SorArg
   const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
   const int nthe = d.nthe, npsi = d.npsi, nzeta = d.nzeta;
   const int tid = threadIdx.x, T = blockDim.x;
-  const int sub = blockIdx.x / CL;
+  const int sub = a.sub0 + blockIdx.x / CL;
   const int r0 = 1, r1 = ALPHA ? nzeta - 1 : npsi - a.nP - 1;
   const int c0 = a.nT, c1 = nthe - a.nT - 1;
   const int nr = r1 - r0 + 1;

@@ -396,6 +396,11 @@ def _scb_lib():
         L.rsg_scb_last_ms.argtypes = [vp]
         L.rsg_scb_last_ms.restype = d
         L.rsg_scb_use_cluster.argtypes = [vp, i]
+        L.rsg_scb_iterate_part.argtypes = [vp, i, d, i, i, i, i, i, i]
+        L.rsg_scb_iterate_finish.argtypes = [vp, i, i, i, C.POINTER(C.c_int), C.POINTER(d), C.POINTER(d), C.POINTER(d),
+                                             C.POINTER(C.c_int), vp]
+        L.rsg_scb_field_device.argtypes = [vp, C.c_char_p, C.POINTER(vp), C.POINTER(C.c_longlong)]
+        L.rsg_scb_set_stream.argtypes = [vp, vp]
         L.rsg_scb_last_cluster.argtypes = [vp]
         L.rsg_scb_launch_count.argtypes = [vp]
         L.rsg_scb_launch_count.restype = ll
@@ -467,6 +472,27 @@ class ScbGpu:
                 C.byref(diffmx), C.byref(fail), ni.ctypes.data))
         return {"nisave": nisave.value, "sumb": sumb.value, "sumdb": sumdb.value, "diffmx": diffmx.value,
                 "SORFail": fail.value, "ni": ni, "ms": self.last_ms()}
+
+    # ---- multi-GPU: sub-problem ranges (include/ramscb_gpu.h: rsg_scb_iterate_part/finish) ----
+    def iterate_part(self, alpha, tol, sub0, nsub, nimax=5001, theChange=4, psiChange=0, ordering=SOR_COLOR4):
+        _sck(self.L.rsg_scb_iterate_part(self.h, 1 if alpha else 0, tol, nimax, theChange, psiChange, ordering, sub0, nsub))
+
+    def iterate_finish(self, alpha, theChange=4, psiChange=0):
+        nisave, fail = C.c_int(), C.c_int()
+        sumb, sumdb, diffmx = C.c_double(), C.c_double(), C.c_double()
+        ni = np.zeros(self.npsi if alpha else self.nzeta, dtype=np.int32)
+        _sck(self.L.rsg_scb_iterate_finish(self.h, 1 if alpha else 0, theChange, psiChange, C.byref(nisave), C.byref(sumb),
+                                           C.byref(sumdb), C.byref(diffmx), C.byref(fail), ni.ctypes.data))
+        return {"nisave": nisave.value, "sumb": sumb.value, "sumdb": sumdb.value, "diffmx": diffmx.value,
+                "SORFail": fail.value, "ni": ni, "ms": self.last_ms()}
+
+    def field_device(self, name):
+        ptr, n = C.c_void_p(), C.c_longlong()
+        _sck(self.L.rsg_scb_field_device(self.h, name.encode(), C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
+
+    def set_stream(self, stream_ptr):
+        _sck(self.L.rsg_scb_set_stream(self.h, C.c_void_p(stream_ptr) if stream_ptr else None))
 
     def iterateAlpha(self, InConAlpha=1e-6, nimax=5001, theChange=4, psiChange=0, ordering=SOR_LEX):
         return self._iterate(self.L.rsg_scb_iterate_alpha, InConAlpha, nimax, theChange, psiChange, ordering, self.npsi)

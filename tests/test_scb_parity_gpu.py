@@ -201,3 +201,20 @@ def test_dipole_field_is_recovered():
     # spline-derivative truncation error only (largest at the high-latitude ends of the lines)
     assert rel.max() < 0.1, rel.max()
     assert np.median(rel) < 2e-3, np.median(rel)
+
+
+def test_multi_gpu_scb_sub_problem_sharding():
+    """2 GPUs: the independent sub-problems of iterateAlpha / iteratePsi split between the ranks,
+    solved planes all-gathered over NCCL -- potentials, sweep counts, residual maxima and sums
+    bit-identical to the single-GPU solve (tests/multi_gpu_scb_check.py under torchrun)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29577", os.path.join(here, "multi_gpu_scb_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "MULTI_GPU_SCB_CHECK_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
