@@ -374,15 +374,28 @@ __global__ void __launch_bounds__(MAXT) k_col_fused(const __grid_constant__ RamD
 
   // ---- stage the block (asynchronous 16-byte copies, all in flight) and its tables -----
   {
-    constexpr int H = PG / 2;                // 16-byte items per (l,k) row
+    // item t = 16 bytes: (l,k) row t/H, half hh = t%H.  Offsets advance incrementally (32-bit: a
+    // species block is < 2^31 doubles); the shared offset skips the pad of the energy stride at
+    // every l wrap.
+    constexpr int H = PG / 2;
     const int rowItems = NE * H;
     int l = tid / rowItems, r = tid - l * rowItems;
     const int dl = T / rowItems, dr = T - dl * rowItems;
+    const int pad = (NEs - NE) * PG;
+    int so = l * RS + (r / H) * PG + 2 * (r % H);
+    int go = (l * NE + r / H) * Pp + p0 + 2 * (r % H);
+    // one step of T items = dl whole l's + dr items; dr items = (dr/H) rows + (dr%H) halves
+    const int so_step = dl * RS + (dr / H) * PG + 2 * (dr % H);
+    const int go_step = (dl * NE + dr / H) * Pp + 2 * (dr % H);
+    int hh = r % H;
+    auto advance = [&]() {
+      r += dr; l += dl; so += so_step; go += go_step; hh += dr % H;
+      if (hh >= H) { hh -= H; so += PG - 2 * H; go += Pp - 2 * H; }    // carry of the half index into the row
+      if (r >= rowItems) { r -= rowItems; ++l; so += pad; }
+    };
     while (l < NPA) {
-      const int k = r / H, hh = r - k * H;
-      cp_async16(sT + (size_t)l * RS + k * PG + 2 * hh, sp.F + ((size_t)l * NE + k) * Pp + p0 + 2 * hh);
-      r += dr; l += dl;
-      if (r >= rowItems) { r -= rowItems; ++l; }
+      cp_async16(sT + so, sp.F + go);
+      advance();
     }
     asm volatile("cp.async.commit_group;");
     for (int t = tid; t < NPA * PG; t += T) {
@@ -621,11 +634,17 @@ __global__ void __launch_bounds__(MAXT) k_col_fused(const __grid_constant__ RamD
     const int rowItems = NE * H;
     int l = tid / rowItems, r = tid - l * rowItems;
     const int dl = T / rowItems, dr = T - dl * rowItems;
+    const int pad = (NEs - NE) * PG;
+    int so = l * RS + (r / H) * PG + 2 * (r % H);
+    int go = (l * NE + r / H) * Pp + p0 + 2 * (r % H);
+    const int so_step = dl * RS + (dr / H) * PG + 2 * (dr % H);
+    const int go_step = (dl * NE + dr / H) * Pp + 2 * (dr % H);
+    int hh = r % H;
     while (l < NPA) {
-      const int k = r / H, hh = r - k * H;
-      *(double2*)(sp.F + ((size_t)l * NE + k) * Pp + p0 + 2 * hh) = *(const double2*)(sT + (size_t)l * RS + k * PG + 2 * hh);
-      r += dr; l += dl;
-      if (r >= rowItems) { r -= rowItems; ++l; }
+      *(double2*)(sp.F + go) = *(const double2*)(sT + so);
+      r += dr; l += dl; so += so_step; go += go_step; hh += dr % H;
+      if (hh >= H) { hh -= H; so += PG - 2 * H; go += Pp - 2 * H; }
+      if (r >= rowItems) { r -= rowItems; ++l; so += pad; }
     }
   }
   block_sum_to<5>(sp.part, blockIdx.x, acc, sRed);

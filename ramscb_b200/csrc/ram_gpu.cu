@@ -147,6 +147,7 @@ struct rsg_ram {
   bool use_fused = true;
   int kcPlane = 0, colT = 0, planeT = 0;
   bool planeOdd = false;
+  int anischLch = 12;   // pitch angles per thread in the ANISCH pitch-angle sums
   bool in_step = false, fwd_half = false;   // set by rsg_ram_part_*: CFL slots are reset once per step
   unsigned long long* d_res_init = nullptr;
 
@@ -594,7 +595,7 @@ int L_finish_fused(rsg_ram* h, int s0, int ns, cudaStream_t st, int l0 = 0, int 
   const double RFAC = 4 * kPI / (kCS * 100);
   RET(prof_mark(h, "k_anisch", st));
   {
-    const int LCH = 6;
+    const int LCH = h->anischLch;
     const int nch = std::max(1, std::min(16, (nl + LCH - 1) / LCH));
     const int lch = (nl + nch - 1) / nch;
     k_anisch_pa_fast<<<dim3(nblk(h->Pp, 32), h->NE, ns), dim3(32, nch), 0, st>>>(h->dev, pk, s0, l0, nl, lch);
@@ -806,6 +807,7 @@ int rsg_ram_create(rsg_ram** out, int nS, int NR, int NT, int NE, int NPA, int d
   if (const char* e = getenv("RSG_COL_T")) h->colT = std::max(32, atoi(e));
   if (const char* e = getenv("RSG_PLANE_T")) h->planeT = std::max(32, atoi(e));
   if (const char* e = getenv("RSG_PLANE_ODD")) h->planeOdd = atoi(e) != 0;
+  if (const char* e = getenv("RSG_ANISCH_LCH")) h->anischLch = std::max(1, atoi(e));
   if (getenv("RSG_NO_GRAPH")) h->use_graph = false;   // kernel-by-kernel launches (profilers)
   RamDev& d = h->dev;
   d.nS = nS; d.NR = NR; d.NT = NT; d.NE = NE; d.NPA = NPA; d.NR1 = h->NR1; d.P = h->P; d.Pp = h->Pp;
