@@ -356,7 +356,7 @@ def main():
             "wall_s_timed_region": wall_s}
     if rank == 0 and world == 1 and not a.no_scb:
         line["scb"] = scb_metrics(local_rank)
-    if rank == 0 and not a.no_cpu_baseline:
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:      # reported at N = 1 only
         v, nthreads, dt = cpu_reference(g, inp, 3 if a.workload == "default" else 1, 1)
         line["cpu_baseline"] = {"value": v, "unit": unit, "cores": nthreads, "kind": "port",
                                 "sample": "full ram_run steps of the same workload on the host cores "
