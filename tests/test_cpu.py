@@ -149,6 +149,58 @@ def test_loss_operators_only_decay(oracle_built, small):
     assert np.all(o.CHARGE[:3, 1:, :, 1:, 1:] < 1.0) and np.all(o.CHARGE[3] == 1.0)
 
 
+def test_flcscatter_matches_wpadif_with_one_coefficient(oracle_built, small):
+    """FLCscatter (src/ModRamLoss.f90:513-575) is WPADIF's tridiagonal with FLC_coef as the only
+    coefficient array: with the same array in ATAW_emic_h (and ATAW_emic_he = 0) the two restatements
+    must agree bit for bit; before the first boundary cycle (T < Dt_bc) it is a no-op."""
+    g, inp = small
+    D = synthetic.synthetic_daa(g, inp) * 20.0
+    a = oracle_built.RamOracle(g, inp, DTs=5.0)
+    b = oracle_built.RamOracle(g, inp, DTs=5.0)
+    a.set_array("FLC_coef", D)
+    b.set_array("ATAW_emic_h", D)
+    a.set_scalar("T", 10.0)
+    assert a.op("flcscatter", 1) == 0 and np.array_equal(a.F2, inp.F2)
+    a.set_scalar("T", 600.0)
+    nv_a = a.op("flcscatter", 1)
+    nv_b = b.op("wpadif", 1)
+    assert nv_a == nv_b
+    assert np.array_equal(a.F2, b.F2) and not np.array_equal(a.F2[0], inp.F2[0])
+
+
+def test_coulomb_operators_properties(oracle_built, small):
+    """COULPARA/COULEN/COULMU (src/ModRamCoul.f90): the drag coefficients are negative (energy
+    loss), vanish at L = NPA (never assigned by the reference), scale linearly with DTs; without
+    plasmasphere electrons (NECR = 0) both operators leave F2 unchanged up to the pitch-angle
+    solve's own round trip; with them F2 stays positive."""
+    g, inp = small
+    o = oracle_built.RamOracle(g, inp, DTs=5.0)
+    o.set_scalar("T", 100.0)
+    o.op("coulpara", 1)
+    ce = o.COULE[0].copy()
+    assert np.all(ce[:, :-1] < 0) and np.all(ce[:, -1] == 0) and np.all(o.ATA[0][:, 1:-1] > 0)
+    o.set_scalar("DTs", 10.0)
+    o.op("coulpara", 1)
+    assert np.allclose(o.COULE[0], 2 * ce, rtol=1e-13, atol=0)
+    o.set_scalar("DTs", 5.0)
+    o.op("coulpara", 1)
+    o.op("coulen", 1)
+    o.op("coulmu", 1)
+    assert np.all(o.F2[0][1:, :, 1:, 1:] > 0) and np.array_equal(o.F2[1:], inp.F2[1:])
+    # no cold electrons -> no drag, and the implicit solve with zero coefficients is the identity
+    import copy
+    inp0 = copy.copy(inp)
+    inp0.NECR = np.zeros_like(inp.NECR)
+    z = oracle_built.RamOracle(g, inp0, DTs=5.0)
+    z.set_scalar("T", 100.0)
+    z.op("coulpara", 1)
+    z.op("coulen", 1)
+    assert np.array_equal(z.F2, inp.F2)
+    z.op("coulmu", 1)
+    f, f0 = z.F2[0][1:, :, 1:, 1:-1], inp.F2[0][1:, :, 1:, 1:-1]
+    assert np.allclose(f, f0, rtol=1e-13, atol=0)
+
+
 def test_scb_steffen_properties(oracle_built):
     """Steffen spline derivative: exact on linear data, zero at local extrema (monotonicity
     preserving), one-sided at the ends; numpy and C++ restatements agree bit for bit."""
