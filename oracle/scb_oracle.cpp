@@ -565,14 +565,14 @@ int iteratePsi(Scb* o, int* ni_out) {
   return fail;
 }
 
-// ---- Compute_convergence, src/ModScbCompute.f90:499-754 (anisotropic branch) ------------
+// ---- Compute_convergence, src/ModScbCompute.f90:499-754 (isotropy 0 and 1) ----------------
 // produces jGradRho/jGradZeta/jGradTheta, Jx..Jz, GradPx..GradPz, jCrossB, GradP and
 // the three norms
 int compute_convergence(Scb* o) {
   DIMS
   const int isotropy = o->I("isotropy");
-  if (isotropy != 0) { std::fprintf(stderr, "scb oracle: Compute_convergence restated for isotropy=0 only\n"); std::abort(); }
   const Spacing s = spacing(o);
+  const double *dPdAlpha = o->D("dPdAlpha"), *dPdPsi = o->D("dPdPsi");
   const double bnormal = o->S("bnormal"), pnormal = o->S("pnormal"), pjconst = o->S("pjconst");
   const double *f = o->D("f"), *fzet = o->D("fzet"), *jac = o->D("jacobian"), *bsq = o->D("bsq"), *sigma = o->D("sigma");
   const double *GRS = o->D("GradRhoSq"), *GTS = o->D("GradThetaSq"), *GZS = o->D("GradZetaSq"), *GRGT = o->D("GradRhoGradTheta"),
@@ -592,6 +592,11 @@ int compute_convergence(Scb* o) {
     for (int j = 1; j <= npsi; ++j)
       for (int k = 1; k <= nzeta; ++k) {
         const double sg = X3(sigma, i, j, k), fj = f[j - 1], fk = fzet[k - 1];
+        if (isotropy == 1) {                                   // :553-556, :575-578
+          X3(jGR, i, j, k) = -1.0 / fj * X3(dPdAlpha, i, j, k);
+          X3(jGZ, i, j, k) = 1.0 / fk * X3(dPdPsi, i, j, k);
+          continue;
+        }
         X3(jGR, i, j, k) = 1.0 / fj * (-1. / sg * X3(dPA, i, j, k) -
                                        1. / (sg * X3(bsq, i, j, k)) * (fj * fj) * fk *
                                            (X3(GRS, i, j, k) * X3(GTGZ, i, j, k) - X3(GRGT, i, j, k) * X3(GRGZ, i, j, k)) *
@@ -632,6 +637,15 @@ int compute_convergence(Scb* o) {
         gPsq[q] = GRS[q] * sq(dPR[q]) + GZS[q] * sq(dPZ[q]) + GTS[q] * sq(dPT[q]) + 2. * dPR[q] * dPZ[q] * GRGZ[q] +
                   2. * dPR[q] * dPT[q] * GRGT[q] + 2. * dPZ[q] * dPT[q] * GTGZ[q] + sq(dDiff[q] / jac[q]) -
                   2. * dPT[q] * dDiff[q] / jac[q];
+        if (isotropy == 1) {                                   // :671-690
+          const double a1 = (fj * dPdPsi[q] * GRS[q] + fk * dPdAlpha[q] * GRGZ[q]);
+          const double a2 = (fj * dPdPsi[q] * GRGZ[q] + fk * dPdAlpha[q] * GZS[q]);
+          const double a3 = (fj * dPdPsi[q] * GRGT[q] + fk * dPdAlpha[q] * GTGZ[q]);
+          GPx[q] = a1 * dXR[q] + a2 * dXZ[q] + a3 * dXT[q];
+          GPy[q] = a1 * dYR[q] + a2 * dYZ[q] + a3 * dYT[q];
+          GPz[q] = a1 * dZR[q] + a2 * dZZ[q] + a3 * dZT[q];
+          continue;
+        }
         const double t1 = (dPR[q] * GRS[q] + dPZ[q] * GRGZ[q] + dPT[q] * GRGT[q]);
         const double t2 = (dPR[q] * GRGZ[q] + dPZ[q] * GZS[q] + dPT[q] * GTGZ[q]);
         const double t3 = (dPR[q] * GRGT[q] + dPZ[q] * GTGZ[q] + dPT[q] * GTS[q]);

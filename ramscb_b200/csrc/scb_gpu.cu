@@ -197,8 +197,14 @@ int rsg_scb_set_pressure(rsg_scb* h, int isotropy, const double* pper, const dou
   h->isotropy = isotropy;
   if (isotropy == 1) {
     SRET(scb_up(h, "dPdAlpha", dPdAlpha)); SRET(scb_up(h, "dPdPsi", dPdPsi));
+    // Compute_convergence reads pper, ppar and dPPerd{Rho,Zeta,Theta} in both branches (:620-631):
+    // whatever the host holds in them is mirrored when given
     if (pper) SRET(scb_up(h, "pper", pper));
     if (ppar) SRET(scb_up(h, "ppar", ppar));
+    if (sigma) SRET(scb_up(h, "sigma", sigma));
+    if (dPPerdTheta) SRET(scb_up(h, "dPPerdTheta", dPPerdTheta));
+    if (dPPerdRho) SRET(scb_up(h, "dPPerdRho", dPPerdRho));
+    if (dPPerdZeta) SRET(scb_up(h, "dPPerdZeta", dPPerdZeta));
   } else {
     SRET(scb_up(h, "pper", pper)); SRET(scb_up(h, "ppar", ppar)); SRET(scb_up(h, "sigma", sigma));
     SRET(scb_up(h, "dPPerdTheta", dPPerdTheta)); SRET(scb_up(h, "dPPerdRho", dPPerdRho)); SRET(scb_up(h, "dPPerdZeta", dPPerdZeta));
@@ -512,11 +518,10 @@ int rsg_scb_iterate_psi(rsg_scb* h, double InConPsi, int nimax, int theChange, i
 int rsg_scb_convergence(rsg_scb* h, double* normDiff, double* normJxB, double* normGradP, int* sorfail) {
   if (!h) return sfail(RSG_ERR_ARG, "null handle");
   if (!h->band_done || !h->press_set) return sfail(RSG_ERR_STATE, "Compute_convergence before computeBandJacob/set_pressure");
-  if (h->isotropy != 0) return sfail(RSG_ERR_UNSUPPORTED, "Compute_convergence: only the anisotropic branch is implemented");
   SCK(cudaSetDevice(h->device));
   dim3 g(nblk(h->nthe, 128), h->npsi, h->nzeta);
   SCK(cudaEventRecord(h->e0, h->st));
-  k_scb_conv1<<<g, 128, 0, h->st>>>(h->dev);
+  k_scb_conv1<<<g, 128, 0, h->st>>>(h->dev, h->isotropy);
   SCKL();
   k_scb_derivs<<<g, 128, 0, h->st>>>(h->dev, h->dev.w1, nullptr, h->dev.w4, nullptr);   // d/drho of jGradThetaPartialRho
   SCKL();
@@ -524,7 +529,7 @@ int rsg_scb_convergence(rsg_scb* h, double* normDiff, double* normJxB, double* n
   SCKL();
   k_scb_derivs<<<g, 128, 0, h->st>>>(h->dev, h->dev.w3, h->dev.w1, nullptr, nullptr);   // d/dtheta of J(pper-ppar) -> w1
   SCKL();
-  k_scb_conv2<<<g, 128, 0, h->st>>>(h->dev, h->bnormal, h->pnormal, h->pjconst, h->d_part);
+  k_scb_conv2<<<g, 128, 0, h->st>>>(h->dev, h->bnormal, h->pnormal, h->pjconst, h->d_part, h->isotropy);
   SCKL();
   SCK(cudaEventRecord(h->e1, h->st));
   h->launches += 5;

@@ -475,15 +475,19 @@ __global__ void k_scb_post_wrap(ScbDev d, double* __restrict__ u, double wrap) {
   S3(u, i, j, d.nzeta) = S3(u, i, j, 1) + wrap;
 }
 
-// ---- Compute_convergence (src/ModScbCompute.f90:553-733), anisotropic branch --------------
+// ---- Compute_convergence (src/ModScbCompute.f90:553-733), isotropy 0 and 1 ----------------
 // stage 1: j.gradRho, j.gradZeta, and the two flux-like fields whose derivatives give j.gradTheta,
 // plus jacobian*(pper-ppar)
-__global__ void __launch_bounds__(128) k_scb_conv1(ScbDev d) {
+__global__ void __launch_bounds__(128) k_scb_conv1(ScbDev d, int isotropy) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = blockIdx.y, k = blockIdx.z;
   if (i >= d.nthe) return;
   const size_t q = (size_t)i + (size_t)d.nthe * ((size_t)j + (size_t)d.npsi * (size_t)k);
   const double sg = d.sigma[q], fj = d.f[j], fk = d.fzet[k];
+  if (isotropy == 1) {                                         // :553-556, :575-578
+    d.jGR[q] = -1.0 / fj * d.dPdAlpha[q];
+    d.jGZ[q] = 1.0 / fk * d.dPdPsi[q];
+  } else {
   d.jGR[q] = 1.0 / fj * (-1. / sg * d.dPA[q] -
                          1. / (sg * d.bsq[q]) * (fj * fj) * fk * (d.GRS[q] * d.GTGZ[q] - d.GRGT[q] * d.GRGZ[q]) *
                              (d.dPT[q] + (1. - sg) * 0.5 * d.dBT[q]) -
@@ -492,13 +496,15 @@ __global__ void __launch_bounds__(128) k_scb_conv1(ScbDev d) {
                          1. / (sg * d.bsq[q]) * fj * (fk * fk) * (d.GRGZ[q] * d.GTGZ[q] - d.GRGT[q] * d.GZS[q]) *
                              (d.dPT[q] + (1. - sg) * 0.5 * d.dBT[q]) +
                          (1. - sg) / sg * 0.5 * d.dBP[q]);
+  }
   d.w1[q] = d.jac[q] * fj * fk * (d.GRGT[q] * d.GRGZ[q] - d.GTGZ[q] * d.GRS[q]);   // jGradThetaPartialRho
   d.w2[q] = d.jac[q] * fj * fk * (d.GRGT[q] * d.GZS[q] - d.GRGZ[q] * d.GTGZ[q]);   // jGradThetaPartialZeta
   d.w3[q] = d.jac[q] * (d.pper[q] - d.ppar[q]);
 }
 // stage 2 (after the derivative passes: w4 = d(w1)/drho, w5 = d(w2)/dzeta, w1 <- d(w3)/dtheta):
 // J, grad P, |J x B|, |grad P| and the per-plane partial sums of the four norms
-__global__ void __launch_bounds__(128) k_scb_conv2(ScbDev d, double bnormal, double pnormal, double pjconst, double* __restrict__ part) {
+__global__ void __launch_bounds__(128) k_scb_conv2(ScbDev d, double bnormal, double pnormal, double pjconst, double* __restrict__ part,
+                                                   int isotropy) {
   __shared__ double sm[4][4];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = blockIdx.y, k = blockIdx.z;
@@ -518,12 +524,22 @@ __global__ void __launch_bounds__(128) k_scb_conv2(ScbDev d, double bnormal, dou
     const double jCBsq = (fj * fj) * (fk * fk) * (GRS * sq(jGZ) + GZS * sq(jGR) - 2.0 * jGZ * jGR * GRGZ);
     const double gPsq = GRS * sq(dPR) + GZS * sq(dPZ) + GTS * sq(dPT) + 2. * dPR * dPZ * GRGZ + 2. * dPR * dPT * GRGT +
                         2. * dPZ * dPT * GTGZ + sq(dD / jac) - 2. * dPT * dD / jac;
+    if (isotropy == 1) {                                       // :671-690
+      const double pP = d.dPdPsi[q], pA = d.dPdAlpha[q];
+      const double a1 = (fj * pP * GRS + fk * pA * GRGZ);
+      const double a2 = (fj * pP * GRGZ + fk * pA * GZS);
+      const double a3 = (fj * pP * GRGT + fk * pA * GTGZ);
+      d.GPx[q] = a1 * d.dXR[q] + a2 * d.dXZ[q] + a3 * d.dXT[q];
+      d.GPy[q] = a1 * d.dYR[q] + a2 * d.dYZ[q] + a3 * d.dYT[q];
+      d.GPz[q] = a1 * d.dZR[q] + a2 * d.dZZ[q] + a3 * d.dZT[q];
+    } else {
     const double t1 = (dPR * GRS + dPZ * GRGZ + dPT * GRGT);
     const double t2 = (dPR * GRGZ + dPZ * GZS + dPT * GTGZ);
     const double t3 = (dPR * GRGT + dPZ * GTGZ + dPT * GTS);
     d.GPx[q] = t1 * d.dXR[q] + t2 * d.dXZ[q] + t3 * d.dXT[q] + dD * GRGT * d.dXR[q] + dD * GTGZ * d.dXZ[q] + dD * GTS * d.dXT[q];
     d.GPy[q] = t1 * d.dYR[q] + t2 * d.dYZ[q] + t3 * d.dYT[q] + dD * GRGT * d.dYR[q] + dD * GTGZ * d.dYZ[q] + dD * GTS * d.dYT[q];
     d.GPz[q] = t1 * d.dZR[q] + t2 * d.dZZ[q] + t3 * d.dZT[q] + dD * GRGT * d.dZR[q] + dD * GTGZ * d.dZZ[q] + dD * GTS * d.dZT[q];
+    }
     const double jCB = sqrt(jCBsq) * bnormal * pjconst;
     const double gP = sqrt(fabs(gPsq)) * pnormal / 6.4;
     d.jCrossB[q] = jCB;

@@ -176,8 +176,9 @@ def test_sor_manufactured_solution(oracle_built):
         assert err <= 1e-9, (order, err)
 
 
-def test_convergence_norms(oracle_built):
-    inp, o, gpu = _pair(oracle_built, **SMALL)
+@pytest.mark.parametrize("isotropy", [0, 1])
+def test_convergence_norms(oracle_built, isotropy):
+    inp, o, gpu = _pair(oracle_built, isotropy=isotropy, **SMALL)
     o.bandjacob(); gpu.computeBandJacob()
     assert o.convergence() == 0
     r = gpu.Compute_convergence()
