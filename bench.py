@@ -345,6 +345,9 @@ def main():
                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": int(alg_bytes),
                     "cell_updates_per_cell_per_launch": ops_per_launch[dom],
+                    "limiter": ("instruction issue, not HBM: the fused kernels move 16 B per cell for "
+                                f"{ops_per_launch[dom]} cell-updates (see traffic) and spend ~42-47 warp instructions per "
+                                "cell-update (profiles/README.md)") if dom in ("k_col_fused", "k_plane_rp") else "see profiles/README.md",
                     "note": "16 B per cell-update (SURVEY 8(d)) x cell-updates of one launch (all cells of the 4 species x the "
                             "operators the kernel fuses); duration = CUDA events on the launching stream inside rsg_ram_run, "
                             "L2 flushed per step.  A fused kernel moves fewer bytes than its algorithmic figure.",
