@@ -41,6 +41,22 @@ def test_plan_slab_sharding_covers_everything():
             assert sa[1] == sb[2] and sa[2] == sb[1]
 
 
+def test_small_grids_leave_extra_ranks_idle():
+    """A species is split among ranks only above parallel.SPLIT_MIN_CELLS cells: below it the
+    first nS ranks take one species each and the others hold nothing (bench.py at N = 8 on the
+    default and 4x grids); at or above it the species x slab groups are used."""
+    small, big = parallel.SPLIT_MIN_CELLS - 1, parallel.SPLIT_MIN_CELLS
+    plans = [parallel.make_plan(8, r, 4, 72, 35, cells_per_species=small) for r in range(8)]
+    assert [p.ns for p in plans] == [1, 1, 1, 1, 0, 0, 0, 0]
+    assert [p.s0 for p in plans[:4]] == [0, 1, 2, 3]
+    assert all(p.G == 1 and p.active == (0, 1, 2, 3) and (p.l0, p.nl, p.k0, p.nk) == (0, 72, 0, 35) for p in plans)
+    plans = [parallel.make_plan(8, r, 4, 72, 35, cells_per_species=big) for r in range(8)]
+    assert all(p.G == 2 and p.ns == 1 and len(p.active) == 8 for p in plans)
+    # never idle when there are enough species
+    assert all(parallel.make_plan(4, r, 4, 72, 35, cells_per_species=small).ns == 1 for r in range(4))
+    assert all(parallel.make_plan(2, r, 4, 72, 35, cells_per_species=small).ns == 2 for r in range(2))
+
+
 def _worker(rank, world, port, NPA, NE, Pp, q):
     import torch
     import torch.distributed as dist
