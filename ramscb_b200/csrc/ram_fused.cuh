@@ -42,14 +42,15 @@ __device__ __forceinline__ void block_sum_to(double* part, size_t cta, double (&
 // the fused path evaluates them here -- once per coefficient set (DRIFTPARA /
 // field / mode change), cached by the host -- instead of inside every sweep.
 // Same expressions and therefore the same bits as the sweeps' own tracking.
-// grid: x = l, y = species
+// grid: x = l, y = energy chunk of KCH, z = species
 // =============================================================================
 __global__ void __launch_bounds__(256) k_cfl_fast(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0,
-                                                  unsigned long long* __restrict__ cfl_all) {
-  const SpecDev& sp = pk.s[s0 + blockIdx.y];
-  unsigned long long* out = cfl_all + 4 * (size_t)(s0 + blockIdx.y);
+                                                  unsigned long long* __restrict__ cfl_all, int KCH) {
+  const SpecDev& sp = pk.s[s0 + blockIdx.z];
+  unsigned long long* out = cfl_all + 4 * (size_t)(s0 + blockIdx.z);
   const int NR = d.NR, NE = d.NE, P = d.P, Pp = d.Pp;
   const int l = blockIdx.x;
+  const int ka = blockIdx.y * KCH, kb = min(NE, ka + KCH);
   double mR = 0.0, mP = 0.0, mE = 0.0, mM = 0.0;
   for (int p = threadIdx.x; p < P; p += blockDim.x) {
     if (d.outp[p]) continue;
@@ -58,7 +59,7 @@ __global__ void __launch_bounds__(256) k_cfl_fast(const __grid_constant__ RamDev
     const double CRp = d.CR[p], gR = d.fRb[o], pa = d.fPa[p], pb = d.fPb[o];
     const double fA = d.fEa[o], fB = d.fEb[o], mA = d.fMa[o], mB = d.fMb[o];
     const double rdmu = d.rDMU[l];
-    for (int k = 0; k < NE; ++k) {
+    for (int k = ka; k < kb; ++k) {
       mR = dmax(mR, fabs(fma(sp.P4[k], gR, CRp)));
       if (i >= 1) {
         if (j >= 1) mP = dmax(mP, fabs(fma(-sp.w2[k], pb, pa)));
@@ -67,7 +68,7 @@ __global__ void __launch_bounds__(256) k_cfl_fast(const __grid_constant__ RamDev
         if (l >= 1) mM = dmax(mM, fabs(fma(sp.wM[k], mB, mA)) * rdmu);
       }
     }
-    if (i >= 1) mE = dmax(mE, 1E-10 * sp.tabE[2]);      // the max(|c|,1e-10) floor of :344 (1/DE largest at K=1)
+    if (i >= 1 && ka == 0) mE = dmax(mE, 1E-10 * sp.tabE[2]);   // the max(|c|,1e-10) floor of :344 (1/DE largest at K=1)
   }
   warp_min_to(out + 0, sp.aRP / dmax(mR, 1E-10));
   warp_min_to(out + 1, sp.aRP / dmax(mP, 1E-10));

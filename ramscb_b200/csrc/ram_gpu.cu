@@ -553,7 +553,8 @@ int L_cfl(rsg_ram* h, int s0, int ns, cudaStream_t st) {
   make_pack(h, pk, s0, ns);
   CK(cudaMemcpy2DAsync(h->d_cfl_all + (size_t)s0 * 4, 4 * sizeof(unsigned long long), h->d_res_init + (size_t)s0 * RES_N,
                        RES_N * sizeof(unsigned long long), 4 * sizeof(unsigned long long), ns, cudaMemcpyDeviceToDevice, st));
-  k_cfl_fast<<<dim3(h->NPA, ns), 256, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0, h->d_cfl_all);
+  const int KCH = 5;
+  k_cfl_fast<<<dim3(h->NPA, (h->NE + KCH - 1) / KCH, ns), 256, 0, st>>>(devfor(h, h->sp[s0].DTs), pk, s0, h->d_cfl_all, KCH);
   CKL();
   h->launches++;
   for (int s = s0; s < s0 + ns; ++s) h->cfl_ok[s] = true;
