@@ -67,14 +67,23 @@ class ClockSampler:
         try:
             import pynvml
             pynvml.nvmlInit()
-            # torch's device index follows CUDA_VISIBLE_DEVICES; NVML's does not
-            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-            phys = index
-            if vis:
-                ids = [v.strip() for v in vis.split(",") if v.strip()]
-                if index < len(ids) and ids[index].isdigit():
-                    phys = int(ids[index])
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            # torch's device index follows CUDA_VISIBLE_DEVICES, NVML's does not: match by PCI address
+            self.h = None
+            try:
+                import torch
+                pr = torch.cuda.get_device_properties(index)
+                bus = f"{pr.pci_domain_id:08X}:{pr.pci_bus_id:02X}:{pr.pci_device_id:02X}.0"
+                self.h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            except Exception:
+                self.h = None
+            if self.h is None:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                phys = index
+                if vis:
+                    ids = [v.strip() for v in vis.split(",") if v.strip()]
+                    if index < len(ids) and ids[index].isdigit():
+                        phys = int(ids[index])
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
             self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
             self.nv = pynvml
         except Exception:
