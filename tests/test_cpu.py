@@ -5,6 +5,7 @@ include/*.h declares (no compute call without a GPU)."""
 import ctypes
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -244,6 +245,27 @@ def test_scb_oracle_dipole_and_sor(oracle_built):
 
 
 # ---- the C-ABI library -------------------------------------------------------------------------
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours) needs no GPU and prints
+    one JSON line with the contract's keys; under torchrun only rank 0 works."""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["higher_is_better"] is True and line["unit"] == "cell-updates/s"
+    assert line["value"] > 0 and line["steps"] == 1 and 1 <= line["warmup"] <= 3
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert "configs[1]" in line["config"]["workload"]
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1"],
+                       capture_output=True, text=True, timeout=120, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
 def test_c_abi_exports_every_declared_symbol():
     from ramscb_b200 import build, host
     build.build()
