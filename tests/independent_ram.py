@@ -1,0 +1,285 @@
+"""A second, independent restatement (numpy, array-at-a-time) of the RAM drift routines, written
+from the Fortran text and not from oracle/ram_oracle.cpp: DRIFTPARA, DRIFTR, DRIFTP, DRIFTE, DRIFTMU
+(src/ModRamDrift.f90:36-473).  The reference cannot be built here, so the
+C++ oracle is "parity unpinned"; two restatements of different shape (scalar loops in C++,
+whole-array expressions here) that agree bit for bit at least rule out transcription slips in
+either.  IEEE double arithmetic, same operation order as the Fortran, no fused multiply-add.
+
+Arrays use the reference's shapes with 0-based numpy indices: F2[S,I,J,K,L], fields [I,J(,L)]
+with the radial ghost row at index NR.
+"""
+import numpy as np
+
+OME = 7.3E-5
+Q, CS = 1.602E-19, 2.998E8
+FRAC_CFL = 0.8
+
+
+def limiter_flux(Fm, Fp, Fn, Fn1, c, chat, sgn, beta):
+    """FBND for every interface of an array of lines.  Fm=F(m), Fp=F(m+1), Fn=F(n), Fn1=F(n-1) with
+    n = m+1-sgn already gathered by the caller.  (:246-259)"""
+    X = Fp - Fm
+    FUP = 0.5 * (Fm + Fp - sgn * X)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        R = (Fn - Fn1) / X
+        LIM = np.maximum(np.minimum(beta * R, 1.), np.minimum(R, beta))
+        CORR = -0.5 * (chat - sgn) * X
+        lim = FUP + LIM * CORR
+    use = (np.abs(X) > 1.E-27) & (R > 0)
+    return np.where(use, lim, FUP)
+
+
+def driftpara(g, S, DTs):
+    """P1(I), P2(I,K), EDOT(I,K) (:64-85); QS = species charge."""
+    s = S - 1
+    QS = float(g.QS[s])
+    RLZ = g.RLZ[:g.NR]
+    P1 = DTs / g.DPHI / 2 / g.MDR / RLZ
+    P2 = DTs * g.EKEV[None, :] * 1000 * (g.GREL[s][None, :] + 1) / g.GREL[s][None, :] / (RLZ[:, None] ** 2) / g.DPHI / QS
+    EDOT = g.EBND[None, :] * DTs / RLZ[:, None] * (g.GRBND[s][None, :] + 1) / g.GRBND[s][None, :] / 2.
+    return QS, P1, P2, EDOT
+
+
+def driftp(g, inp, F2, S, DTs, beta):
+    """DRIFTP for species S; returns (new F2 of the species, DtDriftP)."""
+    NR, NT, NE, NPA = g.NR, g.NT, g.NE, g.NPA
+    s = S - 1
+    QS, P1, P2, EDOT = driftpara(g, S, DTs)
+    F = F2[s].copy()                       # [I,J,K,L]
+    FN, FH, B, VT, EIR = inp.FNIS, inp.FNHS, inp.BNES, inp.VT, inp.EIR
+    RLZ = g.RLZ[:NR]
+    I = np.arange(1, NR)                   # Fortran I = 2..NR
+    Jv = np.arange(1, NT)                  # Fortran J = 2..NT
+    J1 = np.where(Jv == NT - 1, 1, Jv + 1)  # J1 = J+1, 2 when J = NT
+    ix = np.ix_
+    # 3-D pieces [I,J,L]
+    GPA1 = (FN[ix(I, Jv)] + FN[ix(I, J1)] + (FN[ix(I + 1, J1)] + FN[ix(I + 1, Jv)] - FN[ix(I - 1, Jv)] - FN[ix(I - 1, J1)])
+            * RLZ[I][:, None, None] / 2. / g.MDR)
+    GPA2 = (RLZ[I][:, None, None] / 4. / g.MDR * (FN[ix(I, Jv)] + FN[ix(I, J1)] - 2 * FH[ix(I, Jv)] - 2 * FH[ix(I, J1)])
+            * (B[ix(I + 1, J1)] + B[ix(I + 1, Jv)] - B[ix(I - 1, Jv)] - B[ix(I - 1, J1)])[:, :, None]
+            / (B[ix(I, Jv)] + B[ix(I, J1)])[:, :, None])
+    A = ((VT[ix(I + 1, Jv)] + VT[ix(I + 1, J1)] - VT[ix(I - 1, Jv)] - VT[ix(I - 1, J1)]) * P1[I][:, None])      # [I,J]
+    Cterm = (EIR[ix(I, J1)] + EIR[ix(I, Jv)]) / RLZ[I][:, None] * DTs / g.DPHI                                   # [I,J]
+    sB = (B[ix(I, Jv)] + B[ix(I, J1)])                                                                           # [I,J]
+    # CDriftP[I,J,K,L]
+    Bt = P2[I][:, None, :, None] * (GPA1 + GPA2)[:, :, None, :] / (FH[ix(I, Jv)] + FH[ix(I, J1)])[:, :, None, :]
+    CD = (A[:, :, None, None] - Bt - Cterm[:, :, None, None]) / sB[:, :, None, None] + OME * DTs / g.DPHI
+    inside = (inp.outsideMGNP[ix(I, Jv)] == 0)
+    ctemp = np.maximum(np.abs(CD), 1E-10)
+    dts = np.where(inside[:, :, None, None], FRAC_CFL * DTs / ctemp, np.inf)
+    Dt = min(100000.0, float(dts.min()))
+    sgn = np.where(CD < 0, -1.0, 1.0)
+    Fl = F[1:]                              # [I(2..NR), J(1..NT), K, L]
+    Fm, Fp = Fl[:, Jv], Fl[:, J1]
+    # n = J+1-sgn (wrapped: N > NT -> N-NT+1): sgn=+1 -> n=J, n-1=J-1 ; sgn=-1 -> n=J+2, n-1=J+1
+    N2 = Jv + 2
+    N2 = np.where(N2 > NT - 1, N2 - NT + 1, N2)          # 0-based: index > NT-1 wraps to index-NT+1
+    Fn = np.where(sgn > 0, Fm, Fl[:, N2])
+    Fn1 = np.where(sgn > 0, Fl[:, Jv - 1], Fp)
+    FB = limiter_flux(Fm, Fp, Fn, Fn1, CD, CD, sgn, beta)            # FBND(J), J = 2..NT
+    # FBND(1) = FBND(NT), CDriftP(.,1,.,.) = CDriftP(.,NT,.,.)
+    FBm1 = np.concatenate([FB[:, -1:], FB[:, :-1]], axis=1)          # FBND(J-1)
+    CDm1 = np.concatenate([CD[:, -1:], CD[:, :-1]], axis=1)
+    new = Fm - CD * FB + CDm1 * FBm1
+    new = np.where(new < 0, 1E-15, new)
+    out = F.copy()
+    out[1:, 1:] = new
+    out[1:, 0] = out[1:, NT - 1]
+    return out, Dt
+
+
+def drifte(g, inp, F2, S, DTs, beta):
+    """DRIFTE for species S; returns (new F2 of the species, DtDriftE)."""
+    NR, NT, NE, NPA = g.NR, g.NT, g.NE, g.NPA
+    s = S - 1
+    QS, P1, P2, EDOT = driftpara(g, S, DTs)
+    F = F2[s].copy()
+    FN, FH, B, VT, EIR, EIP = inp.FNIS, inp.FNHS, inp.BNES, inp.VT, inp.EIR, inp.EIP
+    RLZ = g.RLZ[:NR]
+    I = np.arange(1, NR)
+    J = np.arange(0, NT)
+    J0 = np.where(J == 0, NT - 2, J - 1)
+    J2 = np.where(J == NT - 1, 1, J + 1)
+    ix = np.ix_
+    R1 = RLZ[I][:, None]
+    DRD1 = (EIP[ix(I, J)] * R1 - (VT[ix(I, J2)] - VT[ix(I, J0)]) / 2. / g.DPHI) / B[ix(I, J)]
+    DPD1 = OME * R1 + ((VT[ix(I + 1, J)] - VT[ix(I - 1, J)]) / 2 / g.MDR - EIR[ix(I, J)]) / B[ix(I, J)]
+    Bc = B[ix(I, J)][:, :, None]
+    R3 = R1[:, :, None]
+    FNc, FHc = FN[ix(I, J)], FH[ix(I, J)]
+    GPA = (1. - FNc / 2. / FHc) / Bc
+    GPR1 = GPA * (B[ix(I + 1, J)] - B[ix(I - 1, J)])[:, :, None] / 2. / g.MDR
+    GPR2 = -FNc / FHc / R3
+    GPR3 = -(FN[ix(I + 1, J)] - FN[ix(I - 1, J)]) / 2. / g.MDR / FHc
+    GPP1 = GPA * (B[ix(I, J2)] - B[ix(I, J0)])[:, :, None] / 2. / g.DPHI
+    GPP2 = -(FN[ix(I, J2)] - FN[ix(I, J0)]) / 2. / g.DPHI / FHc
+    DRD2 = ((FN[ix(I, J2)] - FN[ix(I, J0)]) / 2. / g.DPHI
+            + (FNc - 2 * FHc) * (B[ix(I, J2)] - B[ix(I, J0)])[:, :, None] / 4 / Bc / g.DPHI)
+    DPD2 = (FNc + (FN[ix(I + 1, J)] - FN[ix(I - 1, J)]) * R3 / 2 / g.MDR
+            + R3 * (FNc - 2 * FHc) / 4 / g.MDR * (B[ix(I + 1, J)] - B[ix(I - 1, J)])[:, :, None] / Bc)
+    dBdt1 = inp.dBdt[ix(I, J)][:, :, None] * (1. - FNc / 2. / FHc) * R3 / Bc
+    dIdt1 = -inp.dIdt[ix(I, J)] * R3 / FHc
+    eK = g.EBND * 1e3 * (g.GRBND[s] + 1) / 2 / g.GRBND[s]                  # [K]
+    # [I,J,K,L]
+    EDT1 = eK[None, None, :, None] / FHc[:, :, None, :] / R3[:, :, None, :] / Bc[:, :, None, :] / QS
+    DRDT = DRD1[:, :, None, None] + EDT1 * DRD2[:, :, None, :] * R3[:, :, None, :]
+    DPDT = DPD1[:, :, None, None] - EDT1 * DPD2[:, :, None, :]
+    CD = EDOT[I][:, None, :, None] * ((GPR1 + GPR2 + GPR3)[:, :, None, :] * DRDT + (GPP1 + GPP2)[:, :, None, :] * DPDT
+                                      + dBdt1[:, :, None, :] + dIdt1[:, :, None, :])
+    inside = (inp.outsideMGNP[ix(I, J)] == 0)
+    ctemp = np.maximum(np.abs(CD), 1E-10)
+    dts = np.where(inside[:, :, None, None], FRAC_CFL * DTs * g.DE[None, None, :, None] / ctemp, np.inf)
+    Dt = min(10000.0, float(dts.min()))
+    # line buffer F(0:NE+2): F(1), F(0) ghosts, F(NE+1) = F(NE+2) = 0
+    Fl = F[1:]                                                            # [I,J,K,L]
+    G = g.GREL[s]
+    EZERO = g.EKEV[0] - g.WE[0]
+    GRZ = 1. + EZERO * 1000. * Q / g.RMAS[s] / CS / CS
+    f1 = Fl[:, :, 1] * G[0] / G[1] * np.sqrt((G[1] ** 2 - 1) / (G[0] ** 2 - 1))
+    f0 = f1 * GRZ / G[0] * np.sqrt((G[0] ** 2 - 1) / (GRZ ** 2 - 1))
+    z = np.zeros_like(f1)
+    buf = np.concatenate([f0[:, :, None], f1[:, :, None], Fl[:, :, 1:], z[:, :, None], z[:, :, None]], axis=2)   # index = Fortran K
+    K = np.arange(1, NE + 1)
+    sgn = np.where(CD < 0, -1.0, 1.0)
+    Fm, Fp = buf[:, :, K], buf[:, :, K + 1]
+    Fn = np.where(sgn > 0, Fm, buf[:, :, K + 2])
+    Fn1 = np.where(sgn > 0, buf[:, :, K - 1], Fp)
+    FB = limiter_flux(Fm, Fp, Fn, Fn1, CD, CD / g.DE[None, None, :, None], sgn, beta)          # FBND(1..NE)
+    WE = g.WE[None, None, 1:, None]
+    new = Fl[:, :, 1:] - CD[:, :, 1:] / WE * FB[:, :, 1:] + CD[:, :, :-1] / WE * FB[:, :, :-1]
+    new = np.where(new < 0, 1E-15, new)
+    out = F.copy()
+    out[1:, :, 1:] = new
+    return out, Dt
+
+
+def driftmu(g, inp, F2, S, DTs, beta):
+    """DRIFTMU for species S (:382-473); returns (new F2 of the species, DtDriftMu)."""
+    NR, NT, NE, NPA = g.NR, g.NT, g.NE, g.NPA
+    s = S - 1
+    QS = float(g.QS[s])
+    F = F2[s].copy()
+    BI, BH, B, VT, EIR, EIP, FH = inp.BOUNIS, inp.BOUNHS, inp.BNES, inp.VT, inp.EIR, inp.EIP, inp.FNHS
+    RLZ = g.RLZ[:NR]
+    I = np.arange(1, NR)
+    J = np.arange(0, NT)
+    J0 = np.where(J == 0, NT - 2, J - 1)
+    J1 = np.where(J == NT - 1, 1, J + 1)
+    L = np.arange(1, NPA)                      # Fortran L = 2..NPA
+    ix = np.ix_
+    R1 = RLZ[I][:, None]
+    R3 = R1[:, :, None]
+    DRM1 = (EIP[ix(I, J)] * R1 - (VT[ix(I, J1)] - VT[ix(I, J0)]) / 2 / g.DPHI) / B[ix(I, J)]
+    DPM1 = OME * R1 + ((VT[ix(I + 1, J)] - VT[ix(I - 1, J)]) / 2 / g.MDR - EIR[ix(I, J)]) / B[ix(I, J)]
+    MUBOUN = g.MU + 0.5 * g.WMU
+    MUDOT = (1. - MUBOUN[None, :] ** 2) * DTs / 2 / MUBOUN[None, :] / RLZ[:, None]       # [I,L]
+    MUDOT[:, NPA - 1] = 0.
+    Bc = B[ix(I, J)][:, :, None]
+    BIc, BHc = BI[ix(I, J, L)], BH[ix(I, J, L)]
+    CMUDOT = MUDOT[ix(I, L)][:, None, :] * BIc / BHc                                   # [I,J,L]
+    GMR1 = ((B[ix(I + 1, J)] - B[ix(I - 1, J)]) / 4 / g.MDR / B[ix(I, J)])[:, :, None]
+    GMR2 = 1 / R3
+    GMR3 = (BI[ix(I + 1, J, L)] - BI[ix(I - 1, J, L)]) / 2 / g.MDR / BIc
+    GMP1 = ((B[ix(I, J1)] - B[ix(I, J0)]) / 4 / g.DPHI / B[ix(I, J)])[:, :, None]
+    GMP2 = (BI[ix(I, J1, L)] - BI[ix(I, J0, L)]) / 2 / g.DPHI / BIc
+    DRM2 = ((BI[ix(I, J1, L)] - BI[ix(I, J0, L)]) / 2 / g.DPHI
+            + (BIc - 2 * BHc) * (B[ix(I, J1)] - B[ix(I, J0)])[:, :, None] / 4 / Bc / g.DPHI)
+    DPM2 = (BIc + (BI[ix(I + 1, J, L)] - BI[ix(I - 1, J, L)]) * R3 / 2 / g.MDR
+            + (BIc - 2 * BHc) * R3 / 4 / g.MDR * (B[ix(I + 1, J)] - B[ix(I - 1, J)])[:, :, None] / Bc)
+    dBdt2 = (inp.dBdt[ix(I, J)] / 2. / B[ix(I, J)] * R1)[:, :, None]
+    dIbndt2 = inp.dIbndt[ix(I, J, L)] * R3 / BIc
+    eK = g.EKEV * 1e3 * (g.GREL[s] + 1) / 2 / g.GREL[s]                                  # [K]
+    EDT = eK[None, None, :, None] / BHc[:, :, None, :] / R3[:, :, None, :] / Bc[:, :, None, :] / QS   # [I,J,K,L]
+    DRDM = DRM1[:, :, None, None] + EDT * DRM2[:, :, None, :] * R3[:, :, None, :]
+    DPDM = DPM1[:, :, None, None] - EDT * DPM2[:, :, None, :]
+    CD = -CMUDOT[:, :, None, :] * ((GMR1 + GMR2 + GMR3)[:, :, None, :] * DRDM + (GMP1 + GMP2)[:, :, None, :] * DPDM
+                                   + dBdt2[:, :, None, :] + dIbndt2[:, :, None, :])          # L = 2..NPA
+    inside = (inp.outsideMGNP[ix(I, J)] == 0)
+    ctemp = np.maximum(np.abs(CD), 1E-32)
+    dts = np.where(inside[:, :, None, None], FRAC_CFL * DTs * g.DMU[None, None, None, 1:] / ctemp, np.inf)
+    Dt = min(10000.0, float(dts.min()))
+    Fl = F[1:].copy()                          # [I,J,K,L], line buffer with F(1) = F(2)
+    Fl[:, :, :, 0] = Fl[:, :, :, 1]
+    # limited flux for L = 2..NPA-2 (0-based 1..NPA-3); n = L+1-sgn
+    Lf = np.arange(1, NPA - 2)
+    c = CD[:, :, :, :NPA - 3]                  # CDriftMu at L = 2..NPA-2
+    sgn = np.where(c < 0, -1.0, 1.0)
+    Fm, Fp = Fl[..., Lf], Fl[..., Lf + 1]
+    Fn = np.where(sgn > 0, Fm, Fl[..., Lf + 2])
+    Fn1 = np.where(sgn > 0, Fl[..., Lf - 1], Fp)
+    FBl = limiter_flux(Fm, Fp, Fn, Fn1, c, c / g.DMU[None, None, None, 1:NPA - 2], sgn, beta)
+    # FBND(1) = 0, FBND(2..NPA-2) limited, FBND(NPA-1) = F(NPA); CDriftMu(.,1) = 0
+    FB = np.concatenate([np.zeros_like(FBl[..., :1]), FBl, Fl[..., NPA - 1:NPA]], axis=3)     # index 0..NPA-2 = Fortran L = 1..NPA-1
+    CDf = np.concatenate([np.zeros_like(CD[..., :1]), CD], axis=3)                          # index = Fortran L-1, L = 1..NPA
+    Lu = np.arange(1, NPA - 1)                 # update L = 2..NPA-1
+    WMU = g.WMU[None, None, None, Lu]
+    new = F[1:][..., Lu] - CDf[..., Lu] / WMU * FB[..., Lu] + CDf[..., Lu - 1] / WMU * FB[..., Lu - 1]
+    new = np.where(new < 0, 1E-15, new)
+    out = F.copy()
+    out[1:, :, :, 1:NPA - 1] = new
+    out[1:, :, :, NPA - 1] = (out[1:, :, :, NPA - 2] * FH[ix(I, J)][:, :, None, NPA - 1] * g.MU[NPA - 1]
+                              / FH[ix(I, J)][:, :, None, NPA - 2] / g.MU[NPA - 2])
+    return out, Dt
+
+
+def driftr(g, inp, F2, S, DTs, beta):
+    """DRIFTR for species S (:95-198), line by line in the reference's (K, L, J) order because the
+    ghost cells F(NR+1:NR+2) of the line buffer are only rewritten on inflow lines."""
+    NR, NT, NE, NPA = g.NR, g.NT, g.NE, g.NPA
+    s = S - 1
+    QS = float(g.QS[s])
+    F = F2[s].copy()
+    FN, FH, B, VT, EIP = inp.FNIS, inp.FNHS, inp.BNES, inp.VT, inp.EIP
+    RLZ = g.RLZ[:NR]
+    I = np.arange(0, NR)
+    J = np.arange(0, NT)
+    J0 = np.where(J == 0, NT - 2, J - 1)
+    J1 = np.where(J == NT - 1, 1, J + 1)
+    ix = np.ix_
+    VR = DTs / g.MDR / (RLZ + 0.5 * g.MDR) / 2 / g.DPHI
+    sB = B[ix(I, J)] + B[ix(I + 1, J)]
+    CR = (VR[:, None] * (VT[ix(I, J0)] + VT[ix(I + 1, J0)] - VT[ix(I, J1)] - VT[ix(I + 1, J1)]) / sB
+          + (EIP[ix(I, J)] + EIP[ix(I + 1, J)]) / sB * DTs / g.MDR)                       # [I,J]
+    CGR1 = FN[ix(I + 1, J1)] + FN[ix(I, J1)] - FN[ix(I + 1, J0)] - FN[ix(I, J0)]          # [I,J,L]
+    CGR2 = (B[ix(I + 1, J1)] + B[ix(I, J1)] - B[ix(I + 1, J0)] - B[ix(I, J0)])[:, :, None]
+    CGR3 = CGR1 + (FN[ix(I + 1, J)] + FN[ix(I, J)] - 2 * FH[ix(I + 1, J)] - 2 * FH[ix(I, J)]) * CGR2 / 2. / (B[ix(I + 1, J)] + B[ix(I, J)])[:, :, None]
+    Dt = 100000.0
+    inside = (inp.outsideMGNP == 0)
+    buf = np.zeros(NR + 2)
+    FB = np.zeros(NR)
+    out = F.copy()
+    for K in range(NE):
+        P4 = DTs * g.EKEV[K] * 1000.0 * (g.GREL[s, K] + 1) / g.GREL[s, K] / g.DPHI / g.MDR / QS
+        CGR = CGR3 / (FH[ix(I, J)] + FH[ix(I + 1, J)]) * P4 / 2. / sB[:, :, None] / (RLZ + 0.5 * g.MDR)[:, None, None]
+        CD = CR[:, :, None] + CGR                                                         # [I,J,L]
+        m = np.where(inside[:, :, None], FRAC_CFL * DTs / np.maximum(np.abs(CD), 1E-10), np.inf)
+        Dt = min(Dt, float(m.min()))
+        SG = np.where(CD < 0, -1, 1)
+        for Lq in range(NPA):
+            for j in range(NT):
+                c, sg = CD[:, j, Lq], SG[:, j, Lq]
+                buf[:NR] = F[:, j, K, Lq]
+                if sg[NR - 1] == 1:
+                    FB[0] = 0.
+                    FB[NR - 1] = buf[NR - 1]
+                    UR = NR - 1
+                else:
+                    FB[0] = buf[1]
+                    UR = NR
+                    if inp.outsideMGNP[NR - 1, j] == 1:
+                        buf[NR] = 0.
+                        buf[NR + 1] = 0.
+                    else:
+                        fg = inp.FGEOS[s, j, K, Lq]
+                        buf[NR] = fg * g.CONF1 * FH[NR - 1, j, Lq]
+                        buf[NR + 1] = fg * g.CONF2 * FH[NR - 1, j, Lq]
+                ii = np.arange(1, UR)                                  # Fortran I = 2..UR
+                sgi = sg[ii].astype(float)
+                Fm, Fp = buf[ii], buf[ii + 1]
+                Fn = np.where(sgi > 0, Fm, buf[np.minimum(ii + 2, NR + 1)])
+                Fn1 = np.where(sgi > 0, buf[ii - 1], Fp)
+                FB[ii] = limiter_flux(Fm, Fp, Fn, Fn1, c[ii], c[ii], sgi, beta)
+                iu = np.arange(1, NR)
+                new = buf[iu] - c[iu] * FB[iu] + c[iu - 1] * FB[iu - 1]
+                out[1:, j, K, Lq] = np.where(new < 0, 1E-15, new)
+    return out, Dt

@@ -150,6 +150,41 @@ def test_loss_operators_only_decay(oracle_built, small):
     assert np.all(o.CHARGE[:3, 1:, :, 1:, 1:] < 1.0) and np.all(o.CHARGE[3] == 1.0)
 
 
+@pytest.mark.parametrize("variant", ["noisy_fields", "adversarial", "carry_over"])
+def test_independent_numpy_restatement_of_the_drifts(oracle_built, variant):
+    """tests/independent_ram.py restates DRIFTPARA/DRIFTR/P/E/MU a second time, array-at-a-time in
+    numpy straight from the Fortran text.  The C++ oracle (scalar loops) must agree with it bit for
+    bit -- F2 and the CFL limit -- on inductive fields with an E field and magnetopause flags, on the
+    adversarial distribution, and on an input that triggers DRIFTR's ghost-cell carry-over."""
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import independent_ram as ind
+    g = grids.build_grids(NR=12, NT=9, NE=16)
+    if variant == "noisy_fields":
+        inp = synthetic.make_inputs(g, f2_kind="noisy", inductive=True, efield_ind=True, mgnp=True)
+    elif variant == "adversarial":
+        inp = synthetic.make_inputs(g, f2_kind="adversarial", inductive=True, efield_ind=True, mgnp=True)
+    else:
+        inp = synthetic.make_inputs(g, f2_kind="noisy", efield_ind=True)
+        inp.EIP[g.NR - 1, :] = 6e-4 * np.cos(g.PHI)       # reverse the radial drift between the last two shells
+        inp.EIP[g.NR, :] = -6e-4 * np.cos(g.PHI)
+    beta = 1.5
+    for S in (1, 4):
+        for name, fn, dtn in (("driftr", ind.driftr, "DtDriftR"), ("driftp", ind.driftp, "DtDriftP"),
+                              ("drifte", ind.drifte, "DtDriftE"), ("driftmu", ind.driftmu, "DtDriftMu")):
+            if variant == "carry_over" and name != "driftr":
+                continue
+            o = oracle_built.RamOracle(g, inp, DTs=5.0)
+            o.op("driftpara", S)
+            o.op(name, S)
+            if variant == "carry_over":
+                c = o.cdrift(S, 0)
+                assert np.sum((c[g.NR - 1] >= 0) & (c[g.NR - 2] < 0)) > 0, "input does not trigger the carry-over"
+            new, dt = fn(g, inp, inp.F2, S, 5.0, beta)
+            assert np.array_equal(new, o.F2[S - 1]), (variant, S, name, float(np.abs(new - o.F2[S - 1]).max()))
+            assert dt == getattr(o, dtn)[S - 1], (variant, S, name)
+            assert not np.array_equal(new, inp.F2[S - 1])
+
+
 def test_flcscatter_matches_wpadif_with_one_coefficient(oracle_built, small):
     """FLCscatter (src/ModRamLoss.f90:513-575) is WPADIF's tridiagonal with FLC_coef as the only
     coefficient array: with the same array in ATAW_emic_h (and ATAW_emic_he = 0) the two restatements
