@@ -23,7 +23,9 @@
 // (src/ModRamFunctions.f90:481-482) and the energy ladder feeding every
 // operator against output/test1/dsbnd.ref (tests/golden/).  The operators
 // themselves are "parity unpinned": validated by line-by-line review against
-// the cited Fortran and by conservation / positivity / symmetry properties.
+// the cited Fortran, by conservation / positivity / symmetry properties, and by
+// a second, independent numpy restatement of the drifts, losses, SUMRC, ANISCH
+// and WPADIF (tests/independent_ram.py) that agrees with this file bit for bit.
 // =============================================================================
 #include <algorithm>
 #include <cmath>

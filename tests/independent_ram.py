@@ -283,3 +283,136 @@ def driftr(g, inp, F2, S, DTs, beta):
                 new = buf[iu] - c[iu] * FB[iu] + c[iu - 1] * FB[iu - 1]
                 out[1:, j, K, Lq] = np.where(new < 0, 1E-15, new)
     return out, Dt
+
+
+# ---------------------------------------------------------------------------------------
+# losses, moments, pitch-angle diffusion (src/ModRamLoss.f90:19-170, 457-507;
+# src/ModRamRun.f90:231-259, 343-415; src/ModRamWPI.f90:643-714)
+# exp / pow / log10 go through the C library one value at a time (numpy's vector loops may round
+# the last bit differently from libm, which is what the C++ oracle calls).
+# ---------------------------------------------------------------------------------------
+import math
+
+_exp = np.frompyfunc(math.exp, 1, 1)
+_pow = np.frompyfunc(math.pow, 2, 1)
+
+CEX_POLY = {0: (-18.767, -0.11017, -3.8173e-2, -0.1232, -5.0488e-2),        # Hydrogen
+            2: (-20.789, 0.92316, -0.68017, 0.66153, -0.20998),            # HeliumP1
+            1: (-18.987, -0.10613, -5.4841E-3, -1.6262E-2, -7.0554E-3)}    # OxygenP1
+
+
+def cepara(g, inp, S, DTs):
+    """CHARGE(I,J,K,L) of species S and ATLOS(I,K) (:19-170).  kind: 0 H+, 1 O+, 2 He+, 3 e- (no CEX)."""
+    NR, NT, NE, NPA = g.NR, g.NT, g.NE, g.NPA
+    s = S - 1
+    CH = np.ones((NR, NT, NE, NPA))
+    kind = int(g.kind[s])
+    if kind in CEX_POLY:
+        a0, a1, a2, a3, a4 = CEX_POLY[kind]
+        for K in range(1, NE):
+            X = math.log10(g.EKEV[K])
+            if X < -2.:
+                X = -2.
+            # integer powers as the compiler expands them (powi): X**3 = X*X*X, X**4 = (X*X)*(X*X)
+            Y = a0 + a1 * X + a2 * (X * X) + a3 * (X * X * X) + a4 * ((X * X) * (X * X))
+            ALPHA = math.pow(10., Y) * g.V[s, K] * inp.HDNS[1:NR, :, 1:] * DTs
+            CH[1:, :, K, 1:] = _exp(-ALPHA).astype(float)
+    AT = np.zeros((NR, NE))
+    for K in range(1, NE):
+        for I in range(1, NR):
+            TAUB = 2 * g.RLZ[I] / g.V[s, K]
+            AT[I, K] = math.exp(-DTs / TAUB)
+    return CH, AT
+
+
+def charexchange(F, CH):
+    out = F.copy()
+    out[1:, :, 1:, 1:] = F[1:, :, 1:, 1:] * CH[1:, :, 1:, 1:]
+    return out
+
+
+def atmol(g, inp, F, AT):
+    NR, NPA = g.NR, g.NPA
+    out = F.copy()
+    for I in range(1, NR):
+        u = int(g.UPA[I])                       # Fortran L = u..NPA
+        fac = _pow(AT[I, 1:][None, :, None], 1 / inp.FNHS[I, :, u - 1:][:, None, :]).astype(float)    # [J,K,L]
+        out[I, :, 1:, u - 1:] = F[I, :, 1:, u - 1:] * fac
+    return out
+
+
+def sumrc(g, F):
+    """SETRC in the reference's summation order I, K, L, J (:246-253)."""
+    NR, NT, NE, NPA = g.NR, g.NT, g.NE, g.NPA
+    W = (F[1:, :NT - 1, 1:, 1:] * g.WE[None, None, 1:, None] * g.WMU[None, None, None, 1:])
+    T = g.EKEV[None, None, 1:, None] * W                 # [I,J,K,L]
+    acc = 0.0
+    for v in np.transpose(T, (0, 2, 3, 1)).ravel():      # I, K, L, J order
+        acc = acc + v
+    return acc
+
+
+def anisch_pressures(g, inp, F, S):
+    """PPERT, PPART(I,J) (:343-415) and the side effect F2(.,.,K,1) = F2(.,.,K,2); vectorised over
+    (I,J), energy and pitch-angle sums in the reference's order."""
+    NR, NT, NE, NPA = g.NR, g.NT, g.NE, g.NPA
+    s = S - 1
+    F = F.copy()
+    RFAC = 4 * 3.1415926535897932384626433832795 / (CS * 100)
+    PPERT = np.zeros((NR, NT))
+    PPART = np.zeros((NR, NT))
+    for I in range(1, NR):
+        u = int(g.UPA[I] - 1)
+        klo = 2
+        for iwa in range(5):
+            PPER = np.zeros(NT)
+            PPAR = np.zeros(NT)
+            for K in range(klo, int(g.khi[iwa]) + 1):       # Fortran K
+                F[I, :, K - 1, 0] = F[I, :, K - 1, 1]
+                SUME = np.zeros(NT)
+                SUMA = np.zeros(NT)
+                for L in range(1, u + 1):                   # Fortran L
+                    ERNM = g.WMU[L - 1] / g.FFACTOR[s, I, K - 1, L - 1] / inp.FNHS[I, :, L - 1]
+                    EPMA = ERNM * g.MU[L - 1] * g.MU[L - 1]
+                    EPME = ERNM - EPMA
+                    SUME = SUME + F[I, :, K - 1, L - 1] * EPME
+                    SUMA = SUMA + F[I, :, K - 1, L - 1] * EPMA
+                PPER = PPER + g.EPP[s, K - 1] * SUME
+                PPAR = PPAR + g.EPP[s, K - 1] * SUMA
+            PPAR = 2 * RFAC * PPAR
+            PPER = RFAC * PPER
+            klo = int(g.khi[iwa]) + 1
+            PPERT[I] = PPERT[I] + PPER
+            PPART[I] = PPART[I] + PPAR
+    return PPERT, PPART, F
+
+
+def wpadif(g, inp, F, DA, DB, DTs):
+    """WPADIF with coefficient arrays DA + DB [I,J,K,L] (:643-714); vectorised over (I,J,K)."""
+    NR, NT, NE, NPA = g.NR, g.NT, g.NE, g.NPA
+    out = F.copy()
+    Fl = F[1:, :, 1:, :]                                       # I = 2..NR, K = 2..NE
+    FACMU = (inp.FNHS[1:NR] * g.MU[None, None, :])[:, :, None, :]   # [I,J,1,L]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        f = Fl / FACMU                                         # L = 1 (MU = 0) is never used: F(1) = F(2)
+    RK = np.zeros(Fl.shape)
+    RL = np.zeros(Fl.shape)
+    RL[..., 0] = -1.
+    D = (DA + DB)[1:, :, 1:, :]
+    for L in range(1, NPA - 1):                                # Fortran L = 2..NPA-1
+        AN = D[..., L] / g.DMU[L]
+        GN = D[..., L - 1] / g.DMU[L - 1]
+        AN = AN * DTs / FACMU[..., L] / g.WMU[L]
+        GN = GN * DTs / FACMU[..., L] / g.WMU[L]
+        BN = AN + GN
+        RP = f[..., L]
+        DENOM = BN + GN * RL[..., L - 1] + 1
+        RK[..., L] = (RP + GN * RK[..., L - 1]) / DENOM
+        RL[..., L] = -AN / DENOM
+    new = np.zeros(Fl.shape)
+    new[..., NPA - 2] = RK[..., NPA - 2] / (1 + RL[..., NPA - 2])
+    for L in range(NPA - 3, -1, -1):
+        new[..., L] = RK[..., L] - RL[..., L] * new[..., L + 1]
+    new[..., NPA - 1] = new[..., NPA - 2]
+    out[1:, :, 1:, :] = new * FACMU
+    return out

@@ -185,6 +185,38 @@ def test_independent_numpy_restatement_of_the_drifts(oracle_built, variant):
             assert not np.array_equal(new, inp.F2[S - 1])
 
 
+def test_independent_numpy_restatement_of_losses_and_moments(oracle_built):
+    """Same cross-check for CEPARA (CHARGE, ATLOS), CHAREXCHANGE, ATMOL, SUMRC (reference summation
+    order), the ANISCH pressures (+ the F2(L=1)=F2(L=2) side effect) and WPADIF."""
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import independent_ram as ind
+    g = grids.build_grids(NR=10, NT=9, NE=35)
+    inp = synthetic.make_inputs(g, f2_kind="noisy", inductive=True, mgnp=True)
+    for S in (1, 2, 3, 4):
+        o = oracle_built.RamOracle(g, inp, DTs=5.0)
+        o.op("cepara", S)
+        CH, AT = ind.cepara(g, inp, S, 5.0)
+        assert np.array_equal(CH, o.CHARGE[S - 1]) and np.array_equal(AT[1:, 1:], o.ATLOS[S - 1][1:, 1:]), S
+        o.op("charexchange", S)
+        F1 = ind.charexchange(inp.F2[S - 1], CH)
+        assert np.array_equal(F1, o.F2[S - 1]), S
+        o.op("atmol", S)
+        F2 = ind.atmol(g, inp, F1, AT)
+        assert np.array_equal(F2, o.F2[S - 1]) and not np.array_equal(F2, F1), S
+        o.op("sumrc", S)
+        assert ind.sumrc(g, F2) == o.SETRC[S - 1], S
+        o.op("anisch", S)
+        pe, pa, F3 = ind.anisch_pressures(g, inp, F2, S)
+        assert np.array_equal(pe[1:], o.PPERT[S - 1][1:]) and np.array_equal(pa[1:], o.PPART[S - 1][1:]), S
+        assert np.array_equal(F3, o.F2[S - 1]), S
+    D = synthetic.synthetic_daa(g, inp) * 30
+    o = oracle_built.RamOracle(g, inp, DTs=5.0)
+    o.set_array("ATAC", D)
+    o.op("wpadif", 4)
+    W = ind.wpadif(g, inp, inp.F2[3], np.zeros_like(D), D, 5.0)
+    assert np.array_equal(W, o.F2[3]) and not np.array_equal(W, inp.F2[3])
+
+
 def test_flcscatter_matches_wpadif_with_one_coefficient(oracle_built, small):
     """FLCscatter (src/ModRamLoss.f90:513-575) is WPADIF's tridiagonal with FLC_coef as the only
     coefficient array: with the same array in ATAW_emic_h (and ATAW_emic_he = 0) the two restatements
