@@ -269,6 +269,35 @@ def test_coulomb_operators_properties(oracle_built, small):
     assert np.allclose(f, f0, rtol=1e-13, atol=0)
 
 
+def test_independent_numpy_restatement_of_scb(oracle_built):
+    """tests/independent_scb.py: `metrica` (nine stencil coefficients from the 27-point neighbourhood
+    of x, y, z) and three lexicographic SOR sweeps of `iterateAlpha`, restated a second time in numpy
+    from the Fortran text -- the C++ oracle agrees bit for bit."""
+    import math
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import independent_scb as ind
+    from ramscb_b200 import scb_synthetic as S
+    inp = S.build_scb(nthe=31, npsi=11, nzeta=17, warp=0.3)
+    o = oracle_built.ScbOracle(inp)
+    o.bandjacob(); o.metrica(); o.newk()
+    v = ind.metrica(inp.x, inp.y, inp.z, inp.nthe, inp.npsi, inp.nzeta)
+    for n, a in v.items():
+        assert np.array_equal(getattr(o, n), a), n
+        assert np.abs(a).max() > 0
+    nthe, npsi, nzeta, nT = inp.nthe, inp.npsi, inp.nzeta, 4
+    rjac = 1.0 - 2.0 * math.pi * math.pi / (nzeta * nzeta + nthe * nthe)
+    omopt = 2.0 / (1.0 + math.sqrt(1.0 - rjac * rjac))
+    alfa0 = o.alfa.copy()
+    o.set_int("nimax", 3)
+    o.set_scalar("InConAlpha", 1e-300)
+    fail, ni = o.iterate_alpha()
+    assert fail == 0 and ni[1:-1].max() == 4              # three sweeps done, counter past nimax
+    a, rm = ind.sor_alpha_sweeps(alfa0, {n: getattr(o, n) for n in v}, o.vecx, nthe, npsi, nzeta, nT, 3, [1.0, omopt, omopt])
+    core = (slice(nT, nthe - nT), slice(1, npsi - 1), slice(1, nzeta))       # untouched by the post-processing
+    assert np.array_equal(a[core], o.alfa[core]) and not np.array_equal(a[core], alfa0[core])
+    assert rm.max() == o.get("diffmx")
+
+
 def test_scb_steffen_properties(oracle_built):
     """Steffen spline derivative: exact on linear data, zero at local extrema (monotonicity
     preserving), one-sided at the ends; numpy and C++ restatements agree bit for bit."""
