@@ -22,7 +22,10 @@
 // only tests touching this path are end-to-end (test3/test4 pressure.ref,
 // hI.ref) and need missing input blobs.  Checks that do exist: manufactured
 // solutions for the SOR, exactness of the derivative on linear data and
-// monotonicity preservation, dipole force balance (J x B ~ 0 for p = 0).
+// monotonicity preservation, dipole force balance (J x B ~ 0 for p = 0), and a
+// second, independent numpy restatement of computeBandJacob, metrica, metric,
+// newk and the lexicographic SOR sweep (tests/independent_scb.py, on the numpy
+// Steffen of ramscb_b200/scb_synthetic.py) that agrees with this file bit for bit.
 // =============================================================================
 #include <algorithm>
 #include <cmath>

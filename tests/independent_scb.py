@@ -106,3 +106,121 @@ def sor_alpha_sweeps(alfa, vec, vecx, nthe, npsi, nzeta, nT, nsweeps, om):
                     rm = max(rm, abs(res))
             resmax[jz] = rm
     return a, resmax
+
+
+def _point_metrics(xt, xp, xr, yt, yp, yr, zt, zp, zr):
+    """Jacobian and the gradient products at the five points (:154-242 / :414-502, same text)."""
+    aj, grs, gps, gts, grgp, gpgt, gtgr = {}, {}, {}, {}, {}, {}, {}
+    for q in "abcde":
+        aj[q] = (xr[q] * (yp[q] * zt[q] - yt[q] * zp[q]) + xp[q] * (yt[q] * zr[q] - yr[q] * zt[q])
+                 + xt[q] * (yr[q] * zp[q] - yp[q] * zr[q]))
+        grx = (yp[q] * zt[q] - yt[q] * zp[q]) / aj[q]
+        gry = (zp[q] * xt[q] - zt[q] * xp[q]) / aj[q]
+        grz = (xp[q] * yt[q] - xt[q] * yp[q]) / aj[q]
+        gpx = (yt[q] * zr[q] - yr[q] * zt[q]) / aj[q]
+        gpy = (zt[q] * xr[q] - zr[q] * xt[q]) / aj[q]
+        gpz = (xt[q] * yr[q] - xr[q] * yt[q]) / aj[q]
+        gtx = (yr[q] * zp[q] - yp[q] * zr[q]) / aj[q]
+        gty = (zr[q] * xp[q] - zp[q] * xr[q]) / aj[q]
+        gtz = (xr[q] * yp[q] - xp[q] * yr[q]) / aj[q]
+        grs[q] = (grx ** 2 + gry ** 2 + grz ** 2)
+        gps[q] = (gpx ** 2 + gpy ** 2 + gpz ** 2)
+        gts[q] = (gtx ** 2 + gty ** 2 + gtz ** 2)
+        grgp[q] = (gpx * grx + gpy * gry + gpz * grz)
+        gpgt[q] = (gpx * gtx + gpy * gty + gpz * gtz)
+        gtgr[q] = (gtx * grx + gty * gry + gtz * grz)
+    return aj, grs, gps, gts, grgp, gpgt, gtgr
+
+
+def metric(x, y, z, nthe, npsi, nzeta):
+    """The psi-equation coefficients (src/ModScbEquation.f90:283-540): half points along theta (a, c)
+    and along rho (b, d)."""
+    s = spacing(nthe, npsi, nzeta)
+    rdr = s["rdr"]
+    rdrsq, rdtdr4 = rdr ** 2, 0.25 * s["rdt"] * rdr
+    I, J, K = slice(1, nthe - 1), slice(1, npsi - 1), slice(1, nzeta)
+
+    def sh(a, di, dj, dk):
+        return a[1 + di:nthe - 1 + di, 1 + dj:npsi - 1 + dj, 1 + dk:nzeta + dk]
+
+    def derivs(a):
+        t = {"a": (sh(a, 1, 0, 0) - sh(a, 0, 0, 0)) * s["rdt"],
+             "b": (sh(a, 1, 1, 0) + sh(a, 1, 0, 0) - sh(a, -1, 1, 0) - sh(a, -1, 0, 0)) * s["rdt4"],
+             "c": (sh(a, 0, 0, 0) - sh(a, -1, 0, 0)) * s["rdt"],
+             "d": (sh(a, 1, 0, 0) + sh(a, 1, -1, 0) - sh(a, -1, 0, 0) - sh(a, -1, -1, 0)) * s["rdt4"],
+             "e": (sh(a, 1, 0, 0) - sh(a, -1, 0, 0)) * s["rdt2"]}
+        p = {"a": (sh(a, 1, 0, 1) + sh(a, 0, 0, 1) - sh(a, 1, 0, -1) - sh(a, 0, 0, -1)) * s["rdp4"],
+             "b": (sh(a, 0, 1, 1) + sh(a, 0, 0, 1) - sh(a, 0, 1, -1) - sh(a, 0, 0, -1)) * s["rdp4"],
+             "c": (sh(a, 0, 0, 1) + sh(a, -1, 0, 1) - sh(a, 0, 0, -1) - sh(a, -1, 0, -1)) * s["rdp4"],
+             "d": (sh(a, 0, 0, 1) + sh(a, 0, -1, 1) - sh(a, 0, 0, -1) - sh(a, 0, -1, -1)) * s["rdp4"],
+             "e": (sh(a, 0, 0, 1) - sh(a, 0, 0, -1)) * s["rdp2"]}
+        r = {"a": (sh(a, 1, 1, 0) + sh(a, 0, 1, 0) - sh(a, 1, -1, 0) - sh(a, 0, -1, 0)) * s["rdr4"],
+             "b": (sh(a, 0, 1, 0) - sh(a, 0, 0, 0)) * rdr,
+             "c": (sh(a, 0, 1, 0) + sh(a, -1, 1, 0) - sh(a, 0, -1, 0) - sh(a, -1, -1, 0)) * s["rdr4"],
+             "d": (sh(a, 0, 0, 0) - sh(a, 0, -1, 0)) * rdr,
+             "e": (sh(a, 0, 1, 0) - sh(a, 0, -1, 0)) * s["rdr2"]}
+        return t, p, r
+
+    xt, xp, xr = derivs(x)
+    yt, yp, yr = derivs(y)
+    zt, zp, zr = derivs(z)
+    aj, grs, gps, gts, grgp, gpgt, gtgr = _point_metrics(xt, xp, xr, yt, yp, yr, zt, zp, zr)
+    v1 = {q: (gpgt[q] ** 2 - gps[q] * gts[q]) * aj[q] * s["rdtsq"] for q in "abc"}
+    v2 = {q: (grgp[q] * gpgt[q] - gps[q] * gtgr[q]) * aj[q] * rdtdr4 for q in "abcd"}
+    v3 = {q: (grgp[q] ** 2 - grs[q] * gps[q]) * aj[q] * rdrsq for q in "bcd"}
+    out = {n: np.zeros((nthe, npsi, nzeta)) for n in ("vecd", "vec1", "vec2", "vec3", "vec4", "vec6", "vec7", "vec8", "vec9")}
+    out["vecd"][I, J, K] = (v1["a"] + v1["c"] + v3["b"] + v3["d"])
+    out["vec1"][I, J, K] = (v2["c"] + v2["d"])
+    out["vec2"][I, J, K] = ((v2["c"] - v2["a"]) + v3["d"])
+    out["vec3"][I, J, K] = -(v2["a"] + v2["d"])
+    out["vec4"][I, J, K] = (v1["c"] + (v2["d"] - v2["b"]))
+    out["vec6"][I, J, K] = (v1["a"] + (v2["b"] - v2["d"]))
+    out["vec7"][I, J, K] = -(v2["c"] + v2["b"])
+    out["vec8"][I, J, K] = (v3["b"] + (v2["a"] - v2["c"]))
+    out["vec9"][I, J, K] = (v2["b"] + v2["a"])
+    return out
+
+
+def bandjacob(inp, derivs3d):
+    """computeBandJacob (src/ModScbCompute.f90:412-496) with a given GSL_Derivs restatement
+    (ramscb_b200.scb_synthetic.derivs3d: numpy, independent of the C++ one)."""
+    nthe, npsi, nzeta = inp.nthe, inp.npsi, inp.nzeta
+    X = [derivs3d(inp.thetaVal, inp.rhoVal, inp.zetaVal, np.asfortranarray(a[:, :, :nzeta])) for a in (inp.x, inp.y, inp.z)]
+    (dXT, dXR, dXZ), (dYT, dYR, dYZ), (dZT, dZR, dZZ) = X
+    jac = dXR * (dYZ * dZT - dYT * dZZ) + dXZ * (dYT * dZR - dYR * dZT) + dXT * (dYR * dZZ - dYZ * dZR)
+    gRX = (dYZ * dZT - dYT * dZZ) / jac
+    gRY = (dZZ * dXT - dZT * dXZ) / jac
+    gRZ = (dXZ * dYT - dXT * dYZ) / jac
+    gZX = (dYT * dZR - dYR * dZT) / jac
+    gZY = (dZT * dXR - dZR * dXT) / jac
+    gZZ = (dXT * dYR - dXR * dYT) / jac
+    gTX = (dYR * dZZ - dYZ * dZR) / jac
+    gTY = (dZR * dXZ - dZZ * dXR) / jac
+    gTZ = (dXR * dYZ - dXZ * dYR) / jac
+    out = {"jacobian": jac,
+           "GradRhoSq": gRX ** 2 + gRY ** 2 + gRZ ** 2,
+           "GradRhoGradZeta": gRX * gZX + gRY * gZY + gRZ * gZZ,
+           "GradRhoGradTheta": gRX * gTX + gRY * gTY + gRZ * gTZ,
+           "GradThetaSq": gTX ** 2 + gTY ** 2 + gTZ ** 2,
+           "GradThetaGradZeta": gTX * gZX + gTY * gZY + gTZ * gZZ,
+           "GradZetaSq": gZX ** 2 + gZY ** 2 + gZZ ** 2}
+    ff = inp.f[None, :, None] * inp.fzet[None, None, :nzeta]
+    Bx, By, Bz = ff * dXT / jac, ff * dYT / jac, ff * dZT / jac
+    bsq = (out["GradRhoSq"] * out["GradZetaSq"] - out["GradRhoGradZeta"] ** 2) * ff ** 2
+    for a in (Bx, By, Bz, bsq):
+        a[:, :, 0] = a[:, :, nzeta - 1]
+    out.update(Bx=Bx, By=By, Bz=Bz, bsq=bsq)
+    return out
+
+
+def newk_aniso(inp, m, nthe, npsi, nzeta):
+    """newk, anisotropic Picard branch (src/ModScbEquation.f90:578-590); m = bandjacob() output."""
+    f2 = (inp.f ** 2)[None, :, None]
+    fz = inp.fzet[None, None, :nzeta]
+    sg = inp.sigma[:, :, :nzeta]
+    xpz = (m["GradRhoSq"] * m["GradZetaSq"] - m["GradRhoGradZeta"] ** 2)
+    xpt = (m["GradRhoSq"] * m["GradThetaGradZeta"] - m["GradRhoGradZeta"] * m["GradRhoGradTheta"])
+    c0 = -(f2 * fz) / sg / m["bsq"]
+    tz = inp.dPPerdZeta[:, :, :nzeta] + 0.5 * (1. - sg) * inp.dBsqdZeta[:, :, :nzeta]
+    tt = inp.dPPerdTheta[:, :, :nzeta] + 0.5 * (1. - sg) * inp.dBsqdTheta[:, :, :nzeta]
+    return m["jacobian"] / f2 * c0 * (tz * xpz + tt * xpt)

@@ -270,9 +270,10 @@ def test_coulomb_operators_properties(oracle_built, small):
 
 
 def test_independent_numpy_restatement_of_scb(oracle_built):
-    """tests/independent_scb.py: `metrica` (nine stencil coefficients from the 27-point neighbourhood
-    of x, y, z) and three lexicographic SOR sweeps of `iterateAlpha`, restated a second time in numpy
-    from the Fortran text -- the C++ oracle agrees bit for bit."""
+    """tests/independent_scb.py: `computeBandJacob`, `metrica` / `metric` (nine stencil coefficients from
+    the 27-point neighbourhood of x, y, z), `newk` (anisotropic) and three lexicographic SOR sweeps of
+    `iterateAlpha`, restated a second time in numpy from the Fortran text -- the C++ oracle agrees
+    bit for bit."""
     import math
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     import independent_scb as ind
@@ -284,6 +285,10 @@ def test_independent_numpy_restatement_of_scb(oracle_built):
     for n, a in v.items():
         assert np.array_equal(getattr(o, n), a), n
         assert np.abs(a).max() > 0
+    m = ind.bandjacob(inp, S.derivs3d)                      # computeBandJacob on the numpy Steffen derivatives
+    for n, a in m.items():
+        assert np.array_equal(a, getattr(o, n)[:, :, :a.shape[2]]), n
+    assert np.array_equal(ind.newk_aniso(inp, m, inp.nthe, inp.npsi, inp.nzeta), o.vecx[:, :, :inp.nzeta])
     nthe, npsi, nzeta, nT = inp.nthe, inp.npsi, inp.nzeta, 4
     rjac = 1.0 - 2.0 * math.pi * math.pi / (nzeta * nzeta + nthe * nthe)
     omopt = 2.0 / (1.0 + math.sqrt(1.0 - rjac * rjac))
@@ -296,6 +301,9 @@ def test_independent_numpy_restatement_of_scb(oracle_built):
     core = (slice(nT, nthe - nT), slice(1, npsi - 1), slice(1, nzeta))       # untouched by the post-processing
     assert np.array_equal(a[core], o.alfa[core]) and not np.array_equal(a[core], alfa0[core])
     assert rm.max() == o.get("diffmx")
+    o.metric()                                               # the psi equation's coefficients
+    for n, a in ind.metric(inp.x, inp.y, inp.z, nthe, npsi, nzeta).items():
+        assert np.array_equal(getattr(o, n), a), "metric " + n
 
 
 def test_scb_steffen_properties(oracle_built):
