@@ -416,3 +416,155 @@ def wpadif(g, inp, F, DA, DB, DTs):
     new[..., NPA - 1] = new[..., NPA - 2]
     out[1:, :, 1:, :] = new * FACMU
     return out
+
+
+def wavelo(g, inp, F, DTs, use_plasmasphere=False):
+    """WAVELO (src/ModRamWPI.f90:580-636): electron loss with the piecewise lifetime TAU_LIF."""
+    NR, NT, NE, NPA = g.NR, g.NT, g.NE, g.NPA
+    Bw = 100. if inp.Kp >= 4.0 else 30.
+    RLpp = np.full(NT, 5.39 - 0.382 * inp.Kpmax12)
+    if use_plasmasphere:
+        for J in range(NT):
+            for I in range(1, NR):
+                if inp.NECR[I, J] > 50.:
+                    RLpp[J] = g.LZ[I]
+    out = F.copy()
+    for K in range(1, NE):
+        for I in range(1, NR):
+            for J in range(NT):
+                if g.LZ[I] <= RLpp[J]:
+                    tau = inp.WALOS1[I, K] * ((10. / Bw) ** 2)
+                else:
+                    if g.EKEV[K] <= 1000.:
+                        tau = inp.WALOS2[I, K] * (1 + inp.WALOS3[I, K] / inp.WALOS2[I, K])
+                        if g.EKEV[K] <= 1.1:
+                            tau = tau * 37.5813 * math.exp(-1.81255 * g.EKEV[K])
+                        elif g.EKEV[K] <= 5.:
+                            tau = tau * (7.5 - 1.15 * g.EKEV[K])
+                    else:
+                        tau = 5. * 3600 * 24 / inp.Kp
+                out[I, J, K, 1:] = F[I, J, K, 1:] * math.exp(-DTs / tau)
+    return out
+
+
+# ---------------------------------------------------------------------------------------
+# Coulomb collisions (src/ModRamCoul.f90:17-296)
+# ---------------------------------------------------------------------------------------
+PS_MASS = (5.4462E-4, 1.0, 4.0, 16.0, 14.0, 87.62)      # RAMSpecies(1:6): e-, H+, He+, O+, N+, Sr+
+PS_CHARGE = (-1, 1, 1, 1, 1, 1)
+PS_RATIO = (1.0, 0.77, 0.2, 0.03, 0.0, 0.0)
+MP, RE_M, PI_R = 1.673E-27, 6.371E6, 3.1415926535897932384626433832795
+
+
+def coulpara(g, S, DTs, gcoul):
+    """COULE, COULI, ATA, GTA [K,L] of species S (:17-125).  The collision sums CCE.. are set to zero
+    once, before the energy loop, and therefore accumulate over K (as written in the reference)."""
+    NE, NPA = g.NE, g.NPA
+    s = S - 1
+    EPS, DLN = 8.854E-12, 21.5
+    Zt = float(g.QS[s])
+    QE = (Q ** 2 / EPS)
+    GAMA = Zt ** 2 * DLN / 4. / PI_R * QE * 1E6 * QE
+    CCO = GAMA / Q * DTs / Q / 1E3
+    CCD = GAMA * DTs / (g.RMAS[s] * g.RMAS[s]) / (CS * CS * CS)
+    COULE = np.zeros((NE, NPA)); COULI = np.zeros((NE, NPA)); ATA = np.zeros((NE, NPA)); GTA = np.zeros((NE, NPA))
+    COULDE = np.zeros(NPA); COULDI = np.zeros(NPA)
+    CCE = CDE = CCI = CDI = 0.0
+    for K in range(NE):
+        for b in range(6):
+            RA = PS_RATIO[b]
+            if RA < 1e-9:
+                continue
+            VF = math.sqrt(2. * Q / (MP * PS_MASS[b]))
+            Zb = PS_CHARGE[b]
+            X = g.VBND[s, K] / VF
+            XD = g.V[s, K] / VF
+            if Zb < 0:
+                CCE = CCE + RA * gcoul(X)
+                CDE = CDE + RA * (math.erf(XD) - gcoul(XD))
+            else:
+                CCI = CCI + RA * (Zb * Zb) * gcoul(X)
+                CDI = CDI + RA * (Zb * Zb) * (math.erf(XD) - gcoul(XD))
+        COULE[K, 0] = -CCE * g.VBND[s, K] * CCO * (g.GRBND[s, K] * g.GRBND[s, K])
+        COULI[K, 0] = -CCI * g.VBND[s, K] * CCO * (g.GRBND[s, K] * g.GRBND[s, K])
+        CCDE = CCD * CDE * g.GREL[s, K] / math.pow(g.GREL[s, K] * g.GREL[s, K] - 1, 1.5)
+        CCDI = CCD * CDI * g.GREL[s, K] / math.pow(g.GREL[s, K] * g.GREL[s, K] - 1, 1.5)
+        for L in range(1, NPA - 1):            # Fortran L = 2..NPA-1
+            COULE[K, L] = COULE[K, 0]
+            COULI[K, L] = COULI[K, 0]
+            MUBOUN = g.MU[L] + 0.5 * g.WMU[L]
+            BADIF = (1. - MUBOUN * MUBOUN) / MUBOUN / 2.
+            COULDE[L] = CCDE * BADIF
+            AFER = COULDE[L] / g.MU[L] / g.DMU[L] / g.WMU[L]
+            ASEC = COULDE[L - 1] / g.MU[L] / g.DMU[L - 1] / g.WMU[L]
+            COULDI[L] = CCDI * BADIF
+            AFIR = COULDI[L] / g.MU[L] / g.DMU[L] / g.WMU[L]
+            ASIC = COULDI[L - 1] / g.MU[L] / g.DMU[L - 1] / g.WMU[L]
+            ATA[K, L] = AFIR + AFER
+            GTA[K, L] = ASIC + ASEC
+        ATA[K, NPA - 1] = 0
+    return COULE, COULI, ATA, GTA
+
+
+def coulen(g, inp, F, S, COULE, COULI, beta):
+    """COULEN (:133-221): energy drag, the limiter of DRIFTE on CccolE = (COULE+COULI)*NECR*BANE(L);
+    vectorised over (I, J, L)."""
+    NR, NT, NE, NPA = g.NR, g.NT, g.NE, g.NPA
+    s = S - 1
+    out = F.copy()
+    Fl = F[1:]                                                   # [I,J,K,L]
+    Ls = np.arange(1, NPA)                                       # Fortran L = 2..NPA
+    Lb = np.minimum(Ls, NPA - 12)                                # BANE(L >= NPA-10) = BANE(NPA-11)  (0-based NPA-12)
+    BANE = (1. - inp.FNIS[1:NR][:, :, Lb] / 2. / inp.FNHS[1:NR][:, :, Lb]) / (1. - g.MU[Lb] * g.MU[Lb])[None, None, :]
+    XNE = inp.NECR[1:NR][:, :, None] * BANE                      # [I,J,L]
+    G = g.GREL[s]
+    EZERO = g.EKEV[0] - g.WE[0]
+    GRZ = 1. + EZERO * 1000. * Q / g.RMAS[s] / CS / CS
+    Fs = Fl[:, :, :, 1:]                                         # L = 2..NPA
+    f1 = Fs[:, :, 1] * G[0] / G[1] * np.sqrt((G[0] ** 2 - 1) / (G[1] ** 2 - 1))
+    f0 = f1 * GRZ / G[0] * np.sqrt((GRZ ** 2 - 1) / (G[0] ** 2 - 1))
+    z = np.zeros_like(f1)
+    buf = np.concatenate([f0[:, :, None], f1[:, :, None], Fs[:, :, 1:], z[:, :, None], z[:, :, None]], axis=2)   # index = Fortran K
+    CD = (COULE[:, 1:] + COULI[:, 1:])[None, None, :, :] * XNE[:, :, None, :]           # [I,J,K,L]
+    K = np.arange(1, NE + 1)
+    sgn = np.where(CD < 0, -1.0, 1.0)
+    Fm, Fp = buf[:, :, K], buf[:, :, K + 1]
+    Fn = np.where(sgn > 0, Fm, buf[:, :, K + 2])
+    Fn1 = np.where(sgn > 0, buf[:, :, K - 1], Fp)
+    FB = limiter_flux(Fm, Fp, Fn, Fn1, CD, CD / g.DE[None, None, :, None], sgn, beta)
+    WE = g.WE[None, None, 1:, None]
+    new = Fs[:, :, 1:] - CD[:, :, 1:] / WE * FB[:, :, 1:] + CD[:, :, :-1] / WE * FB[:, :, :-1]
+    new = np.where(new < 0, 1E-15, new)
+    out[1:, :, 1:, 1:] = new
+    return out
+
+
+def coulmu(g, inp, F, S, ATA, GTA, T):
+    """COULMU (:229-296): implicit pitch-angle scattering; vectorised over (I, J, K)."""
+    NR, NT, NE, NPA = g.NR, g.NT, g.NE, g.NPA
+    out = F.copy()
+    Fl = F[1:, :, 1:, :]                                         # I = 2..NR, K = 2..NE
+    XNE = inp.NECR[1:NR][:, :, None]
+    BI, BH, FH = inp.BOUNIS[1:NR], inp.BOUNHS[1:NR], inp.FNHS[1:NR]
+    BAS = XNE * BI / 2. / BH                                     # BASCNE(I,J,L)
+    RK = np.zeros(Fl.shape)
+    RL = np.zeros(Fl.shape)
+    RL[..., 0] = -1.
+    for L in range(1, NPA - 1):
+        AN = ATA[None, None, 1:, L] * BAS[:, :, None, L] / FH[:, :, None, L] * BH[:, :, None, L]
+        GN = GTA[None, None, 1:, L] * BAS[:, :, None, L - 1] / FH[:, :, None, L] * BH[:, :, None, L - 1]
+        BN = AN + GN
+        RP = Fl[..., L] / FH[:, :, None, L] / g.MU[L]
+        DENOM = BN + GN * RL[..., L - 1] + 1
+        RK[..., L] = (RP + GN * RK[..., L - 1]) / DENOM
+        RL[..., L] = -AN / DENOM
+    new = np.zeros(Fl.shape)
+    new[..., NPA - 2] = RK[..., NPA - 2] / (1 + RL[..., NPA - 2])
+    for L in range(NPA - 3, -1, -1):
+        new[..., L] = RK[..., L] - RL[..., L] * new[..., L + 1]
+    new[..., NPA - 1] = new[..., NPA - 2]
+    new = new * FH[:, :, None, :] * g.MU[None, None, None, :]
+    if T > 0:
+        new = np.where(new < 0, 1E-15, new)
+    out[1:, :, 1:, :] = new
+    return out

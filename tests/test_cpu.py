@@ -187,7 +187,8 @@ def test_independent_numpy_restatement_of_the_drifts(oracle_built, variant):
 
 def test_independent_numpy_restatement_of_losses_and_moments(oracle_built):
     """Same cross-check for CEPARA (CHARGE, ATLOS), CHAREXCHANGE, ATMOL, SUMRC (reference summation
-    order), the ANISCH pressures (+ the F2(L=1)=F2(L=2) side effect) and WPADIF."""
+    order), the ANISCH pressures (+ the F2(L=1)=F2(L=2) side effect), WPADIF, WAVELO and the Coulomb
+    operators (COULPARA tables, COULEN, COULMU)."""
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     import independent_ram as ind
     g = grids.build_grids(NR=10, NT=9, NE=35)
@@ -215,6 +216,25 @@ def test_independent_numpy_restatement_of_losses_and_moments(oracle_built):
     o.op("wpadif", 4)
     W = ind.wpadif(g, inp, inp.F2[3], np.zeros_like(D), D, 5.0)
     assert np.array_equal(W, o.F2[3]) and not np.array_equal(W, inp.F2[3])
+    for kp in (2.0, 5.0):                                    # WAVELO: both wave amplitudes
+        inpk = synthetic.make_inputs(g, f2_kind="noisy", Kp=kp)
+        o = oracle_built.RamOracle(g, inpk, DTs=5.0)
+        o.op("wavelo", 4)
+        W = ind.wavelo(g, inpk, inpk.F2[3], 5.0)
+        assert np.array_equal(W, o.F2[3]) and not np.array_equal(W, inpk.F2[3])
+    for S in (1, 2, 4):                                      # COULPARA tables, COULEN, COULMU
+        o = oracle_built.RamOracle(g, inp, DTs=5.0)
+        o.set_scalar("T", 50.0)
+        o.op("coulpara", S)
+        CE, CI, AT, GT = ind.coulpara(g, S, 5.0, grids.gcoul)
+        assert np.array_equal(CE, o.COULE[S - 1]) and np.array_equal(CI, o.COULI[S - 1]), S
+        assert np.array_equal(AT, o.ATA[S - 1]) and np.array_equal(GT, o.GTA[S - 1]), S
+        o.op("coulen", S)
+        F1 = ind.coulen(g, inp, inp.F2[S - 1], S, CE, CI, 1.5)
+        assert np.array_equal(F1, o.F2[S - 1]) and not np.array_equal(F1, inp.F2[S - 1]), S
+        o.op("coulmu", S)
+        F2 = ind.coulmu(g, inp, F1, S, AT, GT, 50.0)
+        assert np.array_equal(F2, o.F2[S - 1]) and not np.array_equal(F2, F1), S
 
 
 def test_flcscatter_matches_wpadif_with_one_coefficient(oracle_built, small):
