@@ -568,3 +568,79 @@ def coulmu(g, inp, F, S, ATA, GTA, T):
         new = np.where(new < 0, 1E-15, new)
     out[1:, :, 1:, :] = new
     return out
+
+
+# ---------------------------------------------------------------------------------------
+# the species loop and epilogue of ram_run (src/ModRamRun.f90:64-222)
+# ---------------------------------------------------------------------------------------
+def ram_run(g, inp, F2, DTs, beta, gcoul, DtsMin=1.0, T=0.0, wpi=False, emic=False, coulomb=False, DAA=None):
+    """One ram_run step of all species with the restatements above, in the reference's call order.
+    Returns F2, DtsNext, SETRC per species, the loss increments LSDR/LSCHA/LSATM/LSWAE/LSCOE/LSCSC and
+    PPERT/PPART.  DAA: (ATAW+ATAC for electrons, ATAW_emic_h+ATAW_emic_he for H+) or None."""
+    nS, NR, NT = g.nS, g.NR, g.NT
+    F2 = F2.copy()
+    dts = {n: np.zeros(nS) for n in ("R", "P", "E", "MU")}
+    loss = {n: np.zeros(nS) for n in ("DR", "CHA", "ATM", "WAE", "COE", "CSC")}
+    SETRC = np.zeros(nS)
+    for S in range(1, nS + 1):
+        s = S - 1
+        kind = int(g.kind[s])
+        sWPI, sCEX, sEMIC = kind == 3, kind != 3, kind == 0
+        CH, AT = cepara(g, inp, S, DTs)
+        CE, CI, ATA, GTA = coulpara(g, S, DTs, gcoul)
+        F = F2[s]
+        setrc = 0.0                     # SETRC(S) before the first SUMRC of the run
+
+        def SUM(key):
+            nonlocal setrc
+            new = sumrc(g, F2[s])
+            loss[key][s] += setrc - new
+            setrc = new
+
+        def put(Fnew):
+            F2[s] = Fnew
+
+        for fn, key in ((driftr, "R"), (driftp, "P"), (drifte, "E"), (driftmu, "MU")):
+            Fn, dt = fn(g, inp, F2, S, DTs, beta)
+            put(Fn)
+            dts[key][s] = dt
+        SUM("DR")
+        if coulomb:
+            put(coulen(g, inp, F2[s], S, CE, CI, beta)); SUM("COE")
+            put(coulmu(g, inp, F2[s], S, ATA, GTA, T)); SUM("CSC")
+
+        def waves():
+            if sWPI:
+                put(wpadif(g, inp, F2[s], DAA[0], DAA[1], DTs) if wpi else wavelo(g, inp, F2[s], DTs)); SUM("WAE")
+
+        def emicw():
+            if sEMIC and emic:
+                put(wpadif(g, inp, F2[s], DAA[2], DAA[3], DTs)); SUM("WAE")
+
+        def cex():
+            if sCEX:
+                put(charexchange(F2[s], CH)); SUM("CHA")
+
+        waves(); emicw(); cex()
+        put(atmol(g, inp, F2[s], AT)); SUM("ATM")
+        put(atmol(g, inp, F2[s], AT)); SUM("ATM")
+        cex(); emicw(); waves()
+        if coulomb:
+            put(coulmu(g, inp, F2[s], S, ATA, GTA, T)); SUM("CSC")
+            put(coulen(g, inp, F2[s], S, CE, CI, beta)); SUM("COE")
+        for fn, key in ((driftmu, "MU"), (drifte, "E"), (driftp, "P"), (driftr, "R")):
+            Fn, dt = fn(g, inp, F2, S, DTs, beta)
+            put(Fn)
+            dts[key][s] = dt
+        SUM("DR")
+        SETRC[s] = setrc
+    F2[:, :, NT - 1] = F2[:, :, 0]
+    out = inp.outsideMGNP == 1
+    F2[:, out] = 1.e-31
+    DtsNext = max(min(dts["R"].min(), dts["P"].min(), dts["E"].min(), dts["MU"].min()), DtsMin)
+    PPERT = np.zeros((nS, NR, NT)); PPART = np.zeros((nS, NR, NT))
+    for S in range(1, nS + 1):
+        pe, pa, Fn = anisch_pressures(g, inp, F2[S - 1], S)
+        F2[S - 1] = Fn
+        PPERT[S - 1], PPART[S - 1] = pe, pa
+    return F2, DtsNext, SETRC, loss, PPERT, PPART

@@ -237,6 +237,32 @@ def test_independent_numpy_restatement_of_losses_and_moments(oracle_built):
         assert np.array_equal(F2, o.F2[S - 1]) and not np.array_equal(F2, F1), S
 
 
+@pytest.mark.parametrize("flags", [0, 2, 1 | 4])
+def test_independent_numpy_restatement_of_ram_run(oracle_built, flags):
+    """The whole species loop + epilogue of ram_run (src/ModRamRun.f90:64-222) composed from the
+    independent numpy routines in the reference's call order -- default operators, Coulomb, WPI+EMIC --
+    against the C++ oracle's ram_run: F2 of all species, DtsNext, SETRC, the six loss accumulators and
+    PPERT/PPART bit for bit."""
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import independent_ram as ind
+    g = grids.build_grids(NR=7, NT=7, NE=35)
+    inp = synthetic.make_inputs(g, f2_kind="noisy", inductive=True, mgnp=True)
+    D = synthetic.synthetic_daa(g, inp)
+    Z = np.zeros_like(D)
+    kw = {0: {}, 2: dict(coulomb=True), 5: dict(wpi=True, emic=True, DAA=(Z, D, D, Z))}[flags]
+    o = oracle_built.RamOracle(g, inp, DTs=5.0)
+    o.set_scalar("T", 25.0)
+    o.set_array("ATAC", D)
+    o.set_array("ATAW_emic_h", D)
+    dtn = o.ram_run(flags=flags)
+    F2, dn, SETRC, loss, pe, pa = ind.ram_run(g, inp, inp.F2, 5.0, 1.5, grids.gcoul, T=25.0, **kw)
+    assert np.array_equal(F2, o.F2) and dn == dtn and np.array_equal(SETRC, o.SETRC)
+    assert np.array_equal(pe[:, 1:], o.PPERT[:, 1:]) and np.array_equal(pa[:, 1:], o.PPART[:, 1:])
+    for k, n in (("DR", "LSDR"), ("CHA", "LSCHA"), ("ATM", "LSATM"), ("WAE", "LSWAE"), ("COE", "LSCOE"), ("CSC", "LSCSC")):
+        assert np.array_equal(loss[k], o.arr[n]), n
+    assert (np.abs(o.arr["LSCOE"]).max() > 0) == bool(flags & 2)
+
+
 def test_flcscatter_matches_wpadif_with_one_coefficient(oracle_built, small):
     """FLCscatter (src/ModRamLoss.f90:513-575) is WPADIF's tridiagonal with FLC_coef as the only
     coefficient array: with the same array in ATAW_emic_h (and ATAW_emic_he = 0) the two restatements
