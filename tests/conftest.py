@@ -10,6 +10,18 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    if os.environ.get("RSG_EMU") == "1":
+        # development aid for a GPU-less container: run the RAM `-m gpu` tests against the kernels
+        # compiled for the host-CPU CUDA emulator (tests/emu/).  Test infrastructure only.
+        use_emulator()
+
+
+def use_emulator():
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+    import build_emu
+    from ramscb_b200 import host
+    host.LIB_PATH = build_emu.build()
+    host._lib = None
 
 
 @pytest.fixture(scope="session")
