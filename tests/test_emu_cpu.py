@@ -1,0 +1,80 @@
+"""The RAM kernels, executed thread for thread by the host-CPU CUDA emulator (tests/emu/), against
+the oracle -- the `-m gpu` parity tests of tests/test_ram_parity_gpu.py re-run on a reduced grid in
+a container without a GPU.  TEST INFRASTRUCTURE: the emulator library is built from a scratch copy
+of ramscb_b200/csrc by tests/emu/build_emu.py and is loaded only here (the product library has no
+CPU path and still fails loudly without a device).  What this buys: indexing, barriers, shuffles,
+shared-memory staging and the arithmetic of every RAM kernel are checked before GPU time is spent.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def emu():
+    """Point ramscb_b200.host at the emulator build for this module only."""
+    import conftest
+    from ramscb_b200 import host
+    saved = (host.LIB_PATH, host._lib)
+    conftest.use_emulator()
+    yield host
+    host.LIB_PATH, host._lib = saved
+
+
+@pytest.fixture(scope="module")
+def small_grids():
+    from ramscb_b200 import grids
+    return grids.build_grids(NR=9, NT=11, NE=35)      # ragged planes; NE stays 35: the ANISCH energy bands (khi, ModRamRun.f90:352) are hard-wired up to K=30
+
+
+@pytest.fixture(scope="module")
+def T():
+    import test_ram_parity_gpu as t
+    return t
+
+
+@pytest.mark.parametrize("op", ["DRIFTR", "DRIFTP", "DRIFTE", "DRIFTMU"])
+def test_emulated_exact_sweeps_bit_identical(emu, T, small_grids, oracle_built, op):
+    T.test_drift_sweeps_bit_exact(small_grids, oracle_built, "adversarial_mgnp", op)
+
+
+@pytest.mark.parametrize("flags", [0, 1 | 2 | 4])
+def test_emulated_full_ram_run_exact(emu, T, small_grids, oracle_built, flags):
+    T.test_full_ram_run(small_grids, oracle_built, flags)
+
+
+def test_emulated_fast_full_ram_run(emu, T, small_grids, oracle_built):
+    T.test_fast_mode_full_ram_run(small_grids, oracle_built)
+
+
+def test_emulated_losses_wpadif_coulomb(emu, T, small_grids, oracle_built):
+    T.test_losses(small_grids, oracle_built, "noisy")
+    T.test_sumrc_and_anisch(small_grids, oracle_built)
+    T.test_wpadif_bit_exact(small_grids, oracle_built, "chorus")
+    T.test_coulomb_operators_bit_exact(small_grids, oracle_built, 1)
+
+
+def test_emulated_fused_equals_unfused_and_graph_replay(emu, T, small_grids):
+    from ramscb_b200 import host, synthetic
+    g = small_grids
+    inp = synthetic.make_inputs(g, f2_kind="noisy", inductive=True, mgnp=True)
+    runs = []
+    for fused, graph in ((False, False), (True, False), (True, True)):
+        gpu = host.RamGpu(g)
+        gpu.set_mode(host.MODE_FAST)
+        gpu.set_inputs(inp)
+        gpu.use_fused(fused)
+        gpu.use_graph(graph)
+        outs = [gpu.ram_run(dts, DtsMin=1.0, flags=0) for dts in (5.0, 5.0, 2.5)]
+        runs.append((gpu.f2_d2h(), outs))
+        gpu.close()
+    for f_b, o_b in runs[1:]:
+        assert np.array_equal(runs[0][0], f_b)
+        for a, b in zip(runs[0][1], o_b):
+            assert np.array_equal(a["DtDrift"], b["DtDrift"]) and a["DtsNext"] == b["DtsNext"]
+            for k in ("PPERT", "PPART", "SETRC"):
+                assert np.allclose(a[k], b[k], rtol=1e-12, atol=0), k
