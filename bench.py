@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- RAM phase-space cell-updates/s per full RAM step (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload default|x4]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload default|x4] [--scaling weak|strong]
 
 One "step" = one pass of the RAM hot path (`ram_run`, src/ModRamRun.f90:64-222)
 over one synthetic input set: for each of the 4 species CEPARA, DRIFTPARA,
@@ -17,6 +17,14 @@ in HBM (CUDA events across the library's streams, L2 flushed between steps);
 host->device and device->host copies inside the timed region (wall clock).
 `--impl reference` times the reference's CPU algorithm (the C++ oracle, the
 reference's own OpenMP-over-species parallelism) on the same workload.
+
+N > 1 (one process per GPU under torchrun).  Species are the independent unit of `ram_run`
+(the OpenMP loop of src/ModRamRun.f90:64), so the default is WEAK scaling with no data-path
+collective: the job advances 4*N species of the named grid, 4 per rank, every rank running exactly
+the N = 1 path on its own species; `value` = cell-updates of all ranks / max-over-ranks device time.
+`--scaling strong` keeps the 4 species fixed and shards them (and, beyond 4 ranks, pitch-angle /
+energy slabs of a species with two NCCL re-shardings per step; ramscb_b200/parallel.py) -- the
+numbers of that mode are in profiles/r1/scaling_r1.txt.
 """
 from __future__ import annotations
 
@@ -157,21 +165,38 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def cpu_reference(g, inp, steps, warmup):
+def cpu_reference(g, inp, steps, warmup, groups=1):
     """The reference's CPU algorithm (C++ oracle; OpenMP over species like
-    src/ModRamRun.f90:64) on the same workload.  Returns (cell-updates/s, threads, s/step)."""
+    src/ModRamRun.f90:64) on the same workload.  `groups` > 1 is the weak-scaling job of N GPUs
+    (4*N species): one oracle instance per group of 4 species, run concurrently, as the reference's
+    species loop would spread 4*N species over the host threads.
+    Returns (cell-updates/s, threads, s/step)."""
+    from concurrent.futures import ThreadPoolExecutor
     from oracle import oracle
     oracle.build()
-    o = oracle.RamOracle(g, inp, DTs=DTS)
-    nthreads = min(g.nS, os.cpu_count() or 1)
-    for _ in range(warmup):
+    ncpu = os.cpu_count() or 1
+    groups = max(1, min(groups, max(1, ncpu // g.nS)))   # no more instances than the cores can hold
+    os_ = [oracle.RamOracle(g, inp, DTs=DTS) for _ in range(groups)]
+    nthreads = min(g.nS, ncpu)
+
+    def one(o):
         o.ram_run(flags=0, nthreads=nthreads)
+
+    def step():
+        if groups == 1:
+            one(os_[0])
+        else:
+            with ThreadPoolExecutor(groups) as ex:      # ctypes releases the GIL inside the call
+                list(ex.map(one, os_))
+
+    for _ in range(warmup):
+        step()
     t0 = time.perf_counter()
     for _ in range(steps):
-        o.ram_run(flags=0, nthreads=nthreads)
+        step()
     dt = (time.perf_counter() - t0) / steps
-    cells = g.nS * g.NR * g.NT * g.NE * g.NPA
-    return OPS_PER_STEP * cells / dt, nthreads, dt
+    cells = groups * g.nS * g.NR * g.NT * g.NE * g.NPA
+    return OPS_PER_STEP * cells / dt, nthreads * groups, dt
 
 
 def scb_metrics(device):
@@ -221,6 +246,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="default", choices=["default", "x4"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = 4 species per rank (4*N in the job), strong = the 4 species sharded over the ranks")
     ap.add_argument("--no-scb", action="store_true", help="skip the SCB solve metrics")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"],
@@ -233,7 +260,11 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     g, inp, desc = workload(a.workload)
-    cells = g.nS * g.NR * g.NT * g.NE * g.NPA
+    weak = a.scaling == "weak"
+    jobs = world if weak else 1                      # independent 4-species sets in the job
+    cells = g.nS * g.NR * g.NT * g.NE * g.NPA        # cells one rank's species set holds
+    if weak and world > 1:
+        desc += f"; weak scaling: {world} x 4 species, 4 per rank"
     unit = "cell-updates/s"
     metric = "RAM phase-space cell-updates/s per full RAM step (8 drift sweeps + losses, 4 species)"
 
@@ -243,14 +274,15 @@ def main():
         # ~0.5 s per step on 4 cores at the default grid: bound the run to about a minute
         cap = 40 if a.workload == "default" else 4
         steps, wu = max(1, min(a.steps, cap)), max(1, min(a.warmup, 3 if a.workload == "default" else 1))
-        v, nthreads, dt = cpu_reference(g, inp, steps, wu)
+        v, nthreads, dt = cpu_reference(g, inp, steps, wu, groups=jobs)
         line = {"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": a.gpus, "steps": steps,
-                "warmup": wu, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+                "warmup": wu, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": a.scaling,
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": desc},
                 "cpu_baseline": {"value": v, "unit": unit, "cores": nthreads, "kind": "port",
                                  "sample": f"{steps} full ram_run steps of the same workload, OpenMP over species "
-                                           f"({nthreads} threads, the reference's own decomposition)"},
+                                           f"({nthreads} threads, the reference's own decomposition"
+                                           + (f"; {nthreads // max(1, min(g.nS, os.cpu_count() or 1))} concurrent 4-species sets" if jobs > 1 else "") + ")"},
                 "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -268,7 +300,9 @@ def main():
     # ---- sharding (ramscb_b200/parallel.py): species over ranks (no data-path collective);
     # beyond nS ranks, (L,K) slabs inside a species with two NCCL re-shardings per step
     from ramscb_b200 import parallel
-    plan = parallel.make_plan(world, rank, g.nS, g.NPA, g.NE, cells_per_species=g.NR * g.NT * g.NE * g.NPA)
+    split = world > 1 and not weak                   # strong scaling: the 4 species are sharded over the ranks
+    plan = parallel.make_plan(world if split else 1, rank if split else 0, g.nS, g.NPA, g.NE,
+                              cells_per_species=g.NR * g.NT * g.NE * g.NPA)
     idle = plan.ns == 0     # more ranks than species on a grid too small to split a species
     gpu = host.RamGpu(g, device=local_rank, mode=host.MODE_FAST if a.mode == "fast" else host.MODE_EXACT)
     gpu.set_inputs(inp)
@@ -276,7 +310,7 @@ def main():
     host.host_register(F2_host)
     flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
     sharded = None
-    if world > 1:
+    if split:
         # a non-default torch stream carries both the library's kernels and the NCCL traffic
         run_stream = torch.cuda.Stream()
         torch.cuda.set_stream(run_stream)
@@ -289,7 +323,7 @@ def main():
         torch.cuda.synchronize()
 
     def step_resident():
-        return gpu.ram_run(DTS, DtsMin=1.0, flags=0) if world == 1 else sharded.ram_run(DTS)
+        return gpu.ram_run(DTS, DtsMin=1.0, flags=0) if not split else sharded.ram_run(DTS)
 
     for _ in range(a.warmup):
         step_resident()
@@ -303,7 +337,7 @@ def main():
     for _ in range(a.steps):
         flush.zero_()                      # evict F2 from the 126 MB L2 (untimed)
         torch.cuda.synchronize()
-        if world == 1:
+        if not split:
             gpu.timer_begin()
             step_resident()
             dev_ms += gpu.timer_end()
@@ -323,7 +357,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms = float(t.item())
     ms_per_step = dev_ms / a.steps
-    value = OPS_PER_STEP * cells / (ms_per_step * 1e-3)
+    value = OPS_PER_STEP * cells * jobs / (ms_per_step * 1e-3)
 
     # ---- end to end through the C ABI with host buffers ---------------------------
     e2e_steps = max(3, min(a.steps, 10))
@@ -345,20 +379,20 @@ def main():
         e2e_s = float(t.item())
     h2d = F2_host.nbytes + 3 * VT.nbytes
     d2h = F2_host.nbytes + (4 + 6 + 1) * g.nS * 8 + 2 * g.nS * g.NR * g.NT * 8
-    e2e = {"value": OPS_PER_STEP * cells / e2e_s, "unit": unit, "h2d_bytes_per_step": int(h2d),
-           "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3,
+    e2e = {"value": OPS_PER_STEP * cells * jobs / e2e_s, "unit": unit, "h2d_bytes_per_step": int(h2d) * jobs,
+           "d2h_bytes_per_step": int(d2h) * jobs, "ms_per_step": e2e_s * 1e3,
            "timer": "wall clock, pinned host F2; F2 goes host->device and back EVERY step (routine-level drop-in, "
                     "INTEGRATION.md 3a): PCIe bound"}
     # for information: the fused integration keeps F2 resident; per step only the
     # E-field arrays go up and the step's results (DtsNext, DtDrift, losses, SETRC, PPERT, PPART) come back
-    if world == 1:
+    if not split:
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             gpu.set_efield(VT, inp.EIR, inp.EIP)
             out = step_resident()
         torch.cuda.synchronize()
         res_s = (time.perf_counter() - t0) / e2e_steps
-        e2e["resident_state"] = {"ms_per_step": res_s * 1e3, "value": OPS_PER_STEP * cells / res_s,
+        e2e["resident_state"] = {"ms_per_step": res_s * 1e3, "value": OPS_PER_STEP * cells / res_s, "per": "rank",
                                  "h2d_bytes_per_step": int(3 * VT.nbytes),
                                  "d2h_bytes_per_step": int((4 + 6 + 1) * g.nS * 8 + 2 * g.nS * g.NR * g.NT * 8),
                                  "note": "F2 stays on the device; not the headline e2e"}
@@ -367,7 +401,7 @@ def main():
     # stream between the stages of rsg_ram_run), dominant kernel roofline ------------
     peak, peak_src = measured_peak()
     roofline = None
-    if world == 1:
+    if not split:                                    # per rank; rank 0's is printed
         gpu.profile(True)
         for _ in range(a.steps):
             flush.zero_()
@@ -406,7 +440,7 @@ def main():
                     "kernel_share_of_step": {k: (v[0] / a.steps) / step_sum for k, v in stages.items() if k != "end"}}
 
     line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "ops_per_cell_per_step": OPS_PER_STEP, "mode": ("fast: separable coefficients + FMA + division-free limiter, fused shared-memory kernels, <=1e-12 of the oracle relative to the "
                                 "stencil neighbourhood (tests/test_ram_parity_gpu.py)") if a.mode == "fast"
@@ -419,8 +453,11 @@ def main():
                                         f"{parallel.SPLIT_MIN_CELLS:.0e} cells (ramscb_b200/parallel.py)"
                                         if len(plan.active) < world else
                                         f"{world} ranks, species-sharded, no data-path collective"))
-                       if world > 1 else "1 GPU, all species per launch"},
-            "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+                       if split else ("1 GPU, all species per launch" if world == 1 else
+                                      f"{world} ranks x 4 species (species are independent in ram_run, src/ModRamRun.f90:64): every rank runs "
+                                      "the 1-GPU path on its own species set, no data-path collective; strong-scaling mode "
+                                      "(species / slab sharding with NCCL re-sharding): --scaling strong, profiles/r1/scaling_r1.txt")},
+            "clocks": clk, "e2e": e2e, "gpu_launches": int(launches) * jobs, "roofline": roofline,
             "wall_s_timed_region": wall_s}
     if rank == 0 and world == 1 and not a.no_scb:
         line["scb"] = scb_metrics(local_rank)
