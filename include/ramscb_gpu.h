@@ -74,9 +74,13 @@ int rsg_ram_sync(rsg_ram* h);
 /* rsg_ram_run replays its launch sequence from a CUDA graph when DTs/flags/mode repeat
  * (default on); 0 disables (every call launches kernel by kernel). */
 int rsg_ram_use_graph(rsg_ram* h, int on);
-/* FAST mode, flags == 0: rsg_ram_run advances F2 with the fused shared-memory kernels
- * (DRIFTR+DRIFTP per plane; DRIFTE, DRIFTMU, losses, DRIFTMU, DRIFTE per column block), default on.
- * 0 selects the one-kernel-per-operator FAST path; F2 is bit-identical either way. */
+/* FAST mode, flags without RSG_F_COULOMB: rsg_ram_run advances F2 with the fused shared-memory
+ * kernels (DRIFTR+DRIFTP per plane; DRIFTE, DRIFTMU, [WPADIF], losses, [WPADIF], DRIFTMU, DRIFTE per
+ * column block), default on.  0 selects the one-kernel-per-operator FAST path; with flags == 0 F2
+ * is bit-identical either way.  With RSG_F_WPI / RSG_F_EMIC the column kernel applies WPADIF
+ * (src/ModRamWPI.f90:643-714) from tabulated elimination factors (k_wpadif_tables; same matrix,
+ * different rounding: <= 1e-12 of the one-kernel-per-operator result); on = 3 keeps WPADIF as its
+ * own bit-exact kernel, which takes such a step to the one-kernel-per-operator path. */
 int rsg_ram_use_fused(rsg_ram* h, int on);
 
 /* ---- static data ----------------------------------------------------------

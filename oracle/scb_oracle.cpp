@@ -11,6 +11,8 @@
 //                                            src/ModScbFunctions.f90:57-76
 //   GSL_Derivs (3-D driver)                  src/ModRamGSL.f90:794-869,
 //                                            src/RamGSL.c:228-291
+//   mapAlpha / mapPsi / mapTheta             src/ModScbEuler.f90:15-147,403-457
+//   GSL_Interpolation_1D (Steffen)           src/ModRamGSL.f90:240-311, src/RamGSL.c:111-174
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's CPU arm may load this.
 //
@@ -568,6 +570,149 @@ int iteratePsi(Scb* o, int* ni_out) {
   return fail;
 }
 
+// ---- GSL_Interpolation_1D, Steffen (src/ModRamGSL.f90:240-311 + interpolation_1d_c,
+// src/RamGSL.c:111-174; gsl interpolation/steffen.c steffen_init + steffen_eval) -----------
+// The Fortran wrapper first drops abscissae that do not increase (:262-273); the C driver
+// extrapolates linearly outside [xa_0, xa_{n-1}] (:159-164, end points included) and evaluates
+// the Steffen cubic d + delx*(c + delx*(b + delx*a)) of the interval found by bisection
+// (gsl_interp_bsearch: xa[i] <= x < xa[i+1]) inside.  Returns GSLerr (0 = ok).
+int interp1d(int n0, const double* x1, const double* f1, int n2, const double* x2, double* f2) {
+  std::vector<double> xa(n0), fa(n0);
+  int n1 = 1;
+  xa[0] = x1[0];
+  fa[0] = f1[0];
+  for (int i = 1; i < n0; ++i)
+    if (x1[i] > xa[n1 - 1]) { xa[n1] = x1[i]; fa[n1] = f1[i]; ++n1; }
+  if (n1 < 3) return 1;   // gsl_interp_steffen needs 3 points (gsl_spline_alloc fails)
+  std::vector<double> yp(n1), a(n1 - 1), b(n1 - 1);
+  {
+    const double h0 = xa[1] - xa[0];
+    yp[0] = (fa[1] - fa[0]) / h0;
+    for (int i = 1; i < n1 - 1; ++i) {
+      const double hi = xa[i + 1] - xa[i];
+      const double him1 = xa[i] - xa[i - 1];
+      const double si = (fa[i + 1] - fa[i]) / hi;
+      const double sim1 = (fa[i] - fa[i - 1]) / him1;
+      const double pi = (sim1 * hi + si * him1) / (him1 + hi);
+      const double m1 = std::fabs(si) < 0.5 * std::fabs(pi) ? std::fabs(si) : 0.5 * std::fabs(pi);
+      const double m2 = std::fabs(sim1) < m1 ? std::fabs(sim1) : m1;
+      yp[i] = (steffen_copysign(1.0, sim1) + steffen_copysign(1.0, si)) * m2;
+    }
+    yp[n1 - 1] = (fa[n1 - 1] - fa[n1 - 2]) / (xa[n1 - 1] - xa[n1 - 2]);
+    for (int i = 0; i < n1 - 1; ++i) {
+      const double hi = xa[i + 1] - xa[i];
+      const double si = (fa[i + 1] - fa[i]) / hi;
+      a[i] = (yp[i] + yp[i + 1] - 2 * si) / hi / hi;
+      b[i] = (3 * si - 2 * yp[i] - yp[i + 1]) / hi;
+    }
+  }
+  for (int q = 0; q < n2; ++q) {
+    const double xb = x2[q];
+    if (xb <= xa[0]) {
+      f2[q] = fa[0] + (xb - xa[0]) / (xa[1] - xa[0]) * (fa[1] - fa[0]);
+    } else if (xb >= xa[n1 - 1]) {
+      f2[q] = fa[n1 - 1] + (xb - xa[n1 - 1]) / (xa[n1 - 2] - xa[n1 - 1]) * (fa[n1 - 2] - fa[n1 - 1]);
+    } else if (xb == xb) {
+      int ilo = 0, ihi = n1 - 1;
+      while (ihi > ilo + 1) {
+        const int i = (ihi + ilo) / 2;
+        if (xa[i] > xb) ihi = i; else ilo = i;
+      }
+      const double delx = xb - xa[ilo];
+      f2[q] = fa[ilo] + delx * (yp[ilo] + delx * (b[ilo] + delx * a[ilo]));
+    } else {
+      return 1;   // NaN abscissa: gsl_spline_eval_e reports GSL_EDOM
+    }
+  }
+  return 0;
+}
+
+void wrap_xyz(Scb* o) {   // periodic boundary conditions in zeta (src/ModScbEuler.f90:66-71)
+  DIMS
+  for (const char* n : {"x", "y", "z"}) {
+    double* a = o->D(n);
+    for (int j = 1; j <= npsi; ++j)
+      for (int i = 1; i <= nthe; ++i) {
+        X3(a, i, j, 1) = X3(a, i, j, nzeta);
+        X3(a, i, j, nzeta + 1) = X3(a, i, j, 2);
+      }
+  }
+}
+
+// ---- mapAlpha, src/ModScbEuler.f90:97-147: move the grid points along zeta so that the computed
+// alfa takes the prescribed values alphaVal(k); then alfges (:82-94) resets alfa --------------
+int mapAlpha(Scb* o) {
+  DIMS
+  double *x = o->D("x"), *y = o->D("y"), *z = o->D("z"), *alfa = o->D("alfa");
+  const double* alphaVal = o->D("alphaVal");
+  const int n = nzeta + 1;
+  std::vector<double> xo(n), yo(n), zo(n), ao(n), out(n);
+  for (int j = 1; j <= npsi; ++j)
+    for (int i = 1; i <= nthe; ++i) {
+      for (int k = 1; k <= n; ++k) { xo[k - 1] = X3(x, i, j, k); yo[k - 1] = X3(y, i, j, k); zo[k - 1] = X3(z, i, j, k); ao[k - 1] = X3(alfa, i, j, k); }
+      double* arrs[3] = {x, y, z};
+      const double* olds[3] = {xo.data(), yo.data(), zo.data()};
+      for (int c = 0; c < 3; ++c) {
+        if (interp1d(n, ao.data(), olds[c], nzeta - 1, alphaVal + 1, out.data())) return 1;   // SORFail
+        for (int k = 2; k <= nzeta; ++k) X3(arrs[c], i, j, k) = out[k - 2];
+      }
+    }
+  wrap_xyz(o);
+  for (int k = 1; k <= n; ++k)
+    for (int j = 1; j <= npsi; ++j)
+      for (int i = 1; i <= nthe; ++i) X3(alfa, i, j, k) = alphaVal[k - 1];
+  return 0;
+}
+
+// ---- mapPsi, src/ModScbEuler.f90:403-457 (+ psiges :387-400) ------------------------------------
+int mapPsi(Scb* o) {
+  DIMS
+  double *x = o->D("x"), *y = o->D("y"), *z = o->D("z"), *psi = o->D("psi");
+  const double* psiVal = o->D("psiVal");
+  std::vector<double> xo(npsi), yo(npsi), zo(npsi), po(npsi), out(npsi);
+  for (int k = 2; k <= nzeta; ++k)
+    for (int i = 1; i <= nthe; ++i) {
+      for (int j = 1; j <= npsi; ++j) { xo[j - 1] = X3(x, i, j, k); yo[j - 1] = X3(y, i, j, k); zo[j - 1] = X3(z, i, j, k); po[j - 1] = X3(psi, i, j, k); }
+      double* arrs[3] = {x, y, z};
+      const double* olds[3] = {xo.data(), yo.data(), zo.data()};
+      for (int c = 0; c < 3; ++c) {
+        if (interp1d(npsi, po.data(), olds[c], npsi, psiVal, out.data())) return 1;
+        for (int j = 1; j <= npsi; ++j) X3(arrs[c], i, j, k) = out[j - 1];
+      }
+    }
+  wrap_xyz(o);
+  for (int k = 1; k <= nzeta + 1; ++k)
+    for (int j = 1; j <= npsi; ++j)
+      for (int i = 1; i <= nthe; ++i) X3(psi, i, j, k) = psiVal[j - 1];
+  return 0;
+}
+
+// ---- mapTheta, src/ModScbEuler.f90:15-75: redistribute the points of every field line to the
+// prescribed arc-length fractions chiVal -------------------------------------------------------
+int mapTheta(Scb* o) {
+  DIMS
+  double *x = o->D("x"), *y = o->D("y"), *z = o->D("z");
+  const double* chiVal = o->D("chiVal");
+  std::vector<double> xo(nthe), yo(nthe), zo(nthe), dist(nthe), chiOld(nthe), out(nthe);
+  for (int k = 2; k <= nzeta; ++k)
+    for (int j = 1; j <= npsi; ++j) {
+      dist[0] = 0.0;
+      for (int i = 1; i <= nthe; ++i) { xo[i - 1] = X3(x, i, j, k); yo[i - 1] = X3(y, i, j, k); zo[i - 1] = X3(z, i, j, k); }
+      for (int i = 2; i <= nthe; ++i)
+        dist[i - 1] = dist[i - 2] + std::sqrt(sq(X3(x, i, j, k) - X3(x, i - 1, j, k)) + sq(X3(y, i, j, k) - X3(y, i - 1, j, k)) +
+                                               sq(X3(z, i, j, k) - X3(z, i - 1, j, k)));
+      for (int i = 0; i < nthe; ++i) chiOld[i] = dist[i] / dist[nthe - 1] * PI_D;
+      double* arrs[3] = {x, y, z};
+      const double* olds[3] = {xo.data(), yo.data(), zo.data()};
+      for (int c = 0; c < 3; ++c) {
+        if (interp1d(nthe, chiOld.data(), olds[c], nthe, chiVal, out.data())) return 1;
+        for (int i = 1; i <= nthe; ++i) X3(arrs[c], i, j, k) = out[i - 1];
+      }
+    }
+  wrap_xyz(o);
+  return 0;
+}
+
 // ---- Compute_convergence, src/ModScbCompute.f90:499-754 (isotropy 0 and 1) ----------------
 // produces jGradRho/jGradZeta/jGradTheta, Jx..Jz, GradPx..GradPz, jCrossB, GradP and
 // the three norms
@@ -708,6 +853,10 @@ int scbo_iterate_alpha(void* h, int* ni) { return iterateAlpha((Scb*)h, ni); }
 int scbo_iterate_psi(void* h, int* ni) { return iteratePsi((Scb*)h, ni); }
 int scbo_convergence(void* h) { return compute_convergence((Scb*)h); }
 void scbo_derivs3d(void* h, const double* f, double* dT, double* dR, double* dZ) { derivs3d((Scb*)h, f, dT, dR, dZ); }
+int scbo_map_alpha(void* h) { return mapAlpha((Scb*)h); }
+int scbo_map_psi(void* h) { return mapPsi((Scb*)h); }
+int scbo_map_theta(void* h) { return mapTheta((Scb*)h); }
+int scbo_interp1d(int n0, const double* x1, const double* f1, int n2, const double* x2, double* f2) { return interp1d(n0, x1, f1, n2, x2, f2); }
 void scbo_steffen(int n, const double* xa, const double* ya, double* dx) {
   std::vector<double> yp;
   steffen_derivs(n, xa, ya, dx, yp);

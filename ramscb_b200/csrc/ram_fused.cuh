@@ -341,9 +341,58 @@ struct ColCfg {
   int nsegL, segL;    // loss block: pitch-angle segments per (k, position) column
   int doA;            // bit s: species s applies its first/last loss operator
   int b0;             // first block of plane positions of the launch (column-sharded ranks)
+  int doW;            // bit s: species s runs WPADIF after the first / before the second DRIFTMU (WPI instantiation only)
+  int wpart_off;      // where the two WPADIF moments of a block go in sp.part
 };
 
-template <int PG, int MAXT>
+// =============================================================================
+// k_wpadif_tables: WPADIF (src/ModRamWPI.f90:643-714) is a tridiagonal solve per (K, position)
+// line whose matrix depends on the diffusion coefficients, the field factors and DTs only -- not
+// on F2.  The elimination factors of the Thomas recurrences are therefore tabulated once per
+// (coefficient set, fields, DTs) and the fused column kernel applies them with two FMAs per cell:
+//   forward   RK(L) = F2(L) * cA(L) + RK(L-1) * cB(L),   cA = 1/(FACMU*DENOM), cB = GN/DENOM
+//   closing   f(NPA-1) = RK(NPA-1) * cA(NPA)             cA(NPA) := 1/(1 + RL(NPA-1))
+//   backward  f(L) = RK(L) - RL(L) * f(L+1),  F2(L) = f(L) * FACMU(L)
+// with AN, GN, DENOM, RL exactly as in the reference (same operation order as k_wpadif).
+// AB holds (cA, cB) pairs, RL the third factor, both [l][k][Pp] like F2.  The count of rows that
+// are not diagonally dominant (the reference's warning, :689) is added to *viol.
+// One thread per line; grid: x = lines of nk*Pp / T
+// =============================================================================
+__global__ void __launch_bounds__(128) k_wpadif_tables(const __grid_constant__ RamDev d, const double* __restrict__ DA,
+                                                       const double* __restrict__ DB, double2* __restrict__ AB,
+                                                       double* __restrict__ RLt, unsigned long long* __restrict__ viol_out) {
+  const int NE = d.NE, NPA = d.NPA, Pp = d.Pp;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)NE * Pp) return;
+  const int k = (int)(t / Pp), p = (int)(t - (long long)k * Pp);
+  const int i = p % d.NR;
+  if (p >= d.P || i < 1 || k < 1) return;
+  const size_t LS = (size_t)NE * Pp;
+  const size_t o = (size_t)k * Pp + p;
+  const double DTs = d.DTs;
+  unsigned long long viol = 0;
+  double rlm = -1.;
+  double Dm = DA[o] + DB[o];   // D(L-1) for L=2
+  for (int L = 2; L <= NPA - 1; ++L) {
+    const double FACMU = d.FNHSc[(size_t)(L - 1) * Pp + p] * d.MU[L - 1];
+    const double Dl = DA[o + (size_t)(L - 1) * LS] + DB[o + (size_t)(L - 1) * LS];
+    double AN = Dl / d.DMU[L - 1];
+    double GN = Dm / d.DMU[L - 2];
+    AN = AN * DTs / FACMU / d.WMU[L - 1];
+    GN = GN * DTs / FACMU / d.WMU[L - 1];
+    const double BN = AN + GN;
+    if (fabs(-1 - BN) < (fabs(AN) + fabs(GN))) ++viol;
+    const double DENOM = BN + GN * rlm + 1;
+    rlm = -AN / DENOM;
+    AB[o + (size_t)(L - 1) * LS] = make_double2(1.0 / (FACMU * DENOM), GN / DENOM);
+    RLt[o + (size_t)(L - 1) * LS] = rlm;
+    Dm = Dl;
+  }
+  AB[o + (size_t)(NPA - 1) * LS] = make_double2(1.0 / (1 + rlm), 0.0);
+  if (viol) atomicAdd(viol_out, viol);
+}
+
+template <int PG, int MAXT, bool WPI>
 __global__ void __launch_bounds__(MAXT) k_col_fused(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0,
                                                     ColCfg cfg) {
   extern __shared__ double smem[];
@@ -372,6 +421,8 @@ __global__ void __launch_bounds__(MAXT) k_col_fused(const __grid_constant__ RamD
   double* sWMZ = sWMU + NPA;
   double* sE2 = sWMZ + NPA;                  // [64] 2^(j/64)
   double* sRed = sE2 + 64;                   // [5][32]
+  double* sFM = sRed + 5 * 32;               // WPI only: [NPA][PG] FNHS*MU (FACMU of WPADIF)
+  const bool doW = WPI && ((cfg.doW >> (s0 + blockIdx.y)) & 1);
 
   // ---- stage the block (asynchronous 16-byte copies, all in flight) and its tables -----
   {
@@ -418,12 +469,58 @@ __global__ void __launch_bounds__(MAXT) k_col_fused(const __grid_constant__ RamD
       sWMZ[t] = (t >= 1) ? d.WMU[t] : 0.0;
     }
     for (int t = tid; t < 64; t += T) sE2[t] = d.exp2tab[t];
+    if (WPI && doW)
+      for (int t = tid; t < NPA * PG; t += T) {
+        const int l2 = t / PG, pp = t - l2 * PG;
+        sFM[t] = d.FNHSc[(size_t)l2 * Pp + p0 + pp] * d.MU[l2];
+      }
     asm volatile("cp.async.wait_group 0;");
   }
   __syncthreads();
 
   const double beta = d.BetaLim;
   double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};   // SUMRC after DRIFTMU, and the four of the loss block
+  double accW[2] = {0.0, 0.0};                 // WPI: SUMRC after the first and after the second WPADIF
+
+  // ---- WPADIF (src/ModRamWPI.f90:643-714) with the tabulated elimination factors of
+  // k_wpadif_tables (sp.DA = (cA,cB) pairs, sp.DB = RL): a thread solves the lines of one
+  // (energy, position); RK overwrites F2 on the way up, F2 is rebuilt on the way down -------
+  auto wpadif = [&](const int which) {
+    const int ntask = NE * PG;
+    for (int e = tid; e < ntask; e += T) {
+      const int pp = e % PG, k = e / PG;
+      const int p = p0 + pp;
+      if (k < 1 || p >= P || p % NR < 1) continue;
+      const size_t LS = (size_t)NE * Pp;
+      const double2* ab = (const double2*)sp.DA + (size_t)k * Pp + p;
+      const double* rl = sp.DB + (size_t)k * Pp + p;
+      double* col = sT + k * PG + pp;                   // F(L) at col[(L-1)*RS]
+      const double* fm = sFM + pp;
+      double rk = 0.0;
+#pragma unroll 4
+      for (int l = 1; l <= NPA - 2; ++l) {
+        const double2 c = ab[(size_t)l * LS];
+        rk = fma(col[(size_t)l * RS], c.x, rk * c.y);
+        col[(size_t)l * RS] = rk;
+      }
+      double f = rk * ab[(size_t)(NPA - 1) * LS].x;      // f(NPA-1) = RK/(1+RL)
+      double fN = f * fm[(NPA - 1) * PG];               // F2(NPA) = f(NPA-1)*FACMU(NPA)
+      double macc = fN * sWMU[NPA - 1];
+      col[(size_t)(NPA - 1) * RS] = fN;
+      fN = f * fm[(NPA - 2) * PG];
+      macc = fma(fN, sWMU[NPA - 2], macc);
+      col[(size_t)(NPA - 2) * RS] = fN;
+#pragma unroll 4
+      for (int l = NPA - 3; l >= 1; --l) {
+        f = fma(-rl[(size_t)l * LS], f, col[(size_t)l * RS]);
+        fN = f * fm[l * PG];
+        macc = fma(fN, sWMU[l], macc);
+        col[(size_t)l * RS] = fN;
+      }
+      col[0] = f * fm[0];                               // RK(1) = 0, RL(1) = -1: f(1) = f(2)
+      if (p < (NT - 1) * NR) accW[which] += macc * (sWE[k] * sEK[k]);
+    }
+  };
 
   // ---- DRIFTE (src/ModRamDrift.f90:285-376) ------------------------------------
   auto drifte = [&]() {
@@ -622,8 +719,10 @@ __global__ void __launch_bounds__(MAXT) k_col_fused(const __grid_constant__ RamD
   __syncthreads();
   driftmu(true);
   __syncthreads();
+  if (WPI && doW) { wpadif(0); __syncthreads(); }       // src/ModRamRun.f90:91-104
   losses();
   __syncthreads();
+  if (WPI && doW) { wpadif(1); __syncthreads(); }       // :140-154
   driftmu(false);
   __syncthreads();
   drifte();
@@ -649,6 +748,44 @@ __global__ void __launch_bounds__(MAXT) k_col_fused(const __grid_constant__ RamD
     }
   }
   block_sum_to<5>(sp.part, blockIdx.x, acc, sRed);
+  if (WPI) {
+    __syncthreads();
+    block_sum_to<2>(sp.part + cfg.wpart_off, blockIdx.x, accW, sRed);
+  }
+}
+
+// =============================================================================
+// k_finalize_wpi: the two WPADIF moments of the fused step (slots 1 and 8 for the electrons'
+// WPI diffusion, 2 and 7 for the EMIC diffusion of H+; src/ModRamRun.f90:91-104, :140-154) and
+// the violation count, after k_finalize.  grid: x = 2, y = species; block = 256
+// =============================================================================
+__global__ void __launch_bounds__(256) k_finalize_wpi(const __grid_constant__ SpecPack pk, int s0, int doW, int nb_col, int wpart_off,
+                                                      int res_n, int nsum, const unsigned long long* __restrict__ viol,
+                                                      unsigned long long* __restrict__ host_res) {
+  __shared__ double sm[32];
+  const int s = s0 + blockIdx.y;
+  if (!((doW >> s) & 1)) return;
+  const SpecDev& sp = pk.s[s];
+  const int q = blockIdx.x;
+  double acc = 0.0;
+  for (int b = threadIdx.x; b < nb_col; b += blockDim.x) acc += sp.part[wpart_off + (size_t)b * 2 + q];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = (threadIdx.x < (blockDim.x >> 5)) ? sm[threadIdx.x] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) {
+      unsigned long long* hr = host_res + (size_t)s * res_n;
+      const bool el = (sp.kind == 3);
+      const int slot = (q == 0) ? (el ? 1 : 2) : (el ? 8 : 7);
+      sp.dt[4 + slot] = dbl_bits(v);
+      hr[4 + slot] = dbl_bits(v);
+      if (q == 0) { sp.dt[4 + nsum] = viol[s]; hr[4 + nsum] = viol[s]; }
+    }
+  }
 }
 
 // =============================================================================

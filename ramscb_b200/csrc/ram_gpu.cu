@@ -74,6 +74,8 @@ struct Spec {
   double* d_tE = nullptr;    // ANISCH scratch [2][nch][NE][Pp]
   double* d_rFFA = nullptr;  // FAST ANISCH: 1/A(S,I,K) [k][i]
   double* d_flc = nullptr;   // FLC_coef of this species [l][k][Pp] (allocated by rsg_ram_set_flc_coef)
+  double* d_wtab = nullptr;  // fused WPADIF: elimination factors (cA,cB) pairs [2*n] then RL [n], n = NPA*NE*Pp (k_wpadif_tables)
+  double wtab_DTs = -1.0;    // DTs the factors were tabulated for (< 0: stale)
   double* d_coul = nullptr;  // COULPARA tables COULE, COULI, ATA, GTA, each [k][l]
   double DTs_coul = -1.0;    // DTs of the last COULPARA
   unsigned long long* d_res = nullptr;  // slice of rsg_ram::d_res_all
@@ -145,11 +147,13 @@ struct rsg_ram {
   bool use_graph = true;
   // fused FAST path (ram_fused.cuh): shared-memory plane / column kernels
   bool use_fused = true;
+  bool use_fused_wpi = true;   // WPADIF inside the column kernel (RSG_NO_FUSE_WPI=1 / rsg_ram_use_fused(h, 1): one kernel per operator with WPI / EMIC)
   int kcPlane = 0, colT = 0, planeT = 0;
   bool planeOdd = false;
   int anischLch = 12;   // pitch angles per thread in the ANISCH pitch-angle sums
   bool in_step = false, fwd_half = false;   // set by rsg_ram_part_*: CFL slots are reset once per step
   unsigned long long* d_res_init = nullptr;
+  unsigned long long* d_wviol = nullptr;    // [nS] rows of the WPADIF matrices that are not diagonally dominant (per tabulation)
 
   cudaStream_t st(int s) { return ext ? ext : sp[s].own; }
   cudaStream_t pst() { return ext ? ext : prepst; }
@@ -464,7 +468,7 @@ int L_anisch(rsg_ram* h, int s0, int ns, cudaStream_t st, int l0 = 0, int nl = -
 // ---- fused FAST path --------------------------------------------------------------
 constexpr int COL_PG = 4;
 struct ColPlan { ColCfg cfg; int T; size_t smem; };
-ColPlan col_plan(const rsg_ram* h) {
+ColPlan col_plan(const rsg_ram* h, bool wpi = false) {
   ColPlan c{};
   const int NE = h->NE, NPA = h->NPA;
   c.cfg.NEs = NE | 1;
@@ -480,10 +484,12 @@ ColPlan col_plan(const rsg_ram* h) {
   segs(NPA - 2, c.T / linesM, &c.cfg.nsegM, &c.cfg.segM);
   segs(NPA, c.T / linesM, &c.cfg.nsegL, &c.cfg.segL);
   c.smem = sizeof(double) * ((size_t)NPA * c.cfg.NEs * COL_PG + 6 * (size_t)NPA * COL_PG + 8 * (size_t)NE + 2 * (size_t)NE * COL_PG +
-                             4 * (size_t)NPA + 64 + 5 * 32);
+                             4 * (size_t)NPA + 64 + 5 * 32 + (wpi ? (size_t)NPA * COL_PG : 0));
   return c;
 }
 int fused_part_off(const rsg_ram* h) { return (((h->P + COL_PG - 1) / COL_PG) * 5 + 15) & ~15; }
+// WPADIF moments of the column kernel: behind the reverse plane kernel's partials (at most NE*NPA of them)
+int fused_wpart_off(const rsg_ram* h) { return (fused_part_off(h) + h->NE * h->NPA + 15) & ~15; }
 struct PlanePlan { PlaneCfg cfg; int T; size_t smem; };
 PlanePlan plane_plan(const rsg_ram* h) {
   PlanePlan c{};
@@ -517,11 +523,21 @@ PlanePlan plane_plan(const rsg_ram* h) {
   return c;
 }
 size_t plane_smem(const rsg_ram* h) { return plane_plan(h).smem; }
-// the fused kernels cover the default operator set on a whole grid in FAST mode
+// species whose step contains WPADIF (src/ModRamRun.f90:91-104): electrons with #USEWPI, H+ with #USEEMIC
+int wpadif_mask(const rsg_ram* h, int flags) {
+  int m = 0;
+  for (int s = 0; s < h->nS; ++s)
+    if (((flags & RSG_F_WPI) && h->kind[s] == RSG_KIND_E) || ((flags & RSG_F_EMIC) && h->kind[s] == RSG_KIND_H)) m |= 1 << s;
+  return m;
+}
+// the fused kernels cover the default operator set, with or without the WPI / EMIC pitch-angle
+// diffusion, on a whole grid in FAST mode (the Coulomb operators run one kernel per operator)
 bool fused_ok(const rsg_ram* h, int flags) {
-  if (!h->use_fused || h->mode != RSG_MODE_FAST || flags != 0) return false;
+  if (!h->use_fused || h->mode != RSG_MODE_FAST || (flags & ~(RSG_F_WPI | RSG_F_EMIC)) != 0) return false;
   if (h->NR < 4 || h->NT < 5 || h->NE < 3 || h->NPA < 4) return false;
-  return col_plan(h).smem <= 220 * 1024 && plane_smem(h) <= 220 * 1024;
+  const bool wpi = wpadif_mask(h, flags) != 0;
+  if (wpi && !h->use_fused_wpi) return false;
+  return col_plan(h, wpi).smem <= 220 * 1024 && plane_smem(h) <= 220 * 1024;
 }
 template <typename K>
 int opt_in_smem(K kernel, size_t smem) {
@@ -560,31 +576,63 @@ int L_cfl(rsg_ram* h, int s0, int ns, cudaStream_t st) {
   for (int s = s0; s < s0 + ns; ++s) h->cfl_ok[s] = true;
   return RSG_OK;
 }
-int L_col(rsg_ram* h, int s0, int ns, int doA, double DTs, cudaStream_t st, int b0 = 0, int nb = -1) {
+// elimination factors of the fused WPADIF for the species of `mask`: tabulated when DTs, the
+// diffusion coefficients or the fields changed, else cached.  Allocates: call outside stream capture.
+int L_wtab(rsg_ram* h, int mask, double DTs, cudaStream_t st) {
+  const size_t n = h->specStride;
+  for (int s = 0; s < h->nS; ++s) {
+    if (!((mask >> s) & 1)) continue;
+    Spec& sp = h->sp[s];
+    const bool el = h->kind[s] == RSG_KIND_E;
+    const double* DA = el ? h->d_diff[0] : h->d_diff[2];
+    const double* DB = el ? h->d_diff[1] : h->d_diff[3];
+    if (!DA && !DB) return fail(RSG_ERR_STATE, "WPADIF before set_diffcoef");
+    if (!sp.d_wtab) RET(h->dalloc(&sp.d_wtab, 3 * n));
+    sp.sd.DA = sp.d_wtab;              // the column kernel reads (cA,cB) through DA and RL through DB
+    sp.sd.DB = sp.d_wtab + 2 * n;
+    if (sp.wtab_DTs == DTs) continue;
+    CK(cudaMemsetAsync(h->d_wviol + s, 0, sizeof(unsigned long long), st));
+    k_wpadif_tables<<<nblk((long long)h->NE * h->Pp, 128), 128, 0, st>>>(devfor(h, DTs), DA ? DA : h->d_zero4, DB ? DB : h->d_zero4,
+                                                                        (double2*)sp.d_wtab, sp.d_wtab + 2 * n, h->d_wviol + s);
+    CKL();
+    h->launches++;
+    sp.wtab_DTs = DTs;
+  }
+  return RSG_OK;
+}
+template <bool WPI>
+int L_col_t(rsg_ram* h, int s0, int ns, int doA, int doW, double DTs, cudaStream_t st, int b0, int nb) {
   SpecPack pk;
   make_pack(h, pk, s0, ns);
-  ColPlan c = col_plan(h);
+  ColPlan c = col_plan(h, WPI);
   c.cfg.doA = doA;
   c.cfg.b0 = b0;
+  c.cfg.doW = doW;
+  c.cfg.wpart_off = fused_wpart_off(h);
   if (nb < 0) nb = (h->P + COL_PG - 1) / COL_PG - b0;
   const dim3 g(nb, ns);
   const RamDev dv = devfor(h, DTs);
   if (c.T <= 320) {          // register budget follows the CTA size
-    RET(opt_in_smem(k_col_fused<COL_PG, 320>, c.smem));
-    k_col_fused<COL_PG, 320><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg);
+    RET(opt_in_smem(k_col_fused<COL_PG, 320, WPI>, c.smem));
+    k_col_fused<COL_PG, 320, WPI><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg);
   } else if (c.T <= 640) {
-    RET(opt_in_smem(k_col_fused<COL_PG, 640>, c.smem));
-    k_col_fused<COL_PG, 640><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg);
+    RET(opt_in_smem(k_col_fused<COL_PG, 640, WPI>, c.smem));
+    k_col_fused<COL_PG, 640, WPI><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg);
   } else if (c.T <= 896) {
-    RET(opt_in_smem(k_col_fused<COL_PG, 896>, c.smem));
-    k_col_fused<COL_PG, 896><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg);
+    RET(opt_in_smem(k_col_fused<COL_PG, 896, WPI>, c.smem));
+    k_col_fused<COL_PG, 896, WPI><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg);
   } else {
-    RET(opt_in_smem(k_col_fused<COL_PG, 1024>, c.smem));
-    k_col_fused<COL_PG, 1024><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg);
+    RET(opt_in_smem(k_col_fused<COL_PG, 1024, WPI>, c.smem));
+    k_col_fused<COL_PG, 1024, WPI><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg);
   }
   CKL();
   h->launches++;
   return RSG_OK;
+}
+int L_col(rsg_ram* h, int s0, int ns, int doA, double DTs, cudaStream_t st, int b0 = 0, int nb = -1, int doW = 0) {
+  for (int s = s0; s < s0 + ns; ++s)
+    if (!((doW >> s) & 1)) { h->sp[s].sd.DA = h->d_zero4; h->sp[s].sd.DB = h->d_zero4; }
+  return doW ? L_col_t<true>(h, s0, ns, doA, doW, DTs, st, b0, nb) : L_col_t<false>(h, s0, ns, doA, 0, DTs, st, b0, nb);
 }
 // pressures of ANISCH in one pass + the result block of the step, both also written to the
 // host-mapped copies (no memcpy nodes in the fused step)
@@ -804,6 +852,7 @@ int rsg_ram_create(rsg_ram** out, int nS, int NR, int NT, int NE, int NPA, int d
   if (const char* e = getenv("RSG_SEG_P")) h->segP = std::max(2, atoi(e));
   if (const char* e = getenv("RSG_KC_R")) h->kcR = std::max(1, atoi(e));
   if (getenv("RSG_NO_FUSE")) h->use_fused = false;
+  if (getenv("RSG_NO_FUSE_WPI")) h->use_fused_wpi = false;
   if (const char* e = getenv("RSG_KC_PLANE")) h->kcPlane = std::max(1, atoi(e));
   if (const char* e = getenv("RSG_COL_T")) h->colT = std::max(32, atoi(e));
   if (const char* e = getenv("RSG_PLANE_T")) h->planeT = std::max(32, atoi(e));
@@ -853,6 +902,7 @@ int rsg_ram_create(rsg_ram** out, int nS, int NR, int NT, int NE, int NPA, int d
   RET(h->dalloc(&h->d_res_all, (size_t)nS * RES_N));
   RET(h->dalloc(&h->d_res_init, (size_t)nS * RES_N));
   RET(h->dalloc(&h->d_cfl_all, (size_t)nS * 4));
+  RET(h->dalloc(&h->d_wviol, (size_t)nS));
   {
     std::vector<unsigned long long> init((size_t)nS * RES_N, 0ull);
     const double dflt[4] = {100000.0, 100000.0, 10000.0, 10000.0};  // :115,223,308,404
@@ -895,7 +945,8 @@ int rsg_ram_create(rsg_ram** out, int nS, int NR, int NT, int NE, int NPA, int d
       // per-plane partials of the reductions, or per-warp partials of the sweeps with a fused SUMRC
       const size_t wR = (size_t)nblk(h->P, 248) * NPA * NE * 8;                       // KC = 1 worst case
       const size_t wM = (size_t)nblk(h->P, 128) * NE * ((NPA - 2 + 1) / 2) * 4;       // SEG = 2 worst case
-      RET(h->dalloc(&sp.d_part, std::max({(size_t)h->nblk_sum * RSG_NMOM, wR, wM})));
+      const size_t wF = (size_t)(nblk(h->P, 4) + 16) * 7 + (size_t)NE * NPA + 64;      // fused step: column + plane + WPADIF partials
+      RET(h->dalloc(&sp.d_part, std::max({(size_t)h->nblk_sum * RSG_NMOM, wR, wM, wF})));
     }
     RET(h->dalloc(&sp.d_tE, (size_t)2 * NE * h->Pp));
     RET(h->dalloc(&sp.d_rFFA, (size_t)NE * NR));
@@ -993,6 +1044,7 @@ int rsg_ram_use_graph(rsg_ram* h, int on) {
 int rsg_ram_use_fused(rsg_ram* h, int on) {
   if (!h) return fail(RSG_ERR_ARG, "null handle");
   h->use_fused = on != 0;
+  h->use_fused_wpi = !(on & 2);        // on = 3: fused kernels for the default operators only, WPADIF as its own kernel
   if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
   return RSG_OK;
 }
@@ -1107,6 +1159,7 @@ int rsg_ram_set_fields(rsg_ram* h, const double* BNES, const double* dBdt, const
   CK(cudaStreamSynchronize(h->pst()));
   h->fields_set = true;
   h->step_dirty = true;
+  for (int s = 0; s < h->nS; ++s) h->sp[s].wtab_DTs = -1.0;   // FACMU = FNHS*MU enters the WPADIF factors
   return RSG_OK;
 }
 
@@ -1167,6 +1220,7 @@ int rsg_ram_set_diffcoef(rsg_ram* h, int which, const double* D) {
   std::vector<double> b;
   to_planes4(h, D, b);
   RET(up(h->d_diff[which], b.data(), b.size()));
+  for (int s = 0; s < h->nS; ++s) h->sp[s].wtab_DTs = -1.0;
   return RSG_OK;
 }
 
@@ -1587,7 +1641,13 @@ int step_prepare(rsg_ram* h, double DTs, int flags, int s0, int ns) {
   RET(ensure_step(h, DTs, st));
   RET(prof_mark(h, "driftr_inflow", st));
   RET(L_inflow(h, s0, ns, st));
-  if (fused_ok(h, flags)) RET(L_cfl(h, s0, ns, st));
+  if (fused_ok(h, flags)) {
+    RET(L_cfl(h, s0, ns, st));
+    int wm = wpadif_mask(h, flags);
+    for (int s = 0; s < h->nS; ++s)
+      if (s < s0 || s >= s0 + ns) wm &= ~(1 << s);
+    if (wm) RET(L_wtab(h, wm, DTs, st));
+  }
   return RSG_OK;
 }
 int enqueue_fwd(rsg_ram* h, int s0, int ns, int l0, int nl);
@@ -1647,11 +1707,22 @@ int enqueue_fused(rsg_ram* h, double DTs, int flags, int s0, int ns) {
   h->in_step = false;
   RET(prof_mark(h, "k_plane_rp", st));
   RET(L_plane_rp(h, s0, ns, st, false));
+  int doW = wpadif_mask(h, flags);
+  for (int s = 0; s < h->nS; ++s)
+    if (s < s0 || s >= s0 + ns) doW &= ~(1 << s);
   RET(prof_mark(h, "k_col_fused", st));
-  RET(L_col(h, s0, ns, doA, DTs, st));
+  RET(L_col(h, s0, ns, doA, DTs, st, 0, -1, doW));
   RET(prof_mark(h, "k_plane_rp", st));
   RET(L_plane_rp(h, s0, ns, st, true));          // ends with the epilogue of ram_run
   RET(L_finish_fused(h, s0, ns, st));
+  if (doW) {                                     // SUMRC moments after the two WPADIFs, violation count
+    SpecPack pk;
+    make_pack(h, pk, s0, ns);
+    k_finalize_wpi<<<dim3(2, ns), 256, 0, st>>>(pk, s0, doW, (h->P + COL_PG - 1) / COL_PG, fused_wpart_off(h), RES_N, NSUM, h->d_wviol,
+                                                h->hd_res_all);
+    CKL();
+    h->launches++;
+  }
   return prof_mark(h, "d2h_results", st);
 }
 }  // namespace
@@ -1738,10 +1809,10 @@ int rsg_ram_part_rev(rsg_ram* h, int s0, int ns, int l0, int nl) {
 // The plane kernels shard by pitch angle, the column kernel by blocks of 4 plane positions:
 //   planes_fwd(l-slab) | exchange | columns(block range) | exchange | planes_rev(l-slab) + finish
 // Moments and pressures are partial sums over the rank's slab / block range.
-int rsg_ram_fused_available(rsg_ram* h, int flags) { return (h && fused_ok(h, flags)) ? 1 : 0; }
+int rsg_ram_fused_available(rsg_ram* h, int flags) { return (h && flags == 0 && fused_ok(h, flags)) ? 1 : 0; }
 int rsg_ram_fpart_planes_fwd(rsg_ram* h, double DTs, int flags, int s0, int ns, int l0, int nl) {
   RET(check_part(h, s0, ns, l0, nl, h ? h->NPA : 0));
-  if (!fused_ok(h, flags)) return fail(RSG_ERR_UNSUPPORTED, "fused kernels not available for this mode / flags / grid");
+  if (flags != 0 || !fused_ok(h, flags)) return fail(RSG_ERR_UNSUPPORTED, "fused kernels not available for this mode / flags / grid");
   CK(cudaSetDevice(h->device));
   RET(step_prepare(h, DTs, flags, s0, ns));
   h->in_step = false;
@@ -1750,7 +1821,7 @@ int rsg_ram_fpart_planes_fwd(rsg_ram* h, double DTs, int flags, int s0, int ns, 
 int rsg_ram_fpart_columns(rsg_ram* h, double DTs, int flags, int s0, int ns, int b0, int nb) {
   const int nbtot = h ? (h->P + COL_PG - 1) / COL_PG : 0;
   RET(check_part(h, s0, ns, b0, nb, nbtot));
-  if (!fused_ok(h, flags)) return fail(RSG_ERR_UNSUPPORTED, "fused kernels not available for this mode / flags / grid");
+  if (flags != 0 || !fused_ok(h, flags)) return fail(RSG_ERR_UNSUPPORTED, "fused kernels not available for this mode / flags / grid");
   CK(cudaSetDevice(h->device));
   int cat[RSG_MAX_SPECIES][NSLOT], doA;
   slot_cats(h, flags, cat, &doA, nullptr);

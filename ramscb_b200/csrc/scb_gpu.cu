@@ -60,6 +60,8 @@ struct rsg_scb {
   bool grid_set = false, geom_set = false, press_set = false, band_done = false;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   double last_ms = 0.0;
+  double *d_alphaVal = nullptr, *d_psiVal = nullptr, *d_chiVal = nullptr, *d_mapw = nullptr;   // map*: targets, workspace
+  bool map_set = false;
   bool use_cluster = true;   // 4-colour SOR on thread-block clusters with the problem resident on chip
   int last_cluster = 0;      // cluster size of the last SOR launch (0: one CTA per sub-problem)
 
@@ -569,6 +571,62 @@ int rsg_scb_derivs(rsg_scb* h, const double* f, double* dT, double* dR, double* 
   SCK(cudaStreamSynchronize(h->st));
   return RSG_OK;
 }
+
+// prescribed node values of the Euler potentials and of the field-line coordinate
+// (alphaVal(nzeta+1), psiVal(npsi): src/ModScbIO.f90:179-203; chiVal(nthe): :167)
+int rsg_scb_set_map_targets(rsg_scb* h, const double* alphaVal, const double* psiVal, const double* chiVal) {
+  if (!h || !alphaVal || !psiVal || !chiVal) return sfail(RSG_ERR_ARG, "null argument");
+  SCK(cudaSetDevice(h->device));
+  if (!h->d_alphaVal) {
+    SRET(h->dalloc(&h->d_alphaVal, h->nzeta + 1, "alphaVal"));
+    SRET(h->dalloc(&h->d_psiVal, h->npsi, "psiVal"));
+    SRET(h->dalloc(&h->d_chiVal, h->nthe, "chiVal"));
+    const size_t nmax = std::max({(size_t)(h->nzeta + 1) * h->nthe * h->npsi, (size_t)h->npsi * h->nthe * (h->nzeta - 1),
+                                  (size_t)h->nthe * h->npsi * (h->nzeta - 1)});
+    SRET(h->dalloc(&h->d_mapw, 7 * nmax, nullptr));
+  }
+  SRET(scb_up(h, "alphaVal", alphaVal)); SRET(scb_up(h, "psiVal", psiVal)); SRET(scb_up(h, "chiVal", chiVal));
+  SCK(cudaStreamSynchronize(h->st));
+  h->map_set = true;
+  return RSG_OK;
+}
+
+// mapAlpha / mapPsi / mapTheta (src/ModScbEuler.f90:97-147, :403-457, :15-75): x, y, z (and the
+// reset alfa / psi) stay on the device for the next computeBandJacob; *sorfail != 0 when a line
+// could not be interpolated (the reference sets SORFail and the caller rolls back)
+static int scb_map(rsg_scb* h, int mode, int* sorfail) {
+  if (!h) return sfail(RSG_ERR_ARG, "null handle");
+  if (!h->geom_set || !h->map_set) return sfail(RSG_ERR_STATE, "map* before set_geometry / set_map_targets");
+  SCK(cudaSetDevice(h->device));
+  const int nthe = h->nthe, npsi = h->npsi, nzeta = h->nzeta;
+  SCK(cudaMemsetAsync(h->d_fail, 0, sizeof(int), h->st));
+  SCK(cudaEventRecord(h->e0, h->st));
+  if (mode == 0) {
+    const int nl = nthe * npsi;
+    k_scb_map<0><<<nblk(nl, 64), 64, 0, h->st>>>(h->dev, h->d_alphaVal, h->d_mapw, nl, h->d_fail);
+  } else if (mode == 1) {
+    const int nl = nthe * (nzeta - 1);
+    k_scb_map<1><<<nblk(nl, 64), 64, 0, h->st>>>(h->dev, h->d_psiVal, h->d_mapw, nl, h->d_fail);
+  } else {
+    const int nl = npsi * (nzeta - 1);
+    k_scb_map<2><<<nblk(nl, 64), 64, 0, h->st>>>(h->dev, h->d_chiVal, h->d_mapw, nl, h->d_fail);
+  }
+  SCKL();
+  h->launches++;
+  SCK(cudaEventRecord(h->e1, h->st));
+  int f = 0;
+  SCK(cudaMemcpyAsync(&f, h->d_fail, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  SCK(cudaStreamSynchronize(h->st));
+  float ms = 0.f;
+  SCK(cudaEventElapsedTime(&ms, h->e0, h->e1));
+  h->last_ms = ms;
+  h->band_done = false;
+  if (sorfail) *sorfail = f != 0;
+  return RSG_OK;
+}
+int rsg_scb_map_alpha(rsg_scb* h, int* sorfail) { return scb_map(h, 0, sorfail); }
+int rsg_scb_map_psi(rsg_scb* h, int* sorfail) { return scb_map(h, 1, sorfail); }
+int rsg_scb_map_theta(rsg_scb* h, int* sorfail) { return scb_map(h, 2, sorfail); }
 
 double rsg_scb_last_ms(rsg_scb* h) { return h ? h->last_ms : 0.0; }
 int rsg_scb_use_cluster(rsg_scb* h, int on) {

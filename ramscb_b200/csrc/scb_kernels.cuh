@@ -571,6 +571,141 @@ __global__ void __launch_bounds__(128) k_scb_conv2(ScbDev d, double bnormal, dou
 }
 
 // =============================================================================
+// k_scb_map<MODE>: mapAlpha (MODE 0, src/ModScbEuler.f90:97-147), mapPsi (1, :403-457) and
+// mapTheta (2, :15-75): move the grid points x,y,z along one coordinate line so that the Euler
+// potential just computed (alfa / psi) -- or the arc-length fraction of the field line -- takes
+// its prescribed node values again.  Per line: GSL_Interpolation_1D with the Steffen spline
+// (src/ModRamGSL.f90:240-311, src/RamGSL.c:111-174): drop non-increasing abscissae, Steffen node
+// slopes, bisection for the interval, Horner evaluation, linear extrapolation outside the data.
+// The three coordinates of a line share abscissae, interval search and the filter.
+// One thread per line; the line's copies (xOld/yOld/zOld of the reference) and slopes live in a
+// workspace W[7][n][nlines] (coalesced across lines).  The thread also does the periodic wrap of
+// its line (:136-141) and alfges / psiges (:82-94, :387-400).  Operation order of the reference
+// (-fmad=false): bit-identical to the oracle.
+// =============================================================================
+template <int MODE>
+__global__ void __launch_bounds__(64) k_scb_map(ScbDev d, const double* __restrict__ tgt, double* __restrict__ W, int nlines,
+                                               int* __restrict__ fail) {
+  const int line = blockIdx.x * blockDim.x + threadIdx.x;
+  if (line >= nlines) return;
+  const int nthe = d.nthe, npsi = d.npsi, nzeta = d.nzeta;
+  const size_t sj = nthe, sk = (size_t)nthe * npsi;
+  // line geometry: n source points from `base` with stride `st`; n2 targets written from point `o0` on
+  size_t base, st;
+  int n, n2, o0, kpl = 0;
+  if (MODE == 0) { base = line; st = sk; n = nzeta + 1; n2 = nzeta - 1; o0 = 1; }                        // line = i + nthe*j
+  else if (MODE == 1) { const int i = line % nthe; kpl = 1 + line / nthe; base = i + sk * kpl; st = sj; n = npsi; n2 = npsi; o0 = 0; }
+  else { const int j = line % npsi; kpl = 1 + line / npsi; base = sj * j + sk * kpl; st = 1; n = nthe; n2 = nthe; o0 = 0; }
+  const size_t NL = nlines;
+  double* Wx = W + line;                    // abscissae
+  double* Wf[3] = {W + (size_t)1 * n * NL + line, W + (size_t)2 * n * NL + line, W + (size_t)3 * n * NL + line};
+  double* Wp[3] = {W + (size_t)4 * n * NL + line, W + (size_t)5 * n * NL + line, W + (size_t)6 * n * NL + line};
+  double* xyz[3] = {d.x, d.y, d.z};
+  const double* absc = (MODE == 0) ? d.alfa : d.psi;
+  double total = 0.0;
+  if (MODE == 2) {                          // arc length along the line (:43-46)
+    double dist = 0.0;
+    Wx[0] = 0.0;
+    for (int q = 1; q < n; ++q) {
+      const size_t o = base + q * st;
+      dist = dist + sqrt(sq(d.x[o] - d.x[o - st]) + sq(d.y[o] - d.y[o - st]) + sq(d.z[o] - d.z[o - st]));
+      Wx[(size_t)q * NL] = dist;
+    }
+    total = dist;
+  }
+  // copy the line, dropping abscissae that do not increase (src/ModRamGSL.f90:262-273)
+  int n1 = 0;
+  double last = 0.0;
+  for (int q = 0; q < n; ++q) {
+    const size_t o = base + q * st;
+    const double xv = (MODE == 2) ? Wx[(size_t)q * NL] / total * 3.141592653589793238462643383279502884197 : absc[o];   // pi_d
+    if (q == 0 || xv > last) {
+      Wx[(size_t)n1 * NL] = xv;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) Wf[c][(size_t)n1 * NL] = xyz[c][o];
+      last = xv;
+      ++n1;
+    }
+  }
+  if (n1 < 3) { atomicAdd(fail, 1); return; }            // GSLerr > 0 => SORFail
+  // Steffen node slopes (gsl interpolation/steffen.c, steffen_init)
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const double* fa = Wf[c];
+    Wp[c][0] = (fa[NL] - fa[0]) / (Wx[NL] - Wx[0]);
+    for (int i = 1; i < n1 - 1; ++i) {
+      const double hi = Wx[(size_t)(i + 1) * NL] - Wx[(size_t)i * NL];
+      const double him1 = Wx[(size_t)i * NL] - Wx[(size_t)(i - 1) * NL];
+      const double si = (fa[(size_t)(i + 1) * NL] - fa[(size_t)i * NL]) / hi;
+      const double sim1 = (fa[(size_t)i * NL] - fa[(size_t)(i - 1) * NL]) / him1;
+      const double pi = (sim1 * hi + si * him1) / (him1 + hi);
+      const double m1 = fabs(si) < 0.5 * fabs(pi) ? fabs(si) : 0.5 * fabs(pi);
+      const double m2 = fabs(sim1) < m1 ? fabs(sim1) : m1;
+      Wp[c][(size_t)i * NL] = (steffen_sgn(sim1) + steffen_sgn(si)) * m2;
+    }
+    Wp[c][(size_t)(n1 - 1) * NL] = (fa[(size_t)(n1 - 1) * NL] - fa[(size_t)(n1 - 2) * NL]) / (Wx[(size_t)(n1 - 1) * NL] - Wx[(size_t)(n1 - 2) * NL]);
+  }
+  // evaluate at the prescribed node values
+  const double xa0 = Wx[0], xa1 = Wx[NL], xaN = Wx[(size_t)(n1 - 1) * NL], xaM = Wx[(size_t)(n1 - 2) * NL];
+  bool bad = false;
+  for (int q = 0; q < n2; ++q) {
+    const double xb = tgt[(MODE == 0) ? q + 1 : q];
+    const size_t o = base + (size_t)(o0 + q) * st;
+    if (xb <= xa0) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) xyz[c][o] = Wf[c][0] + (xb - xa0) / (xa1 - xa0) * (Wf[c][NL] - Wf[c][0]);
+    } else if (xb >= xaN) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        xyz[c][o] = Wf[c][(size_t)(n1 - 1) * NL] + (xb - xaN) / (xaM - xaN) * (Wf[c][(size_t)(n1 - 2) * NL] - Wf[c][(size_t)(n1 - 1) * NL]);
+    } else if (xb == xb) {
+      int ilo = 0, ihi = n1 - 1;
+      while (ihi > ilo + 1) {                            // gsl_interp_bsearch
+        const int i = (ihi + ilo) / 2;
+        if (Wx[(size_t)i * NL] > xb) ihi = i; else ilo = i;
+      }
+      const double xl = Wx[(size_t)ilo * NL];
+      const double hi = Wx[(size_t)(ilo + 1) * NL] - xl;
+      const double delx = xb - xl;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const double f0 = Wf[c][(size_t)ilo * NL];
+        const double si = (Wf[c][(size_t)(ilo + 1) * NL] - f0) / hi;
+        const double y0 = Wp[c][(size_t)ilo * NL], y1 = Wp[c][(size_t)(ilo + 1) * NL];
+        const double a = (y0 + y1 - 2 * si) / hi / hi;
+        const double b = (3 * si - 2 * y0 - y1) / hi;
+        xyz[c][o] = f0 + delx * (y0 + delx * (b + delx * a));
+      }
+    } else {
+      bad = true;
+    }
+  }
+  if (bad) { atomicAdd(fail, 1); return; }
+  // periodic planes (zeta = 1 <- nzeta, nzeta+1 <- 2) and the reset of the potential
+  if (MODE == 0) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      xyz[c][base] = xyz[c][base + (size_t)(nzeta - 1) * st];
+      xyz[c][base + (size_t)nzeta * st] = xyz[c][base + st];
+    }
+    for (int k = 0; k <= nzeta; ++k) d.alfa[base + (size_t)k * st] = tgt[k];          // alfges
+  } else {
+    const long long shift = (kpl == nzeta - 1) ? -(long long)sk * (nzeta - 1) : ((kpl == 1) ? (long long)sk * (nzeta - 1) : 0);
+    for (int q = 0; q < n; ++q) {
+      const size_t o = base + q * st;
+      if (shift != 0) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) xyz[c][(size_t)((long long)o + shift)] = xyz[c][o];
+      }
+      if (MODE == 1) {                                                                // psiges
+        d.psi[o] = tgt[q];
+        if (shift != 0) d.psi[(size_t)((long long)o + shift)] = tgt[q];
+      }
+    }
+  }
+}
+
+// =============================================================================
 // k_scb_sor_cluster: the 4-colour SOR of iterateAlpha / iteratePsi with the WHOLE
 // problem resident on chip.  A thread-block cluster of CL CTAs owns one independent
 // sub-problem (a psi surface for alpha, a zeta plane for psi); the updated rows are cut

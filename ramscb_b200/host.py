@@ -155,8 +155,10 @@ class RamGpu:
     def sync(self):
         _ck(self.L.rsg_ram_sync(self.h))
 
-    def use_fused(self, on=True):
-        _ck(self.L.rsg_ram_use_fused(self.h, 1 if on else 0))
+    def use_fused(self, on=True, wpadif=True):
+        """Fused shared-memory kernels of the FAST step; ``wpadif=False`` keeps WPADIF (WPI / EMIC
+        flags) as its own kernel, which then takes the whole step to the one-kernel-per-operator path."""
+        _ck(self.L.rsg_ram_use_fused(self.h, (1 if wpadif else 3) if on else 0))
 
     def use_graph(self, on=True):
         _ck(self.L.rsg_ram_use_graph(self.h, 1 if on else 0))

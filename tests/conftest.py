@@ -22,6 +22,7 @@ def use_emulator():
     from ramscb_b200 import host
     host.LIB_PATH = build_emu.build()
     host._lib = None
+    os.environ["RSG_SCB_NO_CLUSTER"] = "1"     # thread-block clusters are not emulated (tests/emu/cooperative_groups.h)
 
 
 @pytest.fixture(scope="session")

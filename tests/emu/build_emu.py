@@ -1,8 +1,8 @@
-"""TEST INFRASTRUCTURE ONLY: compile the RAM device library for the host-CPU CUDA emulator.
+"""TEST INFRASTRUCTURE ONLY: compile the device library (RAM and SCB) for the host-CPU CUDA emulator.
 
     python tests/emu/build_emu.py [--force]
 
-Copies ramscb_b200/csrc/{ram_*.cuh, ram_gpu.cu} into tests/emu/_gen/, rewriting only what g++
+Copies ramscb_b200/csrc/{*.cuh, *.cu} into tests/emu/_gen/, rewriting only what g++
 cannot parse -- `kernel<<<grid, block, smem, stream>>>(args);` becomes
 `emu::launch(grid, block, smem, stream, kernel, args);`, `extern __shared__ T name[];` becomes a
 pointer to the emulated dynamic shared memory, and the six `cp.async` inline-PTX statements become
@@ -23,7 +23,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "ramscb_b200", "csrc")
 GEN = os.path.join(HERE, "_gen")
 LIB = os.path.join(GEN, "libramscb_emu.so")
-FILES = ["ram_common.cuh", "ram_kernels.cuh", "ram_fused.cuh", "ram_coulomb.cuh", "ram_gpu.cu"]
+FILES = ["ram_common.cuh", "ram_kernels.cuh", "ram_fused.cuh", "ram_coulomb.cuh", "ram_gpu.cu", "scb_kernels.cuh", "scb_gpu.cu"]
 
 
 def _match(src, i, open_ch, close_ch):
@@ -121,7 +121,7 @@ def build(force=False):
     cmd = ["g++", "-std=c++17", "-O2", "-g", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-DEMU_IMPLEMENT",
            "-fno-stack-protector", "-Wno-unused-result",
            "-I", HERE, "-I", os.path.join(ROOT, "include"), "-I", GEN,
-           "-o", LIB, os.path.join(GEN, "ram_gpu.cpp")]
+           "-o", LIB, os.path.join(GEN, "ram_gpu.cpp"), os.path.join(GEN, "scb_gpu.cpp")]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr[-20000:])

@@ -476,5 +476,22 @@ static inline cudaError_t cudaGraphLaunch(cudaGraphExec_t e, cudaStream_t s) {
   for (auto& op : e->ops) emu::submit(s, op);
   return cudaSuccess;
 }
+// cluster launches are not emulated (cooperative_groups.h stub): refuse them loudly
+enum cudaLaunchAttributeID { cudaLaunchAttributeClusterDimension = 4 };
+struct cudaLaunchAttribute {
+  cudaLaunchAttributeID id;
+  struct { struct { unsigned x, y, z; } clusterDim; } val;
+};
+struct cudaLaunchConfig_t {
+  dim3 gridDim, blockDim;
+  size_t dynamicSmemBytes = 0;
+  cudaStream_t stream = nullptr;
+  cudaLaunchAttribute* attrs = nullptr;
+  unsigned numAttrs = 0;
+};
+template <class K, class... A> static inline cudaError_t cudaLaunchKernelEx(const cudaLaunchConfig_t*, K, A&&...) {
+  fprintf(stderr, "emu: cluster launch requested (set RSG_SCB_NO_CLUSTER=1)\n");
+  return cudaErrorInvalidValue;
+}
 static inline cudaError_t cudaGraphDestroy(cudaGraph_t g) { delete g; return cudaSuccess; }
 static inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t g) { delete g; return cudaSuccess; }

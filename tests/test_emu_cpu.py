@@ -78,3 +78,8 @@ def test_emulated_fused_equals_unfused_and_graph_replay(emu, T, small_grids):
             assert np.array_equal(a["DtDrift"], b["DtDrift"]) and a["DtsNext"] == b["DtsNext"]
             for k in ("PPERT", "PPART", "SETRC"):
                 assert np.allclose(a[k], b[k], rtol=1e-12, atol=0), k
+
+
+@pytest.mark.parametrize("flags", [1 | 4, 1])
+def test_emulated_fused_wpadif_step(emu, T, small_grids, oracle_built, flags):
+    T.test_fused_wpadif_fast_step(small_grids, oracle_built, "default", flags)

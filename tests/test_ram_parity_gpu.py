@@ -427,6 +427,54 @@ def test_fast_mode_full_ram_run(default_grids, oracle_built):
         assert np.allclose(out["SETRC"], o.SETRC, rtol=1e-12, atol=0)
 
 
+@pytest.mark.parametrize("grid", ["default", "odd"])
+@pytest.mark.parametrize("flags", [1 | 4, 1, 4])
+def test_fused_wpadif_fast_step(default_grids, oracle_built, grid, flags):
+    """WPI / EMIC pitch-angle diffusion inside the fused column kernel (BASELINE configs[2]: full step
+    with WPADIF).  The Thomas recurrences use tabulated elimination factors (k_wpadif_tables), i.e. a
+    different rounding than the one-kernel-per-operator path: F2 within 1e-12 of the oracle AND of the
+    unfused FAST path (stencil-neighbourhood scale, as for every FAST test), CFL limits identical,
+    moments / pressures / loss increments to 1e-12, and the fused step must really be taken
+    (5 + 1 launches per step instead of ~30)."""
+    from ramscb_b200 import host
+    g = default_grids if grid == "default" else grids.build_grids(NR=23, NT=31, NE=46, energy_refine=1)
+    inp = _mk(g, f2_kind="noisy", inductive=True, mgnp=True)
+    D = synthetic.synthetic_daa(g, inp)
+    o = oracle_built.RamOracle(g, inp, DTs=DTS)
+    o.set_array("ATAC", D)
+    o.set_array("ATAW_emic_h", D)
+    runs = {}
+    for name, wp in (("unfused", False), ("fused", True)):
+        gpu = host.RamGpu(g)
+        gpu.set_mode(host.MODE_FAST)
+        gpu.set_inputs(inp)
+        gpu.set_diffcoef(1, D)
+        gpu.set_diffcoef(2, D)
+        gpu.use_fused(True, wpadif=wp)
+        outs, n = [], []
+        for dts in (5.0, 5.0, 7.5):
+            n0 = gpu.launch_count()
+            outs.append(gpu.ram_run(dts, DtsMin=1.0, flags=flags))
+            n.append(gpu.launch_count() - n0)
+        runs[name] = (gpu.f2_d2h(), outs, n)
+        gpu.close()
+    for dts in (5.0, 5.0, 7.5):
+        o.set_scalar("DTs", dts)
+        dtn_ref = o.ram_run(flags=flags)
+    (f_u, o_u, n_u), (f_f, o_f, n_f) = runs["unfused"], runs["fused"]
+    assert n_f[1] == 6 and n_u[1] > 20, f"launches per replayed step: fused {n_f}, unfused {n_u}"
+    assert _local_relerr(f_f, f_u) <= 1e-12
+    assert _local_relerr(f_f, o.F2, CLAMP_ABS) <= 1e-12
+    assert abs(o_f[-1]["DtsNext"] - dtn_ref) <= 1e-13 * dtn_ref
+    for a, b in zip(o_u, o_f):
+        assert np.array_equal(a["DtDrift"], b["DtDrift"]) and a["DtsNext"] == b["DtsNext"]
+        for k in ("PPERT", "PPART", "SETRC"):
+            assert np.allclose(a[k], b[k], rtol=1e-12, atol=0), k
+        assert np.all(np.abs(a["losses"] - b["losses"]) <= 1e-11 * np.abs(a["SETRC"])[None, :])
+    assert _relerr(o_f[-1]["PPERT"][:, 1:], o.PPERT[:, 1:]) <= 1e-12
+    assert np.allclose(o_f[-1]["SETRC"], o.SETRC, rtol=1e-12, atol=0)
+
+
 # ---------------------------------------------------------------------------------
 # multi-GPU parts (rsg_ram_part_*): slab-wise execution on one device must reproduce
 # the single-launch step bit for bit (the exchange between the parts is then a no-op:
