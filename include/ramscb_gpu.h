@@ -274,6 +274,18 @@ int rsg_scb_convergence(rsg_scb* h, double* normDiff, double* normJxB, double* n
 /* GSL_Derivs with the Steffen spline (src/ModRamGSL.f90:794-869) of a host (nthe,npsi,nzeta) field;
  * any output may be NULL */
 int rsg_scb_derivs(rsg_scb* h, const double* f, double* dfdTheta, double* dfdRho, double* dfdZeta);
+/* mapAlpha, mapPsi, mapTheta (src/ModScbEuler.f90:97-147, :403-457, :15-75) -- the re-gridding
+ * steps that follow iterateAlpha / iteratePsi inside the SCB outer iteration (src/ModScbRun.f90:
+ * 232-250, 418-430): x, y, z are moved along zeta / rho / theta lines by Steffen interpolation
+ * (GSL_Interpolation_1D, src/ModRamGSL.f90:240-311 + src/RamGSL.c:111-174) so that alfa / psi / the
+ * arc-length coordinate take their prescribed node values again; alfa / psi are reset (alfges,
+ * psiges) and the periodic planes refreshed.  Everything stays on the device for the next
+ * computeBandJacob.  set_map_targets: alphaVal(nzeta+1), psiVal(npsi), chiVal(nthe), once.
+ * *sorfail: a line could not be interpolated (GSLerr > 0 in the reference => SORFail). */
+int rsg_scb_set_map_targets(rsg_scb* h, const double* alphaVal, const double* psiVal, const double* chiVal);
+int rsg_scb_map_alpha(rsg_scb* h, int* sorfail);
+int rsg_scb_map_psi(rsg_scb* h, int* sorfail);
+int rsg_scb_map_theta(rsg_scb* h, int* sorfail);
 /* device time (CUDA events on the launching stream) of the kernels of the last call */
 /* Multi-GPU: the independent sub-problems of a solve (psi surfaces for alpha, zeta planes for psi)
  * split among ranks.  part solves sub-problems [sub0, sub0+nsub) (0-based: q is jz = q+2 / k = q+2);

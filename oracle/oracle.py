@@ -177,7 +177,9 @@ def scb_lib():
         lib.scbo_set_int.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         lib.scbo_get_scalar.argtypes = [C.c_void_p, C.c_char_p]
         lib.scbo_get_scalar.restype = C.c_double
-        for f in ("bandjacob", "convergence"):
+        lib.scbo_interp1d.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        lib.scbo_interp1d.restype = C.c_int
+        for f in ("bandjacob", "convergence", "map_alpha", "map_psi", "map_theta"):
             getattr(lib, "scbo_" + f).argtypes = [C.c_void_p]
             getattr(lib, "scbo_" + f).restype = C.c_int
         for f in ("metrica", "metric", "newk", "newj"):
@@ -201,7 +203,9 @@ class ScbOracle:
         nthe, npsi, nzeta = inp.nthe, inp.npsi, inp.nzeta
         self.h = self.lib.scbo_create(nthe, npsi, nzeta)
         self.arr = {}
-        for n in ("thetaVal", "rhoVal", "zetaVal", "psiVal", "f", "alphaVal", "fzet"):
+        for n in ("thetaVal", "rhoVal", "zetaVal", "psiVal", "f", "alphaVal", "fzet", "chiVal"):
+            if getattr(inp, n, None) is None:
+                continue
             self._set(n, np.ascontiguousarray(getattr(inp, n), dtype=np.float64).copy())
         for n in SCB_IN3P:
             self._set(n, np.asfortranarray(getattr(inp, n)).copy(order="F"))
@@ -252,6 +256,10 @@ class ScbOracle:
 
     def convergence(self):
         return self.lib.scbo_convergence(self.h)
+
+    def map_alpha(self): return self.lib.scbo_map_alpha(self.h)
+    def map_psi(self): return self.lib.scbo_map_psi(self.h)
+    def map_theta(self): return self.lib.scbo_map_theta(self.h)
 
     def derivs3d(self, f3):
         f3 = np.asfortranarray(f3, dtype=np.float64)

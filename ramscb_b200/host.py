@@ -395,6 +395,9 @@ def _scb_lib():
             getattr(L, "rsg_scb_" + n).argtypes = [vp, d, i, i, i, i, _ip, _dp, _dp, _dp, _ip, vp]
         L.rsg_scb_convergence.argtypes = [vp, _dp, _dp, _dp, _ip]
         L.rsg_scb_derivs.argtypes = [vp] * 5
+        L.rsg_scb_set_map_targets.argtypes = [vp, vp, vp, vp]
+        for n in ("map_alpha", "map_psi", "map_theta"):
+            getattr(L, "rsg_scb_" + n).argtypes = [vp, _ip]
         L.rsg_scb_last_ms.argtypes = [vp]
         L.rsg_scb_last_ms.restype = d
         L.rsg_scb_use_cluster.argtypes = [vp, i]
@@ -433,6 +436,8 @@ class ScbGpu:
         self.set_pressure(inp)
         self.set_field("alfa", inp.alfa)
         self.set_field("psi", inp.psi)
+        if getattr(inp, "chiVal", None) is not None:
+            self.set_map_targets(inp.alphaVal, inp.psiVal, inp.chiVal)
 
     def set_pressure(self, inp):
         names = ("pper", "ppar", "sigma", "dPPerdTheta", "dPPerdRho", "dPPerdZeta", "dBsqdTheta", "dBsqdRho", "dBsqdZeta",
@@ -460,6 +465,19 @@ class ScbGpu:
         f = C.c_int()
         _sck(self.L.rsg_scb_bandjacob(self.h, C.byref(f)))
         return f.value
+
+    def set_map_targets(self, alphaVal, psiVal, chiVal):
+        a = [np.ascontiguousarray(v, dtype=np.float64) for v in (alphaVal, psiVal, chiVal)]
+        _sck(self.L.rsg_scb_set_map_targets(self.h, *[v.ctypes.data for v in a]))
+
+    def _map(self, fn):
+        f = C.c_int()
+        _sck(fn(self.h, C.byref(f)))
+        return f.value
+
+    def mapAlpha(self): return self._map(self.L.rsg_scb_map_alpha)     # src/ModScbEuler.f90:97
+    def mapPsi(self): return self._map(self.L.rsg_scb_map_psi)         # :403
+    def mapTheta(self): return self._map(self.L.rsg_scb_map_theta)     # :15
 
     def metrica(self): _sck(self.L.rsg_scb_metrica(self.h))
     def metric(self): _sck(self.L.rsg_scb_metric(self.h))

@@ -90,6 +90,7 @@ class ScbInputs:
     dBsqdAlpha: np.ndarray = None
     dPdAlpha: np.ndarray = None
     dPdPsi: np.ndarray = None
+    chiVal: np.ndarray = None   # (nthe) field-line coordinate nodes, src/ModScbIO.f90:167
     extra: dict = field(default_factory=dict)
 
 
@@ -175,6 +176,7 @@ def build_scb(nthe=101, npsi=45, nzeta=97, constTheta=0.2, xpsiin=1.75, xpsiout=
     inp = ScbInputs(nthe=nthe, npsi=npsi, nzeta=nzeta, isotropy=isotropy, thetaVal=thetaVal, rhoVal=rhoVal, zetaVal=zetaVal,
                     psiVal=psiVal, f=f, alphaVal=alphaVal, fzet=fzet, x=x, y=y, z=z, alfa=alfa, psi=psi, pper=pper, ppar=ppar,
                     sigma=sigma, bsq0=bsq0)
+    inp.chiVal = thetaVal + constTheta * np.sin(2.0 * thetaVal)      # src/ModScbIO.f90:167
     # ---- derivatives the way `pressure` ends (src/ModScbRun.f90:1161-1175) ----------------
     p3 = pper[:, :, :nzeta]
     inp.dPPerdTheta, inp.dPPerdRho, inp.dPPerdZeta = derivs3d(thetaVal, rhoVal, zetaVal, p3)

@@ -118,10 +118,12 @@ def build(force=False):
         src = rewrite(src, f).replace('"../../include/ramscb_gpu.h"', '"ramscb_gpu.h"')
         with open(os.path.join(GEN, f.replace(".cu", ".cpp") if f.endswith(".cu") else f), "w") as fh:
             fh.write(src)
-    cmd = ["g++", "-std=c++17", "-O2", "-g", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-DEMU_IMPLEMENT",
+    with open(os.path.join(GEN, "emu_impl.cpp"), "w") as fh:      # the one definition of the context switch
+        fh.write('#define EMU_IMPLEMENT\n#include "cuda_runtime.h"\n')
+    cmd = ["g++", "-std=c++17", "-O2", "-g", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared",
            "-fno-stack-protector", "-Wno-unused-result",
            "-I", HERE, "-I", os.path.join(ROOT, "include"), "-I", GEN,
-           "-o", LIB, os.path.join(GEN, "ram_gpu.cpp"), os.path.join(GEN, "scb_gpu.cpp")]
+           "-o", LIB, os.path.join(GEN, "ram_gpu.cpp"), os.path.join(GEN, "scb_gpu.cpp"), os.path.join(GEN, "emu_impl.cpp")]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr[-20000:])

@@ -56,6 +56,10 @@ static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y
 static inline double4 make_double4(double x, double y, double z, double w) { double4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 static inline int2 make_int2(int x, int y) { int2 r; r.x = x; r.y = y; return r; }
 
+// the built-in variables: plain globals, threadIdx is set by the scheduler at every fiber switch
+inline uint3 threadIdx{0, 0, 0}, blockIdx{0, 0, 0};
+inline dim3 blockDim, gridDim;
+
 // ---------------------------------------------------------------------------------------------
 // fibers
 namespace emu {
@@ -68,6 +72,7 @@ struct Fiber {
   uint3 tid{0, 0, 0};
   int lin = 0;            // linear thread index
   unsigned shfl_phase = 0;
+  unsigned or_phase = 0;
 };
 
 struct Warp {
@@ -82,15 +87,16 @@ struct Block {
   std::vector<Fiber> f;
   std::vector<Warp> w;
   int nthreads = 0, live = 0, at_barrier = 0;
+  int or_slot[3] = {0, 0, 0};
   void* sched_sp = nullptr;
   std::function<void()> body;
 };
 
 inline Block& blk() { static Block b; return b; }
 inline Fiber*& cur() { static Fiber* c = nullptr; return c; }
-inline uint3& bidx() { static uint3 v; return v; }
-inline dim3& bdim() { static dim3 v; return v; }
-inline dim3& gdim() { static dim3 v; return v; }
+inline uint3& bidx() { return blockIdx; }
+inline dim3& bdim() { return blockDim; }
+inline dim3& gdim() { return gridDim; }
 inline std::vector<char>& dynsmem() { static std::vector<char> v; return v; }
 inline void* dyn_smem() { return dynsmem().data(); }
 
@@ -162,6 +168,7 @@ inline void prepare(Fiber& f) {
   f.done = false;
   f.wait = 0;
   f.shfl_phase = 0;
+  f.or_phase = 0;
 }
 
 // run one block to completion
@@ -173,6 +180,7 @@ inline void run_block(const std::function<void()>& body, dim3 block) {
   b.nthreads = n;
   b.live = n;
   b.at_barrier = 0;
+  b.or_slot[0] = b.or_slot[1] = b.or_slot[2] = 0;
   b.body = body;
   for (int t = 0; t < n; ++t) {
     Fiber& f = b.f[t];
@@ -189,6 +197,7 @@ inline void run_block(const std::function<void()>& body, dim3 block) {
       Fiber& f = b.f[t];
       if (f.done || f.wait) continue;
       cur() = &f;
+      threadIdx = f.tid;
       emu_switch(&b.sched_sp, f.sp);
       progressed = true;
     }
@@ -285,14 +294,20 @@ inline void launch(dim3 grid, dim3 block, size_t smem, void* stream, std::functi
 
 }  // namespace emu
 
-#define threadIdx (emu::cur()->tid)
-#define blockIdx (emu::bidx())
-#define blockDim (emu::bdim())
-#define gridDim (emu::gdim())
 #define warpSize 32
 
 static inline void __syncthreads() { emu::syncthreads(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu::warp_arrive(); }
+static inline int __syncthreads_or(int pred) {
+  // three rotating slots: call n clears the slot of call n+1 before its barrier, so nobody can
+  // still be reading it (its last use was call n-2) and nobody can already be writing it
+  emu::Block& b = emu::blk();
+  const unsigned n = emu::cur()->or_phase++;
+  b.or_slot[(n + 1) % 3] = 0;
+  if (pred) b.or_slot[n % 3] = 1;
+  emu::syncthreads();
+  return b.or_slot[n % 3];
+}
 template <class T> static inline T __shfl_sync(unsigned, T v, int src, int width = 32) { return emu::shfl(v, src, width); }
 template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m, int width = 32) {
   return emu::shfl(v, (emu::cur()->lin & 31) ^ m, 32);

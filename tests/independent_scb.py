@@ -224,3 +224,90 @@ def newk_aniso(inp, m, nthe, npsi, nzeta):
     tz = inp.dPPerdZeta[:, :, :nzeta] + 0.5 * (1. - sg) * inp.dBsqdZeta[:, :, :nzeta]
     tt = inp.dPPerdTheta[:, :, :nzeta] + 0.5 * (1. - sg) * inp.dBsqdTheta[:, :, :nzeta]
     return m["jacobian"] / f2 * c0 * (tz * xpz + tt * xpt)
+
+
+# ---------------------------------------------------------------------------------------------
+# GSL_Interpolation_1D (Steffen) and the three re-gridding maps, restated a second time: whole-line
+# numpy (searchsorted instead of the bisection loop, coefficient arrays a,b,c,d built for every
+# interval as gsl's steffen_init does) straight from src/ModRamGSL.f90:240-311, src/RamGSL.c:111-174
+# and the published steffen.c.
+def interp1d_steffen(x1, f1, x2):
+    x1 = np.asarray(x1, dtype=np.float64)
+    f1 = np.asarray(f1, dtype=np.float64)
+    keep = [0]
+    for i in range(1, len(x1)):                   # monotonicity filter of the Fortran wrapper
+        if x1[i] > x1[keep[-1]]:
+            keep.append(i)
+    xa, fa = x1[keep], f1[keep]
+    n = len(xa)
+    assert n >= 3
+    h = np.diff(xa)
+    s = np.diff(fa) / h
+    yp = np.empty(n)
+    yp[0] = s[0]
+    p = (s[:-1] * h[1:] + s[1:] * h[:-1]) / (h[:-1] + h[1:])
+    sgn = lambda v: np.where(v < 0, -1.0, 1.0)
+    yp[1:-1] = (sgn(s[:-1]) + sgn(s[1:])) * np.minimum(np.abs(s[:-1]), np.minimum(np.abs(s[1:]), 0.5 * np.abs(p)))
+    yp[-1] = s[-1]
+    a = (yp[:-1] + yp[1:] - 2 * s) / h / h
+    b = (3 * s - 2 * yp[:-1] - yp[1:]) / h
+    x2 = np.asarray(x2, dtype=np.float64)
+    out = np.empty_like(x2)
+    lo = x2 <= xa[0]
+    hi = x2 >= xa[-1]
+    out[lo] = fa[0] + (x2[lo] - xa[0]) / (xa[1] - xa[0]) * (fa[1] - fa[0])
+    out[hi] = fa[-1] + (x2[hi] - xa[-1]) / (xa[-2] - xa[-1]) * (fa[-2] - fa[-1])
+    m = ~(lo | hi)
+    idx = np.searchsorted(xa, x2[m], side="right") - 1      # xa[idx] <= x < xa[idx+1]
+    dx = x2[m] - xa[idx]
+    out[m] = fa[idx] + dx * (yp[idx] + dx * (b[idx] + dx * a[idx]))
+    return out
+
+
+def _wrap(a, nzeta):
+    a[:, :, 0] = a[:, :, nzeta - 1]
+    a[:, :, nzeta] = a[:, :, 1]
+
+
+def map_alpha(x, y, z, alfa, alphaVal, nthe, npsi, nzeta):
+    x, y, z, alfa = (np.array(a, order="F") for a in (x, y, z, alfa))
+    for j in range(npsi):
+        for i in range(nthe):
+            ao = alfa[i, j, :].copy()
+            for a in (x, y, z):
+                a[i, j, 1:nzeta] = interp1d_steffen(ao, a[i, j, :].copy(), alphaVal[1:nzeta])
+    for a in (x, y, z):
+        _wrap(a, nzeta)
+    alfa[:, :, :] = alphaVal[None, None, :]
+    return x, y, z, alfa
+
+
+def map_psi(x, y, z, psi, psiVal, nthe, npsi, nzeta):
+    x, y, z, psi = (np.array(a, order="F") for a in (x, y, z, psi))
+    for k in range(1, nzeta):
+        for i in range(nthe):
+            po = psi[i, :, k].copy()
+            for a in (x, y, z):
+                a[i, :, k] = interp1d_steffen(po, a[i, :, k].copy(), psiVal)
+    for a in (x, y, z):
+        _wrap(a, nzeta)
+    psi[:, :, :] = psiVal[None, :, None]
+    return x, y, z, psi
+
+
+def map_theta(x, y, z, chiVal, nthe, npsi, nzeta):
+    x, y, z = (np.array(a, order="F") for a in (x, y, z))
+    PI = 3.141592653589793238462643383279502884197
+    for k in range(1, nzeta):
+        for j in range(npsi):
+            xo, yo, zo = x[:, j, k].copy(), y[:, j, k].copy(), z[:, j, k].copy()
+            seg = np.sqrt((xo[1:] - xo[:-1]) ** 2 + (yo[1:] - yo[:-1]) ** 2 + (zo[1:] - zo[:-1]) ** 2)
+            dist = np.zeros(nthe)
+            for i in range(1, nthe):              # running sum in the reference's order
+                dist[i] = dist[i - 1] + seg[i - 1]
+            chiOld = dist / dist[-1] * PI
+            for a, old in ((x, xo), (y, yo), (z, zo)):
+                a[:, j, k] = interp1d_steffen(chiOld, old, chiVal)
+    for a in (x, y, z):
+        _wrap(a, nzeta)
+    return x, y, z

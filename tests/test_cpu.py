@@ -446,3 +446,80 @@ def test_product_code_does_not_import_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 txt = open(os.path.join(dp, fn)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt.replace("the CPU oracle", ""), fn
+
+
+# ---------------------------------------------------------------------------------------------
+# GSL_Interpolation_1D (Steffen) and mapAlpha / mapPsi / mapTheta of the SCB oracle
+def _interp(oracle_mod, x1, f1, x2):
+    import ctypes as C
+    lib = oracle_mod.scb_lib()
+    x1, f1, x2 = (np.ascontiguousarray(a, dtype=np.float64) for a in (x1, f1, x2))
+    out = np.zeros_like(x2)
+    rc = lib.scbo_interp1d(len(x1), x1.ctypes.data, f1.ctypes.data, len(x2), x2.ctypes.data, out.ctypes.data)
+    return rc, out
+
+
+def test_steffen_interpolation_properties(oracle_built):
+    """interp1d of the oracle (src/ModRamGSL.f90:240-311 + src/RamGSL.c:111-174): reproduces the nodes,
+    is exact on straight lines, never overshoots monotone data (Steffen 1990), extrapolates linearly,
+    drops non-increasing abscissae, and agrees bit for bit with the independent numpy restatement."""
+    import independent_scb as ind
+    rng = np.random.default_rng(11)
+    xa = np.cumsum(rng.uniform(0.1, 1.0, 40))
+    fa = np.cumsum(rng.uniform(0.0, 1.0, 40)) ** 1.5                    # monotone data
+    rc, at_nodes = _interp(oracle_built, xa, fa, xa)
+    assert rc == 0 and np.array_equal(at_nodes, fa)
+    xb = np.sort(rng.uniform(xa[0] - 1.0, xa[-1] + 1.0, 500))
+    rc, fb = _interp(oracle_built, xa, fa, xb)
+    assert rc == 0
+    inside = (xb > xa[0]) & (xb < xa[-1])
+    assert np.all(np.diff(fb[inside]) >= 0), "Steffen's interpolant must be monotone on monotone data"
+    assert np.array_equal(fb, ind.interp1d_steffen(xa, fa, xb))
+    lo = xb <= xa[0]
+    assert np.allclose(fb[lo], fa[0] + (xb[lo] - xa[0]) * (fa[1] - fa[0]) / (xa[1] - xa[0]), rtol=1e-14)
+    rc, lin = _interp(oracle_built, xa, 3.0 * xa - 2.0, xb)
+    assert np.allclose(lin, 3.0 * xb - 2.0, rtol=1e-13, atol=1e-13)
+    # the wrapper's filter: repeated / decreasing abscissae are skipped
+    xd = np.insert(xa, [5, 5, 17], [xa[4], xa[3], xa[16] - 1e-3])
+    fd = np.insert(fa, [5, 5, 17], [1e9, -1e9, 1e9])
+    rc, fb2 = _interp(oracle_built, xd, fd, xb)
+    assert rc == 0 and np.array_equal(fb2, fb)
+    rc, _ = _interp(oracle_built, [0.0, 0.0, 0.0, -1.0], [1.0, 2.0, 3.0, 4.0], [0.5])
+    assert rc != 0                                                    # fewer than 3 usable points: GSLerr
+
+
+def test_map_routines_match_independent_restatement(oracle_built):
+    """mapAlpha / mapPsi / mapTheta of the C++ oracle vs tests/independent_scb.py (bit for bit), on a
+    warped grid with perturbed potentials; plus their defining property: re-gridding with the
+    unperturbed potentials (alfa == alphaVal on every line) leaves x, y, z where they are."""
+    import independent_scb as ind
+    from ramscb_b200 import scb_synthetic as S
+    inp = S.build_scb(nthe=31, npsi=13, nzeta=25, warp=0.3)
+    n = (inp.nthe, inp.npsi, inp.nzeta)
+    o = oracle_built.ScbOracle(inp)
+    x0, y0, z0 = o.x.copy(), o.y.copy(), o.z.copy()
+    assert o.map_alpha() == 0 and o.map_psi() == 0
+    for a, b in ((o.x, x0), (o.y, y0), (o.z, z0)):
+        assert np.allclose(a, b, rtol=0, atol=1e-12), "identity re-gridding moved the points"
+    rng = np.random.default_rng(3)
+    o = oracle_built.ScbOracle(inp)
+    o.alfa[...] = np.asfortranarray(inp.alfa + 0.08 * rng.standard_normal(inp.alfa.shape))
+    o.psi[...] = np.asfortranarray(inp.psi * (1.0 + 0.03 * rng.standard_normal(inp.psi.shape)))
+    rx, ry, rz, ra = ind.map_alpha(o.x, o.y, o.z, o.alfa, inp.alphaVal, *n)
+    assert o.map_alpha() == 0
+    for a, b in ((o.x, rx), (o.y, ry), (o.z, rz), (o.alfa, ra)):
+        assert np.array_equal(a, b)
+    assert np.abs(o.x - x0).max() > 1e-3
+    rx, ry, rz, rp = ind.map_psi(o.x, o.y, o.z, o.psi, inp.psiVal, *n)
+    assert o.map_psi() == 0
+    for a, b in ((o.x, rx), (o.y, ry), (o.z, rz), (o.psi, rp)):
+        assert np.array_equal(a, b)
+    rx, ry, rz = ind.map_theta(o.x, o.y, o.z, inp.chiVal, *n)
+    assert o.map_theta() == 0
+    for a, b in ((o.x, rx), (o.y, ry), (o.z, rz)):
+        assert np.array_equal(a, b)
+    # after mapTheta the points of a line sit at the prescribed arc-length fractions (to the spline's accuracy)
+    j, k = 5, 7
+    seg = np.sqrt(np.diff(o.x[:, j, k]) ** 2 + np.diff(o.y[:, j, k]) ** 2 + np.diff(o.z[:, j, k]) ** 2)
+    frac = np.concatenate([[0.0], np.cumsum(seg)]) / seg.sum()
+    assert np.max(np.abs(frac - inp.chiVal / np.pi)) < 2e-2

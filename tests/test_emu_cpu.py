@@ -83,3 +83,10 @@ def test_emulated_fused_equals_unfused_and_graph_replay(emu, T, small_grids):
 @pytest.mark.parametrize("flags", [1 | 4, 1])
 def test_emulated_fused_wpadif_step(emu, T, small_grids, oracle_built, flags):
     T.test_fused_wpadif_fast_step(small_grids, oracle_built, "default", flags)
+
+
+def test_emulated_scb_maps_and_geometry(emu, oracle_built):
+    """SCB kernels in the emulator: computeBandJacob, metrica/newk, the lexicographic SOR wavefront and
+    mapAlpha / mapPsi / mapTheta, all bit-identical to the oracle (tests/test_scb_parity_gpu.py)."""
+    import test_scb_parity_gpu as TS
+    TS.test_map_alpha_psi_theta_bit_exact(oracle_built)

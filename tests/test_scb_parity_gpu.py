@@ -89,6 +89,66 @@ def test_sor_lexicographic_bit_exact(oracle_built):
     assert np.array_equal(gpu.get_field("psi"), o.psi)
 
 
+def test_map_alpha_psi_theta_bit_exact(oracle_built):
+    """mapAlpha, mapPsi, mapTheta (src/ModScbEuler.f90:97-147, :403-457, :15-75) in the order of
+    one SCB outer iteration (src/ModScbRun.f90:232-250, 418-430): solve alpha, re-grid along zeta,
+    recompute the geometry, solve psi, re-grid along rho, then along theta.  The interpolation is
+    GSL_Interpolation_1D with the Steffen spline in the reference's operation order: x, y, z and the
+    reset potentials must be BIT-IDENTICAL to the oracle after every step, and the following
+    computeBandJacob must agree too (the re-gridded coordinates stay on the device)."""
+    inp, o, gpu = _pair(oracle_built, **SMALL)
+    o.bandjacob(); gpu.computeBandJacob()
+    o.metrica(); o.newk(); gpu.metrica(); gpu.newk()
+    o.iterate_alpha(); gpu.iterateAlpha(1e-6, ordering=0)
+    assert np.array_equal(gpu.get_field("alfa"), o.alfa)
+    x0 = o.x.copy()
+    assert o.map_alpha() == 0 and gpu.mapAlpha() == 0
+    _same(gpu, o, ("x", "y", "z", "alfa"))
+    moved = np.abs(o.x - x0).max()
+    assert moved > 1e-6, "mapAlpha did not move the grid: the test input is too tame"
+    assert np.array_equal(o.alfa[3, 2, :], inp.alphaVal)                    # alfges
+    o.bandjacob(); gpu.computeBandJacob()
+    _same(gpu, o, ("jacobian", "bsq", "Bx"))
+    o.metric(); o.newj(); gpu.metric(); gpu.newj()
+    o.iterate_psi(); gpu.iteratePsi(1e-6, ordering=0)
+    assert np.array_equal(gpu.get_field("psi"), o.psi)
+    x1 = o.x.copy()
+    assert o.map_psi() == 0 and gpu.mapPsi() == 0
+    _same(gpu, o, ("x", "y", "z", "psi"))
+    assert np.abs(o.x - x1).max() > 1e-6
+    x2 = o.x.copy()
+    assert o.map_theta() == 0 and gpu.mapTheta() == 0
+    _same(gpu, o, ("x", "y", "z"))
+    assert np.abs(o.x - x2).max() > 1e-9
+    # periodic planes
+    for a in (gpu.get_field("x"), gpu.get_field("z")):
+        assert np.array_equal(a[:, :, 0], a[:, :, inp.nzeta - 1]) and np.array_equal(a[:, :, inp.nzeta], a[:, :, 1])
+    o.bandjacob(); gpu.computeBandJacob()
+    _same(gpu, o, GEOM_FIELDS)
+
+
+def test_map_full_size_and_degenerate_lines(oracle_built):
+    """Default SCB grid (101 x 45 x 97); alfa / psi perturbed so that some abscissae do not increase
+    (the wrapper's monotonicity filter, src/ModRamGSL.f90:262-273) and some targets fall outside the
+    data (linear extrapolation, src/RamGSL.c:159-164)."""
+    inp, o, gpu = _pair(oracle_built, nthe=101, npsi=45, nzeta=97, warp=0.2)
+    rng = np.random.default_rng(7)
+    alfa = inp.alfa + 0.04 * rng.standard_normal(inp.alfa.shape)             # ~dphi/1.6: many order violations
+    psi = inp.psi * (1.0 + 0.02 * rng.standard_normal(inp.psi.shape))
+    for name, a in (("alfa", alfa), ("psi", psi)):
+        a = np.asfortranarray(a)
+        getattr(o, name)[...] = a
+        gpu.set_field(name, a)
+    nonmono = int(np.sum(np.diff(alfa, axis=2) <= 0))
+    assert nonmono > 1000
+    assert o.map_alpha() == 0 and gpu.mapAlpha() == 0
+    _same(gpu, o, ("x", "y", "z", "alfa"))
+    assert o.map_psi() == 0 and gpu.mapPsi() == 0
+    _same(gpu, o, ("x", "y", "z", "psi"))
+    assert o.map_theta() == 0 and gpu.mapTheta() == 0
+    _same(gpu, o, ("x", "y", "z"))
+
+
 def test_sor_color4_converged_fields(oracle_built):
     """4-colour ordering vs the reference order, both converged tightly: the potentials
     agree within 1e-8 relative (north_star tolerance for the SCB solve)."""
