@@ -235,6 +235,16 @@ def scb_metrics(device):
         full = sweeps / max(nsub, 1)             # equivalent sweeps over all sub-problems
         out[name] = {"ms": rr["ms"], "max_sweeps": int(rr["nisave"]), "mean_sweeps": full, "SORFail": int(rr["SORFail"]),
                      "sweeps_per_s": full / (rr["ms"] * 1e-3), "point_updates_per_s": full * npts / (rr["ms"] * 1e-3)}
+    # the re-gridding steps that follow the solves in the outer iteration (mapAlpha / mapPsi / mapTheta,
+    # src/ModScbEuler.f90): timed once, last, because they move x, y, z
+    try:
+        m = {}
+        for name, fn in (("map_alpha_ms", gpu.mapAlpha), ("map_psi_ms", gpu.mapPsi), ("map_theta_ms", gpu.mapTheta)):
+            fail = fn()
+            m[name] = gpu.last_ms() if not fail else None
+        out.update(m)
+    except Exception as e:      # informational entry: never take the bench line down
+        out["map_error"] = str(e)[:200]
     gpu.close()
     return out
 

@@ -88,6 +88,7 @@ struct Block {
   std::vector<Warp> w;
   int nthreads = 0, live = 0, at_barrier = 0;
   int or_slot[3] = {0, 0, 0};
+  std::vector<int> perm;
   void* sched_sp = nullptr;
   std::function<void()> body;
 };
@@ -191,9 +192,25 @@ inline void run_block(const std::function<void()>& body, dim3 block) {
     f.tid.z = t / (block.x * block.y);
     ++b.w[t >> 5].live;
   }
+  // EMU_ORDER=reverse|random runs the runnable threads of a block in another order between
+  // synchronisation points: results must not depend on it (a difference means a missing barrier)
+  static const int order_mode = [] {
+    const char* e = getenv("EMU_ORDER");
+    return !e ? 0 : (!strcmp(e, "reverse") ? 1 : (!strcmp(e, "random") ? 2 : 0));
+  }();
+  static unsigned long long rng = 0x9E3779B97F4A7C15ull;
+  std::vector<int>& perm = b.perm;
+  perm.resize(n);
+  for (int t = 0; t < n; ++t) perm[t] = order_mode == 1 ? n - 1 - t : t;
   while (b.live > 0) {
     bool progressed = false;
-    for (int t = 0; t < n; ++t) {
+    if (order_mode == 2)
+      for (int t = n - 1; t > 0; --t) {             // Fisher-Yates with xorshift64
+        rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+        std::swap(perm[t], perm[(int)(rng % (unsigned)(t + 1))]);
+      }
+    for (int q = 0; q < n; ++q) {
+      const int t = perm[q];
       Fiber& f = b.f[t];
       if (f.done || f.wait) continue;
       cur() = &f;

@@ -90,3 +90,16 @@ def test_emulated_scb_maps_and_geometry(emu, oracle_built):
     mapAlpha / mapPsi / mapTheta, all bit-identical to the oracle (tests/test_scb_parity_gpu.py)."""
     import test_scb_parity_gpu as TS
     TS.test_map_alpha_psi_theta_bit_exact(oracle_built)
+
+
+def test_emulated_results_do_not_depend_on_thread_order():
+    """Race check: EMU_ORDER=random runs the runnable threads of every block in a fresh random order
+    between synchronisation points.  A kernel whose result depended on the order (a missing barrier
+    between a producer and a consumer stage) would break the bit-exact comparisons of the fused-step
+    tests; they must pass unchanged."""
+    import subprocess
+    env = dict(os.environ, EMU_ORDER="random")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_emu_cpu.py"), "-x", "-q", "-k",
+                        "fused or exact_sweeps or scb_maps"], env=env, capture_output=True, text=True, cwd=os.path.dirname(here))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
