@@ -258,6 +258,9 @@ def main():
     ap.add_argument("--workload", default="default", choices=["default", "x4"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = 4 species per rank (4*N in the job), strong = the 4 species sharded over the ranks")
+    ap.add_argument("--flags", type=int, default=0,
+                    help="rsg_ram_run operator flags: 1 = WPI pitch-angle diffusion (electrons), 4 = EMIC (H+); 5 with "
+                         "--workload x4 is BASELINE configs[2] (full step with WPADIF); default 0 = configs[1]")
     ap.add_argument("--no-scb", action="store_true", help="skip the SCB solve metrics")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"],
@@ -273,6 +276,13 @@ def main():
     weak = a.scaling == "weak"
     jobs = world if weak else 1                      # independent 4-species sets in the job
     cells = g.nS * g.NR * g.NT * g.NE * g.NPA        # cells one rank's species set holds
+    ops_per_step = float(OPS_PER_STEP)               # operator applications per cell, averaged over the species
+    if a.flags:
+        if a.flags & ~5 or a.impl == "reference" or a.scaling == "strong" and world > 1:
+            raise SystemExit("--flags supports 1 (WPI) and 4 (EMIC) on our arm, 1 GPU or weak scaling")
+        nw = sum(1 for sp in g.species if (a.flags & 1 and sp.WPI) or (a.flags & 4 and sp.EMIC))
+        ops_per_step += 2.0 * nw / g.nS               # two WPADIF applications for each species that diffuses
+        desc += f"; flags={a.flags}: WPADIF twice per step for {nw} of the {g.nS} species"
     if weak and world > 1:
         desc += f"; weak scaling: {world} x 4 species, 4 per rank"
     unit = "cell-updates/s"
@@ -298,7 +308,7 @@ def main():
         return
 
     import torch
-    from ramscb_b200 import host
+    from ramscb_b200 import host, synthetic
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
@@ -316,6 +326,10 @@ def main():
     idle = plan.ns == 0     # more ranks than species on a grid too small to split a species
     gpu = host.RamGpu(g, device=local_rank, mode=host.MODE_FAST if a.mode == "fast" else host.MODE_EXACT)
     gpu.set_inputs(inp)
+    if a.flags:
+        D = synthetic.synthetic_daa(g, inp)          # synthetic Daa in ATAC / ATAW_emic_h
+        gpu.set_diffcoef(1, D)
+        gpu.set_diffcoef(2, D)
     F2_host = inp.F2.copy(order="F")
     host.host_register(F2_host)
     flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
@@ -333,7 +347,7 @@ def main():
         torch.cuda.synchronize()
 
     def step_resident():
-        return gpu.ram_run(DTS, DtsMin=1.0, flags=0) if not split else sharded.ram_run(DTS)
+        return gpu.ram_run(DTS, DtsMin=1.0, flags=a.flags) if not split else sharded.ram_run(DTS)
 
     for _ in range(a.warmup):
         step_resident()
@@ -367,7 +381,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms = float(t.item())
     ms_per_step = dev_ms / a.steps
-    value = OPS_PER_STEP * cells * jobs / (ms_per_step * 1e-3)
+    value = ops_per_step * cells * jobs / (ms_per_step * 1e-3)
 
     # ---- end to end through the C ABI with host buffers ---------------------------
     e2e_steps = max(3, min(a.steps, 10))
@@ -389,7 +403,7 @@ def main():
         e2e_s = float(t.item())
     h2d = F2_host.nbytes + 3 * VT.nbytes
     d2h = F2_host.nbytes + (4 + 6 + 1) * g.nS * 8 + 2 * g.nS * g.NR * g.NT * 8
-    e2e = {"value": OPS_PER_STEP * cells * jobs / e2e_s, "unit": unit, "h2d_bytes_per_step": int(h2d) * jobs,
+    e2e = {"value": ops_per_step * cells * jobs / e2e_s, "unit": unit, "h2d_bytes_per_step": int(h2d) * jobs,
            "d2h_bytes_per_step": int(d2h) * jobs, "ms_per_step": e2e_s * 1e3,
            "timer": "wall clock, pinned host F2; F2 goes host->device and back EVERY step (routine-level drop-in, "
                     "INTEGRATION.md 3a): PCIe bound"}
@@ -402,7 +416,7 @@ def main():
             out = step_resident()
         torch.cuda.synchronize()
         res_s = (time.perf_counter() - t0) / e2e_steps
-        e2e["resident_state"] = {"ms_per_step": res_s * 1e3, "value": OPS_PER_STEP * cells / res_s, "per": "rank",
+        e2e["resident_state"] = {"ms_per_step": res_s * 1e3, "value": ops_per_step * cells / res_s, "per": "rank",
                                  "h2d_bytes_per_step": int(3 * VT.nbytes),
                                  "d2h_bytes_per_step": int((4 + 6 + 1) * g.nS * 8 + 2 * g.nS * g.NR * g.NT * 8),
                                  "note": "F2 stays on the device; not the headline e2e"}
@@ -452,7 +466,7 @@ def main():
     line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "ops_per_cell_per_step": OPS_PER_STEP, "mode": ("fast: separable coefficients + FMA + division-free limiter, fused shared-memory kernels, <=1e-12 of the oracle relative to the "
+            "config": {"workload": desc, "ops_per_cell_per_step": ops_per_step, "mode": ("fast: separable coefficients + FMA + division-free limiter, fused shared-memory kernels, <=1e-12 of the oracle relative to the "
                                 "stencil neighbourhood (tests/test_ram_parity_gpu.py)") if a.mode == "fast"
                        else "exact: reference operation order, bit-identical to the oracle",
                        "l2": "flushed between timed steps (512 MB memset, untimed)", "DTs": DTS,
