@@ -286,6 +286,15 @@ int rsg_scb_set_map_targets(rsg_scb* h, const double* alphaVal, const double* ps
 int rsg_scb_map_alpha(rsg_scb* h, int* sorfail);
 int rsg_scb_map_psi(rsg_scb* h, int* sorfail);
 int rsg_scb_map_theta(rsg_scb* h, int* sorfail);
+/* Glue of the outer iteration (src/ModScbRun.f90:232-262, 418-440), so that alfa, psi, x, y, z need
+ * not visit the host between the solves: device snapshots of a named field (alfaSav1, alphaPrev,
+ * xPrev... of the reference; slot 0..3), the blend  field = snap(slot_new)*blend +
+ * snap(slot_sav)*(1-blend)  (:236, :422) and MINVAL(jacobian(2:nthe-1,2:npsi-1,2:nzeta)) (:248, :434;
+ * -1e300 if the Jacobian holds a NaN). */
+int rsg_scb_snapshot(rsg_scb* h, const char* name, int slot);
+int rsg_scb_restore(rsg_scb* h, const char* name, int slot);
+int rsg_scb_blend(rsg_scb* h, const char* name, int slot_new, int slot_sav, double blend);
+int rsg_scb_min_jacobian(rsg_scb* h, double* minjac);
 /* device time (CUDA events on the launching stream) of the kernels of the last call */
 /* Multi-GPU: the independent sub-problems of a solve (psi surfaces for alpha, zeta planes for psi)
  * split among ranks.  part solves sub-problems [sub0, sub0+nsub) (0-based: q is jz = q+2 / k = q+2);

@@ -62,6 +62,7 @@ struct rsg_scb {
   double last_ms = 0.0;
   double *d_alphaVal = nullptr, *d_psiVal = nullptr, *d_chiVal = nullptr, *d_mapw = nullptr;   // map*: targets, workspace
   bool map_set = false;
+  std::map<std::string, double*> snaps;   // "name#slot" -> device copy (rsg_scb_snapshot)
   bool use_cluster = true;   // 4-colour SOR on thread-block clusters with the problem resident on chip
   int last_cluster = 0;      // cluster size of the last SOR launch (0: one CTA per sub-problem)
 
@@ -624,6 +625,67 @@ static int scb_map(rsg_scb* h, int mode, int* sorfail) {
   if (sorfail) *sorfail = f != 0;
   return RSG_OK;
 }
+// ---- glue of the outer iteration (src/ModScbRun.f90:232-262, 418-440) ------------------------
+// snapshot slots hold device copies of a named (nthe,npsi,nzeta+1) field: alfaSav1 / alphaPrev /
+// xPrev ... of the reference.  slot 0..3.
+static int scb_slot(rsg_scb* h, const char* name, int slot, double** field, double** snap, size_t* n) {
+  if (!h || !name) return sfail(RSG_ERR_ARG, "null argument");
+  if (slot < 0 || slot > 3) return sfail(RSG_ERR_ARG, "snapshot slot must be 0..3");
+  auto it = h->arr.find(name);
+  if (it == h->arr.end()) return sfail(RSG_ERR_ARG, std::string("unknown array ") + name);
+  const std::string key = std::string(name) + "#" + std::to_string(slot);
+  auto sn = h->snaps.find(key);
+  if (sn == h->snaps.end()) {
+    double* p = nullptr;
+    SRET(h->dalloc(&p, it->second.second, nullptr));
+    sn = h->snaps.emplace(key, p).first;
+  }
+  *field = it->second.first; *snap = sn->second; *n = it->second.second;
+  return RSG_OK;
+}
+int rsg_scb_snapshot(rsg_scb* h, const char* name, int slot) {
+  double *f, *sn; size_t n;
+  SRET(scb_slot(h, name, slot, &f, &sn, &n));
+  SCK(cudaSetDevice(h->device));
+  SCK(cudaMemcpyAsync(sn, f, n * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+  return RSG_OK;
+}
+int rsg_scb_restore(rsg_scb* h, const char* name, int slot) {
+  double *f, *sn; size_t n;
+  SRET(scb_slot(h, name, slot, &f, &sn, &n));
+  SCK(cudaSetDevice(h->device));
+  SCK(cudaMemcpyAsync(f, sn, n * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+  if (!std::strcmp(name, "x") || !std::strcmp(name, "y") || !std::strcmp(name, "z")) h->band_done = false;
+  return RSG_OK;
+}
+// field = snap(slot_new)*blend + snap(slot_sav)*(1 - blend)       (src/ModScbRun.f90:236, :422)
+int rsg_scb_blend(rsg_scb* h, const char* name, int slot_new, int slot_sav, double blend) {
+  double *f, *a, *b; size_t n;
+  SRET(scb_slot(h, name, slot_new, &f, &a, &n));
+  SRET(scb_slot(h, name, slot_sav, &f, &b, &n));
+  SCK(cudaSetDevice(h->device));
+  k_scb_blend<<<(unsigned)((n + 255) / 256), 256, 0, h->st>>>(f, a, b, blend, n);
+  SCKL();
+  h->launches++;
+  return RSG_OK;
+}
+// MINVAL(jacobian(2:nthe-1,2:npsi-1,2:nzeta)) of the last computeBandJacob (:248); -1e300 if a NaN is present
+int rsg_scb_min_jacobian(rsg_scb* h, double* minjac) {
+  if (!h || !minjac) return sfail(RSG_ERR_ARG, "null argument");
+  SCK(cudaSetDevice(h->device));
+  const int nb = h->nzeta - 1;
+  k_scb_minjac<<<nb, 256, 0, h->st>>>(h->dev, h->d_part);
+  SCKL();
+  h->launches++;
+  std::vector<double> part(nb);
+  SCK(cudaMemcpyAsync(part.data(), h->d_part, nb * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  SCK(cudaStreamSynchronize(h->st));
+  double m = part[0];
+  for (int q = 1; q < nb; ++q) m = part[q] < m ? part[q] : m;
+  *minjac = m;
+  return RSG_OK;
+}
+
 int rsg_scb_map_alpha(rsg_scb* h, int* sorfail) { return scb_map(h, 0, sorfail); }
 int rsg_scb_map_psi(rsg_scb* h, int* sorfail) { return scb_map(h, 1, sorfail); }
 int rsg_scb_map_theta(rsg_scb* h, int* sorfail) { return scb_map(h, 2, sorfail); }

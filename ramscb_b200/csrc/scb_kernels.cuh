@@ -431,6 +431,45 @@ __global__ void __launch_bounds__(256) k_scb_sums(ScbDev d, const double* __rest
   }
 }
 
+// =============================================================================
+// Glue of the SCB outer iteration (src/ModScbRun.f90:232-262, 418-440) so that the 3-D arrays stay
+// on the device between the solves: the blend of the new potential with the one saved at the
+// start of the iteration,  u = uNew*blend + uSav*(1 - blend)  (:236, :422; two roundings per
+// product and one for the sum, as the Fortran expression), and MINVAL(jacobian(2:nthe-1,
+// 2:npsi-1, 2:nzeta)) (:248, :434) whose sign decides whether the moved points are kept.
+// =============================================================================
+__global__ void __launch_bounds__(256) k_scb_blend(double* __restrict__ u, const double* __restrict__ unew,
+                                                   const double* __restrict__ usav, double blend, size_t n) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < n) u[q] = unew[q] * blend + usav[q] * (1.0 - blend);
+}
+// one CTA per zeta plane k = 2..nzeta -> part[k-2]; the host takes the min of nzeta-1 values
+__global__ void __launch_bounds__(256) k_scb_minjac(ScbDev d, double* __restrict__ part) {
+  __shared__ double sm[32];
+  const int k = blockIdx.x + 1;
+  const int ni = d.nthe - 2, nj = d.npsi - 2;
+  double m = 1e300;
+  bool nan = false;
+  for (int w = threadIdx.x; w < ni * nj; w += blockDim.x) {
+    const int jj = w / ni, ii = w - jj * ni;
+    const double v = d.jac[(size_t)(ii + 1) + (size_t)d.nthe * ((size_t)(jj + 1) + (size_t)d.npsi * (size_t)k)];
+    if (v != v) nan = true;
+    m = v < m ? v : m;
+  }
+  if (nan) m = -1e300;          // a NaN Jacobian must not pass the `< 0` test as "fine"
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double t = __shfl_xor_sync(0xffffffffu, m, o);
+    m = t < m ? t : m;
+  }
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int q = 1; q < (int)(blockDim.x >> 5); ++q) m = sm[q] < m ? sm[q] : m;
+    part[blockIdx.x] = m;
+  }
+}
+
 // extap, src/ModScbFunctions.f90:57-76
 __device__ __forceinline__ double extap(double x1, double x2, double x3) {
   double x4 = 3. * x3 - 3. * x2 + x1;

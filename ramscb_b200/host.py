@@ -398,6 +398,10 @@ def _scb_lib():
         L.rsg_scb_set_map_targets.argtypes = [vp, vp, vp, vp]
         for n in ("map_alpha", "map_psi", "map_theta"):
             getattr(L, "rsg_scb_" + n).argtypes = [vp, _ip]
+        L.rsg_scb_snapshot.argtypes = [vp, C.c_char_p, i]
+        L.rsg_scb_restore.argtypes = [vp, C.c_char_p, i]
+        L.rsg_scb_blend.argtypes = [vp, C.c_char_p, i, i, d]
+        L.rsg_scb_min_jacobian.argtypes = [vp, _dp]
         L.rsg_scb_last_ms.argtypes = [vp]
         L.rsg_scb_last_ms.restype = d
         L.rsg_scb_use_cluster.argtypes = [vp, i]
@@ -474,6 +478,16 @@ class ScbGpu:
         f = C.c_int()
         _sck(fn(self.h, C.byref(f)))
         return f.value
+
+    # glue of the outer iteration (src/ModScbRun.f90:232-262): device snapshots, blend, Jacobian sign test
+    def snapshot(self, name, slot): _sck(self.L.rsg_scb_snapshot(self.h, name.encode(), slot))
+    def restore(self, name, slot): _sck(self.L.rsg_scb_restore(self.h, name.encode(), slot))
+    def blend(self, name, slot_new, slot_sav, w): _sck(self.L.rsg_scb_blend(self.h, name.encode(), slot_new, slot_sav, float(w)))
+
+    def min_jacobian(self):
+        v = C.c_double()
+        _sck(self.L.rsg_scb_min_jacobian(self.h, C.byref(v)))
+        return v.value
 
     def mapAlpha(self): return self._map(self.L.rsg_scb_map_alpha)     # src/ModScbEuler.f90:97
     def mapPsi(self): return self._map(self.L.rsg_scb_map_psi)         # :403

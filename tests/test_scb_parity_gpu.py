@@ -149,6 +149,42 @@ def test_map_full_size_and_degenerate_lines(oracle_built):
     _same(gpu, o, ("x", "y", "z"))
 
 
+def test_outer_iteration_alpha_half_stays_on_device(oracle_built):
+    """The alpha half of one SCB outer iteration (src/ModScbRun.f90:214-262) with every 3-D array resident:
+    save alfa, solve, save the solution and the points, blend, mapAlpha, mapTheta, computeBandJacob,
+    MINVAL(jacobian) sign test, revert -- against the oracle routines glued with numpy on the host."""
+    inp, o, gpu = _pair(oracle_built, **SMALL)
+    nthe, npsi, nzeta = inp.nthe, inp.npsi, inp.nzeta
+    alfaSav1 = o.alfa.copy()
+    gpu.snapshot("alfa", 1)
+    o.bandjacob(); gpu.computeBandJacob()
+    o.metrica(); o.newk(); gpu.metrica(); gpu.newk()
+    o.iterate_alpha(); gpu.iterateAlpha(1e-6, ordering=0)
+    alphaPrev = o.alfa.copy()
+    prev = {n: getattr(o, n).copy() for n in ("x", "y", "z")}
+    gpu.snapshot("alfa", 0)
+    for n in ("x", "y", "z"):
+        gpu.snapshot(n, 0)
+    for blend in (0.5, 0.25):                                   # a second, damped attempt re-blends from the same snapshots
+        o.alfa[...] = alphaPrev * blend + alfaSav1 * (1.0 - blend)
+        gpu.blend("alfa", 0, 1, blend)
+        assert np.array_equal(gpu.get_field("alfa"), o.alfa)
+        assert o.map_alpha() == 0 and gpu.mapAlpha() == 0
+        assert o.map_theta() == 0 and gpu.mapTheta() == 0
+        o.bandjacob(); gpu.computeBandJacob()
+        ref = float(o.jacobian[1:nthe - 1, 1:npsi - 1, 1:nzeta].min())
+        assert gpu.min_jacobian() == ref
+        _same(gpu, o, ("x", "y", "z", "jacobian"))
+        for n in ("x", "y", "z"):                               # revert to the previous point configuration (:250-252)
+            getattr(o, n)[...] = prev[n]
+            gpu.restore(n, 0)
+        _same(gpu, o, ("x", "y", "z"))
+    jac = gpu.get_field("jacobian")
+    jac[5, 4, 3] = np.nan
+    gpu.set_field("jacobian", jac)
+    assert gpu.min_jacobian() == -1e300                          # a NaN must fail the sign test
+
+
 def test_sor_color4_converged_fields(oracle_built):
     """4-colour ordering vs the reference order, both converged tightly: the potentials
     agree within 1e-8 relative (north_star tolerance for the SCB solve)."""
