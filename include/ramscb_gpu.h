@@ -286,6 +286,13 @@ int rsg_scb_set_map_targets(rsg_scb* h, const double* alphaVal, const double* ps
 int rsg_scb_map_alpha(rsg_scb* h, int* sorfail);
 int rsg_scb_map_psi(rsg_scb* h, int* sorfail);
 int rsg_scb_map_theta(rsg_scb* h, int* sorfail);
+/* `pressure`, anisotropic branch from the normalised equatorial pressures on (src/ModScbRun.f90:1087-1175):
+ * pperEq, pparEq are (npsi, nzeta+1) host arrays (already divided by pnormal, periodic columns set); the
+ * library maps them along the field lines with the iLossCone = 1 | 2 formulas using bf / bsq of the last
+ * computeBandJacob, builds sigma and tau, optionally reduces the anisotropy of mirror-unstable lines
+ * (iReduceAnisotropy = 1, :1127-1160) and takes the Steffen derivatives dPPerd{Theta,Rho,Zeta,Psi,Alpha},
+ * dBsqd{...} on the device (what rsg_scb_set_pressure would otherwise upload: 15 3-D arrays). */
+int rsg_scb_pressure_aniso(rsg_scb* h, const double* pperEq, const double* pparEq, int iLossCone, int iReduceAnisotropy);
 /* Glue of the outer iteration (src/ModScbRun.f90:232-262, 418-440), so that alfa, psi, x, y, z need
  * not visit the host between the solves: device snapshots of a named field (alfaSav1, alphaPrev,
  * xPrev... of the reference; slot 0..3), the blend  field = snap(slot_new)*blend +

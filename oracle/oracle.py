@@ -182,7 +182,7 @@ def scb_lib():
         for f in ("bandjacob", "convergence", "map_alpha", "map_psi", "map_theta"):
             getattr(lib, "scbo_" + f).argtypes = [C.c_void_p]
             getattr(lib, "scbo_" + f).restype = C.c_int
-        for f in ("metrica", "metric", "newk", "newj"):
+        for f in ("metrica", "metric", "newk", "newj", "pressure_aniso"):
             getattr(lib, "scbo_" + f).argtypes = [C.c_void_p]
             getattr(lib, "scbo_" + f).restype = None
         for f in ("iterate_alpha", "iterate_psi"):
@@ -256,6 +256,16 @@ class ScbOracle:
 
     def convergence(self):
         return self.lib.scbo_convergence(self.h)
+
+    def pressure_aniso(self, pperEq, pparEq, iLossCone=1, iReduceAnisotropy=0):
+        """Tail of `pressure` (src/ModScbRun.f90:1087-1175) from normalised equatorial pressures (npsi, nzeta+1)."""
+        for n, a in (("pperEq", pperEq), ("pparEq", pparEq)):
+            self._set(n, np.asfortranarray(a, dtype=np.float64).copy(order="F"))
+        if "tau" not in self.arr:
+            self._set("tau", _f((self.inp.nthe, self.inp.npsi, self.inp.nzeta + 1)))
+        self.set_int("iLossCone", iLossCone)
+        self.set_int("iReduceAnisotropy", iReduceAnisotropy)
+        self.lib.scbo_pressure_aniso(self.h)
 
     def map_alpha(self): return self.lib.scbo_map_alpha(self.h)
     def map_psi(self): return self.lib.scbo_map_psi(self.h)

@@ -12,6 +12,7 @@
 //   GSL_Derivs (3-D driver)                  src/ModRamGSL.f90:794-869,
 //                                            src/RamGSL.c:228-291
 //   mapAlpha / mapPsi / mapTheta             src/ModScbEuler.f90:15-147,403-457
+//   pressure, anisotropic mapping tail       src/ModScbRun.f90:1087-1175
 //   GSL_Interpolation_1D (Steffen)           src/ModRamGSL.f90:240-311, src/RamGSL.c:111-174
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's CPU arm may load this.
@@ -713,6 +714,90 @@ int mapTheta(Scb* o) {
   return 0;
 }
 
+// ---- pressure, anisotropic branch, from the normalised equatorial pressures on
+// (src/ModScbRun.f90:1087-1175): field-line mapping of pper / ppar with the iLossCone = 1
+// (filled loss cone) or 2 (Liemohn 2004) formulas, sigma, tau, the optional reduction of the
+// anisotropy to marginal mirror stability (:1127-1160), the Steffen derivatives of pper and bsq
+// and their conversion to Euler-potential derivatives.  Inputs: pperEq, pparEq (npsi, nzeta+1),
+// bf, bsq of the last computeBandJacob.  `1./6.` at :1133 is a default-real constant expression:
+// it is evaluated in single precision and then promoted.
+struct AnisoPt { double pper, ppar, sigma, tau; };
+inline AnisoPt aniso_point(double pperEq, double pparEq, double bfEq, double bfI, double bf1, double bsqI, int iLossCone,
+                           bool clampRatio) {
+  const double pEq = (2. * pperEq + pparEq) / 3.;
+  const double aratio = pperEq / pparEq - 1.;
+  const double aL = -aratio / (aratio + 1);
+  double ratioB = bfEq / bfI;
+  if (clampRatio) ratioB = ratioB < 1.0 ? ratioB : 1.0;
+  AnisoPt r;
+  if (iLossCone == 2) {
+    const double q = bf1 / bfI;
+    const double rBI = q > 1. + 1.E-9 ? q : 1. + 1.E-9;
+    const double pparN = pparEq * (1. - (ratioB + aL * ratioB) / (rBI + aL * ratioB));
+    const double pperN = pperEq * (1. - (ratioB + aL * ratioB) / (rBI + aL * ratioB));
+    const double aN = pparN / pperN - 1.;
+    r.ppar = pparN * (aN + 1.) / (1. + aN * ratioB) * std::sqrt((rBI - 1.) / (rBI - ratioB)) * (1. - (1. + aN * ratioB) / (rBI + aN * ratioB));
+    r.pper = r.ppar / (1. + aN * ratioB);
+  } else {
+    const double gParam = 1. / sq(1. + aratio * (1. - ratioB));
+    r.ppar = pEq * 1. / (1. + 2. * aratio / 3.) * std::sqrt(gParam);
+    r.pper = pEq * (aratio + 1.) / (1. + 2. * aratio / 3.) * gParam;
+  }
+  r.sigma = 1. + (r.pper - r.ppar) / bsqI;
+  r.tau = 1. - 2. * (r.pper - r.ppar) / bsqI * r.pper / r.ppar;
+  return r;
+}
+void pressure_aniso(Scb* o) {
+  DIMS
+  const int iLossCone = o->I("iLossCone"), iReduce = o->I("iReduceAnisotropy");
+  const int eq = (nthe + 1) / 2;                     // nThetaEquator, src/ModScbInit.f90:234
+  const double *pperEq = o->D("pperEq"), *pparEq = o->D("pparEq"), *bf = o->D("bf"), *bsq = o->D("bsq");
+  const double *f = o->D("f"), *fzet = o->D("fzet");
+  double *pper = o->D("pper"), *ppar = o->D("ppar"), *sigma = o->D("sigma"), *tau = o->D("tau");
+#define E2(a, j, k) (a)[(size_t)((j)-1) + (size_t)npsi * (size_t)((k)-1)]
+  for (int k = 1; k <= nzeta; ++k)
+    for (int j = 1; j <= npsi; ++j) {
+      for (int i = 1; i <= nthe; ++i) {
+        const AnisoPt r = aniso_point(E2(pperEq, j, k), E2(pparEq, j, k), X3(bf, eq, j, k), X3(bf, i, j, k), X3(bf, 1, j, k),
+                                      X3(bsq, i, j, k), iLossCone, true);
+        X3(pper, i, j, k) = r.pper; X3(ppar, i, j, k) = r.ppar; X3(sigma, i, j, k) = r.sigma; X3(tau, i, j, k) = r.tau;
+      }
+      if (iReduce == 1 && X3(tau, eq, j, k) < 0.) {   // Mirror_unstable, :1130-1158
+        const double pEq = (2. * E2(pperEq, j, k) + E2(pparEq, j, k)) / 3.;
+        const double bEqSq = X3(bsq, eq, j, k);
+        const double sixth = (double)(1.f / 6.f);
+        const double pe = sixth * (3. * pEq - bEqSq + std::sqrt(sq(bEqSq) + 12. * bEqSq * pEq + 9. * sq(pEq)));
+        const double pa = 3. * pEq - 2. * pe;
+        for (int i = 1; i <= nthe; ++i) {
+          AnisoPt r = aniso_point(pe, pa, X3(bf, eq, j, k), X3(bf, i, j, k), X3(bf, 1, j, k), X3(bsq, i, j, k), iLossCone, false);
+          if (iLossCone == 1) {                       // :1149-1151 keeps pEq = press(j,k) of the first pass
+            const double aratio = pe / pa - 1.;
+            const double ratioB = X3(bf, eq, j, k) / X3(bf, i, j, k);
+            const double gParam = 1. / sq(1. + aratio * (1. - ratioB));
+            r.ppar = pEq * 1. / (1. + 2. * aratio / 3.) * std::sqrt(gParam);
+            r.pper = pEq * (aratio + 1.) / (1. + 2. * aratio / 3.) * gParam;
+            r.sigma = 1.0 + (r.pper - r.ppar) / X3(bsq, i, j, k);
+            r.tau = 1. - 2. * (r.pper - r.ppar) / X3(bsq, i, j, k) * r.pper / r.ppar;
+          }
+          X3(pper, i, j, k) = r.pper; X3(ppar, i, j, k) = r.ppar; X3(sigma, i, j, k) = r.sigma; X3(tau, i, j, k) = r.tau;
+        }
+      }
+    }
+#undef E2
+  derivs3d(o, pper, o->D("dPPerdTheta"), o->D("dPPerdRho"), o->D("dPPerdZeta"));
+  derivs3d(o, bsq, o->D("dBsqdTheta"), o->D("dBsqdRho"), o->D("dBsqdZeta"));
+  double *dPR = o->D("dPPerdRho"), *dBR = o->D("dBsqdRho"), *dPZ = o->D("dPPerdZeta"), *dBZ = o->D("dBsqdZeta");
+  double *dPP = o->D("dPPerdPsi"), *dBP = o->D("dBsqdPsi"), *dPA = o->D("dPPerdAlpha"), *dBA = o->D("dBsqdAlpha");
+  for (int k = 1; k <= nzeta; ++k)
+    for (int j = 1; j <= npsi; ++j)
+      for (int i = 1; i <= nthe; ++i) {
+        X3(dPP, i, j, k) = 1. / f[j - 1] * X3(dPR, i, j, k);
+        X3(dBP, i, j, k) = 1. / f[j - 1] * X3(dBR, i, j, k);
+        X3(dPA, i, j, k) = 1. / fzet[k - 1] * X3(dPZ, i, j, k);
+        X3(dBA, i, j, k) = 1. / fzet[k - 1] * X3(dBZ, i, j, k);
+      }
+}
+
 // ---- Compute_convergence, src/ModScbCompute.f90:499-754 (isotropy 0 and 1) ----------------
 // produces jGradRho/jGradZeta/jGradTheta, Jx..Jz, GradPx..GradPz, jCrossB, GradP and
 // the three norms
@@ -830,6 +915,8 @@ void* scbo_create(int nthe, int npsi, int nzeta) {
   o->iv["theChange"] = 4;       // src/ModScbParams.f90
   o->iv["psiChange"] = 0;
   o->iv["isotropy"] = 0;
+  o->iv["iLossCone"] = 1;           // src/ModScbParams.f90:76
+  o->iv["iReduceAnisotropy"] = 0;   // :52
   o->s["InConAlpha"] = 1e-6;    // src/ModScbParams.f90:37-38
   o->s["InConPsi"] = 1e-6;
   const double xzero3 = 6.6 * 6.6 * 6.6;   // src/ModScbInit.f90:246-273
@@ -853,6 +940,7 @@ int scbo_iterate_alpha(void* h, int* ni) { return iterateAlpha((Scb*)h, ni); }
 int scbo_iterate_psi(void* h, int* ni) { return iteratePsi((Scb*)h, ni); }
 int scbo_convergence(void* h) { return compute_convergence((Scb*)h); }
 void scbo_derivs3d(void* h, const double* f, double* dT, double* dR, double* dZ) { derivs3d((Scb*)h, f, dT, dR, dZ); }
+void scbo_pressure_aniso(void* h) { pressure_aniso((Scb*)h); }
 int scbo_map_alpha(void* h) { return mapAlpha((Scb*)h); }
 int scbo_map_psi(void* h) { return mapPsi((Scb*)h); }
 int scbo_map_theta(void* h) { return mapTheta((Scb*)h); }

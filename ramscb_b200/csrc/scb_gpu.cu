@@ -62,6 +62,7 @@ struct rsg_scb {
   double last_ms = 0.0;
   double *d_alphaVal = nullptr, *d_psiVal = nullptr, *d_chiVal = nullptr, *d_mapw = nullptr;   // map*: targets, workspace
   bool map_set = false;
+  double *d_peq = nullptr, *d_tau = nullptr;   // pressure_aniso: equatorial inputs (2 x npsi x (nzeta+1)), tau
   std::map<std::string, double*> snaps;   // "name#slot" -> device copy (rsg_scb_snapshot)
   bool use_cluster = true;   // 4-colour SOR on thread-block clusters with the problem resident on chip
   int last_cluster = 0;      // cluster size of the last SOR launch (0: one CTA per sub-problem)
@@ -625,6 +626,46 @@ static int scb_map(rsg_scb* h, int mode, int* sorfail) {
   if (sorfail) *sorfail = f != 0;
   return RSG_OK;
 }
+// Anisotropic branch of `pressure` from the normalised equatorial pressures pperEq, pparEq
+// (npsi, nzeta+1) on (src/ModScbRun.f90:1087-1175): everything that is 3-D is produced on the device
+// from bf / bsq of the last computeBandJacob -- pper, ppar, sigma, tau, the Steffen derivatives of
+// pper and bsq and their Euler-potential forms.  The host keeps the part before it (RAM pressures
+// interpolated to the SCB equatorial points, smoothing) and uploads two 2-D arrays instead of fifteen
+// 3-D ones.
+int rsg_scb_pressure_aniso(rsg_scb* h, const double* pperEq, const double* pparEq, int iLossCone, int iReduceAnisotropy) {
+  if (!h || !pperEq || !pparEq) return sfail(RSG_ERR_ARG, "null argument");
+  if (iLossCone != 1 && iLossCone != 2) return sfail(RSG_ERR_ARG, "iLossCone must be 1 or 2");
+  if (!h->grid_set || !h->geom_set) return sfail(RSG_ERR_STATE, "pressure before set_grid / set_geometry");
+  SCK(cudaSetDevice(h->device));
+  const int nthe = h->nthe, npsi = h->npsi, nzeta = h->nzeta;
+  const size_t n2 = (size_t)npsi * (nzeta + 1);
+  if (!h->d_peq) {
+    SRET(h->dalloc(&h->d_peq, 2 * n2, nullptr));
+    SRET(h->dalloc(&h->d_tau, (size_t)nthe * npsi * (nzeta + 1), "tau"));
+  }
+  SCK(cudaMemcpyAsync(h->d_peq, pperEq, n2 * sizeof(double), cudaMemcpyHostToDevice, h->st));
+  SCK(cudaMemcpyAsync(h->d_peq + n2, pparEq, n2 * sizeof(double), cudaMemcpyHostToDevice, h->st));
+  SCK(cudaEventRecord(h->e0, h->st));
+  const dim3 g(nblk(nthe, 128), npsi, nzeta);
+  k_scb_press_aniso<<<g, 128, 0, h->st>>>(h->dev, h->d_peq, h->d_peq + n2, h->d_tau, iLossCone, iReduceAnisotropy, (nthe + 1) / 2 - 1);
+  SCKL();
+  k_scb_derivs<<<g, 128, 0, h->st>>>(h->dev, h->dev.pper, h->dev.dPT, h->dev.dPR, h->dev.dPZ);
+  SCKL();
+  k_scb_derivs<<<g, 128, 0, h->st>>>(h->dev, h->dev.bsq, h->dev.dBT, h->dev.dBR, h->dev.dBZ);
+  SCKL();
+  k_scb_press_scale<<<g, 128, 0, h->st>>>(h->dev);
+  SCKL();
+  h->launches += 4;
+  SCK(cudaEventRecord(h->e1, h->st));
+  SCK(cudaStreamSynchronize(h->st));
+  float ms = 0.f;
+  SCK(cudaEventElapsedTime(&ms, h->e0, h->e1));
+  h->last_ms = ms;
+  h->isotropy = 0;
+  h->press_set = true;
+  return RSG_OK;
+}
+
 // ---- glue of the outer iteration (src/ModScbRun.f90:232-262, 418-440) ------------------------
 // snapshot slots hold device copies of a named (nthe,npsi,nzeta+1) field: alfaSav1 / alphaPrev /
 // xPrev ... of the reference.  slot 0..3.

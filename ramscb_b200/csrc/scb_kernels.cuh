@@ -470,6 +470,88 @@ __global__ void __launch_bounds__(256) k_scb_minjac(ScbDev d, double* __restrict
   }
 }
 
+// =============================================================================
+// k_scb_press_aniso: the anisotropic branch of `pressure` from the normalised equatorial pressures
+// on (src/ModScbRun.f90:1087-1160): pper, ppar mapped along the field line with the iLossCone = 1
+// (filled loss cone, :1107-1110) or 2 (Liemohn 2004, :1098-1106) formulas, sigma, tau, and the
+// optional reduction to marginal mirror stability (:1127-1160) of lines whose equatorial tau < 0
+// (every thread of such a line re-derives the equatorial test itself: no second pass).
+// bf, bsq come from computeBandJacob and never leave the device.  Thread per (i, j, k <= nzeta).
+// The Steffen derivatives and the 1/f, 1/fzet scalings (:1162-1175) follow in k_scb_derivs /
+// k_scb_press_scale.  Reference operation order; `1./6.` (:1133) is a single-precision constant.
+// =============================================================================
+struct AnisoPt { double pper, ppar, sigma, tau; };
+__device__ __forceinline__ AnisoPt aniso_point(double pperEq, double pparEq, double bfEq, double bfI, double bf1, double bsqI,
+                                               int iLossCone, bool clampRatio) {
+  const double pEq = (2. * pperEq + pparEq) / 3.;
+  const double aratio = pperEq / pparEq - 1.;
+  const double aL = -aratio / (aratio + 1);
+  double ratioB = bfEq / bfI;
+  if (clampRatio) ratioB = ratioB < 1.0 ? ratioB : 1.0;
+  AnisoPt r;
+  if (iLossCone == 2) {
+    const double q = bf1 / bfI;
+    const double rBI = q > 1. + 1.E-9 ? q : 1. + 1.E-9;
+    const double pparN = pparEq * (1. - (ratioB + aL * ratioB) / (rBI + aL * ratioB));
+    const double pperN = pperEq * (1. - (ratioB + aL * ratioB) / (rBI + aL * ratioB));
+    const double aN = pparN / pperN - 1.;
+    r.ppar = pparN * (aN + 1.) / (1. + aN * ratioB) * sqrt((rBI - 1.) / (rBI - ratioB)) * (1. - (1. + aN * ratioB) / (rBI + aN * ratioB));
+    r.pper = r.ppar / (1. + aN * ratioB);
+  } else {
+    const double gParam = 1. / sq(1. + aratio * (1. - ratioB));
+    r.ppar = pEq * 1. / (1. + 2. * aratio / 3.) * sqrt(gParam);
+    r.pper = pEq * (aratio + 1.) / (1. + 2. * aratio / 3.) * gParam;
+  }
+  r.sigma = 1. + (r.pper - r.ppar) / bsqI;
+  r.tau = 1. - 2. * (r.pper - r.ppar) / bsqI * r.pper / r.ppar;
+  return r;
+}
+__global__ void __launch_bounds__(128) k_scb_press_aniso(ScbDev d, const double* __restrict__ pperEq, const double* __restrict__ pparEq,
+                                                         double* __restrict__ tau, int iLossCone, int iReduce, int eq) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y, k = blockIdx.z;
+  if (i >= d.nthe) return;
+  const size_t e2 = (size_t)j + (size_t)d.npsi * k;
+  const double pe0 = pperEq[e2], pa0 = pparEq[e2];
+  const double bfEq = S3(d.bf, eq, j, k), bfI = S3(d.bf, i, j, k), bf1 = S3(d.bf, 0, j, k), bsqI = S3(d.bsq, i, j, k);
+  AnisoPt r = aniso_point(pe0, pa0, bfEq, bfI, bf1, bsqI, iLossCone, true);
+  if (iReduce == 1) {
+    const double bEqSq = S3(d.bsq, eq, j, k);
+    const AnisoPt q = aniso_point(pe0, pa0, bfEq, bfEq, bf1, bEqSq, iLossCone, true);
+    if (q.tau < 0.) {
+      const double pEq = (2. * pe0 + pa0) / 3.;
+      const double sixth = (double)(1.f / 6.f);
+      const double pe = sixth * (3. * pEq - bEqSq + sqrt(sq(bEqSq) + 12. * bEqSq * pEq + 9. * sq(pEq)));
+      const double pa = 3. * pEq - 2. * pe;
+      r = aniso_point(pe, pa, bfEq, bfI, bf1, bsqI, iLossCone, false);
+      if (iLossCone == 1) {                              // :1149-1151 keep pEq = press(j,k) of the first pass
+        const double aratio = pe / pa - 1.;
+        const double ratioB = bfEq / bfI;
+        const double gParam = 1. / sq(1. + aratio * (1. - ratioB));
+        r.ppar = pEq * 1. / (1. + 2. * aratio / 3.) * sqrt(gParam);
+        r.pper = pEq * (aratio + 1.) / (1. + 2. * aratio / 3.) * gParam;
+        r.sigma = 1.0 + (r.pper - r.ppar) / bsqI;
+        r.tau = 1. - 2. * (r.pper - r.ppar) / bsqI * r.pper / r.ppar;
+      }
+    }
+  }
+  S3(d.pper, i, j, k) = r.pper;
+  S3(d.ppar, i, j, k) = r.ppar;
+  S3(d.sigma, i, j, k) = r.sigma;
+  S3(tau, i, j, k) = r.tau;
+}
+// dPperdPsi = 1/f(j) * dPperdRho, dPperdAlpha = 1/fzet(k) * dPperdZeta, same for bsq (:1168-1175)
+__global__ void __launch_bounds__(128) k_scb_press_scale(ScbDev d) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y, k = blockIdx.z;
+  if (i >= d.nthe) return;
+  const double rf = 1. / d.f[j], rz = 1. / d.fzet[k];
+  S3(d.dPP, i, j, k) = rf * S3(d.dPR, i, j, k);
+  S3(d.dBP, i, j, k) = rf * S3(d.dBR, i, j, k);
+  S3(d.dPA, i, j, k) = rz * S3(d.dPZ, i, j, k);
+  S3(d.dBA, i, j, k) = rz * S3(d.dBZ, i, j, k);
+}
+
 // extap, src/ModScbFunctions.f90:57-76
 __device__ __forceinline__ double extap(double x1, double x2, double x3) {
   double x4 = 3. * x3 - 3. * x2 + x1;

@@ -398,6 +398,7 @@ def _scb_lib():
         L.rsg_scb_set_map_targets.argtypes = [vp, vp, vp, vp]
         for n in ("map_alpha", "map_psi", "map_theta"):
             getattr(L, "rsg_scb_" + n).argtypes = [vp, _ip]
+        L.rsg_scb_pressure_aniso.argtypes = [vp, vp, vp, i, i]
         L.rsg_scb_snapshot.argtypes = [vp, C.c_char_p, i]
         L.rsg_scb_restore.argtypes = [vp, C.c_char_p, i]
         L.rsg_scb_blend.argtypes = [vp, C.c_char_p, i, i, d]
@@ -478,6 +479,11 @@ class ScbGpu:
         f = C.c_int()
         _sck(fn(self.h, C.byref(f)))
         return f.value
+
+    def pressure_aniso(self, pperEq, pparEq, iLossCone=1, iReduceAnisotropy=0):
+        """Tail of `pressure` (src/ModScbRun.f90:1087-1175) from the normalised equatorial pressures."""
+        a, b = (np.asfortranarray(v, dtype=np.float64) for v in (pperEq, pparEq))
+        _sck(self.L.rsg_scb_pressure_aniso(self.h, _p(a), _p(b), iLossCone, iReduceAnisotropy))
 
     # glue of the outer iteration (src/ModScbRun.f90:232-262): device snapshots, blend, Jacobian sign test
     def snapshot(self, name, slot): _sck(self.L.rsg_scb_snapshot(self.h, name.encode(), slot))

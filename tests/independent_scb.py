@@ -311,3 +311,49 @@ def map_theta(x, y, z, chiVal, nthe, npsi, nzeta):
     for a in (x, y, z):
         _wrap(a, nzeta)
     return x, y, z
+
+
+# ---------------------------------------------------------------------------------------------
+# `pressure`, anisotropic mapping from the equatorial pressures (src/ModScbRun.f90:1087-1160), whole-array
+def pressure_aniso(pperEq, pparEq, bf, bsq, nthe, npsi, nzeta, iLossCone=1, iReduce=0):
+    ieq = (nthe + 1) // 2 - 1
+    pe = pperEq[None, :, :nzeta]
+    pa = pparEq[None, :, :nzeta]
+    bfk, bsqk = bf[:, :, :nzeta], bsq[:, :, :nzeta]
+
+    def point(pe, pa, clamp, pEq_keep=None):
+        pEq = (2.0 * pe + pa) / 3.0 if pEq_keep is None else pEq_keep
+        ar = pe / pa - 1.0
+        aL = -ar / (ar + 1)
+        rB = bfk[ieq][None] / bfk
+        if clamp:
+            rB = np.where(rB < 1.0, rB, 1.0)
+        if iLossCone == 2:
+            q = bfk[0][None] / bfk
+            rBI = np.where(q > 1.0 + 1.0e-9, q, 1.0 + 1.0e-9)
+            frac = (rB + aL * rB) / (rBI + aL * rB)
+            pparN = pa * (1.0 - frac)
+            pperN = pe * (1.0 - frac)
+            aN = pparN / pperN - 1.0
+            ppar = pparN * (aN + 1.0) / (1.0 + aN * rB) * np.sqrt((rBI - 1.0) / (rBI - rB)) * (1.0 - (1.0 + aN * rB) / (rBI + aN * rB))
+            pper = ppar / (1.0 + aN * rB)
+        else:
+            t = 1.0 + ar * (1.0 - rB)
+            g = 1.0 / (t * t)
+            ppar = pEq * 1.0 / (1.0 + 2.0 * ar / 3.0) * np.sqrt(g)
+            pper = pEq * (ar + 1.0) / (1.0 + 2.0 * ar / 3.0) * g
+        sigma = 1.0 + (pper - ppar) / bsqk
+        tau = 1.0 - 2.0 * (pper - ppar) / bsqk * pper / ppar
+        return pper, ppar, sigma, tau
+
+    out = point(pe, pa, True)
+    if iReduce == 1:
+        unstable = out[3][ieq] < 0.0                      # (npsi, nzeta)
+        pEq = (2.0 * pe + pa) / 3.0
+        bE = bsqk[ieq][None]
+        sixth = float(np.float32(1.0) / np.float32(6.0))  # the reference's single-precision 1./6.
+        pe2 = sixth * (3.0 * pEq - bE + np.sqrt(bE * bE + 12.0 * bE * pEq + 9.0 * (pEq * pEq)))
+        pa2 = 3.0 * pEq - 2.0 * pe2
+        red = point(pe2, pa2, False, pEq_keep=pEq if iLossCone == 1 else None)
+        out = tuple(np.where(unstable[None], r, o) for r, o in zip(red, out))
+    return out

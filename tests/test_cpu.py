@@ -523,3 +523,37 @@ def test_map_routines_match_independent_restatement(oracle_built):
     seg = np.sqrt(np.diff(o.x[:, j, k]) ** 2 + np.diff(o.y[:, j, k]) ** 2 + np.diff(o.z[:, j, k]) ** 2)
     frac = np.concatenate([[0.0], np.cumsum(seg)]) / seg.sum()
     assert np.max(np.abs(frac - inp.chiVal / np.pi)) < 2e-2
+
+
+@pytest.mark.parametrize("iLossCone,iReduce", [(1, 0), (2, 0), (1, 1), (2, 1)])
+def test_pressure_aniso_oracle_vs_independent_numpy(oracle_built, iLossCone, iReduce):
+    """The oracle's anisotropic pressure mapping (src/ModScbRun.f90:1087-1175) against the whole-array numpy
+    restatement (bit for bit), against the generator of the synthetic inputs (which applies the iLossCone = 1
+    formulas on its own), and the chain rule of the Euler-potential derivatives."""
+    import independent_scb as ind
+    import test_scb_parity_gpu as TS
+    from ramscb_b200 import scb_synthetic as S
+    inp = S.build_scb(nthe=31, npsi=13, nzeta=25, warp=0.3)
+    n = (inp.nthe, inp.npsi, inp.nzeta)
+    o = oracle_built.ScbOracle(inp)
+    o.bandjacob()
+    pe, pa = TS._equatorial_pressures(inp, hot=bool(iReduce))
+    o.pressure_aniso(pe, pa, iLossCone, iReduce)
+    ref = ind.pressure_aniso(pe, pa, o.bf, o.bsq, *n, iLossCone=iLossCone, iReduce=iReduce)
+    nz = inp.nzeta
+    for name, r in zip(("pper", "ppar", "sigma", "tau"), ref):
+        assert np.array_equal(getattr(o, name)[:, :, :nz], r), name
+    assert np.all(o.pper[:, :, :nz] > 0) and np.all(o.ppar[:, :, :nz] > 0)
+    assert np.array_equal(o.dPPerdPsi, (1.0 / inp.f)[None, :, None] * o.dPPerdRho)
+    assert np.array_equal(o.dBsqdAlpha, (1.0 / inp.fzet[:nz])[None, None, :] * o.dBsqdZeta)
+    dT, dR, dZ = S.derivs3d(inp.thetaVal, inp.rhoVal, inp.zetaVal, o.pper[:, :, :nz])
+    assert np.array_equal(o.dPPerdTheta, dT) and np.array_equal(o.dPPerdRho, dR) and np.array_equal(o.dPPerdZeta, dZ)
+    if iLossCone == 1 and iReduce == 0:
+        # the synthetic generator's own 3-D pressure: feed its equatorial values back and recover it
+        ieq = (inp.nthe + 1) // 2 - 1
+        o2 = oracle_built.ScbOracle(inp)
+        o2.bf[...] = np.sqrt(inp.bsq0)
+        o2.bsq[...] = inp.bsq0
+        o2.pressure_aniso(inp.pper[ieq], inp.ppar[ieq], 1, 0)
+        assert np.allclose(o2.pper[:, :, :nz], inp.pper[:, :, :nz], rtol=1e-13, atol=0)
+        assert np.allclose(o2.ppar[:, :, :nz], inp.ppar[:, :, :nz], rtol=1e-13, atol=0)

@@ -91,6 +91,8 @@ def test_emulated_scb_maps_and_geometry(emu, oracle_built):
     import test_scb_parity_gpu as TS
     TS.test_map_alpha_psi_theta_bit_exact(oracle_built)
     TS.test_outer_iteration_alpha_half_stays_on_device(oracle_built)
+    TS.test_pressure_anisotropic_mapping_bit_exact(oracle_built, 1, 1)
+    TS.test_pressure_anisotropic_mapping_bit_exact(oracle_built, 2, 0)
 
 
 def test_emulated_results_do_not_depend_on_thread_order():

@@ -185,6 +185,58 @@ def test_outer_iteration_alpha_half_stays_on_device(oracle_built):
     assert gpu.min_jacobian() == -1e300                          # a NaN must fail the sign test
 
 
+def _equatorial_pressures(inp, hot=False, seed=5):
+    """Normalised equatorial pper/ppar (npsi, nzeta+1) consistent with the synthetic 3-D pressure: smooth radial
+    profile, anisotropy varying in azimuth; `hot`: strongly anisotropic high-beta patches that are mirror unstable."""
+    rng = np.random.default_rng(seed)
+    ieq = (inp.nthe + 1) // 2 - 1
+    pe = np.array(inp.pper[ieq], order="F")
+    k = np.arange(inp.nzeta + 1)
+    a = 0.5 + 0.4 * np.sin(2 * np.pi * (k - 1) / (inp.nzeta - 1))[None, :] + 0.05 * rng.standard_normal(pe.shape)
+    if hot:
+        pe = pe * (1.0 + 400.0 * (rng.random(pe.shape) < 0.2))
+        a = a + 3.0 * (rng.random(pe.shape) < 0.3)
+    pa = pe / (1.0 + a)
+    for v in (pe, pa):
+        v[:, 0] = v[:, inp.nzeta - 1]
+        v[:, inp.nzeta] = v[:, 1]
+    return np.asfortranarray(pe), np.asfortranarray(pa)
+
+
+PRESS_FIELDS = ("pper", "ppar", "sigma", "dPPerdTheta", "dPPerdRho", "dPPerdZeta", "dBsqdTheta", "dBsqdRho", "dBsqdZeta",
+                "dPPerdPsi", "dPPerdAlpha", "dBsqdPsi", "dBsqdAlpha")
+
+
+@pytest.mark.parametrize("iLossCone", [1, 2])
+@pytest.mark.parametrize("iReduce", [0, 1])
+def test_pressure_anisotropic_mapping_bit_exact(oracle_built, iLossCone, iReduce):
+    """`pressure` from the equatorial pressures on (src/ModScbRun.f90:1087-1175) on the device: bf / bsq come
+    from the device's own computeBandJacob; pper, ppar, sigma, tau and the ten derivative arrays must be
+    BIT-IDENTICAL to the oracle, and the following newk / iterateAlpha must see them (vecx identical)."""
+    inp, o, gpu = _pair(oracle_built, **SMALL)
+    o.bandjacob(); gpu.computeBandJacob()
+    pe, pa = _equatorial_pressures(inp, hot=bool(iReduce))
+    o.pressure_aniso(pe, pa, iLossCone, iReduce)
+    gpu.pressure_aniso(pe, pa, iLossCone, iReduce)
+    nz = inp.nzeta
+    for n in ("pper", "ppar", "sigma", "tau"):                      # planes 1..nzeta are (re)computed
+        a, b = gpu.get_field(n)[:, :, :nz], getattr(o, n)[:, :, :nz]
+        assert np.array_equal(a, b), f"{n}: {int(np.sum(a != b))} entries differ, max rel {np.max(np.abs(a - b) / np.abs(b)):.2e}"
+    _same(gpu, o, PRESS_FIELDS[3:])
+    if iReduce:
+        tau0 = o.tau.copy()
+        o.pressure_aniso(pe, pa, iLossCone, 0)
+        ieq = (inp.nthe + 1) // 2 - 1
+        unstable = int(np.sum(o.tau[ieq, :, :nz] < 0))
+        assert unstable > 20, "the test input has no mirror-unstable lines"
+        # reduced to (at least) marginal stability -- up to the reference's single-precision `1./6.` (:1133), ~1e-7;
+        # with the empty-loss-cone formulas the equatorial pressures shrink a little and tau ends up > 0
+        assert np.all(tau0[ieq, :, :nz][o.tau[ieq, :, :nz] < 0] > -1e-5)
+        o.pressure_aniso(pe, pa, iLossCone, iReduce)
+    o.metrica(); o.newk(); gpu.metrica(); gpu.newk()
+    _same(gpu, o, ("vecx",))
+
+
 def test_sor_color4_converged_fields(oracle_built):
     """4-colour ordering vs the reference order, both converged tightly: the potentials
     agree within 1e-8 relative (north_star tolerance for the SCB solve)."""
