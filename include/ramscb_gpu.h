@@ -302,6 +302,22 @@ int rsg_scb_snapshot(rsg_scb* h, const char* name, int slot);
 int rsg_scb_restore(rsg_scb* h, const char* name, int slot);
 int rsg_scb_blend(rsg_scb* h, const char* name, int slot_new, int slot_sav, double blend);
 int rsg_scb_min_jacobian(rsg_scb* h, double* minjac);
+/* Multi-GPU, iterateAlpha sharded along ZETA (the periodic azimuthal axis): a rank relaxes
+ * the zeta planes (0-based rows of the (theta, zeta) problem) [k0, k0+nk) within 1..nzeta-1 of EVERY psi
+ * surface, in the 4-colour order of RSG_SOR_COLOR4 cut at the row parity.  Protocol per sweep:
+ *   half(0); exchange the EVEN edge planes with the zeta neighbours; half(1); exchange the ODD edge
+ *   planes; all-reduce(MAX) the state vector (2*nsub doubles: residual maxima, failure flags); commit
+ * (a plane k is the contiguous block alfa[k*nthe*npsi ...] of rsg_scb_field_device("alfa")).  commit
+ * applies the loop control of src/ModScbEuler.f90:204-262 per surface (ni, EXIT on failure or
+ * convergence, nimax); pending returns how many surfaces still iterate (synchronises; poll it every few
+ * sweeps -- finished surfaces are skipped on the device).  Afterwards all-gather the planes and call
+ * rsg_scb_iterate_finish(alpha = 1): alfa, ni, diffmx, sumb, sumdb are bit-identical to the one-GPU
+ * RSG_SOR_COLOR4 solve.  (iteratePsi's sub-problems ARE zeta planes: rsg_scb_iterate_part.) */
+int rsg_scb_zsolve_begin(rsg_scb* h, double InConAlpha, int nimax, int theChange, int psiChange, int k0, int nk);
+int rsg_scb_zsolve_half(rsg_scb* h, int parity);
+int rsg_scb_zsolve_state_device(rsg_scb* h, void** ptr, long long* n);
+int rsg_scb_zsolve_commit(rsg_scb* h);
+int rsg_scb_zsolve_pending(rsg_scb* h, int* pending);
 /* device time (CUDA events on the launching stream) of the kernels of the last call */
 /* Multi-GPU: the independent sub-problems of a solve (psi surfaces for alpha, zeta planes for psi)
  * split among ranks.  part solves sub-problems [sub0, sub0+nsub) (0-based: q is jz = q+2 / k = q+2);

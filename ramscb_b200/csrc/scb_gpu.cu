@@ -64,6 +64,12 @@ struct rsg_scb {
   bool map_set = false;
   double *d_peq = nullptr, *d_tau = nullptr;   // pressure_aniso: equatorial inputs (2 x npsi x (nzeta+1)), tau
   std::map<std::string, double*> snaps;   // "name#slot" -> device copy (rsg_scb_snapshot)
+  // iterateAlpha sharded along zeta (rsg_scb_zsolve_*): per-surface state of the open solve
+  double* d_zstate = nullptr;
+  int *d_zdone = nullptr, *d_zpend = nullptr;
+  ZArgs z{};
+  int z_sweep = 0;
+  bool z_open = false;
   bool use_cluster = true;   // 4-colour SOR on thread-block clusters with the problem resident on chip
   int last_cluster = 0;      // cluster size of the last SOR launch (0: one CTA per sub-problem)
 
@@ -500,6 +506,90 @@ int rsg_scb_field_device(rsg_scb* h, const char* name, void** ptr, long long* n)
   if (it == h->arr.end()) return sfail(RSG_ERR_ARG, std::string("unknown field ") + name);
   *ptr = it->second.first;
   *n = (long long)it->second.second;
+  return RSG_OK;
+}
+// iterateAlpha sharded along ZETA: this rank relaxes the zeta planes (0-based rows)
+// [k0, k0+nk) of every psi surface; the caller exchanges the edge planes after every half-sweep and
+// all-reduces (MAX) the state vector after every sweep.  Bit-identical to RSG_SOR_COLOR4 on one GPU.
+int rsg_scb_zsolve_begin(rsg_scb* h, double tol, int nimax, int theChange, int psiChange, int k0, int nk) {
+  if (!h) return sfail(RSG_ERR_ARG, "null handle");
+  SCK(cudaSetDevice(h->device));
+  const int nthe = h->nthe, npsi = h->npsi, nzeta = h->nzeta;
+  const int nT = std::max(theChange, 1), nP = std::max(psiChange, 1);
+  if (nT == 1) return sfail(RSG_ERR_UNSUPPORTED, "theChange <= 1 is not supported");
+  if (nthe - 2 * nT < 3) return sfail(RSG_ERR_ARG, "theChange too large for nthe");
+  if (nk < 0 || (nk > 0 && (k0 < 1 || k0 + nk > nzeta))) return sfail(RSG_ERR_ARG, "zeta range outside the updated planes 1..nzeta-1");
+  const int nsub = npsi - nP - 1;
+  if (!h->d_zstate) {
+    const int cap = npsi + 1;
+    SRET(h->dalloc(&h->d_zstate, 2 * (size_t)cap, nullptr));
+    void* q = nullptr;
+    SCK(cudaMalloc(&q, sizeof(int) * (cap + 1)));
+    h->allocs.push_back(q);
+    h->d_zdone = (int*)q;
+    h->d_zpend = h->d_zdone + cap;
+  }
+  const size_t n3p = (size_t)nthe * npsi * (nzeta + 1);
+  SCK(cudaMemcpyAsync(h->d_prev, h->dev.alfa, n3p * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+  std::vector<int> one(std::max(npsi, nzeta) + 2, 0);
+  for (int q = 0; q < nsub; ++q) one[q] = 1;                       // ni = 1 before the first sweep (:205)
+  SCK(cudaMemcpyAsync(h->d_ni, one.data(), sizeof(int) * one.size(), cudaMemcpyHostToDevice, h->st));
+  SCK(cudaMemsetAsync(h->d_resmax, 0, sizeof(double) * (std::max(npsi, nzeta) + 1), h->st));
+  SCK(cudaMemsetAsync(h->d_zstate, 0, sizeof(double) * 2 * (size_t)(npsi + 1), h->st));
+  std::vector<int> done(npsi + 2, nimax < 1 ? 1 : 0);
+  done[npsi + 1] = nimax < 1 ? 0 : nsub;                            // pending
+  SCK(cudaMemcpyAsync(h->d_zdone, done.data(), sizeof(int) * done.size(), cudaMemcpyHostToDevice, h->st));
+  SCK(cudaStreamSynchronize(h->st));                                // `one` / `done` are stack-owned
+  ZArgs& a = h->z;
+  a.tol = tol;
+  a.nT = nT; a.k0 = k0; a.nk = nk; a.nsub = nsub; a.nimax = nimax;
+  a.state = h->d_zstate;
+  a.done = h->d_zdone;
+  a.u0 = h->d_prev;
+  const double rjac = 1.0 - 2.0 * PI_D * PI_D / ((double)nzeta * (double)nzeta + (double)nthe * (double)nthe);
+  a.om = 2.0 / (1.0 + std::sqrt(1.0 - rjac * rjac));                // omegaOpt; the first sweep runs with 1 (:207-214)
+  h->z_sweep = 0;
+  h->z_open = true;
+  SCK(cudaEventRecord(h->e0, h->st));
+  SCK(cudaEventRecord(h->e1, h->st));
+  return RSG_OK;
+}
+int rsg_scb_zsolve_half(rsg_scb* h, int parity) {
+  if (!h || !h->z_open) return sfail(RSG_ERR_ARG, "no open zeta-sharded solve");
+  if (parity != 0 && parity != 1) return sfail(RSG_ERR_ARG, "parity is 0 or 1");
+  SCK(cudaSetDevice(h->device));
+  ZArgs a = h->z;
+  if (h->z_sweep == 0) a.om = 1.0;
+  const int rs = a.k0 + (((a.k0 & 1) == parity) ? 0 : 1);
+  const int nrows = rs < a.k0 + a.nk ? (a.k0 + a.nk - 1 - rs) / 2 + 1 : 0;
+  if (nrows > 0 && a.nsub > 0) {
+    k_scb_zhalf<<<dim3(nrows, a.nsub), 64, 0, h->st>>>(h->dev, a, parity);
+    SCKL();
+    h->launches++;
+  }
+  return RSG_OK;
+}
+int rsg_scb_zsolve_state_device(rsg_scb* h, void** ptr, long long* n) {
+  if (!h || !h->z_open || !ptr || !n) return sfail(RSG_ERR_ARG, "no open zeta-sharded solve");
+  *ptr = h->d_zstate;
+  *n = 2 * (long long)h->z.nsub;
+  return RSG_OK;
+}
+int rsg_scb_zsolve_commit(rsg_scb* h) {
+  if (!h || !h->z_open) return sfail(RSG_ERR_ARG, "no open zeta-sharded solve");
+  SCK(cudaSetDevice(h->device));
+  k_scb_zcommit<<<1, 64, 0, h->st>>>(h->z, h->d_ni, h->d_resmax, h->d_fail, h->d_zpend);
+  SCKL();
+  h->launches++;
+  h->z_sweep++;
+  SCK(cudaEventRecord(h->e1, h->st));
+  return RSG_OK;
+}
+int rsg_scb_zsolve_pending(rsg_scb* h, int* pending) {
+  if (!h || !h->z_open || !pending) return sfail(RSG_ERR_ARG, "no open zeta-sharded solve");
+  SCK(cudaSetDevice(h->device));
+  SCK(cudaMemcpyAsync(pending, h->d_zpend, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  SCK(cudaStreamSynchronize(h->st));
   return RSG_OK;
 }
 int rsg_scb_set_stream(rsg_scb* h, void* stream) {

@@ -403,6 +403,107 @@ __global__ void __launch_bounds__(1024) k_scb_sor(ScbDev d, SorArgs a) {
   }
 }
 
+// =============================================================================
+// iterateAlpha sharded along zeta (the north-star scheme): a rank owns the zeta planes
+// (rows) [k0, k0+nk) of EVERY psi surface and holds rows k0-1 and k0+nk as halo.  The 4-colour sweep
+// of k_scb_sor<true,1> is cut at the row parity: colours 0,1 touch even rows and read odd rows +
+// the row itself, colours 2,3 the other way round -- so ONE halo exchange per HALF-sweep (the rows
+// of that parity at the slab edges) keeps every rank's iterates bit-identical to the single-GPU
+// 4-colour solve.  The unknown stays in global memory (L2): a launch is one half-sweep of all
+// surfaces that are still iterating, one CTA per (row, surface); the per-surface residual maxima are
+// accumulated with atomicMax on the bit pattern (non-negative doubles order like integers) into
+// state[0..nsub), failures into state[nsub..2 nsub) -- the vector the ranks all-reduce with MAX.
+// k_scb_zcommit then applies the loop control of src/ModScbEuler.f90:204-262 per surface.
+// =============================================================================
+struct ZArgs {
+  double tol, om;
+  int nT, k0, nk, nsub, nimax;
+  double* state;        // [resmax accumulators | failure flags], 2*nsub
+  int* done;            // per surface: finished (converged, failed or nimax reached)
+  const double* u0;     // alfa before the solve (restored at a point that blows up, :226-240)
+};
+
+__global__ void __launch_bounds__(64) k_scb_zhalf(ScbDev d, ZArgs a, int parity) {
+  __shared__ double s_red[2];
+  __shared__ int s_fail;
+  const int sub = blockIdx.y;
+  if (a.done[sub]) return;
+  const int rs = a.k0 + (((a.k0 & 1) == parity) ? 0 : 1);
+  const int r = rs + 2 * (int)blockIdx.x;
+  if (r >= a.k0 + a.nk) return;
+  const int nthe = d.nthe, tid = threadIdx.x, T = blockDim.x;
+  const int c0 = a.nT, c1 = nthe - a.nT - 1;
+  const size_t sk = (size_t)nthe * d.npsi;
+  const size_t rowoff = (size_t)nthe * (size_t)(sub + 1) + (size_t)r * sk;
+  double* u = d.alfa;
+  if (tid == 0) s_fail = 0;
+  double rmax = 0.0;
+  bool failed = false;
+  for (int pc = 0; pc < 2; ++pc) {
+    const int cs = c0 + (((c0 & 1) == pc) ? 0 : 1);
+    for (int c = cs + 2 * tid; c <= c1; c += 2 * T) {
+      const size_t q = rowoff + c;
+      const double* um = u + q - sk;
+      const double* uc = u + q;
+      const double* up = u + q + sk;
+      const double vd = d.vecd[q];
+      const double res = -vd * uc[0] + d.vec1[q] * um[-1] + d.vec2[q] * um[0] + d.vec3[q] * um[1] + d.vec4[q] * uc[-1] +
+                         d.vec6[q] * uc[1] + d.vec7[q] * up[-1] + d.vec8[q] * up[0] + d.vec9[q] * up[1] - d.vecx[q];
+      double un = uc[0] + a.om * (res / vd);
+      double rr = res;
+      if (isnan(un) || un >= 1e10) {
+        un = a.u0[q];
+        rr = 0.0;
+        failed = true;
+      }
+      u[q] = un;
+      if (c >= 1 && c <= nthe - 2) rmax = fmax(rmax, fabs(rr));
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+  if ((tid & 31) == 0) s_red[tid >> 5] = rmax;
+  if (failed) s_fail = 1;
+  __syncthreads();
+  if (tid == 0) {
+    double m = s_red[0];
+    if (T > 32) m = fmax(m, s_red[1]);
+    atomicMax((unsigned long long*)(a.state + sub), (unsigned long long)__double_as_longlong(m));
+    if (s_fail) a.state[a.nsub + sub] = 1.0;
+  }
+}
+
+// after the MAX all-reduce of `state`: per surface  IF fail EXIT (ni kept); IF max|resid| < tol EXIT;
+// ni = ni + 1 (loop ends at ni > nimax); the accumulators are cleared for the next sweep
+__global__ void k_scb_zcommit(ZArgs a, int* __restrict__ ni, double* __restrict__ resmax, int* __restrict__ fail,
+                              int* __restrict__ pending) {
+  __shared__ int s_pend;
+  if (threadIdx.x == 0) s_pend = 0;
+  __syncthreads();
+  for (int sub = threadIdx.x; sub < a.nsub; sub += blockDim.x) {
+    if (!a.done[sub]) {
+      const double m = a.state[sub];
+      resmax[sub] = m;
+      if (a.state[a.nsub + sub] != 0.0) {
+        a.done[sub] = 1;
+        *fail = 1;
+      } else if (m < a.tol) {
+        a.done[sub] = 1;
+      } else {
+        const int n = ni[sub] + 1;
+        ni[sub] = n;
+        if (n > a.nimax) a.done[sub] = 1;
+      }
+      if (!a.done[sub]) atomicAdd(&s_pend, 1);
+    }
+    a.state[sub] = 0.0;
+    a.state[a.nsub + sub] = 0.0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *pending = s_pend;
+}
+
 // sumb, sumdb over (2:nthe-1, 2:npsi-1, 2:nzeta) (Fortran), one CTA per zeta plane -> partials
 __global__ void __launch_bounds__(256) k_scb_sums(ScbDev d, const double* __restrict__ u, const double* __restrict__ uprev,
                                                   double* __restrict__ part) {

@@ -411,6 +411,11 @@ def _scb_lib():
                                              C.POINTER(C.c_int), vp]
         L.rsg_scb_field_device.argtypes = [vp, C.c_char_p, C.POINTER(vp), C.POINTER(C.c_longlong)]
         L.rsg_scb_set_stream.argtypes = [vp, vp]
+        L.rsg_scb_zsolve_begin.argtypes = [vp, d, i, i, i, i, i]
+        L.rsg_scb_zsolve_half.argtypes = [vp, i]
+        L.rsg_scb_zsolve_state_device.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_longlong)]
+        L.rsg_scb_zsolve_commit.argtypes = [vp]
+        L.rsg_scb_zsolve_pending.argtypes = [vp, C.POINTER(C.c_int)]
         L.rsg_scb_last_cluster.argtypes = [vp]
         L.rsg_scb_launch_count.argtypes = [vp]
         L.rsg_scb_launch_count.restype = ll
@@ -525,6 +530,23 @@ class ScbGpu:
                                            C.byref(sumdb), C.byref(diffmx), C.byref(fail), ni.ctypes.data))
         return {"nisave": nisave.value, "sumb": sumb.value, "sumdb": sumdb.value, "diffmx": diffmx.value,
                 "SORFail": fail.value, "ni": ni, "ms": self.last_ms()}
+
+    # ---- multi-GPU: iterateAlpha sharded along zeta (include/ramscb_gpu.h: rsg_scb_zsolve_*) ----
+    def zsolve_begin(self, tol, k0, nk, nimax=5001, theChange=4, psiChange=0):
+        _sck(self.L.rsg_scb_zsolve_begin(self.h, tol, nimax, theChange, psiChange, k0, nk))
+
+    def zsolve_half(self, parity): _sck(self.L.rsg_scb_zsolve_half(self.h, parity))
+    def zsolve_commit(self): _sck(self.L.rsg_scb_zsolve_commit(self.h))
+
+    def zsolve_state_device(self):
+        ptr, n = C.c_void_p(), C.c_longlong()
+        _sck(self.L.rsg_scb_zsolve_state_device(self.h, C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
+
+    def zsolve_pending(self):
+        n = C.c_int()
+        _sck(self.L.rsg_scb_zsolve_pending(self.h, C.byref(n)))
+        return n.value
 
     def field_device(self, name):
         ptr, n = C.c_void_p(), C.c_longlong()

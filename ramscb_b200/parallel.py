@@ -347,3 +347,100 @@ class ScbSharded:
             res["nisave"] = int(res["ni"].max())
             res["diffmx"], res["SORFail"] = float(sc[0].item()), int(sc[1].item())
         return res
+
+
+def _dev_tensor(ptr, n, on_cuda=True):
+    """torch view of library-owned memory: device memory on the GPU; with the host-CPU emulator of the
+    test-suite (tests/emu) the "device" pointer is host memory and the view is a CPU tensor."""
+    import torch
+    if on_cuda:
+        return torch.as_tensor(_DevBuf(ptr, n), device="cuda")
+    import ctypes
+    return torch.from_numpy(np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_double)), shape=(n,)))
+
+
+class ScbZetaSharded:
+    """iterateAlpha sharded along the periodic azimuthal axis zeta (north-star scheme).
+
+    Rank p relaxes a contiguous range of the zeta planes 1..nzeta-1 (0-based) of EVERY psi surface
+    (src/ModScbEuler.f90:204-262 couples a surface's planes k-1, k, k+1).  Per sweep: half-sweep of the
+    even planes, the even edge planes go to the zeta neighbours (one plane = nthe*npsi contiguous
+    doubles), half-sweep of the odd planes, the odd edge planes go over, then ONE all-reduce(MAX) of
+    the per-surface residual maxima + failure flags, and the device applies the loop control.  The host
+    only learns every `poll` sweeps whether anything still iterates; surfaces that have finished are
+    skipped on the device, so ni / alfa are bit-identical to the one-GPU RSG_SOR_COLOR4 solve whatever
+    `poll` is.  The periodic images (k = 0, nzeta) are fixed during a solve, as in the reference (they
+    are refreshed by the wrap in rsg_scb_iterate_finish), so there is no wrap-around message.
+    iteratePsi's sub-problems are the zeta planes themselves: ScbSharded covers it with the same
+    partition and no in-solve communication."""
+
+    def __init__(self, gpu, dist, rank, world, on_cuda=True, poll=8):
+        self.gpu, self.dist, self.rank, self.world, self.on_cuda, self.poll = gpu, dist, rank, world, on_cuda, poll
+        self.k0, self.nk = _split(gpu.nzeta - 1, world, rank)
+        self.k0 += 1                                        # planes 1..nzeta-1 are relaxed
+        ptr, n = gpu.field_device("alfa")
+        self.alfa = _dev_tensor(ptr, n, on_cuda).view(gpu.nzeta + 1, gpu.npsi * gpu.nthe)
+        self.messages = 0
+
+    def _edges(self, parity):
+        """P2P ops for the edge planes of this parity: send mine, receive the neighbours' into my halo"""
+        import torch.distributed as td
+        ops = []
+        lo, hi = self.k0, self.k0 + self.nk - 1
+        if self.nk == 0:
+            return ops
+        dn = self._neighbour(-1)
+        up = self._neighbour(+1)
+        if dn is not None:
+            if lo % 2 == parity:
+                ops.append(td.P2POp(td.isend, self.alfa[lo], dn))
+            if (lo - 1) % 2 == parity:
+                ops.append(td.P2POp(td.irecv, self.alfa[lo - 1], dn))
+        if up is not None:
+            if hi % 2 == parity:
+                ops.append(td.P2POp(td.isend, self.alfa[hi], up))
+            if (hi + 1) % 2 == parity:
+                ops.append(td.P2POp(td.irecv, self.alfa[hi + 1], up))
+        return ops
+
+    def _neighbour(self, step):
+        """next rank in that direction that owns planes (ranks beyond nzeta-1 planes own none)"""
+        r = self.rank + step
+        while 0 <= r < self.world:
+            if _split(self.gpu.nzeta - 1, self.world, r)[1] > 0:
+                return r
+            r += step
+        return None
+
+    def iterate(self, tol, nimax=5001, theChange=4, psiChange=0):
+        import torch.distributed as td
+        g = self.gpu
+        g.zsolve_begin(tol, self.k0, self.nk, nimax=nimax, theChange=theChange, psiChange=psiChange)
+        ptr, n = g.zsolve_state_device()
+        state = _dev_tensor(ptr, n, self.on_cuda)
+        sweeps = 0
+        while sweeps < nimax:
+            for _ in range(min(self.poll, nimax - sweeps)):
+                for parity in (0, 1):
+                    g.zsolve_half(parity)
+                    if self.world > 1:
+                        ops = self._edges(parity)
+                        if ops:
+                            self.messages += len(ops)
+                            for w in td.batch_isend_irecv(ops):
+                                w.wait()
+                if self.world > 1:
+                    self.dist.all_reduce(state, op=self.dist.ReduceOp.MAX)
+                g.zsolve_commit()
+                sweeps += 1
+            if g.zsolve_pending() == 0:
+                break
+        # every rank gets the relaxed planes of the others, then the shared post-processing
+        if self.world > 1:
+            for r in range(self.world):
+                r0, rn = _split(g.nzeta - 1, self.world, r)
+                if rn:
+                    self.dist.broadcast(self.alfa[1 + r0:1 + r0 + rn], src=r)
+        res = g.iterate_finish(True, theChange=theChange, psiChange=psiChange)
+        res["sweeps_launched"] = sweeps
+        return res

@@ -1,5 +1,6 @@
-"""torchrun entry: SCB solves with the sub-problems sharded over N GPUs vs the single-GPU solve
-(bit-identical potentials, sweep counts, residual maxima, sums).
+"""torchrun entry: SCB solves with the sub-problems sharded over N GPUs, and iterateAlpha sharded along
+zeta (halo exchange per half-sweep), vs the single-GPU solve (bit-identical potentials, sweep counts,
+residual maxima, sums).
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/multi_gpu_scb_check.py
 """
 import os
@@ -47,6 +48,21 @@ def main():
         print(f"rank {rank} {name}: field identical={same} counts/sums identical={meta} "
               f"wall {times[name]:.2f} ms (1 GPU kernel {r1['ms']:.2f} ms)", flush=True)
         ok = ok and same and meta
+    # iterateAlpha sharded along zeta (halo planes per half-sweep + MAX all-reduce per sweep), same bar
+    gpu.set_field("alfa", inp.alfa)
+    gpu.metrica(); gpu.newk()
+    zs = parallel.ScbZetaSharded(gpu, dist, rank, world, on_cuda=True, poll=16)
+    torch.cuda.synchronize(); dist.barrier()
+    t0 = time.perf_counter()
+    r = zs.iterate(1e-6)
+    torch.cuda.synchronize()
+    tz = (time.perf_counter() - t0) * 1e3
+    same = np.array_equal(gpu.get_field("alfa"), ref.get_field("alfa"))
+    meta = (np.array_equal(r["ni"], ra["ni"]) and r["diffmx"] == ra["diffmx"] and r["sumb"] == ra["sumb"]
+            and r["sumdb"] == ra["sumdb"] and r["SORFail"] == 0)
+    print(f"rank {rank} alpha, zeta-sharded: field identical={same} counts/sums identical={meta} wall {tz:.2f} ms "
+          f"({r['sweeps_launched']} sweeps launched, {zs.messages} halo messages)", flush=True)
+    ok = ok and same and meta
     t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0 and int(t.item()) == 1:

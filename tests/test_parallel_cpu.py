@@ -3,6 +3,7 @@ re-sharding exchanged over a world_size-2 gloo process group (the same code path
 nccl backend drives on GPUs: ramscb_b200.parallel.exchange)."""
 import os
 import socket
+import sys
 
 import numpy as np
 import pytest
@@ -108,3 +109,59 @@ def test_slab_exchange_gloo_world2():
     for pr in procs:
         pr.join(timeout=60)
     assert sorted(res) == [(0, True, True), (1, True, True)]
+
+
+def _zeta_worker(rank, world, port, q):
+    """One rank of the zeta-sharded iterateAlpha: the real kernels (host-CPU emulator build, test
+    infrastructure) + the real ScbZetaSharded protocol over gloo."""
+    import numpy as np
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import conftest
+    conftest.use_emulator()
+    from ramscb_b200 import host, scb_synthetic as S
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    inp = S.build_scb(nthe=41, npsi=13, nzeta=22, warp=0.2)      # 21 relaxed planes: 7+7+7 / 11+10, edges of both parities
+    ref = host.ScbGpu(inp)
+    ref.computeBandJacob(); ref.metrica(); ref.newk()
+    r1 = ref.iterateAlpha(1e-6, ordering=host.SOR_COLOR4)
+    g = host.ScbGpu(inp)
+    g.computeBandJacob(); g.metrica(); g.newk()
+    z = parallel.ScbZetaSharded(g, dist, rank, world, on_cuda=False, poll=7)
+    r = z.iterate(1e-6)
+    same = bool(np.array_equal(g.get_field("alfa"), ref.get_field("alfa")))
+    meta = bool(np.array_equal(r["ni"], r1["ni"]) and r["diffmx"] == r1["diffmx"] and r["sumb"] == r1["sumb"]
+                and r["sumdb"] == r1["sumdb"] and r["SORFail"] == r1["SORFail"] == 0 and r["nisave"] == r1["nisave"])
+    # a sweep limit below convergence: the loop control (ni = nimax + 1 on exit) is the reference's
+    ref.set_field("alfa", inp.alfa); g.set_field("alfa", inp.alfa)
+    r2 = ref.iterateAlpha(1e-6, nimax=9, ordering=host.SOR_COLOR4)
+    r3 = z.iterate(1e-6, nimax=9)
+    capped = bool(np.array_equal(g.get_field("alfa"), ref.get_field("alfa")) and np.array_equal(r3["ni"], r2["ni"])
+                  and r3["diffmx"] == r2["diffmx"] and int(r2["ni"].max()) == 10)
+    q.put((rank, same, meta, capped, z.messages > 0 or world == 1))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_scb_zeta_sharded_alpha_gloo(world):
+    """iterateAlpha sharded along zeta -- halo planes per half-sweep + residual all-reduce over
+    gloo, kernels run by the emulator: alfa, ni, diffmx, sumb, sumdb bit-identical to the one-rank 4-colour solve."""
+    import torch.multiprocessing as mp
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+    import build_emu
+    build_emu.build()                                    # once, before the ranks start
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_zeta_worker, args=(r, world, port, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for pr in procs:
+        pr.join(timeout=60)
+    assert sorted(res) == [(r, True, True, True, True) for r in range(world)]

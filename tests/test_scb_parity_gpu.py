@@ -352,6 +352,68 @@ def test_dipole_field_is_recovered():
     assert np.median(rel) < 2e-3, np.median(rel)
 
 
+@pytest.mark.parametrize("slabs", [1, 3])
+def test_zeta_sharded_alpha_slabs_on_one_device(slabs):
+    """SURVEY 8(e), iterateAlpha sharded along zeta (rsg_scb_zsolve_*): the ranks' kernels and the halo /
+    all-reduce protocol of parallel.ScbZetaSharded, stepped in lock-step for `slabs` handles that share
+    ONE device (plane copies and the MAX of the state vectors done with torch on the library's memory).
+    alfa, ni, diffmx, sumb, sumdb bit-identical to the one-GPU RSG_SOR_COLOR4 solve.  The same protocol
+    over a process group: tests/test_parallel_cpu.py (gloo), tests/multi_gpu_scb_check.py (NCCL)."""
+    import os
+    import torch
+    from ramscb_b200 import host, parallel
+    emu = os.environ.get("RSG_EMU") == "1" or not host.LIB_PATH.endswith("libramscb_gpu.so")
+    inp = S.build_scb(nthe=51, npsi=23, nzeta=50, warp=0.3)       # 49 relaxed planes: slabs of 17 + 16 + 16
+    ref = host.ScbGpu(inp)
+    ref.computeBandJacob(); ref.metrica(); ref.newk()
+    r1 = ref.iterateAlpha(1e-7, ordering=host.SOR_COLOR4)
+    assert r1["SORFail"] == 0 and r1["nisave"] > 20
+    import contextlib
+    tst = None if emu else torch.cuda.Stream()                        # not the legacy default stream (the library's own stream does not wait for it)
+    with (contextlib.nullcontext() if emu else torch.cuda.stream(tst)):
+        gs, al, st, rng = [], [], [], []
+        for r in range(slabs):
+            g = host.ScbGpu(inp)
+            if not emu:
+                g.set_stream(tst.cuda_stream)                             # torch's copies and the kernels: one stream
+            g.computeBandJacob(); g.metrica(); g.newk()
+            k0, nk = parallel._split(inp.nzeta - 1, slabs, r)
+            g.zsolve_begin(1e-7, k0 + 1, nk)
+            ptr, n = g.field_device("alfa")
+            al.append(parallel._dev_tensor(ptr, n, not emu).view(inp.nzeta + 1, -1))
+            ptr, n = g.zsolve_state_device()
+            st.append(parallel._dev_tensor(ptr, n, not emu))
+            gs.append(g); rng.append((k0 + 1, k0 + nk))
+        for sweep in range(5001):
+            for parity in (0, 1):
+                for g in gs:
+                    g.zsolve_half(parity)
+                for r in range(slabs - 1):                                # edge planes of this parity cross the cut
+                    hi, lo = rng[r][1], rng[r + 1][0]
+                    if hi % 2 == parity:
+                        al[r + 1][hi].copy_(al[r][hi])
+                    if lo % 2 == parity:
+                        al[r][lo].copy_(al[r + 1][lo])
+            m = st[0].clone()
+            for t in st[1:]:
+                m = torch.maximum(m, t)
+            for t, g in zip(st, gs):
+                t.copy_(m)
+                g.zsolve_commit()
+            if sweep % 8 == 7 and all(g.zsolve_pending() == 0 for g in gs):
+                break
+        for r, (a, b) in enumerate(rng):                                  # "all-gather" of the relaxed planes
+            for q in range(slabs):
+                if q != r:
+                    al[q][a:b + 1].copy_(al[r][a:b + 1])
+        for g in gs:
+            res = g.iterate_finish(True)
+            assert np.array_equal(g.get_field("alfa"), ref.get_field("alfa"))
+            assert np.array_equal(res["ni"], r1["ni"]) and res["nisave"] == r1["nisave"]
+            assert res["diffmx"] == r1["diffmx"] and res["sumb"] == r1["sumb"] and res["sumdb"] == r1["sumdb"]
+            assert res["SORFail"] == 0
+
+
 def test_multi_gpu_scb_sub_problem_sharding():
     """2 GPUs: the independent sub-problems of iterateAlpha / iteratePsi split between the ranks,
     solved planes all-gathered over NCCL -- potentials, sweep counts, residual maxima and sums
