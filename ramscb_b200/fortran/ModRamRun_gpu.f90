@@ -33,3 +33,36 @@ subroutine ram_run_gpu
      LSWAE(iS) = LSWAE(iS) + ls(4, iS); LSCOE(iS) = LSCOE(iS) + ls(5, iS); LSCSC(iS) = LSCSC(iS) + ls(6, iS)
   end do
 end subroutine ram_run_gpu
+
+!============================================================================
+! Routine-level drop-ins for the two remaining hot routines of MODULE ModRamRun:
+! replace the bodies of SUMRC(S) (src/ModRamRun.f90:231-259) and of the moment part
+! of ANISCH(S) (:343-415) by these (same names, same signatures).  The rest of
+! ANISCH -- the diffusion-coefficient rebuild, :422-605 -- stays on the host.
+!============================================================================
+SUBROUTINE SUMRC(S)
+  use ModRamGpu
+  use ModRamVariables, ONLY: SETRC, ELORC
+  use, intrinsic :: iso_c_binding
+  implicit none
+  integer, intent(in) :: S
+  real(c_double) :: setrc_c, elorc_c
+  call rsg_check(rsg_sumrc(hRam, int(S, c_int), setrc_c, elorc_c), 'SUMRC')
+  SETRC(S) = setrc_c          ! new total, ELORC = old - new (:243-257)
+  ELORC(S) = elorc_c
+END SUBROUTINE SUMRC
+
+SUBROUTINE ANISCH_moments(S)
+  ! PPerT(S,:,:), PParT(S,:,:) (S is the fastest index: contiguous temporaries) and the
+  ! side effect F2(S,I,J,K,1) = F2(S,I,J,K,2) (:366), which the device applies to its F2
+  use ModRamGpu
+  use ModRamGrids,     ONLY: NR, NT
+  use ModRamVariables, ONLY: PPerT, PParT
+  use, intrinsic :: iso_c_binding
+  implicit none
+  integer, intent(in) :: S
+  real(c_double) :: pper(NR, NT), ppar(NR, NT)
+  call rsg_check(rsg_anisch(hRam, int(S, c_int), pper, ppar), 'ANISCH')
+  PPerT(S, :, :) = pper
+  PParT(S, :, :) = ppar
+END SUBROUTINE ANISCH_moments

@@ -1,0 +1,208 @@
+!============================================================================
+! ModScbGpu -- ISO_C_BINDING interface to the SCB half of libramscb_gpu.so
+! (include/ramscb_gpu.h, rsg_scb_*).  Same binding style as ModRamGpu.f90 and as
+! the reference's own C boundary (src/ModRamGSL.f90:10-71).  Field names passed
+! to rsg_scb_set_field / rsg_scb_get_field are the reference's ModScbVariables
+! names ('alfa', 'psi', 'x', 'jacobian', 'bsq', 'GradRhoSq', 'vecd', ...),
+! NUL-terminated.  Shipped uncompiled (no Fortran compiler in the build container).
+!============================================================================
+module ModScbGpu
+
+  use, intrinsic :: iso_c_binding
+  implicit none
+
+  type(c_ptr), save :: hScb = c_null_ptr     ! rsg_scb*
+
+  integer(c_int), parameter :: RSG_SOR_LEX = 0, RSG_SOR_COLOR4 = 1
+  ! production ordering; RSG_SOR_LEX reproduces the reference's sweep order bit for bit
+  integer(c_int), save :: scbSorOrdering = RSG_SOR_COLOR4
+
+  interface
+     function rsg_scb_create(h, nthe, npsi, nzeta, device) bind(C, name='rsg_scb_create') result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), intent(out) :: h
+       integer(c_int), value :: nthe, npsi, nzeta, device
+       integer(c_int) :: ierr
+     end function
+     function rsg_scb_destroy(h) bind(C, name='rsg_scb_destroy') result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       integer(c_int) :: ierr
+     end function
+     function rsg_scb_set_grid(h, thetaVal, rhoVal, zetaVal, f, fzet) bind(C, name='rsg_scb_set_grid') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       real(c_double), intent(in) :: thetaVal(*), rhoVal(*), zetaVal(*), f(*), fzet(*)
+       integer(c_int) :: ierr
+     end function
+     function rsg_scb_set_geometry(h, x, y, z) bind(C, name='rsg_scb_set_geometry') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       real(c_double), intent(in) :: x(*), y(*), z(*)
+       integer(c_int) :: ierr
+     end function
+     function rsg_scb_set_pressure(h, isotropy, pper, ppar, sigma, dPPerdTheta, dPPerdRho, dPPerdZeta, dBsqdTheta, &
+                                   dBsqdRho, dBsqdZeta, dPPerdPsi, dPPerdAlpha, dBsqdPsi, dBsqdAlpha, dPdAlpha, dPdPsi) &
+          bind(C, name='rsg_scb_set_pressure') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       integer(c_int), value :: isotropy
+       real(c_double), intent(in) :: pper(*), ppar(*), sigma(*), dPPerdTheta(*), dPPerdRho(*), dPPerdZeta(*), &
+                                     dBsqdTheta(*), dBsqdRho(*), dBsqdZeta(*), dPPerdPsi(*), dPPerdAlpha(*), &
+                                     dBsqdPsi(*), dBsqdAlpha(*), dPdAlpha(*), dPdPsi(*)
+       integer(c_int) :: ierr
+     end function
+     function rsg_scb_pressure_aniso(h, pperEq, pparEq, iLossCone, iReduceAnisotropy) &
+          bind(C, name='rsg_scb_pressure_aniso') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       real(c_double), intent(in) :: pperEq(*), pparEq(*)
+       integer(c_int), value :: iLossCone, iReduceAnisotropy
+       integer(c_int) :: ierr
+     end function
+     function rsg_scb_set_field(h, name, src) bind(C, name='rsg_scb_set_field') result(ierr)
+       import :: c_ptr, c_int, c_double, c_char
+       type(c_ptr), value :: h
+       character(kind=c_char), intent(in) :: name(*)
+       real(c_double), intent(in) :: src(*)
+       integer(c_int) :: ierr
+     end function
+     function rsg_scb_get_field(h, name, dst) bind(C, name='rsg_scb_get_field') result(ierr)
+       import :: c_ptr, c_int, c_double, c_char
+       type(c_ptr), value :: h
+       character(kind=c_char), intent(in) :: name(*)
+       real(c_double), intent(inout) :: dst(*)
+       integer(c_int) :: ierr
+     end function
+     function rsg_scb_bandjacob(h, sorfail) bind(C, name='rsg_scb_bandjacob') result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       integer(c_int), intent(out) :: sorfail
+       integer(c_int) :: ierr
+     end function
+     function rsg_scb_metrica(h) bind(C, name='rsg_scb_metrica') result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       integer(c_int) :: ierr
+     end function
+     function rsg_scb_metric(h) bind(C, name='rsg_scb_metric') result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       integer(c_int) :: ierr
+     end function
+     function rsg_scb_newk(h) bind(C, name='rsg_scb_newk') result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       integer(c_int) :: ierr
+     end function
+     function rsg_scb_newj(h) bind(C, name='rsg_scb_newj') result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       integer(c_int) :: ierr
+     end function
+     function rsg_scb_iterate_alpha(h, InConAlpha, nimax, theChange, psiChange, ordering, nisave, sumb, sumdb, diffmx, &
+                                    sorfail, ni) bind(C, name='rsg_scb_iterate_alpha') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       real(c_double), value :: InConAlpha
+       integer(c_int), value :: nimax, theChange, psiChange, ordering
+       integer(c_int), intent(out) :: nisave, sorfail
+       real(c_double), intent(out) :: sumb, sumdb, diffmx
+       type(c_ptr), value :: ni                         ! int ni(npsi), or c_null_ptr
+       integer(c_int) :: ierr
+     end function
+     function rsg_scb_iterate_psi(h, InConPsi, nimax, theChange, psiChange, ordering, nisave, sumb, sumdb, diffmx, &
+                                  sorfail, ni) bind(C, name='rsg_scb_iterate_psi') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       real(c_double), value :: InConPsi
+       integer(c_int), value :: nimax, theChange, psiChange, ordering
+       integer(c_int), intent(out) :: nisave, sorfail
+       real(c_double), intent(out) :: sumb, sumdb, diffmx
+       type(c_ptr), value :: ni                         ! int ni(nzeta), or c_null_ptr
+       integer(c_int) :: ierr
+     end function
+     function rsg_scb_convergence(h, normDiff, normJxB, normGradP, sorfail) bind(C, name='rsg_scb_convergence') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       real(c_double), intent(out) :: normDiff, normJxB, normGradP
+       integer(c_int), intent(out) :: sorfail
+       integer(c_int) :: ierr
+     end function
+     function rsg_scb_set_map_targets(h, alphaVal, psiVal, chiVal) bind(C, name='rsg_scb_set_map_targets') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       real(c_double), intent(in) :: alphaVal(*), psiVal(*), chiVal(*)
+       integer(c_int) :: ierr
+     end function
+     function rsg_scb_map_alpha(h, sorfail) bind(C, name='rsg_scb_map_alpha') result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       integer(c_int), intent(out) :: sorfail
+       integer(c_int) :: ierr
+     end function
+     function rsg_scb_map_psi(h, sorfail) bind(C, name='rsg_scb_map_psi') result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       integer(c_int), intent(out) :: sorfail
+       integer(c_int) :: ierr
+     end function
+     function rsg_scb_map_theta(h, sorfail) bind(C, name='rsg_scb_map_theta') result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       integer(c_int), intent(out) :: sorfail
+       integer(c_int) :: ierr
+     end function
+     function rsg_scb_snapshot(h, name, slot) bind(C, name='rsg_scb_snapshot') result(ierr)
+       import :: c_ptr, c_int, c_char
+       type(c_ptr), value :: h
+       character(kind=c_char), intent(in) :: name(*)
+       integer(c_int), value :: slot
+       integer(c_int) :: ierr
+     end function
+     function rsg_scb_restore(h, name, slot) bind(C, name='rsg_scb_restore') result(ierr)
+       import :: c_ptr, c_int, c_char
+       type(c_ptr), value :: h
+       character(kind=c_char), intent(in) :: name(*)
+       integer(c_int), value :: slot
+       integer(c_int) :: ierr
+     end function
+     function rsg_scb_blend(h, name, slot_new, slot_sav, blend) bind(C, name='rsg_scb_blend') result(ierr)
+       import :: c_ptr, c_int, c_double, c_char
+       type(c_ptr), value :: h
+       character(kind=c_char), intent(in) :: name(*)
+       integer(c_int), value :: slot_new, slot_sav
+       real(c_double), value :: blend
+       integer(c_int) :: ierr
+     end function
+     function rsg_scb_min_jacobian(h, minjac) bind(C, name='rsg_scb_min_jacobian') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       real(c_double), intent(out) :: minjac
+       integer(c_int) :: ierr
+     end function
+  end interface
+
+contains
+
+  subroutine rsg_scb_check(ierr, where)
+    ! a failure of the device path itself is fatal (CON_stop, src/Main.f90:135-168);
+    ! numerical failures come back through the sorfail out-parameters and set SORFail,
+    ! which scb_run handles by rolling back (src/ModScbRun.f90:226-229, 398-414)
+    integer(c_int), intent(in) :: ierr
+    character(len=*), intent(in) :: where
+    if (ierr /= 0) call CON_stop('ramscb_gpu (SCB) failure in '//where)
+  end subroutine rsg_scb_check
+
+  subroutine scb_gpu_upload_domain
+    ! after computational_domain / Update_Domain (src/ModScbIO.f90:179-205, 211-519) and
+    ! whenever the host has moved x, y, z, alfa or psi
+    use ModScbVariables, ONLY: x, y, z, alfa, psi, thetaVal, rhoVal, zetaVal, f, fzet, alphaVal, psiVal, chiVal
+    call rsg_scb_check(rsg_scb_set_grid(hScb, thetaVal, rhoVal, zetaVal, f, fzet), 'upload_domain')
+    call rsg_scb_check(rsg_scb_set_geometry(hScb, x, y, z), 'upload_domain')
+    call rsg_scb_check(rsg_scb_set_field(hScb, 'alfa'//c_null_char, alfa), 'upload_domain')
+    call rsg_scb_check(rsg_scb_set_field(hScb, 'psi'//c_null_char, psi), 'upload_domain')
+    call rsg_scb_check(rsg_scb_set_map_targets(hScb, alphaVal, psiVal, chiVal), 'upload_domain')
+  end subroutine scb_gpu_upload_domain
+
+end module ModScbGpu

@@ -557,3 +557,81 @@ def test_pressure_aniso_oracle_vs_independent_numpy(oracle_built, iLossCone, iRe
         o2.pressure_aniso(inp.pper[ieq], inp.ppar[ieq], 1, 0)
         assert np.allclose(o2.pper[:, :, :nz], inp.pper[:, :, :nz], rtol=1e-13, atol=0)
         assert np.allclose(o2.ppar[:, :, :nz], inp.ppar[:, :, :nz], rtol=1e-13, atol=0)
+
+
+def _c_prototypes():
+    """name -> list of (ctype, is_pointer) from include/ramscb_gpu.h"""
+    import re
+    src = open(os.path.join(ROOT, "include", "ramscb_gpu.h")).read()
+    src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(?:int|double|long long|const char\s*\*)\s+(rsg_\w+)\s*\(([^)]*)\)\s*;", src):
+        params = []
+        for p in m.group(2).split(","):
+            p = " ".join(p.split())
+            if p in ("", "void"):
+                continue
+            ptr = "*" in p or "[" in p
+            base = re.sub(r"\bconst\b|\*|\[.*?\]", " ", p).split()
+            ctype = " ".join(base[:-1])          # drop the parameter name
+            params.append((ctype, ptr))
+        out[m.group(1)] = params
+    return out
+
+
+def test_fortran_shims_match_the_c_header():
+    """There is no Fortran compiler in this image, so the ISO_C_BINDING interface blocks of
+    ramscb_b200/fortran/ are checked statically against include/ramscb_gpu.h: every bound name exists
+    in the header and is exported by the library, the argument counts agree, C scalars are passed by
+    `value`, C pointers are arrays / intent(out) scalars / `type(c_ptr), value`, and the kinds agree
+    (int <-> c_int, double <-> c_double, long long <-> c_long_long, char* <-> c_char)."""
+    import glob
+    import re
+    protos = _c_prototypes()
+    assert len(protos) > 90
+    from ramscb_b200 import build, host
+    build.build()
+    L = ctypes.CDLL(host.LIB_PATH)
+    nbound = 0
+    for path in sorted(glob.glob(os.path.join(ROOT, "ramscb_b200", "fortran", "*.f90"))):
+        txt = re.sub(r"&\s*\n\s*", " ", open(path).read())           # join continuation lines
+        txt = "\n".join(l.split("!")[0] if "'" not in l.split("!")[0] or l.split("!")[0].count("'") % 2 == 0 else l
+                        for l in txt.splitlines())
+        for m in re.finditer(r"function\s+(\w+)\s*\(([^)]*)\)\s*bind\(C,\s*name='(\w+)'\)\s*result\(\w+\)(.*?)end function",
+                             txt, flags=re.S | re.I):
+            fname, args, cname, body = m.group(1), [a.strip() for a in m.group(2).split(",") if a.strip()], m.group(3), m.group(4)
+            where = f"{os.path.basename(path)}:{cname}"
+            assert fname == cname, where
+            assert cname in protos, where + " not declared in include/ramscb_gpu.h"
+            assert hasattr(L, cname), where + " not exported by the library"
+            cpar = protos[cname]
+            assert len(cpar) == len(args), f"{where}: {len(args)} dummy arguments, C prototype has {len(cpar)}"
+            decl = {}
+            for line in body.splitlines():
+                if "::" not in line:
+                    continue
+                spec, names = line.split("::", 1)
+                for n in re.split(r",(?![^(]*\))", names):
+                    n = n.strip()
+                    if n:
+                        decl[re.sub(r"\(.*\)", "", n).strip().lower()] = (spec.lower(), "(" in n)
+            for a, (ctype, ptr) in zip(args, cpar):
+                assert a.lower() in decl, f"{where}: dummy {a} is not declared"
+                spec, is_array = decl[a.lower()]
+                by_value = "value" in spec
+                if not ptr:
+                    assert by_value and not is_array, f"{where}: C scalar {ctype} {a} must be passed by value"
+                    kind = {"int": "c_int", "double": "c_double", "long long": "c_long_long"}[ctype]
+                    assert kind in spec, f"{where}: {a} should be {kind}"
+                else:
+                    if by_value:
+                        assert "type(c_ptr)" in spec, f"{where}: pointer {a} passed by value must be type(c_ptr)"
+                    else:
+                        kind = {"int": "c_int", "double": "c_double", "long long": "c_long_long", "char": "c_char",
+                                "void": "c_ptr"}.get(ctype)
+                        if kind:                      # opaque handles (rsg_ram**, rsg_scb**) are type(c_ptr), intent(out)
+                            assert kind in spec, f"{where}: {a} should be {kind} ({spec.strip()})"
+                        else:
+                            assert "type(c_ptr)" in spec, f"{where}: handle {a}"
+            nbound += 1
+    assert nbound >= 55, nbound
