@@ -249,6 +249,129 @@ def scb_metrics(device):
     return out
 
 
+def time_ram_step(workload_name, flags, steps, warmup, device):
+    """Device time of one resident `ram_run` of the named workload with the given operator flags, measured
+    exactly like the headline value (L2 flushed between steps, CUDA events over the library's streams)."""
+    import torch
+    from ramscb_b200 import host, synthetic
+    g, inp, desc = workload(workload_name)
+    gpu = host.RamGpu(g, device=device, mode=host.MODE_FAST)
+    gpu.set_inputs(inp)
+    nw = 0
+    if flags:
+        D = synthetic.synthetic_daa(g, inp)
+        gpu.set_diffcoef(1, D)
+        gpu.set_diffcoef(2, D)
+        nw = sum(1 for sp in g.species if (flags & 1 and sp.WPI) or (flags & 4 and sp.EMIC))
+    flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
+    for _ in range(warmup):
+        gpu.ram_run(DTS, DtsMin=1.0, flags=flags)
+    n0 = gpu.launch_count()
+    ms = 0.0
+    for _ in range(steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        gpu.timer_begin()
+        gpu.ram_run(DTS, DtsMin=1.0, flags=flags)
+        ms += gpu.timer_end()
+    ms /= steps
+    launches = (gpu.launch_count() - n0) / steps
+    gpu.profile(True)
+    for _ in range(3):
+        flush.zero_()
+        torch.cuda.synchronize()
+        gpu.ram_run(DTS, DtsMin=1.0, flags=flags)
+    stages = gpu.profile_get()
+    gpu.profile(False)
+    cells = g.nS * g.NR * g.NT * g.NE * g.NPA
+    ops = OPS_PER_STEP + 2.0 * nw / g.nS
+    out = {"workload": desc, "flags": flags, "ms_per_step": ms, "value": ops * cells / (ms * 1e-3), "unit": "cell-updates/s",
+           "ops_per_cell_per_step": ops, "launches_per_step": launches, "steps": steps, "warmup": warmup,
+           "per_kernel_ms": {k: v[0] / v[1] for k, v in stages.items() if v[1] and k != "end"}}
+    gpu.close()
+    del flush
+    torch.cuda.empty_cache()
+    return out
+
+
+def scb_zeta_metrics(device):
+    """iterateAlpha through the zeta-sharded protocol (rsg_scb_zsolve_*, one launch per half-sweep) on ONE
+    rank, next to the on-chip cluster solve: what the host-driven scheme costs per sweep before any halo
+    traffic.  Wall clock around the whole solve (the protocol is host-driven); results checked identical."""
+    import torch
+    from ramscb_b200 import host, parallel, scb_synthetic
+    inp = scb_synthetic.build_scb(nthe=101, npsi=45, nzeta=97, warp=0.2)
+    ref = host.ScbGpu(inp, device=device)
+    ref.computeBandJacob(); ref.metrica(); ref.newk()
+    r1 = ref.iterateAlpha(1e-6, ordering=host.SOR_COLOR4)
+    gpu = host.ScbGpu(inp, device=device)
+    st = torch.cuda.Stream()
+    out = {}
+    with torch.cuda.stream(st):
+        gpu.set_stream(st.cuda_stream)
+        gpu.computeBandJacob(); gpu.metrica(); gpu.newk()
+        alfa0 = gpu.get_field("alfa").copy()
+        for poll in (16, 64):
+            gpu.set_field("alfa", alfa0)
+            z = parallel.ScbZetaSharded(gpu, None, 0, 1, on_cuda=True, poll=poll)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            r = z.iterate(1e-6)
+            torch.cuda.synchronize()
+            ms = (time.perf_counter() - t0) * 1e3
+            same = bool(np.array_equal(gpu.get_field("alfa"), ref.get_field("alfa")) and np.array_equal(r["ni"], r1["ni"]))
+            out[f"poll{poll}"] = {"wall_ms": ms, "sweeps_launched": r["sweeps_launched"], "us_per_sweep": ms * 1e3 / r["sweeps_launched"],
+                                  "identical_to_cluster_solve": same}
+    out["cluster_solve_ms"] = r1["ms"]
+    out["max_sweeps"] = int(r1["nisave"])
+    gpu.close(); ref.close()
+    return out
+
+
+def scb_run_metrics(device):
+    """configs[3] end to end: scb_run (src/ModScbRun.f90:149-440) with the reference's parameters (InCon 1e-6,
+    MinSCBIterations 11, blend 0.5) on the default SCB grid through ONE rsg_scb_run call; the synthetic
+    pressure front end is the host callback.  Wall clock of the call (it includes the callback and the
+    2-D transfers), 4-colour ordering."""
+    from ramscb_b200 import host, scb_synthetic
+    inp = scb_synthetic.build_scb(nthe=101, npsi=45, nzeta=97, warp=0.2)
+    fn = scb_synthetic.equatorial_pressure_fn()
+    out = {}
+    for rep in range(2):                       # the second run is the warm one
+        gpu = host.ScbGpu(inp, device=device)
+        gpu.set_map_targets(inp.alphaVal, inp.psiVal, inp.chiVal)
+        n0 = gpu.launch_count()
+        t0 = time.perf_counter()
+        r = gpu.scb_run(fn, ordering=host.SOR_COLOR4)
+        ms = (time.perf_counter() - t0) * 1e3
+        out = {"wall_ms": ms, "outer_iterations": r["iterations"], "SORFail": r["SORFail"], "iConvGlobal": r["iConvGlobal"],
+               "nisaveAlpha_last": r["nisaveAlpha"], "nisavePsi_last": r["nisavePsi"], "blendRetries": r["blendRetries"],
+               "normDiff_start_end": [r["normDiffStart"], r["normDiff"]], "normJxB_start_end": [r["normJxBStart"], r["normJxB"]],
+               "normGradP_start_end": [r["normGradPStart"], r["normGradP"]], "launches": int(gpu.launch_count() - n0),
+               "ms_per_outer_iteration": ms / max(r["iterations"], 1)}
+        gpu.close()
+    return out
+
+
+def extras_main(device):
+    """`bench.py --extras-only`: informational measurements beside the headline line (run by the N = 1 bench in a
+    child process, so that nothing here can take the headline down).  One JSON object on stdout."""
+    out = {}
+    jobs = (("ram_default_wpi_emic", lambda: time_ram_step("default", 5, 10, 3, device)),
+            ("ram_x4_configs2_wpi_emic", lambda: time_ram_step("x4", 5, 5, 3, device)),
+            ("ram_x4_no_wpi", lambda: time_ram_step("x4", 0, 5, 3, device)),
+            ("scb_alpha_zeta_protocol_one_rank", lambda: scb_zeta_metrics(device)),
+            ("scb_run_configs3", lambda: scb_run_metrics(device)))
+    for name, fn in jobs:
+        t0 = time.perf_counter()
+        try:
+            out[name] = fn()
+        except Exception as e:           # informational
+            out[name] = {"error": str(e)[:300]}
+        out[name]["wall_s"] = time.perf_counter() - t0
+    print("EXTRAS_JSON " + json.dumps(out))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -263,6 +386,8 @@ def main():
                          "--workload x4 is BASELINE configs[2] (full step with WPADIF); default 0 = configs[1]")
     ap.add_argument("--no-scb", action="store_true", help="skip the SCB solve metrics")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the informational extras (WPI/EMIC steps, 4x grid, zeta protocol)")
+    ap.add_argument("--extras-only", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"],
                     help="arithmetic mode of the sweeps (include/ramscb_gpu.h rsg_mode)")
     a = ap.parse_args()
@@ -271,6 +396,11 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.extras_only:
+        import torch
+        torch.cuda.set_device(local_rank)
+        extras_main(local_rank)
+        return
 
     g, inp, desc = workload(a.workload)
     weak = a.scaling == "weak"
@@ -485,11 +615,39 @@ def main():
             "wall_s_timed_region": wall_s}
     if rank == 0 and world == 1 and not a.no_scb:
         line["scb"] = scb_metrics(local_rank)
+    if rank == 0 and world == 1 and not a.no_cpu_baseline and not a.no_scb:
+        # CPU side of configs[3]: the oracle's scb_run (same loop, same parameters, OpenMP over the sub-problems like
+        # the reference) on the host cores, once -- next to extras.scb_run_configs3
+        try:
+            from oracle import oracle
+            from ramscb_b200 import scb_synthetic
+            oracle.build()
+            sinp = scb_synthetic.build_scb(nthe=101, npsi=45, nzeta=97, warp=0.2)
+            so = oracle.ScbOracle(sinp)
+            t0 = time.perf_counter()
+            sr = so.scb_run(scb_synthetic.equatorial_pressure_fn())
+            line["scb"]["cpu_scb_run"] = {"wall_s": time.perf_counter() - t0, "outer_iterations": sr["iterations"],
+                                          "SORFail": sr["SORFail"], "cores": os.cpu_count(), "kind": "port"}
+        except Exception as e:
+            line["scb"]["cpu_scb_run"] = {"error": str(e)[:200]}
     if rank == 0 and world == 1 and not a.no_cpu_baseline:      # reported at N = 1 only
         v, nthreads, dt = cpu_reference(g, inp, 3 if a.workload == "default" else 1, 1)
         line["cpu_baseline"] = {"value": v, "unit": unit, "cores": nthreads, "kind": "port",
                                 "sample": "full ram_run steps of the same workload on the host cores "
                                           f"({dt:.3f} s/step, OpenMP over species = the reference's decomposition)"}
+    if rank == 0 and world == 1 and not a.no_extras and a.workload == "default" and a.flags == 0:
+        # informational, in a child process (this process's device state is released first): the WPI/EMIC step
+        # (configs[2] on the 4x grid) and the zeta-sharded SOR protocol; never part of `value`
+        try:
+            gpu.close()
+            del flush
+            torch.cuda.empty_cache()
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--extras-only"], capture_output=True, text=True,
+                               timeout=420, env=dict(os.environ, LOCAL_RANK=str(local_rank)))
+            tag = [l for l in r.stdout.splitlines() if l.startswith("EXTRAS_JSON ")]
+            line["extras"] = json.loads(tag[-1][len("EXTRAS_JSON "):]) if tag else {"error": (r.stderr or r.stdout)[-300:]}
+        except Exception as e:
+            line["extras"] = {"error": str(e)[:300]}
     if rank == 0:
         print(json.dumps(line))
     if dist is not None:

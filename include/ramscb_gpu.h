@@ -318,6 +318,35 @@ int rsg_scb_zsolve_half(rsg_scb* h, int parity);
 int rsg_scb_zsolve_state_device(rsg_scb* h, void** ptr, long long* n);
 int rsg_scb_zsolve_commit(rsg_scb* h);
 int rsg_scb_zsolve_pending(rsg_scb* h, int* pending);
+/* scb_run (src/ModScbRun.f90:149-440, method = 2, iAMR = 0): the whole outer iteration of the Euler-
+ * potential solve in ONE call, every 3-D array resident on the device -- the fused level of the drop-in,
+ * like rsg_ram_run for ram_run.  Per outer iteration: computeBandJacob, pressure, metrica, newk,
+ * iterateAlpha, blend + mapAlpha + mapTheta + computeBandJacob + MINVAL(jacobian) test (damped retries),
+ * computeBandJacob, pressure, Compute_convergence, metric, newj, iteratePsi, blend + mapPsi + mapTheta + ...,
+ * then the reference's exit test (errorAlpha/Psi < decreaseConv*, numit, MinSCBIterations).  On SORFail
+ * x, y, z, alfa, psi are restored to their values at entry (:397-413).
+ * `pressure` is the 2-D front end of the reference's routine (src/ModScbRun.f90:753-1086, RAM pressures ->
+ * equatorial points; host): it gets xEq, yEq (npsi, nzeta+1; the foot points x/y(nThetaEquator,j,k)) and
+ * fills the normalised pperEq, pparEq (npsi, nzeta+1, periodic columns set); return 0, non-zero aborts.
+ * Uses snapshot slots 0..2 of x, y, z, alfa, psi.  Needs set_grid, set_geometry, set_map_targets. */
+typedef int (*rsg_scb_pressure_fn)(void* user, int npsi, int nzetap, const double* xEq, const double* yEq, double* pperEq,
+                                   double* pparEq);
+typedef struct rsg_scb_run_params {
+  double InConAlpha, InConPsi;                  /* 1e-6, 1e-6  (src/ModScbParams.f90:37-38) */
+  double blendInitial, blendMin, blendMax;      /* 0.5 (src/ModScbRun.f90:178), 0.01, 1.0 (ModScbParams.f90:35-36) */
+  double damp;                                  /* 0.9 (src/ModScbMain.f90:58) */
+  double decreaseConvAlpha, decreaseConvPsi;    /* 0.5, 0.5 (ModScbParams.f90:29-32, ModScbRun.f90:84-87) */
+  int nimax, theChange, psiChange;              /* 5001, 4, 0 */
+  int numit, MinSCBIterations;                  /* 200, 11 (src/ModScbMain.f90:45, ModScbParams.f90:27) */
+  int ordering;                                 /* RSG_SOR_LEX | RSG_SOR_COLOR4 */
+  int iLossCone, iReduceAnisotropy;             /* 1, 0 */
+} rsg_scb_run_params;
+typedef struct rsg_scb_run_result {
+  int iterations, iConvGlobal, SORFail, nisaveAlpha, nisavePsi, blendRetries;
+  double blendAlpha, blendPsi, errorAlpha, errorPsi, sumbAlpha, sumdbAlpha, sumbPsi, sumdbPsi;
+  double normDiffStart, normJxBStart, normGradPStart, normDiff, normJxB, normGradP;
+} rsg_scb_run_result;
+int rsg_scb_run(rsg_scb* h, const rsg_scb_run_params* p, rsg_scb_pressure_fn pressure, void* user, rsg_scb_run_result* out);
 /* device time (CUDA events on the launching stream) of the kernels of the last call */
 /* Multi-GPU: the independent sub-problems of a solve (psi surfaces for alpha, zeta planes for psi)
  * split among ranks.  part solves sub-problems [sub0, sub0+nsub) (0-based: q is jz = q+2 / k = q+2);

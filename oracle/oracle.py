@@ -271,6 +271,106 @@ class ScbOracle:
     def map_psi(self): return self.lib.scbo_map_psi(self.h)
     def map_theta(self): return self.lib.scbo_map_theta(self.h)
 
+    def scb_run(self, pressure_fn, InConAlpha=1e-6, InConPsi=1e-6, blendInitial=0.5, blendMin=0.01, blendMax=1.0, damp=0.9,
+                decreaseConvAlpha=0.5, decreaseConvPsi=0.5, nimax=5001, numit=200, MinSCBIterations=11, iLossCone=1,
+                iReduceAnisotropy=0):
+        """The outer iteration of scb_run (src/ModScbRun.f90:134-440; method = 2, iAMR = 0) composed from the
+        restated routines.  pressure_fn(xEq, yEq) -> (pperEq, pparEq) is the 2-D front end of `pressure`."""
+        nthe, npsi, nzeta = self.inp.nthe, self.inp.npsi, self.inp.nzeta
+        ieq = (nthe + 1) // 2 - 1
+        self.set_scalar("InConAlpha", InConAlpha); self.set_scalar("InConPsi", InConPsi); self.set_int("nimax", nimax)
+
+        def pressure():
+            pe, pa = pressure_fn(np.array(self.x[ieq], order="F"), np.array(self.y[ieq], order="F"))
+            self.pressure_aniso(pe, pa, iLossCone, iReduceAnisotropy)
+
+        def minjac():
+            j = self.jacobian[1:nthe - 1, 1:npsi - 1, 1:nzeta]
+            return -1e300 if np.isnan(j).any() else float(j.min())
+
+        out = {"blendRetries": 0}
+        start = {n: getattr(self, n).copy() for n in ("x", "y", "z", "alfa", "psi")}           # :134-143
+        fail = self.bandjacob() != 0
+        pressure()
+        fail |= self.convergence() != 0
+        out["normStart"] = (self.get("normDiff"), self.get("normJxB"), self.get("normGradP"))
+        blendAlpha = blendPsi = blendInitial                                                   # :178-180
+        errorAlpha = errorPsi = 0.0
+        iteration, iConvGlobal = 1, 0
+        alfaSav1, psiSav1 = self.alfa.copy(), self.psi.copy()                                   # :206-207
+        while not fail:
+            if self.bandjacob() != 0:                                                           # equation 1, :213-262
+                fail = True; break
+            pressure(); self.metrica(); self.newk()
+            blendAlpha = min(max(blendAlpha, blendMin), blendMax)
+            f, _ = self.iterate_alpha()
+            if f:
+                fail = True; break
+            out["nisaveAlpha"], out["sumdbAlpha"] = int(self.get("nisave")), self.get("sumdb")
+            errorAlpha = self.get("diffmx")
+            prev = {n: getattr(self, n).copy() for n in ("x", "y", "z")}
+            alphaPrev = self.alfa.copy()
+            while True:
+                self.alfa[...] = alphaPrev * blendAlpha + alfaSav1 * (1.0 - blendAlpha)
+                if self.map_alpha() or self.map_theta():
+                    fail = True; break
+                fail |= self.bandjacob() != 0
+                if minjac() < 0.0:
+                    for n in ("x", "y", "z"):
+                        getattr(self, n)[...] = prev[n]
+                    blendAlpha = damp * blendAlpha
+                    out["blendRetries"] += 1
+                    if blendAlpha < blendMin:
+                        fail = True; break
+                    continue
+                break
+            if fail:
+                break
+            if self.bandjacob() != 0:                                                           # equation 2, :285-349
+                fail = True; break
+            pressure()
+            fail |= self.convergence() != 0
+            self.metric(); self.newj()
+            blendPsi = min(max(blendPsi, blendMin), blendMax)
+            f, _ = self.iterate_psi()
+            if f:
+                fail = True; break
+            out["nisavePsi"], out["sumdbPsi"] = int(self.get("nisave")), self.get("sumdb")
+            errorPsi = self.get("diffmx")
+            prev = {n: getattr(self, n).copy() for n in ("x", "y", "z")}
+            psiPrev = self.psi.copy()
+            while True:
+                self.psi[...] = psiPrev * blendPsi + (1.0 - blendPsi) * psiSav1
+                if self.map_psi() or self.map_theta():
+                    fail = True; break
+                fail |= self.bandjacob() != 0
+                if minjac() < 0.0:
+                    for n in ("x", "y", "z"):
+                        getattr(self, n)[...] = prev[n]
+                    blendPsi = damp * blendPsi
+                    out["blendRetries"] += 1
+                    if blendPsi < blendMin:
+                        fail = True; break
+                    continue
+                break
+            if fail:
+                break
+            if errorAlpha < decreaseConvAlpha and errorPsi < decreaseConvPsi:                   # :363-378
+                iConvGlobal = 1
+            if (iteration < numit and iConvGlobal == 0) or iteration < MinSCBIterations:
+                iteration += 1
+                continue
+            break
+        out.update(iterations=iteration, iConvGlobal=iConvGlobal, SORFail=int(fail), blendAlpha=blendAlpha, blendPsi=blendPsi,
+                   errorAlpha=errorAlpha, errorPsi=errorPsi)
+        if fail:                                                                                # :397-413
+            for n, v in start.items():
+                getattr(self, n)[...] = v
+            return out
+        self.bandjacob(); pressure(); self.convergence()                                        # :427-429
+        out["norm"] = (self.get("normDiff"), self.get("normJxB"), self.get("normGradP"))
+        return out
+
     def derivs3d(self, f3):
         f3 = np.asfortranarray(f3, dtype=np.float64)
         out = [_f(f3.shape) for _ in range(3)]

@@ -821,6 +821,135 @@ int rsg_scb_map_alpha(rsg_scb* h, int* sorfail) { return scb_map(h, 0, sorfail);
 int rsg_scb_map_psi(rsg_scb* h, int* sorfail) { return scb_map(h, 1, sorfail); }
 int rsg_scb_map_theta(rsg_scb* h, int* sorfail) { return scb_map(h, 2, sorfail); }
 
+// ---------------------------------------------------------------------------------------------
+// scb_run, src/ModScbRun.f90:149-440 (method = 2, iAMR = 0): the whole outer iteration of the
+// Euler-potential solve with every 3-D array resident.  Only `pressure`'s 2-D front end is the
+// caller's: the callback receives the equatorial foot points of the field lines and returns the
+// normalised equatorial pressures (npsi, nzeta+1); everything downstream (field-line mapping,
+// derivatives, coefficients, SOR, re-gridding, blending, Jacobian test, convergence norms) is here.
+// ---------------------------------------------------------------------------------------------
+static int scb_run_pressure(rsg_scb* h, const rsg_scb_run_params* p, rsg_scb_pressure_fn fn, void* user, std::vector<double>& eq,
+                            std::vector<double>& pe, std::vector<double>& pa) {
+  const size_t n2 = (size_t)h->npsi * (h->nzeta + 1);
+  if (!h->d_peq) {
+    SRET(h->dalloc(&h->d_peq, 2 * n2, nullptr));
+    SRET(h->dalloc(&h->d_tau, (size_t)h->nthe * h->npsi * (h->nzeta + 1), "tau"));
+  }
+  k_scb_gather_eq<<<nblk((long long)n2, 128), 128, 0, h->st>>>(h->dev, (h->nthe + 1) / 2 - 1, h->d_peq);
+  SCKL();
+  h->launches++;
+  SCK(cudaMemcpyAsync(eq.data(), h->d_peq, 2 * n2 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  SCK(cudaStreamSynchronize(h->st));
+  if (fn(user, h->npsi, h->nzeta + 1, eq.data(), eq.data() + n2, pe.data(), pa.data()) != 0)
+    return sfail(RSG_ERR_ARG, "the pressure callback reported a failure");
+  return rsg_scb_pressure_aniso(h, pe.data(), pa.data(), p->iLossCone, p->iReduceAnisotropy);
+}
+
+int rsg_scb_run(rsg_scb* h, const rsg_scb_run_params* p, rsg_scb_pressure_fn pressure, void* user, rsg_scb_run_result* out) {
+  if (!h || !p || !pressure || !out) return sfail(RSG_ERR_ARG, "null argument");
+  if (!h->grid_set || !h->geom_set || !h->map_set) return sfail(RSG_ERR_STATE, "scb_run before set_grid / set_geometry / set_map_targets");
+  SCK(cudaSetDevice(h->device));
+  const size_t n2 = (size_t)h->npsi * (h->nzeta + 1);
+  std::vector<double> eq(2 * n2), pe(n2), pa(n2);
+  *out = rsg_scb_run_result{};
+  int fail = 0, f = 0;
+  const char* xyz[3] = {"x", "y", "z"};
+  // xStart ... alphaStart (:134-143): slot 2
+  for (const char* n : xyz) SRET(rsg_scb_snapshot(h, n, 2));
+  SRET(rsg_scb_snapshot(h, "alfa", 2));
+  SRET(rsg_scb_snapshot(h, "psi", 2));
+  SRET(rsg_scb_bandjacob(h, &f)); fail |= f;                                                     // :148-150
+  SRET(scb_run_pressure(h, p, pressure, user, eq, pe, pa));
+  SRET(rsg_scb_convergence(h, &out->normDiffStart, &out->normJxBStart, &out->normGradPStart, &f)); fail |= f;
+  double blendAlpha = p->blendInitial, blendPsi = p->blendInitial;                               // :178-180
+  double errorAlpha = 0.0, errorPsi = 0.0;
+  int iteration = 1, iConvGlobal = 0;
+  SRET(rsg_scb_snapshot(h, "alfa", 1));                                                          // alfaSav1, psiSav1 (:206-207)
+  SRET(rsg_scb_snapshot(h, "psi", 1));
+  while (!fail) {                                                                                // Outeriters (:209)
+    // ---- equation 1 (:213-262)
+    SRET(rsg_scb_bandjacob(h, &f)); if (f) { fail = 1; break; }
+    SRET(scb_run_pressure(h, p, pressure, user, eq, pe, pa));
+    SRET(rsg_scb_metrica(h));
+    SRET(rsg_scb_newk(h));
+    blendAlpha = std::min(std::max(blendAlpha, p->blendMin), p->blendMax);
+    double sb, sdb, dmx;
+    int nis;
+    SRET(rsg_scb_iterate_alpha(h, p->InConAlpha, p->nimax, p->theChange, p->psiChange, p->ordering, &nis, &sb, &sdb, &dmx, &f, nullptr));
+    if (f) { fail = 1; break; }
+    out->nisaveAlpha = nis; out->sumbAlpha = sb; out->sumdbAlpha = sdb;
+    errorAlpha = dmx;
+    for (const char* n : xyz) SRET(rsg_scb_snapshot(h, n, 0));                                   // xPrev, alphaPrev
+    SRET(rsg_scb_snapshot(h, "alfa", 0));
+    for (;;) {                                                                                   // Move_points_in_alpha_theta
+      SRET(rsg_scb_blend(h, "alfa", 0, 1, blendAlpha));
+      SRET(rsg_scb_map_alpha(h, &f)); if (f) { fail = 1; break; }
+      SRET(rsg_scb_map_theta(h, &f)); if (f) { fail = 1; break; }
+      SRET(rsg_scb_bandjacob(h, &f)); fail |= f;
+      double mj;
+      SRET(rsg_scb_min_jacobian(h, &mj));
+      if (mj < 0.0) {
+        for (const char* n : xyz) SRET(rsg_scb_restore(h, n, 0));
+        blendAlpha = p->damp * blendAlpha;
+        out->blendRetries++;
+        if (blendAlpha < p->blendMin) { fail = 1; break; }
+        continue;
+      }
+      break;
+    }
+    if (fail) break;
+    // ---- equation 2 (:285-349)
+    SRET(rsg_scb_bandjacob(h, &f)); if (f) { fail = 1; break; }
+    SRET(scb_run_pressure(h, p, pressure, user, eq, pe, pa));
+    { double a, b, c; SRET(rsg_scb_convergence(h, &a, &b, &c, &f)); fail |= f; }
+    SRET(rsg_scb_metric(h));
+    SRET(rsg_scb_newj(h));
+    blendPsi = std::min(std::max(blendPsi, p->blendMin), p->blendMax);
+    SRET(rsg_scb_iterate_psi(h, p->InConPsi, p->nimax, p->theChange, p->psiChange, p->ordering, &nis, &sb, &sdb, &dmx, &f, nullptr));
+    if (f) { fail = 1; break; }
+    out->nisavePsi = nis; out->sumbPsi = sb; out->sumdbPsi = sdb;
+    errorPsi = dmx;
+    for (const char* n : xyz) SRET(rsg_scb_snapshot(h, n, 0));
+    SRET(rsg_scb_snapshot(h, "psi", 0));
+    for (;;) {                                                                                   // Move_points_in_psi_theta
+      SRET(rsg_scb_blend(h, "psi", 0, 1, blendPsi));
+      SRET(rsg_scb_map_psi(h, &f)); if (f) { fail = 1; break; }
+      SRET(rsg_scb_map_theta(h, &f)); if (f) { fail = 1; break; }
+      SRET(rsg_scb_bandjacob(h, &f)); fail |= f;
+      double mj;
+      SRET(rsg_scb_min_jacobian(h, &mj));
+      if (mj < 0.0) {
+        for (const char* n : xyz) SRET(rsg_scb_restore(h, n, 0));
+        blendPsi = p->damp * blendPsi;
+        out->blendRetries++;
+        if (blendPsi < p->blendMin) { fail = 1; break; }
+        continue;
+      }
+      break;
+    }
+    if (fail) break;
+    // ---- convergence control (:363-378); SCBIterNeeded = 1 and outDistance > convDistance are constants there
+    if (errorAlpha < p->decreaseConvAlpha && errorPsi < p->decreaseConvPsi) iConvGlobal = 1;
+    if ((iteration < p->numit && iConvGlobal == 0) || iteration < p->MinSCBIterations) { iteration++; continue; }
+    break;
+  }
+  out->iterations = iteration;
+  out->iConvGlobal = iConvGlobal;
+  out->blendAlpha = blendAlpha; out->blendPsi = blendPsi;
+  out->errorAlpha = errorAlpha; out->errorPsi = errorPsi;
+  out->SORFail = fail ? 1 : 0;
+  if (fail) {                                                                                    // :397-413: back to the start
+    for (const char* n : xyz) SRET(rsg_scb_restore(h, n, 2));
+    SRET(rsg_scb_restore(h, "alfa", 2));
+    SRET(rsg_scb_restore(h, "psi", 2));
+    return RSG_OK;
+  }
+  SRET(rsg_scb_bandjacob(h, &f));                                                                // :427-429
+  SRET(scb_run_pressure(h, p, pressure, user, eq, pe, pa));
+  SRET(rsg_scb_convergence(h, &out->normDiff, &out->normJxB, &out->normGradP, &f));
+  return RSG_OK;
+}
+
 double rsg_scb_last_ms(rsg_scb* h) { return h ? h->last_ms : 0.0; }
 int rsg_scb_use_cluster(rsg_scb* h, int on) {
   if (!h) return sfail(RSG_ERR_ARG, "null handle");

@@ -504,6 +504,16 @@ __global__ void k_scb_zcommit(ZArgs a, int* __restrict__ ni, double* __restrict_
   if (threadIdx.x == 0) *pending = s_pend;
 }
 
+// equatorial foot points x(nThetaEquator,j,k), y(nThetaEquator,j,k) of every field line -> out[0..n2), out[n2..2 n2)
+// (what `pressure` needs on the host to look the RAM pressures up, src/ModScbRun.f90:1001-1010)
+__global__ void k_scb_gather_eq(ScbDev d, int ieq, double* __restrict__ out) {
+  const size_t n2 = (size_t)d.npsi * (d.nzeta + 1);
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n2) return;
+  out[q] = d.x[(size_t)ieq + (size_t)d.nthe * q];
+  out[n2 + q] = d.y[(size_t)ieq + (size_t)d.nthe * q];
+}
+
 // sumb, sumdb over (2:nthe-1, 2:npsi-1, 2:nzeta) (Fortran), one CTA per zeta plane -> partials
 __global__ void __launch_bounds__(256) k_scb_sums(ScbDev d, const double* __restrict__ u, const double* __restrict__ uprev,
                                                   double* __restrict__ part) {

@@ -17,6 +17,17 @@ module ModScbGpu
   ! production ordering; RSG_SOR_LEX reproduces the reference's sweep order bit for bit
   integer(c_int), save :: scbSorOrdering = RSG_SOR_COLOR4
 
+  ! rsg_scb_run_params / rsg_scb_run_result of include/ramscb_gpu.h (same member order)
+  type, bind(C) :: rsg_scb_run_params
+     real(c_double) :: InConAlpha, InConPsi, blendInitial, blendMin, blendMax, damp, decreaseConvAlpha, decreaseConvPsi
+     integer(c_int) :: nimax, theChange, psiChange, numit, MinSCBIterations, ordering, iLossCone, iReduceAnisotropy
+  end type
+  type, bind(C) :: rsg_scb_run_result
+     integer(c_int) :: iterations, iConvGlobal, SORFail, nisaveAlpha, nisavePsi, blendRetries
+     real(c_double) :: blendAlpha, blendPsi, errorAlpha, errorPsi, sumbAlpha, sumdbAlpha, sumbPsi, sumdbPsi
+     real(c_double) :: normDiffStart, normJxBStart, normGradPStart, normDiff, normJxB, normGradP
+  end type
+
   interface
      function rsg_scb_create(h, nthe, npsi, nzeta, device) bind(C, name='rsg_scb_create') result(ierr)
        import :: c_ptr, c_int
@@ -173,6 +184,15 @@ module ModScbGpu
        character(kind=c_char), intent(in) :: name(*)
        integer(c_int), value :: slot_new, slot_sav
        real(c_double), value :: blend
+       integer(c_int) :: ierr
+     end function
+     function rsg_scb_run(h, p, pressure, user, res) bind(C, name='rsg_scb_run') result(ierr)
+       import :: c_ptr, c_int, c_funptr, rsg_scb_run_params, rsg_scb_run_result
+       type(c_ptr), value :: h
+       type(rsg_scb_run_params), intent(in) :: p
+       type(c_funptr), value :: pressure                 ! rsg_scb_pressure_fn
+       type(c_ptr), value :: user
+       type(rsg_scb_run_result), intent(out) :: res
        integer(c_int) :: ierr
      end function
      function rsg_scb_min_jacobian(h, minjac) bind(C, name='rsg_scb_min_jacobian') result(ierr)

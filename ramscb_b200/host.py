@@ -374,6 +374,25 @@ SOR_LEX, SOR_COLOR4 = 0, 1
 _scb_ready = False
 
 
+class ScbRunParams(C.Structure):
+    """rsg_scb_run_params (include/ramscb_gpu.h); defaults = the reference's (ModScbParams.f90, ModScbMain.f90)"""
+    _fields_ = [(n, C.c_double) for n in ("InConAlpha", "InConPsi", "blendInitial", "blendMin", "blendMax", "damp",
+                                          "decreaseConvAlpha", "decreaseConvPsi")] + \
+               [(n, C.c_int) for n in ("nimax", "theChange", "psiChange", "numit", "MinSCBIterations", "ordering", "iLossCone",
+                                       "iReduceAnisotropy")]
+
+
+class ScbRunResult(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("iterations", "iConvGlobal", "SORFail", "nisaveAlpha", "nisavePsi", "blendRetries")] + \
+               [(n, C.c_double) for n in ("blendAlpha", "blendPsi", "errorAlpha", "errorPsi", "sumbAlpha", "sumdbAlpha", "sumbPsi",
+                                          "sumdbPsi", "normDiffStart", "normJxBStart", "normGradPStart", "normDiff", "normJxB",
+                                          "normGradP")]
+
+
+SCB_PRESSURE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                              C.POINTER(C.c_double), C.POINTER(C.c_double))
+
+
 def _scb_lib():
     global _scb_ready
     L = lib()
@@ -411,6 +430,7 @@ def _scb_lib():
                                              C.POINTER(C.c_int), vp]
         L.rsg_scb_field_device.argtypes = [vp, C.c_char_p, C.POINTER(vp), C.POINTER(C.c_longlong)]
         L.rsg_scb_set_stream.argtypes = [vp, vp]
+        L.rsg_scb_run.argtypes = [vp, C.POINTER(ScbRunParams), SCB_PRESSURE_FN, vp, C.POINTER(ScbRunResult)]
         L.rsg_scb_zsolve_begin.argtypes = [vp, d, i, i, i, i, i]
         L.rsg_scb_zsolve_half.argtypes = [vp, i]
         L.rsg_scb_zsolve_state_device.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_longlong)]
@@ -530,6 +550,39 @@ class ScbGpu:
                                            C.byref(sumdb), C.byref(diffmx), C.byref(fail), ni.ctypes.data))
         return {"nisave": nisave.value, "sumb": sumb.value, "sumdb": sumdb.value, "diffmx": diffmx.value,
                 "SORFail": fail.value, "ni": ni, "ms": self.last_ms()}
+
+    def scb_run(self, pressure_fn, ordering=SOR_COLOR4, **kw):
+        """scb_run (src/ModScbRun.f90:149-440) in one call, everything resident.  pressure_fn(xEq, yEq) ->
+        (pperEq, pparEq), all (npsi, nzeta+1) Fortran-ordered: the 2-D front end of `pressure`."""
+        p = ScbRunParams(InConAlpha=1e-6, InConPsi=1e-6, blendInitial=0.5, blendMin=0.01, blendMax=1.0, damp=0.9,
+                         decreaseConvAlpha=0.5, decreaseConvPsi=0.5, nimax=5001, theChange=4, psiChange=0, numit=200,
+                         MinSCBIterations=11, ordering=ordering, iLossCone=1, iReduceAnisotropy=0)
+        for k, v in kw.items():
+            if not hasattr(p, k):
+                raise TypeError("unknown scb_run parameter " + k)
+            setattr(p, k, v)
+        shape = (self.npsi, self.nzeta + 1)
+        err = []
+
+        def cb(user, npsi, nzetap, xe, ye, pe, pa):
+            try:
+                n = npsi * nzetap
+                x = np.ctypeslib.as_array(xe, shape=(n,)).reshape(shape, order="F")
+                y = np.ctypeslib.as_array(ye, shape=(n,)).reshape(shape, order="F")
+                a, b = pressure_fn(np.array(x, order="F"), np.array(y, order="F"))
+                np.ctypeslib.as_array(pe, shape=(n,))[:] = np.asarray(a, dtype=np.float64).ravel(order="F")
+                np.ctypeslib.as_array(pa, shape=(n,))[:] = np.asarray(b, dtype=np.float64).ravel(order="F")
+                return 0
+            except Exception as e:          # no exceptions across the C ABI
+                err.append(e)
+                return 1
+
+        res = ScbRunResult()
+        rc = self.L.rsg_scb_run(self.h, C.byref(p), SCB_PRESSURE_FN(cb), None, C.byref(res))
+        if err:
+            raise err[0]
+        _sck(rc)
+        return {n: getattr(res, n) for n, _ in ScbRunResult._fields_}
 
     # ---- multi-GPU: iterateAlpha sharded along zeta (include/ramscb_gpu.h: rsg_scb_zsolve_*) ----
     def zsolve_begin(self, tol, k0, nk, nimax=5001, theChange=4, psiChange=0):

@@ -189,3 +189,25 @@ def build_scb(nthe=101, npsi=45, nzeta=97, constTheta=0.2, xpsiin=1.75, xpsiout=
     inp.dPdAlpha = inp.dPPerdAlpha.copy(order="F")
     inp.extra.update(bnormal=bnormal, pnormal=pnormal, xzero3=xzero3)
     return inp
+
+
+def equatorial_pressure_fn(p0_nPa=2.0, aniso=0.5, xzero=6.6):
+    """The 2-D front end of `pressure` (src/ModScbRun.f90:753-1086) for the synthetic workload: instead of
+    interpolating RAM's PPerT/PParT to the equatorial foot points, evaluate SURVEY 8(d)'s analytic profile
+    there.  Returns f(xEq, yEq) -> (pperEq, pparEq), normalised by pnormal, (npsi, nzeta+1), with the
+    split of the equatorial pressure into p_perp / p_par used by build_scb."""
+    bnormal = 0.31 / xzero ** 3 * 1.0e5
+    pnormal = bnormal * bnormal / (4.0 * PI * 1.0e-7) * 1.0e-9
+
+    def fn(xEq, yEq):
+        req = np.sqrt(xEq ** 2 + yEq ** 2)
+        phi = np.arctan2(yEq, xEq)
+        pEq = (p0_nPa / pnormal) * (req / 4.0) ** -3.5 * np.exp(-((req - 4.0) ** 2) / 4.0) * (1.0 + 0.3 * np.cos(phi))
+        ppar = pEq / (1.0 + 2.0 * aniso / 3.0)
+        pper = pEq * (aniso + 1.0) / (1.0 + 2.0 * aniso / 3.0)
+        for v in (pper, ppar):                       # periodic columns (k = 1 <- nzeta, nzeta+1 <- 2)
+            v[:, 0] = v[:, -2]
+            v[:, -1] = v[:, 1]
+        return np.asfortranarray(pper), np.asfortranarray(ppar)
+
+    return fn

@@ -588,6 +588,7 @@ def test_fortran_shims_match_the_c_header():
     import glob
     import re
     protos = _c_prototypes()
+    hdr_nc = re.sub(r"/\*.*?\*/", " ", open(os.path.join(ROOT, "include", "ramscb_gpu.h")).read(), flags=re.S)
     assert len(protos) > 90
     from ramscb_b200 import build, host
     build.build()
@@ -619,6 +620,9 @@ def test_fortran_shims_match_the_c_header():
                 assert a.lower() in decl, f"{where}: dummy {a} is not declared"
                 spec, is_array = decl[a.lower()]
                 by_value = "value" in spec
+                if not ptr and ctype.endswith("_fn"):       # function-pointer typedef
+                    assert by_value and "type(c_funptr)" in spec, f"{where}: callback {a} must be type(c_funptr), value"
+                    continue
                 if not ptr:
                     assert by_value and not is_array, f"{where}: C scalar {ctype} {a} must be passed by value"
                     kind = {"int": "c_int", "double": "c_double", "long long": "c_long_long"}[ctype]
@@ -631,7 +635,17 @@ def test_fortran_shims_match_the_c_header():
                                 "void": "c_ptr"}.get(ctype)
                         if kind:                      # opaque handles (rsg_ram**, rsg_scb**) are type(c_ptr), intent(out)
                             assert kind in spec, f"{where}: {a} should be {kind} ({spec.strip()})"
-                        else:
+                        elif ctype in ("rsg_ram", "rsg_scb"):
                             assert "type(c_ptr)" in spec, f"{where}: handle {a}"
+                        else:                         # struct passed by reference: a bind(C) derived type of the same name
+                            assert f"type({ctype})" in spec, f"{where}: {a} should be type({ctype})"
+                            m2 = re.search(r"typedef struct " + ctype + r"\s*\{(.*?)\}", hdr_nc, flags=re.S)
+                            cmem = [(t.strip(), [x.strip() for x in names.split(",")]) for t, names in
+                                    re.findall(r"\b(int|double)\s+([^;]+);", m2.group(1))]
+                            f2 = re.search(r"type, bind\(C\) :: " + ctype + r"(.*?)end type", txt, flags=re.S | re.I)
+                            fmem = [("int" if "c_int" in l.split("::")[0] else "double", [x.strip() for x in l.split("::")[1].split(",")])
+                                    for l in f2.group(1).splitlines() if "::" in l]
+                            flat = lambda mem: [(t, n) for t, ns in mem for n in ns]
+                            assert flat(cmem) == flat(fmem), f"{where}: members of {ctype} differ"
             nbound += 1
     assert nbound >= 55, nbound

@@ -95,6 +95,13 @@ def test_emulated_scb_maps_and_geometry(emu, oracle_built):
     TS.test_pressure_anisotropic_mapping_bit_exact(oracle_built, 2, 0)
 
 
+def test_emulated_scb_run_outer_iterations(emu, oracle_built):
+    """rsg_scb_run -- the whole outer iteration of scb_run in one C call, 3-D arrays resident, pressure front
+    end as a host callback -- against the oracle's composition, incl. the SORFail restore path."""
+    import test_scb_parity_gpu as TS
+    TS.test_scb_run_outer_iterations_resident(oracle_built)
+
+
 def test_emulated_results_do_not_depend_on_thread_order():
     """Race check: EMU_ORDER=random runs the runnable threads of every block in a fresh random order
     between synchronisation points.  A kernel whose result depended on the order (a missing barrier

@@ -352,6 +352,57 @@ def test_dipole_field_is_recovered():
     assert np.median(rel) < 2e-3, np.median(rel)
 
 
+def test_scb_run_outer_iterations_resident(oracle_built):
+    """scb_run (src/ModScbRun.f90:149-440) in ONE C call with every 3-D array resident (rsg_scb_run; only the
+    2-D pressure front end is a host callback) against the same loop composed from the oracle's routines:
+    with RSG_SOR_LEX the iteration counts, blends, residuals and x, y, z, alfa, psi are BIT-IDENTICAL; the
+    norms of Compute_convergence agree to 1e-12 (tree vs serial sums).  A second run with the production
+    4-colour ordering must take the same number of outer iterations and land within 1e-6 of the same points
+    (each SOR solve stops at InCon = 1e-6; the orderings share the fixed point, not the iterates)."""
+    from ramscb_b200 import host
+    inp, o, gpu = _pair(oracle_built, **SMALL)
+    fn = S.equatorial_pressure_fn()
+    kw = dict(numit=3, MinSCBIterations=2, decreaseConvAlpha=1e-30, decreaseConvPsi=1e-30)     # exactly 3 outer iterations
+    gpu.set_map_targets(inp.alphaVal, inp.psiVal, inp.chiVal)
+    ro = o.scb_run(fn, **kw)
+    rg = gpu.scb_run(fn, ordering=host.SOR_LEX, **kw)
+    assert ro["SORFail"] == 0 and rg["SORFail"] == 0
+    assert rg["iterations"] == ro["iterations"] == 3
+    for k in ("blendAlpha", "blendPsi", "errorAlpha", "errorPsi", "nisaveAlpha", "nisavePsi", "blendRetries"):
+        assert rg[k] == ro[k], (k, rg[k], ro[k])
+    for k in ("sumdbAlpha", "sumdbPsi"):                       # tree sum vs serial sum
+        assert abs(rg[k] - ro[k]) <= 1e-12 * abs(ro[k]), (k, rg[k], ro[k])
+    _same(gpu, o, ("x", "y", "z", "alfa", "psi", "jacobian", "bsq", "pper", "sigma"))
+    for a, b in zip((rg["normDiff"], rg["normJxB"], rg["normGradP"]), ro["norm"]):
+        assert abs(a - b) <= 1e-12 * abs(b)
+    for a, b in zip((rg["normDiffStart"], rg["normJxBStart"], rg["normGradPStart"]), ro["normStart"]):
+        assert abs(a - b) <= 1e-12 * abs(b)
+    # production ordering from the same start
+    g2 = host.ScbGpu(inp)
+    g2.set_map_targets(inp.alphaVal, inp.psiVal, inp.chiVal)
+    r2 = g2.scb_run(fn, ordering=host.SOR_COLOR4, **kw)
+    assert r2["SORFail"] == 0 and r2["iterations"] == 3
+    for n in ("x", "y", "z"):
+        a, b = g2.get_field(n), getattr(o, n)
+        assert np.max(np.abs(a - b)) <= 1e-6 * np.max(np.abs(b)), (n, np.max(np.abs(a - b)))
+    # failure path: a callback that reports failure aborts the call; one that returns NaN pressures makes the
+    # solve fail (SORFail) and x, y, z, alfa, psi come back as they were at entry (:397-413)
+    g3 = host.ScbGpu(inp)
+    g3.set_map_targets(inp.alphaVal, inp.psiVal, inp.chiVal)
+    with pytest.raises(ZeroDivisionError):
+        g3.scb_run(lambda xe, ye: 1 / 0, **kw)
+
+    def bad(xe, ye):
+        a, b = fn(xe, ye)
+        a[3, 5] = np.nan
+        return a, b
+
+    r3 = g3.scb_run(bad, ordering=host.SOR_LEX, **kw)
+    assert r3["SORFail"] == 1
+    for n in ("x", "y", "z", "alfa", "psi"):
+        assert np.array_equal(g3.get_field(n), getattr(inp, n)), n
+
+
 @pytest.mark.parametrize("slabs", [1, 3])
 def test_zeta_sharded_alpha_slabs_on_one_device(slabs):
     """SURVEY 8(e), iterateAlpha sharded along zeta (rsg_scb_zsolve_*): the ranks' kernels and the halo /
