@@ -285,7 +285,7 @@ def time_ram_step(workload_name, flags, steps, warmup, device):
     gpu.profile(False)
     cells = g.nS * g.NR * g.NT * g.NE * g.NPA
     ops = OPS_PER_STEP + 2.0 * nw / g.nS
-    out = {"workload": desc, "flags": flags, "ms_per_step": ms, "value": ops * cells / (ms * 1e-3), "unit": "cell-updates/s",
+    out = {"workload": desc, "flags": flags, "ms_per_step": ms, "value": ops * cells / (max(ms, 1e-9) * 1e-3), "unit": "cell-updates/s",
            "ops_per_cell_per_step": ops, "launches_per_step": launches, "steps": steps, "warmup": warmup,
            "per_kernel_ms": {k: v[0] / v[1] for k, v in stages.items() if v[1] and k != "end"}}
     gpu.close()
