@@ -142,6 +142,12 @@ int rsg_atmol(rsg_ram* h, int S);              /* :485-507 */
  * PARA_FLC, which stays on the host -- is set per species as a contiguous (NR,NT,NE,NPA) array. */
 int rsg_ram_set_flc_coef(rsg_ram* h, int S, const double* FLC_coef);
 int rsg_flcscatter(rsg_ram* h, int S, double DTs, double T, double Dt_bc, long long* nviolation);
+/* PARA_FLC(S) :342-455 on the device: builds the species' FLC_coef from r_curvEq, zeta1Eq, zeta2Eq (NR,NT) --
+ * the 2-D output of FLC_Radius (:176-340; host: SCB geometry + 2-D interpolation) -- with BNES, BOUNHS of
+ * rsg_ram_set_fields; replaces rsg_ram_set_flc_coef's (NR,NT,NE,NPA) upload per species.  The caller keeps the
+ * reference's "every Dt_bc" gate (:371).  rsg_ram_get_flc_coef: the array as the reference holds it (diagnostics). */
+int rsg_para_flc(rsg_ram* h, int S, const double* r_curvEq, const double* zeta1Eq, const double* zeta2Eq);
+int rsg_ram_get_flc_coef(rsg_ram* h, int S, double* FLC_coef);
 /* ModRamWPI (src/ModRamWPI.f90) */
 int rsg_wavelo(rsg_ram* h, int S, double DTs);                       /* :580-636 */
 int rsg_wpadif(rsg_ram* h, int S, double DTs, long long* nviolation); /* :643-714; nviolation may be NULL */

@@ -43,7 +43,7 @@ def ram_lib():
         lib.orc_set_iarray.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
         lib.orc_set_scalar.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
         for f in ("driftpara", "driftr", "driftp", "drifte", "driftmu", "cepara", "charexchange", "atmol",
-                  "wavelo", "coulpara", "coulen", "coulmu", "sumrc", "anisch"):
+                  "wavelo", "coulpara", "coulen", "coulmu", "sumrc", "anisch", "para_flc"):
             fn = getattr(lib, "orc_" + f)
             fn.argtypes = [C.c_void_p, C.c_int]
             fn.restype = None
@@ -95,6 +95,8 @@ class RamOracle:
         self._set("ATLOS", _f((nS, NR, NE)))
         for name in ("ATAW", "ATAC", "ATAW_emic_h", "ATAW_emic_he", "FLC_coef"):
             self._set(name, _f((NR, NT, NE, NPA)))
+        for name in ("r_curvEq", "zeta1Eq", "zeta2Eq"):          # outputs of FLC_Radius, inputs of PARA_FLC
+            self._set(name, _f((NR, NT)))
         for name in ("COULE", "COULI", "ATA", "GTA", "CEDR", "CIDR"):
             self._set(name, _f((nS, NE, NPA)))
         for name in ("DtDriftR", "DtDriftP", "DtDriftE", "DtDriftMu", "SETRC", "ELORC", "LSDR", "LSCHA", "LSATM",

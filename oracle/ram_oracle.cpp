@@ -635,6 +635,62 @@ long flcscatter(Orc* o, int S) {
 }
 
 // -----------------------------------------------------------------------------
+// PARA_FLC  src/ModRamLoss.f90:342-455: the field-line-curvature pitch-angle diffusion
+// coefficient FLC_coef(S,I,J,K,L) (Young 2002/2008, Ebihara 2011 fits) from the equatorial
+// curvature radius and its zeta parameters r_curvEq, zeta1Eq, zeta2Eq (NR,NT) -- the
+// output of FLC_Radius (:176-340) -- and BNES, BOUNHS.  Integer powers as the compiler
+// evaluates them (x**(-n) = 1/(x*...*x)); everything else left to right.
+void para_flc(Orc* o, int S) {
+  DIMS
+  const double Q = 1.602E-19, REarth = 6.4 * 1.E6;     // ModRamConst.f90:19, ModScbMain.f90:15
+  const double *MU = o->D("MU"), *WMU = o->D("WMU"), *BOUNHS = o->D("BOUNHS"), *BNES = o->D("BNES"), *RMAS = o->D("RMAS"),
+               *LZ = o->D("LZ"), *V = o->D("V"), *rc = o->D("r_curvEq"), *z1 = o->D("zeta1Eq"), *z2 = o->D("zeta2Eq");
+  double* FLC = o->D("FLC_coef");
+  for (size_t q = 0; q < (size_t)NR * NT * NE * NPA; ++q) FLC[q] = 0.0;
+  std::vector<double> Nfactor(NPA), tau_bounce(NPA), D(NPA), Daa(NPA);
+  for (int I = 1; I <= NR; ++I)
+    for (int J = 1; J <= NT; ++J)
+      for (int K = 1; K <= NE; ++K) {
+        double Nmin = 1.0e20;
+        int lmin = 1;
+        for (int L = 1; L <= NPA; ++L) A1(Nfactor, L) = A1(tau_bounce, L) = A1(D, L) = A1(Daa, L) = 0.0;
+        const double Vk = A2(V, nS, S, K);
+        const double r_gyro = A1(RMAS, S) * Vk / std::fabs(BNES_(I, J) * Q);
+        double epsl = r_gyro / A2(rc, NR, I, J);
+        if (epsl > 0.584) epsl = 0.584;
+        if (epsl >= 0.1) {
+          const double e1 = 1.0 / epsl, e2 = 1.0 / (epsl * epsl), e3 = 1.0 / (epsl * epsl * epsl);
+          const double a1 = -0.35533865 + 0.12800347 * e1 + 0.0017113113 * e2;
+          const double a2 = 0.23156321 + 0.15561211 * e1 - 0.001860433 * e2;
+          const double ba = -0.51057275 + 0.93651781 * e1 - 0.031690658 * e2;
+          const double ca = 1.0663037 - 1.0944973 * e1 + 0.016679378 * e2 - 0.000499 * e3;
+          const double da = -0.49667826 - 0.0081941799 * e1 + 0.0013621659 * e2;
+          const double omegaa = 1.0513540 + 0.1351358 * epsl - 0.50787555 * (epsl * epsl);
+          const double Am = std::exp(ca) * (std::pow(A2(z1, NR, I, J), a1) * std::pow(A2(z2, NR, I, J), a2) + da);
+          for (int L = 1; L <= NPA - 1; ++L) {
+            const double MUBOUN = A1(MU, L) + 0.5 * A1(WMU, L);
+            const double alph = std::acos(MUBOUN);
+            A1(Nfactor, L) = 1.0 / (std::sin(omegaa * alph) * std::pow(MUBOUN, ba));
+            A1(tau_bounce, L) = 4 * A1(LZ, I) * REarth * BOUNHS_(I, J, L) / Vk;
+            A1(D, L) = (Am * Am) / (2 * A1(tau_bounce, L));
+            if (A1(Nfactor, L) <= Nmin) {
+              Nmin = A1(Nfactor, L);
+              lmin = L;
+            }
+          }
+          for (int L = 1; L <= NPA - 1; ++L) {
+            const double MUBOUN = A1(MU, L) + 0.5 * A1(WMU, L);
+            const double alph = std::acos(MUBOUN);
+            const double sn = std::sin(omegaa * alph);
+            A1(Daa, L) = A1(D, L) * (A1(Nfactor, lmin) * A1(Nfactor, lmin)) * (sn * sn) * std::pow(MUBOUN, 2 * ba) /
+                         ((1 - MUBOUN * MUBOUN) * (MUBOUN * MUBOUN));
+            A4(FLC, NR, NT, NE, I, J, K, L) = A1(Daa, L) * (1 - MUBOUN * MUBOUN) * MUBOUN * BOUNHS_(I, J, L);
+          }
+        }
+      }
+}
+
+// -----------------------------------------------------------------------------
 // COULPARA  src/ModRamCoul.f90:17-125.  The plasmasphere species table is the
 // reference's RAMSpecies(1:6) (src/ModRamSpecies.f90:42-133): mass, charge,
 // plasmasphereRatio.  NOTE the reference never resets CCE/CDE/EDRE/CCI/CDI/EDRI
@@ -959,6 +1015,7 @@ void orc_atmol(void* h, int S) { atmol((Orc*)h, S); }
 void orc_wavelo(void* h, int S) { wavelo((Orc*)h, S); }
 long orc_wpadif(void* h, int S) { return wpadif((Orc*)h, S); }
 long orc_flcscatter(void* h, int S) { return flcscatter((Orc*)h, S); }
+void orc_para_flc(void* h, int S) { para_flc((Orc*)h, S); }
 void orc_coulpara(void* h, int S) { coulpara((Orc*)h, S); }
 void orc_coulen(void* h, int S) { coulen((Orc*)h, S); }
 void orc_coulmu(void* h, int S) { coulmu((Orc*)h, S); }

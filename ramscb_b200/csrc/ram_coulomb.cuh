@@ -100,3 +100,61 @@ __global__ void k_coulmu(const __grid_constant__ RamDev d, SpecDev sp, const dou
     put(L, f);
   }
 }
+
+
+// =============================================================================
+// PARA_FLC (src/ModRamLoss.f90:342-455): field-line-curvature pitch-angle diffusion coefficient
+// FLC_coef of one species, built on the device from the equatorial curvature radius and zeta
+// parameters (NR,NT; the 2-D output of FLC_Radius) -- the species' (NR,NT,NE,NPA) array no longer
+// crosses the bus.  One thread per (plane position, energy); the two pitch-angle loops of the
+// reference run in the thread (D(l) is recomputed in the second one with the same operations).
+// in: tab = [r_curvEq(P) | zeta1Eq(P) | zeta2Eq(P) | V(S,1:NE) | LZ(1:NR)], out: flc [l][k][Pp]
+// (zero-filled by the caller: L = NPA and the lines with epsilon < 0.1 stay 0).
+// =============================================================================
+__global__ void __launch_bounds__(128) k_para_flc(const __grid_constant__ RamDev d, const double* __restrict__ tab, double rmas,
+                                                  double* __restrict__ flc) {
+  const int P = d.P, NE = d.NE, NPA = d.NPA, NR = d.NR;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= P * NE) return;
+  const int k = q / P, p = q - k * P;
+  const int j = p / NR, i = p - j * NR;
+  const double Q = 1.602E-19, REarth = 6.4 * 1.E6;
+  const double Vk = tab[3 * P + k], LZi = tab[3 * P + NE + i];
+  const size_t f2 = (size_t)i + (size_t)d.NR1 * j;                    // (NR+1,NT) raw field index
+  const double r_gyro = rmas * Vk / fabs(d.BNES[f2] * Q);
+  double epsl = r_gyro / tab[p];
+  if (epsl > 0.584) epsl = 0.584;
+  if (!(epsl >= 0.1)) return;
+  const double e1 = 1.0 / epsl, e2 = 1.0 / (epsl * epsl), e3 = 1.0 / (epsl * epsl * epsl);
+  const double a1 = -0.35533865 + 0.12800347 * e1 + 0.0017113113 * e2;
+  const double a2 = 0.23156321 + 0.15561211 * e1 - 0.001860433 * e2;
+  const double ba = -0.51057275 + 0.93651781 * e1 - 0.031690658 * e2;
+  const double ca = 1.0663037 - 1.0944973 * e1 + 0.016679378 * e2 - 0.000499 * e3;
+  const double da = -0.49667826 - 0.0081941799 * e1 + 0.0013621659 * e2;
+  const double omegaa = 1.0513540 + 0.1351358 * epsl - 0.50787555 * (epsl * epsl);
+  const double Am = exp(ca) * (pow(tab[P + p], a1) * pow(tab[2 * P + p], a2) + da);
+  const size_t n2 = (size_t)d.NR1 * d.NT;
+  double Nmin = 1.0e20, nf1 = 0.0;
+  int lmin = 0;
+  for (int l = 0; l < NPA - 1; ++l) {
+    const double MUBOUN = d.MU[l] + 0.5 * d.WMU[l];
+    const double alph = acos(MUBOUN);
+    const double nf = 1.0 / (sin(omegaa * alph) * pow(MUBOUN, ba));
+    if (l == 0) nf1 = nf;
+    if (nf <= Nmin) {
+      Nmin = nf;
+      lmin = l;
+    }
+  }
+  const double nfm = lmin == 0 ? nf1 : Nmin;                           // Nfactor(lmin), also when no comparison held (NaN)
+  for (int l = 0; l < NPA - 1; ++l) {
+    const double MUBOUN = d.MU[l] + 0.5 * d.WMU[l];
+    const double alph = acos(MUBOUN);
+    const double bh = d.BOUNHS[f2 + n2 * l];
+    const double tau_bounce = 4 * LZi * REarth * bh / Vk;
+    const double D = (Am * Am) / (2 * tau_bounce);
+    const double sn = sin(omegaa * alph);
+    const double Daa = D * (nfm * nfm) * (sn * sn) * pow(MUBOUN, 2 * ba) / ((1 - MUBOUN * MUBOUN) * (MUBOUN * MUBOUN));
+    flc[((size_t)l * NE + k) * d.Pp + p] = Daa * (1 - MUBOUN * MUBOUN) * MUBOUN * bh;
+  }
+}

@@ -101,6 +101,7 @@ struct rsg_ram {
   double* d_stage = nullptr;  // host-layout image of F2 (nS*P*NE*NPA)
   double* d_diff[4] = {nullptr, nullptr, nullptr, nullptr};
   double* d_zero4 = nullptr;  // all-zero diffusion coefficient
+  double* d_flctab = nullptr; // PARA_FLC inputs: r_curvEq, zeta1Eq, zeta2Eq (P each), V(S,:), LZ
   double* d_NECR = nullptr;
   double* d_dtinit = nullptr;
   int* d_outlist = nullptr;   // plane indices p of flagged (outsideMGNP) cells with 2 <= J <= NT-1
@@ -1235,6 +1236,50 @@ int rsg_ram_set_flc_coef(rsg_ram* h, int S, const double* D) {
   std::vector<double> b;
   to_planes4(h, D, b);
   RET(up(sp.d_flc, b.data(), b.size()));
+  return RSG_OK;
+}
+
+// PARA_FLC(S) (src/ModRamLoss.f90:342-455) on the device: r_curvEq, zeta1Eq, zeta2Eq are the (NR,NT)
+// outputs of FLC_Radius (host: SCB geometry + 2-D interpolation, once per Dt_bc); the species'
+// FLC_coef is built where FLCscatter reads it.  The caller keeps the reference's "every Dt_bc" gate (:371).
+int rsg_para_flc(rsg_ram* h, int S, const double* r_curvEq, const double* zeta1Eq, const double* zeta2Eq) {
+  RET(check_S(h, S));
+  if (!r_curvEq || !zeta1Eq || !zeta2Eq) return fail(RSG_ERR_ARG, "null argument");
+  if (!h->grids_set || !h->fields_set) return fail(RSG_ERR_STATE, "PARA_FLC before set_grids / set_fields");
+  CK(cudaSetDevice(h->device));
+  RET(rsg_ram_sync(h));
+  const int s = S - 1, P = h->P, NE = h->NE, NR = h->NR;
+  Spec& sp = h->sp[s];
+  if (!sp.d_flc) RET(h->dalloc(&sp.d_flc, h->specStride));
+  if (!h->d_flctab) RET(h->dalloc(&h->d_flctab, (size_t)3 * P + NE + NR));
+  std::vector<double> tab((size_t)3 * P + NE + NR);
+  std::memcpy(&tab[0], r_curvEq, sizeof(double) * P);
+  std::memcpy(&tab[P], zeta1Eq, sizeof(double) * P);
+  std::memcpy(&tab[2 * (size_t)P], zeta2Eq, sizeof(double) * P);
+  for (int k = 0; k < NE; ++k) tab[3 * (size_t)P + k] = h->V[s + (size_t)h->nS * k];
+  for (int i = 0; i < NR; ++i) tab[3 * (size_t)P + NE + i] = h->LZ[i];
+  RET(up(h->d_flctab, tab.data(), tab.size()));
+  cudaStream_t st = h->st(s);
+  CK(cudaMemsetAsync(sp.d_flc, 0, sizeof(double) * h->specStride, st));
+  k_para_flc<<<nblk((long long)P * NE, 128), 128, 0, st>>>(h->dev, h->d_flctab, h->RMAS[s], sp.d_flc);
+  CKL();
+  h->launches++;
+  CK(cudaStreamSynchronize(st));
+  return RSG_OK;
+}
+// the species' FLC_coef as the reference holds it: contiguous (NR,NT,NE,NPA) (diagnostics / tests)
+int rsg_ram_get_flc_coef(rsg_ram* h, int S, double* D) {
+  RET(check_S(h, S));
+  if (!D) return fail(RSG_ERR_ARG, "null argument");
+  Spec& sp = h->sp[S - 1];
+  if (!sp.d_flc) return fail(RSG_ERR_STATE, "no FLC_coef on the device");
+  CK(cudaSetDevice(h->device));
+  RET(rsg_ram_sync(h));
+  std::vector<double> b(h->specStride);
+  CK(cudaMemcpy(b.data(), sp.d_flc, sizeof(double) * h->specStride, cudaMemcpyDeviceToHost));
+  for (int l = 0; l < h->NPA; ++l)
+    for (int k = 0; k < h->NE; ++k)
+      std::memcpy(&D[((size_t)l * h->NE + k) * h->P], &b[((size_t)l * h->NE + k) * h->Pp], sizeof(double) * h->P);
   return RSG_OK;
 }
 

@@ -222,6 +222,13 @@ module ModRamGpu
        real(c_double), intent(in) :: FLC_coef(*)     ! contiguous copy of FLC_coef(S,:,:,:,:)
        integer(c_int) :: ierr
      end function
+     function rsg_para_flc(h, S, r_curvEq, zeta1Eq, zeta2Eq) bind(C, name='rsg_para_flc') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       integer(c_int), value :: S
+       real(c_double), intent(in) :: r_curvEq(*), zeta1Eq(*), zeta2Eq(*)
+       integer(c_int) :: ierr
+     end function
      function rsg_flcscatter(h, S, DTs, T, Dt_bc, nviolation) bind(C, name='rsg_flcscatter') result(ierr)
        import :: c_ptr, c_int, c_double, c_long_long
        type(c_ptr), value :: h

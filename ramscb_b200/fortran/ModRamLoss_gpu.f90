@@ -4,10 +4,10 @@
 ! FLCscatter(S)); the bodies call the C ABI (include/ramscb_gpu.h).  ram_run
 ! (src/ModRamRun.f90:67-183) compiles against it unchanged.
 !
-! FLC_Radius (src/ModRamLoss.f90:176-340) and PARA_FLC(S) (:342-455) are NOT on the
-! device: they build FLC_coef from the SCB field-line geometry once per SCB call.
-! Keep their reference text in this module unchanged (marked below); PARA_FLC only
-! gains one line at its end that hands the species' coefficients to the library.
+! FLC_Radius (src/ModRamLoss.f90:176-340) is NOT on the device: it derives the (NR,NT)
+! curvature radius and zeta parameters from the SCB field-line geometry with 2-D
+! interpolation once per Dt_bc.  Keep its reference text in this module unchanged
+! (marked below).  PARA_FLC(S) (:342-455) builds FLC_coef on the device from them.
 !
 ! Shipped uncompiled (no Fortran compiler in the build container): see the note in
 ! ModRamGpu.f90.  The C entry points bound here are exercised with the same
@@ -33,21 +33,16 @@ contains
 
   ! --- keep src/ModRamLoss.f90:176-340 (subroutine FLC_Radius) here, unchanged ---
 
-  ! --- keep src/ModRamLoss.f90:342-455 (subroutine PARA_FLC(S)) here and add, before its
-  !     END SUBROUTINE:
-  !        call rsg_flc_upload(S)
-
-  subroutine rsg_flc_upload(S)
-    ! FLC_coef(S,:,:,:,:) is strided (S is the fastest index): hand a contiguous copy over
-    use ModRamGrids,     ONLY: NR, NT, NE, NPA
-    use ModRamVariables, ONLY: FLC_coef
+  subroutine PARA_FLC(S)
+    ! src/ModRamLoss.f90:342-455 on the device: FLC_coef of species S is built from the (NR,NT) outputs of
+    ! FLC_Radius where FLCscatter reads it; the host array FLC_coef is no longer filled (the optional
+    ! DoWriteFLCDiffCoeff dump would need rsg_ram_get_flc_coef).  Same "every Dt_bc" gate as :371.
+    use ModRamTiming,    ONLY: TimeRamElapsed, Dt_bc
+    use ModRamVariables, ONLY: r_curvEq, zeta1Eq, zeta2Eq
     integer, intent(in) :: S
-    real(c_double), allocatable :: slab(:,:,:,:)
-    allocate(slab(NR, NT, NE, NPA))
-    slab = FLC_coef(S, :, :, :, :)
-    call rsg_check(rsg_ram_set_flc_coef(hRam, int(S, c_int), slab), 'PARA_FLC')
-    deallocate(slab)
-  end subroutine rsg_flc_upload
+    if (mod(int(TimeRamElapsed), int(Dt_bc)) .gt. 1e-6) return
+    call rsg_check(rsg_para_flc(hRam, int(S, c_int), r_curvEq, zeta1Eq, zeta2Eq), 'PARA_FLC')
+  end subroutine PARA_FLC
 
   SUBROUTINE CHAREXCHANGE(S)
     ! src/ModRamLoss.f90:457-478

@@ -60,6 +60,8 @@ def lib():
     L.rsg_ram_set_plasmasphere.argtypes = [vp, vp]
     L.rsg_ram_set_flc_coef.argtypes = [vp, i, vp]
     L.rsg_flcscatter.argtypes = [vp, i, d, d, d, C.POINTER(C.c_longlong)]
+    L.rsg_para_flc.argtypes = [vp, i, vp, vp, vp]
+    L.rsg_ram_get_flc_coef.argtypes = [vp, i, vp]
     L.rsg_ram_set_diffcoef.argtypes = [vp, i, vp]
     L.rsg_ram_f2_h2d.argtypes = [vp, vp, i]
     L.rsg_ram_f2_d2h.argtypes = [vp, vp, i]
@@ -230,6 +232,16 @@ class RamGpu:
     def WAVELO(self, S, DTs): _ck(self.L.rsg_wavelo(self.h, S, DTs))
     def set_flc_coef(self, S, D):
         _ck(self.L.rsg_ram_set_flc_coef(self.h, S, _p(np.asfortranarray(D, dtype=np.float64))))
+
+    def PARA_FLC(self, S, r_curvEq, zeta1Eq, zeta2Eq):
+        a = [np.asfortranarray(v, dtype=np.float64) for v in (r_curvEq, zeta1Eq, zeta2Eq)]
+        _ck(self.L.rsg_para_flc(self.h, S, _p(a[0]), _p(a[1]), _p(a[2])))
+
+    def get_flc_coef(self, S):
+        g = self.g
+        out = np.zeros((g.NR, g.NT, g.NE, g.NPA), order="F")
+        _ck(self.L.rsg_ram_get_flc_coef(self.h, S, _p(out)))
+        return out
 
     def FLCscatter(self, S, DTs, T, Dt_bc=300.0):
         nv = C.c_longlong()

@@ -573,6 +573,40 @@ def coulmu(g, inp, F, S, ATA, GTA, T):
 # ---------------------------------------------------------------------------------------
 # the species loop and epilogue of ram_run (src/ModRamRun.f90:64-222)
 # ---------------------------------------------------------------------------------------
+def para_flc(g, inp, S, r_curvEq, zeta1Eq, zeta2Eq):
+    """PARA_FLC (src/ModRamLoss.f90:342-455), whole-array numpy: FLC_coef (NR,NT,NE,NPA) of species S (1-based)."""
+    Q, REarth = 1.602E-19, 6.4 * 1.E6
+    NR, NT, NE, NPA = g.NR, g.NT, g.NE, g.NPA
+    V = g.V[S - 1][None, None, :]                                     # (1,1,NE)
+    BNES = inp.BNES[:NR, :, None]
+    rg = g.RMAS[S - 1] * V / np.abs(BNES * Q)
+    eps = np.minimum(rg / r_curvEq[:, :, None], 0.584)
+    on = eps >= 0.1
+    e = np.where(on, eps, 0.3)                                        # placeholder where the coefficient stays 0
+    e1, e2, e3 = 1.0 / e, 1.0 / (e * e), 1.0 / (e * e * e)
+    a1 = -0.35533865 + 0.12800347 * e1 + 0.0017113113 * e2
+    a2 = 0.23156321 + 0.15561211 * e1 - 0.001860433 * e2
+    ba = -0.51057275 + 0.93651781 * e1 - 0.031690658 * e2
+    ca = 1.0663037 - 1.0944973 * e1 + 0.016679378 * e2 - 0.000499 * e3
+    da = -0.49667826 - 0.0081941799 * e1 + 0.0013621659 * e2
+    om = 1.0513540 + 0.1351358 * e - 0.50787555 * (e * e)
+    Am = np.exp(ca) * (zeta1Eq[:, :, None] ** a1 * zeta2Eq[:, :, None] ** a2 + da)
+    mub = (g.MU + 0.5 * g.WMU)[:NPA - 1]                              # (NPA-1,)
+    alph = np.arccos(mub)
+    sn = np.sin(om[..., None] * alph)                                 # (NR,NT,NE,NPA-1)
+    pw = mub ** ba[..., None]
+    Nf = 1.0 / (sn * pw)
+    lmin = (Nf.shape[-1] - 1) - np.argmin(Nf[..., ::-1], axis=-1)     # `<=` keeps the LAST minimum
+    nfm = np.take_along_axis(Nf, lmin[..., None], axis=-1)
+    bh = inp.BOUNHS[:NR, :, None, :NPA - 1]
+    tau = 4 * g.LZ[:NR, None, None, None] * REarth * bh / V[..., None]
+    D = (Am * Am)[..., None] / (2 * tau)
+    Daa = D * (nfm * nfm) * (sn * sn) * mub ** (2 * ba[..., None]) / ((1 - mub * mub) * (mub * mub))
+    out = np.zeros((NR, NT, NE, NPA), order="F")
+    out[..., :NPA - 1] = np.where(on[..., None], Daa * (1 - mub * mub) * mub * bh, 0.0)
+    return out
+
+
 def ram_run(g, inp, F2, DTs, beta, gcoul, DtsMin=1.0, T=0.0, wpi=False, emic=False, coulomb=False, DAA=None):
     """One ram_run step of all species with the restatements above, in the reference's call order.
     Returns F2, DtsNext, SETRC per species, the loss increments LSDR/LSCHA/LSATM/LSWAE/LSCOE/LSCSC and

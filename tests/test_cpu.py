@@ -282,6 +282,32 @@ def test_flcscatter_matches_wpadif_with_one_coefficient(oracle_built, small):
     assert np.array_equal(a.F2, b.F2) and not np.array_equal(a.F2[0], inp.F2[0])
 
 
+@pytest.mark.parametrize("S", [1, 4])
+def test_para_flc_oracle_vs_independent_numpy(oracle_built, small, S):
+    """PARA_FLC (src/ModRamLoss.f90:342-455): the loop-nest oracle against the whole-array numpy restatement
+    (tests/independent_ram.py).  Same formulas, different evaluation of the powers (libm pow vs numpy): <= 1e-13;
+    properties: zero at L = NPA and where epsilon < 0.1, non-negative, scales as 1/tau_bounce ~ V (same epsilon)."""
+    import independent_ram as ind
+    import test_ram_parity_gpu as T
+    g, inp = small
+    o = oracle_built.RamOracle(g, inp, DTs=5.0)
+    rc, z1, z2 = T.flc_radius_inputs(g, S)
+    for n, a in (("r_curvEq", rc), ("zeta1Eq", z1), ("zeta2Eq", z2)):
+        o.set_array(n, a)
+    o.op("para_flc", S)
+    ref = o.arr["FLC_coef"].copy()
+    mine = ind.para_flc(g, inp, S, rc, z1, z2)
+    assert np.array_equal(ref == 0, mine == 0)
+    nz = ref != 0
+    assert 0.05 < nz.mean() < 0.95
+    assert np.max(np.abs(mine[nz] - ref[nz]) / np.abs(ref[nz])) <= 1e-13
+    assert (ref >= 0).all() and (ref[..., -1] == 0).all()
+    # a larger curvature radius everywhere -> smaller epsilon -> fewer (never more) scattering lines
+    o.set_array("r_curvEq", 3.0 * rc)
+    o.op("para_flc", S)
+    assert ((o.arr["FLC_coef"] != 0) <= nz).all() and (o.arr["FLC_coef"] != 0).sum() < nz.sum()
+
+
 def test_coulomb_operators_properties(oracle_built, small):
     """COULPARA/COULEN/COULMU (src/ModRamCoul.f90): the drag coefficients are negative (energy
     loss), vanish at L = NPA (never assigned by the reference), scale linearly with DTs; without

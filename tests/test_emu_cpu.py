@@ -56,6 +56,7 @@ def test_emulated_losses_wpadif_coulomb(emu, T, small_grids, oracle_built):
     T.test_sumrc_and_anisch(small_grids, oracle_built)
     T.test_wpadif_bit_exact(small_grids, oracle_built, "chorus")
     T.test_coulomb_operators_bit_exact(small_grids, oracle_built, 1)
+    T.test_para_flc_on_device(small_grids, oracle_built, 1)
 
 
 def test_emulated_fused_equals_unfused_and_graph_replay(emu, T, small_grids):
