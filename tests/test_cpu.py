@@ -288,7 +288,7 @@ def test_para_flc_oracle_vs_independent_numpy(oracle_built, small, S):
     (tests/independent_ram.py).  Same formulas, different evaluation of the powers (libm pow vs numpy): <= 1e-13;
     properties: zero at L = NPA and where epsilon < 0.1, non-negative, scales as 1/tau_bounce ~ V (same epsilon)."""
     import independent_ram as ind
-    import test_ram_parity_gpu as T
+    import test_zz_late_additions_gpu as T
     g, inp = small
     o = oracle_built.RamOracle(g, inp, DTs=5.0)
     rc, z1, z2 = T.flc_radius_inputs(g, S)

@@ -56,7 +56,8 @@ def test_emulated_losses_wpadif_coulomb(emu, T, small_grids, oracle_built):
     T.test_sumrc_and_anisch(small_grids, oracle_built)
     T.test_wpadif_bit_exact(small_grids, oracle_built, "chorus")
     T.test_coulomb_operators_bit_exact(small_grids, oracle_built, 1)
-    T.test_para_flc_on_device(small_grids, oracle_built, 1)
+    import test_zz_late_additions_gpu as TZ
+    TZ.test_para_flc_on_device(small_grids, oracle_built, 1)
 
 
 def test_emulated_fused_equals_unfused_and_graph_replay(emu, T, small_grids):
@@ -99,8 +100,8 @@ def test_emulated_scb_maps_and_geometry(emu, oracle_built):
 def test_emulated_scb_run_outer_iterations(emu, oracle_built):
     """rsg_scb_run -- the whole outer iteration of scb_run in one C call, 3-D arrays resident, pressure front
     end as a host callback -- against the oracle's composition, incl. the SORFail restore path."""
-    import test_scb_parity_gpu as TS
-    TS.test_scb_run_outer_iterations_resident(oracle_built)
+    import test_zz_late_additions_gpu as TZ
+    TZ.test_scb_run_outer_iterations_resident(oracle_built)
 
 
 def test_emulated_results_do_not_depend_on_thread_order():

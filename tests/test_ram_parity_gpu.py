@@ -186,45 +186,6 @@ def test_flcscatter_bit_exact(default_grids, oracle_built):
     assert not np.array_equal(got[S - 1], inp.F2[S - 1])
 
 
-def flc_radius_inputs(g, S=1, seed=11):
-    """Synthetic outputs of FLC_Radius (src/ModRamLoss.f90:176-340): curvature radius of the order of the gyroradius
-    of the hot tail (epsilon spans < 0.1, the fitted range and the 0.584 clamp) and zeta parameters of O(1)."""
-    rng = np.random.default_rng(seed)
-    rc = np.asfortranarray(6.4e6 * (0.02 + 0.5 * rng.random((g.NR, g.NT))) * (g.LZ[:g.NR, None] / 6.5) ** 2
-                           * np.sqrt(g.RMAS[S - 1] / g.RMAS[0]))       # gyroradius at fixed energy ~ sqrt(mass)
-    z1 = np.asfortranarray(2.0 + 3.0 * rng.random((g.NR, g.NT)))
-    z2 = np.asfortranarray(2.0 + 3.0 * rng.random((g.NR, g.NT)))
-    return rc, z1, z2
-
-
-@pytest.mark.parametrize("S", [1, 2, 4])
-def test_para_flc_on_device(default_grids, oracle_built, S):
-    """PARA_FLC (src/ModRamLoss.f90:342-455) on the device from the (NR,NT) outputs of FLC_Radius: FLC_coef within
-    1e-12 relative of the oracle (exp / pow / sin / acos of the device library vs libm), zero pattern identical
-    (epsilon < 0.1, L = NPA); then FLCscatter with the device-built coefficient against the oracle chain."""
-    g = default_grids
-    inp = _mk(g, f2_kind="noisy")
-    o, gpu = _pair(g, inp, oracle_built)
-    rc, z1, z2 = flc_radius_inputs(g, S)
-    for n, a in (("r_curvEq", rc), ("zeta1Eq", z1), ("zeta2Eq", z2)):
-        o.set_array(n, a)
-    o.op("para_flc", S)
-    gpu.PARA_FLC(S, rc, z1, z2)
-    ref, got = o.arr["FLC_coef"], gpu.get_flc_coef(S)
-    assert np.isfinite(ref).all() and (ref >= 0).all() and (ref[..., -1] == 0).all()
-    assert np.array_equal(got == 0, ref == 0)
-    nz = ref != 0
-    assert 0.05 < nz.mean() < 0.95                                   # both branches of the epsilon gate are exercised
-    assert np.max(np.abs(got[nz] - ref[nz]) / np.abs(ref[nz])) <= 1e-12
-    o.set_scalar("T", 900.0)
-    nv_ref = o.op("flcscatter", S)
-    nv = gpu.FLCscatter(S, DTS, 900.0)
-    a, b = gpu.f2_d2h()[S - 1], o.F2[S - 1]
-    scale = np.maximum(np.max(np.abs(b), axis=3, keepdims=True), 1e-300)      # per pitch-angle line: the solve couples all L
-    assert np.max(np.abs(a - b) / scale) <= 1e-11, _relerr(a, b)
-    assert nv == nv_ref
-
-
 @pytest.mark.parametrize("S", [1, 2, 4])
 def test_coulomb_operators_bit_exact(default_grids, oracle_built, S):
     """COULPARA tables + COULEN (energy drag) + COULMU (pitch-angle scattering),

@@ -352,119 +352,6 @@ def test_dipole_field_is_recovered():
     assert np.median(rel) < 2e-3, np.median(rel)
 
 
-def test_scb_run_outer_iterations_resident(oracle_built):
-    """scb_run (src/ModScbRun.f90:149-440) in ONE C call with every 3-D array resident (rsg_scb_run; only the
-    2-D pressure front end is a host callback) against the same loop composed from the oracle's routines:
-    with RSG_SOR_LEX the iteration counts, blends, residuals and x, y, z, alfa, psi are BIT-IDENTICAL; the
-    norms of Compute_convergence agree to 1e-12 (tree vs serial sums).  A second run with the production
-    4-colour ordering must take the same number of outer iterations and land within 1e-6 of the same points
-    (each SOR solve stops at InCon = 1e-6; the orderings share the fixed point, not the iterates)."""
-    from ramscb_b200 import host
-    inp, o, gpu = _pair(oracle_built, **SMALL)
-    fn = S.equatorial_pressure_fn()
-    kw = dict(numit=3, MinSCBIterations=2, decreaseConvAlpha=1e-30, decreaseConvPsi=1e-30)     # exactly 3 outer iterations
-    gpu.set_map_targets(inp.alphaVal, inp.psiVal, inp.chiVal)
-    ro = o.scb_run(fn, **kw)
-    rg = gpu.scb_run(fn, ordering=host.SOR_LEX, **kw)
-    assert ro["SORFail"] == 0 and rg["SORFail"] == 0
-    assert rg["iterations"] == ro["iterations"] == 3
-    for k in ("blendAlpha", "blendPsi", "errorAlpha", "errorPsi", "nisaveAlpha", "nisavePsi", "blendRetries"):
-        assert rg[k] == ro[k], (k, rg[k], ro[k])
-    for k in ("sumdbAlpha", "sumdbPsi"):                       # tree sum vs serial sum
-        assert abs(rg[k] - ro[k]) <= 1e-12 * abs(ro[k]), (k, rg[k], ro[k])
-    _same(gpu, o, ("x", "y", "z", "alfa", "psi", "jacobian", "bsq", "pper", "sigma"))
-    for a, b in zip((rg["normDiff"], rg["normJxB"], rg["normGradP"]), ro["norm"]):
-        assert abs(a - b) <= 1e-12 * abs(b)
-    for a, b in zip((rg["normDiffStart"], rg["normJxBStart"], rg["normGradPStart"]), ro["normStart"]):
-        assert abs(a - b) <= 1e-12 * abs(b)
-    # production ordering from the same start
-    g2 = host.ScbGpu(inp)
-    g2.set_map_targets(inp.alphaVal, inp.psiVal, inp.chiVal)
-    r2 = g2.scb_run(fn, ordering=host.SOR_COLOR4, **kw)
-    assert r2["SORFail"] == 0 and r2["iterations"] == 3
-    for n in ("x", "y", "z"):
-        a, b = g2.get_field(n), getattr(o, n)
-        assert np.max(np.abs(a - b)) <= 1e-6 * np.max(np.abs(b)), (n, np.max(np.abs(a - b)))
-    # failure path: a callback that reports failure aborts the call; one that returns NaN pressures makes the
-    # solve fail (SORFail) and x, y, z, alfa, psi come back as they were at entry (:397-413)
-    g3 = host.ScbGpu(inp)
-    g3.set_map_targets(inp.alphaVal, inp.psiVal, inp.chiVal)
-    with pytest.raises(ZeroDivisionError):
-        g3.scb_run(lambda xe, ye: 1 / 0, **kw)
-
-    def bad(xe, ye):
-        a, b = fn(xe, ye)
-        a[3, 5] = np.nan
-        return a, b
-
-    r3 = g3.scb_run(bad, ordering=host.SOR_LEX, **kw)
-    assert r3["SORFail"] == 1
-    for n in ("x", "y", "z", "alfa", "psi"):
-        assert np.array_equal(g3.get_field(n), getattr(inp, n)), n
-
-
-@pytest.mark.parametrize("slabs", [1, 3])
-def test_zeta_sharded_alpha_slabs_on_one_device(slabs):
-    """SURVEY 8(e), iterateAlpha sharded along zeta (rsg_scb_zsolve_*): the ranks' kernels and the halo /
-    all-reduce protocol of parallel.ScbZetaSharded, stepped in lock-step for `slabs` handles that share
-    ONE device (plane copies and the MAX of the state vectors done with torch on the library's memory).
-    alfa, ni, diffmx, sumb, sumdb bit-identical to the one-GPU RSG_SOR_COLOR4 solve.  The same protocol
-    over a process group: tests/test_parallel_cpu.py (gloo), tests/multi_gpu_scb_check.py (NCCL)."""
-    import os
-    import torch
-    from ramscb_b200 import host, parallel
-    emu = os.environ.get("RSG_EMU") == "1" or not host.LIB_PATH.endswith("libramscb_gpu.so")
-    inp = S.build_scb(nthe=51, npsi=23, nzeta=50, warp=0.3)       # 49 relaxed planes: slabs of 17 + 16 + 16
-    ref = host.ScbGpu(inp)
-    ref.computeBandJacob(); ref.metrica(); ref.newk()
-    r1 = ref.iterateAlpha(1e-7, ordering=host.SOR_COLOR4)
-    assert r1["SORFail"] == 0 and r1["nisave"] > 20
-    import contextlib
-    tst = None if emu else torch.cuda.Stream()                        # not the legacy default stream (the library's own stream does not wait for it)
-    with (contextlib.nullcontext() if emu else torch.cuda.stream(tst)):
-        gs, al, st, rng = [], [], [], []
-        for r in range(slabs):
-            g = host.ScbGpu(inp)
-            if not emu:
-                g.set_stream(tst.cuda_stream)                             # torch's copies and the kernels: one stream
-            g.computeBandJacob(); g.metrica(); g.newk()
-            k0, nk = parallel._split(inp.nzeta - 1, slabs, r)
-            g.zsolve_begin(1e-7, k0 + 1, nk)
-            ptr, n = g.field_device("alfa")
-            al.append(parallel._dev_tensor(ptr, n, not emu).view(inp.nzeta + 1, -1))
-            ptr, n = g.zsolve_state_device()
-            st.append(parallel._dev_tensor(ptr, n, not emu))
-            gs.append(g); rng.append((k0 + 1, k0 + nk))
-        for sweep in range(5001):
-            for parity in (0, 1):
-                for g in gs:
-                    g.zsolve_half(parity)
-                for r in range(slabs - 1):                                # edge planes of this parity cross the cut
-                    hi, lo = rng[r][1], rng[r + 1][0]
-                    if hi % 2 == parity:
-                        al[r + 1][hi].copy_(al[r][hi])
-                    if lo % 2 == parity:
-                        al[r][lo].copy_(al[r + 1][lo])
-            m = st[0].clone()
-            for t in st[1:]:
-                m = torch.maximum(m, t)
-            for t, g in zip(st, gs):
-                t.copy_(m)
-                g.zsolve_commit()
-            if sweep % 8 == 7 and all(g.zsolve_pending() == 0 for g in gs):
-                break
-        for r, (a, b) in enumerate(rng):                                  # "all-gather" of the relaxed planes
-            for q in range(slabs):
-                if q != r:
-                    al[q][a:b + 1].copy_(al[r][a:b + 1])
-        for g in gs:
-            res = g.iterate_finish(True)
-            assert np.array_equal(g.get_field("alfa"), ref.get_field("alfa"))
-            assert np.array_equal(res["ni"], r1["ni"]) and res["nisave"] == r1["nisave"]
-            assert res["diffmx"] == r1["diffmx"] and res["sumb"] == r1["sumb"] and res["sumdb"] == r1["sumdb"]
-            assert res["SORFail"] == 0
-
-
 def test_multi_gpu_scb_sub_problem_sharding():
     """2 GPUs: the independent sub-problems of iterateAlpha / iteratePsi split between the ranks,
     solved planes all-gathered over NCCL -- potentials, sweep counts, residual maxima and sums
