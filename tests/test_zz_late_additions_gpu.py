@@ -110,6 +110,29 @@ def test_scb_run_outer_iterations_resident(oracle_built):
         assert np.array_equal(g3.get_field(n), getattr(inp, n)), n
 
 
+@pytest.mark.parametrize("p0,outcome", [(2000.0, "retry"), (20000.0, "fail")])
+def test_scb_run_damped_retries(oracle_built, p0, outcome):
+    """The Move_points loops of scb_run (src/ModScbRun.f90:232-262, 418-440) when the re-gridded points give a
+    negative Jacobian: revert x, y, z, damp the blend, try again -- and give up (SORFail, everything restored)
+    when that does not help.  A pressure 1000x / 10000x the nominal one with blendInitial = 1 drives the psi half
+    into that path; device and oracle must take the same decisions and end bit-identical."""
+    from ramscb_b200 import host
+    inp, o, gpu = _pair(oracle_built, **SMALL)
+    fn = SCBSYN.equatorial_pressure_fn(p0_nPa=p0)
+    kw = dict(numit=2, MinSCBIterations=2, decreaseConvAlpha=1e-30, decreaseConvPsi=1e-30, blendInitial=1.0, damp=0.5)
+    gpu.set_map_targets(inp.alphaVal, inp.psiVal, inp.chiVal)
+    ro = o.scb_run(fn, **kw)
+    rg = gpu.scb_run(fn, ordering=host.SOR_LEX, **kw)
+    assert ro["blendRetries"] >= 1
+    assert ro["SORFail"] == (1 if outcome == "fail" else 0)
+    for k in ("SORFail", "iterations", "blendRetries", "blendAlpha", "blendPsi", "errorAlpha", "errorPsi"):
+        assert rg[k] == ro[k], (k, rg[k], ro[k])
+    _same(gpu, o, ("x", "y", "z", "alfa", "psi"))
+    if outcome == "fail":
+        for n in ("x", "y", "z", "alfa", "psi"):
+            assert np.array_equal(gpu.get_field(n), getattr(inp, n)), n
+
+
 @pytest.mark.parametrize("slabs", [1, 3])
 def test_zeta_sharded_alpha_slabs_on_one_device(slabs):
     """SURVEY 8(e), iterateAlpha sharded along zeta (rsg_scb_zsolve_*): the ranks' kernels and the halo /
