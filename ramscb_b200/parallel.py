@@ -191,6 +191,16 @@ def exchange_lp(p: ShardPlan, bufs, Pp: int, nblocks: int, per: int, to_columns:
         dst.copy_(recv)
 
 
+def _dev_tensor(ptr, n, on_cuda=True):
+    """torch view of library-owned memory: device memory on the GPU; with the host-CPU emulator of the
+    test-suite (tests/emu) the "device" pointer is host memory and the view is a CPU tensor."""
+    import torch
+    if on_cuda:
+        return torch.as_tensor(_DevBuf(ptr, n), device="cuda")
+    import ctypes
+    return torch.from_numpy(np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_double)), shape=(n,)))
+
+
 class _DevBuf:
     """Zero-copy view of library-owned device memory for torch (CUDA array interface)."""
 
@@ -294,16 +304,15 @@ class ScbSharded:
     complete field.  At the default grid the 43 x 4 / 96 x 2 cluster CTAs of one solve need two
     waves on one GPU and one wave on two: that is where the speed-up comes from."""
 
-    def __init__(self, gpu, dist, rank, world):
-        self.gpu, self.dist, self.rank, self.world = gpu, dist, rank, world
+    def __init__(self, gpu, dist, rank, world, on_cuda=True):
+        self.gpu, self.dist, self.rank, self.world, self.on_cuda = gpu, dist, rank, world, on_cuda
         self._fields = {}
 
     def _field(self, name):
-        import torch
         if name not in self._fields:
             ptr, n = self.gpu.field_device(name)
             g = self.gpu
-            self._fields[name] = torch.as_tensor(_DevBuf(ptr, n), device="cuda").view(g.nzeta + 1, g.npsi, g.nthe)
+            self._fields[name] = _dev_tensor(ptr, n, self.on_cuda).view(g.nzeta + 1, g.npsi, g.nthe)
         return self._fields[name]
 
     def iterate(self, alpha, tol, nimax=5001, theChange=4, psiChange=0, ordering=1):
@@ -339,24 +348,15 @@ class ScbSharded:
                     planes(r0, rn).copy_(blk.view(rn, g.npsi, g.nthe))
         res = g.iterate_finish(alpha, theChange=theChange, psiChange=psiChange)
         if self.world > 1:
-            ni = torch.as_tensor(res["ni"].astype(np.int64), device="cuda")
-            sc = torch.tensor([res["diffmx"], float(res["SORFail"])], dtype=torch.float64, device="cuda")
+            dev = "cuda" if self.on_cuda else "cpu"
+            ni = torch.as_tensor(res["ni"].astype(np.int64), device=dev)
+            sc = torch.tensor([res["diffmx"], float(res["SORFail"])], dtype=torch.float64, device=dev)
             self.dist.all_reduce(ni, op=self.dist.ReduceOp.MAX)
             self.dist.all_reduce(sc, op=self.dist.ReduceOp.MAX)
             res["ni"] = ni.cpu().numpy().astype(np.int32)
             res["nisave"] = int(res["ni"].max())
             res["diffmx"], res["SORFail"] = float(sc[0].item()), int(sc[1].item())
         return res
-
-
-def _dev_tensor(ptr, n, on_cuda=True):
-    """torch view of library-owned memory: device memory on the GPU; with the host-CPU emulator of the
-    test-suite (tests/emu) the "device" pointer is host memory and the view is a CPU tensor."""
-    import torch
-    if on_cuda:
-        return torch.as_tensor(_DevBuf(ptr, n), device="cuda")
-    import ctypes
-    return torch.from_numpy(np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_double)), shape=(n,)))
 
 
 class ScbZetaSharded:

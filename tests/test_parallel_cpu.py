@@ -144,6 +144,61 @@ def _zeta_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _subproblem_worker(rank, world, port, q):
+    """One rank of the sub-problem-sharded iterateAlpha / iteratePsi (parallel.ScbSharded) over gloo, kernels in
+    the emulator: bit-identical to the one-rank solves."""
+    import numpy as np
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import conftest
+    conftest.use_emulator()
+    from ramscb_b200 import host, scb_synthetic as S
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    inp = S.build_scb(nthe=41, npsi=14, nzeta=22, warp=0.2)       # 12 psi surfaces, 21 zeta planes: uneven splits
+    ref = host.ScbGpu(inp)
+    ref.computeBandJacob(); ref.metrica(); ref.newk()
+    ra = ref.iterateAlpha(1e-6, ordering=host.SOR_COLOR4)
+    ref.metric(); ref.newj()
+    rp = ref.iteratePsi(1e-6, ordering=host.SOR_COLOR4)
+    g = host.ScbGpu(inp)
+    sh = parallel.ScbSharded(g, dist, rank, world, on_cuda=False)
+    g.computeBandJacob(); g.metrica(); g.newk()
+    ok = True
+    for alpha, r1, fld in ((True, ra, "alfa"), (False, rp, "psi")):
+        if not alpha:
+            g.metric(); g.newj()
+        r = sh.iterate(alpha, 1e-6)
+        ok = ok and bool(np.array_equal(g.get_field(fld), ref.get_field(fld)) and np.array_equal(r["ni"], r1["ni"])
+                         and r["diffmx"] == r1["diffmx"] and r["sumb"] == r1["sumb"] and r["sumdb"] == r1["sumdb"]
+                         and r["SORFail"] == 0 and r["nisave"] == r1["nisave"])
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_scb_sub_problem_sharding_gloo_world2():
+    """SURVEY 8(e), the zero-communication alternative: psi surfaces (alpha) / zeta planes (psi) split between two
+    ranks, solved planes all-gathered over gloo -- the code path tests/multi_gpu_scb_check.py drives over NCCL."""
+    import torch.multiprocessing as mp
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+    import build_emu
+    build_emu.build()
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_subproblem_worker, args=(r, 2, port, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for pr in procs:
+        pr.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
+
+
 @pytest.mark.parametrize("world", [2, 3])
 def test_scb_zeta_sharded_alpha_gloo(world):
     """iterateAlpha sharded along zeta -- halo planes per half-sweep + residual all-reduce over
