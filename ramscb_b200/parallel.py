@@ -211,8 +211,8 @@ class _DevBuf:
 class RamSharded:
     """One rank's share of the RAM step (drop-in for ``RamGpu.ram_run`` at N > 1)."""
 
-    def __init__(self, gpu, plan: ShardPlan, dist=None):
-        self.gpu, self.p, self.dist = gpu, plan, dist
+    def __init__(self, gpu, plan: ShardPlan, dist=None, on_cuda=True):
+        self.gpu, self.p, self.dist, self.on_cuda = gpu, plan, dist, on_cuda
         self.setrc = np.zeros(gpu.g.nS)
         self._views = None
         self._agroup = None
@@ -224,7 +224,7 @@ class RamSharded:
         out = []
         for s in range(self.p.s0, self.p.s0 + self.p.ns):
             ptr, n, pp = self.gpu.f2_device(s + 1)
-            out.append(torch.as_tensor(_DevBuf(ptr, n), device="cuda"))
+            out.append(_dev_tensor(ptr, n, self.on_cuda))
         return out, pp
 
     def _result_views(self):

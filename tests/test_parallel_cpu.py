@@ -144,6 +144,72 @@ def _zeta_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _ram_worker(rank, world, port, q):
+    """One rank of the sharded RAM step (parallel.RamSharded) over gloo, kernels in the emulator, on a reduced
+    ragged grid: nS = 1 -> the two ranks share the species (pitch-angle slabs <-> energy slabs / position ranges,
+    two re-shardings per step); nS = 2 -> one species per rank, no data-path exchange.  Same checks as
+    tests/multi_gpu_check.py (the NCCL run on hardware)."""
+    import numpy as np
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import conftest
+    conftest.use_emulator()
+    from ramscb_b200 import grids, host, synthetic
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    res = []
+    for mode in (host.MODE_EXACT, host.MODE_FAST):
+        for nS in (1, 2):
+            g = grids.build_grids(nS=nS, NR=9, NT=11, NE=35)
+            inp = synthetic.make_inputs(g, f2_kind="noisy", inductive=True)
+            gpu = host.RamGpu(g, mode=mode)
+            gpu.set_inputs(inp)
+            plan = parallel.make_plan(world, rank, nS, g.NPA, g.NE)
+            sh = parallel.RamSharded(gpu, plan, dist, on_cuda=False)
+            ref = host.RamGpu(g, mode=mode)
+            ref.set_inputs(inp)
+            for dts in (5.0, 7.5):
+                out = sh.ram_run(dts)
+                r = ref.ram_run(dts)
+            mine, full = gpu.f2_d2h(), ref.f2_d2h()
+            sl, lsl = slice(plan.s0, plan.s0 + plan.ns), slice(plan.l0, plan.l0 + plan.nl)
+            same = bool(np.array_equal(mine[sl][..., lsl], full[sl][..., lsl]))
+            dt_ok = bool(np.array_equal(out["DtDrift"], r["DtDrift"]) and out["DtsNext"] == r["DtsNext"])
+            pp_ok = bool(np.allclose(out["PPERT"][:, 1:], r["PPERT"][:, 1:], rtol=1e-12, atol=0)
+                         and np.allclose(out["PPART"][:, 1:], r["PPART"][:, 1:], rtol=1e-12, atol=0))
+            res.append((mode, nS, plan.G, same, dt_ok, pp_ok))
+            gpu.close(); ref.close()
+    q.put((rank, res))
+    dist.destroy_process_group()
+
+
+def test_ram_sharded_step_gloo_world2():
+    """The whole N > 1 RAM path on CPU: RamSharded.ram_run at world_size 2 over gloo with the real kernels
+    (emulator): every rank's slab of F2 bit-identical to the one-rank step, CFL steps equal, pressures <= 1e-12."""
+    import torch.multiprocessing as mp
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+    import build_emu
+    build_emu.build()
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ram_worker, args=(r, 2, port, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = dict(q.get(timeout=900) for _ in procs)
+    for pr in procs:
+        pr.join(timeout=60)
+    for rank in (0, 1):
+        assert len(res[rank]) == 4
+        for mode, nS, G, same, dt_ok, pp_ok in res[rank]:
+            assert G == (2 if nS == 1 else 1)
+            assert same and dt_ok and pp_ok, (rank, mode, nS, G, same, dt_ok, pp_ok)
+
+
 def _subproblem_worker(rank, world, port, q):
     """One rank of the sub-problem-sharded iterateAlpha / iteratePsi (parallel.ScbSharded) over gloo, kernels in
     the emulator: bit-identical to the one-rank solves."""
