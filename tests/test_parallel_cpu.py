@@ -159,7 +159,7 @@ def _ram_worker(rank, world, port, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     res = []
-    for mode in (host.MODE_EXACT, host.MODE_FAST):
+    for mode, flags in ((host.MODE_EXACT, 0), (host.MODE_FAST, 0), (host.MODE_FAST, 4)):     # 4: EMIC pitch-angle diffusion (H+)
         for nS in (1, 2):
             g = grids.build_grids(nS=nS, NR=9, NT=11, NE=35)
             inp = synthetic.make_inputs(g, f2_kind="noisy", inductive=True)
@@ -169,9 +169,18 @@ def _ram_worker(rank, world, port, q):
             sh = parallel.RamSharded(gpu, plan, dist, on_cuda=False)
             ref = host.RamGpu(g, mode=mode)
             ref.set_inputs(inp)
+            if flags:
+                # ranks that share a species run WPADIF as its own kernel on their energy slab; one rank by default
+                # runs it inside the fused column kernel with tabulated elimination factors (<= 1e-12 apart):
+                # the bit-exact comparison is against the one-rank step with that stage unfused
+                D = synthetic.synthetic_daa(g, inp)
+                for h in (gpu, ref):
+                    h.set_diffcoef(2, D)
+                if plan.G > 1:
+                    ref.use_fused(True, wpadif=False)
             for dts in (5.0, 7.5):
-                out = sh.ram_run(dts)
-                r = ref.ram_run(dts)
+                out = sh.ram_run(dts, flags=flags)
+                r = ref.ram_run(dts, flags=flags)
             mine, full = gpu.f2_d2h(), ref.f2_d2h()
             sl, lsl = slice(plan.s0, plan.s0 + plan.ns), slice(plan.l0, plan.l0 + plan.nl)
             same = bool(np.array_equal(mine[sl][..., lsl], full[sl][..., lsl]))
@@ -204,7 +213,7 @@ def test_ram_sharded_step_gloo_world2():
     for pr in procs:
         pr.join(timeout=60)
     for rank in (0, 1):
-        assert len(res[rank]) == 4
+        assert len(res[rank]) == 6
         for mode, nS, G, same, dt_ok, pp_ok in res[rank]:
             assert G == (2 if nS == 1 else 1)
             assert same and dt_ok and pp_ok, (rank, mode, nS, G, same, dt_ok, pp_ok)
