@@ -334,7 +334,8 @@ int rsg_scb_zsolve_pending(rsg_scb* h, int* pending);
  * `pressure` is the 2-D front end of the reference's routine (src/ModScbRun.f90:753-1086, RAM pressures ->
  * equatorial points; host): it gets xEq, yEq (npsi, nzeta+1; the foot points x/y(nThetaEquator,j,k)) and
  * fills the normalised pperEq, pparEq (npsi, nzeta+1, periodic columns set); return 0, non-zero aborts.
- * Uses snapshot slots 0..2 of x, y, z, alfa, psi.  Needs set_grid, set_geometry, set_map_targets. */
+ * Anisotropic pressure (isotropy = 0, the reference's RAM-coupled mode) only.  Uses snapshot slots 0..2 of x, y,
+ * z, alfa, psi.  Needs set_grid, set_geometry, set_map_targets. */
 typedef int (*rsg_scb_pressure_fn)(void* user, int npsi, int nzetap, const double* xEq, const double* yEq, double* pperEq,
                                    double* pparEq);
 typedef struct rsg_scb_run_params {

@@ -454,6 +454,19 @@ def test_c_abi_exports_every_declared_symbol():
     assert not missing, missing
 
 
+def test_header_is_plain_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/ramscb_gpu.h must compile as C99 (no C++ or torch types in the
+    signatures) and as C++."""
+    import subprocess
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "ramscb_gpu.h"\nint main(void) { rsg_scb_run_params p; (void)p; return 0; }\n')
+    inc = os.path.join(ROOT, "include")
+    for cmd in (["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only"],
+                ["g++", "-std=c++17", "-fsyntax-only", "-x", "c++"]):
+        r = subprocess.run(cmd + ["-I", inc, str(src)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+
+
 def test_no_gpu_means_loud_failure():
     """There is no CPU fallback: without a device, creating a handle fails with RSG_ERR_CUDA."""
     from ramscb_b200 import host
