@@ -284,7 +284,7 @@ def time_ram_step(workload_name, flags, steps, warmup, device):
     stages = gpu.profile_get()
     gpu.profile(False)
     cells = g.nS * g.NR * g.NT * g.NE * g.NPA
-    ops = OPS_PER_STEP + 2.0 * nw / g.nS
+    ops = OPS_PER_STEP + 2.0 * nw / g.nS + (4.0 if flags & 2 else 0.0)     # Coulomb: COULEN + COULMU in both half steps, all species
     out = {"workload": desc, "flags": flags, "ms_per_step": ms, "value": ops * cells / (max(ms, 1e-9) * 1e-3), "unit": "cell-updates/s",
            "ops_per_cell_per_step": ops, "launches_per_step": launches, "steps": steps, "warmup": warmup,
            "per_kernel_ms": {k: v[0] / v[1] for k, v in stages.items() if v[1] and k != "end"}}
@@ -360,6 +360,7 @@ def extras_main(device):
     jobs = (("ram_default_wpi_emic", lambda: time_ram_step("default", 5, 10, 3, device)),
             ("ram_x4_configs2_wpi_emic", lambda: time_ram_step("x4", 5, 5, 3, device)),
             ("ram_x4_no_wpi", lambda: time_ram_step("x4", 0, 5, 3, device)),
+            ("ram_default_coulomb", lambda: time_ram_step("default", 2, 10, 3, device)),   # one kernel per operator (no fused Coulomb stage)
             ("scb_alpha_zeta_protocol_one_rank", lambda: scb_zeta_metrics(device)),
             ("scb_run_configs3", lambda: scb_run_metrics(device)))
     for name, fn in jobs:
