@@ -14,7 +14,9 @@ import test_ram_parity_gpu as TR          # noqa: E402
 import test_scb_parity_gpu as TS          # noqa: E402
 from ramscb_b200 import scb_synthetic as SCBSYN          # noqa: E402
 
-pytestmark = pytest.mark.gpu
+# first hardware run of these entry points: a device-side loop that never ends must end the run loudly, not hang the
+# box (pytest-timeout's thread method interrupts a blocked C call by exiting the process)
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600, method="thread")]
 
 _mk, _pair_ram, _relerr, DTS = TR._mk, TR._pair, TR._relerr, TR.DTS
 _pair, _same, SMALL = TS._pair, TS._same, TS.SMALL
