@@ -376,6 +376,20 @@ int rsg_scb_use_cluster(rsg_scb* h, int on);
 int rsg_scb_last_cluster(rsg_scb* h);
 long long rsg_scb_launch_count(rsg_scb* h);
 
+/* ---- the integral block of computehI (src/ModRamScb.f90:372-410) ---------------------
+ * Replaces, for all RAM field lines at once, the loop that computes length / r0, fixes the equatorial
+ * field, builds bfMirror and calls GSL_Integration_hI + GSL_BounceAverage (src/ModRamGSL.f90:125-200,
+ * src/RamGSL.c:479-602), then assigns I_cart, H_cart, HDens_cart (nR,nT,nPa) and bZEq_Cart (nR,nT).
+ * Inputs in the reference's shapes: chiVal(nthe), mu(nPa), xRAM / yRAM / zRAM / bRAM / density (nthe,nR,nT),
+ * outsideMGNP(nR,nT); nThetaEquator is 1-based.  HDens_cart is in/out (skipped lines keep their value).
+ * The h / I / bounce-average integrals are summed in closed form per grid segment (the integrands are built
+ * on linear tables), i.e. they are the limit the reference's cquad(1e-3) calls approximate.
+ * ms (may be NULL): device time of the kernel. */
+int rsg_hI_integrals(int device, int nthe, int nR, int nT, int nPa, int nThetaEquator, double bnormal, const double* chiVal,
+                     const double* mu, const double* xRAM, const double* yRAM, const double* zRAM, const double* bRAM,
+                     const double* density, const int* outsideMGNP, double* I_cart, double* H_cart, double* HDens_cart,
+                     double* bZEq_cart, double* ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -384,3 +384,41 @@ class ScbOracle:
             self.lib.scbo_destroy(self.h)
         except Exception:
             pass
+
+
+# ---- computehI integral block (oracle/hi_oracle.cpp) ---------------------------------------------------------
+_hi = None
+
+
+def hi_lib():
+    global _hi
+    if _hi is None:
+        _hi = _load("libhi_oracle.so")
+        _hi.hio_line.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 7
+        _hi.hio_integrals.argtypes = [C.c_int] * 5 + [C.c_double] + [C.c_void_p] * 13
+    return _hi
+
+
+def hi_line(mirror, cVal, bf, var):
+    """integrator_c + bounceaverage_c on one line; returns (mirror after the calls, yI, yH, yV)."""
+    m = np.array(mirror, dtype=np.float64)
+    c, b, v = (np.ascontiguousarray(a, dtype=np.float64) for a in (cVal, bf, var))
+    yI, yH, yV = (np.zeros(len(m)) for _ in range(3))
+    hi_lib().hio_line(len(c), len(m), m.ctypes.data, c.ctypes.data, b.ctypes.data, v.ctypes.data, yI.ctypes.data, yH.ctypes.data,
+                      yV.ctypes.data)
+    return m, yI, yH, yV
+
+
+def hi_integrals(chiVal, mu, xRAM, yRAM, zRAM, bRAM, density, outsideMGNP, nThetaEquator, bnormal, HDens_cart=None):
+    """src/ModRamScb.f90:372-410; returns I_cart, H_cart, HDens_cart, bZEq_Cart, bfMirror."""
+    nthe, nR, nT = bRAM.shape
+    nPa = len(mu)
+    f = lambda a: np.asfortranarray(a, dtype=np.float64)
+    chiVal, mu, xRAM, yRAM, zRAM, bRAM, density = (f(a) for a in (chiVal, mu, xRAM, yRAM, zRAM, bRAM, density))
+    out = np.asfortranarray(outsideMGNP, dtype=np.int32)
+    I, H, M = (_f((nR, nT, nPa)) for _ in range(3))
+    D = _f((nR, nT, nPa)) if HDens_cart is None else f(HDens_cart).copy(order="F")
+    bz = _f((nR, nT))
+    hi_lib().hio_integrals(nthe, nR, nT, nPa, int(nThetaEquator), float(bnormal), *[a.ctypes.data for a in
+                           (chiVal, mu, xRAM, yRAM, zRAM, bRAM, density, out, I, H, D, bz, M)])
+    return I, H, D, bz, M

@@ -10,6 +10,7 @@
 
 #include "../../include/ramscb_gpu.h"
 #include "scb_kernels.cuh"
+#include "hi_kernels.cuh"
 
 namespace {
 
@@ -948,6 +949,78 @@ int rsg_scb_run(rsg_scb* h, const rsg_scb_run_params* p, rsg_scb_pressure_fn pre
   SRET(scb_run_pressure(h, p, pressure, user, eq, pe, pa));
   SRET(rsg_scb_convergence(h, &out->normDiff, &out->normJxB, &out->normGradP, &f));
   return RSG_OK;
+}
+
+// computehI's integral block (src/ModRamScb.f90:372-410): I_cart, H_cart, HDens_cart, bZEq_Cart of every RAM
+// field line from the traced lines (xRAM, yRAM, zRAM, bRAM, density: (nthe,nR,nT)); HDens_cart is in/out
+// (lines with outsideMGNP != 0 keep their value, I_cart / H_cart / bZEq_Cart are zero there).
+// Stateless: buffers live for the call (the arrays are a few MB and the call runs once per SCB update).
+int rsg_hI_integrals(int device, int nthe, int nR, int nT, int nPa, int nThetaEquator, double bnormal, const double* chiVal,
+                     const double* mu, const double* xRAM, const double* yRAM, const double* zRAM, const double* bRAM,
+                     const double* density, const int* outsideMGNP, double* I_cart, double* H_cart, double* HDens_cart,
+                     double* bZEq_cart, double* ms) {
+  if (!chiVal || !mu || !xRAM || !yRAM || !zRAM || !bRAM || !density || !outsideMGNP || !I_cart || !H_cart || !HDens_cart || !bZEq_cart)
+    return sfail(RSG_ERR_ARG, "null argument");
+  if (nthe < 3 || nR < 1 || nT < 1 || nPa < 3 || nThetaEquator < 1 || nThetaEquator > nthe)
+    return sfail(RSG_ERR_ARG, "bad dimensions");
+  SCK(cudaSetDevice(device));
+  const size_t n3 = (size_t)nthe * nR * nT, nl = (size_t)nR * nT, no = nl * nPa;
+  const size_t nd = 5 * n3 + nthe + nPa + 3 * no + nl;
+  double* d = nullptr;
+  int* dout = nullptr;
+  cudaStream_t st = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  int rc = RSG_OK;
+  auto done = [&](int code, const std::string& msg) {
+    if (d) cudaFree(d);
+    if (dout) cudaFree(dout);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (st) cudaStreamDestroy(st);
+    return code == RSG_OK ? RSG_OK : sfail(code, msg);
+  };
+#define HCK(call)                                                                                  \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) return done(RSG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+  HCK(cudaStreamCreate(&st));
+  HCK(cudaEventCreate(&e0));
+  HCK(cudaEventCreate(&e1));
+  HCK(cudaMalloc(&d, nd * sizeof(double)));
+  HCK(cudaMalloc(&dout, nl * sizeof(int)));
+  HiArgs A;
+  A.nthe = nthe; A.nR = nR; A.nT = nT; A.nPa = nPa; A.nThetaEquator = nThetaEquator; A.bnormal = bnormal;
+  double* p = d;
+  auto up = [&](const double* src, size_t n) { double* q = p; p += n; cudaMemcpyAsync(q, src, n * sizeof(double), cudaMemcpyHostToDevice, st); return q; };
+  A.x = up(xRAM, n3); A.y = up(yRAM, n3); A.z = up(zRAM, n3); A.b = up(bRAM, n3); A.dens = up(density, n3);
+  A.chi = up(chiVal, nthe); A.mu = up(mu, nPa);
+  A.Icart = p; p += no;
+  A.Hcart = p; p += no;
+  A.Dcart = up(HDens_cart, no);
+  A.bzeq = p;
+  HCK(cudaMemcpyAsync(dout, outsideMGNP, nl * sizeof(int), cudaMemcpyHostToDevice, st));
+  A.outside = dout;
+  const int threads = std::min(256, ((nPa + 31) / 32) * 32);
+  const size_t smem = (size_t)(4 * nthe + 4 * nPa) * sizeof(double) + 2 * (size_t)nPa * sizeof(int);
+  if (smem > 200 * 1024) return done(RSG_ERR_UNSUPPORTED, "field line does not fit shared memory");
+  if (smem > 48 * 1024) HCK(cudaFuncSetAttribute(k_hi_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  HCK(cudaEventRecord(e0, st));
+  k_hi_lines<<<(unsigned)nl, threads, smem, st>>>(A);
+  HCK(cudaGetLastError());
+  HCK(cudaEventRecord(e1, st));
+  HCK(cudaMemcpyAsync(I_cart, A.Icart, no * sizeof(double), cudaMemcpyDeviceToHost, st));
+  HCK(cudaMemcpyAsync(H_cart, A.Hcart, no * sizeof(double), cudaMemcpyDeviceToHost, st));
+  HCK(cudaMemcpyAsync(HDens_cart, A.Dcart, no * sizeof(double), cudaMemcpyDeviceToHost, st));
+  HCK(cudaMemcpyAsync(bZEq_cart, A.bzeq, nl * sizeof(double), cudaMemcpyDeviceToHost, st));
+  HCK(cudaStreamSynchronize(st));
+  if (ms) {
+    float t = 0.f;
+    HCK(cudaEventElapsedTime(&t, e0, e1));
+    *ms = t;
+  }
+#undef HCK
+  return done(rc, "");
 }
 
 double rsg_scb_last_ms(rsg_scb* h) { return h ? h->last_ms : 0.0; }

@@ -201,6 +201,18 @@ module ModScbGpu
        real(c_double), intent(out) :: minjac
        integer(c_int) :: ierr
      end function
+     function rsg_hI_integrals(device, nthe, nR, nT, nPa, nThetaEquator, bnormal, chiVal, mu, xRAM, yRAM, zRAM, bRAM, &
+          density, outsideMGNP, I_cart, H_cart, HDens_cart, bZEq_cart, ms) bind(C, name='rsg_hI_integrals') result(ierr)
+       ! the integral block of computehI, src/ModRamScb.f90:372-410
+       import :: c_int, c_double
+       integer(c_int), value :: device, nthe, nR, nT, nPa, nThetaEquator
+       real(c_double), value :: bnormal
+       real(c_double), intent(in) :: chiVal(*), mu(*), xRAM(*), yRAM(*), zRAM(*), bRAM(*), density(*)
+       integer(c_int), intent(in) :: outsideMGNP(*)
+       real(c_double), intent(inout) :: I_cart(*), H_cart(*), HDens_cart(*), bZEq_cart(*)
+       real(c_double), intent(out) :: ms
+       integer(c_int) :: ierr
+     end function
   end interface
 
 contains
@@ -224,5 +236,20 @@ contains
     call rsg_scb_check(rsg_scb_set_field(hScb, 'psi'//c_null_char, psi), 'upload_domain')
     call rsg_scb_check(rsg_scb_set_map_targets(hScb, alphaVal, psiVal, chiVal), 'upload_domain')
   end subroutine scb_gpu_upload_domain
+
+  subroutine computehI_integrals_gpu(xRAM, yRAM, zRAM, bRAM, density, I_cart, H_cart, HDens_cart, bZEq_Cart)
+    ! replaces the "BEGIN INTEGRAl CALCULATION" loop nest of computehI (src/ModRamScb.f90:372-410): call it with the
+    ! routine's local arrays in place of the !$OMP PARALLEL DO over (i, j); the scaling / smoothing tail stays as it is
+    use ModRamGrids,     ONLY: nR, nT, nPa
+    use ModRamVariables, ONLY: MU, outsideMGNP
+    use ModScbGrids,     ONLY: nthe
+    use ModScbVariables, ONLY: chiVal, nThetaEquator, bnormal
+    real(c_double), intent(in)    :: xRAM(nthe,nR,nT), yRAM(nthe,nR,nT), zRAM(nthe,nR,nT), bRAM(nthe,nR,nT), density(nthe,nR,nT)
+    real(c_double), intent(inout) :: I_cart(nR,nT,nPa), H_cart(nR,nT,nPa), HDens_cart(nR,nT,nPa), bZEq_Cart(nR,nT)
+    real(c_double) :: ms
+    call rsg_scb_check(rsg_hI_integrals(0_c_int, int(nthe,c_int), int(nR,c_int), int(nT,c_int), int(nPa,c_int), &
+         int(nThetaEquator,c_int), bnormal, chiVal, MU, xRAM, yRAM, zRAM, bRAM, density, outsideMGNP, &
+         I_cart, H_cart, HDens_cart, bZEq_Cart, ms), 'computehI_integrals')
+  end subroutine computehI_integrals_gpu
 
 end module ModScbGpu

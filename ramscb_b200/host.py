@@ -451,6 +451,7 @@ def _scb_lib():
         L.rsg_scb_last_cluster.argtypes = [vp]
         L.rsg_scb_launch_count.argtypes = [vp]
         L.rsg_scb_launch_count.restype = ll
+        L.rsg_hI_integrals.argtypes = [i, i, i, i, i, i, d] + [vp] * 12 + [_dp]
         _scb_ready = True
     return L
 
@@ -660,3 +661,26 @@ class ScbGpu:
             self.close()
         except Exception:
             pass
+
+
+def hI_integrals(chiVal, mu, xRAM, yRAM, zRAM, bRAM, density, outsideMGNP, nThetaEquator, bnormal, HDens_cart=None, device=-1):
+    """The integral block of computehI (src/ModRamScb.f90:372-410) for all RAM field lines in one launch:
+    returns I_cart, H_cart, HDens_cart (nR,nT,nPa), bZEq_Cart (nR,nT) and the kernel's device time in ms.
+    Arrays in the reference's shapes (Fortran order): xRAM .. density (nthe,nR,nT), outsideMGNP (nR,nT)."""
+    L = _scb_lib()
+    nthe, nR, nT = bRAM.shape
+    nPa = len(mu)
+    f = lambda a: np.asfortranarray(a, dtype=np.float64)
+    chiVal, mu, xRAM, yRAM, zRAM, bRAM, density = (f(a) for a in (chiVal, mu, xRAM, yRAM, zRAM, bRAM, density))
+    out = np.asfortranarray(outsideMGNP, dtype=np.int32)
+    I = np.zeros((nR, nT, nPa), order="F")
+    H = np.zeros((nR, nT, nPa), order="F")
+    D = np.zeros((nR, nT, nPa), order="F") if HDens_cart is None else f(HDens_cart).copy(order="F")
+    bz = np.zeros((nR, nT), order="F")
+    ms = C.c_double(0.0)
+    if device < 0:
+        import torch
+        device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    _sck(L.rsg_hI_integrals(device, nthe, nR, nT, nPa, int(nThetaEquator), float(bnormal), _p(chiVal), _p(mu), _p(xRAM), _p(yRAM),
+                            _p(zRAM), _p(bRAM), _p(density), out.ctypes.data, _p(I), _p(H), _p(D), _p(bz), C.byref(ms)))
+    return I, H, D, bz, ms.value

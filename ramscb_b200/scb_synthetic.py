@@ -211,3 +211,39 @@ def equatorial_pressure_fn(p0_nPa=2.0, aniso=0.5, xzero=6.6):
         return np.asfortranarray(pper), np.asfortranarray(ppar)
 
     return fn
+
+
+def ram_field_lines(LZ, MLT, nthe=101, constTheta=0.2, wiggle=0.0, seed=3, outside_fraction=0.0):
+    """Synthetic input of computehI's integral block (src/ModRamScb.f90:372-410): nR x nT dipole field lines through the
+    RAM equatorial points (LZ(2:nR+1), MLT) sampled at the nthe nodes of chiVal = theta + constTheta sin(2 theta)
+    (src/ModScbIO.f90:167), the field strength in units of bnormal and a hydrogen density along each line -- the role
+    get_dipole_lines plays in the reference's 'DIPL' branch (:243-245).  wiggle > 0 adds a smooth perturbation of B with
+    a few local extrema per line (the mirror search of src/RamGSL.c:545-566 is written for non-monotonic B) and moves
+    the minimum off the equatorial node (the fix-up of :388-394); outside_fraction marks random lines outsideMGNP."""
+    rng = np.random.default_rng(seed)
+    LZ = np.asarray(LZ, dtype=np.float64)
+    MLT = np.asarray(MLT, dtype=np.float64)
+    nR, nT = len(LZ), len(MLT)
+    theta = np.linspace(0.0, np.pi, nthe)
+    chiVal = theta + constTheta * np.sin(2.0 * theta)
+    shape = (nthe, nR, nT)
+    x, y, z, b, dens = (np.zeros(shape, order="F") for _ in range(5))
+    for i in range(nR):
+        lam_foot = np.arccos(np.sqrt(1.0 / LZ[i]))
+        lam = lam_foot * (1.0 - 2.0 * chiVal / np.pi)                   # south foot point ... north foot point
+        r = LZ[i] * np.cos(lam) ** 2
+        bd = np.sqrt(1.0 + 3.0 * np.sin(lam) ** 2) / np.cos(lam) ** 6 / LZ[i] ** 3 * (30574.0 / 1.0)   # nT at the surface / bnormal = 1
+        for j in range(nT):
+            phi = MLT[j] * 2.0 * np.pi / 24.0 - np.pi
+            x[:, i, j] = r * np.cos(lam) * np.cos(phi)
+            y[:, i, j] = r * np.cos(lam) * np.sin(phi)
+            z[:, i, j] = r * np.sin(lam)
+            w = 1.0
+            if wiggle:
+                ph = rng.random(3) * 2.0 * np.pi
+                w = 1.0 + wiggle * (np.sin(5.0 * theta + ph[0]) + 0.5 * np.sin(11.0 * theta + ph[1]) + 0.3 * np.sin(2.0 * theta + ph[2]))
+            b[:, i, j] = bd * w
+            dens[:, i, j] = 1.0e3 * (1.0 + 0.3 * rng.random()) * (LZ[i] / r) ** 3 * (1.0 + 0.1 * np.cos(3.0 * theta))
+    outside = np.asfortranarray((rng.random((nR, nT)) < outside_fraction).astype(np.int32))
+    return dict(chiVal=chiVal, xRAM=x, yRAM=y, zRAM=z, bRAM=b, density=dens, outsideMGNP=outside,
+                nThetaEquator=nthe // 2 + 1, bnormal=1.0)

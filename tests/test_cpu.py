@@ -688,3 +688,91 @@ def test_fortran_shims_match_the_c_header():
                             assert flat(cmem) == flat(fmem), f"{where}: members of {ctype} differ"
             nbound += 1
     assert nbound >= 55, nbound
+
+
+def _hi_line_by_quadrature(mirror, cVal, bf, var, quad):
+    """integrator_c / bounceaverage_c (src/RamGSL.c:479-602) restated in Python with the LITERAL integrands
+    (f_I = sqrt(Bm - B), f_h = 1/sqrt(Bm - B), f_D = n/sqrt(Bm - B), zero where B >= Bm; B, n by linear table
+    look-up, :295-448) handed to an adaptive quadrature, as the reference hands them to cquad."""
+    nT, nPa = len(cVal), len(mirror)
+    mirror = mirror.copy()
+    B = lambda t: np.interp(t, cVal, bf)
+    V = lambda t: np.interp(t, cVal, var)
+
+    def integrals(a, b, bm):
+        pts = [c for c in cVal if a < c < b]
+        for k in range(nT - 1):                      # mirror points inside [a, b]: integrable singularities of f_h, f_D
+            if (bf[k] - bm) * (bf[k + 1] - bm) < 0.0:
+                t = cVal[k] + (bm - bf[k]) / (bf[k + 1] - bf[k]) * (cVal[k + 1] - cVal[k])
+                if a < t < b:
+                    pts.append(t)
+        fI = lambda t: 0.0 if B(t) >= bm else np.sqrt(bm - B(t))
+        fH = lambda t: 0.0 if B(t) >= bm else np.sqrt(1.0 / (bm - B(t)))
+        fD = lambda t: 0.0 if B(t) >= bm else V(t) * np.sqrt(1.0 / (bm - B(t)))
+        return [quad(f, a, b, points=sorted(pts), limit=400, epsabs=1e-9, epsrel=1e-9)[0] for f in (fI, fH, fD)]
+
+    a, b, LH, RH = np.zeros(nPa), np.zeros(nPa), np.zeros(nPa, int), np.zeros(nPa, int)
+    for L in range(1, nPa - 1):
+        for i in range(1, nT - 1):
+            if bf[i] <= mirror[L] <= bf[i - 1]:
+                a[L], LH[L] = cVal[i - 1], i - 1
+                break
+        for i in range(nT - 2, 0, -1):
+            if bf[i - 1] <= mirror[L] <= bf[i]:
+                b[L], RH[L] = cVal[i], i
+                break
+    yI, yH, yV = np.zeros(nPa), np.zeros(nPa), np.zeros(nPa)
+    yI[-1], yH[-1], yV[-1] = integrals(cVal[0], cVal[-1], mirror[-1])
+    computed = []
+    for L in range(nPa - 2, 0, -1):
+        if mirror[L] >= bf[1] or a[L] == 0:
+            a[L] = cVal[0]
+        if mirror[L] >= bf[nT - 1] or b[L] == 0:
+            b[L] = cVal[-1]
+        if a[L] <= cVal[0] or b[L] >= cVal[-1]:
+            mirror[L] = mirror[-1]
+            yI[L], yH[L], yV[L] = yI[-1], yH[-1], yV[-1]
+        elif RH[L] - LH[L] <= 4:
+            yI[L], yH[L], yV[L] = yI[L + 1], yH[L + 1], yV[L + 1]
+        else:
+            yI[L], yH[L], yV[L] = integrals(a[L], b[L], mirror[L])
+            computed.append(L)
+            if yI[L] <= 0: yI[L] = yI[L + 1]
+            if yH[L] <= 0: yH[L] = yH[L + 1]
+            if yV[L] <= 0: yV[L] = yV[L + 1]
+    yI[0], yH[0], yV[0] = 0.0, yH[1], yV[1]
+    return mirror, yI, yH, yV, computed
+
+
+@pytest.mark.parametrize("wiggle", [0.0, 0.1])
+def test_hi_oracle_vs_adaptive_quadrature(oracle_built, default_grids, wiggle):
+    """The closed-form segment sums of oracle/hi_oracle.cpp against an independent adaptive quadrature (QUADPACK
+    via scipy) of the reference's literal integrands, with the mirror search and fall-back chain restated a second
+    time in Python: the bar is cquad's own tolerance in the reference (epsrel 1e-3, src/RamGSL.c:351, :402, :455);
+    the closed forms agree with the converged quadrature far inside it."""
+    from scipy.integrate import quad
+    import warnings
+    from ramscb_b200 import scb_synthetic
+    g = default_grids
+    mu = g.MU[::3].copy()
+    mu[-1] = g.MU[-1]
+    d = scb_synthetic.ram_field_lines(g.LZ[1:g.NR + 1:9], g.MLT[:2], nthe=41, wiggle=wiggle, seed=9)
+    _, _, _, _, M = oracle_built.hi_integrals(mu=mu, **d)
+    ncomputed = 0
+    for i in range(d["bRAM"].shape[1]):
+        bf = d["bRAM"][:, i, 1].copy()
+        ke = d["nThetaEquator"] - 1
+        if abs(bf[ke] - bf.min()) > 1e-9:                                 # src/ModRamScb.f90:388-394
+            bf[ke] = 2.0 * bf.min() - bf[ke] if 2.0 * bf.min() - bf[ke] > 0.0 else bf.min() - 0.01
+        mir = np.append(bf[ke] / (1.0 - mu[:-1] ** 2), bf[-1])
+        m1, yI, yH, yV = oracle_built.hi_line(mir, d["chiVal"], bf, d["density"][:, i, 1])
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            m2, qI, qH, qV, computed = _hi_line_by_quadrature(mir, d["chiVal"], bf, d["density"][:, i, 1], quad)
+        assert np.array_equal(m1, m2) and np.array_equal(m1, M[i, 1, :])
+        for name, y, q in (("yI", yI, qI), ("yH", yH, qH), ("yD", yV, qV)):
+            rel = np.abs(y - q) / np.maximum(np.abs(q), 1e-300)
+            assert np.all(rel[1:] < 1e-3), (name, i, rel.max())          # the reference's own quadrature tolerance
+            assert np.all(rel[1:] < 1e-6), (name, i, rel.max())          # what the closed forms actually reach
+        ncomputed += len(computed)
+    assert ncomputed > 20

@@ -97,6 +97,12 @@ def test_emulated_scb_maps_and_geometry(emu, oracle_built):
     TS.test_pressure_anisotropic_mapping_bit_exact(oracle_built, 2, 0)
 
 
+@pytest.mark.parametrize("nthe,wiggle,outside", [(51, 0.0, 0.0), (51, 0.15, 0.1)])
+def test_emulated_hI_integrals(emu, default_grids, oracle_built, nthe, wiggle, outside):
+    import test_zz_late_additions_gpu as TZ
+    TZ.test_hI_integrals_on_device(default_grids, oracle_built, nthe, wiggle, outside)
+
+
 def test_emulated_scb_run_outer_iterations(emu, oracle_built):
     """rsg_scb_run -- the whole outer iteration of scb_run in one C call, 3-D arrays resident, pressure front
     end as a host callback -- against the oracle's composition, incl. the SORFail restore path."""

@@ -195,3 +195,33 @@ def test_zeta_sharded_alpha_slabs_on_one_device(slabs):
             assert np.array_equal(res["ni"], r1["ni"]) and res["nisave"] == r1["nisave"]
             assert res["diffmx"] == r1["diffmx"] and res["sumb"] == r1["sumb"] and res["sumdb"] == r1["sumdb"]
             assert res["SORFail"] == 0
+
+
+@pytest.mark.parametrize("nthe,wiggle,outside", [(101, 0.0, 0.0), (101, 0.05, 0.05), (51, 0.15, 0.1)])
+def test_hI_integrals_on_device(default_grids, oracle_built, nthe, wiggle, outside):
+    """computehI's integral block (src/ModRamScb.f90:372-410: length, r0, the equatorial-B fix-up, bfMirror,
+    GSL_Integration_hI + GSL_BounceAverage, I_cart / H_cart / HDens_cart / bZEq_Cart) through rsg_hI_integrals:
+    bit-identical to the oracle on dipole lines and on lines with non-monotonic B (mirror-search fall-backs,
+    short spans) and skipped (outsideMGNP) lines; HDens_cart keeps its value on skipped lines."""
+    from ramscb_b200 import host
+    g = default_grids
+    d = SCBSYN.ram_field_lines(g.LZ[1:g.NR + 1] if len(g.LZ) > g.NR else g.LZ, g.MLT[:g.NT], nthe=nthe, wiggle=wiggle,
+                               outside_fraction=outside, seed=5)
+    D0 = np.full((g.NR, g.NT, g.NPA), -7.0, order="F")
+    ref = oracle_built.hi_integrals(mu=g.MU, HDens_cart=D0, **d)
+    out = host.hI_integrals(mu=g.MU, HDens_cart=D0, **d)
+    for name, a, b in zip(("I_cart", "H_cart", "HDens_cart", "bZEq_Cart"), ref, out):
+        assert np.all(np.isfinite(b)), name
+        assert np.array_equal(a, b), (name, float(np.max(np.abs(a - b))))
+    I, H, D, bz = out[:4]
+    skipped = d["outsideMGNP"] != 0
+    assert np.all(D[skipped] == -7.0) and np.all(I[skipped] == 0.0) and np.all(bz[skipped] == 0.0)
+    live = ~skipped
+    assert np.all(H[live][:, 1:] > 0.0) and np.all(I[live][:, 1:] > 0.0) and np.all(D[live] > 0.0)
+    if wiggle == 0.0:
+        # dipole: h runs from 0.74 (90 deg) to 1.38 (0 deg); the pitch angles whose mirror points span <= 4 nodes copy
+        # their neighbour (src/RamGSL.c:583-587), so the first values sit a little above 0.74 (h is not monotonic in L: B is a linear table, and the
+        # reference repairs that afterwards, src/ModRamScb.f90:506-514); I grows towards the loss cone
+        assert np.all(H[:, :, 1:] > 0.74) and np.all(H < 1.39) and np.all(H[:, :, 1] < 0.9)
+        assert np.all(np.diff(I[:, :, 4:], axis=2) >= 0.0)
+    assert out[4] >= 0.0
