@@ -353,6 +353,31 @@ def scb_run_metrics(device):
     return out
 
 
+def hi_metrics(device):
+    """computehI's integral block (src/ModRamScb.f90:372-410) through rsg_hI_integrals on the field lines of the
+    default RAM grid (20 x 25 lines) and of the configs[2] grid (80 x 49), nthe = 101, NPA = 72: device time of the
+    kernel (CUDA events inside the call) and wall clock of the whole call (host arrays in and out)."""
+    from ramscb_b200 import grids, host, scb_synthetic
+    out = {}
+    for name, kw in (("default_20x25", {}), ("x4_80x49", dict(NR=80, NT=49, NE=70, energy_refine=2))):
+        g = grids.build_grids(**kw)
+        d = scb_synthetic.ram_field_lines(g.LZ[1:g.NR + 1] if len(g.LZ) > g.NR else g.LZ, g.MLT[:g.NT], nthe=101, wiggle=0.05)
+        ms, wall = [], []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            r = host.hI_integrals(mu=g.MU, device=device, **d)
+            wall.append((time.perf_counter() - t0) * 1e3)
+            ms.append(r[4])
+        lines = g.NR * g.NT
+        bytes_alg = lines * (5 * 101 + 3 * g.NPA + 1) * 8
+        k = sorted(ms)[len(ms) // 2]
+        out[name] = {"lines": lines, "nthe": 101, "NPA": g.NPA, "kernel_ms": k, "call_wall_ms": sorted(wall)[len(wall) // 2],
+                     "integrals_per_s": 3 * lines * g.NPA / (k * 1e-3) if k > 0 else None, "algorithmic_bytes": bytes_alg,
+                     "GBps": bytes_alg / (k * 1e-3) / 1e9 if k > 0 else None,
+                     "bound": "latency (one CTA per line, 500 / 3920 CTAs, serial chain over NPA): far below the HBM roofline by construction"}
+    return out
+
+
 def extras_main(device):
     """`bench.py --extras-only`: informational measurements beside the headline line (run by the N = 1 bench in a
     child process, so that nothing here can take the headline down).  One JSON object on stdout."""
@@ -362,7 +387,8 @@ def extras_main(device):
             ("ram_x4_no_wpi", lambda: time_ram_step("x4", 0, 5, 3, device)),
             ("ram_default_coulomb", lambda: time_ram_step("default", 2, 10, 3, device)),   # one kernel per operator (no fused Coulomb stage)
             ("scb_alpha_zeta_protocol_one_rank", lambda: scb_zeta_metrics(device)),
-            ("scb_run_configs3", lambda: scb_run_metrics(device)))
+            ("scb_run_configs3", lambda: scb_run_metrics(device)),
+            ("computehI_integrals", lambda: hi_metrics(device)))
     for name, fn in jobs:
         t0 = time.perf_counter()
         try:
@@ -631,6 +657,15 @@ def main():
                                           "SORFail": sr["SORFail"], "cores": os.cpu_count(), "kind": "port"}
         except Exception as e:
             line["scb"]["cpu_scb_run"] = {"error": str(e)[:200]}
+        try:        # CPU side of extras.computehI_integrals: the oracle's closed-form loop nest, one thread (the reference
+            # runs adaptive cquad there, ~50-100x more integrand evaluations per integral), default-grid lines
+            from ramscb_b200 import scb_synthetic
+            hd = scb_synthetic.ram_field_lines(g.LZ[1:g.NR + 1] if len(g.LZ) > g.NR else g.LZ, g.MLT[:g.NT], nthe=101, wiggle=0.05)
+            t0 = time.perf_counter()
+            oracle.hi_integrals(mu=g.MU, **hd)
+            line["scb"]["cpu_hI_integrals"] = {"wall_ms": (time.perf_counter() - t0) * 1e3, "lines": g.NR * g.NT, "cores": 1, "kind": "port"}
+        except Exception as e:
+            line["scb"]["cpu_hI_integrals"] = {"error": str(e)[:200]}
     if rank == 0 and world == 1 and not a.no_cpu_baseline:      # reported at N = 1 only
         v, nthreads, dt = cpu_reference(g, inp, 3 if a.workload == "default" else 1, 1)
         line["cpu_baseline"] = {"value": v, "unit": unit, "cores": nthreads, "kind": "port",
