@@ -389,6 +389,17 @@ int rsg_hI_integrals(int device, int nthe, int nR, int nT, int nPa, int nThetaEq
                      const double* mu, const double* xRAM, const double* yRAM, const double* zRAM, const double* bRAM,
                      const double* density, const int* outsideMGNP, double* I_cart, double* H_cart, double* HDens_cart,
                      double* bZEq_cart, double* ms);
+/* The rest of computehI (src/ModRamScb.f90:413-637), on the arrays rsg_hI_integrals returns: scaling at the outer SCB
+ * boundary (ScaleAt(nT): 1-based radial index of the first RAM point outside the SCB domain, 0 = none), MLT continuity,
+ * near-90-degree corrections, negative / too-large repairs, GSL_Interpolation_1D (Steffen) of h and I from PA onto PAbn,
+ * gaussian_kernel(1.0) / convolve smoothing when integral_smooth != 0 (srcExternal/gaussian_filter.f90), then the RAM
+ * variables FNHS, FNIS, BOUNHS, BOUNIS, HDNS (nR+1,nT,nPa), BNES (nR+1,nT) (in: previous values, out: new) with dIdt,
+ * dHdt, dIbndt, dBdt (DthI = TimeRamElapsed - TOld), the I = 1 row and the NaN repair.  Lz(nR+1), PA(nPa), PAbn(nPa).
+ * EIR / EIP(1,J) = 0 (:611-612) stay with the caller.  *gslerr: number of lines the interpolation failed on. */
+int rsg_hI_tail(int device, int nR, int nT, int nPa, double* I_cart, double* H_cart, double* HDens_cart, double* bZEq_cart,
+                const int* ScaleAt, const int* outsideMGNP, const double* Lz, const double* PA, const double* PAbn,
+                int integral_smooth, double DthI, double* FNHS, double* FNIS, double* BOUNHS, double* BOUNIS, double* HDNS,
+                double* BNES, double* dIdt, double* dHdt, double* dIbndt, double* dBdt, int* gslerr, double* ms);
 
 #ifdef __cplusplus
 }

@@ -422,3 +422,28 @@ def hi_integrals(chiVal, mu, xRAM, yRAM, zRAM, bRAM, density, outsideMGNP, nThet
     hi_lib().hio_integrals(nthe, nR, nT, nPa, int(nThetaEquator), float(bnormal), *[a.ctypes.data for a in
                            (chiVal, mu, xRAM, yRAM, zRAM, bRAM, density, out, I, H, D, bz, M)])
     return I, H, D, bz, M
+
+
+def hi_tail(I_cart, H_cart, HDens_cart, bZEq_cart, ScaleAt, outsideMGNP, Lz, PA, PAbn, integral_smooth, DthI, ram):
+    """src/ModRamScb.f90:413-637 (scbo_hi_tail in scb_oracle.cpp); same interface as ramscb_b200.host.hI_tail, plus the
+    interpolated h / I (h_Cart_interp, I_Cart_interp)."""
+    lib = scb_lib()
+    lib.scbo_hi_tail.argtypes = [C.c_int] * 3 + [C.c_void_p] * 9 + [C.c_int, C.c_double] + [C.c_void_p] * 12
+    nR, nT, nPa = I_cart.shape
+    f = lambda a: np.array(a, dtype=np.float64, order="F")
+    out = {"I_cart": f(I_cart), "H_cart": f(H_cart), "HDens_cart": f(HDens_cart), "bZEq_cart": f(bZEq_cart)}
+    for n in ("FNHS", "FNIS", "BOUNHS", "BOUNIS", "HDNS", "BNES"):
+        out[n] = f(ram[n])
+    for n in ("dIdt", "dHdt", "dIbndt"):
+        out[n] = _f((nR + 1, nT, nPa))
+    out["dBdt"] = _f((nR + 1, nT))
+    out["h_interp"], out["I_interp"] = _f((nR, nT, nPa)), _f((nR, nT, nPa))
+    sa = np.ascontiguousarray(ScaleAt, dtype=np.int32)
+    om = np.asfortranarray(outsideMGNP, dtype=np.int32)
+    Lz, PA, PAbn = (np.ascontiguousarray(a, dtype=np.float64) for a in (Lz, PA, PAbn))
+    ptr = lambda a: a.ctypes.data
+    out["gslerr"] = lib.scbo_hi_tail(nR, nT, nPa, ptr(out["I_cart"]), ptr(out["H_cart"]), ptr(out["HDens_cart"]), ptr(out["bZEq_cart"]),
+                                     ptr(sa), ptr(om), ptr(Lz), ptr(PA), ptr(PAbn), 1 if integral_smooth else 0, float(DthI),
+                                     *[ptr(out[n]) for n in ("FNHS", "FNIS", "BOUNHS", "BOUNIS", "HDNS", "BNES", "dIdt", "dHdt", "dIbndt",
+                                                             "dBdt", "h_interp", "I_interp")])
+    return out

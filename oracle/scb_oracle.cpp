@@ -950,3 +950,201 @@ void scbo_steffen(int n, const double* xa, const double* ya, double* dx) {
   steffen_derivs(n, xa, ya, dx, yp);
 }
 }
+
+// ---- computehI, everything after the integral block (src/ModRamScb.f90:413-632) -------------------------------
+// outer-boundary scaling (:413-470), MLT continuity (:472-476), near-90-degree corrections (:478-487), negative and
+// "too large" repairs (:489-514), Steffen interpolation of h, I onto PAbn (:516-529), Gaussian smoothing
+// (:539-563 with gaussian_kernel / convolve of srcExternal/gaussian_filter.f90:19-56, :98-187; 8-byte reals under the
+// reference's -fdefault-real-8), the RAM variables and their time derivatives (:566-606), the I = 1 row (:607-622) and the
+// NaN repair (:625-637).  EIR / EIP(1,J) = 0 (:611-612) are E-field arrays and stay with the caller.  All arrays in
+// the reference's shapes, Fortran order; ScaleAt holds 1-based radial indices (0 = line inside the SCB domain).
+namespace {
+inline size_t h3(int i, int j, int L, int n1, int n2) { return (size_t)i + (size_t)n1 * (j + (size_t)n2 * L); }   // 0-based
+
+void gaussian_kernel9(double* w) {     // sigma = 1.0, truncate 4 -> radius 4
+  const int radius = (int)(4 * 1.0 + 0.5);
+  const double s = 1.0 * 1.0;
+  double sum = 0.0;
+  for (int j = -radius; j <= radius; ++j)
+    for (int i = -radius; i <= radius; ++i) {
+      const double x = i, y = j;
+      const double v = 2.0 * std::exp(-0.5 * (x * x + y * y) / s);
+      w[(i + radius) + 9 * (j + radius)] = v;
+      sum += v;                         // SUM(kernel): array element order
+    }
+  for (int q = 0; q < 81; ++q) w[q] = w[q] / sum;
+}
+
+// convolve without mask: 3x3 reflected tiling, output(i,j) = sum(weights * overlapping) in array element order
+void convolve9(int rows, int cols, const double* in, const double* w, double* out) {
+  auto refl = [](int p, int n) { return p < 0 ? -1 - p : (p >= n ? 2 * n - 1 - p : p); };   // 0-based mirror with edge repeat
+  for (int j = 0; j < cols; ++j)
+    for (int i = 0; i < rows; ++i) {
+      double sum = 0.0;
+      for (int dj = -4; dj <= 4; ++dj)
+        for (int di = -4; di <= 4; ++di) sum += w[(di + 4) + 9 * (dj + 4)] * in[refl(i + di, rows) + (size_t)rows * refl(j + dj, cols)];
+      out[i + (size_t)rows * j] = sum;
+    }
+}
+}  // namespace
+
+extern "C" {
+void scbo_gaussian_kernel9(double* w) { gaussian_kernel9(w); }
+
+int scbo_hi_tail(int nR, int nT, int nPa, double* I_cart, double* H_cart, double* D_cart, double* bZEq, const int* ScaleAt,
+                 const int* outsideMGNP, const double* Lz, const double* PA, const double* PAbn, int integral_smooth, double DthI,
+                 double* FNHS, double* FNIS, double* BOUNHS, double* BOUNIS, double* HDNS, double* BNES, double* dIdt, double* dHdt,
+                 double* dIbndt, double* dBdt, double* h_interp_out, double* I_interp_out) {
+#define C3(a, i, j, L) a[h3((i) - 1, (j) - 1, (L) - 1, nR, nT)]
+#define R3(a, i, j, L) a[h3((i) - 1, (j) - 1, (L) - 1, nR + 1, nT)]
+#define C2(a, i, j) a[((i) - 1) + (size_t)nR * ((j) - 1)]
+#define R2(a, i, j) a[((i) - 1) + (size_t)(nR + 1) * ((j) - 1)]
+  const size_t n3 = (size_t)nR * nT * nPa;
+  std::vector<double> hI(n3, 0.0), iI(n3, 0.0);
+  double scalingI = 0, scalingH = 0, scalingD = 0;
+  for (int j = 2; j <= nT; ++j) {                                                               // :417-470
+    if (ScaleAt[j - 1] == 0) continue;
+    const int ii = ScaleAt[j - 1];
+    for (int L = 2; L <= nPa; ++L) {
+      const double fr = (Lz[ii - 1] - Lz[ii - 2]) / (Lz[ii - 3] - Lz[ii - 2]);
+      const double I_Temp = C3(I_cart, ii - 1, j, L) + fr * (C3(I_cart, ii - 2, j, L) - C3(I_cart, ii - 1, j, L));
+      scalingI = (I_Temp <= 0) ? C3(I_cart, ii - 1, j, L) / C3(I_cart, ii, j, L) : I_Temp / C3(I_cart, ii, j, L);
+      const double H_Temp = C3(H_cart, ii - 1, j, L) + fr * (C3(H_cart, ii - 2, j, L) - C3(H_cart, ii - 1, j, L));
+      scalingH = (H_Temp <= 0) ? C3(H_cart, ii - 1, j, L) / C3(H_cart, ii, j, L) : H_Temp / C3(H_cart, ii, j, L);
+      const double D_Temp = C3(D_cart, ii - 1, j, L) + fr * (C3(D_cart, ii - 2, j, L) - C3(D_cart, ii - 1, j, L));
+      scalingD = (D_Temp <= 0) ? C3(D_cart, ii - 1, j, L) / C3(D_cart, ii, j, L) : D_Temp / C3(D_cart, ii, j, L);
+      for (int i = ii; i <= nR; ++i) {
+        if (C2(outsideMGNP, i, j) == 0) {
+          C3(I_cart, i, j, L) = C3(I_cart, i, j, L) * scalingI;
+          C3(H_cart, i, j, L) = C3(H_cart, i, j, L) * scalingH;
+          C3(D_cart, i, j, L) = C3(D_cart, i, j, L) * scalingD;
+          C2(bZEq, i, j) = C2(bZEq, i - 1, j);
+        } else {
+          C3(I_cart, i, j, L) = C3(I_cart, i - 1, j, L);
+          C3(H_cart, i, j, L) = C3(H_cart, i - 1, j, L);
+          C3(D_cart, i, j, L) = C3(D_cart, i - 1, j, L);
+          C2(bZEq, i, j) = C2(bZEq, i - 1, j);
+        }
+      }
+    }
+  }
+  for (int i = 1; i <= nR; ++i) {                                                               // :472-476
+    for (int L = 1; L <= nPa; ++L) {
+      C3(I_cart, i, 1, L) = C3(I_cart, i, nT, L);
+      C3(H_cart, i, 1, L) = C3(H_cart, i, nT, L);
+      C3(D_cart, i, 1, L) = C3(D_cart, i, nT, L);
+    }
+    C2(bZEq, i, 1) = C2(bZEq, i, nT);
+  }
+  for (int j = 1; j <= nT; ++j)                                                                 // :478-487
+    for (int i = 1; i <= nR; ++i) {
+      C3(I_cart, i, j, 3) = 0.50 * C3(I_cart, i, j, 4);
+      C3(I_cart, i, j, 2) = 0.20 * C3(I_cart, i, j, 3);
+      C3(I_cart, i, j, 1) = 0.0;
+      C3(H_cart, i, j, 3) = 0.99 * C3(H_cart, i, j, 4);
+      C3(H_cart, i, j, 2) = 0.99 * C3(H_cart, i, j, 3);
+      C3(H_cart, i, j, 1) = 0.99 * C3(H_cart, i, j, 2);
+      C3(D_cart, i, j, 3) = 0.999 * C3(D_cart, i, j, 4);
+      C3(D_cart, i, j, 2) = 0.999 * C3(D_cart, i, j, 3);
+      C3(D_cart, i, j, 1) = 0.999 * C3(D_cart, i, j, 2);
+    }
+  bool neg = false;                                                                             // :489-508
+  for (size_t q = 0; q < n3; ++q) neg = neg || H_cart[q] < 0.0 || I_cart[q] < 0.0 || D_cart[q] < 0.0;
+  if (neg)
+    for (int j = 1; j <= nT; ++j)
+      for (int i = 2; i <= nR; ++i)
+        for (int L = 1; L <= nPa; ++L) {
+          if (C3(H_cart, i, j, L) < 0) C3(H_cart, i, j, L) = C3(H_cart, i - 1, j, L);
+          if (C3(I_cart, i, j, L) < 0) C3(I_cart, i, j, L) = C3(I_cart, i - 1, j, L);
+          if (C3(D_cart, i, j, L) < 0) C3(D_cart, i, j, L) = C3(D_cart, i - 1, j, L);
+        }
+  for (int i = 1; i <= nR; ++i)                                                                 // :509-517
+    for (int j = 1; j <= nT; ++j)
+      for (int L = nPa - 1; L >= 1; --L) {
+        if (C3(I_cart, i, j, L) > C3(I_cart, i, j, L + 1)) C3(I_cart, i, j, L) = 0.99 * C3(I_cart, i, j, L + 1);
+        if (C3(H_cart, i, j, L) > C3(H_cart, i, j, L + 1)) C3(H_cart, i, j, L) = 0.99 * C3(H_cart, i, j, L + 1);
+        if (C3(D_cart, i, j, L) > C3(D_cart, i, j, L + 1)) C3(D_cart, i, j, L) = 0.999 * C3(D_cart, i, j, L + 1);
+      }
+  {                                                                                             // :519-532
+    std::vector<double> xa(nPa), fh(nPa), fi(nPa), xb(nPa - 2), oh(nPa - 2), oi(nPa - 2);
+    for (int q = 0; q < nPa; ++q) xa[q] = PA[nPa - 1 - q];                                      // PA(NPA:1:-1)
+    for (int q = 0; q < nPa - 2; ++q) xb[q] = PAbn[nPa - 2 - q];                                // PAbn(NPA-1:2:-1)
+    for (int j = 1; j <= nT; ++j)
+      for (int i = 1; i <= nR; ++i) {
+        for (int q = 0; q < nPa; ++q) { fh[q] = C3(H_cart, i, j, nPa - q); fi[q] = C3(I_cart, i, j, nPa - q); }
+        if (interp1d(nPa, xa.data(), fh.data(), nPa - 2, xb.data(), oh.data())) return 1;
+        if (interp1d(nPa, xa.data(), fi.data(), nPa - 2, xb.data(), oi.data())) return 1;
+        for (int q = 0; q < nPa - 2; ++q) { C3(hI, i, j, nPa - 1 - q) = oh[q]; C3(iI, i, j, nPa - 1 - q) = oi[q]; }
+        C3(hI, i, j, nPa) = C3(hI, i, j, nPa - 1);
+        C3(iI, i, j, nPa) = C3(iI, i, j, nPa - 1);
+        C3(hI, i, j, 1) = C3(hI, i, j, 2);
+        C3(iI, i, j, 1) = C3(iI, i, j, 2);
+      }
+  }
+  if (integral_smooth) {                                                                        // :539-563
+    double w[81];
+    gaussian_kernel9(w);
+    std::vector<double> out((size_t)nR * nT);
+    double* arrs[5] = {H_cart, I_cart, hI.data(), iI.data(), D_cart};
+    for (int L = 2; L <= nPa; ++L)
+      for (double* a : arrs) {
+        double* pl = a + (size_t)nR * nT * (L - 1);
+        convolve9(nR, nT, pl, w, out.data());
+        std::copy(out.begin(), out.end(), pl);
+      }
+  }
+  for (int I = 2; I <= nR + 1; ++I)                                                             // :566-606
+    for (int J = 1; J <= nT; ++J) {
+      const double BNESPrev = R2(BNES, I, J);
+      for (int L = 1; L <= nPa; ++L) {
+        const double FNISPrev = R3(FNIS, I, J, L), FNHSPrev = R3(FNHS, I, J, L);
+        const double BOUNISPrev = R3(BOUNIS, I, J, L), BOUNHSPrev = R3(BOUNHS, I, J, L);
+        R3(FNHS, I, J, L) = C3(H_cart, I - 1, J, L);
+        R3(FNIS, I, J, L) = C3(I_cart, I - 1, J, L);
+        R2(BNES, I, J) = C2(bZEq, I - 1, J);
+        R3(HDNS, I, J, L) = C3(D_cart, I - 1, J, L);
+        R3(BOUNHS, I, J, L) = C3(hI, I - 1, J, L);
+        R3(BOUNIS, I, J, L) = C3(iI, I - 1, J, L);
+        if (std::fabs(DthI) <= 1e-9) {
+          R3(dIdt, I, J, L) = 0; R3(dHdt, I, J, L) = 0; R3(dIbndt, I, J, L) = 0;
+        } else {
+          R3(dIdt, I, J, L) = (R3(FNIS, I, J, L) - FNISPrev) / DthI;
+          R3(dHdt, I, J, L) = (R3(FNHS, I, J, L) - FNHSPrev) / DthI;
+          R3(dIbndt, I, J, L) = (R3(BOUNIS, I, J, L) - BOUNISPrev) / DthI;
+        }
+      }
+      R2(BNES, I, J) = R2(BNES, I, J) / 1e9;
+      R2(dBdt, I, J) = (std::fabs(DthI) <= 1e-9) ? 0.0 : (R2(BNES, I, J) - BNESPrev) / DthI;
+    }
+  for (int J = 1; J <= nT; ++J) {                                                               // :607-622
+    R2(BNES, 1, J) = 0.32 / (Lz[0] * Lz[0] * Lz[0]) / 1.e4;
+    R2(dBdt, 1, J) = 0.0;
+    for (int L = 1; L <= nPa; ++L) {
+      R3(FNHS, 1, J, L) = R3(FNHS, 2, J, L);
+      R3(FNIS, 1, J, L) = R3(FNIS, 2, J, L);
+      R3(BOUNHS, 1, J, L) = R3(BOUNHS, 2, J, L);
+      R3(BOUNIS, 1, J, L) = R3(BOUNIS, 2, J, L);
+      R3(HDNS, 1, J, L) = R3(HDNS, 2, J, L);
+      R3(dIdt, 1, J, L) = 0; R3(dHdt, 1, J, L) = 0; R3(dIbndt, 1, J, L) = 0;
+    }
+  }
+  for (int i = 2; i <= nR + 1; ++i)                                                             // :625-637
+    for (int j = 1; j <= nT; ++j)
+      for (int L = 1; L <= nPa; ++L) {
+        if (std::isnan(R3(FNIS, i, j, L))) R3(FNIS, i, j, L) = R3(FNIS, i - 1, j, L);
+        if (std::isnan(R3(FNHS, i, j, L))) R3(FNHS, i, j, L) = R3(FNHS, i - 1, j, L);
+        if (std::isnan(R3(BOUNIS, i, j, L))) R3(BOUNIS, i, j, L) = R3(BOUNIS, i - 1, j, L);
+        if (std::isnan(R3(BOUNHS, i, j, L))) R3(BOUNHS, i, j, L) = R3(BOUNHS, i - 1, j, L);
+        if (std::isnan(R3(HDNS, i, j, L))) R3(HDNS, i, j, L) = R3(HDNS, i - 1, j, L);
+        if (std::isnan(R3(dIdt, i, j, L))) R3(dIdt, i, j, L) = 0;
+        if (std::isnan(R3(dIbndt, i, j, L))) R3(dIbndt, i, j, L) = 0;
+      }
+  if (h_interp_out) std::copy(hI.begin(), hI.end(), h_interp_out);
+  if (I_interp_out) std::copy(iI.begin(), iI.end(), I_interp_out);
+  return 0;
+#undef C3
+#undef R3
+#undef C2
+#undef R2
+}
+}

@@ -192,3 +192,250 @@ __global__ void k_hi_lines(HiArgs A) {
   }
   if (tid == 0) A.bzeq[line] = bf[ke] * A.bnormal;
 }
+
+// =============================================================================
+// computehI after the integral block (src/ModRamScb.f90:413-637): four small kernels over the (nR, nT, NPA)
+// arrays.  Serial dependences of the reference are kept inside one thread (radial chains per (MLT, pitch angle),
+// the descending pitch-angle repair per line); everything else is pointwise.  Reference operation order,
+// -fmad=false: bit-identical to the oracle (scbo_hi_tail).
+// =============================================================================
+struct HiTailArgs {
+  int nR, nT, nPa, smooth;
+  double DthI, bnes1;                        // bnes1 = 0.32/LZ(1)**3/1.e4 (host)
+  const int *ScaleAt, *outside;              // ScaleAt(nT) 1-based radial index or 0; outsideMGNP(nR,nT)
+  const double *Lz, *PA, *PAbn;
+  double *I0, *H0, *D0, *bz0;                // as the integral block left them
+  double *I1, *H1, *D1, *bz1, *hI, *iI;      // repaired arrays, h / I at PAbn
+  double *I2, *H2, *D2, *hI2, *iI2;          // smoothed
+  double *FNHS, *FNIS, *BOUNHS, *BOUNIS, *HDNS, *BNES, *dIdt, *dHdt, *dIbndt, *dBdt;   // (nR+1,nT,NPA) / (nR+1,nT)
+  int* fail;
+  double w[81];                              // gaussian_kernel(1.0): 9 x 9, column-major
+};
+
+// one column (all radial points of one MLT js and one pitch angle L) after the outer-boundary scaling (:417-470)
+struct HiCol {
+  const double* a; size_t base, st; int nR, ii; bool scale; double s; const int* out;
+  double prev;
+  __device__ void init(const HiTailArgs& A, const double* arr, int js, int L) {
+    a = arr; nR = A.nR; st = 1; base = (size_t)A.nR * (js + (size_t)A.nT * L);
+    ii = A.ScaleAt[js]; out = A.outside + (size_t)A.nR * js;
+    scale = (ii != 0) && js >= 1 && L >= 1;
+    s = 0.0; prev = 0.0;
+    if (scale) {
+      const double fr = (A.Lz[ii - 1] - A.Lz[ii - 2]) / (A.Lz[ii - 3] - A.Lz[ii - 2]);
+      const double t = a[base + ii - 2] + fr * (a[base + ii - 3] - a[base + ii - 2]);
+      s = (t <= 0) ? a[base + ii - 2] / a[base + ii - 1] : t / a[base + ii - 1];
+    }
+  }
+  // call with i = 0 .. nR-1 in order
+  __device__ double get(int i) {
+    double v = a[base + i];
+    if (scale && i >= ii - 1) v = (out[i] == 0) ? v * s : prev;
+    prev = v;
+    return v;
+  }
+};
+
+// thread per (MLT j, pitch angle L): scaling, MLT continuity (column 1 <- column nT), near-90-degree corrections,
+// negative repair (:413-508); out of place (column 1 reads column nT)
+__global__ void k_hi_tail_cols(HiTailArgs A) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= A.nT * A.nPa) return;
+  const int j = t % A.nT, L = t / A.nT;
+  const int js = (j == 0) ? A.nT - 1 : j;
+  const int Ls = L < 3 ? 3 : L;
+  const double* src[3] = {A.I0, A.H0, A.D0};
+  double* dst[3] = {A.I1, A.H1, A.D1};
+  const double f3[3] = {0.50, 0.99, 0.999}, f2[3] = {0.20, 0.99, 0.999};
+  const size_t o = (size_t)A.nR * (j + (size_t)A.nT * L);
+  for (int c = 0; c < 3; c++) {
+    HiCol col;
+    col.init(A, src[c], js, Ls);
+    double last = 0.0;
+    for (int i = 0; i < A.nR; i++) {
+      double v = col.get(i);
+      if (L < 3) {
+        v = f3[c] * v;                                   // L = 3 (1-based)
+        if (L < 2) v = f2[c] * v;                        // L = 2
+        if (L < 1) v = (c == 0) ? 0.0 : f2[c] * v;       // L = 1
+      }
+      if (i >= 1 && v < 0) v = last;                     // :496-504 (a no-op unless something is negative)
+      dst[c][o + i] = v;
+      last = v;
+    }
+  }
+  if (L == 0) {
+    const int ii = A.ScaleAt[js];
+    const bool sc = (ii != 0) && js >= 1 && A.nPa >= 2;
+    double prev = 0.0;
+    for (int i = 0; i < A.nR; i++) {
+      double v = A.bz0[i + (size_t)A.nR * js];
+      if (sc && i >= ii - 1) v = prev;
+      A.bz1[i + (size_t)A.nR * j] = v;
+      prev = v;
+    }
+  }
+}
+
+// CTA per (i, j) line: "too large" repair descending in L (:509-517), then GSL_Interpolation_1D (Steffen) of h and I
+// from PA(NPA:1:-1) onto PAbn(NPA-1:2:-1) (:519-532).  Dynamic shared memory: 8 NPA doubles.
+__global__ void k_hi_tail_lines(HiTailArgs A) {
+  extern __shared__ double hi_sm[];
+  const int nPa = A.nPa;
+  double* lI = hi_sm;            // the line, natural order
+  double* lH = lI + nPa;
+  double* lD = lH + nPa;
+  double* xa = lD + nPa;         // filtered ascending abscissae and values
+  double* fh = xa + nPa;
+  double* fi = fh + nPa;
+  double* yh = fi + nPa;
+  double* yi = yh + nPa;
+  __shared__ int s_n1;
+  const int line = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
+  const size_t nl = (size_t)A.nR * A.nT;
+  for (int L = tid; L < nPa; L += nth) { lI[L] = A.I1[line + nl * L]; lH[L] = A.H1[line + nl * L]; lD[L] = A.D1[line + nl * L]; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int L = nPa - 2; L >= 0; L--) {
+      if (lI[L] > lI[L + 1]) lI[L] = 0.99 * lI[L + 1];
+      if (lH[L] > lH[L + 1]) lH[L] = 0.99 * lH[L + 1];
+      if (lD[L] > lD[L + 1]) lD[L] = 0.999 * lD[L + 1];
+    }
+    int n1 = 1;                                          // src/ModRamGSL.f90:262-273
+    xa[0] = A.PA[nPa - 1]; fh[0] = lH[nPa - 1]; fi[0] = lI[nPa - 1];
+    for (int q = 1; q < nPa; q++) {
+      const double xv = A.PA[nPa - 1 - q];
+      if (xv > xa[n1 - 1]) { xa[n1] = xv; fh[n1] = lH[nPa - 1 - q]; fi[n1] = lI[nPa - 1 - q]; n1++; }
+    }
+    s_n1 = n1;
+  }
+  __syncthreads();
+  const int n1 = s_n1;
+  for (int L = tid; L < nPa; L += nth) { A.I1[line + nl * L] = lI[L]; A.H1[line + nl * L] = lH[L]; A.D1[line + nl * L] = lD[L]; }
+  if (n1 < 3) { if (tid == 0) atomicAdd(A.fail, 1); return; }
+  for (int i = tid; i < n1; i += nth) {                  // steffen_init
+    for (int c = 0; c < 2; c++) {
+      const double* fa = c ? fi : fh;
+      double yp;
+      if (i == 0) yp = (fa[1] - fa[0]) / (xa[1] - xa[0]);
+      else if (i == n1 - 1) yp = (fa[n1 - 1] - fa[n1 - 2]) / (xa[n1 - 1] - xa[n1 - 2]);
+      else {
+        const double hi = xa[i + 1] - xa[i], him1 = xa[i] - xa[i - 1];
+        const double si = (fa[i + 1] - fa[i]) / hi, sim1 = (fa[i] - fa[i - 1]) / him1;
+        const double pi = (sim1 * hi + si * him1) / (him1 + hi);
+        const double m1 = fabs(si) < 0.5 * fabs(pi) ? fabs(si) : 0.5 * fabs(pi);
+        const double m2 = fabs(sim1) < m1 ? fabs(sim1) : m1;
+        yp = (((sim1 < 0) ? -1.0 : 1.0) + ((si < 0) ? -1.0 : 1.0)) * m2;
+      }
+      (c ? yi : yh)[i] = yp;
+    }
+  }
+  __syncthreads();
+  bool bad = false;
+  for (int q = tid; q < nPa - 2; q += nth) {
+    const int Lt = nPa - 2 - q;                          // 0-based pitch-angle index of target q
+    const double xb = A.PAbn[Lt];
+    double r[2];
+    for (int c = 0; c < 2; c++) {
+      const double* fa = c ? fi : fh;
+      const double* yp = c ? yi : yh;
+      if (xb <= xa[0]) r[c] = fa[0] + (xb - xa[0]) / (xa[1] - xa[0]) * (fa[1] - fa[0]);
+      else if (xb >= xa[n1 - 1]) r[c] = fa[n1 - 1] + (xb - xa[n1 - 1]) / (xa[n1 - 2] - xa[n1 - 1]) * (fa[n1 - 2] - fa[n1 - 1]);
+      else if (xb == xb) {
+        int ilo = 0, ihi = n1 - 1;
+        while (ihi > ilo + 1) {
+          const int m = (ihi + ilo) / 2;
+          if (xa[m] > xb) ihi = m; else ilo = m;
+        }
+        const double hi = xa[ilo + 1] - xa[ilo], delx = xb - xa[ilo];
+        const double si = (fa[ilo + 1] - fa[ilo]) / hi;
+        const double a = (yp[ilo] + yp[ilo + 1] - 2 * si) / hi / hi;
+        const double b = (3 * si - 2 * yp[ilo] - yp[ilo + 1]) / hi;
+        r[c] = fa[ilo] + delx * (yp[ilo] + delx * (b + delx * a));
+      } else { bad = true; r[c] = xb; }
+    }
+    A.hI[line + nl * Lt] = r[0];
+    A.iI[line + nl * Lt] = r[1];
+    if (Lt == nPa - 2) { A.hI[line + nl * (nPa - 1)] = r[0]; A.iI[line + nl * (nPa - 1)] = r[1]; }
+    if (Lt == 1) { A.hI[line + nl * 0] = r[0]; A.iI[line + nl * 0] = r[1]; }
+  }
+  if (bad) atomicAdd(A.fail, 1);
+}
+
+// Gaussian smoothing of the five arrays, planes L = 2 .. NPA (:539-563): thread per (i, j, L), 9 x 9 window on the
+// 3 x 3 reflected tiling of convolve (srcExternal/gaussian_filter.f90:98-187), products summed in array element order
+__global__ void k_hi_smooth(HiTailArgs A) {
+  const size_t nl = (size_t)A.nR * A.nT;
+  const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= nl * A.nPa) return;
+  const int i = (int)(t % A.nR), j = (int)((t / A.nR) % A.nT), L = (int)(t / nl);
+  const double* src[5] = {A.H1, A.I1, A.hI, A.iI, A.D1};
+  double* dst[5] = {A.H2, A.I2, A.hI2, A.iI2, A.D2};
+  if (L == 0) {
+    for (int c = 0; c < 5; c++) dst[c][t] = src[c][t];
+    return;
+  }
+  double sum[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  for (int dj = -4; dj <= 4; dj++) {
+    int jj = j + dj;
+    jj = jj < 0 ? -1 - jj : (jj >= A.nT ? 2 * A.nT - 1 - jj : jj);
+    for (int di = -4; di <= 4; di++) {
+      int ir = i + di;
+      ir = ir < 0 ? -1 - ir : (ir >= A.nR ? 2 * A.nR - 1 - ir : ir);
+      const double w = A.w[(di + 4) + 9 * (dj + 4)];
+      const size_t o = ir + (size_t)A.nR * jj + nl * L;
+      for (int c = 0; c < 5; c++) sum[c] += w * src[c][o];
+    }
+  }
+  for (int c = 0; c < 5; c++) dst[c][t] = sum[c];
+}
+
+// thread per (MLT J, pitch angle L): the RAM variables, their time derivatives, the I = 1 row and the NaN repair
+// (:566-637), serial in the radial index like the reference
+__global__ void k_hi_fill(HiTailArgs A) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= A.nT * A.nPa) return;
+  const int J = t % A.nT, L = t / A.nT, nR = A.nR;
+  const double* H = A.smooth ? A.H2 : A.H1;
+  const double* I = A.smooth ? A.I2 : A.I1;
+  const double* D = A.smooth ? A.D2 : A.D1;
+  const double* hI = A.smooth ? A.hI2 : A.hI;
+  const double* iI = A.smooth ? A.iI2 : A.iI;
+  const size_t oc = (size_t)nR * (J + (size_t)A.nT * L);              // column in (nR,nT,NPA)
+  const size_t orr = (size_t)(nR + 1) * (J + (size_t)A.nT * L);        // column in (nR+1,nT,NPA)
+  const bool still = fabs(A.DthI) <= 1e-9;
+  for (int i = 1; i <= nR; i++) {                                      // 0-based row of the RAM arrays
+    const double pI = A.FNIS[orr + i], pH = A.FNHS[orr + i], pbI = A.BOUNIS[orr + i];
+    const double nH = H[oc + i - 1], nI = I[oc + i - 1], nbI = iI[oc + i - 1];
+    A.FNHS[orr + i] = nH; A.FNIS[orr + i] = nI;
+    A.HDNS[orr + i] = D[oc + i - 1];
+    A.BOUNHS[orr + i] = hI[oc + i - 1]; A.BOUNIS[orr + i] = nbI;
+    A.dIdt[orr + i] = still ? 0.0 : (nI - pI) / A.DthI;
+    A.dHdt[orr + i] = still ? 0.0 : (nH - pH) / A.DthI;
+    A.dIbndt[orr + i] = still ? 0.0 : (nbI - pbI) / A.DthI;
+  }
+  A.FNHS[orr] = A.FNHS[orr + 1]; A.FNIS[orr] = A.FNIS[orr + 1];
+  A.BOUNHS[orr] = A.BOUNHS[orr + 1]; A.BOUNIS[orr] = A.BOUNIS[orr + 1];
+  A.HDNS[orr] = A.HDNS[orr + 1];
+  A.dIdt[orr] = 0.0; A.dHdt[orr] = 0.0; A.dIbndt[orr] = 0.0;
+  for (int i = 1; i <= nR; i++) {
+    if (isnan(A.FNIS[orr + i])) A.FNIS[orr + i] = A.FNIS[orr + i - 1];
+    if (isnan(A.FNHS[orr + i])) A.FNHS[orr + i] = A.FNHS[orr + i - 1];
+    if (isnan(A.BOUNIS[orr + i])) A.BOUNIS[orr + i] = A.BOUNIS[orr + i - 1];
+    if (isnan(A.BOUNHS[orr + i])) A.BOUNHS[orr + i] = A.BOUNHS[orr + i - 1];
+    if (isnan(A.HDNS[orr + i])) A.HDNS[orr + i] = A.HDNS[orr + i - 1];
+    if (isnan(A.dIdt[orr + i])) A.dIdt[orr + i] = 0.0;
+    if (isnan(A.dIbndt[orr + i])) A.dIbndt[orr + i] = 0.0;
+  }
+  if (L == 0) {
+    const size_t o2 = (size_t)(nR + 1) * J;
+    for (int i = 1; i <= nR; i++) {
+      const double prev = A.BNES[o2 + i];
+      const double v = A.bz1[i - 1 + (size_t)nR * J] / 1e9;
+      A.BNES[o2 + i] = v;
+      A.dBdt[o2 + i] = still ? 0.0 : (v - prev) / A.DthI;
+    }
+    A.BNES[o2] = A.bnes1;
+    A.dBdt[o2] = 0.0;
+  }
+}

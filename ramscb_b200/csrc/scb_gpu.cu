@@ -1023,6 +1023,111 @@ int rsg_hI_integrals(int device, int nthe, int nR, int nT, int nPa, int nThetaEq
   return done(rc, "");
 }
 
+// computehI after the integral block (src/ModRamScb.f90:413-637): outer-boundary scaling, MLT continuity, near-90-degree
+// corrections, repairs, Steffen interpolation of h / I onto PAbn, Gaussian smoothing, the RAM variables (FNHS, FNIS,
+// BOUNHS, BOUNIS, HDNS, BNES) with their time derivatives, the I = 1 row and the NaN repair.  I_cart, H_cart,
+// HDens_cart, bZEq_cart come back as the reference leaves them.  *gslerr != 0: a line could not be interpolated.
+int rsg_hI_tail(int device, int nR, int nT, int nPa, double* I_cart, double* H_cart, double* HDens_cart, double* bZEq_cart,
+                const int* ScaleAt, const int* outsideMGNP, const double* Lz, const double* PA, const double* PAbn,
+                int integral_smooth, double DthI, double* FNHS, double* FNIS, double* BOUNHS, double* BOUNIS, double* HDNS,
+                double* BNES, double* dIdt, double* dHdt, double* dIbndt, double* dBdt, int* gslerr, double* ms) {
+  if (!I_cart || !H_cart || !HDens_cart || !bZEq_cart || !ScaleAt || !outsideMGNP || !Lz || !PA || !PAbn || !FNHS || !FNIS ||
+      !BOUNHS || !BOUNIS || !HDNS || !BNES || !dIdt || !dHdt || !dIbndt || !dBdt)
+    return sfail(RSG_ERR_ARG, "null argument");
+  if (nR < 3 || nT < 2 || nPa < 5) return sfail(RSG_ERR_ARG, "bad dimensions");
+  if (integral_smooth && (nR < 9 || nT < 9)) return sfail(RSG_ERR_ARG, "grid smaller than the 9 x 9 smoothing kernel");
+  for (int j = 0; j < nT; j++)
+    if (ScaleAt[j] != 0 && (ScaleAt[j] < 3 || ScaleAt[j] > nR)) return sfail(RSG_ERR_ARG, "ScaleAt out of range");
+  SCK(cudaSetDevice(device));
+  const size_t nl = (size_t)nR * nT, n3 = nl * nPa, nr2 = (size_t)(nR + 1) * nT, nr3 = nr2 * nPa;
+  const size_t nd = 13 * n3 + 2 * nl + 8 * nr3 + 2 * nr2 + (nR + 1) + 2 * (size_t)nPa;
+  double* d = nullptr;
+  int* di = nullptr;
+  cudaStream_t st = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  auto done = [&](int code, const std::string& msg) {
+    if (d) cudaFree(d);
+    if (di) cudaFree(di);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (st) cudaStreamDestroy(st);
+    return code == RSG_OK ? RSG_OK : sfail(code, msg);
+  };
+#define HCK(call)                                                                                  \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) return done(RSG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+  HCK(cudaStreamCreate(&st));
+  HCK(cudaEventCreate(&e0));
+  HCK(cudaEventCreate(&e1));
+  HCK(cudaMalloc(&d, nd * sizeof(double)));
+  HCK(cudaMalloc(&di, (nl + nT + 1) * sizeof(int)));
+  HiTailArgs A;
+  A.nR = nR; A.nT = nT; A.nPa = nPa; A.smooth = integral_smooth ? 1 : 0; A.DthI = DthI;
+  A.bnes1 = 0.32 / (Lz[0] * Lz[0] * Lz[0]) / 1.e4;                                  // :609
+  {                                                                                 // gaussian_kernel(1.0), srcExternal/gaussian_filter.f90:19-56
+    double sum = 0.0;
+    for (int j = -4; j <= 4; j++)
+      for (int i = -4; i <= 4; i++) {
+        const double x = i, y = j;
+        const double v = 2.0 * std::exp(-0.5 * (x * x + y * y) / 1.0);
+        A.w[(i + 4) + 9 * (j + 4)] = v;
+        sum += v;
+      }
+    for (int q = 0; q < 81; q++) A.w[q] = A.w[q] / sum;
+  }
+  double* p = d;
+  auto take = [&](size_t n) { double* q = p; p += n; return q; };
+  auto up = [&](const double* src, size_t n) { double* q = take(n); cudaMemcpyAsync(q, src, n * sizeof(double), cudaMemcpyHostToDevice, st); return q; };
+  A.I0 = up(I_cart, n3); A.H0 = up(H_cart, n3); A.D0 = up(HDens_cart, n3); A.bz0 = up(bZEq_cart, nl);
+  A.I1 = take(n3); A.H1 = take(n3); A.D1 = take(n3); A.bz1 = take(nl); A.hI = take(n3); A.iI = take(n3);
+  A.I2 = take(n3); A.H2 = take(n3); A.D2 = take(n3); A.hI2 = take(n3); A.iI2 = take(n3);
+  A.FNHS = up(FNHS, nr3); A.FNIS = up(FNIS, nr3); A.BOUNHS = up(BOUNHS, nr3); A.BOUNIS = up(BOUNIS, nr3); A.HDNS = up(HDNS, nr3);
+  A.dIdt = take(nr3); A.dHdt = take(nr3); A.dIbndt = take(nr3);
+  A.BNES = up(BNES, nr2); A.dBdt = take(nr2);
+  A.Lz = up(Lz, nR + 1); A.PA = up(PA, nPa); A.PAbn = up(PAbn, nPa);
+  HCK(cudaMemcpyAsync(di, outsideMGNP, nl * sizeof(int), cudaMemcpyHostToDevice, st));
+  HCK(cudaMemcpyAsync(di + nl, ScaleAt, nT * sizeof(int), cudaMemcpyHostToDevice, st));
+  HCK(cudaMemsetAsync(di + nl + nT, 0, sizeof(int), st));
+  A.outside = di; A.ScaleAt = di + nl; A.fail = di + nl + nT;
+  const int ncol = nT * nPa;
+  const int lthreads = std::min(256, ((nPa + 31) / 32) * 32);
+  const size_t lsmem = (size_t)8 * nPa * sizeof(double);
+  if (lsmem > 48 * 1024) return done(RSG_ERR_UNSUPPORTED, "pitch-angle line does not fit shared memory");
+  HCK(cudaEventRecord(e0, st));
+  k_hi_tail_cols<<<nblk(ncol, 128), 128, 0, st>>>(A);
+  HCK(cudaGetLastError());
+  k_hi_tail_lines<<<(unsigned)nl, lthreads, lsmem, st>>>(A);
+  HCK(cudaGetLastError());
+  if (A.smooth) {
+    k_hi_smooth<<<nblk((long long)n3, 128), 128, 0, st>>>(A);
+    HCK(cudaGetLastError());
+  }
+  k_hi_fill<<<nblk(ncol, 128), 128, 0, st>>>(A);
+  HCK(cudaGetLastError());
+  HCK(cudaEventRecord(e1, st));
+  auto down = [&](double* dst, const double* src, size_t n) { return cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost, st); };
+  HCK(down(I_cart, A.smooth ? A.I2 : A.I1, n3));
+  HCK(down(H_cart, A.smooth ? A.H2 : A.H1, n3));
+  HCK(down(HDens_cart, A.smooth ? A.D2 : A.D1, n3));
+  HCK(down(bZEq_cart, A.bz1, nl));
+  HCK(down(FNHS, A.FNHS, nr3)); HCK(down(FNIS, A.FNIS, nr3)); HCK(down(BOUNHS, A.BOUNHS, nr3)); HCK(down(BOUNIS, A.BOUNIS, nr3));
+  HCK(down(HDNS, A.HDNS, nr3)); HCK(down(dIdt, A.dIdt, nr3)); HCK(down(dHdt, A.dHdt, nr3)); HCK(down(dIbndt, A.dIbndt, nr3));
+  HCK(down(BNES, A.BNES, nr2)); HCK(down(dBdt, A.dBdt, nr2));
+  int nfail = 0;
+  HCK(cudaMemcpyAsync(&nfail, A.fail, sizeof(int), cudaMemcpyDeviceToHost, st));
+  HCK(cudaStreamSynchronize(st));
+  if (gslerr) *gslerr = nfail;
+  if (ms) {
+    float t = 0.f;
+    HCK(cudaEventElapsedTime(&t, e0, e1));
+    *ms = t;
+  }
+#undef HCK
+  return done(RSG_OK, "");
+}
+
 double rsg_scb_last_ms(rsg_scb* h) { return h ? h->last_ms : 0.0; }
 int rsg_scb_use_cluster(rsg_scb* h, int on) {
   if (!h) return sfail(RSG_ERR_ARG, "null handle");

@@ -452,6 +452,7 @@ def _scb_lib():
         L.rsg_scb_launch_count.argtypes = [vp]
         L.rsg_scb_launch_count.restype = ll
         L.rsg_hI_integrals.argtypes = [i, i, i, i, i, i, d] + [vp] * 12 + [_dp]
+        L.rsg_hI_tail.argtypes = [i, i, i, i] + [vp] * 9 + [i, d] + [vp] * 10 + [_ip, _dp]
         _scb_ready = True
     return L
 
@@ -684,3 +685,34 @@ def hI_integrals(chiVal, mu, xRAM, yRAM, zRAM, bRAM, density, outsideMGNP, nThet
     _sck(L.rsg_hI_integrals(device, nthe, nR, nT, nPa, int(nThetaEquator), float(bnormal), _p(chiVal), _p(mu), _p(xRAM), _p(yRAM),
                             _p(zRAM), _p(bRAM), _p(density), out.ctypes.data, _p(I), _p(H), _p(D), _p(bz), C.byref(ms)))
     return I, H, D, bz, ms.value
+
+
+HI_RAM_NAMES = ("FNHS", "FNIS", "BOUNHS", "BOUNIS", "HDNS", "BNES")
+
+
+def hI_tail(I_cart, H_cart, HDens_cart, bZEq_cart, ScaleAt, outsideMGNP, Lz, PA, PAbn, integral_smooth, DthI, ram, device=-1):
+    """computehI after the integral block (src/ModRamScb.f90:413-637).  `ram`: dict with the previous FNHS, FNIS, BOUNHS,
+    BOUNIS, HDNS (nR+1,nT,nPa) and BNES (nR+1,nT).  Returns a dict with the new RAM variables, dIdt, dHdt, dIbndt, dBdt,
+    the four *_cart arrays as the reference leaves them, gslerr and the device time in ms."""
+    L = _scb_lib()
+    nR, nT, nPa = I_cart.shape
+    f = lambda a: np.array(a, dtype=np.float64, order="F")
+    out = {"I_cart": f(I_cart), "H_cart": f(H_cart), "HDens_cart": f(HDens_cart), "bZEq_cart": f(bZEq_cart)}
+    for n in HI_RAM_NAMES:
+        out[n] = f(ram[n])
+    for n in ("dIdt", "dHdt", "dIbndt"):
+        out[n] = np.zeros((nR + 1, nT, nPa), order="F")
+    out["dBdt"] = np.zeros((nR + 1, nT), order="F")
+    sa = np.ascontiguousarray(ScaleAt, dtype=np.int32)
+    om = np.asfortranarray(outsideMGNP, dtype=np.int32)
+    Lz, PA, PAbn = (np.ascontiguousarray(a, dtype=np.float64) for a in (Lz, PA, PAbn))
+    err, ms = C.c_int(0), C.c_double(0.0)
+    if device < 0:
+        import torch
+        device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    _sck(L.rsg_hI_tail(device, nR, nT, nPa, _p(out["I_cart"]), _p(out["H_cart"]), _p(out["HDens_cart"]), _p(out["bZEq_cart"]),
+                       sa.ctypes.data, om.ctypes.data, _p(Lz), _p(PA), _p(PAbn), 1 if integral_smooth else 0, float(DthI),
+                       *[_p(out[n]) for n in HI_RAM_NAMES], _p(out["dIdt"]), _p(out["dHdt"]), _p(out["dIbndt"]), _p(out["dBdt"]),
+                       C.byref(err), C.byref(ms)))
+    out["gslerr"], out["ms"] = err.value, ms.value
+    return out

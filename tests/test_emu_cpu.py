@@ -103,6 +103,12 @@ def test_emulated_hI_integrals(emu, default_grids, oracle_built, nthe, wiggle, o
     TZ.test_hI_integrals_on_device(default_grids, oracle_built, nthe, wiggle, outside)
 
 
+@pytest.mark.parametrize("smooth,DthI,variant", [(1, 300.0, "scaled"), (0, 0.0, "plain"), (1, 300.0, "repairs")])
+def test_emulated_hI_tail(emu, default_grids, oracle_built, smooth, DthI, variant):
+    import test_zz_late_additions_gpu as TZ
+    TZ.test_hI_tail_on_device(default_grids, oracle_built, smooth, DthI, variant)
+
+
 def test_emulated_scb_run_outer_iterations(emu, oracle_built):
     """rsg_scb_run -- the whole outer iteration of scb_run in one C call, 3-D arrays resident, pressure front
     end as a host callback -- against the oracle's composition, incl. the SORFail restore path."""

@@ -225,3 +225,56 @@ def test_hI_integrals_on_device(default_grids, oracle_built, nthe, wiggle, outsi
         assert np.all(H[:, :, 1:] > 0.74) and np.all(H < 1.39) and np.all(H[:, :, 1] < 0.9)
         assert np.all(np.diff(I[:, :, 4:], axis=2) >= 0.0)
     assert out[4] >= 0.0
+
+
+def hi_tail_inputs(g, seed, scale_cols=True, negatives=False, nans=False):
+    """Integral-block output on perturbed dipole lines plus the ingredients of the tail: an outer SCB boundary (ScaleAt)
+    on part of the MLT sectors with some points outside the magnetopause, previous RAM variables, optionally negative
+    and NaN entries (the repairs of src/ModRamScb.f90:489-508 and :625-637)."""
+    rng = np.random.default_rng(seed)
+    d = SCBSYN.ram_field_lines(g.LZ[1:g.NR + 1] if len(g.LZ) > g.NR else g.LZ, g.MLT[:g.NT], nthe=41, wiggle=0.05, seed=seed)
+    ScaleAt = np.zeros(g.NT, dtype=np.int32)
+    if scale_cols:
+        for j in range(g.NT):
+            if rng.random() < 0.5:
+                ScaleAt[j] = rng.integers(max(3, g.NR - 6), g.NR + 1)
+                for i in range(ScaleAt[j], g.NR):        # the point the scaling is anchored on stays inside
+                    if rng.random() < 0.3:
+                        d["outsideMGNP"][i, j] = 1
+    return d, ScaleAt, rng
+
+
+@pytest.mark.parametrize("smooth,DthI,variant", [(1, 300.0, "scaled"), (0, 0.0, "plain"), (1, 300.0, "repairs")])
+def test_hI_tail_on_device(default_grids, oracle_built, smooth, DthI, variant):
+    """The rest of computehI (src/ModRamScb.f90:413-637) through rsg_hI_tail: every output bit-identical to the oracle
+    -- with an outer SCB boundary and points outside the magnetopause, without (and DthI = 0), and with negative / NaN /
+    non-monotonic entries that trigger the repairs."""
+    from ramscb_b200 import host
+    g = default_grids
+    d, ScaleAt, rng = hi_tail_inputs(g, seed=21, scale_cols=variant != "plain")
+    I, H, D, bz, _ = oracle_built.hi_integrals(mu=g.MU, **d)
+    D = np.where(np.isfinite(D), D, 1.0)
+    if variant == "repairs":
+        for a in (I, H, D):
+            m = rng.random(a.shape) < 0.01
+            a[m] = -a[m]                                     # negatives (:489-508)
+            m = rng.random(a.shape) < 0.01
+            a[m] = 3.0 * a[m]                                # too large relative to L+1 (:509-517)
+        H[rng.random(H.shape) < 0.002] = np.nan              # NaN repair (:625-637)
+    shape3 = (g.NR + 1, g.NT, g.NPA)
+    ram = {n: np.asfortranarray(rng.random(shape3)) for n in ("FNHS", "FNIS", "BOUNHS", "BOUNIS", "HDNS")}
+    ram["BNES"] = np.asfortranarray(1e-7 * rng.random((g.NR + 1, g.NT)))
+    Lz = g.LZ[:g.NR + 1] if len(g.LZ) > g.NR else np.append(2 * g.LZ[0] - g.LZ[1], g.LZ)
+    args = (I, H, D, bz, ScaleAt, d["outsideMGNP"], Lz, g.PA, g.PAbn, smooth, DthI, ram)
+    ref = oracle_built.hi_tail(*args)
+    out = host.hI_tail(*args)
+    assert ref["gslerr"] == 0 and out["gslerr"] == 0
+    for n in ("I_cart", "H_cart", "HDens_cart", "bZEq_cart", "FNHS", "FNIS", "BOUNHS", "BOUNIS", "HDNS", "BNES", "dIdt", "dHdt",
+              "dIbndt", "dBdt"):
+        assert np.array_equal(ref[n], out[n], equal_nan=True), (n, float(np.nanmax(np.abs(ref[n] - out[n]))))
+    assert np.array_equal(out["FNHS"][0], out["FNHS"][1], equal_nan=True) and np.all(out["dIdt"][0] == 0.0)
+    if variant != "repairs":
+        assert all(np.all(np.isfinite(out[n])) for n in ("FNHS", "FNIS", "BOUNHS", "BOUNIS", "HDNS", "BNES", "dIdt", "dBdt"))
+        assert np.all(np.diff(out["FNIS"][1:], axis=2) >= 0.0) if not smooth else True
+    if DthI == 0.0:
+        assert not out["dIdt"].any() and not out["dHdt"].any() and not out["dIbndt"].any() and not out["dBdt"].any()
