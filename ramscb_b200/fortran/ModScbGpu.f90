@@ -213,6 +213,22 @@ module ModScbGpu
        real(c_double), intent(out) :: ms
        integer(c_int) :: ierr
      end function
+     function rsg_hI_tail(device, nR, nT, nPa, I_cart, H_cart, HDens_cart, bZEq_cart, ScaleAt, outsideMGNP, Lz, PA, PAbn, &
+          integral_smooth, DthI, FNHS, FNIS, BOUNHS, BOUNIS, HDNS, BNES, dIdt, dHdt, dIbndt, dBdt, gslerr, ms) &
+          bind(C, name='rsg_hI_tail') result(ierr)
+       ! computehI after the integral block, src/ModRamScb.f90:413-637
+       import :: c_int, c_double
+       integer(c_int), value :: device, nR, nT, nPa, integral_smooth
+       real(c_double), value :: DthI
+       real(c_double), intent(inout) :: I_cart(*), H_cart(*), HDens_cart(*), bZEq_cart(*)
+       integer(c_int), intent(in) :: ScaleAt(*), outsideMGNP(*)
+       real(c_double), intent(in) :: Lz(*), PA(*), PAbn(*)
+       real(c_double), intent(inout) :: FNHS(*), FNIS(*), BOUNHS(*), BOUNIS(*), HDNS(*), BNES(*)
+       real(c_double), intent(inout) :: dIdt(*), dHdt(*), dIbndt(*), dBdt(*)
+       integer(c_int), intent(out) :: gslerr
+       real(c_double), intent(out) :: ms
+       integer(c_int) :: ierr
+     end function
   end interface
 
 contains
@@ -251,5 +267,24 @@ contains
          int(nThetaEquator,c_int), bnormal, chiVal, MU, xRAM, yRAM, zRAM, bRAM, density, outsideMGNP, &
          I_cart, H_cart, HDens_cart, bZEq_Cart, ms), 'computehI_integrals')
   end subroutine computehI_integrals_gpu
+
+  subroutine computehI_tail_gpu(I_cart, H_cart, HDens_cart, bZEq_Cart, ScaleAt, DthI)
+    ! replaces computehI from "Scale based on outer SCB boundary" to the NaN check (src/ModRamScb.f90:413-637);
+    ! the caller keeps EIR(1,:) = EIP(1,:) = 0 (:611-612) and TOld = TimeRamElapsed (:623)
+    use ModRamGrids,     ONLY: nR, nT, nPa
+    use ModRamParams,    ONLY: integral_smooth
+    use ModRamVariables, ONLY: FNHS, FNIS, BOUNHS, BOUNIS, HDNS, BNES, dIdt, dHdt, dIbndt, dBdt, LZ, PA, PAbn, outsideMGNP
+    real(c_double), intent(inout) :: I_cart(nR,nT,nPa), H_cart(nR,nT,nPa), HDens_cart(nR,nT,nPa), bZEq_Cart(nR,nT)
+    integer(c_int), intent(in)    :: ScaleAt(nT)
+    real(c_double), intent(in)    :: DthI
+    integer(c_int) :: gslerr, ismooth
+    real(c_double) :: ms
+    ismooth = 0
+    if (integral_smooth) ismooth = 1
+    call rsg_scb_check(rsg_hI_tail(0_c_int, int(nR,c_int), int(nT,c_int), int(nPa,c_int), I_cart, H_cart, HDens_cart, &
+         bZEq_Cart, ScaleAt, outsideMGNP, LZ, PA, PAbn, ismooth, DthI, FNHS, FNIS, BOUNHS, BOUNIS, HDNS, BNES, &
+         dIdt, dHdt, dIbndt, dBdt, gslerr, ms), 'computehI_tail')
+    if (gslerr /= 0) call CON_stop('computehI_tail_gpu: GSL_Interpolation_1D failed on a pitch-angle line')
+  end subroutine computehI_tail_gpu
 
 end module ModScbGpu

@@ -776,3 +776,105 @@ def test_hi_oracle_vs_adaptive_quadrature(oracle_built, default_grids, wiggle):
             assert np.all(rel[1:] < 1e-6), (name, i, rel.max())          # what the closed forms actually reach
         ncomputed += len(computed)
     assert ncomputed > 20
+
+
+def _hi_tail_numpy(I, H, D, bz, ScaleAt, outside, Lz, PA, PAbn, smooth, DthI, ram):
+    """computehI after the integral block (src/ModRamScb.f90:413-637) a second time, in whole-array numpy straight from
+    the Fortran array statements; smoothing through scipy.ndimage (mode 'reflect' = the 3 x 3 reflected tiling of
+    srcExternal/gaussian_filter.f90, which says it mirrors a Python implementation)."""
+    import independent_scb as ind
+    from scipy import ndimage
+    I, H, D, bz = (np.array(a, order="F") for a in (I, H, D, bz))
+    nR, nT, nPa = I.shape
+    for j in range(1, nT):
+        ii = ScaleAt[j]
+        if ii == 0:
+            continue
+        fr = (Lz[ii - 1] - Lz[ii - 2]) / (Lz[ii - 3] - Lz[ii - 2])
+        for a in (I, H, D):
+            t = a[ii - 2, j, 1:] + fr * (a[ii - 3, j, 1:] - a[ii - 2, j, 1:])
+            s = np.where(t <= 0, a[ii - 2, j, 1:] / a[ii - 1, j, 1:], t / a[ii - 1, j, 1:])
+            for i in range(ii - 1, nR):
+                a[i, j, 1:] = a[i, j, 1:] * s if outside[i, j] == 0 else a[i - 1, j, 1:]
+        bz[ii - 1:, j] = bz[ii - 2, j]
+    for a in (I, H, D):
+        a[:, 0, :] = a[:, nT - 1, :]
+    bz[:, 0] = bz[:, nT - 1]
+    I[:, :, 2] = 0.50 * I[:, :, 3]; I[:, :, 1] = 0.20 * I[:, :, 2]; I[:, :, 0] = 0.0
+    H[:, :, 2] = 0.99 * H[:, :, 3]; H[:, :, 1] = 0.99 * H[:, :, 2]; H[:, :, 0] = 0.99 * H[:, :, 1]
+    D[:, :, 2] = 0.999 * D[:, :, 3]; D[:, :, 1] = 0.999 * D[:, :, 2]; D[:, :, 0] = 0.999 * D[:, :, 1]
+    if min(np.nanmin(H), np.nanmin(I), np.nanmin(D)) < 0:
+        for i in range(1, nR):
+            for a in (H, I, D):
+                a[i] = np.where(a[i] < 0, a[i - 1], a[i])
+    for L in range(nPa - 2, -1, -1):
+        for a, f in ((I, 0.99), (H, 0.99), (D, 0.999)):
+            a[:, :, L] = np.where(a[:, :, L] > a[:, :, L + 1], f * a[:, :, L + 1], a[:, :, L])
+    hI, iI = np.zeros_like(H), np.zeros_like(I)
+    for i in range(nR):
+        for j in range(nT):
+            hI[i, j, nPa - 2:0:-1] = ind.interp1d_steffen(PA[::-1], H[i, j, ::-1], PAbn[nPa - 2:0:-1])
+            iI[i, j, nPa - 2:0:-1] = ind.interp1d_steffen(PA[::-1], I[i, j, ::-1], PAbn[nPa - 2:0:-1])
+    for a in (hI, iI):
+        a[:, :, nPa - 1] = a[:, :, nPa - 2]
+        a[:, :, 0] = a[:, :, 1]
+    if smooth:
+        xx, yy = np.meshgrid(np.arange(-4, 5.0), np.arange(-4, 5.0), indexing="ij")
+        k = 2.0 * np.exp(-0.5 * (xx ** 2 + yy ** 2) / 1.0)
+        k = k / k.sum()
+        for L in range(1, nPa):
+            for a in (H, I, hI, iI, D):
+                a[:, :, L] = ndimage.correlate(a[:, :, L], k, mode="reflect")
+    out = {n: np.array(ram[n], order="F") for n in ("FNHS", "FNIS", "BOUNHS", "BOUNIS", "HDNS", "BNES")}
+    prev = {n: out[n].copy() for n in out}
+    out["FNHS"][1:], out["FNIS"][1:], out["HDNS"][1:], out["BOUNHS"][1:], out["BOUNIS"][1:] = H, I, D, hI, iI
+    out["BNES"][1:] = bz / 1e9
+    still = abs(DthI) <= 1e-9
+    for dn, n in (("dIdt", "FNIS"), ("dHdt", "FNHS"), ("dIbndt", "BOUNIS"), ("dBdt", "BNES")):
+        out[dn] = np.zeros_like(out[n]) if still else (out[n] - prev[n]) / DthI
+        out[dn][0] = 0.0
+    for n in ("FNHS", "FNIS", "BOUNHS", "BOUNIS", "HDNS"):
+        out[n][0] = out[n][1]
+    out["BNES"][0] = 0.32 / Lz[0] ** 3 / 1.e4
+    for i in range(1, nR + 1):
+        for n in ("FNIS", "FNHS", "BOUNIS", "BOUNHS", "HDNS"):
+            out[n][i] = np.where(np.isnan(out[n][i]), out[n][i - 1], out[n][i])
+    for n in ("dIdt", "dIbndt"):
+        out[n][1:] = np.where(np.isnan(out[n][1:]), 0.0, out[n][1:])
+    out.update(I_cart=I, H_cart=H, HDens_cart=D, bZEq_cart=bz, h_interp=hI, I_interp=iI)
+    return out
+
+
+@pytest.mark.parametrize("smooth,DthI,variant", [(0, 300.0, "scaled"), (1, 300.0, "repairs"), (1, 0.0, "plain")])
+def test_hi_tail_oracle_vs_independent_numpy(oracle_built, default_grids, smooth, DthI, variant):
+    """scbo_hi_tail (scalar loops in the reference's statement order) against a whole-array numpy restatement written
+    from the Fortran array statements, with scipy.ndimage as the smoothing: bit-identical without smoothing, within
+    3e-11 of each array's maximum with it (ndimage sums the 81 products in another order; the time derivatives
+    divide differences of smoothed values)."""
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import test_zz_late_additions_gpu as TZ
+    g = default_grids
+    d, ScaleAt, rng = TZ.hi_tail_inputs(g, seed=33, scale_cols=variant != "plain")
+    I, H, D, bz, _ = oracle_built.hi_integrals(mu=g.MU, **d)
+    if variant == "repairs":
+        for a in (I, H, D):
+            m = rng.random(a.shape) < 0.01
+            a[m] = -a[m]
+            m = rng.random(a.shape) < 0.01
+            a[m] = 3.0 * a[m]
+        if not smooth:
+            H[rng.random(H.shape) < 0.002] = np.nan
+    shape3 = (g.NR + 1, g.NT, g.NPA)
+    ram = {n: np.asfortranarray(rng.random(shape3)) for n in ("FNHS", "FNIS", "BOUNHS", "BOUNIS", "HDNS")}
+    ram["BNES"] = np.asfortranarray(1e-7 * rng.random((g.NR + 1, g.NT)))
+    Lz = g.LZ[:g.NR + 1] if len(g.LZ) > g.NR else np.append(2 * g.LZ[0] - g.LZ[1], g.LZ)
+    args = (I, H, D, bz, ScaleAt, d["outsideMGNP"], Lz, g.PA, g.PAbn, smooth, DthI, ram)
+    ref = oracle_built.hi_tail(*args)
+    ind = _hi_tail_numpy(*args)
+    for n in ("I_cart", "H_cart", "HDens_cart", "bZEq_cart", "h_interp", "I_interp", "FNHS", "FNIS", "BOUNHS", "BOUNIS", "HDNS",
+              "BNES", "dIdt", "dHdt", "dIbndt", "dBdt"):
+        if smooth:
+            scale = np.nanmax(np.abs(ref[n])) + 1e-300
+            assert np.allclose(ref[n], ind[n], rtol=0, atol=1e-13 * scale * 300, equal_nan=True), (n, float(np.nanmax(np.abs(ref[n] - ind[n])) / scale))
+        else:
+            assert np.array_equal(ref[n], ind[n], equal_nan=True), (n, float(np.nanmax(np.abs(ref[n] - ind[n]))))
