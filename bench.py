@@ -371,7 +371,23 @@ def hi_metrics(device):
         lines = g.NR * g.NT
         bytes_alg = lines * (5 * 101 + 3 * g.NPA + 1) * 8
         k = sorted(ms)[len(ms) // 2]
-        out[name] = {"lines": lines, "nthe": 101, "NPA": g.NPA, "kernel_ms": k, "call_wall_ms": sorted(wall)[len(wall) // 2],
+        try:        # the rest of computehI (rsg_hI_tail: 4 kernels) on the arrays just computed
+            rng = np.random.default_rng(1)
+            shape3 = (g.NR + 1, g.NT, g.NPA)
+            ram = {n: np.asfortranarray(rng.random(shape3)) for n in ("FNHS", "FNIS", "BOUNHS", "BOUNIS", "HDNS")}
+            ram["BNES"] = np.asfortranarray(1e-7 * rng.random((g.NR + 1, g.NT)))
+            Lz = g.LZ[:g.NR + 1] if len(g.LZ) > g.NR else np.append(2 * g.LZ[0] - g.LZ[1], g.LZ)
+            tms, twall = [], []
+            for _ in range(5):
+                t0 = time.perf_counter()
+                tr = host.hI_tail(r[0], r[1], np.where(np.isfinite(r[2]), r[2], 1.0), r[3], np.zeros(g.NT, dtype=np.int32),
+                                  d["outsideMGNP"], Lz, g.PA, g.PAbn, 1, 300.0, ram, device=device)
+                twall.append((time.perf_counter() - t0) * 1e3)
+                tms.append(tr["ms"])
+            tail = {"kernels_ms": sorted(tms)[2], "call_wall_ms": sorted(twall)[2], "launches": 4, "integral_smooth": 1}
+        except Exception as e:
+            tail = {"error": str(e)[:200]}
+        out[name] = {"tail": tail, "lines": lines, "nthe": 101, "NPA": g.NPA, "kernel_ms": k, "call_wall_ms": sorted(wall)[len(wall) // 2],
                      "integrals_per_s": 3 * lines * g.NPA / (k * 1e-3) if k > 0 else None, "algorithmic_bytes": bytes_alg,
                      "GBps": bytes_alg / (k * 1e-3) / 1e9 if k > 0 else None,
                      "bound": "latency (one CTA per line, 500 / 3920 CTAs, serial chain over NPA): far below the HBM roofline by construction"}
