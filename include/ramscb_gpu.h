@@ -400,6 +400,15 @@ int rsg_hI_tail(int device, int nR, int nT, int nPa, double* I_cart, double* H_c
                 const int* ScaleAt, const int* outsideMGNP, const double* Lz, const double* PA, const double* PAbn,
                 int integral_smooth, double DthI, double* FNHS, double* FNIS, double* BOUNHS, double* BOUNIS, double* HDNS,
                 double* BNES, double* dIdt, double* dHdt, double* dIbndt, double* dBdt, int* gslerr, double* ms);
+/* The first block of computehI, "Convert SCB field lines to RAM field lines" (src/ModRamScb.f90:252-300): winding-number
+ * test of every RAM equatorial point (Lz(i+1), MLT(j)) against the outer SCB ring, psiRAM and then x, y, z, bf of every
+ * node of the line by GSL_Interpolation_2D = Interpolation_2D_NN_point + NN_Interpolation_2D (src/ModRamGSL.f90:368-422,
+ * :872-917: 9 nearest scattered points, inverse-distance-squared weights).  SCB arrays (nthe,npsi,nzeta+1), outputs
+ * xRAM .. bRAM (nthe,nR,nT) (zero on lines outside the SCB domain) and outsideSCB(nR,nT).  The Geopack tracing of the
+ * outside lines (:302-368) stays on the host. */
+int rsg_hI_convert_lines(int device, int nthe, int npsi, int nzeta, int nR, int nT, int nThetaEquator, const double* x,
+                         const double* y, const double* z, const double* bf, const double* psi, const double* alfa, const double* Lz,
+                         const double* MLT, double* xRAM, double* yRAM, double* zRAM, double* bRAM, int* outsideSCB, double* ms);
 
 #ifdef __cplusplus
 }

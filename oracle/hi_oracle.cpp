@@ -161,3 +161,97 @@ void hio_integrals(int nthe, int nR, int nT, int nPa, int nThetaEquator, double 
 }
 
 }  // extern "C"
+
+// ---- computehI, "Convert SCB field lines to RAM field lines" (src/ModRamScb.f90:252-300) -------------------------
+// winding-number test against the ring (nThetaEquator, npsi-1, :), psiRAM by GSL_Interpolation_2D on the scattered
+// equatorial points, then x, y, z, bf of every node k of the line by GSL_Interpolation_2D in (psi, alfa) space.  The
+// generic resolves to Interpolation_2D_NN_point (src/ModRamGSL.f90:368-422): the 9 nearest scattered points by nine
+// MINLOC passes, then NN_Interpolation_2D (:872-917), inverse-distance-squared weights.  Pure Fortran in the
+// reference (no GSL call), restated literally.  Arrays (nthe,npsi,nzeta+1), Fortran order.
+namespace {
+double nn9(int n1, int m1, const double* x1, const double* y1, size_t s1, size_t s2, const double* const* f1, int nf, double x2,
+           double y2, std::vector<double>& distance, double* f2) {
+  // x1(i,j) = x1[i*s1 + j*s2]; scatter order of :391-399: i outer, j inner
+  const int nTotal = n1 * m1;
+  int it = 0;
+  for (int i = 0; i < n1; i++)
+    for (int j = 0; j < m1; j++, it++) {
+      const double dx = x1[i * s1 + j * s2] - x2, dy = y1[i * s1 + j * s2] - y2;
+      distance[it] = dx * dx + dy * dy;
+    }
+  size_t near[9];
+  for (int k = 0; k < 9; k++) {
+    int best = 0;
+    for (int q = 1; q < nTotal; q++)
+      if (distance[q] < distance[best]) best = q;      // MINLOC: first minimum
+    near[k] = (size_t)(best / m1) * s1 + (size_t)(best % m1) * s2;
+    distance[best] = 999999.9;
+  }
+  double w[9], wsum = 0.0;                              // NN_Interpolation_2D
+  for (int i = 0; i < 9; i++) {
+    const double dx = x1[near[i]] - x2, dy = y1[near[i]] - y2;
+    const double d = std::sqrt(dx * dx + dy * dy);
+    if (std::fabs(d) <= 1e-9) {
+      for (int q = 0; q < 9; q++) w[q] = 0.0;
+      w[i] = 1.0; wsum = 1.0;
+      break;
+    }
+    w[i] = 1 / (d * d);
+    wsum = wsum + w[i];
+  }
+  for (int c = 0; c < nf; c++) {
+    double v = 0.0;
+    for (int i = 0; i < 9; i++) v = v + f1[c][near[i]] * w[i] / wsum;
+    f2[c] = v;
+  }
+  return wsum;
+}
+}  // namespace
+
+extern "C" void hio_convert_lines(int nthe, int npsi, int nzeta, int nR, int nT, int nThetaEquator, const double* x, const double* y,
+                                  const double* z, const double* bf, const double* psi, const double* alfa, const double* Lz,
+                                  const double* MLT, double* xRAM, double* yRAM, double* zRAM, double* bRAM, int* outsideSCB,
+                                  double* psiRAM_out) {
+  const double pi_d = 3.141592653589793238462643383279502884197, twopi_d = 2.0 * pi_d;
+  const size_t sj = nthe, sk = (size_t)nthe * npsi;
+  const int ke = nThetaEquator - 1;
+#pragma omp parallel for collapse(2) schedule(dynamic)
+  for (int i = 0; i < nR; i++)
+    for (int j = 0; j < nT; j++) {
+      std::vector<double> distance((size_t)npsi * (nzeta - 1));
+      const size_t line = i + (size_t)nR * j;
+      for (int k = 0; k < nthe; k++) { xRAM[k + nthe * line] = 0; yRAM[k + nthe * line] = 0; zRAM[k + nthe * line] = 0; bRAM[k + nthe * line] = 0; }
+      const double xo = Lz[i + 1] * std::cos(MLT[j] * 2.0 * pi_d / 24.0 - pi_d);
+      const double yo = Lz[i + 1] * std::sin(MLT[j] * 2.0 * pi_d / 24.0 - pi_d);
+      int wn = 0;
+      for (int k = 0; k < nzeta; k++) {                                  // ring (nThetaEquator, npsi-1, k), k = 1..nzeta
+        const size_t o = ke + sj * (npsi - 2) + sk * k;
+        const double yn = y[o], yp = y[o + sk], xn = x[o], xp = x[o + sk];
+        if (yn <= yo) {
+          if (yp > yo)
+            if (((xp - xn) * (yo - yn) - (yp - yn) * (xo - xn)) > 0) wn = wn + 1;
+        } else {
+          if (yp <= yo)
+            if (((xp - xn) * (yo - yn) - (yp - yn) * (xo - xn)) < 0) wn = wn - 1;
+        }
+      }
+      outsideSCB[line] = 0;
+      if (psiRAM_out) psiRAM_out[line] = 0.0;
+      if (std::abs(wn) > 0) {
+        double alphaRAM = MLT[j] * pi_d / 12.0 + pi_d;
+        if (alphaRAM > twopi_d) alphaRAM = alphaRAM - twopi_d;
+        double psiRAM;
+        const double* fp[1] = {psi + ke + sk};                         // (nThetaEquator, :, 2:nzeta)
+        nn9(npsi, nzeta - 1, x + ke + sk, y + ke + sk, sj, sk, fp, 1, xo, yo, distance, &psiRAM);
+        if (psiRAM_out) psiRAM_out[line] = psiRAM;
+        for (int k = 0; k < nthe; k++) {
+          const double* f4[4] = {x + k + sk, y + k + sk, z + k + sk, bf + k + sk};
+          double r[4];
+          nn9(npsi, nzeta - 1, psi + k + sk, alfa + k + sk, sj, sk, f4, 4, psiRAM, alphaRAM, distance, r);
+          xRAM[k + nthe * line] = r[0]; yRAM[k + nthe * line] = r[1]; zRAM[k + nthe * line] = r[2]; bRAM[k + nthe * line] = r[3];
+        }
+      } else {
+        outsideSCB[line] = 1;
+      }
+    }
+}

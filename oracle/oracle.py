@@ -447,3 +447,20 @@ def hi_tail(I_cart, H_cart, HDens_cart, bZEq_cart, ScaleAt, outsideMGNP, Lz, PA,
                                      *[ptr(out[n]) for n in ("FNHS", "FNIS", "BOUNHS", "BOUNIS", "HDNS", "BNES", "dIdt", "dHdt", "dIbndt",
                                                              "dBdt", "h_interp", "I_interp")])
     return out
+
+
+def hi_convert_lines(x, y, z, bf, psi, alfa, Lz, MLT, nThetaEquator):
+    """src/ModRamScb.f90:252-300 (hio_convert_lines); returns xRAM, yRAM, zRAM, bRAM, outsideSCB, psiRAM."""
+    lib = hi_lib()
+    lib.hio_convert_lines.argtypes = [C.c_int] * 6 + [C.c_void_p] * 14
+    nthe, npsi, nz1 = x.shape
+    f = lambda a: np.asfortranarray(a, dtype=np.float64)
+    x, y, z, bf, psi, alfa = (f(a) for a in (x, y, z, bf, psi, alfa))
+    Lz, MLT = (np.ascontiguousarray(a, dtype=np.float64) for a in (Lz, MLT))
+    nR, nT = len(Lz) - 1, len(MLT)
+    out = [_f((nthe, nR, nT)) for _ in range(4)]
+    outside = np.zeros((nR, nT), dtype=np.int32, order="F")
+    psiRAM = _f((nR, nT))
+    lib.hio_convert_lines(nthe, npsi, nz1 - 1, nR, nT, int(nThetaEquator), *[a.ctypes.data for a in (x, y, z, bf, psi, alfa, Lz, MLT)],
+                          *[a.ctypes.data for a in out], outside.ctypes.data, psiRAM.ctypes.data)
+    return (*out, outside, psiRAM)

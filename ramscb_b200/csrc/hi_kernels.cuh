@@ -439,3 +439,123 @@ __global__ void k_hi_fill(HiTailArgs A) {
     A.dBdt[o2] = 0.0;
   }
 }
+
+// =============================================================================
+// computehI, "Convert SCB field lines to RAM field lines" (src/ModRamScb.f90:252-300): for every RAM equatorial point
+// the winding-number test against the outer SCB ring, psiRAM by GSL_Interpolation_2D over the equatorial (x, y)
+// scatter, then x, y, z, bf at every node k by GSL_Interpolation_2D over the (psi, alfa) scatter of that k.  The
+// generic is Interpolation_2D_NN_point (src/ModRamGSL.f90:368-422): nine MINLOC passes over npsi (nzeta-1) squared
+// distances, then NN_Interpolation_2D (:872-917).  This is the brute-force part of the routine (NR NT nthe queries x
+// 4320 candidates x 9 passes in the reference).
+//
+// One CTA per (point set, slice of the queries): the candidate coordinates sit in shared memory in the reference's
+// scatter order; a warp takes a query, every pass each lane scans its candidates for the smallest (distance, index)
+// pair that follows the previous pick in lexicographic order -- which is what MINLOC + overwriting the pick with
+// 999999.9 produces (first minimum wins ties) -- and a shuffle reduction elects the pick.  Weights and the 1 or 4
+// weighted sums in the reference's order: bit-identical to the oracle.
+// MODE 0: point set = equatorial plane (x, y) -> psiRAM, outsideSCB;  MODE 1: point set k = blockIdx.x, (psi, alfa) -> x, y, z, bf.
+// =============================================================================
+struct HiConvArgs {
+  int nthe, npsi, nzeta, nR, nT, nThetaEquator;
+  const double *x, *y, *z, *bf, *psi, *alfa;     // (nthe,npsi,nzeta+1)
+  const double *qx, *qy, *alphaRAM;              // xo, yo (nR,nT); alphaRAM(nT)  (host tables: cos / sin of libm)
+  double* psiRAM;                                // (nR,nT)
+  int* outside;                                  // outsideSCB(nR,nT)
+  double *xRAM, *yRAM, *zRAM, *bRAM;             // (nthe,nR,nT)
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k_hi_nn9(HiConvArgs A) {
+  extern __shared__ double hi_sm[];
+  const int m1 = A.nzeta - 1, M = A.npsi * m1;
+  double* cx = hi_sm;
+  double* cy = cx + M;
+  const size_t sj = A.nthe, sk = (size_t)A.nthe * A.npsi;
+  const int k = (MODE == 0) ? A.nThetaEquator - 1 : blockIdx.x;
+  const double* px = (MODE == 0) ? A.x : A.psi;
+  const double* py = (MODE == 0) ? A.y : A.alfa;
+  for (int s = threadIdx.x; s < M; s += blockDim.x) {
+    const size_t o = k + sj * (s / m1) + sk * (s % m1 + 1);
+    cx[s] = px[o]; cy[s] = py[o];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int nq = A.nR * A.nT;
+  for (int q = blockIdx.y * nwarp + warp; q < nq; q += gridDim.y * nwarp) {
+    const int j = q / A.nR;
+    double x2, y2;
+    if (MODE == 0) {
+      x2 = A.qx[q]; y2 = A.qy[q];
+      int wn = 0;                                                        // :262-280
+      const size_t ring = (A.nThetaEquator - 1) + sj * (A.npsi - 2);
+      for (int kz = lane; kz < A.nzeta; kz += 32) {
+        const double yn = A.y[ring + sk * kz], yp = A.y[ring + sk * (kz + 1)], xn = A.x[ring + sk * kz], xp = A.x[ring + sk * (kz + 1)];
+        if (yn <= y2) {
+          if (yp > y2 && ((xp - xn) * (y2 - yn) - (yp - yn) * (x2 - xn)) > 0) wn++;
+        } else {
+          if (yp <= y2 && ((xp - xn) * (y2 - yn) - (yp - yn) * (x2 - xn)) < 0) wn--;
+        }
+      }
+      for (int o = 16; o > 0; o >>= 1) wn += __shfl_xor_sync(0xffffffffu, wn, o);
+      if (wn == 0) {
+        if (lane == 0) { A.outside[q] = 1; A.psiRAM[q] = 0.0; }
+        continue;
+      }
+      if (lane == 0) A.outside[q] = 0;
+    } else {
+      if (A.outside[q] != 0) {
+        if (lane == 0) {
+          const size_t o = k + (size_t)A.nthe * q;
+          A.xRAM[o] = 0.0; A.yRAM[o] = 0.0; A.zRAM[o] = 0.0; A.bRAM[o] = 0.0;
+        }
+        continue;
+      }
+      x2 = A.psiRAM[q]; y2 = A.alphaRAM[j];
+    }
+    int near[9];
+    double dl = -1.0;
+    int il = -1;
+    for (int r = 0; r < 9; r++) {
+      double bd = 1.7976931348623157e308;
+      int bi = 0x7fffffff;
+      for (int s = lane; s < M; s += 32) {
+        const double dx = cx[s] - x2, dy = cy[s] - y2;
+        const double d = dx * dx + dy * dy;
+        const bool after = d > dl || (d == dl && s > il);
+        if (after && (d < bd || (d == bd && s < bi))) { bd = d; bi = s; }
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+      }
+      near[r] = bi; dl = bd; il = bi;
+    }
+    double w[9], wsum = 0.0;                                             // NN_Interpolation_2D
+    for (int i = 0; i < 9; i++) {
+      const double dx = cx[near[i]] - x2, dy = cy[near[i]] - y2;
+      const double d = sqrt(dx * dx + dy * dy);
+      if (fabs(d) <= 1e-9) {
+        for (int c = 0; c < 9; c++) w[c] = 0.0;
+        w[i] = 1.0; wsum = 1.0;
+        break;
+      }
+      w[i] = 1 / (d * d);
+      wsum = wsum + w[i];
+    }
+    const int nf = (MODE == 0) ? 1 : 4;
+    if (lane < nf) {
+      const double* f = (MODE == 0) ? A.psi : (lane == 0 ? A.x : lane == 1 ? A.y : lane == 2 ? A.z : A.bf);
+      double v = 0.0;
+      for (int i = 0; i < 9; i++) {
+        const size_t o = k + sj * (near[i] / m1) + sk * (near[i] % m1 + 1);
+        v = v + f[o] * w[i] / wsum;
+      }
+      if (MODE == 0) A.psiRAM[q] = v;
+      else {
+        double* dst = lane == 0 ? A.xRAM : lane == 1 ? A.yRAM : lane == 2 ? A.zRAM : A.bRAM;
+        dst[k + (size_t)A.nthe * q] = v;
+      }
+    }
+  }
+}

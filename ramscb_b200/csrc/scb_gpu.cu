@@ -1128,6 +1128,89 @@ int rsg_hI_tail(int device, int nR, int nT, int nPa, double* I_cart, double* H_c
   return done(RSG_OK, "");
 }
 
+// computehI, "Convert SCB field lines to RAM field lines" (src/ModRamScb.f90:252-300): xRAM, yRAM, zRAM, bRAM
+// (nthe,nR,nT) and outsideSCB(nR,nT) from the SCB arrays x, y, z, bf, psi, alfa (nthe,npsi,nzeta+1), Lz(nR+1), MLT(nT).
+// Lines outside the SCB domain come back zero with outsideSCB = 1 (the reference traces them with Geopack afterwards).
+int rsg_hI_convert_lines(int device, int nthe, int npsi, int nzeta, int nR, int nT, int nThetaEquator, const double* x,
+                         const double* y, const double* z, const double* bf, const double* psi, const double* alfa, const double* Lz,
+                         const double* MLT, double* xRAM, double* yRAM, double* zRAM, double* bRAM, int* outsideSCB, double* ms) {
+  if (!x || !y || !z || !bf || !psi || !alfa || !Lz || !MLT || !xRAM || !yRAM || !zRAM || !bRAM || !outsideSCB)
+    return sfail(RSG_ERR_ARG, "null argument");
+  if (nthe < 1 || npsi < 3 || nzeta < 3 || nR < 1 || nT < 1 || nThetaEquator < 1 || nThetaEquator > nthe || (long long)npsi * (nzeta - 1) < 9)
+    return sfail(RSG_ERR_ARG, "bad dimensions");
+  SCK(cudaSetDevice(device));
+  const size_t n3 = (size_t)nthe * npsi * (nzeta + 1), nl = (size_t)nR * nT, no = (size_t)nthe * nl;
+  const size_t nd = 6 * n3 + 3 * nl + nT + 4 * no;
+  double* d = nullptr;
+  int* dout = nullptr;
+  cudaStream_t st = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  auto done = [&](int code, const std::string& msg) {
+    if (d) cudaFree(d);
+    if (dout) cudaFree(dout);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (st) cudaStreamDestroy(st);
+    return code == RSG_OK ? RSG_OK : sfail(code, msg);
+  };
+#define HCK(call)                                                                                  \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) return done(RSG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+  HCK(cudaStreamCreate(&st));
+  HCK(cudaEventCreate(&e0));
+  HCK(cudaEventCreate(&e1));
+  HCK(cudaMalloc(&d, nd * sizeof(double)));
+  HCK(cudaMalloc(&dout, nl * sizeof(int)));
+  std::vector<double> qx(nl), qy(nl), al(nT);                       // :258-259, :283-284 (cos / sin of the host libm)
+  const double twopi = 2.0 * PI_D;
+  for (int j = 0; j < nT; j++) {
+    for (int i = 0; i < nR; i++) {
+      qx[i + (size_t)nR * j] = Lz[i + 1] * std::cos(MLT[j] * 2.0 * PI_D / 24.0 - PI_D);
+      qy[i + (size_t)nR * j] = Lz[i + 1] * std::sin(MLT[j] * 2.0 * PI_D / 24.0 - PI_D);
+    }
+    al[j] = MLT[j] * PI_D / 12.0 + PI_D;
+    if (al[j] > twopi) al[j] = al[j] - twopi;
+  }
+  HiConvArgs A;
+  A.nthe = nthe; A.npsi = npsi; A.nzeta = nzeta; A.nR = nR; A.nT = nT; A.nThetaEquator = nThetaEquator;
+  double* p = d;
+  auto take = [&](size_t n) { double* q = p; p += n; return q; };
+  auto up = [&](const double* src, size_t n) { double* q = take(n); cudaMemcpyAsync(q, src, n * sizeof(double), cudaMemcpyHostToDevice, st); return q; };
+  A.x = up(x, n3); A.y = up(y, n3); A.z = up(z, n3); A.bf = up(bf, n3); A.psi = up(psi, n3); A.alfa = up(alfa, n3);
+  A.qx = up(qx.data(), nl); A.qy = up(qy.data(), nl); A.alphaRAM = up(al.data(), nT);
+  A.psiRAM = take(nl);
+  A.xRAM = take(no); A.yRAM = take(no); A.zRAM = take(no); A.bRAM = take(no);
+  A.outside = dout;
+  const size_t smem = 2 * (size_t)npsi * (nzeta - 1) * sizeof(double);
+  if (smem > 200 * 1024) return done(RSG_ERR_UNSUPPORTED, "SCB surface does not fit shared memory");
+  HCK(cudaFuncSetAttribute(k_hi_nn9<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  HCK(cudaFuncSetAttribute(k_hi_nn9<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  HCK(cudaStreamSynchronize(st));                                   // the host tables go out of scope with the call only, but keep it simple
+  HCK(cudaEventRecord(e0, st));
+  const int q0 = std::max(1, std::min(148, (int)((nl + 7) / 8)));   // one point set, queries spread over the SMs
+  k_hi_nn9<0><<<dim3(1, q0), 256, smem, st>>>(A);
+  HCK(cudaGetLastError());
+  const int q1 = std::max(1, std::min((int)((nl + 7) / 8), (3 * 148 + nthe - 1) / nthe));   // ~3 resident CTAs per SM
+  k_hi_nn9<1><<<dim3(nthe, q1), 256, smem, st>>>(A);
+  HCK(cudaGetLastError());
+  HCK(cudaEventRecord(e1, st));
+  HCK(cudaMemcpyAsync(xRAM, A.xRAM, no * sizeof(double), cudaMemcpyDeviceToHost, st));
+  HCK(cudaMemcpyAsync(yRAM, A.yRAM, no * sizeof(double), cudaMemcpyDeviceToHost, st));
+  HCK(cudaMemcpyAsync(zRAM, A.zRAM, no * sizeof(double), cudaMemcpyDeviceToHost, st));
+  HCK(cudaMemcpyAsync(bRAM, A.bRAM, no * sizeof(double), cudaMemcpyDeviceToHost, st));
+  HCK(cudaMemcpyAsync(outsideSCB, dout, nl * sizeof(int), cudaMemcpyDeviceToHost, st));
+  HCK(cudaStreamSynchronize(st));
+  if (ms) {
+    float t = 0.f;
+    HCK(cudaEventElapsedTime(&t, e0, e1));
+    *ms = t;
+  }
+#undef HCK
+  return done(RSG_OK, "");
+}
+
 double rsg_scb_last_ms(rsg_scb* h) { return h ? h->last_ms : 0.0; }
 int rsg_scb_use_cluster(rsg_scb* h, int on) {
   if (!h) return sfail(RSG_ERR_ARG, "null handle");

@@ -229,6 +229,17 @@ module ModScbGpu
        real(c_double), intent(out) :: ms
        integer(c_int) :: ierr
      end function
+     function rsg_hI_convert_lines(device, nthe, npsi, nzeta, nR, nT, nThetaEquator, x, y, z, bf, psi, alfa, Lz, MLT, &
+          xRAM, yRAM, zRAM, bRAM, outsideSCB, ms) bind(C, name='rsg_hI_convert_lines') result(ierr)
+       ! computehI, "Convert SCB field lines to RAM field lines", src/ModRamScb.f90:252-300
+       import :: c_int, c_double
+       integer(c_int), value :: device, nthe, npsi, nzeta, nR, nT, nThetaEquator
+       real(c_double), intent(in) :: x(*), y(*), z(*), bf(*), psi(*), alfa(*), Lz(*), MLT(*)
+       real(c_double), intent(inout) :: xRAM(*), yRAM(*), zRAM(*), bRAM(*)
+       integer(c_int), intent(inout) :: outsideSCB(*)
+       real(c_double), intent(out) :: ms
+       integer(c_int) :: ierr
+     end function
   end interface
 
 contains
@@ -286,5 +297,19 @@ contains
          dIdt, dHdt, dIbndt, dBdt, gslerr, ms), 'computehI_tail')
     if (gslerr /= 0) call CON_stop('computehI_tail_gpu: GSL_Interpolation_1D failed on a pitch-angle line')
   end subroutine computehI_tail_gpu
+
+  subroutine computehI_convert_lines_gpu(xRAM, yRAM, zRAM, bRAM, outsideSCB)
+    ! replaces the first !$OMP PARALLEL DO of computehI's default branch (src/ModRamScb.f90:252-300)
+    use ModRamGrids,     ONLY: nR, nT
+    use ModRamVariables, ONLY: LZ, MLT
+    use ModScbGrids,     ONLY: nthe, npsi, nzeta
+    use ModScbVariables, ONLY: x, y, z, bf, psi, alfa, nThetaEquator
+    real(c_double), intent(inout) :: xRAM(nthe,nR,nT), yRAM(nthe,nR,nT), zRAM(nthe,nR,nT), bRAM(nthe,nR,nT)
+    integer(c_int), intent(inout) :: outsideSCB(nR,nT)
+    real(c_double) :: ms
+    call rsg_scb_check(rsg_hI_convert_lines(0_c_int, int(nthe,c_int), int(npsi,c_int), int(nzeta,c_int), int(nR,c_int), &
+         int(nT,c_int), int(nThetaEquator,c_int), x, y, z, bf, psi, alfa, LZ, MLT, xRAM, yRAM, zRAM, bRAM, outsideSCB, ms), &
+         'computehI_convert_lines')
+  end subroutine computehI_convert_lines_gpu
 
 end module ModScbGpu

@@ -452,6 +452,7 @@ def _scb_lib():
         L.rsg_scb_launch_count.argtypes = [vp]
         L.rsg_scb_launch_count.restype = ll
         L.rsg_hI_integrals.argtypes = [i, i, i, i, i, i, d] + [vp] * 12 + [_dp]
+        L.rsg_hI_convert_lines.argtypes = [i] * 7 + [vp] * 13 + [_dp]
         L.rsg_hI_tail.argtypes = [i, i, i, i] + [vp] * 9 + [i, d] + [vp] * 10 + [_ip, _dp]
         _scb_ready = True
     return L
@@ -716,3 +717,23 @@ def hI_tail(I_cart, H_cart, HDens_cart, bZEq_cart, ScaleAt, outsideMGNP, Lz, PA,
                        C.byref(err), C.byref(ms)))
     out["gslerr"], out["ms"] = err.value, ms.value
     return out
+
+
+def hI_convert_lines(x, y, z, bf, psi, alfa, Lz, MLT, nThetaEquator, device=-1):
+    """computehI's "Convert SCB field lines to RAM field lines" (src/ModRamScb.f90:252-300): returns xRAM, yRAM, zRAM,
+    bRAM (nthe,nR,nT), outsideSCB (nR,nT) and the device time in ms.  SCB arrays (nthe,npsi,nzeta+1); Lz(nR+1), MLT(nT)."""
+    L = _scb_lib()
+    nthe, npsi, nz1 = x.shape
+    f = lambda a: np.asfortranarray(a, dtype=np.float64)
+    x, y, z, bf, psi, alfa = (f(a) for a in (x, y, z, bf, psi, alfa))
+    Lz, MLT = (np.ascontiguousarray(a, dtype=np.float64) for a in (Lz, MLT))
+    nR, nT = len(Lz) - 1, len(MLT)
+    out = [np.zeros((nthe, nR, nT), order="F") for _ in range(4)]
+    outside = np.zeros((nR, nT), dtype=np.int32, order="F")
+    ms = C.c_double(0.0)
+    if device < 0:
+        import torch
+        device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    _sck(L.rsg_hI_convert_lines(device, nthe, npsi, nz1 - 1, nR, nT, int(nThetaEquator), _p(x), _p(y), _p(z), _p(bf), _p(psi), _p(alfa),
+                                _p(Lz), _p(MLT), *[_p(a) for a in out], outside.ctypes.data, C.byref(ms)))
+    return (*out, outside, ms.value)

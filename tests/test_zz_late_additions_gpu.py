@@ -278,3 +278,38 @@ def test_hI_tail_on_device(default_grids, oracle_built, smooth, DthI, variant):
         assert np.all(np.diff(out["FNIS"][1:], axis=2) >= 0.0) if not smooth else True
     if DthI == 0.0:
         assert not out["dIdt"].any() and not out["dHdt"].any() and not out["dIbndt"].any() and not out["dBdt"].any()
+
+
+@pytest.mark.parametrize("dims", [(41, 25, 33, 10, 12), (101, 45, 97, 20, 25)])
+def test_hI_convert_lines_on_device(oracle_built, dims):
+    """computehI's field-line conversion (src/ModRamScb.f90:252-300: winding-number test, psiRAM, then x, y, z, bf of every
+    node through Interpolation_2D_NN_point = nine MINLOC passes + inverse-distance-squared weights) through
+    rsg_hI_convert_lines: bit-identical to the oracle, inside and outside the SCB domain (RAM shells beyond the last SCB
+    surface), incl. a RAM point that coincides with an SCB node (the d <= 1e-9 branch of NN_Interpolation_2D)."""
+    from ramscb_b200 import host
+    nthe, npsi, nzeta, nR, nT = dims
+    inp = SCBSYN.build_scb(nthe=nthe, npsi=npsi, nzeta=nzeta, warp=0.2)
+    ke = nthe // 2 + 1
+    r = np.sqrt(inp.x ** 2 + inp.y ** 2 + inp.z ** 2)
+    bf = np.asfortranarray(30574.0 / r ** 3 * np.sqrt(1.0 + 3.0 * (inp.z / r) ** 2))
+    Lz = np.linspace(1.75, 8.5, nR + 1)                       # the SCB domain ends at 7.5: the outer shells are outside
+    MLT = np.linspace(0.0, 24.0, nT)
+    # one RAM point exactly on an SCB equatorial node
+    jn, kn = npsi // 2, nzeta // 3
+    xe, ye = inp.x[ke - 1, jn, kn], inp.y[ke - 1, jn, kn]
+    Lz[3] = np.hypot(xe, ye)
+    MLT[2] = ((np.arctan2(ye, xe) + np.pi) * 24.0 / (2.0 * np.pi)) % 24.0
+    args = (inp.x, inp.y, inp.z, bf, inp.psi, inp.alfa, Lz, MLT, ke)
+    ref = oracle_built.hi_convert_lines(*args)
+    out = host.hI_convert_lines(*args)
+    assert np.array_equal(ref[4], out[4]) and 0 < out[4].sum() < out[4].size
+    for name, a, b in zip(("xRAM", "yRAM", "zRAM", "bRAM"), ref, out):
+        assert np.all(np.isfinite(b)), name
+        assert np.array_equal(a, b), (name, float(np.max(np.abs(a - b))))
+    inside = out[4] == 0
+    # the interpolated equatorial foot points land near the RAM points they were asked for
+    xo = Lz[1:, None] * np.cos(MLT[None, :] * 2 * np.pi / 24 - np.pi)
+    yo = Lz[1:, None] * np.sin(MLT[None, :] * 2 * np.pi / 24 - np.pi)
+    err = np.hypot(out[0][ke - 1] - xo, out[1][ke - 1] - yo)[inside]
+    # (nine unnormalised nearest neighbours in (psi, alfa): 0.04 RE median at the default SCB grid, coarser grids are worse)
+    assert np.all(out[0][:, ~inside] == 0.0) and (nthe < 101 or np.median(err) < 0.1)
