@@ -391,6 +391,25 @@ def hi_metrics(device):
                      "integrals_per_s": 3 * lines * g.NPA / (k * 1e-3) if k > 0 else None, "algorithmic_bytes": bytes_alg,
                      "GBps": bytes_alg / (k * 1e-3) / 1e9 if k > 0 else None,
                      "bound": "latency (one CTA per line, 500 / 3920 CTAs, serial chain over NPA): far below the HBM roofline by construction"}
+    try:        # the first block of computehI: SCB field lines -> RAM field lines (rsg_hI_convert_lines), configs[3] SCB grid
+        inp = scb_synthetic.build_scb(nthe=101, npsi=45, nzeta=97, warp=0.2)
+        rr = np.sqrt(inp.x ** 2 + inp.y ** 2 + inp.z ** 2)
+        bf = np.asfortranarray(30574.0 / rr ** 3 * np.sqrt(1.0 + 3.0 * (inp.z / rr) ** 2))
+        g = grids.build_grids()
+        Lz = g.LZ[:g.NR + 1] if len(g.LZ) > g.NR else np.append(2 * g.LZ[0] - g.LZ[1], g.LZ)
+        ms, wall = [], []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            r = host.hI_convert_lines(inp.x, inp.y, inp.z, bf, inp.psi, inp.alfa, Lz, g.MLT[:g.NT], 51, device=device)
+            wall.append((time.perf_counter() - t0) * 1e3)
+            ms.append(r[5])
+        nq = int((r[4] == 0).sum()) * 101
+        k = sorted(ms)[1]
+        out["convert_lines_default"] = {"kernels_ms": k, "call_wall_ms": sorted(wall)[1], "queries": nq, "candidates_per_query": 45 * 96,
+                                        "passes": 9, "distance_evaluations_per_s": nq * 45 * 96 * 9 / (k * 1e-3) if k > 0 else None,
+                                        "bound": "shared-memory bandwidth / FP64 issue (candidates resident in shared memory, no HBM traffic to speak of)"}
+    except Exception as e:
+        out["convert_lines_default"] = {"error": str(e)[:200]}
     return out
 
 
@@ -682,6 +701,14 @@ def main():
             line["scb"]["cpu_hI_integrals"] = {"wall_ms": (time.perf_counter() - t0) * 1e3, "lines": g.NR * g.NT, "cores": 1, "kind": "port"}
         except Exception as e:
             line["scb"]["cpu_hI_integrals"] = {"error": str(e)[:200]}
+        try:        # CPU side of extras.computehI_integrals.convert_lines_default (OpenMP over the RAM points like the reference)
+            rr = np.sqrt(sinp.x ** 2 + sinp.y ** 2 + sinp.z ** 2)
+            t0 = time.perf_counter()
+            oracle.hi_convert_lines(sinp.x, sinp.y, sinp.z, np.asfortranarray(30574.0 / rr ** 3), sinp.psi, sinp.alfa,
+                                    g.LZ[:g.NR + 1] if len(g.LZ) > g.NR else np.append(2 * g.LZ[0] - g.LZ[1], g.LZ), g.MLT[:g.NT], 51)
+            line["scb"]["cpu_hI_convert_lines"] = {"wall_ms": (time.perf_counter() - t0) * 1e3, "cores": os.cpu_count(), "kind": "port"}
+        except Exception as e:
+            line["scb"]["cpu_hI_convert_lines"] = {"error": str(e)[:200]}
     if rank == 0 and world == 1 and not a.no_cpu_baseline:      # reported at N = 1 only
         v, nthreads, dt = cpu_reference(g, inp, 3 if a.workload == "default" else 1, 1)
         line["cpu_baseline"] = {"value": v, "unit": unit, "cores": nthreads, "kind": "port",

@@ -878,3 +878,64 @@ def test_hi_tail_oracle_vs_independent_numpy(oracle_built, default_grids, smooth
             assert np.allclose(ref[n], ind[n], rtol=0, atol=1e-13 * scale * 300, equal_nan=True), (n, float(np.nanmax(np.abs(ref[n] - ind[n])) / scale))
         else:
             assert np.array_equal(ref[n], ind[n], equal_nan=True), (n, float(np.nanmax(np.abs(ref[n] - ind[n]))))
+
+
+def test_hi_convert_oracle_vs_independent_numpy(oracle_built):
+    """hio_convert_lines (nine MINLOC passes, literal) against a numpy restatement that takes the nine nearest scattered
+    points from ONE stable argsort of the squared distances -- the same sequence MINLOC + overwrite produces -- and
+    NN_Interpolation_2D's weights (src/ModRamGSL.f90:368-422, :872-917); winding number from src/ModRamScb.f90:262-280
+    in array form.  Bit-identical."""
+    from ramscb_b200 import scb_synthetic
+    nthe, npsi, nzeta, nR, nT = 9, 13, 15, 7, 9
+    inp = scb_synthetic.build_scb(nthe=nthe, npsi=npsi, nzeta=nzeta, warp=0.2)
+    ke = nthe // 2 + 1
+    r = np.sqrt(inp.x ** 2 + inp.y ** 2 + inp.z ** 2)
+    bf = np.asfortranarray(30574.0 / r ** 3)
+    Lz = np.linspace(1.75, 8.5, nR + 1)
+    MLT = np.linspace(0.0, 24.0, nT)
+    xR, yR, zR, bR, outside, psiR = oracle_built.hi_convert_lines(inp.x, inp.y, inp.z, bf, inp.psi, inp.alfa, Lz, MLT, ke)
+
+    def nn9(X, Y, Fs, x2, y2):               # X, Y, F: (npsi, nzeta-1); scatter order = C order of that shape
+        xs, ys = X.ravel(order="C"), Y.ravel(order="C")
+        d2 = (xs - x2) ** 2 + (ys - y2) ** 2
+        near = np.argsort(d2, kind="stable")[:9]
+        w, wsum = np.zeros(9), 0.0
+        for i, n in enumerate(near):
+            d = np.sqrt((xs[n] - x2) ** 2 + (ys[n] - y2) ** 2)
+            if abs(d) <= 1e-9:
+                w[:] = 0.0
+                w[i] = 1.0
+                wsum = 1.0
+                break
+            w[i] = 1 / (d * d)               # gfortran expands d**2 to d*d; Python's pow(d, 2) is not always the rounded product
+            wsum = wsum + w[i]
+        res = []
+        for F in Fs:
+            fs, v = F.ravel(order="C"), 0.0
+            for i, n in enumerate(near):
+                v = v + fs[n] * w[i] / wsum
+            res.append(v)
+        return res
+
+    pi = np.pi
+    for i in range(nR):
+        for j in range(nT):
+            xo = Lz[i + 1] * np.cos(MLT[j] * 2.0 * pi / 24.0 - pi)
+            yo = Lz[i + 1] * np.sin(MLT[j] * 2.0 * pi / 24.0 - pi)
+            xn, yn = inp.x[ke - 1, npsi - 2, :nzeta], inp.y[ke - 1, npsi - 2, :nzeta]
+            xp, yp = inp.x[ke - 1, npsi - 2, 1:nzeta + 1], inp.y[ke - 1, npsi - 2, 1:nzeta + 1]
+            cross = (xp - xn) * (yo - yn) - (yp - yn) * (xo - xn)
+            wn = np.sum((yn <= yo) & (yp > yo) & (cross > 0)) - np.sum((yn > yo) & (yp <= yo) & (cross < 0))
+            assert outside[i, j] == (0 if wn != 0 else 1)
+            if wn == 0:
+                assert not xR[:, i, j].any() and not bR[:, i, j].any()
+                continue
+            al = MLT[j] * pi / 12.0 + pi
+            if al > 2.0 * pi:
+                al = al - 2.0 * pi
+            sl = (slice(None), slice(1, nzeta))
+            psiRAM, = nn9(inp.x[ke - 1][sl], inp.y[ke - 1][sl], [inp.psi[ke - 1][sl]], xo, yo)
+            assert psiRAM == psiR[i, j]
+            for k in range(nthe):
+                v = nn9(inp.psi[k][sl], inp.alfa[k][sl], [inp.x[k][sl], inp.y[k][sl], inp.z[k][sl], bf[k][sl]], psiRAM, al)
+                assert v == [xR[k, i, j], yR[k, i, j], zR[k, i, j], bR[k, i, j]], (i, j, k)
