@@ -737,3 +737,38 @@ def hI_convert_lines(x, y, z, bf, psi, alfa, Lz, MLT, nThetaEquator, device=-1):
     _sck(L.rsg_hI_convert_lines(device, nthe, npsi, nz1 - 1, nR, nT, int(nThetaEquator), _p(x), _p(y), _p(z), _p(bf), _p(psi), _p(alfa),
                                 _p(Lz), _p(MLT), *[_p(a) for a in out], outside.ctypes.data, C.byref(ms)))
     return (*out, outside, ms.value)
+
+
+def computehI(scb, Lz, MLT, mu, PA, PAbn, ram, DthI, integral_smooth=True, density_fn=None, trace_fn=None, device=-1, _impl=None):
+    """computehI (src/ModRamScb.f90:141-637, default branch) composed from the three device calls, with the reference's
+    host-side steps in between: `scb` carries x, y, z, bf, psi, alfa (nthe,npsi,nzeta+1), chiVal, nThetaEquator, bnormal;
+    `ram` the previous FNHS, FNIS, BOUNHS, BOUNIS, HDNS, BNES.  Lines outside the SCB domain set ScaleAt (:306-310) and go
+    to `trace_fn(i, j, xo, yo)` -> (x, y, z, b) arrays of nthe nodes or None; without a tracer they are flagged
+    outsideMGNP like the reference's 'SWMF' branch (:311-314).  `density_fn(distance)` is the bounce-averaged quantity
+    (RAIRDEN polynomial in the reference, :365-371).  `_impl` (tests only) swaps the three calls for another
+    implementation with the same signatures."""
+    conv, integ, tail = _impl if _impl else (hI_convert_lines, hI_integrals, hI_tail)
+    kw = {} if _impl else {"device": device}
+    xR, yR, zR, bR, outsideSCB = conv(scb["x"], scb["y"], scb["z"], scb["bf"], scb["psi"], scb["alfa"], Lz, MLT, scb["nThetaEquator"], **kw)[:5]
+    nR, nT = outsideSCB.shape
+    ScaleAt = np.zeros(nT, dtype=np.int32)
+    outsideMGNP = np.zeros((nR, nT), dtype=np.int32, order="F")
+    for j in range(nT):
+        for i in range(nR):
+            if outsideSCB[i, j] == 1:
+                if ScaleAt[j] == 0:
+                    ScaleAt[j] = i + 1
+                line = None
+                if trace_fn is not None:
+                    ang = MLT[j] * 2.0 * np.pi / 24.0 - np.pi
+                    line = trace_fn(i, j, Lz[i + 1] * np.cos(ang), Lz[i + 1] * np.sin(ang))
+                if line is None:
+                    outsideMGNP[i, j] = 1
+                else:
+                    xR[:, i, j], yR[:, i, j], zR[:, i, j], bR[:, i, j] = line
+    distance = np.sqrt(xR ** 2 + yR ** 2 + zR ** 2)
+    density = np.asfortranarray(density_fn(distance) if density_fn else np.zeros_like(distance))
+    I, H, D, bz = integ(scb["chiVal"], mu, xR, yR, zR, bR, density, outsideMGNP, scb["nThetaEquator"], scb["bnormal"], **kw)[:4]
+    out = tail(I, H, D, bz, ScaleAt, outsideMGNP, Lz, PA, PAbn, integral_smooth, DthI, ram, **kw)
+    out.update(xRAM=xR, yRAM=yR, zRAM=zR, bRAM=bR, outsideSCB=outsideSCB, outsideMGNP=outsideMGNP, ScaleAt=ScaleAt)
+    return out

@@ -313,3 +313,32 @@ def test_hI_convert_lines_on_device(oracle_built, dims):
     err = np.hypot(out[0][ke - 1] - xo, out[1][ke - 1] - yo)[inside]
     # (nine unnormalised nearest neighbours in (psi, alfa): 0.04 RE median at the default SCB grid, coarser grids are worse)
     assert np.all(out[0][:, ~inside] == 0.0) and (nthe < 101 or np.median(err) < 0.1)
+
+
+@pytest.mark.parametrize("dims", [(41, 25, 33), (101, 45, 97)])
+def test_computehI_composed_on_device(default_grids, oracle_built, dims):
+    """computehI end to end (conversion -> ScaleAt / outsideMGNP on the host -> integrals -> tail) through
+    host.computehI against the same composition of the oracle's three restatements: every RAM variable and time derivative
+    bit-identical, with RAM shells beyond the SCB domain (no tracer: flagged outsideMGNP like the 'SWMF' branch)."""
+    from ramscb_b200 import host
+    g = default_grids
+    nthe, npsi, nzeta = dims
+    inp = SCBSYN.build_scb(nthe=nthe, npsi=npsi, nzeta=nzeta, warp=0.2)
+    r = np.sqrt(inp.x ** 2 + inp.y ** 2 + inp.z ** 2)
+    scb = dict(x=inp.x, y=inp.y, z=inp.z, psi=inp.psi, alfa=inp.alfa, chiVal=inp.chiVal, nThetaEquator=nthe // 2 + 1, bnormal=1.0,
+               bf=np.asfortranarray(30574.0 / r ** 3 * np.sqrt(1.0 + 3.0 * (inp.z / r) ** 2)))
+    Lz = np.linspace(1.75, 8.0, g.NR + 1)                    # the last shells lie outside the SCB domain (7.5)
+    rng = np.random.default_rng(4)
+    shape3 = (g.NR + 1, g.NT, g.NPA)
+    ram = {n: np.asfortranarray(rng.random(shape3)) for n in ("FNHS", "FNIS", "BOUNHS", "BOUNIS", "HDNS")}
+    ram["BNES"] = np.asfortranarray(1e-7 * rng.random((g.NR + 1, g.NT)))
+    dens = lambda dist: 10 ** (13.326 - 3.6908 * dist + 1.1362 * dist ** 2 - 0.16984 * dist ** 3 + 0.009553 * dist ** 4)   # RAIRDEN
+    args = (scb, Lz, g.MLT[:g.NT], g.MU, g.PA, g.PAbn, ram, 300.0)
+    out = host.computehI(*args, integral_smooth=True, density_fn=dens)
+    ref = host.computehI(*args, integral_smooth=True, density_fn=dens,
+                         _impl=(oracle_built.hi_convert_lines, oracle_built.hi_integrals, oracle_built.hi_tail))
+    assert out["ScaleAt"].any() and np.array_equal(out["ScaleAt"], ref["ScaleAt"]) and np.array_equal(out["outsideMGNP"], ref["outsideMGNP"])
+    for n in ("xRAM", "bRAM", "FNHS", "FNIS", "BOUNHS", "BOUNIS", "HDNS", "BNES", "dIdt", "dHdt", "dIbndt", "dBdt"):
+        assert np.array_equal(ref[n], out[n], equal_nan=True), (n, float(np.nanmax(np.abs(ref[n] - out[n]))))
+    inside = out["outsideMGNP"] == 0
+    assert np.all(np.isfinite(out["FNHS"][1:][inside])) and np.all(out["FNHS"][1:][inside][:, 4:] > 0.0)
