@@ -19,3 +19,10 @@ ncu --set full --clock-control none --import-source on -k "$K" --launch-skip 18 
 ncu -i $O/full_x4_wpi.ncu-rep --page raw --csv > $O/full_x4_wpi_raw.csv
 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $O/launches_scb_run.csv \
     python -c "import bench, json; print(json.dumps(bench.scb_run_metrics(0)))" > $O/launches_scb_run.log 2>&1
+#   4. computehI (rsg_hI_convert_lines / rsg_hI_integrals / rsg_hI_tail): launch list and a --set full capture of the
+#      nearest-neighbour kernel and of the integral kernel (both have never run on hardware before step 0)
+ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $O/launches_computehI.csv \
+    python -c "import bench, json; print(json.dumps(bench.hi_metrics(0)))" > $O/launches_computehI.log 2>&1
+ncu --set full --clock-control none --import-source on -k 'regex:^(k_hi_nn9|k_hi_lines|k_hi_smooth)' --launch-count 4 \
+    -o $O/full_computehI -f python -c "import bench; bench.hi_metrics(0)" > $O/full_computehI.log 2>&1
+ncu -i $O/full_computehI.ncu-rep --page raw --csv > $O/full_computehI_raw.csv
