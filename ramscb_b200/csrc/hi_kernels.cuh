@@ -449,9 +449,9 @@ __global__ void k_hi_fill(HiTailArgs A) {
 // 4320 candidates x 9 passes in the reference).
 //
 // One CTA per (point set, slice of the queries): the candidate coordinates sit in shared memory in the reference's
-// scatter order; a warp takes a query, every pass each lane scans its candidates for the smallest (distance, index)
-// pair that follows the previous pick in lexicographic order -- which is what MINLOC + overwriting the pick with
-// 999999.9 produces (first minimum wins ties) -- and a shuffle reduction elects the pick.  Weights and the 1 or 4
+// scatter order; a warp takes a query.  MINLOC + overwriting the pick with 999999.9, nine times, yields the nine
+// smallest (distance, index) pairs in lexicographic order (first minimum wins ties): every lane keeps the nine smallest
+// pairs of its own candidates in registers during ONE scan, and nine shuffle elections pop the picks from the lane heads.  Weights and the 1 or 4
 // weighted sums in the reference's order: bit-identical to the oracle.
 // MODE 0: point set = equatorial plane (x, y) -> psiRAM, outsideSCB;  MODE 1: point set k = blockIdx.x, (psi, alfa) -> x, y, z, bf.
 // =============================================================================
@@ -512,24 +512,42 @@ __global__ void __launch_bounds__(256) k_hi_nn9(HiConvArgs A) {
       }
       x2 = A.psiRAM[q]; y2 = A.alphaRAM[j];
     }
-    int near[9];
-    double dl = -1.0;
-    int il = -1;
-    for (int r = 0; r < 9; r++) {
-      double bd = 1.7976931348623157e308;
-      int bi = 0x7fffffff;
-      for (int s = lane; s < M; s += 32) {
-        const double dx = cx[s] - x2, dy = cy[s] - y2;
-        const double d = dx * dx + dy * dy;
-        const bool after = d > dl || (d == dl && s > il);
-        if (after && (d < bd || (d == bd && s < bi))) { bd = d; bi = s; }
+    // one pass: every lane keeps the nine smallest (distance, index) pairs of its candidates, sorted; the nine picks of
+    // the MINLOC sequence are then popped from the lane heads by nine shuffle elections
+    double ld[9];
+    int li[9];
+#pragma unroll
+    for (int t = 0; t < 9; t++) { ld[t] = 1.7976931348623157e308; li[t] = 0x7fffffff; }
+    for (int s = lane; s < M; s += 32) {
+      const double dx = cx[s] - x2, dy = cy[s] - y2;
+      const double d = dx * dx + dy * dy;
+      if (d < ld[8] || (d == ld[8] && s < li[8])) {
+        ld[8] = d; li[8] = s;
+#pragma unroll
+        for (int t = 8; t > 0; t--) {
+          if (ld[t] < ld[t - 1] || (ld[t] == ld[t - 1] && li[t] < li[t - 1])) {
+            const double td = ld[t]; ld[t] = ld[t - 1]; ld[t - 1] = td;
+            const int ti = li[t]; li[t] = li[t - 1]; li[t - 1] = ti;
+          }
+        }
       }
+    }
+    int near[9];
+#pragma unroll
+    for (int r = 0; r < 9; r++) {
+      double bd = ld[0];
+      int bi = li[0];
       for (int o = 16; o > 0; o >>= 1) {
         const double od = __shfl_xor_sync(0xffffffffu, bd, o);
         const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
         if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
       }
-      near[r] = bi; dl = bd; il = bi;
+      near[r] = bi;
+      if (li[0] == bi) {                                                 // the owner pops its head
+#pragma unroll
+        for (int t = 0; t < 8; t++) { ld[t] = ld[t + 1]; li[t] = li[t + 1]; }
+        ld[8] = 1.7976931348623157e308; li[8] = 0x7fffffff;
+      }
     }
     double w[9], wsum = 0.0;                                             // NN_Interpolation_2D
     for (int i = 0; i < 9; i++) {
