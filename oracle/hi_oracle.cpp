@@ -11,7 +11,8 @@
 // This oracle integrates the same piecewise-linear integrands in closed form per grid segment, i.e.
 // it returns the limit cquad converges to; tests/test_cpu.py::test_hi_oracle_vs_adaptive_quadrature
 // checks it against an independent adaptive quadrature (QUADPACK) of the literal integrands at
-// cquad's tolerance.  Layouts are the reference's (Fortran order, theta fastest).
+// cquad's tolerance, and test_hi_integrals_reproduce_reference_dipole_functions pins H_cart / I_cart on dipole
+// lines to the reference's own closed forms funt / funi (src/ModRamFunctions.f90:90-143) to 1e-3.  Layouts are the reference's (Fortran order, theta fastest).
 #include <cmath>
 #include <vector>
 

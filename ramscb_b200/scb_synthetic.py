@@ -230,7 +230,12 @@ def ram_field_lines(LZ, MLT, nthe=101, constTheta=0.2, wiggle=0.0, seed=3, outsi
     x, y, z, b, dens = (np.zeros(shape, order="F") for _ in range(5))
     for i in range(nR):
         lam_foot = np.arccos(np.sqrt(1.0 / LZ[i]))
-        lam = lam_foot * (1.0 - 2.0 * chiVal / np.pi)                   # south foot point ... north foot point
+        # nodes at arc-length fraction chiVal / pi, as mapTheta leaves them (src/ModScbEuler.f90:15-75): computehI turns
+        # the integrals over chi into integrals over arc length with the factor length / pi (src/ModRamScb.f90:402-405)
+        lam_d = np.linspace(lam_foot, -lam_foot, 20001)
+        ds = LZ[i] * np.cos(lam_d) * np.sqrt(1.0 + 3.0 * np.sin(lam_d) ** 2)          # |ds / dlambda| of a dipole line
+        s_d = np.concatenate(([0.0], np.cumsum(0.5 * (ds[1:] + ds[:-1]) * np.abs(np.diff(lam_d)))))
+        lam = np.interp(chiVal / np.pi * s_d[-1], s_d, lam_d)           # foot point ... equator ... conjugate foot point
         r = LZ[i] * np.cos(lam) ** 2
         bd = np.sqrt(1.0 + 3.0 * np.sin(lam) ** 2) / np.cos(lam) ** 6 / LZ[i] ** 3 * (30574.0 / 1.0)   # nT at the surface / bnormal = 1
         for j in range(nT):

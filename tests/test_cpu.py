@@ -939,3 +939,38 @@ def test_hi_convert_oracle_vs_independent_numpy(oracle_built):
             for k in range(nthe):
                 v = nn9(inp.psi[k][sl], inp.alfa[k][sl], [inp.x[k][sl], inp.y[k][sl], inp.z[k][sl], bf[k][sl]], psiRAM, al)
                 assert v == [xR[k, i, j], yR[k, i, j], zR[k, i, j], bR[k, i, j]], (i, j, k)
+
+
+def test_hi_integrals_reproduce_reference_dipole_functions(oracle_built, default_grids):
+    """Known-answer pin of the computehI integral block against the reference's OWN dipole closed forms: funt(mu) = h and
+    funi(mu) = I of Ejiri (1978) (src/ModRamFunctions.f90:90-143, what the reference initialises FNHS / FNIS with).  On
+    dipole lines with nodes at equal arc-length fractions of chiVal (as mapTheta leaves them) H_cart and I_cart of
+    src/ModRamScb.f90:372-410 converge to them as nthe grows; the residual 1e-3 is the accuracy of Ejiri's fit."""
+    from ramscb_b200 import scb_synthetic
+    g = default_grids
+
+    def funt(x):
+        y = np.sqrt(1 - x * x)
+        al = 1. + np.log(2. + np.sqrt(3.)) / 2. / np.sqrt(3.)
+        be = al / 2. - np.pi * np.sqrt(2.) / 12.
+        return al - be * (y + np.sqrt(y)) + 0.055 * y ** (1. / 3.) - 0.037 * y ** (2. / 3.) - 0.074 * y + 0.056 * y ** (4. / 3.)
+
+    def funi(x):
+        y = np.sqrt(1 - x * x)
+        yl = np.log(y)
+        al = 1. + np.log(2. + np.sqrt(3.)) / 2. / np.sqrt(3.)
+        be = al / 2. - np.pi * np.sqrt(2.) / 12.
+        return (2. * al * (1. - y) + 2. * be * y * yl + 4. * be * (y - np.sqrt(y)) + 3. * 0.055 * (y ** (1. / 3.) - y)
+                + 6. * (-0.037) * (y ** (2. / 3.) - y) + 6. * 0.056 * (y - y ** (4. / 3.)) - 2. * (-0.074) * y * yl)
+
+    Ls = np.array([3.0, 5.0, 6.5])
+    for nthe, tol_max, tol_med in ((101, 3e-2, 4e-3), (801, 3e-3, 1.5e-3)):
+        d = scb_synthetic.ram_field_lines(Ls, g.MLT[:2], nthe=nthe)
+        I, H, _, _, _ = oracle_built.hi_integrals(mu=g.MU, **d)
+        for i in range(len(Ls)):
+            mu_lc = np.sqrt(1.0 - d["bRAM"][nthe // 2, i, 0] / d["bRAM"][-1, i, 0])       # mirror point at the foot of the line
+            sel = (g.MU < 0.95 * mu_lc) & (np.arange(g.NPA) >= 4)
+            assert sel.sum() > 40
+            eH = np.abs(H[i, 0, sel] / funt(g.MU[sel]) - 1.0)
+            eI = np.abs(I[i, 0, sel] / funi(g.MU[sel]) - 1.0)
+            assert eH.max() < tol_max and eI.max() < tol_max and np.median(eH) < tol_med and np.median(eI) < tol_med, (nthe, Ls[i], eH.max(), eI.max())
