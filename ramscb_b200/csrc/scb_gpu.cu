@@ -1192,7 +1192,7 @@ int rsg_hI_convert_lines(int device, int nthe, int npsi, int nzeta, int nR, int 
   const int q0 = std::max(1, std::min(148, (int)((nl + 7) / 8)));   // one point set, queries spread over the SMs
   k_hi_nn9<0><<<dim3(1, q0), 256, smem, st>>>(A);
   HCK(cudaGetLastError());
-  const int q1 = std::max(1, std::min((int)((nl + 7) / 8), (3 * 148 + nthe - 1) / nthe));   // ~3 resident CTAs per SM
+  const int q1 = std::max(1, std::min((int)((nl + 7) / 8), (3 * 148) / nthe));   // one wave: 3 resident CTAs (69 KB each) per SM
   k_hi_nn9<1><<<dim3(nthe, q1), 256, smem, st>>>(A);
   HCK(cudaGetLastError());
   HCK(cudaEventRecord(e1, st));
