@@ -135,5 +135,5 @@ def test_emulated_results_do_not_depend_on_thread_order():
     env = dict(os.environ, EMU_ORDER="random")
     here = os.path.dirname(os.path.abspath(__file__))
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_emu_cpu.py"), "-x", "-q", "-k",
-                        "fused_equals or (fused_wpadif and 5) or exact_sweeps or scb_maps or hI"], env=env, capture_output=True, text=True, cwd=os.path.dirname(here))
+                        "fused_equals or (fused_wpadif and 5) or exact_sweeps or scb_maps or hI_integrals or hI_tail or hI_convert"], env=env, capture_output=True, text=True, cwd=os.path.dirname(here))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
