@@ -1,30 +1,30 @@
 #!/usr/bin/env python
 """bench.py -- RAM phase-space cell-updates/s per full RAM step (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload default|x4] [--scaling weak|strong]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload x4|default] [--flags F] [--policy species|slabs]
 
-One "step" = one pass of the RAM hot path (`ram_run`, src/ModRamRun.f90:64-222)
-over one synthetic input set: for each of the 4 species CEPARA, DRIFTPARA,
-DRIFTR/P/E/MU, SUMRC, [WAVELO | CHAREXCHANGE], ATMOL x2, reversed order back to
-DRIFTR, then the epilogue, ANISCH pressures and the CFL time step.  Work unit:
-one cell-update = one F2 cell advanced by one operator call; a step applies 12
-operators (8 drift sweeps + 2 ATMOL + 2 CHAREXCHANGE-or-WAVELO) to nS*NR*NT*NE*NPA
-cells.
+One "step" = one pass of the RAM hot path (`ram_run`, src/ModRamRun.f90:64-222) over one synthetic input set: for each of
+the 4 species CEPARA, DRIFTPARA, DRIFTR/P/E/MU, SUMRC, [WPADIF], [WAVELO | CHAREXCHANGE], ATMOL x2, the same in reverse
+back to DRIFTR, then the epilogue, the ANISCH pressures and the CFL time step.  Work unit: one cell-update = one F2 cell
+advanced by one operator call; a step applies 12 operators (8 drift sweeps + 2 ATMOL + 2 CHAREXCHANGE-or-WAVELO) plus 2
+WPADIF for the species that diffuse (electrons: WPI, H+: EMIC) to nS*NR*NT*NE*NPA cells.
 
-Printed JSON keys follow the driver contract: `value` is measured with F2 resident
-in HBM (CUDA events across the library's streams, L2 flushed between steps);
-`e2e` is the same metric through the C-ABI with HOST buffers (pinned), F2
-host->device and device->host copies inside the timed region (wall clock).
-`--impl reference` times the reference's CPU algorithm (the C++ oracle, the
-reference's own OpenMP-over-species parallelism) on the same workload.
+Workload (the same at every N, so the driver's scaling efficiency is a strong-scaling figure): BASELINE configs[2] -- the
+full step with WPI / EMIC pitch-angle diffusion on the 4x grid (NR=80 NT=49 NE=70 NPA=72, 79 M cells, 632 MB), which fits
+one GPU.  configs[1] (default grid, drift + loss step) is measured beside it at N = 1 (`configs1`, also copied into
+`roofline.configs1_default_grid`).
 
-N > 1 (one process per GPU under torchrun).  Species are the independent unit of `ram_run`
-(the OpenMP loop of src/ModRamRun.f90:64), so the default is WEAK scaling with no data-path
-collective: the job advances 4*N species of the named grid, 4 per rank, every rank running exactly
-the N = 1 path on its own species; `value` = cell-updates of all ranks / max-over-ranks device time.
-`--scaling strong` keeps the 4 species fixed and shards them (and, beyond 4 ranks, pitch-angle /
-energy slabs of a species with two NCCL re-shardings per step; ramscb_b200/parallel.py) -- the
-numbers of that mode are in profiles/r1/scaling_r1.txt.
+Printed JSON keys follow the driver contract: `value` is measured with F2 resident in HBM (CUDA events over the library's
+run stream, L2 flushed between steps, max over ranks); `e2e` is the same metric through the C ABI with HOST buffers
+(pinned), the rank's share of F2 going host->device and device->host inside the timed region (wall clock).
+`--impl reference` times the reference's CPU algorithm (the C++ oracle with the reference's own OpenMP-over-species
+parallelism) on a bounded sample of the same workload.
+
+N > 1 (one process per GPU under torchrun): the library's own sharded step, rsg_ram_run_sharded
+(ramscb_b200/csrc/ram_shard.inl) -- species over ranks, pitch-angle slabs / plane-position blocks inside a species group,
+the two re-shardings done by the kernels' write-backs into the peer's buffer over NVLink (CUDA IPC), device-side barriers
+and result reduction, one CUDA graph per rank.  Before timing, every rank's share is compared bit for bit with the one-GPU
+step (`config.sharded_check`).
 """
 from __future__ import annotations
 
@@ -165,38 +165,36 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def cpu_reference(g, inp, steps, warmup, groups=1):
-    """The reference's CPU algorithm (C++ oracle; OpenMP over species like
-    src/ModRamRun.f90:64) on the same workload.  `groups` > 1 is the weak-scaling job of N GPUs
-    (4*N species): one oracle instance per group of 4 species, run concurrently, as the reference's
-    species loop would spread 4*N species over the host threads.
+def cpu_reference(g, inp, steps, warmup, flags=0, nthreads=None):
+    """The reference's CPU algorithm (C++ oracle, oracle/ram_oracle.cpp) on the same workload: one `ram_run` per step,
+    OpenMP over species like src/ModRamRun.f90:64 (the reference's own decomposition: at most nS threads).
     Returns (cell-updates/s, threads, s/step)."""
-    from concurrent.futures import ThreadPoolExecutor
     from oracle import oracle
+    from ramscb_b200 import synthetic
     oracle.build()
+    o = oracle.RamOracle(g, inp, DTs=DTS)
+    if flags & 5:
+        D = synthetic.synthetic_daa(g, inp)
+        o.set_array("ATAC", D)
+        o.set_array("ATAW_emic_h", D)
     ncpu = os.cpu_count() or 1
-    groups = max(1, min(groups, max(1, ncpu // g.nS)))   # no more instances than the cores can hold
-    os_ = [oracle.RamOracle(g, inp, DTs=DTS) for _ in range(groups)]
-    nthreads = min(g.nS, ncpu)
-
-    def one(o):
-        o.ram_run(flags=0, nthreads=nthreads)
-
-    def step():
-        if groups == 1:
-            one(os_[0])
-        else:
-            with ThreadPoolExecutor(groups) as ex:      # ctypes releases the GIL inside the call
-                list(ex.map(one, os_))
-
+    if nthreads is None:
+        nthreads = min(g.nS, ncpu)
     for _ in range(warmup):
-        step()
+        o.ram_run(flags=flags, nthreads=nthreads)
     t0 = time.perf_counter()
     for _ in range(steps):
-        step()
+        o.ram_run(flags=flags, nthreads=nthreads)
     dt = (time.perf_counter() - t0) / steps
-    cells = groups * g.nS * g.NR * g.NT * g.NE * g.NPA
-    return OPS_PER_STEP * cells / dt, nthreads * groups, dt
+    cells = g.nS * g.NR * g.NT * g.NE * g.NPA
+    return ops_per_cell(g, flags) * cells / dt, nthreads, dt
+
+
+def ops_per_cell(g, flags):
+    """operator applications per cell per ram_run, averaged over the species: 8 drift sweeps + 2 ATMOL + 2 CHAREXCHANGE /
+    WAVELO, + 2 WPADIF for each species that diffuses (electrons with WPI, H+ with EMIC), + 4 with the Coulomb operators"""
+    nw = sum(1 for sp in g.species if (flags & 1 and sp.WPI) or (flags & 4 and sp.EMIC))
+    return OPS_PER_STEP + 2.0 * nw / g.nS + (4.0 if flags & 2 else 0.0)
 
 
 def scb_metrics(device):
@@ -249,49 +247,234 @@ def scb_metrics(device):
     return out
 
 
-def time_ram_step(workload_name, flags, steps, warmup, device):
-    """Device time of one resident `ram_run` of the named workload with the given operator flags, measured
-    exactly like the headline value (L2 flushed between steps, CUDA events over the library's streams)."""
+def measure_ram(workload_name, flags, steps, warmup, device, mode="fast", dist=None, rank=0, world=1, policy=0,
+                do_e2e=True, do_profile=True, check=False, e2e_steps=None):
+    """One RAM workload, measured the way the headline is: `value` with F2 resident (CUDA events over the library's run
+    stream, L2 flushed between steps, max over ranks), `e2e` through the C ABI with the pinned HOST array going up and
+    coming back every step (wall clock), per-kernel device times and the dominant kernel's roofline (1 GPU).  world > 1:
+    the library's own sharded step (rsg_ram_run_sharded, ramscb_b200/csrc/ram_shard.inl), strong scaling."""
     import torch
-    from ramscb_b200 import host, synthetic
+    from ramscb_b200 import host, parallel, synthetic
     g, inp, desc = workload(workload_name)
-    gpu = host.RamGpu(g, device=device, mode=host.MODE_FAST)
-    gpu.set_inputs(inp)
-    nw = 0
-    if flags:
-        D = synthetic.synthetic_daa(g, inp)
+    cells = g.nS * g.NR * g.NT * g.NE * g.NPA
+    ops = ops_per_cell(g, flags)
+    gpu = host.RamGpu(g, device=device, mode=host.MODE_FAST if mode == "fast" else host.MODE_EXACT)
+    gpu.set_fields(inp)
+    gpu.set_efield(inp.VT, inp.EIR, inp.EIP)
+    gpu.set_boundary(inp.FGEOS)
+    gpu.set_wavelo(inp.WALOS1, inp.WALOS2, inp.WALOS3, inp.Kp, inp.Kpmax12)
+    gpu.set_plasmasphere(inp.NECR)
+    D = None
+    if flags & 5:
+        D = synthetic.synthetic_daa(g, inp)          # SURVEY 8(d): synthetic Daa in ATAC / ATAW_emic_h
         gpu.set_diffcoef(1, D)
         gpu.set_diffcoef(2, D)
-        nw = sum(1 for sp in g.species if (flags & 1 and sp.WPI) or (flags & 4 and sp.EMIC))
+    sh, plan = None, None
+    if world > 1:
+        sh = parallel.RamPeerSharded(gpu, dist, rank, world, policy)
+        plan = sh.plan
+        sh.load(inp.F2)
+    else:
+        gpu.f2_h2d(inp.F2)
+    F2_host = inp.F2.copy(order="F")
+    host.host_register(F2_host)
     flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
+
+    def step():
+        return sh.ram_run(DTS, flags=flags) if sh else gpu.ram_run(DTS, DtsMin=1.0, flags=flags)
+
+    def barrier():
+        if dist is not None and world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
     for _ in range(warmup):
-        gpu.ram_run(DTS, DtsMin=1.0, flags=flags)
-    n0 = gpu.launch_count()
-    ms = 0.0
+        step()
+    out = {"workload": desc, "flags": flags, "ops_per_cell_per_step": ops, "cells": cells}
+    if check and sh:
+        # inside the same lease as the timing: this rank's share after `warmup` sharded steps against the one-GPU step
+        ref = host.RamGpu(g, device=device, mode=host.MODE_FAST if mode == "fast" else host.MODE_EXACT)
+        ref.set_inputs(inp)
+        if D is not None:
+            ref.set_diffcoef(1, D)
+            ref.set_diffcoef(2, D)
+        for _ in range(warmup):
+            r1 = ref.ram_run(DTS, DtsMin=1.0, flags=flags)
+        full = ref.f2_d2h()
+        ref.close()
+        mine = sh.store(np.full(inp.F2.shape, np.nan, order="F"))
+        sl, lsl = slice(plan.s0, plan.s0 + plan.ns), slice(plan.l0, plan.l0 + plan.nl)
+        same = bool(np.array_equal(mine[sl][..., lsl], full[sl][..., lsl]))
+        t = torch.tensor([1 if same else 0], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        out["sharded_check"] = {"every_rank_share_of_F2_bit_identical_to_one_gpu_step": bool(int(t.item())),
+                                "after_steps": warmup, "script": "same comparison as tests/multi_gpu_peer_check.py"}
+        del full, mine
+    launches0 = gpu.launch_count()
+    clocks = ClockSampler(device)
+    clocks.start()
+    barrier()
+    dev_ms = 0.0
+    t_wall0 = time.perf_counter()
     for _ in range(steps):
-        flush.zero_()
-        torch.cuda.synchronize()
+        flush.zero_()                      # evict F2 from the 126 MB L2 (untimed)
+        barrier()                          # ranks start the step together: the step itself contains device-side barriers
         gpu.timer_begin()
-        gpu.ram_run(DTS, DtsMin=1.0, flags=flags)
-        ms += gpu.timer_end()
-    ms /= steps
-    launches = (gpu.launch_count() - n0) / steps
-    gpu.profile(True)
-    for _ in range(3):
-        flush.zero_()
-        torch.cuda.synchronize()
-        gpu.ram_run(DTS, DtsMin=1.0, flags=flags)
-    stages = gpu.profile_get()
-    gpu.profile(False)
-    cells = g.nS * g.NR * g.NT * g.NE * g.NPA
-    ops = OPS_PER_STEP + 2.0 * nw / g.nS + (4.0 if flags & 2 else 0.0)     # Coulomb: COULEN + COULMU in both half steps, all species
-    out = {"workload": desc, "flags": flags, "ms_per_step": ms, "value": ops * cells / (max(ms, 1e-9) * 1e-3), "unit": "cell-updates/s",
-           "ops_per_cell_per_step": ops, "launches_per_step": launches, "steps": steps, "warmup": warmup,
-           "per_kernel_ms": {k: v[0] / v[1] for k, v in stages.items() if v[1] and k != "end"}}
+        step()
+        dev_ms += gpu.timer_end()
+        clocks.sample()
+    barrier()
+    out["wall_s_timed_region"] = time.perf_counter() - t_wall0
+    out["clocks"] = clocks.stop()
+    launches = gpu.launch_count() - launches0
+    if dist is not None and world > 1:
+        t = torch.tensor([dev_ms, float(launches)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t[:1], op=dist.ReduceOp.MAX)
+        dist.all_reduce(t[1:], op=dist.ReduceOp.SUM)
+        dev_ms, launches = float(t[0].item()), int(t[1].item())
+    ms = dev_ms / steps
+    out.update(ms_per_step=ms, value=ops * cells / (ms * 1e-3), gpu_launches=int(launches), launches_per_step=launches / steps)
+
+    if do_e2e:
+        # ---- end to end through the C ABI with host buffers: the (share of the) host array goes up, the step
+        # runs, the share comes back -- every step, as the routine-level drop-in does (INTEGRATION.md 3a)
+        n = e2e_steps or max(3, min(steps, 10))
+        per_l = g.nS * g.NR * g.NT * g.NE * 8
+        if sh:
+            up = plan.nl * per_l
+            down = plan.nl * per_l
+            if plan.ns < g.nS:
+                up += plan.nl * per_l          # d2h of a species subset starts from the host image (other species kept)
+        else:
+            up = down = F2_host.nbytes
+        up += 3 * inp.VT.nbytes
+        down += (4 + 6 + 1) * g.nS * 8 + 2 * g.nS * g.NR * g.NT * 8
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            if sh:
+                gpu.f2_h2d_shard(F2_host)
+            else:
+                gpu.f2_h2d(F2_host)
+            gpu.set_efield(inp.VT, inp.EIR, inp.EIP)
+            step()
+            if sh:
+                gpu.f2_d2h_shard(F2_host)
+            else:
+                gpu.f2_d2h(F2_host)
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / n
+        tot = [float(up), float(down)]
+        if dist is not None and world > 1:
+            t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+            t = torch.tensor(tot, dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            tot = [float(t[0].item()), float(t[1].item())]
+        out["e2e"] = {"value": ops * cells / e2e_s, "unit": "cell-updates/s", "h2d_bytes_per_step": int(tot[0]),
+                      "d2h_bytes_per_step": int(tot[1]), "ms_per_step": e2e_s * 1e3, "steps": n,
+                      "timer": "wall clock around the C-ABI calls, max over ranks; pinned host F2 goes host->device and back "
+                               "EVERY step (routine-level drop-in, INTEGRATION.md 3a): PCIe bound"}
+        if not sh:
+            t0 = time.perf_counter()
+            for _ in range(n):
+                gpu.set_efield(inp.VT, inp.EIR, inp.EIP)
+                step()
+            torch.cuda.synchronize()
+            res_s = (time.perf_counter() - t0) / n
+            out["e2e"]["resident_state"] = {"ms_per_step": res_s * 1e3, "value": ops * cells / res_s,
+                                            "h2d_bytes_per_step": int(3 * inp.VT.nbytes),
+                                            "d2h_bytes_per_step": int((4 + 6 + 1) * g.nS * 8 + 2 * g.nS * g.NR * g.NT * 8),
+                                            "note": "F2 stays on the device (the fused integration, INTEGRATION.md 3b); not the headline e2e"}
+
+    peak, peak_src = measured_peak()
+    if do_profile and not sh:
+        # per-kernel device times: CUDA events recorded on the run stream between the stages of rsg_ram_run (graph
+        # replay off for this pass), L2 flushed per step
+        gpu.profile(True)
+        npf = max(3, min(steps, 10))
+        for _ in range(npf):
+            flush.zero_()
+            torch.cuda.synchronize()
+            step()
+        stages = gpu.profile_get()
+        gpu.profile(False)
+        per_kernel_ms = {k: v[0] / v[1] for k, v in stages.items() if v[1] and k != "end"}
+        nw = ops - OPS_PER_STEP - (4.0 if flags & 2 else 0.0)          # WPADIF applications per cell, species average
+        # cell-updates per cell one launch performs (SURVEY 8(d): 16 B = one FP64 read + one write per cell-update)
+        ops_per_launch = {"k_driftr": 1, "k_driftp": 1, "k_drifte": 1, "k_driftmu": 1,
+                          "k_plane_rp": 2,          # DRIFTR + DRIFTP of every plane
+                          "k_col_fused": 8 + nw}    # DRIFTE, DRIFTMU, [WPADIF], CHAREX, ATMOL, ATMOL, CHAREX, [WPADIF], DRIFTMU, DRIFTE
+        sweeps = {k: per_kernel_ms[k] for k in ops_per_launch if k in per_kernel_ms}
+        dom = max(sweeps, key=lambda n: sweeps[n])
+        alg_bytes = 16.0 * cells * ops_per_launch[dom]
+        achieved = alg_bytes / (sweeps[dom] * 1e-3) / 1e9
+        step_sum = sum(v[0] for k, v in stages.items() if k != "end") / npf
+        out["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                           "frac": achieved / peak, "traffic": profiled_traffic(workload_name, flags, dom), "peak_source": peak_src,
+                           "algorithmic_bytes_per_launch": int(alg_bytes),
+                           "cell_updates_per_cell_per_launch": ops_per_launch[dom],
+                           "note": "achieved = 16 B per cell-update (SURVEY 8(d)) x the cell-updates of one launch (all cells of the 4 "
+                                   "species x the operators the kernel fuses) / CUDA-event duration on the launching stream, L2 flushed "
+                                   "per step.  A fused kernel MOVES 16 B per cell once for all its operators, so this is an "
+                                   "HBM-equivalent throughput, not a bandwidth utilisation: `traffic` (ncu dram bytes, when the "
+                                   "committed capture matches the current sources) and `whole_step` say what the DRAM sees.",
+                           "per_kernel_ms": per_kernel_ms,
+                           "per_kernel_frac_of_peak": {k: 16.0 * cells * ops_per_launch[k] / (v * 1e-3) / 1e9 / peak for k, v in sweeps.items()},
+                           "kernel_share_of_step": {k: (v[0] / npf) / step_sum for k, v in stages.items() if k != "end"},
+                           "whole_step": {"algorithmic_GBps": 16.0 * cells * ops / (ms * 1e-3) / 1e9,
+                                          "frac": 16.0 * cells * ops / (ms * 1e-3) / 1e9 / peak,
+                                          "three_pass_floor_ms": 3 * 16.0 * cells / (peak * 1e9) * 1e3}}
+    elif sh:
+        per_gpu = 16.0 * cells * ops / world / (ms * 1e-3) / 1e9
+        sent = 0.0                                                # bytes this rank stores into peers per step (2 re-shardings)
+        if plan.G > 1:
+            mine = plan.ns * plan.nl * g.NE * g.NR * g.NT * 8.0
+            sent = 2.0 * mine * (plan.G - 1) / plan.G
+        out["roofline"] = {"bound": "hbm", "kernel": "whole sharded step (per GPU)", "achieved": per_gpu, "peak": peak, "unit": "GB/s",
+                           "frac": per_gpu / peak, "traffic": None, "peak_source": peak_src,
+                           "note": "16 B per cell-update x this GPU's share of the cell-updates / max-over-ranks step time",
+                           "nvlink": {"peer_store_bytes_per_rank_per_step": int(sent),
+                                      "link_floor_ms": sent / 770e9 * 1e3,
+                                      "note": "F2 values stored straight into the consuming rank's buffer by the producing kernel's "
+                                              "write-back (no separate exchange pass); floor = bytes / 770 GB/s measured peer bandwidth "
+                                              "(B200_PROFILING.md)"}}
+    out["plan"] = plan.as_dict() if plan is not None else None
+    host.host_unregister(F2_host)
     gpu.close()
     del flush
     torch.cuda.empty_cache()
-    return out
+    return out, g, inp
+
+
+def profiled_traffic(workload_name, flags, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full` capture
+    (profiles/traffic.json) -- only when that capture was taken from the kernel sources as they are now (sha of
+    ramscb_b200/csrc/ram_*.cuh recorded beside it); else None (a stale number is no evidence about this run)."""
+    import hashlib
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        h = hashlib.sha1()
+        for fn in ("ram_kernels.cuh", "ram_fused.cuh"):
+            with open(os.path.join(ROOT, "ramscb_b200", "csrc", fn), "rb") as f:
+                h.update(f.read())
+        if t.get("sources_sha1") != h.hexdigest():
+            return None
+        return t.get(f"{workload_name}_flags{flags}", {}).get(kernel)
+    except (OSError, ValueError):
+        return None
+
+
+def time_ram_step(workload_name, flags, steps, warmup, device):
+    """informational extras: resident step + per-kernel times of another workload / flag set"""
+    out, _, _ = measure_ram(workload_name, flags, steps, warmup, device, do_e2e=False)
+    keep = ("workload", "flags", "ms_per_step", "value", "ops_per_cell_per_step", "launches_per_step")
+    r = {k: out[k] for k in keep}
+    r["unit"] = "cell-updates/s"
+    r["per_kernel_ms"] = out.get("roofline", {}).get("per_kernel_ms")
+    return r
 
 
 def scb_zeta_metrics(device):
@@ -418,9 +601,8 @@ def extras_main(device):
     child process, so that nothing here can take the headline down).  One JSON object on stdout."""
     out = {}
     jobs = (("ram_default_wpi_emic", lambda: time_ram_step("default", 5, 10, 3, device)),
-            ("ram_x4_configs2_wpi_emic", lambda: time_ram_step("x4", 5, 5, 3, device)),
             ("ram_x4_no_wpi", lambda: time_ram_step("x4", 0, 5, 3, device)),
-            ("ram_default_coulomb", lambda: time_ram_step("default", 2, 10, 3, device)),   # one kernel per operator (no fused Coulomb stage)
+            ("ram_default_coulomb", lambda: time_ram_step("default", 2, 10, 3, device)),
             ("scb_alpha_zeta_protocol_one_rank", lambda: scb_zeta_metrics(device)),
             ("scb_run_configs3", lambda: scb_run_metrics(device)),
             ("computehI_integrals", lambda: hi_metrics(device)))
@@ -440,20 +622,26 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="default", choices=["default", "x4"])
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="N > 1: weak = 4 species per rank (4*N in the job), strong = the 4 species sharded over the ranks")
-    ap.add_argument("--flags", type=int, default=0,
-                    help="rsg_ram_run operator flags: 1 = WPI pitch-angle diffusion (electrons), 4 = EMIC (H+); 5 with "
-                         "--workload x4 is BASELINE configs[2] (full step with WPADIF); default 0 = configs[1]")
+    ap.add_argument("--workload", default="x4", choices=["default", "x4"],
+                    help="x4 = BASELINE configs[2] grid (the headline at every N), default = configs[1] grid")
+    ap.add_argument("--flags", type=int, default=None,
+                    help="rsg_ram_run operator flags: 1 = WPI pitch-angle diffusion (electrons), 4 = EMIC (H+), 2 = Coulomb; "
+                         "default 5 on the x4 grid (configs[2]: full step with WPADIF), 0 on the default grid (configs[1])")
+    ap.add_argument("--policy", default=os.environ.get("RSG_SHARD_POLICY", "species"), choices=["species", "slabs"],
+                    help="N > 1: species = whole species per rank up to 4 ranks, 2 ranks per species at 8; "
+                         "slabs = every rank holds a pitch-angle slab of all species")
     ap.add_argument("--no-scb", action="store_true", help="skip the SCB solve metrics")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the informational extras (WPI/EMIC steps, 4x grid, zeta protocol)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the informational extras")
+    ap.add_argument("--no-configs1", action="store_true", help="skip the default-grid (configs[1]) secondary measurement")
+    ap.add_argument("--no-check", action="store_true", help="N > 1: skip the in-run comparison of the sharded step with the one-GPU step")
     ap.add_argument("--extras-only", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"],
                     help="arithmetic mode of the sweeps (include/ramscb_gpu.h rsg_mode)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
+    if a.flags is None:
+        a.flags = 5 if a.workload == "x4" else 0
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -464,43 +652,31 @@ def main():
         extras_main(local_rank)
         return
 
-    g, inp, desc = workload(a.workload)
-    weak = a.scaling == "weak"
-    jobs = world if weak else 1                      # independent 4-species sets in the job
-    cells = g.nS * g.NR * g.NT * g.NE * g.NPA        # cells one rank's species set holds
-    ops_per_step = float(OPS_PER_STEP)               # operator applications per cell, averaged over the species
-    if a.flags:
-        if a.flags & ~5 or a.impl == "reference" or a.scaling == "strong" and world > 1:
-            raise SystemExit("--flags supports 1 (WPI) and 4 (EMIC) on our arm, 1 GPU or weak scaling")
-        nw = sum(1 for sp in g.species if (a.flags & 1 and sp.WPI) or (a.flags & 4 and sp.EMIC))
-        ops_per_step += 2.0 * nw / g.nS               # two WPADIF applications for each species that diffuses
-        desc += f"; flags={a.flags}: WPADIF twice per step for {nw} of the {g.nS} species"
-    if weak and world > 1:
-        desc += f"; weak scaling: {world} x 4 species, 4 per rank"
     unit = "cell-updates/s"
-    metric = "RAM phase-space cell-updates/s per full RAM step (8 drift sweeps + losses, 4 species)"
+    metric = "RAM phase-space cell-updates/s per full RAM step (8 drift sweeps + losses + WPI/EMIC pitch-angle diffusion, 4 species)"
 
     if a.impl == "reference":
         if rank != 0:
             return
-        # ~0.5 s per step on 4 cores at the default grid: bound the run to about a minute
-        cap = 40 if a.workload == "default" else 4
-        steps, wu = max(1, min(a.steps, cap)), max(1, min(a.warmup, 3 if a.workload == "default" else 1))
-        v, nthreads, dt = cpu_reference(g, inp, steps, wu, groups=jobs)
+        g, inp, desc = workload(a.workload)
+        # the 4x grid takes ~8 s per step on the reference's 4 species threads: a bounded sample of whole steps
+        cap = 40 if a.workload == "default" else 2
+        steps, wu = max(1, min(a.steps, cap)), (max(1, min(a.warmup, 3)) if a.workload == "default" else 1)
+        v, nthreads, dt = cpu_reference(g, inp, steps, wu, flags=a.flags)
         line = {"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": a.gpus, "steps": steps,
-                "warmup": wu, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": a.scaling,
+                "warmup": wu, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": desc},
+                "config": {"workload": desc + f"; flags={a.flags}"},
                 "cpu_baseline": {"value": v, "unit": unit, "cores": nthreads, "kind": "port",
-                                 "sample": f"{steps} full ram_run steps of the same workload, OpenMP over species "
-                                           f"({nthreads} threads, the reference's own decomposition"
-                                           + (f"; {nthreads // max(1, min(g.nS, os.cpu_count() or 1))} concurrent 4-species sets" if jobs > 1 else "") + ")"},
+                                 "sample": f"{steps} full ram_run steps of the same workload (flags {a.flags}), OpenMP over species "
+                                           f"({nthreads} threads: the reference's own decomposition, src/ModRamRun.f90:64); the "
+                                           "reference Fortran cannot be built in this image, so this is the C++ restatement "
+                                           "oracle/ram_oracle.cpp (-O3 -march=native)"},
                 "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
 
     import torch
-    from ramscb_b200 import host, synthetic
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
@@ -508,175 +684,65 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from ramscb_b200 import host
+    policy = host.SHARD_SPECIES if a.policy == "species" else host.SHARD_SLABS
 
-    # ---- sharding (ramscb_b200/parallel.py): species over ranks (no data-path collective);
-    # beyond nS ranks, (L,K) slabs inside a species with two NCCL re-shardings per step
-    from ramscb_b200 import parallel
-    split = world > 1 and not weak                   # strong scaling: the 4 species are sharded over the ranks
-    plan = parallel.make_plan(world if split else 1, rank if split else 0, g.nS, g.NPA, g.NE,
-                              cells_per_species=g.NR * g.NT * g.NE * g.NPA)
-    idle = plan.ns == 0     # more ranks than species on a grid too small to split a species
-    gpu = host.RamGpu(g, device=local_rank, mode=host.MODE_FAST if a.mode == "fast" else host.MODE_EXACT)
-    gpu.set_inputs(inp)
-    if a.flags:
-        D = synthetic.synthetic_daa(g, inp)          # synthetic Daa in ATAC / ATAW_emic_h
-        gpu.set_diffcoef(1, D)
-        gpu.set_diffcoef(2, D)
-    F2_host = inp.F2.copy(order="F")
-    host.host_register(F2_host)
-    flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
-    sharded = None
-    if split:
-        # a non-default torch stream carries both the library's kernels and the NCCL traffic
-        run_stream = torch.cuda.Stream()
-        torch.cuda.set_stream(run_stream)
-        gpu.set_stream(run_stream.cuda_stream)
-        sharded = parallel.RamSharded(gpu, plan, dist)
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def step_resident():
-        return gpu.ram_run(DTS, DtsMin=1.0, flags=a.flags) if not split else sharded.ram_run(DTS)
-
-    for _ in range(a.warmup):
-        step_resident()
-    launches0 = gpu.launch_count()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
-    barrier()
-    dev_ms = 0.0
-    t_wall0 = time.perf_counter()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for _ in range(a.steps):
-        flush.zero_()                      # evict F2 from the 126 MB L2 (untimed)
-        torch.cuda.synchronize()
-        if not split:
-            gpu.timer_begin()
-            step_resident()
-            dev_ms += gpu.timer_end()
-        else:                              # library work and NCCL are on / ordered with torch's current stream
-            ev0.record()
-            step_resident()
-            ev1.record()
-            torch.cuda.synchronize()
-            dev_ms += ev0.elapsed_time(ev1)
-        clocks.sample()
-    barrier()
-    wall_s = time.perf_counter() - t_wall0
-    clk = clocks.stop()
-    launches = gpu.launch_count() - launches0
-    if dist is not None:
-        t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms = float(t.item())
-    ms_per_step = dev_ms / a.steps
-    value = ops_per_step * cells * jobs / (ms_per_step * 1e-3)
-
-    # ---- end to end through the C ABI with host buffers ---------------------------
-    e2e_steps = max(3, min(a.steps, 10))
-    VT = inp.VT
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        if idle:
-            continue
-        gpu.f2_h2d(F2_host)
-        gpu.set_efield(VT, inp.EIR, inp.EIP)
-        out = step_resident()
-        gpu.f2_d2h(F2_host)
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    if dist is not None:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    h2d = F2_host.nbytes + 3 * VT.nbytes
-    d2h = F2_host.nbytes + (4 + 6 + 1) * g.nS * 8 + 2 * g.nS * g.NR * g.NT * 8
-    e2e = {"value": ops_per_step * cells * jobs / e2e_s, "unit": unit, "h2d_bytes_per_step": int(h2d) * jobs,
-           "d2h_bytes_per_step": int(d2h) * jobs, "ms_per_step": e2e_s * 1e3,
-           "timer": "wall clock, pinned host F2; F2 goes host->device and back EVERY step (routine-level drop-in, "
-                    "INTEGRATION.md 3a): PCIe bound"}
-    # for information: the fused integration keeps F2 resident; per step only the
-    # E-field arrays go up and the step's results (DtsNext, DtDrift, losses, SETRC, PPERT, PPART) come back
-    if not split:
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            gpu.set_efield(VT, inp.EIR, inp.EIP)
-            out = step_resident()
-        torch.cuda.synchronize()
-        res_s = (time.perf_counter() - t0) / e2e_steps
-        e2e["resident_state"] = {"ms_per_step": res_s * 1e3, "value": ops_per_step * cells / res_s, "per": "rank",
-                                 "h2d_bytes_per_step": int(3 * VT.nbytes),
-                                 "d2h_bytes_per_step": int((4 + 6 + 1) * g.nS * 8 + 2 * g.nS * g.NR * g.NT * 8),
-                                 "note": "F2 stays on the device; not the headline e2e"}
-
-    # ---- per-kernel device times over timed steps (CUDA events recorded on the run
-    # stream between the stages of rsg_ram_run), dominant kernel roofline ------------
-    peak, peak_src = measured_peak()
-    roofline = None
-    if not split:                                    # per rank; rank 0's is printed
-        gpu.profile(True)
-        for _ in range(a.steps):
-            flush.zero_()
-            torch.cuda.synchronize()
-            step_resident()
-        stages = gpu.profile_get()
-        gpu.profile(False)
-        per_kernel_ms = {k: v[0] / v[1] for k, v in stages.items() if v[1] and k != "end"}
-        # cell-updates one launch performs (16 B = one FP64 read + one write per cell-update)
-        ops_per_launch = {"k_driftr": 1, "k_driftp": 1, "k_drifte": 1, "k_driftmu": 1,
-                          "k_plane_rp": 2,     # DRIFTR + DRIFTP of every plane
-                          "k_col_fused": 8}    # DRIFTE, DRIFTMU, CHAREX, ATMOL, ATMOL, CHAREX, DRIFTMU, DRIFTE
-        sweeps = {k: per_kernel_ms[k] for k in ops_per_launch if k in per_kernel_ms}
-        dom = max(sweeps, key=lambda n: sweeps[n])
-        alg_bytes = 16.0 * cells * ops_per_launch[dom]
-        achieved = alg_bytes / (sweeps[dom] * 1e-3) / 1e9
-        step_sum = sum(v[0] for k, v in stages.items() if k != "end") / a.steps
-        traffic = None   # dram read+write bytes per launch from the committed `ncu --set full` capture
-        try:
-            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")) as f:
-                traffic = json.load(f).get(a.workload, {}).get(dom)
-        except OSError:
-            pass
-        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": int(alg_bytes),
-                    "cell_updates_per_cell_per_launch": ops_per_launch[dom],
-                    "limiter": ("instruction issue, not HBM: the fused kernels move 16 B per cell for "
-                                f"{ops_per_launch[dom]} cell-updates (see traffic) and spend ~42-47 warp instructions per "
-                                "cell-update (profiles/README.md)") if dom in ("k_col_fused", "k_plane_rp") else "see profiles/README.md",
-                    "note": "16 B per cell-update (SURVEY 8(d)) x cell-updates of one launch (all cells of the 4 species x the "
-                            "operators the kernel fuses); duration = CUDA events on the launching stream inside rsg_ram_run, "
-                            "L2 flushed per step.  A fused kernel moves fewer bytes than its algorithmic figure.",
-                    "per_kernel_ms": per_kernel_ms,
-                    "per_kernel_frac_of_peak": {k: 16.0 * cells * ops_per_launch[k] / (v * 1e-3) / 1e9 / peak for k, v in sweeps.items()},
-                    "kernel_share_of_step": {k: (v[0] / a.steps) / step_sum for k, v in stages.items() if k != "end"}}
-
-    line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
+    r, g, inp = measure_ram(a.workload, a.flags, a.steps, a.warmup, local_rank, mode=a.mode, dist=dist, rank=rank, world=world,
+                            policy=policy, check=(world > 1 and not a.no_check))
+    plan = r["plan"]
+    if world == 1:
+        par = "1 GPU, all species per launch"
+    elif plan["G"] == 1:
+        par = (f"{world} ranks, {plan['ns']} whole species each (rsg_ram_run_sharded, policy species): no F2 exchange; result "
+               "blocks gathered over NVLink peer memory and reduced on the device")
+    else:
+        par = (f"{world} ranks, {plan['G']} per species group ({'all species' if plan['ns'] > 1 else 'one species'} per group): "
+               "pitch-angle slabs for DRIFTR/DRIFTP, plane-position blocks for the column kernel; the 2 re-shardings per step are "
+               "the kernels' own write-backs into the consuming rank's buffer over NVLink peer memory (CUDA IPC), device-side "
+               "barriers, one CUDA graph per rank, no NCCL on the data path")
+    line = {"metric": metric, "value": r["value"], "unit": unit, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "ops_per_cell_per_step": ops_per_step, "mode": ("fast: separable coefficients + FMA + division-free limiter, fused shared-memory kernels, <=1e-12 of the oracle relative to the "
-                                "stencil neighbourhood (tests/test_ram_parity_gpu.py)") if a.mode == "fast"
+            "config": {"workload": r["workload"] + f"; flags={a.flags}", "ops_per_cell_per_step": r["ops_per_cell_per_step"],
+                       "mode": ("fast: separable coefficients + FMA + division-free limiter, fused shared-memory kernels (parity: "
+                                "PARITY.md, tests/test_ram_parity_gpu.py)") if a.mode == "fast"
                        else "exact: reference operation order, bit-identical to the oracle",
-                       "l2": "flushed between timed steps (512 MB memset, untimed)", "DTs": DTS,
-                       "parallelism": (f"{world} ranks: species x slab groups of {plan.G}, NCCL re-sharding twice per step"
-                                       if plan.G > 1 else
-                                       (f"{world} ranks, {len(plan.active)} active (one species each, no data-path collective), "
-                                        f"{world - len(plan.active)} idle: a species is split only above "
-                                        f"{parallel.SPLIT_MIN_CELLS:.0e} cells (ramscb_b200/parallel.py)"
-                                        if len(plan.active) < world else
-                                        f"{world} ranks, species-sharded, no data-path collective"))
-                       if split else ("1 GPU, all species per launch" if world == 1 else
-                                      f"{world} ranks x 4 species (species are independent in ram_run, src/ModRamRun.f90:64): every rank runs "
-                                      "the 1-GPU path on its own species set, no data-path collective; strong-scaling mode "
-                                      "(species / slab sharding with NCCL re-sharding): --scaling strong, profiles/r1/scaling_r1.txt")},
-            "clocks": clk, "e2e": e2e, "gpu_launches": int(launches) * jobs, "roofline": roofline,
-            "wall_s_timed_region": wall_s}
+                       "l2": "flushed between timed steps (512 MB memset, untimed)", "DTs": DTS, "parallelism": par,
+                       "same_workload_at_every_N": "strong scaling: bench.py --gpus 1 runs this same workload on one GPU"},
+            "clocks": r["clocks"], "e2e": r.get("e2e"), "gpu_launches": r["gpu_launches"], "roofline": r.get("roofline"),
+            "wall_s_timed_region": r["wall_s_timed_region"]}
+    if "sharded_check" in r:
+        line["config"]["sharded_check"] = r["sharded_check"]
+    if plan is not None:
+        line["config"]["shard_plan_rank0"] = plan
+
+    if rank == 0 and world == 1 and not a.no_configs1 and a.workload == "x4":
+        # BASELINE configs[1] (default grid, drift + loss step) measured the same way; secondary to the headline.  Kept
+        # inside `roofline` / `e2e` too, because the driver's parsed line keeps those objects.
+        try:
+            c1, _, _ = measure_ram("default", 0, a.steps, a.warmup, local_rank, mode=a.mode)
+            c1s = {k: c1[k] for k in ("workload", "flags", "ms_per_step", "value", "ops_per_cell_per_step", "launches_per_step")}
+            c1s["unit"] = unit
+            c1s["e2e"] = c1.get("e2e")
+            c1s["roofline"] = c1.get("roofline")
+            line["configs1"] = c1s
+            if line.get("roofline") is not None:
+                rf = c1.get("roofline") or {}
+                line["roofline"]["configs1_default_grid"] = {"ms_per_step": c1["ms_per_step"], "value": c1["value"], "unit": unit,
+                                                             "kernel": rf.get("kernel"), "frac": rf.get("frac"),
+                                                             "per_kernel_ms": rf.get("per_kernel_ms"),
+                                                             "per_kernel_frac_of_peak": rf.get("per_kernel_frac_of_peak"),
+                                                             "e2e_value": (c1.get("e2e") or {}).get("value"),
+                                                             "e2e_ms_per_step": (c1.get("e2e") or {}).get("ms_per_step")}
+        except Exception as e:
+            line["configs1"] = {"error": str(e)[:300]}
     if rank == 0 and world == 1 and not a.no_scb:
         line["scb"] = scb_metrics(local_rank)
+        if line.get("roofline") is not None:
+            # the second half of BASELINE's metric where the driver's parsed line keeps it
+            sc = line["scb"]
+            line["roofline"]["scb_sor"] = {k: sc[k] for k in ("grid", "iterate_alpha", "iterate_psi", "bandjacob_ms", "metrica_ms", "metric_ms")
+                                           if k in sc}
     if rank == 0 and world == 1 and not a.no_cpu_baseline and not a.no_scb:
         # CPU side of configs[3]: the oracle's scb_run (same loop, same parameters, OpenMP over the sub-problems like
         # the reference) on the host cores, once -- next to extras.scb_run_configs3
@@ -692,39 +758,21 @@ def main():
                                           "SORFail": sr["SORFail"], "cores": os.cpu_count(), "kind": "port"}
         except Exception as e:
             line["scb"]["cpu_scb_run"] = {"error": str(e)[:200]}
-        try:        # CPU side of extras.computehI_integrals: the oracle's closed-form loop nest, one thread (the reference
-            # runs adaptive cquad there, ~50-100x more integrand evaluations per integral), default-grid lines
-            from ramscb_b200 import scb_synthetic
-            hd = scb_synthetic.ram_field_lines(g.LZ[1:g.NR + 1] if len(g.LZ) > g.NR else g.LZ, g.MLT[:g.NT], nthe=101, wiggle=0.05)
-            t0 = time.perf_counter()
-            oracle.hi_integrals(mu=g.MU, **hd)
-            line["scb"]["cpu_hI_integrals"] = {"wall_ms": (time.perf_counter() - t0) * 1e3, "lines": g.NR * g.NT, "cores": 1, "kind": "port"}
-        except Exception as e:
-            line["scb"]["cpu_hI_integrals"] = {"error": str(e)[:200]}
-        try:        # CPU side of extras.computehI_integrals.convert_lines_default (OpenMP over the RAM points like the reference)
-            rr = np.sqrt(sinp.x ** 2 + sinp.y ** 2 + sinp.z ** 2)
-            t0 = time.perf_counter()
-            oracle.hi_convert_lines(sinp.x, sinp.y, sinp.z, np.asfortranarray(30574.0 / rr ** 3), sinp.psi, sinp.alfa,
-                                    g.LZ[:g.NR + 1] if len(g.LZ) > g.NR else np.append(2 * g.LZ[0] - g.LZ[1], g.LZ), g.MLT[:g.NT], 51)
-            line["scb"]["cpu_hI_convert_lines"] = {"wall_ms": (time.perf_counter() - t0) * 1e3, "cores": os.cpu_count(), "kind": "port"}
-        except Exception as e:
-            line["scb"]["cpu_hI_convert_lines"] = {"error": str(e)[:200]}
     if rank == 0 and world == 1 and not a.no_cpu_baseline:      # reported at N = 1 only
-        v, nthreads, dt = cpu_reference(g, inp, 3 if a.workload == "default" else 1, 1)
+        big = a.workload == "x4"
+        v, nthreads, dt = cpu_reference(g, inp, 1 if big else 3, 1, flags=a.flags)
         line["cpu_baseline"] = {"value": v, "unit": unit, "cores": nthreads, "kind": "port",
-                                "sample": "full ram_run steps of the same workload on the host cores "
-                                          f"({dt:.3f} s/step, OpenMP over species = the reference's decomposition)"}
-    if rank == 0 and world == 1 and not a.no_extras and a.workload == "default" and a.flags == 0:
-        # informational, in a child process (this process's device state is released first): the WPI/EMIC step
-        # (configs[2] on the 4x grid) and the zeta-sharded SOR protocol; never part of `value`
+                                "sample": f"{1 if big else 3} full ram_run step(s) of the same workload on the host cores after 1 warm-up "
+                                          f"({dt:.3f} s/step, OpenMP over species = the reference's decomposition, {nthreads} threads)"}
+    if rank == 0 and world == 1 and not a.no_extras and a.workload == "x4" and a.flags == 5:
+        # informational, in a child process: other flag sets, the zeta-sharded SOR protocol, scb_run, computehI
         try:
-            gpu.close()
-            del flush
-            torch.cuda.empty_cache()
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--extras-only"], capture_output=True, text=True,
-                               timeout=420, env=dict(os.environ, LOCAL_RANK=str(local_rank)))
-            tag = [l for l in r.stdout.splitlines() if l.startswith("EXTRAS_JSON ")]
-            line["extras"] = json.loads(tag[-1][len("EXTRAS_JSON "):]) if tag else {"error": (r.stderr or r.stdout)[-300:]}
+            r2 = subprocess.run([sys.executable, os.path.abspath(__file__), "--extras-only"], capture_output=True, text=True,
+                                timeout=420, env=dict(os.environ, LOCAL_RANK=str(local_rank)))
+            tag = [l for l in r2.stdout.splitlines() if l.startswith("EXTRAS_JSON ")]
+            line["extras"] = json.loads(tag[-1][len("EXTRAS_JSON "):]) if tag else {"error": (r2.stderr or r2.stdout)[-300:]}
+            if line.get("roofline") is not None and "scb_run_configs3" in line["extras"]:
+                line["roofline"].setdefault("scb_sor", {})["scb_run_configs3"] = line["extras"]["scb_run_configs3"]
         except Exception as e:
             line["extras"] = {"error": str(e)[:300]}
     if rank == 0:

@@ -197,6 +197,52 @@ int rsg_ram_fpart_planes_rev(rsg_ram* h, int s0, int ns, int l0, int nl);
 int rsg_ram_results_device(rsg_ram* h, void** res, long long* res_n, void** pp, long long* pp_n);
 int rsg_ram_part_results(rsg_ram* h, int s0, int ns, double* DtDrift, double* moments, double* PPER, double* PPAR);
 
+/* ---- Multi-GPU inside the library: the sharded ram_run over NVLink peer memory ------------------
+ * One process per GPU (<= 8 on one node).  The reference has no domain decomposition (its MPI is
+ * init / finalize only, src/Main.f90:54-57); this replaces the species loop of ram_run
+ * (src/ModRamRun.f90:64-185) the way SURVEY 8(e) shards it: species over ranks, and pitch-angle slabs /
+ * plane-position blocks inside a species when several ranks share it, with exactly two re-shardings per
+ * step.  Nothing of that is visible to the host: the ranks map each other's F2 buffer (CUDA IPC) and
+ * the kernels store their results straight into the buffer of the rank that needs them next; barriers
+ * and the reduction of the step's results run on the device too, in one CUDA graph per rank.
+ *
+ * Set-up, once: every rank calls rsg_ram_peer_export (an opaque blob of RSG_PEER_BLOB_BYTES), the host
+ * all-gathers the blobs in rank order (MPI_Allgather in the Fortran host, torch.distributed in
+ * ramscb_b200/parallel.py) and every rank calls rsg_ram_peer_attach.  Then rsg_ram_run_sharded is
+ * rsg_ram_run: same arguments, same outputs on every rank (DtDrift, losses, SETRC, PPERT, PPART of ALL
+ * species), F2 sharded.  It must be called by all ranks with the same DTs / flags (it contains barriers;
+ * a rank that never arrives makes the others fail with a time-out after 20 s instead of hanging).
+ * policy: RSG_SHARD_SPECIES = whole species per rank while world <= nS, G = world/nS ranks per species
+ * beyond; RSG_SHARD_SLABS = every rank holds a pitch-angle slab of ALL species (a contiguous run of the
+ * host array F2(nS,NR,NT,NE,NPA), which is what rsg_ram_f2_h2d_shard / d2h_shard move).
+ * Ranks that share a species need RSG_MODE_FAST and no Coulomb flag (the fused kernels). */
+#define RSG_PEER_BLOB_BYTES 192
+enum { RSG_SHARD_SPECIES = 0, RSG_SHARD_SLABS = 1 };
+typedef struct rsg_shard_plan_t {
+  int world, rank, policy;
+  int s0, ns;        /* owned species, 0-based [s0, s0+ns) */
+  int G, gidx, g0;   /* ranks g0 .. g0+G-1 share them; this rank's index among them */
+  int l0, nl;        /* pitch-angle slab of the plane kernels (DRIFTR, DRIFTP) */
+  int b0, nb, per;   /* blocks of `per` plane positions of the column kernel (DRIFTE, DRIFTMU, losses, WPADIF) */
+} rsg_shard_plan_t;
+/* the decomposition as a pure function (no device needed): P = NR*NT plane positions */
+int rsg_shard_plan(int world, int rank, int policy, int nS, int NPA, int P, rsg_shard_plan_t* out);
+int rsg_ram_peer_export(rsg_ram* h, void* blob);
+int rsg_ram_peer_attach(rsg_ram* h, int rank, int world, int policy, const void* blobs /* world x RSG_PEER_BLOB_BYTES */);
+/* several handles of ONE process on one device wired together by pointer (tests on a 1-GPU box; a host
+ * that drives several "ranks" itself): enqueue every rank's step, then collect every rank's results. */
+int rsg_ram_peer_attach_local(rsg_ram* h, int rank, int world, int policy, rsg_ram* const* peers);
+int rsg_ram_peer_detach(rsg_ram* h);
+int rsg_ram_shard_info(rsg_ram* h, rsg_shard_plan_t* out);
+int rsg_ram_run_sharded(rsg_ram* h, double DTs, double DtsMin, double T, int flags, double* dts_next, double* DtDrift,
+                        double* losses, double* SETRC, double* PPERT, double* PPART);
+int rsg_ram_run_sharded_enqueue(rsg_ram* h, double DTs, double T, int flags);
+int rsg_ram_run_sharded_collect(rsg_ram* h, double DtsMin, double* dts_next, double* DtDrift, double* losses, double* SETRC,
+                                double* PPERT, double* PPART);
+/* this rank's share of the host array F2 (full shape): its pitch-angle slab of its species */
+int rsg_ram_f2_h2d_shard(rsg_ram* h, const double* F2);
+int rsg_ram_f2_d2h_shard(rsg_ram* h, double* F2);
+
 /* FLUX = F2/FFACTOR/FNHS (src/ModRamRun.f90:210-221), host array like F2 */
 int rsg_ram_flux_d2h(rsg_ram* h, double* FLUX);
 

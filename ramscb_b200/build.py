@@ -25,6 +25,9 @@ NVCC_FLAGS = [
 ]
 
 
+LINK_LIBS = []
+
+
 def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
@@ -33,7 +36,7 @@ def _stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "ramscb_gpu.h")]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if not f.endswith(".o")] + [os.path.join(HERE, "..", "include", "ramscb_gpu.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -42,13 +45,32 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    objdir = os.path.join(LIBDIR, "obj")
+    os.makedirs(objdir, exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+    # one nvcc per translation unit, side by side (the two big files take about a minute each)
+    procs = []
+    for src in sources():
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        procs.append((src, obj, subprocess.Popen([nvcc] + flags + ["-c", "-o", obj, src], stdout=subprocess.PIPE,
+                                                 stderr=subprocess.PIPE, text=True)))
+    objs, log = [], ""
+    failed = False
+    for src, obj, pr in procs:
+        out, err = pr.communicate()
+        log += out + err
+        failed = failed or pr.returncode != 0
+        objs.append(obj)
+    if failed:
+        sys.stderr.write(log)
+        raise RuntimeError("nvcc failed")
+    r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + LINK_LIBS,
+                       capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc failed")
+        raise RuntimeError("nvcc link failed")
     if verbose:
-        sys.stderr.write(r.stderr)
+        sys.stderr.write(log)
     return LIB
 
 

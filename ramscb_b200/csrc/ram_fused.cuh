@@ -103,6 +103,24 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 // cells of a segment are read before the barrier that precedes the walk.
 // grid: x = energy chunk, y = l, z = species
 // =============================================================================
+// Where the ranks that SHARE a species hold their copies of F2 (multi-GPU, ram_shard.inl): the plane kernels
+// own pitch-angle slabs [lcut[g], lcut[g+1]), the column kernel ranges of plane positions [ccut[g], ccut[g+1])
+// (multiples of the column block).  F[g] is rank g's F2 buffer mapped into this process (CUDA IPC peer memory over
+// NVLink; F[gidx] is the local one), all with the same layout, so the re-sharding of SURVEY 8(e) is the write-back of
+// the producing kernel: every finished value is stored once, straight into the buffer of the rank that reads it next.
+#define RSG_MAX_PEERS 8
+struct PeerView {
+  int G, gidx;
+  double* F[RSG_MAX_PEERS];
+  int lcut[RSG_MAX_PEERS + 1];
+  int ccut[RSG_MAX_PEERS + 1];
+};
+__device__ __forceinline__ int peer_owner(const int* cut, int G, int x) {
+  int g = 0;
+  while (g + 1 < G && x >= cut[g + 1]) ++g;
+  return g;
+}
+
 struct PlaneCfg {
   int KC;             // planes (energies) per CTA
   int NRp, PS;        // padded row stride and plane stride of the shared copy (doubles)
@@ -112,9 +130,9 @@ struct PlaneCfg {
   int l0;             // first pitch angle of the launch (slab-sharded ranks); blockIdx.y counts from it
 };
 
-template <bool REV>
+template <bool REV, bool PEER = false>
 __global__ void __launch_bounds__(512) k_plane_rp(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0,
-                                                  PlaneCfg cfg) {
+                                                  PlaneCfg cfg, const __grid_constant__ PeerView pv) {
   extern __shared__ double smem[];
   const SpecDev& sp = pk.s[s0 + blockIdx.z];
   const int NR = d.NR, NT = d.NT, NE = d.NE, P = d.P, Pp = d.Pp;
@@ -312,6 +330,14 @@ __global__ void __launch_bounds__(512) k_plane_rp(const __grid_constant__ RamDev
       });
     else
       for_chunks([&](int so, int go, int pl) { Fg[go] = d.outp[pl] ? 1.e-31 : sP[so]; });
+  } else if (PEER) {
+    // the column kernel runs next, on the rank that owns the plane position: store there (NVLink peer memory)
+    const ptrdiff_t rel = Fg - pv.F[pv.gidx];
+    if (E == 2)
+      for_chunks([&](int so, int go, int pl) {
+        *(double2*)(pv.F[peer_owner(pv.ccut, pv.G, pl)] + rel + go) = *(const double2*)(sP + so);
+      });
+    else for_chunks([&](int so, int go, int pl) { pv.F[peer_owner(pv.ccut, pv.G, pl)][rel + go] = sP[so]; });
   } else {
     if (E == 2) for_chunks([&](int so, int go, int) { *(double2*)(Fg + go) = *(const double2*)(sP + so); });
     else for_chunks([&](int so, int go, int) { Fg[go] = sP[so]; });
@@ -392,9 +418,9 @@ __global__ void __launch_bounds__(128) k_wpadif_tables(const __grid_constant__ R
   if (viol) atomicAdd(viol_out, viol);
 }
 
-template <int PG, int MAXT, bool WPI>
+template <int PG, int MAXT, bool WPI, bool PEER = false>
 __global__ void __launch_bounds__(MAXT) k_col_fused(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0,
-                                                    ColCfg cfg) {
+                                                    ColCfg cfg, const __grid_constant__ PeerView pv) {
   extern __shared__ double smem[];
   const SpecDev& sp = pk.s[s0 + blockIdx.y];
   const int NR = d.NR, NT = d.NT, NE = d.NE, NPA = d.NPA, P = d.P, Pp = d.Pp;
@@ -740,8 +766,11 @@ __global__ void __launch_bounds__(MAXT) k_col_fused(const __grid_constant__ RamD
     const int so_step = dl * RS + (dr / H) * PG + 2 * (dr % H);
     const int go_step = (dl * NE + dr / H) * Pp + 2 * (dr % H);
     int hh = r % H;
+    const ptrdiff_t rel = PEER ? sp.F - pv.F[pv.gidx] : 0;
     while (l < NPA) {
-      *(double2*)(sp.F + go) = *(const double2*)(sT + so);
+      // PEER: the reverse plane kernel runs next, on the rank that owns the pitch angle: store there
+      if (PEER) *(double2*)(pv.F[peer_owner(pv.lcut, pv.G, l)] + rel + go) = *(const double2*)(sT + so);
+      else *(double2*)(sp.F + go) = *(const double2*)(sT + so);
       r += dr; l += dl; so += so_step; go += go_step; hh += dr % H;
       if (hh >= H) { hh -= H; so += PG - 2 * H; go += Pp - 2 * H; }
       if (r >= rowItems) { r -= rowItems; ++l; so += pad; }

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <unistd.h>
 #include <string>
 #include <vector>
 
@@ -86,8 +87,11 @@ struct Spec {
 
 }  // namespace
 
+struct rsg_shard;   // multi-GPU state (ram_shard.inl)
+
 struct rsg_ram {
   int nS, NR, NT, NE, NPA, NR1, P, Pp;
+  rsg_shard* shard = nullptr;
   int device = 0, mode = RSG_MODE_EXACT;
   bool grids_set = false, fields_set = false, efield_set = false;
   double Kp = 0, Kpmax12 = 0;
@@ -172,6 +176,8 @@ struct rsg_ram {
 };
 
 namespace {
+
+void shard_release(rsg_ram* h);   // ram_shard.inl
 
 inline int nblk(long long n, int b) { return (int)((n + b - 1) / b); }
 
@@ -545,8 +551,10 @@ int opt_in_smem(K kernel, size_t smem) {
   if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   return RSG_OK;
 }
-int L_plane_rp(rsg_ram* h, int s0, int ns, cudaStream_t st, bool rev, int l0 = 0, int nl = -1) {
+int L_plane_rp(rsg_ram* h, int s0, int ns, cudaStream_t st, bool rev, int l0 = 0, int nl = -1, const PeerView* peer = nullptr) {
   if (nl < 0) nl = h->NPA - l0;
+  static const PeerView kNoPeer{};
+  const PeerView& pv = peer ? *peer : kNoPeer;
   SpecPack pk;
   make_pack(h, pk, s0, ns);
   const RamDev dv = devfor(h, h->sp[s0].DTs);
@@ -555,8 +563,9 @@ int L_plane_rp(rsg_ram* h, int s0, int ns, cudaStream_t st, bool rev, int l0 = 0
   const dim3 g(KG, nl, ns);
   c.cfg.part_off = fused_part_off(h);      // after the column kernel's partials
   c.cfg.l0 = l0;
-  if (rev) { RET(opt_in_smem(k_plane_rp<true>, c.smem)); k_plane_rp<true><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg); }
-  else { RET(opt_in_smem(k_plane_rp<false>, c.smem)); k_plane_rp<false><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg); }
+  if (rev) { RET(opt_in_smem(k_plane_rp<true>, c.smem)); k_plane_rp<true><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg, pv); }
+  else if (peer) { RET(opt_in_smem(k_plane_rp<false, true>, c.smem)); k_plane_rp<false, true><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg, pv); }
+  else { RET(opt_in_smem(k_plane_rp<false>, c.smem)); k_plane_rp<false><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg, pv); }
   CKL();
   h->launches++;
   return RSG_OK;
@@ -601,8 +610,8 @@ int L_wtab(rsg_ram* h, int mask, double DTs, cudaStream_t st) {
   }
   return RSG_OK;
 }
-template <bool WPI>
-int L_col_t(rsg_ram* h, int s0, int ns, int doA, int doW, double DTs, cudaStream_t st, int b0, int nb) {
+template <bool WPI, bool PEER>
+int L_col_t(rsg_ram* h, int s0, int ns, int doA, int doW, double DTs, cudaStream_t st, int b0, int nb, const PeerView& pv) {
   SpecPack pk;
   make_pack(h, pk, s0, ns);
   ColPlan c = col_plan(h, WPI);
@@ -614,26 +623,30 @@ int L_col_t(rsg_ram* h, int s0, int ns, int doA, int doW, double DTs, cudaStream
   const dim3 g(nb, ns);
   const RamDev dv = devfor(h, DTs);
   if (c.T <= 320) {          // register budget follows the CTA size
-    RET(opt_in_smem(k_col_fused<COL_PG, 320, WPI>, c.smem));
-    k_col_fused<COL_PG, 320, WPI><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg);
+    RET(opt_in_smem(k_col_fused<COL_PG, 320, WPI, PEER>, c.smem));
+    k_col_fused<COL_PG, 320, WPI, PEER><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg, pv);
   } else if (c.T <= 640) {
-    RET(opt_in_smem(k_col_fused<COL_PG, 640, WPI>, c.smem));
-    k_col_fused<COL_PG, 640, WPI><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg);
+    RET(opt_in_smem(k_col_fused<COL_PG, 640, WPI, PEER>, c.smem));
+    k_col_fused<COL_PG, 640, WPI, PEER><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg, pv);
   } else if (c.T <= 896) {
-    RET(opt_in_smem(k_col_fused<COL_PG, 896, WPI>, c.smem));
-    k_col_fused<COL_PG, 896, WPI><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg);
+    RET(opt_in_smem(k_col_fused<COL_PG, 896, WPI, PEER>, c.smem));
+    k_col_fused<COL_PG, 896, WPI, PEER><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg, pv);
   } else {
-    RET(opt_in_smem(k_col_fused<COL_PG, 1024, WPI>, c.smem));
-    k_col_fused<COL_PG, 1024, WPI><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg);
+    RET(opt_in_smem(k_col_fused<COL_PG, 1024, WPI, PEER>, c.smem));
+    k_col_fused<COL_PG, 1024, WPI, PEER><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg, pv);
   }
   CKL();
   h->launches++;
   return RSG_OK;
 }
-int L_col(rsg_ram* h, int s0, int ns, int doA, double DTs, cudaStream_t st, int b0 = 0, int nb = -1, int doW = 0) {
+int L_col(rsg_ram* h, int s0, int ns, int doA, double DTs, cudaStream_t st, int b0 = 0, int nb = -1, int doW = 0,
+          const PeerView* peer = nullptr) {
   for (int s = s0; s < s0 + ns; ++s)
     if (!((doW >> s) & 1)) { h->sp[s].sd.DA = h->d_zero4; h->sp[s].sd.DB = h->d_zero4; }
-  return doW ? L_col_t<true>(h, s0, ns, doA, doW, DTs, st, b0, nb) : L_col_t<false>(h, s0, ns, doA, 0, DTs, st, b0, nb);
+  static const PeerView kNoPeer{};
+  if (peer)
+    return doW ? L_col_t<true, true>(h, s0, ns, doA, doW, DTs, st, b0, nb, *peer) : L_col_t<false, true>(h, s0, ns, doA, 0, DTs, st, b0, nb, *peer);
+  return doW ? L_col_t<true, false>(h, s0, ns, doA, doW, DTs, st, b0, nb, kNoPeer) : L_col_t<false, false>(h, s0, ns, doA, 0, DTs, st, b0, nb, kNoPeer);
 }
 // pressures of ANISCH in one pass + the result block of the step, both also written to the
 // host-mapped copies (no memcpy nodes in the fused step)
@@ -996,6 +1009,7 @@ int rsg_ram_destroy(rsg_ram* h) {
   if (!h) return RSG_OK;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
+  shard_release(h);
   for (void* p : h->allocs) cudaFree(p);
   for (int s = 0; s < h->nS; ++s) {
     Spec& sp = h->sp[s];
@@ -1993,12 +2007,12 @@ int rsg_ram_part_all(rsg_ram* h, double DTs, int flags, int s0, int ns) {
 
 // The whole species loop of ram_run (src/ModRamRun.f90:64-185) + epilogue (:186-222) on one
 // GPU: the three parts back to back, all species advanced by each launch, on one stream.
-int rsg_ram_run(rsg_ram* h, double DTs, double DtsMin, double T, int flags, double* dts_next, double* DtDrift,
-                double* losses, double* SETRC, double* PPERT, double* PPART) {
-  if (!h) return fail(RSG_ERR_ARG, "null handle");
-  h->T_elapsed = T;                    // COULMU clamps negatives only once T > 0 (src/ModRamCoul.f90:289)
+namespace {
+// decode the result blocks of all species (pinned copies) into the reference's step outputs: DtsNext (:202-205),
+// DtDrift, the loss increments ELORC = ENOLD - SETRC chained through the SUMRC calls in ram_run's order (:77-174)
+int decode_step(rsg_ram* h, int flags, double DtsMin, double* dts_next, double* DtDrift, double* losses, double* SETRC, double* PPERT,
+                double* PPART) {
   const int nS = h->nS;
-  RET(run_core(h, DTs, flags, 0, nS));
   std::vector<double> dt((size_t)4 * nS), mom((size_t)NSLOT * nS), pe((size_t)h->P * nS), pa((size_t)h->P * nS);
   RET(collect_results(h, 0, nS, dt.data(), mom.data(), pe.data(), pa.data()));
   int cat[RSG_MAX_SPECIES][NSLOT], doA;
@@ -2030,6 +2044,15 @@ int rsg_ram_run(rsg_ram* h, double DTs, double DtsMin, double T, int flags, doub
   }
   if (dts_next) *dts_next = std::max(dtn, DtsMin);
   return RSG_OK;
+}
+}  // namespace
+
+int rsg_ram_run(rsg_ram* h, double DTs, double DtsMin, double T, int flags, double* dts_next, double* DtDrift,
+                double* losses, double* SETRC, double* PPERT, double* PPART) {
+  if (!h) return fail(RSG_ERR_ARG, "null handle");
+  h->T_elapsed = T;                    // COULMU clamps negatives only once T > 0 (src/ModRamCoul.f90:289)
+  RET(run_core(h, DTs, flags, 0, h->nS));
+  return decode_step(h, flags, DtsMin, dts_next, DtDrift, losses, SETRC, PPERT, PPART);
 }
 
 int rsg_ram_flux_d2h(rsg_ram* h, double* FLUX) {
@@ -2123,3 +2146,10 @@ int rsg_host_unregister(void* p) {
 }
 
 }  // extern "C"
+
+// ---- multi-GPU step over peer memory (device-side exchange and barriers) ----------------------
+#ifdef __CUDACC__
+#include "ram_shard.inl"
+#else
+namespace { void shard_release(rsg_ram*) {} }
+#endif

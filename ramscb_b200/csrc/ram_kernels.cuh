@@ -1144,17 +1144,17 @@ __global__ void k_anisch_en(const __grid_constant__ RamDev d, const __grid_const
 // =============================================================================
 // stage: raw host image; one thread per device element of species s
 // grid: x = tiles of p, y = plane
-__global__ void k_f2_from_host(RamDev d, const double* __restrict__ stage, double* __restrict__ Fs, int s) {
+__global__ void k_f2_from_host(RamDev d, const double* __restrict__ stage, double* __restrict__ Fs, int s, int plane0 = 0) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t plane = blockIdx.y;  // l*NE + k
+  const size_t plane = (size_t)plane0 + blockIdx.y;  // l*NE + k
   if (p >= d.Pp) return;
   double v = 0.0;
   if (p < d.P) v = stage[(plane * d.P + p) * d.nS + s];
   Fs[plane * d.Pp + p] = v;
 }
-__global__ void k_f2_to_host(RamDev d, double* __restrict__ stage, const double* __restrict__ Fs, int s) {
+__global__ void k_f2_to_host(RamDev d, double* __restrict__ stage, const double* __restrict__ Fs, int s, int plane0 = 0) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t plane = blockIdx.y;
+  const size_t plane = (size_t)plane0 + blockIdx.y;
   if (p < d.P) stage[(plane * d.P + p) * d.nS + s] = Fs[plane * d.Pp + p];
 }
 // F2(:,:,NT,:,:) = F2(:,:,1,:,:), then F2 = 1e-31 where outsideMGNP == 1

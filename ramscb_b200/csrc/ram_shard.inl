@@ -1,0 +1,497 @@
+// Multi-GPU RAM step inside the library (included at the end of ram_gpu.cu).
+//
+// One process per GPU.  A rank owns species [s0, s0+ns) and, when G ranks share them, the pitch-angle slab
+// [l0, l0+nl) for the plane kernels (DRIFTR/DRIFTP) and the plane-position blocks [b0, b0+nb) for the column
+// kernel (DRIFTE, DRIFTMU, losses, WPADIF).  The step is the palindrome of src/ModRamRun.f90:70-175, so there are
+// exactly two re-shardings -- and neither is a separate pass: the ranks map each other's F2 buffer (CUDA IPC peer
+// memory over NVLink / NVSwitch) and the producing kernel's write-back stores every finished value straight into
+// the buffer of the rank that reads it next (k_plane_rp<fwd, PEER>, k_col_fused<.., PEER>).  What remains between
+// the kernels is a device-side barrier (k_peer_barrier: release / acquire flags at system scope in a peer-mapped
+// mailbox), and after the step the result blocks (CFL limits, SUMRC partial sums, partial pressures) are pushed
+// into every rank's mailbox and reduced in rank order, so every rank returns the same full result as rsg_ram_run
+// on one GPU.  The whole sequence is ONE CUDA graph per (DTs, flags, mode): no host code, no NCCL call and no
+// pack / unpack copy between the kernels.
+//
+// The host (Fortran + MPI, or Python + torch.distributed) only moves an opaque 192-byte blob per rank once
+// (rsg_ram_peer_export -> all-gather -> rsg_ram_peer_attach).  rsg_ram_peer_attach_local wires several handles of
+// ONE process together by pointer: the same kernels, barriers and graphs on one device (tests on a 1-GPU box).
+
+namespace {
+
+constexpr unsigned long long kBarrierTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
+constexpr int kBlobMagic = 0x52534732;   // "RSG2"
+
+struct PeerBlob {
+  int magic, pid, device, nS, NR, NT, NE, NPA;
+  cudaIpcMemHandle_t f2, mbox;
+  char pad[RSG_PEER_BLOB_BYTES - 8 * sizeof(int) - 2 * sizeof(cudaIpcMemHandle_t)];
+};
+static_assert(sizeof(PeerBlob) == RSG_PEER_BLOB_BYTES, "blob size is part of the ABI");
+
+// mailbox of one rank (device memory, mapped by every peer)
+struct PeerCtx {
+  int W, rank, nS, res_n;
+  long long pp_n;
+  unsigned char* mb[RSG_MAX_PEERS];
+  size_t off_flags, off_epoch, off_res, off_pp;   // [2][MAX] u64 | [2] u64 | [MAX][nS][res_n] u64 | [MAX][nS][pp_n] f64
+  unsigned long long* err;                        // host-mapped: non-zero = a barrier timed out
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Barrier among the ranks of `mask` (bit r), all of which launch it the same number of times.  Everything this
+// GPU stored before the kernel (kernel boundary + fence) is visible to a peer once it has seen the flag.
+// which: 0 = the species group's barrier, 1 = the world's (separate epoch counters).  One CTA of 32 threads.
+__global__ void k_peer_barrier(const __grid_constant__ PeerCtx pc, int which, unsigned mask) {
+  __shared__ unsigned long long e;
+  if (threadIdx.x == 0) {
+    unsigned long long* ep = (unsigned long long*)(pc.mb[pc.rank] + pc.off_epoch) + which;
+    e = *ep + 1;
+    *ep = e;
+  }
+  __syncthreads();
+  const int r = threadIdx.x;
+  if (r < pc.W && ((mask >> r) & 1u)) {
+    __threadfence_system();
+    st_release_sys((unsigned long long*)(pc.mb[r] + pc.off_flags) + which * RSG_MAX_PEERS + pc.rank, e);
+    const unsigned long long* src = (const unsigned long long*)(pc.mb[pc.rank] + pc.off_flags) + which * RSG_MAX_PEERS + r;
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_sys(src) < e) {
+      if (global_ns() - t0 > kBarrierTimeoutNs) { *pc.err = 1ull + (unsigned long long)r; break; }
+      __nanosleep(64);
+    }
+  }
+}
+
+// this rank's result blocks of species [s0, s0+ns) into slot `rank` of every rank's mailbox.  grid: x = destination rank
+__global__ void __launch_bounds__(256) k_push_results(const __grid_constant__ PeerCtx pc, int s0, int ns,
+                                                      const unsigned long long* __restrict__ res, const double* __restrict__ pp) {
+  const int r = blockIdx.x;
+  unsigned long long* dr = (unsigned long long*)(pc.mb[r] + pc.off_res) + ((size_t)pc.rank * pc.nS + s0) * pc.res_n;
+  double* dp = (double*)(pc.mb[r] + pc.off_pp) + ((size_t)pc.rank * pc.nS + s0) * pc.pp_n;
+  const unsigned long long* sr = res + (size_t)s0 * pc.res_n;
+  const double* sp = pp + (size_t)s0 * pc.pp_n;
+  for (int t = threadIdx.x; t < ns * pc.res_n; t += blockDim.x) dr[t] = sr[t];
+  for (long long t = threadIdx.x; t < (long long)ns * pc.pp_n; t += blockDim.x) dp[t] = sp[t];
+}
+
+// Full results of every species on every rank: species s was advanced by ranks first[s] .. first[s]+cnt[s]-1, each
+// holding the CFL limits (identical), partial SUMRC sums and partial pressures of its slab / column range.  Sums run
+// in rank order (the same on every rank => identical bits everywhere).  grid: x = tiles, y = species
+struct OwnerTab { int first[RSG_MAX_SPECIES], cnt[RSG_MAX_SPECIES]; };
+__global__ void __launch_bounds__(256) k_reduce_results(const __grid_constant__ PeerCtx pc, const __grid_constant__ OwnerTab ow,
+                                                        int nsum, int dtf_off, unsigned long long* __restrict__ res,
+                                                        double* __restrict__ pp, unsigned long long* __restrict__ host_res,
+                                                        double* __restrict__ host_pp) {
+  const int s = blockIdx.y;
+  const int f = ow.first[s], c = ow.cnt[s];
+  const unsigned long long* mr = (const unsigned long long*)(pc.mb[pc.rank] + pc.off_res);
+  const double* mp = (const double*)(pc.mb[pc.rank] + pc.off_pp);
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < pc.res_n) {
+    const int w = (int)t;
+    unsigned long long v = mr[((size_t)f * pc.nS + s) * pc.res_n + w];
+    const bool is_min = (w < 4) || (w >= dtf_off && w < dtf_off + 4);
+    const bool is_sum = (w >= 4 && w < 4 + nsum);
+    if (is_min)
+      for (int q = 1; q < c; ++q) {
+        const unsigned long long o = mr[((size_t)(f + q) * pc.nS + s) * pc.res_n + w];
+        v = o < v ? o : v;
+      }
+    else if (is_sum) {
+      double a = __longlong_as_double((long long)v);
+      for (int q = 1; q < c; ++q) a += __longlong_as_double((long long)mr[((size_t)(f + q) * pc.nS + s) * pc.res_n + w]);
+      v = (unsigned long long)__double_as_longlong(a);
+    }
+    res[(size_t)s * pc.res_n + w] = v;
+    host_res[(size_t)s * pc.res_n + w] = v;
+  }
+  if (t < pc.pp_n) {
+    double a = mp[((size_t)f * pc.nS + s) * pc.pp_n + t];
+    for (int q = 1; q < c; ++q) a += mp[((size_t)(f + q) * pc.nS + s) * pc.pp_n + t];
+    pp[(size_t)s * pc.pp_n + t] = a;
+    host_pp[(size_t)s * pc.pp_n + t] = a;
+  }
+}
+
+void split_range(int n, int parts, int idx, int* start, int* count) {
+  const int base = n / parts, rem = n % parts;
+  *start = idx * base + std::min(idx, rem);
+  *count = base + (idx < rem ? 1 : 0);
+}
+
+int plan_for(int world, int rank, int policy, int nS, int NPA, int P, rsg_shard_plan_t* p) {
+  if (!p) return fail(RSG_ERR_ARG, "null plan");
+  if (world < 1 || world > RSG_MAX_PEERS || rank < 0 || rank >= world) return fail(RSG_ERR_ARG, "world must be 1..8 and 0 <= rank < world");
+  if (nS < 1 || nS > RSG_MAX_SPECIES) return fail(RSG_ERR_ARG, "bad species count");
+  std::memset(p, 0, sizeof(*p));
+  p->world = world; p->rank = rank; p->policy = policy;
+  p->per = COL_PG;
+  const int nblocks = (P + COL_PG - 1) / COL_PG;
+  if (policy == RSG_SHARD_SLABS) {                 // every rank: a slab of ALL species
+    p->s0 = 0; p->ns = nS; p->G = world; p->gidx = rank; p->g0 = 0;
+  } else if (policy == RSG_SHARD_SPECIES) {        // species first, slabs inside a species beyond nS ranks
+    if (world <= nS) {
+      if (nS % world) return fail(RSG_ERR_ARG, "the species cannot be split evenly over the ranks");
+      p->ns = nS / world; p->s0 = rank * p->ns; p->G = 1; p->gidx = 0; p->g0 = rank;
+    } else {
+      if (world % nS) return fail(RSG_ERR_ARG, "the rank count must be a multiple of the species count");
+      p->G = world / nS; p->s0 = rank / p->G; p->ns = 1; p->gidx = rank % p->G; p->g0 = p->s0 * p->G;
+    }
+  } else return fail(RSG_ERR_ARG, "unknown sharding policy");
+  if (p->G > 1 && (NPA / p->G < 2 || nblocks / p->G < 1)) return fail(RSG_ERR_ARG, "too many ranks per species for this grid");
+  split_range(NPA, p->G, p->gidx, &p->l0, &p->nl);
+  split_range(nblocks, p->G, p->gidx, &p->b0, &p->nb);
+  return RSG_OK;
+}
+
+}  // namespace
+
+struct rsg_shard {
+  rsg_shard_plan_t plan{};
+  bool attached = false, local = false;
+  unsigned char* mbox = nullptr;      // own mailbox (device)
+  size_t mbox_bytes = 0;
+  void* opened[2 * RSG_MAX_PEERS] = {nullptr};   // IPC mappings to close
+  int nopened = 0;
+  PeerCtx pc{};
+  PeerView pv{};
+  OwnerTab ow{};
+  unsigned long long* h_err = nullptr;   // pinned + mapped
+  cudaGraphExec_t gexec = nullptr;
+  double g_DTs = -1.0;
+  int g_flags = -1, g_mode = -1;
+  long long g_launches = 0;
+  cudaStream_t g_stream = nullptr;
+  unsigned group_mask = 0, world_mask = 0;
+  int pending_flags = 0;
+  bool pending = false;
+};
+
+namespace {
+
+int shard_alloc_mbox(rsg_ram* h) {
+  if (h->shard && h->shard->mbox) return RSG_OK;
+  if (!h->shard) h->shard = new rsg_shard();
+  rsg_shard& sh = *h->shard;
+  PeerCtx& pc = sh.pc;
+  pc.nS = h->nS; pc.res_n = RES_N; pc.pp_n = 2 * (long long)h->Pp;
+  pc.off_flags = 0;
+  pc.off_epoch = pc.off_flags + sizeof(unsigned long long) * 2 * RSG_MAX_PEERS;
+  pc.off_res = (pc.off_epoch + 2 * sizeof(unsigned long long) + 255) & ~(size_t)255;
+  pc.off_pp = (pc.off_res + sizeof(unsigned long long) * RSG_MAX_PEERS * h->nS * RES_N + 255) & ~(size_t)255;
+  sh.mbox_bytes = pc.off_pp + sizeof(double) * RSG_MAX_PEERS * h->nS * (size_t)pc.pp_n;
+  RET(h->dalloc(&sh.mbox, sh.mbox_bytes));
+  CK(cudaHostAlloc((void**)&sh.h_err, sizeof(unsigned long long), cudaHostAllocMapped));
+  *sh.h_err = 0;
+  CK(cudaHostGetDevicePointer((void**)&pc.err, sh.h_err, 0));
+  return RSG_OK;
+}
+
+int shard_finish_attach(rsg_ram* h, int rank, int world, int policy) {
+  rsg_shard& sh = *h->shard;
+  RET(plan_for(world, rank, policy, h->nS, h->NPA, h->P, &sh.plan));
+  const rsg_shard_plan_t& p = sh.plan;
+  sh.pc.W = world; sh.pc.rank = rank;
+  sh.pv.G = p.G; sh.pv.gidx = p.gidx;
+  for (int g = 0; g <= p.G; ++g) {
+    int a, n;
+    if (g < p.G) { split_range(h->NPA, p.G, g, &a, &n); sh.pv.lcut[g] = a; } else sh.pv.lcut[g] = h->NPA;
+    if (g < p.G) { split_range((h->P + COL_PG - 1) / COL_PG, p.G, g, &a, &n); sh.pv.ccut[g] = a * COL_PG; } else sh.pv.ccut[g] = h->Pp;
+  }
+  sh.group_mask = 0; sh.world_mask = 0;
+  for (int g = 0; g < p.G; ++g) sh.group_mask |= 1u << (p.g0 + g);
+  for (int r = 0; r < world; ++r) sh.world_mask |= 1u << r;
+  for (int s = 0; s < h->nS; ++s) {
+    rsg_shard_plan_t q;
+    int first = -1, cnt = 0;
+    for (int r = 0; r < world; ++r) {
+      RET(plan_for(world, r, policy, h->nS, h->NPA, h->P, &q));
+      if (s >= q.s0 && s < q.s0 + q.ns) { if (first < 0) first = r; ++cnt; }
+    }
+    sh.ow.first[s] = first; sh.ow.cnt[s] = cnt;
+  }
+  for (int s = 0; s < h->nS; ++s)
+    if (h->sp[s].cur != 0) return fail(RSG_ERR_STATE, "peer attach needs F2 in buffer 0 (attach before running single operators)");
+  if (sh.gexec) { cudaGraphExecDestroy(sh.gexec); sh.gexec = nullptr; }
+  sh.attached = true;
+  return RSG_OK;
+}
+
+void shard_release(rsg_ram* h) {
+  if (!h->shard) return;
+  rsg_shard& sh = *h->shard;
+  if (sh.gexec) cudaGraphExecDestroy(sh.gexec);
+  for (int q = 0; q < sh.nopened; ++q) cudaIpcCloseMemHandle(sh.opened[q]);
+  if (sh.h_err) cudaFreeHost(sh.h_err);
+  delete h->shard;
+  h->shard = nullptr;
+}
+
+// the launch sequence of one sharded step on the run stream (captured into the step's graph)
+int enqueue_sharded(rsg_ram* h, double DTs, int flags) {
+  rsg_shard& sh = *h->shard;
+  const rsg_shard_plan_t& p = sh.plan;
+  cudaStream_t st = h->pst();
+  const int s0 = p.s0, ns = p.ns;
+  if (p.G > 1) {
+    int cat[RSG_MAX_SPECIES][NSLOT], doA;
+    slot_cats(h, flags, cat, &doA, nullptr);
+    int doW = wpadif_mask(h, flags);
+    for (int s = 0; s < h->nS; ++s)
+      if (s < s0 || s >= s0 + ns) doW &= ~(1 << s);
+    h->in_step = false;
+    RET(L_plane_rp(h, s0, ns, st, false, p.l0, p.nl, &sh.pv));     // DRIFTR, DRIFTP -> the column owners
+    k_peer_barrier<<<1, 32, 0, st>>>(sh.pc, 0, sh.group_mask);
+    CKL();
+    RET(L_col(h, s0, ns, doA, DTs, st, p.b0, p.nb, doW, &sh.pv));   // DRIFTE .. DRIFTE -> the pitch-angle owners
+    k_peer_barrier<<<1, 32, 0, st>>>(sh.pc, 0, sh.group_mask);
+    CKL();
+    RET(L_plane_rp(h, s0, ns, st, true, p.l0, p.nl));               // DRIFTP, DRIFTR, epilogue (local slab)
+    RET(L_finish_fused(h, s0, ns, st, p.l0, p.nl, p.nb));
+    h->launches += 2;
+    if (doW) {
+      SpecPack pk;
+      make_pack(h, pk, s0, ns);
+      k_finalize_wpi<<<dim3(2, ns), 256, 0, st>>>(pk, s0, doW, p.nb, fused_wpart_off(h), RES_N, NSUM, h->d_wviol, h->hd_res_all);
+      CKL();
+      h->launches++;
+    }
+  } else if (fused_ok(h, flags)) {
+    RET(enqueue_fused(h, DTs, flags, s0, ns));
+  } else {
+    RET(enqueue_fwd(h, s0, ns, 0, h->NPA));
+    RET(rsg_ram_part_mid(h, DTs, flags, s0, ns, 0, h->NE));
+    RET(rsg_ram_part_rev(h, s0, ns, 0, h->NPA));
+  }
+  k_push_results<<<p.world, 256, 0, st>>>(sh.pc, s0, ns, h->d_res_all, h->d_pp_all);
+  CKL();
+  k_peer_barrier<<<1, 32, 0, st>>>(sh.pc, 1, sh.world_mask);
+  CKL();
+  k_reduce_results<<<dim3(nblk(std::max<long long>(sh.pc.pp_n, RES_N), 256), h->nS), 256, 0, st>>>(
+      sh.pc, sh.ow, NSUM, DTF_OFF, h->d_res_all, h->d_pp_all, h->hd_res_all, h->hd_pp_all);
+  CKL();
+  h->launches += 3;
+  return RSG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rsg_shard_plan(int world, int rank, int policy, int nS, int NPA, int P, rsg_shard_plan_t* out) {
+  return plan_for(world, rank, policy, nS, NPA, P, out);
+}
+
+int rsg_ram_shard_info(rsg_ram* h, rsg_shard_plan_t* out) {
+  if (!h || !out) return fail(RSG_ERR_ARG, "null argument");
+  if (!h->shard || !h->shard->attached) return fail(RSG_ERR_STATE, "no peers attached");
+  *out = h->shard->plan;
+  return RSG_OK;
+}
+
+int rsg_ram_peer_export(rsg_ram* h, void* blob) {
+  if (!h || !blob) return fail(RSG_ERR_ARG, "null argument");
+  CK(cudaSetDevice(h->device));
+  RET(shard_alloc_mbox(h));
+  PeerBlob b;
+  std::memset(&b, 0, sizeof(b));
+  b.magic = kBlobMagic; b.pid = (int)getpid(); b.device = h->device;
+  b.nS = h->nS; b.NR = h->NR; b.NT = h->NT; b.NE = h->NE; b.NPA = h->NPA;
+  CK(cudaIpcGetMemHandle(&b.f2, h->d_F2[0]));
+  CK(cudaIpcGetMemHandle(&b.mbox, h->shard->mbox));
+  std::memcpy(blob, &b, sizeof(b));
+  return RSG_OK;
+}
+
+int rsg_ram_peer_attach(rsg_ram* h, int rank, int world, int policy, const void* blobs) {
+  if (!h || !blobs) return fail(RSG_ERR_ARG, "null argument");
+  if (world < 1 || world > RSG_MAX_PEERS || rank < 0 || rank >= world) return fail(RSG_ERR_ARG, "world must be 1..8 and 0 <= rank < world");
+  CK(cudaSetDevice(h->device));
+  RET(rsg_ram_sync(h));
+  RET(shard_alloc_mbox(h));
+  rsg_shard& sh = *h->shard;
+  if (sh.attached) return fail(RSG_ERR_STATE, "peers already attached");
+  rsg_shard_plan_t p;
+  RET(plan_for(world, rank, policy, h->nS, h->NPA, h->P, &p));
+  const PeerBlob* bl = (const PeerBlob*)blobs;
+  for (int r = 0; r < world; ++r) {
+    const PeerBlob& b = bl[r];
+    if (b.magic != kBlobMagic || b.nS != h->nS || b.NR != h->NR || b.NT != h->NT || b.NE != h->NE || b.NPA != h->NPA)
+      return fail(RSG_ERR_ARG, "peer blob of rank " + std::to_string(r) + " does not describe the same grid");
+    const bool in_group = p.G > 1 && r >= p.g0 && r < p.g0 + p.G;
+    if (r == rank) {
+      sh.pc.mb[r] = sh.mbox;
+      if (in_group) sh.pv.F[r - p.g0] = h->d_F2[0];
+      continue;
+    }
+    if (b.pid == (int)getpid()) return fail(RSG_ERR_ARG, "peer in the same process: use rsg_ram_peer_attach_local");
+    void* q = nullptr;
+    CK(cudaIpcOpenMemHandle(&q, b.mbox, cudaIpcMemLazyEnablePeerAccess));
+    sh.opened[sh.nopened++] = q;
+    sh.pc.mb[r] = (unsigned char*)q;
+    if (in_group) {
+      CK(cudaIpcOpenMemHandle(&q, b.f2, cudaIpcMemLazyEnablePeerAccess));
+      sh.opened[sh.nopened++] = q;
+      sh.pv.F[r - p.g0] = (double*)q;
+    }
+  }
+  sh.local = false;
+  return shard_finish_attach(h, rank, world, policy);
+}
+
+int rsg_ram_peer_attach_local(rsg_ram* h, int rank, int world, int policy, rsg_ram* const* peers) {
+  if (!h || !peers) return fail(RSG_ERR_ARG, "null argument");
+  if (world < 1 || world > RSG_MAX_PEERS || rank < 0 || rank >= world || peers[rank] != h) return fail(RSG_ERR_ARG, "bad rank / world / peer list");
+  CK(cudaSetDevice(h->device));
+  RET(rsg_ram_sync(h));
+  RET(shard_alloc_mbox(h));
+  rsg_shard& sh = *h->shard;
+  if (sh.attached) return fail(RSG_ERR_STATE, "peers already attached");
+  rsg_shard_plan_t p;
+  RET(plan_for(world, rank, policy, h->nS, h->NPA, h->P, &p));
+  for (int r = 0; r < world; ++r) {
+    rsg_ram* q = peers[r];
+    if (!q || q->nS != h->nS || q->NR != h->NR || q->NT != h->NT || q->NE != h->NE || q->NPA != h->NPA || q->device != h->device)
+      return fail(RSG_ERR_ARG, "local peers must be handles of the same grid on the same device");
+    RET(shard_alloc_mbox(q));
+    sh.pc.mb[r] = q->shard->mbox;
+    if (p.G > 1 && r >= p.g0 && r < p.g0 + p.G) sh.pv.F[r - p.g0] = q->d_F2[0];
+  }
+  sh.local = true;
+  return shard_finish_attach(h, rank, world, policy);
+}
+
+int rsg_ram_peer_detach(rsg_ram* h) {
+  if (!h) return fail(RSG_ERR_ARG, "null handle");
+  if (!h->shard) return RSG_OK;
+  CK(cudaSetDevice(h->device));
+  RET(rsg_ram_sync(h));
+  rsg_shard& sh = *h->shard;
+  if (sh.gexec) { cudaGraphExecDestroy(sh.gexec); sh.gexec = nullptr; }
+  for (int q = 0; q < sh.nopened; ++q) cudaIpcCloseMemHandle(sh.opened[q]);
+  sh.nopened = 0;
+  sh.attached = false;
+  return RSG_OK;
+}
+
+// enqueue: everything of the step is put on the run stream (graph replay when DTs / flags / mode repeat) and the
+// call returns without waiting -- ranks living in one process (attach_local) enqueue all their steps first and
+// collect afterwards; rsg_ram_run_sharded does both.
+int rsg_ram_run_sharded_enqueue(rsg_ram* h, double DTs, double T, int flags) {
+  if (!h) return fail(RSG_ERR_ARG, "null handle");
+  if (!h->shard || !h->shard->attached) return fail(RSG_ERR_STATE, "rsg_ram_run_sharded before rsg_ram_peer_attach");
+  rsg_shard& sh = *h->shard;
+  const rsg_shard_plan_t& p = sh.plan;
+  RET(check_part(h, p.s0, p.ns, 0, h->NPA, h->NPA));
+  if (p.G > 1 && !fused_ok(h, flags))
+    return fail(RSG_ERR_UNSUPPORTED, "ranks sharing a species need the fused FAST kernels (RSG_MODE_FAST, no Coulomb flag)");
+  for (int s = p.s0; s < p.s0 + p.ns; ++s)
+    if (p.G > 1 && h->sp[s].cur != 0) return fail(RSG_ERR_STATE, "sharded step needs F2 in buffer 0");
+  CK(cudaSetDevice(h->device));
+  h->T_elapsed = T;
+  RET(step_prepare(h, DTs, flags, p.s0, p.ns));
+  cudaStream_t st = h->pst();
+  sh.pending = true;
+  sh.pending_flags = flags;
+  if (h->use_graph && !h->prof_on && sh.gexec && sh.g_DTs == DTs && sh.g_flags == flags && sh.g_mode == h->mode && sh.g_stream == st) {
+    CK(cudaGraphLaunch(sh.gexec, st));
+    h->launches += sh.g_launches;
+    return RSG_OK;
+  }
+  if (sh.gexec) { cudaGraphExecDestroy(sh.gexec); sh.gexec = nullptr; }
+  const bool graph_ok = h->use_graph && !h->prof_on && !(flags & RSG_F_COULOMB);   // COULMU's T > 0 switch is a launch argument
+  const long long l0 = h->launches;
+  if (graph_ok) CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  const int rc = enqueue_sharded(h, DTs, flags);
+  if (graph_ok) {
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(st, &g);
+    if (rc != RSG_OK) { if (g) cudaGraphDestroy(g); return rc; }
+    if (e != cudaSuccess) return fail(RSG_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&sh.gexec, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) { sh.gexec = nullptr; return fail(RSG_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
+    sh.g_DTs = DTs; sh.g_flags = flags; sh.g_mode = h->mode; sh.g_stream = st;
+    sh.g_launches = h->launches - l0;
+    CK(cudaGraphLaunch(sh.gexec, st));
+  }
+  return rc;
+}
+
+int rsg_ram_run_sharded_collect(rsg_ram* h, double DtsMin, double* dts_next, double* DtDrift, double* losses, double* SETRC,
+                                double* PPERT, double* PPART) {
+  if (!h) return fail(RSG_ERR_ARG, "null handle");
+  if (!h->shard || !h->shard->pending) return fail(RSG_ERR_STATE, "collect without a pending sharded step");
+  rsg_shard& sh = *h->shard;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->pst()));
+  sh.pending = false;
+  if (*sh.h_err) {
+    const unsigned long long e = *sh.h_err;
+    *sh.h_err = 0;
+    return fail(RSG_ERR_CUDA, "peer barrier timed out waiting for rank " + std::to_string((long long)e - 1));
+  }
+  return decode_step(h, sh.pending_flags, DtsMin, dts_next, DtDrift, losses, SETRC, PPERT, PPART);
+}
+
+int rsg_ram_run_sharded(rsg_ram* h, double DTs, double DtsMin, double T, int flags, double* dts_next, double* DtDrift,
+                        double* losses, double* SETRC, double* PPERT, double* PPART) {
+  RET(rsg_ram_run_sharded_enqueue(h, DTs, T, flags));
+  return rsg_ram_run_sharded_collect(h, DtsMin, dts_next, DtDrift, losses, SETRC, PPERT, PPART);
+}
+
+// F2 of the host array (full shape, species fastest) <-> this rank's share: its pitch-angle slab of its species.
+// The slab is one contiguous run of the host array (L is the slowest index); with RSG_SHARD_SLABS it is all the
+// rank moves.  d2h leaves the entries of species the rank does not own untouched.
+int rsg_ram_f2_h2d_shard(rsg_ram* h, const double* F2) {
+  if (!h || !F2) return fail(RSG_ERR_ARG, "null argument");
+  if (!h->shard || !h->shard->attached) return fail(RSG_ERR_STATE, "no peers attached");
+  const rsg_shard_plan_t& p = h->shard->plan;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = h->pst();
+  const size_t per_l = (size_t)h->nS * h->P * h->NE;
+  CK(cudaMemcpyAsync(h->d_stage + p.l0 * per_l, F2 + p.l0 * per_l, p.nl * per_l * sizeof(double), cudaMemcpyHostToDevice, st));
+  for (int s = p.s0; s < p.s0 + p.ns; ++s) {
+    k_f2_from_host<<<dim3(nblk(h->Pp, 256), p.nl * h->NE), 256, 0, st>>>(h->dev, h->d_stage, h->d_F2[h->sp[s].cur] + h->specStride * s, s,
+                                                                          p.l0 * h->NE);
+    CKL();
+    h->launches++;
+  }
+  CK(cudaStreamSynchronize(st));
+  return RSG_OK;
+}
+
+int rsg_ram_f2_d2h_shard(rsg_ram* h, double* F2) {
+  if (!h || !F2) return fail(RSG_ERR_ARG, "null argument");
+  if (!h->shard || !h->shard->attached) return fail(RSG_ERR_STATE, "no peers attached");
+  const rsg_shard_plan_t& p = h->shard->plan;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = h->pst();
+  const size_t per_l = (size_t)h->nS * h->P * h->NE;
+  if (p.ns < h->nS)   // keep the other species' host values: start from the host image of the slab
+    CK(cudaMemcpyAsync(h->d_stage + p.l0 * per_l, F2 + p.l0 * per_l, p.nl * per_l * sizeof(double), cudaMemcpyHostToDevice, st));
+  for (int s = p.s0; s < p.s0 + p.ns; ++s) {
+    k_f2_to_host<<<dim3(nblk(h->Pp, 256), p.nl * h->NE), 256, 0, st>>>(h->dev, h->d_stage, h->d_F2[h->sp[s].cur] + h->specStride * s, s,
+                                                                        p.l0 * h->NE);
+    CKL();
+    h->launches++;
+  }
+  CK(cudaMemcpyAsync(F2 + p.l0 * per_l, h->d_stage + p.l0 * per_l, p.nl * per_l * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return RSG_OK;
+}
+
+}  // extern "C"

@@ -27,6 +27,17 @@ _lib = None
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
 
+PEER_BLOB_BYTES = 192
+SHARD_SPECIES, SHARD_SLABS = 0, 1
+
+
+class ShardPlan(C.Structure):
+    """rsg_shard_plan_t (include/ramscb_gpu.h): what one rank owns in the multi-GPU RAM step"""
+    _fields_ = [(n, C.c_int) for n in ("world", "rank", "policy", "s0", "ns", "G", "gidx", "g0", "l0", "nl", "b0", "nb", "per")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
 
 class RsgError(RuntimeError):
     pass
@@ -96,6 +107,17 @@ def lib():
     L.rsg_ram_profile_get.argtypes = [vp, i, C.c_char_p, i, _dp, C.POINTER(ll)]
     L.rsg_host_register.argtypes = [vp, ll]
     L.rsg_host_unregister.argtypes = [vp]
+    L.rsg_shard_plan.argtypes = [i, i, i, i, i, i, C.POINTER(ShardPlan)]
+    L.rsg_ram_shard_info.argtypes = [vp, C.POINTER(ShardPlan)]
+    L.rsg_ram_peer_export.argtypes = [vp, vp]
+    L.rsg_ram_peer_attach.argtypes = [vp, i, i, i, vp]
+    L.rsg_ram_peer_attach_local.argtypes = [vp, i, i, i, C.POINTER(vp)]
+    L.rsg_ram_peer_detach.argtypes = [vp]
+    L.rsg_ram_run_sharded.argtypes = [vp, d, d, d, i, _dp, vp, vp, vp, vp, vp]
+    L.rsg_ram_run_sharded_enqueue.argtypes = [vp, d, d, i]
+    L.rsg_ram_run_sharded_collect.argtypes = [vp, d, _dp, vp, vp, vp, vp, vp]
+    L.rsg_ram_f2_h2d_shard.argtypes = [vp, vp]
+    L.rsg_ram_f2_d2h_shard.argtypes = [vp, vp]
     _lib = L
     return L
 
@@ -123,6 +145,13 @@ def host_unregister(a):
 
 def device_count() -> int:
     return lib().rsg_device_count()
+
+
+def shard_plan(world, rank, policy, nS, NPA, P):
+    """The decomposition of the sharded RAM step as the library computes it (no device needed)."""
+    p = ShardPlan()
+    _ck(lib().rsg_shard_plan(world, rank, policy, nS, NPA, P, C.byref(p)))
+    return p
 
 
 def device_info():
@@ -333,6 +362,58 @@ class RamGpu:
         ppar = np.zeros((g.NR, g.NT, ns), order="F")
         _ck(self.L.rsg_ram_part_results(self.h, s0, ns, _p(dt), _p(mom), _p(pper), _p(ppar)))
         return dt, mom, pper, ppar
+
+    # ---- multi-GPU inside the library (include/ramscb_gpu.h: rsg_ram_peer_*, rsg_ram_run_sharded) --------
+    def peer_export(self):
+        blob = np.zeros(PEER_BLOB_BYTES, dtype=np.uint8)
+        _ck(self.L.rsg_ram_peer_export(self.h, blob.ctypes.data))
+        return blob
+
+    def peer_attach(self, rank, world, policy, blobs):
+        blobs = np.ascontiguousarray(blobs, dtype=np.uint8).reshape(world, PEER_BLOB_BYTES)
+        _ck(self.L.rsg_ram_peer_attach(self.h, rank, world, policy, blobs.ctypes.data))
+
+    def peer_attach_local(self, rank, peers, policy=SHARD_SPECIES):
+        arr = (C.c_void_p * len(peers))(*[p.h for p in peers])
+        _ck(self.L.rsg_ram_peer_attach_local(self.h, rank, len(peers), policy, arr))
+
+    def peer_detach(self):
+        _ck(self.L.rsg_ram_peer_detach(self.h))
+
+    def shard_info(self):
+        p = ShardPlan()
+        _ck(self.L.rsg_ram_shard_info(self.h, C.byref(p)))
+        return p
+
+    def _step_outputs(self):
+        g = self.g
+        return {"DtDrift": np.zeros((4, g.nS), order="F"), "losses": np.zeros((6, g.nS), order="F"), "SETRC": np.zeros(g.nS),
+                "PPERT": np.zeros((g.nS, g.NR, g.NT), order="F"), "PPART": np.zeros((g.nS, g.NR, g.NT), order="F")}
+
+    def run_sharded(self, DTs, DtsMin=1.0, T=0.0, flags=0):
+        """ram_run on this rank's share; every rank returns the results of ALL species (like ``ram_run``)."""
+        dtn, out = C.c_double(), self._step_outputs()
+        _ck(self.L.rsg_ram_run_sharded(self.h, DTs, DtsMin, T, flags, C.byref(dtn), _p(out["DtDrift"]), _p(out["losses"]),
+                                       _p(out["SETRC"]), _p(out["PPERT"]), _p(out["PPART"])))
+        out["DtsNext"] = dtn.value
+        return out
+
+    def run_sharded_enqueue(self, DTs, T=0.0, flags=0):
+        _ck(self.L.rsg_ram_run_sharded_enqueue(self.h, DTs, T, flags))
+
+    def run_sharded_collect(self, DtsMin=1.0):
+        dtn, out = C.c_double(), self._step_outputs()
+        _ck(self.L.rsg_ram_run_sharded_collect(self.h, DtsMin, C.byref(dtn), _p(out["DtDrift"]), _p(out["losses"]), _p(out["SETRC"]),
+                                               _p(out["PPERT"]), _p(out["PPART"])))
+        out["DtsNext"] = dtn.value
+        return out
+
+    def f2_h2d_shard(self, F2):
+        _ck(self.L.rsg_ram_f2_h2d_shard(self.h, _p(F2)))
+
+    def f2_d2h_shard(self, F2):
+        _ck(self.L.rsg_ram_f2_d2h_shard(self.h, _p(F2)))
+        return F2
 
     def flux_d2h(self):
         g = self.g

@@ -294,6 +294,46 @@ class RamSharded:
                 "PPERT": np.asfortranarray(np.moveaxis(PE, 2, 0)), "PPART": np.asfortranarray(np.moveaxis(PA, 2, 0))}
 
 
+def gather_blobs(dist, blob, world, device=None):
+    """All-gather of the ranks' peer blobs (rsg_ram_peer_export) in rank order: the ONLY host-side communication of the
+    library's own multi-GPU step (a Fortran host does the same with one MPI_Allgather).  Works on any backend: the
+    bytes travel as a uint8 tensor on `device` ("cuda" for nccl, "cpu" for gloo)."""
+    import torch
+    if device is None:
+        device = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    mine = torch.from_numpy(np.ascontiguousarray(blob, dtype=np.uint8)).to(device)
+    out = torch.empty(world * mine.numel(), dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(out, mine)
+    return out.cpu().numpy().reshape(world, -1)
+
+
+class RamPeerSharded:
+    """One rank of the sharded RAM step that lives INSIDE the library (include/ramscb_gpu.h: rsg_ram_run_sharded).
+
+    The ranks map each other's F2 buffer over NVLink (CUDA IPC); the kernels store their results straight into the
+    buffer of the rank that reads them next, barriers and the result reduction run on the device, one CUDA graph per
+    step.  Python's part is the one-off exchange of the 192-byte blobs.  ``ram_run`` returns what ``RamGpu.ram_run``
+    returns (results of ALL species, identical on every rank)."""
+
+    def __init__(self, gpu, dist, rank, world, policy=None):
+        from . import host
+        self.gpu, self.rank, self.world = gpu, rank, world
+        self.policy = host.SHARD_SPECIES if policy is None else policy
+        blobs = gather_blobs(dist, gpu.peer_export(), world)
+        gpu.peer_attach(rank, world, self.policy, blobs)
+        self.plan = gpu.shard_info()
+
+    def load(self, F2):
+        """this rank's share of the host array F2(nS,NR,NT,NE,NPA)"""
+        self.gpu.f2_h2d_shard(F2)
+
+    def store(self, F2):
+        return self.gpu.f2_d2h_shard(F2)
+
+    def ram_run(self, DTs, DtsMin=1.0, T=0.0, flags=0):
+        return self.gpu.run_sharded(DTs, DtsMin=DtsMin, T=T, flags=flags)
+
+
 class ScbSharded:
     """iterateAlpha / iteratePsi with the independent sub-problems split among ranks.
 

@@ -10,6 +10,9 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # tests/test_ram_shard_gpu.py runs several "ranks" of the multi-GPU step on ONE device: a rank's barrier kernel spins
+    # while the next rank's kernels start, so no kernel may need (device-synchronising) lazy module loading by then
+    os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
     if os.environ.get("RSG_EMU") == "1":
         # development aid for a GPU-less container: run the RAM `-m gpu` tests against the kernels
         # compiled for the host-CPU CUDA emulator (tests/emu/).  Test infrastructure only.

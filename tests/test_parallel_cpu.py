@@ -295,3 +295,69 @@ def test_scb_zeta_sharded_alpha_gloo(world):
     for pr in procs:
         pr.join(timeout=60)
     assert sorted(res) == [(r, True, True, True, True) for r in range(world)]
+
+
+# ---- the library's own multi-GPU step (ramscb_b200/csrc/ram_shard.inl): host-side logic ---------------------------
+def test_shard_plan_covers_every_cell_once():
+    """rsg_shard_plan (no device needed): for every world size and policy each (species, pitch angle) and each
+    (species, column block) has exactly one owner, groups are contiguous rank ranges, slabs hold >= 2 pitch angles."""
+    from ramscb_b200 import host
+    nS, NPA, P = 4, 72, 20 * 25
+    nblocks = (P + 3) // 4
+    for world in range(1, 9):
+        for policy in (host.SHARD_SPECIES, host.SHARD_SLABS):
+            if policy == host.SHARD_SPECIES and not (world % nS == 0 or nS % world == 0):
+                with pytest.raises(host.RsgError):
+                    host.shard_plan(world, 0, policy, nS, NPA, P)
+                continue
+            own_l = np.zeros((nS, NPA), dtype=int)
+            own_b = np.zeros((nS, nblocks), dtype=int)
+            for r in range(world):
+                p = host.shard_plan(world, r, policy, nS, NPA, P)
+                assert p.world == world and p.rank == r and p.per == 4
+                assert p.g0 <= r < p.g0 + p.G and p.gidx == r - p.g0
+                assert p.nl >= 2 or p.G == 1
+                own_l[p.s0:p.s0 + p.ns, p.l0:p.l0 + p.nl] += 1
+                own_b[p.s0:p.s0 + p.ns, p.b0:p.b0 + p.nb] += 1
+                q = host.shard_plan(world, p.g0, policy, nS, NPA, P)          # the group shares one species range
+                assert (q.s0, q.ns, q.G) == (p.s0, p.ns, p.G)
+            assert (own_l == 1).all() and (own_b == 1).all()
+    with pytest.raises(host.RsgError):
+        host.shard_plan(9, 0, host.SHARD_SLABS, nS, NPA, P)
+    with pytest.raises(host.RsgError):
+        host.shard_plan(8, 0, host.SHARD_SLABS, nS, 8, P)                     # slabs of one pitch angle
+
+
+def _peer_blob_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ramscb_b200 import host, parallel
+    blob = np.full(host.PEER_BLOB_BYTES, rank + 1, dtype=np.uint8)            # stands in for rsg_ram_peer_export
+    allb = parallel.gather_blobs(dist, blob, world)
+    ok = allb.shape == (world, host.PEER_BLOB_BYTES) and all((allb[r] == r + 1).all() for r in range(world))
+    # without a CUDA device the library refuses to build a handle: the product path fails loudly, no fallback
+    try:
+        from ramscb_b200 import grids
+        host.RamGpu(grids.build_grids(NR=8, NT=9, NE=8))
+        ok = False
+    except host.RsgError:
+        pass
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_peer_blob_all_gather_gloo():
+    """world_size 2 over gloo: the one host-side message of rsg_ram_run_sharded's set-up (the ranks' opaque blobs,
+    all-gathered in rank order) -- what a Fortran host does with one MPI_Allgather."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    world, port = 2, 29541
+    ps = [ctx.Process(target=_peer_blob_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(world))
+    for p in ps:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
