@@ -44,8 +44,11 @@ enum rsg_status {
 enum rsg_mode {
   RSG_MODE_EXACT = 0, /* reference operation order, no FMA contraction: drift
                          sweeps / WPADIF are bit-identical to the CPU oracle   */
-  RSG_MODE_FAST = 1   /* separable coefficients a+w(K)*b, FMA, division-free
-                         limiter: same maths, results within ~1e-14 relative   */
+  RSG_MODE_FAST = 1   /* separable coefficients a+w(K)*b, FMA, division-free limiter: same maths, other
+                         rounding.  Per cell within 1e-12 relative of the EXACT result after a sweep, and
+                         after whole ram_run steps within 1e-12 for all but a handful of 1e-20 .. 1e-65
+                         cells (<= 3e-12 measured; PARITY.md) -- the reference's own FMA-contracted
+                         build moves by up to 5e-10                                               */
 };
 
 /* species kinds: select the charge-exchange cross-section polynomial

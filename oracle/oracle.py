@@ -30,12 +30,25 @@ def _load(name):
 
 
 _ram = None
+_ram_variants = {}
 
 
-def ram_lib():
+def ram_lib(variant=""):
+    """variant "fma": the same source built with FMA contraction allowed (oracle/Makefile) -- a measuring stick for the
+    reference's own compiler-dependent rounding, never the parity oracle."""
     global _ram
+    if variant:
+        if variant not in _ram_variants:
+            _ram_variants[variant] = _ram_lib_from("libram_oracle_" + variant + ".so")
+        return _ram_variants[variant]
     if _ram is None:
-        lib = _load("libram_oracle.so")
+        _ram = _ram_lib_from("libram_oracle.so")
+    return _ram
+
+
+def _ram_lib_from(name):
+    if True:
+        lib = _load(name)
         lib.orc_create.restype = C.c_void_p
         lib.orc_create.argtypes = [C.c_int] * 5
         lib.orc_destroy.argtypes = [C.c_void_p]
@@ -59,8 +72,7 @@ def ram_lib():
             fn.argtypes = [C.c_double]
             fn.restype = C.c_double
         lib.orc_max_threads.restype = C.c_int
-        _ram = lib
-    return _ram
+    return lib
 
 
 def _f(shape, dtype=np.float64):
@@ -71,8 +83,8 @@ class RamOracle:
     """Holds one complete RAM state (reference layouts) and runs the restated
     operators on it.  Species index S is 1-based, as in the reference."""
 
-    def __init__(self, g, inp, DTs=5.0):
-        self.lib = ram_lib()
+    def __init__(self, g, inp, DTs=5.0, variant=""):
+        self.lib = ram_lib(variant)
         self.g = g
         nS, NR, NT, NE, NPA = g.nS, g.NR, g.NT, g.NE, g.NPA
         self.h = self.lib.orc_create(nS, NR, NT, NE, NPA)

@@ -71,7 +71,9 @@ __device__ __forceinline__ double limited_flux(double Fm1, double F0, double Fp1
 // gives lim = 0 anyway; the product's underflow to 0 below 1e-308 is the only difference).
 __device__ __forceinline__ double limited_flux_d(double F0, double Fp1, double dm1, double d0, double dp1, bool neg, double achat,
                                                  double beta) {
-  const double U = neg ? Fp1 : F0;
+  // the upwind value as the reference forms it, FUP = 0.5*((F0+Fp1) - sgn*X) (:172 etc.): algebraically U, but its
+  // rounding noise (ulp of the LARGER of the two cells) is part of the reference's result next to steep gradients
+  const double U = 0.5 * ((F0 + Fp1) + (neg ? d0 : -d0));
   const double ds = neg ? dp1 : dm1;
   const int hs = __double2hiint(ds), h0 = __double2hiint(d0);
   const double an = __hiloint2double(hs & 0x7fffffff, __double2loint(ds));

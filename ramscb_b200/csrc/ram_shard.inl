@@ -126,37 +126,6 @@ __global__ void __launch_bounds__(256) k_reduce_results(const __grid_constant__ 
   }
 }
 
-void split_range(int n, int parts, int idx, int* start, int* count) {
-  const int base = n / parts, rem = n % parts;
-  *start = idx * base + std::min(idx, rem);
-  *count = base + (idx < rem ? 1 : 0);
-}
-
-int plan_for(int world, int rank, int policy, int nS, int NPA, int P, rsg_shard_plan_t* p) {
-  if (!p) return fail(RSG_ERR_ARG, "null plan");
-  if (world < 1 || world > RSG_MAX_PEERS || rank < 0 || rank >= world) return fail(RSG_ERR_ARG, "world must be 1..8 and 0 <= rank < world");
-  if (nS < 1 || nS > RSG_MAX_SPECIES) return fail(RSG_ERR_ARG, "bad species count");
-  std::memset(p, 0, sizeof(*p));
-  p->world = world; p->rank = rank; p->policy = policy;
-  p->per = COL_PG;
-  const int nblocks = (P + COL_PG - 1) / COL_PG;
-  if (policy == RSG_SHARD_SLABS) {                 // every rank: a slab of ALL species
-    p->s0 = 0; p->ns = nS; p->G = world; p->gidx = rank; p->g0 = 0;
-  } else if (policy == RSG_SHARD_SPECIES) {        // species first, slabs inside a species beyond nS ranks
-    if (world <= nS) {
-      if (nS % world) return fail(RSG_ERR_ARG, "the species cannot be split evenly over the ranks");
-      p->ns = nS / world; p->s0 = rank * p->ns; p->G = 1; p->gidx = 0; p->g0 = rank;
-    } else {
-      if (world % nS) return fail(RSG_ERR_ARG, "the rank count must be a multiple of the species count");
-      p->G = world / nS; p->s0 = rank / p->G; p->ns = 1; p->gidx = rank % p->G; p->g0 = p->s0 * p->G;
-    }
-  } else return fail(RSG_ERR_ARG, "unknown sharding policy");
-  if (p->G > 1 && (NPA / p->G < 2 || nblocks / p->G < 1)) return fail(RSG_ERR_ARG, "too many ranks per species for this grid");
-  split_range(NPA, p->G, p->gidx, &p->l0, &p->nl);
-  split_range(nblocks, p->G, p->gidx, &p->b0, &p->nb);
-  return RSG_OK;
-}
-
 }  // namespace
 
 struct rsg_shard {
@@ -290,10 +259,6 @@ int enqueue_sharded(rsg_ram* h, double DTs, int flags) {
 }  // namespace
 
 extern "C" {
-
-int rsg_shard_plan(int world, int rank, int policy, int nS, int NPA, int P, rsg_shard_plan_t* out) {
-  return plan_for(world, rank, policy, nS, NPA, P, out);
-}
 
 int rsg_ram_shard_info(rsg_ram* h, rsg_shard_plan_t* out) {
   if (!h || !out) return fail(RSG_ERR_ARG, "null argument");
