@@ -716,6 +716,16 @@ def main():
     if plan is not None:
         line["config"]["shard_plan_rank0"] = plan
 
+    if rank == 0 and world == 1 and a.mode == "fast":
+        # the bit-faithful arithmetic mode (reference operation order, no FMA contraction) on the same workload
+        try:
+            ex, _, _ = measure_ram(a.workload, a.flags, 5, 3, local_rank, mode="exact", do_e2e=False, do_profile=False)
+            line["config"]["modes"] = {"fast_ms_per_step": r["ms_per_step"], "exact_ms_per_step": ex["ms_per_step"],
+                                       "exact": "reference operation order, sweeps bit-identical to the oracle (PARITY.md)"}
+            if line.get("roofline") is not None:
+                line["roofline"]["exact_mode_ms_per_step"] = ex["ms_per_step"]
+        except Exception as e:
+            line["config"]["modes"] = {"error": str(e)[:200]}
     if rank == 0 and world == 1 and not a.no_configs1 and a.workload == "x4":
         # BASELINE configs[1] (default grid, drift + loss step) measured the same way; secondary to the headline.  Kept
         # inside `roofline` / `e2e` too, because the driver's parsed line keeps those objects.

@@ -410,17 +410,23 @@ inline void extap(double x1, double x2, double x3, double& x4) {
 }
 
 // post-processing shared by iterateAlpha / iteratePsi (:262-292 / :575-605)
-void sor_post(Scb* o, double* u, int nT, int nP, double wrap) {
+void sor_post(Scb* o, double* u, int nT, int nP, double wrap, bool alpha_variant) {
   DIMS
   for (int k = 2; k <= nzeta; ++k)
     for (int i = 1 + nT; i <= nthe - nT; ++i)
       for (int j = nP; j >= 1; --j) extap(X3(u, i, npsi - j - 2, k), X3(u, i, npsi - j - 1, k), X3(u, i, npsi - j + 0, k), X3(u, i, npsi - j + 1, k));
   if (nT == 1) {
-    // NOTE: the alpha variant loops k = 2..nthe-1 here (:274, a reference quirk that only
-    // matters for theChange <= 1); the psi variant loops k = 2..nzeta.  nT = 1 is not a
-    // configuration any shipped PARAM uses (theChange = 4); not restated.
-    std::fprintf(stderr, "scb oracle: theChange <= 1 is not supported\n");
-    std::abort();
+    // theChange <= 1 (:272-279 / :585-591): the theta end points are extrapolated with extap instead of the linear fill.
+    // The psi variant loops k = 2..nzeta.  The alpha variant loops k = 2..nthe-1 over the ZETA index of an array with
+    // nzeta+1 planes (:274, a reference quirk): out of bounds whenever nthe-1 > nzeta+1, as on the default grid (101 vs
+    // 98) -- restated with the loop clipped to the planes that exist.  No shipped PARAM uses theChange <= 1 (default 4);
+    // the device library answers RSG_ERR_UNSUPPORTED for it.
+    const int kend = alpha_variant ? std::min(nthe - 1, nzeta + 1) : nzeta;
+    for (int k = 2; k <= kend; ++k)
+      for (int j = 1; j <= npsi; ++j) {
+        extap(X3(u, nthe - 3, j, k), X3(u, nthe - 2, j, k), X3(u, nthe - 1, j, k), X3(u, nthe, j, k));
+        extap(X3(u, 4, j, k), X3(u, 3, j, k), X3(u, 2, j, k), X3(u, 1, j, k));
+      }
   } else {
     for (int j = 1; j <= npsi; ++j)
       for (int k = 1; k <= nzeta; ++k)
@@ -500,7 +506,7 @@ int iterateAlpha(Scb* o, int* ni_out) {
   o->s["nisave"] = nisave; o->s["sumdb"] = sumdb; o->s["sumb"] = sumb; o->s["diffmx"] = diffmx;
   if (ni_out)
     for (int jz = 1; jz <= npsi; ++jz) ni_out[jz - 1] = ni[jz];
-  sor_post(o, alfa, nT, nP, 2.0 * PI_D);
+  sor_post(o, alfa, nT, nP, 2.0 * PI_D, true);
   return fail;
 }
 
@@ -567,7 +573,7 @@ int iteratePsi(Scb* o, int* ni_out) {
   o->s["nisave"] = nisave; o->s["sumdb"] = sumdb; o->s["sumb"] = sumb; o->s["diffmx"] = diffmx;
   if (ni_out)
     for (int k = 1; k <= nzeta; ++k) ni_out[k - 1] = ni[k];
-  sor_post(o, psi, nT, nP, 0.0);
+  sor_post(o, psi, nT, nP, 0.0, false);
   return fail;
 }
 
