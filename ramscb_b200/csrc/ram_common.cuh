@@ -67,6 +67,7 @@ struct SpecDev {
   const double* wfac;                     // WAVELO factor exp(-DTs/TAU_LIF) [NE][Pp]
   const double *DA, *DB;                  // WPADIF coefficient pair [l][k][Pp]
   double *tE, *tA;                        // ANISCH scratch [NE][Pp]
+  double *aE2, *aA2;                      // fused step: ANISCH rows written by k_plane_rp<REV> [NPA * energy chunks][Pp]
   double *pper, *ppar;                    // ANISCH results [Pp]
   double GREL1, GREL2, sqrtA, GRZERO, sqrtB;  // DRIFTE ghost cells
   double aRP;                             // FracCFL*DTs

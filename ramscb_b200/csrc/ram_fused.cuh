@@ -128,6 +128,7 @@ struct PlaneCfg {
   int nsegP, segP;    // DRIFTP (cells J=2..NT)
   int part_off;       // REV: offset of this kernel's SUMRC partials in SpecDev::part
   int l0;             // first pitch angle of the launch (slab-sharded ranks); blockIdx.y counts from it
+  int anisch;         // REV: also write this CTA's share of the ANISCH pitch-angle / energy sums (SpecDev::aE2 / aA2)
 };
 
 template <bool REV, bool PEER = false>
@@ -320,6 +321,43 @@ __global__ void __launch_bounds__(512) k_plane_rp(const __grid_constant__ RamDev
       sP[(size_t)q * PS + (NT - 1) * NRp + i] = sP[(size_t)q * PS + i];
     }
     __syncthreads();
+    // ---- ANISCH (src/ModRamRun.f90:360-400) rides along too: the step's final F2 of this pitch angle and these
+    // energies is in shared memory, so the CTA writes its share of  sum_K EPP(K)/A(S,I,K) * sum_L F2 * w(L)/FNHS  for every
+    // plane position (one row of [slab pitch angles x energy chunks][Pp] per CTA; k_finalize adds the rows in a fixed
+    // order).  L = 1 carries the value of L = 2 (the side effect F2(L=1) = F2(L=2), :366, is applied by k_finalize).
+    if (cfg.anisch) {
+      const size_t row = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+      double* oE = sp.aE2 + row * Pp;
+      double* oA = sp.aA2 + row * Pp;
+      const double wE = (l >= 1) ? d.wPE[l] : 0.0, wA = (l >= 1) ? d.wPA[l] : 0.0;
+      const double wE1 = (l == 1) ? d.wPE[0] : 0.0, wA1 = (l == 1) ? d.wPA[0] : 0.0;
+      for (int p = tid; p < Pp; p += T) {
+        double se = 0.0, sa = 0.0;
+        if (p < P) {
+          const int j = p / NR, i = p - j * NR;
+          if (i >= 1 && l + 1 <= d.UPA[i] - 1) {              // Fortran L = l+1 inside the loss-cone edge
+            double acc = 0.0;
+            const bool outm = d.outp[p] != 0;
+            for (int q = 0; q < KCa; ++q) {
+              const int k = k0 + q;
+              if (k < 1) continue;
+              const double f = outm ? 1.e-31 : sP[(size_t)q * PS + j * NRp + i];
+              acc = fma(f, sp.EPP[k] * sp.rFFA[k * NR + i], acc);
+            }
+            const double r0 = d.rFNHS[(size_t)l * Pp + p];
+            se = acc * (r0 * wE);
+            sa = acc * (r0 * wA);
+            if (l == 1) {                                      // the L = 1 term, with F2(L=1) := F2(L=2)
+              const double r1 = d.rFNHS[p];
+              se = fma(acc, r1 * wE1, se);
+              sa = fma(acc, r1 * wA1, sa);
+            }
+          }
+        }
+        oE[p] = se;
+        oA[p] = sa;
+      }
+    }
     if (E == 2)
       for_chunks([&](int so, int go, int pl) {
         double2 v = *(const double2*)(sP + so);
@@ -522,12 +560,28 @@ __global__ void __launch_bounds__(MAXT) k_col_fused(const __grid_constant__ RamD
       const double* rl = sp.DB + (size_t)k * Pp + p;
       double* col = sT + k * PG + pp;                   // F(L) at col[(L-1)*RS]
       const double* fm = sFM + pp;
+      // The factors come from global memory (three F2-sized tables: L2 / HBM latency per access) and the
+      // recurrences are serial in L: the loads of the next WB cells are issued before the current WB cells
+      // are eliminated, so a line always has 2*WB table reads in flight instead of waiting on each one.
+      constexpr int WB = 8;
       double rk = 0.0;
-#pragma unroll 4
-      for (int l = 1; l <= NPA - 2; ++l) {
-        const double2 c = ab[(size_t)l * LS];
-        rk = fma(col[(size_t)l * RS], c.x, rk * c.y);
-        col[(size_t)l * RS] = rk;
+      {
+        double2 nx[WB];
+#pragma unroll
+        for (int b = 0; b < WB; ++b) nx[b] = (1 + b <= NPA - 2) ? ab[(size_t)(1 + b) * LS] : make_double2(0.0, 0.0);
+        for (int l0 = 1; l0 <= NPA - 2; l0 += WB) {
+          double2 cu[WB];
+#pragma unroll
+          for (int b = 0; b < WB; ++b) cu[b] = nx[b];
+#pragma unroll
+          for (int b = 0; b < WB; ++b) if (l0 + WB + b <= NPA - 2) nx[b] = ab[(size_t)(l0 + WB + b) * LS];
+#pragma unroll
+          for (int b = 0; b < WB; ++b)
+            if (l0 + b <= NPA - 2) {
+              rk = fma(col[(size_t)(l0 + b) * RS], cu[b].x, rk * cu[b].y);
+              col[(size_t)(l0 + b) * RS] = rk;
+            }
+        }
       }
       double f = rk * ab[(size_t)(NPA - 1) * LS].x;      // f(NPA-1) = RK/(1+RL)
       double fN = f * fm[(NPA - 1) * PG];               // F2(NPA) = f(NPA-1)*FACMU(NPA)
@@ -536,12 +590,26 @@ __global__ void __launch_bounds__(MAXT) k_col_fused(const __grid_constant__ RamD
       fN = f * fm[(NPA - 2) * PG];
       macc = fma(fN, sWMU[NPA - 2], macc);
       col[(size_t)(NPA - 2) * RS] = fN;
-#pragma unroll 4
-      for (int l = NPA - 3; l >= 1; --l) {
-        f = fma(-rl[(size_t)l * LS], f, col[(size_t)l * RS]);
-        fN = f * fm[l * PG];
-        macc = fma(fN, sWMU[l], macc);
-        col[(size_t)l * RS] = fN;
+      {
+        double nx[WB];
+#pragma unroll
+        for (int b = 0; b < WB; ++b) nx[b] = (NPA - 3 - b >= 1) ? rl[(size_t)(NPA - 3 - b) * LS] : 0.0;
+        for (int l0 = NPA - 3; l0 >= 1; l0 -= WB) {
+          double cu[WB];
+#pragma unroll
+          for (int b = 0; b < WB; ++b) cu[b] = nx[b];
+#pragma unroll
+          for (int b = 0; b < WB; ++b) if (l0 - WB - b >= 1) nx[b] = rl[(size_t)(l0 - WB - b) * LS];
+#pragma unroll
+          for (int b = 0; b < WB; ++b)
+            if (l0 - b >= 1) {
+              const int l = l0 - b;
+              f = fma(-cu[b], f, col[(size_t)l * RS]);
+              fN = f * fm[l * PG];
+              macc = fma(fN, sWMU[l], macc);
+              col[(size_t)l * RS] = fN;
+            }
+        }
       }
       col[0] = f * fm[0];                               // RK(1) = 0, RL(1) = -1: f(1) = f(2)
       if (p < (NT - 1) * NR) accW[which] += macc * (sWE[k] * sEK[k]);
@@ -830,19 +898,30 @@ __global__ void __launch_bounds__(256) k_finalize_wpi(const __grid_constant__ Sp
 __global__ void __launch_bounds__(256) k_finalize(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0,
                                                   int nb_col, int off_rev, int nb_rev,
                                                   const unsigned long long* __restrict__ cfl_all, int res_n, int nsum,
-                                                  unsigned long long* __restrict__ host_res, double RFAC, double* __restrict__ host_pp) {
+                                                  unsigned long long* __restrict__ host_res, double RFAC, double* __restrict__ host_pp,
+                                                  int anisch_rows, int anisch_l0) {
   __shared__ double sm[32];
   const int s = s0 + blockIdx.y;
   const SpecDev& sp = pk.s[s];
   if (blockIdx.x >= 6) {
-    // 32 positions x 8 energy lanes; the 8 partial sums are combined in a fixed order
+    // 32 positions x 8 lanes over the rows; the 8 partial sums are combined in a fixed order
     __shared__ double sE[8][32], sA[8][32];
     const int pl = threadIdx.x & 31, kl = threadIdx.x >> 5;
     const int p = (blockIdx.x - 6) * 32 + pl;
     double pe = 0.0, pa = 0.0;
     const bool act = (p < d.P) && (p % d.NR >= 1);
-    if (act)
+    if (anisch_rows > 0) {
+      // rows written by k_plane_rp<REV>: one per (slab pitch angle, energy chunk)
+      if (act)
+        for (int r = kl; r < anisch_rows; r += 8) { pe += sp.aE2[(size_t)r * d.Pp + p]; pa += sp.aA2[(size_t)r * d.Pp + p]; }
+      // F2(S,I,J,K,1) = F2(S,I,J,K,2) for I, K >= 2 (:366); the slab that holds L = 1, 2 does it
+      if (anisch_l0 == 0 && act) {
+        const size_t LS = (size_t)d.NE * d.Pp;
+        for (int k = 1 + kl; k < d.NE; k += 8) sp.F[(size_t)k * d.Pp + p] = sp.F[LS + (size_t)k * d.Pp + p];
+      }
+    } else if (act) {
       for (int k = 1 + kl; k < d.NE; k += 8) { pe += sp.tE[(size_t)k * d.Pp + p]; pa += sp.tA[(size_t)k * d.Pp + p]; }
+    }
     sE[kl][pl] = pe;
     sA[kl][pl] = pa;
     __syncthreads();

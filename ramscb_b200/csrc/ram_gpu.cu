@@ -73,6 +73,7 @@ struct Spec {
   double* d_ghost = nullptr; // DRIFTR ghost cells per line
   double* d_part = nullptr;  // moment partials [nblk_sum][RSG_NMOM]
   double* d_tE = nullptr;    // ANISCH scratch [2][nch][NE][Pp]
+  double* d_aE2 = nullptr;   // fused step: ANISCH rows of k_plane_rp<REV> [2][NPA * energy chunks][Pp] (allocated on first use)
   double* d_rFFA = nullptr;  // FAST ANISCH: 1/A(S,I,K) [k][i]
   double* d_flc = nullptr;   // FLC_coef of this species [l][k][Pp] (allocated by rsg_ram_set_flc_coef)
   double* d_wtab = nullptr;  // fused WPADIF: elimination factors (cA,cB) pairs [2*n] then RL [n], n = NPA*NE*Pp (k_wpadif_tables)
@@ -563,6 +564,7 @@ int L_plane_rp(rsg_ram* h, int s0, int ns, cudaStream_t st, bool rev, int l0 = 0
   const dim3 g(KG, nl, ns);
   c.cfg.part_off = fused_part_off(h);      // after the column kernel's partials
   c.cfg.l0 = l0;
+  c.cfg.anisch = (rev && h->sp[s0].d_aE2) ? 1 : 0;
   if (rev) { RET(opt_in_smem(k_plane_rp<true>, c.smem)); k_plane_rp<true><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg, pv); }
   else if (peer) { RET(opt_in_smem(k_plane_rp<false, true>, c.smem)); k_plane_rp<false, true><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg, pv); }
   else { RET(opt_in_smem(k_plane_rp<false>, c.smem)); k_plane_rp<false><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg, pv); }
@@ -656,21 +658,23 @@ int L_finish_fused(rsg_ram* h, int s0, int ns, cudaStream_t st, int l0 = 0, int 
   SpecPack pk;
   make_pack(h, pk, s0, ns);
   const double RFAC = 4 * kPI / (kCS * 100);
-  RET(prof_mark(h, "k_anisch", st));
-  {
+  const bool folded = h->sp[s0].d_aE2 != nullptr;     // ANISCH sums written by k_plane_rp<REV>
+  if (!folded) {
+    RET(prof_mark(h, "k_anisch", st));
     const int LCH = h->anischLch;
     const int nch = std::max(1, std::min(16, (nl + LCH - 1) / LCH));
     const int lch = (nl + nch - 1) / nch;
     k_anisch_pa_fast<<<dim3(nblk(h->Pp, 32), h->NE, ns), dim3(32, nch), 0, st>>>(h->dev, pk, s0, l0, nl, lch);
     CKL();
+    h->launches++;
   }
   RET(prof_mark(h, "k_finalize", st));
   const PlanePlan c = plane_plan(h);
   const int KG = (h->NE + c.cfg.KC - 1) / c.cfg.KC;
   k_finalize<<<dim3(6 + nblk(h->P, 32), ns), 256, 0, st>>>(h->dev, pk, s0, nb_col, fused_part_off(h), KG * nl, h->d_cfl_all, RES_N, NSUM,
-                                                           h->hd_res_all, RFAC, h->hd_pp_all);
+                                                           h->hd_res_all, RFAC, h->hd_pp_all, folded ? KG * nl : 0, l0);
   CKL();
-  h->launches += 2;
+  h->launches++;
   return RSG_OK;
 }
 
@@ -1701,6 +1705,17 @@ int step_prepare(rsg_ram* h, double DTs, int flags, int s0, int ns) {
   RET(prof_mark(h, "driftr_inflow", st));
   RET(L_inflow(h, s0, ns, st));
   if (fused_ok(h, flags)) {
+    if (!getenv("RSG_NO_ANISCH_FOLD")) {
+      const PlanePlan c = plane_plan(h);
+      const size_t rows = (size_t)h->NPA * ((h->NE + c.cfg.KC - 1) / c.cfg.KC);
+      for (int s = s0; s < s0 + ns; ++s)
+        if (!h->sp[s].d_aE2) {
+          RET(h->dalloc(&h->sp[s].d_aE2, 2 * rows * h->Pp));
+          h->sp[s].sd.aE2 = h->sp[s].d_aE2;
+          h->sp[s].sd.aA2 = h->sp[s].d_aE2 + rows * h->Pp;
+          if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+        }
+    }
     RET(L_cfl(h, s0, ns, st));
     int wm = wpadif_mask(h, flags);
     for (int s = 0; s < h->nS; ++s)
