@@ -118,6 +118,22 @@ int rsg_ram_set_plasmasphere(rsg_ram* h, const double* NECR);
  * which = 0 ATAW, 1 ATAC, 2 ATAW_emic_h, 3 ATAW_emic_he */
 int rsg_ram_set_diffcoef(rsg_ram* h, int which, const double* D);
 
+/* ANISCH, second half (src/ModRamRun.f90:422-605): the rebuild of those coefficients on the device, so a
+ * WPI / EMIC run needs no host-built ATAW / ATAC / ATAW_emic_*.  set_wave_tables, once: the tabulated bounce-averaged
+ * diffusion coefficients the reference reads at start-up (src/ModRamWPI.f90:185-470) -- ENOR(ENG), fpofc(NCF),
+ * NDAAJ(NR,ENG,NPA,NCF) [hiss], CDAAR(NR,NT,NE,NPA) with use_bas = 1 (DoUseBASdiff) or BDAAR with 0 [chorus];
+ * EKEV_emic(ENG_emic), fp2c_emic(NCF_emic), Daa_emic_h / _he(NR,ENG_emic,NPA,NCF_emic), Ihs_emic / Ihes_emic(4,NR,NT)
+ * [EMIC]; PAbn(NPA).  Either group may be NULL.  rsg_anisch_diffcoef(S): chorus -> ATAC by the Steffen spline of
+ * GSL_Interpolation_1D, hiss -> ATAW and EMIC -> ATAW_emic_h / _he by the bilinear rule of GSL_Interpolation_2D, for the
+ * species S the flags select (RSG_F_WPI: electrons, RSG_F_EMIC: H+); XNE(NR,NT) plasmaspheric density, AE index.  The
+ * caller keeps the reference's MOD(INT(T),INT(Dt_bc)) == 0 gate.  get_diffcoef: the arrays as the reference holds them. */
+int rsg_ram_set_wave_tables(rsg_ram* h, int ENG, int NCF, const double* ENOR, const double* fpofc, const double* NDAAJ,
+                            const double* DAAR, int use_bas, int ENG_emic, int NCF_emic, const double* EKEV_emic,
+                            const double* fp2c_emic, const double* Daa_emic_h, const double* Daa_emic_he, const double* Ihs_emic,
+                            const double* Ihes_emic, const double* PAbn);
+int rsg_anisch_diffcoef(rsg_ram* h, int S, int flags, const double* XNE, int AE, int* gslerr);
+int rsg_ram_get_diffcoef(rsg_ram* h, int which, double* D);
+
 /* ---- phase-space density ---------------------------------------------------
  * F2(nS,NR,NT,NE,NPA), species fastest (src/ModRamInit.f90:72).  S = 0 moves
  * all species, S >= 1 one species (the host array is always the full one). */

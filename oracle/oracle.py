@@ -64,6 +64,8 @@ def _ram_lib_from(name):
         lib.orc_wpadif.restype = C.c_long
         lib.orc_flcscatter.argtypes = [C.c_void_p, C.c_int]
         lib.orc_flcscatter.restype = C.c_long
+        lib.orc_anisch_diffcoef.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        lib.orc_anisch_diffcoef.restype = C.c_int
         lib.orc_ram_run.argtypes = [C.c_void_p, C.c_int, C.c_int]
         lib.orc_ram_run.restype = C.c_double
         lib.orc_get_cdrift.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
@@ -151,6 +153,19 @@ class RamOracle:
         out = _f((g.NR, g.NT, g.NE, g.NPA))
         self.lib.orc_get_cdrift(self.h, S, which, out.ctypes.data)
         return out
+
+    def anisch_diffcoef(self, S, flags, t, AE=0, use_bas=True):
+        """second half of ANISCH (src/ModRamRun.f90:422-605) from the table dict `t` (synthetic.synthetic_wave_tables);
+        fills ATAW / ATAC or ATAW_emic_h / ATAW_emic_he; returns the GSLerr count"""
+        for name in ("ENOR", "fpofc", "NDAAJ", "CDAAR", "BDAAR", "EKEV_emic", "fp2c_emic", "Daa_emic_h", "Daa_emic_he", "Ihs_emic",
+                     "Ihes_emic", "XNE", "PAbn"):
+            self._set(name, np.asfortranarray(t[name], dtype=np.float64).copy(order="F"))
+        for name in ("ENG", "NCF", "ENG_emic", "NCF_emic"):
+            self.set_scalar(name, t[name])
+        self.set_scalar("AE", AE)
+        self.set_scalar("DoUseBASdiff", 1.0 if use_bas else 0.0)
+        self.set_scalar("electron_species", 1 + int(np.argmax(self.g.kind == 3)))
+        return self.lib.orc_anisch_diffcoef(self.h, int(S), int(flags))
 
     def ram_run(self, flags=0, nthreads=None):
         if nthreads is None:

@@ -902,6 +902,181 @@ void anisch(Orc* o, int S) {
     }
 }
 
+// ---- GSL pieces of the diffusion-coefficient rebuild (GNU GSL 2.5 / 2.6, un-vendored: restated from the published
+// algorithms, like the Steffen spline of oracle/scb_oracle.cpp) ----------------------------------------------------------
+// GSL_Interpolation_1D -> Interpolation_1D_array (src/ModRamGSL.f90:240-311) + interpolation_1d_c (src/RamGSL.c:111-174):
+// the wrapper drops abscissae that do not increase, the C driver extrapolates linearly outside [xa_0, xa_n-1] (end points
+// included) and evaluates the Steffen cubic (gsl interpolation/steffen.c) of the bisection interval inside.
+inline double copysign1(double y) { return (y < 0.0) ? -1.0 : 1.0; }   // steffen_copysign(1.0, y) of gsl steffen.c
+int interp1d_steffen(int n0, const double* x1, const double* f1, int n2, const double* x2, double* f2) {
+  std::vector<double> xa(n0), fa(n0);
+  int n1 = 1;
+  xa[0] = x1[0];
+  fa[0] = f1[0];
+  for (int i = 1; i < n0; ++i)
+    if (x1[i] > xa[n1 - 1]) { xa[n1] = x1[i]; fa[n1] = f1[i]; ++n1; }
+  if (n1 < 3) return 1;
+  std::vector<double> yp(n1), a(n1 - 1), b(n1 - 1);
+  yp[0] = (fa[1] - fa[0]) / (xa[1] - xa[0]);
+  for (int i = 1; i < n1 - 1; ++i) {
+    const double hi = xa[i + 1] - xa[i], him1 = xa[i] - xa[i - 1];
+    const double si = (fa[i + 1] - fa[i]) / hi, sim1 = (fa[i] - fa[i - 1]) / him1;
+    const double pi = (sim1 * hi + si * him1) / (him1 + hi);
+    const double m1 = std::fabs(si) < 0.5 * std::fabs(pi) ? std::fabs(si) : 0.5 * std::fabs(pi);
+    const double m2 = std::fabs(sim1) < m1 ? std::fabs(sim1) : m1;
+    yp[i] = (copysign1(sim1) + copysign1(si)) * m2;
+  }
+  yp[n1 - 1] = (fa[n1 - 1] - fa[n1 - 2]) / (xa[n1 - 1] - xa[n1 - 2]);
+  for (int i = 0; i < n1 - 1; ++i) {
+    const double hi = xa[i + 1] - xa[i];
+    const double si = (fa[i + 1] - fa[i]) / hi;
+    a[i] = (yp[i] + yp[i + 1] - 2 * si) / hi / hi;
+    b[i] = (3 * si - 2 * yp[i] - yp[i + 1]) / hi;
+  }
+  for (int q = 0; q < n2; ++q) {
+    const double xb = x2[q];
+    if (xb <= xa[0]) f2[q] = fa[0] + (xb - xa[0]) / (xa[1] - xa[0]) * (fa[1] - fa[0]);
+    else if (xb >= xa[n1 - 1]) f2[q] = fa[n1 - 1] + (xb - xa[n1 - 1]) / (xa[n1 - 2] - xa[n1 - 1]) * (fa[n1 - 2] - fa[n1 - 1]);
+    else if (xb == xb) {
+      int ilo = 0, ihi = n1 - 1;
+      while (ihi > ilo + 1) {
+        const int i = (ihi + ilo) / 2;
+        if (xa[i] > xb) ihi = i; else ilo = i;
+      }
+      const double delx = xb - xa[ilo];
+      f2[q] = fa[ilo] + delx * (yp[ilo] + delx * (b[ilo] + delx * a[ilo]));
+    } else return 1;
+  }
+  return 0;
+}
+// GSL_Interpolation_2D -> Interpolation_2D_point (src/ModRamGSL.f90:489-533) + interpolation_2d_c (src/RamGSL.c:178-214):
+// gsl_interp2d_bilinear evaluated with gsl_interp2d_eval_extrap (no domain check: the edge cell is used outside the
+// table).  Index search = gsl_interp_bsearch(xa, x, 0, n-1): xa[i] <= x < xa[i+1], clipped to [0, n-2].
+inline int gsl_bsearch(const double* xa, double x, int n) {
+  int ilo = 0, ihi = n - 1;
+  while (ihi > ilo + 1) {
+    const int i = (ihi + ilo) / 2;
+    if (xa[i] > x) ihi = i; else ilo = i;
+  }
+  return ilo;
+}
+inline double interp2d_bilinear(int n1, int m1, const double* xa, const double* ya, const double* za, double x, double y) {
+  const int xi = gsl_bsearch(xa, x, n1), yi = gsl_bsearch(ya, y, m1);
+  const double xmin = xa[xi], xmax = xa[xi + 1], ymin = ya[yi], ymax = ya[yi + 1];
+  const double zminmin = za[(size_t)yi * n1 + xi], zminmax = za[(size_t)(yi + 1) * n1 + xi];
+  const double zmaxmin = za[(size_t)yi * n1 + xi + 1], zmaxmax = za[(size_t)(yi + 1) * n1 + xi + 1];
+  const double dx = xmax - xmin, dy = ymax - ymin;
+  const double t = (x - xmin) / dx, u = (y - ymin) / dy;
+  return (1. - t) * (1. - u) * zminmin + t * (1. - u) * zmaxmin + (1. - t) * u * zminmax + t * u * zmaxmax;
+}
+
+// ANISCH, second half: the pitch-angle diffusion coefficients of WPADIF, rebuilt every Dt_bc
+// (src/ModRamRun.f90:422-605).  Electrons with DoUseWPI: chorus outside the plasmapause (XNE <= 50; Steffen interpolation
+// of log10 <Daa> from the table's pitch angles PA onto PAbn -> ATAC) and hiss inside (bilinear interpolation of the
+// normalised table in (log10 E, fpe/fce) -> ATAW).  Species with EMIC (H+) and DoUseEMIC: bilinear interpolation of the
+// H-band / He-band tables, scaled by the wave intensity of I_emic (src/ModRamWPI.f90:720-750) -> ATAW_emic_h / _he.
+// The caller keeps the MOD(INT(T), INT(Dt_bc)) == 0 gate.  Returns the number of failed 1-D interpolations.
+int anisch_diffcoef(Orc* o, int S, int flags) {
+  DIMS
+  const double CS = 2.998E8, PI = 3.1415926535897932384626433832795, Q = 1.602E-19;
+  const int kind = A1(o->I("kind"), S);
+  const bool DoUseWPI = flags & 1, DoUseEMIC = flags & 4;
+  const double *MU = o->D("MU"), *WMU = o->D("WMU"), *EKEV = o->D("EKEV"), *RMAS = o->D("RMAS"), *BNES = o->D("BNES"),
+               *BOUNHS = o->D("BOUNHS"), *GREL = o->D("GREL"), *XNE = o->D("XNE"), *PAbn = o->D("PAbn");
+  const double cv = CS * 100, esu = Q * 3E9, gausgam = 1.E-5;
+  int nerr = 0;
+  if (DoUseWPI && kind == 3) {
+    double *ATAW = o->D("ATAW"), *ATAC = o->D("ATAC");
+    const double *CDAAR = o->D("CDAAR"), *BDAAR = o->D("BDAAR"), *NDAAJ = o->D("NDAAJ"), *ENOR = o->D("ENOR"), *fpofc = o->D("fpofc");
+    const int ENG = (int)o->S("ENG"), NCF = (int)o->S("NCF");
+    const bool DoUseBASdiff = o->S("DoUseBASdiff") != 0.0;
+    for (size_t q = 0; q < (size_t)NR * NT * NE * NPA; ++q) { ATAW[q] = 0.0; ATAC[q] = 0.0; }
+    std::vector<double> PA(NPA), DAMR1(NPA), Y(NPA);
+    for (int L = 1; L <= NPA; ++L) A1(PA, L) = 180.0 / PI * std::acos(A1(MU, NPA - L + 1));    // ACOSD, src/ModRamFunctions.f90:172
+    for (int I = 2; I <= NR; ++I)
+      for (int J = 1; J <= NT; ++J)
+        if (A2(XNE, NR, I, J) <= 50.) {                                                         // outside the plasmapause
+          const double fnorm = 1;
+          for (int K = 2; K <= NE; ++K) {
+            for (int L = 1; L <= NPA; ++L)
+              A1(DAMR1, L) = DoUseBASdiff ? std::log10(CD4(CDAAR, I, J, K, NPA - L + 1)) : std::log10(CD4(BDAAR, I, J, K, L));
+            // the reference interpolates one target per call; the spline of a line is the same for all of them
+            if (interp1d_steffen(NPA, PA.data(), DAMR1.data(), NPA, PAbn, Y.data())) ++nerr;
+            for (int L = 1; L <= NPA; ++L) {
+              const double MUBOUN = A1(MU, L) + 0.5 * A1(WMU, L);
+              double taudaa = std::pow(10., A1(Y, L)) * fnorm;
+              if (taudaa > 1e0) taudaa = 1e-1;
+              if (taudaa < 1e-30) taudaa = 1e-30;
+              CD4(ATAC, I, J, K, L) = taudaa * (1. - MUBOUN * MUBOUN) * MUBOUN * BOUNHS_(I, J, L);
+            }
+          }
+        }
+    double Bw = 30.;
+    if (o->S("Kp") >= 4.0) Bw = 100.;
+    std::vector<double> ALENOR(ENG), DUMP((size_t)ENG * NCF);
+    for (int KN = 1; KN <= ENG; ++KN) A1(ALENOR, KN) = std::log10(A1(ENOR, KN));
+    for (int I = 2; I <= NR; ++I)
+      for (int J = 1; J <= NT; ++J)
+        if (A2(XNE, NR, I, J) > 50.) {                                                          // inside the plasmapause
+          const double omega = esu * 10 * BNES_(I, J) / (A1(RMAS, S) * cv);
+          double xfrl = CS * std::sqrt(A2(XNE, NR, I, J) * A1(RMAS, S) * 40 * PI) / 10. / BNES_(I, J);
+          if (xfrl > 18) xfrl = 18.;
+          if (xfrl < 2) xfrl = 2.;
+          const double fnorm = omega * ((Bw * 1e-3) * (Bw * 1e-3)) * (gausgam * gausgam) / 1e8 / BNES_(I, J) / BNES_(I, J);
+          for (int L = 1; L <= NPA; ++L) {
+            const double MUBOUN = A1(MU, L) + 0.5 * A1(WMU, L);
+            for (int IZ = 1; IZ <= NCF; ++IZ)
+              for (int KN = 1; KN <= ENG; ++KN) A2(DUMP, ENG, KN, IZ) = std::log10(A4(NDAAJ, NR, ENG, NPA, I, KN, L, IZ));
+            for (int K = 2; K <= NE; ++K) {
+              const double ER1 = std::log10(A1(EKEV, K));
+              const double Yv = interp2d_bilinear(ENG, NCF, ALENOR.data(), fpofc, DUMP.data(), ER1, xfrl);
+              CD4(ATAW, I, J, K, L) = std::pow(10., Yv) * fnorm / (GREL_(S, K) * GREL_(S, K)) * (1. - MUBOUN * MUBOUN) / MUBOUN;
+            }
+          }
+        }
+  }
+  if (DoUseEMIC && kind == 0) {
+    double *AH = o->D("ATAW_emic_h"), *AHE = o->D("ATAW_emic_he");
+    const double *DH = o->D("Daa_emic_h"), *DHE = o->D("Daa_emic_he"), *EKEV_emic = o->D("EKEV_emic"), *fp2c = o->D("fp2c_emic"),
+                 *Ihs = o->D("Ihs_emic"), *Ihes = o->D("Ihes_emic");
+    const int ENGe = (int)o->S("ENG_emic"), NCFe = (int)o->S("NCF_emic");
+    const int AE = (int)o->S("AE");
+    const int eleS = (int)o->S("electron_species");        // RMAS(4) in the reference: the electron's index
+    for (size_t q = 0; q < (size_t)NR * NT * NE * NPA; ++q) { AH[q] = 0.0; AHE[q] = 0.0; }
+    std::vector<double> logE(ENGe), D1((size_t)ENGe * NCFe), D2((size_t)ENGe * NCFe);
+    for (int KN = 1; KN <= ENGe; ++KN) A1(logE, KN) = std::log10(A1(EKEV_emic, KN));
+    int cls = 0;                                            // I_emic: AE class 1..4 (0: none, intensities stay 0)
+    if (AE >= 0 && AE < 100) cls = 1; else if (AE >= 100 && AE < 300) cls = 2; else if (AE >= 300 && AE < 400) cls = 3; else if (AE >= 400) cls = 4;
+    for (int I = 2; I <= NR; ++I)
+      for (int J = 1; J <= NT; ++J) {
+        double xfrl = CS * std::sqrt(A2(XNE, NR, I, J) * A1(RMAS, eleS) * 40 * PI) / 10. / BNES_(I, J);
+        if (xfrl > 20) xfrl = 20.;
+        if (xfrl < 2) xfrl = 2.;
+        const double fnorm_h = cls ? A3(Ihs, 4, NR, cls, I, J) : 0.0, fnorm_he = cls ? A3(Ihes, 4, NR, cls, I, J) : 0.0;
+        for (int L = 1; L <= NPA; ++L) {
+          const double MUBOUN = A1(MU, L) + 0.5 * A1(WMU, L);
+          for (int IZ = 1; IZ <= NCFe; ++IZ)
+            for (int KN = 1; KN <= ENGe; ++KN) {
+              A2(D1, ENGe, KN, IZ) = std::log10(A4(DH, NR, ENGe, NPA, I, KN, L, IZ));
+              A2(D2, ENGe, KN, IZ) = std::log10(A4(DHE, NR, ENGe, NPA, I, KN, L, IZ));
+            }
+          for (int K = 2; K <= NE; ++K) {
+            const double ER1 = std::log10(A1(EKEV, K));
+            double Yv = interp2d_bilinear(ENGe, NCFe, logE.data(), fp2c, D1.data(), ER1, xfrl);
+            double vh = std::pow(10., Yv) * fnorm_h * (1. - MUBOUN * MUBOUN) * MUBOUN * BOUNHS_(I, J, L);
+            Yv = interp2d_bilinear(ENGe, NCFe, logE.data(), fp2c, D2.data(), ER1, xfrl);
+            double vhe = std::pow(10., Yv) * fnorm_he * (1. - MUBOUN * MUBOUN) * MUBOUN * BOUNHS_(I, J, L);
+            if (vh <= 1.0e-20) vh = 1.0e-31;
+            if (vhe <= 1.0e-20) vhe = 1.0e-31;
+            CD4(AH, I, J, K, L) = vh;
+            CD4(AHE, I, J, K, L) = vhe;
+          }
+        }
+      }
+  }
+  return nerr;
+}
+
 // flags for ram_run
 enum { F_WPI = 1, F_COULOMB = 2, F_EMIC = 4 };
 
@@ -1022,6 +1197,7 @@ void orc_coulmu(void* h, int S) { coulmu((Orc*)h, S); }
 void orc_sumrc(void* h, int S) { sumrc((Orc*)h, S); }
 void orc_anisch(void* h, int S) { anisch((Orc*)h, S); }
 double orc_ram_run(void* h, int flags, int nthreads) { return ram_run((Orc*)h, flags, nthreads); }
+int orc_anisch_diffcoef(void* h, int S, int flags) { return anisch_diffcoef((Orc*)h, S, flags); }
 // copy of a species' drift coefficient array (NR,NT,NE,NPA), which: 0=R 1=P 2=E 3=Mu
 void orc_get_cdrift(void* h, int S, int which, double* out) {
   Orc* o = (Orc*)h;

@@ -93,6 +93,36 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
 }
 
+// ---- TMA bulk copies (cp.async.bulk + mbarrier): one instruction moves a whole row of a plane between global and
+// shared memory; the copy engine does the addressing, the threads only wait on the barrier ----
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned done = 0;
+  while (!done) {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store(void* gdst, const void* smem_src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_store_fence() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_commit_wait() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 // =============================================================================
 // k_plane_rp: DRIFTR (src/ModRamDrift.f90:95-198) and DRIFTP (:204-279) of KC
 // consecutive (K,L) planes, back to back on a shared-memory copy; REV = reverse half
@@ -129,6 +159,7 @@ struct PlaneCfg {
   int part_off;       // REV: offset of this kernel's SUMRC partials in SpecDev::part
   int l0;             // first pitch angle of the launch (slab-sharded ranks); blockIdx.y counts from it
   int anisch;         // REV: also write this CTA's share of the ANISCH pitch-angle / energy sums (SpecDev::aE2 / aA2)
+  int tma;            // stage rows with TMA bulk copies when the layout allows (NR even)
 };
 
 template <bool REV, bool PEER = false>
@@ -166,8 +197,21 @@ __global__ void __launch_bounds__(512) k_plane_rp(const __grid_constant__ RamDev
       while (j >= NT) { j -= NT; ++q; so += PS - NT * NRp; go += Pp - P; p -= P; }
     }
   };
+  // NR even: every row of a plane is a 16-byte aligned run of NR*8 bytes on both sides -- one TMA bulk copy per row
+  // (cp.async.bulk, completion counted on an mbarrier); else 8-byte cp.async chunks.
+  __shared__ unsigned long long mbar;
+  const bool tma = (E == 2) && cfg.tma;
+  const int nrows = KCa * NT;
   {
-    if (E == 2) for_chunks([&](int so, int go, int) { cp_async16(sP + so, Fg + go); });
+    if (tma) {
+      if (tid == 0) mbar_init(&mbar, 1);
+      __syncthreads();
+      if (tid == 0) mbar_expect_tx(&mbar, (unsigned)(nrows * NR * 8));
+      for (int t = tid; t < nrows; t += T) {
+        const int q = t / NT, j = t - q * NT;
+        tma_load(sP + (size_t)q * PS + j * NRp, Fg + (size_t)q * Pp + j * NR, (unsigned)(NR * 8), &mbar);
+      }
+    } else if (E == 2) for_chunks([&](int so, int go, int) { cp_async16(sP + so, Fg + go); });
     else for_chunks([&](int so, int go, int) { cp_async8(sP + so, Fg + go); });
     asm volatile("cp.async.commit_group;");
     for (int t = tid; t < KCa * NT; t += T) {
@@ -178,6 +222,7 @@ __global__ void __launch_bounds__(512) k_plane_rp(const __grid_constant__ RamDev
       sG[2 * t + 1] = sp.ghost[2 * (size_t)line + 1];
     }
     asm volatile("cp.async.wait_group 0;");
+    if (tma) mbar_wait(&mbar, 0);
   }
   __syncthreads();
   double macc = 0.0;
@@ -358,7 +403,21 @@ __global__ void __launch_bounds__(512) k_plane_rp(const __grid_constant__ RamDev
         oA[p] = sa;
       }
     }
-    if (E == 2)
+    if (tma) {
+      // the magnetopause mask on the shared copy, then one bulk store per row
+      for (int p = tid; p < P; p += T)
+        if (d.outp[p]) {
+          const int j = p / NR, i = p - j * NR;
+          for (int q = 0; q < KCa; ++q) sP[(size_t)q * PS + j * NRp + i] = 1.e-31;
+        }
+      tma_store_fence();
+      __syncthreads();
+      for (int t = tid; t < nrows; t += T) {
+        const int q = t / NT, j = t - q * NT;
+        tma_store(Fg + (size_t)q * Pp + j * NR, sP + (size_t)q * PS + j * NRp, (unsigned)(NR * 8));
+      }
+      tma_store_commit_wait();
+    } else if (E == 2)
       for_chunks([&](int so, int go, int pl) {
         double2 v = *(const double2*)(sP + so);
         const unsigned short o2 = *(const unsigned short*)(d.outp + pl);
@@ -376,6 +435,14 @@ __global__ void __launch_bounds__(512) k_plane_rp(const __grid_constant__ RamDev
         *(double2*)(pv.F[peer_owner(pv.ccut, pv.G, pl)] + rel + go) = *(const double2*)(sP + so);
       });
     else for_chunks([&](int so, int go, int pl) { pv.F[peer_owner(pv.ccut, pv.G, pl)][rel + go] = sP[so]; });
+  } else if (tma) {
+    tma_store_fence();
+    __syncthreads();
+    for (int t = tid; t < nrows; t += T) {
+      const int q = t / NT, j = t - q * NT;
+      tma_store(Fg + (size_t)q * Pp + j * NR, sP + (size_t)q * PS + j * NRp, (unsigned)(NR * 8));
+    }
+    tma_store_commit_wait();
   } else {
     if (E == 2) for_chunks([&](int so, int go, int) { *(double2*)(Fg + go) = *(const double2*)(sP + so); });
     else for_chunks([&](int so, int go, int) { Fg[go] = sP[so]; });

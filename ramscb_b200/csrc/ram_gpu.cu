@@ -16,6 +16,7 @@
 #include "ram_kernels.cuh"
 #include "ram_fused.cuh"
 #include "ram_coulomb.cuh"
+#include "ram_diffcoef.cuh"
 
 namespace {
 
@@ -108,6 +109,11 @@ struct rsg_ram {
   double* d_zero4 = nullptr;  // all-zero diffusion coefficient
   double* d_flctab = nullptr; // PARA_FLC inputs: r_curvEq, zeta1Eq, zeta2Eq (P each), V(S,:), LZ
   double* d_NECR = nullptr;
+  DiffTabs dtab{};             // wave tables of the ANISCH diffusion-coefficient rebuild (rsg_ram_set_wave_tables)
+  bool dtab_set = false;
+  double* d_XNE = nullptr;
+  int* d_dcerr = nullptr;
+  double* d_dcgrel = nullptr;
   double* d_dtinit = nullptr;
   int* d_outlist = nullptr;   // plane indices p of flagged (outsideMGNP) cells with 2 <= J <= NT-1
   int nout = 0;
@@ -156,6 +162,7 @@ struct rsg_ram {
   bool use_fused_wpi = true;   // WPADIF inside the column kernel (RSG_NO_FUSE_WPI=1 / rsg_ram_use_fused(h, 1): one kernel per operator with WPI / EMIC)
   int kcPlane = 0, colT = 0, planeT = 0;
   bool planeOdd = false;
+  bool planeTma = true;     // k_plane_rp stages plane rows with TMA bulk copies (RSG_PLANE_TMA=0: cp.async chunks)
   int anischLch = 12;   // pitch angles per thread in the ANISCH pitch-angle sums
   bool in_step = false, fwd_half = false;   // set by rsg_ram_part_*: CFL slots are reset once per step
   unsigned long long* d_res_init = nullptr;
@@ -565,6 +572,7 @@ int L_plane_rp(rsg_ram* h, int s0, int ns, cudaStream_t st, bool rev, int l0 = 0
   c.cfg.part_off = fused_part_off(h);      // after the column kernel's partials
   c.cfg.l0 = l0;
   c.cfg.anisch = (rev && h->sp[s0].d_aE2) ? 1 : 0;
+  c.cfg.tma = h->planeTma ? 1 : 0;
   if (rev) { RET(opt_in_smem(k_plane_rp<true>, c.smem)); k_plane_rp<true><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg, pv); }
   else if (peer) { RET(opt_in_smem(k_plane_rp<false, true>, c.smem)); k_plane_rp<false, true><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg, pv); }
   else { RET(opt_in_smem(k_plane_rp<false>, c.smem)); k_plane_rp<false><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg, pv); }
@@ -875,6 +883,7 @@ int rsg_ram_create(rsg_ram** out, int nS, int NR, int NT, int NE, int NPA, int d
   if (const char* e = getenv("RSG_COL_T")) h->colT = std::max(32, atoi(e));
   if (const char* e = getenv("RSG_PLANE_T")) h->planeT = std::max(32, atoi(e));
   if (const char* e = getenv("RSG_PLANE_ODD")) h->planeOdd = atoi(e) != 0;
+  if (const char* e = getenv("RSG_PLANE_TMA")) h->planeTma = atoi(e) != 0;
   if (const char* e = getenv("RSG_ANISCH_LCH")) h->anischLch = std::max(1, atoi(e));
   if (getenv("RSG_NO_GRAPH")) h->use_graph = false;   // kernel-by-kernel launches (profilers)
   RamDev& d = h->dev;
@@ -1295,6 +1304,153 @@ int rsg_ram_get_flc_coef(rsg_ram* h, int S, double* D) {
   RET(rsg_ram_sync(h));
   std::vector<double> b(h->specStride);
   CK(cudaMemcpy(b.data(), sp.d_flc, sizeof(double) * h->specStride, cudaMemcpyDeviceToHost));
+  for (int l = 0; l < h->NPA; ++l)
+    for (int k = 0; k < h->NE; ++k)
+      std::memcpy(&D[((size_t)l * h->NE + k) * h->P], &b[((size_t)l * h->NE + k) * h->Pp], sizeof(double) * h->P);
+  return RSG_OK;
+}
+
+// ---- ANISCH, second half: rebuild of the WPADIF diffusion coefficients on the device (src/ModRamRun.f90:422-605) ----
+int rsg_ram_set_wave_tables(rsg_ram* h, int ENG, int NCF, const double* ENOR, const double* fpofc, const double* NDAAJ,
+                            const double* DAAR, int use_bas, int ENG_emic, int NCF_emic, const double* EKEV_emic,
+                            const double* fp2c_emic, const double* Daa_emic_h, const double* Daa_emic_he, const double* Ihs_emic,
+                            const double* Ihes_emic, const double* PAbn) {
+  if (!h || !PAbn) return fail(RSG_ERR_ARG, "null argument");
+  if (!h->grids_set) return fail(RSG_ERR_STATE, "set_wave_tables before set_grids");
+  const bool wpi = ENOR && fpofc && NDAAJ && DAAR, emic = EKEV_emic && fp2c_emic && Daa_emic_h && Daa_emic_he && Ihs_emic && Ihes_emic;
+  if (!wpi && !emic) return fail(RSG_ERR_ARG, "neither the WPI (ENOR, fpofc, NDAAJ, C/BDAAR) nor the EMIC tables are complete");
+  if ((wpi && (ENG < 2 || NCF < 2)) || (emic && (ENG_emic < 2 || NCF_emic < 2))) return fail(RSG_ERR_ARG, "tables need >= 2 nodes per axis");
+  CK(cudaSetDevice(h->device));
+  RET(rsg_ram_sync(h));
+  const int NR = h->NR, NT = h->NT, NE = h->NE, NPA = h->NPA;
+  DiffTabs& t = h->dtab;
+  t = DiffTabs{};
+  auto upv = [&](const double** dst, const std::vector<double>& v) -> int {
+    double* p = nullptr;
+    RET(h->dalloc(&p, v.size()));
+    RET(up(p, v.data(), v.size()));
+    *dst = p;
+    return RSG_OK;
+  };
+  auto upa = [&](const double** dst, const double* src, size_t n) -> int { return upv(dst, std::vector<double>(src, src + n)); };
+  // abscissae of the chorus interpolation: PA(L) = ACOSD(MU(NPA-L+1)) (:437), through the wrapper's monotonicity filter
+  {
+    std::vector<double> xa;
+    std::vector<int> idx;
+    for (int L = 1; L <= NPA; ++L) {
+      const double pa = 180.0 / kPI * std::acos(h->MU[NPA - L]);
+      if (xa.empty() || pa > xa.back()) { xa.push_back(pa); idx.push_back(L - 1); }
+    }
+    t.n1 = (int)xa.size();
+    RET(upv(&t.PAx, xa));
+    int* pi = nullptr;
+    RET(h->dalloc(&pi, idx.size()));
+    RET(up(pi, idx.data(), idx.size()));
+    t.PAidx = pi;
+  }
+  RET(upa(&t.PAbn, PAbn, NPA));
+  if (wpi) {
+    t.ENG = ENG; t.NCF = NCF; t.use_bas = use_bas ? 1 : 0;
+    std::vector<double> al(ENG);
+    for (int q = 0; q < ENG; ++q) al[q] = std::log10(ENOR[q]);
+    RET(upv(&t.ALENOR, al));
+    RET(upa(&t.fpofc, fpofc, NCF));
+    RET(upa(&t.NDAAJ, NDAAJ, (size_t)NR * ENG * NPA * NCF));
+    RET(upa(&t.DAAR, DAAR, (size_t)NR * NT * NE * NPA));
+  }
+  if (emic) {
+    t.ENGe = ENG_emic; t.NCFe = NCF_emic;
+    std::vector<double> al(ENG_emic);
+    for (int q = 0; q < ENG_emic; ++q) al[q] = std::log10(EKEV_emic[q]);
+    RET(upv(&t.logEe, al));
+    RET(upa(&t.fp2c, fp2c_emic, NCF_emic));
+    RET(upa(&t.DH, Daa_emic_h, (size_t)NR * ENG_emic * NPA * NCF_emic));
+    RET(upa(&t.DHE, Daa_emic_he, (size_t)NR * ENG_emic * NPA * NCF_emic));
+    RET(upa(&t.Ihs, Ihs_emic, (size_t)4 * NR * NT));
+    RET(upa(&t.Ihes, Ihes_emic, (size_t)4 * NR * NT));
+  }
+  if (!h->d_XNE) RET(h->dalloc(&h->d_XNE, (size_t)NR * NT));
+  if (!h->d_dcerr) RET(h->dalloc(&h->d_dcerr, 1));
+  h->dtab_set = true;
+  return RSG_OK;
+}
+
+// S: 1-based species; flags: RSG_F_WPI (electrons: ATAW + ATAC) | RSG_F_EMIC (H+: ATAW_emic_h + ATAW_emic_he); XNE(NR,NT):
+// plasmaspheric electron density; AE index (I_emic).  Kp comes from rsg_ram_set_wavelo.  The caller keeps the reference's
+// "every Dt_bc" gate (:422, :520).  *gslerr: lines whose 1-D interpolation failed (GSLerr of the reference).
+int rsg_anisch_diffcoef(rsg_ram* h, int S, int flags, const double* XNE, int AE, int* gslerr) {
+  RET(check_S(h, S));
+  if (!XNE) return fail(RSG_ERR_ARG, "null argument");
+  if (!h->dtab_set) return fail(RSG_ERR_STATE, "ANISCH diffusion coefficients before rsg_ram_set_wave_tables");
+  if (!h->fields_set) return fail(RSG_ERR_STATE, "ANISCH diffusion coefficients before set_fields");
+  CK(cudaSetDevice(h->device));
+  RET(rsg_ram_sync(h));
+  const int s = S - 1, NR = h->NR, NT = h->NT, NE = h->NE, NPA = h->NPA;
+  RET(up(h->d_XNE, XNE, (size_t)NR * NT));
+  DiffTabs t = h->dtab;
+  t.XNE = h->d_XNE;
+  t.RMASs = h->RMAS[s];
+  t.RMASe = h->RMAS[s];
+  for (int q = 0; q < h->nS; ++q)
+    if (h->kind[q] == RSG_KIND_E) t.RMASe = h->RMAS[q];       // RMAS(4) of the reference: the electrons
+  t.Bw = (h->Kp >= 4.0) ? 100. : 30.;
+  t.cls = (AE >= 0 && AE < 100) ? 1 : ((AE >= 100 && AE < 300) ? 2 : ((AE >= 300 && AE < 400) ? 3 : (AE >= 400 ? 4 : 0)));
+  {
+    std::vector<double> g(NE);
+    for (int k = 0; k < NE; ++k) g[k] = h->GREL[s + (size_t)h->nS * k];
+    if (!h->d_dcgrel) RET(h->dalloc(&h->d_dcgrel, NE));
+    RET(up(h->d_dcgrel, g.data(), NE));
+    t.GRELs = h->d_dcgrel;
+  }
+  cudaStream_t st = h->st(s);
+  CK(cudaMemsetAsync(h->d_dcerr, 0, sizeof(int), st));
+  auto ensure = [&](int which) -> int {
+    if (!h->d_diff[which]) {
+      RET(h->dalloc(&h->d_diff[which], h->specStride));
+      if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+    }
+    CK(cudaMemsetAsync(h->d_diff[which], 0, sizeof(double) * h->specStride, st));
+    return RSG_OK;
+  };
+  bool did = false;
+  if ((flags & RSG_F_WPI) && h->kind[s] == RSG_KIND_E) {
+    if (!t.DAAR) return fail(RSG_ERR_STATE, "the WPI tables were not set");
+    RET(ensure(0)); RET(ensure(1));
+    const long long nlines = (long long)(NR - 1) * NT * (NE - 1);
+    k_diffcoef_chorus<<<nblk(nlines, 4), 128, sizeof(double) * 4 * 2 * NPA, st>>>(h->dev, t, h->d_diff[1], h->d_dcerr);
+    CKL();
+    k_diffcoef_bilinear<<<nblk(nlines * NPA, 128), 128, 0, st>>>(h->dev, t, 0, h->d_diff[0], nullptr);
+    CKL();
+    h->launches += 2;
+    did = true;
+  }
+  if ((flags & RSG_F_EMIC) && h->kind[s] == RSG_KIND_H) {
+    if (!t.DH) return fail(RSG_ERR_STATE, "the EMIC tables were not set");
+    RET(ensure(2)); RET(ensure(3));
+    const long long n = (long long)(NR - 1) * NT * (NE - 1) * NPA;
+    k_diffcoef_bilinear<<<nblk(n, 128), 128, 0, st>>>(h->dev, t, 1, h->d_diff[2], h->d_diff[3]);
+    CKL();
+    h->launches++;
+    did = true;
+  }
+  int err = 0;
+  CK(cudaMemcpyAsync(&err, h->d_dcerr, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (gslerr) *gslerr = err;
+  if (did)
+    for (int q = 0; q < h->nS; ++q) h->sp[q].wtab_DTs = -1.0;     // the fused WPADIF factors are stale
+  return RSG_OK;
+}
+
+// which = 0 ATAW, 1 ATAC, 2 ATAW_emic_h, 3 ATAW_emic_he as the reference holds them: (NR,NT,NE,NPA)
+int rsg_ram_get_diffcoef(rsg_ram* h, int which, double* D) {
+  if (!h || !D) return fail(RSG_ERR_ARG, "null argument");
+  if (which < 0 || which > 3) return fail(RSG_ERR_ARG, "which must be 0..3");
+  if (!h->d_diff[which]) return fail(RSG_ERR_STATE, "this diffusion coefficient is not on the device");
+  CK(cudaSetDevice(h->device));
+  RET(rsg_ram_sync(h));
+  std::vector<double> b(h->specStride);
+  CK(cudaMemcpy(b.data(), h->d_diff[which], sizeof(double) * h->specStride, cudaMemcpyDeviceToHost));
   for (int l = 0; l < h->NPA; ++l)
     for (int k = 0; k < h->NE; ++k)
       std::memcpy(&D[((size_t)l * h->NE + k) * h->P], &b[((size_t)l * h->NE + k) * h->Pp], sizeof(double) * h->P);

@@ -74,6 +74,9 @@ def lib():
     L.rsg_para_flc.argtypes = [vp, i, vp, vp, vp]
     L.rsg_ram_get_flc_coef.argtypes = [vp, i, vp]
     L.rsg_ram_set_diffcoef.argtypes = [vp, i, vp]
+    L.rsg_ram_set_wave_tables.argtypes = [vp, i, i, vp, vp, vp, vp, i, i, i, vp, vp, vp, vp, vp, vp, vp]
+    L.rsg_anisch_diffcoef.argtypes = [vp, i, i, vp, i, _ip]
+    L.rsg_ram_get_diffcoef.argtypes = [vp, i, vp]
     L.rsg_ram_f2_h2d.argtypes = [vp, vp, i]
     L.rsg_ram_f2_d2h.argtypes = [vp, vp, i]
     L.rsg_ram_f2_device.argtypes = [vp, i, C.POINTER(vp), C.POINTER(ll), _ip]
@@ -222,6 +225,31 @@ class RamGpu:
 
     def set_diffcoef(self, which, D):
         _ck(self.L.rsg_ram_set_diffcoef(self.h, which, _p(D)))
+
+    def set_wave_tables(self, t, use_bas=True):
+        """the tabulated diffusion coefficients (dict of synthetic.synthetic_wave_tables / the reference's start-up files)"""
+        f = lambda n: np.asfortranarray(t[n], dtype=np.float64)
+        a = {n: f(n) for n in ("ENOR", "fpofc", "NDAAJ", "CDAAR" if use_bas else "BDAAR", "EKEV_emic", "fp2c_emic", "Daa_emic_h",
+                               "Daa_emic_he", "Ihs_emic", "Ihes_emic", "PAbn")}
+        self._keep.append(a)
+        _ck(self.L.rsg_ram_set_wave_tables(self.h, int(t["ENG"]), int(t["NCF"]), a["ENOR"].ctypes.data, a["fpofc"].ctypes.data,
+                                           a["NDAAJ"].ctypes.data, a["CDAAR" if use_bas else "BDAAR"].ctypes.data, 1 if use_bas else 0,
+                                           int(t["ENG_emic"]), int(t["NCF_emic"]), a["EKEV_emic"].ctypes.data, a["fp2c_emic"].ctypes.data,
+                                           a["Daa_emic_h"].ctypes.data, a["Daa_emic_he"].ctypes.data, a["Ihs_emic"].ctypes.data,
+                                           a["Ihes_emic"].ctypes.data, a["PAbn"].ctypes.data))
+
+    def ANISCH_diffcoef(self, S, flags, XNE, AE=0):
+        """second half of ANISCH (src/ModRamRun.f90:422-605): rebuild ATAW/ATAC (electrons, WPI) or ATAW_emic_h/_he (H+, EMIC)
+        on the device; returns the reference's GSLerr count"""
+        err = C.c_int()
+        _ck(self.L.rsg_anisch_diffcoef(self.h, S, flags, _p(np.asfortranarray(XNE, dtype=np.float64)), int(AE), C.byref(err)))
+        return err.value
+
+    def get_diffcoef(self, which):
+        g = self.g
+        out = np.zeros((g.NR, g.NT, g.NE, g.NPA), order="F")
+        _ck(self.L.rsg_ram_get_diffcoef(self.h, which, _p(out)))
+        return out
 
     def set_inputs(self, inp):
         """Everything a RamInputs carries, F2 included."""

@@ -204,3 +204,37 @@ def synthetic_daa(g: G.RamGrids, inp: RamInputs):
     D = (tau[None, None, :, None] * ((1.0 - mub ** 2) * mub)[None, None, None, :]
          * inp.BOUNHS[:NR, :, None, :])
     return np.asfortranarray(np.clip(D, 1e-30, None))
+
+
+def synthetic_wave_tables(g: G.RamGrids, inp: RamInputs, seed: int = 7):
+    """Synthetic stand-ins for the tabulated bounce-averaged diffusion coefficients the reference reads at start-up
+    (src/ModRamWPI.f90:185-470; the files are missing blobs) -- same shapes, axes and orders of magnitude -- and the
+    plasmaspheric density XNE with a plasmapause near L = 4.5, so that both branches of the ANISCH rebuild
+    (src/ModRamRun.f90:447-515: chorus outside, hiss inside) are taken.  Returns a dict of Fortran-ordered arrays."""
+    rng = np.random.default_rng(seed)
+    NR, NT, NE, NPA = g.NR, g.NT, g.NE, g.NPA
+    ENG, NCF, ENGe, NCFe = 45, 5, 41, 10                       # src/ModRamGrids.f90:31-34, :51
+    t = {"ENG": ENG, "NCF": NCF, "ENG_emic": ENGe, "NCF_emic": NCFe}
+    t["ENOR"] = np.logspace(-2.0, 3.5, ENG)                     # normalised energies, ascending
+    t["fpofc"] = 2.0 + 4.0 * np.arange(NCF)                     # src/ModRamWPI.f90:351-362
+    t["EKEV_emic"] = np.logspace(-1.0, 3.0, ENGe)               # 0.1 keV .. 1000 keV
+    t["fp2c_emic"] = 2.0 * (1 + np.arange(NCFe))                # :232
+    mu = g.MU
+    shape_l = 0.2 + np.sin(np.pi * np.clip(mu, 0.02, 0.98)) ** 2
+
+    def smooth(shape, lo, hi):
+        return np.asfortranarray(10.0 ** (lo + (hi - lo) * rng.random(shape)))
+
+    t["NDAAJ"] = np.asfortranarray(smooth((NR, ENG, NPA, NCF), -3.0, 1.0) * shape_l[None, None, :, None])
+    t["CDAAR"] = np.asfortranarray(smooth((NR, NT, NE, NPA), -7.0, -3.0) * shape_l[None, None, None, :])
+    t["BDAAR"] = np.asfortranarray(smooth((NR, NT, NE, NPA), -7.0, -3.0) * shape_l[None, None, None, :])
+    t["Daa_emic_h"] = np.asfortranarray(smooth((NR, ENGe, NPA, NCFe), -8.0, -2.0) * shape_l[None, None, :, None])
+    t["Daa_emic_he"] = np.asfortranarray(smooth((NR, ENGe, NPA, NCFe), -9.0, -3.0) * shape_l[None, None, :, None])
+    t["Daa_emic_h"][:, :, ::7, :] *= 1e-30                      # some entries below the 1e-20 floor (:585-586)
+    t["Ihs_emic"] = np.asfortranarray(0.1 + rng.random((4, NR, NT)))
+    t["Ihes_emic"] = np.asfortranarray(0.05 + rng.random((4, NR, NT)))
+    LZ = g.LZ[:NR]
+    XNE = np.asfortranarray(inp.NECR[:NR, :NT] * np.where(LZ[:, None] > 4.5, 0.05, 1.0))
+    t["XNE"] = XNE
+    t["PAbn"] = np.asfortranarray(g.PAbn, dtype=np.float64)
+    return t

@@ -23,7 +23,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "ramscb_b200", "csrc")
 GEN = os.path.join(HERE, "_gen")
 LIB = os.path.join(GEN, "libramscb_emu.so")
-FILES = ["ram_common.cuh", "ram_kernels.cuh", "ram_fused.cuh", "ram_coulomb.cuh", "ram_gpu.cu", "scb_kernels.cuh", "hi_kernels.cuh", "scb_gpu.cu"]
+FILES = ["ram_common.cuh", "ram_kernels.cuh", "ram_fused.cuh", "ram_coulomb.cuh", "ram_diffcoef.cuh", "ram_gpu.cu", "scb_kernels.cuh", "hi_kernels.cuh", "scb_gpu.cu"]
 
 
 def _match(src, i, open_ch, close_ch):
@@ -101,6 +101,12 @@ def rewrite(src, name):
     src = re.sub(r'asm volatile\("cp\.async\.ca\.shared\.global[^\n]*\n', "memcpy(smem_dst, gsrc, 8);\n", src)
     src = re.sub(r'asm volatile\("cp\.async\.cg\.shared\.global[^\n]*\n', "memcpy(smem_dst, gsrc, 16);\n", src)
     src = re.sub(r'asm volatile\("cp\.async\.(commit_group|wait_group \d+);"\);', ";", src)
+    # TMA bulk copies and their mbarrier (ram_fused.cuh): the copy happens at once, the barrier is always passed --
+    # the kernels follow the wait with a __syncthreads(), which is what orders the emulated threads
+    src = re.sub(r'asm volatile\("cp\.async\.bulk\.shared::cluster\.global[^\n]*\n', "memcpy(smem_dst, gsrc, bytes);\n", src)
+    src = re.sub(r'asm volatile\("cp\.async\.bulk\.global\.shared::cta[^\n]*\n', "memcpy(gdst, smem_src, bytes);\n", src)
+    src = re.sub(r'asm volatile\("\{ \.reg \.pred p; mbarrier\.try_wait[^\n]*\n', "done = 1;\n", src)
+    src = re.sub(r'asm volatile\("(mbarrier\.|fence\.|cp\.async\.bulk\.(commit_group|wait_group))[^\n]*\n', ";\n", src)
     if "asm volatile" in src or "asm(" in src:
         raise SystemExit(f"{name}: inline PTX the emulator does not know")
     return rewrite_launches(src)

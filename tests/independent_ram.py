@@ -678,3 +678,71 @@ def ram_run(g, inp, F2, DTs, beta, gcoul, DtsMin=1.0, T=0.0, wpi=False, emic=Fal
         F2[S - 1] = Fn
         PPERT[S - 1], PPART[S - 1] = pe, pa
     return F2, DtsNext, SETRC, loss, PPERT, PPART
+
+
+# ---------------------------------------------------------------------------------------------
+# ANISCH, second half: the diffusion-coefficient rebuild (src/ModRamRun.f90:422-605), restated a second time:
+# whole-array numpy, the Steffen spline through tests/independent_scb.interp1d_steffen (searchsorted instead of the
+# bisection loop), the bilinear rule written on index arrays.
+def anisch_diffcoef(g, inp, t, S, wpi, emic, Kp, AE=0, use_bas=True):
+    from independent_scb import interp1d_steffen
+    NR, NT, NE, NPA = g.NR, g.NT, g.NE, g.NPA
+    s = S - 1
+    CSv, PI = 2.998E8, 3.1415926535897932384626433832795
+    MUB = g.MU + 0.5 * g.WMU
+    XNE, B, BH = t["XNE"], inp.BNES, inp.BOUNHS
+    out = {}
+
+    def bilinear(xa, ya, za, x, y):                     # za[i, j] = f(xa[i], ya[j]); x, y arrays of equal shape
+        xi = np.clip(np.searchsorted(xa, x, side="right") - 1, 0, len(xa) - 2)
+        yi = np.clip(np.searchsorted(ya, y, side="right") - 1, 0, len(ya) - 2)
+        tt = (x - xa[xi]) / (xa[xi + 1] - xa[xi])
+        u = (y - ya[yi]) / (ya[yi + 1] - ya[yi])
+        return ((1. - tt) * (1. - u) * za[xi, yi] + tt * (1. - u) * za[xi + 1, yi] + (1. - tt) * u * za[xi, yi + 1]
+                + tt * u * za[xi + 1, yi + 1])
+
+    if wpi and g.kind[s] == 3:
+        ATAW = np.zeros((NR, NT, NE, NPA), order="F")
+        ATAC = np.zeros((NR, NT, NE, NPA), order="F")
+        PA = 180.0 / PI * np.arccos(g.MU[::-1])
+        tab = t["CDAAR"][..., ::-1] if use_bas else t["BDAAR"]
+        Bw = 100. if Kp >= 4.0 else 30.
+        esu, cv, gausgam = 1.602E-19 * 3E9, CSv * 100, 1.E-5
+        ALENOR = np.log10(t["ENOR"])
+        ER1 = np.log10(g.EKEV[1:])
+        for I in range(1, NR):
+            for J in range(NT):
+                if XNE[I, J] <= 50.:
+                    for K in range(1, NE):
+                        Y = interp1d_steffen(PA, np.log10(tab[I, J, K, :]), t["PAbn"])
+                        tau = 10. ** Y * 1
+                        tau = np.where(tau > 1e0, 1e-1, tau)
+                        tau = np.where(tau < 1e-30, 1e-30, tau)
+                        ATAC[I, J, K, :] = tau * (1. - MUB * MUB) * MUB * BH[I, J, :]
+                else:
+                    omega = esu * 10 * B[I, J] / (g.RMAS[s] * cv)
+                    xfrl = min(max(CSv * np.sqrt(XNE[I, J] * g.RMAS[s] * 40 * PI) / 10. / B[I, J], 2.), 18.)
+                    fnorm = omega * ((Bw * 1e-3) * (Bw * 1e-3)) * (gausgam * gausgam) / 1e8 / B[I, J] / B[I, J]
+                    for L in range(NPA):
+                        Y = bilinear(ALENOR, t["fpofc"], np.log10(t["NDAAJ"][I, :, L, :]), ER1, np.full_like(ER1, xfrl))
+                        ATAW[I, J, 1:, L] = 10. ** Y * fnorm / (g.GREL[s, 1:] * g.GREL[s, 1:]) * (1. - MUB[L] * MUB[L]) / MUB[L]
+        out["ATAW"], out["ATAC"] = ATAW, ATAC
+    if emic and g.kind[s] == 0:
+        AH = np.zeros((NR, NT, NE, NPA), order="F")
+        AHE = np.zeros((NR, NT, NE, NPA), order="F")
+        cls = 1 if 0 <= AE < 100 else (2 if 100 <= AE < 300 else (3 if 300 <= AE < 400 else (4 if AE >= 400 else 0)))
+        me = g.RMAS[int(np.argmax(g.kind == 3))]
+        logE = np.log10(t["EKEV_emic"])
+        ER1 = np.log10(g.EKEV[1:])
+        for I in range(1, NR):
+            for J in range(NT):
+                xfrl = min(max(CSv * np.sqrt(XNE[I, J] * me * 40 * PI) / 10. / B[I, J], 2.), 20.)
+                fh = t["Ihs_emic"][cls - 1, I, J] if cls else 0.0
+                fhe = t["Ihes_emic"][cls - 1, I, J] if cls else 0.0
+                for L in range(NPA):
+                    for arr, tab, f in ((AH, t["Daa_emic_h"], fh), (AHE, t["Daa_emic_he"], fhe)):
+                        Y = bilinear(logE, t["fp2c_emic"], np.log10(tab[I, :, L, :]), ER1, np.full_like(ER1, xfrl))
+                        v = 10. ** Y * f * (1. - MUB[L] * MUB[L]) * MUB[L] * BH[I, J, L]
+                        arr[I, J, 1:, L] = np.where(v <= 1.0e-20, 1.0e-31, v)
+        out["ATAW_emic_h"], out["ATAW_emic_he"] = AH, AHE
+    return out

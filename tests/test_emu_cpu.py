@@ -137,3 +137,43 @@ def test_emulated_results_do_not_depend_on_thread_order():
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_emu_cpu.py"), "-x", "-q", "-k",
                         "fused_equals or (fused_wpadif and 5) or exact_sweeps or scb_maps or hI_integrals or hI_tail or hI_convert"], env=env, capture_output=True, text=True, cwd=os.path.dirname(here))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("use_bas", [True, False])
+def test_anisch_diffusion_coefficient_rebuild(emu, use_bas):
+    """ANISCH, second half (src/ModRamRun.f90:422-605): chorus (Steffen 1-D), hiss and EMIC (bilinear 2-D)
+    coefficients rebuilt by the device kernels (emulated) against the oracle -- the kernels keep the reference's operation
+    order, so ATAW, ATAC, ATAW_emic_h, ATAW_emic_he are BIT-IDENTICAL -- and the oracle against a second, whole-array numpy
+    restatement (<= 1e-13: np.log10 / ** vs libm differ in the last bit)."""
+    import independent_ram as ir
+    from oracle import oracle
+    from ramscb_b200 import grids, synthetic
+    g = grids.build_grids(NR=9, NT=7, NE=8)
+    inp = synthetic.make_inputs(g, f2_kind="smooth")
+    t = synthetic.synthetic_wave_tables(g, inp)
+    assert 0 < (t["XNE"] > 50).sum() < t["XNE"].size          # both sides of the plasmapause are exercised
+    o = oracle.RamOracle(g, inp)
+    gpu = emu.RamGpu(g)
+    gpu.set_inputs(inp)
+    with pytest.raises(emu.RsgError, match="set_wave_tables"):
+        gpu.ANISCH_diffcoef(4, 1, t["XNE"])
+    gpu.set_wave_tables(t, use_bas=use_bas)
+    for S, fl in ((4, emu.F_WPI), (1, emu.F_EMIC)):
+        assert o.anisch_diffcoef(S, fl, t, AE=150, use_bas=use_bas) == 0
+        assert gpu.ANISCH_diffcoef(S, fl, t["XNE"], AE=150) == 0
+    ref2 = {}
+    ref2.update(ir.anisch_diffcoef(g, inp, t, 4, True, False, inp.Kp, AE=150, use_bas=use_bas))
+    ref2.update(ir.anisch_diffcoef(g, inp, t, 1, False, True, inp.Kp, AE=150, use_bas=use_bas))
+    for which, name in enumerate(("ATAW", "ATAC", "ATAW_emic_h", "ATAW_emic_he")):
+        a, b = gpu.get_diffcoef(which), getattr(o, name)
+        assert (b != 0).sum() > 1000
+        assert np.array_equal(a, b), name
+        c = ref2[name]
+        assert np.array_equal(c == 0, b == 0), name
+        assert np.max(np.abs(c - b) / np.maximum(np.abs(b), 1e-300)) <= 1e-13, name
+    assert (o.ATAW_emic_h == 1e-31).sum() > 0                 # the 1e-20 floor of :585 is hit
+    # species the flags do not select are left alone
+    before = gpu.get_diffcoef(1)
+    assert gpu.ANISCH_diffcoef(2, emu.F_WPI | emu.F_EMIC, t["XNE"]) == 0
+    assert np.array_equal(gpu.get_diffcoef(1), before)
+    gpu.close()

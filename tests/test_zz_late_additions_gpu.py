@@ -342,3 +342,32 @@ def test_computehI_composed_on_device(default_grids, oracle_built, dims):
         assert np.array_equal(ref[n], out[n], equal_nan=True), (n, float(np.nanmax(np.abs(ref[n] - out[n]))))
     inside = out["outsideMGNP"] == 0
     assert np.all(np.isfinite(out["FNHS"][1:][inside])) and np.all(out["FNHS"][1:][inside][:, 4:] > 0.0)
+
+
+def test_anisch_diffcoef_rebuild_feeds_the_wpi_step(default_grids, oracle_built):
+    """ANISCH's diffusion-coefficient rebuild (src/ModRamRun.f90:422-605) on the device, then a WPI + EMIC
+    ram_run that never sees a host-built coefficient array.  Coefficients <= 1e-13 of the oracle's (device log10 / pow vs
+    libm; the kernels keep the reference's operation order and are bit-identical in the emulator), zero pattern and the
+    1e-31 floor identical; the step with them within the bars of the WPADIF tests."""
+    from ramscb_b200 import host
+    g = default_grids
+    inp = synthetic.make_inputs(g, f2_kind="noisy", inductive=True)
+    t = synthetic.synthetic_wave_tables(g, inp)
+    o = oracle_built.RamOracle(g, inp, DTs=5.0)
+    gpu = host.RamGpu(g, mode=host.MODE_EXACT)
+    gpu.set_inputs(inp)
+    gpu.set_wave_tables(t)
+    for S, fl in ((4, host.F_WPI), (1, host.F_EMIC)):
+        assert o.anisch_diffcoef(S, fl, t, AE=350) == 0
+        assert gpu.ANISCH_diffcoef(S, fl, t["XNE"], AE=350) == 0
+    for which, name in enumerate(("ATAW", "ATAC", "ATAW_emic_h", "ATAW_emic_he")):
+        a, b = gpu.get_diffcoef(which), getattr(o, name)
+        assert np.array_equal(a == 0, b == 0) and np.array_equal(a == 1e-31, b == 1e-31), name
+        assert np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)) <= 1e-13, name
+    dtn = o.ram_run(flags=5)
+    out = gpu.ram_run(5.0, DtsMin=1.0, flags=5)
+    got = gpu.f2_d2h()
+    strict = np.abs(got - o.F2) / np.maximum(np.abs(o.F2), 1e-300)
+    assert strict.max() <= 1e-11 and int((strict > 1e-12).sum()) <= 50, (strict.max(), int((strict > 1e-12).sum()))
+    assert abs(out["DtsNext"] - dtn) <= 1e-13 * dtn
+    gpu.close()
