@@ -13,6 +13,7 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import test_ram_parity_gpu as TR          # noqa: E402
 import test_scb_parity_gpu as TS          # noqa: E402
 from ramscb_b200 import scb_synthetic as SCBSYN          # noqa: E402
+from ramscb_b200 import synthetic          # noqa: E402
 
 # first hardware run of these entry points: a device-side loop that never ends must end the run loudly, not hang the
 # box (pytest-timeout's thread method interrupts a blocked C call by exiting the process)
