@@ -259,6 +259,71 @@ module ModRamGpu
        real(c_double), intent(out) :: dts_next, DtDrift(*), losses(*), SETRC(*), PPERT(*), PPART(*)
        integer(c_int) :: ierr
      end function
+     ! ---- ANISCH, second half: the diffusion-coefficient rebuild on the device (src/ModRamRun.f90:422-605) ----
+     function rsg_ram_set_wave_tables(h, ENG, NCF, ENOR, fpofc, NDAAJ, DAAR, use_bas, ENG_emic, NCF_emic, EKEV_emic, &
+          fp2c_emic, Daa_emic_h, Daa_emic_he, Ihs_emic, Ihes_emic, PAbn) bind(C, name='rsg_ram_set_wave_tables') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       integer(c_int), value :: ENG, NCF, use_bas, ENG_emic, NCF_emic
+       real(c_double), intent(in) :: ENOR(*), fpofc(*), NDAAJ(*), DAAR(*), EKEV_emic(*), fp2c_emic(*), Daa_emic_h(*), &
+                                     Daa_emic_he(*), Ihs_emic(*), Ihes_emic(*), PAbn(*)
+       integer(c_int) :: ierr
+     end function
+     function rsg_anisch_diffcoef(h, S, flags, XNE, AE, gslerr) bind(C, name='rsg_anisch_diffcoef') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       integer(c_int), value :: S, flags, AE
+       real(c_double), intent(in) :: XNE(*)
+       integer(c_int), intent(out) :: gslerr
+       integer(c_int) :: ierr
+     end function
+     function rsg_ram_get_diffcoef(h, which, D) bind(C, name='rsg_ram_get_diffcoef') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       integer(c_int), value :: which
+       real(c_double), intent(out) :: D(*)
+       integer(c_int) :: ierr
+     end function
+     ! ---- the multi-GPU step inside the library (one process / MPI rank per GPU; include/ramscb_gpu.h) ----
+     function rsg_ram_peer_export(h, blob) bind(C, name='rsg_ram_peer_export') result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       type(c_ptr), value :: blob            ! c_loc of RSG_PEER_BLOB_BYTES = 192 bytes
+       integer(c_int) :: ierr
+     end function
+     function rsg_ram_peer_attach(h, rank, world, policy, blobs) bind(C, name='rsg_ram_peer_attach') result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       integer(c_int), value :: rank, world, policy
+       type(c_ptr), value :: blobs           ! c_loc of world x 192 bytes, in rank order
+       integer(c_int) :: ierr
+     end function
+     function rsg_ram_peer_detach(h) bind(C, name='rsg_ram_peer_detach') result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       integer(c_int) :: ierr
+     end function
+     function rsg_ram_run_sharded(h, DTs, DtsMin, T, flags, dts_next, DtDrift, losses, SETRC, PPERT, PPART) &
+          bind(C, name='rsg_ram_run_sharded') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       real(c_double), value :: DTs, DtsMin, T
+       integer(c_int), value :: flags
+       real(c_double), intent(out) :: dts_next, DtDrift(*), losses(*), SETRC(*), PPERT(*), PPART(*)
+       integer(c_int) :: ierr
+     end function
+     function rsg_ram_f2_h2d_shard(h, F2) bind(C, name='rsg_ram_f2_h2d_shard') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       real(c_double), intent(in) :: F2(*)
+       integer(c_int) :: ierr
+     end function
+     function rsg_ram_f2_d2h_shard(h, F2) bind(C, name='rsg_ram_f2_d2h_shard') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       real(c_double), intent(inout) :: F2(*)
+       integer(c_int) :: ierr
+     end function
      function rsg_host_register(p, bytes) bind(C, name='rsg_host_register') result(ierr)
        import :: c_ptr, c_int, c_long_long
        type(c_ptr), value :: p

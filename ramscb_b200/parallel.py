@@ -208,14 +208,39 @@ class _DevBuf:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
 
 
+def _bind_stream(gpu, on_cuda):
+    """The library's kernels and torch.distributed's NCCL traffic must share ONE stream: the exchanges read / write the
+    library's buffers through zero-copy views, and only stream order keeps a send behind the kernels that produce its data
+    and the next kernels behind the scatter of what was received.  The classes below bind the handle to torch's current
+    stream when they are built and check that it still is the current one whenever they run (the host-CPU emulator of the
+    test-suite is synchronous: nothing to bind)."""
+    if not on_cuda:
+        return None
+    import torch
+    ptr = torch.cuda.current_stream().cuda_stream
+    gpu.set_stream(ptr)
+    return ptr
+
+
+def _check_stream(ptr):
+    if ptr is None:
+        return
+    import torch
+    if torch.cuda.current_stream().cuda_stream != ptr:
+        raise RuntimeError("the handle was bound to another CUDA stream: build and run the sharded step under the same "
+                           "torch.cuda.stream(...) (see ramscb_b200.parallel._bind_stream)")
+
+
 class RamSharded:
-    """One rank's share of the RAM step (drop-in for ``RamGpu.ram_run`` at N > 1)."""
+    """One rank's share of the RAM step (drop-in for ``RamGpu.ram_run`` at N > 1).  Python-driven exchange over
+    torch.distributed (round 1); the library's own multi-GPU step is ``RamPeerSharded`` below."""
 
     def __init__(self, gpu, plan: ShardPlan, dist=None, on_cuda=True):
         self.gpu, self.p, self.dist, self.on_cuda = gpu, plan, dist, on_cuda
         self.setrc = np.zeros(gpu.g.nS)
         self._views = None
         self._agroup = None
+        self._stream = _bind_stream(gpu, on_cuda and dist is not None and plan.world > 1)
         if dist is not None and plan.world > 1 and len(plan.active) < plan.world:
             self._agroup = dist.new_group(ranks=list(plan.active))   # collective: every rank calls it
 
@@ -239,7 +264,8 @@ class RamSharded:
         import torch
         g, p, gpu = self.gpu.g, self.p, self.gpu
         if p.ns == 0:
-            return None                      # idle rank (small grid, more ranks than species)
+            return None                      # idle rank (small grid, more ranks than species): takes part in NO collective
+        _check_stream(self._stream)
         if p.G == 1:
             # species-sharded: the whole step is local (fused kernels, graph replay)
             gpu.part_all(DTs, flags, p.s0, p.ns)
@@ -279,12 +305,13 @@ class RamSharded:
         PA = np.zeros((g.NR, g.NT, g.nS))
         sl = slice(p.s0, p.s0 + p.ns)
         DT[:, sl], MOM[:, sl], PE[:, :, sl], PA[:, :, sl] = dt, mom, pper, ppar
-        if self.dist is not None and p.world > 1:
+        if self.dist is not None and p.world > 1 and len(p.active) > 1:
+            # only the ranks that hold species take part (idle ranks returned above): the group of the active ranks
             dev = "cuda" if self.dist.get_backend() == "nccl" else "cpu"
             t_min = torch.as_tensor(DT, device=dev)
             t_sum = torch.as_tensor(np.concatenate([MOM.ravel(), PE.ravel(), PA.ravel()]), device=dev)
-            self.dist.all_reduce(t_min, op=self.dist.ReduceOp.MIN)
-            self.dist.all_reduce(t_sum, op=self.dist.ReduceOp.SUM)
+            self.dist.all_reduce(t_min, op=self.dist.ReduceOp.MIN, group=self._agroup)
+            self.dist.all_reduce(t_sum, op=self.dist.ReduceOp.SUM, group=self._agroup)
             DT = t_min.cpu().numpy()
             v = t_sum.cpu().numpy()
             MOM = v[:MOM.size].reshape(MOM.shape)
@@ -347,6 +374,7 @@ class ScbSharded:
     def __init__(self, gpu, dist, rank, world, on_cuda=True):
         self.gpu, self.dist, self.rank, self.world, self.on_cuda = gpu, dist, rank, world, on_cuda
         self._fields = {}
+        self._stream = _bind_stream(gpu, on_cuda and dist is not None and world > 1)
 
     def _field(self, name):
         if name not in self._fields:
@@ -357,6 +385,7 @@ class ScbSharded:
 
     def iterate(self, alpha, tol, nimax=5001, theChange=4, psiChange=0, ordering=1):
         import torch
+        _check_stream(self._stream)
         g = self.gpu
         nP = max(psiChange, 1)
         nsub = (g.npsi - nP - 1) if alpha else (g.nzeta - 1)
@@ -416,6 +445,7 @@ class ScbZetaSharded:
 
     def __init__(self, gpu, dist, rank, world, on_cuda=True, poll=8):
         self.gpu, self.dist, self.rank, self.world, self.on_cuda, self.poll = gpu, dist, rank, world, on_cuda, poll
+        self._stream = _bind_stream(gpu, on_cuda and dist is not None and world > 1)
         self.k0, self.nk = _split(gpu.nzeta - 1, world, rank)
         self.k0 += 1                                        # planes 1..nzeta-1 are relaxed
         ptr, n = gpu.field_device("alfa")
@@ -454,6 +484,7 @@ class ScbZetaSharded:
 
     def iterate(self, tol, nimax=5001, theChange=4, psiChange=0):
         import torch.distributed as td
+        _check_stream(self._stream)
         g = self.gpu
         g.zsolve_begin(tol, self.k0, self.nk, nimax=nimax, theChange=theChange, psiChange=psiChange)
         ptr, n = g.zsolve_state_device()
