@@ -572,7 +572,7 @@ int L_plane_rp(rsg_ram* h, int s0, int ns, cudaStream_t st, bool rev, int l0 = 0
   c.cfg.part_off = fused_part_off(h);      // after the column kernel's partials
   c.cfg.l0 = l0;
   c.cfg.anisch = (rev && h->sp[s0].d_aE2) ? 1 : 0;
-  c.cfg.tma = h->planeTma ? 1 : 0;
+  c.cfg.tma = (h->planeTma && h->NR * 8 >= 512) ? 1 : 0;   // rows shorter than 512 B: the per-copy overhead shows (measured)
   if (rev) { RET(opt_in_smem(k_plane_rp<true>, c.smem)); k_plane_rp<true><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg, pv); }
   else if (peer) { RET(opt_in_smem(k_plane_rp<false, true>, c.smem)); k_plane_rp<false, true><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg, pv); }
   else { RET(opt_in_smem(k_plane_rp<false>, c.smem)); k_plane_rp<false><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg, pv); }
@@ -1861,7 +1861,10 @@ int step_prepare(rsg_ram* h, double DTs, int flags, int s0, int ns) {
   RET(prof_mark(h, "driftr_inflow", st));
   RET(L_inflow(h, s0, ns, st));
   if (fused_ok(h, flags)) {
-    if (!getenv("RSG_NO_ANISCH_FOLD")) {
+    // measured on the B200 (profiles/r2): the fold trades k_anisch_pa_fast's read of F2 for 2 x rows x Pp doubles written by
+    // the plane kernel and read back by k_finalize -- a wash at the default grid, a loss at the 4x grid (3 energies per
+    // CTA => rows ~ 0.7 of F2).  Kept as an option.
+    if (getenv("RSG_ANISCH_FOLD")) {
       const PlanePlan c = plane_plan(h);
       const size_t rows = (size_t)h->NPA * ((h->NE + c.cfg.KC - 1) / c.cfg.KC);
       for (int s = s0; s < s0 + ns; ++s)

@@ -66,10 +66,13 @@ def test_scb_default_grid_color4_cluster_kernel_vs_oracle(oracle_built):
     o, gpu = oracle_built.ScbOracle(inp), ScbGpu(inp)
     o.bandjacob(); gpu.computeBandJacob()
     o.metrica(); o.newk(); gpu.metrica(); gpu.newk()
-    o.set_scalar("InConAlpha", 1e-11)
+    # 1e-11 is below the rounding floor of the residual on this grid (|alfa| ~ 6, |vecd| ~ 1e3: the 4-colour solve runs
+    # into nimax); 1e-10 is reached by both orderings
+    o.set_scalar("InConAlpha", 1e-10)
     fail, ni = o.iterate_alpha()
-    r = gpu.iterateAlpha(1e-11, ordering=1)
-    assert fail == 0 and r["SORFail"] == 0 and r["nisave"] < 5001
+    r = gpu.iterateAlpha(1e-10, ordering=1)
+    print(f"\nalpha: oracle sweeps {int(ni.max())}, 4-colour cluster sweeps {r['nisave']}")
+    assert fail == 0 and r["SORFail"] == 0 and r["nisave"] < 5001 and ni.max() < 5001
     assert gpu.last_cluster() == 4
     a, b = gpu.get_field("alfa"), o.alfa
     rel = np.abs(a - b) / np.maximum(np.abs(b), 1e-2 * np.abs(b).max())

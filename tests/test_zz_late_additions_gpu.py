@@ -365,10 +365,11 @@ def test_anisch_diffcoef_rebuild_feeds_the_wpi_step(default_grids, oracle_built)
         a, b = gpu.get_diffcoef(which), getattr(o, name)
         assert np.array_equal(a == 0, b == 0) and np.array_equal(a == 1e-31, b == 1e-31), name
         assert np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)) <= 1e-13, name
+        o.set_array(name, a)     # the step below compares the kernels, not the last bit of pow / log10: same coefficients on both sides
     dtn = o.ram_run(flags=5)
     out = gpu.ram_run(5.0, DtsMin=1.0, flags=5)
     got = gpu.f2_d2h()
     strict = np.abs(got - o.F2) / np.maximum(np.abs(o.F2), 1e-300)
-    assert strict.max() <= 1e-11 and int((strict > 1e-12).sum()) <= 50, (strict.max(), int((strict > 1e-12).sum()))
-    assert abs(out["DtsNext"] - dtn) <= 1e-13 * dtn
+    assert strict.max() <= 1e-12, (strict.max(), int((strict > 1e-12).sum()))          # EXACT mode, bar of test_full_ram_run
+    assert out["DtsNext"] == dtn
     gpu.close()
