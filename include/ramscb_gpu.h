@@ -364,6 +364,18 @@ int rsg_scb_map_theta(rsg_scb* h, int* sorfail);
  * (iReduceAnisotropy = 1, :1127-1160) and takes the Steffen derivatives dPPerd{Theta,Rho,Zeta,Psi,Alpha},
  * dBsqd{...} on the device (what rsg_scb_set_pressure would otherwise upload: 15 3-D arrays). */
 int rsg_scb_pressure_aniso(rsg_scb* h, const double* pperEq, const double* pparEq, int iLossCone, int iReduceAnisotropy);
+/* The 2-D FRONT END of `pressure` on the device (src/ModScbRun.f90:838-1086, anisotropic branch with RAM pressures): with it
+ * an SCB outer iteration has no host hop left.  set_ram_pressure, once per scb_run (the RAM pressures do not change while SCB
+ * iterates): PPerT, PParT (nS,NR,NT) of ram_run / ANISCH, scb[nS] = species%SCB, LZ(NR+1), PHI(NT); the library sums the
+ * species on the RAM grid, extends it radially (PressMode 0 SKD | 1 ROE | 2 EXT | 3 FLT; ModScbParams default SKD) and smooths
+ * (iSm2 0 none | 1 SavGol7 | 3 Gaussian | 4 both, default 4; SavGolIters default 11).  pressure_front = one `pressure` call:
+ * equatorial foot points -> bilinear interpolation in (r^2, azimuth) (GSL_Interpolation_2D), extap inside 2 RE, floor, periodic
+ * columns, normalisation, then the 3-D tail of rsg_scb_pressure_aniso; pperEq / pparEq (npsi, nzeta+1; may be NULL) return the
+ * equatorial pressures.  rsg_scb_run with pressure == NULL uses it. */
+int rsg_scb_set_ram_pressure(rsg_scb* h, int nS, int NR, int NT, const double* PPerT, const double* PParT, const int* scb,
+                             const double* LZ, const double* PHI, int PressMode, int iSm2, int SavGolIters);
+int rsg_scb_get_ram_pressure(rsg_scb* h, int* nX, int* nAz, double* rad2, double* azim, double* per, double* par);
+int rsg_scb_pressure_front(rsg_scb* h, int iLossCone, int iReduceAnisotropy, double* pperEq, double* pparEq);
 /* Glue of the outer iteration (src/ModScbRun.f90:232-262, 418-440), so that alfa, psi, x, y, z need
  * not visit the host between the solves: device snapshots of a named field (alfaSav1, alphaPrev,
  * xPrev... of the reference; slot 0..3), the blend  field = snap(slot_new)*blend +
@@ -399,6 +411,7 @@ int rsg_scb_zsolve_pending(rsg_scb* h, int* pending);
  * `pressure` is the 2-D front end of the reference's routine (src/ModScbRun.f90:753-1086, RAM pressures ->
  * equatorial points; host): it gets xEq, yEq (npsi, nzeta+1; the foot points x/y(nThetaEquator,j,k)) and
  * fills the normalised pperEq, pparEq (npsi, nzeta+1, periodic columns set); return 0, non-zero aborts.
+ * pressure == NULL: the front end runs on the device too (rsg_scb_set_ram_pressure before the call).
  * Anisotropic pressure (isotropy = 0, the reference's RAM-coupled mode) only.  Uses snapshot slots 0..2 of x, y,
  * z, alfa, psi.  Needs set_grid, set_geometry, set_map_targets. */
 typedef int (*rsg_scb_pressure_fn)(void* user, int npsi, int nzetap, const double* xEq, const double* yEq, double* pperEq,

@@ -217,6 +217,11 @@ def scb_lib():
         for f in ("iterate_alpha", "iterate_psi"):
             getattr(lib, "scbo_" + f).argtypes = [C.c_void_p, C.c_void_p]
             getattr(lib, "scbo_" + f).restype = C.c_int
+        lib.scbo_pressure_raw.argtypes = [C.c_int] * 3 + [C.c_void_p] * 5 + [C.c_int] * 3 + [C.c_void_p] * 4
+        lib.scbo_pressure_raw.restype = C.c_int
+        lib.scbo_pressure_eq.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_double,
+                                                                                                                            C.c_void_p, C.c_void_p]
+        lib.scbo_pressure_eq.restype = None
         lib.scbo_derivs3d.argtypes = [C.c_void_p] * 5
         lib.scbo_steffen.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         _scb = lib
@@ -296,6 +301,36 @@ class ScbOracle:
         self.set_int("iReduceAnisotropy", iReduceAnisotropy)
         self.lib.scbo_pressure_aniso(self.h)
 
+    PRESS_MODES = {"SKD": 0, "ROE": 1, "EXT": 2, "FLT": 3}
+
+    def pressure_raw(self, PPerT, PParT, scb, LZ, PHI, PressMode="SKD", iSm2=4, SavGolIters=11):
+        """front end of `pressure`, part 1 (src/ModScbRun.f90:858-980): RAM pressures summed over the species%SCB species,
+        extended radially and smoothed; kept for pressure_front()."""
+        a, b = np.asfortranarray(PPerT, dtype=np.float64), np.asfortranarray(PParT, dtype=np.float64)
+        nS, NR, NT = a.shape
+        nX = NR + 2 * int(np.floor(1.5 / (5. / NR)))
+        flags = np.ascontiguousarray(scb, dtype=np.int32)
+        lz, ph = np.ascontiguousarray(LZ, dtype=np.float64), np.ascontiguousarray(PHI, dtype=np.float64)
+        r2, az = np.zeros(nX), np.zeros(NT)
+        per, par = _f((nX, NT)), _f((nX, NT))
+        rc = self.lib.scbo_pressure_raw(nS, NR, NT, a.ctypes.data, b.ctypes.data, flags.ctypes.data, lz.ctypes.data, ph.ctypes.data,
+                                        self.PRESS_MODES[PressMode], iSm2, SavGolIters, r2.ctypes.data, az.ctypes.data,
+                                        per.ctypes.data, par.ctypes.data)
+        assert rc == 0, "unsupported PressMode / iSm2"
+        self._raw = (r2, az, per, par)
+        return self._raw
+
+    def pressure_front(self):
+        """front end of `pressure`, part 2 (:838-850, :1060-1086): normalised equatorial pressures (npsi, nzeta+1)"""
+        nthe, npsi, nzeta = self.inp.nthe, self.inp.npsi, self.inp.nzeta
+        ieq = (nthe + 1) // 2 - 1
+        xe, ye = np.array(self.x[ieq], order="F"), np.array(self.y[ieq], order="F")
+        r2, az, per, par = self._raw
+        pe, pa = _f((npsi, nzeta + 1)), _f((npsi, nzeta + 1))
+        self.lib.scbo_pressure_eq(npsi, nzeta, xe.ctypes.data, ye.ctypes.data, len(r2), len(az), r2.ctypes.data, az.ctypes.data,
+                                  per.ctypes.data, par.ctypes.data, self.get("pnormal"), pe.ctypes.data, pa.ctypes.data)
+        return pe, pa
+
     def map_alpha(self): return self.lib.scbo_map_alpha(self.h)
     def map_psi(self): return self.lib.scbo_map_psi(self.h)
     def map_theta(self): return self.lib.scbo_map_theta(self.h)
@@ -310,7 +345,10 @@ class ScbOracle:
         self.set_scalar("InConAlpha", InConAlpha); self.set_scalar("InConPsi", InConPsi); self.set_int("nimax", nimax)
 
         def pressure():
-            pe, pa = pressure_fn(np.array(self.x[ieq], order="F"), np.array(self.y[ieq], order="F"))
+            if pressure_fn is None:          # the restated front end (pressure_raw before the call)
+                pe, pa = self.pressure_front()
+            else:
+                pe, pa = pressure_fn(np.array(self.x[ieq], order="F"), np.array(self.y[ieq], order="F"))
             self.pressure_aniso(pe, pa, iLossCone, iReduceAnisotropy)
 
         def minjac():

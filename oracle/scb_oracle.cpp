@@ -913,6 +913,175 @@ int compute_convergence(Scb* o) {
 
 }  // namespace
 
+// ---- `pressure`, 2-D front end (src/ModScbRun.f90:838-1086, anisotropic branch with RAM pressures) ----------------------------
+// Part 1 (independent of the SCB geometry): the RAM pressures of the species with species%SCB summed on the RAM grid
+// (:858-875), the radial extension of the grid (:877-881) and of the pressures (PressMode SKD / ROE / EXT / FLT, :884-938), the
+// smoothing (iSm2: 1 SavGol7, 3 Gaussian, 4 both; :947-980 with SavGol7 of src/ModScbFunctions.f90:137-230 and gaussian_kernel /
+// convolve of srcExternal/gaussian_filter.f90).  Outputs rad2(nXRawExt) = radRawExt**2, azim(nAz), per / par(nXRawExt, nAz).
+namespace {
+void gaussian_kernel9(double* w);                                                   // defined with the computehI tail below
+void convolve9(int rows, int cols, const double* in, const double* w, double* out);
+void savgol7(int nrad, int nphi, int iters, std::vector<double>& pres) {
+  static const double vals[49] = {32, 5, 1, -2, -2, -1, 5, 15, 4, 3, 3, 1, 0, -3, 3, 3, 4, 6, 3, 1, -6, -4, 2, 4, 7, 4, 2, -4,
+                                  -6, 1, 3, 6, 4, 3, 3, -3, 0, 1, 3, 3, 4, 15, 5, -1, -2, -2, 1, 5, 32};
+  auto B = [&](int r, int c) { return vals[(c - 1) * 7 + (r - 1)]; };       // RESHAPE fills by columns
+  auto P = [&](std::vector<double>& a, int j, int k) -> double& { return a[(size_t)(j - 1) + (size_t)nrad * (k - 1)]; };
+  double mn = pres[0];
+  for (double v : pres) mn = v < mn ? v : mn;                                // MINVAL(pres)
+  std::vector<double> pres0 = pres, pres1(pres.size()), pres2(pres.size());
+  for (int it = 0; it < iters; ++it) {
+    for (int k = 1; k <= nphi; ++k)
+      for (int j = 1; j <= nrad; ++j) {
+        if (j > 3 && j < nrad - 2) {
+          double sum = 0.0;
+          for (int m = 1; m <= 7; ++m) sum += (B(4, m) / 21.) * P(pres0, j - 4 + m, k);
+          P(pres1, j, k) = sum;
+        } else if (j <= 3) {
+          P(pres1, j, k) = P(pres0, j, k);
+        } else {
+          const int row = (j == nrad - 2) ? 5 : ((j == nrad - 1) ? 6 : 7);
+          const double den = (row == 7) ? 42. : 14.;
+          double sum = 0.0;
+          for (int m = 1; m <= 7; ++m) sum += (B(row, m) / den) * P(pres0, nrad - 7 + m, k);
+          P(pres1, j, k) = sum;
+        }
+      }
+    for (int j = 1; j <= nrad; ++j)
+      for (int k = 1; k <= nphi; ++k) {
+        int idx[7];
+        if (k > 3 && k < nphi - 2) { for (int m = 0; m < 7; ++m) idx[m] = k - 3 + m; }
+        else if (k == 1 || k == nphi) { const int t[7] = {nphi - 3, nphi - 2, nphi - 1, 1, 2, 3, 4}; for (int m = 0; m < 7; ++m) idx[m] = t[m]; }
+        else if (k == 2) { const int t[7] = {nphi - 2, nphi - 1, 1, 2, 3, 4, 5}; for (int m = 0; m < 7; ++m) idx[m] = t[m]; }
+        else if (k == nphi - 1) { const int t[7] = {nphi - 4, nphi - 3, nphi - 2, nphi - 1, 1, 2, 3}; for (int m = 0; m < 7; ++m) idx[m] = t[m]; }
+        else if (k == 3) { const int t[7] = {nphi - 1, 1, 2, 3, 4, 5, 6}; for (int m = 0; m < 7; ++m) idx[m] = t[m]; }
+        else { const int t[7] = {nphi - 5, nphi - 4, nphi - 3, nphi - 2, nphi - 1, 1, 2}; for (int m = 0; m < 7; ++m) idx[m] = t[m]; }
+        double sum = 0.0;
+        for (int m = 1; m <= 7; ++m) sum += (B(4, m) / 21.) * P(pres1, j, idx[m - 1]);
+        P(pres2, j, k) = sum;
+      }
+    pres0 = pres2;
+  }
+  pres = pres2;
+  for (double& v : pres) if (v < 0) v = mn;
+}
+}  // namespace
+
+extern "C" {
+// returns 0, or 1 for an unsupported PressMode / iSm2
+int scbo_pressure_raw(int nS, int NR, int NT, const double* PPerT, const double* PParT, const int* scb, const double* LZ,
+                      const double* PHI, int PressMode, int iSm2, int SavGolIters, double* rad2, double* azim, double* per, double* par) {
+  const int nXRaw = NR - 1, nAz = NT, nXRawExt = NR + 2 * (int)std::floor(1.5 / (5. / NR));
+  std::vector<double> radRaw(nXRaw), radExt(nXRawExt);
+  for (int j1 = 1; j1 <= nXRaw; ++j1) radRaw[j1 - 1] = LZ[j1];                       // LZ(j1+1)
+  for (int k1 = 1; k1 <= nAz; ++k1) azim[k1 - 1] = ((PHI[k1 - 1] * 12 / PI_D) * 360. / 24) * PI_D / 180.;
+  for (int j1 = 1; j1 <= nXRaw; ++j1) radExt[j1 - 1] = radRaw[j1 - 1];
+  for (int j1 = nXRaw + 1; j1 <= nXRawExt; ++j1)
+    radExt[j1 - 1] = radRaw[nXRaw - 1] + (double)(j1 - nXRaw) * (radRaw[nXRaw - 1] - radRaw[0]) / ((double)(nXRaw - 1));
+  std::vector<double> pe((size_t)nXRawExt * nAz, 0.0), pa((size_t)nXRawExt * nAz, 0.0);
+  auto E = [&](std::vector<double>& a, int j, int k) -> double& { return a[(size_t)(j - 1) + (size_t)nXRawExt * (k - 1)]; };
+  for (int k1 = 1; k1 <= nAz; ++k1)
+    for (int j1 = 1; j1 <= nXRaw; ++j1) {
+      double sp = 0.0, sa = 0.0;
+      for (int iS = 1; iS <= nS; ++iS)
+        if (scb[iS - 1]) {
+          sp = sp + PPerT[(size_t)(iS - 1) + (size_t)nS * (j1 + (size_t)NR * (k1 - 1))];   // PPerT(iS, j1+1, k1)
+          sa = sa + PParT[(size_t)(iS - 1) + (size_t)nS * (j1 + (size_t)NR * (k1 - 1))];
+        }
+      E(pe, j1, k1) = 0.16 * sp;                                                      // keV/cm^3 -> nPa
+      E(pa, j1, k1) = 0.16 * sa;
+    }
+  auto R = [&](int j) { return radExt[j - 1]; };
+  for (int k1 = 1; k1 <= nAz; ++k1) {
+    if (PressMode == 0) {                                                              // SKD (:884-897)
+      const double den = 89. * std::exp(-0.59 * R(nXRaw - 2)) + 8.9 * std::pow(R(nXRaw - 2), -1.53);
+      for (int j1 = nXRaw - 1; j1 <= nXRawExt; ++j1) {
+        const double num = 89. * std::exp(-0.59 * R(j1)) + 8.9 * std::pow(R(j1), -1.53);
+        E(pe, j1, k1) = E(pe, nXRaw - 2, k1) * num / den;
+        E(pa, j1, k1) = E(pa, nXRaw - 2, k1) * num / den;
+      }
+    } else if (PressMode == 1) {                                                       // ROE (:898-909), pRoeRad ModScbFunctions.f90:118-134
+      auto roe = [](double r) { return 8.4027 * std::exp(-1.7845 * r) + 90.3150 * std::exp(-0.7659 * r); };
+      for (int j1 = nXRaw + 1; j1 <= nXRawExt; ++j1) {
+        E(pe, j1, k1) = E(pe, nXRaw, k1) * roe(R(j1)) / roe(R(nXRaw));
+        E(pa, j1, k1) = E(pa, nXRaw, k1) * roe(R(j1)) / roe(R(nXRaw));
+      }
+    } else if (PressMode == 2) {                                                       // EXT (:910-925)
+      for (int j1 = nXRaw + 1; j1 <= nXRawExt; ++j1) {
+        E(pe, j1, k1) = E(pe, j1 - 1, k1) + (R(j1) - R(j1 - 1)) / (R(j1 - 2) - R(j1 - 1)) * (E(pe, j1 - 2, k1) - E(pe, j1 - 1, k1));
+        E(pa, j1, k1) = E(pa, j1 - 1, k1) + (R(j1) - R(j1 - 1)) / (R(j1 - 2) - R(j1 - 1)) * (E(pa, j1 - 2, k1) - E(pa, j1 - 1, k1));
+      }
+    } else if (PressMode == 3) {                                                       // FLT (:926-938)
+      for (int j1 = nXRaw + 1; j1 <= nXRawExt - 1; ++j1) { E(pe, j1, k1) = E(pe, nXRaw, k1); E(pa, j1, k1) = E(pa, nXRaw, k1); }
+      E(pe, nXRawExt, k1) = 0.0;
+      E(pa, nXRawExt, k1) = 0.0;
+    } else return 1;
+  }
+  if (iSm2 == 1 || iSm2 == 4) { savgol7(nXRawExt, nAz, SavGolIters, pe); savgol7(nXRawExt, nAz, SavGolIters, pa); }
+  if (iSm2 == 3 || iSm2 == 4) {
+    double w[81];
+    gaussian_kernel9(w);
+    std::vector<double> out(pe.size());
+    convolve9(nXRawExt, nAz, pe.data(), w, out.data()); pe = out;
+    convolve9(nXRawExt, nAz, pa.data(), w, out.data()); pa = out;
+  } else if (iSm2 != 0 && iSm2 != 1) return 1;                                         // 2 = B-spline fit (GSL bspline): not restated
+  for (int j1 = 0; j1 < nXRawExt; ++j1) rad2[j1] = radExt[j1] * radExt[j1];
+  for (size_t q = 0; q < pe.size(); ++q) { per[q] = pe[q]; par[q] = pa[q]; }
+  return 0;
+}
+
+// Part 2, per call of `pressure`: the equatorial foot points of the SCB lines -> radius / angle (:838-850), bilinear
+// interpolation of the extended RAM pressures in (r**2, azimuth) (GSL_Interpolation_2D -> gsl_interp2d_bilinear with
+// eval_extrap, :1060-1065), extap inside 2 RE (:1069-1076), the <= 0 floor, periodic columns, normalisation (:1077-1086).
+// xEq, yEq, pperEq, pparEq: (npsi, nzeta+1).
+void scbo_pressure_eq(int npsi, int nzeta, const double* xEq, const double* yEq, int nX, int nAz, const double* rad2, const double* azim,
+                      const double* per, const double* par, double pnormal, double* pperEq, double* pparEq) {
+  auto Q = [&](const double* a, int j, int k) { return a[(size_t)(j - 1) + (size_t)npsi * (k - 1)]; };
+  auto W = [&](double* a, int j, int k) -> double& { return a[(size_t)(j - 1) + (size_t)npsi * (k - 1)]; };
+  auto bsearch = [](const double* xa, double x, int n) {
+    int ilo = 0, ihi = n - 1;
+    while (ihi > ilo + 1) { const int i = (ihi + ilo) / 2; if (xa[i] > x) ihi = i; else ilo = i; }
+    return ilo;
+  };
+  auto bilin = [&](const double* za, double x, double y) {
+    const int xi = bsearch(rad2, x, nX), yi = bsearch(azim, y, nAz);
+    const double xmin = rad2[xi], xmax = rad2[xi + 1], ymin = azim[yi], ymax = azim[yi + 1];
+    const double zminmin = za[(size_t)yi * nX + xi], zminmax = za[(size_t)(yi + 1) * nX + xi];
+    const double zmaxmin = za[(size_t)yi * nX + xi + 1], zmaxmax = za[(size_t)(yi + 1) * nX + xi + 1];
+    const double dx = xmax - xmin, dy = ymax - ymin;
+    const double t = (x - xmin) / dx, u = (y - ymin) / dy;
+    return (1. - t) * (1. - u) * zminmin + t * (1. - u) * zmaxmin + (1. - t) * u * zminmax + t * u * zmaxmax;
+  };
+  std::vector<double> radGrid((size_t)npsi * (nzeta + 1), 0.0);
+  for (size_t q = 0; q < (size_t)npsi * (nzeta + 1); ++q) { pperEq[q] = 0.0; pparEq[q] = 0.0; }
+  for (int k = 2; k <= nzeta; ++k)
+    for (int j = 1; j <= npsi; ++j) {
+      const double xe = Q(xEq, j, k), ye = Q(yEq, j, k);
+      const double radius = std::sqrt(xe * xe + ye * ye);
+      double angle = std::asin(ye / radius) + PI_D;
+      if (xe <= 0 && ye >= 0) angle = 2.0 * PI_D - std::asin(ye / radius);
+      if (xe <= 0 && ye <= 0) angle = -std::asin(ye / radius);
+      radGrid[(size_t)(j - 1) + (size_t)npsi * (k - 1)] = radius;
+      W(pperEq, j, k) = bilin(per, radius * radius, angle);
+      W(pparEq, j, k) = bilin(par, radius * radius, angle);
+    }
+  for (int k = 1; k <= nzeta; ++k)
+    for (int j = 10; j >= 1; --j)
+      if (radGrid[(size_t)(j - 1) + (size_t)npsi * (k - 1)] < 2.0) {
+        extap(Q(pperEq, j + 3, k), Q(pperEq, j + 2, k), Q(pperEq, j + 1, k), W(pperEq, j, k));
+        extap(Q(pparEq, j + 3, k), Q(pparEq, j + 2, k), Q(pparEq, j + 1, k), W(pparEq, j, k));
+      }
+  for (size_t q = 0; q < (size_t)npsi * (nzeta + 1); ++q) {
+    if (pperEq[q] <= 0.0) pperEq[q] = 1e-1 / pnormal;
+    if (pparEq[q] <= 0.0) pparEq[q] = 1e-1 / pnormal;
+  }
+  for (int j = 1; j <= npsi; ++j) {
+    W(pperEq, j, nzeta + 1) = Q(pperEq, j, 2); W(pparEq, j, nzeta + 1) = Q(pparEq, j, 2);
+    W(pperEq, j, 1) = Q(pperEq, j, nzeta); W(pparEq, j, 1) = Q(pparEq, j, nzeta);
+  }
+  for (size_t q = 0; q < (size_t)npsi * (nzeta + 1); ++q) { pperEq[q] = pperEq[q] / pnormal; pparEq[q] = pparEq[q] / pnormal; }
+}
+}  // extern "C"
+
 extern "C" {
 void* scbo_create(int nthe, int npsi, int nzeta) {
   Scb* o = new Scb();

@@ -10,6 +10,7 @@
 
 #include "../../include/ramscb_gpu.h"
 #include "scb_kernels.cuh"
+#include "scb_press_front.cuh"
 #include "hi_kernels.cuh"
 
 namespace {
@@ -64,6 +65,10 @@ struct rsg_scb {
   double *d_alphaVal = nullptr, *d_psiVal = nullptr, *d_chiVal = nullptr, *d_mapw = nullptr;   // map*: targets, workspace
   bool map_set = false;
   double *d_peq = nullptr, *d_tau = nullptr;   // pressure_aniso: equatorial inputs (2 x npsi x (nzeta+1)), tau
+  // `pressure` front end on the device (rsg_scb_set_ram_pressure): extended + smoothed RAM pressures and their axes
+  double *d_pf = nullptr, *d_rad2 = nullptr, *d_azim = nullptr, *d_rper = nullptr, *d_rpar = nullptr;
+  int pf_nX = 0, pf_nAz = 0;
+  bool pf_set = false;
   std::map<std::string, double*> snaps;   // "name#slot" -> device copy (rsg_scb_snapshot)
   // iterateAlpha sharded along zeta (rsg_scb_zsolve_*): per-surface state of the open solve
   double* d_zstate = nullptr;
@@ -723,22 +728,11 @@ static int scb_map(rsg_scb* h, int mode, int* sorfail) {
 // pper and bsq and their Euler-potential forms.  The host keeps the part before it (RAM pressures
 // interpolated to the SCB equatorial points, smoothing) and uploads two 2-D arrays instead of fifteen
 // 3-D ones.
-int rsg_scb_pressure_aniso(rsg_scb* h, const double* pperEq, const double* pparEq, int iLossCone, int iReduceAnisotropy) {
-  if (!h || !pperEq || !pparEq) return sfail(RSG_ERR_ARG, "null argument");
-  if (iLossCone != 1 && iLossCone != 2) return sfail(RSG_ERR_ARG, "iLossCone must be 1 or 2");
-  if (!h->grid_set || !h->geom_set) return sfail(RSG_ERR_STATE, "pressure before set_grid / set_geometry");
-  SCK(cudaSetDevice(h->device));
+static int scb_pressure_aniso_core(rsg_scb* h, const double* d_pe, const double* d_pa, int iLossCone, int iReduceAnisotropy) {
   const int nthe = h->nthe, npsi = h->npsi, nzeta = h->nzeta;
-  const size_t n2 = (size_t)npsi * (nzeta + 1);
-  if (!h->d_peq) {
-    SRET(h->dalloc(&h->d_peq, 2 * n2, nullptr));
-    SRET(h->dalloc(&h->d_tau, (size_t)nthe * npsi * (nzeta + 1), "tau"));
-  }
-  SCK(cudaMemcpyAsync(h->d_peq, pperEq, n2 * sizeof(double), cudaMemcpyHostToDevice, h->st));
-  SCK(cudaMemcpyAsync(h->d_peq + n2, pparEq, n2 * sizeof(double), cudaMemcpyHostToDevice, h->st));
   SCK(cudaEventRecord(h->e0, h->st));
   const dim3 g(nblk(nthe, 128), npsi, nzeta);
-  k_scb_press_aniso<<<g, 128, 0, h->st>>>(h->dev, h->d_peq, h->d_peq + n2, h->d_tau, iLossCone, iReduceAnisotropy, (nthe + 1) / 2 - 1);
+  k_scb_press_aniso<<<g, 128, 0, h->st>>>(h->dev, d_pe, d_pa, h->d_tau, iLossCone, iReduceAnisotropy, (nthe + 1) / 2 - 1);
   SCKL();
   k_scb_derivs<<<g, 128, 0, h->st>>>(h->dev, h->dev.pper, h->dev.dPT, h->dev.dPR, h->dev.dPZ);
   SCKL();
@@ -755,6 +749,138 @@ int rsg_scb_pressure_aniso(rsg_scb* h, const double* pperEq, const double* pparE
   h->isotropy = 0;
   h->press_set = true;
   return RSG_OK;
+}
+static int scb_press_buffers(rsg_scb* h) {
+  const size_t n2 = (size_t)h->npsi * (h->nzeta + 1);
+  if (!h->d_peq) {
+    SRET(h->dalloc(&h->d_peq, 2 * n2, nullptr));
+    SRET(h->dalloc(&h->d_tau, (size_t)h->nthe * h->npsi * (h->nzeta + 1), "tau"));
+  }
+  return RSG_OK;
+}
+int rsg_scb_pressure_aniso(rsg_scb* h, const double* pperEq, const double* pparEq, int iLossCone, int iReduceAnisotropy) {
+  if (!h || !pperEq || !pparEq) return sfail(RSG_ERR_ARG, "null argument");
+  if (iLossCone != 1 && iLossCone != 2) return sfail(RSG_ERR_ARG, "iLossCone must be 1 or 2");
+  if (!h->grid_set || !h->geom_set) return sfail(RSG_ERR_STATE, "pressure before set_grid / set_geometry");
+  SCK(cudaSetDevice(h->device));
+  const size_t n2 = (size_t)h->npsi * (h->nzeta + 1);
+  SRET(scb_press_buffers(h));
+  SCK(cudaMemcpyAsync(h->d_peq, pperEq, n2 * sizeof(double), cudaMemcpyHostToDevice, h->st));
+  SCK(cudaMemcpyAsync(h->d_peq + n2, pparEq, n2 * sizeof(double), cudaMemcpyHostToDevice, h->st));
+  return scb_pressure_aniso_core(h, h->d_peq, h->d_peq + n2, iLossCone, iReduceAnisotropy);
+}
+
+// ---- `pressure`, 2-D front end on the device (src/ModScbRun.f90:838-1086; scb_press_front.cuh) ------------------
+// set_ram_pressure, once per scb_run (the RAM pressures do not change while SCB iterates): PPerT, PParT (nS,NR,NT) of
+// ram_run / ANISCH, scb[nS] = species%SCB, LZ(NR+1), PHI(NT); PressMode 0 SKD | 1 ROE | 2 EXT | 3 FLT (ModScbParams
+// default SKD), iSm2 0 none | 1 SavGol7 | 3 Gaussian | 4 both (default 4), SavGolIters (default 11).
+int rsg_scb_set_ram_pressure(rsg_scb* h, int nS, int NR, int NT, const double* PPerT, const double* PParT, const int* scb,
+                             const double* LZ, const double* PHI, int PressMode, int iSm2, int SavGolIters) {
+  if (!h || !PPerT || !PParT || !scb || !LZ || !PHI) return sfail(RSG_ERR_ARG, "null argument");
+  if (nS < 1 || NR < 10 || NT < 8) return sfail(RSG_ERR_ARG, "bad RAM dimensions");
+  if (PressMode < 0 || PressMode > 3) return sfail(RSG_ERR_UNSUPPORTED, "PressMode must be SKD (0), ROE (1), EXT (2) or FLT (3); BAT needs the SWMF coupler");
+  if (iSm2 != 0 && iSm2 != 1 && iSm2 != 3 && iSm2 != 4) return sfail(RSG_ERR_UNSUPPORTED, "iSm2 = 2 (GSL B-spline fit) is not available on the device");
+  SCK(cudaSetDevice(h->device));
+  SCK(cudaStreamSynchronize(h->st));
+  const int nXRaw = NR - 1, nAz = NT, nX = NR + 2 * (int)std::floor(1.5 / (5. / NR));
+  if (nXRaw < 7 || nX < 9 || nAz < 9) return sfail(RSG_ERR_ARG, "RAM grid too small for the 7-point filter");
+  const size_t n = (size_t)nX * nAz;
+  std::vector<double> radExt(nX), rad2(nX), azim(nAz), fac(nX, 0.0), w(81);
+  for (int j1 = 1; j1 <= nXRaw; ++j1) radExt[j1 - 1] = LZ[j1];
+  for (int j1 = nXRaw + 1; j1 <= nX; ++j1)
+    radExt[j1 - 1] = radExt[nXRaw - 1] + (double)(j1 - nXRaw) * (radExt[nXRaw - 1] - radExt[0]) / ((double)(nXRaw - 1));
+  for (int k1 = 0; k1 < nAz; ++k1) azim[k1] = ((PHI[k1] * 12 / PI_D) * 360. / 24) * PI_D / 180.;
+  for (int j1 = 0; j1 < nX; ++j1) {
+    const double r = radExt[j1];
+    rad2[j1] = r * r;
+    fac[j1] = (PressMode == 0) ? 89. * std::exp(-0.59 * r) + 8.9 * std::pow(r, -1.53)
+                               : 8.4027 * std::exp(-1.7845 * r) + 90.3150 * std::exp(-0.7659 * r);
+  }
+  {
+    double sum = 0.0;
+    for (int j = -4; j <= 4; ++j)
+      for (int i = -4; i <= 4; ++i) {
+        const double x = i, y = j;
+        const double v = 2.0 * std::exp(-0.5 * (x * x + y * y) / 1.0);
+        w[(i + 4) + 9 * (j + 4)] = v;
+        sum += v;
+      }
+    for (double& v : w) v = v / sum;
+  }
+  // (re)allocate: the RAM grid may differ between calls only if the handle is rebuilt; sizes are fixed afterwards
+  if (!h->d_rad2 || h->pf_nX != nX || h->pf_nAz != nAz) {
+    SRET(h->dalloc(&h->d_rad2, nX, nullptr));
+    SRET(h->dalloc(&h->d_azim, nAz, nullptr));
+    SRET(h->dalloc(&h->d_rper, n, nullptr));
+    SRET(h->dalloc(&h->d_rpar, n, nullptr));
+    h->pf_nX = nX; h->pf_nAz = nAz;
+  }
+  double *d_in = nullptr, *d_tab = nullptr, *d_tmp = nullptr;
+  int* d_scb = nullptr;
+  const size_t nin = (size_t)nS * NR * NT;
+  SCK(cudaMalloc((void**)&d_in, 2 * nin * sizeof(double)));
+  SCK(cudaMalloc((void**)&d_tab, (2 * (size_t)nX + 81) * sizeof(double)));
+  SCK(cudaMalloc((void**)&d_tmp, 6 * n * sizeof(double)));
+  SCK(cudaMalloc((void**)&d_scb, nS * sizeof(int)));
+  SCK(cudaMemcpy(d_in, PPerT, nin * sizeof(double), cudaMemcpyHostToDevice));
+  SCK(cudaMemcpy(d_in + nin, PParT, nin * sizeof(double), cudaMemcpyHostToDevice));
+  SCK(cudaMemcpy(d_tab, radExt.data(), nX * sizeof(double), cudaMemcpyHostToDevice));
+  SCK(cudaMemcpy(d_tab + nX, fac.data(), nX * sizeof(double), cudaMemcpyHostToDevice));
+  SCK(cudaMemcpy(d_tab + 2 * nX, w.data(), 81 * sizeof(double), cudaMemcpyHostToDevice));
+  SCK(cudaMemcpy(d_scb, scb, nS * sizeof(int), cudaMemcpyHostToDevice));
+  SCK(cudaMemcpy(h->d_rad2, rad2.data(), nX * sizeof(double), cudaMemcpyHostToDevice));
+  SCK(cudaMemcpy(h->d_azim, azim.data(), nAz * sizeof(double), cudaMemcpyHostToDevice));
+  PressRawArgs A{};
+  A.nS = nS; A.NR = NR; A.NT = NT; A.nX = nX; A.nXRaw = nXRaw; A.nAz = nAz; A.mode = PressMode; A.iSm2 = iSm2; A.iters = SavGolIters;
+  A.PPerT = d_in; A.PParT = d_in + nin; A.scb = d_scb; A.radExt = d_tab; A.fac = d_tab + nX; A.w = d_tab + 2 * nX;
+  A.per = h->d_rper; A.par = h->d_rpar; A.t0 = d_tmp; A.t1 = d_tmp + 2 * n; A.t2 = d_tmp + 4 * n;
+  k_scb_press_raw<<<1, 256, 0, h->st>>>(A);
+  SCKL();
+  h->launches++;
+  SCK(cudaStreamSynchronize(h->st));
+  cudaFree(d_in); cudaFree(d_tab); cudaFree(d_tmp); cudaFree(d_scb);
+  h->pf_set = true;
+  return RSG_OK;
+}
+// the extended, smoothed RAM pressures and their axes (diagnostics / tests): rad2(nX), azim(nAz), per, par (nX,nAz)
+int rsg_scb_get_ram_pressure(rsg_scb* h, int* nX, int* nAz, double* rad2, double* azim, double* per, double* par) {
+  if (!h || !nX || !nAz) return sfail(RSG_ERR_ARG, "null argument");
+  if (!h->pf_set) return sfail(RSG_ERR_STATE, "no RAM pressures on the device");
+  *nX = h->pf_nX; *nAz = h->pf_nAz;
+  SCK(cudaSetDevice(h->device));
+  const size_t n = (size_t)h->pf_nX * h->pf_nAz;
+  if (rad2) SCK(cudaMemcpy(rad2, h->d_rad2, h->pf_nX * sizeof(double), cudaMemcpyDeviceToHost));
+  if (azim) SCK(cudaMemcpy(azim, h->d_azim, h->pf_nAz * sizeof(double), cudaMemcpyDeviceToHost));
+  if (per) SCK(cudaMemcpy(per, h->d_rper, n * sizeof(double), cudaMemcpyDeviceToHost));
+  if (par) SCK(cudaMemcpy(par, h->d_rpar, n * sizeof(double), cudaMemcpyDeviceToHost));
+  return RSG_OK;
+}
+// `pressure` (anisotropic, RAM-coupled) entirely on the device: front end + rsg_scb_pressure_aniso's 3-D tail.
+// pperEq / pparEq (npsi, nzeta+1; may be NULL) return the normalised equatorial pressures.
+static int scb_pressure_front(rsg_scb* h, int iLossCone, int iReduceAnisotropy, double* pperEq, double* pparEq) {
+  if (!h->pf_set) return sfail(RSG_ERR_STATE, "pressure front end before rsg_scb_set_ram_pressure");
+  if (iLossCone != 1 && iLossCone != 2) return sfail(RSG_ERR_ARG, "iLossCone must be 1 or 2");
+  const int npsi = h->npsi, nzeta = h->nzeta;
+  const size_t n2 = (size_t)npsi * (nzeta + 1);
+  SRET(scb_press_buffers(h));
+  if (!h->d_pf) SRET(h->dalloc(&h->d_pf, 4 * n2, nullptr));
+  k_scb_gather_eq<<<nblk((long long)n2, 128), 128, 0, h->st>>>(h->dev, (h->nthe + 1) / 2 - 1, h->d_peq);
+  SCKL();
+  k_scb_press_eq<<<nblk(nzeta + 1, 64), 64, 0, h->st>>>(npsi, nzeta, h->d_peq, h->pf_nX, h->pf_nAz, h->d_rad2, h->d_azim, h->d_rper,
+                                                        h->d_rpar, h->pnormal, h->d_pf);
+  SCKL();
+  k_scb_press_wrap<<<nblk((long long)(2 * n2), 128), 128, 0, h->st>>>(npsi, nzeta, h->pnormal, h->d_pf);
+  SCKL();
+  h->launches += 3;
+  if (pperEq) SCK(cudaMemcpyAsync(pperEq, h->d_pf + 2 * n2, n2 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  if (pparEq) SCK(cudaMemcpyAsync(pparEq, h->d_pf + 3 * n2, n2 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  return scb_pressure_aniso_core(h, h->d_pf + 2 * n2, h->d_pf + 3 * n2, iLossCone, iReduceAnisotropy);
+}
+int rsg_scb_pressure_front(rsg_scb* h, int iLossCone, int iReduceAnisotropy, double* pperEq, double* pparEq) {
+  if (!h) return sfail(RSG_ERR_ARG, "null handle");
+  if (!h->grid_set || !h->geom_set) return sfail(RSG_ERR_STATE, "pressure before set_grid / set_geometry");
+  SCK(cudaSetDevice(h->device));
+  return scb_pressure_front(h, iLossCone, iReduceAnisotropy, pperEq, pparEq);
 }
 
 // ---- glue of the outer iteration (src/ModScbRun.f90:232-262, 418-440) ------------------------
@@ -832,10 +958,8 @@ int rsg_scb_map_theta(rsg_scb* h, int* sorfail) { return scb_map(h, 2, sorfail);
 static int scb_run_pressure(rsg_scb* h, const rsg_scb_run_params* p, rsg_scb_pressure_fn fn, void* user, std::vector<double>& eq,
                             std::vector<double>& pe, std::vector<double>& pa) {
   const size_t n2 = (size_t)h->npsi * (h->nzeta + 1);
-  if (!h->d_peq) {
-    SRET(h->dalloc(&h->d_peq, 2 * n2, nullptr));
-    SRET(h->dalloc(&h->d_tau, (size_t)h->nthe * h->npsi * (h->nzeta + 1), "tau"));
-  }
+  if (!fn) return scb_pressure_front(h, p->iLossCone, p->iReduceAnisotropy, nullptr, nullptr);   // no host hop at all
+  SRET(scb_press_buffers(h));
   k_scb_gather_eq<<<nblk((long long)n2, 128), 128, 0, h->st>>>(h->dev, (h->nthe + 1) / 2 - 1, h->d_peq);
   SCKL();
   h->launches++;
@@ -847,8 +971,9 @@ static int scb_run_pressure(rsg_scb* h, const rsg_scb_run_params* p, rsg_scb_pre
 }
 
 int rsg_scb_run(rsg_scb* h, const rsg_scb_run_params* p, rsg_scb_pressure_fn pressure, void* user, rsg_scb_run_result* out) {
-  if (!h || !p || !pressure || !out) return sfail(RSG_ERR_ARG, "null argument");
+  if (!h || !p || !out) return sfail(RSG_ERR_ARG, "null argument");
   if (!h->grid_set || !h->geom_set || !h->map_set) return sfail(RSG_ERR_STATE, "scb_run before set_grid / set_geometry / set_map_targets");
+  if (!pressure && !h->pf_set) return sfail(RSG_ERR_STATE, "scb_run without a pressure callback needs rsg_scb_set_ram_pressure");
   SCK(cudaSetDevice(h->device));
   const size_t n2 = (size_t)h->npsi * (h->nzeta + 1);
   std::vector<double> eq(2 * n2), pe(n2), pa(n2);

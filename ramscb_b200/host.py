@@ -525,6 +525,9 @@ def _scb_lib():
         L.rsg_scb_set_grid.argtypes = [vp] * 6
         L.rsg_scb_set_geometry.argtypes = [vp] * 4
         L.rsg_scb_set_pressure.argtypes = [vp, i] + [vp] * 15
+        L.rsg_scb_set_ram_pressure.argtypes = [vp, i, i, i, vp, vp, vp, vp, vp, i, i, i]
+        L.rsg_scb_get_ram_pressure.argtypes = [vp, _ip, _ip, vp, vp, vp, vp]
+        L.rsg_scb_pressure_front.argtypes = [vp, i, i, vp, vp]
         L.rsg_scb_set_field.argtypes = [vp, C.c_char_p, vp]
         L.rsg_scb_get_field.argtypes = [vp, C.c_char_p, vp]
         L.rsg_scb_field_size.argtypes = [vp, C.c_char_p, C.POINTER(ll)]
@@ -675,6 +678,35 @@ class ScbGpu:
         return {"nisave": nisave.value, "sumb": sumb.value, "sumdb": sumdb.value, "diffmx": diffmx.value,
                 "SORFail": fail.value, "ni": ni, "ms": self.last_ms()}
 
+    PRESS_MODES = {"SKD": 0, "ROE": 1, "EXT": 2, "FLT": 3}
+
+    def set_ram_pressure(self, PPerT, PParT, scb, LZ, PHI, PressMode="SKD", iSm2=4, SavGolIters=11):
+        """RAM pressures (nS,NR,NT) for the device front end of `pressure` (src/ModScbRun.f90:858-980): summed over the
+        species%SCB species, extended radially, smoothed -- once per scb_run."""
+        a, b = np.asfortranarray(PPerT, dtype=np.float64), np.asfortranarray(PParT, dtype=np.float64)
+        nS, NR, NT = a.shape
+        flags = np.ascontiguousarray(scb, dtype=np.int32)
+        lz, ph = np.ascontiguousarray(LZ, dtype=np.float64), np.ascontiguousarray(PHI, dtype=np.float64)
+        assert len(lz) >= NR + 1 and len(ph) >= NT
+        _sck(self.L.rsg_scb_set_ram_pressure(self.h, nS, NR, NT, a.ctypes.data, b.ctypes.data, flags.ctypes.data, lz.ctypes.data,
+                                             ph.ctypes.data, self.PRESS_MODES[PressMode], iSm2, SavGolIters))
+
+    def get_ram_pressure(self):
+        nX, nAz = C.c_int(), C.c_int()
+        _sck(self.L.rsg_scb_get_ram_pressure(self.h, C.byref(nX), C.byref(nAz), None, None, None, None))
+        r2, az = np.zeros(nX.value), np.zeros(nAz.value)
+        per, par = np.zeros((nX.value, nAz.value), order="F"), np.zeros((nX.value, nAz.value), order="F")
+        _sck(self.L.rsg_scb_get_ram_pressure(self.h, C.byref(nX), C.byref(nAz), r2.ctypes.data, az.ctypes.data, per.ctypes.data,
+                                             par.ctypes.data))
+        return r2, az, per, par
+
+    def pressure_front(self, iLossCone=1, iReduceAnisotropy=0):
+        """one `pressure` call entirely on the device; returns the normalised equatorial pressures (npsi, nzeta+1)"""
+        pe = np.zeros((self.npsi, self.nzeta + 1), order="F")
+        pa = np.zeros((self.npsi, self.nzeta + 1), order="F")
+        _sck(self.L.rsg_scb_pressure_front(self.h, iLossCone, iReduceAnisotropy, pe.ctypes.data, pa.ctypes.data))
+        return pe, pa
+
     def scb_run(self, pressure_fn, ordering=SOR_COLOR4, **kw):
         """scb_run (src/ModScbRun.f90:149-440) in one call, everything resident.  pressure_fn(xEq, yEq) ->
         (pperEq, pparEq), all (npsi, nzeta+1) Fortran-ordered: the 2-D front end of `pressure`."""
@@ -702,7 +734,10 @@ class ScbGpu:
                 return 1
 
         res = ScbRunResult()
-        rc = self.L.rsg_scb_run(self.h, C.byref(p), SCB_PRESSURE_FN(cb), None, C.byref(res))
+        if pressure_fn is None:          # `pressure` front end on the device (set_ram_pressure before): no callback
+            rc = self.L.rsg_scb_run(self.h, C.byref(p), C.cast(None, SCB_PRESSURE_FN), None, C.byref(res))
+        else:
+            rc = self.L.rsg_scb_run(self.h, C.byref(p), SCB_PRESSURE_FN(cb), None, C.byref(res))
         if err:
             raise err[0]
         _sck(rc)

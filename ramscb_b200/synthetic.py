@@ -235,6 +235,13 @@ def synthetic_wave_tables(g: G.RamGrids, inp: RamInputs, seed: int = 7):
     t["Ihes_emic"] = np.asfortranarray(0.05 + rng.random((4, NR, NT)))
     LZ = g.LZ[:NR]
     XNE = np.asfortranarray(inp.NECR[:NR, :NT] * np.where(LZ[:, None] > 4.5, 0.05, 1.0))
+    # J = NT is the J = 1 meridian (PHI = 2 pi): every (I,J) input of the reference repeats there, and the step relies on it
+    # (F2(J=1) = F2(J=NT) is maintained by DRIFTP, src/ModRamDrift.f90:272, and by ram_run's epilogue)
+    XNE[:, -1] = XNE[:, 0]
+    for n in ("CDAAR", "BDAAR"):
+        t[n][:, -1] = t[n][:, 0]
+    for n in ("Ihs_emic", "Ihes_emic"):
+        t[n][:, :, -1] = t[n][:, :, 0]
     t["XNE"] = XNE
     t["PAbn"] = np.asfortranarray(g.PAbn, dtype=np.float64)
     return t

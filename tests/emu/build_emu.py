@@ -23,7 +23,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "ramscb_b200", "csrc")
 GEN = os.path.join(HERE, "_gen")
 LIB = os.path.join(GEN, "libramscb_emu.so")
-FILES = ["ram_common.cuh", "ram_kernels.cuh", "ram_fused.cuh", "ram_coulomb.cuh", "ram_diffcoef.cuh", "ram_gpu.cu", "scb_kernels.cuh", "hi_kernels.cuh", "scb_gpu.cu"]
+FILES = ["ram_common.cuh", "ram_kernels.cuh", "ram_fused.cuh", "ram_coulomb.cuh", "ram_diffcoef.cuh", "ram_gpu.cu", "scb_kernels.cuh", "scb_press_front.cuh", "hi_kernels.cuh", "scb_gpu.cu"]
 
 
 def _match(src, i, open_ch, close_ch):

@@ -144,7 +144,7 @@ def test_ram_configs2_grid_full_step_vs_oracle(ram_x4, mode):
         DtR, DtP, DtE, DtM = o.DtDriftR, o.DtDriftP, o.DtDriftE, o.DtDriftMu
         assert np.array_equal(out["DtDrift"], np.stack([DtR, DtP, DtE, DtM]))
     else:
-        assert launches <= 12, "the fused path was not taken"
+        assert launches <= 16, "the fused path was not taken"        # 6 per step + the one-off table / CFL / inflow kernels
         assert n <= max(20, int(1e-5 * strict.size)) and strict.max() <= 1e-11
         assert abs(out["DtsNext"] - dtn) <= 1e-13 * dtn
     assert np.allclose(out["SETRC"], o.SETRC, rtol=1e-12, atol=0)

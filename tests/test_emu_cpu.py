@@ -177,3 +177,77 @@ def test_anisch_diffusion_coefficient_rebuild(emu, use_bas):
     assert gpu.ANISCH_diffcoef(2, emu.F_WPI | emu.F_EMIC, t["XNE"]) == 0
     assert np.array_equal(gpu.get_diffcoef(1), before)
     gpu.close()
+
+
+def _ram_pressures(g):
+    """synthetic ring-current-like RAM pressures PPerT, PParT (nS,NR,NT) [keV/cm^3] and species%SCB flags"""
+    rng = np.random.default_rng(3)
+    LZ, PHI = g.LZ[:g.NR + 1], g.PHI[:g.NT]
+    base = 12.0 * np.exp(-((LZ[:g.NR, None] - 4.0) / 1.2) ** 2) * (1 + 0.3 * np.cos(PHI[None, :]))
+    PPerT = np.asfortranarray(np.stack([base * f * (1 + 0.05 * rng.random(base.shape)) for f in (1.0, 0.3, 0.1, 0.05)]))
+    PParT = np.asfortranarray(0.7 * PPerT * (1 + 0.05 * rng.random(PPerT.shape)))
+    return PPerT, PParT, np.array([1, 1, 1, 0], dtype=np.int32), LZ, PHI
+
+
+def test_pressure_front_end_on_device(emu):
+    """SURVEY 8(f)-2, the 2-D front end of `pressure` (src/ModScbRun.f90:838-1086): RAM pressures summed over the SCB species,
+    radial extension (all four PressModes), SavGol7 / Gaussian smoothing, bilinear interpolation to the equatorial foot points,
+    extap / floor / periodic columns.  Device kernels (emulated) BIT-IDENTICAL to the oracle; the oracle's pieces against
+    scipy (Savitzky-Golay interior points, RegularGridInterpolator); then scb_run with NO host callback against the oracle's
+    composition of the same loop."""
+    from oracle import oracle
+    from scipy.interpolate import RegularGridInterpolator
+    from scipy.signal import savgol_coeffs
+    from ramscb_b200 import grids, scb_synthetic as S
+    g = grids.build_grids()
+    PPerT, PParT, scb, LZ, PHI = _ram_pressures(g)
+    sinp = S.build_scb(nthe=51, npsi=23, nzeta=49, warp=0.3)
+    o, gpu = oracle.ScbOracle(sinp), emu.ScbGpu(sinp)
+    with pytest.raises(emu.RsgError, match="set_ram_pressure"):
+        gpu.pressure_front()
+    for mode, ism in (("ROE", 1), ("EXT", 3), ("FLT", 0), ("SKD", 4)):
+        r = o.pressure_raw(PPerT, PParT, scb, LZ, PHI, PressMode=mode, iSm2=ism)
+        gpu.set_ram_pressure(PPerT, PParT, scb, LZ, PHI, PressMode=mode, iSm2=ism)
+        for a, b in zip(r, gpu.get_ram_pressure()):
+            assert np.array_equal(a, b), mode
+        o.bandjacob(); gpu.computeBandJacob()
+        pe, pa = o.pressure_front()
+        ge, ga = gpu.pressure_front()
+        assert np.array_equal(pe, ge) and np.array_equal(pa, ga), mode
+        assert pe.min() > 0 and np.array_equal(pe[:, 0], pe[:, -2]) and np.array_equal(pe[:, -1], pe[:, 1])
+        o.pressure_aniso(pe, pa)                 # the 3-D tail (gpu.pressure_front ran it already)
+        _same = lambda n: np.array_equal(gpu.get_field(n), getattr(o, n))
+        assert all(_same(n) for n in ("pper", "ppar", "sigma", "dPPerdTheta", "dBsqdRho"))
+    # independent checks of the oracle's pieces: one Savitzky-Golay pass (interior points) and the bilinear rule
+    r2, az, per0, _ = o.pressure_raw(PPerT, PParT, scb, LZ, PHI, PressMode="FLT", iSm2=0)
+    _, _, per1, _ = o.pressure_raw(PPerT, PParT, scb, LZ, PHI, PressMode="FLT", iSm2=1, SavGolIters=1)
+    c = savgol_coeffs(7, 2)
+    rad_pass = per0.copy()
+    for j in range(3, per0.shape[0] - 3):
+        rad_pass[j] = sum(c[m] * per0[j - 3 + m] for m in range(7))
+    want = sum(c[m] * rad_pass[5:-5, 10 - 3 + m] for m in range(7))
+    assert np.max(np.abs(per1[5:-5, 10] - want)) <= 1e-13 * np.abs(want).max()
+    o.pressure_raw(PPerT, PParT, scb, LZ, PHI, PressMode="FLT", iSm2=0)
+    pe, _ = o.pressure_front()
+    ieq = (sinp.nthe + 1) // 2 - 1
+    xe, ye = o.x[ieq][:, 1:-1], o.y[ieq][:, 1:-1]
+    ang = np.where(xe > 0, np.arcsin(ye / np.hypot(xe, ye)) + np.pi, np.where(ye >= 0, 2 * np.pi - np.arcsin(ye / np.hypot(xe, ye)),
+                                                                              -np.arcsin(ye / np.hypot(xe, ye))))
+    rgi = RegularGridInterpolator((r2, az), per0, bounds_error=False, fill_value=None)
+    want = rgi(np.stack([(xe ** 2 + ye ** 2).ravel(), ang.ravel()], axis=1)).reshape(xe.shape) / o.get("pnormal")
+    far = np.hypot(xe, ye) >= 2.0                                      # inside 2 RE the extap repair takes over
+    sel = far & (want > 0)
+    assert np.max(np.abs(pe[:, 1:-1][sel] - want[sel]) / want[sel]) <= 1e-12
+    # the whole outer iteration without a host callback
+    o.pressure_raw(PPerT, PParT, scb, LZ, PHI)
+    gpu.set_ram_pressure(PPerT, PParT, scb, LZ, PHI)
+    gpu.set_map_targets(sinp.alphaVal, sinp.psiVal, sinp.chiVal)
+    kw = dict(numit=2, MinSCBIterations=2, decreaseConvAlpha=1e-30, decreaseConvPsi=1e-30)
+    ro = o.scb_run(None, **kw)
+    rg = gpu.scb_run(None, ordering=emu.SOR_LEX, **kw)
+    assert ro["SORFail"] == 0 and rg["SORFail"] == 0 and rg["iterations"] == ro["iterations"] == 2
+    for k in ("blendAlpha", "blendPsi", "errorAlpha", "errorPsi", "nisaveAlpha", "nisavePsi"):
+        assert rg[k] == ro[k], k
+    for n in ("x", "y", "z", "alfa", "psi", "pper", "sigma"):
+        assert np.array_equal(gpu.get_field(n), getattr(o, n)), n
+    gpu.close()
