@@ -376,6 +376,12 @@ int rsg_scb_set_ram_pressure(rsg_scb* h, int nS, int NR, int NT, const double* P
                              const double* LZ, const double* PHI, int PressMode, int iSm2, int SavGolIters);
 int rsg_scb_get_ram_pressure(rsg_scb* h, int* nX, int* nAz, double* rad2, double* azim, double* per, double* par);
 int rsg_scb_pressure_front(rsg_scb* h, int iLossCone, int iReduceAnisotropy, double* pperEq, double* pparEq);
+/* FLC_Radius (src/ModRamLoss.f90:176-336): curvature radius of the field lines and the zeta parameters of the
+ * field-line-curvature scattering model from x, y, z and Bx, By, Bz of the last computeBandJacob (resident), interpolated
+ * to the RAM equatorial points radRaw(i) (cos, sin)(azimRaw(j) 2 pi / 24 - pi) by GSL_Interpolation_2D (the 9-nearest-
+ * neighbour rule).  r_curvEq, zeta1Eq, zeta2Eq (nR,nT) are what rsg_para_flc takes.  REarth = 6.4e6 m. */
+int rsg_scb_flc_radius(rsg_scb* h, int nR, int nT, const double* radRaw, const double* azimRaw, double REarth, double* r_curvEq,
+                       double* zeta1Eq, double* zeta2Eq);
 /* Glue of the outer iteration (src/ModScbRun.f90:232-262, 418-440), so that alfa, psi, x, y, z need
  * not visit the host between the solves: device snapshots of a named field (alfaSav1, alphaPrev,
  * xPrev... of the reference; slot 0..3), the blend  field = snap(slot_new)*blend +

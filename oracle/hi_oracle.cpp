@@ -256,3 +256,95 @@ extern "C" void hio_convert_lines(int nthe, int npsi, int nzeta, int nR, int nT,
       }
     }
 }
+
+
+// ---- FLC_Radius (src/ModRamLoss.f90:176-336): field-line curvature radius and the zeta parameters of the FLC scattering
+// model on the SCB grid, then their values at the RAM equatorial points by GSL_Interpolation_2D = the 9-nearest-neighbour
+// inverse-distance rule above (Interpolation_2D_NN_point).  x, y, z (nthe,npsi,nzeta+1); bx, by, bz (nthe,npsi,nzeta) of
+// computeBandJacob; radRaw(1:nR) and azimRaw(1:nT) as the reference holds them; outputs (nR,nT).  Only the equatorial
+// slice of the 3-D fields is read at the end; the slots the reference leaves unassigned (theta ends of the second
+// differences) are never touched by it and are left at 0 here.  The caller keeps the "every Dt_bc" gate (:207).
+extern "C" void hio_flc_radius(int nthe, int npsi, int nzeta, int nR, int nT, int nThetaEquator, double bnormal, double REarth,
+                               const double* x, const double* y, const double* z, const double* bx, const double* by, const double* bz,
+                               const double* radRaw, const double* azimRaw, double* r_curvEq, double* zeta1Eq, double* zeta2Eq) {
+  const double PI = 3.1415926535897932384626433832795;      // ModRamConst PI = cPi
+  const size_t sj = nthe, sk3 = (size_t)nthe * npsi;          // strides of both (…,nzeta) and (…,nzeta+1) arrays
+  const size_t n3 = sk3 * nzeta;
+  auto X3 = [&](const double* a, int i, int j, int k) { return a[(size_t)(i - 1) + sj * (j - 1) + sk3 * (k - 1)]; };
+  std::vector<double> bb(n3), vbx(n3), vby(n3), vbz(n3), ax(n3, 0.0), ay(n3, 0.0), az(n3, 0.0), ds(n3, 0.0), rc(n3, 0.0), dBdS(n3, 0.0),
+      dRcdS(n3, 0.0), d2B(n3, 0.0), d2R(n3, 0.0);
+  auto W3 = [&](std::vector<double>& a, int i, int j, int k) -> double& { return a[(size_t)(i - 1) + sj * (j - 1) + sk3 * (k - 1)]; };
+  for (size_t q = 0; q < n3; ++q) {
+    bb[q] = std::sqrt(bx[q] * bx[q] + by[q] * by[q] + bz[q] * bz[q]);
+    vbx[q] = bx[q] / bb[q]; vby[q] = by[q] / bb[q]; vbz[q] = bz[q] / bb[q];
+  }
+  for (int i = 2; i <= nthe - 1; ++i)
+    for (int j = 1; j <= npsi; ++j)
+      for (int k = 1; k <= nzeta; ++k) {
+        const double dx = X3(x, i + 1, j, k) - X3(x, i, j, k), dy = X3(y, i + 1, j, k) - X3(y, i, j, k), dz = X3(z, i + 1, j, k) - X3(z, i, j, k);
+        const double dvx = W3(vbx, i + 1, j, k) - W3(vbx, i, j, k), dvy = W3(vby, i + 1, j, k) - W3(vby, i, j, k),
+                     dvz = W3(vbz, i + 1, j, k) - W3(vbz, i, j, k);
+        const double bxv = W3(vbx, i, j, k), byv = W3(vby, i, j, k), bzv = W3(vbz, i, j, k);
+        if (dx == 0.0) {
+          W3(ax, i, j, k) = byv * (dvx / dy) + bzv * (dvx / dz);
+          W3(ay, i, j, k) = byv * (dvy / dy) + bzv * (dvy / dz);
+          W3(az, i, j, k) = byv * (dvz / dy) + bzv * (dvz / dz);
+        } else if (dy == 0.0) {
+          W3(ax, i, j, k) = bxv * (dvx / dx) + bzv * (dvx / dz);
+          W3(ay, i, j, k) = bxv * (dvy / dx) + bzv * (dvy / dz);
+          W3(az, i, j, k) = bxv * (dvz / dx) + bzv * (dvz / dz);
+        } else {
+          W3(ax, i, j, k) = bxv * dvx / dx + byv * dvx / dy + bzv * dvx / dz;
+          W3(ay, i, j, k) = bxv * dvy / dx + byv * dvy / dy + bzv * dvy / dz;
+          W3(az, i, j, k) = bxv * dvz / dx + byv * dvz / dy + bzv * dvz / dz;
+        }
+        W3(ds, i, j, k) = std::sqrt(dx * dx + dy * dy + dz * dz) * REarth;
+      }
+  for (size_t q = 0; q < n3; ++q) rc[q] = 1. / std::sqrt(ax[q] * ax[q] + ay[q] * ay[q] + az[q] * az[q]) * REarth;
+  for (int j = 1; j <= npsi; ++j)
+    for (int k = 1; k <= nzeta; ++k) { W3(rc, 1, j, k) = W3(rc, 2, j, k); W3(rc, nthe, j, k) = W3(rc, nthe - 1, j, k); }
+  for (int i = 2; i <= nthe - 1; ++i)
+    for (int j = 1; j <= npsi; ++j)
+      for (int k = 1; k <= nzeta; ++k) {
+        W3(dBdS, i, j, k) = bnormal * (W3(bb, i + 1, j, k) - W3(bb, i, j, k)) * 1.0e-9 / W3(ds, i, j, k);
+        W3(dRcdS, i, j, k) = (W3(rc, i + 1, j, k) - W3(rc, i, j, k)) / W3(ds, i, j, k);
+      }
+  for (int j = 1; j <= npsi; ++j)
+    for (int k = 1; k <= nzeta; ++k) { W3(dBdS, 1, j, k) = W3(dBdS, 2, j, k); W3(dRcdS, 1, j, k) = W3(dRcdS, 2, j, k); }
+  for (int i = 2; i <= nthe - 2; ++i)
+    for (int j = 1; j <= npsi; ++j)
+      for (int k = 1; k <= nzeta; ++k) {
+        W3(d2B, i, j, k) = (W3(dBdS, i + 1, j, k) - W3(dBdS, i, j, k)) / W3(ds, i, j, k);
+        W3(d2R, i, j, k) = (W3(dRcdS, i + 1, j, k) - W3(dRcdS, i, j, k)) / W3(ds, i, j, k);
+      }
+  // equatorial slices (1:npsi, 2:nzeta) as contiguous (npsi, nzeta-1) arrays
+  const int ie = nThetaEquator, m1 = nzeta - 1;
+  std::vector<double> xe((size_t)npsi * m1), ye(xe.size()), f_rc(xe.size()), f_z1(xe.size()), f_z2(xe.size()), distance(xe.size());
+  for (int j = 1; j <= npsi; ++j)
+    for (int k = 2; k <= nzeta; ++k) {
+      const size_t o = (size_t)(j - 1) + (size_t)npsi * (k - 2);
+      xe[o] = X3(x, ie, j, k); ye[o] = X3(y, ie, j, k);
+      const double r = W3(rc, ie, j, k);
+      f_rc[o] = r;
+      f_z1[o] = r * W3(d2R, ie, j, k);
+      f_z2[o] = r * r / (bnormal * 1.0e-9 * W3(bb, ie, j, k)) * W3(d2B, ie, j, k);
+    }
+  const double* fp[3] = {f_rc.data(), f_z1.data(), f_z2.data()};
+  for (int i = 2; i <= nR; ++i)
+    for (int j = 1; j <= nT - 1; ++j) {
+      const double c1 = radRaw[i - 1] * std::cos(azimRaw[j - 1] * 2 * PI / 24. - PI);
+      const double c2 = radRaw[i - 1] * std::sin(azimRaw[j - 1] * 2 * PI / 24. - PI);
+      double r[3];
+      nn9(npsi, m1, xe.data(), ye.data(), 1, (size_t)npsi, fp, 3, c1, c2, distance, r);
+      const size_t o = (size_t)(i - 1) + (size_t)nR * (j - 1);
+      r_curvEq[o] = r[0]; zeta1Eq[o] = r[1]; zeta2Eq[o] = r[2];
+    }
+  for (int i = 1; i <= nR; ++i) {                    // MLT = 24 is MLT = 0
+    const size_t a = (size_t)(i - 1) + (size_t)nR * (nT - 1), b = (size_t)(i - 1);
+    r_curvEq[a] = r_curvEq[b]; zeta1Eq[a] = zeta1Eq[b]; zeta2Eq[a] = zeta2Eq[b];
+  }
+  for (int j = 1; j <= nT; ++j) {                    // the innermost circle
+    const size_t a = (size_t)nR * (j - 1);
+    r_curvEq[a] = r_curvEq[a + 1]; zeta1Eq[a] = zeta1Eq[a + 1]; zeta2Eq[a] = zeta2Eq[a + 1];
+  }
+}

@@ -529,3 +529,17 @@ def hi_convert_lines(x, y, z, bf, psi, alfa, Lz, MLT, nThetaEquator):
     lib.hio_convert_lines(nthe, npsi, nz1 - 1, nR, nT, int(nThetaEquator), *[a.ctypes.data for a in (x, y, z, bf, psi, alfa, Lz, MLT)],
                           *[a.ctypes.data for a in out], outside.ctypes.data, psiRAM.ctypes.data)
     return (*out, outside, psiRAM)
+
+
+def flc_radius(x, y, z, bx, by, bz, radRaw, azimRaw, nThetaEquator, bnormal, REarth=6.4e6):
+    """FLC_Radius (src/ModRamLoss.f90:176-336; hio_flc_radius): r_curvEq, zeta1Eq, zeta2Eq (nR,nT)."""
+    lib = hi_lib()
+    lib.hio_flc_radius.argtypes = [C.c_int] * 6 + [C.c_double] * 2 + [C.c_void_p] * 11
+    lib.hio_flc_radius.restype = None
+    nthe, npsi, nz1 = x.shape
+    a = [np.asfortranarray(v, dtype=np.float64) for v in (x, y, z, bx, by, bz)]
+    rr, az = np.ascontiguousarray(radRaw, dtype=np.float64), np.ascontiguousarray(azimRaw, dtype=np.float64)
+    out = [_f((len(rr), len(az))) for _ in range(3)]
+    lib.hio_flc_radius(nthe, npsi, nz1 - 1, len(rr), len(az), int(nThetaEquator), float(bnormal), float(REarth),
+                       *[v.ctypes.data for v in a], rr.ctypes.data, az.ctypes.data, *[o.ctypes.data for o in out])
+    return out

@@ -577,3 +577,163 @@ __global__ void __launch_bounds__(256) k_hi_nn9(HiConvArgs A) {
     }
   }
 }
+
+// =============================================================================
+// FLC_Radius (src/ModRamLoss.f90:176-336): curvature radius of the field lines and the zeta parameters of the field-line-
+// curvature scattering model at the SCB equatorial points, then at the RAM equatorial points by the same 9-nearest-
+// neighbour rule as above (GSL_Interpolation_2D -> Interpolation_2D_NN_point).  Only the equatorial slice of the
+// reference's 3-D work arrays is ever read, so k_flc_curv evaluates the theta stencil i .. i+3 of that slice directly
+// (same expressions, same operation order; compiled with -fmad=false).
+// =============================================================================
+struct FlcArgs {
+  int nthe, npsi, nzeta, nR, nT, ie;             // ie: 0-based equatorial theta index
+  double bnormal, REarth;
+  const double *x, *y, *z;                       // (nthe,npsi,nzeta+1)
+  const double *bx, *by, *bz;                    // (nthe,npsi,nzeta)
+  double *xe, *ye, *rc, *z1, *z2;                // (npsi, nzeta-1) in the scatter order of the interpolation: s = j*(nzeta-1) + (k-1)
+  const double *qx, *qy;                         // query points (nR,nT) (host: cos / sin of libm)
+  double *rcEq, *z1Eq, *z2Eq;                    // (nR,nT)
+};
+
+struct FlcNode { double bb, vx, vy, vz; };
+__device__ __forceinline__ FlcNode flc_node(const FlcArgs& A, size_t o) {
+  FlcNode n;
+  const double bx = A.bx[o], by = A.by[o], bz = A.bz[o];
+  n.bb = sqrt(bx * bx + by * by + bz * bz);
+  n.vx = bx / n.bb; n.vy = by / n.bb; n.vz = bz / n.bb;
+  return n;
+}
+// ax, ay, az and ds at theta node i (1-based 2 .. nthe-1) of line (j, k): |a| -> r_curv
+__device__ __forceinline__ void flc_accel(const FlcArgs& A, int i, size_t line, double* rcurv, double* ds_out, double* bb_i, double* bb_ip1) {
+  const size_t o = (size_t)(i - 1) + line, o1 = o + 1;
+  const FlcNode a = flc_node(A, o), b = flc_node(A, o1);
+  const double dx = A.x[o1] - A.x[o], dy = A.y[o1] - A.y[o], dz = A.z[o1] - A.z[o];
+  const double dvx = b.vx - a.vx, dvy = b.vy - a.vy, dvz = b.vz - a.vz;
+  double ax, ay, az;
+  if (dx == 0.0) {
+    ax = a.vy * (dvx / dy) + a.vz * (dvx / dz);
+    ay = a.vy * (dvy / dy) + a.vz * (dvy / dz);
+    az = a.vy * (dvz / dy) + a.vz * (dvz / dz);
+  } else if (dy == 0.0) {
+    ax = a.vx * (dvx / dx) + a.vz * (dvx / dz);
+    ay = a.vx * (dvy / dx) + a.vz * (dvy / dz);
+    az = a.vx * (dvz / dx) + a.vz * (dvz / dz);
+  } else {
+    ax = a.vx * dvx / dx + a.vy * dvx / dy + a.vz * dvx / dz;
+    ay = a.vx * dvy / dx + a.vy * dvy / dy + a.vz * dvy / dz;
+    az = a.vx * dvz / dx + a.vy * dvz / dy + a.vz * dvz / dz;
+  }
+  *rcurv = 1. / sqrt(ax * ax + ay * ay + az * az) * A.REarth;
+  *ds_out = sqrt(dx * dx + dy * dy + dz * dz) * A.REarth;
+  *bb_i = a.bb; *bb_ip1 = b.bb;
+}
+// r_curv(i) with the end rules r_curv(1) = r_curv(2), r_curv(nthe) = r_curv(nthe-1)   (:276-278)
+__device__ __forceinline__ double flc_rcurv(const FlcArgs& A, int i, size_t line) {
+  const int ii = (i < 2) ? 2 : ((i > A.nthe - 1) ? A.nthe - 1 : i);
+  double rc, ds, b0, b1;
+  flc_accel(A, ii, line, &rc, &ds, &b0, &b1);
+  return rc;
+}
+// thread per equatorial point (j, k), k = 2..nzeta (Fortran)
+__global__ void k_flc_curv(FlcArgs A) {
+  const int m1 = A.nzeta - 1;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= A.npsi * m1) return;
+  const int j = t / m1, kk = t - j * m1;                   // kk = k - 2
+  const size_t line = (size_t)A.nthe * (j + (size_t)A.npsi * (kk + 1));
+  const int i = A.ie + 1;                                  // 1-based theta index of the equator; needs 2 <= i <= nthe-3
+  double rc[3], ds[2], b0[2], b1[2];
+  for (int q = 0; q < 2; ++q) flc_accel(A, i + q, line, &rc[q], &ds[q], &b0[q], &b1[q]);
+  rc[0] = flc_rcurv(A, i, line); rc[1] = flc_rcurv(A, i + 1, line); rc[2] = flc_rcurv(A, i + 2, line);
+  // dBdS, dRcdS at i and i+1 (:280-283), second differences at i (:288-291)
+  const double dBdS0 = A.bnormal * (b1[0] - b0[0]) * 1.0e-9 / ds[0], dBdS1 = A.bnormal * (b1[1] - b0[1]) * 1.0e-9 / ds[1];
+  const double dRdS0 = (rc[1] - rc[0]) / ds[0], dRdS1 = (rc[2] - rc[1]) / ds[1];
+  const double d2B = (dBdS1 - dBdS0) / ds[0], d2R = (dRdS1 - dRdS0) / ds[0];
+  const size_t o = (size_t)(i - 1) + line;
+  A.xe[t] = A.x[o]; A.ye[t] = A.y[o];
+  A.rc[t] = rc[0];
+  A.z1[t] = rc[0] * d2R;
+  A.z2[t] = rc[0] * rc[0] / (A.bnormal * 1.0e-9 * b0[0]) * d2B;
+}
+
+// 9-nearest-neighbour interpolation of rc, z1, z2 to the RAM points: a warp per query, candidates in shared memory
+// (selection = the single-scan form of k_hi_nn9: nine smallest (distance, index) pairs per lane, nine shuffle elections)
+__global__ void __launch_bounds__(256) k_flc_nn9(FlcArgs A) {
+  extern __shared__ double hi_sm[];
+  const int m1 = A.nzeta - 1, M = A.npsi * m1;
+  double* cx = hi_sm;
+  double* cy = cx + M;
+  for (int s = threadIdx.x; s < M; s += blockDim.x) { cx[s] = A.xe[s]; cy[s] = A.ye[s]; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int nq = (A.nR - 1) * (A.nT - 1);
+  for (int q = blockIdx.x * nwarp + warp; q < nq; q += gridDim.x * nwarp) {
+    const int i = 1 + q % (A.nR - 1), j = q / (A.nR - 1);                // 0-based (Fortran i = 2..nR, j = 1..nT-1)
+    const size_t oq = (size_t)i + (size_t)A.nR * j;
+    const double x2 = A.qx[oq], y2 = A.qy[oq];
+    double ld[9];
+    int li[9];
+#pragma unroll
+    for (int t = 0; t < 9; t++) { ld[t] = 1.7976931348623157e308; li[t] = 0x7fffffff; }
+    for (int s = lane; s < M; s += 32) {
+      const double dx = cx[s] - x2, dy = cy[s] - y2;
+      const double d = dx * dx + dy * dy;
+      if (d < ld[8] || (d == ld[8] && s < li[8])) {
+        ld[8] = d; li[8] = s;
+#pragma unroll
+        for (int t = 8; t > 0; t--) {
+          if (ld[t] < ld[t - 1] || (ld[t] == ld[t - 1] && li[t] < li[t - 1])) {
+            const double td = ld[t]; ld[t] = ld[t - 1]; ld[t - 1] = td;
+            const int ti = li[t]; li[t] = li[t - 1]; li[t - 1] = ti;
+          }
+        }
+      }
+    }
+    int near[9];
+#pragma unroll
+    for (int r = 0; r < 9; r++) {
+      double bd = ld[0];
+      int bi = li[0];
+      for (int o = 16; o > 0; o >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+      }
+      near[r] = bi;
+      if (li[0] == bi) {
+#pragma unroll
+        for (int t = 0; t < 8; t++) { ld[t] = ld[t + 1]; li[t] = li[t + 1]; }
+        ld[8] = 1.7976931348623157e308; li[8] = 0x7fffffff;
+      }
+    }
+    double w[9], wsum = 0.0;                                             // NN_Interpolation_2D (src/ModRamGSL.f90:872-917)
+    for (int c = 0; c < 9; c++) {
+      const double dx = cx[near[c]] - x2, dy = cy[near[c]] - y2;
+      const double d = sqrt(dx * dx + dy * dy);
+      if (fabs(d) <= 1e-9) {
+        for (int e = 0; e < 9; e++) w[e] = 0.0;
+        w[c] = 1.0; wsum = 1.0;
+        break;
+      }
+      w[c] = 1 / (d * d);
+      wsum = wsum + w[c];
+    }
+    if (lane < 3) {
+      const double* f = lane == 0 ? A.rc : (lane == 1 ? A.z1 : A.z2);
+      double v = 0.0;
+      // the oracle's candidate order is i-outer / j-inner over (npsi, nzeta-1) stored (npsi fastest): s = j*m1 + kk here
+      for (int c = 0; c < 9; c++) v = v + f[near[c]] * w[c] / wsum;
+      (lane == 0 ? A.rcEq : (lane == 1 ? A.z1Eq : A.z2Eq))[oq] = v;
+    }
+  }
+}
+// MLT = 24 is MLT = 0, the innermost circle repeats the second one (:311-316); thread per (i, j)
+__global__ void k_flc_edges(FlcArgs A) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= A.nR * A.nT) return;
+  const int i = t % A.nR, j = t / A.nR;
+  if (i != 0 && j != A.nT - 1) return;
+  const int js = (j == A.nT - 1) ? 0 : j, is = (i == 0) ? 1 : i;
+  const size_t src = (size_t)is + (size_t)A.nR * js;
+  A.rcEq[t] = A.rcEq[src]; A.z1Eq[t] = A.z1Eq[src]; A.z2Eq[t] = A.z2Eq[src];
+}

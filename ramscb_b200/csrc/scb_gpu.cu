@@ -883,6 +883,59 @@ int rsg_scb_pressure_front(rsg_scb* h, int iLossCone, int iReduceAnisotropy, dou
   return scb_pressure_front(h, iLossCone, iReduceAnisotropy, pperEq, pparEq);
 }
 
+// FLC_Radius (src/ModRamLoss.f90:176-336) from the geometry and field of the last computeBandJacob, both resident:
+// r_curvEq, zeta1Eq, zeta2Eq (nR,nT) for PARA_FLC (rsg_para_flc).  radRaw(1:nR), azimRaw(1:nT) as the reference holds them
+// (src/ModRamEField.f90:100-107); REarth = 6.4e6 (src/ModScbMain.f90:15).  The caller keeps the "every Dt_bc" gate (:207).
+int rsg_scb_flc_radius(rsg_scb* h, int nR, int nT, const double* radRaw, const double* azimRaw, double REarth, double* r_curvEq,
+                       double* zeta1Eq, double* zeta2Eq) {
+  if (!h || !radRaw || !azimRaw || !r_curvEq || !zeta1Eq || !zeta2Eq) return sfail(RSG_ERR_ARG, "null argument");
+  if (nR < 2 || nT < 2) return sfail(RSG_ERR_ARG, "bad RAM dimensions");
+  if (!h->geom_set || !h->band_done) return sfail(RSG_ERR_STATE, "FLC_Radius needs computeBandJacob on the current geometry");
+  const int nthe = h->nthe, npsi = h->npsi, nzeta = h->nzeta, m1 = nzeta - 1;
+  const int ie = (nthe + 1) / 2 - 1;
+  if (ie + 1 < 2 || ie + 1 > nthe - 3 || (long long)npsi * m1 < 9) return sfail(RSG_ERR_ARG, "grid too small for FLC_Radius");
+  SCK(cudaSetDevice(h->device));
+  const size_t ne = (size_t)npsi * m1, nq = (size_t)nR * nT;
+  const size_t smem = 2 * ne * sizeof(double);
+  if (smem > 200 * 1024) return sfail(RSG_ERR_UNSUPPORTED, "equatorial plane too large for the shared-memory candidate set");
+  double* buf = nullptr;
+  SCK(cudaMalloc((void**)&buf, (5 * ne + 5 * nq) * sizeof(double)));
+  std::vector<double> q(2 * nq, 0.0);
+  const double PI = 3.1415926535897932384626433832795;
+  for (int i = 2; i <= nR; ++i)
+    for (int j = 1; j <= nT - 1; ++j) {
+      q[(size_t)(i - 1) + (size_t)nR * (j - 1)] = radRaw[i - 1] * std::cos(azimRaw[j - 1] * 2 * PI / 24. - PI);
+      q[nq + (size_t)(i - 1) + (size_t)nR * (j - 1)] = radRaw[i - 1] * std::sin(azimRaw[j - 1] * 2 * PI / 24. - PI);
+    }
+  FlcArgs A{};
+  A.nthe = nthe; A.npsi = npsi; A.nzeta = nzeta; A.nR = nR; A.nT = nT; A.ie = ie; A.bnormal = h->bnormal; A.REarth = REarth;
+  A.x = h->dev.x; A.y = h->dev.y; A.z = h->dev.z; A.bx = h->dev.Bx; A.by = h->dev.By; A.bz = h->dev.Bz;
+  A.xe = buf; A.ye = buf + ne; A.rc = buf + 2 * ne; A.z1 = buf + 3 * ne; A.z2 = buf + 4 * ne;
+  double* dq = buf + 5 * ne;
+  A.qx = dq; A.qy = dq + nq; A.rcEq = dq + 2 * nq; A.z1Eq = dq + 3 * nq; A.z2Eq = dq + 4 * nq;
+  SCK(cudaMemcpyAsync(dq, q.data(), 2 * nq * sizeof(double), cudaMemcpyHostToDevice, h->st));
+  SCK(cudaMemsetAsync(dq + 2 * nq, 0, 3 * nq * sizeof(double), h->st));
+  SCK(cudaEventRecord(h->e0, h->st));
+  k_flc_curv<<<nblk((long long)ne, 128), 128, 0, h->st>>>(A);
+  SCKL();
+  if (smem > 48 * 1024) SCK(cudaFuncSetAttribute(k_flc_nn9, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_flc_nn9<<<std::max(1, std::min(148, (int)(((size_t)(nR - 1) * (nT - 1) + 7) / 8))), 256, smem, h->st>>>(A);
+  SCKL();
+  k_flc_edges<<<nblk((long long)nq, 128), 128, 0, h->st>>>(A);
+  SCKL();
+  h->launches += 3;
+  SCK(cudaEventRecord(h->e1, h->st));
+  SCK(cudaMemcpyAsync(r_curvEq, A.rcEq, nq * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  SCK(cudaMemcpyAsync(zeta1Eq, A.z1Eq, nq * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  SCK(cudaMemcpyAsync(zeta2Eq, A.z2Eq, nq * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  SCK(cudaStreamSynchronize(h->st));
+  float ms = 0.f;
+  SCK(cudaEventElapsedTime(&ms, h->e0, h->e1));
+  h->last_ms = ms;
+  cudaFree(buf);
+  return RSG_OK;
+}
+
 // ---- glue of the outer iteration (src/ModScbRun.f90:232-262, 418-440) ------------------------
 // snapshot slots hold device copies of a named (nthe,npsi,nzeta+1) field: alfaSav1 / alphaPrev /
 // xPrev ... of the reference.  slot 0..3.

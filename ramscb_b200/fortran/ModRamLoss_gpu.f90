@@ -44,6 +44,20 @@ contains
     call rsg_check(rsg_para_flc(hRam, int(S, c_int), r_curvEq, zeta1Eq, zeta2Eq), 'PARA_FLC')
   end subroutine PARA_FLC
 
+  subroutine FLC_Radius
+    ! src/ModRamLoss.f90:176-336 on the device: curvature radius and zeta parameters from the SCB geometry / field that
+    ! computeBandJacob left resident (hScb), interpolated to the RAM equatorial points; same "every Dt_bc" gate as :207
+    use ModRamGrids,     ONLY: NR, NT
+    use ModRamTiming,    ONLY: TimeRamElapsed, Dt_bc
+    use ModRamVariables, ONLY: r_curvEq, zeta1Eq, zeta2Eq
+    use ModScbMain,      ONLY: REarth
+    use ModScbVariables, ONLY: radRaw, azimRaw
+    use ModScbGpu,       ONLY: hScb, rsg_scb_flc_radius
+    if (mod(int(TimeRamElapsed), int(Dt_bc)) .gt. 1e-6) return
+    call rsg_check(rsg_scb_flc_radius(hScb, int(NR, c_int), int(NT, c_int), radRaw(1:NR), azimRaw, real(REarth, c_double), &
+                                      r_curvEq, zeta1Eq, zeta2Eq), 'FLC_Radius')
+  end subroutine FLC_Radius
+
   SUBROUTINE CHAREXCHANGE(S)
     ! src/ModRamLoss.f90:457-478
     integer, intent(in) :: S

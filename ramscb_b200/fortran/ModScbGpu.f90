@@ -63,6 +63,33 @@ module ModScbGpu
                                      dBsqdPsi(*), dBsqdAlpha(*), dPdAlpha(*), dPdPsi(*)
        integer(c_int) :: ierr
      end function
+     function rsg_scb_flc_radius(h, nR, nT, radRaw, azimRaw, REarth, r_curvEq, zeta1Eq, zeta2Eq) &
+          bind(C, name='rsg_scb_flc_radius') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       integer(c_int), value :: nR, nT
+       real(c_double), value :: REarth
+       real(c_double), intent(in) :: radRaw(*), azimRaw(*)
+       real(c_double), intent(out) :: r_curvEq(*), zeta1Eq(*), zeta2Eq(*)
+       integer(c_int) :: ierr
+     end function
+     function rsg_scb_set_ram_pressure(h, nS, NR, NT, PPerT, PParT, scb, LZ, PHI, PressMode, iSm2, SavGolIters) &
+          bind(C, name='rsg_scb_set_ram_pressure') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       integer(c_int), value :: nS, NR, NT, PressMode, iSm2, SavGolIters
+       real(c_double), intent(in) :: PPerT(*), PParT(*), LZ(*), PHI(*)
+       integer(c_int), intent(in) :: scb(*)
+       integer(c_int) :: ierr
+     end function
+     function rsg_scb_pressure_front(h, iLossCone, iReduceAnisotropy, pperEq, pparEq) &
+          bind(C, name='rsg_scb_pressure_front') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       integer(c_int), value :: iLossCone, iReduceAnisotropy
+       real(c_double), intent(out) :: pperEq(*), pparEq(*)
+       integer(c_int) :: ierr
+     end function
      function rsg_scb_pressure_aniso(h, pperEq, pparEq, iLossCone, iReduceAnisotropy) &
           bind(C, name='rsg_scb_pressure_aniso') result(ierr)
        import :: c_ptr, c_int, c_double

@@ -525,6 +525,7 @@ def _scb_lib():
         L.rsg_scb_set_grid.argtypes = [vp] * 6
         L.rsg_scb_set_geometry.argtypes = [vp] * 4
         L.rsg_scb_set_pressure.argtypes = [vp, i] + [vp] * 15
+        L.rsg_scb_flc_radius.argtypes = [vp, i, i, vp, vp, d, vp, vp, vp]
         L.rsg_scb_set_ram_pressure.argtypes = [vp, i, i, i, vp, vp, vp, vp, vp, i, i, i]
         L.rsg_scb_get_ram_pressure.argtypes = [vp, _ip, _ip, vp, vp, vp, vp]
         L.rsg_scb_pressure_front.argtypes = [vp, i, i, vp, vp]
@@ -677,6 +678,14 @@ class ScbGpu:
                                            C.byref(sumdb), C.byref(diffmx), C.byref(fail), ni.ctypes.data))
         return {"nisave": nisave.value, "sumb": sumb.value, "sumdb": sumdb.value, "diffmx": diffmx.value,
                 "SORFail": fail.value, "ni": ni, "ms": self.last_ms()}
+
+    def FLC_Radius(self, radRaw, azimRaw, REarth=6.4e6):
+        """FLC_Radius (src/ModRamLoss.f90:176-336) from the resident geometry / field of the last computeBandJacob:
+        r_curvEq, zeta1Eq, zeta2Eq (nR,nT), the inputs of RamGpu.PARA_FLC"""
+        rr, az = np.ascontiguousarray(radRaw, dtype=np.float64), np.ascontiguousarray(azimRaw, dtype=np.float64)
+        out = [np.zeros((len(rr), len(az)), order="F") for _ in range(3)]
+        _sck(self.L.rsg_scb_flc_radius(self.h, len(rr), len(az), rr.ctypes.data, az.ctypes.data, REarth, *[o.ctypes.data for o in out]))
+        return out
 
     PRESS_MODES = {"SKD": 0, "ROE": 1, "EXT": 2, "FLT": 3}
 

@@ -251,3 +251,29 @@ def test_pressure_front_end_on_device(emu):
     for n in ("x", "y", "z", "alfa", "psi", "pper", "sigma"):
         assert np.array_equal(gpu.get_field(n), getattr(o, n)), n
     gpu.close()
+
+
+def test_flc_radius_on_device(emu):
+    """R12, FLC_Radius (src/ModRamLoss.f90:176-336): field-line curvature radius and zeta parameters from the resident SCB
+    geometry / field, interpolated to the RAM points by the 9-nearest-neighbour rule.  Device (emulated) BIT-IDENTICAL to
+    the oracle; known answer: on dipole field lines the equatorial curvature radius is r / 3."""
+    from oracle import oracle
+    from ramscb_b200 import grids, scb_synthetic as S
+    g = grids.build_grids()
+    radRaw = 1.75 + (6.75 - 1.75) * np.arange(1, g.NR + 1) / g.NR          # radRaw(1:nR), src/ModRamEField.f90:100-103
+    azimRaw = 24.0 * np.arange(g.NT) / (g.NT - 1)
+    for warp in (0.3, 0.0):
+        sinp = S.build_scb(nthe=51, npsi=23, nzeta=49, warp=warp)
+        o, gpu = oracle.ScbOracle(sinp), emu.ScbGpu(sinp)
+        with pytest.raises(emu.RsgError, match="computeBandJacob"):
+            gpu.FLC_Radius(radRaw, azimRaw)
+        o.bandjacob(); gpu.computeBandJacob()
+        ref = oracle.flc_radius(o.x, o.y, o.z, o.Bx, o.By, o.Bz, radRaw, azimRaw, (sinp.nthe + 1) // 2, o.get("bnormal"))
+        got = gpu.FLC_Radius(radRaw, azimRaw)
+        for a, b in zip(got, ref):
+            assert np.array_equal(a, b)
+            assert np.array_equal(b[:, -1], b[:, 0]) and np.array_equal(b[0], b[1])
+        if warp == 0.0:
+            rc = ref[0][1:, :-1] / 6.4e6                     # in RE
+            assert np.max(np.abs(rc / (radRaw[1:, None] / 3.0) - 1.0)) < 0.05, np.max(np.abs(rc / (radRaw[1:, None] / 3.0) - 1.0))
+        gpu.close()

@@ -373,3 +373,40 @@ def test_anisch_diffcoef_rebuild_feeds_the_wpi_step(default_grids, oracle_built)
     assert strict.max() <= 1e-12, (strict.max(), int((strict > 1e-12).sum()))          # EXACT mode, bar of test_full_ram_run
     assert out["DtsNext"] == dtn
     gpu.close()
+
+
+def test_flc_radius_and_pressure_front_end_on_hardware(default_grids, oracle_built):
+    """The two device paths written in round 2 for the RAM <-> SCB coupling, on the configs[3] grid: FLC_Radius (R12) and the 2-D
+    front end of `pressure` (8(f)-2).  Same kernels are bit-identical to the oracle in the emulator (tests/test_emu_cpu.py); on
+    hardware asin / sqrt / division of the device library round like libm except in the last bit of asin: <= 1e-13."""
+    import test_emu_cpu as TE
+    from ramscb_b200 import host
+    g = default_grids
+    sinp = SCBSYN.build_scb(nthe=101, npsi=45, nzeta=97, warp=0.2)
+    o, gpu = oracle_built.ScbOracle(sinp), host.ScbGpu(sinp)
+    o.bandjacob(); gpu.computeBandJacob()
+    radRaw = 1.75 + (6.75 - 1.75) * np.arange(1, g.NR + 1) / g.NR
+    azimRaw = 24.0 * np.arange(g.NT) / (g.NT - 1)
+    ref = oracle_built.flc_radius(o.x, o.y, o.z, o.Bx, o.By, o.Bz, radRaw, azimRaw, (sinp.nthe + 1) // 2, o.get("bnormal"))
+    for a, b in zip(gpu.FLC_Radius(radRaw, azimRaw), ref):
+        assert np.array_equal(a, b)                      # +, -, *, /, sqrt only: correctly rounded on the device too
+    PPerT, PParT, scb, LZ, PHI = TE._ram_pressures(g)
+    r = o.pressure_raw(PPerT, PParT, scb, LZ, PHI)
+    gpu.set_ram_pressure(PPerT, PParT, scb, LZ, PHI)
+    for a, b in zip(r, gpu.get_ram_pressure()):
+        assert np.array_equal(a, b)
+    pe, pa = o.pressure_front()
+    ge, ga = gpu.pressure_front()
+    assert np.max(np.abs(ge - pe) / pe) <= 1e-13 and np.max(np.abs(ga - pa) / pa) <= 1e-13
+    # scb_run without a host callback: same decisions as the oracle's composition, fields to 1e-10
+    gpu.set_map_targets(sinp.alphaVal, sinp.psiVal, sinp.chiVal)
+    kw = dict(numit=2, MinSCBIterations=2, decreaseConvAlpha=1e-30, decreaseConvPsi=1e-30)
+    ro = o.scb_run(None, **kw)
+    n0 = gpu.launch_count()
+    rg = gpu.scb_run(None, ordering=host.SOR_LEX, **kw)
+    assert ro["SORFail"] == 0 and rg["SORFail"] == 0 and rg["iterations"] == ro["iterations"] == 2
+    assert rg["nisaveAlpha"] == ro["nisaveAlpha"] and rg["nisavePsi"] == ro["nisavePsi"]
+    for n in ("x", "y", "z", "alfa", "psi"):
+        a, b = gpu.get_field(n), getattr(o, n)
+        assert np.max(np.abs(a - b)) <= 1e-10 * np.max(np.abs(b)), n
+    gpu.close()
