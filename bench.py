@@ -513,27 +513,36 @@ def scb_zeta_metrics(device):
 
 def scb_run_metrics(device):
     """configs[3] end to end: scb_run (src/ModScbRun.f90:149-440) with the reference's parameters (InCon 1e-6,
-    MinSCBIterations 11, blend 0.5) on the default SCB grid through ONE rsg_scb_run call; the synthetic
-    pressure front end is the host callback.  Wall clock of the call (it includes the callback and the
-    2-D transfers), 4-colour ordering."""
-    from ramscb_b200 import host, scb_synthetic
+    MinSCBIterations 11, blend 0.5) on the default SCB grid through ONE rsg_scb_run call, 4-colour ordering.  Two variants:
+    `device_front_end` -- `pressure` entirely on the device from synthetic RAM pressures (rsg_scb_set_ram_pressure; no host
+    hop inside the outer iteration) -- and `host_callback` (round 1: the 2-D front end as a host callback, a synthetic
+    analytic pressure).  Wall clock of the call; the second of two runs (warm)."""
+    from ramscb_b200 import grids, host, scb_synthetic
     inp = scb_synthetic.build_scb(nthe=101, npsi=45, nzeta=97, warp=0.2)
     fn = scb_synthetic.equatorial_pressure_fn()
-    out = {}
-    for rep in range(2):                       # the second run is the warm one
-        gpu = host.ScbGpu(inp, device=device)
-        gpu.set_map_targets(inp.alphaVal, inp.psiVal, inp.chiVal)
-        n0 = gpu.launch_count()
-        t0 = time.perf_counter()
-        r = gpu.scb_run(fn, ordering=host.SOR_COLOR4)
-        ms = (time.perf_counter() - t0) * 1e3
-        out = {"wall_ms": ms, "outer_iterations": r["iterations"], "SORFail": r["SORFail"], "iConvGlobal": r["iConvGlobal"],
-               "nisaveAlpha_last": r["nisaveAlpha"], "nisavePsi_last": r["nisavePsi"], "blendRetries": r["blendRetries"],
-               "normDiff_start_end": [r["normDiffStart"], r["normDiff"]], "normJxB_start_end": [r["normJxBStart"], r["normJxB"]],
-               "normGradP_start_end": [r["normGradPStart"], r["normGradP"]], "launches": int(gpu.launch_count() - n0),
-               "ms_per_outer_iteration": ms / max(r["iterations"], 1)}
-        gpu.close()
-    return out
+    g = grids.build_grids()
+    PPerT, PParT, scb, LZ, PHI = scb_synthetic.synthetic_ram_pressures(g)
+    res = {}
+    for name, cb in (("device_front_end", None), ("host_callback", fn)):
+        out = {}
+        for rep in range(2):                       # the second run is the warm one
+            gpu = host.ScbGpu(inp, device=device)
+            gpu.set_map_targets(inp.alphaVal, inp.psiVal, inp.chiVal)
+            if cb is None:
+                gpu.set_ram_pressure(PPerT, PParT, scb, LZ, PHI)
+            n0 = gpu.launch_count()
+            t0 = time.perf_counter()
+            r = gpu.scb_run(cb, ordering=host.SOR_COLOR4)
+            ms = (time.perf_counter() - t0) * 1e3
+            out = {"wall_ms": ms, "outer_iterations": r["iterations"], "SORFail": r["SORFail"], "iConvGlobal": r["iConvGlobal"],
+                   "nisaveAlpha_last": r["nisaveAlpha"], "nisavePsi_last": r["nisavePsi"], "blendRetries": r["blendRetries"],
+                   "normDiff_start_end": [r["normDiffStart"], r["normDiff"]], "normJxB_start_end": [r["normJxBStart"], r["normJxB"]],
+                   "normGradP_start_end": [r["normGradPStart"], r["normGradP"]], "launches": int(gpu.launch_count() - n0),
+                   "ms_per_outer_iteration": ms / max(r["iterations"], 1)}
+            gpu.close()
+        res[name] = out
+    res.update(res["device_front_end"])            # the headline entries = the callback-free run
+    return res
 
 
 def hi_metrics(device):

@@ -371,16 +371,28 @@ static int scb_iterate_part(rsg_scb* h, bool alpha, double tol, int nimax, int t
   bool in_regs = false;     // coefficients in registers: one point per colour per thread (<= 576)
   if (ordering != RSG_SOR_LEX && h->use_cluster && !getenv("RSG_SCB_NO_CLUSTER")) {
     const int nc = nthe - 2 * nT;
-    if (!getenv("RSG_SCB_NO_REGS"))
-      for (int c = 1; c <= 8; c *= 2) {
+    if (!getenv("RSG_SCB_NO_REGS")) {
+      // smallest cluster whose CTAs hold at most one point per colour per thread; 768 threads (85 registers) are allowed
+      // when that lets ALL sub-problems run in one wave of the device's SMs (alpha on the default grid: 43 x 3 CTAs
+      // instead of 43 x 4 = 172 on 148 SMs, i.e. two waves)
+      int sms = 148;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+      const int wide = getenv("RSG_SCB_NO_WIDE") ? 576 : 768;
+      int best = 0;
+      for (int c = 1; c <= 8; ++c) {
         const int nl = (nr + c - 1) / c;
         const int npc = ((nl + 1) / 2) * ((nc + 1) / 2);
-        if (npc <= 576 && nl >= 2) {
-          CL = c; nloc_max = nl; npc_max = npc; in_regs = true;
-          csmem = sizeof(double) * (size_t)(nl + 2) * nthe;
-          break;
-        }
+        if (nl < 2 || npc > wide) continue;
+        const bool one_wave = nsub * c <= sms;
+        if (npc <= 576 && (c & (c - 1)) == 0 && !best) best = c;          // round 1's choice: power of two, 576 threads
+        if (one_wave && (npc <= 576 || wide > 576)) { best = c; break; }   // first (smallest) cluster that fits one wave
       }
+      if (best) {
+        const int nl = (nr + best - 1) / best;
+        CL = best; nloc_max = nl; npc_max = ((nl + 1) / 2) * ((nc + 1) / 2); in_regs = true;
+        csmem = sizeof(double) * (size_t)(nl + 2) * nthe;
+      }
+    }
     for (int c = 1; c <= 8 && !in_regs; c *= 2) {
       const int nl = (nr + c - 1) / c;
       const int npc = ((nl + 1) / 2) * ((nc + 1) / 2);
@@ -405,7 +417,14 @@ static int scb_iterate_part(rsg_scb* h, bool alpha, double tol, int nimax, int t
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    if (in_regs && alpha) {
+    const bool wideT = npc_max > 576;
+    if (in_regs && alpha && wideT) {
+      SCK(cudaFuncSetAttribute(k_scb_sor_cluster_reg<true, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+      SCK(cudaLaunchKernelEx(&cfg, k_scb_sor_cluster_reg<true, 768>, h->dev, a, nloc_max));
+    } else if (in_regs && wideT) {
+      SCK(cudaFuncSetAttribute(k_scb_sor_cluster_reg<false, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+      SCK(cudaLaunchKernelEx(&cfg, k_scb_sor_cluster_reg<false, 768>, h->dev, a, nloc_max));
+    } else if (in_regs && alpha) {
       SCK(cudaFuncSetAttribute(k_scb_sor_cluster_reg<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
       SCK(cudaLaunchKernelEx(&cfg, k_scb_sor_cluster_reg<true>, h->dev, a, nloc_max));
     } else if (in_regs) {

@@ -1095,8 +1095,8 @@ __global__ void __launch_bounds__(1024) k_scb_sor_cluster(ScbDev d, SorArgs a, i
 // coefficient traffic at all, not even from shared memory.  Same arithmetic, colour order,
 // halo pushes and barriers as k_scb_sor_cluster: bit-identical results.
 // =============================================================================
-template <bool ALPHA>
-__global__ void __launch_bounds__(576, 1) k_scb_sor_cluster_reg(ScbDev d, SorArgs a, int nloc_max) {
+template <bool ALPHA, int MAXT = 576>
+__global__ void __launch_bounds__(MAXT, 1) k_scb_sor_cluster_reg(ScbDev d, SorArgs a, int nloc_max) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ double su[];

@@ -252,3 +252,17 @@ def ram_field_lines(LZ, MLT, nthe=101, constTheta=0.2, wiggle=0.0, seed=3, outsi
     outside = np.asfortranarray((rng.random((nR, nT)) < outside_fraction).astype(np.int32))
     return dict(chiVal=chiVal, xRAM=x, yRAM=y, zRAM=z, bRAM=b, density=dens, outsideMGNP=outside,
                 nThetaEquator=nthe // 2 + 1, bnormal=1.0)
+
+
+def synthetic_ram_pressures(g, seed=3):
+    """Synthetic ring-current-like RAM pressures for the device front end of `pressure` (src/ModScbRun.f90:858-875):
+    PPerT, PParT (nS,NR,NT) [keV/cm^3], the species%SCB flags, LZ(NR+1), PHI(NT).  Peak ~ 12 keV/cm^3 near L = 4 with a
+    day-night asymmetry (the magnitudes of output/test1/pressure.ref), anisotropy p_par = 0.7 p_perp, 5 % seeded noise."""
+    rng = np.random.default_rng(seed)
+    LZ, PHI = g.LZ[:g.NR + 1], g.PHI[:g.NT]
+    base = 12.0 * np.exp(-((LZ[:g.NR, None] - 4.0) / 1.2) ** 2) * (1 + 0.3 * np.cos(PHI[None, :]))
+    frac = (1.0, 0.3, 0.1, 0.05)[:g.nS]
+    PPerT = np.asfortranarray(np.stack([base * f * (1 + 0.05 * rng.random(base.shape)) for f in frac]))
+    PParT = np.asfortranarray(0.7 * PPerT * (1 + 0.05 * rng.random(PPerT.shape)))
+    scb = np.array([1, 1, 1, 0][:g.nS], dtype=np.int32)
+    return PPerT, PParT, scb, LZ, PHI

@@ -180,13 +180,8 @@ def test_anisch_diffusion_coefficient_rebuild(emu, use_bas):
 
 
 def _ram_pressures(g):
-    """synthetic ring-current-like RAM pressures PPerT, PParT (nS,NR,NT) [keV/cm^3] and species%SCB flags"""
-    rng = np.random.default_rng(3)
-    LZ, PHI = g.LZ[:g.NR + 1], g.PHI[:g.NT]
-    base = 12.0 * np.exp(-((LZ[:g.NR, None] - 4.0) / 1.2) ** 2) * (1 + 0.3 * np.cos(PHI[None, :]))
-    PPerT = np.asfortranarray(np.stack([base * f * (1 + 0.05 * rng.random(base.shape)) for f in (1.0, 0.3, 0.1, 0.05)]))
-    PParT = np.asfortranarray(0.7 * PPerT * (1 + 0.05 * rng.random(PPerT.shape)))
-    return PPerT, PParT, np.array([1, 1, 1, 0], dtype=np.int32), LZ, PHI
+    from ramscb_b200 import scb_synthetic
+    return scb_synthetic.synthetic_ram_pressures(g)
 
 
 def test_pressure_front_end_on_device(emu):
