@@ -567,3 +567,50 @@ def test_multi_gpu_nccl_exchange():
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "MULTI_GPU_CHECK_OK" in r.stdout
+
+
+def test_concurrent_calls_with_different_species(default_grids, oracle_built):
+    """The ABI's threading contract (include/ramscb_gpu.h; the reference calls these routines from `!$OMP PARALLEL DO` over
+    species, src/ModRamRun.f90:64): four host threads drive the operator sequence of one species each, at the same time,
+    through one handle.  Every species must end bit-identical to the same sequence issued from one thread, and to the oracle
+    (EXACT mode)."""
+    import threading
+    from ramscb_b200.host import RamGpu
+    g = default_grids
+    inp = _mk(g, f2_kind="noisy", inductive=True)
+    seq = ("DRIFTR", "DRIFTP", "DRIFTE", "DRIFTMU", "CHAREXCHANGE", "ATMOL", "ATMOL", "CHAREXCHANGE", "DRIFTMU", "DRIFTE", "DRIFTP", "DRIFTR")
+
+    def species(gpu, S, out):
+        try:
+            for rep in range(3):
+                gpu.CEPARA(S, DTS); gpu.DRIFTPARA(S, DTS)
+                for name in seq:
+                    getattr(gpu, name)(S)
+                out[S] = (gpu.SUMRC(S), gpu.dtdrift(S))
+        except Exception as e:       # surfaces in the main thread
+            out[S] = e
+
+    serial, res_s = RamGpu(g), {}
+    serial.set_inputs(inp)
+    for S in range(1, g.nS + 1):
+        species(serial, S, res_s)
+    F_serial = serial.f2_d2h()
+    par, res_p = RamGpu(g), {}
+    par.set_inputs(inp)
+    ths = [threading.Thread(target=species, args=(par, S, res_p)) for S in range(1, g.nS + 1)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    for S in range(1, g.nS + 1):
+        assert not isinstance(res_p[S], Exception), res_p[S]
+        assert res_p[S][0] == res_s[S][0] and np.array_equal(res_p[S][1], res_s[S][1])
+    assert np.array_equal(par.f2_d2h(), F_serial)
+    o = oracle_built.RamOracle(g, inp, DTs=DTS)
+    for S in range(1, g.nS + 1):
+        for rep in range(3):
+            o.op("cepara", S); o.op("driftpara", S)
+            for name in seq:
+                o.op(name.lower(), S)
+    assert _relerr(F_serial, o.F2) <= 1e-12
+    serial.close(); par.close()
