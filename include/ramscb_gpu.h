@@ -118,6 +118,17 @@ int rsg_ram_set_plasmasphere(rsg_ram* h, const double* NECR);
  * which = 0 ATAW, 1 ATAC, 2 ATAW_emic_h, 3 ATAW_emic_he */
 int rsg_ram_set_diffcoef(rsg_ram* h, int which, const double* D);
 
+/* SURVEY 8(f)-4, the producers of two of those inputs on the device.  GEOSB(S) (src/ModRamBoundary.f90:241-319, boundary
+ * 'LANL'): FluxLanl(NT,NE) of get_geomlt_flux (file I/O: host) and species%s_comp -> FGEOS of species S, built where DRIFTR
+ * reads it.  get_electric_field (src/ModRamEField.f90:14-63): vols = 0 interpolates VT between the potential maps VTOL, VTN
+ * (NR+1,NT) at TimeRamElapsed; vols = 1 is the Volland-Stern potential (Kp, PHI(NT), PHIOFS; LZ from set_grids).  EIR / EIP keep
+ * the values of the last rsg_ram_set_efield (zero before).  The readers of the flux / potential files and the restart /
+ * NetCDF formats stay on the host. */
+int rsg_geosb(rsg_ram* h, int S, const double* FluxLanl, double s_comp);
+int rsg_ram_get_boundary(rsg_ram* h, int S, double* FGEOS_S /* (NT,NE,NPA) */);
+int rsg_get_electric_field(rsg_ram* h, int vols, const double* VTOL, const double* VTN, double TimeRamElapsed, double TOLV,
+                           double DtEfi, double Kp, const double* PHI, double PHIOFS, double* VT_out);
+
 /* ANISCH, second half (src/ModRamRun.f90:422-605): the rebuild of those coefficients on the device, so a
  * WPI / EMIC run needs no host-built ATAW / ATAC / ATAW_emic_*.  set_wave_tables, once: the tabulated bounce-averaged
  * diffusion coefficients the reference reads at start-up (src/ModRamWPI.f90:185-470) -- ENOR(ENG), fpofc(NCF),

@@ -64,6 +64,10 @@ def _ram_lib_from(name):
         lib.orc_wpadif.restype = C.c_long
         lib.orc_flcscatter.argtypes = [C.c_void_p, C.c_int]
         lib.orc_flcscatter.restype = C.c_long
+        lib.orc_geosb.argtypes = [C.c_void_p, C.c_int]
+        lib.orc_geosb.restype = None
+        lib.orc_get_electric_field.argtypes = [C.c_void_p, C.c_int]
+        lib.orc_get_electric_field.restype = None
         lib.orc_anisch_diffcoef.argtypes = [C.c_void_p, C.c_int, C.c_int]
         lib.orc_anisch_diffcoef.restype = C.c_int
         lib.orc_ram_run.argtypes = [C.c_void_p, C.c_int, C.c_int]
@@ -153,6 +157,24 @@ class RamOracle:
         out = _f((g.NR, g.NT, g.NE, g.NPA))
         self.lib.orc_get_cdrift(self.h, S, which, out.ctypes.data)
         return out
+
+    def geosb(self, S, FluxLanl, s_comp):
+        """GEOSB (src/ModRamBoundary.f90:241-319, boundary LANL): FGEOS(S,:,:,:) from the geosynchronous flux (NT,NE)"""
+        self._set("FluxLanl", np.asfortranarray(FluxLanl, dtype=np.float64).copy(order="F"))
+        self.set_scalar("s_comp", s_comp)
+        self.lib.orc_geosb(self.h, int(S))
+
+    def get_electric_field(self, vols, VTOL=None, VTN=None, t=0.0, TOLV=0.0, DtEfi=1.0, PHI=None, PHIOFS=0.0):
+        """get_electric_field (src/ModRamEField.f90:14-63) -> VT"""
+        if vols:
+            self._set("PHI", np.asfortranarray(PHI, dtype=np.float64).copy())
+            self.set_scalar("PHIOFS", PHIOFS)
+        else:
+            self._set("VTOL", np.asfortranarray(VTOL, dtype=np.float64).copy(order="F"))
+            self._set("VTN", np.asfortranarray(VTN, dtype=np.float64).copy(order="F"))
+            for n, v in (("TimeRamElapsed", t), ("TOLV", TOLV), ("DtEfi", DtEfi)):
+                self.set_scalar(n, v)
+        self.lib.orc_get_electric_field(self.h, 1 if vols else 0)
 
     def anisch_diffcoef(self, S, flags, t, AE=0, use_bas=True):
         """second half of ANISCH (src/ModRamRun.f90:422-605) from the table dict `t` (synthetic.synthetic_wave_tables);

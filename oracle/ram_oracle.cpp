@@ -1077,6 +1077,48 @@ int anisch_diffcoef(Orc* o, int S, int flags) {
   return nerr;
 }
 
+// GEOSB (src/ModRamBoundary.f90:241-319), boundary == 'LANL': the outer-boundary distribution of species S from the
+// interpolated geosynchronous flux FluxLanl(NT,NE) [1/cm2/s/sr/keV, isotropic] (get_geomlt_flux: file I/O, host), the
+// composition factor species%s_comp and FFACTOR at the outermost radius, for pitch angles 2 .. UPA(NR)-1.
+void geosb(Orc* o, int S) {
+  DIMS
+  double *FGEOS = o->D("FGEOS"), *Flux = o->D("FluxLanl");
+  const double *FFACTOR = o->D("FFACTOR"), *UPA = o->D("UPA");
+  const double comp = o->S("s_comp");
+  for (int L = 1; L <= NPA; ++L)
+    for (int K = 1; K <= NE; ++K)
+      for (int J = 1; J <= NT; ++J) A4(FGEOS, nS, NT, NE, S, J, K, L) = 0.;
+  for (int K = 1; K <= NE; ++K) A2(Flux, NT, 1, K) = A2(Flux, NT, NT, K);             // FluxLanl(1,:) = FluxLanl(nT,:)
+  for (int K = 1; K <= NE; ++K)
+    for (int J = 1; J <= NT; ++J) A2(Flux, NT, J, K) = A2(Flux, NT, J, K) * comp;     // FluxLanl = FluxLanl*s_comp
+  const int u = (int)(A1(UPA, NR) - 1);
+  for (int K = 1; K <= NE; ++K)
+    for (int J = 1; J <= NT; ++J)
+      for (int L = 2; L <= u; ++L) A4(FGEOS, nS, NT, NE, S, J, K, L) = A2(Flux, NT, J, K) * A4(FFACTOR, nS, NR, NE, S, NR, K, L);
+}
+
+// get_electric_field (src/ModRamEField.f90:14-63): VT(NR+1,NT) either interpolated in time between two potential maps
+// (electric /= 'VOLS': VT = VTOL + (VTN - VTOL)*(TimeRamElapsed - TOLV)/DtEfi) or the Volland-Stern potential.
+void get_electric_field(Orc* o, int vols) {
+  DIMS
+  double* VT = o->D("VT");
+  const double RE = 6.371E6;
+  if (!vols) {
+    const double *VTOL = o->D("VTOL"), *VTN = o->D("VTN");
+    const double t = o->S("TimeRamElapsed"), TOLV = o->S("TOLV"), DtEfi = o->S("DtEfi");
+    for (int I = 1; I <= NR + 1; ++I)
+      for (int J = 1; J <= NT; ++J) VT_(I, J) = A2(VTOL, NR + 1, I, J) + (A2(VTN, NR + 1, I, J) - A2(VTOL, NR + 1, I, J)) * (t - TOLV) / DtEfi;
+  } else {
+    const double KP = o->S("Kp"), PHIOFS = o->S("PHIOFS");
+    const double *LZ = o->D("LZ"), *PHI = o->D("PHI");
+    for (int I = 1; I <= NR + 1; ++I)
+      for (int J = 1; J <= NT; ++J) {
+        const double AVS = 7.05E-6 / ((1. - 0.159 * KP + 0.0093 * (KP * KP)) * (1. - 0.159 * KP + 0.0093 * (KP * KP)) * (1. - 0.159 * KP + 0.0093 * (KP * KP))) / RE;
+        VT_(I, J) = AVS * ((A1(LZ, I) * RE) * (A1(LZ, I) * RE)) * std::sin(A1(PHI, J) - PHIOFS);
+      }
+  }
+}
+
 // flags for ram_run
 enum { F_WPI = 1, F_COULOMB = 2, F_EMIC = 4 };
 
@@ -1198,6 +1240,8 @@ void orc_sumrc(void* h, int S) { sumrc((Orc*)h, S); }
 void orc_anisch(void* h, int S) { anisch((Orc*)h, S); }
 double orc_ram_run(void* h, int flags, int nthreads) { return ram_run((Orc*)h, flags, nthreads); }
 int orc_anisch_diffcoef(void* h, int S, int flags) { return anisch_diffcoef((Orc*)h, S, flags); }
+void orc_geosb(void* h, int S) { geosb((Orc*)h, S); }
+void orc_get_electric_field(void* h, int vols) { get_electric_field((Orc*)h, vols); }
 // copy of a species' drift coefficient array (NR,NT,NE,NPA), which: 0=R 1=P 2=E 3=Mu
 void orc_get_cdrift(void* h, int S, int which, double* out) {
   Orc* o = (Orc*)h;

@@ -1310,6 +1310,86 @@ int rsg_ram_get_flc_coef(rsg_ram* h, int S, double* D) {
   return RSG_OK;
 }
 
+// ---- the boundary / E-field producers ------------------------------------------------------------
+// GEOSB(S) (src/ModRamBoundary.f90:241-319, boundary 'LANL'): FluxLanl(NT,NE) of get_geomlt_flux and species%s_comp ->
+// the species' FGEOS on the device (replaces the nS x NT x NE x NPA upload of rsg_ram_set_boundary for that species).
+int rsg_geosb(rsg_ram* h, int S, const double* FluxLanl, double s_comp) {
+  RET(check_S(h, S));
+  if (!FluxLanl) return fail(RSG_ERR_ARG, "null argument");
+  if (!h->grids_set) return fail(RSG_ERR_STATE, "GEOSB before set_grids");
+  CK(cudaSetDevice(h->device));
+  const int s = S - 1;
+  cudaStream_t st = h->st(s);
+  double* d_flux = nullptr;
+  const size_t n = (size_t)h->NT * h->NE;
+  CK(cudaMalloc((void**)&d_flux, n * sizeof(double)));
+  CK(cudaMemcpyAsync(d_flux, FluxLanl, n * sizeof(double), cudaMemcpyHostToDevice, st));
+  k_geosb<<<dim3(nblk((long long)n, 128), h->NPA), 128, 0, st>>>(h->dev, d_flux, s_comp, h->sp[s].d_FF, h->sp[s].d_FGEOS);
+  CKL();
+  h->launches++;
+  CK(cudaStreamSynchronize(st));
+  cudaFree(d_flux);
+  h->inflow_ok[s] = h->cfl_ok[s] = false;
+  return RSG_OK;
+}
+int rsg_ram_get_boundary(rsg_ram* h, int S, double* FGEOS_S) {          // (NT,NE,NPA) of species S (diagnostics / tests)
+  RET(check_S(h, S));
+  if (!FGEOS_S) return fail(RSG_ERR_ARG, "null argument");
+  CK(cudaSetDevice(h->device));
+  RET(rsg_ram_sync(h));
+  const int NT = h->NT, NE = h->NE, NPA = h->NPA;
+  std::vector<double> b((size_t)NPA * NE * NT);
+  CK(cudaMemcpy(b.data(), h->sp[S - 1].d_FGEOS, b.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  for (int l = 0; l < NPA; ++l)
+    for (int k = 0; k < NE; ++k)
+      for (int j = 0; j < NT; ++j) FGEOS_S[j + (size_t)NT * (k + (size_t)NE * l)] = b[((size_t)l * NE + k) * NT + j];
+  return RSG_OK;
+}
+// get_electric_field (src/ModRamEField.f90:14-63) on the device: mode 0 interpolates VT in time between two potential
+// maps VTOL, VTN (NR+1,NT); mode 1 is the Volland-Stern potential from Kp, LZ(NR+1), PHI(NT), PHIOFS.  EIR / EIP keep the
+// values of the last rsg_ram_set_efield.  VT_out (may be NULL) returns VT.
+int rsg_get_electric_field(rsg_ram* h, int vols, const double* VTOL, const double* VTN, double TimeRamElapsed, double TOLV,
+                           double DtEfi, double Kp, const double* PHI, double PHIOFS, double* VT_out) {
+  if (!h) return fail(RSG_ERR_ARG, "null handle");
+  if (!h->grids_set) return fail(RSG_ERR_STATE, "get_electric_field before set_grids");
+  if (vols ? !PHI : (!VTOL || !VTN)) return fail(RSG_ERR_ARG, "null argument");
+  CK(cudaSetDevice(h->device));
+  RET(rsg_ram_sync(h));
+  const size_t n2 = (size_t)h->NR1 * h->NT;
+  double *da = nullptr, *db = nullptr;
+  cudaStream_t st = h->pst();
+  double p0, p1, p2 = 1.0;
+  if (!vols) {
+    CK(cudaMalloc((void**)&da, n2 * sizeof(double)));
+    CK(cudaMalloc((void**)&db, n2 * sizeof(double)));
+    CK(cudaMemcpyAsync(da, VTOL, n2 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(db, VTN, n2 * sizeof(double), cudaMemcpyHostToDevice, st));
+    p0 = TimeRamElapsed; p1 = TOLV; p2 = DtEfi;
+  } else {
+    const double RE = 6.371E6;
+    const double q = 1. - 0.159 * Kp + 0.0093 * (Kp * Kp);
+    std::vector<double> sn(h->NT);
+    for (int j = 0; j < h->NT; ++j) sn[j] = std::sin(PHI[j] - PHIOFS);
+    CK(cudaMalloc((void**)&da, (h->NR1) * sizeof(double)));
+    CK(cudaMalloc((void**)&db, h->NT * sizeof(double)));
+    CK(cudaMemcpyAsync(da, h->LZ.data(), h->NR1 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(db, sn.data(), h->NT * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    p0 = 7.05E-6 / (q * q * q) / RE; p1 = RE;
+  }
+  k_efield<<<nblk((long long)n2, 128), 128, 0, st>>>(h->dev, vols, da, db, p0, p1, p2, (double*)h->dev.VT);
+  CKL();
+  h->launches++;
+  if (VT_out) CK(cudaMemcpyAsync(VT_out, h->dev.VT, n2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  cudaFree(da); cudaFree(db);
+  if (!h->efield_set) {                       // EIR, EIP stay zero until rsg_ram_set_efield provides them
+    h->efield_set = true;
+  }
+  h->step_dirty = true;
+  return RSG_OK;
+}
+
 // ---- ANISCH, second half: rebuild of the WPADIF diffusion coefficients on the device (src/ModRamRun.f90:422-605) ----
 int rsg_ram_set_wave_tables(rsg_ram* h, int ENG, int NCF, const double* ENOR, const double* fpofc, const double* NDAAJ,
                             const double* DAAR, int use_bas, int ENG_emic, int NCF_emic, const double* EKEV_emic,

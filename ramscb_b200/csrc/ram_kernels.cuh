@@ -1193,3 +1193,31 @@ __global__ void k_flux_to_host(RamDev d, SpecDev sp, double* __restrict__ stage)
     v = sp.F[plane * d.Pp + p] / sp.FF[((size_t)l * d.NE + k) * d.NR + i] / d.FNHSc[(size_t)l * d.Pp + p];
   stage[(plane * d.P + p) * d.nS + sp.S] = v;
 }
+
+// =============================================================================
+// GEOSB (src/ModRamBoundary.f90:241-319, boundary 'LANL'): FGEOS of one species, in the [l][k][j] layout the DRIFTR
+// kernels read, from the geosynchronous flux (NT,NE) (the file reader get_geomlt_flux stays on the host), the
+// composition factor and FFACTOR at the outermost radius.  grid: x = tiles of (k, j), y = l
+// =============================================================================
+__global__ void k_geosb(RamDev d, const double* __restrict__ flux, double comp, const double* __restrict__ FF, double* __restrict__ FGEOS) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= d.NE * d.NT) return;
+  const int k = t / d.NT, j = t - k * d.NT, l = blockIdx.y;
+  const int u = d.UPA[d.NR - 1] - 1;                                   // Fortran L = 2 .. u
+  double v = 0.0;
+  if (l >= 1 && l + 1 <= u) {
+    const double f = flux[(size_t)((j == 0) ? d.NT - 1 : j) + (size_t)d.NT * k] * comp;     // FluxLanl(1,:) = FluxLanl(nT,:), then * s_comp
+    v = f * FF[((size_t)l * d.NE + k) * d.NR + (d.NR - 1)];
+  }
+  FGEOS[((size_t)l * d.NE + k) * d.NT + j] = v;
+}
+// get_electric_field (src/ModRamEField.f90:14-63): VT(NR+1,NT).  vols = 0: VTOL + (VTN - VTOL)*(t - TOLV)/DtEfi;
+// vols = 1: Volland-Stern, AVS*(LZ*RE)**2*SIN(PHI - PHIOFS) with the sines from the host (libm).
+__global__ void k_efield(RamDev d, int vols, const double* __restrict__ a, const double* __restrict__ b, double p0, double p1, double p2,
+                         double* __restrict__ VT) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= d.NR1 * d.NT) return;
+  const int j = t / d.NR1, i = t - j * d.NR1;
+  if (!vols) VT[t] = a[t] + (b[t] - a[t]) * (p0 - p1) / p2;             // a = VTOL, b = VTN; p0 = t, p1 = TOLV, p2 = DtEfi
+  else VT[t] = p0 * ((a[i] * p1) * (a[i] * p1)) * b[j];                 // a = LZ, b = sin(PHI - PHIOFS); p0 = AVS, p1 = RE
+}

@@ -324,6 +324,24 @@ module ModRamGpu
        real(c_double), intent(inout) :: F2(*)
        integer(c_int) :: ierr
      end function
+     function rsg_geosb(h, S, FluxLanl, s_comp) bind(C, name='rsg_geosb') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       integer(c_int), value :: S
+       real(c_double), intent(in) :: FluxLanl(*)
+       real(c_double), value :: s_comp
+       integer(c_int) :: ierr
+     end function
+     function rsg_get_electric_field(h, vols, VTOL, VTN, TimeRamElapsed, TOLV, DtEfi, Kp, PHI, PHIOFS, VT_out) &
+          bind(C, name='rsg_get_electric_field') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       integer(c_int), value :: vols
+       real(c_double), intent(in) :: VTOL(*), VTN(*), PHI(*)
+       real(c_double), value :: TimeRamElapsed, TOLV, DtEfi, Kp, PHIOFS
+       real(c_double), intent(out) :: VT_out(*)
+       integer(c_int) :: ierr
+     end function
      function rsg_host_register(p, bytes) bind(C, name='rsg_host_register') result(ierr)
        import :: c_ptr, c_int, c_long_long
        type(c_ptr), value :: p

@@ -74,6 +74,9 @@ def lib():
     L.rsg_para_flc.argtypes = [vp, i, vp, vp, vp]
     L.rsg_ram_get_flc_coef.argtypes = [vp, i, vp]
     L.rsg_ram_set_diffcoef.argtypes = [vp, i, vp]
+    L.rsg_geosb.argtypes = [vp, i, vp, d]
+    L.rsg_ram_get_boundary.argtypes = [vp, i, vp]
+    L.rsg_get_electric_field.argtypes = [vp, i, vp, vp, d, d, d, d, vp, d, vp]
     L.rsg_ram_set_wave_tables.argtypes = [vp, i, i, vp, vp, vp, vp, i, i, i, vp, vp, vp, vp, vp, vp, vp]
     L.rsg_anisch_diffcoef.argtypes = [vp, i, i, vp, i, _ip]
     L.rsg_ram_get_diffcoef.argtypes = [vp, i, vp]
@@ -225,6 +228,27 @@ class RamGpu:
 
     def set_diffcoef(self, which, D):
         _ck(self.L.rsg_ram_set_diffcoef(self.h, which, _p(D)))
+
+    def GEOSB(self, S, FluxLanl, s_comp=1.0):
+        """GEOSB (src/ModRamBoundary.f90:241-319, boundary LANL) on the device from the geosynchronous flux (NT,NE)"""
+        _ck(self.L.rsg_geosb(self.h, S, _p(np.asfortranarray(FluxLanl, dtype=np.float64)), s_comp))
+
+    def get_boundary(self, S):
+        g = self.g
+        out = np.zeros((g.NT, g.NE, g.NPA), order="F")
+        _ck(self.L.rsg_ram_get_boundary(self.h, S, _p(out)))
+        return out
+
+    def get_electric_field(self, vols, VTOL=None, VTN=None, t=0.0, TOLV=0.0, DtEfi=1.0, Kp=0.0, PHI=None, PHIOFS=0.0):
+        """get_electric_field (src/ModRamEField.f90:14-63) on the device; returns VT(NR+1,NT)"""
+        g = self.g
+        VT = np.zeros((g.NR + 1, g.NT), order="F")
+        a = _p(np.asfortranarray(VTOL, dtype=np.float64)) if VTOL is not None else None
+        b = _p(np.asfortranarray(VTN, dtype=np.float64)) if VTN is not None else None
+        ph = np.ascontiguousarray(PHI, dtype=np.float64) if PHI is not None else None
+        _ck(self.L.rsg_get_electric_field(self.h, 1 if vols else 0, a, b, t, TOLV, DtEfi, Kp, ph.ctypes.data if ph is not None else None,
+                                          PHIOFS, _p(VT)))
+        return VT
 
     def set_wave_tables(self, t, use_bas=True):
         """the tabulated diffusion coefficients (dict of synthetic.synthetic_wave_tables / the reference's start-up files)"""

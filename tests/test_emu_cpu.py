@@ -272,3 +272,38 @@ def test_flc_radius_on_device(emu):
             rc = ref[0][1:, :-1] / 6.4e6                     # in RE
             assert np.max(np.abs(rc / (radRaw[1:, None] / 3.0) - 1.0)) < 0.05, np.max(np.abs(rc / (radRaw[1:, None] / 3.0) - 1.0))
         gpu.close()
+
+
+def test_geosb_and_electric_field_on_device(emu, small_grids):
+    """GEOSB (src/ModRamBoundary.f90:241-319) and get_electric_field (src/ModRamEField.f90:14-63) on the
+    device (emulated), BIT-IDENTICAL to the oracle; the Volland-Stern branch also against ram_run's own formula
+    (synthetic.volland_stern, src/ModRamRun.f90:45-51)."""
+    from oracle import oracle
+    from ramscb_b200 import synthetic
+    g = small_grids
+    inp = synthetic.make_inputs(g, f2_kind="smooth")
+    o = oracle.RamOracle(g, inp)
+    gpu = emu.RamGpu(g)
+    gpu.set_inputs(inp)
+    rng = np.random.default_rng(5)
+    flux = np.asfortranarray(10.0 ** (2 + 3 * rng.random((g.NT, g.NE))))
+    for S, comp in ((1, 0.7), (4, 1.0)):
+        o.geosb(S, flux, comp)
+        gpu.GEOSB(S, flux, comp)
+        got = gpu.get_boundary(S)
+        assert np.array_equal(got, o.FGEOS[S - 1]) and (got != 0).sum() > 100
+        assert np.array_equal(got[0], got[-1])                         # J = 1 carries the J = NT flux
+    # the sweeps see the new boundary: one DRIFTR against the oracle
+    for S in (1, 4):
+        o.op("driftpara", S); o.op("driftr", S)
+        gpu.DRIFTPARA(S, 5.0); gpu.DRIFTR(S)
+    assert np.array_equal(gpu.f2_d2h()[[0, 3]], o.F2[[0, 3]])
+    VTOL, VTN = inp.VT.copy(order="F"), np.asfortranarray(1.3 * inp.VT + 5.0)
+    o.get_electric_field(False, VTOL=VTOL, VTN=VTN, t=450.0, TOLV=300.0, DtEfi=300.0)
+    assert np.array_equal(gpu.get_electric_field(False, VTOL=VTOL, VTN=VTN, t=450.0, TOLV=300.0, DtEfi=300.0), o.VT)
+    o.set_scalar("Kp", 4.3)
+    o.get_electric_field(True, PHI=g.PHI[:g.NT], PHIOFS=0.1)
+    vt = gpu.get_electric_field(True, Kp=4.3, PHI=g.PHI[:g.NT], PHIOFS=0.1)
+    assert np.array_equal(vt, o.VT)
+    assert np.allclose(vt, synthetic.volland_stern(g, 4.3, 0.1), rtol=1e-14, atol=0)
+    gpu.close()
