@@ -718,15 +718,32 @@ static int scb_map(rsg_scb* h, int mode, int* sorfail) {
   const int nthe = h->nthe, npsi = h->npsi, nzeta = h->nzeta;
   SCK(cudaMemsetAsync(h->d_fail, 0, sizeof(int), h->st));
   SCK(cudaEventRecord(h->e0, h->st));
+  constexpr int LPB = 8;                                    // lines per CTA (8 warps): 64-byte runs of the tile loads
+  const bool serial = getenv("RSG_SCB_MAP_SERIAL") != nullptr;   // round 1's thread-per-line kernel (A/B)
   if (mode == 0) {
     const int nl = nthe * npsi;
-    k_scb_map<0><<<nblk(nl, 64), 64, 0, h->st>>>(h->dev, h->d_alphaVal, h->d_mapw, nl, h->d_fail);
+    const size_t sm = sizeof(double) * LPB * 7 * (size_t)(nzeta + 1);
+    if (serial) k_scb_map<0><<<nblk(nl, 64), 64, 0, h->st>>>(h->dev, h->d_alphaVal, h->d_mapw, nl, h->d_fail);
+    else {
+      if (sm > 48 * 1024) SCK(cudaFuncSetAttribute(k_scb_map_w<0, LPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      k_scb_map_w<0, LPB><<<nblk(nl, LPB), 32 * LPB, sm, h->st>>>(h->dev, h->d_alphaVal, nl, h->d_fail);
+    }
   } else if (mode == 1) {
     const int nl = nthe * (nzeta - 1);
-    k_scb_map<1><<<nblk(nl, 64), 64, 0, h->st>>>(h->dev, h->d_psiVal, h->d_mapw, nl, h->d_fail);
+    const size_t sm = sizeof(double) * LPB * 7 * (size_t)npsi;
+    if (serial) k_scb_map<1><<<nblk(nl, 64), 64, 0, h->st>>>(h->dev, h->d_psiVal, h->d_mapw, nl, h->d_fail);
+    else {
+      if (sm > 48 * 1024) SCK(cudaFuncSetAttribute(k_scb_map_w<1, LPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      k_scb_map_w<1, LPB><<<nblk(nl, LPB), 32 * LPB, sm, h->st>>>(h->dev, h->d_psiVal, nl, h->d_fail);
+    }
   } else {
     const int nl = npsi * (nzeta - 1);
-    k_scb_map<2><<<nblk(nl, 64), 64, 0, h->st>>>(h->dev, h->d_chiVal, h->d_mapw, nl, h->d_fail);
+    const size_t sm = sizeof(double) * LPB * 7 * (size_t)nthe;
+    if (serial) k_scb_map<2><<<nblk(nl, 64), 64, 0, h->st>>>(h->dev, h->d_chiVal, h->d_mapw, nl, h->d_fail);
+    else {
+      if (sm > 48 * 1024) SCK(cudaFuncSetAttribute(k_scb_map_w<2, LPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      k_scb_map_w<2, LPB><<<nblk(nl, LPB), 32 * LPB, sm, h->st>>>(h->dev, h->d_chiVal, nl, h->d_fail);
+    }
   }
   SCKL();
   h->launches++;

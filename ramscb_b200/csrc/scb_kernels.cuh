@@ -1224,3 +1224,177 @@ __global__ void __launch_bounds__(MAXT, 1) k_scb_sor_cluster_reg(ScbDev d, SorAr
   }
   cluster.sync();
 }
+
+
+// =============================================================================
+// k_scb_map_w<MODE>: the same re-gridding maps as k_scb_map (mapAlpha 0, mapPsi 1, mapTheta 2), one WARP per grid line
+// with the line in shared memory.  k_scb_map walks a line with one thread through a global workspace -- ~100 dependent
+// global round trips per line and only a few thousand threads on the device: it was 26 % of scb_run (ncu launch list,
+// profiles/r2).  Here the CTA loads LPB lines as one coalesced tile, lane 0 of each warp does the two inherently serial
+// prefixes (arc length, monotonicity filter) in shared memory, and the Steffen slopes and the evaluation at the target
+// node values run one point per lane.  Per point the arithmetic is k_scb_map's, operation for operation: bit-identical.
+// block = 32 * LPB threads; dynamic shared memory: LPB * 7 * nmax doubles.  grid: x = ceil(nlines / LPB)
+// =============================================================================
+template <int MODE, int LPB>
+__global__ void __launch_bounds__(32 * LPB) k_scb_map_w(ScbDev d, const double* __restrict__ tgt, int nlines, int* __restrict__ fail) {
+  extern __shared__ double mw_sm[];
+  __shared__ int s_n1[LPB];
+  __shared__ double s_tot[LPB];
+  const int nthe = d.nthe, npsi = d.npsi, nzeta = d.nzeta;
+  const size_t sj = nthe, sk = (size_t)nthe * npsi;
+  const int n = (MODE == 0) ? nzeta + 1 : ((MODE == 1) ? npsi : nthe);
+  const int n2 = (MODE == 0) ? nzeta - 1 : n, o0 = (MODE == 0) ? 1 : 0;
+  const size_t st = (MODE == 0) ? sk : ((MODE == 1) ? sj : 1);
+  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, w = tid >> 5;
+  const int line0 = blockIdx.x * LPB;
+  const int nl = min(LPB, nlines - line0);
+  auto line_base = [&](int line, int* kpl) -> size_t {
+    if (MODE == 0) { *kpl = 0; return (size_t)line; }
+    if (MODE == 1) { const int i = line % nthe; *kpl = 1 + line / nthe; return (size_t)i + sk * (*kpl); }
+    const int j = line % npsi; *kpl = 1 + line / npsi; return sj * j + sk * (*kpl);
+  };
+  double* L = mw_sm;                                          // [line][7][n]: x-abscissa, f[3], yp[3]
+  auto arr = [&](int lw, int a) -> double* { return L + ((size_t)lw * 7 + a) * n; };
+  double* xyz[3] = {d.x, d.y, d.z};
+  const double* absc = (MODE == 0) ? d.alfa : d.psi;
+  // ---- load the tile: lines are adjacent along the fastest index for MODE 0 / 1, contiguous themselves for MODE 2
+  for (int e = tid; e < nl * n; e += T) {
+    int lw, q;
+    if (MODE == 2) { lw = e / n; q = e - lw * n; } else { q = e / nl; lw = e - q * nl; }
+    int kpl;
+    const size_t o = line_base(line0 + lw, &kpl) + (size_t)q * st;
+    arr(lw, 1)[q] = d.x[o]; arr(lw, 2)[q] = d.y[o]; arr(lw, 3)[q] = d.z[o];
+    if (MODE != 2) arr(lw, 0)[q] = absc[o];
+  }
+  __syncthreads();
+  const bool have = w < nl;
+  // ---- serial prefixes, lane 0 of the line's warp
+  if (have && lane == 0) {
+    double* Wx = arr(w, 0);
+    double *f0 = arr(w, 1), *f1 = arr(w, 2), *f2 = arr(w, 3);
+    double total = 0.0;
+    if (MODE == 2) {                                          // arc length along the line (src/ModScbEuler.f90:43-46)
+      double dist = 0.0;
+      Wx[0] = 0.0;
+      for (int q = 1; q < n; ++q) {
+        dist = dist + sqrt(sq(f0[q] - f0[q - 1]) + sq(f1[q] - f1[q - 1]) + sq(f2[q] - f2[q - 1]));
+        Wx[q] = dist;
+      }
+      total = dist;
+    }
+    int n1 = 0;                                               // drop abscissae that do not increase (src/ModRamGSL.f90:262-273)
+    double last = 0.0;
+    for (int q = 0; q < n; ++q) {
+      const double xv = (MODE == 2) ? Wx[q] / total * 3.141592653589793238462643383279502884197 : Wx[q];
+      if (q == 0 || xv > last) {
+        Wx[n1] = xv; f0[n1] = f0[q]; f1[n1] = f1[q]; f2[n1] = f2[q];
+        last = xv;
+        ++n1;
+      }
+    }
+    s_n1[w] = n1;
+    s_tot[w] = total;
+    if (n1 < 3) atomicAdd(fail, 1);                           // GSLerr > 0 => SORFail
+  }
+  __syncthreads();
+  const int n1 = have ? s_n1[w] : 0;
+  const bool ok = have && n1 >= 3;
+  // ---- Steffen node slopes (gsl interpolation/steffen.c, steffen_init), a node per lane
+  if (ok) {
+    const double* Wx = arr(w, 0);
+    for (int i = lane; i < n1; i += 32) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const double* fa = arr(w, 1 + c);
+        double v;
+        if (i == 0) v = (fa[1] - fa[0]) / (Wx[1] - Wx[0]);
+        else if (i == n1 - 1) v = (fa[n1 - 1] - fa[n1 - 2]) / (Wx[n1 - 1] - Wx[n1 - 2]);
+        else {
+          const double hi = Wx[i + 1] - Wx[i];
+          const double him1 = Wx[i] - Wx[i - 1];
+          const double si = (fa[i + 1] - fa[i]) / hi;
+          const double sim1 = (fa[i] - fa[i - 1]) / him1;
+          const double pi = (sim1 * hi + si * him1) / (him1 + hi);
+          const double m1 = fabs(si) < 0.5 * fabs(pi) ? fabs(si) : 0.5 * fabs(pi);
+          const double m2 = fabs(sim1) < m1 ? fabs(sim1) : m1;
+          v = (steffen_sgn(sim1) + steffen_sgn(si)) * m2;
+        }
+        arr(w, 4 + c)[i] = v;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- evaluate at the prescribed node values, a target per lane; results straight to global memory
+  int kpl = 0;
+  const size_t base = have ? line_base(line0 + w, &kpl) : 0;
+  bool bad = false;
+  if (ok) {
+    const double* Wx = arr(w, 0);
+    const double xa0 = Wx[0], xa1 = Wx[1], xaN = Wx[n1 - 1], xaM = Wx[n1 - 2];
+    for (int q = lane; q < n2; q += 32) {
+      const double xb = tgt[(MODE == 0) ? q + 1 : q];
+      const size_t o = base + (size_t)(o0 + q) * st;
+      if (xb <= xa0) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { const double* Wf = arr(w, 1 + c); xyz[c][o] = Wf[0] + (xb - xa0) / (xa1 - xa0) * (Wf[1] - Wf[0]); }
+      } else if (xb >= xaN) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { const double* Wf = arr(w, 1 + c); xyz[c][o] = Wf[n1 - 1] + (xb - xaN) / (xaM - xaN) * (Wf[n1 - 2] - Wf[n1 - 1]); }
+      } else if (xb == xb) {
+        int ilo = 0, ihi = n1 - 1;
+        while (ihi > ilo + 1) {                              // gsl_interp_bsearch
+          const int i = (ihi + ilo) / 2;
+          if (Wx[i] > xb) ihi = i; else ilo = i;
+        }
+        const double xl = Wx[ilo];
+        const double hi = Wx[ilo + 1] - xl;
+        const double delx = xb - xl;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const double* Wf = arr(w, 1 + c);
+          const double* Wp = arr(w, 4 + c);
+          const double f0 = Wf[ilo];
+          const double si = (Wf[ilo + 1] - f0) / hi;
+          const double y0 = Wp[ilo], y1 = Wp[ilo + 1];
+          const double a = (y0 + y1 - 2 * si) / hi / hi;
+          const double b = (3 * si - 2 * y0 - y1) / hi;
+          xyz[c][o] = f0 + delx * (y0 + delx * (b + delx * a));
+        }
+      } else {
+        bad = true;
+      }
+    }
+  }
+  {
+    int b = bad ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) b |= __shfl_xor_sync(0xffffffffu, b, o);
+    bad = b != 0;
+  }
+  if (bad && lane == 0) atomicAdd(fail, 1);
+  __syncwarp();                                               // orders this warp's global writes before the copies below
+  // ---- periodic planes (zeta = 1 <- nzeta, nzeta+1 <- 2) and the reset of the potential; a line that failed keeps its points
+  if (ok && !bad) {
+    if (MODE == 0) {
+      if (lane < 3) {
+        double* a = xyz[lane];
+        a[base] = a[base + (size_t)(nzeta - 1) * st];
+        a[base + (size_t)nzeta * st] = a[base + st];
+      }
+      for (int k = lane; k <= nzeta; k += 32) d.alfa[base + (size_t)k * st] = tgt[k];          // alfges
+    } else {
+      const long long shift = (kpl == nzeta - 1) ? -(long long)sk * (nzeta - 1) : ((kpl == 1) ? (long long)sk * (nzeta - 1) : 0);
+      for (int q = lane; q < n; q += 32) {
+        const size_t o = base + (size_t)q * st;
+        if (shift != 0) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) xyz[c][(size_t)((long long)o + shift)] = xyz[c][o];
+        }
+        if (MODE == 1) {                                                                        // psiges
+          d.psi[o] = tgt[q];
+          if (shift != 0) d.psi[(size_t)((long long)o + shift)] = tgt[q];
+        }
+      }
+    }
+  }
+}
