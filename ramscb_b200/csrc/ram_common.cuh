@@ -66,6 +66,9 @@ struct SpecDev {
   const double* EPP;                      // [NE]
   const double* wfac;                     // WAVELO factor exp(-DTs/TAU_LIF) [NE][Pp]
   const double *DA, *DB;                  // WPADIF coefficient pair [l][k][Pp]
+  const double *CA, *CB;                  // fused COULMU: elimination factors (cA,cB) pairs and RL, like the fused WPADIF's (k_coulmu_tables)
+  const double* cK;                       // fused COULEN: COULE + COULI per energy [NE] (the same for every L < NPA, src/ModRamCoul.f90:98-101)
+  double cg1, cg0;                        // COULEN ghost-cell ratios sqrt((GREL1^2-1)/(GREL2^2-1)), sqrt((GRZERO^2-1)/(GREL1^2-1)) (:182-183)
   double *tE, *tA;                        // ANISCH scratch [NE][Pp]
   double *aE2, *aA2;                      // fused step: ANISCH rows written by k_plane_rp<REV> [NPA * energy chunks][Pp]
   double *pper, *ppar;                    // ANISCH results [Pp]

@@ -474,6 +474,10 @@ struct ColCfg {
   int b0;             // first block of plane positions of the launch (column-sharded ranks)
   int doW;            // bit s: species s runs WPADIF after the first / before the second DRIFTMU (WPI instantiation only)
   int wpart_off;      // where the two WPADIF moments of a block go in sp.part
+  int doC;            // Coulomb operators (COULEN, COULMU | COULMU, COULEN around the loss block) for every species (WPI instantiation only)
+  int tpos;           // TimeRamElapsed > 0: COULMU clamps negatives (src/ModRamCoul.f90:289)
+  int cpart_off;      // where the four Coulomb moments of a block go in sp.part
+  const double* NECR; // plasmaspheric density [j][i] (NR,NT)
 };
 
 // =============================================================================
@@ -523,6 +527,42 @@ __global__ void __launch_bounds__(128) k_wpadif_tables(const __grid_constant__ R
   if (viol) atomicAdd(viol_out, viol);
 }
 
+// =============================================================================
+// k_coulmu_tables: the same idea for COULMU (src/ModRamCoul.f90:229-296): its tridiagonal matrix depends on the rate
+// tables ATA / GTA (COULPARA), the plasmaspheric density and the field factors only -- AN, GN, DENOM in the reference's
+// operation order (k_coulmu), factors laid out like k_wpadif_tables' so the fused column kernel applies them with the
+// same stage.  One thread per (K, position) line.
+// =============================================================================
+__global__ void __launch_bounds__(128) k_coulmu_tables(const __grid_constant__ RamDev d, const double* __restrict__ ATA,
+                                                       const double* __restrict__ GTA, const double* __restrict__ NECR,
+                                                       double2* __restrict__ AB, double* __restrict__ RLt) {
+  const int NE = d.NE, NPA = d.NPA, Pp = d.Pp;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)NE * Pp) return;
+  const int k = (int)(t / Pp), p = (int)(t - (long long)k * Pp);
+  const int j = p / d.NR, i = p - j * d.NR;
+  if (p >= d.P || i < 1 || k < 1) return;
+  const int I = i + 1, J = j + 1;
+  const size_t LS = (size_t)NE * Pp;
+  const size_t o = (size_t)k * Pp + p;
+  const double XNE = NECR[p];
+  double rlm = -1.;
+  double BASm = XNE * R3(d.BOUNIS, I, J, 1) / 2. / R3(d.BOUNHS, I, J, 1);
+  for (int L = 2; L <= NPA - 1; ++L) {
+    const double BOUNHSl = R3(d.BOUNHS, I, J, L), FNHSl = R3(d.FNHS, I, J, L);
+    const double BAS = XNE * R3(d.BOUNIS, I, J, L) / 2. / BOUNHSl;
+    const double AN = ATA[(size_t)k * NPA + (L - 1)] * BAS / FNHSl * BOUNHSl;
+    const double GN = GTA[(size_t)k * NPA + (L - 1)] * BASm / FNHSl * R3(d.BOUNHS, I, J, L - 1);
+    const double BN = AN + GN;
+    const double DENOM = BN + GN * rlm + 1;
+    rlm = -AN / DENOM;
+    AB[o + (size_t)(L - 1) * LS] = make_double2(1.0 / (FNHSl * d.MU[L - 1] * DENOM), GN / DENOM);
+    RLt[o + (size_t)(L - 1) * LS] = rlm;
+    BASm = BAS;
+  }
+  AB[o + (size_t)(NPA - 1) * LS] = make_double2(1.0 / (1 + rlm), 0.0);
+}
+
 template <int PG, int MAXT, bool WPI, bool PEER = false>
 __global__ void __launch_bounds__(MAXT) k_col_fused(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0,
                                                     ColCfg cfg, const __grid_constant__ PeerView pv) {
@@ -552,8 +592,11 @@ __global__ void __launch_bounds__(MAXT) k_col_fused(const __grid_constant__ RamD
   double* sWMZ = sWMU + NPA;
   double* sE2 = sWMZ + NPA;                  // [64] 2^(j/64)
   double* sRed = sE2 + 64;                   // [5][32]
-  double* sFM = sRed + 5 * 32;               // WPI only: [NPA][PG] FNHS*MU (FACMU of WPADIF)
+  double* sFM = sRed + 5 * 32;               // WPI only: [NPA][PG] FNHS*MU (FACMU of WPADIF / COULMU)
+  double* sXc = sFM + NPA * PG;              // WPI only: [NPA][PG] NECR*BANE(L) of COULEN (src/ModRamCoul.f90:170-176)
+  double* sTabC = sXc + NPA * PG;            // WPI only: [NE][4] COULE+COULI, 0, 1/DE, 1/WE
   const bool doW = WPI && ((cfg.doW >> (s0 + blockIdx.y)) & 1);
+  const bool doC = WPI && cfg.doC;
 
   // ---- stage the block (asynchronous 16-byte copies, all in flight) and its tables -----
   {
@@ -600,11 +643,28 @@ __global__ void __launch_bounds__(MAXT) k_col_fused(const __grid_constant__ RamD
       sWMZ[t] = (t >= 1) ? d.WMU[t] : 0.0;
     }
     for (int t = tid; t < 64; t += T) sE2[t] = d.exp2tab[t];
-    if (WPI && doW)
+    if (WPI && (doW || doC))
       for (int t = tid; t < NPA * PG; t += T) {
         const int l2 = t / PG, pp = t - l2 * PG;
         sFM[t] = d.FNHSc[(size_t)l2 * Pp + p0 + pp] * d.MU[l2];
       }
+    if (WPI && doC) {
+      for (int t = tid; t < NPA * PG; t += T) {
+        const int l2 = t / PG, pp = t - l2 * PG;
+        const int p = min(p0 + pp, P - 1);
+        const int j = p / NR, i = p - j * NR;
+        // BANE(L) = (1 - FNIS/2/FNHS)/(1 - MU^2), L >= NPA-10 repeat L = NPA-11; L = 1 is not advanced by COULEN
+        const int Lb = min(l2 + 1, NPA - 11);
+        const double bane = (1. - R3(d.FNIS, i + 1, j + 1, Lb) / 2. / R3(d.FNHS, i + 1, j + 1, Lb)) / (1. - d.MU[Lb - 1] * d.MU[Lb - 1]);
+        sXc[t] = (l2 == NPA - 1) ? 0.0 : cfg.NECR[p] * bane;   // COULE, COULI are never assigned at L = NPA (:98-101): c = 0 there
+      }
+      for (int t = tid; t < NE; t += T) {
+        sTabC[4 * t] = sp.cK[t];
+        sTabC[4 * t + 1] = 0.0;
+        sTabC[4 * t + 2] = sp.tabE[4 * t + 2];
+        sTabC[4 * t + 3] = sp.tabE[4 * t + 3];
+      }
+    }
     asm volatile("cp.async.wait_group 0;");
   }
   __syncthreads();
@@ -612,19 +672,20 @@ __global__ void __launch_bounds__(MAXT) k_col_fused(const __grid_constant__ RamD
   const double beta = d.BetaLim;
   double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};   // SUMRC after DRIFTMU, and the four of the loss block
   double accW[2] = {0.0, 0.0};                 // WPI: SUMRC after the first and after the second WPADIF
+  double accC[4] = {0.0, 0.0, 0.0, 0.0};       // Coulomb: SUMRC after COULEN, COULMU | COULMU, COULEN (slots 10..13)
 
   // ---- WPADIF (src/ModRamWPI.f90:643-714) with the tabulated elimination factors of
   // k_wpadif_tables (sp.DA = (cA,cB) pairs, sp.DB = RL): a thread solves the lines of one
   // (energy, position); RK overwrites F2 on the way up, F2 is rebuilt on the way down -------
-  auto wpadif = [&](const int which) {
+  auto thomas = [&](const double2* abBase, const double* rlBase, double& accum, const bool clamp) {
     const int ntask = NE * PG;
     for (int e = tid; e < ntask; e += T) {
       const int pp = e % PG, k = e / PG;
       const int p = p0 + pp;
       if (k < 1 || p >= P || p % NR < 1) continue;
       const size_t LS = (size_t)NE * Pp;
-      const double2* ab = (const double2*)sp.DA + (size_t)k * Pp + p;
-      const double* rl = sp.DB + (size_t)k * Pp + p;
+      const double2* ab = abBase + (size_t)k * Pp + p;
+      const double* rl = rlBase + (size_t)k * Pp + p;
       double* col = sT + k * PG + pp;                   // F(L) at col[(L-1)*RS]
       const double* fm = sFM + pp;
       // The factors come from global memory (three F2-sized tables: L2 / HBM latency per access) and the
@@ -652,9 +713,11 @@ __global__ void __launch_bounds__(MAXT) k_col_fused(const __grid_constant__ RamD
       }
       double f = rk * ab[(size_t)(NPA - 1) * LS].x;      // f(NPA-1) = RK/(1+RL)
       double fN = f * fm[(NPA - 1) * PG];               // F2(NPA) = f(NPA-1)*FACMU(NPA)
+      if (clamp && fN < 0.0) fN = 1E-15;                // COULMU with TimeRamElapsed > 0 (src/ModRamCoul.f90:289)
       double macc = fN * sWMU[NPA - 1];
       col[(size_t)(NPA - 1) * RS] = fN;
       fN = f * fm[(NPA - 2) * PG];
+      if (clamp && fN < 0.0) fN = 1E-15;
       macc = fma(fN, sWMU[NPA - 2], macc);
       col[(size_t)(NPA - 2) * RS] = fN;
       {
@@ -673,18 +736,27 @@ __global__ void __launch_bounds__(MAXT) k_col_fused(const __grid_constant__ RamD
               const int l = l0 - b;
               f = fma(-cu[b], f, col[(size_t)l * RS]);
               fN = f * fm[l * PG];
+              if (clamp && fN < 0.0) fN = 1E-15;
               macc = fma(fN, sWMU[l], macc);
               col[(size_t)l * RS] = fN;
             }
         }
       }
-      col[0] = f * fm[0];                               // RK(1) = 0, RL(1) = -1: f(1) = f(2)
-      if (p < (NT - 1) * NR) accW[which] += macc * (sWE[k] * sEK[k]);
+      {
+        double f1 = f * fm[0];                          // RK(1) = 0, RL(1) = -1: f(1) = f(2)
+        if (clamp && f1 < 0.0) f1 = 1E-15;
+        col[0] = f1;
+      }
+      if (p < (NT - 1) * NR) accum += macc * (sWE[k] * sEK[k]);
     }
   };
+  auto wpadif = [&](const int which) { thomas((const double2*)sp.DA, sp.DB, accW[which], false); };
+  auto coulmu = [&](const int which) { thomas((const double2*)sp.CA, sp.CB, accC[which], cfg.tpos != 0); };
 
   // ---- DRIFTE (src/ModRamDrift.f90:285-376) ------------------------------------
-  auto drifte = [&]() {
+  // COUL: the same walk is COULEN (src/ModRamCoul.f90:133-221) -- coefficient (COULE+COULI)(K) * NECR*BANE(L), ghost cells
+  // with COULEN's own ratios, pitch angles L >= 2 only, optionally with the SUMRC moment of the result
+  auto ewalk = [&](const bool COUL, double* mom) {
     const int ntask = NPA * PG * cfg.nsegE;
     const int nround = (ntask + T - 1) / T;
     for (int rd = 0; rd < nround; ++rd) {
@@ -692,7 +764,7 @@ __global__ void __launch_bounds__(MAXT) k_col_fused(const __grid_constant__ RamD
       const int pp = e % PG, lq = e / PG;
       const int l = lq % NPA, seg = lq / NPA;
       const int p = p0 + pp;
-      const bool act = (e < ntask) && (p < P) && (p % NR != 0);
+      const bool act = (e < ntask) && (p < P) && (p % NR != 0) && (!COUL || l >= 1);
       const int ka = 1 + seg * cfg.segE, kb = min(NE, ka + cfg.segE - 1);
       const int K0 = max(ka - 1, 1);
       double* col = sT + (size_t)l * RS + pp;           // F(K) at col[(K-1)*PG]
@@ -701,8 +773,8 @@ __global__ void __launch_bounds__(MAXT) k_col_fused(const __grid_constant__ RamD
         double F1 = 0.0, Fz = 0.0;
         if (K0 <= 2) {
           const double f2 = col[PG];
-          F1 = f2 * sp.GREL1 / sp.GREL2 * sp.sqrtA;
-          Fz = F1 * sp.GRZERO / sp.GREL1 * sp.sqrtB;
+          F1 = f2 * sp.GREL1 / sp.GREL2 * (COUL ? sp.cg1 : sp.sqrtA);
+          Fz = F1 * sp.GRZERO / sp.GREL1 * (COUL ? sp.cg0 : sp.sqrtB);
         }
 #define GETFK(K) (((K) > NE) ? 0.0 : (((K) >= 2) ? col[((K)-1) * PG] : (((K) == 1) ? F1 : Fz)))
         Fm1 = GETFK(K0 - 1); F0 = GETFK(K0); Fp1 = GETFK(K0 + 1); Fp2 = GETFK(K0 + 2);
@@ -711,8 +783,11 @@ __global__ void __launch_bounds__(MAXT) k_col_fused(const __grid_constant__ RamD
       }
       if (cfg.nsegE > 1) __syncthreads();               // halo reads before anybody's in-place walk
       if (act) {
-        const double fA = sEa[l * PG + pp], fB = sEb[l * PG + pp];
-        const double4* tab = (const double4*)sTab + (K0 - 1);
+        const double fA = COUL ? sXc[l * PG + pp] : sEa[l * PG + pp], fB = COUL ? 0.0 : sEb[l * PG + pp];
+        const double4* tab = (const double4*)(COUL ? sTabC : sTab) + (K0 - 1);
+        double macc = 0.0;
+        const double wl = sWMU[l];
+        int Kc = K0 + 1;                                // 1-based energy of the cell the next step() writes
         double FBprev;
         double dm1 = F0 - Fm1, d0 = Fp1 - F0, dp1 = Fp2 - Fp1;
         {                                               // peeled first interface K0: flux only
@@ -735,15 +810,20 @@ __global__ void __launch_bounds__(MAXT) k_col_fused(const __grid_constant__ RamD
           *pO = fn;
           pO += PG;
           FBprev = FB;
+          if (mom) macc = fma(fn, sWE[Kc - 1] * sEK[Kc - 1], macc);
+          ++Kc;
         };
         int K = K0 + 1;
 #pragma unroll 4
         for (; K + 2 <= kb; ++K) step(pO[2 * PG]);      // F(K+2): own cell, not yet rewritten
         if (K + 1 <= kb) { step(hi1); ++K; }            // K = kb-1: F(kb+1)
         if (K <= kb) step(hi2);                         // K = kb:   F(kb+2)
+        if (mom && p < (NT - 1) * NR) *mom += macc * wl;
       }
     }
   };
+  auto drifte = [&]() { ewalk(false, nullptr); };
+  auto coulen = [&](const int which) { ewalk(true, &accC[which]); };
 
   // ---- DRIFTMU (src/ModRamDrift.f90:382-473), optionally with the SUMRC moment ----
   auto driftmu = [&](const bool mom) {
@@ -880,10 +960,12 @@ __global__ void __launch_bounds__(MAXT) k_col_fused(const __grid_constant__ RamD
   __syncthreads();
   driftmu(true);
   __syncthreads();
-  if (WPI && doW) { wpadif(0); __syncthreads(); }       // src/ModRamRun.f90:91-104
+  if (WPI && doC) { coulen(0); __syncthreads(); coulmu(1); __syncthreads(); }   // src/ModRamRun.f90:79-88
+  if (WPI && doW) { wpadif(0); __syncthreads(); }       // :91-104
   losses();
   __syncthreads();
   if (WPI && doW) { wpadif(1); __syncthreads(); }       // :140-154
+  if (WPI && doC) { coulmu(2); __syncthreads(); coulen(3); __syncthreads(); }   // :156-165
   driftmu(false);
   __syncthreads();
   drifte();
@@ -915,6 +997,10 @@ __global__ void __launch_bounds__(MAXT) k_col_fused(const __grid_constant__ RamD
   if (WPI) {
     __syncthreads();
     block_sum_to<2>(sp.part + cfg.wpart_off, blockIdx.x, accW, sRed);
+    if (doC) {
+      __syncthreads();
+      block_sum_to<4>(sp.part + cfg.cpart_off, blockIdx.x, accC, sRed);
+    }
   }
 }
 
@@ -948,6 +1034,31 @@ __global__ void __launch_bounds__(256) k_finalize_wpi(const __grid_constant__ Sp
       sp.dt[4 + slot] = dbl_bits(v);
       hr[4 + slot] = dbl_bits(v);
       if (q == 0) { sp.dt[4 + nsum] = viol[s]; hr[4 + nsum] = viol[s]; }
+    }
+  }
+}
+
+// k_finalize_coul: the four Coulomb moments of the fused step (slots 10..13: COULEN, COULMU | COULMU, COULEN;
+// src/ModRamRun.f90:79-88, :156-165).  grid: x = 4, y = species; block = 256
+__global__ void __launch_bounds__(256) k_finalize_coul(const __grid_constant__ SpecPack pk, int s0, int nb_col, int cpart_off, int res_n,
+                                                       unsigned long long* __restrict__ host_res) {
+  __shared__ double sm[32];
+  const int s = s0 + blockIdx.y;
+  const SpecDev& sp = pk.s[s];
+  const int q = blockIdx.x;
+  double acc = 0.0;
+  for (int b = threadIdx.x; b < nb_col; b += blockDim.x) acc += sp.part[cpart_off + (size_t)b * 4 + q];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = (threadIdx.x < (blockDim.x >> 5)) ? sm[threadIdx.x] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) {
+      sp.dt[4 + 10 + q] = dbl_bits(v);
+      host_res[(size_t)s * res_n + 4 + 10 + q] = dbl_bits(v);
     }
   }
 }

@@ -79,7 +79,9 @@ struct Spec {
   double* d_flc = nullptr;   // FLC_coef of this species [l][k][Pp] (allocated by rsg_ram_set_flc_coef)
   double* d_wtab = nullptr;  // fused WPADIF: elimination factors (cA,cB) pairs [2*n] then RL [n], n = NPA*NE*Pp (k_wpadif_tables)
   double wtab_DTs = -1.0;    // DTs the factors were tabulated for (< 0: stale)
-  double* d_coul = nullptr;  // COULPARA tables COULE, COULI, ATA, GTA, each [k][l]
+  double* d_coul = nullptr;  // COULPARA tables COULE, COULI, ATA, GTA, each [k][l], then cK = (COULE + COULI)(K) [NE] for the fused COULEN
+  double* d_ctab = nullptr;  // fused COULMU: elimination factors (cA,cB) pairs [2*n] then RL [n] (k_coulmu_tables)
+  double ctab_DTs = -1.0;    // DTs the factors were tabulated for (< 0: stale)
   double DTs_coul = -1.0;    // DTs of the last COULPARA
   unsigned long long* d_res = nullptr;  // slice of rsg_ram::d_res_all
   unsigned long long* h_res = nullptr;  // slice of rsg_ram::h_res_all (pinned)
@@ -499,12 +501,14 @@ ColPlan col_plan(const rsg_ram* h, bool wpi = false) {
   segs(NPA - 2, c.T / linesM, &c.cfg.nsegM, &c.cfg.segM);
   segs(NPA, c.T / linesM, &c.cfg.nsegL, &c.cfg.segL);
   c.smem = sizeof(double) * ((size_t)NPA * c.cfg.NEs * COL_PG + 6 * (size_t)NPA * COL_PG + 8 * (size_t)NE + 2 * (size_t)NE * COL_PG +
-                             4 * (size_t)NPA + 64 + 5 * 32 + (wpi ? (size_t)NPA * COL_PG : 0));
+                             4 * (size_t)NPA + 64 + 5 * 32 + (wpi ? 2 * (size_t)NPA * COL_PG + 4 * (size_t)NE : 0));
   return c;
 }
 int fused_part_off(const rsg_ram* h) { return (((h->P + COL_PG - 1) / COL_PG) * 5 + 15) & ~15; }
 // WPADIF moments of the column kernel: behind the reverse plane kernel's partials (at most NE*NPA of them)
 int fused_wpart_off(const rsg_ram* h) { return (fused_part_off(h) + h->NE * h->NPA + 15) & ~15; }
+// Coulomb moments of the column kernel: behind the two WPADIF moments of every block
+int fused_cpart_off(const rsg_ram* h) { return (fused_wpart_off(h) + ((h->P + COL_PG - 1) / COL_PG) * 2 + 15) & ~15; }
 struct PlanePlan { PlaneCfg cfg; int T; size_t smem; };
 PlanePlan plane_plan(const rsg_ram* h) {
   PlanePlan c{};
@@ -548,9 +552,9 @@ int wpadif_mask(const rsg_ram* h, int flags) {
 // the fused kernels cover the default operator set, with or without the WPI / EMIC pitch-angle
 // diffusion, on a whole grid in FAST mode (the Coulomb operators run one kernel per operator)
 bool fused_ok(const rsg_ram* h, int flags) {
-  if (!h->use_fused || h->mode != RSG_MODE_FAST || (flags & ~(RSG_F_WPI | RSG_F_EMIC)) != 0) return false;
-  if (h->NR < 4 || h->NT < 5 || h->NE < 3 || h->NPA < 4) return false;
-  const bool wpi = wpadif_mask(h, flags) != 0;
+  if (!h->use_fused || h->mode != RSG_MODE_FAST || (flags & ~(RSG_F_WPI | RSG_F_EMIC | RSG_F_COULOMB)) != 0) return false;
+  if (h->NR < 4 || h->NT < 5 || h->NE < 3 || h->NPA < 13) return false;
+  const bool wpi = wpadif_mask(h, flags) != 0 || (flags & RSG_F_COULOMB);
   if (wpi && !h->use_fused_wpi) return false;
   return col_plan(h, wpi).smem <= 220 * 1024 && plane_smem(h) <= 220 * 1024;
 }
@@ -621,7 +625,7 @@ int L_wtab(rsg_ram* h, int mask, double DTs, cudaStream_t st) {
   return RSG_OK;
 }
 template <bool WPI, bool PEER>
-int L_col_t(rsg_ram* h, int s0, int ns, int doA, int doW, double DTs, cudaStream_t st, int b0, int nb, const PeerView& pv) {
+int L_col_t(rsg_ram* h, int s0, int ns, int doA, int doW, double DTs, cudaStream_t st, int b0, int nb, const PeerView& pv, int doC) {
   SpecPack pk;
   make_pack(h, pk, s0, ns);
   ColPlan c = col_plan(h, WPI);
@@ -629,6 +633,10 @@ int L_col_t(rsg_ram* h, int s0, int ns, int doA, int doW, double DTs, cudaStream
   c.cfg.b0 = b0;
   c.cfg.doW = doW;
   c.cfg.wpart_off = fused_wpart_off(h);
+  c.cfg.doC = doC;
+  c.cfg.tpos = h->T_elapsed > 0.0 ? 1 : 0;
+  c.cfg.cpart_off = fused_cpart_off(h);
+  c.cfg.NECR = h->d_NECR;
   if (nb < 0) nb = (h->P + COL_PG - 1) / COL_PG - b0;
   const dim3 g(nb, ns);
   const RamDev dv = devfor(h, DTs);
@@ -650,13 +658,34 @@ int L_col_t(rsg_ram* h, int s0, int ns, int doA, int doW, double DTs, cudaStream
   return RSG_OK;
 }
 int L_col(rsg_ram* h, int s0, int ns, int doA, double DTs, cudaStream_t st, int b0 = 0, int nb = -1, int doW = 0,
-          const PeerView* peer = nullptr) {
+          const PeerView* peer = nullptr, int doC = 0) {
   for (int s = s0; s < s0 + ns; ++s)
     if (!((doW >> s) & 1)) { h->sp[s].sd.DA = h->d_zero4; h->sp[s].sd.DB = h->d_zero4; }
   static const PeerView kNoPeer{};
+  const bool ext = doW || doC;          // the extended instantiation: WPADIF and / or the Coulomb operators as extra stages
   if (peer)
-    return doW ? L_col_t<true, true>(h, s0, ns, doA, doW, DTs, st, b0, nb, *peer) : L_col_t<false, true>(h, s0, ns, doA, 0, DTs, st, b0, nb, *peer);
-  return doW ? L_col_t<true, false>(h, s0, ns, doA, doW, DTs, st, b0, nb, kNoPeer) : L_col_t<false, false>(h, s0, ns, doA, 0, DTs, st, b0, nb, kNoPeer);
+    return ext ? L_col_t<true, true>(h, s0, ns, doA, doW, DTs, st, b0, nb, *peer, doC) : L_col_t<false, true>(h, s0, ns, doA, 0, DTs, st, b0, nb, *peer, 0);
+  return ext ? L_col_t<true, false>(h, s0, ns, doA, doW, DTs, st, b0, nb, kNoPeer, doC) : L_col_t<false, false>(h, s0, ns, doA, 0, DTs, st, b0, nb, kNoPeer, 0);
+}
+// elimination factors of the fused COULMU (k_coulmu_tables) for species [s0, s0+ns): tabulated when DTs (through COULPARA's
+// rate tables), the fields or the plasmasphere changed, else cached.  Allocates: call outside stream capture.
+int L_ctab(rsg_ram* h, int s0, int ns, double DTs, cudaStream_t st) {
+  const size_t n = h->specStride;
+  for (int s = s0; s < s0 + ns; ++s) {
+    Spec& sp = h->sp[s];
+    if (sp.DTs_coul < 0) return fail(RSG_ERR_STATE, "COULMU before COULPARA");
+    if (!sp.d_ctab) RET(h->dalloc(&sp.d_ctab, 3 * n));
+    sp.sd.CA = sp.d_ctab;
+    sp.sd.CB = sp.d_ctab + 2 * n;
+    if (sp.ctab_DTs == DTs) continue;
+    const size_t nt = (size_t)h->NE * h->NPA;
+    k_coulmu_tables<<<nblk((long long)h->NE * h->Pp, 128), 128, 0, st>>>(devfor(h, DTs), sp.d_coul + 2 * nt, sp.d_coul + 3 * nt, h->d_NECR,
+                                                                        (double2*)sp.d_ctab, sp.d_ctab + 2 * n);
+    CKL();
+    h->launches++;
+    sp.ctab_DTs = DTs;
+  }
+  return RSG_OK;
 }
 // pressures of ANISCH in one pass + the result block of the step, both also written to the
 // host-mapped copies (no memcpy nodes in the fused step)
@@ -972,12 +1001,12 @@ int rsg_ram_create(rsg_ram** out, int nS, int NR, int NT, int NE, int NPA, int d
       // per-plane partials of the reductions, or per-warp partials of the sweeps with a fused SUMRC
       const size_t wR = (size_t)nblk(h->P, 248) * NPA * NE * 8;                       // KC = 1 worst case
       const size_t wM = (size_t)nblk(h->P, 128) * NE * ((NPA - 2 + 1) / 2) * 4;       // SEG = 2 worst case
-      const size_t wF = (size_t)(nblk(h->P, 4) + 16) * 7 + (size_t)NE * NPA + 64;      // fused step: column + plane + WPADIF partials
+      const size_t wF = (size_t)(nblk(h->P, 4) + 16) * 11 + (size_t)NE * NPA + 128;    // fused step: column + plane + WPADIF + Coulomb partials
       RET(h->dalloc(&sp.d_part, std::max({(size_t)h->nblk_sum * RSG_NMOM, wR, wM, wF})));
     }
     RET(h->dalloc(&sp.d_tE, (size_t)2 * NE * h->Pp));
     RET(h->dalloc(&sp.d_rFFA, (size_t)NE * NR));
-    RET(h->dalloc(&sp.d_coul, (size_t)4 * NE * NPA));
+    RET(h->dalloc(&sp.d_coul, (size_t)4 * NE * NPA + NE));
     sp.d_res = h->d_res_all + (size_t)s * RES_N;
     sp.h_res = h->h_res_all + (size_t)s * RES_N;
     sp.d_pp = h->d_pp_all + (size_t)s * 2 * h->Pp;
@@ -1187,7 +1216,7 @@ int rsg_ram_set_fields(rsg_ram* h, const double* BNES, const double* dBdt, const
   CK(cudaStreamSynchronize(h->pst()));
   h->fields_set = true;
   h->step_dirty = true;
-  for (int s = 0; s < h->nS; ++s) h->sp[s].wtab_DTs = -1.0;   // FACMU = FNHS*MU enters the WPADIF factors
+  for (int s = 0; s < h->nS; ++s) h->sp[s].wtab_DTs = h->sp[s].ctab_DTs = -1.0;   // FACMU = FNHS*MU enters the WPADIF / COULMU factors
   return RSG_OK;
 }
 
@@ -1233,6 +1262,7 @@ int rsg_ram_set_plasmasphere(rsg_ram* h, const double* NECR) {
   CK(cudaSetDevice(h->device));
   RET(rsg_ram_sync(h));
   RET(up(h->d_NECR, NECR, (size_t)h->NR * h->NT));
+  for (int s = 0; s < h->nS; ++s) h->sp[s].ctab_DTs = -1.0;
   return RSG_OK;
 }
 
@@ -1782,7 +1812,19 @@ int tables_coulomb(rsg_ram* h, int s, double DTs) {
   (void)RE; (void)funt_h; (void)funi_h;
   CK(cudaStreamSynchronize(h->st(s)));
   RET(up(sp.d_coul, tab.data(), tab.size()));
+  {
+    std::vector<double> ck(NE);
+    for (int k = 0; k < NE; ++k) ck[k] = COULE[(size_t)k * NPA] + COULI[(size_t)k * NPA];
+    RET(up(sp.d_coul + (size_t)4 * NE * NPA, ck.data(), NE));
+    sp.sd.cK = sp.d_coul + (size_t)4 * NE * NPA;
+    const double EZERO = h->EKEV[0] - h->WE[0];
+    const double GRZERO = 1. + EZERO * 1000. * kQ / h->RMAS[s] / kCS / kCS;
+    const double GREL1 = h->GREL[s], GREL2 = h->GREL[s + (size_t)h->nS];
+    sp.sd.cg1 = std::sqrt((GREL1 * GREL1 - 1) / (GREL2 * GREL2 - 1));
+    sp.sd.cg0 = std::sqrt((GRZERO * GRZERO - 1) / (GREL1 * GREL1 - 1));
+  }
   sp.DTs_coul = DTs;
+  sp.ctab_DTs = -1.0;
   return RSG_OK;
 }
 int L_coulen(rsg_ram* h, int s, cudaStream_t st) {
@@ -1960,6 +2002,7 @@ int step_prepare(rsg_ram* h, double DTs, int flags, int s0, int ns) {
     for (int s = 0; s < h->nS; ++s)
       if (s < s0 || s >= s0 + ns) wm &= ~(1 << s);
     if (wm) RET(L_wtab(h, wm, DTs, st));
+    if (flags & RSG_F_COULOMB) RET(L_ctab(h, s0, ns, DTs, st));
   }
   return RSG_OK;
 }
@@ -2023,11 +2066,19 @@ int enqueue_fused(rsg_ram* h, double DTs, int flags, int s0, int ns) {
   int doW = wpadif_mask(h, flags);
   for (int s = 0; s < h->nS; ++s)
     if (s < s0 || s >= s0 + ns) doW &= ~(1 << s);
+  const int doC = (flags & RSG_F_COULOMB) ? 1 : 0;
   RET(prof_mark(h, "k_col_fused", st));
-  RET(L_col(h, s0, ns, doA, DTs, st, 0, -1, doW));
+  RET(L_col(h, s0, ns, doA, DTs, st, 0, -1, doW, nullptr, doC));
   RET(prof_mark(h, "k_plane_rp", st));
   RET(L_plane_rp(h, s0, ns, st, true));          // ends with the epilogue of ram_run
   RET(L_finish_fused(h, s0, ns, st));
+  if (doC) {                                     // SUMRC moments after COULEN, COULMU | COULMU, COULEN
+    SpecPack pk;
+    make_pack(h, pk, s0, ns);
+    k_finalize_coul<<<dim3(4, ns), 256, 0, st>>>(pk, s0, (h->P + COL_PG - 1) / COL_PG, fused_cpart_off(h), RES_N, h->hd_res_all);
+    CKL();
+    h->launches++;
+  }
   if (doW) {                                     // SUMRC moments after the two WPADIFs, violation count
     SpecPack pk;
     make_pack(h, pk, s0, ns);

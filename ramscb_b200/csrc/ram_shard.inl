@@ -141,7 +141,7 @@ struct rsg_shard {
   unsigned long long* h_err = nullptr;   // pinned + mapped
   cudaGraphExec_t gexec = nullptr;
   double g_DTs = -1.0;
-  int g_flags = -1, g_mode = -1;
+  int g_flags = -1, g_mode = -1, g_tpos = -1;
   long long g_launches = 0;
   cudaStream_t g_stream = nullptr;
   unsigned group_mask = 0, world_mask = 0;
@@ -225,7 +225,8 @@ int enqueue_sharded(rsg_ram* h, double DTs, int flags) {
     RET(L_plane_rp(h, s0, ns, st, false, p.l0, p.nl, &sh.pv));     // DRIFTR, DRIFTP -> the column owners
     k_peer_barrier<<<1, 32, 0, st>>>(sh.pc, 0, sh.group_mask);
     CKL();
-    RET(L_col(h, s0, ns, doA, DTs, st, p.b0, p.nb, doW, &sh.pv));   // DRIFTE .. DRIFTE -> the pitch-angle owners
+    const int doC = (flags & RSG_F_COULOMB) ? 1 : 0;
+    RET(L_col(h, s0, ns, doA, DTs, st, p.b0, p.nb, doW, &sh.pv, doC));   // DRIFTE .. DRIFTE -> the pitch-angle owners
     k_peer_barrier<<<1, 32, 0, st>>>(sh.pc, 0, sh.group_mask);
     CKL();
     RET(L_plane_rp(h, s0, ns, st, true, p.l0, p.nl));               // DRIFTP, DRIFTR, epilogue (local slab)
@@ -235,6 +236,13 @@ int enqueue_sharded(rsg_ram* h, double DTs, int flags) {
       SpecPack pk;
       make_pack(h, pk, s0, ns);
       k_finalize_wpi<<<dim3(2, ns), 256, 0, st>>>(pk, s0, doW, p.nb, fused_wpart_off(h), RES_N, NSUM, h->d_wviol, h->hd_res_all);
+      CKL();
+      h->launches++;
+    }
+    if (doC) {
+      SpecPack pk;
+      make_pack(h, pk, s0, ns);
+      k_finalize_coul<<<dim3(4, ns), 256, 0, st>>>(pk, s0, p.nb, fused_cpart_off(h), RES_N, h->hd_res_all);
       CKL();
       h->launches++;
     }
@@ -362,7 +370,7 @@ int rsg_ram_run_sharded_enqueue(rsg_ram* h, double DTs, double T, int flags) {
   const rsg_shard_plan_t& p = sh.plan;
   RET(check_part(h, p.s0, p.ns, 0, h->NPA, h->NPA));
   if (p.G > 1 && !fused_ok(h, flags))
-    return fail(RSG_ERR_UNSUPPORTED, "ranks sharing a species need the fused FAST kernels (RSG_MODE_FAST, no Coulomb flag)");
+    return fail(RSG_ERR_UNSUPPORTED, "ranks sharing a species need the fused FAST kernels (RSG_MODE_FAST)");
   for (int s = p.s0; s < p.s0 + p.ns; ++s)
     if (p.G > 1 && h->sp[s].cur != 0) return fail(RSG_ERR_STATE, "sharded step needs F2 in buffer 0");
   CK(cudaSetDevice(h->device));
@@ -371,13 +379,13 @@ int rsg_ram_run_sharded_enqueue(rsg_ram* h, double DTs, double T, int flags) {
   cudaStream_t st = h->pst();
   sh.pending = true;
   sh.pending_flags = flags;
-  if (h->use_graph && !h->prof_on && sh.gexec && sh.g_DTs == DTs && sh.g_flags == flags && sh.g_mode == h->mode && sh.g_stream == st) {
+  if (h->use_graph && !h->prof_on && sh.gexec && sh.g_DTs == DTs && sh.g_flags == flags && sh.g_mode == h->mode && sh.g_stream == st && sh.g_tpos == (T > 0.0)) {
     CK(cudaGraphLaunch(sh.gexec, st));
     h->launches += sh.g_launches;
     return RSG_OK;
   }
   if (sh.gexec) { cudaGraphExecDestroy(sh.gexec); sh.gexec = nullptr; }
-  const bool graph_ok = h->use_graph && !h->prof_on && !(flags & RSG_F_COULOMB);   // COULMU's T > 0 switch is a launch argument
+  const bool graph_ok = h->use_graph && !h->prof_on;   // COULMU's T > 0 switch is a launch argument: part of the graph's key
   const long long l0 = h->launches;
   if (graph_ok) CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
   const int rc = enqueue_sharded(h, DTs, flags);
@@ -389,7 +397,7 @@ int rsg_ram_run_sharded_enqueue(rsg_ram* h, double DTs, double T, int flags) {
     e = cudaGraphInstantiate(&sh.gexec, g, 0);
     cudaGraphDestroy(g);
     if (e != cudaSuccess) { sh.gexec = nullptr; return fail(RSG_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
-    sh.g_DTs = DTs; sh.g_flags = flags; sh.g_mode = h->mode; sh.g_stream = st;
+    sh.g_DTs = DTs; sh.g_flags = flags; sh.g_mode = h->mode; sh.g_stream = st; sh.g_tpos = T > 0.0;
     sh.g_launches = h->launches - l0;
     CK(cudaGraphLaunch(sh.gexec, st));
   }

@@ -87,6 +87,11 @@ def test_emulated_fused_wpadif_step(emu, T, small_grids, oracle_built, flags):
     T.test_fused_wpadif_fast_step(small_grids, oracle_built, "default", flags)
 
 
+@pytest.mark.parametrize("flags", [2, 1 | 2 | 4])
+def test_emulated_fused_coulomb_step(emu, T, small_grids, oracle_built, flags):
+    T.test_fused_coulomb_fast_step(small_grids, oracle_built, flags)
+
+
 def test_emulated_scb_maps_and_geometry(emu, oracle_built):
     """SCB kernels in the emulator: computeBandJacob, metrica/newk, the lexicographic SOR wavefront and
     mapAlpha / mapPsi / mapTheta, all bit-identical to the oracle (tests/test_scb_parity_gpu.py)."""

@@ -488,6 +488,53 @@ def test_fused_wpadif_fast_step(default_grids, oracle_built, grid, flags):
     assert np.allclose(o_f[-1]["SETRC"], o.SETRC, rtol=1e-12, atol=0)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("flags", [2, 1 | 2 | 4])
+def test_fused_coulomb_fast_step(default_grids, oracle_built, flags):
+    """Coulomb collisions (COULEN, COULMU | COULMU, COULEN; src/ModRamRun.f90:79-88, :156-165) as four more stages of
+    the fused column kernel: energy walks with the plasmaspheric density folded into the Courant number, and the
+    pitch-angle Thomas recurrences from tabulated factors (k_coulmu_tables).  Strict bar against the oracle and the
+    one-kernel-per-operator FAST path, all 14 loss increments, and the launch count of the replayed step."""
+    from ramscb_b200 import host
+    g = default_grids
+    inp = _mk(g, f2_kind="noisy", inductive=True, mgnp=True)
+    D = synthetic.synthetic_daa(g, inp)
+    o = oracle_built.RamOracle(g, inp, DTs=DTS)
+    o.set_array("ATAC", D)
+    o.set_array("ATAW_emic_h", D)
+    runs = {}
+    for name, wp in (("unfused", False), ("fused", True)):
+        gpu = host.RamGpu(g)
+        gpu.set_mode(host.MODE_FAST)
+        gpu.set_inputs(inp)
+        gpu.set_diffcoef(1, D)
+        gpu.set_diffcoef(2, D)
+        gpu.use_fused(True, wpadif=wp)
+        outs, n = [], []
+        for dts in (5.0, 5.0, 7.5):
+            n0 = gpu.launch_count()
+            outs.append(gpu.ram_run(dts, DtsMin=1.0, flags=flags))
+            n.append(gpu.launch_count() - n0)
+        runs[name] = (gpu.f2_d2h(), outs, n)
+        gpu.close()
+    for dts in (5.0, 5.0, 7.5):
+        o.set_scalar("DTs", dts)
+        dtn_ref = o.ram_run(flags=flags)
+    (f_u, o_u, n_u), (f_f, o_f, n_f) = runs["unfused"], runs["fused"]
+    assert n_f[1] <= 8 and n_u[1] > 20, f"launches per replayed step: fused {n_f}, unfused {n_u}"
+    mx_u, n_over_u = _strict_bar(f_f, f_u, "fused Coulomb vs one kernel per operator")
+    mx_o, n_over_o = _strict_bar(f_f, o.F2, "fused Coulomb step vs oracle", strict_all=STRICT_ALL)
+    print(f"\nfused Coulomb flags={flags}: strict vs unfused {mx_u:.2e} ({n_over_u} cells > 1e-12), vs oracle {mx_o:.2e} ({n_over_o}); launches {n_f}")
+    assert abs(o_f[-1]["DtsNext"] - dtn_ref) <= 1e-13 * dtn_ref
+    for a, b in zip(o_u, o_f):
+        assert np.array_equal(a["DtDrift"], b["DtDrift"]) and a["DtsNext"] == b["DtsNext"]
+        for k in ("PPERT", "PPART", "SETRC"):
+            assert np.allclose(a[k], b[k], rtol=1e-12, atol=0), k
+        assert np.all(np.abs(a["losses"] - b["losses"]) <= 1e-11 * np.abs(a["SETRC"])[None, :])
+    assert _relerr(o_f[-1]["PPERT"][:, 1:], o.PPERT[:, 1:]) <= 1e-12
+    assert np.allclose(o_f[-1]["SETRC"], o.SETRC, rtol=1e-12, atol=0)
+
+
 # ---------------------------------------------------------------------------------
 # multi-GPU parts (rsg_ram_part_*): slab-wise execution on one device must reproduce
 # the single-launch step bit for bit (the exchange between the parts is then a no-op:

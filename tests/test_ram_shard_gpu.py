@@ -90,6 +90,19 @@ def test_sharded_step_matches_one_gpu_fast(default_grids, world, policy, flags):
     _check(F1, o1, FN, oN, plans)
 
 
+@pytest.mark.parametrize("world,policy", [(8, 0), (4, 1)])
+def test_sharded_step_with_coulomb_stages(default_grids, world, policy):
+    """flags 7: WPI + Coulomb + EMIC, ranks sharing a species: the Coulomb stages run inside the sharded column kernel,
+    their four moments are reduced with the others"""
+    from ramscb_b200 import host
+    g = default_grids
+    inp = synthetic.make_inputs(g, f2_kind="noisy", inductive=True, mgnp=True)
+    D = synthetic.synthetic_daa(g, inp)
+    F1, o1 = _single(g, inp, host.MODE_FAST, 7, D)
+    FN, oN, plans = _sharded(g, inp, host.MODE_FAST, 7, world, policy, D)
+    _check(F1, o1, FN, oN, plans)
+
+
 def test_sharded_step_ragged_grid():
     """odd sizes: NR odd (8-byte staging path of the plane kernel), slabs and column ranges that do not divide evenly"""
     from ramscb_b200 import host
