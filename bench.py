@@ -719,6 +719,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
+    from ramscb_b200 import parallel as _par
+    numa = {"bound": False, "why": "RSG_NO_NUMA_BIND"} if os.environ.get("RSG_NO_NUMA_BIND") else _par.bind_to_gpu_numa(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -747,6 +749,7 @@ def main():
                                 "PARITY.md, tests/test_ram_parity_gpu.py)") if a.mode == "fast"
                        else "exact: reference operation order, bit-identical to the oracle",
                        "l2": "flushed between timed steps (512 MB memset, untimed)", "DTs": DTS, "parallelism": par,
+                       "host_numa_binding_rank0": numa,
                        "same_workload_at_every_N": "strong scaling: bench.py --gpus 1 runs this same workload on one GPU"},
             "clocks": r["clocks"], "e2e": r.get("e2e"), "gpu_launches": r["gpu_launches"], "roofline": r.get("roofline"),
             "wall_s_timed_region": r["wall_s_timed_region"]}

@@ -14,6 +14,7 @@
 // bit-identical to the unfused FAST path (tests/test_ram_parity_gpu.py); only the
 // summation order of the SUMRC moments differs.  All updates are in place.
 #pragma once
+#include <type_traits>
 #include "ram_kernels.cuh"
 
 // CTA-wide sum of NM per-thread values -> part[cta*NM + q] (fixed order => reproducible).
@@ -563,10 +564,13 @@ __global__ void __launch_bounds__(128) k_coulmu_tables(const __grid_constant__ R
   AB[o + (size_t)(NPA - 1) * LS] = make_double2(1.0 / (1 + rlm), 0.0);
 }
 
-template <int PG, int MAXT, bool WPI, bool PEER = false>
+// EXT: 0 = drift + loss stages only, 1 = + WPADIF, 2 = + WPADIF and the Coulomb operators (own instantiation: the extra
+// stages cost registers the flags-5 step should not pay for)
+template <int PG, int MAXT, int EXT, bool PEER = false>
 __global__ void __launch_bounds__(MAXT) k_col_fused(const __grid_constant__ RamDev d, const __grid_constant__ SpecPack pk, int s0,
                                                     ColCfg cfg, const __grid_constant__ PeerView pv) {
   extern __shared__ double smem[];
+  constexpr bool WPI = EXT >= 1, CO = EXT >= 2;
   const SpecDev& sp = pk.s[s0 + blockIdx.y];
   const int NR = d.NR, NT = d.NT, NE = d.NE, NPA = d.NPA, P = d.P, Pp = d.Pp;
   const int T = blockDim.x, tid = threadIdx.x;
@@ -596,7 +600,7 @@ __global__ void __launch_bounds__(MAXT) k_col_fused(const __grid_constant__ RamD
   double* sXc = sFM + NPA * PG;              // WPI only: [NPA][PG] NECR*BANE(L) of COULEN (src/ModRamCoul.f90:170-176)
   double* sTabC = sXc + NPA * PG;            // WPI only: [NE][4] COULE+COULI, 0, 1/DE, 1/WE
   const bool doW = WPI && ((cfg.doW >> (s0 + blockIdx.y)) & 1);
-  const bool doC = WPI && cfg.doC;
+  const bool doC = CO && cfg.doC;
 
   // ---- stage the block (asynchronous 16-byte copies, all in flight) and its tables -----
   {
@@ -648,7 +652,7 @@ __global__ void __launch_bounds__(MAXT) k_col_fused(const __grid_constant__ RamD
         const int l2 = t / PG, pp = t - l2 * PG;
         sFM[t] = d.FNHSc[(size_t)l2 * Pp + p0 + pp] * d.MU[l2];
       }
-    if (WPI && doC) {
+    if (CO && doC) {
       for (int t = tid; t < NPA * PG; t += T) {
         const int l2 = t / PG, pp = t - l2 * PG;
         const int p = min(p0 + pp, P - 1);
@@ -756,7 +760,8 @@ __global__ void __launch_bounds__(MAXT) k_col_fused(const __grid_constant__ RamD
   // ---- DRIFTE (src/ModRamDrift.f90:285-376) ------------------------------------
   // COUL: the same walk is COULEN (src/ModRamCoul.f90:133-221) -- coefficient (COULE+COULI)(K) * NECR*BANE(L), ghost cells
   // with COULEN's own ratios, pitch angles L >= 2 only, optionally with the SUMRC moment of the result
-  auto ewalk = [&](const bool COUL, double* mom) {
+  auto ewalk = [&](auto coulTag, double* mom) {
+    constexpr bool COUL = decltype(coulTag)::value;
     const int ntask = NPA * PG * cfg.nsegE;
     const int nround = (ntask + T - 1) / T;
     for (int rd = 0; rd < nround; ++rd) {
@@ -822,8 +827,8 @@ __global__ void __launch_bounds__(MAXT) k_col_fused(const __grid_constant__ RamD
       }
     }
   };
-  auto drifte = [&]() { ewalk(false, nullptr); };
-  auto coulen = [&](const int which) { ewalk(true, &accC[which]); };
+  auto drifte = [&]() { ewalk(std::false_type{}, nullptr); };
+  auto coulen = [&](const int which) { ewalk(std::true_type{}, &accC[which]); };
 
   // ---- DRIFTMU (src/ModRamDrift.f90:382-473), optionally with the SUMRC moment ----
   auto driftmu = [&](const bool mom) {
@@ -960,12 +965,12 @@ __global__ void __launch_bounds__(MAXT) k_col_fused(const __grid_constant__ RamD
   __syncthreads();
   driftmu(true);
   __syncthreads();
-  if (WPI && doC) { coulen(0); __syncthreads(); coulmu(1); __syncthreads(); }   // src/ModRamRun.f90:79-88
+  if constexpr (CO) if (doC) { coulen(0); __syncthreads(); coulmu(1); __syncthreads(); }   // src/ModRamRun.f90:79-88
   if (WPI && doW) { wpadif(0); __syncthreads(); }       // :91-104
   losses();
   __syncthreads();
   if (WPI && doW) { wpadif(1); __syncthreads(); }       // :140-154
-  if (WPI && doC) { coulmu(2); __syncthreads(); coulen(3); __syncthreads(); }   // :156-165
+  if constexpr (CO) if (doC) { coulmu(2); __syncthreads(); coulen(3); __syncthreads(); }   // :156-165
   driftmu(false);
   __syncthreads();
   drifte();

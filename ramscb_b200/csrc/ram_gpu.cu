@@ -624,11 +624,11 @@ int L_wtab(rsg_ram* h, int mask, double DTs, cudaStream_t st) {
   }
   return RSG_OK;
 }
-template <bool WPI, bool PEER>
+template <int EXT, bool PEER>
 int L_col_t(rsg_ram* h, int s0, int ns, int doA, int doW, double DTs, cudaStream_t st, int b0, int nb, const PeerView& pv, int doC) {
   SpecPack pk;
   make_pack(h, pk, s0, ns);
-  ColPlan c = col_plan(h, WPI);
+  ColPlan c = col_plan(h, EXT >= 1);
   c.cfg.doA = doA;
   c.cfg.b0 = b0;
   c.cfg.doW = doW;
@@ -641,17 +641,17 @@ int L_col_t(rsg_ram* h, int s0, int ns, int doA, int doW, double DTs, cudaStream
   const dim3 g(nb, ns);
   const RamDev dv = devfor(h, DTs);
   if (c.T <= 320) {          // register budget follows the CTA size
-    RET(opt_in_smem(k_col_fused<COL_PG, 320, WPI, PEER>, c.smem));
-    k_col_fused<COL_PG, 320, WPI, PEER><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg, pv);
+    RET(opt_in_smem(k_col_fused<COL_PG, 320, EXT, PEER>, c.smem));
+    k_col_fused<COL_PG, 320, EXT, PEER><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg, pv);
   } else if (c.T <= 640) {
-    RET(opt_in_smem(k_col_fused<COL_PG, 640, WPI, PEER>, c.smem));
-    k_col_fused<COL_PG, 640, WPI, PEER><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg, pv);
+    RET(opt_in_smem(k_col_fused<COL_PG, 640, EXT, PEER>, c.smem));
+    k_col_fused<COL_PG, 640, EXT, PEER><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg, pv);
   } else if (c.T <= 896) {
-    RET(opt_in_smem(k_col_fused<COL_PG, 896, WPI, PEER>, c.smem));
-    k_col_fused<COL_PG, 896, WPI, PEER><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg, pv);
+    RET(opt_in_smem(k_col_fused<COL_PG, 896, EXT, PEER>, c.smem));
+    k_col_fused<COL_PG, 896, EXT, PEER><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg, pv);
   } else {
-    RET(opt_in_smem(k_col_fused<COL_PG, 1024, WPI, PEER>, c.smem));
-    k_col_fused<COL_PG, 1024, WPI, PEER><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg, pv);
+    RET(opt_in_smem(k_col_fused<COL_PG, 1024, EXT, PEER>, c.smem));
+    k_col_fused<COL_PG, 1024, EXT, PEER><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg, pv);
   }
   CKL();
   h->launches++;
@@ -664,8 +664,10 @@ int L_col(rsg_ram* h, int s0, int ns, int doA, double DTs, cudaStream_t st, int 
   static const PeerView kNoPeer{};
   const bool ext = doW || doC;          // the extended instantiation: WPADIF and / or the Coulomb operators as extra stages
   if (peer)
-    return ext ? L_col_t<true, true>(h, s0, ns, doA, doW, DTs, st, b0, nb, *peer, doC) : L_col_t<false, true>(h, s0, ns, doA, 0, DTs, st, b0, nb, *peer, 0);
-  return ext ? L_col_t<true, false>(h, s0, ns, doA, doW, DTs, st, b0, nb, kNoPeer, doC) : L_col_t<false, false>(h, s0, ns, doA, 0, DTs, st, b0, nb, kNoPeer, 0);
+    return doC ? L_col_t<2, true>(h, s0, ns, doA, doW, DTs, st, b0, nb, *peer, doC)
+         : ext ? L_col_t<1, true>(h, s0, ns, doA, doW, DTs, st, b0, nb, *peer, 0) : L_col_t<0, true>(h, s0, ns, doA, 0, DTs, st, b0, nb, *peer, 0);
+  return doC ? L_col_t<2, false>(h, s0, ns, doA, doW, DTs, st, b0, nb, kNoPeer, doC)
+       : ext ? L_col_t<1, false>(h, s0, ns, doA, doW, DTs, st, b0, nb, kNoPeer, 0) : L_col_t<0, false>(h, s0, ns, doA, 0, DTs, st, b0, nb, kNoPeer, 0);
 }
 // elimination factors of the fused COULMU (k_coulmu_tables) for species [s0, s0+ns): tabulated when DTs (through COULPARA's
 // rate tables), the fields or the plasmasphere changed, else cached.  Allocates: call outside stream capture.

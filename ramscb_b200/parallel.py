@@ -321,6 +321,34 @@ class RamSharded:
                 "PPERT": np.asfortranarray(np.moveaxis(PE, 2, 0)), "PPART": np.asfortranarray(np.moveaxis(PA, 2, 0))}
 
 
+def bind_to_gpu_numa(device_index: int) -> dict:
+    """Pin the calling process to the host cores next to its GPU (NVML's ideal CPU affinity for the device, found through
+    the PCI bus id so that CUDA_VISIBLE_DEVICES remapping does not matter).  Call it BEFORE allocating the host arrays a
+    rank hands to rsg_ram_f2_h2d(_shard): first touch then places them on the GPU's NUMA node, and the pinned copies do
+    not cross the socket interconnect.  The reference's MPI ranks get the same from `mpirun --bind-to`; torchrun binds
+    nothing.  Returns what was done (never raises: an unbound process is slower, not wrong)."""
+    import os
+    try:
+        import pynvml
+        import torch
+        pr = torch.cuda.get_device_properties(device_index)
+        bus = f"{pr.pci_domain_id:08X}:{pr.pci_bus_id:02X}:{pr.pci_device_id:02X}.0"
+        pynvml.nvmlInit()
+        hdl = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(hdl, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = sorted(cpus & allowed)
+        if not cpus:
+            return {"bound": False, "why": "NVML affinity mask empty within the allowed cpus"}
+        if len(cpus) < len(allowed):
+            os.sched_setaffinity(0, cpus)
+        return {"bound": len(cpus) < len(allowed), "cpus": len(cpus), "first_cpu": cpus[0], "last_cpu": cpus[-1], "pci": bus}
+    except Exception as e:                                  # no NVML, container without the right, ...
+        return {"bound": False, "why": f"{type(e).__name__}: {e}"[:160]}
+
+
 def gather_blobs(dist, blob, world, device=None):
     """All-gather of the ranks' peer blobs (rsg_ram_peer_export) in rank order: the ONLY host-side communication of the
     library's own multi-GPU step (a Fortran host does the same with one MPI_Allgather).  Works on any backend: the
