@@ -632,6 +632,41 @@ def hi_metrics(device):
                                         "bound": "shared-memory bandwidth / FP64 issue (candidates resident in shared memory, no HBM traffic to speak of)"}
     except Exception as e:
         out["convert_lines_default"] = {"error": str(e)[:200]}
+    try:        # the whole routine resident on the device (rsg_hi): nothing but the SCB arrays go in, or nothing at all
+        from ramscb_b200 import synthetic
+        inp = scb_synthetic.build_scb(nthe=101, npsi=45, nzeta=97, warp=0.2)
+        g = grids.build_grids()
+        Lz = g.LZ[:g.NR + 1] if len(g.LZ) > g.NR else np.append(2 * g.LZ[0] - g.LZ[1], g.LZ)
+        rng = np.random.default_rng(1)
+        shape3 = (g.NR + 1, g.NT, g.NPA)
+        ram = {n: np.asfortranarray(rng.random(shape3)) for n in ("FNHS", "FNIS", "BOUNHS", "BOUNIS", "HDNS")}
+        ram["BNES"] = np.asfortranarray(1e-7 * rng.random((g.NR + 1, g.NT)))
+        sg = host.ScbGpu(inp, device=device)
+        sg.computeBandJacob()                                     # leaves bf on the device
+        scb = dict(x=inp.x, y=inp.y, z=inp.z, psi=inp.psi, alfa=inp.alfa, bf=sg.get_field("bf"))
+        hi = host.HiGpu(101, 45, 97, Lz, g.MLT[:g.NT], g.MU, g.PA, g.PAbn, inp.chiVal, 51, 1.0, device=device)
+        hi.set_ram_fields(ram)
+        res = {}
+        for label, src in (("scb_arrays_from_host", scb), ("scb_arrays_from_rsg_scb_handle", sg)):
+            wall, ms = [], []
+            for _ in range(7):
+                t0 = time.perf_counter()
+                hi.computehI(src, 300.0, True)
+                wall.append((time.perf_counter() - t0) * 1e3)
+                ms.append(hi.last_ms())
+            res[label] = {"call_wall_ms": sorted(wall)[3], "kernels_ms": sorted(ms)[3]}
+        rg = host.RamGpu(g, device=device)
+        rg.set_inputs(synthetic.make_inputs(g, f2_kind="smooth"))
+        t0 = time.perf_counter()
+        hi.push_to_ram(rg)
+        res["push_to_rsg_ram_wall_ms"] = (time.perf_counter() - t0) * 1e3
+        res["launches_per_call"] = 9
+        res["note"] = ("rsg_computehI: convert -> ScaleAt -> RAIRDEN -> integrals -> tail on one stream, intermediates resident; wall "
+                       "includes the final synchronisation (and the 21 MB upload of the six SCB arrays in the host variant)")
+        out["computehI_resident_default"] = res
+        rg.close(); hi.close(); sg.close()
+    except Exception as e:
+        out["computehI_resident_default"] = {"error": str(e)[:300]}
     return out
 
 

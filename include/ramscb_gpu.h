@@ -505,6 +505,46 @@ int rsg_hI_convert_lines(int device, int nthe, int npsi, int nzeta, int nR, int 
                          const double* y, const double* z, const double* bf, const double* psi, const double* alfa, const double* Lz,
                          const double* MLT, double* xRAM, double* yRAM, double* zRAM, double* bRAM, int* outsideSCB, double* ms);
 
+
+/* ---- computehI resident on the device (src/ModRamScb.f90:249-637 in one object) ---------------------------------
+ * The three calls above move every intermediate array through the host; rsg_hi keeps them on the device: the SCB arrays
+ * come from the host once per call or straight from an rsg_scb handle, xRAM .. bRAM, I_cart .. bZEq_Cart stay resident
+ * between the blocks, HDens_cart and the previous FNHS .. BNES persist between calls like the reference's module
+ * variables (ModRamVariables), and the new field arrays go device-to-device into an rsg_ram handle
+ * (rsg_hi_device_fields + rsg_ram_set_fields_device).  Same kernels, same results as the three stateless calls. */
+typedef struct rsg_hi rsg_hi;
+int rsg_hi_create(rsg_hi** out, int device, int nthe, int npsi, int nzeta, int nR, int nT, int nPa, int nThetaEquator, double bnormal,
+                  const double* chiVal, const double* mu, const double* Lz, const double* MLT, const double* PA, const double* PAbn);
+void rsg_hi_destroy(rsg_hi* h);
+/* previous RAM variables (the module arrays at entry); HDens_cart may be NULL */
+int rsg_hi_set_ram_fields(rsg_hi* h, const double* FNHS, const double* FNIS, const double* BOUNHS, const double* BOUNIS, const double* HDNS,
+                          const double* BNES, const double* HDens_cart);
+/* block 1 (:252-300): host SCB arrays x, y, z, bf, psi, alfa (nthe,npsi,nzeta+1), or all six NULL and an rsg_scb handle on
+ * the same device.  outsideSCB(nR,nT) and *nOutside may be NULL (then nothing is read back). */
+int rsg_hi_convert(rsg_hi* h, const double* x, const double* y, const double* z, const double* bf, const double* psi, const double* alfa,
+                   rsg_scb* scb, int* outsideSCB, int* nOutside);
+/* a line the host traced (Geopack, :330-362) for RAM point (i,j), 1-based: nthe nodes each of x, y, z, b / bnormal */
+int rsg_hi_set_line(rsg_hi* h, int i, int j, const double* xl, const double* yl, const double* zl, const double* bl);
+/* blocks 2 and 3.  ScaleAt(nT) + outsideMGNP(nR,nT) from the host's magnetopause logic (:306-329), or both NULL: the 'SWMF'
+ * branch on the device (first outside point per MLT, every outside line flagged).  density(nthe,nR,nT) or NULL = RAIRDEN
+ * (:362-371) on the device. */
+int rsg_hi_finish(rsg_hi* h, const int* ScaleAt, const int* outsideMGNP, const double* density, int integral_smooth, double DthI,
+                  int* gslerr);
+/* convert + finish with the device-side defaults: nothing but the SCB arrays in (or nothing at all with an rsg_scb handle) */
+int rsg_computehI(rsg_hi* h, const double* x, const double* y, const double* z, const double* bf, const double* psi, const double* alfa,
+                  rsg_scb* scb, int integral_smooth, double DthI, int* gslerr);
+/* results by name: xRAM yRAM zRAM bRAM density (nthe,nR,nT), psiRAM bZEq_cart (nR,nT), I_cart H_cart HDens_cart (nR,nT,nPa),
+ * FNHS FNIS BOUNHS BOUNIS HDNS dIdt dHdt dIbndt (nR+1,nT,nPa), BNES dBdt (nR+1,nT) */
+int rsg_hi_get(rsg_hi* h, const char* name, double* host);
+/* which = 0 outsideSCB(nR,nT), 1 outsideMGNP(nR,nT), 2 ScaleAt(nT) */
+int rsg_hi_get_int(rsg_hi* h, int which, int* host);
+double rsg_hi_last_ms(rsg_hi* h);            /* device time convert .. tail of the last rsg_hi_finish */
+long long rsg_hi_launch_count(rsg_hi* h);
+/* device pointers of the new field arrays, in the order rsg_ram_set_fields_device takes them */
+int rsg_hi_device_fields(rsg_hi* h, const double** ptrs9, const int** outsideMGNP);
+/* rsg_ram_set_fields from DEVICE arrays: BNES, dBdt, FNHS, FNIS, BOUNHS, BOUNIS, HDNS, dIdt, dIbndt; outsideMGNP(NR,NT) */
+int rsg_ram_set_fields_device(rsg_ram* h, const double* const* ptrs9, const int* d_outsideMGNP);
+
 #ifdef __cplusplus
 }
 #endif

@@ -450,8 +450,7 @@ __global__ void k_hi_fill(HiTailArgs A) {
 //
 // One CTA per (point set, slice of the queries): the candidate coordinates sit in shared memory in the reference's
 // scatter order; a warp takes a query.  MINLOC + overwriting the pick with 999999.9, nine times, yields the nine
-// smallest (distance, index) pairs in lexicographic order (first minimum wins ties): every lane keeps the nine smallest
-// pairs of its own candidates in registers during ONE scan, and nine shuffle elections pop the picks from the lane heads.  Weights and the 1 or 4
+// smallest (distance, index) pairs in lexicographic order (first minimum wins ties): nn9_select below.  Weights and the 1 or 4
 // weighted sums in the reference's order: bit-identical to the oracle.
 // MODE 0: point set = equatorial plane (x, y) -> psiRAM, outsideSCB;  MODE 1: point set k = blockIdx.x, (psi, alfa) -> x, y, z, bf.
 // =============================================================================
@@ -463,6 +462,80 @@ struct HiConvArgs {
   int* outside;                                  // outsideSCB(nR,nT)
   double *xRAM, *yRAM, *zRAM, *bRAM;             // (nthe,nR,nT)
 };
+
+// The nine picks of Interpolation_2D_NN_point (src/ModRamGSL.f90:368-422: MINLOC, overwrite the pick with 999999.9, nine
+// times) = the nine smallest (distance, index) pairs in lexicographic order.  A warp takes a query in two scans of the
+// candidates in shared memory: the first finds every lane's own smallest distance; the ninth smallest of those 32 values
+// bounds the ninth pick from above (nine distinct candidates are no farther), so the second scan runs the sorted insertion
+// only for the handful of candidates within the bound instead of through the warm-up of every lane's list.  Nine shuffle
+// elections then pop the picks from the lane heads.  The distances are the same expression in both scans (-fmad=false).
+__device__ __forceinline__ void nn9_select(const double* __restrict__ cx, const double* __restrict__ cy, int M, double x2, double y2,
+                                           int lane, int near[9]) {
+  const double BIG = 1.7976931348623157e308;
+  double m0 = BIG, m1 = BIG;
+  int s = lane;
+  for (; s + 32 < M; s += 64) {                                          // two independent chains
+    const double dx0 = cx[s] - x2, dy0 = cy[s] - y2, dx1 = cx[s + 32] - x2, dy1 = cy[s + 32] - y2;
+    const double d0 = dx0 * dx0 + dy0 * dy0, d1 = dx1 * dx1 + dy1 * dy1;
+    m0 = d0 < m0 ? d0 : m0;
+    m1 = d1 < m1 ? d1 : m1;
+  }
+  if (s < M) {
+    const double dx0 = cx[s] - x2, dy0 = cy[s] - y2;
+    const double d0 = dx0 * dx0 + dy0 * dy0;
+    m0 = d0 < m0 ? d0 : m0;
+  }
+  double v = m1 < m0 ? m1 : m0, bound = BIG;
+#pragma unroll 1
+  for (int r = 0; r < 9; r++) {                                          // ninth smallest of the lane minima
+    double b = v;
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, b, o);
+      b = ob < b ? ob : b;
+    }
+    bound = b;
+    int c = (v == b) ? lane : 32;
+    for (int o = 16; o > 0; o >>= 1) {
+      const int oc = __shfl_xor_sync(0xffffffffu, c, o);
+      c = oc < c ? oc : c;
+    }
+    if (lane == c) v = BIG;
+  }
+  double ld[9];
+  int li[9];
+#pragma unroll
+  for (int t = 0; t < 9; t++) { ld[t] = BIG; li[t] = 0x7fffffff; }
+  for (s = lane; s < M; s += 32) {
+    const double dx = cx[s] - x2, dy = cy[s] - y2;
+    const double d = dx * dx + dy * dy;
+    if (d <= bound && (d < ld[8] || (d == ld[8] && s < li[8]))) {
+      ld[8] = d; li[8] = s;
+#pragma unroll
+      for (int t = 8; t > 0; t--) {
+        if (ld[t] < ld[t - 1] || (ld[t] == ld[t - 1] && li[t] < li[t - 1])) {
+          const double td = ld[t]; ld[t] = ld[t - 1]; ld[t - 1] = td;
+          const int ti = li[t]; li[t] = li[t - 1]; li[t - 1] = ti;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 9; r++) {
+    double bd = ld[0];
+    int bi = li[0];
+    for (int o = 16; o > 0; o >>= 1) {
+      const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+    }
+    near[r] = bi;
+    if (li[0] == bi) {                                                   // the owner pops its head
+#pragma unroll
+      for (int t = 0; t < 8; t++) { ld[t] = ld[t + 1]; li[t] = li[t + 1]; }
+      ld[8] = BIG; li[8] = 0x7fffffff;
+    }
+  }
+}
 
 template <int MODE>
 __global__ void __launch_bounds__(256) k_hi_nn9(HiConvArgs A) {
@@ -512,43 +585,8 @@ __global__ void __launch_bounds__(256) k_hi_nn9(HiConvArgs A) {
       }
       x2 = A.psiRAM[q]; y2 = A.alphaRAM[j];
     }
-    // one pass: every lane keeps the nine smallest (distance, index) pairs of its candidates, sorted; the nine picks of
-    // the MINLOC sequence are then popped from the lane heads by nine shuffle elections
-    double ld[9];
-    int li[9];
-#pragma unroll
-    for (int t = 0; t < 9; t++) { ld[t] = 1.7976931348623157e308; li[t] = 0x7fffffff; }
-    for (int s = lane; s < M; s += 32) {
-      const double dx = cx[s] - x2, dy = cy[s] - y2;
-      const double d = dx * dx + dy * dy;
-      if (d < ld[8] || (d == ld[8] && s < li[8])) {
-        ld[8] = d; li[8] = s;
-#pragma unroll
-        for (int t = 8; t > 0; t--) {
-          if (ld[t] < ld[t - 1] || (ld[t] == ld[t - 1] && li[t] < li[t - 1])) {
-            const double td = ld[t]; ld[t] = ld[t - 1]; ld[t - 1] = td;
-            const int ti = li[t]; li[t] = li[t - 1]; li[t - 1] = ti;
-          }
-        }
-      }
-    }
     int near[9];
-#pragma unroll
-    for (int r = 0; r < 9; r++) {
-      double bd = ld[0];
-      int bi = li[0];
-      for (int o = 16; o > 0; o >>= 1) {
-        const double od = __shfl_xor_sync(0xffffffffu, bd, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
-      }
-      near[r] = bi;
-      if (li[0] == bi) {                                                 // the owner pops its head
-#pragma unroll
-        for (int t = 0; t < 8; t++) { ld[t] = ld[t + 1]; li[t] = li[t + 1]; }
-        ld[8] = 1.7976931348623157e308; li[8] = 0x7fffffff;
-      }
-    }
+    nn9_select(cx, cy, M, x2, y2, lane, near);
     double w[9], wsum = 0.0;                                             // NN_Interpolation_2D
     for (int i = 0; i < 9; i++) {
       const double dx = cx[near[i]] - x2, dy = cy[near[i]] - y2;
@@ -576,6 +614,30 @@ __global__ void __launch_bounds__(256) k_hi_nn9(HiConvArgs A) {
       }
     }
   }
+}
+
+// ScaleAt / outsideMGNP as the reference's NameBoundMag = 'SWMF' branch derives them (src/ModRamScb.f90:306-314): per MLT
+// the first radial point outside the SCB domain, every outside line flagged.  Thread per MLT.
+__global__ void k_hi_scaleat(int nR, int nT, const int* __restrict__ outsideSCB, int* __restrict__ outsideMGNP, int* __restrict__ ScaleAt,
+                             int* /*unused*/) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nT) return;
+  int sa = 0;
+  for (int i = 0; i < nR; i++) {
+    const int o = outsideSCB[i + (size_t)nR * j];
+    if (o == 1 && sa == 0) sa = i + 1;
+    outsideMGNP[i + (size_t)nR * j] = (o == 1) ? 1 : 0;
+  }
+  ScaleAt[j] = sa;
+}
+// densityMode "RAIRDEN" (src/ModRamScb.f90:362-371): 10**(polynomial of the geocentric distance), left-to-right like the Fortran
+__global__ void k_hi_rairden(size_t n, const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+                             double* __restrict__ dens) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const double r = sqrt(x[t] * x[t] + y[t] * y[t] + z[t] * z[t]);
+  const double r2 = r * r;
+  dens[t] = pow(10.0, 13.326 - 3.6908 * r + 1.1362 * r2 - 0.16984 * (r2 * r) + 0.009553 * (r2 * r2));
 }
 
 // =============================================================================
@@ -671,41 +733,8 @@ __global__ void __launch_bounds__(256) k_flc_nn9(FlcArgs A) {
     const int i = 1 + q % (A.nR - 1), j = q / (A.nR - 1);                // 0-based (Fortran i = 2..nR, j = 1..nT-1)
     const size_t oq = (size_t)i + (size_t)A.nR * j;
     const double x2 = A.qx[oq], y2 = A.qy[oq];
-    double ld[9];
-    int li[9];
-#pragma unroll
-    for (int t = 0; t < 9; t++) { ld[t] = 1.7976931348623157e308; li[t] = 0x7fffffff; }
-    for (int s = lane; s < M; s += 32) {
-      const double dx = cx[s] - x2, dy = cy[s] - y2;
-      const double d = dx * dx + dy * dy;
-      if (d < ld[8] || (d == ld[8] && s < li[8])) {
-        ld[8] = d; li[8] = s;
-#pragma unroll
-        for (int t = 8; t > 0; t--) {
-          if (ld[t] < ld[t - 1] || (ld[t] == ld[t - 1] && li[t] < li[t - 1])) {
-            const double td = ld[t]; ld[t] = ld[t - 1]; ld[t - 1] = td;
-            const int ti = li[t]; li[t] = li[t - 1]; li[t - 1] = ti;
-          }
-        }
-      }
-    }
     int near[9];
-#pragma unroll
-    for (int r = 0; r < 9; r++) {
-      double bd = ld[0];
-      int bi = li[0];
-      for (int o = 16; o > 0; o >>= 1) {
-        const double od = __shfl_xor_sync(0xffffffffu, bd, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
-      }
-      near[r] = bi;
-      if (li[0] == bi) {
-#pragma unroll
-        for (int t = 0; t < 8; t++) { ld[t] = ld[t + 1]; li[t] = li[t + 1]; }
-        ld[8] = 1.7976931348623157e308; li[8] = 0x7fffffff;
-      }
-    }
+    nn9_select(cx, cy, M, x2, y2, lane, near);
     double w[9], wsum = 0.0;                                             // NN_Interpolation_2D (src/ModRamGSL.f90:872-917)
     for (int c = 0; c < 9; c++) {
       const double dx = cx[near[c]] - x2, dy = cy[near[c]] - y2;

@@ -1222,6 +1222,44 @@ int rsg_ram_set_fields(rsg_ram* h, const double* BNES, const double* dBdt, const
   return RSG_OK;
 }
 
+// rsg_ram_set_fields with DEVICE pointers (what rsg_hi_device_fields returns: the resident computehI, same process and
+// device): nine device-to-device copies instead of the host round trip.  Order: BNES, dBdt, FNHS, FNIS, BOUNHS, BOUNIS,
+// HDNS, dIdt, dIbndt.  The list of lines beyond the magnetopause (the step's DRIFTP repair) is rebuilt from the flags.
+int rsg_ram_set_fields_device(rsg_ram* h, const double* const* ptrs9, const int* d_outsideMGNP) {
+  if (!h || !ptrs9 || !d_outsideMGNP) return fail(RSG_ERR_ARG, "null argument");
+  for (int q = 0; q < 9; ++q)
+    if (!ptrs9[q]) return fail(RSG_ERR_ARG, "null field pointer");
+  if (!h->grids_set) return fail(RSG_ERR_STATE, "set_fields before set_grids");
+  CK(cudaSetDevice(h->device));
+  RET(rsg_ram_sync(h));
+  RamDev& d = h->dev;
+  const size_t n2 = (size_t)h->NR1 * h->NT, n3 = n2 * h->NPA;
+  double* dst[9] = {(double*)d.BNES, (double*)d.dBdt, (double*)d.FNHS, (double*)d.FNIS, (double*)d.BOUNHS, (double*)d.BOUNIS,
+                    (double*)d.HDNS, (double*)d.dIdt, (double*)d.dIbndt};
+  cudaStream_t st = h->pst();
+  for (int q = 0; q < 9; ++q) CK(cudaMemcpyAsync(dst[q], ptrs9[q], (q < 2 ? n2 : n3) * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync((int*)d.outside, d_outsideMGNP, (size_t)h->NR * h->NT * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  std::vector<int> om((size_t)h->NR * h->NT);
+  CK(cudaMemcpyAsync(om.data(), d_outsideMGNP, om.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  {
+    std::vector<int> lst;
+    for (int j = 1; j < h->NT - 1; ++j)
+      for (int i = 0; i < h->NR; ++i)
+        if (om[(size_t)j * h->NR + i] != 0) lst.push_back(j * h->NR + i);
+    h->nout = (int)lst.size();
+    if (h->nout) RET(up(h->d_outlist, lst.data(), lst.size()));
+  }
+  k_prep_fields<<<nblk((long long)h->NPA * h->Pp, 256), 256, 0, st>>>(d);
+  CKL();
+  h->launches++;
+  CK(cudaStreamSynchronize(st));
+  h->fields_set = true;
+  h->step_dirty = true;
+  for (int s = 0; s < h->nS; ++s) h->sp[s].wtab_DTs = h->sp[s].ctab_DTs = -1.0;
+  return RSG_OK;
+}
+
 int rsg_ram_set_efield(rsg_ram* h, const double* VT, const double* EIR, const double* EIP) {
   if (!h) return fail(RSG_ERR_ARG, "null handle");
   if (!VT || !EIR || !EIP) return fail(RSG_ERR_ARG, "null e-field pointer");

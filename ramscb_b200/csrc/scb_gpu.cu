@@ -1165,6 +1165,74 @@ int rsg_scb_run(rsg_scb* h, const rsg_scb_run_params* p, rsg_scb_pressure_fn pre
   return RSG_OK;
 }
 
+// ---- launch sequences of the three computehI blocks, shared by the stateless calls and the resident handle (rsg_hi) ----
+static int hi_launch_lines(const HiArgs& A, cudaStream_t st) {
+  const int threads = std::min(256, ((A.nPa + 31) / 32) * 32);
+  const size_t smem = (size_t)(4 * A.nthe + 4 * A.nPa) * sizeof(double) + 2 * (size_t)A.nPa * sizeof(int);
+  if (smem > 200 * 1024) return sfail(RSG_ERR_UNSUPPORTED, "field line does not fit shared memory");
+  if (smem > 48 * 1024) SCK(cudaFuncSetAttribute(k_hi_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_hi_lines<<<(unsigned)(A.nR * A.nT), threads, smem, st>>>(A);
+  SCK(cudaGetLastError());
+  return RSG_OK;
+}
+static void hi_gauss_weights(double* w) {                             // gaussian_kernel(1.0), srcExternal/gaussian_filter.f90:19-56
+  double sum = 0.0;
+  for (int j = -4; j <= 4; j++)
+    for (int i = -4; i <= 4; i++) {
+      const double x = i, y = j;
+      const double v = 2.0 * std::exp(-0.5 * (x * x + y * y) / 1.0);
+      w[(i + 4) + 9 * (j + 4)] = v;
+      sum += v;
+    }
+  for (int q = 0; q < 81; q++) w[q] = w[q] / sum;
+}
+static int hi_launch_tail(const HiTailArgs& A, cudaStream_t st) {
+  const int ncol = A.nT * A.nPa;
+  const size_t nl = (size_t)A.nR * A.nT, n3 = nl * A.nPa;
+  const int lthreads = std::min(256, ((A.nPa + 31) / 32) * 32);
+  const size_t lsmem = (size_t)8 * A.nPa * sizeof(double);
+  if (lsmem > 48 * 1024) return sfail(RSG_ERR_UNSUPPORTED, "pitch-angle line does not fit shared memory");
+  k_hi_tail_cols<<<nblk(ncol, 128), 128, 0, st>>>(A);
+  SCK(cudaGetLastError());
+  k_hi_tail_lines<<<(unsigned)nl, lthreads, lsmem, st>>>(A);
+  SCK(cudaGetLastError());
+  if (A.smooth) {
+    k_hi_smooth<<<nblk((long long)n3, 128), 128, 0, st>>>(A);
+    SCK(cudaGetLastError());
+  }
+  k_hi_fill<<<nblk(ncol, 128), 128, 0, st>>>(A);
+  SCK(cudaGetLastError());
+  return RSG_OK;
+}
+static int hi_launch_convert(const HiConvArgs& A, cudaStream_t st) {
+  const size_t nl = (size_t)A.nR * A.nT;
+  const size_t smem = 2 * (size_t)A.npsi * (A.nzeta - 1) * sizeof(double);
+  if (smem > 200 * 1024) return sfail(RSG_ERR_UNSUPPORTED, "SCB surface does not fit shared memory");
+  SCK(cudaFuncSetAttribute(k_hi_nn9<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SCK(cudaFuncSetAttribute(k_hi_nn9<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int q0 = std::max(1, std::min(148, (int)((nl + 7) / 8)));   // one point set, queries spread over the SMs
+  k_hi_nn9<0><<<dim3(1, q0), 256, smem, st>>>(A);
+  SCK(cudaGetLastError());
+  const int q1 = std::max(1, std::min((int)((nl + 7) / 8), (3 * 148) / A.nthe));   // one wave: 3 resident CTAs (69 KB each) per SM
+  k_hi_nn9<1><<<dim3(A.nthe, q1), 256, smem, st>>>(A);
+  SCK(cudaGetLastError());
+  return RSG_OK;
+}
+// xo, yo of the RAM equatorial points and alphaRAM (src/ModRamScb.f90:258-259, :283-284; cos / sin of the host libm)
+static void hi_query_tables(int nR, int nT, const double* Lz, const double* MLT, std::vector<double>& qx, std::vector<double>& qy,
+                            std::vector<double>& al) {
+  qx.resize((size_t)nR * nT); qy.resize((size_t)nR * nT); al.resize(nT);
+  const double twopi = 2.0 * PI_D;
+  for (int j = 0; j < nT; j++) {
+    for (int i = 0; i < nR; i++) {
+      qx[i + (size_t)nR * j] = Lz[i + 1] * std::cos(MLT[j] * 2.0 * PI_D / 24.0 - PI_D);
+      qy[i + (size_t)nR * j] = Lz[i + 1] * std::sin(MLT[j] * 2.0 * PI_D / 24.0 - PI_D);
+    }
+    al[j] = MLT[j] * PI_D / 12.0 + PI_D;
+    if (al[j] > twopi) al[j] = al[j] - twopi;
+  }
+}
+
 // computehI's integral block (src/ModRamScb.f90:372-410): I_cart, H_cart, HDens_cart, bZEq_Cart of every RAM
 // field line from the traced lines (xRAM, yRAM, zRAM, bRAM, density: (nthe,nR,nT)); HDens_cart is in/out
 // (lines with outsideMGNP != 0 keep their value, I_cart / H_cart / bZEq_Cart are zero there).
@@ -1215,13 +1283,8 @@ int rsg_hI_integrals(int device, int nthe, int nR, int nT, int nPa, int nThetaEq
   A.bzeq = p;
   HCK(cudaMemcpyAsync(dout, outsideMGNP, nl * sizeof(int), cudaMemcpyHostToDevice, st));
   A.outside = dout;
-  const int threads = std::min(256, ((nPa + 31) / 32) * 32);
-  const size_t smem = (size_t)(4 * nthe + 4 * nPa) * sizeof(double) + 2 * (size_t)nPa * sizeof(int);
-  if (smem > 200 * 1024) return done(RSG_ERR_UNSUPPORTED, "field line does not fit shared memory");
-  if (smem > 48 * 1024) HCK(cudaFuncSetAttribute(k_hi_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   HCK(cudaEventRecord(e0, st));
-  k_hi_lines<<<(unsigned)nl, threads, smem, st>>>(A);
-  HCK(cudaGetLastError());
+  if ((rc = hi_launch_lines(A, st)) != RSG_OK) return done(rc, g_serr);
   HCK(cudaEventRecord(e1, st));
   HCK(cudaMemcpyAsync(I_cart, A.Icart, no * sizeof(double), cudaMemcpyDeviceToHost, st));
   HCK(cudaMemcpyAsync(H_cart, A.Hcart, no * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1280,17 +1343,7 @@ int rsg_hI_tail(int device, int nR, int nT, int nPa, double* I_cart, double* H_c
   HiTailArgs A;
   A.nR = nR; A.nT = nT; A.nPa = nPa; A.smooth = integral_smooth ? 1 : 0; A.DthI = DthI;
   A.bnes1 = 0.32 / (Lz[0] * Lz[0] * Lz[0]) / 1.e4;                                  // :609
-  {                                                                                 // gaussian_kernel(1.0), srcExternal/gaussian_filter.f90:19-56
-    double sum = 0.0;
-    for (int j = -4; j <= 4; j++)
-      for (int i = -4; i <= 4; i++) {
-        const double x = i, y = j;
-        const double v = 2.0 * std::exp(-0.5 * (x * x + y * y) / 1.0);
-        A.w[(i + 4) + 9 * (j + 4)] = v;
-        sum += v;
-      }
-    for (int q = 0; q < 81; q++) A.w[q] = A.w[q] / sum;
-  }
+  hi_gauss_weights(A.w);
   double* p = d;
   auto take = [&](size_t n) { double* q = p; p += n; return q; };
   auto up = [&](const double* src, size_t n) { double* q = take(n); cudaMemcpyAsync(q, src, n * sizeof(double), cudaMemcpyHostToDevice, st); return q; };
@@ -1305,21 +1358,8 @@ int rsg_hI_tail(int device, int nR, int nT, int nPa, double* I_cart, double* H_c
   HCK(cudaMemcpyAsync(di + nl, ScaleAt, nT * sizeof(int), cudaMemcpyHostToDevice, st));
   HCK(cudaMemsetAsync(di + nl + nT, 0, sizeof(int), st));
   A.outside = di; A.ScaleAt = di + nl; A.fail = di + nl + nT;
-  const int ncol = nT * nPa;
-  const int lthreads = std::min(256, ((nPa + 31) / 32) * 32);
-  const size_t lsmem = (size_t)8 * nPa * sizeof(double);
-  if (lsmem > 48 * 1024) return done(RSG_ERR_UNSUPPORTED, "pitch-angle line does not fit shared memory");
   HCK(cudaEventRecord(e0, st));
-  k_hi_tail_cols<<<nblk(ncol, 128), 128, 0, st>>>(A);
-  HCK(cudaGetLastError());
-  k_hi_tail_lines<<<(unsigned)nl, lthreads, lsmem, st>>>(A);
-  HCK(cudaGetLastError());
-  if (A.smooth) {
-    k_hi_smooth<<<nblk((long long)n3, 128), 128, 0, st>>>(A);
-    HCK(cudaGetLastError());
-  }
-  k_hi_fill<<<nblk(ncol, 128), 128, 0, st>>>(A);
-  HCK(cudaGetLastError());
+  { const int rc = hi_launch_tail(A, st); if (rc != RSG_OK) return done(rc, g_serr); }
   HCK(cudaEventRecord(e1, st));
   auto down = [&](double* dst, const double* src, size_t n) { return cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost, st); };
   HCK(down(I_cart, A.smooth ? A.I2 : A.I1, n3));
@@ -1377,16 +1417,8 @@ int rsg_hI_convert_lines(int device, int nthe, int npsi, int nzeta, int nR, int 
   HCK(cudaEventCreate(&e1));
   HCK(cudaMalloc(&d, nd * sizeof(double)));
   HCK(cudaMalloc(&dout, nl * sizeof(int)));
-  std::vector<double> qx(nl), qy(nl), al(nT);                       // :258-259, :283-284 (cos / sin of the host libm)
-  const double twopi = 2.0 * PI_D;
-  for (int j = 0; j < nT; j++) {
-    for (int i = 0; i < nR; i++) {
-      qx[i + (size_t)nR * j] = Lz[i + 1] * std::cos(MLT[j] * 2.0 * PI_D / 24.0 - PI_D);
-      qy[i + (size_t)nR * j] = Lz[i + 1] * std::sin(MLT[j] * 2.0 * PI_D / 24.0 - PI_D);
-    }
-    al[j] = MLT[j] * PI_D / 12.0 + PI_D;
-    if (al[j] > twopi) al[j] = al[j] - twopi;
-  }
+  std::vector<double> qx, qy, al;
+  hi_query_tables(nR, nT, Lz, MLT, qx, qy, al);
   HiConvArgs A;
   A.nthe = nthe; A.npsi = npsi; A.nzeta = nzeta; A.nR = nR; A.nT = nT; A.nThetaEquator = nThetaEquator;
   double* p = d;
@@ -1397,18 +1429,9 @@ int rsg_hI_convert_lines(int device, int nthe, int npsi, int nzeta, int nR, int 
   A.psiRAM = take(nl);
   A.xRAM = take(no); A.yRAM = take(no); A.zRAM = take(no); A.bRAM = take(no);
   A.outside = dout;
-  const size_t smem = 2 * (size_t)npsi * (nzeta - 1) * sizeof(double);
-  if (smem > 200 * 1024) return done(RSG_ERR_UNSUPPORTED, "SCB surface does not fit shared memory");
-  HCK(cudaFuncSetAttribute(k_hi_nn9<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  HCK(cudaFuncSetAttribute(k_hi_nn9<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   HCK(cudaStreamSynchronize(st));                                   // the host tables go out of scope with the call only, but keep it simple
   HCK(cudaEventRecord(e0, st));
-  const int q0 = std::max(1, std::min(148, (int)((nl + 7) / 8)));   // one point set, queries spread over the SMs
-  k_hi_nn9<0><<<dim3(1, q0), 256, smem, st>>>(A);
-  HCK(cudaGetLastError());
-  const int q1 = std::max(1, std::min((int)((nl + 7) / 8), (3 * 148) / nthe));   // one wave: 3 resident CTAs (69 KB each) per SM
-  k_hi_nn9<1><<<dim3(nthe, q1), 256, smem, st>>>(A);
-  HCK(cudaGetLastError());
+  { const int rc = hi_launch_convert(A, st); if (rc != RSG_OK) return done(rc, g_serr); }
   HCK(cudaEventRecord(e1, st));
   HCK(cudaMemcpyAsync(xRAM, A.xRAM, no * sizeof(double), cudaMemcpyDeviceToHost, st));
   HCK(cudaMemcpyAsync(yRAM, A.yRAM, no * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1423,6 +1446,303 @@ int rsg_hI_convert_lines(int device, int nthe, int npsi, int nzeta, int nR, int 
   }
 #undef HCK
   return done(RSG_OK, "");
+}
+
+// =============================================================================
+// rsg_hi: computehI (src/ModRamScb.f90:249-637) with everything resident -- the SCB arrays come from the host once
+// per call or straight from an rsg_scb handle's device arrays, xRAM .. bRAM, I_cart .. bZEq_Cart and the RAM variables
+// never leave the device between the three blocks, HDens_cart and the previous FNHS .. BNES persist between calls like
+// the reference's module variables, and the new field arrays can go device-to-device into an rsg_ram handle.
+// =============================================================================
+struct rsg_hi {
+  int device = 0, nthe = 0, npsi = 0, nzeta = 0, nR = 0, nT = 0, nPa = 0, nThetaEquator = 0;
+  double bnormal = 1.0, Lz0 = 1.0;
+  cudaStream_t st = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  std::vector<void*> allocs;
+  std::map<std::string, std::pair<double*, size_t>> arr;
+  double *d_scb[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // x, y, z, bf, psi, alfa (own copies when the host supplies them)
+  HiConvArgs C{};
+  HiArgs I{};
+  HiTailArgs T{};
+  double* d_dens = nullptr;
+  int *d_outSCB = nullptr, *d_outMGNP = nullptr, *d_scale = nullptr, *d_fail = nullptr;
+  bool converted = false, fields_set = false, finished = false;
+  double last_ms = 0.0;
+  long long launches = 0;
+  int dalloc(double** p, size_t n, const char* name) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, n * sizeof(double));
+    if (e != cudaSuccess) return sfail(RSG_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    cudaMemset(q, 0, n * sizeof(double));
+    allocs.push_back(q);
+    *p = (double*)q;
+    if (name) arr[name] = {(double*)q, n};
+    return RSG_OK;
+  }
+};
+
+void rsg_hi_destroy(rsg_hi* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->st) { cudaStreamSynchronize(h->st); cudaStreamDestroy(h->st); }
+  if (h->e0) cudaEventDestroy(h->e0);
+  if (h->e1) cudaEventDestroy(h->e1);
+  for (void* q : h->allocs) cudaFree(q);
+  delete h;
+}
+
+int rsg_hi_create(rsg_hi** out, int device, int nthe, int npsi, int nzeta, int nR, int nT, int nPa, int nThetaEquator, double bnormal,
+                  const double* chiVal, const double* mu, const double* Lz, const double* MLT, const double* PA, const double* PAbn) {
+  if (!out || !chiVal || !mu || !Lz || !MLT || !PA || !PAbn) return sfail(RSG_ERR_ARG, "null argument");
+  if (nthe < 3 || npsi < 3 || nzeta < 3 || nR < 3 || nT < 2 || nPa < 5 || nThetaEquator < 1 || nThetaEquator > nthe ||
+      (long long)npsi * (nzeta - 1) < 9)
+    return sfail(RSG_ERR_ARG, "bad dimensions");
+  if (device >= 0) SCK(cudaSetDevice(device));
+  rsg_hi* h = new rsg_hi();
+  auto bail = [&](int rc) { rsg_hi_destroy(h); return rc; };
+  if (cudaGetDevice(&h->device) != cudaSuccess) return bail(sfail(RSG_ERR_CUDA, "cudaGetDevice"));
+  h->nthe = nthe; h->npsi = npsi; h->nzeta = nzeta; h->nR = nR; h->nT = nT; h->nPa = nPa; h->nThetaEquator = nThetaEquator;
+  h->bnormal = bnormal; h->Lz0 = Lz[0];
+  if (cudaStreamCreate(&h->st) != cudaSuccess || cudaEventCreate(&h->e0) != cudaSuccess || cudaEventCreate(&h->e1) != cudaSuccess)
+    return bail(sfail(RSG_ERR_CUDA, "stream / event creation failed"));
+  const size_t n3s = (size_t)nthe * npsi * (nzeta + 1), nl = (size_t)nR * nT, no = (size_t)nthe * nl, n3 = nl * nPa;
+  const size_t nr2 = (size_t)(nR + 1) * nT, nr3 = nr2 * nPa;
+#define HA(ptr, n, name) do { int rc_ = h->dalloc((double**)&(ptr), (n), (name)); if (rc_ != RSG_OK) return bail(rc_); } while (0)
+  static const char* scbn[6] = {"x", "y", "z", "bf", "psi", "alfa"};
+  for (int q = 0; q < 6; q++) HA(h->d_scb[q], n3s, scbn[q]);
+  HiConvArgs& C = h->C;
+  C.nthe = nthe; C.npsi = npsi; C.nzeta = nzeta; C.nR = nR; C.nT = nT; C.nThetaEquator = nThetaEquator;
+  HA(C.qx, nl, nullptr); HA(C.qy, nl, nullptr); HA(C.alphaRAM, nT, nullptr);
+  HA(C.psiRAM, nl, "psiRAM");
+  HA(C.xRAM, no, "xRAM"); HA(C.yRAM, no, "yRAM"); HA(C.zRAM, no, "zRAM"); HA(C.bRAM, no, "bRAM");
+  HiArgs& I = h->I;
+  I.nthe = nthe; I.nR = nR; I.nT = nT; I.nPa = nPa; I.nThetaEquator = nThetaEquator; I.bnormal = bnormal;
+  I.x = C.xRAM; I.y = C.yRAM; I.z = C.zRAM; I.b = C.bRAM;
+  HA(h->d_dens, no, "density");
+  I.dens = h->d_dens;
+  HA(I.chi, nthe, nullptr); HA(I.mu, nPa, nullptr);
+  HA(I.Icart, n3, nullptr); HA(I.Hcart, n3, nullptr); HA(I.Dcart, n3, nullptr); HA(I.bzeq, nl, nullptr);
+  HiTailArgs& T = h->T;
+  T.nR = nR; T.nT = nT; T.nPa = nPa; T.smooth = 0; T.DthI = 0.0;
+  T.bnes1 = 0.32 / (Lz[0] * Lz[0] * Lz[0]) / 1.e4;                                  // :609
+  hi_gauss_weights(T.w);
+  T.I0 = I.Icart; T.H0 = I.Hcart; T.D0 = I.Dcart; T.bz0 = I.bzeq;
+  HA(T.I1, n3, nullptr); HA(T.H1, n3, nullptr); HA(T.D1, n3, nullptr); HA(T.bz1, nl, nullptr); HA(T.hI, n3, nullptr); HA(T.iI, n3, nullptr);
+  HA(T.I2, n3, nullptr); HA(T.H2, n3, nullptr); HA(T.D2, n3, nullptr); HA(T.hI2, n3, nullptr); HA(T.iI2, n3, nullptr);
+  HA(T.FNHS, nr3, "FNHS"); HA(T.FNIS, nr3, "FNIS"); HA(T.BOUNHS, nr3, "BOUNHS"); HA(T.BOUNIS, nr3, "BOUNIS"); HA(T.HDNS, nr3, "HDNS");
+  HA(T.dIdt, nr3, "dIdt"); HA(T.dHdt, nr3, "dHdt"); HA(T.dIbndt, nr3, "dIbndt");
+  HA(T.BNES, nr2, "BNES"); HA(T.dBdt, nr2, "dBdt");
+  HA(T.Lz, nR + 1, nullptr); HA(T.PA, nPa, nullptr); HA(T.PAbn, nPa, nullptr);
+#undef HA
+  {
+    void* q = nullptr;
+    if (cudaMalloc(&q, (2 * nl + nT + 1) * sizeof(int)) != cudaSuccess) return bail(sfail(RSG_ERR_CUDA, "cudaMalloc"));
+    cudaMemset(q, 0, (2 * nl + nT + 1) * sizeof(int));
+    h->allocs.push_back(q);
+    h->d_outSCB = (int*)q; h->d_outMGNP = h->d_outSCB + nl; h->d_scale = h->d_outMGNP + nl; h->d_fail = h->d_scale + nT;
+  }
+  C.outside = h->d_outSCB;
+  I.outside = h->d_outMGNP;
+  T.outside = h->d_outMGNP; T.ScaleAt = h->d_scale; T.fail = h->d_fail;
+  std::vector<double> qx, qy, al;
+  hi_query_tables(nR, nT, Lz, MLT, qx, qy, al);
+  auto upl = [&](const double* dst, const double* src, size_t n) {
+    return cudaMemcpy((void*)dst, src, n * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess;
+  };
+  if (!upl(C.qx, qx.data(), nl) || !upl(C.qy, qy.data(), nl) || !upl(C.alphaRAM, al.data(), nT) || !upl(I.chi, chiVal, nthe) ||
+      !upl(I.mu, mu, nPa) || !upl(T.Lz, Lz, nR + 1) || !upl(T.PA, PA, nPa) || !upl(T.PAbn, PAbn, nPa))
+    return bail(sfail(RSG_ERR_CUDA, "upload of the grid tables failed"));
+  *out = h;
+  return RSG_OK;
+}
+
+static int hi_named(rsg_hi* h, const char* name, double** p, size_t* n) {
+  if (!h || !name) return sfail(RSG_ERR_ARG, "null argument");
+  const size_t nl = (size_t)h->nR * h->nT, n3 = nl * h->nPa;
+  const std::string k(name);
+  // the *_cart arrays as the reference leaves them after the routine: smoothed when IntegralSmooth
+  if (k == "I_cart") { *p = h->T.smooth ? h->T.I2 : h->T.I1; *n = n3; return RSG_OK; }
+  if (k == "H_cart") { *p = h->T.smooth ? h->T.H2 : h->T.H1; *n = n3; return RSG_OK; }
+  if (k == "HDens_cart") { *p = h->I.Dcart; *n = n3; return RSG_OK; }
+  if (k == "bZEq_cart") { *p = h->T.bz1; *n = nl; return RSG_OK; }
+  auto it = h->arr.find(k);
+  if (it == h->arr.end()) return sfail(RSG_ERR_ARG, std::string("unknown array '") + name + "'");
+  *p = it->second.first; *n = it->second.second;
+  return RSG_OK;
+}
+
+/* previous values of the RAM variables (the reference's module arrays at entry): FNHS, FNIS, BOUNHS, BOUNIS, HDNS
+ * (nR+1,nT,nPa), BNES (nR+1,nT); HDens_cart (nR,nT,nPa) may be NULL (zeros / what the last call left) */
+int rsg_hi_set_ram_fields(rsg_hi* h, const double* FNHS, const double* FNIS, const double* BOUNHS, const double* BOUNIS, const double* HDNS,
+                          const double* BNES, const double* HDens_cart) {
+  if (!h || !FNHS || !FNIS || !BOUNHS || !BOUNIS || !HDNS || !BNES) return sfail(RSG_ERR_ARG, "null argument");
+  SCK(cudaSetDevice(h->device));
+  const size_t nr2 = (size_t)(h->nR + 1) * h->nT, nr3 = nr2 * h->nPa;
+  auto up = [&](double* dst, const double* src, size_t n) { return cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyHostToDevice, h->st); };
+  SCK(up(h->T.FNHS, FNHS, nr3)); SCK(up(h->T.FNIS, FNIS, nr3)); SCK(up(h->T.BOUNHS, BOUNHS, nr3)); SCK(up(h->T.BOUNIS, BOUNIS, nr3));
+  SCK(up(h->T.HDNS, HDNS, nr3)); SCK(up(h->T.BNES, BNES, nr2));
+  if (HDens_cart) SCK(up(h->I.Dcart, HDens_cart, (size_t)h->nR * h->nT * h->nPa));
+  SCK(cudaStreamSynchronize(h->st));
+  h->fields_set = true;
+  return RSG_OK;
+}
+
+/* block 1 (src/ModRamScb.f90:252-300).  The SCB arrays x, y, z, bf, psi, alfa (nthe,npsi,nzeta+1) come from the host, or --
+ * all six NULL and scb given -- from the device arrays of an rsg_scb handle on the same device (no copy at all).
+ * outsideSCB (nR,nT; may be NULL) comes back; *nOutside (may be NULL) counts its ones. */
+int rsg_hi_convert(rsg_hi* h, const double* x, const double* y, const double* z, const double* bf, const double* psi, const double* alfa,
+                   rsg_scb* scb, int* outsideSCB, int* nOutside) {
+  if (!h) return sfail(RSG_ERR_ARG, "null handle");
+  SCK(cudaSetDevice(h->device));
+  const size_t n3s = (size_t)h->nthe * h->npsi * (h->nzeta + 1), nl = (size_t)h->nR * h->nT;
+  HiConvArgs& C = h->C;
+  if (x || y || z || bf || psi || alfa) {
+    if (!x || !y || !z || !bf || !psi || !alfa) return sfail(RSG_ERR_ARG, "give all six SCB arrays or none (with an rsg_scb handle)");
+    const double* src[6] = {x, y, z, bf, psi, alfa};
+    for (int q = 0; q < 6; q++) SCK(cudaMemcpyAsync(h->d_scb[q], src[q], n3s * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    C.x = h->d_scb[0]; C.y = h->d_scb[1]; C.z = h->d_scb[2]; C.bf = h->d_scb[3]; C.psi = h->d_scb[4]; C.alfa = h->d_scb[5];
+  } else {
+    if (!scb) return sfail(RSG_ERR_ARG, "no SCB arrays and no rsg_scb handle");
+    if (scb->device != h->device || scb->nthe != h->nthe || scb->npsi != h->npsi || scb->nzeta != h->nzeta)
+      return sfail(RSG_ERR_ARG, "rsg_scb handle on another device or with other dimensions");
+    SCK(cudaStreamSynchronize(scb->st));                           // what the SCB solve left
+    C.x = scb->dev.x; C.y = scb->dev.y; C.z = scb->dev.z; C.bf = scb->dev.bf; C.psi = scb->dev.psi; C.alfa = scb->dev.alfa;
+  }
+  SCK(cudaEventRecord(h->e0, h->st));
+  SRET(hi_launch_convert(C, h->st));
+  h->launches += 2;
+  h->converted = true;
+  h->finished = false;
+  if (outsideSCB || nOutside) {
+    std::vector<int> tmp;
+    int* dst = outsideSCB;
+    if (!dst) { tmp.resize(nl); dst = tmp.data(); }
+    SCK(cudaMemcpyAsync(dst, h->d_outSCB, nl * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    SCK(cudaStreamSynchronize(h->st));
+    if (nOutside) {
+      int c = 0;
+      for (size_t q = 0; q < nl; q++) c += dst[q] != 0;
+      *nOutside = c;
+    }
+  }
+  return RSG_OK;
+}
+
+/* one traced line (src/ModRamScb.f90:330-362, the host's Geopack tracer) for the RAM point (i, j), 1-based: nthe nodes each */
+int rsg_hi_set_line(rsg_hi* h, int i, int j, const double* xl, const double* yl, const double* zl, const double* bl) {
+  if (!h || !xl || !yl || !zl || !bl) return sfail(RSG_ERR_ARG, "null argument");
+  if (i < 1 || i > h->nR || j < 1 || j > h->nT) return sfail(RSG_ERR_ARG, "point out of range");
+  if (!h->converted) return sfail(RSG_ERR_STATE, "rsg_hi_set_line before rsg_hi_convert");
+  SCK(cudaSetDevice(h->device));
+  const size_t o = (size_t)h->nthe * ((i - 1) + (size_t)h->nR * (j - 1)), nb = (size_t)h->nthe * sizeof(double);
+  SCK(cudaMemcpyAsync(h->C.xRAM + o, xl, nb, cudaMemcpyHostToDevice, h->st));
+  SCK(cudaMemcpyAsync(h->C.yRAM + o, yl, nb, cudaMemcpyHostToDevice, h->st));
+  SCK(cudaMemcpyAsync(h->C.zRAM + o, zl, nb, cudaMemcpyHostToDevice, h->st));
+  SCK(cudaMemcpyAsync(h->C.bRAM + o, bl, nb, cudaMemcpyHostToDevice, h->st));
+  SCK(cudaStreamSynchronize(h->st));
+  return RSG_OK;
+}
+
+/* blocks 2 and 3 (:302-637 without the tracer): ScaleAt(nT) / outsideMGNP(nR,nT) from the host's magnetopause logic, or both
+ * NULL: derived on the device as the reference's 'SWMF' branch does (:306-314: ScaleAt = first outside point of the MLT,
+ * every outside line flagged).  density (nthe,nR,nT) from the host, or NULL: the RAIRDEN polynomial of the distance
+ * (:365-371) on the device.  Then the integral block, the tail and the RAM variables, all on the handle's stream. */
+int rsg_hi_finish(rsg_hi* h, const int* ScaleAt, const int* outsideMGNP, const double* density, int integral_smooth, double DthI,
+                  int* gslerr) {
+  if (!h) return sfail(RSG_ERR_ARG, "null handle");
+  if (!h->converted) return sfail(RSG_ERR_STATE, "rsg_hi_finish before rsg_hi_convert");
+  if (!h->fields_set) return sfail(RSG_ERR_STATE, "rsg_hi_finish before rsg_hi_set_ram_fields");
+  if ((ScaleAt == nullptr) != (outsideMGNP == nullptr)) return sfail(RSG_ERR_ARG, "give ScaleAt and outsideMGNP together or neither");
+  if (integral_smooth && (h->nR < 9 || h->nT < 9)) return sfail(RSG_ERR_ARG, "grid smaller than the 9 x 9 smoothing kernel");
+  SCK(cudaSetDevice(h->device));
+  const size_t nl = (size_t)h->nR * h->nT, no = (size_t)h->nthe * nl, n3 = nl * h->nPa;
+  cudaStream_t st = h->st;
+  if (ScaleAt) {
+    for (int j = 0; j < h->nT; j++)
+      if (ScaleAt[j] != 0 && (ScaleAt[j] < 3 || ScaleAt[j] > h->nR)) return sfail(RSG_ERR_ARG, "ScaleAt out of range");
+    SCK(cudaMemcpyAsync(h->d_scale, ScaleAt, h->nT * sizeof(int), cudaMemcpyHostToDevice, st));
+    SCK(cudaMemcpyAsync(h->d_outMGNP, outsideMGNP, nl * sizeof(int), cudaMemcpyHostToDevice, st));
+  } else {
+    k_hi_scaleat<<<nblk(h->nT, 64), 64, 0, st>>>(h->nR, h->nT, h->d_outSCB, h->d_outMGNP, h->d_scale, h->d_fail + 0);
+    SCK(cudaGetLastError());
+    h->launches++;
+  }
+  if (density) {
+    SCK(cudaMemcpyAsync(h->d_dens, density, no * sizeof(double), cudaMemcpyHostToDevice, st));
+  } else {
+    k_hi_rairden<<<nblk((long long)no, 256), 256, 0, st>>>(no, h->C.xRAM, h->C.yRAM, h->C.zRAM, h->d_dens);
+    SCK(cudaGetLastError());
+    h->launches++;
+  }
+  SCK(cudaMemsetAsync(h->d_fail, 0, sizeof(int), st));
+  SRET(hi_launch_lines(h->I, st));
+  h->T.smooth = integral_smooth ? 1 : 0;
+  h->T.DthI = DthI;
+  SRET(hi_launch_tail(h->T, st));
+  h->launches += 4 + (integral_smooth ? 1 : 0);
+  // HDens_cart persists into the next call as the reference's module variable does (skipped lines keep their value, :399)
+  SCK(cudaMemcpyAsync(h->I.Dcart, h->T.smooth ? h->T.D2 : h->T.D1, n3 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  SCK(cudaEventRecord(h->e1, st));
+  int nfail = 0;
+  SCK(cudaMemcpyAsync(&nfail, h->d_fail, sizeof(int), cudaMemcpyDeviceToHost, st));
+  SCK(cudaStreamSynchronize(st));
+  if (!ScaleAt) {                                                  // the device-derived ScaleAt obeys the same range rule
+    std::vector<int> sa(h->nT);
+    SCK(cudaMemcpy(sa.data(), h->d_scale, h->nT * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int j = 0; j < h->nT; j++)
+      if (sa[j] != 0 && sa[j] < 3) return sfail(RSG_ERR_ARG, "ScaleAt out of range (SCB domain ends inside the second RAM shell)");
+  }
+  if (gslerr) *gslerr = nfail;
+  float t = 0.f;
+  if (cudaEventElapsedTime(&t, h->e0, h->e1) == cudaSuccess) h->last_ms = t;
+  h->finished = true;
+  return RSG_OK;
+}
+
+/* the whole routine in one call: convert + finish with the device-side defaults ('SWMF' boundary branch, RAIRDEN density) */
+int rsg_computehI(rsg_hi* h, const double* x, const double* y, const double* z, const double* bf, const double* psi, const double* alfa,
+                  rsg_scb* scb, int integral_smooth, double DthI, int* gslerr) {
+  SRET(rsg_hi_convert(h, x, y, z, bf, psi, alfa, scb, nullptr, nullptr));
+  return rsg_hi_finish(h, nullptr, nullptr, nullptr, integral_smooth, DthI, gslerr);
+}
+
+/* any resident array to the host by name: xRAM yRAM zRAM bRAM density (nthe,nR,nT), psiRAM (nR,nT), I_cart H_cart HDens_cart
+ * (nR,nT,nPa), bZEq_cart (nR,nT), FNHS FNIS BOUNHS BOUNIS HDNS dIdt dHdt dIbndt (nR+1,nT,nPa), BNES dBdt (nR+1,nT) */
+int rsg_hi_get(rsg_hi* h, const char* name, double* host) {
+  if (!host) return sfail(RSG_ERR_ARG, "null argument");
+  double* p = nullptr;
+  size_t n = 0;
+  SRET(hi_named(h, name, &p, &n));
+  SCK(cudaSetDevice(h->device));
+  SCK(cudaMemcpyAsync(host, p, n * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  SCK(cudaStreamSynchronize(h->st));
+  return RSG_OK;
+}
+/* integer results: which = 0 outsideSCB (nR,nT), 1 outsideMGNP (nR,nT), 2 ScaleAt (nT) */
+int rsg_hi_get_int(rsg_hi* h, int which, int* host) {
+  if (!h || !host) return sfail(RSG_ERR_ARG, "null argument");
+  if (which < 0 || which > 2) return sfail(RSG_ERR_ARG, "which out of range");
+  SCK(cudaSetDevice(h->device));
+  const size_t nl = (size_t)h->nR * h->nT;
+  const int* src = which == 0 ? h->d_outSCB : (which == 1 ? h->d_outMGNP : h->d_scale);
+  SCK(cudaMemcpyAsync(host, src, (which == 2 ? (size_t)h->nT : nl) * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  SCK(cudaStreamSynchronize(h->st));
+  return RSG_OK;
+}
+double rsg_hi_last_ms(rsg_hi* h) { return h ? h->last_ms : 0.0; }
+long long rsg_hi_launch_count(rsg_hi* h) { return h ? h->launches : 0; }
+
+/* device pointers of the new field arrays for rsg_ram_set_fields_device (same process, same device):
+ * order BNES, dBdt, FNHS, FNIS, BOUNHS, BOUNIS, HDNS, dIdt, dIbndt; *outsideMGNP the integer array (nR,nT) */
+int rsg_hi_device_fields(rsg_hi* h, const double** ptrs9, const int** outsideMGNP) {
+  if (!h || !ptrs9 || !outsideMGNP) return sfail(RSG_ERR_ARG, "null argument");
+  if (!h->finished) return sfail(RSG_ERR_STATE, "rsg_hi_device_fields before rsg_hi_finish");
+  const HiTailArgs& T = h->T;
+  const double* p[9] = {T.BNES, T.dBdt, T.FNHS, T.FNIS, T.BOUNHS, T.BOUNIS, T.HDNS, T.dIdt, T.dIbndt};
+  for (int q = 0; q < 9; q++) ptrs9[q] = p[q];
+  *outsideMGNP = h->d_outMGNP;
+  return RSG_OK;
 }
 
 double rsg_scb_last_ms(rsg_scb* h) { return h ? h->last_ms : 0.0; }

@@ -267,6 +267,71 @@ module ModScbGpu
        real(c_double), intent(out) :: ms
        integer(c_int) :: ierr
      end function
+     function rsg_hi_create(hOut, device, nthe, npsi, nzeta, nR, nT, nPa, nThetaEquator, bnormal, chiVal, mu, Lz, MLT, PA, PAbn) &
+          bind(C, name='rsg_hi_create') result(ierr)
+       ! the resident computehI (src/ModRamScb.f90:249-637 as one device object)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), intent(out) :: hOut
+       integer(c_int), value :: device, nthe, npsi, nzeta, nR, nT, nPa, nThetaEquator
+       real(c_double), value :: bnormal
+       real(c_double), intent(in) :: chiVal(*), mu(*), Lz(*), MLT(*), PA(*), PAbn(*)
+       integer(c_int) :: ierr
+     end function
+     function rsg_hi_set_ram_fields(h, FNHS, FNIS, BOUNHS, BOUNIS, HDNS, BNES, HDens_cart) &
+          bind(C, name='rsg_hi_set_ram_fields') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       real(c_double), intent(in) :: FNHS(*), FNIS(*), BOUNHS(*), BOUNIS(*), HDNS(*), BNES(*)
+       type(c_ptr), value :: HDens_cart                        ! c_loc(HDens_cart) or c_null_ptr
+       integer(c_int) :: ierr
+     end function
+     function rsg_hi_convert(h, x, y, z, bf, psi, alfa, scb, outsideSCB, nOutside) bind(C, name='rsg_hi_convert') result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h, x, y, z, bf, psi, alfa, scb    ! six c_loc(array) and c_null_ptr, or six c_null_ptr and hScb
+       integer(c_int), intent(inout) :: outsideSCB(*)
+       integer(c_int), intent(out) :: nOutside
+       integer(c_int) :: ierr
+     end function
+     function rsg_hi_set_line(h, i, j, xl, yl, zl, bl) bind(C, name='rsg_hi_set_line') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       integer(c_int), value :: i, j
+       real(c_double), intent(in) :: xl(*), yl(*), zl(*), bl(*)
+       integer(c_int) :: ierr
+     end function
+     function rsg_hi_finish(h, ScaleAt, outsideMGNP, density, integral_smooth, DthI, gslerr) bind(C, name='rsg_hi_finish') result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h, ScaleAt, outsideMGNP, density  ! c_loc(...) or c_null_ptr: device-side defaults
+       integer(c_int), value :: integral_smooth
+       real(c_double), value :: DthI
+       integer(c_int), intent(out) :: gslerr
+       integer(c_int) :: ierr
+     end function
+     function rsg_hi_get(h, name, dst) bind(C, name='rsg_hi_get') result(ierr)
+       import :: c_ptr, c_int, c_double, c_char
+       type(c_ptr), value :: h
+       character(kind=c_char), intent(in) :: name(*)
+       real(c_double), intent(inout) :: dst(*)
+       integer(c_int) :: ierr
+     end function
+     function rsg_hi_get_int(h, which, dst) bind(C, name='rsg_hi_get_int') result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       integer(c_int), value :: which
+       integer(c_int), intent(inout) :: dst(*)
+       integer(c_int) :: ierr
+     end function
+     function rsg_hi_device_fields(h, ptrs9, outsideMGNP) bind(C, name='rsg_hi_device_fields') result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       type(c_ptr), value :: ptrs9, outsideMGNP                ! c_loc of a type(c_ptr) array(9) / of a type(c_ptr) scalar
+       integer(c_int) :: ierr
+     end function
+     function rsg_ram_set_fields_device(h, ptrs9, d_outsideMGNP) bind(C, name='rsg_ram_set_fields_device') result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h, ptrs9, d_outsideMGNP
+       integer(c_int) :: ierr
+     end function
   end interface
 
 contains
@@ -338,5 +403,60 @@ contains
          int(nT,c_int), int(nThetaEquator,c_int), x, y, z, bf, psi, alfa, LZ, MLT, xRAM, yRAM, zRAM, bRAM, outsideSCB, ms), &
          'computehI_convert_lines')
   end subroutine computehI_convert_lines_gpu
+
+  subroutine computehI_gpu(hRam, DthI)
+    ! replaces computehI's default branch from "Convert SCB field lines to RAM field lines" to the NaN check
+    ! (src/ModRamScb.f90:249-637) with everything resident on the device: SCB arrays from the host, the RAM field arrays
+    ! kept in the rsg_hi object between calls and handed device-to-device to the RAM state hRam.  Points outside the SCB
+    ! domain that the reference traces with Geopack (:330-362) are traced here by the host exactly as before and uploaded
+    ! line by line; magnetopause logic (ScaleAt / outsideMGNP, :306-329) stays on the host.
+    use ModRamGrids,     ONLY: nR, nT, nPa
+    use ModRamParams,    ONLY: integral_smooth
+    use ModRamVariables, ONLY: FNHS, FNIS, BOUNHS, BOUNIS, HDNS, BNES, dIdt, dHdt, dIbndt, dBdt, LZ, MLT, MU, PA, PAbn, outsideMGNP
+    use ModScbGrids,     ONLY: nthe, npsi, nzeta
+    use ModScbVariables, ONLY: x, y, z, bf, psi, alfa, chiVal, nThetaEquator, bnormal
+    type(c_ptr), intent(in)    :: hRam
+    real(c_double), intent(in) :: DthI
+    type(c_ptr), save :: hHi = c_null_ptr
+    type(c_ptr), target :: ptrs(9), pOut
+    integer(c_int), target :: ScaleAt(nT), outsideSCB(nR,nT)
+    integer(c_int) :: nOutside, gslerr, ismooth, i, j
+    if (.not. c_associated(hHi)) then
+       call rsg_scb_check(rsg_hi_create(hHi, 0_c_int, int(nthe,c_int), int(npsi,c_int), int(nzeta,c_int), int(nR,c_int), &
+            int(nT,c_int), int(nPa,c_int), int(nThetaEquator,c_int), bnormal, chiVal, MU, LZ, MLT, PA, PAbn), 'computehI')
+       call rsg_scb_check(rsg_hi_set_ram_fields(hHi, FNHS, FNIS, BOUNHS, BOUNIS, HDNS, BNES, c_null_ptr), 'computehI')
+    end if
+    call rsg_scb_check(rsg_hi_convert(hHi, c_loc(x), c_loc(y), c_loc(z), c_loc(bf), c_loc(psi), c_loc(alfa), c_null_ptr, &
+         outsideSCB, nOutside), 'computehI')
+    ScaleAt = 0
+    outsideMGNP = 0
+    do j = 1, nT
+       do i = 1, nR
+          if (outsideSCB(i,j) == 1) then
+             if (ScaleAt(j) == 0) ScaleAt(j) = i
+             ! the reference's magnetopause test and Geopack trace (:311-362) go here unchanged; a traced line is handed
+             ! over with rsg_hi_set_line(hHi, i, j, xRAM(:,i,j), yRAM(:,i,j), zRAM(:,i,j), bRAM(:,i,j)); without a tracer:
+             outsideMGNP(i,j) = 1
+          end if
+       end do
+    end do
+    ismooth = 0
+    if (integral_smooth) ismooth = 1
+    call rsg_scb_check(rsg_hi_finish(hHi, c_loc(ScaleAt), c_loc(outsideMGNP), c_null_ptr, ismooth, DthI, gslerr), 'computehI')
+    if (gslerr /= 0) call CON_stop('computehI_gpu: GSL_Interpolation_1D failed on a pitch-angle line')
+    ! the new field arrays: device-to-device into the RAM state, and to the host copies the rest of the code reads
+    call rsg_scb_check(rsg_hi_device_fields(hHi, c_loc(ptrs), c_loc(pOut)), 'computehI')
+    call rsg_scb_check(rsg_ram_set_fields_device(hRam, c_loc(ptrs), pOut), 'computehI')
+    call rsg_scb_check(rsg_hi_get(hHi, 'FNHS'//c_null_char, FNHS), 'computehI')
+    call rsg_scb_check(rsg_hi_get(hHi, 'FNIS'//c_null_char, FNIS), 'computehI')
+    call rsg_scb_check(rsg_hi_get(hHi, 'BOUNHS'//c_null_char, BOUNHS), 'computehI')
+    call rsg_scb_check(rsg_hi_get(hHi, 'BOUNIS'//c_null_char, BOUNIS), 'computehI')
+    call rsg_scb_check(rsg_hi_get(hHi, 'HDNS'//c_null_char, HDNS), 'computehI')
+    call rsg_scb_check(rsg_hi_get(hHi, 'BNES'//c_null_char, BNES), 'computehI')
+    call rsg_scb_check(rsg_hi_get(hHi, 'dIdt'//c_null_char, dIdt), 'computehI')
+    call rsg_scb_check(rsg_hi_get(hHi, 'dHdt'//c_null_char, dHdt), 'computehI')
+    call rsg_scb_check(rsg_hi_get(hHi, 'dIbndt'//c_null_char, dIbndt), 'computehI')
+    call rsg_scb_check(rsg_hi_get(hHi, 'dBdt'//c_null_char, dBdt), 'computehI')
+  end subroutine computehI_gpu
 
 end module ModScbGpu

@@ -550,6 +550,22 @@ def _scb_lib():
         L.rsg_scb_set_geometry.argtypes = [vp] * 4
         L.rsg_scb_set_pressure.argtypes = [vp, i] + [vp] * 15
         L.rsg_scb_flc_radius.argtypes = [vp, i, i, vp, vp, d, vp, vp, vp]
+        L.rsg_hi_create.argtypes = [C.POINTER(vp), i, i, i, i, i, i, i, i, d] + [vp] * 6
+        L.rsg_hi_destroy.argtypes = [vp]
+        L.rsg_hi_destroy.restype = None
+        L.rsg_hi_set_ram_fields.argtypes = [vp] * 8
+        L.rsg_hi_convert.argtypes = [vp] * 8 + [vp, _ip]
+        L.rsg_hi_set_line.argtypes = [vp, i, i, vp, vp, vp, vp]
+        L.rsg_hi_finish.argtypes = [vp, vp, vp, vp, i, d, _ip]
+        L.rsg_computehI.argtypes = [vp] * 8 + [i, d, _ip]
+        L.rsg_hi_get.argtypes = [vp, C.c_char_p, vp]
+        L.rsg_hi_get_int.argtypes = [vp, i, vp]
+        L.rsg_hi_last_ms.argtypes = [vp]
+        L.rsg_hi_last_ms.restype = d
+        L.rsg_hi_launch_count.argtypes = [vp]
+        L.rsg_hi_launch_count.restype = ll
+        L.rsg_hi_device_fields.argtypes = [vp, vp, vp]
+        L.rsg_ram_set_fields_device.argtypes = [vp, vp, vp]
         L.rsg_scb_set_ram_pressure.argtypes = [vp, i, i, i, vp, vp, vp, vp, vp, i, i, i]
         L.rsg_scb_get_ram_pressure.argtypes = [vp, _ip, _ip, vp, vp, vp, vp]
         L.rsg_scb_pressure_front.argtypes = [vp, i, i, vp, vp]
@@ -914,6 +930,121 @@ def hI_convert_lines(x, y, z, bf, psi, alfa, Lz, MLT, nThetaEquator, device=-1):
     _sck(L.rsg_hI_convert_lines(device, nthe, npsi, nz1 - 1, nR, nT, int(nThetaEquator), _p(x), _p(y), _p(z), _p(bf), _p(psi), _p(alfa),
                                 _p(Lz), _p(MLT), *[_p(a) for a in out], outside.ctypes.data, C.byref(ms)))
     return (*out, outside, ms.value)
+
+
+class HiGpu:
+    """computehI resident on the device (rsg_hi, include/ramscb_gpu.h; src/ModRamScb.f90:249-637): the three blocks run
+    back to back on one stream, the intermediate arrays never leave the device, HDens_cart and the RAM variables persist
+    between calls like the reference's module arrays.  `scb` in convert()/computehI() is a dict with x, y, z, bf, psi, alfa
+    (host arrays) or a ScbGpu (its device arrays are read in place)."""
+
+    NAMES3 = ("xRAM", "yRAM", "zRAM", "bRAM", "density")
+    NAMES_CART = ("I_cart", "H_cart", "HDens_cart")
+    NAMES_RAM3 = ("FNHS", "FNIS", "BOUNHS", "BOUNIS", "HDNS", "dIdt", "dHdt", "dIbndt")
+    NAMES_RAM2 = ("BNES", "dBdt")
+
+    def __init__(self, nthe, npsi, nzeta, Lz, MLT, mu, PA, PAbn, chiVal, nThetaEquator, bnormal, device: int = -1):
+        self.L = _scb_lib()
+        c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        Lz, MLT, mu, PA, PAbn, chiVal = (c(a) for a in (Lz, MLT, mu, PA, PAbn, chiVal))
+        self.nthe, self.npsi, self.nzeta = int(nthe), int(npsi), int(nzeta)
+        self.nR, self.nT, self.nPa = len(Lz) - 1, len(MLT), len(mu)
+        if device < 0:
+            import torch
+            device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        self.h = C.c_void_p()
+        _sck(self.L.rsg_hi_create(C.byref(self.h), device, self.nthe, self.npsi, self.nzeta, self.nR, self.nT, self.nPa,
+                                  int(nThetaEquator), float(bnormal), _p(chiVal), _p(mu), _p(Lz), _p(MLT), _p(PA), _p(PAbn)))
+
+    def close(self):
+        if self.h:
+            self.L.rsg_hi_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_ram_fields(self, ram, HDens_cart=None):
+        f = lambda a: np.asfortranarray(a, dtype=np.float64)
+        a = [f(ram[n]) for n in HI_RAM_NAMES]
+        hd = f(HDens_cart) if HDens_cart is not None else None
+        _sck(self.L.rsg_hi_set_ram_fields(self.h, *[_p(x) for x in a], _p(hd) if hd is not None else None))
+
+    def _scb_args(self, scb):
+        if isinstance(scb, ScbGpu):
+            return [None] * 6 + [scb.h], []
+        f = lambda a: np.asfortranarray(a, dtype=np.float64)
+        keep = [f(scb[n]) for n in ("x", "y", "z", "bf", "psi", "alfa")]
+        return [_p(a) for a in keep] + [None], keep
+
+    def convert(self, scb, want_outside=True):
+        args, keep = self._scb_args(scb)
+        out = np.zeros((self.nR, self.nT), dtype=np.int32, order="F") if want_outside else None
+        n = C.c_int(0)
+        _sck(self.L.rsg_hi_convert(self.h, *args, out.ctypes.data if out is not None else None, C.byref(n) if want_outside else None))
+        return out, n.value
+
+    def set_line(self, i, j, x, y, z, b):
+        c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        x, y, z, b = c(x), c(y), c(z), c(b)
+        _sck(self.L.rsg_hi_set_line(self.h, int(i), int(j), _p(x), _p(y), _p(z), _p(b)))
+
+    def finish(self, DthI, integral_smooth=True, ScaleAt=None, outsideMGNP=None, density=None):
+        sa = np.ascontiguousarray(ScaleAt, dtype=np.int32) if ScaleAt is not None else None
+        om = np.asfortranarray(outsideMGNP, dtype=np.int32) if outsideMGNP is not None else None
+        de = np.asfortranarray(density, dtype=np.float64) if density is not None else None
+        err = C.c_int(0)
+        _sck(self.L.rsg_hi_finish(self.h, sa.ctypes.data if sa is not None else None, om.ctypes.data if om is not None else None,
+                                  _p(de) if de is not None else None, 1 if integral_smooth else 0, float(DthI), C.byref(err)))
+        return err.value
+
+    def computehI(self, scb, DthI, integral_smooth=True):
+        args, keep = self._scb_args(scb)
+        err = C.c_int(0)
+        _sck(self.L.rsg_computehI(self.h, *args, 1 if integral_smooth else 0, float(DthI), C.byref(err)))
+        return err.value
+
+    def get(self, name):
+        if name in self.NAMES3:
+            out = np.zeros((self.nthe, self.nR, self.nT), order="F")
+        elif name in self.NAMES_CART:
+            out = np.zeros((self.nR, self.nT, self.nPa), order="F")
+        elif name in self.NAMES_RAM3:
+            out = np.zeros((self.nR + 1, self.nT, self.nPa), order="F")
+        elif name in self.NAMES_RAM2:
+            out = np.zeros((self.nR + 1, self.nT), order="F")
+        else:
+            out = np.zeros((self.nR, self.nT), order="F")          # psiRAM, bZEq_cart
+        _sck(self.L.rsg_hi_get(self.h, name.encode(), _p(out)))
+        return out
+
+    def get_int(self, which):
+        k = {"outsideSCB": 0, "outsideMGNP": 1, "ScaleAt": 2}[which]
+        out = np.zeros(self.nT if k == 2 else (self.nR, self.nT), dtype=np.int32, order="F")
+        _sck(self.L.rsg_hi_get_int(self.h, k, out.ctypes.data))
+        return out
+
+    def results(self):
+        out = {n: self.get(n) for n in self.NAMES_RAM3 + self.NAMES_RAM2 + self.NAMES_CART + ("bZEq_cart", "xRAM", "yRAM", "zRAM", "bRAM")}
+        for n in ("outsideSCB", "outsideMGNP", "ScaleAt"):
+            out[n] = self.get_int(n)
+        return out
+
+    def push_to_ram(self, ram_gpu):
+        """the new BNES .. dIbndt and outsideMGNP device-to-device into a RamGpu on the same device (rsg_ram_set_fields)"""
+        ptrs = (C.c_void_p * 9)()
+        om = C.c_void_p()
+        _sck(self.L.rsg_hi_device_fields(self.h, C.cast(ptrs, C.c_void_p), C.cast(C.byref(om), C.c_void_p)))
+        _ck(self.L.rsg_ram_set_fields_device(ram_gpu.h, C.cast(ptrs, C.c_void_p), om))
+
+    def last_ms(self):
+        return float(self.L.rsg_hi_last_ms(self.h))
+
+    def launch_count(self):
+        return int(self.L.rsg_hi_launch_count(self.h))
 
 
 def computehI(scb, Lz, MLT, mu, PA, PAbn, ram, DthI, integral_smooth=True, density_fn=None, trace_fn=None, device=-1, _impl=None):

@@ -674,7 +674,7 @@ def test_fortran_shims_match_the_c_header():
                                 "void": "c_ptr"}.get(ctype)
                         if kind:                      # opaque handles (rsg_ram**, rsg_scb**) are type(c_ptr), intent(out)
                             assert kind in spec, f"{where}: {a} should be {kind} ({spec.strip()})"
-                        elif ctype in ("rsg_ram", "rsg_scb"):
+                        elif ctype in ("rsg_ram", "rsg_scb", "rsg_hi"):
                             assert "type(c_ptr)" in spec, f"{where}: handle {a}"
                         else:                         # struct passed by reference: a bind(C) derived type of the same name
                             assert f"type({ctype})" in spec, f"{where}: {a} should be type({ctype})"

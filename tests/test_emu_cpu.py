@@ -124,6 +124,11 @@ def test_emulated_computehI_composed(emu, default_grids, oracle_built):
     TZ.test_computehI_composed_on_device(default_grids, oracle_built, (21, 19, 25))
 
 
+def test_emulated_computehI_resident(emu, default_grids, oracle_built):
+    import test_zz_late_additions_gpu as TZ
+    TZ.test_computehI_resident_handle(default_grids, oracle_built, (21, 15, 25))
+
+
 def test_emulated_scb_run_outer_iterations(emu, oracle_built):
     """rsg_scb_run -- the whole outer iteration of scb_run in one C call, 3-D arrays resident, pressure front
     end as a host callback -- against the oracle's composition, incl. the SORFail restore path."""

@@ -345,6 +345,95 @@ def test_computehI_composed_on_device(default_grids, oracle_built, dims):
     assert np.all(np.isfinite(out["FNHS"][1:][inside])) and np.all(out["FNHS"][1:][inside][:, 4:] > 0.0)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("dims", [(51, 25, 41)])
+def test_computehI_resident_handle(default_grids, oracle_built, dims):
+    """rsg_hi (the resident computehI): same kernels as the three stateless calls with nothing going through the host in
+    between.  (a) host-driven middle (ScaleAt / outsideMGNP / density from the host) bit-identical to host.computehI and so
+    to the oracle's composition; (b) a second call continues from the persisted HDens_cart and RAM variables exactly as
+    the stateless chain fed with its own outputs does; (c) the all-device defaults ('SWMF' boundary branch, RAIRDEN on the
+    device): flags identical, fields within the last bits of pow(); (d) the new field arrays device-to-device into a RamGpu
+    give the same ram_run as set_fields from the host."""
+    from ramscb_b200 import host
+    g = default_grids
+    nthe, npsi, nzeta = dims
+    inp = SCBSYN.build_scb(nthe=nthe, npsi=npsi, nzeta=nzeta, warp=0.2)
+    r = np.sqrt(inp.x ** 2 + inp.y ** 2 + inp.z ** 2)
+    scb = dict(x=inp.x, y=inp.y, z=inp.z, psi=inp.psi, alfa=inp.alfa, chiVal=inp.chiVal, nThetaEquator=nthe // 2 + 1, bnormal=1.0,
+               bf=np.asfortranarray(30574.0 / r ** 3 * np.sqrt(1.0 + 3.0 * (inp.z / r) ** 2)))
+    Lz = np.linspace(1.75, 8.0, g.NR + 1)
+    rng = np.random.default_rng(4)
+    shape3 = (g.NR + 1, g.NT, g.NPA)
+    ram = {n: np.asfortranarray(rng.random(shape3)) for n in ("FNHS", "FNIS", "BOUNHS", "BOUNIS", "HDNS")}
+    ram["BNES"] = np.asfortranarray(1e-7 * rng.random((g.NR + 1, g.NT)))
+
+    def dens(d):        # RAIRDEN with the Fortran's integer powers (x**3 = x*x*x, x**4 = (x*x)*(x*x))
+        d2 = d * d
+        return 10.0 ** (13.326 - 3.6908 * d + 1.1362 * d2 - 0.16984 * (d2 * d) + 0.009553 * (d2 * d2))
+
+    MLT = g.MLT[:g.NT]
+    args = (scb, Lz, MLT, g.MU, g.PA, g.PAbn)
+    ref1 = host.computehI(*args, ram, 300.0, integral_smooth=True, density_fn=dens)
+    ram2 = {n: ref1[n] for n in host.HI_RAM_NAMES}
+    hi = host.HiGpu(nthe, npsi, nzeta, Lz, MLT, g.MU, g.PA, g.PAbn, inp.chiVal, nthe // 2 + 1, 1.0)
+    hi.set_ram_fields(ram)
+    # (a) host-driven middle
+    outside, nout = hi.convert(scb)
+    assert nout > 0 and np.array_equal(outside, ref1["outsideSCB"])
+    xR, yR, zR = hi.get("xRAM"), hi.get("yRAM"), hi.get("zRAM")
+    assert np.array_equal(xR, ref1["xRAM"]) and np.array_equal(hi.get("bRAM"), ref1["bRAM"])
+    err = hi.finish(300.0, True, ScaleAt=ref1["ScaleAt"], outsideMGNP=ref1["outsideMGNP"],
+                    density=dens(np.sqrt(xR ** 2 + yR ** 2 + zR ** 2)))
+    assert err == ref1["gslerr"]
+    got = hi.results()
+    for n in ("FNHS", "FNIS", "BOUNHS", "BOUNIS", "HDNS", "BNES", "dIdt", "dHdt", "dIbndt", "dBdt", "I_cart", "H_cart", "HDens_cart", "bZEq_cart"):
+        assert np.array_equal(ref1[n], got[n], equal_nan=True), n
+    # (b) second call: state persisted on the device
+    warped = dict(scb)
+    warped["bf"] = np.asfortranarray(scb["bf"] * 1.01)
+    hi.convert(warped, want_outside=False)
+    xR, yR, zR = hi.get("xRAM"), hi.get("yRAM"), hi.get("zRAM")
+    hi.finish(60.0, True, ScaleAt=ref1["ScaleAt"], outsideMGNP=ref1["outsideMGNP"], density=dens(np.sqrt(xR ** 2 + yR ** 2 + zR ** 2)))
+    xR2, yR2, zR2, bR2, _o = host.hI_convert_lines(warped["x"], warped["y"], warped["z"], warped["bf"], warped["psi"], warped["alfa"], Lz, MLT,
+                                                   nthe // 2 + 1)[:5]
+    I, H, D, bz = host.hI_integrals(inp.chiVal, g.MU, xR2, yR2, zR2, bR2, dens(np.sqrt(xR2 ** 2 + yR2 ** 2 + zR2 ** 2)), ref1["outsideMGNP"],
+                                    nthe // 2 + 1, 1.0, HDens_cart=ref1["HDens_cart"])[:4]
+    ref2 = host.hI_tail(I, H, D, bz, ref1["ScaleAt"], ref1["outsideMGNP"], Lz, g.PA, g.PAbn, True, 60.0, ram2)
+    got2 = hi.results()
+    for n in ("FNHS", "FNIS", "BOUNHS", "BOUNIS", "HDNS", "BNES", "dIdt", "dHdt", "dIbndt", "dBdt", "HDens_cart"):
+        assert np.array_equal(ref2[n], got2[n], equal_nan=True), n
+    # (c) everything on the device in one call
+    hi2 = host.HiGpu(nthe, npsi, nzeta, Lz, MLT, g.MU, g.PA, g.PAbn, inp.chiVal, nthe // 2 + 1, 1.0)
+    hi2.set_ram_fields(ram)
+    n0 = hi2.launch_count()
+    assert hi2.computehI(scb, 300.0, True) == ref1["gslerr"]
+    assert hi2.launch_count() - n0 == 9          # nn9 x2, ScaleAt, RAIRDEN, lines, tail x4
+    got3 = hi2.results()
+    assert np.array_equal(got3["ScaleAt"], ref1["ScaleAt"]) and np.array_equal(got3["outsideMGNP"], ref1["outsideMGNP"])
+    for n in ("FNHS", "FNIS", "BOUNHS", "BOUNIS", "BNES", "dIdt", "dIbndt", "dBdt"):
+        assert np.array_equal(ref1[n], got3[n], equal_nan=True), n
+    for n in ("HDNS", "dHdt"):                   # the bounce-averaged density sees pow() of the device
+        assert np.allclose(ref1[n], got3[n], rtol=1e-13, atol=0, equal_nan=True), n
+    # (d) straight into the RAM state
+    inp_r = synthetic.make_inputs(g, f2_kind="smooth", inductive=True)
+    outs = []
+    for dev_path in (False, True):
+        gpu = host.RamGpu(g)
+        gpu.set_inputs(inp_r)
+        if dev_path:
+            hi2.push_to_ram(gpu)
+        else:
+            L = host.lib()
+            a = [np.asfortranarray(got3[n]) for n in ("BNES", "dBdt", "FNHS", "FNIS", "BOUNHS", "BOUNIS", "HDNS", "dIdt", "dIbndt")]
+            om = np.asfortranarray(got3["outsideMGNP"], dtype=np.int32)
+            host._ck(L.rsg_ram_set_fields(gpu.h, *[host._p(x) for x in a], om.ctypes.data))
+        gpu.ram_run(5.0, DtsMin=1.0, flags=0)
+        outs.append(gpu.f2_d2h())
+        gpu.close()
+    assert np.array_equal(outs[0], outs[1], equal_nan=True)
+    hi.close(); hi2.close()
+
+
 def test_anisch_diffcoef_rebuild_feeds_the_wpi_step(default_grids, oracle_built):
     """ANISCH's diffusion-coefficient rebuild (src/ModRamRun.f90:422-605) on the device, then a WPI + EMIC
     ram_run that never sees a host-built coefficient array.  Coefficients <= 1e-13 of the oracle's (device log10 / pow vs
