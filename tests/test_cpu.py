@@ -420,6 +420,62 @@ def test_scb_oracle_dipole_and_sor(oracle_built):
     assert np.max(np.abs(res[1:-1, :, 1:-1])) < 5e-5
 
 
+def test_scb_oracle_theChange_one_branch(oracle_built):
+    """theChange <= 1 (src/ModScbEuler.f90:272-279 / :585-591): the theta end points are extrapolated with extap
+    (src/ModScbFunctions.f90:57-76) instead of the linear fill.  The oracle used to abort() here.  Checked:
+    the post-processing against a literal numpy transcription applied to the same pre-image (the interior rows the SOR
+    sweeps leave are untouched by the end-point rule, so the pre-image is recoverable), for iteratePsi (k = 2..nzeta) and
+    iterateAlpha (the reference's k = 2..nthe-1 over the zeta index, clipped to the planes that exist: oracle header)."""
+    from ramscb_b200 import scb_synthetic as S
+
+    def extap(x1, x2, x3):
+        x4 = 3. * x3 - 3. * x2 + x1
+        ddx1, ddx2 = x3 - x2, x2 - x1
+        if (x4 - x3) * ddx1 > 0.:
+            return x4
+        if abs(ddx2) <= 1e-9:
+            return 2. * x3 - x2
+        return x3 + (ddx1 * ddx1) / ddx2
+
+    inp = S.build_scb(nthe=25, npsi=13, nzeta=17, warp=0.1)
+    nthe, npsi, nzeta = inp.nthe, inp.npsi, inp.nzeta
+    for which in ("psi", "alpha"):
+        o = oracle_built.ScbOracle(inp)
+        assert o.bandjacob() == 0
+        o.set_int("theChange", 1)
+        o.set_int("nimax", 30)
+        if which == "psi":
+            o.metric(); o.newj()
+            o.iterate_psi()
+            u = o.psi.copy()
+            kend, wrap = nzeta, 0.0
+        else:
+            o.metrica(); o.newk()
+            o.iterate_alpha()
+            u = o.alfa.copy()
+            kend, wrap = min(nthe - 1, nzeta + 1), 2.0 * np.pi
+        assert np.all(np.isfinite(u))
+        v = u.copy()
+        for k in range(2, kend + 1):                       # Fortran k; arrays are (nthe, npsi, nzeta+1)
+            for j in range(1, npsi + 1):
+                v[nthe - 1, j - 1, k - 1] = extap(v[nthe - 4, j - 1, k - 1], v[nthe - 3, j - 1, k - 1], v[nthe - 2, j - 1, k - 1])
+                v[0, j - 1, k - 1] = extap(v[3, j - 1, k - 1], v[2, j - 1, k - 1], v[1, j - 1, k - 1])
+        v[:, :, 0] = v[:, :, nzeta - 1] - wrap
+        v[:, :, nzeta] = v[:, :, 1] + wrap
+        # the end points are a pure function of rows 2..4 / nthe-3..nthe-1, which the rule does not touch: idempotent image
+        assert np.array_equal(u, v), which
+        # and it is NOT the linear fill of the default branch (which with nT = 1 would leave the end points unchanged)
+        o4 = oracle_built.ScbOracle(inp)
+        o4.bandjacob()
+        o4.set_int("nimax", 30)
+        if which == "psi":
+            o4.metric(); o4.newj(); o4.iterate_psi()
+            assert not np.array_equal(o4.psi[0], u[0])
+        else:
+            o4.metrica(); o4.newk(); o4.iterate_alpha()
+            assert not np.array_equal(o4.alfa[0], u[0])
+
+
 # ---- the C-ABI library -------------------------------------------------------------------------
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` (the CPU arm the driver runs next to ours) needs no GPU and prints
