@@ -457,6 +457,26 @@ def measure_ram(workload_name, flags, steps, warmup, device, mode="fast", dist=N
                                           "frac": 16.0 * cells * ops / (ms * 1e-3) / 1e9 / peak,
                                           "three_pass_floor_ms": 3 * 16.0 * cells / (peak * 1e9) * 1e3}}
     elif sh:
+        per_stage = None
+        if do_profile:
+            # per-stage device times of the sharded step (CUDA events on the run stream between its launches, graph replay
+            # off for this pass); a stage that ends in a device-side barrier includes the wait for the slowest peer
+            gpu.profile(True)
+            npf = 5
+            for _ in range(npf):
+                flush.zero_()
+                barrier()
+                step()
+            stages = gpu.profile_get()
+            gpu.profile(False)
+            names = [k for k in stages if k != "end"]
+            t = torch.tensor([stages[k][0] / max(stages[k][1], 1) for k in names], dtype=torch.float64, device="cuda")
+            tmax = t.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            per_stage = {"rank0_ms": {k: float(v) for k, v in zip(names, t.tolist())},
+                         "max_over_ranks_ms": {k: float(v) for k, v in zip(names, tmax.tolist())},
+                         "column_resharding": "bulk push after the column kernel (RSG_PEER_PUSH=1)" if os.environ.get("RSG_PEER_PUSH", "0") not in ("", "0")
+                         else "the column kernel's own write-back into the peers"}
         per_gpu = 16.0 * cells * ops / world / (ms * 1e-3) / 1e9
         sent = 0.0                                                # bytes this rank stores into peers per step (2 re-shardings)
         if plan.G > 1:
@@ -465,6 +485,7 @@ def measure_ram(workload_name, flags, steps, warmup, device, mode="fast", dist=N
         out["roofline"] = {"bound": "hbm", "kernel": "whole sharded step (per GPU)", "achieved": per_gpu, "peak": peak, "unit": "GB/s",
                            "frac": per_gpu / peak, "traffic": None, "peak_source": peak_src,
                            "note": "16 B per cell-update x this GPU's share of the cell-updates / max-over-ranks step time",
+                           "per_stage": per_stage,
                            "nvlink": {"peer_store_bytes_per_rank_per_step": int(sent),
                                       "link_floor_ms": sent / 770e9 * 1e3,
                                       "note": "F2 values stored straight into the consuming rank's buffer by the producing kernel's "

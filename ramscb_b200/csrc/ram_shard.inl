@@ -75,6 +75,28 @@ __global__ void k_peer_barrier(const __grid_constant__ PeerCtx pc, int which, un
   }
 }
 
+// Second re-sharding of the step, bulk form: the column kernel has written its block range [c0, c1) of plane positions
+// into the LOCAL buffer; every (l, k) row of that range whose pitch angle belongs to another rank goes to that rank's
+// buffer as ONE contiguous run (c1 - c0 doubles, 3.9 KB at 8 ranks on the 4x grid) of 16-byte stores -- full NVLink
+// packets, where the column kernel's own write-back can only send the 32 bytes a CTA holds of a row.  The source was
+// written a moment ago: an L2 read.  Warp per row; grid: x = row tiles, y = species.
+__global__ void __launch_bounds__(256) k_peer_push_cols(const __grid_constant__ PeerView pv, const __grid_constant__ SpecPack pk, int s0,
+                                                        int NE, int NPA, int Pp, int c0, int c1) {
+  const SpecDev& sp = pk.s[s0 + blockIdx.y];
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= NE * NPA) return;
+  const int l = row / NE;
+  const int o = peer_owner(pv.lcut, pv.G, l);
+  if (o == pv.gidx) return;
+  const double* src = sp.F + (size_t)row * Pp;
+  double* dst = pv.F[o] + (sp.F - pv.F[pv.gidx]) + (size_t)row * Pp;
+  int c = c0;
+  if ((c & 1) && c < c1) { if (lane == 0) dst[c] = src[c]; ++c; }                  // Pp is even: rows start 16-byte aligned
+  const int n2 = (c1 - c) >> 1;
+  for (int t = lane; t < n2; t += 32) *(double2*)(dst + c + 2 * t) = *(const double2*)(src + c + 2 * t);
+  if (((c1 - c) & 1) && lane == 0) dst[c1 - 1] = src[c1 - 1];
+}
+
 // this rank's result blocks of species [s0, s0+ns) into slot `rank` of every rank's mailbox.  grid: x = destination rank
 __global__ void __launch_bounds__(256) k_push_results(const __grid_constant__ PeerCtx pc, int s0, int ns,
                                                       const unsigned long long* __restrict__ res, const double* __restrict__ pp) {
@@ -147,6 +169,7 @@ struct rsg_shard {
   unsigned group_mask = 0, world_mask = 0;
   int pending_flags = 0;
   bool pending = false;
+  bool push_cols = false;   // second re-sharding as a bulk push after the column kernel (RSG_PEER_PUSH) instead of its own write-back
 };
 
 namespace {
@@ -195,6 +218,7 @@ int shard_finish_attach(rsg_ram* h, int rank, int world, int policy) {
   for (int s = 0; s < h->nS; ++s)
     if (h->sp[s].cur != 0) return fail(RSG_ERR_STATE, "peer attach needs F2 in buffer 0 (attach before running single operators)");
   if (sh.gexec) { cudaGraphExecDestroy(sh.gexec); sh.gexec = nullptr; }
+  if (const char* e = getenv("RSG_PEER_PUSH")) sh.push_cols = std::atoi(e) != 0;
   sh.attached = true;
   return RSG_OK;
 }
@@ -222,14 +246,32 @@ int enqueue_sharded(rsg_ram* h, double DTs, int flags) {
     for (int s = 0; s < h->nS; ++s)
       if (s < s0 || s >= s0 + ns) doW &= ~(1 << s);
     h->in_step = false;
+    RET(prof_mark(h, "k_plane_rp_fwd(peer stores)", st));
     RET(L_plane_rp(h, s0, ns, st, false, p.l0, p.nl, &sh.pv));     // DRIFTR, DRIFTP -> the column owners
+    RET(prof_mark(h, "barrier_1", st));
     k_peer_barrier<<<1, 32, 0, st>>>(sh.pc, 0, sh.group_mask);
     CKL();
     const int doC = (flags & RSG_F_COULOMB) ? 1 : 0;
-    RET(L_col(h, s0, ns, doA, DTs, st, p.b0, p.nb, doW, &sh.pv, doC));   // DRIFTE .. DRIFTE -> the pitch-angle owners
+    if (sh.push_cols) {
+      RET(prof_mark(h, "k_col_fused(local)", st));
+      RET(L_col(h, s0, ns, doA, DTs, st, p.b0, p.nb, doW, nullptr, doC));  // DRIFTE .. DRIFTE into the local buffer
+      RET(prof_mark(h, "k_peer_push_cols", st));
+      SpecPack pk;
+      make_pack(h, pk, s0, ns);
+      const int c0 = p.b0 * COL_PG, c1 = std::min(h->P, (p.b0 + p.nb) * COL_PG);
+      k_peer_push_cols<<<dim3(nblk((long long)h->NE * h->NPA, 8), ns), 256, 0, st>>>(sh.pv, pk, s0, h->NE, h->NPA, h->Pp, c0, c1);
+      CKL();
+      h->launches++;
+    } else {
+      RET(prof_mark(h, "k_col_fused(peer stores)", st));
+      RET(L_col(h, s0, ns, doA, DTs, st, p.b0, p.nb, doW, &sh.pv, doC));   // DRIFTE .. DRIFTE -> the pitch-angle owners
+    }
+    RET(prof_mark(h, "barrier_2", st));
     k_peer_barrier<<<1, 32, 0, st>>>(sh.pc, 0, sh.group_mask);
     CKL();
+    RET(prof_mark(h, "k_plane_rp_rev", st));
     RET(L_plane_rp(h, s0, ns, st, true, p.l0, p.nl));               // DRIFTP, DRIFTR, epilogue (local slab)
+    RET(prof_mark(h, "anisch+finalize", st));
     RET(L_finish_fused(h, s0, ns, st, p.l0, p.nl, p.nb));
     h->launches += 2;
     if (doW) {
@@ -253,6 +295,7 @@ int enqueue_sharded(rsg_ram* h, double DTs, int flags) {
     RET(rsg_ram_part_mid(h, DTs, flags, s0, ns, 0, h->NE));
     RET(rsg_ram_part_rev(h, s0, ns, 0, h->NPA));
   }
+  RET(prof_mark(h, "results: push, world barrier, reduce", st));
   k_push_results<<<p.world, 256, 0, st>>>(sh.pc, s0, ns, h->d_res_all, h->d_pp_all);
   CKL();
   k_peer_barrier<<<1, 32, 0, st>>>(sh.pc, 1, sh.world_mask);
@@ -260,6 +303,7 @@ int enqueue_sharded(rsg_ram* h, double DTs, int flags) {
   k_reduce_results<<<dim3(nblk(std::max<long long>(sh.pc.pp_n, RES_N), 256), h->nS), 256, 0, st>>>(
       sh.pc, sh.ow, NSUM, DTF_OFF, h->d_res_all, h->d_pp_all, h->hd_res_all, h->hd_pp_all);
   CKL();
+  RET(prof_mark(h, "end", st));
   h->launches += 3;
   return RSG_OK;
 }
@@ -412,6 +456,7 @@ int rsg_ram_run_sharded_collect(rsg_ram* h, double DtsMin, double* dts_next, dou
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->pst()));
   sh.pending = false;
+  RET(prof_fold(h));
   if (*sh.h_err) {
     const unsigned long long e = *sh.h_err;
     *sh.h_err = 0;

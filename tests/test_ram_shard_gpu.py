@@ -6,6 +6,8 @@ of tests/multi_gpu_check.py, which differs only in how the peer pointers are obt
 Bars: the re-assembled F2 of the ranks is BIT-IDENTICAL to rsg_ram_run on one handle (the kernels do the same per-cell
 arithmetic; only the owner of a cell changes), CFL limits identical, SUMRC moments / pressures <= 1e-12 (partial sums
 are added in rank order instead of block order), and every rank returns the same bits."""
+import os
+
 import numpy as np
 import pytest
 
@@ -103,6 +105,20 @@ def test_sharded_step_with_coulomb_stages(default_grids, world, policy):
     _check(F1, o1, FN, oN, plans)
 
 
+@pytest.mark.parametrize("world,policy", [(8, 1), (8, 0), (3, 1)])
+def test_sharded_step_bulk_push_of_the_column_resharding(default_grids, monkeypatch, world, policy):
+    """RSG_PEER_PUSH=1: the column kernel writes its block range locally and k_peer_push_cols sends every (l, k) row to
+    the pitch angle's owner as one contiguous run -- same bits as the kernel's own peer write-back"""
+    from ramscb_b200 import host
+    monkeypatch.setenv("RSG_PEER_PUSH", "1")
+    g = default_grids
+    inp = synthetic.make_inputs(g, f2_kind="noisy", inductive=True, mgnp=True)
+    D = synthetic.synthetic_daa(g, inp)
+    F1, o1 = _single(g, inp, host.MODE_FAST, 5, D)
+    FN, oN, plans = _sharded(g, inp, host.MODE_FAST, 5, world, policy, D)
+    _check(F1, o1, FN, oN, plans)
+
+
 def test_sharded_step_ragged_grid():
     """odd sizes: NR odd (8-byte staging path of the plane kernel), slabs and column ranges that do not divide evenly"""
     from ramscb_b200 import host
@@ -112,6 +128,12 @@ def test_sharded_step_ragged_grid():
     for world, policy in ((8, 0), (5, 1)):
         FN, oN, plans = _sharded(g, inp, host.MODE_FAST, 0, world, policy)
         _check(F1, o1, FN, oN, plans)
+    os.environ["RSG_PEER_PUSH"] = "1"            # odd column cuts: the scalar head / tail of the bulk push
+    try:
+        FN, oN, plans = _sharded(g, inp, host.MODE_FAST, 0, 5, 1)
+        _check(F1, o1, FN, oN, plans)
+    finally:
+        del os.environ["RSG_PEER_PUSH"]
 
 
 @pytest.mark.parametrize("world", [2, 4])
