@@ -473,6 +473,7 @@ struct ColCfg {
   int nsegL, segL;    // loss block: pitch-angle segments per (k, position) column
   int doA;            // bit s: species s applies its first/last loss operator
   int b0;             // first block of plane positions of the launch (column-sharded ranks)
+  int pb0;            // partial-sum slot of the launch's first block (chunked launches of one rank's block range)
   int doW;            // bit s: species s runs WPADIF after the first / before the second DRIFTMU (WPI instantiation only)
   int wpart_off;      // where the two WPADIF moments of a block go in sp.part
   int doC;            // Coulomb operators (COULEN, COULMU | COULMU, COULEN around the loss block) for every species (WPI instantiation only)
@@ -998,13 +999,13 @@ __global__ void __launch_bounds__(MAXT) k_col_fused(const __grid_constant__ RamD
       if (r >= rowItems) { r -= rowItems; ++l; so += pad; }
     }
   }
-  block_sum_to<5>(sp.part, blockIdx.x, acc, sRed);
+  block_sum_to<5>(sp.part, cfg.pb0 + blockIdx.x, acc, sRed);
   if (WPI) {
     __syncthreads();
-    block_sum_to<2>(sp.part + cfg.wpart_off, blockIdx.x, accW, sRed);
+    block_sum_to<2>(sp.part + cfg.wpart_off, cfg.pb0 + blockIdx.x, accW, sRed);
     if (doC) {
       __syncthreads();
-      block_sum_to<4>(sp.part + cfg.cpart_off, blockIdx.x, accC, sRed);
+      block_sum_to<4>(sp.part + cfg.cpart_off, cfg.pb0 + blockIdx.x, accC, sRed);
     }
   }
 }

@@ -625,12 +625,13 @@ int L_wtab(rsg_ram* h, int mask, double DTs, cudaStream_t st) {
   return RSG_OK;
 }
 template <int EXT, bool PEER>
-int L_col_t(rsg_ram* h, int s0, int ns, int doA, int doW, double DTs, cudaStream_t st, int b0, int nb, const PeerView& pv, int doC) {
+int L_col_t(rsg_ram* h, int s0, int ns, int doA, int doW, double DTs, cudaStream_t st, int b0, int nb, const PeerView& pv, int doC, int pb0) {
   SpecPack pk;
   make_pack(h, pk, s0, ns);
   ColPlan c = col_plan(h, EXT >= 1);
   c.cfg.doA = doA;
   c.cfg.b0 = b0;
+  c.cfg.pb0 = pb0;
   c.cfg.doW = doW;
   c.cfg.wpart_off = fused_wpart_off(h);
   c.cfg.doC = doC;
@@ -643,9 +644,9 @@ int L_col_t(rsg_ram* h, int s0, int ns, int doA, int doW, double DTs, cudaStream
   if (c.T <= 320) {          // register budget follows the CTA size
     RET(opt_in_smem(k_col_fused<COL_PG, 320, EXT, PEER>, c.smem));
     k_col_fused<COL_PG, 320, EXT, PEER><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg, pv);
-  } else if (c.T <= 640) {
-    RET(opt_in_smem(k_col_fused<COL_PG, 640, EXT, PEER>, c.smem));
-    k_col_fused<COL_PG, 640, EXT, PEER><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg, pv);
+  } else if (c.T <= 576) {   // 576 = 2 x 288: the configs[2] shape; 112 registers, no spill in the WPI instantiation
+    RET(opt_in_smem(k_col_fused<COL_PG, 576, EXT, PEER>, c.smem));
+    k_col_fused<COL_PG, 576, EXT, PEER><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg, pv);
   } else if (c.T <= 896) {
     RET(opt_in_smem(k_col_fused<COL_PG, 896, EXT, PEER>, c.smem));
     k_col_fused<COL_PG, 896, EXT, PEER><<<g, c.T, c.smem, st>>>(dv, pk, s0, c.cfg, pv);
@@ -658,16 +659,16 @@ int L_col_t(rsg_ram* h, int s0, int ns, int doA, int doW, double DTs, cudaStream
   return RSG_OK;
 }
 int L_col(rsg_ram* h, int s0, int ns, int doA, double DTs, cudaStream_t st, int b0 = 0, int nb = -1, int doW = 0,
-          const PeerView* peer = nullptr, int doC = 0) {
+          const PeerView* peer = nullptr, int doC = 0, int pb0 = 0) {
   for (int s = s0; s < s0 + ns; ++s)
     if (!((doW >> s) & 1)) { h->sp[s].sd.DA = h->d_zero4; h->sp[s].sd.DB = h->d_zero4; }
   static const PeerView kNoPeer{};
   const bool ext = doW || doC;          // the extended instantiation: WPADIF and / or the Coulomb operators as extra stages
   if (peer)
-    return doC ? L_col_t<2, true>(h, s0, ns, doA, doW, DTs, st, b0, nb, *peer, doC)
-         : ext ? L_col_t<1, true>(h, s0, ns, doA, doW, DTs, st, b0, nb, *peer, 0) : L_col_t<0, true>(h, s0, ns, doA, 0, DTs, st, b0, nb, *peer, 0);
-  return doC ? L_col_t<2, false>(h, s0, ns, doA, doW, DTs, st, b0, nb, kNoPeer, doC)
-       : ext ? L_col_t<1, false>(h, s0, ns, doA, doW, DTs, st, b0, nb, kNoPeer, 0) : L_col_t<0, false>(h, s0, ns, doA, 0, DTs, st, b0, nb, kNoPeer, 0);
+    return doC ? L_col_t<2, true>(h, s0, ns, doA, doW, DTs, st, b0, nb, *peer, doC, pb0)
+         : ext ? L_col_t<1, true>(h, s0, ns, doA, doW, DTs, st, b0, nb, *peer, 0, pb0) : L_col_t<0, true>(h, s0, ns, doA, 0, DTs, st, b0, nb, *peer, 0, pb0);
+  return doC ? L_col_t<2, false>(h, s0, ns, doA, doW, DTs, st, b0, nb, kNoPeer, doC, pb0)
+       : ext ? L_col_t<1, false>(h, s0, ns, doA, doW, DTs, st, b0, nb, kNoPeer, 0, pb0) : L_col_t<0, false>(h, s0, ns, doA, 0, DTs, st, b0, nb, kNoPeer, 0, pb0);
 }
 // elimination factors of the fused COULMU (k_coulmu_tables) for species [s0, s0+ns): tabulated when DTs (through COULPARA's
 // rate tables), the fields or the plasmasphere changed, else cached.  Allocates: call outside stream capture.

@@ -75,19 +75,30 @@ __global__ void k_peer_barrier(const __grid_constant__ PeerCtx pc, int which, un
   }
 }
 
-// Second re-sharding of the step, bulk form: the column kernel has written its block range [c0, c1) of plane positions
-// into the LOCAL buffer; every (l, k) row of that range whose pitch angle belongs to another rank goes to that rank's
-// buffer as ONE contiguous run (c1 - c0 doubles, 3.9 KB at 8 ranks on the 4x grid) of 16-byte stores -- full NVLink
-// packets, where the column kernel's own write-back can only send the 32 bytes a CTA holds of a row.  The source was
-// written a moment ago: an L2 read.  Warp per row; grid: x = row tiles, y = species.
-__global__ void __launch_bounds__(256) k_peer_push_cols(const __grid_constant__ PeerView pv, const __grid_constant__ SpecPack pk, int s0,
-                                                        int NE, int NPA, int Pp, int c0, int c1) {
+// The two re-shardings of the step in bulk form (RSG_PEER_PUSH): the producing kernel writes into the LOCAL buffer and
+// this kernel sends the rows to their next owner as contiguous runs of 16-byte stores -- full NVLink packets -- while
+// the producer already works on its next chunk (second stream).  The source was written a moment ago: an L2 read.
+//   mode 0 (after the forward plane kernel): rows [row0, row0+nrows) are this rank's (l, k) rows; blockIdx.z = the
+//           destination rank, which receives its block range of plane positions [ccut[z], ccut[z+1]) of every row;
+//   mode 1 (after the column kernel): all (l, k) rows whose pitch angle belongs to another rank; that rank receives the
+//           columns [c0, c1) this launch of the column kernel has produced (3.9 KB per row at 8 ranks on the 4x grid,
+//           where the column kernel's own write-back can only send the 32 bytes a CTA holds of a row).
+// Warp per row; grid: x = row tiles, y = species, z = destinations (mode 0) / 1.
+__global__ void __launch_bounds__(256) k_peer_push(const __grid_constant__ PeerView pv, const __grid_constant__ SpecPack pk, int s0,
+                                                   int NE, int Pp, int P, int row0, int nrows, int c0, int c1, int mode) {
   const SpecDev& sp = pk.s[s0 + blockIdx.y];
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (row >= NE * NPA) return;
-  const int l = row / NE;
-  const int o = peer_owner(pv.lcut, pv.G, l);
-  if (o == pv.gidx) return;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= nrows) return;
+  const int row = row0 + r;
+  int o;
+  if (mode == 0) {
+    o = blockIdx.z;
+    c0 = pv.ccut[o];
+    c1 = min(pv.ccut[o + 1], P);
+  } else {
+    o = peer_owner(pv.lcut, pv.G, row / NE);
+  }
+  if (o == pv.gidx || c1 <= c0) return;
   const double* src = sp.F + (size_t)row * Pp;
   double* dst = pv.F[o] + (sp.F - pv.F[pv.gidx]) + (size_t)row * Pp;
   int c = c0;
@@ -169,7 +180,11 @@ struct rsg_shard {
   unsigned group_mask = 0, world_mask = 0;
   int pending_flags = 0;
   bool pending = false;
-  bool push_cols = false;   // second re-sharding as a bulk push after the column kernel (RSG_PEER_PUSH) instead of its own write-back
+  // RSG_PEER_PUSH: 0 = the kernels' own write-backs go to the peers; 1 = the column kernel writes locally, one bulk push
+  // follows; 2 = both re-shardings in `nchunk` chunks, the push of chunk c on a second stream beside the kernel of chunk c+1
+  int push_mode = 0, nchunk = 4;
+  cudaStream_t st2 = nullptr;
+  cudaEvent_t ev[2 * 8 + 2] = {nullptr};
 };
 
 namespace {
@@ -218,7 +233,12 @@ int shard_finish_attach(rsg_ram* h, int rank, int world, int policy) {
   for (int s = 0; s < h->nS; ++s)
     if (h->sp[s].cur != 0) return fail(RSG_ERR_STATE, "peer attach needs F2 in buffer 0 (attach before running single operators)");
   if (sh.gexec) { cudaGraphExecDestroy(sh.gexec); sh.gexec = nullptr; }
-  if (const char* e = getenv("RSG_PEER_PUSH")) sh.push_cols = std::atoi(e) != 0;
+  if (const char* e = getenv("RSG_PEER_PUSH")) sh.push_mode = std::max(0, std::min(2, std::atoi(e)));
+  if (const char* e = getenv("RSG_PEER_CHUNKS")) sh.nchunk = std::max(1, std::min(8, std::atoi(e)));
+  if (sh.push_mode == 2 && !sh.st2) {
+    CK(cudaStreamCreateWithFlags(&sh.st2, cudaStreamNonBlocking));
+    for (auto& e : sh.ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
   sh.attached = true;
   return RSG_OK;
 }
@@ -227,6 +247,8 @@ void shard_release(rsg_ram* h) {
   if (!h->shard) return;
   rsg_shard& sh = *h->shard;
   if (sh.gexec) cudaGraphExecDestroy(sh.gexec);
+  if (sh.st2) cudaStreamDestroy(sh.st2);
+  for (auto& e : sh.ev) if (e) cudaEventDestroy(e);
   for (int q = 0; q < sh.nopened; ++q) cudaIpcCloseMemHandle(sh.opened[q]);
   if (sh.h_err) cudaFreeHost(sh.h_err);
   delete h->shard;
@@ -246,25 +268,57 @@ int enqueue_sharded(rsg_ram* h, double DTs, int flags) {
     for (int s = 0; s < h->nS; ++s)
       if (s < s0 || s >= s0 + ns) doW &= ~(1 << s);
     h->in_step = false;
-    RET(prof_mark(h, "k_plane_rp_fwd(peer stores)", st));
-    RET(L_plane_rp(h, s0, ns, st, false, p.l0, p.nl, &sh.pv));     // DRIFTR, DRIFTP -> the column owners
-    RET(prof_mark(h, "barrier_1", st));
-    k_peer_barrier<<<1, 32, 0, st>>>(sh.pc, 0, sh.group_mask);
-    CKL();
     const int doC = (flags & RSG_F_COULOMB) ? 1 : 0;
-    if (sh.push_cols) {
-      RET(prof_mark(h, "k_col_fused(local)", st));
-      RET(L_col(h, s0, ns, doA, DTs, st, p.b0, p.nb, doW, nullptr, doC));  // DRIFTE .. DRIFTE into the local buffer
-      RET(prof_mark(h, "k_peer_push_cols", st));
-      SpecPack pk;
-      make_pack(h, pk, s0, ns);
-      const int c0 = p.b0 * COL_PG, c1 = std::min(h->P, (p.b0 + p.nb) * COL_PG);
-      k_peer_push_cols<<<dim3(nblk((long long)h->NE * h->NPA, 8), ns), 256, 0, st>>>(sh.pv, pk, s0, h->NE, h->NPA, h->Pp, c0, c1);
-      CKL();
+    SpecPack pk;
+    make_pack(h, pk, s0, ns);
+    auto push = [&](cudaStream_t q, int row0, int nrows, int c0, int c1, int mode) {
+      k_peer_push<<<dim3(nblk(nrows, 8), ns, mode == 0 ? p.G : 1), 256, 0, q>>>(sh.pv, pk, s0, h->NE, h->Pp, h->P, row0, nrows, c0, c1, mode);
       h->launches++;
+      return cudaGetLastError();
+    };
+    if (sh.push_mode == 2) {
+      // both re-shardings chunked: kernel of chunk c on the run stream, its bulk push on the second stream beside chunk c+1
+      const int NC = std::max(1, std::min({sh.nchunk, p.nl, p.nb}));
+      RET(prof_mark(h, "k_plane_rp_fwd(local) || k_peer_push", st));
+      for (int c = 0; c < NC; ++c) {
+        int a, n;
+        split_range(p.nl, NC, c, &a, &n);
+        RET(L_plane_rp(h, s0, ns, st, false, p.l0 + a, n));
+        CK(cudaEventRecord(sh.ev[c], st));
+        CK(cudaStreamWaitEvent(sh.st2, sh.ev[c], 0));
+        CK(push(sh.st2, (p.l0 + a) * h->NE, n * h->NE, 0, 0, 0));
+      }
+      CK(cudaEventRecord(sh.ev[16], sh.st2));
+      CK(cudaStreamWaitEvent(st, sh.ev[16], 0));
+      RET(prof_mark(h, "barrier_1", st));
+      k_peer_barrier<<<1, 32, 0, st>>>(sh.pc, 0, sh.group_mask);
+      CKL();
+      RET(prof_mark(h, "k_col_fused(local) || k_peer_push", st));
+      for (int c = 0; c < NC; ++c) {
+        int a, n;
+        split_range(p.nb, NC, c, &a, &n);
+        RET(L_col(h, s0, ns, doA, DTs, st, p.b0 + a, n, doW, nullptr, doC, a));
+        CK(cudaEventRecord(sh.ev[8 + c], st));
+        CK(cudaStreamWaitEvent(sh.st2, sh.ev[8 + c], 0));
+        CK(push(sh.st2, 0, h->NE * h->NPA, (p.b0 + a) * COL_PG, std::min(h->P, (p.b0 + a + n) * COL_PG), 1));
+      }
+      CK(cudaEventRecord(sh.ev[17], sh.st2));
+      CK(cudaStreamWaitEvent(st, sh.ev[17], 0));
     } else {
-      RET(prof_mark(h, "k_col_fused(peer stores)", st));
-      RET(L_col(h, s0, ns, doA, DTs, st, p.b0, p.nb, doW, &sh.pv, doC));   // DRIFTE .. DRIFTE -> the pitch-angle owners
+      RET(prof_mark(h, "k_plane_rp_fwd(peer stores)", st));
+      RET(L_plane_rp(h, s0, ns, st, false, p.l0, p.nl, &sh.pv));     // DRIFTR, DRIFTP -> the column owners
+      RET(prof_mark(h, "barrier_1", st));
+      k_peer_barrier<<<1, 32, 0, st>>>(sh.pc, 0, sh.group_mask);
+      CKL();
+      if (sh.push_mode == 1) {
+        RET(prof_mark(h, "k_col_fused(local)", st));
+        RET(L_col(h, s0, ns, doA, DTs, st, p.b0, p.nb, doW, nullptr, doC));  // DRIFTE .. DRIFTE into the local buffer
+        RET(prof_mark(h, "k_peer_push", st));
+        CK(push(st, 0, h->NE * h->NPA, p.b0 * COL_PG, std::min(h->P, (p.b0 + p.nb) * COL_PG), 1));
+      } else {
+        RET(prof_mark(h, "k_col_fused(peer stores)", st));
+        RET(L_col(h, s0, ns, doA, DTs, st, p.b0, p.nb, doW, &sh.pv, doC));   // DRIFTE .. DRIFTE -> the pitch-angle owners
+      }
     }
     RET(prof_mark(h, "barrier_2", st));
     k_peer_barrier<<<1, 32, 0, st>>>(sh.pc, 0, sh.group_mask);

@@ -105,12 +105,15 @@ def test_sharded_step_with_coulomb_stages(default_grids, world, policy):
     _check(F1, o1, FN, oN, plans)
 
 
+@pytest.mark.parametrize("push", ["1", "2"])
 @pytest.mark.parametrize("world,policy", [(8, 1), (8, 0), (3, 1)])
-def test_sharded_step_bulk_push_of_the_column_resharding(default_grids, monkeypatch, world, policy):
-    """RSG_PEER_PUSH=1: the column kernel writes its block range locally and k_peer_push_cols sends every (l, k) row to
-    the pitch angle's owner as one contiguous run -- same bits as the kernel's own peer write-back"""
+def test_sharded_step_bulk_push_of_the_resharding(default_grids, monkeypatch, world, policy, push):
+    """RSG_PEER_PUSH=1: the column kernel writes its block range locally and k_peer_push sends every (l, k) row to the
+    pitch angle's owner as one contiguous run; =2: both re-shardings that way, in chunks, the push of a chunk on a second
+    stream beside the kernel of the next (fork / join inside the step's graph) -- same bits as the kernels' own peer
+    write-backs"""
     from ramscb_b200 import host
-    monkeypatch.setenv("RSG_PEER_PUSH", "1")
+    monkeypatch.setenv("RSG_PEER_PUSH", push)
     g = default_grids
     inp = synthetic.make_inputs(g, f2_kind="noisy", inductive=True, mgnp=True)
     D = synthetic.synthetic_daa(g, inp)
@@ -128,12 +131,13 @@ def test_sharded_step_ragged_grid():
     for world, policy in ((8, 0), (5, 1)):
         FN, oN, plans = _sharded(g, inp, host.MODE_FAST, 0, world, policy)
         _check(F1, o1, FN, oN, plans)
-    os.environ["RSG_PEER_PUSH"] = "1"            # odd column cuts: the scalar head / tail of the bulk push
-    try:
-        FN, oN, plans = _sharded(g, inp, host.MODE_FAST, 0, 5, 1)
-        _check(F1, o1, FN, oN, plans)
-    finally:
-        del os.environ["RSG_PEER_PUSH"]
+    for push in ("1", "2"):                      # odd column cuts: the scalar head / tail of the bulk push
+        os.environ["RSG_PEER_PUSH"] = push
+        try:
+            FN, oN, plans = _sharded(g, inp, host.MODE_FAST, 0, 5, 1)
+            _check(F1, o1, FN, oN, plans)
+        finally:
+            del os.environ["RSG_PEER_PUSH"]
 
 
 @pytest.mark.parametrize("world", [2, 4])
