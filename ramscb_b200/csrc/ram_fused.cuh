@@ -323,7 +323,8 @@ __global__ void __launch_bounds__(512) k_plane_rp(const __grid_constant__ RamDev
         double prev;
         {
           const double c = fma(-w2k, *pb, *pa);
-          prev = c * limited_flux_d(F0, Fp1, dm1, d0, dp1, c < 0.0, fabs(c), beta);
+          // interface NT-1 (a segment that starts at J = NT): far-upwind difference F(2) - F(1), see limited_flux_num
+          prev = c * limited_flux_d(F0, Fp1, dm1, d0, (Jpe == NT - 1) ? Fp2 - F1row : dp1, c < 0.0, fabs(c), beta);
         }
         if (ja == 2) d0 = Fp1 - F1row;                  // cell J=2 sees the stored F(1), not F(NT)
         pa = d.fPa + (ja - 1) * NR + i;
@@ -331,13 +332,14 @@ __global__ void __launch_bounds__(512) k_plane_rp(const __grid_constant__ RamDev
         double cnext = fma(-w2k, *pb, *pa);
         double* pO = colp + (size_t)(ja - 1) * NRp;
         double fnew = 0.0;
-        auto step = [&](const double nn, const bool more) {
+        // wrapfix: this step's interface is J = NT-1, whose far-upwind difference is F(2) - F(1) (limited_flux_num)
+        auto step = [&](const double nn, const bool more, const bool wrapfix) {
           F0 = Fp1; Fp1 = Fp2; Fp2 = nn;
           dm1 = d0; d0 = dp1; dp1 = Fp2 - Fp1;
           const double c = cnext;
           pa += NR; pb += NR;
           if (more) cnext = fma(-w2k, *pb, *pa);
-          const double cur = c * limited_flux_d(F0, Fp1, dm1, d0, dp1, c < 0.0, fabs(c), beta);
+          const double cur = c * limited_flux_d(F0, Fp1, dm1, d0, wrapfix ? Fp2 - F1row : dp1, c < 0.0, fabs(c), beta);
           fnew = F0 - cur + prev;                       // :266
           if (fnew < 0.0) fnew = 1E-15;
           *pO = fnew;
@@ -346,9 +348,9 @@ __global__ void __launch_bounds__(512) k_plane_rp(const __grid_constant__ RamDev
         };
         int J = ja;
 #pragma unroll 4
-        for (; J + 2 <= jb; ++J) step(pO[2 * (size_t)NRp], true);
-        if (J + 1 <= jb) { step(hi1, true); ++J; }
-        if (J <= jb) step(hi2, false);
+        for (; J + 2 <= jb; ++J) step(pO[2 * (size_t)NRp], true, false);     // J <= NT-2 here
+        if (J + 1 <= jb) { step(hi1, true, J == NT - 1); ++J; }
+        if (J <= jb) step(hi2, false, J == NT - 1);
         if (jb == NT) colp[0] = fnew;                   // F2(J=1) = F2(J=NT)  (:272)
       }
     }

@@ -60,6 +60,29 @@ __device__ __forceinline__ double limited_flux(double Fm1, double F0, double Fp1
   return FB;
 }
 
+// DRIFTP's interface J = NT-1 with a negative coefficient: the reference's far-upwind index N = J+2 wraps to N-NT+1 = 2, so
+// its difference is F(2) - F(1) with the STORED F(1) (src/ModRamDrift.f90:251-254), not F(NT+1) - F(NT).  The two agree
+// while every (I,J) input is periodic in MLT; computehI's smoothed field arrays are not (the 9 x 9 Gaussian reflects at
+// the MLT edges after the continuity fix of src/ModRamScb.f90:474-477), and then F2(J=1) and F2(J=NT) part between two
+// DRIFTP sweeps.  numneg = that difference.
+__device__ __forceinline__ double limited_flux_num(double Fm1, double F0, double Fp1, double numneg, double c, double chat,
+                                                   double beta) {
+  const double sgn = (c < 0.0) ? -1.0 : 1.0;
+  const double X = Fp1 - F0;
+  const double FUP = 0.5 * ((F0 + Fp1) - sgn * X);
+  double FB = FUP;
+  if (fabs(X) > 1.E-27) {
+    const double num = (c < 0.0) ? numneg : (F0 - Fm1);
+    const double R = num / X;
+    if (R > 0.0) {
+      const double LIM = dmax(dmin(beta * R, 1.0), dmin(R, beta));
+      const double CORR = (-0.5 * (chat - sgn)) * X;
+      FB = FUP + LIM * CORR;
+    }
+  }
+  return FB;
+}
+
 // FAST mode: the same limiter in upwind form, without the division.  With
 // U/D/UU the upwind, downwind and far-upwind cells, dU=U-UU, dD=D-U, R=dU/dD:
 //   FBND = U + 0.5*(1-|chat|) * LIM(R)*dD,  LIM(R)*|dD| = min(max(|dU|,|dD|), beta*min(|dU|,|dD|))
@@ -547,6 +570,11 @@ __global__ void __launch_bounds__(128) k_driftp(const __grid_constant__ RamDev d
       auto lim = [&](double a, double b, double c_, double e, double cc) -> double {
         return FAST ? limited_flux_fast(a, b, c_, e, cc < 0.0, fabs(cc), beta) : limited_flux(a, b, c_, e, cc, cc, beta);
       };
+      // interface NT-1: far-upwind difference F(2) - F(1) with the stored F(1) (limited_flux_num)
+      const double numw = f2 - F[0];
+      auto limw = [&](double a, double b, double c_, double cc) -> double {
+        return FAST ? limited_flux_d(b, c_, b - a, c_ - b, numw, cc < 0.0, fabs(cc), beta) : limited_flux_num(a, b, c_, numw, cc, cc, beta);
+      };
       // flux through the segment's lower edge: interface ja-1, or NT for ja==2 (:261-262)
       double prev;
       if (ja == 2) {
@@ -555,7 +583,8 @@ __global__ void __launch_bounds__(128) k_driftp(const __grid_constant__ RamDev d
       } else {
         const double c = coef((ja - 2) * NR);
         const double e = (ja + 1 <= NT) ? F[ja * NR] : f2;
-        prev = c * lim(F[(ja - 3) * NR], F[(ja - 2) * NR], F[(ja - 1) * NR], e, c);
+        prev = c * ((ja - 1 == NT - 1) ? limw(F[(ja - 3) * NR], F[(ja - 2) * NR], F[(ja - 1) * NR], c)
+                                       : lim(F[(ja - 3) * NR], F[(ja - 2) * NR], F[(ja - 1) * NR], e, c));
       }
       // rolling window F(J-1), F(J), F(J+1), F(J+2) with wrap J=NT+1->2, NT+2->3
       int q = (ja - 1) * NR;                       // offset of F(J)
@@ -572,7 +601,7 @@ __global__ void __launch_bounds__(128) k_driftp(const __grid_constant__ RamDev d
         const double cnn = coef(min(q + NR, qNT));
         const double c = cn;
         if (!d.outp[q + i]) cmax = dmax(cmax, fabs(c));
-        const double cur = c * lim(Fm1, F0, Fp1, Fp2, c);
+        const double cur = c * ((J == NT - 1) ? limw(Fm1, F0, Fp1, c) : lim(Fm1, F0, Fp1, Fp2, c));
         fnew = F0 - cur + prev;                         // :266
         if (fnew < 0.0) fnew = 1E-15;
         Fo[q] = fnew;

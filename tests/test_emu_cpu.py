@@ -51,6 +51,11 @@ def test_emulated_fast_full_ram_run(emu, T, small_grids, oracle_built):
     T.test_fast_mode_full_ram_run(small_grids, oracle_built)
 
 
+@pytest.mark.parametrize("mode", ["exact", "fast", "fast_unfused"])
+def test_emulated_driftp_wrap_nonperiodic_fields(emu, T, small_grids, oracle_built, mode):
+    T.test_driftp_wrap_with_fields_not_periodic_in_mlt(small_grids, oracle_built, mode)
+
+
 def test_emulated_losses_wpadif_coulomb(emu, T, small_grids, oracle_built):
     T.test_losses(small_grids, oracle_built, "noisy")
     T.test_sumrc_and_anisch(small_grids, oracle_built)
@@ -127,6 +132,11 @@ def test_emulated_computehI_composed(emu, default_grids, oracle_built):
 def test_emulated_computehI_resident(emu, default_grids, oracle_built):
     import test_zz_late_additions_gpu as TZ
     TZ.test_computehI_resident_handle(default_grids, oracle_built, (21, 15, 25))
+
+
+def test_emulated_coupled_cycle(emu, default_grids, oracle_built):
+    import test_zz_late_additions_gpu as TZ
+    TZ.test_coupled_ram_scb_cycle_stays_on_the_device(default_grids, oracle_built, (21, 15, 25))
 
 
 def test_emulated_scb_run_outer_iterations(emu, oracle_built):

@@ -247,6 +247,53 @@ def test_full_ram_run(default_grids, oracle_built, flags):
     assert _relerr(flux[:, 1:, :-1, 1:, 1:], o.FLUX[:, 1:, :-1, 1:, 1:]) <= 1e-12
 
 
+@pytest.mark.parametrize("mode", ["exact", "fast", "fast_unfused"])
+def test_driftp_wrap_with_fields_not_periodic_in_mlt(default_grids, oracle_built, mode):
+    """DRIFTP's far-upwind index at J = NT-1 with a negative coefficient wraps to N = 2, so the reference reads
+    F(2) - F(1) with the STORED F(1) (src/ModRamDrift.f90:251-254).  While every (I,J) input is periodic in MLT that
+    equals F(NT+1) - F(NT); computehI's smoothed field arrays are not periodic (the 9 x 9 Gaussian reflects at the MLT
+    edges after the continuity fix, src/ModRamScb.f90:474-477), and then F2(J=1) and F2(J=NT) part between two DRIFTP
+    sweeps.  Fields AND the entry F2 made non-periodic here: EXACT stays bit-identical to the oracle through two
+    steps, FAST within the strict bar.  (Found by the coupled-cycle test; the device used F(NT) until round 2.)"""
+    import copy
+    from ramscb_b200 import host
+    g = default_grids
+    inp = copy.copy(_mk(g, f2_kind="noisy", inductive=True, mgnp=False))
+    rng = np.random.default_rng(11)
+    for n in ("BNES", "dBdt", "FNHS", "FNIS", "BOUNHS", "BOUNIS", "HDNS", "dIdt", "dIbndt"):
+        a = getattr(inp, n)
+        setattr(inp, n, np.asfortranarray(a * (1 + 0.05 * rng.random(a.shape))))
+    F2 = inp.F2.copy(order="F")
+    F2[:, :, 0] *= 1 + 0.1 * rng.random(F2[:, :, 0].shape)
+    inp.F2 = F2
+    o = oracle_built.RamOracle(g, inp, DTs=DTS)
+    gpu = host.RamGpu(g, mode=host.MODE_EXACT if mode == "exact" else host.MODE_FAST)
+    gpu.set_inputs(inp)
+    if mode == "fast_unfused":
+        gpu.use_fused(False)
+    for dts in (5.0, 7.5):
+        o.set_scalar("DTs", dts)
+        dtn = o.ram_run(flags=0)
+        out = gpu.ram_run(dts, DtsMin=1.0, flags=0)
+        F = gpu.f2_d2h()
+        if mode == "exact":
+            assert out["DtsNext"] == dtn
+            assert _relerr(F, o.F2) <= 1e-12
+        else:
+            assert abs(out["DtsNext"] - dtn) <= 1e-13 * dtn
+            _strict_bar(F, o.F2, f"non-periodic fields, {mode}")
+    if mode == "exact":       # single sweep: bit-identical
+        o2 = oracle_built.RamOracle(g, inp, DTs=DTS)
+        g2 = host.RamGpu(g, mode=host.MODE_EXACT)
+        g2.set_inputs(inp)
+        for S in range(1, g.nS + 1):
+            o2.op("driftpara", S); g2.DRIFTPARA(S, DTS)
+            o2.op("driftp", S); g2.DRIFTP(S)
+        assert np.array_equal(g2.f2_d2h(), o2.F2)
+        g2.close()
+    gpu.close()
+
+
 @pytest.mark.parametrize("mode", ["exact", "fast"])
 def test_graph_replay_matches_kernel_by_kernel(default_grids, mode):
     """rsg_ram_run replays a captured CUDA graph when (DTs, flags, mode) repeat: the

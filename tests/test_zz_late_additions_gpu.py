@@ -434,6 +434,78 @@ def test_computehI_resident_handle(default_grids, oracle_built, dims):
     hi.close(); hi2.close()
 
 
+@pytest.mark.gpu
+def test_coupled_ram_scb_cycle_stays_on_the_device(default_grids, oracle_built, dims=(51, 23, 49)):
+    """BASELINE configs[4] in miniature -- the coupled cycle ram_run -> pressure -> scb_run -> computehI -> ram_run
+    (src/ModRamScbRun.f90:60-130) composed from the device entry points so that no 3-D or 4-D array crosses PCIe between
+    the two hot paths: the (nS,NR,NT) pressures of ram_run go to rsg_scb_set_ram_pressure, rsg_scb_run runs with the front
+    end on the device, rsg_computehI reads the SCB handle's arrays in place, rsg_ram_set_fields_device takes the new field
+    arrays.  Against the oracle's composition of the same cycle: SCB decisions identical and fields <= 1e-9 (the two
+    pressures differ in the last bits of the RAM moments), computehI's RAM variables <= 1e-7 of the oracle chain fed with
+    the oracle's own SCB state, and the second ram_run -- both sides on the DEVICE-built fields -- to the EXACT-mode bars."""
+    from ramscb_b200 import host
+    g = default_grids
+    nthe, npsi, nzeta = dims
+    inp = synthetic.make_inputs(g, f2_kind="smooth", inductive=True)
+    sinp = SCBSYN.build_scb(nthe=nthe, npsi=npsi, nzeta=nzeta, warp=0.3)
+    ram, o = host.RamGpu(g, mode=host.MODE_EXACT), oracle_built.RamOracle(g, inp, DTs=5.0)
+    ram.set_inputs(inp)
+    out = ram.ram_run(5.0, DtsMin=1.0, flags=0)
+    o.ram_run(flags=0)
+    assert np.allclose(out["PPERT"], o.PPERT, rtol=1e-12, atol=0)
+    # pressures of the synthetic F2 are not ring-current sized: one scale on both sides (12 keV/cm^3 peak, output/test1)
+    scale = 12.0 / float(out["PPERT"].max())
+    flags_scb = np.array([1, 1, 1, 0][:g.nS], dtype=np.int32)
+    LZ, PHI = g.LZ[:g.NR + 1], g.PHI[:g.NT]
+    sg, so = host.ScbGpu(sinp), oracle_built.ScbOracle(sinp)
+    sg.set_ram_pressure(out["PPERT"] * scale, out["PPART"] * scale, flags_scb, LZ, PHI)
+    so.pressure_raw(np.asfortranarray(o.PPERT * scale), np.asfortranarray(o.PPART * scale), flags_scb, LZ, PHI)
+    sg.set_map_targets(sinp.alphaVal, sinp.psiVal, sinp.chiVal)
+    kw = dict(numit=2, MinSCBIterations=2, decreaseConvAlpha=1e-30, decreaseConvPsi=1e-30)
+    ro = so.scb_run(None, **kw)
+    rg = sg.scb_run(None, ordering=host.SOR_LEX, **kw)
+    assert ro["SORFail"] == 0 and rg["SORFail"] == 0 and rg["iterations"] == ro["iterations"] == 2
+    assert rg["nisaveAlpha"] == ro["nisaveAlpha"] and rg["nisavePsi"] == ro["nisavePsi"]
+    for n in ("x", "y", "z", "alfa", "psi", "bf"):
+        a, b = sg.get_field(n), getattr(so, n)
+        assert np.max(np.abs(a - b)) <= 1e-9 * np.max(np.abs(b)), n
+    # computehI on the SCB handle's device arrays, new fields device-to-device into the RAM state
+    ieq = nthe // 2 + 1
+    bnormal = so.get("bnormal")
+    prev = {n: getattr(inp, n) for n in host.HI_RAM_NAMES}
+    hi = host.HiGpu(nthe, npsi, nzeta, LZ, g.MLT[:g.NT], g.MU, g.PA, g.PAbn, sinp.chiVal, ieq, bnormal)
+    hi.set_ram_fields(prev)
+    assert hi.computehI(sg, 300.0, True) == 0
+    hi.push_to_ram(ram)
+    new = hi.results()
+    assert not new["outsideSCB"].any()                     # the RAM domain (L <= 6.5) lies inside this SCB domain
+
+    def dens(d):
+        d2 = d * d
+        return 10.0 ** (13.326 - 3.6908 * d + 1.1362 * d2 - 0.16984 * (d2 * d) + 0.009553 * (d2 * d2))
+
+    scb_o = dict(x=so.x, y=so.y, z=so.z, bf=so.bf, psi=so.psi, alfa=so.alfa, chiVal=sinp.chiVal, nThetaEquator=ieq, bnormal=bnormal)
+    ref = host.computehI(scb_o, LZ, g.MLT[:g.NT], g.MU, g.PA, g.PAbn, prev, 300.0, integral_smooth=True, density_fn=dens,
+                         _impl=(oracle_built.hi_convert_lines, oracle_built.hi_integrals, oracle_built.hi_tail))
+    for n in ("FNHS", "FNIS", "BOUNHS", "BOUNIS", "HDNS", "BNES"):
+        a, b = new[n], ref[n]
+        ok = np.isfinite(b)
+        assert np.array_equal(np.isfinite(a), ok), n
+        assert np.max(np.abs(a[ok] - b[ok])) <= 1e-7 * np.max(np.abs(b[ok])), (n, float(np.max(np.abs(a[ok] - b[ok]))))
+    # second RAM step: the device on the arrays it was handed on the device, the oracle on copies of the same arrays
+    for n in ("BNES", "dBdt", "FNHS", "FNIS", "BOUNHS", "BOUNIS", "HDNS", "dIdt", "dIbndt"):
+        o.set_array(n, new[n])
+    o.set_array("outsideMGNP", new["outsideMGNP"])
+    out2 = ram.ram_run(5.0, DtsMin=1.0, flags=0)
+    dtn = o.ram_run(flags=0)
+    assert abs(out2["DtsNext"] - dtn) <= 1e-13 * dtn
+    F = ram.f2_d2h()
+    assert np.all(np.isfinite(F))
+    assert np.max(np.abs(F - o.F2) / np.maximum(np.abs(o.F2), 1e-300)) <= 1e-12
+    assert np.allclose(out2["PPERT"], o.PPERT, rtol=1e-12, atol=0)
+    hi.close(); sg.close(); ram.close()
+
+
 def test_anisch_diffcoef_rebuild_feeds_the_wpi_step(default_grids, oracle_built):
     """ANISCH's diffusion-coefficient rebuild (src/ModRamRun.f90:422-605) on the device, then a WPI + EMIC
     ram_run that never sees a host-built coefficient array.  Coefficients <= 1e-13 of the oracle's (device log10 / pow vs
