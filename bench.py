@@ -567,7 +567,7 @@ def scb_run_metrics(device):
     MinSCBIterations 11, blend 0.5) on the default SCB grid through ONE rsg_scb_run call, 4-colour ordering.  Two variants:
     `device_front_end` -- `pressure` entirely on the device from synthetic RAM pressures (rsg_scb_set_ram_pressure; no host
     hop inside the outer iteration) -- and `host_callback` (round 1: the 2-D front end as a host callback, a synthetic
-    analytic pressure).  Wall clock of the call; the second of two runs (warm)."""
+    analytic pressure).  Wall clock of the call: one cold run, then the fastest of three warm ones."""
     from ramscb_b200 import grids, host, scb_synthetic
     inp = scb_synthetic.build_scb(nthe=101, npsi=45, nzeta=97, warp=0.2)
     fn = scb_synthetic.equatorial_pressure_fn()
@@ -576,7 +576,7 @@ def scb_run_metrics(device):
     res = {}
     for name, cb in (("device_front_end", None), ("host_callback", fn)):
         out = {}
-        for rep in range(2):                       # the second run is the warm one
+        for rep in range(4):                       # one cold run, then the fastest of three warm ones (wall clock on a shared host)
             gpu = host.ScbGpu(inp, device=device)
             gpu.set_map_targets(inp.alphaVal, inp.psiVal, inp.chiVal)
             if cb is None:
@@ -585,6 +585,9 @@ def scb_run_metrics(device):
             t0 = time.perf_counter()
             r = gpu.scb_run(cb, ordering=host.SOR_COLOR4)
             ms = (time.perf_counter() - t0) * 1e3
+            if rep >= 2 and ms >= out["wall_ms"]:
+                gpu.close()
+                continue
             out = {"wall_ms": ms, "outer_iterations": r["iterations"], "SORFail": r["SORFail"], "iConvGlobal": r["iConvGlobal"],
                    "nisaveAlpha_last": r["nisaveAlpha"], "nisavePsi_last": r["nisavePsi"], "blendRetries": r["blendRetries"],
                    "normDiff_start_end": [r["normDiffStart"], r["normDiff"]], "normJxB_start_end": [r["normJxBStart"], r["normJxB"]],

@@ -1274,13 +1274,20 @@ int rsg_hI_integrals(int device, int nthe, int nR, int nT, int nPa, int nThetaEq
   HiArgs A;
   A.nthe = nthe; A.nR = nR; A.nT = nT; A.nPa = nPa; A.nThetaEquator = nThetaEquator; A.bnormal = bnormal;
   double* p = d;
-  auto up = [&](const double* src, size_t n) { double* q = p; p += n; cudaMemcpyAsync(q, src, n * sizeof(double), cudaMemcpyHostToDevice, st); return q; };
+  cudaError_t uerr = cudaSuccess;      // first failed upload (checked after the batch)
+  auto up = [&](const double* src, size_t n) {
+    double* q = p; p += n;
+    const cudaError_t e_ = cudaMemcpyAsync(q, src, n * sizeof(double), cudaMemcpyHostToDevice, st);
+    if (e_ != cudaSuccess && uerr == cudaSuccess) uerr = e_;
+    return q;
+  };
   A.x = up(xRAM, n3); A.y = up(yRAM, n3); A.z = up(zRAM, n3); A.b = up(bRAM, n3); A.dens = up(density, n3);
   A.chi = up(chiVal, nthe); A.mu = up(mu, nPa);
   A.Icart = p; p += no;
   A.Hcart = p; p += no;
   A.Dcart = up(HDens_cart, no);
   A.bzeq = p;
+  HCK(uerr);
   HCK(cudaMemcpyAsync(dout, outsideMGNP, nl * sizeof(int), cudaMemcpyHostToDevice, st));
   A.outside = dout;
   HCK(cudaEventRecord(e0, st));
@@ -1346,7 +1353,13 @@ int rsg_hI_tail(int device, int nR, int nT, int nPa, double* I_cart, double* H_c
   hi_gauss_weights(A.w);
   double* p = d;
   auto take = [&](size_t n) { double* q = p; p += n; return q; };
-  auto up = [&](const double* src, size_t n) { double* q = take(n); cudaMemcpyAsync(q, src, n * sizeof(double), cudaMemcpyHostToDevice, st); return q; };
+  cudaError_t uerr = cudaSuccess;      // first failed upload (checked after the batch)
+  auto up = [&](const double* src, size_t n) {
+    double* q = take(n);
+    const cudaError_t e_ = cudaMemcpyAsync(q, src, n * sizeof(double), cudaMemcpyHostToDevice, st);
+    if (e_ != cudaSuccess && uerr == cudaSuccess) uerr = e_;
+    return q;
+  };
   A.I0 = up(I_cart, n3); A.H0 = up(H_cart, n3); A.D0 = up(HDens_cart, n3); A.bz0 = up(bZEq_cart, nl);
   A.I1 = take(n3); A.H1 = take(n3); A.D1 = take(n3); A.bz1 = take(nl); A.hI = take(n3); A.iI = take(n3);
   A.I2 = take(n3); A.H2 = take(n3); A.D2 = take(n3); A.hI2 = take(n3); A.iI2 = take(n3);
@@ -1354,6 +1367,7 @@ int rsg_hI_tail(int device, int nR, int nT, int nPa, double* I_cart, double* H_c
   A.dIdt = take(nr3); A.dHdt = take(nr3); A.dIbndt = take(nr3);
   A.BNES = up(BNES, nr2); A.dBdt = take(nr2);
   A.Lz = up(Lz, nR + 1); A.PA = up(PA, nPa); A.PAbn = up(PAbn, nPa);
+  HCK(uerr);
   HCK(cudaMemcpyAsync(di, outsideMGNP, nl * sizeof(int), cudaMemcpyHostToDevice, st));
   HCK(cudaMemcpyAsync(di + nl, ScaleAt, nT * sizeof(int), cudaMemcpyHostToDevice, st));
   HCK(cudaMemsetAsync(di + nl + nT, 0, sizeof(int), st));
@@ -1423,9 +1437,16 @@ int rsg_hI_convert_lines(int device, int nthe, int npsi, int nzeta, int nR, int 
   A.nthe = nthe; A.npsi = npsi; A.nzeta = nzeta; A.nR = nR; A.nT = nT; A.nThetaEquator = nThetaEquator;
   double* p = d;
   auto take = [&](size_t n) { double* q = p; p += n; return q; };
-  auto up = [&](const double* src, size_t n) { double* q = take(n); cudaMemcpyAsync(q, src, n * sizeof(double), cudaMemcpyHostToDevice, st); return q; };
+  cudaError_t uerr = cudaSuccess;      // first failed upload (checked after the batch)
+  auto up = [&](const double* src, size_t n) {
+    double* q = take(n);
+    const cudaError_t e_ = cudaMemcpyAsync(q, src, n * sizeof(double), cudaMemcpyHostToDevice, st);
+    if (e_ != cudaSuccess && uerr == cudaSuccess) uerr = e_;
+    return q;
+  };
   A.x = up(x, n3); A.y = up(y, n3); A.z = up(z, n3); A.bf = up(bf, n3); A.psi = up(psi, n3); A.alfa = up(alfa, n3);
   A.qx = up(qx.data(), nl); A.qy = up(qy.data(), nl); A.alphaRAM = up(al.data(), nT);
+  HCK(uerr);
   A.psiRAM = take(nl);
   A.xRAM = take(no); A.yRAM = take(no); A.zRAM = take(no); A.bRAM = take(no);
   A.outside = dout;
