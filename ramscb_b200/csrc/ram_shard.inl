@@ -18,7 +18,7 @@
 
 namespace {
 
-constexpr unsigned long long kBarrierTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
+constexpr unsigned long long kBarrierTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;   // RSG_BARRIER_TIMEOUT_MS overrides (tests)
 constexpr int kBlobMagic = 0x52534732;   // "RSG2"
 
 struct PeerBlob {
@@ -33,8 +33,9 @@ struct PeerCtx {
   int W, rank, nS, res_n;
   long long pp_n;
   unsigned char* mb[RSG_MAX_PEERS];
-  size_t off_flags, off_epoch, off_res, off_pp;   // [2][MAX] u64 | [2] u64 | [MAX][nS][res_n] u64 | [MAX][nS][pp_n] f64
+  size_t off_flags, off_epoch, off_res, off_pp;   // [4][MAX] u64 | [4] u64 | [MAX][nS][res_n] u64 | [MAX][nS][pp_n] f64
   unsigned long long* err;                        // host-mapped: non-zero = a barrier timed out
+  unsigned long long timeout_ns;
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
@@ -53,7 +54,8 @@ __device__ __forceinline__ unsigned long long global_ns() {
 
 // Barrier among the ranks of `mask` (bit r), all of which launch it the same number of times.  Everything this
 // GPU stored before the kernel (kernel boundary + fence) is visible to a peer once it has seen the flag.
-// which: 0 = the species group's barrier, 1 = the world's (separate epoch counters).  One CTA of 32 threads.
+// which: 0 = the species group's barrier, 1 = the world's, 2 = the group's barrier of the second species pipeline
+// (RSG_PEER_PIPES=2); separate epoch counters.  One CTA of 32 threads.
 __global__ void k_peer_barrier(const __grid_constant__ PeerCtx pc, int which, unsigned mask) {
   __shared__ unsigned long long e;
   if (threadIdx.x == 0) {
@@ -69,7 +71,7 @@ __global__ void k_peer_barrier(const __grid_constant__ PeerCtx pc, int which, un
     const unsigned long long* src = (const unsigned long long*)(pc.mb[pc.rank] + pc.off_flags) + which * RSG_MAX_PEERS + r;
     const unsigned long long t0 = global_ns();
     while (ld_acquire_sys(src) < e) {
-      if (global_ns() - t0 > kBarrierTimeoutNs) { *pc.err = 1ull + (unsigned long long)r; break; }
+      if (global_ns() - t0 > pc.timeout_ns) { *pc.err = 1ull + (unsigned long long)r; break; }
       __nanosleep(64);
     }
   }
@@ -183,6 +185,9 @@ struct rsg_shard {
   // RSG_PEER_PUSH: 0 = the kernels' own write-backs go to the peers; 1 = the column kernel writes locally, one bulk push
   // follows; 2 = both re-shardings in `nchunk` chunks, the push of chunk c on a second stream beside the kernel of chunk c+1
   int push_mode = 0, nchunk = 4;
+  // RSG_PEER_PIPES=2: the rank's species run as two independent pipelines (planes | barrier | columns | barrier | planes) on
+  // two streams, so one pipeline computes while the other waits for its peers' stores, and fills the other's last wave
+  int pipes = 1;
   cudaStream_t st2 = nullptr;
   cudaEvent_t ev[2 * 8 + 2] = {nullptr};
 };
@@ -196,14 +201,16 @@ int shard_alloc_mbox(rsg_ram* h) {
   PeerCtx& pc = sh.pc;
   pc.nS = h->nS; pc.res_n = RES_N; pc.pp_n = 2 * (long long)h->Pp;
   pc.off_flags = 0;
-  pc.off_epoch = pc.off_flags + sizeof(unsigned long long) * 2 * RSG_MAX_PEERS;
-  pc.off_res = (pc.off_epoch + 2 * sizeof(unsigned long long) + 255) & ~(size_t)255;
+  pc.off_epoch = pc.off_flags + sizeof(unsigned long long) * 4 * RSG_MAX_PEERS;
+  pc.off_res = (pc.off_epoch + 4 * sizeof(unsigned long long) + 255) & ~(size_t)255;
   pc.off_pp = (pc.off_res + sizeof(unsigned long long) * RSG_MAX_PEERS * h->nS * RES_N + 255) & ~(size_t)255;
   sh.mbox_bytes = pc.off_pp + sizeof(double) * RSG_MAX_PEERS * h->nS * (size_t)pc.pp_n;
   RET(h->dalloc(&sh.mbox, sh.mbox_bytes));
   CK(cudaHostAlloc((void**)&sh.h_err, sizeof(unsigned long long), cudaHostAllocMapped));
   *sh.h_err = 0;
   CK(cudaHostGetDevicePointer((void**)&pc.err, sh.h_err, 0));
+  pc.timeout_ns = kBarrierTimeoutNs;
+  if (const char* e = getenv("RSG_BARRIER_TIMEOUT_MS")) pc.timeout_ns = (unsigned long long)std::max(1, std::atoi(e)) * 1000000ull;
   return RSG_OK;
 }
 
@@ -235,7 +242,11 @@ int shard_finish_attach(rsg_ram* h, int rank, int world, int policy) {
   if (sh.gexec) { cudaGraphExecDestroy(sh.gexec); sh.gexec = nullptr; }
   if (const char* e = getenv("RSG_PEER_PUSH")) sh.push_mode = std::max(0, std::min(2, std::atoi(e)));
   if (const char* e = getenv("RSG_PEER_CHUNKS")) sh.nchunk = std::max(1, std::min(8, std::atoi(e)));
-  if (sh.push_mode == 2 && !sh.st2) {
+  // two species pipelines by default with one process per GPU (measured: 0.849 -> 0.820 ms at 8 GPUs, 1.30 -> 1.22 at 4, 2.10 -> 2.03
+  // at 2); several in-process "ranks" on ONE device (attach_local, the test harness) stall each other's barriers with forked graphs
+  sh.pipes = sh.local ? 1 : 2;
+  if (const char* e = getenv("RSG_PEER_PIPES")) sh.pipes = std::max(1, std::min(2, std::atoi(e)));
+  if ((sh.push_mode == 2 || sh.pipes == 2) && !sh.st2) {
     CK(cudaStreamCreateWithFlags(&sh.st2, cudaStreamNonBlocking));
     for (auto& e : sh.ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
@@ -269,78 +280,96 @@ int enqueue_sharded(rsg_ram* h, double DTs, int flags) {
       if (s < s0 || s >= s0 + ns) doW &= ~(1 << s);
     h->in_step = false;
     const int doC = (flags & RSG_F_COULOMB) ? 1 : 0;
-    SpecPack pk;
-    make_pack(h, pk, s0, ns);
-    auto push = [&](cudaStream_t q, int row0, int nrows, int c0, int c1, int mode) {
-      k_peer_push<<<dim3(nblk(nrows, 8), ns, mode == 0 ? p.G : 1), 256, 0, q>>>(sh.pv, pk, s0, h->NE, h->Pp, h->P, row0, nrows, c0, c1, mode);
-      h->launches++;
-      return cudaGetLastError();
-    };
-    if (sh.push_mode == 2) {
-      // both re-shardings chunked: kernel of chunk c on the run stream, its bulk push on the second stream beside chunk c+1
-      const int NC = std::max(1, std::min({sh.nchunk, p.nl, p.nb}));
-      RET(prof_mark(h, "k_plane_rp_fwd(local) || k_peer_push", st));
-      for (int c = 0; c < NC; ++c) {
-        int a, n;
-        split_range(p.nl, NC, c, &a, &n);
-        RET(L_plane_rp(h, s0, ns, st, false, p.l0 + a, n));
-        CK(cudaEventRecord(sh.ev[c], st));
-        CK(cudaStreamWaitEvent(sh.st2, sh.ev[c], 0));
-        CK(push(sh.st2, (p.l0 + a) * h->NE, n * h->NE, 0, 0, 0));
-      }
-      CK(cudaEventRecord(sh.ev[16], sh.st2));
-      CK(cudaStreamWaitEvent(st, sh.ev[16], 0));
-      RET(prof_mark(h, "barrier_1", st));
-      k_peer_barrier<<<1, 32, 0, st>>>(sh.pc, 0, sh.group_mask);
-      CKL();
-      RET(prof_mark(h, "k_col_fused(local) || k_peer_push", st));
-      for (int c = 0; c < NC; ++c) {
-        int a, n;
-        split_range(p.nb, NC, c, &a, &n);
-        RET(L_col(h, s0, ns, doA, DTs, st, p.b0 + a, n, doW, nullptr, doC, a));
-        CK(cudaEventRecord(sh.ev[8 + c], st));
-        CK(cudaStreamWaitEvent(sh.st2, sh.ev[8 + c], 0));
-        CK(push(sh.st2, 0, h->NE * h->NPA, (p.b0 + a) * COL_PG, std::min(h->P, (p.b0 + a + n) * COL_PG), 1));
-      }
-      CK(cudaEventRecord(sh.ev[17], sh.st2));
-      CK(cudaStreamWaitEvent(st, sh.ev[17], 0));
-    } else {
-      RET(prof_mark(h, "k_plane_rp_fwd(peer stores)", st));
-      RET(L_plane_rp(h, s0, ns, st, false, p.l0, p.nl, &sh.pv));     // DRIFTR, DRIFTP -> the column owners
-      RET(prof_mark(h, "barrier_1", st));
-      k_peer_barrier<<<1, 32, 0, st>>>(sh.pc, 0, sh.group_mask);
-      CKL();
-      if (sh.push_mode == 1) {
-        RET(prof_mark(h, "k_col_fused(local)", st));
-        RET(L_col(h, s0, ns, doA, DTs, st, p.b0, p.nb, doW, nullptr, doC));  // DRIFTE .. DRIFTE into the local buffer
-        RET(prof_mark(h, "k_peer_push", st));
-        CK(push(st, 0, h->NE * h->NPA, p.b0 * COL_PG, std::min(h->P, (p.b0 + p.nb) * COL_PG), 1));
+    const int doW_all = doW;
+    auto pipeline = [&](const int s0, const int ns, cudaStream_t st, const int bar) -> int {
+      int doW = doW_all;
+      for (int s = 0; s < h->nS; ++s)
+        if (s < s0 || s >= s0 + ns) doW &= ~(1 << s);
+      SpecPack pk;
+      make_pack(h, pk, s0, ns);
+      auto push = [&](cudaStream_t q, int row0, int nrows, int c0, int c1, int mode) {
+        k_peer_push<<<dim3(nblk(nrows, 8), ns, mode == 0 ? p.G : 1), 256, 0, q>>>(sh.pv, pk, s0, h->NE, h->Pp, h->P, row0, nrows, c0, c1, mode);
+        h->launches++;
+        return cudaGetLastError();
+      };
+      if (sh.push_mode == 2) {
+        // both re-shardings chunked: kernel of chunk c on the run stream, its bulk push on the second stream beside chunk c+1
+        const int NC = std::max(1, std::min({sh.nchunk, p.nl, p.nb}));
+        RET(prof_mark(h, "k_plane_rp_fwd(local) || k_peer_push", st));
+        for (int c = 0; c < NC; ++c) {
+          int a, n;
+          split_range(p.nl, NC, c, &a, &n);
+          RET(L_plane_rp(h, s0, ns, st, false, p.l0 + a, n));
+          CK(cudaEventRecord(sh.ev[c], st));
+          CK(cudaStreamWaitEvent(sh.st2, sh.ev[c], 0));
+          CK(push(sh.st2, (p.l0 + a) * h->NE, n * h->NE, 0, 0, 0));
+        }
+        CK(cudaEventRecord(sh.ev[16], sh.st2));
+        CK(cudaStreamWaitEvent(st, sh.ev[16], 0));
+        RET(prof_mark(h, "barrier_1", st));
+        k_peer_barrier<<<1, 32, 0, st>>>(sh.pc, bar, sh.group_mask);
+        CKL();
+        RET(prof_mark(h, "k_col_fused(local) || k_peer_push", st));
+        for (int c = 0; c < NC; ++c) {
+          int a, n;
+          split_range(p.nb, NC, c, &a, &n);
+          RET(L_col(h, s0, ns, doA, DTs, st, p.b0 + a, n, doW, nullptr, doC, a));
+          CK(cudaEventRecord(sh.ev[8 + c], st));
+          CK(cudaStreamWaitEvent(sh.st2, sh.ev[8 + c], 0));
+          CK(push(sh.st2, 0, h->NE * h->NPA, (p.b0 + a) * COL_PG, std::min(h->P, (p.b0 + a + n) * COL_PG), 1));
+        }
+        CK(cudaEventRecord(sh.ev[17], sh.st2));
+        CK(cudaStreamWaitEvent(st, sh.ev[17], 0));
       } else {
-        RET(prof_mark(h, "k_col_fused(peer stores)", st));
-        RET(L_col(h, s0, ns, doA, DTs, st, p.b0, p.nb, doW, &sh.pv, doC));   // DRIFTE .. DRIFTE -> the pitch-angle owners
+        RET(prof_mark(h, "k_plane_rp_fwd(peer stores)", st));
+        RET(L_plane_rp(h, s0, ns, st, false, p.l0, p.nl, &sh.pv));     // DRIFTR, DRIFTP -> the column owners
+        RET(prof_mark(h, "barrier_1", st));
+        k_peer_barrier<<<1, 32, 0, st>>>(sh.pc, bar, sh.group_mask);
+        CKL();
+        if (sh.push_mode == 1) {
+          RET(prof_mark(h, "k_col_fused(local)", st));
+          RET(L_col(h, s0, ns, doA, DTs, st, p.b0, p.nb, doW, nullptr, doC));  // DRIFTE .. DRIFTE into the local buffer
+          RET(prof_mark(h, "k_peer_push", st));
+          CK(push(st, 0, h->NE * h->NPA, p.b0 * COL_PG, std::min(h->P, (p.b0 + p.nb) * COL_PG), 1));
+        } else {
+          RET(prof_mark(h, "k_col_fused(peer stores)", st));
+          RET(L_col(h, s0, ns, doA, DTs, st, p.b0, p.nb, doW, &sh.pv, doC));   // DRIFTE .. DRIFTE -> the pitch-angle owners
+        }
       }
-    }
-    RET(prof_mark(h, "barrier_2", st));
-    k_peer_barrier<<<1, 32, 0, st>>>(sh.pc, 0, sh.group_mask);
-    CKL();
-    RET(prof_mark(h, "k_plane_rp_rev", st));
-    RET(L_plane_rp(h, s0, ns, st, true, p.l0, p.nl));               // DRIFTP, DRIFTR, epilogue (local slab)
-    RET(prof_mark(h, "anisch+finalize", st));
-    RET(L_finish_fused(h, s0, ns, st, p.l0, p.nl, p.nb));
-    h->launches += 2;
-    if (doW) {
-      SpecPack pk;
-      make_pack(h, pk, s0, ns);
-      k_finalize_wpi<<<dim3(2, ns), 256, 0, st>>>(pk, s0, doW, p.nb, fused_wpart_off(h), RES_N, NSUM, h->d_wviol, h->hd_res_all);
+      RET(prof_mark(h, "barrier_2", st));
+      k_peer_barrier<<<1, 32, 0, st>>>(sh.pc, bar, sh.group_mask);
       CKL();
-      h->launches++;
-    }
-    if (doC) {
-      SpecPack pk;
-      make_pack(h, pk, s0, ns);
-      k_finalize_coul<<<dim3(4, ns), 256, 0, st>>>(pk, s0, p.nb, fused_cpart_off(h), RES_N, h->hd_res_all);
-      CKL();
-      h->launches++;
+      RET(prof_mark(h, "k_plane_rp_rev", st));
+      RET(L_plane_rp(h, s0, ns, st, true, p.l0, p.nl));               // DRIFTP, DRIFTR, epilogue (local slab)
+      RET(prof_mark(h, "anisch+finalize", st));
+      RET(L_finish_fused(h, s0, ns, st, p.l0, p.nl, p.nb));
+      h->launches += 2;
+      if (doW) {
+        SpecPack pk;
+        make_pack(h, pk, s0, ns);
+        k_finalize_wpi<<<dim3(2, ns), 256, 0, st>>>(pk, s0, doW, p.nb, fused_wpart_off(h), RES_N, NSUM, h->d_wviol, h->hd_res_all);
+        CKL();
+        h->launches++;
+      }
+      if (doC) {
+        SpecPack pk;
+        make_pack(h, pk, s0, ns);
+        k_finalize_coul<<<dim3(4, ns), 256, 0, st>>>(pk, s0, p.nb, fused_cpart_off(h), RES_N, h->hd_res_all);
+        CKL();
+        h->launches++;
+      }
+      return RSG_OK;
+    };
+    if (sh.pipes == 2 && ns >= 2 && sh.push_mode != 2 && !h->prof_on) {   // (per-stage timing needs one stream)
+      const int na = ns / 2;
+      CK(cudaEventRecord(sh.ev[0], st));
+      CK(cudaStreamWaitEvent(sh.st2, sh.ev[0], 0));
+      RET(pipeline(s0, na, st, 0));
+      RET(pipeline(s0 + na, ns - na, sh.st2, 2));
+      CK(cudaEventRecord(sh.ev[1], sh.st2));
+      CK(cudaStreamWaitEvent(st, sh.ev[1], 0));
+    } else {
+      RET(pipeline(s0, ns, st, 0));
     }
   } else if (fused_ok(h, flags)) {
     RET(enqueue_fused(h, DTs, flags, s0, ns));

@@ -13,6 +13,11 @@ def pytest_configure(config):
     # tests/test_ram_shard_gpu.py runs several "ranks" of the multi-GPU step on ONE device: a rank's barrier kernel spins
     # while the next rank's kernels start, so no kernel may need (device-synchronising) lazy module loading by then
     os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+    # ... and no two active streams may share a hardware queue (a spinning barrier at the head of a queue would block the
+    # kernels it waits for): 8 in-process ranks x 2 streams need more than the default 8 connections.  A failed in-process
+    # barrier should cost seconds, not the production 20 s.
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+    os.environ.setdefault("RSG_BARRIER_TIMEOUT_MS", "4000")
     if os.environ.get("RSG_EMU") == "1":
         # development aid for a GPU-less container: run the RAM `-m gpu` tests against the kernels
         # compiled for the host-CPU CUDA emulator (tests/emu/).  Test infrastructure only.

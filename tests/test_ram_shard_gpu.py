@@ -169,9 +169,12 @@ def test_sharded_errors(default_grids):
     a.close(); b.close()
 
 
-def test_multi_gpu_peer_memory():
+@pytest.mark.parametrize("pipes", ["1", "2"])
+def test_multi_gpu_peer_memory(pipes):
     """>= 2 GPUs: one process per GPU, peer pointers through CUDA IPC (tests/multi_gpu_peer_check.py).  Skipped on a
-    1-GPU box, where the in-process tests above run the same kernels, barriers and graphs."""
+    1-GPU box, where the in-process tests above run the same kernels, barriers and graphs.  pipes = 2: the rank's species
+    as two pipelines on two streams (RSG_PEER_PIPES; own barrier ids, fork / join in the step's graph) -- only testable
+    with one process per GPU: several in-process "ranks" with forked graphs on ONE device stall each other's barriers."""
     import os
     import subprocess
     import sys
@@ -182,7 +185,7 @@ def test_multi_gpu_peer_memory():
     n = 8 if n >= 8 else (4 if n >= 4 else 2)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
-                        "127.0.0.1", "--master-port", "29519", os.path.join(root, "tests", "multi_gpu_peer_check.py")],
-                       capture_output=True, text=True, timeout=900)
+                        "127.0.0.1", "--master-port", "2951" + pipes, os.path.join(root, "tests", "multi_gpu_peer_check.py")],
+                       capture_output=True, text=True, timeout=900, env=dict(os.environ, RSG_PEER_PIPES=pipes))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "MULTI_GPU_PEER_CHECK_OK" in r.stdout
