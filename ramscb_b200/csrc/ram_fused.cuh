@@ -339,7 +339,8 @@ __global__ void __launch_bounds__(512) k_plane_rp(const __grid_constant__ RamDev
           const double c = cnext;
           pa += NR; pb += NR;
           if (more) cnext = fma(-w2k, *pb, *pa);
-          const double cur = c * limited_flux_d(F0, Fp1, dm1, d0, wrapfix ? Fp2 - F1row : dp1, c < 0.0, fabs(c), beta);
+          // (colp[0] = the stored F(1): only this thread rewrites it, after its last step; re-read so that it is not live in the loop)
+          const double cur = c * limited_flux_d(F0, Fp1, dm1, d0, wrapfix ? Fp2 - colp[0] : dp1, c < 0.0, fabs(c), beta);
           fnew = F0 - cur + prev;                       // :266
           if (fnew < 0.0) fnew = 1E-15;
           *pO = fnew;

@@ -538,6 +538,13 @@ PlanePlan plane_plan(const rsg_ram* h) {
   };
   segs(NR - 1, c.T / linesR, &c.cfg.nsegR, &c.cfg.segR);
   segs(NT - 1, c.T / linesP, &c.cfg.nsegP, &c.cfg.segP);
+  // DRIFTP: the cells J = NT-1 and J = NT must belong to ONE thread -- the step at interface NT-1 re-reads the stored F(1)
+  // (colp[0]), which the thread that owns J = NT overwrites at its end (k_plane_rp, wrapfix).  A last segment of one cell
+  // is avoided by one more cell per segment.
+  while (c.cfg.nsegP > 1 && (NT - 1) - (c.cfg.nsegP - 1) * c.cfg.segP < 2) {
+    c.cfg.segP++;
+    c.cfg.nsegP = (NT - 1 + c.cfg.segP - 1) / c.cfg.segP;
+  }
   c.smem = sizeof(double) * ((size_t)KC * c.cfg.PS + 2 * (size_t)KC * NT + 32) + sizeof(int) * (((size_t)KC * NT + 1) & ~(size_t)1);
   return c;
 }
