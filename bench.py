@@ -379,19 +379,34 @@ def measure_ram(workload_name, flags, steps, warmup, device, mode="fast", dist=N
             up = down = F2_host.nbytes
         up += 3 * inp.VT.nbytes
         down += (4 + 6 + 1) * g.nS * 8 + 2 * g.nS * g.NR * g.NT * 8
+        def e2e_step(pipelined):
+            gpu.set_efield(inp.VT, inp.EIR, inp.EIP)
+            if sh:
+                gpu.f2_h2d_shard(F2_host)
+                step()
+                gpu.f2_d2h_shard(F2_host)
+            elif pipelined:       # one C call: upload | DRIFTR, DRIFTP per chunk of pitch angles ... | download
+                gpu.ram_run_host(F2_host, DTS, DtsMin=1.0, flags=flags)
+            else:
+                gpu.f2_h2d(F2_host)
+                step()
+                gpu.f2_d2h(F2_host)
+
+        seq_s = None
+        if not sh:                # the three calls one after the other (round 1's e2e), for comparison
+            e2e_step(False)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(max(3, n // 2)):
+                e2e_step(False)
+            barrier()
+            seq_s = (time.perf_counter() - t0) / max(3, n // 2)
+            F2_host[...] = inp.F2
+            e2e_step(True)        # warm the pipelined path (stream, events)
         barrier()
         t0 = time.perf_counter()
         for _ in range(n):
-            if sh:
-                gpu.f2_h2d_shard(F2_host)
-            else:
-                gpu.f2_h2d(F2_host)
-            gpu.set_efield(inp.VT, inp.EIR, inp.EIP)
-            step()
-            if sh:
-                gpu.f2_d2h_shard(F2_host)
-            else:
-                gpu.f2_d2h(F2_host)
+            e2e_step(True)
         barrier()
         e2e_s = (time.perf_counter() - t0) / n
         tot = [float(up), float(down)]
@@ -405,7 +420,11 @@ def measure_ram(workload_name, flags, steps, warmup, device, mode="fast", dist=N
         out["e2e"] = {"value": ops * cells / e2e_s, "unit": "cell-updates/s", "h2d_bytes_per_step": int(tot[0]),
                       "d2h_bytes_per_step": int(tot[1]), "ms_per_step": e2e_s * 1e3, "steps": n,
                       "timer": "wall clock around the C-ABI calls, max over ranks; pinned host F2 goes host->device and back "
-                               "EVERY step (routine-level drop-in, INTEGRATION.md 3a): PCIe bound"}
+                               "EVERY step (routine-level drop-in, INTEGRATION.md 3a): PCIe bound",
+                      "call": "rsg_ram_f2_h2d_shard + rsg_ram_run_sharded + rsg_ram_f2_d2h_shard" if sh else
+                              "rsg_ram_run_host (upload, step and download pipelined over chunks of pitch angles)"}
+        if seq_s is not None:
+            out["e2e"]["three_calls_ms_per_step"] = seq_s * 1e3
         if not sh:
             t0 = time.perf_counter()
             for _ in range(n):

@@ -170,6 +170,10 @@ struct rsg_ram {
   unsigned long long* d_res_init = nullptr;
   unsigned long long* d_wviol = nullptr;    // [nS] rows of the WPADIF matrices that are not diagonally dominant (per tabulation)
 
+  // rsg_ram_run_host: copy stream and per-chunk events of the pipelined host <-> device step
+  cudaStream_t copyst = nullptr;
+  cudaEvent_t evh[2 * 16] = {nullptr};
+
   cudaStream_t st(int s) { return ext ? ext : sp[s].own; }
   cudaStream_t pst() { return ext ? ext : prepst; }
   template <class T>
@@ -570,7 +574,29 @@ int opt_in_smem(K kernel, size_t smem) {
   if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   return RSG_OK;
 }
-int L_plane_rp(rsg_ram* h, int s0, int ns, cudaStream_t st, bool rev, int l0 = 0, int nl = -1, const PeerView* peer = nullptr) {
+void split_range(int n, int parts, int idx, int* start, int* count);
+// host layout <-> device layout for ALL species of a range of (l, k) planes in one pass: a thread moves the nS contiguous
+// doubles of one (plane, position) between the staging image and the species buffers (k_f2_from_host / to_host make one
+// strided pass per species).  grid: x = tiles of p, y = planes of the range
+struct SpecPtrs { double* F[RSG_MAX_SPECIES]; };
+template <bool TO_HOST>
+__global__ void __launch_bounds__(256) k_f2_host_all(RamDev d, double* __restrict__ stage, SpecPtrs sp, int plane0) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t plane = (size_t)plane0 + blockIdx.y;
+  if (p >= d.Pp) return;
+  if (p < d.P) {
+    double* q = stage + (plane * d.P + p) * d.nS;
+    for (int s = 0; s < d.nS; ++s) {
+      if (TO_HOST) q[s] = sp.F[s][plane * d.Pp + p];
+      else sp.F[s][plane * d.Pp + p] = q[s];
+    }
+  } else if (!TO_HOST) {
+    for (int s = 0; s < d.nS; ++s) sp.F[s][plane * d.Pp + p] = 0.0;
+  }
+}
+
+int L_plane_rp(rsg_ram* h, int s0, int ns, cudaStream_t st, bool rev, int l0 = 0, int nl = -1, const PeerView* peer = nullptr,
+               int part_l0 = -1) {
   if (nl < 0) nl = h->NPA - l0;
   static const PeerView kNoPeer{};
   const PeerView& pv = peer ? *peer : kNoPeer;
@@ -581,6 +607,9 @@ int L_plane_rp(rsg_ram* h, int s0, int ns, cudaStream_t st, bool rev, int l0 = 0
   const int KG = (h->NE + c.cfg.KC - 1) / c.cfg.KC;
   const dim3 g(KG, nl, ns);
   c.cfg.part_off = fused_part_off(h);      // after the column kernel's partials
+  // a launch over [l0, l0+nl) writes its reduction rows from row 0; chunked launches of one range (rsg_ram_run_host) place
+  // their rows behind those of the pitch angles part_l0 .. l0-1
+  if (part_l0 >= 0) c.cfg.part_off += (l0 - part_l0) * KG;
   c.cfg.l0 = l0;
   c.cfg.anisch = (rev && h->sp[s0].d_aE2) ? 1 : 0;
   c.cfg.tma = (h->planeTma && h->NR * 8 >= 512) ? 1 : 0;   // rows shorter than 512 B: the per-copy overhead shows (measured)
@@ -1074,6 +1103,8 @@ int rsg_ram_destroy(rsg_ram* h) {
   if (h->h_res_all) cudaFreeHost(h->h_res_all);
   if (h->h_pp_all) cudaFreeHost(h->h_pp_all);
   if (h->prepst) cudaStreamDestroy(h->prepst);
+  if (h->copyst) cudaStreamDestroy(h->copyst);
+  for (auto& e : h->evh) if (e) cudaEventDestroy(e);
   if (h->prepev) cudaEventDestroy(h->prepev);
   if (h->t0) cudaEventDestroy(h->t0);
   if (h->t1) cudaEventDestroy(h->t1);
@@ -2405,6 +2436,98 @@ int rsg_ram_run(rsg_ram* h, double DTs, double DtsMin, double T, int flags, doub
   if (!h) return fail(RSG_ERR_ARG, "null handle");
   h->T_elapsed = T;                    // COULMU clamps negatives only once T > 0 (src/ModRamCoul.f90:289)
   RET(run_core(h, DTs, flags, 0, h->nS));
+  return decode_step(h, flags, DtsMin, dts_next, DtDrift, losses, SETRC, PPERT, PPART);
+}
+
+// ---- the step with F2 coming from and returning to the HOST array (the routine-level drop-in's every step) ----------
+// rsg_ram_f2_h2d + rsg_ram_run + rsg_ram_f2_d2h in one call, pipelined over chunks of pitch angles (L is the slowest index of
+// the host array, so a chunk is one contiguous run): the upload of chunk c+1 runs beside the layout conversion and the
+// forward plane kernel (DRIFTR, DRIFTP) of chunk c; after the column kernel the reverse plane kernel of a chunk is followed
+// at once by its conversion and download, beside the next chunk's kernel.  Same kernels, same per-cell arithmetic as
+// rsg_ram_run (F2 and the CFL limits bit-identical; moments summed in the same order).  What cannot overlap: upload and
+// download themselves -- the column kernel needs every pitch angle of a position, the plane kernels every position of a
+// pitch angle.  Steps the fused kernels do not cover (EXACT mode, RSG_NO_FUSE) run the three calls one after the other.
+int rsg_ram_run_host(rsg_ram* h, double* F2, double DTs, double DtsMin, double T, int flags, double* dts_next, double* DtDrift,
+                     double* losses, double* SETRC, double* PPERT, double* PPART) {
+  if (!h || !F2) return fail(RSG_ERR_ARG, "null argument");
+  const int NC = std::min(12, h->NPA / 4);
+  bool same_buf = true;
+  for (int s = 0; s < h->nS; ++s) same_buf = same_buf && h->sp[s].cur == 0;
+  if (!fused_ok(h, flags) || !same_buf || h->ext || NC < 2 || h->sp[0].d_aE2 || getenv("RSG_NO_HOST_PIPELINE")) {
+    RET(rsg_ram_f2_h2d(h, F2, 0));
+    RET(rsg_ram_run(h, DTs, DtsMin, T, flags, dts_next, DtDrift, losses, SETRC, PPERT, PPART));
+    return rsg_ram_f2_d2h(h, F2, 0);
+  }
+  CK(cudaSetDevice(h->device));
+  RET(rsg_ram_sync(h));
+  h->T_elapsed = T;
+  const int nS = h->nS;
+  RET(step_prepare(h, DTs, flags, 0, nS));
+  if (!h->copyst) {
+    CK(cudaStreamCreateWithFlags(&h->copyst, cudaStreamNonBlocking));
+    for (auto& e : h->evh) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  cudaStream_t st = h->pst(), cs = h->copyst;
+  const size_t per_l = (size_t)nS * h->P * h->NE;
+  SpecPtrs sp;
+  for (int s = 0; s < RSG_MAX_SPECIES; ++s) sp.F[s] = s < nS ? h->d_F2[0] + h->specStride * s : nullptr;
+  const dim3 tb(nblk(h->Pp, 256));
+  int cat[RSG_MAX_SPECIES][NSLOT], doA;
+  slot_cats(h, flags, cat, &doA, nullptr);
+  const int doW = wpadif_mask(h, flags), doC = (flags & RSG_F_COULOMB) ? 1 : 0;
+  h->in_step = false;
+  CK(cudaEventRecord(h->evh[0], st));                     // the copies start after whatever the run stream still holds
+  CK(cudaStreamWaitEvent(cs, h->evh[0], 0));
+  for (int c = 0; c < NC; ++c) {                          // up: copy | convert + DRIFTR, DRIFTP
+    int a, n;
+    split_range(h->NPA, NC, c, &a, &n);
+    CK(cudaMemcpyAsync(h->d_stage + a * per_l, F2 + a * per_l, n * per_l * sizeof(double), cudaMemcpyHostToDevice, cs));
+    CK(cudaEventRecord(h->evh[1 + c], cs));
+    CK(cudaStreamWaitEvent(st, h->evh[1 + c], 0));
+    k_f2_host_all<false><<<dim3(tb.x, n * h->NE), 256, 0, st>>>(h->dev, h->d_stage, sp, a * h->NE);
+    CKL();
+    RET(L_plane_rp(h, 0, nS, st, false, a, n));
+    h->launches++;
+  }
+  RET(L_col(h, 0, nS, doA, DTs, st, 0, -1, doW, nullptr, doC));
+  auto down = [&](int c, int a, int n) -> int {          // convert + copy of a finished chunk
+    k_f2_host_all<true><<<dim3(tb.x, n * h->NE), 256, 0, st>>>(h->dev, h->d_stage, sp, a * h->NE);
+    CKL();
+    h->launches++;
+    CK(cudaEventRecord(h->evh[16 + c], st));
+    CK(cudaStreamWaitEvent(cs, h->evh[16 + c], 0));
+    CK(cudaMemcpyAsync(F2 + a * per_l, h->d_stage + a * per_l, n * per_l * sizeof(double), cudaMemcpyDeviceToHost, cs));
+    return RSG_OK;
+  };
+  for (int c = NC - 1; c >= 0; --c) {                     // down: DRIFTP, DRIFTR, epilogue | convert + copy
+    int a, n;
+    split_range(h->NPA, NC, c, &a, &n);
+    RET(L_plane_rp(h, 0, nS, st, true, a, n, nullptr, 0));
+    if (c > 0) RET(down(c, a, n));
+  }
+  RET(L_finish_fused(h, 0, nS, st));                     // ANISCH sums, second stage of the reductions; sets F2(L=1) = F2(L=2)
+  {
+    int a, n;
+    split_range(h->NPA, NC, 0, &a, &n);
+    RET(down(0, a, n));
+  }
+  if (doC) {
+    SpecPack pk;
+    make_pack(h, pk, 0, nS);
+    k_finalize_coul<<<dim3(4, nS), 256, 0, st>>>(pk, 0, (h->P + COL_PG - 1) / COL_PG, fused_cpart_off(h), RES_N, h->hd_res_all);
+    CKL();
+    h->launches++;
+  }
+  if (doW) {
+    SpecPack pk;
+    make_pack(h, pk, 0, nS);
+    k_finalize_wpi<<<dim3(2, nS), 256, 0, st>>>(pk, 0, doW, (h->P + COL_PG - 1) / COL_PG, fused_wpart_off(h), RES_N, NSUM, h->d_wviol,
+                                                h->hd_res_all);
+    CKL();
+    h->launches++;
+  }
+  CK(cudaStreamSynchronize(st));
+  CK(cudaStreamSynchronize(cs));
   return decode_step(h, flags, DtsMin, dts_next, DtDrift, losses, SETRC, PPERT, PPART);
 }
 

@@ -259,6 +259,17 @@ module ModRamGpu
        real(c_double), intent(out) :: dts_next, DtDrift(*), losses(*), SETRC(*), PPERT(*), PPART(*)
        integer(c_int) :: ierr
      end function
+     function rsg_ram_run_host(h, F2, DTs, DtsMin, T, flags, dts_next, DtDrift, losses, SETRC, PPERT, PPART) &
+          bind(C, name='rsg_ram_run_host') result(ierr)
+       ! rsg_ram_f2_h2d + rsg_ram_run + rsg_ram_f2_d2h in one pipelined call
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       real(c_double), intent(inout) :: F2(*)
+       real(c_double), value :: DTs, DtsMin, T
+       integer(c_int), value :: flags
+       real(c_double), intent(out) :: dts_next, DtDrift(*), losses(*), SETRC(*), PPERT(*), PPART(*)
+       integer(c_int) :: ierr
+     end function
      ! ---- ANISCH, second half: the diffusion-coefficient rebuild on the device (src/ModRamRun.f90:422-605) ----
      function rsg_ram_set_wave_tables(h, ENG, NCF, ENOR, fpofc, NDAAJ, DAAR, use_bas, ENG_emic, NCF_emic, EKEV_emic, &
           fp2c_emic, Daa_emic_h, Daa_emic_he, Ihs_emic, Ihes_emic, PAbn) bind(C, name='rsg_ram_set_wave_tables') result(ierr)

@@ -31,10 +31,10 @@ subroutine ram_run_gpu
   if (DoUseCoulomb) flags = ior(flags, RSG_F_COULOMB)
   if (DoUseEMIC) flags = ior(flags, RSG_F_EMIC)
   call rsg_check(rsg_ram_set_efield(hRam, VT, EIR, EIP), 'ram_run')            ! VT changes every call (:45-54)
-  call rsg_check(rsg_ram_f2_h2d(hRam, F2, 0_c_int), 'ram_run')                 ! skip when F2 was not touched on the host
-  call rsg_check(rsg_ram_run(hRam, real(DTs, c_double), real(DtsMin, c_double), real(TimeRamElapsed, c_double), &
-                             flags, dtn, dt, ls, SETRC, PPerT, PParT), 'ram_run')
-  call rsg_check(rsg_ram_f2_d2h(hRam, F2, 0_c_int), 'ram_run')                 ! needed by outputs / restart / Compute3DFlux
+  ! F2 up, the step, F2 back (outputs / restart / Compute3DFlux read it) in ONE call, pipelined over chunks of pitch angles.
+  ! A host that leaves F2 untouched between steps calls rsg_ram_run instead and fetches F2 (rsg_ram_f2_d2h) when it writes output.
+  call rsg_check(rsg_ram_run_host(hRam, F2, real(DTs, c_double), real(DtsMin, c_double), real(TimeRamElapsed, c_double), &
+                                  flags, dtn, dt, ls, SETRC, PPerT, PParT), 'ram_run')
   DtsNext = dtn
   do iS = 1, nS
      DtDriftR(iS) = dt(1, iS); DtDriftP(iS) = dt(2, iS); DtDriftE(iS) = dt(3, iS); DtDriftMu(iS) = dt(4, iS)

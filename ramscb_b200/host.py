@@ -93,6 +93,7 @@ def lib():
     L.rsg_sumrc.argtypes = [vp, i, _dp, _dp]
     L.rsg_anisch.argtypes = [vp, i, vp, vp]
     L.rsg_ram_run.argtypes = [vp, d, d, d, i, _dp, vp, vp, vp, vp, vp]
+    L.rsg_ram_run_host.argtypes = [vp, vp, d, d, d, i, _dp, vp, vp, vp, vp, vp]
     L.rsg_ram_part_fwd.argtypes = [vp, d, i, i, i, i, i]
     L.rsg_ram_part_all.argtypes = [vp, d, i, i, i]
     L.rsg_ram_fused_available.argtypes = [vp, i]
@@ -367,6 +368,24 @@ class RamGpu:
         }
         _ck(self.L.rsg_ram_run(self.h, DTs, DtsMin, T, flags, C.byref(dtn), _p(out["DtDrift"]), _p(out["losses"]),
                                _p(out["SETRC"]), _p(out["PPERT"]), _p(out["PPART"])))
+        out["DtsNext"] = dtn.value
+        return out
+
+    def ram_run_host(self, F2, DTs, DtsMin=1.0, T=0.0, flags=0):
+        """ram_run with F2 (the host array, Fortran order (nS,NR,NT,NE,NPA), updated in place) going up and coming back
+        inside the call, pipelined over chunks of pitch angles (rsg_ram_run_host)."""
+        g = self.g
+        assert F2.flags.f_contiguous and F2.dtype == np.float64 and F2.shape == (g.nS, g.NR, g.NT, g.NE, g.NPA)
+        dtn = C.c_double()
+        out = {
+            "DtDrift": np.zeros((4, g.nS), order="F"),
+            "losses": np.zeros((6, g.nS), order="F"),
+            "SETRC": np.zeros(g.nS),
+            "PPERT": np.zeros((g.nS, g.NR, g.NT), order="F"),
+            "PPART": np.zeros((g.nS, g.NR, g.NT), order="F"),
+        }
+        _ck(self.L.rsg_ram_run_host(self.h, F2.ctypes.data, DTs, DtsMin, T, flags, C.byref(dtn), _p(out["DtDrift"]), _p(out["losses"]),
+                                    _p(out["SETRC"]), _p(out["PPERT"]), _p(out["PPART"])))
         out["DtsNext"] = dtn.value
         return out
 

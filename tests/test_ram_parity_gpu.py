@@ -294,6 +294,44 @@ def test_driftp_wrap_with_fields_not_periodic_in_mlt(default_grids, oracle_built
     gpu.close()
 
 
+@pytest.mark.parametrize("mode,flags", [("fast", 0), ("fast", 5), ("fast", 7), ("exact", 0)])
+def test_ram_run_host_pipelined_equals_three_calls(default_grids, mode, flags):
+    """rsg_ram_run_host = rsg_ram_f2_h2d + rsg_ram_run + rsg_ram_f2_d2h in one call, pipelined over chunks of pitch angles
+    (upload | convert + DRIFTR, DRIFTP per chunk; column kernel; DRIFTP, DRIFTR | convert + download per chunk).  Same
+    kernels and the same reduction order: the host array and every result bit-identical to the three calls, over three
+    steps that start from the previous step's host array.  EXACT mode takes the sequential fallback inside the call."""
+    from ramscb_b200 import host
+    g = default_grids
+    inp = _mk(g, f2_kind="noisy", inductive=True, mgnp=True)
+    D = synthetic.synthetic_daa(g, inp)
+    res = []
+    for piped in (False, True):
+        gpu = host.RamGpu(g, mode=host.MODE_FAST if mode == "fast" else host.MODE_EXACT)
+        gpu.set_inputs(inp)
+        gpu.set_diffcoef(1, D)
+        gpu.set_diffcoef(2, D)
+        F = inp.F2.copy(order="F")
+        host.host_register(F)
+        outs = []
+        for step, dts in enumerate((5.0, 5.0, 7.5)):
+            if piped:
+                outs.append(gpu.ram_run_host(F, dts, DtsMin=1.0, T=5.0 * step, flags=flags))
+            else:
+                gpu.f2_h2d(F)
+                outs.append(gpu.ram_run(dts, DtsMin=1.0, T=5.0 * step, flags=flags))
+                gpu.f2_d2h(F)
+        host.host_unregister(F)
+        res.append((F, outs))
+        gpu.close()
+    (Fa, oa), (Fb, ob) = res
+    assert np.array_equal(Fa, Fb), f"{int((Fa != Fb).sum())} cells differ"
+    assert not np.array_equal(Fa, inp.F2)
+    for a, b in zip(oa, ob):
+        assert a["DtsNext"] == b["DtsNext"]
+        for k in ("DtDrift", "losses", "SETRC", "PPERT", "PPART"):
+            assert np.array_equal(a[k], b[k]), k
+
+
 @pytest.mark.parametrize("mode", ["exact", "fast"])
 def test_graph_replay_matches_kernel_by_kernel(default_grids, mode):
     """rsg_ram_run replays a captured CUDA graph when (DTs, flags, mode) repeat: the

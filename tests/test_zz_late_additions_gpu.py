@@ -62,7 +62,7 @@ def test_para_flc_on_device(default_grids, oracle_built, S):
     assert nv == nv_ref
 
 
-def test_scb_run_outer_iterations_resident(oracle_built):
+def test_scb_run_outer_iterations_resident(oracle_built, numit=3, color4=True):
     """scb_run (src/ModScbRun.f90:149-440) in ONE C call with every 3-D array resident (rsg_scb_run; only the
     2-D pressure front end is a host callback) against the same loop composed from the oracle's routines:
     with RSG_SOR_LEX the iteration counts, blends, residuals and x, y, z, alfa, psi are BIT-IDENTICAL; the
@@ -72,12 +72,12 @@ def test_scb_run_outer_iterations_resident(oracle_built):
     from ramscb_b200 import host
     inp, o, gpu = _pair(oracle_built, **SMALL)
     fn = SCBSYN.equatorial_pressure_fn()
-    kw = dict(numit=3, MinSCBIterations=2, decreaseConvAlpha=1e-30, decreaseConvPsi=1e-30)     # exactly 3 outer iterations
+    kw = dict(numit=numit, MinSCBIterations=2, decreaseConvAlpha=1e-30, decreaseConvPsi=1e-30)     # exactly `numit` outer iterations
     gpu.set_map_targets(inp.alphaVal, inp.psiVal, inp.chiVal)
     ro = o.scb_run(fn, **kw)
     rg = gpu.scb_run(fn, ordering=host.SOR_LEX, **kw)
     assert ro["SORFail"] == 0 and rg["SORFail"] == 0
-    assert rg["iterations"] == ro["iterations"] == 3
+    assert rg["iterations"] == ro["iterations"] == numit
     for k in ("blendAlpha", "blendPsi", "errorAlpha", "errorPsi", "nisaveAlpha", "nisavePsi", "blendRetries"):
         assert rg[k] == ro[k], (k, rg[k], ro[k])
     for k in ("sumdbAlpha", "sumdbPsi"):                       # tree sum vs serial sum
@@ -88,13 +88,14 @@ def test_scb_run_outer_iterations_resident(oracle_built):
     for a, b in zip((rg["normDiffStart"], rg["normJxBStart"], rg["normGradPStart"]), ro["normStart"]):
         assert abs(a - b) <= 1e-12 * abs(b)
     # production ordering from the same start
-    g2 = host.ScbGpu(inp)
-    g2.set_map_targets(inp.alphaVal, inp.psiVal, inp.chiVal)
-    r2 = g2.scb_run(fn, ordering=host.SOR_COLOR4, **kw)
-    assert r2["SORFail"] == 0 and r2["iterations"] == 3
-    for n in ("x", "y", "z"):
-        a, b = g2.get_field(n), getattr(o, n)
-        assert np.max(np.abs(a - b)) <= 1e-6 * np.max(np.abs(b)), (n, np.max(np.abs(a - b)))
+    if color4:
+        g2 = host.ScbGpu(inp)
+        g2.set_map_targets(inp.alphaVal, inp.psiVal, inp.chiVal)
+        r2 = g2.scb_run(fn, ordering=host.SOR_COLOR4, **kw)
+        assert r2["SORFail"] == 0 and r2["iterations"] == numit
+        for n in ("x", "y", "z"):
+            a, b = g2.get_field(n), getattr(o, n)
+            assert np.max(np.abs(a - b)) <= 1e-6 * np.max(np.abs(b)), (n, np.max(np.abs(a - b)))
     # failure path: a callback that reports failure aborts the call; one that returns NaN pressures makes the
     # solve fail (SORFail) and x, y, z, alfa, psi come back as they were at entry (:397-413)
     g3 = host.ScbGpu(inp)
