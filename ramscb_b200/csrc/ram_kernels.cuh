@@ -1122,10 +1122,20 @@ __global__ void __launch_bounds__(512) k_anisch_pa_fast(const __grid_constant__ 
     double* F = sp.F + (size_t)k * Pp + p;
     const int La = l0 + 1 + ch * LCH;                               // Fortran L range of this chunk
     const int Lb = min(min(d.UPA[i] - 1, l0 + nl), La + LCH - 1);
-    for (int L = La; L <= Lb; ++L) {
-      double f;
-      if (L == 1) { f = F[LS]; F[0] = f; }                         // F2(S,I,J,K,1) = F2(S,I,J,K,2)  (:366)
-      else f = F[(size_t)(L - 1) * LS];
+    int L = La;
+    if (L == 1 && L <= Lb) {                                       // F2(S,I,J,K,1) = F2(S,I,J,K,2)  (:366)
+      const double f = F[LS];
+      F[0] = f;
+      const double g = f * d.rFNHS[p];
+      se = fma(g, d.wPE[0], se);
+      sa = fma(g, d.wPA[0], sa);
+      ++L;
+    }
+    // same summation order; unrolled so that a thread has four independent 8-byte loads in flight (the kernel is a pure
+    // read of F2: at one load per warp it reached 2.1 TB/s, a third of HBM)
+#pragma unroll 4
+    for (; L <= Lb; ++L) {
+      const double f = F[(size_t)(L - 1) * LS];
       const double g = f * d.rFNHS[(size_t)(L - 1) * Pp + p];
       se = fma(g, d.wPE[L - 1], se);
       sa = fma(g, d.wPA[L - 1], sa);
