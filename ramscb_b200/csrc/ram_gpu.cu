@@ -952,6 +952,9 @@ int rsg_ram_create(rsg_ram** out, int nS, int NR, int NT, int NE, int NPA, int d
   if (const char* e = getenv("RSG_PLANE_T")) h->planeT = std::max(32, atoi(e));
   if (const char* e = getenv("RSG_PLANE_ODD")) h->planeOdd = atoi(e) != 0;
   if (const char* e = getenv("RSG_PLANE_TMA")) h->planeTma = atoi(e) != 0;
+  // measured (profiles/r2/anisch_lch_sweep.txt): 12 at the default grid; at the configs[2] grid longer chunks keep more loads in
+  // flight per thread (0.199 -> 0.171 ms with 18)
+  h->anischLch = ((double)NR * NT * NE * NPA > 8e6) ? 18 : 12;
   if (const char* e = getenv("RSG_ANISCH_LCH")) h->anischLch = std::max(1, atoi(e));
   if (getenv("RSG_NO_GRAPH")) h->use_graph = false;   // kernel-by-kernel launches (profilers)
   RamDev& d = h->dev;
