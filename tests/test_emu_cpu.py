@@ -133,14 +133,16 @@ def test_emulated_computehI_composed(emu, default_grids, oracle_built):
     TZ.test_computehI_composed_on_device(default_grids, oracle_built, (21, 19, 25))
 
 
-def test_emulated_computehI_resident(emu, default_grids, oracle_built):
+def test_emulated_computehI_resident(emu, small_grids, oracle_built):
     import test_zz_late_additions_gpu as TZ
-    TZ.test_computehI_resident_handle(default_grids, oracle_built, (21, 15, 25))
+    TZ.test_computehI_resident_handle(small_grids, oracle_built, (21, 15, 25))      # (the GPU run uses the default RAM grid)
 
 
-def test_emulated_coupled_cycle(emu, default_grids, oracle_built):
+def test_emulated_coupled_cycle(emu, oracle_built):
     import test_zz_late_additions_gpu as TZ
-    TZ.test_coupled_ram_scb_cycle_stays_on_the_device(default_grids, oracle_built, (21, 15, 25))
+    from ramscb_b200 import grids
+    g = grids.build_grids(NR=11, NT=11, NE=35)      # the pressure front end needs NR >= 10 (GPU: default RAM grid)
+    TZ.test_coupled_ram_scb_cycle_stays_on_the_device(g, oracle_built, (21, 15, 25))
 
 
 def test_emulated_scb_run_outer_iterations(emu, oracle_built):
@@ -159,7 +161,7 @@ def test_emulated_results_do_not_depend_on_thread_order():
     env = dict(os.environ, EMU_ORDER="random")
     here = os.path.dirname(os.path.abspath(__file__))
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_emu_cpu.py"), "-x", "-q", "-k",
-                        "(fused_wpadif and 5) or (exact_sweeps and DRIFTP) or scb_maps or hI_tail or hI_convert"], env=env, capture_output=True, text=True, cwd=os.path.dirname(here))
+                        "(fused_wpadif and 5) or (exact_sweeps and DRIFTP) or hI_tail or hI_convert"], env=env, capture_output=True, text=True, cwd=os.path.dirname(here))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
