@@ -152,3 +152,49 @@ def test_ram_configs2_grid_full_step_vs_oracle(ram_x4, mode):
     assert np.allclose(out["SETRC"], o.SETRC, rtol=2e-11, atol=0)
     assert np.max(np.abs(out["PPERT"][:, 1:] - o.PPERT[:, 1:]) / np.maximum(np.abs(o.PPERT[:, 1:]), 1e-300)) <= 1e-12
     assert np.max(np.abs(out["PPART"][:, 1:] - o.PPART[:, 1:]) / np.maximum(np.abs(o.PPART[:, 1:]), 1e-300)) <= 1e-12
+
+
+# ---- RAM at the size of configs[4]'s grid (8 x the default: 4 x NR, 4 x NT, 2 x NE = 156 M cells, 1.25 GB) -----------
+def test_ram_configs4_size_properties(dims=(80, 97, 70, 2)):
+    """No oracle run at this size (the CPU restatement needs minutes per step): the size-independent properties the path
+    offers instead.  (i) default operators: the fused FAST step and the one-kernel-per-operator FAST step give bit-identical
+    F2 and CFL limits (same per-cell arithmetic, different kernels, launch shapes and staging); (ii) flags 5: rsg_ram_run_host
+    (12 pipelined chunks) equals the three calls bit for bit; (iii) F2 stays positive and finite, J = NT repeats J = 1; (iv) a checksum of
+    checksums: the SETRC the device returns equals the moment recomputed on the host from the returned F2
+    (src/ModRamRun.f90:246-253) to 1e-11."""
+    from ramscb_b200 import host
+    g = grids.build_grids(NR=dims[0], NT=dims[1], NE=dims[2], energy_refine=dims[3])
+    inp = synthetic.make_inputs(g, f2_kind="noisy", inductive=True)
+    D = synthetic.synthetic_daa(g, inp)
+    res = {}
+    for name, flags in (("unfused", 0), ("fused0", 0), ("fused", 5), ("host", 5)):
+        gpu = host.RamGpu(g, mode=host.MODE_FAST)
+        gpu.set_inputs(inp)
+        gpu.set_diffcoef(1, D)
+        gpu.set_diffcoef(2, D)
+        gpu.use_fused(name != "unfused")
+        if name == "host":
+            F = inp.F2.copy(order="F")
+            out = gpu.ram_run_host(F, 5.0, DtsMin=1.0, flags=flags)
+        else:
+            out = gpu.ram_run(5.0, DtsMin=1.0, flags=flags)
+            F = gpu.f2_d2h()
+        res[name] = (F, out)
+        gpu.close()
+    Fu, ou = res.pop("unfused")
+    F0, o0 = res.pop("fused0")
+    # (with WPADIF the fused stage applies tabulated Thomas factors: bit-identity holds for the default operator set)
+    assert np.array_equal(Fu, F0), f"fused vs unfused: {int((Fu != F0).sum())} of {Fu.size} cells differ"
+    assert np.array_equal(ou["DtDrift"], o0["DtDrift"]) and ou["DtsNext"] == o0["DtsNext"]
+    del Fu, F0
+    Ff, of = res["fused"]
+    Fh, oh = res["host"]
+    assert np.array_equal(Ff, Fh) and np.array_equal(of["SETRC"], oh["SETRC"]) and np.array_equal(of["PPERT"], oh["PPERT"])
+    assert np.all(np.isfinite(Ff)) and Ff.min() > 0.0
+    assert np.array_equal(Ff[:, :, -1], Ff[:, :, 0])
+    assert not np.array_equal(Ff, inp.F2)
+    # SUMRC on the host: sum over I = 2..NR, J = 1..NT-1, K = 2..NE, L = 2..NPA of F2 * WE(K) * WMU(L) * EKEV(K)
+    w = (g.WE[1:g.NE] * g.EKEV[1:g.NE])[:, None] * g.WMU[1:g.NPA][None, :]
+    for s in range(g.nS):
+        want = float(np.einsum("ijkl,kl->", Ff[s, 1:, :-1, 1:, 1:], w))
+        assert abs(of["SETRC"][s] - want) <= 1e-11 * abs(want), (s, of["SETRC"][s], want)
