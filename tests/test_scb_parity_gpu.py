@@ -259,7 +259,8 @@ def test_sor_color4_converged_fields(oracle_built):
     assert np.max(np.abs(a - b) / np.abs(b)) <= 1e-8
 
 
-@pytest.mark.parametrize("grid", [SMALL, dict(nthe=101, npsi=45, nzeta=97, warp=0.2), dict(nthe=75, npsi=30, nzeta=64, warp=0.25)])
+@pytest.mark.parametrize("grid", [SMALL, dict(nthe=101, npsi=45, nzeta=97, warp=0.2), dict(nthe=75, npsi=30, nzeta=64, warp=0.25),
+                                  dict(nthe=201, npsi=89, nzeta=97, warp=0.2)])     # the last: 4 x the default grid (configs[4])
 def test_sor_cluster_matches_single_cta(grid):
     """The cluster/distributed-shared-memory SOR kernel (coefficients resident on chip, halo rows
     pushed between the CTAs of a cluster) keeps the per-point arithmetic and the colour order of
