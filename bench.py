@@ -713,6 +713,19 @@ def hi_metrics(device):
     return out
 
 
+def coupled_cycle_metrics():
+    """BASELINE configs[4]'s physics in miniature: one coupled RAM <-> SCB cycle composed from the device entry points on ONE
+    GPU at the default grids (scripts/time_coupled_cycle.py: 300 s of RAM steps -> pressure -> scb_run -> computehI -> new
+    fields into the RAM state, three consecutive cycles; wall clock per phase).  The last cycle is reported."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "time_coupled_cycle.py")], capture_output=True, text=True, timeout=120)
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    out = dict(d["cycles"][-1])
+    out["cycles_run"] = len(d["cycles"])
+    out["all_cycles_SORFail_0"] = all(c["SORFail"] == 0 for c in d["cycles"])
+    out["F2_finite"] = d["F2_finite"]
+    return out
+
+
 def extras_main(device):
     """`bench.py --extras-only`: informational measurements beside the headline line (run by the N = 1 bench in a
     child process, so that nothing here can take the headline down).  One JSON object on stdout."""
@@ -722,7 +735,8 @@ def extras_main(device):
             ("ram_default_coulomb", lambda: time_ram_step("default", 2, 10, 3, device)),
             ("scb_alpha_zeta_protocol_one_rank", lambda: scb_zeta_metrics(device)),
             ("scb_run_configs3", lambda: scb_run_metrics(device)),
-            ("computehI_integrals", lambda: hi_metrics(device)))
+            ("computehI_integrals", lambda: hi_metrics(device)),
+            ("coupled_cycle_default_grids", lambda: coupled_cycle_metrics()))
     for name, fn in jobs:
         t0 = time.perf_counter()
         try:
@@ -909,6 +923,8 @@ def main():
             line["extras"] = json.loads(tag[-1][len("EXTRAS_JSON "):]) if tag else {"error": (r2.stderr or r2.stdout)[-300:]}
             if line.get("roofline") is not None and "scb_run_configs3" in line["extras"]:
                 line["roofline"].setdefault("scb_sor", {})["scb_run_configs3"] = line["extras"]["scb_run_configs3"]
+            if line.get("roofline") is not None and "coupled_cycle_default_grids" in line["extras"]:
+                line["roofline"].setdefault("scb_sor", {})["coupled_cycle_default_grids"] = line["extras"]["coupled_cycle_default_grids"]
         except Exception as e:
             line["extras"] = {"error": str(e)[:300]}
     if rank == 0:
