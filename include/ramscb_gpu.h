@@ -196,7 +196,7 @@ int rsg_anisch(rsg_ram* h, int S, double* PPERT_S, double* PPART_S);     /* :343
  * LSCOE,LSCSC; SETRC(nS); PPERT,PPART(nS,NR,NT).  Returns DtsNext in *dts_next. */
 int rsg_ram_run(rsg_ram* h, double DTs, double DtsMin, double T, int flags, double* dts_next, double* DtDrift,
                 double* losses, double* SETRC, double* PPERT, double* PPART);
-/* The same step with F2 coming from and returning to the HOST array -- what the routine-level drop-in does every step
+/* The same step (src/ModRamRun.f90:64-222) with F2 coming from and returning to the HOST array -- what the routine-level drop-in does every step
  * (rsg_ram_f2_h2d, rsg_ram_run, rsg_ram_f2_d2h) in one call, pipelined over chunks of pitch angles: the upload of a chunk
  * runs beside the layout conversion and DRIFTR / DRIFTP of the previous one, and after the column kernel each chunk is
  * downloaded as soon as its reverse DRIFTP / DRIFTR are done.  F2 (nS,NR,NT,NE,NPA) in / out, best page-locked
